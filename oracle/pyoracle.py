@@ -1,0 +1,359 @@
+"""ctypes front end of the CPU oracle (oracle/rmcrt_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  The product (uintah_b200/)
+never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "librmcrt_oracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle (and oracle/_ref when /root/reference is present)."""
+    src = os.path.join(_HERE, "rmcrt_oracle.cpp")
+    stale = (not os.path.exists(_LIB_PATH)) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src)
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "all"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+class Params(C.Structure):
+    _fields_ = [("nDivQRays", C.c_int), ("nFluxRays", C.c_int), ("threshold", C.c_double),
+                ("allowReflect", C.c_int), ("CCRays", C.c_int), ("isSeedRandom", C.c_int),
+                ("solveDivQ", C.c_int), ("solveBoundaryFlux", C.c_int), ("fixedRandom", C.c_int),
+                ("flowCell", C.c_int), ("dataOnionFluxFlowGuard", C.c_int)]
+
+
+class CLevel(C.Structure):
+    _fields_ = [("abskg", C.c_void_p), ("sigmaT4", C.c_void_p), ("cellType", C.c_void_p),
+                ("isFloat", C.c_int), ("lo", C.c_int * 3), ("hi", C.c_int * 3),
+                ("dx", C.c_double * 3), ("anchor", C.c_double * 3), ("refineRatio", C.c_int * 3),
+                ("interiorLo", C.c_int * 3), ("interiorHi", C.c_int * 3)]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.oracle_default_params.argtypes = [C.POINTER(Params)]
+    return _lib
+
+
+def default_params(**kw) -> Params:
+    p = Params()
+    lib().oracle_default_params(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def _i3(v):
+    return (C.c_int * 3)(*[int(x) for x in v])
+
+
+def _d3(v):
+    return (C.c_double * 3)(*[float(x) for x in v])
+
+
+class Level:
+    """A level's property arrays, numpy [z][y][x] (x fastest) over window [lo,hi)."""
+
+    def __init__(self, abskg, sigmaT4, cellType, lo, hi, dx, anchor=(0, 0, 0), refine_ratio=(1, 1, 1),
+                 interior_lo=None, interior_hi=None):
+        self.abskg = np.ascontiguousarray(abskg)
+        self.sigmaT4 = np.ascontiguousarray(sigmaT4, dtype=self.abskg.dtype)
+        self.cellType = np.ascontiguousarray(cellType, dtype=np.int32)
+        assert self.abskg.dtype in (np.float32, np.float64)
+        self.lo = tuple(int(x) for x in lo)
+        self.hi = tuple(int(x) for x in hi)
+        shape = (self.hi[2] - self.lo[2], self.hi[1] - self.lo[1], self.hi[0] - self.lo[0])
+        assert self.abskg.shape == shape and self.sigmaT4.shape == shape and self.cellType.shape == shape, \
+            (self.abskg.shape, shape)
+        self.dx = tuple(float(x) for x in dx)
+        self.anchor = tuple(float(x) for x in anchor)
+        self.rr = tuple(int(x) for x in refine_ratio)
+        self.interior_lo = tuple(interior_lo) if interior_lo is not None else tuple(x + 1 for x in self.lo)
+        self.interior_hi = tuple(interior_hi) if interior_hi is not None else tuple(x - 1 for x in self.hi)
+
+    @property
+    def is_float(self):
+        return self.abskg.dtype == np.float32
+
+    def c(self) -> CLevel:
+        L = CLevel()
+        L.abskg = self.abskg.ctypes.data
+        L.sigmaT4 = self.sigmaT4.ctypes.data
+        L.cellType = self.cellType.ctypes.data
+        L.isFloat = 1 if self.is_float else 0
+        L.lo = _i3(self.lo); L.hi = _i3(self.hi)
+        L.dx = _d3(self.dx); L.anchor = _d3(self.anchor)
+        L.refineRatio = _i3(self.rr)
+        L.interiorLo = _i3(self.interior_lo); L.interiorHi = _i3(self.interior_hi)
+        return L
+
+
+# ---------------------------------------------------------------- MT19937
+def mt_u32(seed, n):
+    out = np.empty(n, np.uint32)
+    lib().oracle_mt_u32(C.c_uint32(seed), n, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def mt_rand(seed, n):
+    out = np.empty(n, np.float64)
+    lib().oracle_mt_rand(C.c_uint32(seed), n, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def mt_randDblExc(seed, n):
+    out = np.empty(n, np.float64)
+    lib().oracle_mt_randDblExc(C.c_uint32(seed), n, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+# ---------------------------------------------------------------- problem set-up
+SIGMA = 5.67051e-8  # Ray.cc:165
+
+
+def sigmaT4(temp, dtype=np.float64, sigma=SIGMA):
+    temp = np.ascontiguousarray(temp, dtype=np.float64)
+    out = np.empty(temp.shape, dtype)
+    lib().oracle_sigmaT4(temp.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                         1 if dtype == np.float32 else 0, C.c_int64(temp.size), C.c_double(sigma))
+    return out
+
+
+def burns_christon(N, dtype=np.float64, T_gas=64.804, abskg_wall=1.0, T_wall=0.0, wall_type=8) -> Level:
+    """RMCRT_bm1_1L.ups at resolution N^3: unit cube, one layer of extra cells, cold black walls."""
+    M = N + 2
+    abskg = np.empty((M, M, M), np.float64)
+    temp = np.empty((M, M, M), np.float64)
+    ct = np.empty((M, M, M), np.int32)
+    lib().oracle_burns_christon(N, abskg.ctypes.data_as(C.c_void_p), temp.ctypes.data_as(C.c_void_p),
+                                ct.ctypes.data_as(C.c_void_p), C.c_double(T_gas), C.c_double(abskg_wall),
+                                C.c_double(T_wall), wall_type)
+    s4 = sigmaT4(temp, dtype)
+    return Level(abskg.astype(dtype), s4, ct, (-1, -1, -1), (N + 1, N + 1, N + 1), (1.0 / N,) * 3,
+                 interior_lo=(0, 0, 0), interior_hi=(N, N, N))
+
+
+def parallel_plates(N, dtype=np.float64, T_gas=1500.0, T_wall=1000.0, kappa=1.0, mirror_faces=("x-", "y-"),
+                    wall_type=8, black_abskg=1.0) -> Level:
+    """Benchmark 2 as configured by RMCRT_1L_perf.ups:24-90,108-110: abskg==1, T_m 1500 K, walls 1000 K,
+    listed faces are perfect mirrors (abskg 0), the others black."""
+    M = N + 2
+    abskg = np.full((M, M, M), kappa, np.float64)
+    temp = np.full((M, M, M), T_gas, np.float64)
+    ct = np.full((M, M, M), -1, np.int32)
+    faces = {"x-": (2, 0), "x+": (2, M - 1), "y-": (1, 0), "y+": (1, M - 1), "z-": (0, 0), "z+": (0, M - 1)}
+    for name, (axis, idx) in faces.items():
+        sl = [slice(None)] * 3
+        sl[axis] = idx
+        sl = tuple(sl)
+        ct[sl] = wall_type
+        temp[sl] = T_wall
+    # abskg on walls: black first then mirrors, so shared edges follow the face order x-,x+,y-,y+,z-,z+ of setBC
+    for name in ("x-", "x+", "y-", "y+", "z-", "z+"):
+        axis, idx = faces[name]
+        sl = [slice(None)] * 3
+        sl[axis] = idx
+        abskg[tuple(sl)] = 0.0 if name in mirror_faces else black_abskg
+    s4 = sigmaT4(temp, dtype)
+    return Level(abskg.astype(dtype), s4, ct, (-1, -1, -1), (N + 1, N + 1, N + 1), (1.0 / N,) * 3,
+                 interior_lo=(0, 0, 0), interior_hi=(N, N, N))
+
+
+# ---------------------------------------------------------------- single rays
+def update_sumI(p: Params, lv: Level, direction, ray_origin, origin_cell, max_path=0):
+    cl = lv.c()
+    sumI = C.c_double(0)
+    n = C.c_uint64(0)
+    npath = C.c_int(0)
+    path = np.zeros((max(max_path, 1), 3), np.int32)
+    lib().oracle_updateSumI(C.byref(p), C.byref(cl), _d3(direction), _d3(ray_origin), _i3(origin_cell),
+                            C.byref(sumI), C.byref(n), path.ctypes.data_as(C.c_void_p) if max_path else None,
+                            max_path, C.byref(npath))
+    return sumI.value, n.value, path[:min(npath.value, max_path)]
+
+
+def compute_extents(levels, patch_lo, patch_hi, halo):
+    nl = len(levels)
+    arr = (CLevel * nl)(*[l.c() for l in levels])
+    roiLo = (C.c_int * 3)(); roiHi = (C.c_int * 3)()
+    regLo = (C.c_int * (3 * nl))(); regHi = (C.c_int * (3 * nl))()
+    lib().oracle_computeExtents(arr, nl, _i3(patch_lo), _i3(patch_hi), _i3(halo), roiLo, roiHi, regLo, regHi)
+    return (tuple(roiLo), tuple(roiHi), np.array(regLo).reshape(nl, 3).copy(), np.array(regHi).reshape(nl, 3).copy())
+
+
+def update_sumI_ML(p: Params, levels, roi_lo, roi_hi, region_lo, region_hi, direction, ray_origin, origin_cell,
+                   max_path=0):
+    nl = len(levels)
+    arr = (CLevel * nl)(*[l.c() for l in levels])
+    regLo = np.ascontiguousarray(region_lo, np.int32)
+    regHi = np.ascontiguousarray(region_hi, np.int32)
+    sumI = C.c_double(0)
+    n = C.c_uint64(0)
+    npath = C.c_int(0)
+    path = np.zeros((max(max_path, 1), 4), np.int32)
+    lib().oracle_updateSumI_ML(C.byref(p), arr, nl, _i3(roi_lo), _i3(roi_hi), regLo.ctypes.data_as(C.c_void_p),
+                               regHi.ctypes.data_as(C.c_void_p), _d3(direction), _d3(ray_origin), _i3(origin_cell),
+                               C.byref(sumI), C.byref(n), path.ctypes.data_as(C.c_void_p) if max_path else None,
+                               max_path, C.byref(npath))
+    return sumI.value, n.value, path[:min(npath.value, max_path)]
+
+
+# ---------------------------------------------------------------- patch solves
+def _split(lo, hi, parts):
+    """Split box [lo,hi) into parts[0]*parts[1]*parts[2] patches like <patches> does."""
+    edges = []
+    for d in range(3):
+        n = hi[d] - lo[d]
+        e = [lo[d] + (n * i) // parts[d] for i in range(parts[d] + 1)]
+        edges.append(e)
+    out = []
+    for k in range(parts[2]):
+        for j in range(parts[1]):
+            for i in range(parts[0]):
+                out.append(((edges[0][i], edges[1][j], edges[2][k]), (edges[0][i + 1], edges[1][j + 1], edges[2][k + 1])))
+    return out
+
+
+def ray_trace(p: Params, lv: Level, patch_lo=None, patch_hi=None, seed=1, patches=(1, 1, 1), threads=1):
+    """Ray::rayTrace over [patch_lo,patch_hi) (default: interior), split into `patches` tasks.
+    Task t uses MT seed `seed + t` when isSeedRandom.  Returns dict(divQ, radiationVolq, boundFlux, steps, fluxSteps);
+    output arrays cover the whole level window (extra cells stay 0)."""
+    patch_lo = lv.interior_lo if patch_lo is None else tuple(patch_lo)
+    patch_hi = lv.interior_hi if patch_hi is None else tuple(patch_hi)
+    shape = lv.abskg.shape
+    divQ = np.zeros(shape, np.float64)
+    volq = np.zeros(shape, np.float64)
+    bflux = np.zeros(shape + (7,), np.float64)
+    cl = lv.c()
+    tasks = _split(patch_lo, patch_hi, patches)
+    steps = [0] * len(tasks)
+    fsteps = [0] * len(tasks)
+
+    def run(t):
+        lo, hi = tasks[t]
+        n = C.c_uint64(0)
+        nf = C.c_uint64(0)
+        lib().oracle_rayTrace(C.byref(p), C.byref(cl), _i3(lo), _i3(hi), C.c_uint32(seed + t),
+                              divQ.ctypes.data_as(C.c_void_p), volq.ctypes.data_as(C.c_void_p),
+                              bflux.ctypes.data_as(C.c_void_p), _i3(lv.lo), _i3(lv.hi), C.byref(n), C.byref(nf))
+        steps[t] = n.value
+        fsteps[t] = nf.value
+
+    if threads > 1 and len(tasks) > 1:
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            list(ex.map(run, range(len(tasks))))
+    else:
+        for t in range(len(tasks)):
+            run(t)
+    return dict(divQ=divQ, radiationVolq=volq, boundFlux=bflux, steps=sum(steps), fluxSteps=sum(fsteps))
+
+
+def ray_trace_data_onion(p: Params, levels, halo, patch_lo=None, patch_hi=None, seed=1, patches=(1, 1, 1), threads=1):
+    """Ray::rayTrace_dataOnion over the fine level's interior split into `patches` fine patches."""
+    fine = levels[-1]
+    patch_lo = fine.interior_lo if patch_lo is None else tuple(patch_lo)
+    patch_hi = fine.interior_hi if patch_hi is None else tuple(patch_hi)
+    nl = len(levels)
+    arr = (CLevel * nl)(*[l.c() for l in levels])
+    shape = fine.abskg.shape
+    divQ = np.zeros(shape, np.float64)
+    volq = np.zeros(shape, np.float64)
+    bflux = np.zeros(shape + (7,), np.float64)
+    tasks = _split(patch_lo, patch_hi, patches)
+    steps = [0] * len(tasks)
+    fsteps = [0] * len(tasks)
+
+    def run(t):
+        lo, hi = tasks[t]
+        n = C.c_uint64(0)
+        nf = C.c_uint64(0)
+        lib().oracle_rayTrace_dataOnion(C.byref(p), arr, nl, _i3(lo), _i3(hi), _i3(halo), C.c_uint32(seed + t),
+                                        divQ.ctypes.data_as(C.c_void_p), volq.ctypes.data_as(C.c_void_p),
+                                        bflux.ctypes.data_as(C.c_void_p), _i3(fine.lo), _i3(fine.hi),
+                                        C.byref(n), C.byref(nf))
+        steps[t] = n.value
+        fsteps[t] = nf.value
+
+    if threads > 1 and len(tasks) > 1:
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            list(ex.map(run, range(len(tasks))))
+    else:
+        for t in range(len(tasks)):
+            run(t)
+    return dict(divQ=divQ, radiationVolq=volq, boundFlux=bflux, steps=sum(steps), fluxSteps=sum(fsteps))
+
+
+def coarsen_level(fine: Level, rr=(4, 4, 4), logic=0, wall_abskg=None, wall_sigmaT4=None, wall_type=None) -> Level:
+    """Build the coarse level the Data-Onion needs: Ray::coarsen_Q interior average of abskg and sigmaT4 and
+    Ray::computeCellType; coarse extra cells are then filled the way sched_setBoundaryConditions does for
+    Dirichlet walls (taken from the fine level's extra-cell corner value unless given)."""
+    fl, fh = fine.interior_lo, fine.interior_hi
+    cil = tuple(fl[d] // rr[d] for d in range(3))
+    cih = tuple(fh[d] // rr[d] for d in range(3))
+    clo = tuple(x - 1 for x in cil)
+    chi = tuple(x + 1 for x in cih)
+    shape = (chi[2] - clo[2], chi[1] - clo[1], chi[0] - clo[0])
+    dt = fine.abskg.dtype
+    ab = np.zeros(shape, dt)
+    s4 = np.zeros(shape, dt)
+    ct = np.zeros(shape, np.int32)
+    isf = 1 if fine.is_float else 0
+    for src, dst in ((fine.abskg, ab), (fine.sigmaT4, s4)):
+        lib().oracle_coarsen_interior(src.ctypes.data_as(C.c_void_p), isf, _i3(fine.lo), _i3(fine.hi),
+                                      dst.ctypes.data_as(C.c_void_p), _i3(clo), _i3(chi), _i3(cil), _i3(cih), _i3(rr))
+    lib().oracle_computeCellType(fine.cellType.ctypes.data_as(C.c_void_p), _i3(fine.lo), _i3(fine.hi),
+                                 ct.ctypes.data_as(C.c_void_p), _i3(clo), _i3(chi), _i3(cil), _i3(cih), _i3(rr), logic)
+    # extra cells: copy the fine level's face values (uniform Dirichlet in all BASELINE decks)
+    def face_fill(dst, src, override):
+        M = dst.shape
+        for axis, idx, fidx in ((2, 0, 0), (2, M[2] - 1, -1), (1, 0, 0), (1, M[1] - 1, -1), (0, 0, 0), (0, M[0] - 1, -1)):
+            sl = [slice(None)] * 3
+            sl[axis] = idx
+            fsl = [1, 1, 1]
+            fsl[axis] = fidx
+            dst[tuple(sl)] = src[tuple(fsl)] if override is None else override
+    face_fill(ab, fine.abskg, wall_abskg)
+    face_fill(s4, fine.sigmaT4, wall_sigmaT4)
+    face_fill(ct, fine.cellType, wall_type)
+    cdx = tuple(fine.dx[d] * rr[d] for d in range(3))
+    return Level(ab, s4, ct, clo, chi, cdx, fine.anchor, (1, 1, 1), cil, cih)
+
+
+# ---------------------------------------------------------------- golden: Burns & Christon centre line
+# parametricStudies/postProcessTools/RMCRT.m:22-35 (x = 0:1/40:1, symmetric about 0.5)
+_BC_HALF = [3.07561, 2.94305, 2.81667, 2.69362, 2.57196, 2.45069, 2.32896, 2.20616, 2.08181, 1.95549, 1.82691,
+            1.69575, 1.56180, 1.42485, 1.28473, 1.1413, .99443, .84405, .6901, .53255, .37165]
+
+
+def burns_christon_exact(x_cc):
+    """pchip interpolation of the exact centre line to cell centres (RMCRT.m:37-38)."""
+    from scipy.interpolate import PchipInterpolator
+    xs = np.linspace(0.0, 1.0, 41)
+    ys = -np.array(_BC_HALF[::-1][:-1] + _BC_HALF)
+    return PchipInterpolator(xs, ys)(np.asarray(x_cc))
+
+
+def centreline_L2(divQ_level, N):
+    """L2 = sqrt(sum((sim-exact)^2)/n) along the x centre line (RMCRT.m:387-413); divQ_level has the (N+2)^3 window."""
+    mid = N // 2
+    line = divQ_level[mid + 1, mid + 1, 1:N + 1]
+    x = (np.arange(N) + 0.5) / N
+    ex = burns_christon_exact(x)
+    return float(np.sqrt(np.sum((line - ex) ** 2) / N)), line, ex

@@ -1,0 +1,127 @@
+/*
+ * rmcrt_oracle.h -- CPU restatement of the reference RMCRT hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product path (uintah_b200/, include/)
+ * may include, link or call this.  Only tests/, __graft_entry__.smoke() and the
+ * cpu_baseline / --impl reference legs of bench.py use it, and there only as the
+ * checker / the CPU baseline.
+ *
+ * Every function cites the reference file:line it follows (paths relative to
+ * /root/reference/src; RMCRT/ = CCA/Components/Models/Radiation/RMCRT/).
+ *
+ * Pinning (see DESIGN.md "Oracle"):
+ *   - MT19937 stream + rand()/randDblExc() conversions: checked against the
+ *     reference's own Core/Math/MersenneTwister.h compiled from where it lies
+ *     (oracle/_ref, built by oracle/Makefile) and against tests/golden/mt19937.json
+ *     generated from it.
+ *   - Burns & Christon exact centre line (parametricStudies/postProcessTools/RMCRT.m:22-38).
+ *   - Modest parallel-plate closed form (RMCRT.m:44-94).
+ *   The bit-level results of Ray.cc itself are NOT pinned in the reference tree
+ *   (gold-standard UDAs live outside the repo) and sus cannot be built here.
+ */
+#ifndef RMCRT_ORACLE_H
+#define RMCRT_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* mirrors the statics/members read by the trace: Ray.h:162-181, RMCRTCommon.h:287-293 */
+typedef struct oracle_params {
+  int    nDivQRays;          /* Ray.cc:162 default 10   */
+  int    nFluxRays;          /* Ray.cc:168 default 1    */
+  double threshold;          /* Ray.cc:163 default 0.01 */
+  int    allowReflect;       /* Ray.cc:170 default true */
+  int    CCRays;             /* Ray.cc:167 default false*/
+  int    isSeedRandom;       /* Ray.cc:164 default true */
+  int    solveDivQ;          /* Ray.cc:171 default true */
+  int    solveBoundaryFlux;  /* Ray.cc:166 default false*/
+  int    fixedRandom;        /* MersenneTwister.h:93 FIXED_RANDOM_NUM: every draw == 0.3 */
+  int    flowCell;           /* RMCRTCommon.cc:116, hard-wired -1 */
+  int    dataOnionFluxFlowGuard; /* 0 = reference (Ray.cc:1098-1107 has no flow-cell guard) */
+} oracle_params;
+
+/* one level's property arrays: x-fastest Array3 window [lo,hi) (Array3Data.h:93,212-220) */
+typedef struct oracle_level {
+  const void*    abskg;      /* float or double, see isFloat */
+  const void*    sigmaT4;    /* sigma T^4 / pi */
+  const int32_t* cellType;
+  int    isFloat;
+  int    lo[3], hi[3];       /* array window, hi exclusive (includes extra cells) */
+  double dx[3];
+  double anchor[3];          /* Level::m_anchor (Level.cc:473-477) */
+  int    refineRatio[3];     /* ratio to the next COARSER level (Level.cc:1285-1307) */
+  int    interiorLo[3], interiorHi[3]; /* findInteriorCellIndexRange */
+} oracle_level;
+
+void oracle_default_params(oracle_params* p);
+
+/* ---- MT19937 (MersenneTwister.h:172-258,339-370) ---- */
+void oracle_mt_u32(uint32_t seed, int n, uint32_t* out);
+void oracle_mt_rand(uint32_t seed, int n, double* out);        /* rand()       [0,1] */
+void oracle_mt_randDblExc(uint32_t seed, int n, double* out);  /* randDblExc() (0,1) */
+
+/* ---- one ray, single level: RMCRTCommon::updateSumI (RMCRTCommon.cc:607-904) ----
+ * path: optional [maxPath][3] buffer receiving every `cur` visited; nPath receives the count. */
+void oracle_updateSumI(const oracle_params* p, const oracle_level* lv,
+                       const double dir[3], const double rayOrigin[3], const int originCell[3],
+                       double* sumI, uint64_t* nRaySteps,
+                       int* path, int maxPath, int* nPath);
+
+/* ---- one ray, multi level: Ray::updateSumI_ML (Ray.cc:2349-2627) ---- */
+void oracle_updateSumI_ML(const oracle_params* p, const oracle_level* levels, int maxLevels,
+                          const int roiLo[3], const int roiHi[3],
+                          const int* regionLo /*[maxLevels][3]*/, const int* regionHi,
+                          const double dir[3], const double rayOrigin[3], const int originCell[3],
+                          double* sumI, uint64_t* nRaySteps,
+                          int* path /*[maxPath][4] = i,j,k,L*/, int maxPath, int* nPath);
+
+/* ---- Ray::rayTrace<T> for one patch [patchLo,patchHi) (Ray.cc:513-818) ----
+ * Outputs are x-fastest arrays over window [outLo,outHi); they must be zero-initialised
+ * by the caller (Ray.cc:581-587).  boundFlux = Stencil7 AoS, 7 doubles/cell (Stencil7.h:38-76).
+ * mtSeed: the per-task MTRand seed when isSeedRandom (replaces hash(time,clock), Ray.cc:539). */
+void oracle_rayTrace(const oracle_params* p, const oracle_level* lv,
+                     const int patchLo[3], const int patchHi[3], uint32_t mtSeed,
+                     double* divQ, double* radiationVolq, double* boundFlux,
+                     const int outLo[3], const int outHi[3],
+                     uint64_t* nRaySteps, uint64_t* nFluxRaySteps);
+
+/* ---- Ray::computeExtents, patch_based ROI (Ray.cc:1279-1358) ---- */
+void oracle_computeExtents(const oracle_level* levels, int maxLevels,
+                           const int patchLo[3], const int patchHi[3], const int haloCells[3],
+                           int roiLo[3], int roiHi[3], int* regionLo, int* regionHi);
+
+/* ---- Ray::rayTrace_dataOnion<T> for one fine patch (Ray.cc:943-1274) ----
+ * levels[maxLevels-1] is the fine level; its arrays must cover at least the ROI. */
+void oracle_rayTrace_dataOnion(const oracle_params* p, const oracle_level* levels, int maxLevels,
+                               const int patchLo[3], const int patchHi[3], const int haloCells[3],
+                               uint32_t mtSeed,
+                               double* divQ, double* radiationVolq, double* boundFlux,
+                               const int outLo[3], const int outHi[3],
+                               uint64_t* nRaySteps, uint64_t* nFluxRaySteps);
+
+/* ---- property preparation ---- */
+/* RMCRTCommon::sigmaT4<T> (RMCRTCommon.cc:304-343): out = (sigma/pi) T^2 T^2 */
+void oracle_sigmaT4(const double* temp, void* out, int isFloat, int64_t n, double sigma);
+/* RMCRT_Test::initialize benchmark 1 (RMCRT_Test.cc:653-680) + Dirichlet walls of RMCRT_bm1_1L.ups:28-93.
+ * Fills (N+2)^3 arrays with window lo=-1: abskg, temperature ("color"), cellType. */
+void oracle_burns_christon(int N, double* abskg, double* temperature, int32_t* cellType,
+                           double T_gas, double abskg_wall, double T_wall, int wallType);
+/* Ray::coarsen_Q<T> interior average (Ray.cc:2103-2145 via fineToCoarseOperator, computesAve) */
+void oracle_coarsen_interior(const void* fine, int isFloat, const int fLo[3], const int fHi[3],
+                             void* coarse, const int cLo[3], const int cHi[3],
+                             const int cIntLo[3], const int cIntHi[3], const int rr[3]);
+/* Ray::computeCellType (Ray.cc:2272-2345): logic 0 = ROUNDUP, 1 = ROUNDDOWN */
+void oracle_computeCellType(const int32_t* fine, const int fLo[3], const int fHi[3],
+                            int32_t* coarse, const int cLo[3], const int cHi[3],
+                            const int cIntLo[3], const int cIntHi[3], const int rr[3], int logic);
+
+/* Level::mapCellToCoarser including its negative-index behaviour (Level.cc:1285-1307) */
+void oracle_mapCellToCoarser(const int idx[3], const int rr[3], int out[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
