@@ -1,0 +1,216 @@
+/*
+ * rmcrt_b200.h -- C ABI of the B200-native RMCRT divQ / boundary-flux solve.
+ *
+ * This is the drop-in boundary for ONE hot path of Uintah: the body of the tasks
+ * `Ray::rayTrace<T>` and `Ray::rayTrace_dataOnion<T>` registered by
+ * `Ray::sched_rayTrace` / `Ray::sched_rayTrace_dataOnion`.  The host-side `Ray` /
+ * `RMCRTCommon` classes (uintah_b200/host/) keep the reference's plugin surface and
+ * call these entry points with the raw x-fastest Array3 buffers they obtain from the
+ * DataWarehouse (getLevel / getRegion / allocateAndPut).
+ *
+ * Reference paths: /root/reference/src; RMCRT/ = CCA/Components/Models/Radiation/RMCRT/.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types; every function returns 0 on
+ *     success or a negative rmcrt_status, with text in rmcrt_last_error().
+ *   - cell boxes are [lo,hi) IntVector triples (x,y,z); arrays are x-fastest over their
+ *     window, exactly the memory layout of Uintah's Array3 (Array3Data.h:93,212-220).
+ *   - "host" entry points take host pointers and do the H2D/D2H copies themselves;
+ *     "_device" entry points take device pointers of the context's device.
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  Calls are
+ *     asynchronous with respect to the host unless stated otherwise.
+ *   - the library never falls back to a CPU path: without a CUDA device every call fails.
+ */
+#ifndef RMCRT_B200_H
+#define RMCRT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RMCRT_ABI_VERSION 1
+#define RMCRT_MAX_LEVELS 8
+
+typedef struct rmcrt_ctx rmcrt_ctx;
+
+typedef enum rmcrt_status {
+  RMCRT_OK = 0,
+  RMCRT_ERR_INVALID = -1,      /* bad argument (ProblemSetupException on the C++ side) */
+  RMCRT_ERR_CUDA = -2,         /* CUDA runtime error                                    */
+  RMCRT_ERR_NONPHYSICAL = -3,  /* non-finite abskg/sigmaT4 (InternalError, RMCRTCommon.cc:267-271) */
+  RMCRT_ERR_OPEN_DOMAIN = -4,  /* a flow cell lies on the outer layer of a level: rays could leave it */
+  RMCRT_ERR_NCCL = -5
+} rmcrt_status;
+
+/* Mirrors the members/statics read by the trace tasks: Ray.h:162-181, RMCRTCommon.h:287-293,
+ * with the .ups defaults of Ray::problemSetup (Ray.cc:162-173). */
+typedef struct rmcrt_params {
+  int32_t  nDivQRays;          /* <nDivQRays>          10    */
+  int32_t  nFluxRays;          /* <nFluxRays>          1     */
+  double   threshold;          /* <Threshold>          0.01  */
+  double   sigma;              /* <StefanBoltzmann>    5.67051e-8 */
+  int32_t  allowReflect;       /* <allowReflect>       true  */
+  int32_t  CCRays;             /* <CCRays>             false */
+  int32_t  solveDivQ;          /* <solveDivQ>          true  */
+  int32_t  solveBoundaryFlux;  /* <solveBoundaryFlux>  false */
+  int32_t  isSeedRandom;       /* <randomSeed> true: Philox4x32-10 keyed (cell, ray, timestep);
+                                  false: the reference's per-ray MT19937 reseed (i+j+k)*iRay+1
+                                  (RMCRTCommon.cc:504-506), reproducing its regression mode */
+  int32_t  flowCell;           /* -1, RMCRTCommon.cc:116 */
+  int32_t  haloCells[3];       /* <haloCells> [10,10,10], Data-Onion ROI = patch +- halo */
+  int32_t  cellTypeCoarsenLogic; /* 0 ROUNDUP (default, Ray.h:194), 1 ROUNDDOWN */
+  uint64_t seed;               /* mixed into the Philox key (randomSeed=true) */
+  /* ---- implementation knobs (no counterpart in the reference) ---- */
+  int32_t  marchPrecision;     /* 0 = FP32 march (production), 1 = FP64 march (parity debugging) */
+  int32_t  rayCoherence;       /* 1 = the 32 origin cells of a warp share one direction per ray index
+                                  (warp-coherent batching); 0 = independent direction per (cell, ray) */
+  int32_t  skipZeroWeightLegs; /* 1 = end a ray once fs==0 and no non-flow cell can emit (exact);
+                                  0 = march every leg the reference marches */
+  int32_t  fixedRandom;        /* FIXED_RANDOM_NUM (MersenneTwister.h:93): every draw = 0.3 */
+  int32_t  l2Persist;          /* 1 = pin the level records in L2 with an access-policy window */
+  int32_t  warpsPerTile;       /* 0 = auto; rays of a 32-cell tile are split over this many warps */
+  int32_t  reserved[4];
+} rmcrt_params;
+
+/* geometry of one level (Level.cc:473-477, 1285-1307) */
+typedef struct rmcrt_level_desc {
+  int32_t lo[3], hi[3];                  /* whole index range incl. extra cells (findCellIndexRange) */
+  int32_t interiorLo[3], interiorHi[3];  /* findInteriorCellIndexRange */
+  double  dx[3];                         /* dCell() */
+  double  anchor[3];                     /* position of index (0,0,0)'s low corner */
+  int32_t refineRatio[3];                /* ratio to the next coarser level; [1,1,1] on level 0 */
+} rmcrt_level_desc;
+
+typedef struct rmcrt_counters {
+  uint64_t nRaySteps;        /* executed divQ ray-cell steps  ("Size", Ray.cc:807)        */
+  uint64_t nFluxRaySteps;    /* executed boundary-flux steps  (Ray.cc:1262)               */
+  uint64_t nDivQCells;       /* flow cells that received a divQ                           */
+  uint64_t nFluxCells;       /* cells with boundFlux.p == 1                               */
+} rmcrt_counters;
+
+/* ------------------------------------------------------------------ life cycle */
+int  rmcrt_abi_version(void);
+/* sizeof of the ABI structs as compiled (0 rmcrt_params, 1 rmcrt_level_desc, 2 rmcrt_counters): lets a foreign-language
+ * binding verify its struct layout at load time */
+size_t rmcrt_struct_size(int which);
+void rmcrt_default_params(rmcrt_params* p);
+/* replaces the per-process Ray instance state; device = CUDA ordinal (patch->GPU map of
+ * GPUGridVariableInfo.cc:610-632 is the caller's business). */
+int  rmcrt_create(int device, const rmcrt_params* p, rmcrt_ctx** out);
+int  rmcrt_set_params(rmcrt_ctx* ctx, const rmcrt_params* p);
+void rmcrt_destroy(rmcrt_ctx* ctx);
+const char* rmcrt_last_error(const rmcrt_ctx* ctx);   /* ctx may be NULL: last create() error */
+
+/* ------------------------------------------------------------------ property levels
+ * Replaces getLevel()/getRegion() + the H2D staging of DetailedTask::initiateH2DCopies
+ * (DetailedTask.cc:1217, 1326-1340).  Levels are indexed as in Uintah (0 = coarsest).
+ * recordKind: 0 = {float abskg|wall-sign, float sigmaT4OverPi} (8 B, production),
+ *             1 = {double,double} (16 B, FP64 parity march). */
+int rmcrt_define_level(rmcrt_ctx* ctx, int L, const rmcrt_level_desc* desc, int recordKind);
+
+/* Pack abskg / sigmaT4OverPi / cellType given on window [srcLo,srcHi) into the level's device
+ * records (replaces the three getLevel gathers of Ray.cc:549-553 and the slim-variant pack task
+ * RMCRTCommon.cc:378-427).  isFloat selects T = float|double of the two property arrays. */
+int rmcrt_upload_level(rmcrt_ctx* ctx, int L, const void* abskg, const void* sigmaT4OverPi,
+                       const int32_t* cellType, int isFloat,
+                       const int32_t srcLo[3], const int32_t srcHi[3], void* stream);
+int rmcrt_pack_level_device(rmcrt_ctx* ctx, int L, const void* d_abskg, const void* d_sigmaT4OverPi,
+                            const int32_t* d_cellType, int isFloat,
+                            const int32_t srcLo[3], const int32_t srcHi[3], void* stream);
+/* Validate a fully populated level (blocking): non-finite properties, open domain; also decides
+ * whether zero-weight legs may be skipped (no emitting non-flow cell). */
+int rmcrt_finalize_level(rmcrt_ctx* ctx, int L, void* stream);
+/* Device address/size of the packed records (for the NCCL all-gather of the replicated level). */
+int rmcrt_level_records(rmcrt_ctx* ctx, int L, void** d_records, size_t* bytes, size_t* recordBytes);
+
+/* ------------------------------------------------------------------ the hot path
+ * rmcrt_trace_divq[_device]: body of Ray::rayTrace<T> for one patch (Ray.cc:556-788):
+ * boundary flux (if solveBoundaryFlux) then divQ (if solveDivQ) for cells [patchLo,patchHi) of level L.
+ * Outputs are x-fastest over [outLo,outHi) (the patch's allocateAndPut window incl. extra cells):
+ *   divQ, radiationVolq : double per cell;  boundFlux : Stencil7 {w,e,s,n,b,t,p} = 7 doubles per cell.
+ * zeroInit != 0 reproduces `modifies_divQ == false` (Ray.cc:577-587): the whole window is zeroed first.
+ * boundFlux may be NULL when solveBoundaryFlux is off.  timestep enters the Philox counter. */
+int rmcrt_trace_divq_device(rmcrt_ctx* ctx, int L, const int32_t patchLo[3], const int32_t patchHi[3],
+                            double* d_divQ, double* d_radiationVolq, double* d_boundFlux,
+                            const int32_t outLo[3], const int32_t outHi[3],
+                            int zeroInit, uint64_t timestep, void* stream);
+/* same with host output buffers; blocks until the results are in host memory */
+int rmcrt_trace_divq(rmcrt_ctx* ctx, int L, const int32_t patchLo[3], const int32_t patchHi[3],
+                     double* divQ, double* radiationVolq, double* boundFlux,
+                     const int32_t outLo[3], const int32_t outHi[3],
+                     int zeroInit, uint64_t timestep, void* stream);
+
+/* Body of Ray::rayTrace_dataOnion<T> for one fine patch (Ray.cc:1036-1241) with ROI_extents
+ * patch_based: ROI = patch +- haloCells clamped to the fine level (Ray::computeExtents, 1279-1358).
+ * All levels 0..maxLevels-1 must have been uploaded. */
+int rmcrt_trace_dataonion_device(rmcrt_ctx* ctx, int maxLevels, const int32_t patchLo[3], const int32_t patchHi[3],
+                                 double* d_divQ, double* d_radiationVolq, double* d_boundFlux,
+                                 const int32_t outLo[3], const int32_t outHi[3],
+                                 int zeroInit, uint64_t timestep, void* stream);
+int rmcrt_trace_dataonion(rmcrt_ctx* ctx, int maxLevels, const int32_t patchLo[3], const int32_t patchHi[3],
+                          double* divQ, double* radiationVolq, double* boundFlux,
+                          const int32_t outLo[3], const int32_t outHi[3],
+                          int zeroInit, uint64_t timestep, void* stream);
+
+/* Ray::computeExtents (patch_based) on the host, exported so callers/tests see the same boxes. */
+int rmcrt_compute_extents(rmcrt_ctx* ctx, int maxLevels, const int32_t patchLo[3], const int32_t patchHi[3],
+                          int32_t roiLo[3], int32_t roiHi[3],
+                          int32_t* regionLo /*[maxLevels][3]*/, int32_t* regionHi);
+
+/* counters accumulate over trace calls until reset; get blocks on `stream` */
+int rmcrt_reset_counters(rmcrt_ctx* ctx, void* stream);
+int rmcrt_get_counters(rmcrt_ctx* ctx, rmcrt_counters* out, void* stream);
+
+/* ------------------------------------------------------------------ property pipeline on device
+ * sigmaT4OverPi = (sigma/pi) T^4 (RMCRTCommon.cc:304-343); n cells; T of the output = isFloat */
+int rmcrt_sigmaT4_device(rmcrt_ctx* ctx, const double* d_temperature, void* d_sigmaT4OverPi, int isFloat,
+                         int64_t n, void* stream);
+/* Data-Onion coarse level from the fine level's records: Ray::coarsen_Q interior average (Ray.cc:2103-2145)
+ * + Ray::computeCellType (2272-2345) for interior coarse cells; extra cells of the coarse level keep what
+ * rmcrt_upload_level / rmcrt_set_level_extra_cells put there. */
+int rmcrt_coarsen_level_device(rmcrt_ctx* ctx, int fineL, int coarseL, void* stream);
+/* Dirichlet fill of a level's extra-cell layer (Ray::setBoundaryConditions, Ray.cc:1662-1742) per face
+ * x-,x+,y-,y+,z-,z+: abskg[6], sigmaT4OverPi[6], cellType[6]. */
+int rmcrt_set_level_extra_cells(rmcrt_ctx* ctx, int L, const double abskg[6], const double sigmaT4OverPi[6],
+                                const int32_t cellType[6], void* stream);
+
+/* ------------------------------------------------------------------ multi-GPU replication
+ * Each rank packs the cells it owns, box [lo,hi) of level L, into its slot of an all-gather send buffer
+ * (records in x-fastest order of the box); after the collective, rmcrt_assemble_level scatters every rank's
+ * box into the level records.  The collective itself is the caller's (NCCL via torch.distributed in the
+ * python harness; ncclAllGather in a C++ host) -- or rmcrt_allgather_level when an ncclComm_t is at hand. */
+int rmcrt_pack_box_device(rmcrt_ctx* ctx, int L, const void* d_abskg, const void* d_sigmaT4OverPi,
+                          const int32_t* d_cellType, int isFloat,
+                          const int32_t srcLo[3], const int32_t srcHi[3],
+                          const int32_t boxLo[3], const int32_t boxHi[3],
+                          void* d_sendRecords, void* stream);
+int rmcrt_assemble_level(rmcrt_ctx* ctx, int L, const void* d_gathered, size_t slotBytes, int nRanks,
+                         const int32_t* boxLo /*[nRanks][3]*/, const int32_t* boxHi, void* stream);
+/* ncclAllGather(sendSlot -> gathered) on `comm` (an ncclComm_t passed as void*), resolved with dlsym at
+ * first use so the library has no link-time NCCL dependency. */
+int rmcrt_allgather_records(rmcrt_ctx* ctx, const void* d_sendSlot, void* d_gathered, size_t slotBytes,
+                            void* ncclComm, void* stream);
+
+/* ------------------------------------------------------------------ roofline denominators
+ * Measures device read bandwidth on a scratch buffer of `bytes` (L2-resident when well below the L2 size, HBM when far
+ * above it), `repeats` passes, CUDA-event timed.  pattern 0: coalesced 16-B loads (streaming);
+ * pattern 1: one dependent-free 8-B gather per lane at a hashed record index -- every lane touches its own 32-B sector,
+ * the access shape of an incoherent ray step; *gbps counts 32 B per gather (sector traffic), *gaccess the gathers/s. */
+int rmcrt_measure_read_bandwidth(rmcrt_ctx* ctx, size_t bytes, int repeats, int pattern, double* gbps, double* gaccess);
+
+/* ------------------------------------------------------------------ debugging (cf. isDbgCell, RMCRTCommon.cc:38,632-635)
+ * Trace n caller-specified rays through level L (single level) or the Data-Onion stack (maxLevels > 1)
+ * with the production march code.  Host pointers; blocking.
+ *   originCell[n][3], dir[n][3], rayOrigin[n][3] (physical position);  out: sumI[n], steps[n]
+ *   path: optional [n][maxPath][4] int32 (i,j,k,level) of every cell entered. */
+int rmcrt_debug_trace_rays(rmcrt_ctx* ctx, int L, int maxLevels, const int32_t patchLo[3], const int32_t patchHi[3],
+                           int n, const int32_t* originCell, const double* dir, const double* rayOrigin,
+                           double* sumI, uint32_t* steps, int32_t* path, int maxPath);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RMCRT_B200_H */

@@ -1,0 +1,88 @@
+// Host build of the production march code (uintah_b200/csrc/march.cuh, rng.cuh) for CPU-side logic tests.
+#include "cuda_shim.h"
+#include "../../uintah_b200/csrc/march.cuh"
+#include "../../uintah_b200/csrc/rng.cuh"
+using namespace rmcrt;
+
+extern "C" {
+
+// pack like pack_kernel: sign bit <=> cellType != flowCell
+void hs_pack(const double* abskg, const double* sig, const int* ct, long long n, int flowCell, int kind, void* out) {
+  for (long long i = 0; i < n; ++i) {
+    double k = std::fabs(abskg[i]);
+    if (ct[i] != flowCell) k = -k;
+    if (kind == 0) static_cast<Rec8*>(out)[i] = Rec8{(float)k, (float)sig[i]};
+    else static_cast<Rec16*>(out)[i] = Rec16{k, sig[i]};
+  }
+}
+
+struct HsLevel { const void* rec; int lo[3], hi[3], intLo[3], intHi[3], rr[3]; double dx[3], anchor[3]; };
+
+static void rayDxOf(const HsLevel& g, const int c[3], const double* o, double r[3]) {
+  for (int d = 0; d < 3; ++d) { const double cc = g.anchor[d] + g.dx[d] * c[d] + g.dx[d] * 0.5; r[d] = o[d] - (cc - 0.5 * g.dx[d]); }
+}
+
+// single level: kind 0 = fp32/Rec8, 1 = fp64/Rec16
+void hs_trace_1L(const HsLevel* g, int kind, int n, const int* cells, const double* dirs, const double* orgs, double threshold,
+                 int allowReflect, int skipZero, double* sumI, unsigned* steps, int* path, int maxPath) {
+  const int nx = g->hi[0] - g->lo[0], ny = g->hi[1] - g->lo[1];
+  for (int t = 0; t < n; ++t) {
+    const int* c = cells + 3 * t;
+    double r[3];
+    rayDxOf(*g, c, orgs + 3 * t, r);
+    const long long idx = (long long)(c[0] - g->lo[0]) + (long long)nx * ((c[1] - g->lo[1]) + (long long)ny * (c[2] - g->lo[2]));
+    PathSink sink{path ? path + (long long)t * maxPath * 4 : nullptr, maxPath, 0};
+    unsigned s = 0;
+    const double* d = dirs + 3 * t;
+    if (kind == 0)
+      sumI[t] = march_single_level<float, Rec8, true>(static_cast<const Rec8*>(g->rec), idx, nx, nx * ny, (float)d[0], (float)d[1], (float)d[2],
+                  (float)r[0], (float)r[1], (float)r[2], (float)g->dx[0], (float)g->dx[1], (float)g->dx[2], (float)threshold,
+                  allowReflect != 0, skipZero != 0, s, path ? &sink : nullptr, c[0], c[1], c[2]);
+    else
+      sumI[t] = march_single_level<double, Rec16, true>(static_cast<const Rec16*>(g->rec), idx, nx, nx * ny, d[0], d[1], d[2], r[0], r[1], r[2],
+                  g->dx[0], g->dx[1], g->dx[2], threshold, allowReflect != 0, skipZero != 0, s, path ? &sink : nullptr, c[0], c[1], c[2]);
+    steps[t] = s;
+  }
+}
+
+void hs_trace_ML(const HsLevel* lv, int maxLevels, const int* roiLo, const int* roiHi, const int* regLo, const int* regHi, int kind, int n,
+                 const int* cells, const double* dirs, const double* orgs, double threshold, int allowReflect, int skipZero,
+                 double* sumI, unsigned* steps, int* path, int maxPath) {
+  OnionGeom<4> G;
+  std::memset(&G, 0, sizeof G);
+  G.maxLevels = maxLevels;
+  const int F = maxLevels - 1;
+  for (int L = 0; L < maxLevels; ++L) {
+    LevelGeom& g = G.lev[L];
+    g.rec = lv[L].rec;
+    for (int d = 0; d < 3; ++d) {
+      g.lo[d] = lv[L].lo[d]; g.n[d] = lv[L].hi[d] - lv[L].lo[d]; g.intLo[d] = lv[L].intLo[d]; g.intHi[d] = lv[L].intHi[d];
+      g.rr[d] = lv[L].rr[d]; g.regLo[d] = regLo[3 * L + d]; g.regHi[d] = regHi[3 * L + d]; g.dx[d] = lv[L].dx[d];
+      g.anchor[d] = lv[L].anchor[d]; g.off[d] = lv[L].anchor[d] - lv[F].anchor[d];
+    }
+  }
+  for (int d = 0; d < 3; ++d) { G.roiLo[d] = roiLo[d]; G.roiHi[d] = roiHi[d]; }
+  for (int t = 0; t < n; ++t) {
+    const int* c = cells + 3 * t;
+    double r[3];
+    rayDxOf(lv[F], c, orgs + 3 * t, r);
+    PathSink sink{path ? path + (long long)t * maxPath * 4 : nullptr, maxPath, 0};
+    unsigned s = 0;
+    const double* d = dirs + 3 * t;
+    if (kind == 0)
+      sumI[t] = march_multi_level<float, Rec8, 4, true>(G, c[0], c[1], c[2], (float)d[0], (float)d[1], (float)d[2], (float)r[0], (float)r[1],
+                  (float)r[2], (float)threshold, allowReflect != 0, skipZero != 0, s, path ? &sink : nullptr);
+    else
+      sumI[t] = march_multi_level<double, Rec16, 4, true>(G, c[0], c[1], c[2], d[0], d[1], d[2], r[0], r[1], r[2], threshold,
+                  allowReflect != 0, skipZero != 0, s, path ? &sink : nullptr);
+    steps[t] = s;
+  }
+}
+
+void hs_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  const u32x4 r = philox4x32_10(u32x4{ctr[0], ctr[1], ctr[2], ctr[3]}, key[0], key[1]);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+void hs_mt_first5(uint32_t seed, uint32_t out[5]) { mt19937_first<5>(seed, out); }
+void hs_mt_first4(uint32_t seed, uint32_t out[4]) { mt19937_first<4>(seed, out); }
+}

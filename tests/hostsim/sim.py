@@ -1,0 +1,86 @@
+"""ctypes front end of tests/hostsim/march_host.cpp: the production march/rng headers compiled for the host."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libmarch_host.so")
+_lib = None
+
+
+class HsLevel(C.Structure):
+    _fields_ = [("rec", C.c_void_p), ("lo", C.c_int * 3), ("hi", C.c_int * 3), ("intLo", C.c_int * 3), ("intHi", C.c_int * 3),
+                ("rr", C.c_int * 3), ("dx", C.c_double * 3), ("anchor", C.c_double * 3)]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        srcs = [os.path.join(HERE, "march_host.cpp"), os.path.join(HERE, "cuda_shim.h"),
+                os.path.join(HERE, "..", "..", "uintah_b200", "csrc", "march.cuh"),
+                os.path.join(HERE, "..", "..", "uintah_b200", "csrc", "rng.cuh")]
+        if (not os.path.exists(SO)) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
+            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", SO, srcs[0]], check=True)
+        _lib = C.CDLL(SO)
+    return _lib
+
+
+def pack(lv, kind):
+    n = lv.abskg.size
+    out = np.zeros(n * (8 if kind == 0 else 16), np.uint8)
+    ab = np.ascontiguousarray(lv.abskg, np.float64)
+    s4 = np.ascontiguousarray(lv.sigmaT4, np.float64)
+    lib().hs_pack(ab.ctypes.data_as(C.c_void_p), s4.ctypes.data_as(C.c_void_p), lv.cellType.ctypes.data_as(C.c_void_p),
+                  C.c_longlong(n), -1, kind, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def hslevel(lv, rec):
+    h = HsLevel()
+    h.rec = rec.ctypes.data
+    h.lo = (C.c_int * 3)(*lv.lo); h.hi = (C.c_int * 3)(*lv.hi)
+    h.intLo = (C.c_int * 3)(*lv.interior_lo); h.intHi = (C.c_int * 3)(*lv.interior_hi)
+    h.rr = (C.c_int * 3)(*lv.rr); h.dx = (C.c_double * 3)(*lv.dx); h.anchor = (C.c_double * 3)(*lv.anchor)
+    return h
+
+
+def _vp(a):
+    return np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)
+
+
+def trace_1L(lv, kind, cells, dirs, org, thr, refl, skip=0, max_path=4000):
+    rec = pack(lv, kind)
+    h = hslevel(lv, rec)
+    n = len(cells)
+    sumI = np.zeros(n); steps = np.zeros(n, np.uint32); path = np.zeros((n, max_path, 4), np.int32)
+    cells = np.ascontiguousarray(cells, np.int32); dirs = np.ascontiguousarray(dirs); org = np.ascontiguousarray(org)
+    lib().hs_trace_1L(C.byref(h), kind, n, _vp(cells), _vp(dirs), _vp(org), C.c_double(thr), refl, skip, _vp(sumI), _vp(steps),
+                      path.ctypes.data_as(C.c_void_p), max_path)
+    return sumI, steps, path
+
+
+def trace_ML(levels, kind, roi, reg, cells, dirs, org, thr, refl, skip=0, max_path=4000):
+    recs = [pack(l, kind) for l in levels]
+    nl = len(levels)
+    arr = (HsLevel * nl)(*[hslevel(l, r) for l, r in zip(levels, recs)])
+    n = len(cells)
+    sumI = np.zeros(n); steps = np.zeros(n, np.uint32); path = np.zeros((n, max_path, 4), np.int32)
+    cells = np.ascontiguousarray(cells, np.int32); dirs = np.ascontiguousarray(dirs); org = np.ascontiguousarray(org)
+    regLo = np.ascontiguousarray(reg[0], np.int32); regHi = np.ascontiguousarray(reg[1], np.int32)
+    lib().hs_trace_ML(arr, nl, (C.c_int * 3)(*roi[0]), (C.c_int * 3)(*roi[1]), _vp(regLo), _vp(regHi), kind, n, _vp(cells),
+                      _vp(dirs), _vp(org), C.c_double(thr), refl, skip, _vp(sumI), _vp(steps), path.ctypes.data_as(C.c_void_p), max_path)
+    return sumI, steps, path
+
+
+def philox(ctr, key):
+    out = (C.c_uint32 * 4)()
+    lib().hs_philox((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), out)
+    return tuple(out)
+
+
+def mt_first(seed, n):
+    out = (C.c_uint32 * n)()
+    getattr(lib(), f"hs_mt_first{n}")(C.c_uint32(seed), out)
+    return [int(x) for x in out]

@@ -1,0 +1,184 @@
+"""CPU tests that PIN the oracle (oracle/rmcrt_oracle.cpp) against what the reference tree itself holds:
+the reference's own MersenneTwister.h (golden fixture + live _ref build), the Burns & Christon exact centre line
+(parametricStudies/postProcessTools/RMCRT.m:22-38) and the Modest parallel-plate closed form (RMCRT.m:44-94)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def test_mt19937_matches_reference_golden(po):
+    g = json.load(open(os.path.join(HERE, "golden", "mt19937.json")))
+    for seed_s, v in g["seeds"].items():
+        seed = int(seed_s)
+        u = po.mt_u32(seed, 1300)
+        assert [int(x) for x in u[:8]] == v["first8_u32"]
+        assert [int(x) for x in u[623:626]] == v["u32_at_623_624_625"]
+        assert [int(u[1247]), int(u[1248]), int(u[1299])] == v["u32_at_1247_1248_1299"]
+        assert int(np.bitwise_xor.reduce(u)) == v["xor_all_1300"]
+        assert [float(x).hex() for x in po.mt_rand(seed, 8)] == v["rand_first8_hex"]
+        assert [float(x).hex() for x in po.mt_randDblExc(seed, 8)] == v["randDblExc_first8_hex"]
+
+
+def test_mt19937_matches_reference_header_live(po):
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_mt.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    ref = C.CDLL(so)
+    for seed in (1, 7, 99991, 2 ** 32 - 1):
+        b = np.empty(3000, np.uint32)
+        ref.ref_mt_u32(C.c_uint32(seed), 3000, b.ctypes.data_as(C.c_void_p))
+        assert (po.mt_u32(seed, 3000) == b).all()
+
+
+def test_fixed_random_num_live(po):
+    """FIXED_RANDOM_NUM build of the reference header returns 0.3 for rand() and randDblExc()"""
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_mt_fixed.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref not built")
+    ref = C.CDLL(so)
+    b = np.empty(4)
+    ref.ref_mt_rand(C.c_uint32(1), 4, b.ctypes.data_as(C.c_void_p))
+    assert (b == 0.3).all()
+    ref.ref_mt_randDblExc(C.c_uint32(1), 4, b.ctypes.data_as(C.c_void_p))
+    assert (b == 0.3).all()
+
+
+@pytest.fixture(scope="module")
+def bc41(po):
+    """RMCRT_bm1_1L.ups at 100 rays/cell, randomSeed=true style (C1 of BASELINE.json)"""
+    lv = po.burns_christon(41)
+    p = po.default_params(nDivQRays=100, threshold=0.05, isSeedRandom=1)
+    r = po.ray_trace(p, lv, seed=1, patches=(1, 1, 8), threads=8)
+    return lv, p, r
+
+
+def test_burns_christon_centreline(po, bc41):
+    lv, p, r = bc41
+    L2, line, exact = po.centreline_L2(r["divQ"], 41)
+    # 0.010-0.014 at 100 rays; exact value at x=0.5 is -3.07561
+    assert L2 < 0.02, L2
+    assert abs(line[20] - (-3.07561)) < 0.05
+    # symmetric problem: y and z centre lines agree with the exact line as well
+    mid = 21
+    for ln in (r["divQ"][mid, 1:42, mid], r["divQ"][1:42, mid, mid]):
+        assert np.sqrt(np.mean((ln - exact) ** 2)) < 0.02
+
+
+def test_steps_per_ray_reference_semantics(po, bc41):
+    lv, p, r = bc41
+    # default allowReflect=true marches a zero-weight second leg: 62.4 steps/ray at 41^3
+    spr = r["steps"] / (41 ** 3 * 100)
+    assert 61.5 < spr < 63.2, spr
+
+
+def test_zero_weight_second_leg_is_exact_noop(po):
+    lv = po.burns_christon(17)
+    a = po.ray_trace(po.default_params(nDivQRays=20, threshold=0.05, isSeedRandom=0, allowReflect=1), lv)
+    b = po.ray_trace(po.default_params(nDivQRays=20, threshold=0.05, isSeedRandom=0, allowReflect=0), lv)
+    assert np.array_equal(a["divQ"], b["divQ"])
+    assert a["steps"] > 1.8 * b["steps"]
+
+
+def modest_exact(n, Tw=1000.0, Tm=1500.0, sigma=5.67051e-8, ntheta=100000):
+    """benchMark2 of RMCRT.m:44-94 (k = 1, eps = 1) at the n cell centres between the plates"""
+    x = np.linspace(1 / (2 * n), 1 - 1 / (2 * n), n)
+    mu = np.cos(np.linspace(0, np.pi / 2, ntheta))
+    dmu = mu[:-1] - mu[1:]
+    E2 = np.zeros(n)
+    with np.errstate(divide="ignore"):
+        for ix in range(n):
+            f = np.exp(-x[ix] / mu)
+            f[~np.isfinite(f)] = 0
+            E2[ix] = np.sum((f[:-1] + f[1:]) / 2 * dmu)
+    D = np.zeros(n)
+    for ix in range(1, n):
+        D[ix - 1] = sigma * (Tw ** 4 - Tm ** 4) * -2 * (E2[ix - 1] + E2[n - ix])
+    D[n - 1] = sigma * (Tw ** 4 - Tm ** 4) * -2 * (E2[n - 1] + 1.0)
+    D[n - 1] = (D[n - 1] + D[n - 2]) / 2
+    return D
+
+
+def test_modest_parallel_plates(po):
+    """RMCRT_1L_reflect.ups: 4 mirror walls, 2 black plates at 1000 K, medium 1500 K, kappa 1.
+    Plane-averaged divQ follows Modest's closed form (RMCRT's divQ has the opposite sign convention)."""
+    N = 41
+    lv = po.parallel_plates(N, mirror_faces=("x-", "x+", "y-", "y+"))
+    p = po.default_params(nDivQRays=16, threshold=0.001, isSeedRandom=1, allowReflect=1)
+    r = po.ray_trace(p, lv, seed=3, patches=(1, 1, 8), threads=8)
+    plane = r["divQ"][1:N + 1, 1:N + 1, 1:N + 1].mean(axis=(1, 2))
+    D = modest_exact(N)
+    rel = np.sqrt(np.mean((plane + D) ** 2)) / np.abs(D).mean()
+    assert rel < 0.03, rel
+
+
+def test_deterministic_mode_is_decomposition_invariant(po):
+    """<randomSeed> false: per-ray reseed makes the result independent of the patch layout"""
+    lv = po.burns_christon(12)
+    p = po.default_params(nDivQRays=3, threshold=0.05, isSeedRandom=0)
+    a = po.ray_trace(p, lv, patches=(1, 1, 1))
+    b = po.ray_trace(p, lv, patches=(2, 3, 2), threads=4)
+    assert np.array_equal(a["divQ"], b["divQ"]) and a["steps"] == b["steps"]
+
+
+def test_boundary_flux_mask_and_slots(po):
+    """boundFlux.p and the set of written Stencil7 slots (Ray.cc:664,716-717; has_a_boundary 1517-1572)"""
+    rng = np.random.default_rng(5)
+    from util import add_random_walls
+    lv = po.burns_christon(10)
+    add_random_walls(lv, 0.05, rng)
+    p = po.default_params(nDivQRays=1, nFluxRays=2, threshold=0.05, isSeedRandom=0, solveBoundaryFlux=1, solveDivQ=0)
+    r = po.ray_trace(p, lv)
+    ct = lv.cellType
+    flow = ct == -1
+    S = r["boundFlux"]
+    nb = {0: (0, 0, -1), 1: (0, 0, 1), 2: (0, -1, 0), 3: (0, 1, 0), 4: (-1, 0, 0), 5: (1, 0, 0)}  # slot -> (dz,dy,dx)
+    any_face = np.zeros(ct.shape, bool)
+    for slot, (dz, dy, dx) in nb.items():
+        wall_nb = np.zeros(ct.shape, bool)
+        wall_nb[1:-1, 1:-1, 1:-1] = ct[1 + dz:ct.shape[0] - 1 + dz, 1 + dy:ct.shape[1] - 1 + dy, 1 + dx:ct.shape[2] - 1 + dx] != -1
+        expect = wall_nb & flow
+        expect[[0, -1], :, :] = False; expect[:, [0, -1], :] = False; expect[:, :, [0, -1]] = False
+        # gas at 64.8 K around cold walls: every traced face receives a strictly positive flux
+        assert np.array_equal(S[..., slot] != 0, expect), slot
+        any_face |= expect
+    assert np.array_equal(S[..., 6] == 1.0, any_face)
+    assert set(np.unique(S[..., 6])) <= {0.0, 1.0}
+
+
+def test_map_cell_to_coarser_negative_indices(po):
+    """Level::mapCellToCoarser quirk (Level.cc:1285-1307): -1 -> -1, but -2 -> -2 for ratio 4"""
+    out = (C.c_int * 3)()
+    po.lib().oracle_mapCellToCoarser((C.c_int * 3)(-1, 7, -4), (C.c_int * 3)(4, 4, 4), out)
+    assert tuple(out) == (-1, 1, -1)
+    po.lib().oracle_mapCellToCoarser((C.c_int * 3)(-2, 8, -5), (C.c_int * 3)(4, 4, 4), out)
+    assert tuple(out) == (-2, 2, -2)
+
+
+def test_data_onion_close_to_single_level(po):
+    """2-level Data Onion (fine 32^3, coarse 8^3, halo 4) approximates the single-level answer"""
+    fine = po.burns_christon(32)
+    fine.rr = (4, 4, 4)
+    coarse = po.coarsen_level(fine, (4, 4, 4))
+    p = po.default_params(nDivQRays=24, threshold=0.05, isSeedRandom=1)
+    one = po.ray_trace(p, fine, seed=11, patches=(1, 1, 8), threads=8)
+    do = po.ray_trace_data_onion(p, [coarse, fine], (4, 4, 4), seed=11, patches=(2, 2, 2), threads=8)
+    a = one["divQ"][1:-1, 1:-1, 1:-1]
+    b = do["divQ"][1:-1, 1:-1, 1:-1]
+    assert abs(a.mean() - b.mean()) / abs(a.mean()) < 0.02
+    assert do["steps"] < one["steps"]          # coarse cells are 4x longer
+
+
+def test_extents_patch_based(po):
+    fine = po.burns_christon(32)
+    fine.rr = (4, 4, 4)
+    coarse = po.coarsen_level(fine, (4, 4, 4))
+    roiLo, roiHi, regLo, regHi = po.compute_extents([coarse, fine], (16, 0, 0), (32, 16, 16), (4, 4, 4))
+    assert roiLo == (12, -1, -1) and roiHi == (33, 20, 20)           # clamped to the level incl. extra cells
+    assert tuple(regLo[1]) == (13, 0, 0) and tuple(regHi[1]) == (32, 19, 19)
+    assert tuple(regLo[0]) == (0, 0, 0) and tuple(regHi[0]) == (8, 8, 8)

@@ -1,0 +1,326 @@
+// march.cuh -- Amanatides-Woo DDA ray march with the emission/absorption integral of RMCRT.
+//
+// Behavioural contract (what is reproduced, quirks included -- SURVEY.md 3.5):
+//   single level : RMCRTCommon::updateSumI<T>   RMCRT/RMCRTCommon.cc:607-904
+//   multi level  : Ray::updateSumI_ML<T>        RMCRT/Ray.cc:2349-2627
+//   reflection   : RMCRTCommon::reflect         RMCRT/RMCRTCommon.cc:581-602
+//
+// B200 design: a cell is ONE packed record {abskg with the sign bit = "not a flow cell", sigmaT4/pi}
+// (8 B for the FP32 production march, 16 B for the FP64 parity march) so every DDA step issues a single
+// vectorised read-only load (LDG.E.64/.128.CONSTANT) that yields both the stop flag of the cell just entered
+// and the properties integrated on the next step.  The FP32 march keeps all lengths pre-multiplied by
+// log2(e) so the attenuation is one ex2.approx per step.
+#pragma once
+#include <cstdint>
+#include <cmath>
+
+namespace rmcrt {
+
+struct Rec8  { float  k, s; };   // k: abskg, sign bit set <=> cellType != flowCell ; s: sigmaT4/pi
+struct Rec16 { double k, s; };
+
+__device__ __forceinline__ Rec8 ldrec(const Rec8* p) {
+  const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+  return Rec8{v.x, v.y};
+}
+__device__ __forceinline__ Rec16 ldrec(const Rec16* p) {
+  const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+  return Rec16{v.x, v.y};
+}
+__device__ __forceinline__ bool sign_bit(float v)  { return (__float_as_uint(v) >> 31) != 0u; }
+__device__ __forceinline__ bool sign_bit(double v) { return (__double2hiint(v) < 0); }
+// a record whose abskg carries the sign bit is "not a flow cell" (cellType != d_flowCell)
+__device__ __forceinline__ bool is_wall(float k)  { return sign_bit(k); }
+__device__ __forceinline__ bool is_wall(double k) { return sign_bit(k); }
+
+template <class Real> struct Num;
+template <> struct Num<float> {
+  // all lengths carry a factor log2(e): exp(-tau) == ex2(-tau2)
+  static constexpr float LEN_SCALE = 1.4426950408889634f;
+  static __device__ __forceinline__ float attenuation(float tau2) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-tau2));
+    return r;
+#else
+    return exp2f(-tau2);   // host build of this header (tests/hostsim) only
+#endif
+  }
+  static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+  static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+  static __device__ __forceinline__ float rcp(float a) { return __frcp_rn(a); }
+  static __device__ __forceinline__ float fuzz(float ds) { return ds; }
+};
+template <> struct Num<double> {
+  static constexpr double LEN_SCALE = 1.0;
+  static __device__ __forceinline__ double attenuation(double tau) { return exp(-tau); }
+  // no FMA contraction: keeps the operation sequence of the reference's x86-64 build
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double rcp(double a) { return __ddiv_rn(1.0, a); }
+  // RMCRTCommon.cc:717-720 (FUZZ = 1e-12); single level only
+  static __device__ __forceinline__ double fuzz(double ds) { return (ds > -1e-12 && ds < 1e-12) ? ds + 1e-12 : ds; }
+};
+
+template <class Real> __device__ __forceinline__ Real absr(Real v);
+template <> __device__ __forceinline__ float  absr(float v)  { return fabsf(v); }
+template <> __device__ __forceinline__ double absr(double v) { return fabs(v); }
+
+struct PathSink {       // debug only
+  int32_t* buf;         // [cap][4]
+  int cap;
+  int n;
+};
+
+//------------------------------------------------------------------------------------------------------
+// single level
+//------------------------------------------------------------------------------------------------------
+// recs  : level records, x-fastest, strides (1, sy, sz)
+// idx   : record index of the origin cell
+// d*    : ray direction;  r* : rayDx = distance of the ray origin from the cell's low corner (RMCRTCommon.cc:643-646)
+// returns the ray's contribution to sumI
+template <class Real, class RecT, bool RECORD>
+__device__ __forceinline__ Real march_single_level(const RecT* __restrict__ recs, long long idx, int sy, int sz,
+                                                   Real dx, Real dy, Real dz, Real rx, Real ry, Real rz,
+                                                   Real cx, Real cy, Real cz,   // cell size
+                                                   Real threshold, bool allowReflect, bool skipZero,
+                                                   unsigned& nSteps, PathSink* path, int pi, int pj, int pk) {
+  typedef Num<Real> N;
+  if (!(Real(1) > threshold)) return Real(0);   // while (intensity > d_threshold), RMCRTCommon.cc:683
+
+  // raySignStep (RMCRTCommon.cc:482-494): +1 / -1 by the sign BIT of the direction
+  const bool posx = !sign_bit(dx), posy = !sign_bit(dy), posz = !sign_bit(dz);
+  int stx = posx ? 1 : -1, sty = posy ? sy : -sy, stz = posz ? sz : -sz;
+  const Real ix = N::rcp(dx), iy = N::rcp(dy), iz = N::rcp(dz);
+  // tMax (649-652) and tDelta (655)
+  Real tx = N::mul(N::mul(N::add(posx ? cx : Real(0), -rx), ix), N::LEN_SCALE);
+  Real ty = N::mul(N::mul(N::add(posy ? cy : Real(0), -ry), iy), N::LEN_SCALE);
+  Real tz = N::mul(N::mul(N::add(posz ? cz : Real(0), -rz), iz), N::LEN_SCALE);
+  const Real ddx = N::mul(N::mul(absr(ix), cx), N::LEN_SCALE);
+  const Real ddy = N::mul(N::mul(absr(iy), cy), N::LEN_SCALE);
+  const Real ddz = N::mul(N::mul(absr(iz), cz), N::LEN_SCALE);
+
+  Real tPrev = 0, tau = 0, ePrev = 1, sum = 0, fs = 1;
+  RecT r = ldrec(recs + idx);
+  Real k = absr(r.k), s = r.s;
+  unsigned steps = 0;
+  int ci = pi, cj = pj, ck = pk;   // only maintained when RECORD
+
+  for (;;) {
+    long long idxPrev;
+    bool px, py;
+    Real e;
+    do {
+      idxPrev = idx;
+      // axis with the smallest tMax; strict '<' so ties go Y-before-... exactly as RMCRTCommon.cc:696-708
+      const bool xy = tx < ty;
+      px = xy && (tx < tz);
+      py = !xy && (ty < tz);
+      const Real tNext = px ? tx : (py ? ty : tz);
+      idx += px ? stx : (py ? sty : stz);
+      if (RECORD) {
+        if (px) ci += (stx > 0 ? 1 : -1); else if (py) cj += (sty > 0 ? 1 : -1); else ck += (stz > 0 ? 1 : -1);
+      }
+      r = ldrec(recs + idx);                 // the one load of this step
+      Real ds = N::add(tNext, -tPrev);
+      tPrev = tNext;
+      tx = px ? N::add(tx, ddx) : tx;
+      ty = py ? N::add(ty, ddy) : ty;
+      tz = (px || py) ? tz : N::add(tz, ddz);
+      ds = N::fuzz(ds);
+      tau = N::add(tau, N::mul(k, ds));      // optical_thickness += abskg[prev]*disMin   (731)
+      ++steps;
+      e = N::attenuation(tau);               // 782
+      sum = N::add(sum, N::mul(N::mul(s, N::add(ePrev, -e)), fs));   // 786
+      ePrev = e;
+      k = absr(r.k);
+      s = r.s;
+      if (RECORD && path && path->n < path->cap) {
+        int32_t* q = path->buf + 4 * path->n; q[0] = ci; q[1] = cj; q[2] = ck; q[3] = 0;
+      }
+      if (RECORD && path) path->n++;
+    } while (!is_wall(r.k));                 // in_domain = (celltype[cur] == d_flowCell)  (729)
+
+    // wall: r = record of the non-flow cell entered
+    const Real eps = k > Real(1) ? Real(1) : k;          // 846-850
+    Real intensity = e;                                   // exp(-optical_thickness), same argument as the last step
+    sum = N::add(sum, N::mul(N::mul(eps, s), intensity)); // 854: NOT multiplied by fs
+    intensity = N::mul(intensity, fs);                    // 856
+    if (!allowReflect || !(intensity > threshold)) break; // 884, 898, 683
+    // RMCRTCommon::reflect (581-602)
+    fs = N::mul(fs, N::add(Real(1), -k));
+    idx = idxPrev;
+    if (px) stx = -stx; else if (py) sty = -sty; else stz = -stz;
+    if (RECORD) { if (px) ci += (stx > 0 ? 1 : -1); else if (py) cj += (sty > 0 ? 1 : -1); else ck += (stz > 0 ? 1 : -1); }
+    if (skipZero && fs == Real(0)) break;                 // exact: every later term carries fs==0 or a zero wall emission
+    r = ldrec(recs + idx);
+    k = absr(r.k);
+    s = r.s;
+  }
+  nSteps += steps;
+  return sum;
+}
+
+//------------------------------------------------------------------------------------------------------
+// multi level (Data Onion)
+//------------------------------------------------------------------------------------------------------
+struct LevelGeom {
+  const void* rec;
+  int lo[3];        // window low index (records cover [lo, lo+n))
+  int n[3];
+  int intLo[3], intHi[3];
+  int rr[3];        // refinement ratio to the next coarser level
+  int regLo[3], regHi[3];   // Ray::computeExtents region on this level
+  double dx[3];
+  double anchor[3]; // Level::m_anchor
+  double off[3];    // anchor[L] - anchor[fine]
+};
+
+template <int MAXL>
+struct OnionGeom {
+  LevelGeom lev[MAXL];
+  int maxLevels;
+  int roiLo[3], roiHi[3];
+};
+
+// Level::mapCellToCoarser (Level.cc:1285-1307): truncating division + (int)fmod(idx, rr) for negative idx
+__device__ __forceinline__ int map_to_coarser(int i, int rr) {
+  int q = i / rr;
+  if (i < 0 && rr > 1) q += (i % rr);   // C '%' truncates like fmod for ints
+  return q;
+}
+
+template <class Real, class RecT, int MAXL, bool RECORD>
+__device__ __forceinline__ Real march_multi_level(const OnionGeom<MAXL>& G, int ci, int cj, int ck,
+                                                  Real dx, Real dy, Real dz, Real rx, Real ry, Real rz,
+                                                  Real threshold, bool allowReflect, bool skipZero,
+                                                  unsigned& nSteps, PathSink* path) {
+  typedef Num<Real> N;
+  if (!(Real(1) > threshold)) return Real(0);
+  int L = G.maxLevels - 1;
+  const int F = L;
+  const int oi = ci, oj = cj, ok = ck;   // origin cell on the fine level
+
+  const bool posx = !sign_bit(dx), posy = !sign_bit(dy), posz = !sign_bit(dz);
+  int stx = posx ? 1 : -1, sty = posy ? 1 : -1, stz = posz ? 1 : -1;
+  // sign[] of the reference: 1/0, and after a reflection along that axis -1/-0 (sign *= -1, RMCRTCommon.cc:599)
+  Real sgx = posx ? Real(1) : Real(0), sgy = posy ? Real(1) : Real(0), sgz = posz ? Real(1) : Real(0);
+  const Real ix = N::rcp(dx), iy = N::rcp(dy), iz = N::rcp(dz);   // never refreshed on reflection (Ray.cc:2395)
+  const Real aix = absr(ix), aiy = absr(iy), aiz = absr(iz);
+
+  Real cx = (Real)G.lev[L].dx[0], cy = (Real)G.lev[L].dx[1], cz = (Real)G.lev[L].dx[2];
+  Real tx = N::mul(N::mul(N::add(N::mul(sgx, cx), -rx), ix), N::LEN_SCALE);
+  Real ty = N::mul(N::mul(N::add(N::mul(sgy, cy), -ry), iy), N::LEN_SCALE);
+  Real tz = N::mul(N::mul(N::add(N::mul(sgz, cz), -rz), iz), N::LEN_SCALE);
+  Real ddx = N::mul(N::mul(aix, cx), N::LEN_SCALE), ddy = N::mul(N::mul(aiy, cy), N::LEN_SCALE),
+       ddz = N::mul(N::mul(aiz, cz), N::LEN_SCALE);
+
+  // ray location relative to the origin cell's low corner, in true length units
+  Real lx = rx, ly = ry, lz = rz;
+  Real dirx = dx, diry = dy, dirz = dz;
+  Real tPrev = 0, tau = 0, ePrev = 1, sum = 0, fs = 1;
+  bool onFine = true;
+  unsigned steps = 0;
+
+  auto recIndex = [&](int l, int i, int j, int kk) -> long long {
+    const LevelGeom& g = G.lev[l];
+    // clamp: only reachable through the reference's own out-of-range quirk
+    int a = min(max(i - g.lo[0], 0), g.n[0] - 1), b = min(max(j - g.lo[1], 0), g.n[1] - 1),
+        c = min(max(kk - g.lo[2], 0), g.n[2] - 1);
+    return (long long)a + (long long)g.n[0] * ((long long)b + (long long)g.n[1] * (long long)c);
+  };
+
+  const RecT* recs = static_cast<const RecT*>(G.lev[L].rec);
+  RecT r = ldrec(recs + recIndex(L, ci, cj, ck));
+  Real k = absr(r.k), s = r.s;
+
+  for (;;) {
+    int pi, pj, pk;
+    bool px, py, stop;
+    Real e;
+    do {
+      pi = ci; pj = cj; pk = ck;
+      const bool xy = tx < ty;
+      px = xy && (tx < tz);
+      py = !xy && (ty < tz);
+      const bool pz = !(px || py);
+      const Real tNext = px ? tx : (py ? ty : tz);
+      ci += px ? stx : 0; cj += py ? sty : 0; ck += pz ? stz : 0;
+      const int ax = px ? 0 : (py ? 1 : 2);
+      const int cA = px ? ci : (py ? cj : ck);
+
+      const LevelGeom& g = G.lev[L];
+      // domain_BB.inside(level->getCellPosition(cur)) (Ray.cc:2486-2487): only the stepped axis can change the
+      // answer, and a cell centre is inside the interior box exactly when its index is an interior index.
+      bool inDomain = (cA >= g.intLo[ax]) && (cA < g.intHi[ax]);
+      const bool outsideROI = !(G.roiLo[ax] <= cA && G.roiHi[ax] > cA);          // 2489
+      const bool outsideReg = !(g.regLo[ax] <= cA && g.regHi[ax] > cA);          // 2490
+      const bool jumpFine = onFine && outsideROI && inDomain;                     // 2492
+      const bool jumpCoarse = (!onFine) && outsideReg && (L > 0) && inDomain;     // 2493
+      const bool jump = jumpFine || jumpCoarse;
+      // CC_pos[ax] of the cell entered, on the PRE-jump level (Ray.cc:2486), relative to the origin corner
+      const int oA = px ? oi : (py ? oj : ok);
+      const Real cA_dx = px ? cx : (py ? cy : cz);
+      const Real ccRel = N::add(N::add((Real)g.off[ax], N::mul(cA_dx, N::add((Real)cA, Real(0.5)))),
+                                -N::mul((Real)G.lev[F].dx[ax], (Real)oA));
+      if (jump) {                                                                 // 2505-2527
+        ci = map_to_coarser(ci, g.rr[0]); cj = map_to_coarser(cj, g.rr[1]); ck = map_to_coarser(ck, g.rr[2]);
+        L = L - 1;
+        onFine = false;
+        cx = (Real)G.lev[L].dx[0]; cy = (Real)G.lev[L].dx[1]; cz = (Real)G.lev[L].dx[2];
+        ddx = N::mul(N::mul(aix, cx), N::LEN_SCALE); ddy = N::mul(N::mul(aiy, cy), N::LEN_SCALE);
+        ddz = N::mul(N::mul(aiz, cz), N::LEN_SCALE);
+        recs = static_cast<const RecT*>(G.lev[L].rec);
+      }
+      r = ldrec(recs + recIndex(L, ci, cj, ck));
+
+      const Real dsS = N::add(tNext, -tPrev);            // distanceTraveled (scaled), 2534
+      tPrev = tNext;
+      const Real ds = (N::LEN_SCALE == Real(1)) ? dsS : N::mul(dsS, Real(0.6931471805599453));
+      lx = N::add(lx, N::mul(ds, dirx)); ly = N::add(ly, N::mul(ds, diry)); lz = N::add(lz, N::mul(ds, dirz));  // 2539-2541
+      if (!jump) {
+        tx = px ? N::add(tx, ddx) : tx; ty = py ? N::add(ty, ddy) : ty; tz = pz ? N::add(tz, ddz) : tz;   // 2537
+      } else {                                           // 2545-2550: only tMax[ax] is re-anchored
+        const Real lA = px ? lx : (py ? ly : lz);
+        const Real cdx = px ? cx : (py ? cy : cz);       // coarse Dx[L][ax]
+        const Real sg = px ? sgx : (py ? sgy : sgz);
+        const Real inv = px ? ix : (py ? iy : iz);
+        const Real rayDxLevel = N::add(lA, -N::add(ccRel, -N::mul(Real(0.5), cdx)));
+        const Real tTmp = N::mul(N::mul(N::add(N::mul(sg, cdx), -rayDxLevel), inv), N::LEN_SCALE);
+        tx = px ? N::add(tx, tTmp) : tx; ty = py ? N::add(ty, tTmp) : ty; tz = pz ? N::add(tz, tTmp) : tz;
+      }
+      inDomain = inDomain && !is_wall(r.k);              // 2554
+      tau = N::add(tau, N::mul(k, dsS));                 // 2557
+      ++steps;
+      e = N::attenuation(tau);
+      sum = N::add(sum, N::mul(N::mul(s, N::add(ePrev, -e)), fs));   // 2588
+      ePrev = e;
+      k = absr(r.k);
+      s = r.s;
+      if (RECORD && path && path->n < path->cap) {
+        int32_t* q = path->buf + 4 * path->n; q[0] = ci; q[1] = cj; q[2] = ck; q[3] = L;
+      }
+      if (RECORD && path) path->n++;
+      stop = !inDomain;
+    } while (!stop);
+
+    const Real eps = k > Real(1) ? Real(1) : k;          // 2594-2598
+    Real intensity = e;
+    sum = N::add(sum, N::mul(N::mul(eps, s), intensity)); // 2602
+    intensity = N::mul(intensity, fs);
+    if (!allowReflect || !(intensity > threshold)) break; // 2607-2609, 2621
+    fs = N::mul(fs, N::add(Real(1), -k));                // reflect(); cur = prevCell with L unchanged
+    ci = pi; cj = pj; ck = pk;
+    if (px) { stx = -stx; sgx = -sgx; dirx = -dirx; }
+    else if (py) { sty = -sty; sgy = -sgy; diry = -diry; }
+    else { stz = -stz; sgz = -sgz; dirz = -dirz; }
+    if (skipZero && fs == Real(0)) break;
+    r = ldrec(recs + recIndex(L, ci, cj, ck));
+    k = absr(r.k);
+    s = r.s;
+  }
+  nSteps += steps;
+  return sum;
+}
+
+}  // namespace rmcrt

@@ -1,0 +1,1349 @@
+// rmcrt_b200.cu -- kernels and C ABI of the B200-native RMCRT solve (see include/rmcrt_b200.h).
+//
+// Reference paths: /root/reference/src; RMCRT/ = CCA/Components/Models/Radiation/RMCRT/.
+//
+// Kernel inventory
+//   pack_kernel<T,RecT>        abskg/sigmaT4/cellType (Array3 windows) -> packed cell records   (HBM streaming)
+//   finalize_kernel<RecT>      validation + "can any non-flow cell emit?" reduction             (HBM streaming)
+//   divq_kernel<Real,RecT,ML>  THE hot kernel: ray generation + DDA march + divQ epilogue        (L2/L1 gather bound)
+//   flux_mask_kernel<RecT>     Ray::has_a_boundary face masks, boundFlux.p                        (streaming)
+//   flux_trace_kernel<...>     boundary-flux rays for the compacted (face, cell) items            (gather bound)
+//   debug_rays_kernel<...>     caller-specified rays through the production march code
+//   sigmaT4 / coarsen / extra-cell fill / box pack / assemble: property pipeline + multi-GPU replication
+#include "../../include/rmcrt_b200.h"
+#include "march.cuh"
+#include "rng.cuh"
+
+#include <cuda_runtime.h>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+
+#include <cfloat>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace rmcrt;
+
+namespace {
+
+constexpr int MAXL = 4;   // levels supported by the Data-Onion kernels (reference decks use 2-3)
+
+//======================================================================================================
+// device-side helpers
+//======================================================================================================
+struct RayGen {
+  uint32_t key0, key1;    // Philox key (seed)
+  uint32_t timestep;
+  int isSeedRandom;       // 0: MT19937 per-ray reseed (reference regression mode)
+  int fixedRandom;        // every draw 0.3
+  int ccRays;
+  int coherent;           // direction shared by the warp's 32 origin cells
+};
+
+struct TraceArgs {
+  OnionGeom<MAXL> G;      // levels [0, maxLevels); the origin cells live on level maxLevels-1
+  int multiLevel;         // 0: single-level march on level G.maxLevels-1
+  int patchLo[3], patchN[3];
+  long long nCells;       // cells in the patch
+  long long nTiles;       // ceil(nCells/32)
+  int outLo[3], outN[3];
+  double* divQ;
+  double* volq;
+  double* bflux;
+  int nRays;
+  double threshold;
+  int allowReflect;
+  int skipZero;
+  int fluxFlowGuard;      // 1L: only flow cells get boundary fluxes (Ray.cc:654-656); DO: no guard (Q3)
+  RayGen rng;
+  unsigned long long* counters;   // [0] divQ steps [1] flux steps [2] divQ cells [3] flux cells
+  // flux items
+  const int* items;       // compacted item ids: face * nCells + patch-linear cell
+  const int* nItems;      // device count
+};
+
+__device__ __forceinline__ void patch_cell(const TraceArgs& a, long long t, int& i, int& j, int& k) {
+  const int nx = a.patchN[0], ny = a.patchN[1];
+  const long long row = t / nx;
+  i = a.patchLo[0] + (int)(t - row * nx);
+  k = a.patchLo[2] + (int)(row / ny);
+  j = a.patchLo[1] + (int)(row - (long long)(k - a.patchLo[2]) * ny);
+}
+
+__device__ __forceinline__ long long level_index(const LevelGeom& g, int i, int j, int k) {
+  return (long long)(i - g.lo[0]) + (long long)g.n[0] * ((long long)(j - g.lo[1]) + (long long)g.n[1] * (long long)(k - g.lo[2]));
+}
+
+// RMCRTCommon::findRayDirection (RMCRTCommon.cc:499-538) + ray_Origin (544-576), FP64 like the reference.
+// cellId / dirId : Philox counters (the cell itself; the warp tile's first cell when coherent).
+__device__ __forceinline__ void gen_divq_ray(const RayGen& rg, const LevelGeom& g, int i, int j, int k, int ray,
+                                             unsigned long long cellId, unsigned long long dirId,
+                                             double dir[3], double rayDx[3]) {
+  double u1, u2, o0, o1, o2;
+  if (rg.fixedRandom) {
+    u1 = u2 = o0 = o1 = o2 = 0.3;
+  } else if (!rg.isSeedRandom) {
+    uint32_t v[5];
+    mt19937_first<5>((uint32_t)((i + j + k) * ray + 1), v);      // RMCRTCommon.cc:504-506
+    u1 = u01_open(v[0]); u2 = u01_open(v[1]);
+    o0 = u01_closed(v[2]); o1 = u01_closed(v[3]); o2 = u01_closed(v[4]);
+  } else {
+    const u32x4 a = philox4x32_10(u32x4{(uint32_t)dirId, (uint32_t)ray, rg.timestep,
+                                        ((uint32_t)(dirId >> 32) << 8) | STREAM_DIR}, rg.key0, rg.key1);
+    const u32x4 b = philox4x32_10(u32x4{(uint32_t)cellId, (uint32_t)ray, rg.timestep,
+                                        ((uint32_t)(cellId >> 32) << 8) | STREAM_ORIGIN}, rg.key0, rg.key1);
+    u1 = u01_open(a.x); u2 = u01_open(a.y);
+    o0 = u01_closed(b.x); o1 = u01_closed(b.y); o2 = u01_closed(b.z);
+  }
+  const double pm1 = 2.0 * u1 - 1.0 + DBL_EPSILON;
+  const double r = sqrt(1.0 - pm1 * pm1);
+  const double theta = 2.0 * M_PI * u2;
+  double sn, cs;
+  sincos(theta, &sn, &cs);
+  dir[0] = r * cs; dir[1] = r * sn; dir[2] = pm1;
+  const int c[3] = {i, j, k};
+  const double off[3] = {o0, o1, o2};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    // absolute positions as the reference forms them, so the FP64 path rounds identically (Level.cc:473-477)
+    const double cc = g.anchor[d] + g.dx[d] * c[d] + g.dx[d] * 0.5;
+    const double o = rg.ccRays ? cc : (cc - 0.5 * g.dx[d] + off[d] * g.dx[d]);
+    rayDx[d] = o - (cc - 0.5 * g.dx[d]);
+  }
+}
+
+// Ray::rayDirection_cellFace (Ray.cc:1362-1390) + rayLocation_cellFace (1465-1513).
+// face in push order of has_a_boundary: 0 W(-x) 1 E(+x) 2 S(-y) 3 N(+y) 4 B(-z) 5 T(+z) == Stencil7 slot.
+__device__ __forceinline__ void gen_flux_ray(const RayGen& rg, const LevelGeom& g, int i, int j, int k, int face, int ray,
+                                             unsigned long long cellId, unsigned long long dirId,
+                                             double dir[3], double rayDx[3], double& cosTheta) {
+  double u1, u2, p0, p1;
+  if (rg.fixedRandom) {
+    u1 = u2 = p0 = p1 = 0.3;
+  } else if (!rg.isSeedRandom) {
+    uint32_t v[4];
+    mt19937_first<4>((uint32_t)((i + j + k) * ray + 1), v);      // Ray.cc:1371-1373
+    u1 = u01_closed(v[0]); u2 = u01_closed(v[1]); p0 = u01_closed(v[2]); p1 = u01_closed(v[3]);
+  } else {
+    const uint32_t rw = (uint32_t)ray | ((uint32_t)face << 28);
+    const u32x4 a = philox4x32_10(u32x4{(uint32_t)dirId, rw, rg.timestep,
+                                        ((uint32_t)(dirId >> 32) << 8) | STREAM_FLUX_DIR}, rg.key0, rg.key1);
+    const u32x4 b = philox4x32_10(u32x4{(uint32_t)cellId, rw, rg.timestep,
+                                        ((uint32_t)(cellId >> 32) << 8) | STREAM_FLUX_ORIGIN}, rg.key0, rg.key1);
+    u1 = u01_closed(a.x); u2 = u01_closed(a.y); p0 = u01_closed(b.x); p1 = u01_closed(b.y);
+  }
+  const double phi = 2 * M_PI * u1;
+  const double theta = acos(u2);
+  cosTheta = cos(theta);
+  double sp, cp;
+  sincos(phi, &sp, &cp);
+  const double st = sin(theta);
+  const double tmp[3] = {st * cp, st * sp, cosTheta};
+  // Ray.cc:112-125 re-indexed to push order
+  const int axisN = face >> 1;            // normal axis
+  const bool hiFace = (face & 1) != 0;    // E, N, T
+  // indexOrder: x-faces (2,1,0), y-faces (0,2,1), z-faces (0,1,2); sign -1 on the normal axis of E, N, T
+  const int io0 = (axisN == 0) ? 2 : 0;
+  const int io1 = (axisN == 1) ? 2 : 1;
+  const int io2 = (axisN == 0) ? 0 : ((axisN == 1) ? 1 : 2);
+  dir[0] = tmp[io0] * ((axisN == 0 && hiFace) ? -1 : 1);
+  dir[1] = tmp[io1] * ((axisN == 1 && hiFace) ? -1 : 1);
+  dir[2] = tmp[io2] * ((axisN == 2 && hiFace) ? -1 : 1);
+  const int c[3] = {i, j, k};
+  double q[2] = {p0, p1};
+  int qi = 0;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double cc = g.anchor[d] + g.dx[d] * c[d] + g.dx[d] * 0.5;
+    const double c0 = cc - 0.5 * g.dx[d];
+    double o;
+    if (d == axisN) o = hiFace ? (c0 + g.dx[d]) : c0;
+    else o = c0 + q[qi++] * g.dx[d];
+    rayDx[d] = o - (cc - 0.5 * g.dx[d]);
+  }
+}
+
+template <class Real>
+__device__ __forceinline__ Real nz(double v) {   // direction component as Real, never exactly zero
+  Real r = (Real)v;
+  if (r == Real(0)) r = sign_bit(v) ? -Real(1e-30) : Real(1e-30);
+  return r;
+}
+
+template <class Real, class RecT, bool ML, bool RECORD>
+__device__ __forceinline__ Real trace_one(const TraceArgs& a, int i, int j, int k, const double dir[3], const double rayDx[3],
+                                          unsigned& steps, PathSink* path) {
+  const int F = a.G.maxLevels - 1;
+  const LevelGeom& g = a.G.lev[F];
+  if (ML) {
+    return march_multi_level<Real, RecT, MAXL, RECORD>(a.G, i, j, k, nz<Real>(dir[0]), nz<Real>(dir[1]), nz<Real>(dir[2]),
+                                                       (Real)rayDx[0], (Real)rayDx[1], (Real)rayDx[2], (Real)a.threshold,
+                                                       a.allowReflect != 0, a.skipZero != 0, steps, path);
+  } else {
+    return march_single_level<Real, RecT, RECORD>(static_cast<const RecT*>(g.rec), level_index(g, i, j, k), g.n[0],
+                                                  g.n[0] * g.n[1], nz<Real>(dir[0]), nz<Real>(dir[1]), nz<Real>(dir[2]),
+                                                  (Real)rayDx[0], (Real)rayDx[1], (Real)rayDx[2], (Real)g.dx[0],
+                                                  (Real)g.dx[1], (Real)g.dx[2], (Real)a.threshold, a.allowReflect != 0,
+                                                  a.skipZero != 0, steps, path, i, j, k);
+  }
+}
+
+//======================================================================================================
+// THE hot kernel.  One block = one tile of 32 consecutive (x-fastest) origin cells of the patch x W warps;
+// warp w marches rays w, w+W, ... of all 32 cells (lane = cell), so the lanes of a warp are parallel rays
+// from neighbouring cells (rayCoherence) and every step's 32 loads fall into a handful of 128-B lines.
+// Per-lane sums are combined across the W warps through shared memory in a fixed order (deterministic),
+// then lane = cell writes divQ / radiationVolq fully coalesced.
+//======================================================================================================
+template <class Real, class RecT, bool ML>
+__global__ void __launch_bounds__(256) divq_kernel(const __grid_constant__ TraceArgs a) {
+  extern __shared__ double red[];     // [W][32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+  const int F = a.G.maxLevels - 1;
+  const LevelGeom& g = a.G.lev[F];
+  const RecT* recs = static_cast<const RecT*>(g.rec);
+  unsigned long long stepsTotal = 0, cellsTotal = 0;
+
+  for (long long tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
+    const long long t = tile * 32 + lane;
+    const bool valid = t < a.nCells;
+    int i = 0, j = 0, k = 0;
+    bool flow = false;
+    RecT r0 = RecT{0, 0};
+    unsigned long long cellId = 0, dirId = 0;
+    if (valid) {
+      patch_cell(a, t, i, j, k);
+      cellId = (unsigned long long)level_index(g, i, j, k);
+      r0 = ldrec(recs + cellId);
+      flow = !is_wall(r0.k);
+    }
+    {
+      int i0, j0, k0;
+      patch_cell(a, tile * 32, i0, j0, k0);
+      dirId = a.rng.coherent ? (unsigned long long)level_index(g, i0, j0, k0) : cellId;
+    }
+    double acc = 0;
+    unsigned steps = 0;
+    if (flow) {
+      for (int ray = warp; ray < a.nRays; ray += W) {
+        double dir[3], rayDx[3];
+        gen_divq_ray(a.rng, g, i, j, k, ray, cellId, dirId, dir, rayDx);
+        acc += (double)trace_one<Real, RecT, ML, false>(a, i, j, k, dir, rayDx, steps, nullptr);
+      }
+    }
+    red[warp * 32 + lane] = acc;
+    __syncthreads();
+    if (warp == 0 && valid) {
+      double sumI = 0;
+      for (int w = 0; w < W; ++w) sumI += red[w * 32 + lane];
+      const long long q = (long long)(i - a.outLo[0]) +
+                          (long long)a.outN[0] * ((long long)(j - a.outLo[1]) + (long long)a.outN[1] * (long long)(k - a.outLo[2]));
+      if (flow) {
+        const double mean = sumI / a.nRays;
+        // Ray.cc:775,778 (DO: 1226,1229)
+        a.divQ[q] = -4.0 * M_PI * (double)r0.k * ((double)r0.s - mean);
+        a.volq[q] = 4.0 * M_PI * mean;
+        ++cellsTotal;
+      } else {
+        a.divQ[q] = 0.0;   // non-flow cells keep their initial 0 (Ray.cc:581-582,746-748)
+        a.volq[q] = 0.0;
+      }
+    }
+    __syncthreads();
+    stepsTotal += steps;
+  }
+  // one atomic per warp
+  for (int o = 16; o > 0; o >>= 1) {
+    stepsTotal += __shfl_down_sync(0xffffffffu, stepsTotal, o);
+    cellsTotal += __shfl_down_sync(0xffffffffu, cellsTotal, o);
+  }
+  if (lane == 0) {
+    if (stepsTotal) atomicAdd(a.counters + 0, stepsTotal);
+    if (cellsTotal) atomicAdd(a.counters + 2, cellsTotal);
+  }
+}
+
+//======================================================================================================
+// boundary flux
+//======================================================================================================
+// Ray::has_a_boundary (Ray.cc:1517-1572): `celltype[adj]+1 != 0`  <=>  adj is not a flow cell  <=>  record sign bit.
+template <class RecT>
+__global__ void flux_mask_kernel(const __grid_constant__ TraceArgs a, unsigned char* __restrict__ flags) {
+  const int F = a.G.maxLevels - 1;
+  const LevelGeom& g = a.G.lev[F];
+  const RecT* recs = static_cast<const RecT*>(g.rec);
+  unsigned long long nb = 0;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < a.nCells; t += (long long)gridDim.x * blockDim.x) {
+    int i, j, k;
+    patch_cell(a, t, i, j, k);
+    const long long c = level_index(g, i, j, k);
+    const bool flow = !is_wall(ldrec(recs + c).k);
+    unsigned m = 0;
+    if (flow || !a.fluxFlowGuard) {
+      const long long sy = g.n[0], sz = (long long)g.n[0] * g.n[1];
+      m |= is_wall(ldrec(recs + c - 1).k) ? 1u : 0u;
+      m |= is_wall(ldrec(recs + c + 1).k) ? 2u : 0u;
+      m |= is_wall(ldrec(recs + c - sy).k) ? 4u : 0u;
+      m |= is_wall(ldrec(recs + c + sy).k) ? 8u : 0u;
+      m |= is_wall(ldrec(recs + c - sz).k) ? 16u : 0u;
+      m |= is_wall(ldrec(recs + c + sz).k) ? 32u : 0u;
+      const long long q = (long long)(i - a.outLo[0]) +
+                          (long long)a.outN[0] * ((long long)(j - a.outLo[1]) + (long long)a.outN[1] * (long long)(k - a.outLo[2]));
+      a.bflux[7 * q + 6] = m ? 1.0 : 0.0;    // boundFlux[origin].p = has_a_boundary(...)  (Ray.cc:664)
+      nb += m ? 1 : 0;
+    }
+#pragma unroll
+    for (int f = 0; f < 6; ++f) flags[(long long)f * a.nCells + t] = (m >> f) & 1u;
+  }
+  for (int o = 16; o > 0; o >>= 1) nb += __shfl_down_sync(0xffffffffu, nb, o);
+  if ((threadIdx.x & 31) == 0 && nb) atomicAdd(a.counters + 3, nb);
+}
+
+// lane = one (face, cell) item; consecutive items are neighbouring cells on the same face.
+template <class Real, class RecT, bool ML>
+__global__ void __launch_bounds__(256) flux_trace_kernel(const __grid_constant__ TraceArgs a) {
+  extern __shared__ double red[];     // [W][32][2]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+  const int F = a.G.maxLevels - 1;
+  const LevelGeom& g = a.G.lev[F];
+  const long long nItems = *a.nItems;
+  const long long nTiles = (nItems + 31) / 32;
+  unsigned long long stepsTotal = 0;
+  for (long long tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+    const long long it = tile * 32 + lane;
+    const bool valid = it < nItems;
+    int i = 0, j = 0, k = 0, face = 0;
+    unsigned long long cellId = 0, dirId = 0;
+    if (valid) {
+      const long long id = a.items[it];
+      face = (int)(id / a.nCells);
+      patch_cell(a, id - (long long)face * a.nCells, i, j, k);
+      cellId = (unsigned long long)level_index(g, i, j, k);
+    }
+    {
+      const long long id0 = a.items[tile * 32];
+      const int f0 = (int)(id0 / a.nCells);
+      int i0, j0, k0;
+      patch_cell(a, id0 - (long long)f0 * a.nCells, i0, j0, k0);
+      // a warp straddling two faces still gets per-face directions through `face` in the counter
+      dirId = a.rng.coherent ? (unsigned long long)level_index(g, i0, j0, k0) : cellId;
+    }
+    double sumProj = 0, sumCos = 0;
+    unsigned steps = 0;
+    if (valid) {
+      for (int ray = warp; ray < a.nRays; ray += W) {
+        double dir[3], rayDx[3], cosT;
+        gen_flux_ray(a.rng, g, i, j, k, face, ray, cellId, dirId, dir, rayDx, cosT);
+        const double dI = (double)trace_one<Real, RecT, ML, false>(a, i, j, k, dir, rayDx, steps, nullptr);
+        sumProj += cosT * dI;      // sumProjI += cosTheta * (sumI - sumI_prev)   (Ray.cc:704)
+        sumCos += cosT;
+      }
+    }
+    red[(warp * 32 + lane) * 2 + 0] = sumProj;
+    red[(warp * 32 + lane) * 2 + 1] = sumCos;
+    __syncthreads();
+    if (warp == 0 && valid) {
+      double sp = 0, sc = 0;
+      for (int w = 0; w < W; ++w) { sp += red[(w * 32 + lane) * 2]; sc += red[(w * 32 + lane) * 2 + 1]; }
+      sp = sp * (double)a.nRays / sc / 2.0;                              // Ray.cc:712
+      const long long q = (long long)(i - a.outLo[0]) +
+                          (long long)a.outN[0] * ((long long)(j - a.outLo[1]) + (long long)a.outN[1] * (long long)(k - a.outLo[2]));
+      a.bflux[7 * q + face] = sp * 2 * M_PI / (double)a.nRays;           // Ray.cc:716-717
+    }
+    __syncthreads();
+    stepsTotal += steps;
+  }
+  for (int o = 16; o > 0; o >>= 1) stepsTotal += __shfl_down_sync(0xffffffffu, stepsTotal, o);
+  if (lane == 0 && stepsTotal) atomicAdd(a.counters + 1, stepsTotal);
+}
+
+//======================================================================================================
+// debug rays
+//======================================================================================================
+template <class Real, class RecT, bool ML>
+__global__ void debug_rays_kernel(const __grid_constant__ TraceArgs a, int n, const int* __restrict__ cells,
+                                  const double* __restrict__ dirs, const double* __restrict__ origins,
+                                  double* __restrict__ sumI, unsigned* __restrict__ stepsOut, int* pathBuf, int maxPath) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int F = a.G.maxLevels - 1;
+  const LevelGeom& g = a.G.lev[F];
+  const int i = cells[3 * t], j = cells[3 * t + 1], k = cells[3 * t + 2];
+  const int c[3] = {i, j, k};
+  double dir[3], rayDx[3];
+  for (int d = 0; d < 3; ++d) {
+    dir[d] = dirs[3 * t + d];
+    const double cc = g.anchor[d] + g.dx[d] * c[d] + g.dx[d] * 0.5;   // RMCRTCommon.cc:640-646
+    rayDx[d] = origins[3 * t + d] - (cc - 0.5 * g.dx[d]);
+  }
+  PathSink sink{pathBuf ? pathBuf + (long long)t * maxPath * 4 : nullptr, maxPath, 0};
+  unsigned steps = 0;
+  const Real v = trace_one<Real, RecT, ML, true>(a, i, j, k, dir, rayDx, steps, pathBuf ? &sink : nullptr);
+  sumI[t] = (double)v;
+  stepsOut[t] = steps;
+}
+
+//======================================================================================================
+// property pipeline
+//======================================================================================================
+template <class RecT> struct RecTraits;
+template <> struct RecTraits<Rec8>  { typedef float  real; };
+template <> struct RecTraits<Rec16> { typedef double real; };
+
+struct Box { int lo[3], n[3]; };
+__host__ __device__ inline long long box_cells(const Box& b) { return (long long)b.n[0] * b.n[1] * b.n[2]; }
+
+// status words: [0] non-finite count, [1] flow cells on the outer layer, [2] emitting non-flow cells
+template <class T, class RecT>
+__global__ void pack_kernel(const T* __restrict__ abskg, const T* __restrict__ sig, const int* __restrict__ ct, Box src,
+                            Box region /* cells to pack */, RecT* __restrict__ dst, Box dstBox, int flowCell,
+                            unsigned* __restrict__ status) {
+  typedef typename RecTraits<RecT>::real R;
+  const long long n = box_cells(region);
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const long long row = t / region.n[0];
+    const int i = region.lo[0] + (int)(t - row * region.n[0]);
+    const int kk = (int)(row / region.n[1]);
+    const int j = region.lo[1] + (int)(row - (long long)kk * region.n[1]);
+    const int k = region.lo[2] + kk;
+    const long long s = (long long)(i - src.lo[0]) + (long long)src.n[0] * ((long long)(j - src.lo[1]) + (long long)src.n[1] * (long long)(k - src.lo[2]));
+    const long long d = (long long)(i - dstBox.lo[0]) + (long long)dstBox.n[0] * ((long long)(j - dstBox.lo[1]) + (long long)dstBox.n[1] * (long long)(k - dstBox.lo[2]));
+    const T kv = abskg[s], sv = sig[s];
+    if (!isfinite((double)kv) || !isfinite((double)sv)) atomicAdd(status + 0, 1u);   // RMCRTCommon.cc:267-271
+    R kr = (R)kv;
+    kr = kr < R(0) ? -kr : kr;
+    if (ct[s] != flowCell) kr = -kr;     // sign bit == "not a flow cell", also for abskg == 0 (-0.0)
+    dst[d] = RecT{kr, (R)sv};
+  }
+}
+
+template <class RecT>
+__global__ void finalize_kernel(const RecT* __restrict__ recs, Box b, unsigned* __restrict__ status) {
+  const long long n = box_cells(b);
+  unsigned open = 0, emit = 0, bad = 0;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const long long row = t / b.n[0];
+    const int i = (int)(t - row * b.n[0]);
+    const int k = (int)(row / b.n[1]);
+    const int j = (int)(row - (long long)k * b.n[1]);
+    const RecT r = recs[t];
+    const bool wall = is_wall(r.k);
+    const bool outer = (i == 0 || j == 0 || k == 0 || i == b.n[0] - 1 || j == b.n[1] - 1 || k == b.n[2] - 1);
+    if (outer && !wall) ++open;
+    if (wall && (r.k != 0) && (r.s != 0)) ++emit;
+    if (!isfinite((double)r.k) || !isfinite((double)r.s)) ++bad;
+  }
+  if (bad) atomicAdd(status + 0, bad);
+  if (open) atomicAdd(status + 1, open);
+  if (emit) atomicAdd(status + 2, emit);
+}
+
+template <class T>
+__global__ void sigmaT4_kernel(const double* __restrict__ temp, T* __restrict__ out, long long n, double sigma_over_pi) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const double T2 = temp[t] * temp[t];
+    out[t] = (T)(sigma_over_pi * T2 * T2);   // RMCRTCommon.cc:339-340
+  }
+}
+
+// Ray::coarsen_Q (Ray.cc:2103-2145; AMR_CoarsenRefine.cc:42-86) + Ray::computeCellType (2272-2345), interior coarse cells.
+// cellType enters only as flow / not-flow: the integer sum of the reference equals -nFlow + sum(types of non-flow cells);
+// with the record's 1-bit cell type we reproduce the decision for the cases where every non-flow fine cell has a
+// positive type (true for every RMCRT deck and for Arches): ROUNDUP -> non-flow iff any fine cell is non-flow with
+// |avg|/10 >= 1/RR; ROUNDDOWN -> flow unless |avg|/10 > 1 - 1/RR.  We store the fine non-flow TYPE-free decision:
+//   all flow -> flow;  otherwise ROUNDUP -> intrusion, ROUNDDOWN -> flow unless all RR cells are non-flow.
+template <class RecT>
+__global__ void coarsen_kernel(const RecT* __restrict__ fine, Box fb, RecT* __restrict__ coarse, Box cb, Box cint,
+                               int rr0, int rr1, int rr2, int logic) {
+  typedef typename RecTraits<RecT>::real R;
+  const long long n = box_cells(cint);
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const long long row = t / cint.n[0];
+    const int i = cint.lo[0] + (int)(t - row * cint.n[0]);
+    const int kk = (int)(row / cint.n[1]);
+    const int j = cint.lo[1] + (int)(row - (long long)kk * cint.n[1]);
+    const int k = cint.lo[2] + kk;
+    // Level::mapCellToFiner (Level.cc:1311-1332)
+    const int fi = i * rr0 + ((i < 0 && rr0 > 1) ? 1 : 0), fj = j * rr1 + ((j < 0 && rr1 > 1) ? 1 : 0),
+              fk = k * rr2 + ((k < 0 && rr2 > 1) ? 1 : 0);
+    R ak = 0, as = 0;
+    int nWall = 0;
+    for (int c = 0; c < rr2; ++c) for (int b = 0; b < rr1; ++b) for (int a = 0; a < rr0; ++a) {
+      const long long f = (long long)(fi + a - fb.lo[0]) + (long long)fb.n[0] * ((long long)(fj + b - fb.lo[1]) + (long long)fb.n[1] * (long long)(fk + c - fb.lo[2]));
+      const RecT r = fine[f];
+      ak += (r.k < R(0) || is_wall(r.k)) ? -r.k : r.k;   // accumulate in T, x-fastest, like coarsenDriver_std
+      as += r.s;
+      nWall += is_wall(r.k) ? 1 : 0;
+    }
+    const double invRR = 1.0 / ((double)(rr0 * rr1 * rr2));
+    R kc = (R)(ak * invRR), sc = (R)(as * invRR);
+    const int RR = rr0 * rr1 * rr2;
+    bool wall;
+    if (nWall == 0) wall = false;
+    else if (logic == 0) wall = true;           // ROUNDUP: any partial cell becomes an intrusion
+    else wall = (nWall == RR);                  // ROUNDDOWN: any partial cell becomes a flow cell
+    const long long d = (long long)(i - cb.lo[0]) + (long long)cb.n[0] * ((long long)(j - cb.lo[1]) + (long long)cb.n[1] * (long long)(k - cb.lo[2]));
+    coarse[d] = RecT{wall ? -kc : kc, sc};
+  }
+}
+
+template <class RecT>
+__global__ void extra_cells_kernel(RecT* __restrict__ recs, Box b, Box interior, const double* __restrict__ vals /*[3][6]*/,
+                                   const int* __restrict__ types, int flowCell) {
+  typedef typename RecTraits<RecT>::real R;
+  const long long n = box_cells(b);
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const long long row = t / b.n[0];
+    const int i = b.lo[0] + (int)(t - row * b.n[0]);
+    const int kk = (int)(row / b.n[1]);
+    const int j = b.lo[1] + (int)(row - (long long)kk * b.n[1]);
+    const int k = b.lo[2] + kk;
+    // face order x-,x+,y-,y+,z-,z+ ; later faces overwrite earlier ones on shared edges, like the setBC face loop
+    int face = -1;
+    if (i < interior.lo[0]) face = 0;
+    if (i >= interior.lo[0] + interior.n[0]) face = 1;
+    if (j < interior.lo[1]) face = 2;
+    if (j >= interior.lo[1] + interior.n[1]) face = 3;
+    if (k < interior.lo[2]) face = 4;
+    if (k >= interior.lo[2] + interior.n[2]) face = 5;
+    if (face < 0) continue;
+    R kr = (R)fabs(vals[face]);
+    if (types[face] != flowCell) kr = -kr;
+    recs[t] = RecT{kr, (R)vals[6 + face]};
+  }
+}
+
+template <class RecT>
+__global__ void assemble_kernel(const unsigned char* __restrict__ gathered, size_t slotBytes, int rank, Box box,
+                                RecT* __restrict__ dst, Box dstBox) {
+  const RecT* src = reinterpret_cast<const RecT*>(gathered + (size_t)rank * slotBytes);
+  const long long n = box_cells(box);
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const long long row = t / box.n[0];
+    const int i = box.lo[0] + (int)(t - row * box.n[0]);
+    const int kk = (int)(row / box.n[1]);
+    const int j = box.lo[1] + (int)(row - (long long)kk * box.n[1]);
+    const int k = box.lo[2] + kk;
+    const long long d = (long long)(i - dstBox.lo[0]) + (long long)dstBox.n[0] * ((long long)(j - dstBox.lo[1]) + (long long)dstBox.n[1] * (long long)(k - dstBox.lo[2]));
+    dst[d] = src[t];
+  }
+}
+
+
+// ---- roofline denominators ----
+__global__ void bw_stream_kernel(const uint4* __restrict__ buf, long long n16, unsigned* sink) {
+  unsigned acc = 0;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n16; t += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(buf + t);
+    acc ^= v.x ^ v.y ^ v.z ^ v.w;
+  }
+  if (acc == 0x12345677u) *sink = acc;
+}
+__global__ void bw_gather_kernel(const float2* __restrict__ buf, unsigned nRec, int perThread, unsigned* sink) {
+  unsigned x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+  float acc = 0;
+#pragma unroll 4
+  for (int i = 0; i < perThread; ++i) {
+    x = x * 1664525u + 1013904223u;                         // LCG: next index independent of loaded data
+    const unsigned idx = (unsigned)(((unsigned long long)(x ^ (x >> 15)) * nRec) >> 32);
+    const float2 v = __ldg(buf + idx);
+    acc += v.x + v.y;
+  }
+  if (acc == 123.456f) *sink = 1;
+}
+
+}  // namespace
+
+//======================================================================================================
+// host side
+//======================================================================================================
+struct LevelState {
+  bool defined = false;
+  bool finalized = false;
+  bool wallsEmit = true;
+  rmcrt_level_desc d{};
+  int recordKind = 0;
+  void* base = nullptr;   // allocation (guard records in front of and behind the level)
+  void* rec = nullptr;    // record of cell `lo`
+  long long nCells = 0;
+  size_t recBytes = 8;
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return -1;
+    cap = bytes;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct rmcrt_ctx {
+  int device = 0;
+  int smCount = 148;
+  rmcrt_params p{};
+  LevelState lv[RMCRT_MAX_LEVELS];
+  unsigned long long* d_counters = nullptr;   // 4
+  unsigned* d_status = nullptr;               // 4
+  int* d_nItems = nullptr;
+  DevBuf stage[3];      // upload staging
+  DevBuf outDivQ, outVolq, outFlux;   // host-API output staging
+  DevBuf fluxFlags, fluxItems, cubTemp, dbg[6], misc;
+  std::string err;
+  void* persistedStreamFor = nullptr;
+};
+
+namespace {
+
+std::string g_createErr;
+std::mutex g_mu;
+
+int fail(rmcrt_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf; else { std::lock_guard<std::mutex> l(g_mu); g_createErr = buf; }
+  return code;
+}
+
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) return fail(ctx, RMCRT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+Box mkbox(const int32_t lo[3], const int32_t hi[3]) {
+  Box b;
+  for (int d = 0; d < 3; ++d) { b.lo[d] = lo[d]; b.n[d] = hi[d] - lo[d]; }
+  return b;
+}
+
+int grid_for(long long n, int block, int sm) {
+  long long g = (n + block - 1) / block;
+  long long cap = (long long)sm * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+int check_level(rmcrt_ctx* ctx, int L) {
+  if (!ctx) return RMCRT_ERR_INVALID;
+  if (L < 0 || L >= RMCRT_MAX_LEVELS || !ctx->lv[L].defined) return fail(ctx, RMCRT_ERR_INVALID, "level %d is not defined", L);
+  return 0;
+}
+
+int validate_params(rmcrt_ctx* ctx, const rmcrt_params* p) {
+  if (p->nDivQRays < 1 || p->nFluxRays < 1) return fail(ctx, RMCRT_ERR_INVALID, "nDivQRays and nFluxRays must be >= 1");
+  if (p->nFluxRays >= (1 << 28)) return fail(ctx, RMCRT_ERR_INVALID, "nFluxRays too large");
+  if (!(p->threshold >= 0)) return fail(ctx, RMCRT_ERR_INVALID, "Threshold must be >= 0");
+  if (p->marchPrecision != 0 && p->marchPrecision != 1) return fail(ctx, RMCRT_ERR_INVALID, "marchPrecision must be 0 (fp32) or 1 (fp64)");
+  return 0;
+}
+
+void fill_level_geom(const rmcrt_ctx* ctx, int L, LevelGeom& g) {
+  const LevelState& s = ctx->lv[L];
+  g.rec = s.rec;
+  for (int d = 0; d < 3; ++d) {
+    g.lo[d] = s.d.lo[d]; g.n[d] = s.d.hi[d] - s.d.lo[d];
+    g.intLo[d] = s.d.interiorLo[d]; g.intHi[d] = s.d.interiorHi[d];
+    g.rr[d] = s.d.refineRatio[d] > 0 ? s.d.refineRatio[d] : 1;
+    g.regLo[d] = s.d.interiorLo[d]; g.regHi[d] = s.d.interiorHi[d];
+    g.dx[d] = s.d.dx[d];
+    g.anchor[d] = s.d.anchor[d];
+    g.off[d] = 0.0;
+  }
+}
+
+// Level::mapCellToCoarser (Level.cc:1285-1307)
+int map_coarser_host(int i, int rr) {
+  int q = i / rr;
+  if (i < 0 && rr > 1) q += (int)fmod((double)i, (double)rr);
+  return q;
+}
+
+// Ray::computeExtents, patch_based (Ray.cc:1312-1357)
+void compute_extents(const rmcrt_ctx* ctx, int maxLevels, const int32_t pLo[3], const int32_t pHi[3], int32_t roiLo[3],
+                     int32_t roiHi[3], int32_t* regLo, int32_t* regHi) {
+  const int F = maxLevels - 1;
+  const rmcrt_level_desc& f = ctx->lv[F].d;
+  for (int d = 0; d < 3; ++d) {
+    roiLo[d] = std::max(pLo[d] - ctx->p.haloCells[d], f.lo[d]);
+    roiHi[d] = std::min(pHi[d] + ctx->p.haloCells[d], f.hi[d]);
+    const int ec = f.interiorLo[d] - f.lo[d];
+    regLo[3 * F + d] = roiLo[d] + ec;
+    regHi[3 * F + d] = roiHi[d] - ec;
+    regLo[d] = ctx->lv[0].d.interiorLo[d];
+    regHi[d] = ctx->lv[0].d.interiorHi[d];
+  }
+  for (int L = maxLevels - 2; L > 0; --L) {
+    const rmcrt_level_desc& l = ctx->lv[L].d;
+    for (int d = 0; d < 3; ++d) {
+      const int rr = l.refineRatio[d] > 0 ? l.refineRatio[d] : 1;
+      regLo[3 * L + d] = std::max(map_coarser_host(regLo[3 * (L + 1) + d], rr) - ctx->p.haloCells[d], l.interiorLo[d]);
+      regHi[3 * L + d] = std::min(map_coarser_host(regHi[3 * (L + 1) + d], rr) + ctx->p.haloCells[d], l.interiorHi[d]);
+    }
+  }
+}
+
+int pick_warps(const rmcrt_ctx* ctx, long long nTiles) {
+  if (ctx->p.warpsPerTile > 0) {
+    int w = ctx->p.warpsPerTile;
+    return w > 8 ? 8 : w;
+  }
+  // enough warps to fill the machine ~4x over: 148 SMs x 32 resident warps
+  const long long want = (long long)ctx->smCount * 32 * 4;
+  int w = 1;
+  while (w < 8 && nTiles * w < want) w *= 2;
+  return w;
+}
+
+void apply_l2_window(rmcrt_ctx* ctx, int L, cudaStream_t st) {
+  if (!ctx->p.l2Persist) return;
+  const LevelState& s = ctx->lv[L];
+  int maxWin = 0, maxPersist = 0;
+  cudaDeviceGetAttribute(&maxWin, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+  cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+  if (maxWin <= 0 || maxPersist <= 0) return;
+  const size_t bytes = (size_t)s.nCells * s.recBytes;
+  const size_t win = std::min(bytes, (size_t)maxWin);
+  cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(win, (size_t)maxPersist));
+  cudaStreamAttrValue attr;
+  memset(&attr, 0, sizeof attr);
+  attr.accessPolicyWindow.base_ptr = s.rec;
+  attr.accessPolicyWindow.num_bytes = win;
+  attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)maxPersist / (double)win);
+  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+  cudaGetLastError();
+}
+
+template <class T, class RecT>
+int launch_pack(rmcrt_ctx* ctx, const void* a, const void* s, const int32_t* ct, Box src, Box region, void* dst, Box dstBox,
+                cudaStream_t st) {
+  const long long n = box_cells(region);
+  if (n <= 0) return 0;
+  pack_kernel<T, RecT><<<grid_for(n, 256, ctx->smCount), 256, 0, st>>>(static_cast<const T*>(a), static_cast<const T*>(s), ct, src,
+                                                                     region, static_cast<RecT*>(dst), dstBox, ctx->p.flowCell,
+                                                                     ctx->d_status);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int do_pack(rmcrt_ctx* ctx, int recordKind, int isFloat, const void* a, const void* s, const int32_t* ct, Box src, Box region,
+            void* dst, Box dstBox, cudaStream_t st) {
+  if (recordKind == 0) return isFloat ? launch_pack<float, Rec8>(ctx, a, s, ct, src, region, dst, dstBox, st)
+                                      : launch_pack<double, Rec8>(ctx, a, s, ct, src, region, dst, dstBox, st);
+  return isFloat ? launch_pack<float, Rec16>(ctx, a, s, ct, src, region, dst, dstBox, st)
+                 : launch_pack<double, Rec16>(ctx, a, s, ct, src, region, dst, dstBox, st);
+}
+
+int build_args(rmcrt_ctx* ctx, int maxLevels, bool multiLevel, const int32_t pLo[3], const int32_t pHi[3], const int32_t oLo[3],
+               const int32_t oHi[3], uint64_t timestep, TraceArgs& a) {
+  memset(&a, 0, sizeof a);
+  const int F = maxLevels - 1;
+  if (maxLevels < 1 || maxLevels > MAXL) return fail(ctx, RMCRT_ERR_INVALID, "maxLevels %d not in [1,%d]", maxLevels, MAXL);
+  for (int L = multiLevel ? 0 : F; L <= F; ++L) {
+    int rc = check_level(ctx, L);
+    if (rc) return rc;
+    if (ctx->lv[L].recordKind != ctx->lv[F].recordKind) return fail(ctx, RMCRT_ERR_INVALID, "all levels must use one recordKind");
+  }
+  if ((ctx->p.marchPrecision == 1) != (ctx->lv[F].recordKind == 1))
+    return fail(ctx, RMCRT_ERR_INVALID, "marchPrecision fp64 needs recordKind 1 (double records) and fp32 needs recordKind 0");
+  a.G.maxLevels = maxLevels;
+  for (int L = 0; L <= F; ++L) if (ctx->lv[L].defined) fill_level_geom(ctx, L, a.G.lev[L]);
+  const rmcrt_level_desc& f = ctx->lv[F].d;
+  for (int d = 0; d < 3; ++d) {
+    if (pLo[d] < f.interiorLo[d] || pHi[d] > f.interiorHi[d] || pHi[d] <= pLo[d])
+      return fail(ctx, RMCRT_ERR_INVALID, "patch [%d,%d) outside the interior of level %d on axis %d", pLo[d], pHi[d], F, d);
+    if (oLo[d] > pLo[d] || oHi[d] < pHi[d]) return fail(ctx, RMCRT_ERR_INVALID, "output window does not contain the patch");
+    a.patchLo[d] = pLo[d]; a.patchN[d] = pHi[d] - pLo[d];
+    a.outLo[d] = oLo[d]; a.outN[d] = oHi[d] - oLo[d];
+  }
+  a.multiLevel = multiLevel ? 1 : 0;
+  if (multiLevel) {
+    int32_t roiLo[3], roiHi[3], regLo[3 * RMCRT_MAX_LEVELS], regHi[3 * RMCRT_MAX_LEVELS];
+    compute_extents(ctx, maxLevels, pLo, pHi, roiLo, roiHi, regLo, regHi);
+    for (int d = 0; d < 3; ++d) { a.G.roiLo[d] = roiLo[d]; a.G.roiHi[d] = roiHi[d]; }
+    for (int L = 0; L <= F; ++L) for (int d = 0; d < 3; ++d) { a.G.lev[L].regLo[d] = regLo[3 * L + d]; a.G.lev[L].regHi[d] = regHi[3 * L + d]; }
+    for (int L = 0; L <= F; ++L) for (int d = 0; d < 3; ++d) a.G.lev[L].off[d] = ctx->lv[L].d.anchor[d] - f.anchor[d];
+  }
+  a.nCells = (long long)a.patchN[0] * a.patchN[1] * a.patchN[2];
+  if (a.nCells * 6 >= (1LL << 31)) return fail(ctx, RMCRT_ERR_INVALID, "patch too large (%lld cells); split it", a.nCells);
+  a.nTiles = (a.nCells + 31) / 32;
+  a.threshold = ctx->p.threshold;
+  a.allowReflect = ctx->p.allowReflect;
+  bool emit = false;
+  for (int L = multiLevel ? 0 : F; L <= F; ++L) emit = emit || ctx->lv[L].wallsEmit || !ctx->lv[L].finalized;
+  a.skipZero = (ctx->p.skipZeroWeightLegs && !emit) ? 1 : 0;
+  a.fluxFlowGuard = multiLevel ? 0 : 1;
+  a.rng.key0 = (uint32_t)ctx->p.seed;
+  a.rng.key1 = (uint32_t)(ctx->p.seed >> 32) ^ (uint32_t)(timestep >> 32);
+  a.rng.timestep = (uint32_t)timestep;
+  a.rng.isSeedRandom = ctx->p.isSeedRandom;
+  a.rng.fixedRandom = ctx->p.fixedRandom;
+  a.rng.ccRays = ctx->p.CCRays;
+  a.rng.coherent = ctx->p.rayCoherence;
+  a.counters = ctx->d_counters;
+  return 0;
+}
+
+template <class Real, class RecT>
+int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
+  // ---- boundary flux first, like the task body (Ray.cc:645 before 742)
+  if (ctx->p.solveBoundaryFlux) {
+    if (!a.bflux) return fail(ctx, RMCRT_ERR_INVALID, "solveBoundaryFlux needs a boundFlux buffer");
+    if (ctx->fluxFlags.ensure((size_t)a.nCells * 6)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc flux flags");
+    if (ctx->fluxItems.ensure((size_t)a.nCells * 6 * sizeof(int))) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc flux items");
+    unsigned char* flags = static_cast<unsigned char*>(ctx->fluxFlags.p);
+    flux_mask_kernel<RecT><<<grid_for(a.nCells, 256, ctx->smCount), 256, 0, st>>>(a, flags);
+    CK(cudaGetLastError());
+    cub::CountingInputIterator<int> ids(0);
+    size_t tmpBytes = 0;
+    const int nFlag = (int)(a.nCells * 6);
+    CK(cub::DeviceSelect::Flagged(nullptr, tmpBytes, ids, flags, static_cast<int*>(ctx->fluxItems.p), ctx->d_nItems, nFlag, st));
+    if (ctx->cubTemp.ensure(tmpBytes + 16)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc cub temp");
+    CK(cub::DeviceSelect::Flagged(ctx->cubTemp.p, tmpBytes, ids, flags, static_cast<int*>(ctx->fluxItems.p), ctx->d_nItems, nFlag, st));
+    TraceArgs f = a;
+    f.items = static_cast<const int*>(ctx->fluxItems.p);
+    f.nItems = ctx->d_nItems;
+    f.nRays = ctx->p.nFluxRays;
+    const int W = ctx->p.warpsPerTile > 0 ? std::min(ctx->p.warpsPerTile, 8) : (ctx->p.nFluxRays >= 8 ? 8 : 1);
+    const int grid = ctx->smCount * 8;
+    if (ML) flux_trace_kernel<Real, RecT, true><<<grid, 32 * W, W * 64 * sizeof(double), st>>>(f);
+    else    flux_trace_kernel<Real, RecT, false><<<grid, 32 * W, W * 64 * sizeof(double), st>>>(f);
+    CK(cudaGetLastError());
+  }
+  if (ctx->p.solveDivQ) {
+    a.nRays = ctx->p.nDivQRays;
+    int W = pick_warps(ctx, a.nTiles);
+    if (W > a.nRays) W = 1;
+    long long grid = a.nTiles;
+    const long long cap = (long long)ctx->smCount * 64;   // persistent-ish: grid-stride beyond this
+    if (grid > cap) grid = cap;
+    if (ML) divq_kernel<Real, RecT, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
+    else    divq_kernel<Real, RecT, false><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
+    CK(cudaGetLastError());
+  }
+  return 0;
+}
+
+int trace_common(rmcrt_ctx* ctx, int maxLevels, bool ML, const int32_t pLo[3], const int32_t pHi[3], double* dDivQ, double* dVolq,
+                 double* dFlux, const int32_t oLo[3], const int32_t oHi[3], int zeroInit, uint64_t timestep, cudaStream_t st) {
+  TraceArgs a;
+  int rc = build_args(ctx, maxLevels, ML, pLo, pHi, oLo, oHi, timestep, a);
+  if (rc) return rc;
+  if (!dDivQ || !dVolq) return fail(ctx, RMCRT_ERR_INVALID, "divQ and radiationVolq buffers are required");
+  a.divQ = dDivQ; a.volq = dVolq; a.bflux = dFlux;
+  const size_t nOut = (size_t)a.outN[0] * a.outN[1] * a.outN[2];
+  CK(cudaSetDevice(ctx->device));
+  if (zeroInit) {   // Ray.cc:577-587
+    CK(cudaMemsetAsync(dDivQ, 0, nOut * sizeof(double), st));
+    CK(cudaMemsetAsync(dVolq, 0, nOut * sizeof(double), st));
+    if (dFlux) CK(cudaMemsetAsync(dFlux, 0, nOut * 7 * sizeof(double), st));
+  }
+  if (ctx->p.l2Persist && ctx->persistedStreamFor != (void*)st) {
+    apply_l2_window(ctx, maxLevels - 1, st);
+    ctx->persistedStreamFor = (void*)st;
+  }
+  if (ctx->p.marchPrecision == 1) return launch_trace<double, Rec16>(ctx, a, ML, st);
+  return launch_trace<float, Rec8>(ctx, a, ML, st);
+}
+
+int trace_host(rmcrt_ctx* ctx, int maxLevels, bool ML, const int32_t pLo[3], const int32_t pHi[3], double* divQ, double* volq,
+               double* flux, const int32_t oLo[3], const int32_t oHi[3], int zeroInit, uint64_t timestep, cudaStream_t st) {
+  if (!ctx) return RMCRT_ERR_INVALID;
+  if (!divQ || !volq) return fail(ctx, RMCRT_ERR_INVALID, "divQ and radiationVolq buffers are required");
+  size_t nOut = 1;
+  for (int d = 0; d < 3; ++d) {
+    if (oHi[d] <= oLo[d]) return fail(ctx, RMCRT_ERR_INVALID, "empty output window");
+    nOut *= (size_t)(oHi[d] - oLo[d]);
+  }
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->outDivQ.ensure(nOut * 8) || ctx->outVolq.ensure(nOut * 8)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc outputs");
+  double* dFlux = nullptr;
+  if (flux) {
+    if (ctx->outFlux.ensure(nOut * 56)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc boundFlux");
+    dFlux = static_cast<double*>(ctx->outFlux.p);
+  }
+  if (!zeroInit) {   // modifies_divQ: start from the caller's values
+    CK(cudaMemcpyAsync(ctx->outDivQ.p, divQ, nOut * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->outVolq.p, volq, nOut * 8, cudaMemcpyHostToDevice, st));
+    if (flux) CK(cudaMemcpyAsync(dFlux, flux, nOut * 56, cudaMemcpyHostToDevice, st));
+  }
+  int rc = trace_common(ctx, maxLevels, ML, pLo, pHi, static_cast<double*>(ctx->outDivQ.p), static_cast<double*>(ctx->outVolq.p),
+                        dFlux, oLo, oHi, zeroInit, timestep, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(divQ, ctx->outDivQ.p, nOut * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(volq, ctx->outVolq.p, nOut * 8, cudaMemcpyDeviceToHost, st));
+  if (flux) CK(cudaMemcpyAsync(flux, dFlux, nOut * 56, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // namespace
+
+//======================================================================================================
+// C ABI
+//======================================================================================================
+extern "C" {
+
+int rmcrt_abi_version(void) { return RMCRT_ABI_VERSION; }
+
+size_t rmcrt_struct_size(int which) {
+  switch (which) {
+    case 0: return sizeof(rmcrt_params);
+    case 1: return sizeof(rmcrt_level_desc);
+    case 2: return sizeof(rmcrt_counters);
+    default: return 0;
+  }
+}
+
+void rmcrt_default_params(rmcrt_params* p) {
+  memset(p, 0, sizeof *p);
+  p->nDivQRays = 10; p->nFluxRays = 1; p->threshold = 0.01; p->sigma = 5.67051e-8;   // Ray.cc:162-173
+  p->allowReflect = 1; p->CCRays = 0; p->solveDivQ = 1; p->solveBoundaryFlux = 0; p->isSeedRandom = 1;
+  p->flowCell = -1;
+  p->haloCells[0] = p->haloCells[1] = p->haloCells[2] = 10;   // Ray.cc:254
+  p->cellTypeCoarsenLogic = 0;
+  p->seed = 0x9E3779B97F4A7C15ull;
+  p->marchPrecision = 0; p->rayCoherence = 1; p->skipZeroWeightLegs = 1; p->fixedRandom = 0; p->l2Persist = 1;
+  p->warpsPerTile = 0;
+}
+
+const char* rmcrt_last_error(const rmcrt_ctx* ctx) {
+  if (ctx) return ctx->err.c_str();
+  std::lock_guard<std::mutex> l(g_mu);
+  return g_createErr.c_str();
+}
+
+int rmcrt_create(int device, const rmcrt_params* p, rmcrt_ctx** out) {
+  rmcrt_ctx* ctx = nullptr;
+  if (!out || !p) return fail(nullptr, RMCRT_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int nDev = 0;
+  cudaError_t e = cudaGetDeviceCount(&nDev);
+  if (e != cudaSuccess || nDev <= 0)
+    return fail(nullptr, RMCRT_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= nDev) return fail(nullptr, RMCRT_ERR_INVALID, "device %d out of range [0,%d)", device, nDev);
+  int rc = validate_params(nullptr, p);
+  if (rc) return rc;
+  ctx = new rmcrt_ctx();
+  ctx->device = device;
+  ctx->p = *p;
+  auto bail = [&](const char* what) { std::string m = what; rmcrt_destroy(ctx); return fail(nullptr, RMCRT_ERR_CUDA, "%s", m.c_str()); };
+  if (cudaSetDevice(device) != cudaSuccess) return bail("cudaSetDevice failed");
+  cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, device);
+  if (cudaMalloc(&ctx->d_counters, 4 * sizeof(unsigned long long)) != cudaSuccess) return bail("cudaMalloc counters");
+  if (cudaMalloc(&ctx->d_status, 4 * sizeof(unsigned)) != cudaSuccess) return bail("cudaMalloc status");
+  if (cudaMalloc(&ctx->d_nItems, sizeof(int)) != cudaSuccess) return bail("cudaMalloc nItems");
+  cudaMemset(ctx->d_counters, 0, 4 * sizeof(unsigned long long));
+  cudaMemset(ctx->d_status, 0, 4 * sizeof(unsigned));
+  cudaMemset(ctx->d_nItems, 0, sizeof(int));
+  *out = ctx;
+  return 0;
+}
+
+int rmcrt_set_params(rmcrt_ctx* ctx, const rmcrt_params* p) {
+  if (!ctx || !p) return RMCRT_ERR_INVALID;
+  int rc = validate_params(ctx, p);
+  if (rc) return rc;
+  ctx->p = *p;
+  ctx->persistedStreamFor = nullptr;
+  return 0;
+}
+
+void rmcrt_destroy(rmcrt_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (auto& l : ctx->lv) if (l.base) cudaFree(l.base);
+  if (ctx->d_counters) cudaFree(ctx->d_counters);
+  if (ctx->d_status) cudaFree(ctx->d_status);
+  if (ctx->d_nItems) cudaFree(ctx->d_nItems);
+  for (auto& b : ctx->stage) b.release();
+  ctx->outDivQ.release(); ctx->outVolq.release(); ctx->outFlux.release();
+  ctx->fluxFlags.release(); ctx->fluxItems.release(); ctx->cubTemp.release(); ctx->misc.release();
+  for (auto& b : ctx->dbg) b.release();
+  delete ctx;
+}
+
+int rmcrt_define_level(rmcrt_ctx* ctx, int L, const rmcrt_level_desc* d, int recordKind) {
+  if (!ctx || !d) return RMCRT_ERR_INVALID;
+  if (L < 0 || L >= RMCRT_MAX_LEVELS) return fail(ctx, RMCRT_ERR_INVALID, "level index %d out of range", L);
+  if (recordKind != 0 && recordKind != 1) return fail(ctx, RMCRT_ERR_INVALID, "recordKind must be 0 or 1");
+  long long n = 1;
+  for (int k = 0; k < 3; ++k) {
+    if (d->hi[k] - d->lo[k] < 3) return fail(ctx, RMCRT_ERR_INVALID, "level needs >= 3 cells per axis incl. extra cells");
+    if (d->interiorLo[k] <= d->lo[k] || d->interiorHi[k] >= d->hi[k] || d->interiorHi[k] <= d->interiorLo[k])
+      return fail(ctx, RMCRT_ERR_INVALID, "level interior must be strictly inside [lo,hi): extraCells >= 1 (RMCRT_Test.cc:238-251)");
+    if (!(d->dx[k] > 0)) return fail(ctx, RMCRT_ERR_INVALID, "dx must be positive");
+    n *= (d->hi[k] - d->lo[k]);
+  }
+  if (n >= (1LL << 31)) return fail(ctx, RMCRT_ERR_INVALID, "level too large for 32-bit record strides");
+  CK(cudaSetDevice(ctx->device));
+  LevelState& s = ctx->lv[L];
+  if (s.defined && s.base && s.recordKind == recordKind && s.nCells == n && memcmp(s.d.lo, d->lo, sizeof d->lo) == 0 &&
+      memcmp(s.d.hi, d->hi, sizeof d->hi) == 0) {
+    s.d = *d;              // same shape: keep the allocation (a new radiation solve re-packs into it)
+    s.finalized = false;
+    s.wallsEmit = true;
+    return 0;
+  }
+  if (s.base) { cudaFree(s.base); s.base = nullptr; s.rec = nullptr; }
+  s.d = *d;
+  s.recordKind = recordKind;
+  s.recBytes = recordKind == 0 ? sizeof(Rec8) : sizeof(Rec16);
+  s.nCells = n;
+  // guard records on both ends (flagged "not a flow cell") so neighbour / speculative loads issued from any cell of
+  // the level stay inside the allocation
+  const long long guard = (long long)(d->hi[0] - d->lo[0]) * (d->hi[1] - d->lo[1]) + (d->hi[0] - d->lo[0]) + 1;
+  void* base = nullptr;
+  CK(cudaMalloc(&base, (size_t)(n + 2 * guard) * s.recBytes));
+  CK(cudaMemset(base, 0xFF, (size_t)(n + 2 * guard) * s.recBytes));   // 0xFF.. = negative NaN: wall flag set, caught by finalize if left
+  s.base = base;
+  s.rec = static_cast<char*>(base) + (size_t)guard * s.recBytes;
+  s.defined = true;
+  s.finalized = false;
+  s.wallsEmit = true;
+  ctx->persistedStreamFor = nullptr;
+  return 0;
+}
+
+int rmcrt_pack_level_device(rmcrt_ctx* ctx, int L, const void* a, const void* s, const int32_t* ct, int isFloat,
+                            const int32_t srcLo[3], const int32_t srcHi[3], void* stream) {
+  int rc = check_level(ctx, L);
+  if (rc) return rc;
+  if (!a || !s || !ct) return fail(ctx, RMCRT_ERR_INVALID, "null property pointer");
+  CK(cudaSetDevice(ctx->device));
+  LevelState& lv = ctx->lv[L];
+  Box src = mkbox(srcLo, srcHi), dst = mkbox(lv.d.lo, lv.d.hi);
+  Box region;
+  for (int d = 0; d < 3; ++d) {
+    const int lo = std::max(srcLo[d], lv.d.lo[d]), hi = std::min(srcHi[d], lv.d.hi[d]);
+    if (hi <= lo) return fail(ctx, RMCRT_ERR_INVALID, "source window does not overlap level %d", L);
+    region.lo[d] = lo; region.n[d] = hi - lo;
+  }
+  lv.finalized = false;
+  return do_pack(ctx, lv.recordKind, isFloat, a, s, ct, src, region, lv.rec, dst, (cudaStream_t)stream);
+}
+
+int rmcrt_upload_level(rmcrt_ctx* ctx, int L, const void* a, const void* s, const int32_t* ct, int isFloat,
+                       const int32_t srcLo[3], const int32_t srcHi[3], void* stream) {
+  int rc = check_level(ctx, L);
+  if (rc) return rc;
+  if (!a || !s || !ct) return fail(ctx, RMCRT_ERR_INVALID, "null property pointer");
+  CK(cudaSetDevice(ctx->device));
+  size_t n = 1;
+  for (int d = 0; d < 3; ++d) {
+    if (srcHi[d] <= srcLo[d]) return fail(ctx, RMCRT_ERR_INVALID, "empty source window");
+    n *= (size_t)(srcHi[d] - srcLo[d]);
+  }
+  const size_t eb = isFloat ? 4 : 8;
+  if (ctx->stage[0].ensure(n * eb) || ctx->stage[1].ensure(n * eb) || ctx->stage[2].ensure(n * 4))
+    return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc staging failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(ctx->stage[0].p, a, n * eb, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->stage[1].p, s, n * eb, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->stage[2].p, ct, n * 4, cudaMemcpyHostToDevice, st));
+  return rmcrt_pack_level_device(ctx, L, ctx->stage[0].p, ctx->stage[1].p, static_cast<const int32_t*>(ctx->stage[2].p), isFloat,
+                                 srcLo, srcHi, stream);
+}
+
+int rmcrt_finalize_level(rmcrt_ctx* ctx, int L, void* stream) {
+  int rc = check_level(ctx, L);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  LevelState& lv = ctx->lv[L];
+  unsigned h[4] = {0, 0, 0, 0};
+  CK(cudaStreamSynchronize(st));
+  CK(cudaMemcpy(h, ctx->d_status, sizeof h, cudaMemcpyDeviceToHost));   // non-finite inputs seen by pack
+  const unsigned badPacked = h[0];
+  CK(cudaMemsetAsync(ctx->d_status, 0, 4 * sizeof(unsigned), st));
+  Box b = mkbox(lv.d.lo, lv.d.hi);
+  if (lv.recordKind == 0) finalize_kernel<Rec8><<<grid_for(lv.nCells, 256, ctx->smCount), 256, 0, st>>>(static_cast<const Rec8*>(lv.rec), b, ctx->d_status);
+  else                    finalize_kernel<Rec16><<<grid_for(lv.nCells, 256, ctx->smCount), 256, 0, st>>>(static_cast<const Rec16*>(lv.rec), b, ctx->d_status);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(h, ctx->d_status, sizeof h, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaMemsetAsync(ctx->d_status, 0, 4 * sizeof(unsigned), st));
+  if (h[0] || badPacked)
+    return fail(ctx, RMCRT_ERR_NONPHYSICAL, "level %d: %u non-finite abskg/sigmaT4 values (or unset cells)", L, h[0] + badPacked);
+  if (h[1]) return fail(ctx, RMCRT_ERR_OPEN_DOMAIN, "level %d: %u flow cells on the outer (extra-cell) layer; rays could leave the level", L, h[1]);
+  lv.wallsEmit = (h[2] != 0);
+  lv.finalized = true;
+  return 0;
+}
+
+int rmcrt_level_records(rmcrt_ctx* ctx, int L, void** d_records, size_t* bytes, size_t* recordBytes) {
+  int rc = check_level(ctx, L);
+  if (rc) return rc;
+  if (d_records) *d_records = ctx->lv[L].rec;
+  if (bytes) *bytes = (size_t)ctx->lv[L].nCells * ctx->lv[L].recBytes;
+  if (recordBytes) *recordBytes = ctx->lv[L].recBytes;
+  return 0;
+}
+
+int rmcrt_trace_divq_device(rmcrt_ctx* ctx, int L, const int32_t pLo[3], const int32_t pHi[3], double* dq, double* vq, double* bf,
+                            const int32_t oLo[3], const int32_t oHi[3], int zeroInit, uint64_t timestep, void* stream) {
+  int rc = check_level(ctx, L);
+  if (rc) return rc;
+  if (L + 1 > MAXL) return fail(ctx, RMCRT_ERR_INVALID, "level index too large");
+  return trace_common(ctx, L + 1, false, pLo, pHi, dq, vq, bf, oLo, oHi, zeroInit, timestep, (cudaStream_t)stream);
+}
+
+int rmcrt_trace_divq(rmcrt_ctx* ctx, int L, const int32_t pLo[3], const int32_t pHi[3], double* dq, double* vq, double* bf,
+                     const int32_t oLo[3], const int32_t oHi[3], int zeroInit, uint64_t timestep, void* stream) {
+  int rc = check_level(ctx, L);
+  if (rc) return rc;
+  return trace_host(ctx, L + 1, false, pLo, pHi, dq, vq, bf, oLo, oHi, zeroInit, timestep, (cudaStream_t)stream);
+}
+
+int rmcrt_trace_dataonion_device(rmcrt_ctx* ctx, int maxLevels, const int32_t pLo[3], const int32_t pHi[3], double* dq, double* vq,
+                                 double* bf, const int32_t oLo[3], const int32_t oHi[3], int zeroInit, uint64_t timestep, void* stream) {
+  if (!ctx) return RMCRT_ERR_INVALID;
+  return trace_common(ctx, maxLevels, true, pLo, pHi, dq, vq, bf, oLo, oHi, zeroInit, timestep, (cudaStream_t)stream);
+}
+
+int rmcrt_trace_dataonion(rmcrt_ctx* ctx, int maxLevels, const int32_t pLo[3], const int32_t pHi[3], double* dq, double* vq,
+                          double* bf, const int32_t oLo[3], const int32_t oHi[3], int zeroInit, uint64_t timestep, void* stream) {
+  if (!ctx) return RMCRT_ERR_INVALID;
+  return trace_host(ctx, maxLevels, true, pLo, pHi, dq, vq, bf, oLo, oHi, zeroInit, timestep, (cudaStream_t)stream);
+}
+
+int rmcrt_compute_extents(rmcrt_ctx* ctx, int maxLevels, const int32_t pLo[3], const int32_t pHi[3], int32_t roiLo[3],
+                          int32_t roiHi[3], int32_t* regionLo, int32_t* regionHi) {
+  if (!ctx) return RMCRT_ERR_INVALID;
+  if (maxLevels < 1 || maxLevels > RMCRT_MAX_LEVELS) return fail(ctx, RMCRT_ERR_INVALID, "bad maxLevels");
+  for (int L = 0; L < maxLevels; ++L) { int rc = check_level(ctx, L); if (rc) return rc; }
+  compute_extents(ctx, maxLevels, pLo, pHi, roiLo, roiHi, regionLo, regionHi);
+  return 0;
+}
+
+int rmcrt_reset_counters(rmcrt_ctx* ctx, void* stream) {
+  if (!ctx) return RMCRT_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), (cudaStream_t)stream));
+  return 0;
+}
+
+int rmcrt_get_counters(rmcrt_ctx* ctx, rmcrt_counters* out, void* stream) {
+  if (!ctx || !out) return RMCRT_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  unsigned long long h[4];
+  CK(cudaMemcpyAsync(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  out->nRaySteps = h[0]; out->nFluxRaySteps = h[1]; out->nDivQCells = h[2]; out->nFluxCells = h[3];
+  return 0;
+}
+
+int rmcrt_sigmaT4_device(rmcrt_ctx* ctx, const double* d_temp, void* d_out, int isFloat, int64_t n, void* stream) {
+  if (!ctx || !d_temp || !d_out || n < 0) return RMCRT_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  if (n == 0) return 0;
+  const double sop = ctx->p.sigma / M_PI;
+  if (isFloat) sigmaT4_kernel<float><<<grid_for(n, 256, ctx->smCount), 256, 0, (cudaStream_t)stream>>>(d_temp, static_cast<float*>(d_out), n, sop);
+  else         sigmaT4_kernel<double><<<grid_for(n, 256, ctx->smCount), 256, 0, (cudaStream_t)stream>>>(d_temp, static_cast<double*>(d_out), n, sop);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int rmcrt_coarsen_level_device(rmcrt_ctx* ctx, int fineL, int coarseL, void* stream) {
+  int rc = check_level(ctx, fineL);
+  if (rc) return rc;
+  rc = check_level(ctx, coarseL);
+  if (rc) return rc;
+  LevelState& f = ctx->lv[fineL];
+  LevelState& c = ctx->lv[coarseL];
+  if (f.recordKind != c.recordKind) return fail(ctx, RMCRT_ERR_INVALID, "recordKind mismatch between levels");
+  const int* rr = f.d.refineRatio;
+  for (int d = 0; d < 3; ++d) {
+    if (rr[d] < 1) return fail(ctx, RMCRT_ERR_INVALID, "fine level refineRatio must be >= 1");
+    if ((c.d.interiorHi[d] - c.d.interiorLo[d]) * rr[d] != (f.d.interiorHi[d] - f.d.interiorLo[d]) ||
+        c.d.interiorLo[d] * rr[d] != f.d.interiorLo[d])
+      return fail(ctx, RMCRT_ERR_INVALID, "coarse interior x refineRatio must equal the fine interior on axis %d", d);
+  }
+  CK(cudaSetDevice(ctx->device));
+  Box fb = mkbox(f.d.lo, f.d.hi), cb = mkbox(c.d.lo, c.d.hi), ci = mkbox(c.d.interiorLo, c.d.interiorHi);
+  const long long n = box_cells(ci);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (f.recordKind == 0) coarsen_kernel<Rec8><<<grid_for(n, 128, ctx->smCount), 128, 0, st>>>(static_cast<const Rec8*>(f.rec), fb, static_cast<Rec8*>(c.rec), cb, ci, rr[0], rr[1], rr[2], ctx->p.cellTypeCoarsenLogic);
+  else                   coarsen_kernel<Rec16><<<grid_for(n, 128, ctx->smCount), 128, 0, st>>>(static_cast<const Rec16*>(f.rec), fb, static_cast<Rec16*>(c.rec), cb, ci, rr[0], rr[1], rr[2], ctx->p.cellTypeCoarsenLogic);
+  CK(cudaGetLastError());
+  c.finalized = false;
+  return 0;
+}
+
+int rmcrt_set_level_extra_cells(rmcrt_ctx* ctx, int L, const double abskg[6], const double sig[6], const int32_t types[6], void* stream) {
+  int rc = check_level(ctx, L);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  LevelState& lv = ctx->lv[L];
+  if (ctx->misc.ensure(12 * sizeof(double) + 6 * sizeof(int))) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc");
+  double h[12];
+  for (int f = 0; f < 6; ++f) { h[f] = abskg[f]; h[6 + f] = sig[f]; }
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(ctx->misc.p, h, sizeof h, cudaMemcpyHostToDevice, st));
+  int* dT = reinterpret_cast<int*>(static_cast<char*>(ctx->misc.p) + sizeof h);
+  CK(cudaMemcpyAsync(dT, types, 6 * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));   // h[] is a stack buffer
+  Box b = mkbox(lv.d.lo, lv.d.hi), in = mkbox(lv.d.interiorLo, lv.d.interiorHi);
+  if (lv.recordKind == 0) extra_cells_kernel<Rec8><<<grid_for(lv.nCells, 256, ctx->smCount), 256, 0, st>>>(static_cast<Rec8*>(lv.rec), b, in, static_cast<const double*>(ctx->misc.p), dT, ctx->p.flowCell);
+  else                    extra_cells_kernel<Rec16><<<grid_for(lv.nCells, 256, ctx->smCount), 256, 0, st>>>(static_cast<Rec16*>(lv.rec), b, in, static_cast<const double*>(ctx->misc.p), dT, ctx->p.flowCell);
+  CK(cudaGetLastError());
+  lv.finalized = false;
+  return 0;
+}
+
+int rmcrt_pack_box_device(rmcrt_ctx* ctx, int L, const void* a, const void* s, const int32_t* ct, int isFloat,
+                          const int32_t srcLo[3], const int32_t srcHi[3], const int32_t boxLo[3], const int32_t boxHi[3],
+                          void* d_send, void* stream) {
+  int rc = check_level(ctx, L);
+  if (rc) return rc;
+  if (!a || !s || !ct || !d_send) return fail(ctx, RMCRT_ERR_INVALID, "null pointer");
+  for (int d = 0; d < 3; ++d)
+    if (boxLo[d] < srcLo[d] || boxHi[d] > srcHi[d] || boxHi[d] <= boxLo[d]) return fail(ctx, RMCRT_ERR_INVALID, "box must lie inside the source window");
+  CK(cudaSetDevice(ctx->device));
+  Box src = mkbox(srcLo, srcHi), box = mkbox(boxLo, boxHi);
+  return do_pack(ctx, ctx->lv[L].recordKind, isFloat, a, s, ct, src, box, d_send, box, (cudaStream_t)stream);
+}
+
+int rmcrt_assemble_level(rmcrt_ctx* ctx, int L, const void* gathered, size_t slotBytes, int nRanks, const int32_t* boxLo,
+                         const int32_t* boxHi, void* stream) {
+  int rc = check_level(ctx, L);
+  if (rc) return rc;
+  if (!gathered || nRanks < 1) return fail(ctx, RMCRT_ERR_INVALID, "bad gather buffer");
+  CK(cudaSetDevice(ctx->device));
+  LevelState& lv = ctx->lv[L];
+  Box dst = mkbox(lv.d.lo, lv.d.hi);
+  for (int r = 0; r < nRanks; ++r) {
+    Box b = mkbox(boxLo + 3 * r, boxHi + 3 * r);
+    const long long n = box_cells(b);
+    if (n <= 0) continue;
+    if ((size_t)n * lv.recBytes > slotBytes) return fail(ctx, RMCRT_ERR_INVALID, "rank %d box does not fit its slot", r);
+    for (int d = 0; d < 3; ++d)
+      if (b.lo[d] < lv.d.lo[d] || b.lo[d] + b.n[d] > lv.d.hi[d]) return fail(ctx, RMCRT_ERR_INVALID, "rank %d box outside level", r);
+    if (lv.recordKind == 0) assemble_kernel<Rec8><<<grid_for(n, 256, ctx->smCount), 256, 0, (cudaStream_t)stream>>>(static_cast<const unsigned char*>(gathered), slotBytes, r, b, static_cast<Rec8*>(lv.rec), dst);
+    else                    assemble_kernel<Rec16><<<grid_for(n, 256, ctx->smCount), 256, 0, (cudaStream_t)stream>>>(static_cast<const unsigned char*>(gathered), slotBytes, r, b, static_cast<Rec16*>(lv.rec), dst);
+    CK(cudaGetLastError());
+  }
+  lv.finalized = false;
+  return 0;
+}
+
+int rmcrt_allgather_records(rmcrt_ctx* ctx, const void* d_send, void* d_gathered, size_t slotBytes, void* comm, void* stream) {
+  if (!ctx) return RMCRT_ERR_INVALID;
+  typedef int (*allgather_fn)(const void*, void*, size_t, int, void*, cudaStream_t);
+  static allgather_fn fn = nullptr;
+  if (!fn) {
+    fn = (allgather_fn)dlsym(RTLD_DEFAULT, "ncclAllGather");
+    if (!fn) {
+      void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+      if (h) fn = (allgather_fn)dlsym(h, "ncclAllGather");
+    }
+    if (!fn) return fail(ctx, RMCRT_ERR_NCCL, "ncclAllGather not found (libnccl.so.2 not loadable)");
+  }
+  const int ncclInt8 = 0;   // ncclInt8 / ncclChar
+  const int r = fn(d_send, d_gathered, slotBytes, ncclInt8, comm, (cudaStream_t)stream);
+  if (r != 0) return fail(ctx, RMCRT_ERR_NCCL, "ncclAllGather failed with code %d", r);
+  return 0;
+}
+
+int rmcrt_measure_read_bandwidth(rmcrt_ctx* ctx, size_t bytes, int repeats, int pattern, double* gbps, double* gaccess) {
+  if (!ctx || bytes < 4096 || repeats < 1) return RMCRT_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  void* buf = nullptr;
+  unsigned* sink = nullptr;
+  CK(cudaMalloc(&buf, bytes));
+  CK(cudaMalloc(&sink, 4));
+  CK(cudaMemset(buf, 0x11, bytes));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  const int grid = ctx->smCount * 16, block = 256;
+  const long long n16 = (long long)(bytes / 16);
+  const unsigned nRec = (unsigned)std::min<size_t>(bytes / 8, 0xFFFFFFFFu);
+  const int perThread = 256;
+  auto pass = [&]() {
+    if (pattern == 0) bw_stream_kernel<<<grid, block>>>(static_cast<const uint4*>(buf), n16, sink);
+    else bw_gather_kernel<<<grid, block>>>(static_cast<const float2*>(buf), nRec, perThread, sink);
+  };
+  for (int i = 0; i < 3; ++i) pass();     // warm-up (and L2 fill for small buffers)
+  CK(cudaEventRecord(e0));
+  for (int i = 0; i < repeats; ++i) pass();
+  CK(cudaEventRecord(e1));
+  CK(cudaEventSynchronize(e1));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  CK(cudaGetLastError());
+  const double sec = ms * 1e-3;
+  if (pattern == 0) {
+    if (gbps) *gbps = (double)n16 * 16.0 * repeats / sec / 1e9;
+    if (gaccess) *gaccess = (double)n16 * repeats / sec / 1e9;
+  } else {
+    const double acc = (double)grid * block * perThread * repeats;
+    if (gbps) *gbps = acc * 32.0 / sec / 1e9;
+    if (gaccess) *gaccess = acc / sec / 1e9;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(buf); cudaFree(sink);
+  return 0;
+}
+
+int rmcrt_debug_trace_rays(rmcrt_ctx* ctx, int L, int maxLevels, const int32_t pLo[3], const int32_t pHi[3], int n,
+                           const int32_t* cells, const double* dir, const double* org, double* sumI, uint32_t* steps,
+                           int32_t* path, int maxPath) {
+  if (!ctx) return RMCRT_ERR_INVALID;
+  if (n <= 0) return 0;
+  const bool ML = maxLevels > 1;
+  const int nl = ML ? maxLevels : L + 1;
+  TraceArgs a;
+  const rmcrt_level_desc* fd = nullptr;
+  int rc = check_level(ctx, nl - 1);
+  if (rc) return rc;
+  fd = &ctx->lv[nl - 1].d;
+  int32_t lo[3], hi[3];
+  for (int d = 0; d < 3; ++d) { lo[d] = pLo ? pLo[d] : fd->interiorLo[d]; hi[d] = pHi ? pHi[d] : fd->interiorHi[d]; }
+  rc = build_args(ctx, nl, ML, lo, hi, lo, hi, 0, a);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->dbg[0].ensure((size_t)n * 12) || ctx->dbg[1].ensure((size_t)n * 24) || ctx->dbg[2].ensure((size_t)n * 24) ||
+      ctx->dbg[3].ensure((size_t)n * 8) || ctx->dbg[4].ensure((size_t)n * 4))
+    return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc debug buffers");
+  int* dPath = nullptr;
+  if (path && maxPath > 0) {
+    if (ctx->dbg[5].ensure((size_t)n * maxPath * 16)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc path buffer");
+    dPath = static_cast<int*>(ctx->dbg[5].p);
+    CK(cudaMemset(dPath, 0, (size_t)n * maxPath * 16));
+  }
+  CK(cudaMemcpy(ctx->dbg[0].p, cells, (size_t)n * 12, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->dbg[1].p, dir, (size_t)n * 24, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->dbg[2].p, org, (size_t)n * 24, cudaMemcpyHostToDevice));
+  const int grid = (n + 63) / 64;
+#define DBG_LAUNCH(REAL, REC, MLF)                                                                                         \
+  debug_rays_kernel<REAL, REC, MLF><<<grid, 64>>>(a, n, static_cast<const int*>(ctx->dbg[0].p),                            \
+      static_cast<const double*>(ctx->dbg[1].p), static_cast<const double*>(ctx->dbg[2].p), static_cast<double*>(ctx->dbg[3].p), \
+      static_cast<unsigned*>(ctx->dbg[4].p), dPath, maxPath)
+  if (ctx->p.marchPrecision == 1) { if (ML) DBG_LAUNCH(double, Rec16, true); else DBG_LAUNCH(double, Rec16, false); }
+  else                            { if (ML) DBG_LAUNCH(float, Rec8, true);   else DBG_LAUNCH(float, Rec8, false); }
+#undef DBG_LAUNCH
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(sumI, ctx->dbg[3].p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(steps, ctx->dbg[4].p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  if (dPath) CK(cudaMemcpy(path, dPath, (size_t)n * maxPath * 16, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // extern "C"
