@@ -244,6 +244,7 @@ def run_ours(args):
             g.pack_box_device(0, d_ab, d_s4, d_ct, blo, bhi, blo, bhi, send, stream=stream)
             dist.all_gather_into_tensor(gathered, send)
             g.assemble_level(0, gathered, slot, boxes_lo, boxes_hi, stream=stream)
+        g.finalize_level_async(0, stream)     # device-side validation scan; no host round trip
 
     def device_step(ts):
         replicate()
@@ -252,7 +253,7 @@ def run_ours(args):
     # one validated set-up solve
     replicate()
     g.finalize_level(0, stream)
-    kernels_per_step = 2 if world == 1 else 2 + world         # pack + divq (+ assemble per rank box)
+    kernels_per_step = 3 if world == 1 else 3 + world         # pack + finalize + divq (+ assemble per rank box)
 
     def barrier():
         if world > 1:
@@ -382,7 +383,7 @@ def run_ours(args):
                         "binding roofline is L2 (see roofline_l2), HBM peak shown because MEASURED_PEAKS.json has no L2 figure"}
     # L2 denominators measured live with the library's microbenchmarks (16 MiB scratch, L2-resident)
     try:
-        l2_stream, _ = g.measure_read_bandwidth(16 << 20, repeats=200, pattern=0)
+        l2_stream, _ = g.measure_read_bandwidth(16 << 20, repeats=10, pattern=0)
         l2_gather, l2_gacc = g.measure_read_bandwidth(16 << 20, repeats=20, pattern=1)
         hbm_stream, _ = g.measure_read_bandwidth(2 << 30, repeats=5, pattern=0)
         roofline_l2 = {"bound": "l2", "achieved": achieved, "peak": l2_stream, "unit": "GB/s", "frac": achieved / l2_stream,

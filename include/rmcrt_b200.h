@@ -123,6 +123,10 @@ int rmcrt_pack_level_device(rmcrt_ctx* ctx, int L, const void* d_abskg, const vo
 /* Validate a fully populated level (blocking): non-finite properties, open domain; also decides
  * whether zero-weight legs may be skipped (no emitting non-flow cell). */
 int rmcrt_finalize_level(rmcrt_ctx* ctx, int L, void* stream);
+/* Same scan without the host round trip: the result stays in device status words that the trace kernels read (the
+ * zero-weight-leg skip is enabled only for levels whose status is valid and shows no emitting wall).  Validation
+ * errors are then reported by the next blocking rmcrt_finalize_level. */
+int rmcrt_finalize_level_async(rmcrt_ctx* ctx, int L, void* stream);
 /* Device address/size of the packed records (for the NCCL all-gather of the replicated level). */
 int rmcrt_level_records(rmcrt_ctx* ctx, int L, void** d_records, size_t* bytes, size_t* recordBytes);
 

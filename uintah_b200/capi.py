@@ -18,7 +18,7 @@ RMCRT_MAX_LEVELS = 8
 SYMBOLS = [
     "rmcrt_abi_version", "rmcrt_struct_size", "rmcrt_default_params", "rmcrt_create", "rmcrt_set_params", "rmcrt_destroy",
     "rmcrt_last_error", "rmcrt_define_level", "rmcrt_upload_level", "rmcrt_pack_level_device",
-    "rmcrt_finalize_level", "rmcrt_level_records", "rmcrt_trace_divq_device", "rmcrt_trace_divq",
+    "rmcrt_finalize_level", "rmcrt_finalize_level_async", "rmcrt_level_records", "rmcrt_trace_divq_device", "rmcrt_trace_divq",
     "rmcrt_trace_dataonion_device", "rmcrt_trace_dataonion", "rmcrt_compute_extents", "rmcrt_reset_counters",
     "rmcrt_get_counters", "rmcrt_sigmaT4_device", "rmcrt_coarsen_level_device", "rmcrt_set_level_extra_cells",
     "rmcrt_pack_box_device", "rmcrt_assemble_level", "rmcrt_allgather_records", "rmcrt_measure_read_bandwidth", "rmcrt_debug_trace_rays",
@@ -88,6 +88,7 @@ def load_library(path: str | None = None):
     lib.rmcrt_upload_level.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, i3, i3, vp]
     lib.rmcrt_pack_level_device.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, i3, i3, vp]
     lib.rmcrt_finalize_level.argtypes = [vp, C.c_int, vp]
+    lib.rmcrt_finalize_level_async.argtypes = [vp, C.c_int, vp]
     lib.rmcrt_level_records.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     for name in ("rmcrt_trace_divq_device", "rmcrt_trace_divq", "rmcrt_trace_dataonion_device", "rmcrt_trace_dataonion"):
         getattr(lib, name).argtypes = [vp, C.c_int, i3, i3, vp, vp, vp, i3, i3, C.c_int, C.c_uint64, vp]

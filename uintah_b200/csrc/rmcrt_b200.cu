@@ -33,6 +33,12 @@ namespace {
 
 constexpr int MAXL = 4;   // levels supported by the Data-Onion kernels (reference decks use 2-3)
 
+// per-level status words living on the device, so that a radiation solve needs no host round trip:
+//   [0] non-finite records  [1] flow cells on the outer layer  [2] non-flow cells that can emit (k*s != 0)
+//   [3] valid: set by finalize_kernel's last block, cleared by every kernel that modifies the level
+//   [4] ticket for "last block"      [5] non-finite inputs seen by the pack kernels
+constexpr int LSTAT_WORDS = 8;
+
 //======================================================================================================
 // device-side helpers
 //======================================================================================================
@@ -62,6 +68,8 @@ struct TraceArgs {
   int fluxFlowGuard;      // 1L: only flow cells get boundary fluxes (Ray.cc:654-656); DO: no guard (Q3)
   RayGen rng;
   unsigned long long* counters;   // [0] divQ steps [1] flux steps [2] divQ cells [3] flux cells
+  const unsigned* lstat;          // per-level device status words [MAXL][LSTAT_WORDS] (see finalize_kernel)
+  int firstLevel;                 // levels [firstLevel, maxLevels) take part in this trace
   // flux items
   const int* items;       // compacted item ids: face * nCells + patch-linear cell
   const int* nItems;      // device count
@@ -168,6 +176,15 @@ __device__ __forceinline__ void gen_flux_ray(const RayGen& rg, const LevelGeom& 
   }
 }
 
+// zero-weight legs may be skipped only when every level in play has been finalized and none of its non-flow cells emits
+__device__ __forceinline__ bool skip_allowed(const TraceArgs& a) {
+  if (!a.skipZero) return false;
+  bool ok = true;
+  for (int L = a.firstLevel; L < a.G.maxLevels; ++L)
+    ok = ok && (a.lstat[L * LSTAT_WORDS + 3] != 0u) && (a.lstat[L * LSTAT_WORDS + 2] == 0u);
+  return ok;
+}
+
 template <class Real>
 __device__ __forceinline__ Real nz(double v) {   // direction component as Real, never exactly zero
   Real r = (Real)v;
@@ -176,20 +193,20 @@ __device__ __forceinline__ Real nz(double v) {   // direction component as Real,
 }
 
 template <class Real, class RecT, bool ML, bool RECORD>
-__device__ __forceinline__ Real trace_one(const TraceArgs& a, int i, int j, int k, const double dir[3], const double rayDx[3],
+__device__ __forceinline__ Real trace_one(const TraceArgs& a, bool skipZero, int i, int j, int k, const double dir[3], const double rayDx[3],
                                           unsigned& steps, PathSink* path) {
   const int F = a.G.maxLevels - 1;
   const LevelGeom& g = a.G.lev[F];
   if (ML) {
     return march_multi_level<Real, RecT, MAXL, RECORD>(a.G, i, j, k, nz<Real>(dir[0]), nz<Real>(dir[1]), nz<Real>(dir[2]),
                                                        (Real)rayDx[0], (Real)rayDx[1], (Real)rayDx[2], (Real)a.threshold,
-                                                       a.allowReflect != 0, a.skipZero != 0, steps, path);
+                                                       a.allowReflect != 0, skipZero, steps, path);
   } else {
     return march_single_level<Real, RecT, RECORD>(static_cast<const RecT*>(g.rec), level_index(g, i, j, k), g.n[0],
                                                   g.n[0] * g.n[1], nz<Real>(dir[0]), nz<Real>(dir[1]), nz<Real>(dir[2]),
                                                   (Real)rayDx[0], (Real)rayDx[1], (Real)rayDx[2], (Real)g.dx[0],
                                                   (Real)g.dx[1], (Real)g.dx[2], (Real)a.threshold, a.allowReflect != 0,
-                                                  a.skipZero != 0, steps, path, i, j, k);
+                                                  skipZero, steps, path, i, j, k);
   }
 }
 
@@ -207,6 +224,7 @@ __global__ void __launch_bounds__(256) divq_kernel(const __grid_constant__ Trace
   const int F = a.G.maxLevels - 1;
   const LevelGeom& g = a.G.lev[F];
   const RecT* recs = static_cast<const RecT*>(g.rec);
+  const bool skipZero = skip_allowed(a);
   unsigned long long stepsTotal = 0, cellsTotal = 0;
 
   for (long long tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
@@ -233,7 +251,7 @@ __global__ void __launch_bounds__(256) divq_kernel(const __grid_constant__ Trace
       for (int ray = warp; ray < a.nRays; ray += W) {
         double dir[3], rayDx[3];
         gen_divq_ray(a.rng, g, i, j, k, ray, cellId, dirId, dir, rayDx);
-        acc += (double)trace_one<Real, RecT, ML, false>(a, i, j, k, dir, rayDx, steps, nullptr);
+        acc += (double)trace_one<Real, RecT, ML, false>(a, skipZero, i, j, k, dir, rayDx, steps, nullptr);
       }
     }
     red[warp * 32 + lane] = acc;
@@ -312,6 +330,7 @@ __global__ void __launch_bounds__(256) flux_trace_kernel(const __grid_constant__
   const int F = a.G.maxLevels - 1;
   const LevelGeom& g = a.G.lev[F];
   const long long nItems = *a.nItems;
+  const bool skipZero = skip_allowed(a);
   const long long nTiles = (nItems + 31) / 32;
   unsigned long long stepsTotal = 0;
   for (long long tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
@@ -339,7 +358,7 @@ __global__ void __launch_bounds__(256) flux_trace_kernel(const __grid_constant__
       for (int ray = warp; ray < a.nRays; ray += W) {
         double dir[3], rayDx[3], cosT;
         gen_flux_ray(a.rng, g, i, j, k, face, ray, cellId, dirId, dir, rayDx, cosT);
-        const double dI = (double)trace_one<Real, RecT, ML, false>(a, i, j, k, dir, rayDx, steps, nullptr);
+        const double dI = (double)trace_one<Real, RecT, ML, false>(a, skipZero, i, j, k, dir, rayDx, steps, nullptr);
         sumProj += cosT * dI;      // sumProjI += cosTheta * (sumI - sumI_prev)   (Ray.cc:704)
         sumCos += cosT;
       }
@@ -383,7 +402,7 @@ __global__ void debug_rays_kernel(const __grid_constant__ TraceArgs a, int n, co
   }
   PathSink sink{pathBuf ? pathBuf + (long long)t * maxPath * 4 : nullptr, maxPath, 0};
   unsigned steps = 0;
-  const Real v = trace_one<Real, RecT, ML, true>(a, i, j, k, dir, rayDx, steps, pathBuf ? &sink : nullptr);
+  const Real v = trace_one<Real, RecT, ML, true>(a, skip_allowed(a), i, j, k, dir, rayDx, steps, pathBuf ? &sink : nullptr);
   sumI[t] = (double)v;
   stepsOut[t] = steps;
 }
@@ -398,7 +417,6 @@ template <> struct RecTraits<Rec16> { typedef double real; };
 struct Box { int lo[3], n[3]; };
 __host__ __device__ inline long long box_cells(const Box& b) { return (long long)b.n[0] * b.n[1] * b.n[2]; }
 
-// status words: [0] non-finite count, [1] flow cells on the outer layer, [2] emitting non-flow cells
 template <class T, class RecT>
 __global__ void pack_kernel(const T* __restrict__ abskg, const T* __restrict__ sig, const int* __restrict__ ct, Box src,
                             Box region /* cells to pack */, RecT* __restrict__ dst, Box dstBox, int flowCell,
@@ -414,7 +432,7 @@ __global__ void pack_kernel(const T* __restrict__ abskg, const T* __restrict__ s
     const long long s = (long long)(i - src.lo[0]) + (long long)src.n[0] * ((long long)(j - src.lo[1]) + (long long)src.n[1] * (long long)(k - src.lo[2]));
     const long long d = (long long)(i - dstBox.lo[0]) + (long long)dstBox.n[0] * ((long long)(j - dstBox.lo[1]) + (long long)dstBox.n[1] * (long long)(k - dstBox.lo[2]));
     const T kv = abskg[s], sv = sig[s];
-    if (!isfinite((double)kv) || !isfinite((double)sv)) atomicAdd(status + 0, 1u);   // RMCRTCommon.cc:267-271
+    if (!isfinite((double)kv) || !isfinite((double)sv)) atomicAdd(status + 5, 1u);   // RMCRTCommon.cc:267-271
     R kr = (R)kv;
     kr = kr < R(0) ? -kr : kr;
     if (ct[s] != flowCell) kr = -kr;     // sign bit == "not a flow cell", also for abskg == 0 (-0.0)
@@ -441,6 +459,13 @@ __global__ void finalize_kernel(const RecT* __restrict__ recs, Box b, unsigned* 
   if (bad) atomicAdd(status + 0, bad);
   if (open) atomicAdd(status + 1, open);
   if (emit) atomicAdd(status + 2, emit);
+  // the last block to finish publishes the result (words 0..2 were zeroed before the launch)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(status + 4, 1u);
+    if (t == gridDim.x - 1) { __threadfence(); atomicExch(status + 3, 1u); }
+  }
 }
 
 template <class T>
@@ -536,11 +561,18 @@ __global__ void assemble_kernel(const unsigned char* __restrict__ gathered, size
 
 
 // ---- roofline denominators ----
-__global__ void bw_stream_kernel(const uint4* __restrict__ buf, long long n16, unsigned* sink) {
+__global__ void bw_stream_kernel(const uint4* __restrict__ buf, long long n16, int inner, unsigned* sink) {
   unsigned acc = 0;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n16; t += (long long)gridDim.x * blockDim.x) {
-    const uint4 v = __ldg(buf + t);
-    acc ^= v.x ^ v.y ^ v.z ^ v.w;
+  for (int it = 0; it < inner; ++it) {
+    // rotate the start so consecutive sweeps of one thread do not hit its own L1 lines
+    const long long shift = (long long)it * 7919 * blockDim.x;
+#pragma unroll 4
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n16; t += (long long)gridDim.x * blockDim.x) {
+      long long u = t + shift;
+      if (u >= n16) u -= n16 * (u / n16);
+      const uint4 v = __ldg(buf + u);
+      acc ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
   }
   if (acc == 0x12345677u) *sink = acc;
 }
@@ -594,7 +626,7 @@ struct rmcrt_ctx {
   rmcrt_params p{};
   LevelState lv[RMCRT_MAX_LEVELS];
   unsigned long long* d_counters = nullptr;   // 4
-  unsigned* d_status = nullptr;               // 4
+  unsigned* d_lstat = nullptr;                // [RMCRT_MAX_LEVELS][LSTAT_WORDS]
   int* d_nItems = nullptr;
   DevBuf stage[3];      // upload staging
   DevBuf outDivQ, outVolq, outFlux;   // host-API output staging
@@ -697,6 +729,15 @@ void compute_extents(const rmcrt_ctx* ctx, int maxLevels, const int32_t pLo[3], 
   }
 }
 
+unsigned* lstat_of(const rmcrt_ctx* ctx, int L) { return ctx->d_lstat + (size_t)L * LSTAT_WORDS; }
+
+// every modification of a level clears its device-side "valid" word (stream-ordered)
+int invalidate_level(rmcrt_ctx* ctx, int L, cudaStream_t st) {
+  ctx->lv[L].finalized = false;
+  CK(cudaMemsetAsync(lstat_of(ctx, L) + 3, 0, sizeof(unsigned), st));
+  return 0;
+}
+
 int pick_warps(const rmcrt_ctx* ctx, long long nTiles) {
   if (ctx->p.warpsPerTile > 0) {
     int w = ctx->p.warpsPerTile;
@@ -732,22 +773,22 @@ void apply_l2_window(rmcrt_ctx* ctx, int L, cudaStream_t st) {
 
 template <class T, class RecT>
 int launch_pack(rmcrt_ctx* ctx, const void* a, const void* s, const int32_t* ct, Box src, Box region, void* dst, Box dstBox,
-                cudaStream_t st) {
+                unsigned* status, cudaStream_t st) {
   const long long n = box_cells(region);
   if (n <= 0) return 0;
   pack_kernel<T, RecT><<<grid_for(n, 256, ctx->smCount), 256, 0, st>>>(static_cast<const T*>(a), static_cast<const T*>(s), ct, src,
                                                                      region, static_cast<RecT*>(dst), dstBox, ctx->p.flowCell,
-                                                                     ctx->d_status);
+                                                                     status);
   CK(cudaGetLastError());
   return 0;
 }
 
 int do_pack(rmcrt_ctx* ctx, int recordKind, int isFloat, const void* a, const void* s, const int32_t* ct, Box src, Box region,
-            void* dst, Box dstBox, cudaStream_t st) {
-  if (recordKind == 0) return isFloat ? launch_pack<float, Rec8>(ctx, a, s, ct, src, region, dst, dstBox, st)
-                                      : launch_pack<double, Rec8>(ctx, a, s, ct, src, region, dst, dstBox, st);
-  return isFloat ? launch_pack<float, Rec16>(ctx, a, s, ct, src, region, dst, dstBox, st)
-                 : launch_pack<double, Rec16>(ctx, a, s, ct, src, region, dst, dstBox, st);
+            void* dst, Box dstBox, unsigned* status, cudaStream_t st) {
+  if (recordKind == 0) return isFloat ? launch_pack<float, Rec8>(ctx, a, s, ct, src, region, dst, dstBox, status, st)
+                                      : launch_pack<double, Rec8>(ctx, a, s, ct, src, region, dst, dstBox, status, st);
+  return isFloat ? launch_pack<float, Rec16>(ctx, a, s, ct, src, region, dst, dstBox, status, st)
+                 : launch_pack<double, Rec16>(ctx, a, s, ct, src, region, dst, dstBox, status, st);
 }
 
 int build_args(rmcrt_ctx* ctx, int maxLevels, bool multiLevel, const int32_t pLo[3], const int32_t pHi[3], const int32_t oLo[3],
@@ -785,9 +826,9 @@ int build_args(rmcrt_ctx* ctx, int maxLevels, bool multiLevel, const int32_t pLo
   a.nTiles = (a.nCells + 31) / 32;
   a.threshold = ctx->p.threshold;
   a.allowReflect = ctx->p.allowReflect;
-  bool emit = false;
-  for (int L = multiLevel ? 0 : F; L <= F; ++L) emit = emit || ctx->lv[L].wallsEmit || !ctx->lv[L].finalized;
-  a.skipZero = (ctx->p.skipZeroWeightLegs && !emit) ? 1 : 0;
+  a.skipZero = ctx->p.skipZeroWeightLegs ? 1 : 0;   // the kernels AND this with the device-side level status
+  a.lstat = ctx->d_lstat;
+  a.firstLevel = multiLevel ? 0 : F;
   a.fluxFlowGuard = multiLevel ? 0 : 1;
   a.rng.key0 = (uint32_t)ctx->p.seed;
   a.rng.key1 = (uint32_t)(ctx->p.seed >> 32) ^ (uint32_t)(timestep >> 32);
@@ -947,10 +988,10 @@ int rmcrt_create(int device, const rmcrt_params* p, rmcrt_ctx** out) {
   if (cudaSetDevice(device) != cudaSuccess) return bail("cudaSetDevice failed");
   cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, device);
   if (cudaMalloc(&ctx->d_counters, 4 * sizeof(unsigned long long)) != cudaSuccess) return bail("cudaMalloc counters");
-  if (cudaMalloc(&ctx->d_status, 4 * sizeof(unsigned)) != cudaSuccess) return bail("cudaMalloc status");
+  if (cudaMalloc(&ctx->d_lstat, RMCRT_MAX_LEVELS * LSTAT_WORDS * sizeof(unsigned)) != cudaSuccess) return bail("cudaMalloc status");
   if (cudaMalloc(&ctx->d_nItems, sizeof(int)) != cudaSuccess) return bail("cudaMalloc nItems");
   cudaMemset(ctx->d_counters, 0, 4 * sizeof(unsigned long long));
-  cudaMemset(ctx->d_status, 0, 4 * sizeof(unsigned));
+  cudaMemset(ctx->d_lstat, 0, RMCRT_MAX_LEVELS * LSTAT_WORDS * sizeof(unsigned));
   cudaMemset(ctx->d_nItems, 0, sizeof(int));
   *out = ctx;
   return 0;
@@ -970,7 +1011,7 @@ void rmcrt_destroy(rmcrt_ctx* ctx) {
   cudaSetDevice(ctx->device);
   for (auto& l : ctx->lv) if (l.base) cudaFree(l.base);
   if (ctx->d_counters) cudaFree(ctx->d_counters);
-  if (ctx->d_status) cudaFree(ctx->d_status);
+  if (ctx->d_lstat) cudaFree(ctx->d_lstat);
   if (ctx->d_nItems) cudaFree(ctx->d_nItems);
   for (auto& b : ctx->stage) b.release();
   ctx->outDivQ.release(); ctx->outVolq.release(); ctx->outFlux.release();
@@ -998,7 +1039,7 @@ int rmcrt_define_level(rmcrt_ctx* ctx, int L, const rmcrt_level_desc* d, int rec
       memcmp(s.d.hi, d->hi, sizeof d->hi) == 0) {
     s.d = *d;              // same shape: keep the allocation (a new radiation solve re-packs into it)
     s.finalized = false;
-    s.wallsEmit = true;
+    CK(cudaMemset(lstat_of(ctx, L), 0, LSTAT_WORDS * sizeof(unsigned)));
     return 0;
   }
   if (s.base) { cudaFree(s.base); s.base = nullptr; s.rec = nullptr; }
@@ -1016,7 +1057,7 @@ int rmcrt_define_level(rmcrt_ctx* ctx, int L, const rmcrt_level_desc* d, int rec
   s.rec = static_cast<char*>(base) + (size_t)guard * s.recBytes;
   s.defined = true;
   s.finalized = false;
-  s.wallsEmit = true;
+  CK(cudaMemset(lstat_of(ctx, L), 0, LSTAT_WORDS * sizeof(unsigned)));
   ctx->persistedStreamFor = nullptr;
   return 0;
 }
@@ -1035,8 +1076,9 @@ int rmcrt_pack_level_device(rmcrt_ctx* ctx, int L, const void* a, const void* s,
     if (hi <= lo) return fail(ctx, RMCRT_ERR_INVALID, "source window does not overlap level %d", L);
     region.lo[d] = lo; region.n[d] = hi - lo;
   }
-  lv.finalized = false;
-  return do_pack(ctx, lv.recordKind, isFloat, a, s, ct, src, region, lv.rec, dst, (cudaStream_t)stream);
+  int rci = invalidate_level(ctx, L, (cudaStream_t)stream);
+  if (rci) return rci;
+  return do_pack(ctx, lv.recordKind, isFloat, a, s, ct, src, region, lv.rec, dst, lstat_of(ctx, L), (cudaStream_t)stream);
 }
 
 int rmcrt_upload_level(rmcrt_ctx* ctx, int L, const void* a, const void* s, const int32_t* ct, int isFloat,
@@ -1061,26 +1103,38 @@ int rmcrt_upload_level(rmcrt_ctx* ctx, int L, const void* a, const void* s, cons
                                  srcLo, srcHi, stream);
 }
 
+static int finalize_launch(rmcrt_ctx* ctx, int L, cudaStream_t st) {
+  LevelState& lv = ctx->lv[L];
+  unsigned* ls = lstat_of(ctx, L);
+  CK(cudaMemsetAsync(ls, 0, 5 * sizeof(unsigned), st));      // words 0..4; word 5 (pack-time input check) survives
+  Box b = mkbox(lv.d.lo, lv.d.hi);
+  if (lv.recordKind == 0) finalize_kernel<Rec8><<<grid_for(lv.nCells, 256, ctx->smCount), 256, 0, st>>>(static_cast<const Rec8*>(lv.rec), b, ls);
+  else                    finalize_kernel<Rec16><<<grid_for(lv.nCells, 256, ctx->smCount), 256, 0, st>>>(static_cast<const Rec16*>(lv.rec), b, ls);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int rmcrt_finalize_level_async(rmcrt_ctx* ctx, int L, void* stream) {
+  int rc = check_level(ctx, L);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  return finalize_launch(ctx, L, (cudaStream_t)stream);
+}
+
 int rmcrt_finalize_level(rmcrt_ctx* ctx, int L, void* stream) {
   int rc = check_level(ctx, L);
   if (rc) return rc;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
   LevelState& lv = ctx->lv[L];
-  unsigned h[4] = {0, 0, 0, 0};
+  rc = finalize_launch(ctx, L, st);
+  if (rc) return rc;
+  unsigned h[LSTAT_WORDS];
+  CK(cudaMemcpyAsync(h, lstat_of(ctx, L), sizeof h, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  CK(cudaMemcpy(h, ctx->d_status, sizeof h, cudaMemcpyDeviceToHost));   // non-finite inputs seen by pack
-  const unsigned badPacked = h[0];
-  CK(cudaMemsetAsync(ctx->d_status, 0, 4 * sizeof(unsigned), st));
-  Box b = mkbox(lv.d.lo, lv.d.hi);
-  if (lv.recordKind == 0) finalize_kernel<Rec8><<<grid_for(lv.nCells, 256, ctx->smCount), 256, 0, st>>>(static_cast<const Rec8*>(lv.rec), b, ctx->d_status);
-  else                    finalize_kernel<Rec16><<<grid_for(lv.nCells, 256, ctx->smCount), 256, 0, st>>>(static_cast<const Rec16*>(lv.rec), b, ctx->d_status);
-  CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(h, ctx->d_status, sizeof h, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  CK(cudaMemsetAsync(ctx->d_status, 0, 4 * sizeof(unsigned), st));
-  if (h[0] || badPacked)
-    return fail(ctx, RMCRT_ERR_NONPHYSICAL, "level %d: %u non-finite abskg/sigmaT4 values (or unset cells)", L, h[0] + badPacked);
+  if (h[5]) CK(cudaMemsetAsync(lstat_of(ctx, L) + 5, 0, sizeof(unsigned), st));
+  if (h[0] || h[5])
+    return fail(ctx, RMCRT_ERR_NONPHYSICAL, "level %d: %u non-finite abskg/sigmaT4 values (or cells never packed)", L, h[0] + h[5]);
   if (h[1]) return fail(ctx, RMCRT_ERR_OPEN_DOMAIN, "level %d: %u flow cells on the outer (extra-cell) layer; rays could leave the level", L, h[1]);
   lv.wallsEmit = (h[2] != 0);
   lv.finalized = true;
@@ -1182,8 +1236,7 @@ int rmcrt_coarsen_level_device(rmcrt_ctx* ctx, int fineL, int coarseL, void* str
   if (f.recordKind == 0) coarsen_kernel<Rec8><<<grid_for(n, 128, ctx->smCount), 128, 0, st>>>(static_cast<const Rec8*>(f.rec), fb, static_cast<Rec8*>(c.rec), cb, ci, rr[0], rr[1], rr[2], ctx->p.cellTypeCoarsenLogic);
   else                   coarsen_kernel<Rec16><<<grid_for(n, 128, ctx->smCount), 128, 0, st>>>(static_cast<const Rec16*>(f.rec), fb, static_cast<Rec16*>(c.rec), cb, ci, rr[0], rr[1], rr[2], ctx->p.cellTypeCoarsenLogic);
   CK(cudaGetLastError());
-  c.finalized = false;
-  return 0;
+  return invalidate_level(ctx, coarseL, st);
 }
 
 int rmcrt_set_level_extra_cells(rmcrt_ctx* ctx, int L, const double abskg[6], const double sig[6], const int32_t types[6], void* stream) {
@@ -1203,8 +1256,7 @@ int rmcrt_set_level_extra_cells(rmcrt_ctx* ctx, int L, const double abskg[6], co
   if (lv.recordKind == 0) extra_cells_kernel<Rec8><<<grid_for(lv.nCells, 256, ctx->smCount), 256, 0, st>>>(static_cast<Rec8*>(lv.rec), b, in, static_cast<const double*>(ctx->misc.p), dT, ctx->p.flowCell);
   else                    extra_cells_kernel<Rec16><<<grid_for(lv.nCells, 256, ctx->smCount), 256, 0, st>>>(static_cast<Rec16*>(lv.rec), b, in, static_cast<const double*>(ctx->misc.p), dT, ctx->p.flowCell);
   CK(cudaGetLastError());
-  lv.finalized = false;
-  return 0;
+  return invalidate_level(ctx, L, st);
 }
 
 int rmcrt_pack_box_device(rmcrt_ctx* ctx, int L, const void* a, const void* s, const int32_t* ct, int isFloat,
@@ -1217,7 +1269,7 @@ int rmcrt_pack_box_device(rmcrt_ctx* ctx, int L, const void* a, const void* s, c
     if (boxLo[d] < srcLo[d] || boxHi[d] > srcHi[d] || boxHi[d] <= boxLo[d]) return fail(ctx, RMCRT_ERR_INVALID, "box must lie inside the source window");
   CK(cudaSetDevice(ctx->device));
   Box src = mkbox(srcLo, srcHi), box = mkbox(boxLo, boxHi);
-  return do_pack(ctx, ctx->lv[L].recordKind, isFloat, a, s, ct, src, box, d_send, box, (cudaStream_t)stream);
+  return do_pack(ctx, ctx->lv[L].recordKind, isFloat, a, s, ct, src, box, d_send, box, lstat_of(ctx, L), (cudaStream_t)stream);
 }
 
 int rmcrt_assemble_level(rmcrt_ctx* ctx, int L, const void* gathered, size_t slotBytes, int nRanks, const int32_t* boxLo,
@@ -1239,8 +1291,7 @@ int rmcrt_assemble_level(rmcrt_ctx* ctx, int L, const void* gathered, size_t slo
     else                    assemble_kernel<Rec16><<<grid_for(n, 256, ctx->smCount), 256, 0, (cudaStream_t)stream>>>(static_cast<const unsigned char*>(gathered), slotBytes, r, b, static_cast<Rec16*>(lv.rec), dst);
     CK(cudaGetLastError());
   }
-  lv.finalized = false;
-  return 0;
+  return invalidate_level(ctx, L, (cudaStream_t)stream);
 }
 
 int rmcrt_allgather_records(rmcrt_ctx* ctx, const void* d_send, void* d_gathered, size_t slotBytes, void* comm, void* stream) {
@@ -1276,8 +1327,10 @@ int rmcrt_measure_read_bandwidth(rmcrt_ctx* ctx, size_t bytes, int repeats, int 
   const long long n16 = (long long)(bytes / 16);
   const unsigned nRec = (unsigned)std::min<size_t>(bytes / 8, 0xFFFFFFFFu);
   const int perThread = 256;
+  // small (L2-resident) buffers: sweep them many times inside one launch so launch latency does not dominate
+  const int inner = bytes <= (64u << 20) ? 64 : 1;
   auto pass = [&]() {
-    if (pattern == 0) bw_stream_kernel<<<grid, block>>>(static_cast<const uint4*>(buf), n16, sink);
+    if (pattern == 0) bw_stream_kernel<<<grid, block>>>(static_cast<const uint4*>(buf), n16, inner, sink);
     else bw_gather_kernel<<<grid, block>>>(static_cast<const float2*>(buf), nRec, perThread, sink);
   };
   for (int i = 0; i < 3; ++i) pass();     // warm-up (and L2 fill for small buffers)
@@ -1290,8 +1343,8 @@ int rmcrt_measure_read_bandwidth(rmcrt_ctx* ctx, size_t bytes, int repeats, int 
   CK(cudaGetLastError());
   const double sec = ms * 1e-3;
   if (pattern == 0) {
-    if (gbps) *gbps = (double)n16 * 16.0 * repeats / sec / 1e9;
-    if (gaccess) *gaccess = (double)n16 * repeats / sec / 1e9;
+    if (gbps) *gbps = (double)n16 * 16.0 * repeats * inner / sec / 1e9;
+    if (gaccess) *gaccess = (double)n16 * repeats * inner / sec / 1e9;
   } else {
     const double acc = (double)grid * block * perThread * repeats;
     if (gbps) *gbps = acc * 32.0 / sec / 1e9;

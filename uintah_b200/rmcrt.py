@@ -152,6 +152,9 @@ class RMCRT:
     def finalize_level(self, L: int, stream=None):
         check(self.ctx, self.lib.rmcrt_finalize_level(self.ctx, L, _stream_handle(stream)))
 
+    def finalize_level_async(self, L: int, stream=None):
+        check(self.ctx, self.lib.rmcrt_finalize_level_async(self.ctx, L, _stream_handle(stream)))
+
     def level_records(self, L: int):
         """torch uint8 view of the packed records of level L (for the all-gather)."""
         import torch
