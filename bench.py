@@ -207,7 +207,8 @@ def run_ours(args):
 
     skip = 0 if args.reference_semantics else 1
     g = RMCRT(device=local, nDivQRays=rays, threshold=0.05, seed=1234, skipZeroWeightLegs=skip,
-              rayCoherence=args.coherence, l2Persist=args.l2persist, warpsPerTile=args.warps)
+              rayCoherence=args.coherence, l2Persist=args.l2persist, warpsPerTile=args.warps,
+              genericMarch=args.generic_march)
     stream = torch.cuda.current_stream()
     desc = LevelData(None, None, None, lo, hi, dx, interior_lo=(0, 0, 0), interior_hi=shape).desc()
     g.define_level(0, desc)
@@ -442,6 +443,7 @@ def main():
     ap.add_argument("--coherence", type=int, default=1)
     ap.add_argument("--l2persist", type=int, default=1)
     ap.add_argument("--warps", type=int, default=0)
+    ap.add_argument("--generic-march", type=int, default=0, help="1: generic march template instead of the tuned fast path (A/B)")
     ap.add_argument("--reference-semantics", action="store_true", help="march the zero-weight reflected legs like the reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

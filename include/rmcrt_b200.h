@@ -72,7 +72,9 @@ typedef struct rmcrt_params {
   int32_t  fixedRandom;        /* FIXED_RANDOM_NUM (MersenneTwister.h:93): every draw = 0.3 */
   int32_t  l2Persist;          /* 1 = pin the level records in L2 with an access-policy window */
   int32_t  warpsPerTile;       /* 0 = auto; rays of a 32-cell tile are split over this many warps */
-  int32_t  reserved[4];
+  int32_t  genericMarch;       /* 1 = run the FP32 solve through the generic march template instead of the tuned
+                                  single-level fast path (A/B measurements, debugging); results agree to FP32 round-off */
+  int32_t  reserved[3];
 } rmcrt_params;
 
 /* geometry of one level (Level.cc:473-477, 1285-1307) */

@@ -45,6 +45,24 @@ void hs_trace_1L(const HsLevel* g, int kind, int n, const int* cells, const doub
   }
 }
 
+// production FP32 fast path (march_single_level_fast), same inputs as hs_trace_1L kind 0
+void hs_trace_1L_fast(const HsLevel* g, int n, const int* cells, const double* dirs, const double* orgs, double threshold,
+                      int allowReflect, int skipZero, double* sumI, unsigned* steps) {
+  const int nx = g->hi[0] - g->lo[0], ny = g->hi[1] - g->lo[1];
+  for (int t = 0; t < n; ++t) {
+    const int* c = cells + 3 * t;
+    double r[3];
+    rayDxOf(*g, c, orgs + 3 * t, r);
+    const int idx = (c[0] - g->lo[0]) + nx * ((c[1] - g->lo[1]) + ny * (c[2] - g->lo[2]));
+    unsigned s = 0;
+    const double* d = dirs + 3 * t;
+    sumI[t] = march_single_level_fast(static_cast<const Rec8*>(g->rec), idx, nx, nx * ny, (float)d[0], (float)d[1], (float)d[2],
+                                      (float)r[0], (float)r[1], (float)r[2], (float)g->dx[0], (float)g->dx[1], (float)g->dx[2],
+                                      (float)threshold, allowReflect != 0, skipZero != 0, s);
+    steps[t] = s;
+  }
+}
+
 void hs_trace_ML(const HsLevel* lv, int maxLevels, const int* roiLo, const int* roiHi, const int* regLo, const int* regHi, int kind, int n,
                  const int* cells, const double* dirs, const double* orgs, double threshold, int allowReflect, int skipZero,
                  double* sumI, unsigned* steps, int* path, int maxPath) {

@@ -61,6 +61,16 @@ def trace_1L(lv, kind, cells, dirs, org, thr, refl, skip=0, max_path=4000):
     return sumI, steps, path
 
 
+def trace_1L_fast(lv, cells, dirs, org, thr, refl, skip=0):
+    rec = pack(lv, 0)
+    h = hslevel(lv, rec)
+    n = len(cells)
+    sumI = np.zeros(n); steps = np.zeros(n, np.uint32)
+    cells = np.ascontiguousarray(cells, np.int32); dirs = np.ascontiguousarray(dirs); org = np.ascontiguousarray(org)
+    lib().hs_trace_1L_fast(C.byref(h), n, _vp(cells), _vp(dirs), _vp(org), C.c_double(thr), refl, skip, _vp(sumI), _vp(steps))
+    return sumI, steps
+
+
 def trace_ML(levels, kind, roi, reg, cells, dirs, org, thr, refl, skip=0, max_path=4000):
     recs = [pack(l, kind) for l in levels]
     nl = len(levels)

@@ -15,7 +15,10 @@ def _compare_1L(po, lv, thr, refl, n=200, seed=0):
     ref = [po.update_sumI(p, lv, dirs[t], org[t], cells[t], max_path=4000) for t in range(n)]
     s64, n64, p64 = sim.trace_1L(lv, 1, cells, dirs, org, thr, refl)
     s32, n32, _ = sim.trace_1L(lv, 0, cells, dirs, org, thr, refl)
+    sfa, nfa = sim.trace_1L_fast(lv, cells, dirs, org, thr, refl)      # the production FP32 kernel's march
+    assert (nfa == n32).mean() > 0.98 and (nfa == np.array([r[1] for r in ref])).mean() > 0.98
     for t, (s, ns, path) in enumerate(ref):
+        assert s == pytest.approx(sfa[t], rel=5e-4, abs=1e-6 * max(1.0, abs(s)))
         assert ns == n64[t]
         assert np.array_equal(path, p64[t, :ns, :3])
         assert s == pytest.approx(s64[t], rel=1e-13, abs=1e-300)

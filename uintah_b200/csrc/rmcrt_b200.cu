@@ -25,6 +25,7 @@
 #include <dlfcn.h>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 using namespace rmcrt;
@@ -192,11 +193,17 @@ __device__ __forceinline__ Real nz(double v) {   // direction component as Real,
   return r;
 }
 
-template <class Real, class RecT, bool ML, bool RECORD>
+template <class Real, class RecT, bool ML, bool RECORD, bool FAST = false>
 __device__ __forceinline__ Real trace_one(const TraceArgs& a, bool skipZero, int i, int j, int k, const double dir[3], const double rayDx[3],
                                           unsigned& steps, PathSink* path) {
   const int F = a.G.maxLevels - 1;
   const LevelGeom& g = a.G.lev[F];
+  if constexpr (FAST && !ML && !RECORD && std::is_same<Real, float>::value && std::is_same<RecT, Rec8>::value) {
+    return march_single_level_fast(static_cast<const Rec8*>(g.rec), (int)level_index(g, i, j, k), g.n[0], g.n[0] * g.n[1],
+                                   nz<float>(dir[0]), nz<float>(dir[1]), nz<float>(dir[2]), (float)rayDx[0], (float)rayDx[1],
+                                   (float)rayDx[2], (float)g.dx[0], (float)g.dx[1], (float)g.dx[2], (float)a.threshold,
+                                   a.allowReflect != 0, skipZero, steps);
+  } else
   if (ML) {
     return march_multi_level<Real, RecT, MAXL, RECORD>(a.G, i, j, k, nz<Real>(dir[0]), nz<Real>(dir[1]), nz<Real>(dir[2]),
                                                        (Real)rayDx[0], (Real)rayDx[1], (Real)rayDx[2], (Real)a.threshold,
@@ -217,7 +224,7 @@ __device__ __forceinline__ Real trace_one(const TraceArgs& a, bool skipZero, int
 // Per-lane sums are combined across the W warps through shared memory in a fixed order (deterministic),
 // then lane = cell writes divQ / radiationVolq fully coalesced.
 //======================================================================================================
-template <class Real, class RecT, bool ML>
+template <class Real, class RecT, bool ML, bool FAST = false>
 __global__ void __launch_bounds__(256) divq_kernel(const __grid_constant__ TraceArgs a) {
   extern __shared__ double red[];     // [W][32]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
@@ -251,7 +258,7 @@ __global__ void __launch_bounds__(256) divq_kernel(const __grid_constant__ Trace
       for (int ray = warp; ray < a.nRays; ray += W) {
         double dir[3], rayDx[3];
         gen_divq_ray(a.rng, g, i, j, k, ray, cellId, dirId, dir, rayDx);
-        acc += (double)trace_one<Real, RecT, ML, false>(a, skipZero, i, j, k, dir, rayDx, steps, nullptr);
+        acc += (double)trace_one<Real, RecT, ML, false, FAST>(a, skipZero, i, j, k, dir, rayDx, steps, nullptr);
       }
     }
     red[warp * 32 + lane] = acc;
@@ -875,6 +882,8 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
     const long long cap = (long long)ctx->smCount * 64;   // persistent-ish: grid-stride beyond this
     if (grid > cap) grid = cap;
     if (ML) divq_kernel<Real, RecT, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
+    else if (std::is_same<Real, float>::value && !ctx->p.genericMarch)
+      divq_kernel<Real, RecT, false, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
     else    divq_kernel<Real, RecT, false><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
     CK(cudaGetLastError());
   }
