@@ -170,50 +170,59 @@ __device__ __forceinline__ Real march_single_level(const RecT* __restrict__ recs
 //     re-bases A with the next cell's k -- no tPrev, no separate ds;
 //   * the per-leg integral is accumulated without fs and scaled once per wall hit (fs is constant on a leg);
 //   * the step is unrolled by two so the loop-carried (ePrev, k, s) need no register moves;
+//   * the record of the NEXT step is requested before the wall test of the current one (see below);
 //   * executed steps are counted in an FP32 register (exact below 2^24 per ray; FADD runs on the FMA pipe).
 // The axis choice keeps the reference's strict-'<' tie order (RMCRTCommon.cc:696-708).
 //------------------------------------------------------------------------------------------------------
-struct FastStep {
+// DDA state of one ray; advanced in place.  Only the stepping axis changes, and its old tMax is exactly the returned t,
+// so a speculative advance can be undone bit-exactly (dda_undo).
+struct Dda {
   float tx, ty, tz;      // tMax, scaled by log2(e)
+  int idx;               // record index of the current cell
+};
+
+__device__ __forceinline__ void dda_advance(Dda& d, float ddx, float ddy, float ddz, int stx, int sty, int stz,
+                                            float& t, bool& px, bool& py) {
+  const bool a = d.tx < d.ty;
+  const float m = fminf(d.tx, d.ty);
+  const bool nz_ = m < d.tz;                 // false: z is the stepping axis
+  px = a && nz_;
+  py = !a && nz_;
+  t = fminf(m, d.tz);                        // == px ? tx : py ? ty : tz
+  d.idx += px ? stx : (py ? sty : stz);
+  d.tx = px ? d.tx + ddx : d.tx;
+  d.ty = py ? d.ty + ddy : d.ty;
+  d.tz = nz_ ? d.tz : d.tz + ddz;
+}
+__device__ __forceinline__ void dda_undo(Dda& d, int stx, int sty, int stz, float t, bool px, bool py) {
+  d.idx -= px ? stx : (py ? sty : stz);
+  if (px) d.tx = t; else if (py) d.ty = t; else d.tz = t;
+}
+
+// emission/absorption integral state along one ray
+struct Integ {
   float A;               // tau(t) = A + k t inside the current cell
   float k, s;            // properties of the current cell
   float ePrev;           // exp(-tau) on entry to the current cell
   float leg;             // sum over the leg of s (ePrev - e)
   float nsteps;
-  int idx;
-  bool px, py;
-  float e;
-  float rk;              // raw abskg word of the cell just entered (sign bit = wall)
-  float t, tau;          // tMax and optical thickness of the step just taken (needed only at a wall)
+  float tau;             // optical thickness at the last cell face crossed
 };
-
-__device__ __forceinline__ void fast_step(FastStep& q, const Rec8* __restrict__ recs, float ddx, float ddy, float ddz,
-                                          int stx, int sty, int stz) {
-  typedef Num<float> N;
-  const bool a = q.tx < q.ty;
-  const float m = fminf(q.tx, q.ty);
-  const bool nz_ = m < q.tz;                 // false: z is the stepping axis
-  q.px = a && nz_;
-  q.py = !a && nz_;
-  const float tNext = fminf(m, q.tz);        // == px ? tx : py ? ty : tz
-  q.idx += q.px ? stx : (q.py ? sty : stz);
-  const Rec8 r = ldrec(recs + q.idx);        // the one load of this step
-  q.tx = q.px ? q.tx + ddx : q.tx;
-  q.ty = q.py ? q.ty + ddy : q.ty;
-  q.tz = nz_ ? q.tz : q.tz + ddz;
-  const float tau = fmaf(q.k, tNext, q.A);   // optical thickness at the cell exit (RMCRTCommon.cc:731)
-  q.e = N::attenuation(tau);                 // 782
-  q.leg = fmaf(q.s, q.ePrev - q.e, q.leg);   // 786 (fs applied per leg)
-  q.ePrev = q.e;
+// cross the face at t into the cell whose record is r
+__device__ __forceinline__ void integ_cross(Integ& q, float t, const Rec8 r) {
+  q.tau = fmaf(q.k, t, q.A);                          // optical thickness at the cell exit (RMCRTCommon.cc:731)
+  const float e = Num<float>::attenuation(q.tau);     // 782
+  q.leg = fmaf(q.s, q.ePrev - e, q.leg);              // 786 (fs applied per leg)
+  q.ePrev = e;
   q.nsteps += 1.0f;
-  q.rk = r.k;
   q.k = fabsf(r.k);
   q.s = r.s;
-  q.A = fmaf(-q.k, tNext, tau);              // re-base for the cell just entered
-  q.t = tNext;
-  q.tau = tau;
+  q.A = fmaf(-q.k, t, q.tau);                         // re-base for the cell just entered
 }
 
+// The loads are software-pipelined: the DDA does not depend on the loaded data, so the record of step n+1 is requested
+// before the wall test of step n resolves (two records in flight per ray).  The speculative step past a wall reads a
+// neighbour of a non-flow cell -- inside the level, or inside the guard records rmcrt_define_level puts around it.
 __device__ __forceinline__ float march_single_level_fast(const Rec8* __restrict__ recs, int idx0, int sy, int sz,
                                                          float dx, float dy, float dz, float rx, float ry, float rz,
                                                          float cx, float cy, float cz, float threshold, bool allowReflect,
@@ -223,40 +232,49 @@ __device__ __forceinline__ float march_single_level_fast(const Rec8* __restrict_
   const bool posx = !sign_bit(dx), posy = !sign_bit(dy), posz = !sign_bit(dz);
   int stx = posx ? 1 : -1, sty = posy ? sy : -sy, stz = posz ? sz : -sz;
   const float ix = N::rcp(dx), iy = N::rcp(dy), iz = N::rcp(dz);
-  FastStep q;
-  q.tx = ((posx ? cx : 0.0f) - rx) * ix * N::LEN_SCALE;
-  q.ty = ((posy ? cy : 0.0f) - ry) * iy * N::LEN_SCALE;
-  q.tz = ((posz ? cz : 0.0f) - rz) * iz * N::LEN_SCALE;
+  Dda d;
+  d.tx = ((posx ? cx : 0.0f) - rx) * ix * N::LEN_SCALE;
+  d.ty = ((posy ? cy : 0.0f) - ry) * iy * N::LEN_SCALE;
+  d.tz = ((posz ? cz : 0.0f) - rz) * iz * N::LEN_SCALE;
   const float ddx = fabsf(ix) * cx * N::LEN_SCALE, ddy = fabsf(iy) * cy * N::LEN_SCALE, ddz = fabsf(iz) * cz * N::LEN_SCALE;
-  q.idx = idx0;
+  d.idx = idx0;
+  Integ q;
   {
     const Rec8 r = ldrec(recs + idx0);
-    q.k = fabsf(r.k); q.s = r.s; q.rk = r.k;
+    q.k = fabsf(r.k); q.s = r.s;
   }
-  q.A = 0.0f; q.ePrev = 1.0f; q.nsteps = 0.0f; q.e = 1.0f; q.px = q.py = false; q.t = 0.0f; q.tau = 0.0f;
+  q.A = 0.0f; q.ePrev = 1.0f; q.nsteps = 0.0f; q.tau = 0.0f;
   float sum = 0.0f, fs = 1.0f;
   for (;;) {
     q.leg = 0.0f;
+    float t, t1, t2;
+    bool px, py, px1, py1, px2, py2;
+    dda_advance(d, ddx, ddy, ddz, stx, sty, stz, t1, px1, py1);
+    Rec8 r1 = ldrec(recs + d.idx), r2;
     for (;;) {
-      fast_step(q, recs, ddx, ddy, ddz, stx, sty, stz);
-      if (is_wall(q.rk)) break;
-      fast_step(q, recs, ddx, ddy, ddz, stx, sty, stz);
-      if (is_wall(q.rk)) break;
+      dda_advance(d, ddx, ddy, ddz, stx, sty, stz, t2, px2, py2);   // speculative
+      r2 = ldrec(recs + d.idx);
+      integ_cross(q, t1, r1);
+      if (is_wall(r1.k)) { dda_undo(d, stx, sty, stz, t2, px2, py2); t = t1; px = px1; py = py1; break; }
+      dda_advance(d, ddx, ddy, ddz, stx, sty, stz, t1, px1, py1);   // speculative
+      r1 = ldrec(recs + d.idx);
+      integ_cross(q, t2, r2);
+      if (is_wall(r2.k)) { dda_undo(d, stx, sty, stz, t1, px1, py1); t = t2; px = px2; py = py2; break; }
     }
     sum = fmaf(q.leg, fs, sum);
-    // wall: (q.k, q.s) = record of the non-flow cell entered, q.e = exp(-tau) at its face
+    // wall: (q.k, q.s) = record of the non-flow cell entered, q.ePrev = exp(-tau) at its face
     const float eps = q.k > 1.0f ? 1.0f : q.k;                 // 846-850
-    sum = fmaf(eps * q.s, q.e, sum);                           // 854: NOT multiplied by fs
-    const float intensity = q.e * fs;                          // 856
+    sum = fmaf(eps * q.s, q.ePrev, sum);                       // 854: NOT multiplied by fs
+    const float intensity = q.ePrev * fs;                      // 856
     if (!allowReflect || !(intensity > threshold)) break;      // 884, 898, 683
     // RMCRTCommon::reflect (581-602): back to the cell the ray came from, flip the stepping axis
     fs *= (1.0f - q.k);
     if (skipZero && fs == 0.0f) break;
-    q.idx -= q.px ? stx : (q.py ? sty : stz);
-    if (q.px) stx = -stx; else if (q.py) sty = -sty; else stz = -stz;
-    const Rec8 r = ldrec(recs + q.idx);
-    q.k = fabsf(r.k); q.s = r.s; q.rk = r.k;
-    q.A = fmaf(-q.k, q.t, q.tau);                              // tMax is NOT recomputed on reflection (reference behaviour)
+    d.idx -= px ? stx : (py ? sty : stz);
+    if (px) stx = -stx; else if (py) sty = -sty; else stz = -stz;
+    const Rec8 r = ldrec(recs + d.idx);
+    q.k = fabsf(r.k); q.s = r.s;
+    q.A = fmaf(-q.k, t, q.tau);                                // tMax is NOT recomputed on reflection (reference behaviour)
   }
   nSteps += (unsigned)q.nsteps;
   return sum;
