@@ -258,6 +258,33 @@ def test_skip_zero_weight_legs_is_exact(gpu_lib, po):
     assert steps[0] == steps[1]
 
 
+@pytest.mark.parametrize("case", ["bc_walls", "plates_mirrors", "bc_refsem"])
+def test_tuned_march_matches_generic_march(gpu_lib, po, case):
+    """The production FP32 kernel (PTX leg loop, pipelined loads, offset-form tau) against the generic march template
+    on the same Philox rays: same executed steps up to FP32 ties, same divQ to FP32 round-off."""
+    rng = np.random.default_rng(3)
+    kw = dict(nDivQRays=16, threshold=0.05, seed=11)
+    if case == "bc_walls":
+        lv = po.burns_christon(24, dtype=np.float32)
+        add_random_walls(lv, 0.02, rng)
+    elif case == "plates_mirrors":       # reflections off mirrors, hot black walls: every leg is marched
+        lv = po.parallel_plates(20, dtype=np.float32, mirror_faces=("x-", "y-"))
+        kw["threshold"] = 0.001
+    else:
+        lv = po.burns_christon(24, dtype=np.float32)
+        kw["skipZeroWeightLegs"] = 0
+    out = {}
+    for gm in (0, 1):
+        g = make(gpu_lib, genericMarch=gm, **kw)
+        g.upload_level(0, lv)
+        out[gm] = (g.trace_divq(0, timestep=5)["divQ"], g.counters().nRaySteps)
+    (a, na), (b, nb) = out[0], out[1]
+    assert abs(int(na) - int(nb)) <= 2e-4 * nb, (na, nb)
+    assert np.array_equal(a == 0, b == 0)
+    scale = np.abs(b).max()
+    assert np.abs(a - b).max() <= 2e-4 * scale, np.abs(a - b).max() / scale
+
+
 def test_reproducible_and_keyed_on_timestep(gpu_lib, po):
     lv = po.burns_christon(16, dtype=np.float32)
     g = make(gpu_lib, nDivQRays=6, threshold=0.05, seed=99)

@@ -174,29 +174,35 @@ __device__ __forceinline__ Real march_single_level(const RecT* __restrict__ recs
 //   * executed steps are counted in an FP32 register (exact below 2^24 per ray; FADD runs on the FMA pipe).
 // The axis choice keeps the reference's strict-'<' tie order (RMCRTCommon.cc:696-708).
 //------------------------------------------------------------------------------------------------------
-// DDA state of one ray; advanced in place.  Only the stepping axis changes, and its old tMax is exactly the returned t,
-// so a speculative advance can be undone bit-exactly (dda_undo).
+// DDA state of one ray.  A step is split into PEEK (which axis steps next, at which t, into which record -- no state
+// change) and COMMIT (advance tMax of that axis and the index), so the record of step n+1 can be requested before the wall
+// test of step n resolves while the state still is exactly "after step n" if that test fires.
 struct Dda {
   float tx, ty, tz;      // tMax, scaled by log2(e)
   int idx;               // record index of the current cell
 };
-
-__device__ __forceinline__ void dda_advance(Dda& d, float ddx, float ddy, float ddz, int stx, int sty, int stz,
-                                            float& t, bool& px, bool& py) {
+struct Peek {
+  float t;               // == px ? tx : py ? ty : tz
+  bool px, py, pz;       // stepping axis; strict '<' tie order of RMCRTCommon.cc:696-708
+  int idx;               // record index of the cell the step enters
+};
+__device__ __forceinline__ Peek dda_peek(const Dda& d, int stx, int sty, int stz) {
+  Peek p;
   const bool a = d.tx < d.ty;
   const float m = fminf(d.tx, d.ty);
   const bool nz_ = m < d.tz;                 // false: z is the stepping axis
-  px = a && nz_;
-  py = !a && nz_;
-  t = fminf(m, d.tz);                        // == px ? tx : py ? ty : tz
-  d.idx += px ? stx : (py ? sty : stz);
-  d.tx = px ? d.tx + ddx : d.tx;
-  d.ty = py ? d.ty + ddy : d.ty;
-  d.tz = nz_ ? d.tz : d.tz + ddz;
+  p.px = a && nz_;
+  p.py = !a && nz_;
+  p.pz = !nz_;
+  p.t = fminf(m, d.tz);
+  p.idx = d.idx + (p.px ? stx : (p.py ? sty : stz));
+  return p;
 }
-__device__ __forceinline__ void dda_undo(Dda& d, int stx, int sty, int stz, float t, bool px, bool py) {
-  d.idx -= px ? stx : (py ? sty : stz);
-  if (px) d.tx = t; else if (py) d.ty = t; else d.tz = t;
+__device__ __forceinline__ void dda_commit(Dda& d, const Peek& p, float ddx, float ddy, float ddz) {
+  d.idx = p.idx;
+  d.tx = p.px ? d.tx + ddx : d.tx;      // predicated in-place adds, no branches
+  d.ty = p.py ? d.ty + ddy : d.ty;
+  d.tz = p.pz ? d.tz + ddz : d.tz;
 }
 
 // emission/absorption integral state along one ray
@@ -220,9 +226,116 @@ __device__ __forceinline__ void integ_cross(Integ& q, float t, const Rec8 r) {
   q.A = fmaf(-q.k, t, q.tau);                         // re-base for the cell just entered
 }
 
+// One LEG of a ray: march from the current cell until a non-flow cell is entered.
+//
 // The loads are software-pipelined: the DDA does not depend on the loaded data, so the record of step n+1 is requested
-// before the wall test of step n resolves (two records in flight per ray).  The speculative step past a wall reads a
-// neighbour of a non-flow cell -- inside the level, or inside the guard records rmcrt_define_level puts around it.
+// before the wall test of step n resolves (two records in flight per ray), while the DDA state is only committed after
+// that test -- at a wall the state is exactly "after step n".  The speculative request past a wall reads a neighbour of
+// a non-flow cell: inside the level, or inside the guard records rmcrt_define_level puts around it.
+//
+// On the device the loop is written in PTX: three steps per iteration so that the three cells in play (being left, being
+// entered, in flight) rotate through fixed registers without moves, predicated in-place tMax updates, and no
+// re-association by the compiler; ~21 SASS instructions per ray-cell step.  The C++ version below it is the same
+// algorithm statement by statement and is what the host-side simulation (tests/hostsim) steps against the oracle.
+struct LegOut {
+  float t;        // tMax of the step that entered the wall
+  int axis;       // stepping axis of that step: 0 x, 1 y, 2 z
+};
+
+#if defined(__CUDA_ARCH__)
+#define RM_PEEK(J, IB)                                      \
+  "min.f32 m, %0, %1;\n\t"                                  \
+  "setp.lt.f32 n" #J ", m, %2;\n\t"                         \
+  "setp.lt.and.f32 x" #J ", %0, %1, n" #J ";\n\t"           \
+  "setp.ge.and.f32 y" #J ", %0, %1, n" #J ";\n\t"           \
+  "min.f32 t" #J ", m, %2;\n\t"                             \
+  "selp.s32 i" #J ", %17, %19, x" #J ";\n\t"                \
+  "@y" #J " mov.s32 i" #J ", %18;\n\t"                      \
+  "add.s32 i" #J ", i" #J ", " IB ";\n\t"                   \
+  "mad.wide.s32 ad, i" #J ", 8, %13;\n\t"                   \
+  "ld.global.nc.v2.f32 {k" #J ", s" #J "}, [ad];\n\t"
+#define RM_COMMIT(J)                                        \
+  "@x" #J " add.f32 %0, %0, %14;\n\t"                       \
+  "@y" #J " add.f32 %1, %1, %15;\n\t"                       \
+  "@!n" #J " add.f32 %2, %2, %16;\n\t"
+// leave the cell in slot P at t<C>, enter the cell in slot C
+#define RM_INTEG(P, C)                                      \
+  "fma.rn.f32 ta, a" #P ", t" #C ", %4;\n\t"                \
+  "neg.f32 d, ta;\n\t"                                      \
+  "ex2.approx.ftz.f32 e" #C ", d;\n\t"                      \
+  "sub.f32 d, e" #P ", e" #C ";\n\t"                        \
+  "fma.rn.f32 %8, s" #P ", d, %8;\n\t"                      \
+  "add.f32 %9, %9, 0f3F800000;\n\t"                         \
+  "abs.f32 a" #C ", k" #C ";\n\t"                           \
+  "neg.f32 d, a" #C ";\n\t"                                 \
+  "fma.rn.f32 %4, d, t" #C ", ta;\n\t"                      \
+  "setp.lt.s32 w, k" #C ", 0;\n\t"                          \
+  "@w bra EXIT" #C ";\n\t"
+#define RM_EXIT(C)                                          \
+  "EXIT" #C ":\n\t"                                         \
+  "mov.s32 %3, i" #C ";\n\t"                                \
+  "mov.f32 %10, t" #C ";\n\t"                               \
+  "selp.s32 %11, 1, 2, y" #C ";\n\t"                        \
+  "@x" #C " mov.s32 %11, 0;\n\t"                            \
+  "mov.f32 %5, a" #C ";\n\t"                                \
+  "mov.f32 %6, s" #C ";\n\t"                                \
+  "mov.f32 %7, e" #C ";\n\t"                                \
+  "bra DONE;\n\t"
+
+__device__ __forceinline__ LegOut march_leg(Dda& d, Integ& q, const Rec8* __restrict__ recs, float ddx, float ddy, float ddz,
+                                            int stx, int sty, int stz) {
+  LegOut o;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred x0, y0, n0, x1, y1, n1, x2, y2, n2, w;\n\t"
+      ".reg .f32 m, d, ta, t0, t1, t2, s0, s1, s2, e0, e1, e2, a0, a1, a2;\n\t"
+      ".reg .b32 k0, k1, k2;\n\t"
+      ".reg .s32 i0, i1, i2;\n\t"
+      ".reg .s64 ad;\n\t"
+      // slot 2 = the cell the leg starts in
+      "mov.f32 a2, %5;\n\t"
+      "mov.f32 s2, %6;\n\t"
+      "mov.f32 e2, %7;\n\t"
+      RM_PEEK(0, "%3")
+      "LOOP:\n\t"
+      RM_COMMIT(0) RM_PEEK(1, "i0") RM_INTEG(2, 0)
+      RM_COMMIT(1) RM_PEEK(2, "i1") RM_INTEG(0, 1)
+      RM_COMMIT(2) RM_PEEK(0, "i2") RM_INTEG(1, 2)
+      "bra LOOP;\n\t"
+      RM_EXIT(0) RM_EXIT(1) RM_EXIT(2)
+      "DONE:\n\t"
+      "mov.f32 %12, ta;\n\t"
+      "}"
+      : "+f"(d.tx), "+f"(d.ty), "+f"(d.tz), "+r"(d.idx), "+f"(q.A), "+f"(q.k), "+f"(q.s), "+f"(q.ePrev), "+f"(q.leg),
+        "+f"(q.nsteps), "=f"(o.t), "=r"(o.axis), "=f"(q.tau)
+      : "l"(recs), "f"(ddx), "f"(ddy), "f"(ddz), "r"(stx), "r"(sty), "r"(stz)
+      : "memory");
+  return o;
+}
+#undef RM_PEEK
+#undef RM_COMMIT
+#undef RM_INTEG
+#undef RM_EXIT
+#else
+__device__ __forceinline__ LegOut march_leg(Dda& d, Integ& q, const Rec8* __restrict__ recs, float ddx, float ddy, float ddz,
+                                            int stx, int sty, int stz) {
+  Peek p1 = dda_peek(d, stx, sty, stz), p2;
+  Rec8 r1 = ldrec(recs + p1.idx), r2;
+  for (;;) {
+    dda_commit(d, p1, ddx, ddy, ddz);
+    p2 = dda_peek(d, stx, sty, stz);          // speculative: issued before r1's wall test
+    r2 = ldrec(recs + p2.idx);
+    integ_cross(q, p1.t, r1);
+    if (is_wall(r1.k)) return LegOut{p1.t, p1.px ? 0 : (p1.py ? 1 : 2)};
+    dda_commit(d, p2, ddx, ddy, ddz);
+    p1 = dda_peek(d, stx, sty, stz);
+    r1 = ldrec(recs + p1.idx);
+    integ_cross(q, p2.t, r2);
+    if (is_wall(r2.k)) return LegOut{p2.t, p2.px ? 0 : (p2.py ? 1 : 2)};
+  }
+}
+#endif
+
 __device__ __forceinline__ float march_single_level_fast(const Rec8* __restrict__ recs, int idx0, int sy, int sz,
                                                          float dx, float dy, float dz, float rx, float ry, float rz,
                                                          float cx, float cy, float cz, float threshold, bool allowReflect,
@@ -247,20 +360,7 @@ __device__ __forceinline__ float march_single_level_fast(const Rec8* __restrict_
   float sum = 0.0f, fs = 1.0f;
   for (;;) {
     q.leg = 0.0f;
-    float t, t1, t2;
-    bool px, py, px1, py1, px2, py2;
-    dda_advance(d, ddx, ddy, ddz, stx, sty, stz, t1, px1, py1);
-    Rec8 r1 = ldrec(recs + d.idx), r2;
-    for (;;) {
-      dda_advance(d, ddx, ddy, ddz, stx, sty, stz, t2, px2, py2);   // speculative
-      r2 = ldrec(recs + d.idx);
-      integ_cross(q, t1, r1);
-      if (is_wall(r1.k)) { dda_undo(d, stx, sty, stz, t2, px2, py2); t = t1; px = px1; py = py1; break; }
-      dda_advance(d, ddx, ddy, ddz, stx, sty, stz, t1, px1, py1);   // speculative
-      r1 = ldrec(recs + d.idx);
-      integ_cross(q, t2, r2);
-      if (is_wall(r2.k)) { dda_undo(d, stx, sty, stz, t1, px1, py1); t = t2; px = px2; py = py2; break; }
-    }
+    const LegOut w = march_leg(d, q, recs, ddx, ddy, ddz, stx, sty, stz);
     sum = fmaf(q.leg, fs, sum);
     // wall: (q.k, q.s) = record of the non-flow cell entered, q.ePrev = exp(-tau) at its face
     const float eps = q.k > 1.0f ? 1.0f : q.k;                 // 846-850
@@ -270,11 +370,11 @@ __device__ __forceinline__ float march_single_level_fast(const Rec8* __restrict_
     // RMCRTCommon::reflect (581-602): back to the cell the ray came from, flip the stepping axis
     fs *= (1.0f - q.k);
     if (skipZero && fs == 0.0f) break;
-    d.idx -= px ? stx : (py ? sty : stz);
-    if (px) stx = -stx; else if (py) sty = -sty; else stz = -stz;
+    d.idx -= w.axis == 0 ? stx : (w.axis == 1 ? sty : stz);
+    if (w.axis == 0) stx = -stx; else if (w.axis == 1) sty = -sty; else stz = -stz;
     const Rec8 r = ldrec(recs + d.idx);
     q.k = fabsf(r.k); q.s = r.s;
-    q.A = fmaf(-q.k, t, q.tau);                                // tMax is NOT recomputed on reflection (reference behaviour)
+    q.A = fmaf(-q.k, w.t, q.tau);                                // tMax is NOT recomputed on reflection (reference behaviour)
   }
   nSteps += (unsigned)q.nsteps;
   return sum;
