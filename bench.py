@@ -418,7 +418,7 @@ def run_ours(args):
                                 f"packed-record all-gather per solve (BASELINE configs[2] at 8 GPUs)"),
                    "executed_steps_per_ray": all_steps / (all_cells * rays),
                    "zero_weight_legs": "marched (reference semantics)" if not skip else "skipped (exact: cold black walls, fs==0)",
-                   "ray_coherence": "warp-shared direction" if args.coherence else "independent per cell",
+                   "ray_coherence": {0: "independent per cell", 1: "warp-shared direction", 2: "warp-shared direction and in-cell offset"}[args.coherence],
                    "l2": "flushed between steps (256 MiB fill); level records (%.1f MB) re-packed every step" % (np.prod([h - l for l, h in zip(lo, hi)]) * 8 / 1e6),
                    "timing": "CUDA events on the launching stream per step, max over ranks"},
         "roofline": roofline, "roofline_l2": roofline_l2, "cpu_baseline": cpu_baseline, "e2e": e2e,

@@ -66,7 +66,9 @@ typedef struct rmcrt_params {
   /* ---- implementation knobs (no counterpart in the reference) ---- */
   int32_t  marchPrecision;     /* 0 = FP32 march (production), 1 = FP64 march (parity debugging) */
   int32_t  rayCoherence;       /* 1 = the 32 origin cells of a warp share one direction per ray index
-                                  (warp-coherent batching); 0 = independent direction per (cell, ray) */
+                                  (warp-coherent batching); 0 = independent direction per (cell, ray);
+                                  2 = they also share the in-cell origin offset, so the 32 rays are exact translates
+                                  of each other and march in lockstep (divQ rays only) */
   int32_t  skipZeroWeightLegs; /* 1 = end a ray once fs==0 and no non-flow cell can emit (exact);
                                   0 = march every leg the reference marches */
   int32_t  fixedRandom;        /* FIXED_RANDOM_NUM (MersenneTwister.h:93): every draw = 0.3 */
@@ -174,6 +176,8 @@ int rmcrt_get_counters(rmcrt_ctx* ctx, rmcrt_counters* out, void* stream);
  * sigmaT4OverPi = (sigma/pi) T^4 (RMCRTCommon.cc:304-343); n cells; T of the output = isFloat */
 int rmcrt_sigmaT4_device(rmcrt_ctx* ctx, const double* d_temperature, void* d_sigmaT4OverPi, int isFloat,
                          int64_t n, void* stream);
+/* same with host buffers (H2D, kernel, D2H; blocking): the body of the RMCRTCommon::sigmaT4<T> task for one patch */
+int rmcrt_sigmaT4(rmcrt_ctx* ctx, const double* temperature, void* sigmaT4OverPi, int isFloat, int64_t n, void* stream);
 /* Data-Onion coarse level from the fine level's records: Ray::coarsen_Q interior average (Ray.cc:2103-2145)
  * + Ray::computeCellType (2272-2345) for interior coarse cells; extra cells of the coarse level keep what
  * rmcrt_upload_level / rmcrt_set_level_extra_cells put there. */

@@ -1,0 +1,192 @@
+"""The C++ host mirror of the reference plugin surface (uintah_b200/host: Ray, RMCRTCommon, RMCRT_Test driver).
+
+CPU part (-m "not gpu"): the decks parse, the same tasks with the same labels/dependencies/task graphs as the reference's
+Ray::sched_* get registered, input errors raise ProblemSetupException, and without a GPU the solve fails loudly.
+GPU part: `rmcrt_test <deck> --dump` end to end (deck -> grid -> DataWarehouse -> tasks -> C ABI -> kernels) against the oracle.
+"""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+HOST = os.path.join(ROOT, "uintah_b200", "host")
+EXE = os.path.join(HOST, "rmcrt_test")
+DECKS = os.path.join(HERE, "decks")
+
+
+@pytest.fixture(scope="module")
+def exe():
+    from uintah_b200 import build
+    build.build()
+    subprocess.run(["make", "-C", HOST, "-j4"], check=True, capture_output=True)
+    return EXE
+
+
+def run(exe, deck, *args, check=True):
+    r = subprocess.run([exe, os.path.join(DECKS, deck), *args], capture_output=True, text=True, timeout=600)
+    if check:
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return r
+
+
+def tasks_of(stdout):
+    tasks, cur = [], None
+    for line in stdout.splitlines():
+        if line.startswith("TASK "):
+            f = line.split()
+            cur = {"name": f[1], **{k: v for k, v in (x.split("=") for x in f[2:])}, "deps": []}
+            tasks.append(cur)
+        elif line.startswith("  ") and cur is not None:
+            f = line.split()
+            cur["deps"].append((f[0], f[1], *f[2:]))
+    return tasks
+
+
+# ------------------------------------------------------------------------------------------------ CPU: surface
+def test_single_level_schedule_matches_reference_surface(exe):
+    """Ray::sched_rayTrace (Ray.cc:422-506): task name, labels, SHRT_MAX ghosts, TG_RMCRT; carry-forward on TG_CARRY_FORWARD"""
+    t = tasks_of(run(exe, "bm1_1L_double.ups", "--parse-only").stdout)
+    names = [x["name"] for x in t]
+    assert names == ["RMCRT_Test::initialize", "RMCRT_Test::initProperties", "RMCRTCommon::carryForward_VarLabels",
+                     "RMCRTCommon::sigmaT4", "Ray::setBoundaryConditions", "Ray::rayTrace"]
+    rt = t[-1]
+    assert rt["tg"] == "1" and rt["device"] == "1"
+    req = [d for d in rt["deps"] if d[0] == "requires"]
+    assert [d[1] for d in req] == ["abskg", "sigmaT4", "cellType"]
+    assert all(d[3] == "ghost=32767" and d[2] == "dw=NewDW" for d in req)
+    assert [d[1] for d in rt["deps"] if d[0] == "computes"] == ["divQ", "RMCRTboundFlux", "radiationVolq"]
+    cf = t[2]
+    assert cf["tg"] == "0" and {d[1] for d in cf["deps"]} == {"divQ", "RMCRTboundFlux", "radiationVolq", "sigmaT4"}
+
+
+def test_float_mode_creates_abskgRMCRT(exe):
+    """<RMCRT type="float"> with a double abskg: DoubleToFloat -> "abskgRMCRT" (RMCRTCommon.cc:188-191, 211-237)"""
+    t = tasks_of(run(exe, "bm1_1L_float_8patches.ups", "--parse-only").stdout)
+    d2f = [x for x in t if x["name"] == "RMCRTCommon::DoubleToFloat"]
+    assert len(d2f) == 1 and ("computes", "abskgRMCRT", "dw=NewDW", "ghost=0", "domain=normal", "offset=0") in d2f[0]["deps"]
+    rt = [x for x in t if x["name"] == "Ray::rayTrace"][0]
+    assert rt["patches"] == "8" and rt["deps"][0][1] == "abskgRMCRT"
+
+
+def test_data_onion_schedule(exe):
+    """Ray::sched_rayTrace_dataOnion (Ray.cc:824-938): finest level only, halo ghosts on the fine level, whole coarser levels"""
+    t = tasks_of(run(exe, "bm1_DO.ups", "--parse-only").stdout)
+    rt = [x for x in t if x["name"] == "Ray::rayTrace_dataOnion"]
+    assert len(rt) == 1 and rt[0]["level"] == "1" and rt[0]["patches"] == "8" and rt[0]["tg"] == "1"
+    fine = [d for d in rt[0]["deps"] if d[0] == "requires" and d[4] == "domain=normal"]
+    coarse = [d for d in rt[0]["deps"] if d[0] == "requires" and d[4] == "domain=coarse"]
+    assert [d[3] for d in fine] == ["ghost=4"] * 3
+    assert [d[1] for d in coarse] == ["abskg", "sigmaT4", "cellType"] and all(d[3] == "ghost=32767" and d[5] == "offset=1" for d in coarse)
+    names = [x["name"] for x in t]
+    assert names.index("Ray::coarsenAll") < names.index("Ray::rayTrace_dataOnion")
+
+
+@pytest.mark.parametrize("edit,needle", [
+    (("<nDivQRays>          3          </nDivQRays>", "<nDivQRays> 3 </nDivQRays> <sigmaScat> 0.5 </sigmaScat>"), "--enable-ray-scatter"),
+    (("<periodic> [0,0,0] </periodic>", "<periodic> [1,0,0] </periodic>"), "Periodic boundary conditions are not allowed"),
+    (("<extraCells> [1,1,1]   </extraCells>", "<extraCells> [0,0,0] </extraCells>"), "one extraCell"),
+    (('<BCType id="0" label="abskg"    var="Dirichlet"> <value> 1.0 </value> </BCType>', ""), "boundary condition for (abskg)"),
+    (("<Temperature>    64.804 </Temperature>", ""), "<Temperature>"),
+])
+def test_input_errors_raise_problem_setup_exception(exe, tmp_path, edit, needle):
+    src = open(os.path.join(DECKS, "bm1_1L_double.ups")).read()
+    assert edit[0] in src, edit[0]
+    deck = tmp_path / "bad.ups"
+    deck.write_text(src.replace(edit[0], edit[1], 1))
+    r = subprocess.run([exe, str(deck), "--parse-only"], capture_output=True, text=True)
+    assert r.returncode == 1 and "ProblemSetupException" in r.stderr and needle in r.stderr, r.stderr
+
+
+def test_data_onion_needs_patch_based_roi(exe, tmp_path):
+    """GPU bullet proofing of Ray::problemSetup (Ray.cc:338-345)"""
+    src = open(os.path.join(DECKS, "bm1_DO.ups")).read()
+    deck = tmp_path / "bad.ups"
+    deck.write_text(src.replace('<ROI_extents type="patch_based"/>', '<ROI_extents type="dynamic"> <abskgd_threshold> 0.1 </abskgd_threshold> </ROI_extents>'))
+    r = subprocess.run([exe, str(deck), "--parse-only"], capture_output=True, text=True)
+    assert r.returncode == 1 and 'only ROI_extents type="patch_based" work on the GPU' in r.stderr
+
+
+def test_no_gpu_fails_loudly(exe):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = run(exe, "bm1_1L_double.ups", check=False)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr and "no CPU fallback" in r.stderr
+
+
+# ------------------------------------------------------------------------------------------------ GPU: end to end
+def load_dump(d):
+    meta = json.load(open(os.path.join(d, "meta.json")))
+    out = {"report": meta["report"]}
+    for k, m in meta.items():
+        if k == "report":
+            continue
+        a = np.fromfile(os.path.join(d, m["file"]), dtype=np.dtype("<" + m["dtype"]))
+        shape = tuple(m["hi"][i] - m["lo"][i] for i in (2, 1, 0))
+        out[k] = a.reshape(shape + ((m["components"],) if m["components"] > 1 else ()))
+    return out
+
+
+@pytest.mark.gpu
+def test_bm1_single_level_double_deterministic(exe, po, tmp_path, gpu_lib):
+    """RMCRT_bm1_1L pattern: <randomSeed> false, type double -> FP64 march, agreement with the oracle to round-off"""
+    out = load_dump(run(exe, "bm1_1L_double.ups", "--dump", str(tmp_path)).args[3])
+    lv = po.burns_christon(21)
+    # the driver's own initialisation + sigmaT4 + setBoundaryConditions reproduce the oracle's input fields bit for bit
+    assert np.array_equal(out["abskg"], lv.abskg) and np.array_equal(out["cellType"], lv.cellType)
+    np.testing.assert_allclose(out["sigmaT4"], lv.sigmaT4, rtol=1e-15, atol=0)
+    ref = po.ray_trace(po.default_params(nDivQRays=3, threshold=0.05, isSeedRandom=0), lv)
+    assert out["report"]["nRaySteps"] == ref["steps"] and out["report"]["nDivQCells"] == 21 ** 3
+    np.testing.assert_allclose(out["divQ"], ref["divQ"], rtol=1e-9, atol=1e-10 * np.abs(ref["divQ"]).max())
+    np.testing.assert_allclose(out["radiationVolq"], ref["radiationVolq"], rtol=1e-9, atol=1e-12)
+    assert not out["RMCRTboundFlux"].any()          # solveBoundaryFlux false: zero-initialised Stencil7 (Ray.cc:583-587)
+
+
+@pytest.mark.gpu
+def test_bm1_float_eight_patches_equals_whole_level_solve(exe, po, tmp_path, gpu_lib):
+    """8 patches through the C++ task == one whole-level solve through the python harness (Philox keyed on the cell,
+    rayCoherence 0, so the result is independent of the patch layout), and within Monte-Carlo error of the oracle"""
+    from uintah_b200 import RMCRT
+    out = load_dump(run(exe, "bm1_1L_float_8patches.ups", "--dump", str(tmp_path), "--knob", "rayCoherence=0").args[3])
+    lv = po.burns_christon(32, dtype=np.float32)
+    assert out["report"]["nDivQCells"] == 32 ** 3
+    g = RMCRT(device=0, nDivQRays=32, threshold=0.05, rayCoherence=0)
+    g.upload_level(0, lv)
+    whole = g.trace_divq(0, timestep=2)["divQ"]      # the deck runs 2 time steps, both on TG_RMCRT (calc_frequency 2)
+    np.testing.assert_allclose(out["divQ"], whole, rtol=1e-12, atol=1e-14)
+    ref = po.ray_trace(po.default_params(nDivQRays=32, threshold=0.05), lv, seed=3, patches=(1, 1, 8), threads=8)["divQ"]
+    assert np.linalg.norm(out["divQ"] - ref) / np.linalg.norm(ref) < 0.04
+
+
+@pytest.mark.gpu
+def test_bm1_data_onion_deterministic(exe, po, tmp_path, gpu_lib):
+    """RMCRT_bm1_DO pattern (fine 32^3 in 8 patches, coarse 8^3, RR 4, halo 4): device coarsening + coarse BCs + DO trace"""
+    out = load_dump(run(exe, "bm1_DO.ups", "--dump", str(tmp_path)).args[3])
+    fine = po.burns_christon(32)
+    fine.rr = (4, 4, 4)
+    coarse = po.coarsen_level(fine, (4, 4, 4))
+    ref = po.ray_trace_data_onion(po.default_params(nDivQRays=3, threshold=0.05, isSeedRandom=0), [coarse, fine], (4, 4, 4),
+                                  patches=(2, 2, 2), threads=8)
+    assert out["report"]["nRaySteps"] == ref["steps"]
+    np.testing.assert_allclose(out["divQ"], ref["divQ"], rtol=1e-9, atol=1e-10 * np.abs(ref["divQ"]).max())
+
+
+@pytest.mark.gpu
+def test_bm2_boundary_flux_and_reflections(exe, po, tmp_path, gpu_lib):
+    """RMCRT_1L_perf pattern: hot walls, x-/y- mirrors, solveBoundaryFlux, 2 patches: masks bit-exact, fluxes to round-off"""
+    out = load_dump(run(exe, "bm2_1L_flux_reflect.ups", "--dump", str(tmp_path)).args[3])
+    lv = po.parallel_plates(16, mirror_faces=("x-", "y-"))
+    assert np.array_equal(out["abskg"], lv.abskg) and np.array_equal(out["cellType"], lv.cellType)
+    np.testing.assert_allclose(out["sigmaT4"], lv.sigmaT4, rtol=1e-14, atol=0)
+    p = po.default_params(nDivQRays=4, nFluxRays=4, threshold=0.001, isSeedRandom=0, solveBoundaryFlux=1, allowReflect=1)
+    ref = po.ray_trace(p, lv)
+    S, R = out["RMCRTboundFlux"], ref["boundFlux"]
+    assert np.array_equal(S[..., 6], R[..., 6])                        # boundFlux.p
+    assert np.array_equal(S[..., :6] != 0, R[..., :6] != 0)            # face selection
+    assert out["report"]["nRaySteps"] == ref["steps"] and out["report"]["nFluxRaySteps"] == ref["fluxSteps"]
+    np.testing.assert_allclose(S, R, rtol=1e-9, atol=0)
+    np.testing.assert_allclose(out["divQ"], ref["divQ"], rtol=1e-9, atol=1e-9 * np.abs(ref["divQ"]).max())

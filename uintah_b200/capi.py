@@ -20,7 +20,7 @@ SYMBOLS = [
     "rmcrt_last_error", "rmcrt_define_level", "rmcrt_upload_level", "rmcrt_pack_level_device",
     "rmcrt_finalize_level", "rmcrt_finalize_level_async", "rmcrt_level_records", "rmcrt_trace_divq_device", "rmcrt_trace_divq",
     "rmcrt_trace_dataonion_device", "rmcrt_trace_dataonion", "rmcrt_compute_extents", "rmcrt_reset_counters",
-    "rmcrt_get_counters", "rmcrt_sigmaT4_device", "rmcrt_coarsen_level_device", "rmcrt_set_level_extra_cells",
+    "rmcrt_get_counters", "rmcrt_sigmaT4_device", "rmcrt_sigmaT4", "rmcrt_coarsen_level_device", "rmcrt_set_level_extra_cells",
     "rmcrt_pack_box_device", "rmcrt_assemble_level", "rmcrt_allgather_records", "rmcrt_measure_read_bandwidth", "rmcrt_debug_trace_rays",
 ]
 
@@ -96,6 +96,7 @@ def load_library(path: str | None = None):
     lib.rmcrt_reset_counters.argtypes = [vp, vp]
     lib.rmcrt_get_counters.argtypes = [vp, C.POINTER(Counters), vp]
     lib.rmcrt_sigmaT4_device.argtypes = [vp, vp, vp, C.c_int, C.c_int64, vp]
+    lib.rmcrt_sigmaT4.argtypes = [vp, vp, vp, C.c_int, C.c_int64, vp]
     lib.rmcrt_coarsen_level_device.argtypes = [vp, C.c_int, C.c_int, vp]
     lib.rmcrt_set_level_extra_cells.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), i3, vp]
     lib.rmcrt_pack_box_device.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, i3, i3, i3, i3, vp, vp]

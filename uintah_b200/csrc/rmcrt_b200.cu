@@ -104,8 +104,9 @@ __device__ __forceinline__ void gen_divq_ray(const RayGen& rg, const LevelGeom& 
   } else {
     const u32x4 a = philox4x32_10(u32x4{(uint32_t)dirId, (uint32_t)ray, rg.timestep,
                                         ((uint32_t)(dirId >> 32) << 8) | STREAM_DIR}, rg.key0, rg.key1);
-    const u32x4 b = philox4x32_10(u32x4{(uint32_t)cellId, (uint32_t)ray, rg.timestep,
-                                        ((uint32_t)(cellId >> 32) << 8) | STREAM_ORIGIN}, rg.key0, rg.key1);
+    const unsigned long long orgId = rg.coherent == 2 ? dirId : cellId;   // 2: the tile also shares the in-cell origin offset
+    const u32x4 b = philox4x32_10(u32x4{(uint32_t)orgId, (uint32_t)ray, rg.timestep,
+                                        ((uint32_t)(orgId >> 32) << 8) | STREAM_ORIGIN}, rg.key0, rg.key1);
     u1 = u01_open(a.x); u2 = u01_open(a.y);
     o0 = u01_closed(b.x); o1 = u01_closed(b.y); o2 = u01_closed(b.z);
   }
@@ -1220,6 +1221,21 @@ int rmcrt_sigmaT4_device(rmcrt_ctx* ctx, const double* d_temp, void* d_out, int 
   if (isFloat) sigmaT4_kernel<float><<<grid_for(n, 256, ctx->smCount), 256, 0, (cudaStream_t)stream>>>(d_temp, static_cast<float*>(d_out), n, sop);
   else         sigmaT4_kernel<double><<<grid_for(n, 256, ctx->smCount), 256, 0, (cudaStream_t)stream>>>(d_temp, static_cast<double*>(d_out), n, sop);
   CK(cudaGetLastError());
+  return 0;
+}
+
+int rmcrt_sigmaT4(rmcrt_ctx* ctx, const double* temp, void* out, int isFloat, int64_t n, void* stream) {
+  if (!ctx || !temp || !out || n < 0) return RMCRT_ERR_INVALID;
+  if (n == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t ob = (size_t)n * (isFloat ? 4 : 8);
+  if (ctx->stage[0].ensure((size_t)n * 8) || ctx->stage[1].ensure(ob)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc staging failed");
+  CK(cudaMemcpyAsync(ctx->stage[0].p, temp, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  int rc = rmcrt_sigmaT4_device(ctx, static_cast<const double*>(ctx->stage[0].p), ctx->stage[1].p, isFloat, n, stream);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(out, ctx->stage[1].p, ob, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   return 0;
 }
 

@@ -1,0 +1,436 @@
+// RMCRT_Test.cc -- stand-alone driver of the host plugin, mirroring the reference's example component
+// CCA/Components/Examples/RMCRT_Test.{h,cc} (problemSetup 111-260, scheduleInitialize 317-341, scheduleTimeAdvance 365-600,
+// initialize 619-821, sched_initProperties 944-958, task-graph choice 989-994) on top of UintahShim.h.
+//
+//   rmcrt_test <deck.ups> [--dump DIR] [--timesteps N] [--devices N] [--seed S] [--knob name=value]... [--parse-only]
+//
+// --parse-only stops after problemSetup + scheduling and prints every registered task with its dependencies (no GPU needed).
+//
+// It reads the same .ups decks (the <Grid>, <Temperature>/<abskg>/<benchmark>/<calc_frequency> keys and the <RMCRT> block),
+// builds the grid, runs the time loop with the two task graphs (TG_CARRY_FORWARD / TG_RMCRT) and, with --dump, writes the
+// finest level's divQ / radiationVolq / RMCRTboundFlux / abskg / sigmaT4 / cellType as raw arrays for the parity tests.
+#include "Ray.h"
+
+#include <sys/stat.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+
+using namespace Uintah;
+
+namespace Uintah {
+ProblemSpecP ProblemSpec::parseFile(const std::string& path) {
+  std::ifstream in(path);
+  if (!in) throw ProblemSetupException("cannot open input deck " + path, __FILE__, __LINE__);
+  std::stringstream ss;
+  ss << in.rdbuf();
+  return parseString(ss.str());
+}
+}  // namespace Uintah
+
+namespace {
+
+class RMCRT_Test {
+ public:
+  enum Algo { dataOnion, dataOnionSlim, coarseLevel, singleLevel, radiometerOnly };   // RMCRT_Test.h:166-171
+
+  RMCRT_Test() {
+    d_colorLabel = VarLabel::create("color", TypeDescription::double_type);
+    d_compAbskgLabel = VarLabel::create("abskg", TypeDescription::double_type);
+    d_divQLabel = VarLabel::create("divQ", TypeDescription::double_type);
+    d_cellTypeLabel = VarLabel::create("cellType", TypeDescription::int_type);
+  }
+  ~RMCRT_Test() {
+    d_RMCRT.reset();
+    VarLabel::destroy(d_colorLabel);
+    VarLabel::destroy(d_compAbskgLabel);
+    VarLabel::destroy(d_divQLabel);
+    VarLabel::destroy(d_cellTypeLabel);
+  }
+
+  //______________________________________________________________________ <Grid>
+  static GridP buildGrid(const ProblemSpecP& root) {
+    ProblemSpecP grid_ps = root->findBlock("Grid");
+    if (!grid_ps) throw ProblemSetupException("no <Grid> block", __FILE__, __LINE__);
+    auto grid = std::make_shared<Grid>();
+    static const char* sides[6] = {"x-", "x+", "y-", "y+", "z-", "z+"};
+    if (ProblemSpecP bc_ps = grid_ps->findBlock("BoundaryConditions")) {
+      for (ProblemSpecP face = bc_ps->findBlock("Face"); face; face = face->findNextBlock("Face")) {
+        std::string side;
+        if (!face->getAttribute("side", side)) throw ProblemSetupException("<Face> without side (only side= faces are supported)", __FILE__, __LINE__);
+        int f = -1;
+        for (int i = 0; i < 6; ++i) if (side == sides[i]) f = i;
+        if (f < 0) throw ProblemSetupException("unknown face side " + side, __FILE__, __LINE__);
+        for (ProblemSpecP bc = face->findBlock("BCType"); bc; bc = bc->findNextBlock("BCType")) {
+          BCEntry e;
+          std::string label;
+          bc->getAttribute("label", label);
+          bc->getAttribute("var", e.var);
+          bc->get("value", e.value);
+          grid->setBC(f, label, e);
+        }
+      }
+    }
+    int index = 0;
+    IntVector prevRes(0, 0, 0);
+    for (ProblemSpecP level_ps = grid_ps->findBlock("Level"); level_ps; level_ps = level_ps->findNextBlock("Level"), ++index) {
+      ProblemSpecP box = level_ps->findBlock("Box");
+      if (!box) throw ProblemSetupException("<Level> without <Box>", __FILE__, __LINE__);
+      if (box->findNextBlock("Box")) throw ProblemSetupException("multi-box levels are not supported by this driver", __FILE__, __LINE__);
+      Vector lower, upper;
+      IntVector res, patches(1, 1, 1), extra(0, 0, 0);
+      box->require("lower", lower);
+      box->require("upper", upper);
+      box->require("resolution", res);
+      box->getWithDefault("patches", patches, IntVector(1, 1, 1));
+      box->getWithDefault("extraCells", extra, IntVector(0, 0, 0));
+      Vector periodic(0, 0, 0);
+      level_ps->getWithDefault("periodic", periodic, Vector(0, 0, 0));
+      grid->periodic = IntVector((int)periodic.x(), (int)periodic.y(), (int)periodic.z());
+      const Vector dx((upper.x() - lower.x()) / res.x(), (upper.y() - lower.y()) / res.y(), (upper.z() - lower.z()) / res.z());
+      IntVector rr(1, 1, 1);
+      if (index > 0) {
+        for (int d = 0; d < 3; ++d) {
+          if (res[d] % prevRes[d] != 0) throw ProblemSetupException("level resolution is not a multiple of the coarser level's", __FILE__, __LINE__);
+          rr[d] = res[d] / prevRes[d];
+        }
+      }
+      auto level = std::make_shared<Level>(grid.get(), index, lower, dx, extra, rr);
+      level->setInterior(IntVector(0, 0, 0), res);
+      int id = index * 100000;
+      for (int pk = 0; pk < patches.z(); ++pk)
+        for (int pj = 0; pj < patches.y(); ++pj)
+          for (int pi = 0; pi < patches.x(); ++pi) {
+            const IntVector pidx(pi, pj, pk);
+            IntVector lo, hi, exLo, exHi;
+            for (int d = 0; d < 3; ++d) {
+              if (res[d] % patches[d] != 0) throw ProblemSetupException("resolution is not divisible by patches", __FILE__, __LINE__);
+              const int n = res[d] / patches[d];
+              lo[d] = pidx[d] * n; hi[d] = lo[d] + n;
+              exLo[d] = lo[d] - (pidx[d] == 0 ? extra[d] : 0);
+              exHi[d] = hi[d] + (pidx[d] == patches[d] - 1 ? extra[d] : 0);
+            }
+            level->addPatch(std::unique_ptr<Patch>(new Patch(id++, level.get(), lo, hi, exLo, exHi)));
+          }
+      grid->addLevel(level);
+      prevRes = res;
+    }
+    if (grid->numLevels() == 0) throw ProblemSetupException("no <Level> in <Grid>", __FILE__, __LINE__);
+    return grid;
+  }
+
+  //______________________________________________________________________ RMCRT_Test.cc:111-260
+  void problemSetup(const ProblemSpecP& prob_spec, GridP& grid, SchedulerP& sched) {
+    d_grid = grid;
+    sched->setNumTaskGraphs(RMCRTCommon::NUM_GRAPHS);   // TG-0 carry forward, TG-1 RMCRT
+    prob_spec->getWithDefault("calc_frequency", d_radCalc_freq, 1);
+    prob_spec->require("Temperature", d_initColor);
+    prob_spec->require("abskg", d_initAbskg);
+    prob_spec->getWithDefault("benchmark", d_benchmark, 0);
+    if (d_benchmark > 8 || d_benchmark < 0) {
+      std::ostringstream warn;
+      warn << "RMCRT:ERROR:  Benchmark (" << d_benchmark << ") only valid options are 1-7\n";
+      throw ProblemSetupException(warn.str(), __FILE__, __LINE__);
+    }
+    if (d_benchmark > 3)
+      throw ProblemSetupException("rmcrt_test: only benchmarks 0-3 are initialised by this driver", __FILE__, __LINE__);
+
+    ProblemSpecP rmcrt_ps = prob_spec->findBlock("RMCRT");
+    if (!rmcrt_ps) throw ProblemSetupException("no <RMCRT> block", __FILE__, __LINE__);
+    std::map<std::string, std::string> type;
+    rmcrt_ps->getAttributes(type);
+    d_RMCRT.reset(new Ray(type["type"] == "float" ? TypeDescription::float_type : TypeDescription::double_type));
+
+    d_whichAlgo = singleLevel;
+    if (ProblemSpecP alg_ps = rmcrt_ps->findBlock("algorithm")) {
+      std::string t = "nullptr";
+      alg_ps->getAttribute("type", t);
+      if (t == "dataOnion") d_whichAlgo = dataOnion;
+      else if (t == "dataOnionSlim") d_whichAlgo = dataOnionSlim;
+      else if (t == "RMCRT_coarseLevel") d_whichAlgo = coarseLevel;
+      else if (t == "singleLevel") d_whichAlgo = singleLevel;
+      else if (t == "radiometerOnly") d_whichAlgo = radiometerOnly;
+      if (d_whichAlgo == dataOnion) {
+        ProblemSpecP amr = prob_spec->findBlock("AMR");
+        bool lockstep = false;
+        if (amr) amr->get("useLockStep", lockstep);
+        if (!lockstep) throw ProblemSetupException("\n ERROR: You must add \n <useLockStep> true </useLockStep> \n inside of the <AMR> section. \n", __FILE__, __LINE__);
+      }
+    }
+    // the caller-private enum is passed as a bare int; Ray only compares it with radiometerOnly
+    int ray_algo = RMCRTCommon::singleLevel;
+    if (d_whichAlgo == dataOnion || d_whichAlgo == dataOnionSlim) ray_algo = RMCRTCommon::dataOnion;
+    else if (d_whichAlgo == coarseLevel) ray_algo = RMCRTCommon::coarseLevel;
+    d_RMCRT->registerVariables(0, d_compAbskgLabel, d_colorLabel, d_cellTypeLabel, d_divQLabel, ray_algo);
+    d_RMCRT->problemSetup(prob_spec, rmcrt_ps, grid);
+    d_RMCRT->BC_bulletproofing(rmcrt_ps, true, true);
+
+    // one extra cell (or periodicity) in each direction (RMCRT_Test.cc:238-251)
+    const IntVector extraCells = grid->getLevel(0)->getExtraCells();
+    for (int dir = 0; dir < 3; ++dir)
+      if (grid->periodic[dir] != 1 && extraCells[dir] != 1) {
+        std::ostringstream warn;
+        warn << "\n \n INPUT FILE ERROR: \n You must have either a periodic boundary " << grid->periodic << " or one extraCell "
+             << extraCells << " specified in each direction";
+        throw ProblemSetupException(warn.str(), __FILE__, __LINE__);
+      }
+  }
+
+  //______________________________________________________________________ RMCRT_Test.cc:317-341
+  void scheduleInitialize(const LevelP& level, SchedulerP& sched) {
+    Task* task = new Task("RMCRT_Test::initialize", this, &RMCRT_Test::initialize);
+    task->computesVar(d_colorLabel);
+    task->computesVar(d_compAbskgLabel);
+    task->computesVar(d_cellTypeLabel);
+    sched->addTask(task, level->eachPatch(), RMCRTCommon::d_matlSet);
+  }
+
+  //______________________________________________________________________ RMCRT_Test.cc:365-600
+  void scheduleTimeAdvance(const LevelP& level, SchedulerP& sched) {
+    if (level->getIndex() > 0) return;   // only schedule once
+    GridP grid = d_grid;
+    const int maxLevels = grid->numLevels();
+    const LevelP& finestLevel = grid->getLevel(maxLevels - 1);
+    sched_initProperties(finestLevel, sched);
+
+    std::vector<const VarLabel*> fineLevelVarLabels = {RMCRTCommon::d_divQLabel, RMCRTCommon::d_boundFluxLabel,
+                                                       RMCRTCommon::d_radiationVolqLabel, RMCRTCommon::d_sigmaT4Label};
+    const bool includeExtraCells = true;
+    Task::WhichDW notUsed = Task::None;
+
+    if (d_whichAlgo == dataOnion || d_whichAlgo == dataOnionSlim) {      // 385-460
+      Task::WhichDW temp_dw = Task::NewDW, sigmaT4_dw = Task::NewDW, celltype_dw = Task::NewDW;
+      const bool backoutTemp = true, modifies_abskg = false, modifies_sigmaT4 = false, modifies_divQ = false;
+      const LevelP& fineLevel = finestLevel;
+      d_RMCRT->set_abskg_dw_perLevel(fineLevel, Task::NewDW);
+      d_RMCRT->sched_DoubleToFloat(fineLevel, sched, notUsed);
+      d_RMCRT->sched_sigmaT4(fineLevel, sched, temp_dw, includeExtraCells);
+      d_RMCRT->sched_setBoundaryConditions(fineLevel, sched, temp_dw);
+      d_RMCRT->sched_carryForward_VarLabels(fineLevel, sched, fineLevelVarLabels);
+      // coarse-level abskg/sigmaT4 live on the device only (Ray::coarsenAll), so there is nothing to carry forward there
+      for (int l = maxLevels - 2; l >= 0; l--) {
+        const LevelP& lev = grid->getLevel(l);
+        d_RMCRT->sched_CoarsenAll(lev, sched, modifies_abskg, modifies_sigmaT4);
+        if (d_RMCRT->d_coarsenExtraCells == false) d_RMCRT->sched_setBoundaryConditions(lev, sched, notUsed, backoutTemp);
+      }
+      d_RMCRT->sched_ROI_Extents(fineLevel, sched);
+      d_RMCRT->sched_rayTrace_dataOnion(fineLevel, sched, notUsed, sigmaT4_dw, celltype_dw, modifies_divQ);
+    }
+
+    if (d_whichAlgo == singleLevel) {                                     // 527-557
+      Task::WhichDW temp_dw = Task::NewDW, sigmaT4_dw = Task::NewDW, celltype_dw = Task::NewDW;
+      const bool modifies_divQ = false, backoutTemp = true;
+      d_RMCRT->set_abskg_dw_perLevel(level, Task::NewDW);
+      d_RMCRT->sched_carryForward_VarLabels(level, sched, fineLevelVarLabels);
+      d_RMCRT->sched_DoubleToFloat(level, sched, notUsed);
+      d_RMCRT->sched_sigmaT4(level, sched, temp_dw, includeExtraCells);
+      d_RMCRT->sched_setBoundaryConditions(level, sched, temp_dw, backoutTemp);
+      d_RMCRT->sched_rayTrace(level, sched, notUsed, sigmaT4_dw, celltype_dw, modifies_divQ);
+    }
+    if (d_whichAlgo == coarseLevel || d_whichAlgo == radiometerOnly)
+      throw ProblemSetupException("rmcrt_test: algorithm not supported by the B200 back end", __FILE__, __LINE__);
+  }
+
+  // RMCRT_Test.cc:944-958: carry abskg, color, cellType Old -> New to mimic what a component would compute
+  void sched_initProperties(const LevelP& level, SchedulerP& sched) {
+    Task* tsk = new Task("RMCRT_Test::initProperties", this, &RMCRT_Test::initProperties);
+    tsk->requiresVar(Task::OldDW, d_colorLabel);
+    tsk->requiresVar(Task::OldDW, d_compAbskgLabel);
+    tsk->requiresVar(Task::OldDW, d_cellTypeLabel);
+    tsk->computesVar(d_colorLabel);
+    tsk->computesVar(d_compAbskgLabel);
+    tsk->computesVar(d_cellTypeLabel);
+    sched->addTask(tsk, level->eachPatch(), RMCRTCommon::d_matlSet, Scheduler::ALL_GRAPHS);
+  }
+  void initProperties(const ProcessorGroup*, const PatchSubset* patches, const MaterialSubset* matls, DataWarehouse* old_dw, DataWarehouse* new_dw) {
+    new_dw->transferFrom(old_dw, d_colorLabel, patches, matls);
+    new_dw->transferFrom(old_dw, d_compAbskgLabel, patches, matls);
+    new_dw->transferFrom(old_dw, d_cellTypeLabel, patches, matls);
+  }
+
+  //______________________________________________________________________ RMCRT_Test.cc:619-821
+  void initialize(const ProcessorGroup*, const PatchSubset* patches, const MaterialSubset*, DataWarehouse*, DataWarehouse* new_dw) {
+    const Level* level = getLevel(patches);
+    for (int p = 0; p < patches->size(); p++) {
+      const Patch* patch = patches->get(p);
+      const int matl = 0;
+      CCVariable<double> color, abskg;
+      CCVariable<int> cellType;
+      new_dw->allocateAndPut(color, d_colorLabel, matl, patch);
+      new_dw->allocateAndPut(abskg, d_compAbskgLabel, matl, patch);
+      new_dw->allocateAndPut(cellType, d_cellTypeLabel, matl, patch);
+      color.initialize(d_initColor);
+      abskg.initialize(d_initAbskg);
+      const IntVector lo = patch->getCellLowIndex(), hi = patch->getCellHighIndex();
+
+      if (d_benchmark == 1 || d_benchmark == 3) {      // Burns & Christon (653-680)
+        IntVector pLow, pHigh;
+        level->findInteriorCellIndexRange(pLow, pHigh);
+        const IntVector Nx = pHigh - pLow;
+        const Vector Dx = patch->dCell();
+        for (int k = lo.z(); k < hi.z(); ++k)
+          for (int j = lo.y(); j < hi.y(); ++j)
+            for (int i = lo.x(); i < hi.x(); ++i) {
+              const IntVector c(i, j, k);
+              abskg[c] = 0.90 * (1.0 - 2.0 * std::fabs((c[0] - (Nx.x() - 1.0) / 2.0) * Dx.x()))
+                              * (1.0 - 2.0 * std::fabs((c[1] - (Nx.y() - 1.0) / 2.0) * Dx.y()))
+                              * (1.0 - 2.0 * std::fabs((c[2] - (Nx.z() - 1.0) / 2.0) * Dx.z())) + 0.1;
+            }
+      }
+      if (d_benchmark == 2) abskg.initialize(1);       // 682-684
+      if (d_benchmark == 3)                            // 686-691
+        for (int k = lo.z(); k < hi.z(); ++k)
+          for (int j = lo.y(); j < hi.y(); ++j)
+            for (int i = lo.x(); i < hi.x(); ++i) { const IntVector c(i, j, k); color[c] = 1000 * abskg[c]; }
+
+      // cellType: flow everywhere, then the boundary conditions on the extra cells (776-786)
+      cellType.initialize(d_RMCRT->d_flowCell);
+      d_RMCRT->setBC<int, int>(cellType, d_cellTypeLabel->getName(), patch, matl);
+      d_RMCRT->setBC<double, double>(color, d_colorLabel->getName(), patch, matl);
+      d_RMCRT->setBC<double, double>(abskg, d_compAbskgLabel->getName(), patch, matl);
+    }
+  }
+
+  // RMCRT_Test.cc:989-994 decides the task graph of the NEXT step; equivalently, for step ts:
+  int taskGraphFor(int ts) const { return (ts % d_radCalc_freq == 0 || ts == 1) ? RMCRTCommon::TG_RMCRT : RMCRTCommon::TG_CARRY_FORWARD; }
+
+  std::unique_ptr<Ray> d_RMCRT;
+  const VarLabel *d_colorLabel, *d_compAbskgLabel, *d_divQLabel, *d_cellTypeLabel;
+  GridP d_grid;
+  double d_initColor = 0, d_initAbskg = 0;
+  int d_radCalc_freq = 1, d_benchmark = 0, d_whichAlgo = singleLevel;
+};
+
+template <class T>
+void dumpVar(const std::string& dir, const std::string& name, const char* dtype, int comps, DataWarehouse* dw, const VarLabel* label,
+             const Level* level, std::ostream& meta, bool& first) {
+  constCCVariable<T> v;
+  dw->getLevel(v, label, 0, level);
+  const std::string file = name + ".bin";
+  std::ofstream out(dir + "/" + file, std::ios::binary);
+  out.write(reinterpret_cast<const char*>(v.getPointer()), (std::streamsize)(v.cells() * sizeof(T)));
+  const IntVector lo = v.getLowIndex(), hi = v.getHighIndex();
+  meta << (first ? "" : ",\n") << "  \"" << name << "\": {\"file\": \"" << file << "\", \"dtype\": \"" << dtype << "\", \"components\": " << comps
+       << ", \"lo\": [" << lo.x() << "," << lo.y() << "," << lo.z() << "], \"hi\": [" << hi.x() << "," << hi.y() << "," << hi.z() << "]}";
+  first = false;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  std::string deck, dumpDir;
+  int timesteps = -1, devices = 0;
+  unsigned long long seed = 0;
+  bool haveSeed = false, parseOnly = false;
+  std::vector<std::pair<std::string, int>> knobs;
+  for (int i = 1; i < argc; ++i) {
+    const std::string a = argv[i];
+    auto next = [&]() -> std::string { if (i + 1 >= argc) { std::cerr << "missing value after " << a << "\n"; std::exit(2); } return argv[++i]; };
+    if (a == "--parse-only") parseOnly = true;
+    else if (a == "--dump") dumpDir = next();
+    else if (a == "--timesteps") timesteps = std::atoi(next().c_str());
+    else if (a == "--devices") devices = std::atoi(next().c_str());
+    else if (a == "--seed") { seed = std::strtoull(next().c_str(), nullptr, 0); haveSeed = true; }
+    else if (a == "--knob") {
+      const std::string kv = next();
+      const size_t eq = kv.find('=');
+      if (eq == std::string::npos) { std::cerr << "--knob needs name=value\n"; return 2; }
+      knobs.emplace_back(kv.substr(0, eq), std::atoi(kv.substr(eq + 1).c_str()));
+    } else if (a[0] == '-') { std::cerr << "unknown option " << a << "\n"; return 2; }
+    else deck = a;
+  }
+  if (deck.empty()) {
+    std::cerr << "usage: rmcrt_test <deck.ups> [--dump DIR] [--timesteps N] [--devices N] [--seed S] [--knob name=value]...\n";
+    return 2;
+  }
+  try {
+    ProblemSpecP ups = ProblemSpec::parseFile(deck);
+    if (ups->getNodeName() != "Uintah_specification") throw ProblemSetupException("root element must be <Uintah_specification>", __FILE__, __LINE__);
+    std::string comp;
+    if (ProblemSpecP sc = ups->findBlock("SimulationComponent")) sc->getAttribute("type", comp);
+    if (comp != "RMCRT_Test") throw ProblemSetupException("<SimulationComponent type> must be RMCRT_Test, got '" + comp + "'", __FILE__, __LINE__);
+    int maxTimesteps = 1;
+    if (ProblemSpecP time_ps = ups->findBlock("Time")) time_ps->getWithDefault("max_Timesteps", maxTimesteps, 1);
+    if (timesteps > 0) maxTimesteps = timesteps;
+
+    RMCRTCommon::setMaxDevices(devices);
+    GridP grid = RMCRT_Test::buildGrid(ups);
+    SchedulerP sched = std::make_shared<Scheduler>();
+    RMCRT_Test app;
+    app.problemSetup(ups, grid, sched);
+    if (haveSeed) app.d_RMCRT->setSeed(seed);
+    for (auto& kv : knobs) app.d_RMCRT->setKnob(kv.first, kv.second);
+
+    if (parseOnly) {
+      for (int l = 0; l < grid->numLevels(); ++l) app.scheduleInitialize(grid->getLevel(l), sched);
+      for (int l = 0; l < grid->numLevels(); ++l) app.scheduleTimeAdvance(grid->getLevel(l), sched);
+      static const char* kinds[3] = {"requires", "computes", "modifies"};
+      for (auto& e : sched->tasks()) {
+        std::cout << "TASK " << e.task->getName() << " level=" << getLevel(e.patches)->getIndex() << " patches=" << e.patches->size()
+                  << " tg=" << e.tg << " device=" << (e.task->usesDevice() ? 1 : 0) << "\n";
+        for (auto& d : e.task->dependencies())
+          std::cout << "  " << kinds[d.kind] << " " << d.label->getName() << " dw=" << (d.dw == Task::OldDW ? "OldDW" : "NewDW")
+                    << " ghost=" << d.numGhost << " domain=" << (d.domain == Task::NormalDomain ? "normal" : d.domain == Task::CoarseLevel ? "coarse" : "fine")
+                    << " offset=" << d.levelOffset << "\n";
+      }
+      return 0;
+    }
+    // initialisation "time step": every level gets its properties (sus: scheduleInitialize per level)
+    sched->advanceDataWarehouse(0);
+    for (int l = 0; l < grid->numLevels(); ++l) app.scheduleInitialize(grid->getLevel(l), sched);
+    sched->execute(Scheduler::ALL_GRAPHS);
+    sched->clearTasks();
+
+    for (int l = 0; l < grid->numLevels(); ++l) app.scheduleTimeAdvance(grid->getLevel(l), sched);
+    std::cout << "rmcrt_test: " << grid->numLevels() << " level(s), task graph TG_RMCRT:";
+    for (auto& e : sched->tasks())
+      if (e.tg == Scheduler::ALL_GRAPHS || e.tg == RMCRTCommon::TG_RMCRT) std::cout << " " << e.task->getName() << "[L" << getLevel(e.patches)->getIndex() << "]";
+    std::cout << std::endl;
+
+    for (int ts = 1; ts <= maxTimesteps; ++ts) {
+      sched->advanceDataWarehouse(ts);
+      const int tg = app.taskGraphFor(ts);
+      std::cout << "timestep " << ts << ": task graph " << (tg == RMCRTCommon::TG_RMCRT ? "TG_RMCRT" : "TG_CARRY_FORWARD") << std::endl;
+      sched->execute(tg);
+    }
+
+    const Level* fine = grid->getLevel(grid->numLevels() - 1).get();
+    DataWarehouse* dw = sched->get_dw(Task::NewDW);
+    {   // centre line of divQ along x (what RMCRT.m / lineextract look at)
+      constCCVariable<double> divQ;
+      dw->getLevel(divQ, app.d_divQLabel, 0, fine);
+      IntVector lo, hi;
+      fine->findInteriorCellIndexRange(lo, hi);
+      const int j = (lo.y() + hi.y()) / 2, k = (lo.z() + hi.z()) / 2;
+      std::cout << "divQ centre line (j=" << j << ", k=" << k << "):";
+      const int stride = std::max(1, (hi.x() - lo.x()) / 8);
+      for (int i = lo.x(); i < hi.x(); i += stride) std::cout << " " << divQ[IntVector(i, j, k)];
+      std::cout << std::endl;
+    }
+    if (!dumpDir.empty()) {
+      mkdir(dumpDir.c_str(), 0755);
+      std::ofstream meta(dumpDir + "/meta.json");
+      meta << "{\n";
+      bool first = true;
+      dumpVar<double>(dumpDir, "divQ", "f8", 1, dw, app.d_divQLabel, fine, meta, first);
+      dumpVar<double>(dumpDir, "radiationVolq", "f8", 1, dw, RMCRTCommon::d_radiationVolqLabel, fine, meta, first);
+      dumpVar<Stencil7>(dumpDir, "RMCRTboundFlux", "f8", 7, dw, RMCRTCommon::d_boundFluxLabel, fine, meta, first);
+      dumpVar<double>(dumpDir, "abskg", "f8", 1, dw, app.d_compAbskgLabel, fine, meta, first);
+      dumpVar<int>(dumpDir, "cellType", "i4", 1, dw, app.d_cellTypeLabel, fine, meta, first);
+      if (RMCRTCommon::d_sigmaT4Label->typeDescription() == TypeDescription::float_type)
+        dumpVar<float>(dumpDir, "sigmaT4", "f4", 1, dw, RMCRTCommon::d_sigmaT4Label, fine, meta, first);
+      else
+        dumpVar<double>(dumpDir, "sigmaT4", "f8", 1, dw, RMCRTCommon::d_sigmaT4Label, fine, meta, first);
+      const Ray::Report& r = app.d_RMCRT->lastReport();
+      meta << ",\n  \"report\": {\"seconds\": " << r.seconds << ", \"nRaySteps\": " << r.nRaySteps << ", \"nFluxRaySteps\": " << r.nFluxRaySteps
+           << ", \"nDivQCells\": " << r.nDivQCells << ", \"nFluxCells\": " << r.nFluxCells << ", \"devicesUsed\": " << r.devicesUsed << "}\n}\n";
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    std::cerr << "rmcrt_test: caught exception: " << e.what() << std::endl;
+    return 1;
+  }
+}
