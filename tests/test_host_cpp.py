@@ -134,7 +134,7 @@ def load_dump(d):
 @pytest.mark.gpu
 def test_bm1_single_level_double_deterministic(exe, po, tmp_path, gpu_lib):
     """RMCRT_bm1_1L pattern: <randomSeed> false, type double -> FP64 march, agreement with the oracle to round-off"""
-    out = load_dump(run(exe, "bm1_1L_double.ups", "--dump", str(tmp_path)).args[3])
+    out = load_dump(run(exe, "bm1_1L_double.ups", "--dump", str(tmp_path), "--knob", "skipZeroWeightLegs=0").args[3])
     lv = po.burns_christon(21)
     # the driver's own initialisation + sigmaT4 + setBoundaryConditions reproduce the oracle's input fields bit for bit
     assert np.array_equal(out["abskg"], lv.abskg) and np.array_equal(out["cellType"], lv.cellType)
@@ -165,7 +165,7 @@ def test_bm1_float_eight_patches_equals_whole_level_solve(exe, po, tmp_path, gpu
 @pytest.mark.gpu
 def test_bm1_data_onion_deterministic(exe, po, tmp_path, gpu_lib):
     """RMCRT_bm1_DO pattern (fine 32^3 in 8 patches, coarse 8^3, RR 4, halo 4): device coarsening + coarse BCs + DO trace"""
-    out = load_dump(run(exe, "bm1_DO.ups", "--dump", str(tmp_path)).args[3])
+    out = load_dump(run(exe, "bm1_DO.ups", "--dump", str(tmp_path), "--knob", "skipZeroWeightLegs=0").args[3])
     fine = po.burns_christon(32)
     fine.rr = (4, 4, 4)
     coarse = po.coarsen_level(fine, (4, 4, 4))
@@ -178,7 +178,7 @@ def test_bm1_data_onion_deterministic(exe, po, tmp_path, gpu_lib):
 @pytest.mark.gpu
 def test_bm2_boundary_flux_and_reflections(exe, po, tmp_path, gpu_lib):
     """RMCRT_1L_perf pattern: hot walls, x-/y- mirrors, solveBoundaryFlux, 2 patches: masks bit-exact, fluxes to round-off"""
-    out = load_dump(run(exe, "bm2_1L_flux_reflect.ups", "--dump", str(tmp_path)).args[3])
+    out = load_dump(run(exe, "bm2_1L_flux_reflect.ups", "--dump", str(tmp_path), "--knob", "skipZeroWeightLegs=0").args[3])
     lv = po.parallel_plates(16, mirror_faces=("x-", "y-"))
     assert np.array_equal(out["abskg"], lv.abskg) and np.array_equal(out["cellType"], lv.cellType)
     np.testing.assert_allclose(out["sigmaT4"], lv.sigmaT4, rtol=1e-14, atol=0)

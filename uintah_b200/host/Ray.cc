@@ -404,7 +404,7 @@ void Ray::traceCommon(bool dataOnion, const PatchSubset* patches, DataWarehouse*
   // Ray.cc:803-812 prints this for patch 0
   const unsigned long long size = d_report.nRaySteps + d_report.nFluxRaySteps;
   std::cout << "\n RMCRT REPORT: Patch " << patches->get(0)->getID() << " +" << patches->size() - 1 << " more on " << d_report.devicesUsed
-            << " GPU(s)\n Used " << d_report.seconds * 1000 << " milliseconds of wall time (H2D of nothing, trace, D2H of the results)\n"
+            << " GPU(s)\n Used " << d_report.seconds * 1000 << " milliseconds of wall time (trace kernels + D2H of divQ / radiationVolq / boundFlux)\n"
             << " Size: " << size << " ray-cell steps\n Efficiency: " << size / d_report.seconds << " steps per sec\n" << std::endl;
 }
 
