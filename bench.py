@@ -131,7 +131,7 @@ def cpu_reference_sample(n_cells_side, rays, shape_cells, slab_cells, threads, r
     lo = (-1, -1, -1)
     hi = tuple(s + 1 for s in shape_cells)
     ab, s4, ct = burns_christon_fields(shape_cells, lo, hi, np.float32)
-    lv = po.Level(ab, s4, ct, lo, hi, (1.0 / n_cells_side,) * 3, interior_lo=(0, 0, 0), interior_hi=tuple(shape_cells))
+    lv = po.Level(ab, s4, ct, lo, hi, tuple(1.0 / s for s in shape_cells), interior_lo=(0, 0, 0), interior_hi=tuple(shape_cells))
     p = po.default_params(nDivQRays=rays, threshold=0.05, isSeedRandom=1)      # reference semantics: allowReflect default
     z0 = shape_cells[2] // 2 - slab_cells // 2
     plo, phi = (0, 0, z0), (shape_cells[0], shape_cells[1], z0 + slab_cells)
@@ -178,7 +178,8 @@ def run_reference(args):
 
 # --------------------------------------------------------------------------------------------------- our arm
 def patch_grid(n_gpus):
-    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(n_gpus, (n_gpus, 1, 1))
+    from uintah_b200.partition import patch_grid as pg
+    return pg(n_gpus)
 
 
 def run_ours(args):
@@ -199,10 +200,9 @@ def run_ours(args):
     pg = patch_grid(world)
     shape = tuple(P * g for g in pg)          # level interior
     lo, hi = (-1, -1, -1), tuple(s + 1 for s in shape)
-    dx = (1.0 / P,) * 3 if world > 1 else (1.0 / P,) * 3
-    pi_, pj_, pk_ = rank % pg[0], (rank // pg[0]) % pg[1], rank // (pg[0] * pg[1])
-    plo = (pi_ * P, pj_ * P, pk_ * P)
-    phi = (plo[0] + P, plo[1] + P, plo[2] + P)
+    dx = tuple(1.0 / s for s in shape)       # unit-cube domain like every Burns & Christon deck
+    from uintah_b200 import partition
+    plo, phi = partition.rank_patch(rank, pg, P)
     rays = args.rays
 
     skip = 0 if args.reference_semantics else 1
@@ -215,19 +215,11 @@ def run_ours(args):
     g.levels[0] = LevelData(None, None, None, lo, hi, dx, interior_lo=(0, 0, 0), interior_hi=shape)
 
     # ---- the rank's own property box (its patch plus the extra cells it touches), resident on the device
-    blo = tuple(-1 if plo[d] == 0 else plo[d] for d in range(3))
-    bhi = tuple(shape[d] + 1 if phi[d] == shape[d] else phi[d] for d in range(3))
+    blo, bhi = partition.owner_box(plo, phi, shape)
     ab, s4, ct = burns_christon_fields(shape, blo, bhi, np.float32)
     d_ab, d_s4, d_ct = (torch.from_numpy(x).to(dev) for x in (ab, s4, ct))
-    box_cells = int(np.prod([bhi[d] - blo[d] for d in range(3)]))
-    slot = (P + 1) ** 3 * 8 if world > 1 else box_cells * 8
-    boxes_lo, boxes_hi = [], []
-    for r in range(world):
-        a, b, c = r % pg[0], (r // pg[0]) % pg[1], r // (pg[0] * pg[1])
-        l = (a * P, b * P, c * P)
-        h = (l[0] + P, l[1] + P, l[2] + P)
-        boxes_lo.append(tuple(-1 if l[d] == 0 else l[d] for d in range(3)))
-        boxes_hi.append(tuple(shape[d] + 1 if h[d] == shape[d] else h[d] for d in range(3)))
+    boxes_lo, boxes_hi = partition.all_owner_boxes(world, pg, P, shape)
+    slot = partition.slot_bytes(boxes_lo, boxes_hi)
     send = torch.zeros(slot, dtype=torch.uint8, device=dev)
     gathered = torch.zeros(slot * world, dtype=torch.uint8, device=dev) if world > 1 else None
 

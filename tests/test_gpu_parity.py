@@ -211,7 +211,7 @@ def bc41_stats(po):
     return lv, runs
 
 
-@pytest.mark.parametrize("coherent", [1, 0])
+@pytest.mark.parametrize("coherent", [1, 0, 2])
 def test_burns_christon_monte_carlo_tolerance(gpu_lib, po, bc41_stats, coherent):
     """BASELINE config 1 (RMCRT_bm1_1L, 41^3, 100 rays/cell): SURVEY 8c acceptance (i)-(iii)"""
     lv, runs = bc41_stats
