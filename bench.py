@@ -208,7 +208,7 @@ def run_ours(args):
     skip = 0 if args.reference_semantics else 1
     g = RMCRT(device=local, nDivQRays=rays, threshold=0.05, seed=1234, skipZeroWeightLegs=skip,
               rayCoherence=args.coherence, l2Persist=args.l2persist, warpsPerTile=args.warps,
-              genericMarch=args.generic_march)
+              genericMarch=args.generic_march, half_records=bool(args.half_records))
     stream = torch.cuda.current_stream()
     desc = LevelData(None, None, None, lo, hi, dx, interior_lo=(0, 0, 0), interior_hi=shape).desc()
     g.define_level(0, desc)
@@ -219,7 +219,8 @@ def run_ours(args):
     ab, s4, ct = burns_christon_fields(shape, blo, bhi, np.float32)
     d_ab, d_s4, d_ct = (torch.from_numpy(x).to(dev) for x in (ab, s4, ct))
     boxes_lo, boxes_hi = partition.all_owner_boxes(world, pg, P, shape)
-    slot = partition.slot_bytes(boxes_lo, boxes_hi)
+    rec_bytes = 4 if args.half_records else 8
+    slot = partition.slot_bytes(boxes_lo, boxes_hi, rec_bytes)
     send = torch.zeros(slot, dtype=torch.uint8, device=dev)
     gathered = torch.zeros(slot * world, dtype=torch.uint8, device=dev) if world > 1 else None
 
@@ -411,7 +412,7 @@ def run_ours(args):
                    "executed_steps_per_ray": all_steps / (all_cells * rays),
                    "zero_weight_legs": "marched (reference semantics)" if not skip else "skipped (exact: cold black walls, fs==0)",
                    "ray_coherence": {0: "independent per cell", 1: "warp-shared direction", 2: "warp-shared direction and in-cell offset"}[args.coherence],
-                   "l2": "flushed between steps (256 MiB fill); level records (%.1f MB) re-packed every step" % (np.prod([h - l for l, h in zip(lo, hi)]) * 8 / 1e6),
+                   "l2": "flushed between steps (256 MiB fill); level records (%.1f MB, %d B/cell) re-packed every step" % (np.prod([h - l for l, h in zip(lo, hi)]) * rec_bytes / 1e6, rec_bytes),
                    "timing": "CUDA events on the launching stream per step, max over ranks"},
         "roofline": roofline, "roofline_l2": roofline_l2, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "gpu_launches": kernels_per_step * args.steps, "clocks": clocks,
@@ -435,6 +436,7 @@ def main():
     ap.add_argument("--coherence", type=int, default=1)
     ap.add_argument("--l2persist", type=int, default=1)
     ap.add_argument("--warps", type=int, default=0)
+    ap.add_argument("--half-records", type=int, default=0, help="1: 4-B half-packed level records (fp16 abskg|wall, fp16 sigmaT4/pi)")
     ap.add_argument("--generic-march", type=int, default=0, help="1: generic march template instead of the tuned fast path (A/B)")
     ap.add_argument("--reference-semantics", action="store_true", help="march the zero-weight reflected legs like the reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -112,7 +112,10 @@ const char* rmcrt_last_error(const rmcrt_ctx* ctx);   /* ctx may be NULL: last c
  * Replaces getLevel()/getRegion() + the H2D staging of DetailedTask::initiateH2DCopies
  * (DetailedTask.cc:1217, 1326-1340).  Levels are indexed as in Uintah (0 = coarsest).
  * recordKind: 0 = {float abskg|wall-sign, float sigmaT4OverPi} (8 B, production),
- *             1 = {double,double} (16 B, FP64 parity march). */
+ *             1 = {double,double} (16 B, FP64 parity march),
+ *             2 = half-packed {fp16 abskg|wall-sign, fp16 sigmaT4OverPi/32} (4 B) for levels that do not fit the L2 as
+ *                 8-B records (256^3: 69 MB instead of 137 MB); needs 18 K < T < 3270 K and abskg < 65504 (else
+ *                 RMCRT_ERR_NONPHYSICAL); a float copy of the level is kept for the divQ epilogue of the origin cells. */
 int rmcrt_define_level(rmcrt_ctx* ctx, int L, const rmcrt_level_desc* desc, int recordKind);
 
 /* Pack abskg / sigmaT4OverPi / cellType given on window [srcLo,srcHi) into the level's device

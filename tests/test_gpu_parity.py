@@ -285,6 +285,60 @@ def test_tuned_march_matches_generic_march(gpu_lib, po, case):
     assert np.abs(a - b).max() <= 2e-4 * scale, np.abs(a - b).max() / scale
 
 
+def test_half_packed_records(gpu_lib, po):
+    """recordKind 2 (fp16 abskg|wall, fp16 sigmaT4/pi * 2^-5): same rays as the float records; divQ differs only by the
+    fp16 rounding of the properties seen along the rays (<= 2^-11 relative each, averaging down along a path), masks and
+    executed steps are identical up to FP32 ties, and the isothermal-enclosure identity still holds exactly."""
+    from uintah_b200 import RMCRT
+    rng = np.random.default_rng(9)
+    lv = po.burns_christon(32, dtype=np.float32)
+    add_random_walls(lv, 0.01, rng)
+    out = {}
+    for half in (False, True):
+        g = RMCRT(device=0, half_records=half, nDivQRays=32, threshold=0.05, seed=21)
+        g.upload_level(0, lv)
+        out[half] = (g.trace_divq(0, timestep=3)["divQ"], g.counters().nRaySteps, g.level_records(0)[1])
+    (a, na, ra), (b, nb, rb) = out[False], out[True]
+    assert (ra, rb) == (8, 4)
+    assert abs(int(na) - int(nb)) <= 5e-4 * na
+    assert np.array_equal(a == 0, b == 0)
+    scale = np.abs(a).max()
+    diff = np.abs(a - b)[a != 0]
+    # a handful of rays sit at the reflection threshold (intensity*fs vs Threshold) and gain / lose a whole leg when the
+    # attenuation moves in the 4th digit: a discrete, unbiased change of Monte-Carlo size in single cells
+    assert np.percentile(diff, 99.5) < 1.5e-3 * scale, np.percentile(diff, 99.5) / scale
+    assert diff.max() < 1.5e-2 * scale, diff.max() / scale
+    assert np.linalg.norm(a - b) / np.linalg.norm(a) < 1e-3, np.linalg.norm(a - b) / np.linalg.norm(a)
+    # uniform sigmaT4/pi: every cell carries the same fp16 rounding (<= 2^-11 relative), i.e. a common factor on sumI
+    assert abs((a - b).mean()) < 2e-4 * scale
+    # Burns & Christon centre line with half records is as good as with float records
+    lv41 = po.burns_christon(41, dtype=np.float32)
+    g = RMCRT(device=0, half_records=True, nDivQRays=100, threshold=0.05, seed=5)
+    g.upload_level(0, lv41)
+    assert po.centreline_L2(g.trace_divq(0)["divQ"], 41)[0] < 0.02
+    # isothermal black enclosure: divQ == 0 to round-off whatever abskg is (sigmaT4/pi = 0.75 is exact in fp16)
+    M = 34
+    ab = rng.uniform(0.1, 1.0, (M, M, M)).astype(np.float32)
+    s4 = np.full((M, M, M), 0.75, np.float32)
+    ct = np.full((M, M, M), -1, np.int32)
+    for ax in range(3):
+        for idx in (0, M - 1):
+            sl = [slice(None)] * 3; sl[ax] = idx
+            ct[tuple(sl)] = 8; ab[tuple(sl)] = 1.0
+    iso = po.Level(ab, s4, ct, (-1,) * 3, (33,) * 3, (1.0 / 32,) * 3, interior_lo=(0,) * 3, interior_hi=(32,) * 3)
+    g = RMCRT(device=0, half_records=True, nDivQRays=8, threshold=0.001, allowReflect=0)
+    g.upload_level(0, iso)
+    assert np.abs(g.trace_divq(0)["divQ"]).max() < 2e-5 * 4 * np.pi * 0.75
+    # out-of-range properties are refused, not silently saturated
+    hot = po.burns_christon(8, dtype=np.float32)
+    hot.sigmaT4[4, 4, 4] = 5.0e6
+    from uintah_b200 import RmcrtError
+    g = RMCRT(device=0, half_records=True)
+    with pytest.raises(RmcrtError) as e:
+        g.upload_level(0, hot)
+    assert e.value.code == -3
+
+
 def test_reproducible_and_keyed_on_timestep(gpu_lib, po):
     lv = po.burns_christon(16, dtype=np.float32)
     g = make(gpu_lib, nDivQRays=6, threshold=0.05, seed=99)

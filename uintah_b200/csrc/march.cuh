@@ -13,11 +13,23 @@
 #pragma once
 #include <cstdint>
 #include <cmath>
+#if defined(__CUDACC__)
+#include <cuda_fp16.h>
+#endif
 
 namespace rmcrt {
 
 struct Rec8  { float  k, s; };   // k: abskg, sign bit set <=> cellType != flowCell ; s: sigmaT4/pi
 struct Rec16 { double k, s; };
+// half-packed record (4 B): high half = fp16 abskg with the wall flag in ITS sign bit (bit 31 of the word), low half = fp16 of
+// sigmaT4/pi * HALF_S_SCALE.  The scale is a fixed power of two (exact), chosen so that 18 K < T < 3270 K stays in fp16's
+// normal range; the march integrates in scaled units and the per-ray result is multiplied by 1/HALF_S_SCALE once.
+struct Rec4  { uint32_t w; };
+constexpr float HALF_S_SCALE = 1.0f / 32.0f;
+template <class RecT> struct RecInfo;
+template <> struct RecInfo<Rec8>  { typedef Rec8  decoded; typedef float  real; static constexpr float  unscale = 1.0f; };
+template <> struct RecInfo<Rec16> { typedef Rec16 decoded; typedef double real; static constexpr double unscale = 1.0;  };
+template <> struct RecInfo<Rec4>  { typedef Rec8  decoded; typedef float  real; static constexpr float  unscale = 1.0f / HALF_S_SCALE; };
 
 __device__ __forceinline__ Rec8 ldrec(const Rec8* p) {
   const float2 v = __ldg(reinterpret_cast<const float2*>(p));
@@ -27,6 +39,16 @@ __device__ __forceinline__ Rec16 ldrec(const Rec16* p) {
   const double2 v = __ldg(reinterpret_cast<const double2*>(p));
   return Rec16{v.x, v.y};
 }
+#if defined(__CUDACC__)
+__device__ __forceinline__ Rec8 ldrec(const Rec4* p) {       // decoded: k signed, s still scaled by HALF_S_SCALE
+  const uint32_t w = __ldg(reinterpret_cast<const unsigned int*>(p));
+  return Rec8{__half2float(__ushort_as_half((unsigned short)(w >> 16))), __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu)))};
+}
+__device__ __forceinline__ Rec4 encode_rec4(float kSigned, float s) {
+  const uint32_t hk = __half_as_ushort(__float2half_rn(kSigned)), hs = __half_as_ushort(__float2half_rn(s * HALF_S_SCALE));
+  return Rec4{(hk << 16) | hs};
+}
+#endif
 __device__ __forceinline__ bool sign_bit(float v)  { return (__float_as_uint(v) >> 31) != 0u; }
 __device__ __forceinline__ bool sign_bit(double v) { return (__double2hiint(v) < 0); }
 // a record whose abskg carries the sign bit is "not a flow cell" (cellType != d_flowCell)
@@ -101,7 +123,7 @@ __device__ __forceinline__ Real march_single_level(const RecT* __restrict__ recs
   const Real ddz = N::mul(N::mul(absr(iz), cz), N::LEN_SCALE);
 
   Real tPrev = 0, tau = 0, ePrev = 1, sum = 0, fs = 1;
-  RecT r = ldrec(recs + idx);
+  typename RecInfo<RecT>::decoded r = ldrec(recs + idx);
   Real k = absr(r.k), s = r.s;
   unsigned steps = 0;
   int ci = pi, cj = pj, ck = pk;   // only maintained when RECORD
@@ -243,7 +265,13 @@ struct LegOut {
 };
 
 #if defined(__CUDA_ARCH__)
-#define RM_PEEK(J, IB)                                      \
+// record-type specific pieces: request the record of slot J / decode slot C into a<C> = |abskg|, s<C> (k<C> keeps the raw word
+// whose bit 31 is the wall flag for both layouts)
+#define RM_LD8(J)  "mad.wide.s32 ad, i" #J ", 8, %13;\n\t" "ld.global.nc.v2.f32 {k" #J ", s" #J "}, [ad];\n\t"
+#define RM_LD4(J)  "mad.wide.s32 ad, i" #J ", 4, %13;\n\t" "ld.global.nc.b32 k" #J ", [ad];\n\t"
+#define RM_DEC8(C) "abs.f32 a" #C ", k" #C ";\n\t"
+#define RM_DEC4(C) "mov.b32 {hl, hh}, k" #C ";\n\t" "cvt.f32.f16 s" #C ", hl;\n\t" "cvt.f32.f16 a" #C ", hh;\n\t" "abs.f32 a" #C ", a" #C ";\n\t"
+#define RM_PEEK(J, IB, LD)                                  \
   "min.f32 m, %0, %1;\n\t"                                  \
   "setp.lt.f32 n" #J ", m, %2;\n\t"                         \
   "setp.lt.and.f32 x" #J ", %0, %1, n" #J ";\n\t"           \
@@ -252,21 +280,20 @@ struct LegOut {
   "selp.s32 i" #J ", %17, %19, x" #J ";\n\t"                \
   "@y" #J " mov.s32 i" #J ", %18;\n\t"                      \
   "add.s32 i" #J ", i" #J ", " IB ";\n\t"                   \
-  "mad.wide.s32 ad, i" #J ", 8, %13;\n\t"                   \
-  "ld.global.nc.v2.f32 {k" #J ", s" #J "}, [ad];\n\t"
+  LD(J)
 #define RM_COMMIT(J)                                        \
   "@x" #J " add.f32 %0, %0, %14;\n\t"                       \
   "@y" #J " add.f32 %1, %1, %15;\n\t"                       \
   "@!n" #J " add.f32 %2, %2, %16;\n\t"
 // leave the cell in slot P at t<C>, enter the cell in slot C
-#define RM_INTEG(P, C)                                      \
+#define RM_INTEG(P, C, DEC)                                 \
   "fma.rn.f32 ta, a" #P ", t" #C ", %4;\n\t"                \
   "neg.f32 d, ta;\n\t"                                      \
   "ex2.approx.ftz.f32 e" #C ", d;\n\t"                      \
   "sub.f32 d, e" #P ", e" #C ";\n\t"                        \
   "fma.rn.f32 %8, s" #P ", d, %8;\n\t"                      \
   "add.f32 %9, %9, 0f3F800000;\n\t"                         \
-  "abs.f32 a" #C ", k" #C ";\n\t"                           \
+  DEC(C)                                                    \
   "neg.f32 d, a" #C ";\n\t"                                 \
   "fma.rn.f32 %4, d, t" #C ", ta;\n\t"                      \
   "setp.lt.s32 w, k" #C ", 0;\n\t"                          \
@@ -281,41 +308,55 @@ struct LegOut {
   "mov.f32 %6, s" #C ";\n\t"                                \
   "mov.f32 %7, e" #C ";\n\t"                                \
   "bra DONE;\n\t"
+#define RM_ASM(LD, DEC)                                                                                              \
+  asm volatile(                                                                                                      \
+      "{\n\t"                                                                                                        \
+      ".reg .pred x0, y0, n0, x1, y1, n1, x2, y2, n2, w;\n\t"                                                        \
+      ".reg .f32 m, d, ta, t0, t1, t2, s0, s1, s2, e0, e1, e2, a0, a1, a2;\n\t"                                      \
+      ".reg .b32 k0, k1, k2;\n\t"                                                                                    \
+      ".reg .b16 hl, hh;\n\t"                                                                                        \
+      ".reg .s32 i0, i1, i2;\n\t"                                                                                    \
+      ".reg .s64 ad;\n\t"                                                                                            \
+      /* slot 2 = the cell the leg starts in */                                                                      \
+      "mov.f32 a2, %5;\n\t"                                                                                          \
+      "mov.f32 s2, %6;\n\t"                                                                                          \
+      "mov.f32 e2, %7;\n\t"                                                                                          \
+      RM_PEEK(0, "%3", LD)                                                                                           \
+      "LOOP:\n\t"                                                                                                    \
+      RM_COMMIT(0) RM_PEEK(1, "i0", LD) RM_INTEG(2, 0, DEC)                                                          \
+      RM_COMMIT(1) RM_PEEK(2, "i1", LD) RM_INTEG(0, 1, DEC)                                                          \
+      RM_COMMIT(2) RM_PEEK(0, "i2", LD) RM_INTEG(1, 2, DEC)                                                          \
+      "bra LOOP;\n\t"                                                                                                \
+      RM_EXIT(0) RM_EXIT(1) RM_EXIT(2)                                                                               \
+      "DONE:\n\t"                                                                                                    \
+      "mov.f32 %12, ta;\n\t"                                                                                         \
+      "}"                                                                                                            \
+      : "+f"(d.tx), "+f"(d.ty), "+f"(d.tz), "+r"(d.idx), "+f"(q.A), "+f"(q.k), "+f"(q.s), "+f"(q.ePrev), "+f"(q.leg),  \
+        "+f"(q.nsteps), "=f"(o.t), "=r"(o.axis), "=f"(q.tau)                                                         \
+      : "l"(recs), "f"(ddx), "f"(ddy), "f"(ddz), "r"(stx), "r"(sty), "r"(stz)                                        \
+      : "memory")
 
 __device__ __forceinline__ LegOut march_leg(Dda& d, Integ& q, const Rec8* __restrict__ recs, float ddx, float ddy, float ddz,
                                             int stx, int sty, int stz) {
   LegOut o;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred x0, y0, n0, x1, y1, n1, x2, y2, n2, w;\n\t"
-      ".reg .f32 m, d, ta, t0, t1, t2, s0, s1, s2, e0, e1, e2, a0, a1, a2;\n\t"
-      ".reg .b32 k0, k1, k2;\n\t"
-      ".reg .s32 i0, i1, i2;\n\t"
-      ".reg .s64 ad;\n\t"
-      // slot 2 = the cell the leg starts in
-      "mov.f32 a2, %5;\n\t"
-      "mov.f32 s2, %6;\n\t"
-      "mov.f32 e2, %7;\n\t"
-      RM_PEEK(0, "%3")
-      "LOOP:\n\t"
-      RM_COMMIT(0) RM_PEEK(1, "i0") RM_INTEG(2, 0)
-      RM_COMMIT(1) RM_PEEK(2, "i1") RM_INTEG(0, 1)
-      RM_COMMIT(2) RM_PEEK(0, "i2") RM_INTEG(1, 2)
-      "bra LOOP;\n\t"
-      RM_EXIT(0) RM_EXIT(1) RM_EXIT(2)
-      "DONE:\n\t"
-      "mov.f32 %12, ta;\n\t"
-      "}"
-      : "+f"(d.tx), "+f"(d.ty), "+f"(d.tz), "+r"(d.idx), "+f"(q.A), "+f"(q.k), "+f"(q.s), "+f"(q.ePrev), "+f"(q.leg),
-        "+f"(q.nsteps), "=f"(o.t), "=r"(o.axis), "=f"(q.tau)
-      : "l"(recs), "f"(ddx), "f"(ddy), "f"(ddz), "r"(stx), "r"(sty), "r"(stz)
-      : "memory");
+  RM_ASM(RM_LD8, RM_DEC8);
   return o;
 }
+__device__ __forceinline__ LegOut march_leg(Dda& d, Integ& q, const Rec4* __restrict__ recs, float ddx, float ddy, float ddz,
+                                            int stx, int sty, int stz) {
+  LegOut o;
+  RM_ASM(RM_LD4, RM_DEC4);
+  return o;
+}
+#undef RM_ASM
 #undef RM_PEEK
 #undef RM_COMMIT
 #undef RM_INTEG
 #undef RM_EXIT
+#undef RM_LD8
+#undef RM_LD4
+#undef RM_DEC8
+#undef RM_DEC4
 #else
 __device__ __forceinline__ LegOut march_leg(Dda& d, Integ& q, const Rec8* __restrict__ recs, float ddx, float ddy, float ddz,
                                             int stx, int sty, int stz) {
@@ -336,7 +377,8 @@ __device__ __forceinline__ LegOut march_leg(Dda& d, Integ& q, const Rec8* __rest
 }
 #endif
 
-__device__ __forceinline__ float march_single_level_fast(const Rec8* __restrict__ recs, int idx0, int sy, int sz,
+template <class RecT>
+__device__ __forceinline__ float march_single_level_fast(const RecT* __restrict__ recs, int idx0, int sy, int sz,
                                                          float dx, float dy, float dz, float rx, float ry, float rz,
                                                          float cx, float cy, float cz, float threshold, bool allowReflect,
                                                          bool skipZero, unsigned& nSteps) {
@@ -385,6 +427,7 @@ __device__ __forceinline__ float march_single_level_fast(const Rec8* __restrict_
 //------------------------------------------------------------------------------------------------------
 struct LevelGeom {
   const void* rec;
+  const void* recFull;   // half-packed levels: float {abskg|wall, sigmaT4/pi} copy read by the divQ epilogue only
   int lo[3];        // window low index (records cover [lo, lo+n))
   int n[3];
   int intLo[3], intHi[3];
@@ -450,7 +493,7 @@ __device__ __forceinline__ Real march_multi_level(const OnionGeom<MAXL>& G, int 
   };
 
   const RecT* recs = static_cast<const RecT*>(G.lev[L].rec);
-  RecT r = ldrec(recs + recIndex(L, ci, cj, ck));
+  typename RecInfo<RecT>::decoded r = ldrec(recs + recIndex(L, ci, cj, ck));
   Real k = absr(r.k), s = r.s;
 
   for (;;) {

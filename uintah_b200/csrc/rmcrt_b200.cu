@@ -199,18 +199,19 @@ __device__ __forceinline__ Real trace_one(const TraceArgs& a, bool skipZero, int
                                           unsigned& steps, PathSink* path) {
   const int F = a.G.maxLevels - 1;
   const LevelGeom& g = a.G.lev[F];
-  if constexpr (FAST && !ML && !RECORD && std::is_same<Real, float>::value && std::is_same<RecT, Rec8>::value) {
-    return march_single_level_fast(static_cast<const Rec8*>(g.rec), (int)level_index(g, i, j, k), g.n[0], g.n[0] * g.n[1],
+  constexpr Real UNSCALE = (Real)RecInfo<RecT>::unscale;   // half-packed records carry sigmaT4/pi scaled by a power of two
+  if constexpr (FAST && !ML && !RECORD && std::is_same<Real, float>::value) {
+    return UNSCALE * march_single_level_fast(static_cast<const RecT*>(g.rec), (int)level_index(g, i, j, k), g.n[0], g.n[0] * g.n[1],
                                    nz<float>(dir[0]), nz<float>(dir[1]), nz<float>(dir[2]), (float)rayDx[0], (float)rayDx[1],
                                    (float)rayDx[2], (float)g.dx[0], (float)g.dx[1], (float)g.dx[2], (float)a.threshold,
                                    a.allowReflect != 0, skipZero, steps);
   } else
   if (ML) {
-    return march_multi_level<Real, RecT, MAXL, RECORD>(a.G, i, j, k, nz<Real>(dir[0]), nz<Real>(dir[1]), nz<Real>(dir[2]),
+    return UNSCALE * march_multi_level<Real, RecT, MAXL, RECORD>(a.G, i, j, k, nz<Real>(dir[0]), nz<Real>(dir[1]), nz<Real>(dir[2]),
                                                        (Real)rayDx[0], (Real)rayDx[1], (Real)rayDx[2], (Real)a.threshold,
                                                        a.allowReflect != 0, skipZero, steps, path);
   } else {
-    return march_single_level<Real, RecT, RECORD>(static_cast<const RecT*>(g.rec), level_index(g, i, j, k), g.n[0],
+    return UNSCALE * march_single_level<Real, RecT, RECORD>(static_cast<const RecT*>(g.rec), level_index(g, i, j, k), g.n[0],
                                                   g.n[0] * g.n[1], nz<Real>(dir[0]), nz<Real>(dir[1]), nz<Real>(dir[2]),
                                                   (Real)rayDx[0], (Real)rayDx[1], (Real)rayDx[2], (Real)g.dx[0],
                                                   (Real)g.dx[1], (Real)g.dx[2], (Real)a.threshold, a.allowReflect != 0,
@@ -240,12 +241,14 @@ __global__ void __launch_bounds__(256) divq_kernel(const __grid_constant__ Trace
     const bool valid = t < a.nCells;
     int i = 0, j = 0, k = 0;
     bool flow = false;
-    RecT r0 = RecT{0, 0};
+    typename std::conditional<std::is_same<RecT, Rec16>::value, Rec16, Rec8>::type r0{0, 0};
     unsigned long long cellId = 0, dirId = 0;
     if (valid) {
       patch_cell(a, t, i, j, k);
       cellId = (unsigned long long)level_index(g, i, j, k);
-      r0 = ldrec(recs + cellId);
+      // epilogue properties of the origin cell: full precision (half-packed levels keep a float copy for exactly this)
+      if constexpr (std::is_same<RecT, Rec4>::value) r0 = ldrec(static_cast<const Rec8*>(g.recFull) + cellId);
+      else r0 = ldrec(recs + cellId);
       flow = !is_wall(r0.k);
     }
     {
@@ -421,6 +424,15 @@ __global__ void debug_rays_kernel(const __grid_constant__ TraceArgs a, int n, co
 template <class RecT> struct RecTraits;
 template <> struct RecTraits<Rec8>  { typedef float  real; };
 template <> struct RecTraits<Rec16> { typedef double real; };
+template <> struct RecTraits<Rec4>  { typedef float  real; };
+template <class RecT, class R> __device__ __forceinline__ RecT make_rec(R kSigned, R s) { return RecT{kSigned, s}; }
+template <> __device__ __forceinline__ Rec4 make_rec<Rec4, float>(float kSigned, float s) { return encode_rec4(kSigned, s); }
+// true (unscaled) values of a record
+template <class RecT> __device__ __forceinline__ typename RecInfo<RecT>::decoded load_true(const RecT* p) {
+  typename RecInfo<RecT>::decoded r = ldrec(p);
+  r.s = r.s * (typename RecInfo<RecT>::real)RecInfo<RecT>::unscale;
+  return r;
+}
 
 struct Box { int lo[3], n[3]; };
 __host__ __device__ inline long long box_cells(const Box& b) { return (long long)b.n[0] * b.n[1] * b.n[2]; }
@@ -428,7 +440,7 @@ __host__ __device__ inline long long box_cells(const Box& b) { return (long long
 template <class T, class RecT>
 __global__ void pack_kernel(const T* __restrict__ abskg, const T* __restrict__ sig, const int* __restrict__ ct, Box src,
                             Box region /* cells to pack */, RecT* __restrict__ dst, Box dstBox, int flowCell,
-                            unsigned* __restrict__ status) {
+                            unsigned* __restrict__ status, Rec8* __restrict__ full, Box fullBox) {
   typedef typename RecTraits<RecT>::real R;
   const long long n = box_cells(region);
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
@@ -444,7 +456,16 @@ __global__ void pack_kernel(const T* __restrict__ abskg, const T* __restrict__ s
     R kr = (R)kv;
     kr = kr < R(0) ? -kr : kr;
     if (ct[s] != flowCell) kr = -kr;     // sign bit == "not a flow cell", also for abskg == 0 (-0.0)
-    dst[d] = RecT{kr, (R)sv};
+    const RecT rec = make_rec<RecT, R>(kr, (R)sv);
+    dst[d] = rec;
+    if (std::is_same<RecT, Rec4>::value) {
+      const auto back = ldrec(&dst[d]);   // fp16 overflow (T > 3270 K or abskg > 65504) must not pass silently
+      if (isinf((float)back.k) || isinf((float)back.s)) atomicAdd(status + 5, 1u);
+      if (full) {
+        const long long f = (long long)(i - fullBox.lo[0]) + (long long)fullBox.n[0] * ((long long)(j - fullBox.lo[1]) + (long long)fullBox.n[1] * (long long)(k - fullBox.lo[2]));
+        full[f] = Rec8{(float)kr, (float)sv};
+      }
+    }
   }
 }
 
@@ -457,7 +478,7 @@ __global__ void finalize_kernel(const RecT* __restrict__ recs, Box b, unsigned* 
     const int i = (int)(t - row * b.n[0]);
     const int k = (int)(row / b.n[1]);
     const int j = (int)(row - (long long)k * b.n[1]);
-    const RecT r = recs[t];
+    const auto r = ldrec(recs + t);
     const bool wall = is_wall(r.k);
     const bool outer = (i == 0 || j == 0 || k == 0 || i == b.n[0] - 1 || j == b.n[1] - 1 || k == b.n[2] - 1);
     if (outer && !wall) ++open;
@@ -492,7 +513,7 @@ __global__ void sigmaT4_kernel(const double* __restrict__ temp, T* __restrict__ 
 //   all flow -> flow;  otherwise ROUNDUP -> intrusion, ROUNDDOWN -> flow unless all RR cells are non-flow.
 template <class RecT>
 __global__ void coarsen_kernel(const RecT* __restrict__ fine, Box fb, RecT* __restrict__ coarse, Box cb, Box cint,
-                               int rr0, int rr1, int rr2, int logic) {
+                               int rr0, int rr1, int rr2, int logic, Rec8* __restrict__ coarseFull) {
   typedef typename RecTraits<RecT>::real R;
   const long long n = box_cells(cint);
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
@@ -508,7 +529,7 @@ __global__ void coarsen_kernel(const RecT* __restrict__ fine, Box fb, RecT* __re
     int nWall = 0;
     for (int c = 0; c < rr2; ++c) for (int b = 0; b < rr1; ++b) for (int a = 0; a < rr0; ++a) {
       const long long f = (long long)(fi + a - fb.lo[0]) + (long long)fb.n[0] * ((long long)(fj + b - fb.lo[1]) + (long long)fb.n[1] * (long long)(fk + c - fb.lo[2]));
-      const RecT r = fine[f];
+      const auto r = load_true(fine + f);
       ak += (r.k < R(0) || is_wall(r.k)) ? -r.k : r.k;   // accumulate in T, x-fastest, like coarsenDriver_std
       as += r.s;
       nWall += is_wall(r.k) ? 1 : 0;
@@ -521,13 +542,14 @@ __global__ void coarsen_kernel(const RecT* __restrict__ fine, Box fb, RecT* __re
     else if (logic == 0) wall = true;           // ROUNDUP: any partial cell becomes an intrusion
     else wall = (nWall == RR);                  // ROUNDDOWN: any partial cell becomes a flow cell
     const long long d = (long long)(i - cb.lo[0]) + (long long)cb.n[0] * ((long long)(j - cb.lo[1]) + (long long)cb.n[1] * (long long)(k - cb.lo[2]));
-    coarse[d] = RecT{wall ? -kc : kc, sc};
+    coarse[d] = make_rec<RecT, R>(wall ? -kc : kc, sc);
+    if (coarseFull) coarseFull[d] = Rec8{(float)(wall ? -kc : kc), (float)sc};
   }
 }
 
 template <class RecT>
 __global__ void extra_cells_kernel(RecT* __restrict__ recs, Box b, Box interior, const double* __restrict__ vals /*[3][6]*/,
-                                   const int* __restrict__ types, int flowCell) {
+                                   const int* __restrict__ types, int flowCell, Rec8* __restrict__ full) {
   typedef typename RecTraits<RecT>::real R;
   const long long n = box_cells(b);
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
@@ -547,7 +569,8 @@ __global__ void extra_cells_kernel(RecT* __restrict__ recs, Box b, Box interior,
     if (face < 0) continue;
     R kr = (R)fabs(vals[face]);
     if (types[face] != flowCell) kr = -kr;
-    recs[t] = RecT{kr, (R)vals[6 + face]};
+    recs[t] = make_rec<RecT, R>(kr, (R)vals[6 + face]);
+    if (full) full[t] = Rec8{(float)kr, (float)vals[6 + face]};
   }
 }
 
@@ -610,6 +633,7 @@ struct LevelState {
   int recordKind = 0;
   void* base = nullptr;   // allocation (guard records in front of and behind the level)
   void* rec = nullptr;    // record of cell `lo`
+  void* recFull = nullptr;   // recordKind 2: float records of the same cells (epilogue of the divQ kernel)
   long long nCells = 0;
   size_t recBytes = 8;
 };
@@ -695,6 +719,7 @@ int validate_params(rmcrt_ctx* ctx, const rmcrt_params* p) {
 void fill_level_geom(const rmcrt_ctx* ctx, int L, LevelGeom& g) {
   const LevelState& s = ctx->lv[L];
   g.rec = s.rec;
+  g.recFull = s.recFull;
   for (int d = 0; d < 3; ++d) {
     g.lo[d] = s.d.lo[d]; g.n[d] = s.d.hi[d] - s.d.lo[d];
     g.intLo[d] = s.d.interiorLo[d]; g.intHi[d] = s.d.interiorHi[d];
@@ -781,22 +806,25 @@ void apply_l2_window(rmcrt_ctx* ctx, int L, cudaStream_t st) {
 
 template <class T, class RecT>
 int launch_pack(rmcrt_ctx* ctx, const void* a, const void* s, const int32_t* ct, Box src, Box region, void* dst, Box dstBox,
-                unsigned* status, cudaStream_t st) {
+                unsigned* status, void* full, Box fullBox, cudaStream_t st) {
   const long long n = box_cells(region);
   if (n <= 0) return 0;
   pack_kernel<T, RecT><<<grid_for(n, 256, ctx->smCount), 256, 0, st>>>(static_cast<const T*>(a), static_cast<const T*>(s), ct, src,
                                                                      region, static_cast<RecT*>(dst), dstBox, ctx->p.flowCell,
-                                                                     status);
+                                                                     status, static_cast<Rec8*>(full), fullBox);
   CK(cudaGetLastError());
   return 0;
 }
 
+// full / fullBox: float copy of the level (recordKind 2 only), written alongside the half-packed records
 int do_pack(rmcrt_ctx* ctx, int recordKind, int isFloat, const void* a, const void* s, const int32_t* ct, Box src, Box region,
-            void* dst, Box dstBox, unsigned* status, cudaStream_t st) {
-  if (recordKind == 0) return isFloat ? launch_pack<float, Rec8>(ctx, a, s, ct, src, region, dst, dstBox, status, st)
-                                      : launch_pack<double, Rec8>(ctx, a, s, ct, src, region, dst, dstBox, status, st);
-  return isFloat ? launch_pack<float, Rec16>(ctx, a, s, ct, src, region, dst, dstBox, status, st)
-                 : launch_pack<double, Rec16>(ctx, a, s, ct, src, region, dst, dstBox, status, st);
+            void* dst, Box dstBox, unsigned* status, void* full, Box fullBox, cudaStream_t st) {
+  if (recordKind == 0) return isFloat ? launch_pack<float, Rec8>(ctx, a, s, ct, src, region, dst, dstBox, status, nullptr, fullBox, st)
+                                      : launch_pack<double, Rec8>(ctx, a, s, ct, src, region, dst, dstBox, status, nullptr, fullBox, st);
+  if (recordKind == 2) return isFloat ? launch_pack<float, Rec4>(ctx, a, s, ct, src, region, dst, dstBox, status, full, fullBox, st)
+                                      : launch_pack<double, Rec4>(ctx, a, s, ct, src, region, dst, dstBox, status, full, fullBox, st);
+  return isFloat ? launch_pack<float, Rec16>(ctx, a, s, ct, src, region, dst, dstBox, status, nullptr, fullBox, st)
+                 : launch_pack<double, Rec16>(ctx, a, s, ct, src, region, dst, dstBox, status, nullptr, fullBox, st);
 }
 
 int build_args(rmcrt_ctx* ctx, int maxLevels, bool multiLevel, const int32_t pLo[3], const int32_t pHi[3], const int32_t oLo[3],
@@ -810,7 +838,7 @@ int build_args(rmcrt_ctx* ctx, int maxLevels, bool multiLevel, const int32_t pLo
     if (ctx->lv[L].recordKind != ctx->lv[F].recordKind) return fail(ctx, RMCRT_ERR_INVALID, "all levels must use one recordKind");
   }
   if ((ctx->p.marchPrecision == 1) != (ctx->lv[F].recordKind == 1))
-    return fail(ctx, RMCRT_ERR_INVALID, "marchPrecision fp64 needs recordKind 1 (double records) and fp32 needs recordKind 0");
+    return fail(ctx, RMCRT_ERR_INVALID, "marchPrecision fp64 needs recordKind 1 (double records) and fp32 needs recordKind 0 or 2");
   a.G.maxLevels = maxLevels;
   for (int L = 0; L <= F; ++L) if (ctx->lv[L].defined) fill_level_geom(ctx, L, a.G.lev[L]);
   const rmcrt_level_desc& f = ctx->lv[F].d;
@@ -883,7 +911,7 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
     const long long cap = (long long)ctx->smCount * 64;   // persistent-ish: grid-stride beyond this
     if (grid > cap) grid = cap;
     if (ML) divq_kernel<Real, RecT, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
-    else if (std::is_same<Real, float>::value && !ctx->p.genericMarch)
+    else if (std::is_same<Real, float>::value && (!ctx->p.genericMarch || std::is_same<RecT, Rec4>::value))
       divq_kernel<Real, RecT, false, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
     else    divq_kernel<Real, RecT, false><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
     CK(cudaGetLastError());
@@ -910,6 +938,7 @@ int trace_common(rmcrt_ctx* ctx, int maxLevels, bool ML, const int32_t pLo[3], c
     ctx->persistedStreamFor = (void*)st;
   }
   if (ctx->p.marchPrecision == 1) return launch_trace<double, Rec16>(ctx, a, ML, st);
+  if (ctx->lv[maxLevels - 1].recordKind == 2) return launch_trace<float, Rec4>(ctx, a, ML, st);
   return launch_trace<float, Rec8>(ctx, a, ML, st);
 }
 
@@ -1019,7 +1048,7 @@ int rmcrt_set_params(rmcrt_ctx* ctx, const rmcrt_params* p) {
 void rmcrt_destroy(rmcrt_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  for (auto& l : ctx->lv) if (l.base) cudaFree(l.base);
+  for (auto& l : ctx->lv) { if (l.base) cudaFree(l.base); if (l.recFull) cudaFree(l.recFull); }
   if (ctx->d_counters) cudaFree(ctx->d_counters);
   if (ctx->d_lstat) cudaFree(ctx->d_lstat);
   if (ctx->d_nItems) cudaFree(ctx->d_nItems);
@@ -1033,7 +1062,7 @@ void rmcrt_destroy(rmcrt_ctx* ctx) {
 int rmcrt_define_level(rmcrt_ctx* ctx, int L, const rmcrt_level_desc* d, int recordKind) {
   if (!ctx || !d) return RMCRT_ERR_INVALID;
   if (L < 0 || L >= RMCRT_MAX_LEVELS) return fail(ctx, RMCRT_ERR_INVALID, "level index %d out of range", L);
-  if (recordKind != 0 && recordKind != 1) return fail(ctx, RMCRT_ERR_INVALID, "recordKind must be 0 or 1");
+  if (recordKind < 0 || recordKind > 2) return fail(ctx, RMCRT_ERR_INVALID, "recordKind must be 0 (float), 1 (double) or 2 (half-packed)");
   long long n = 1;
   for (int k = 0; k < 3; ++k) {
     if (d->hi[k] - d->lo[k] < 3) return fail(ctx, RMCRT_ERR_INVALID, "level needs >= 3 cells per axis incl. extra cells");
@@ -1053,9 +1082,10 @@ int rmcrt_define_level(rmcrt_ctx* ctx, int L, const rmcrt_level_desc* d, int rec
     return 0;
   }
   if (s.base) { cudaFree(s.base); s.base = nullptr; s.rec = nullptr; }
+  if (s.recFull) { cudaFree(s.recFull); s.recFull = nullptr; }
   s.d = *d;
   s.recordKind = recordKind;
-  s.recBytes = recordKind == 0 ? sizeof(Rec8) : sizeof(Rec16);
+  s.recBytes = recordKind == 0 ? sizeof(Rec8) : (recordKind == 1 ? sizeof(Rec16) : sizeof(Rec4));
   s.nCells = n;
   // guard records on both ends (flagged "not a flow cell") so neighbour / speculative loads issued from any cell of
   // the level stay inside the allocation
@@ -1065,6 +1095,10 @@ int rmcrt_define_level(rmcrt_ctx* ctx, int L, const rmcrt_level_desc* d, int rec
   CK(cudaMemset(base, 0xFF, (size_t)(n + 2 * guard) * s.recBytes));   // 0xFF.. = negative NaN: wall flag set, caught by finalize if left
   s.base = base;
   s.rec = static_cast<char*>(base) + (size_t)guard * s.recBytes;
+  if (recordKind == 2) {
+    CK(cudaMalloc(&s.recFull, (size_t)n * sizeof(Rec8)));
+    CK(cudaMemset(s.recFull, 0xFF, (size_t)n * sizeof(Rec8)));
+  }
   s.defined = true;
   s.finalized = false;
   CK(cudaMemset(lstat_of(ctx, L), 0, LSTAT_WORDS * sizeof(unsigned)));
@@ -1088,7 +1122,7 @@ int rmcrt_pack_level_device(rmcrt_ctx* ctx, int L, const void* a, const void* s,
   }
   int rci = invalidate_level(ctx, L, (cudaStream_t)stream);
   if (rci) return rci;
-  return do_pack(ctx, lv.recordKind, isFloat, a, s, ct, src, region, lv.rec, dst, lstat_of(ctx, L), (cudaStream_t)stream);
+  return do_pack(ctx, lv.recordKind, isFloat, a, s, ct, src, region, lv.rec, dst, lstat_of(ctx, L), lv.recFull, dst, (cudaStream_t)stream);
 }
 
 int rmcrt_upload_level(rmcrt_ctx* ctx, int L, const void* a, const void* s, const int32_t* ct, int isFloat,
@@ -1118,8 +1152,9 @@ static int finalize_launch(rmcrt_ctx* ctx, int L, cudaStream_t st) {
   unsigned* ls = lstat_of(ctx, L);
   CK(cudaMemsetAsync(ls, 0, 5 * sizeof(unsigned), st));      // words 0..4; word 5 (pack-time input check) survives
   Box b = mkbox(lv.d.lo, lv.d.hi);
-  if (lv.recordKind == 0) finalize_kernel<Rec8><<<grid_for(lv.nCells, 256, ctx->smCount), 256, 0, st>>>(static_cast<const Rec8*>(lv.rec), b, ls);
-  else                    finalize_kernel<Rec16><<<grid_for(lv.nCells, 256, ctx->smCount), 256, 0, st>>>(static_cast<const Rec16*>(lv.rec), b, ls);
+  if (lv.recordKind == 0)      finalize_kernel<Rec8><<<grid_for(lv.nCells, 256, ctx->smCount), 256, 0, st>>>(static_cast<const Rec8*>(lv.rec), b, ls);
+  else if (lv.recordKind == 2) finalize_kernel<Rec4><<<grid_for(lv.nCells, 256, ctx->smCount), 256, 0, st>>>(static_cast<const Rec4*>(lv.rec), b, ls);
+  else                         finalize_kernel<Rec16><<<grid_for(lv.nCells, 256, ctx->smCount), 256, 0, st>>>(static_cast<const Rec16*>(lv.rec), b, ls);
   CK(cudaGetLastError());
   return 0;
 }
@@ -1258,8 +1293,9 @@ int rmcrt_coarsen_level_device(rmcrt_ctx* ctx, int fineL, int coarseL, void* str
   Box fb = mkbox(f.d.lo, f.d.hi), cb = mkbox(c.d.lo, c.d.hi), ci = mkbox(c.d.interiorLo, c.d.interiorHi);
   const long long n = box_cells(ci);
   cudaStream_t st = (cudaStream_t)stream;
-  if (f.recordKind == 0) coarsen_kernel<Rec8><<<grid_for(n, 128, ctx->smCount), 128, 0, st>>>(static_cast<const Rec8*>(f.rec), fb, static_cast<Rec8*>(c.rec), cb, ci, rr[0], rr[1], rr[2], ctx->p.cellTypeCoarsenLogic);
-  else                   coarsen_kernel<Rec16><<<grid_for(n, 128, ctx->smCount), 128, 0, st>>>(static_cast<const Rec16*>(f.rec), fb, static_cast<Rec16*>(c.rec), cb, ci, rr[0], rr[1], rr[2], ctx->p.cellTypeCoarsenLogic);
+  if (f.recordKind == 0)      coarsen_kernel<Rec8><<<grid_for(n, 128, ctx->smCount), 128, 0, st>>>(static_cast<const Rec8*>(f.rec), fb, static_cast<Rec8*>(c.rec), cb, ci, rr[0], rr[1], rr[2], ctx->p.cellTypeCoarsenLogic, nullptr);
+  else if (f.recordKind == 2) coarsen_kernel<Rec4><<<grid_for(n, 128, ctx->smCount), 128, 0, st>>>(static_cast<const Rec4*>(f.rec), fb, static_cast<Rec4*>(c.rec), cb, ci, rr[0], rr[1], rr[2], ctx->p.cellTypeCoarsenLogic, static_cast<Rec8*>(c.recFull));
+  else                        coarsen_kernel<Rec16><<<grid_for(n, 128, ctx->smCount), 128, 0, st>>>(static_cast<const Rec16*>(f.rec), fb, static_cast<Rec16*>(c.rec), cb, ci, rr[0], rr[1], rr[2], ctx->p.cellTypeCoarsenLogic, nullptr);
   CK(cudaGetLastError());
   return invalidate_level(ctx, coarseL, st);
 }
@@ -1278,8 +1314,9 @@ int rmcrt_set_level_extra_cells(rmcrt_ctx* ctx, int L, const double abskg[6], co
   CK(cudaMemcpyAsync(dT, types, 6 * sizeof(int), cudaMemcpyHostToDevice, st));
   CK(cudaStreamSynchronize(st));   // h[] is a stack buffer
   Box b = mkbox(lv.d.lo, lv.d.hi), in = mkbox(lv.d.interiorLo, lv.d.interiorHi);
-  if (lv.recordKind == 0) extra_cells_kernel<Rec8><<<grid_for(lv.nCells, 256, ctx->smCount), 256, 0, st>>>(static_cast<Rec8*>(lv.rec), b, in, static_cast<const double*>(ctx->misc.p), dT, ctx->p.flowCell);
-  else                    extra_cells_kernel<Rec16><<<grid_for(lv.nCells, 256, ctx->smCount), 256, 0, st>>>(static_cast<Rec16*>(lv.rec), b, in, static_cast<const double*>(ctx->misc.p), dT, ctx->p.flowCell);
+  if (lv.recordKind == 0)      extra_cells_kernel<Rec8><<<grid_for(lv.nCells, 256, ctx->smCount), 256, 0, st>>>(static_cast<Rec8*>(lv.rec), b, in, static_cast<const double*>(ctx->misc.p), dT, ctx->p.flowCell, nullptr);
+  else if (lv.recordKind == 2) extra_cells_kernel<Rec4><<<grid_for(lv.nCells, 256, ctx->smCount), 256, 0, st>>>(static_cast<Rec4*>(lv.rec), b, in, static_cast<const double*>(ctx->misc.p), dT, ctx->p.flowCell, static_cast<Rec8*>(lv.recFull));
+  else                         extra_cells_kernel<Rec16><<<grid_for(lv.nCells, 256, ctx->smCount), 256, 0, st>>>(static_cast<Rec16*>(lv.rec), b, in, static_cast<const double*>(ctx->misc.p), dT, ctx->p.flowCell, nullptr);
   CK(cudaGetLastError());
   return invalidate_level(ctx, L, st);
 }
@@ -1294,7 +1331,9 @@ int rmcrt_pack_box_device(rmcrt_ctx* ctx, int L, const void* a, const void* s, c
     if (boxLo[d] < srcLo[d] || boxHi[d] > srcHi[d] || boxHi[d] <= boxLo[d]) return fail(ctx, RMCRT_ERR_INVALID, "box must lie inside the source window");
   CK(cudaSetDevice(ctx->device));
   Box src = mkbox(srcLo, srcHi), box = mkbox(boxLo, boxHi);
-  return do_pack(ctx, ctx->lv[L].recordKind, isFloat, a, s, ct, src, box, d_send, box, lstat_of(ctx, L), (cudaStream_t)stream);
+  // half-packed levels: the float copy of the rank's own cells goes straight into the level (only origin cells need it)
+  return do_pack(ctx, ctx->lv[L].recordKind, isFloat, a, s, ct, src, box, d_send, box, lstat_of(ctx, L), ctx->lv[L].recFull,
+                 mkbox(ctx->lv[L].d.lo, ctx->lv[L].d.hi), (cudaStream_t)stream);
 }
 
 int rmcrt_assemble_level(rmcrt_ctx* ctx, int L, const void* gathered, size_t slotBytes, int nRanks, const int32_t* boxLo,
@@ -1312,8 +1351,9 @@ int rmcrt_assemble_level(rmcrt_ctx* ctx, int L, const void* gathered, size_t slo
     if ((size_t)n * lv.recBytes > slotBytes) return fail(ctx, RMCRT_ERR_INVALID, "rank %d box does not fit its slot", r);
     for (int d = 0; d < 3; ++d)
       if (b.lo[d] < lv.d.lo[d] || b.lo[d] + b.n[d] > lv.d.hi[d]) return fail(ctx, RMCRT_ERR_INVALID, "rank %d box outside level", r);
-    if (lv.recordKind == 0) assemble_kernel<Rec8><<<grid_for(n, 256, ctx->smCount), 256, 0, (cudaStream_t)stream>>>(static_cast<const unsigned char*>(gathered), slotBytes, r, b, static_cast<Rec8*>(lv.rec), dst);
-    else                    assemble_kernel<Rec16><<<grid_for(n, 256, ctx->smCount), 256, 0, (cudaStream_t)stream>>>(static_cast<const unsigned char*>(gathered), slotBytes, r, b, static_cast<Rec16*>(lv.rec), dst);
+    if (lv.recordKind == 0)      assemble_kernel<Rec8><<<grid_for(n, 256, ctx->smCount), 256, 0, (cudaStream_t)stream>>>(static_cast<const unsigned char*>(gathered), slotBytes, r, b, static_cast<Rec8*>(lv.rec), dst);
+    else if (lv.recordKind == 2) assemble_kernel<Rec4><<<grid_for(n, 256, ctx->smCount), 256, 0, (cudaStream_t)stream>>>(static_cast<const unsigned char*>(gathered), slotBytes, r, b, static_cast<Rec4*>(lv.rec), dst);
+    else                         assemble_kernel<Rec16><<<grid_for(n, 256, ctx->smCount), 256, 0, (cudaStream_t)stream>>>(static_cast<const unsigned char*>(gathered), slotBytes, r, b, static_cast<Rec16*>(lv.rec), dst);
     CK(cudaGetLastError());
   }
   return invalidate_level(ctx, L, (cudaStream_t)stream);
@@ -1415,6 +1455,7 @@ int rmcrt_debug_trace_rays(rmcrt_ctx* ctx, int L, int maxLevels, const int32_t p
       static_cast<const double*>(ctx->dbg[1].p), static_cast<const double*>(ctx->dbg[2].p), static_cast<double*>(ctx->dbg[3].p), \
       static_cast<unsigned*>(ctx->dbg[4].p), dPath, maxPath)
   if (ctx->p.marchPrecision == 1) { if (ML) DBG_LAUNCH(double, Rec16, true); else DBG_LAUNCH(double, Rec16, false); }
+  else if (ctx->lv[nl - 1].recordKind == 2) { if (ML) DBG_LAUNCH(float, Rec4, true); else DBG_LAUNCH(float, Rec4, false); }
   else                            { if (ML) DBG_LAUNCH(float, Rec8, true);   else DBG_LAUNCH(float, Rec8, false); }
 #undef DBG_LAUNCH
   CK(cudaGetLastError());

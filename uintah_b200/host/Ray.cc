@@ -173,7 +173,7 @@ void Ray::BC_bulletproofing(const ProblemSpecP& rmcrtps, const bool chk_temp, co
 
 //______________________________________________________________________
 void Ray::setKnob(const std::string& name, int value) {
-  static const char* known[] = {"rayCoherence", "skipZeroWeightLegs", "l2Persist", "genericMarch", "marchPrecision", "warpsPerTile", "fixedRandom"};
+  static const char* known[] = {"rayCoherence", "skipZeroWeightLegs", "l2Persist", "genericMarch", "marchPrecision", "warpsPerTile", "fixedRandom", "halfRecords"};
   for (auto k : known)
     if (name == k) { d_knobs[name] = value; return; }
   throw ProblemSetupException("RMCRT (B200 back end): unknown knob " + name, __FILE__, __LINE__);
@@ -277,6 +277,13 @@ void Ray::sched_rayTrace_dataOnion(const LevelP& level, SchedulerP& sched, Task:
 }
 
 //______________________________________________________________________
+// 0 float records, 1 double records (FP64 parity march), 2 half-packed records (knob halfRecords; for levels beyond the L2)
+int Ray::recordKind(const rmcrt_params& p) const {
+  if (p.marchPrecision == 1) return 1;
+  auto it = d_knobs.find("halfRecords");
+  return (it != d_knobs.end() && it->second) ? 2 : 0;
+}
+
 rmcrt_level_desc Ray::describe(const Level* level) {
   rmcrt_level_desc d;
   IntVector lo, hi, ilo, ihi;
@@ -315,7 +322,7 @@ void Ray::uploadLevel(const Level* level, DataWarehouse* abskg_dw, DataWarehouse
   fillParams(p);
   for (auto& dev : devs) {
     check(dev.ctx, rmcrt_set_params(dev.ctx, &p), "rmcrt_set_params");
-    check(dev.ctx, rmcrt_define_level(dev.ctx, L, &desc, p.marchPrecision == 1 ? 1 : 0), "rmcrt_define_level");
+    check(dev.ctx, rmcrt_define_level(dev.ctx, L, &desc, recordKind(p)), "rmcrt_define_level");
     check(dev.ctx, rmcrt_upload_level(dev.ctx, L, abskg.getPointer(), sigmaT4OverPi.getPointer(), celltype.getPointer(),
                                       sizeof(T) == 4 ? 1 : 0, desc.lo, desc.hi, nullptr), "rmcrt_upload_level");
     dev.levelStamp[L] = stamp;
@@ -475,7 +482,7 @@ void Ray::coarsenAll(const ProcessorGroup*, const PatchSubset* patches, const Ma
   rmcrt_params p;
   fillParams(p);
   for (auto& dev : devices()) {
-    check(dev.ctx, rmcrt_define_level(dev.ctx, cL, &desc, p.marchPrecision == 1 ? 1 : 0), "rmcrt_define_level");
+    check(dev.ctx, rmcrt_define_level(dev.ctx, cL, &desc, recordKind(p)), "rmcrt_define_level");
     check(dev.ctx, rmcrt_coarsen_level_device(dev.ctx, fL, cL, nullptr), "rmcrt_coarsen_level_device");
     dev.levelStamp[cL] = stamp;
   }

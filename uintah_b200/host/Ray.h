@@ -113,6 +113,7 @@ class Ray : public RMCRTCommon {
 
   //__________________________________ helpers
   static rmcrt_level_desc describe(const Level* level);
+  int recordKind(const rmcrt_params& p) const;
   /** getLevel() the three property arrays of `level` and pack them on every device, once per DataWarehouse generation */
   template <class T>
   void uploadLevel(const Level* level, DataWarehouse* abskg_dw, DataWarehouse* sigmaT4_dw, DataWarehouse* celltype_dw, long long stamp);

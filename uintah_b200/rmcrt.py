@@ -80,8 +80,10 @@ class _DevView:
 class RMCRT:
     """Owner of one rmcrt_ctx (one per process / GPU, like the per-process Ray instance)."""
 
-    def __init__(self, device: int = 0, params: Params | None = None, **overrides):
+    def __init__(self, device: int = 0, params: Params | None = None, half_records: bool = False, **overrides):
+        """half_records: levels are stored as 4-B half-packed records (recordKind 2) instead of 8-B float records"""
         self.lib = capi.load_library()
+        self.half_records = bool(half_records)
         self.params = params if params is not None else capi.default_params(**overrides)
         if params is not None:
             for k, v in overrides.items():
@@ -119,7 +121,7 @@ class RMCRT:
 
     @property
     def record_kind(self) -> int:
-        return 1 if self.params.marchPrecision == 1 else 0
+        return 1 if self.params.marchPrecision == 1 else (2 if self.half_records else 0)
 
     # ------------------------------------------------------------------ levels
     def define_level(self, L: int, desc: LevelDesc, record_kind: int | None = None):
