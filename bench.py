@@ -205,10 +205,12 @@ def run_ours(args):
     plo, phi = partition.rank_patch(rank, pg, P)
     rays = args.rays
 
+    if args.half_records < 0:     # policy: keep the replicated level L2-resident
+        args.half_records = 1 if int(np.prod([h - l for l, h in zip(lo, hi)])) * 8 > 64e6 else 0
     skip = 0 if args.reference_semantics else 1
     g = RMCRT(device=local, nDivQRays=rays, threshold=0.05, seed=1234, skipZeroWeightLegs=skip,
               rayCoherence=args.coherence, l2Persist=args.l2persist, warpsPerTile=args.warps,
-              genericMarch=args.generic_march, half_records=bool(args.half_records))
+              genericMarch=args.generic_march, maxBlocksPerSM=args.max_blocks_per_sm, half_records=bool(args.half_records))
     stream = torch.cuda.current_stream()
     desc = LevelData(None, None, None, lo, hi, dx, interior_lo=(0, 0, 0), interior_hi=shape).desc()
     g.define_level(0, desc)
@@ -436,7 +438,10 @@ def main():
     ap.add_argument("--coherence", type=int, default=1)
     ap.add_argument("--l2persist", type=int, default=1)
     ap.add_argument("--warps", type=int, default=0)
-    ap.add_argument("--half-records", type=int, default=0, help="1: 4-B half-packed level records (fp16 abskg|wall, fp16 sigmaT4/pi)")
+    ap.add_argument("--half-records", type=int, default=-1,
+                    help="1: 4-B half-packed level records (fp16 abskg|wall, fp16 sigmaT4/pi); 0: 8-B float records; "
+                         "-1 (default): half-packed when the float records of the level would exceed 64 MB (beyond the L2)")
+    ap.add_argument("--max-blocks-per-sm", type=int, default=0, help="cap the divQ grid (0: one tile per block)")
     ap.add_argument("--generic-march", type=int, default=0, help="1: generic march template instead of the tuned fast path (A/B)")
     ap.add_argument("--reference-semantics", action="store_true", help="march the zero-weight reflected legs like the reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -76,7 +76,9 @@ typedef struct rmcrt_params {
   int32_t  warpsPerTile;       /* 0 = auto; rays of a 32-cell tile are split over this many warps */
   int32_t  genericMarch;       /* 1 = run the FP32 solve through the generic march template instead of the tuned
                                   single-level fast path (A/B measurements, debugging); results agree to FP32 round-off */
-  int32_t  reserved[3];
+  int32_t  maxBlocksPerSM;     /* 0 = one tile per block (hardware balances the tail); > 0 caps the divQ grid at this many
+                                  blocks per SM and grid-strides over the tiles (A/B measurements) */
+  int32_t  reserved[2];
 } rmcrt_params;
 
 /* geometry of one level (Level.cc:473-477, 1285-1307) */

@@ -39,7 +39,7 @@ class Params(C.Structure):
         ("haloCells", C.c_int32 * 3), ("cellTypeCoarsenLogic", C.c_int32), ("seed", C.c_uint64),
         ("marchPrecision", C.c_int32), ("rayCoherence", C.c_int32), ("skipZeroWeightLegs", C.c_int32),
         ("fixedRandom", C.c_int32), ("l2Persist", C.c_int32), ("warpsPerTile", C.c_int32),
-        ("genericMarch", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("genericMarch", C.c_int32), ("maxBlocksPerSM", C.c_int32), ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -63,7 +63,7 @@ def load_library(path: str | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("RMCRT_B200_LIB") or LIB_PATH     # RMCRT_B200_LIB: A/B builds of the same ABI
     if not os.path.exists(p):
         raise RmcrtError(-2, f"{p} not found: build it with `python -m uintah_b200.build` "
                              "(there is no CPU fallback for the RMCRT hot path)")

@@ -127,6 +127,28 @@ __device__ __forceinline__ void gen_divq_ray(const RayGen& rg, const LevelGeom& 
   }
 }
 
+// The same ray in FP32 for the FP32 production march with Philox draws: the march consumes float directions and offsets
+// anyway, and the FP64 sincos / sqrt of the reference formula cost as much as ~4 DDA steps per ray.  24-bit uniforms,
+// direction (r cos, r sin, z) with z = 2u-1 uniform in (-1,1) and phi = 2 pi u uniform (RMCRTCommon.cc:517-530), origin =
+// low corner + u*Dx per axis (553-558).
+__device__ __forceinline__ void gen_divq_ray_f32(const RayGen& rg, const LevelGeom& g, int ray, unsigned long long cellId,
+                                                 unsigned long long dirId, float dir[3], float rayDx[3]) {
+  const u32x4 a = philox4x32_10(u32x4{(uint32_t)dirId, (uint32_t)ray, rg.timestep,
+                                      ((uint32_t)(dirId >> 32) << 8) | STREAM_DIR}, rg.key0, rg.key1);
+  const unsigned long long orgId = rg.coherent == 2 ? dirId : cellId;
+  const u32x4 b = philox4x32_10(u32x4{(uint32_t)orgId, (uint32_t)ray, rg.timestep,
+                                      ((uint32_t)(orgId >> 32) << 8) | STREAM_ORIGIN}, rg.key0, rg.key1);
+  const float S = 1.0f / 16777216.0f;                     // 2^-24
+  const float z = fmaf((float)(a.x >> 8) + 0.5f, 2.0f * S, -1.0f);      // (-1,1), never +-1
+  const float r = sqrtf(fmaxf(0.0f, fmaf(-z, z, 1.0f)));
+  float sn, cs;
+  sincospif(((float)(a.y >> 8) + 0.5f) * (2.0f * S), &sn, &cs);
+  dir[0] = r * cs; dir[1] = r * sn; dir[2] = z;
+  const float off[3] = {(float)(b.x >> 8) * S, (float)(b.y >> 8) * S, (float)(b.z >> 8) * S};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) rayDx[d] = (rg.ccRays ? 0.5f : off[d]) * (float)g.dx[d];
+}
+
 // Ray::rayDirection_cellFace (Ray.cc:1362-1390) + rayLocation_cellFace (1465-1513).
 // face in push order of has_a_boundary: 0 W(-x) 1 E(+x) 2 S(-y) 3 N(+y) 4 B(-z) 5 T(+z) == Stencil7 slot.
 __device__ __forceinline__ void gen_flux_ray(const RayGen& rg, const LevelGeom& g, int i, int j, int k, int face, int ray,
@@ -187,32 +209,32 @@ __device__ __forceinline__ bool skip_allowed(const TraceArgs& a) {
   return ok;
 }
 
-template <class Real>
-__device__ __forceinline__ Real nz(double v) {   // direction component as Real, never exactly zero
+template <class Real, class D>
+__device__ __forceinline__ Real nz(D v) {   // direction component as Real, never exactly zero
   Real r = (Real)v;
   if (r == Real(0)) r = sign_bit(v) ? -Real(1e-30) : Real(1e-30);
   return r;
 }
 
-template <class Real, class RecT, bool ML, bool RECORD, bool FAST = false>
-__device__ __forceinline__ Real trace_one(const TraceArgs& a, bool skipZero, int i, int j, int k, const double dir[3], const double rayDx[3],
+template <class Real, class RecT, bool ML, bool RECORD, bool FAST = false, class D = double>
+__device__ __forceinline__ Real trace_one(const TraceArgs& a, bool skipZero, int i, int j, int k, const D dir[3], const D rayDx[3],
                                           unsigned& steps, PathSink* path) {
   const int F = a.G.maxLevels - 1;
   const LevelGeom& g = a.G.lev[F];
   constexpr Real UNSCALE = (Real)RecInfo<RecT>::unscale;   // half-packed records carry sigmaT4/pi scaled by a power of two
   if constexpr (FAST && !ML && !RECORD && std::is_same<Real, float>::value) {
     return UNSCALE * march_single_level_fast(static_cast<const RecT*>(g.rec), (int)level_index(g, i, j, k), g.n[0], g.n[0] * g.n[1],
-                                   nz<float>(dir[0]), nz<float>(dir[1]), nz<float>(dir[2]), (float)rayDx[0], (float)rayDx[1],
+                                   nz<float, D>(dir[0]), nz<float, D>(dir[1]), nz<float, D>(dir[2]), (float)rayDx[0], (float)rayDx[1],
                                    (float)rayDx[2], (float)g.dx[0], (float)g.dx[1], (float)g.dx[2], (float)a.threshold,
                                    a.allowReflect != 0, skipZero, steps);
   } else
   if (ML) {
-    return UNSCALE * march_multi_level<Real, RecT, MAXL, RECORD>(a.G, i, j, k, nz<Real>(dir[0]), nz<Real>(dir[1]), nz<Real>(dir[2]),
+    return UNSCALE * march_multi_level<Real, RecT, MAXL, RECORD>(a.G, i, j, k, nz<Real, D>(dir[0]), nz<Real, D>(dir[1]), nz<Real, D>(dir[2]),
                                                        (Real)rayDx[0], (Real)rayDx[1], (Real)rayDx[2], (Real)a.threshold,
                                                        a.allowReflect != 0, skipZero, steps, path);
   } else {
     return UNSCALE * march_single_level<Real, RecT, RECORD>(static_cast<const RecT*>(g.rec), level_index(g, i, j, k), g.n[0],
-                                                  g.n[0] * g.n[1], nz<Real>(dir[0]), nz<Real>(dir[1]), nz<Real>(dir[2]),
+                                                  g.n[0] * g.n[1], nz<Real, D>(dir[0]), nz<Real, D>(dir[1]), nz<Real, D>(dir[2]),
                                                   (Real)rayDx[0], (Real)rayDx[1], (Real)rayDx[2], (Real)g.dx[0],
                                                   (Real)g.dx[1], (Real)g.dx[2], (Real)a.threshold, a.allowReflect != 0,
                                                   skipZero, steps, path, i, j, k);
@@ -227,7 +249,14 @@ __device__ __forceinline__ Real trace_one(const TraceArgs& a, bool skipZero, int
 // then lane = cell writes divQ / radiationVolq fully coalesced.
 //======================================================================================================
 template <class Real, class RecT, bool ML, bool FAST = false>
-__global__ void __launch_bounds__(256) divq_kernel(const __grid_constant__ TraceArgs a) {
+// Register budget: the tuned single-level kernel is built for 32 registers/thread (8 x 256-thread blocks per SM = 64
+// resident warps).  Measured at 128^3 x 100 rays: 96 regs 5.5e11, 80 regs 6.5e11, 64 regs 8.0e11, 48 regs 8.5e11,
+// 40 regs 8.8e11, 32 regs 9.3e11 steps/s -- latency hiding by occupancy beats the spills, which sit in the per-ray
+// set-up outside the PTX leg loop.  The generic / Data-Onion / FP64 instantiations keep 64 registers.
+#ifndef RMCRT_FAST_MIN_BLOCKS
+#define RMCRT_FAST_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(256, (FAST ? RMCRT_FAST_MIN_BLOCKS : 4)) divq_kernel(const __grid_constant__ TraceArgs a) {
   extern __shared__ double red[];     // [W][32]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
   const int F = a.G.maxLevels - 1;
@@ -259,10 +288,18 @@ __global__ void __launch_bounds__(256) divq_kernel(const __grid_constant__ Trace
     double acc = 0;
     unsigned steps = 0;
     if (flow) {
-      for (int ray = warp; ray < a.nRays; ray += W) {
-        double dir[3], rayDx[3];
-        gen_divq_ray(a.rng, g, i, j, k, ray, cellId, dirId, dir, rayDx);
-        acc += (double)trace_one<Real, RecT, ML, false, FAST>(a, skipZero, i, j, k, dir, rayDx, steps, nullptr);
+      if (std::is_same<Real, float>::value && a.rng.isSeedRandom && !a.rng.fixedRandom) {
+        for (int ray = warp; ray < a.nRays; ray += W) {      // production: Philox draws, FP32 ray set-up
+          float dir[3], rayDx[3];
+          gen_divq_ray_f32(a.rng, g, ray, cellId, dirId, dir, rayDx);
+          acc += (double)trace_one<Real, RecT, ML, false, FAST, float>(a, skipZero, i, j, k, dir, rayDx, steps, nullptr);
+        }
+      } else {
+        for (int ray = warp; ray < a.nRays; ray += W) {      // regression modes (MT19937 reseed, FIXED_RANDOM_NUM) and the FP64 march
+          double dir[3], rayDx[3];
+          gen_divq_ray(a.rng, g, i, j, k, ray, cellId, dirId, dir, rayDx);
+          acc += (double)trace_one<Real, RecT, ML, false, FAST>(a, skipZero, i, j, k, dir, rayDx, steps, nullptr);
+        }
       }
     }
     red[warp * 32 + lane] = acc;
@@ -369,7 +406,7 @@ __global__ void __launch_bounds__(256) flux_trace_kernel(const __grid_constant__
       for (int ray = warp; ray < a.nRays; ray += W) {
         double dir[3], rayDx[3], cosT;
         gen_flux_ray(a.rng, g, i, j, k, face, ray, cellId, dirId, dir, rayDx, cosT);
-        const double dI = (double)trace_one<Real, RecT, ML, false>(a, skipZero, i, j, k, dir, rayDx, steps, nullptr);
+        const double dI = (double)trace_one<Real, RecT, ML, false, true>(a, skipZero, i, j, k, dir, rayDx, steps, nullptr);
         sumProj += cosT * dI;      // sumProjI += cosTheta * (sumI - sumI_prev)   (Ray.cc:704)
         sumCos += cosT;
       }
@@ -776,9 +813,10 @@ int pick_warps(const rmcrt_ctx* ctx, long long nTiles) {
     int w = ctx->p.warpsPerTile;
     return w > 8 ? 8 : w;
   }
-  // enough warps to fill the machine ~4x over: 148 SMs x 32 resident warps
-  const long long want = (long long)ctx->smCount * 32 * 4;
-  int w = 1;
+  // 128-thread blocks (4 warps share a tile's rays) reach the 64 resident warps per SM that 32 registers allow; small
+  // patches get more warps per tile so the machine is still filled ~4x over
+  const long long want = (long long)ctx->smCount * 64 * 4;
+  int w = 4;
   while (w < 8 && nTiles * w < want) w *= 2;
   return w;
 }
@@ -908,7 +946,9 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
     int W = pick_warps(ctx, a.nTiles);
     if (W > a.nRays) W = 1;
     long long grid = a.nTiles;
-    const long long cap = (long long)ctx->smCount * 64;   // persistent-ish: grid-stride beyond this
+    // one tile per block up to a large cap: the hardware block scheduler then balances the uneven ray lengths (a
+    // grid-stride loop over ~7 tiles per block left a ~10 % tail at 128^3)
+    const long long cap = ctx->p.maxBlocksPerSM > 0 ? (long long)ctx->smCount * ctx->p.maxBlocksPerSM : (1LL << 22);
     if (grid > cap) grid = cap;
     if (ML) divq_kernel<Real, RecT, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
     else if (std::is_same<Real, float>::value && (!ctx->p.genericMarch || std::is_same<RecT, Rec4>::value))
