@@ -58,7 +58,7 @@ void hs_trace_1L_fast(const HsLevel* g, int n, const int* cells, const double* d
     const double* d = dirs + 3 * t;
     sumI[t] = march_single_level_fast(static_cast<const Rec8*>(g->rec), idx, nx, nx * ny, (float)d[0], (float)d[1], (float)d[2],
                                       (float)r[0], (float)r[1], (float)r[2], (float)g->dx[0], (float)g->dx[1], (float)g->dx[2],
-                                      (float)threshold, allowReflect != 0, skipZero != 0, s);
+                                      (float)threshold, allowReflect != 0, skipZero != 0, s, 8);
     steps[t] = s;
   }
 }

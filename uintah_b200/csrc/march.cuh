@@ -267,16 +267,17 @@ struct LegOut {
 #if defined(__CUDA_ARCH__)
 // record-type specific pieces: request the record of slot J / decode slot C into a<C> = |abskg|, s<C> (k<C> keeps the raw word
 // whose bit 31 is the wall flag for both layouts)
+// (%20 = record size in a REGISTER: with an immediate ptxas turns the address into two ALU-pipe LEAs; with a register it
+// is one IMAD.WIDE on the FMA pipe, and the ALU pipe is the one that saturates)
 #define RM_LD8(J)  "mad.wide.s32 ad, i" #J ", 8, %13;\n\t" "ld.global.nc.v2.f32 {k" #J ", s" #J "}, [ad];\n\t"
 #define RM_LD4(J)  "mad.wide.s32 ad, i" #J ", 4, %13;\n\t" "ld.global.nc.b32 k" #J ", [ad];\n\t"
 #define RM_DEC8(C) "abs.f32 a" #C ", k" #C ";\n\t"
 #define RM_DEC4(C) "mov.b32 {hl, hh}, k" #C ";\n\t" "cvt.f32.f16 s" #C ", hl;\n\t" "cvt.f32.f16 a" #C ", hh;\n\t" "abs.f32 a" #C ", a" #C ";\n\t"
 #define RM_PEEK(J, IB, LD)                                  \
-  "min.f32 m, %0, %1;\n\t"                                  \
-  "setp.lt.f32 n" #J ", m, %2;\n\t"                         \
+  "min.f32 t" #J ", %0, %1, %2;\n\t"                        \
+  "setp.neu.f32 n" #J ", t" #J ", %2;\n\t"                  \
   "setp.lt.and.f32 x" #J ", %0, %1, n" #J ";\n\t"           \
   "setp.ge.and.f32 y" #J ", %0, %1, n" #J ";\n\t"           \
-  "min.f32 t" #J ", m, %2;\n\t"                             \
   "selp.s32 i" #J ", %17, %19, x" #J ";\n\t"                \
   "@y" #J " mov.s32 i" #J ", %18;\n\t"                      \
   "add.s32 i" #J ", i" #J ", " IB ";\n\t"                   \
@@ -312,7 +313,7 @@ struct LegOut {
   asm volatile(                                                                                                      \
       "{\n\t"                                                                                                        \
       ".reg .pred x0, y0, n0, x1, y1, n1, x2, y2, n2, w;\n\t"                                                        \
-      ".reg .f32 m, d, ta, t0, t1, t2, s0, s1, s2, e0, e1, e2, a0, a1, a2;\n\t"                                      \
+      ".reg .f32 d, ta, t0, t1, t2, s0, s1, s2, e0, e1, e2, a0, a1, a2;\n\t"                                      \
       ".reg .b32 k0, k1, k2;\n\t"                                                                                    \
       ".reg .b16 hl, hh;\n\t"                                                                                        \
       ".reg .s32 i0, i1, i2;\n\t"                                                                                    \
@@ -333,17 +334,17 @@ struct LegOut {
       "}"                                                                                                            \
       : "+f"(d.tx), "+f"(d.ty), "+f"(d.tz), "+r"(d.idx), "+f"(q.A), "+f"(q.k), "+f"(q.s), "+f"(q.ePrev), "+f"(q.leg),  \
         "+f"(q.nsteps), "=f"(o.t), "=r"(o.axis), "=f"(q.tau)                                                         \
-      : "l"(recs), "f"(ddx), "f"(ddy), "f"(ddz), "r"(stx), "r"(sty), "r"(stz)                                        \
+      : "l"(recs), "f"(ddx), "f"(ddy), "f"(ddz), "r"(stx), "r"(sty), "r"(stz), "r"(recBytes)                         \
       : "memory")
 
 __device__ __forceinline__ LegOut march_leg(Dda& d, Integ& q, const Rec8* __restrict__ recs, float ddx, float ddy, float ddz,
-                                            int stx, int sty, int stz) {
+                                            int stx, int sty, int stz, int recBytes) {
   LegOut o;
   RM_ASM(RM_LD8, RM_DEC8);
   return o;
 }
 __device__ __forceinline__ LegOut march_leg(Dda& d, Integ& q, const Rec4* __restrict__ recs, float ddx, float ddy, float ddz,
-                                            int stx, int sty, int stz) {
+                                            int stx, int sty, int stz, int recBytes) {
   LegOut o;
   RM_ASM(RM_LD4, RM_DEC4);
   return o;
@@ -359,7 +360,7 @@ __device__ __forceinline__ LegOut march_leg(Dda& d, Integ& q, const Rec4* __rest
 #undef RM_DEC4
 #else
 __device__ __forceinline__ LegOut march_leg(Dda& d, Integ& q, const Rec8* __restrict__ recs, float ddx, float ddy, float ddz,
-                                            int stx, int sty, int stz) {
+                                            int stx, int sty, int stz, int /*recBytes*/) {
   Peek p1 = dda_peek(d, stx, sty, stz), p2;
   Rec8 r1 = ldrec(recs + p1.idx), r2;
   for (;;) {
@@ -381,7 +382,7 @@ template <class RecT>
 __device__ __forceinline__ float march_single_level_fast(const RecT* __restrict__ recs, int idx0, int sy, int sz,
                                                          float dx, float dy, float dz, float rx, float ry, float rz,
                                                          float cx, float cy, float cz, float threshold, bool allowReflect,
-                                                         bool skipZero, unsigned& nSteps) {
+                                                         bool skipZero, unsigned& nSteps, int recBytes) {
   typedef Num<float> N;
   if (!(1.0f > threshold)) return 0.0f;
   const bool posx = !sign_bit(dx), posy = !sign_bit(dy), posz = !sign_bit(dz);
@@ -402,7 +403,7 @@ __device__ __forceinline__ float march_single_level_fast(const RecT* __restrict_
   float sum = 0.0f, fs = 1.0f;
   for (;;) {
     q.leg = 0.0f;
-    const LegOut w = march_leg(d, q, recs, ddx, ddy, ddz, stx, sty, stz);
+    const LegOut w = march_leg(d, q, recs, ddx, ddy, ddz, stx, sty, stz, recBytes);
     sum = fmaf(q.leg, fs, sum);
     // wall: (q.k, q.s) = record of the non-flow cell entered, q.ePrev = exp(-tau) at its face
     const float eps = q.k > 1.0f ? 1.0f : q.k;                 // 846-850

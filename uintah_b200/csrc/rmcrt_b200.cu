@@ -71,6 +71,7 @@ struct TraceArgs {
   unsigned long long* counters;   // [0] divQ steps [1] flux steps [2] divQ cells [3] flux cells
   const unsigned* lstat;          // per-level device status words [MAXL][LSTAT_WORDS] (see finalize_kernel)
   int firstLevel;                 // levels [firstLevel, maxLevels) take part in this trace
+  int recBytes;                   // sizeof(record); a kernel PARAMETER on purpose (see RM_LD8 in march.cuh)
   // flux items
   const int* items;       // compacted item ids: face * nCells + patch-linear cell
   const int* nItems;      // device count
@@ -226,7 +227,7 @@ __device__ __forceinline__ Real trace_one(const TraceArgs& a, bool skipZero, int
     return UNSCALE * march_single_level_fast(static_cast<const RecT*>(g.rec), (int)level_index(g, i, j, k), g.n[0], g.n[0] * g.n[1],
                                    nz<float, D>(dir[0]), nz<float, D>(dir[1]), nz<float, D>(dir[2]), (float)rayDx[0], (float)rayDx[1],
                                    (float)rayDx[2], (float)g.dx[0], (float)g.dx[1], (float)g.dx[2], (float)a.threshold,
-                                   a.allowReflect != 0, skipZero, steps);
+                                   a.allowReflect != 0, skipZero, steps, a.recBytes);
   } else
   if (ML) {
     return UNSCALE * march_multi_level<Real, RecT, MAXL, RECORD>(a.G, i, j, k, nz<Real, D>(dir[0]), nz<Real, D>(dir[1]), nz<Real, D>(dir[2]),
@@ -903,6 +904,7 @@ int build_args(rmcrt_ctx* ctx, int maxLevels, bool multiLevel, const int32_t pLo
   a.skipZero = ctx->p.skipZeroWeightLegs ? 1 : 0;   // the kernels AND this with the device-side level status
   a.lstat = ctx->d_lstat;
   a.firstLevel = multiLevel ? 0 : F;
+  a.recBytes = (int)ctx->lv[F].recBytes;
   a.fluxFlowGuard = multiLevel ? 0 : 1;
   a.rng.key0 = (uint32_t)ctx->p.seed;
   a.rng.key1 = (uint32_t)(ctx->p.seed >> 32) ^ (uint32_t)(timestep >> 32);
