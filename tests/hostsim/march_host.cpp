@@ -1,5 +1,6 @@
 // Host build of the production march code (uintah_b200/csrc/march.cuh, rng.cuh) for CPU-side logic tests.
 #include "cuda_shim.h"
+#include <vector>
 #include "../../uintah_b200/csrc/march.cuh"
 #include "../../uintah_b200/csrc/rng.cuh"
 using namespace rmcrt;
@@ -93,6 +94,51 @@ void hs_trace_ML(const HsLevel* lv, int maxLevels, const int* roiLo, const int* 
     else
       sumI[t] = march_multi_level<double, Rec16, 4, true>(G, c[0], c[1], c[2], d[0], d[1], d[2], r[0], r[1], r[2], threshold,
                   allowReflect != 0, skipZero != 0, s, path ? &sink : nullptr);
+    steps[t] = s;
+  }
+}
+
+// production 2-level Data-Onion fast path (march_onion2_fast): builds the shell-wrapped ROI copy the way roi_copy_kernel
+// does and marches the same rays as hs_trace_ML kind 0
+void hs_trace_DO2_fast(const HsLevel* lv, const int* roiLo, const int* roiHi, const int* regLo, const int* regHi, int n,
+                       const int* cells, const double* dirs, const double* orgs, double threshold, int allowReflect, int skipZero,
+                       double* sumI, unsigned* steps) {
+  OnionGeom<4> G;
+  std::memset(&G, 0, sizeof G);
+  G.maxLevels = 2;
+  for (int L = 0; L < 2; ++L) {
+    LevelGeom& g = G.lev[L];
+    g.rec = lv[L].rec;
+    for (int d = 0; d < 3; ++d) {
+      g.lo[d] = lv[L].lo[d]; g.n[d] = lv[L].hi[d] - lv[L].lo[d]; g.intLo[d] = lv[L].intLo[d]; g.intHi[d] = lv[L].intHi[d];
+      g.rr[d] = lv[L].rr[d]; g.regLo[d] = regLo[3 * L + d]; g.regHi[d] = regHi[3 * L + d]; g.dx[d] = lv[L].dx[d];
+      g.anchor[d] = lv[L].anchor[d]; g.off[d] = lv[L].anchor[d] - lv[1].anchor[d];
+    }
+  }
+  RoiBox roi;
+  long long cellsB = 1;
+  for (int d = 0; d < 3; ++d) { roi.lo[d] = roiLo[d] - 1; roi.n[d] = roiHi[d] - roiLo[d] + 2; cellsB *= roi.n[d]; }
+  const long long guard = (long long)roi.n[0] * roi.n[1] + roi.n[0] + 1;
+  std::vector<Rec8> buf((size_t)(cellsB + 2 * guard), Rec8{-INFINITY, 0.0f});
+  Rec8* base = buf.data() + guard;
+  const LevelGeom& gf = G.lev[1];
+  const Rec8* fine = static_cast<const Rec8*>(gf.rec);
+  for (int k = roiLo[2]; k < roiHi[2]; ++k)
+    for (int j = roiLo[1]; j < roiHi[1]; ++j)
+      for (int i = roiLo[0]; i < roiHi[0]; ++i) {
+        const long long src = (long long)(i - gf.lo[0]) + (long long)gf.n[0] * ((j - gf.lo[1]) + (long long)gf.n[1] * (k - gf.lo[2]));
+        const long long dst = (long long)(i - roi.lo[0]) + (long long)roi.n[0] * ((j - roi.lo[1]) + (long long)roi.n[1] * (k - roi.lo[2]));
+        base[dst] = fine[src];
+      }
+  roi.rec = base;
+  for (int t = 0; t < n; ++t) {
+    const int* c = cells + 3 * t;
+    double r[3];
+    rayDxOf(lv[1], c, orgs + 3 * t, r);
+    unsigned s = 0;
+    const double* d = dirs + 3 * t;
+    sumI[t] = march_onion2_fast<Rec8, 4>(G, roi, c[0], c[1], c[2], (float)d[0], (float)d[1], (float)d[2], (float)r[0], (float)r[1],
+                                         (float)r[2], (float)threshold, allowReflect != 0, skipZero != 0, s, 8);
     steps[t] = s;
   }
 }

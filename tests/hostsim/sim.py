@@ -84,6 +84,19 @@ def trace_ML(levels, kind, roi, reg, cells, dirs, org, thr, refl, skip=0, max_pa
     return sumI, steps, path
 
 
+def trace_DO2_fast(levels, roi, reg, cells, dirs, org, thr, refl, skip=0):
+    assert len(levels) == 2
+    recs = [pack(l, 0) for l in levels]
+    arr = (HsLevel * 2)(*[hslevel(l, r) for l, r in zip(levels, recs)])
+    n = len(cells)
+    sumI = np.zeros(n); steps = np.zeros(n, np.uint32)
+    cells = np.ascontiguousarray(cells, np.int32); dirs = np.ascontiguousarray(dirs); org = np.ascontiguousarray(org)
+    regLo = np.ascontiguousarray(reg[0], np.int32); regHi = np.ascontiguousarray(reg[1], np.int32)
+    lib().hs_trace_DO2_fast(arr, (C.c_int * 3)(*roi[0]), (C.c_int * 3)(*roi[1]), _vp(regLo), _vp(regHi), n, _vp(cells), _vp(dirs),
+                            _vp(org), C.c_double(thr), refl, skip, _vp(sumI), _vp(steps))
+    return sumI, steps
+
+
 def philox(ctr, key):
     out = (C.c_uint32 * 4)()
     lib().hs_philox((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), out)

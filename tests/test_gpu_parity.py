@@ -386,6 +386,33 @@ def test_data_onion_deterministic(gpu_lib, po):
     np.testing.assert_allclose(divQ2, divQ, rtol=1e-12, atol=0)
 
 
+@pytest.mark.parametrize("case", ["bc", "plates_mirrors"])
+def test_data_onion_fast_path_matches_generic_march(gpu_lib, po, case):
+    """2-level Data Onion: the production path (per-patch ROI copy with a marker shell + the tuned leg loop on both levels)
+    against the generic multi-level march on the same Philox rays."""
+    if case == "bc":
+        fine, thr = po.burns_christon(32, dtype=np.float32), 0.05
+    else:
+        fine, thr = po.parallel_plates(32, dtype=np.float32, mirror_faces=("x-", "y-")), 0.001
+    fine.rr = (4, 4, 4)
+    coarse = po.coarsen_level(fine, (4, 4, 4))
+    res = {}
+    for gm in (0, 1):
+        g = make(gpu_lib, nDivQRays=16, threshold=thr, haloCells=(4, 4, 4), seed=17, genericMarch=gm)
+        g.upload_level(0, coarse)
+        g.upload_level(1, fine)
+        divQ = np.zeros(fine.abskg.shape); vol = np.zeros_like(divQ)
+        for plo, phi in po._split((0, 0, 0), (32, 32, 32), (2, 2, 2)):
+            g.trace_dataonion(2, plo, phi, zero_init=False, outputs=(divQ, vol, None), timestep=4)
+        res[gm] = (divQ, g.counters().nRaySteps)
+    (a, na), (b, nb) = res[0], res[1]
+    assert abs(int(na) - int(nb)) <= 3e-4 * nb, (na, nb)
+    assert np.array_equal(a == 0, b == 0)
+    scale = np.abs(b).max()
+    diff = np.abs(a - b)
+    assert np.percentile(diff, 99.9) <= 2e-4 * scale and diff.max() <= 2e-2 * scale, (np.percentile(diff, 99.9) / scale, diff.max() / scale)
+
+
 def test_data_onion_statistical(gpu_lib, po):
     """C4 in miniature (fine 64^3 / coarse 16^3, RR 4, halo 4, 2x2x2 fine patches), FP32 Philox vs the DO oracle"""
     fine = po.burns_christon(64, dtype=np.float32)

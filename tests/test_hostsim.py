@@ -55,6 +55,8 @@ def test_multi_level(po, case):
         cells, dirs, org = random_rays(fine, 120, rng, plo, phi)
         s64, n64, p64 = sim.trace_ML(levels, 1, (roiLo, roiHi), (regLo, regHi), cells, dirs, org, thr, 1)
         s32, n32, _ = sim.trace_ML(levels, 0, (roiLo, roiHi), (regLo, regHi), cells, dirs, org, thr, 1)
+        sfa, nfa = sim.trace_DO2_fast(levels, (roiLo, roiHi), (regLo, regHi), cells, dirs, org, thr, 1)   # production DO march
+        assert (nfa == n32).mean() >= 0.97
         same32 = 0
         for t in range(len(cells)):
             s, ns, path = po.update_sumI_ML(p, levels, roiLo, roiHi, regLo, regHi, dirs[t], org[t], cells[t], max_path=4000)
@@ -62,6 +64,8 @@ def test_multi_level(po, case):
             assert np.array_equal(path, p64[t, :ns])          # (i,j,k,level) of every cell entered
             assert s == pytest.approx(s64[t], rel=1e-11)
             assert s == pytest.approx(s32[t], rel=1e-3, abs=1e-6 * max(1.0, abs(s)))
+            if nfa[t] == ns:
+                assert s == pytest.approx(sfa[t], rel=1e-3, abs=1e-6 * max(1.0, abs(s)))
             same32 += ns == n32[t]
         assert same32 >= 0.97 * len(cells)
 

@@ -453,6 +453,116 @@ __device__ __forceinline__ int map_to_coarser(int i, int rr) {
   return q;
 }
 
+//------------------------------------------------------------------------------------------------------
+// 2-level Data Onion, production FP32 fast path (same behaviour as march_multi_level<float, RecT, MAXL, false> for
+// maxLevels == 2, i.e. BASELINE config C4 / RMCRT_bm1_DO).
+//
+// The reference copies the fine level's region of interest per patch (getRegion(ROI), Ray.cc:1060-1075).  So do we, on the
+// device, into a compact box with a ONE-CELL SHELL whose records carry the wall flag and abskg = inf.  Inside the ROI the
+// ray then runs the very same PTX leg loop as the single-level solve (no per-step ROI test, no per-step position update);
+// entering the shell ends the leg like a wall does, and the "wall" being infinite identifies it as the ROI exit of
+// Ray.cc:2489-2527: map the cell to the coarse level, re-anchor tMax of the stepping axis exactly as the reference does
+// (SURVEY Q10), switch strides / tDelta to the coarse level and keep marching there with the same leg loop (level 0's
+// region is the whole level, so only walls end it).  The ray position the re-anchoring needs is reconstructed from the
+// crossing time instead of being accumulated every step.
+//------------------------------------------------------------------------------------------------------
+struct RoiBox {
+  const void* rec;   // records of the shell-inclusive box [lo, lo+n), x-fastest
+  int lo[3], n[3];
+};
+
+__device__ __forceinline__ float sel3(int ax, float a, float b, float c) { return ax == 0 ? a : (ax == 1 ? b : c); }
+__device__ __forceinline__ int sel3(int ax, int a, int b, int c) { return ax == 0 ? a : (ax == 1 ? b : c); }
+
+template <class RecT, int MAXL>
+__device__ __forceinline__ float march_onion2_fast(const OnionGeom<MAXL>& G, const RoiBox& roi, int ci, int cj, int ck,
+                                                   float dx, float dy, float dz, float rx, float ry, float rz, float threshold,
+                                                   bool allowReflect, bool skipZero, unsigned& nSteps, int recBytes) {
+  typedef Num<float> N;
+  if (!(1.0f > threshold)) return 0.0f;
+  const LevelGeom& gf = G.lev[1];
+  const LevelGeom& gc = G.lev[0];
+  const float LN2 = 0.6931471805599453f;
+  const bool posx = !sign_bit(dx), posy = !sign_bit(dy), posz = !sign_bit(dz);
+  int sy = roi.n[0], sz = roi.n[0] * roi.n[1];
+  int stx = posx ? 1 : -1, sty = posy ? sy : -sy, stz = posz ? sz : -sz;
+  // sign[] of the reference: 1/0, after a reflection along that axis -1/-0 (RMCRTCommon.cc:599)
+  float sgx = posx ? 1.0f : 0.0f, sgy = posy ? 1.0f : 0.0f, sgz = posz ? 1.0f : 0.0f;
+  const float ix = N::rcp(dx), iy = N::rcp(dy), iz = N::rcp(dz);     // never refreshed on reflection (Ray.cc:2395)
+  const float fx = (float)gf.dx[0], fy = (float)gf.dx[1], fz = (float)gf.dx[2];
+  Dda d;
+  d.tx = (sgx * fx - rx) * ix * N::LEN_SCALE;
+  d.ty = (sgy * fy - ry) * iy * N::LEN_SCALE;
+  d.tz = (sgz * fz - rz) * iz * N::LEN_SCALE;
+  float ddx = fabsf(ix) * fx * N::LEN_SCALE, ddy = fabsf(iy) * fy * N::LEN_SCALE, ddz = fabsf(iz) * fz * N::LEN_SCALE;
+  d.idx = (ci - roi.lo[0]) + sy * (cj - roi.lo[1]) + sz * (ck - roi.lo[2]);
+  const RecT* cur = static_cast<const RecT*>(roi.rec);
+  Integ q;
+  {
+    const Rec8 r = ldrec(cur + d.idx);
+    q.k = fabsf(r.k); q.s = r.s;
+  }
+  q.A = 0.0f; q.ePrev = 1.0f; q.nsteps = 0.0f; q.tau = 0.0f;
+  // position along each axis relative to the origin cell's low corner: l(t) = lb + (t - tb) ln2 * dir   (t is scaled by log2 e)
+  float lbx = rx, lby = ry, lbz = rz, tbx = 0.0f, tby = 0.0f, tbz = 0.0f, dvx = dx, dvy = dy, dvz = dz;
+  bool onFine = true;
+  float sum = 0.0f, fs = 1.0f;
+  for (;;) {
+    q.leg = 0.0f;
+    const LegOut w = march_leg(d, q, cur, ddx, ddy, ddz, stx, sty, stz, recBytes);
+    sum = fmaf(q.leg, fs, sum);
+    const int ax = w.axis;
+    if (onFine && q.k > 3.0e38f) {                   // stepped into the shell: leave the ROI (Ray.cc:2489-2527)
+      int b = d.idx;
+      const int bk = b / sz; b -= bk * sz;
+      const int bj = b / sy;
+      const int bi = b - bj * sy;
+      const int c0 = roi.lo[0] + bi, c1 = roi.lo[1] + bj, c2 = roi.lo[2] + bk;     // fine cell just entered
+      // re-anchor tMax of the stepping axis from the ray position and the centre of that fine cell (Ray.cc:2486,2534-2550)
+      const float fA = sel3(ax, fx, fy, fz);
+      const float ccRel = fA * ((float)sel3(ax, c0, c1, c2) + 0.5f) - fA * (float)sel3(ax, ci, cj, ck);
+      const float lA = fmaf((w.t - sel3(ax, tbx, tby, tbz)) * LN2, sel3(ax, dvx, dvy, dvz), sel3(ax, lbx, lby, lbz));
+      const float cdx = (float)sel3(ax, (float)gc.dx[0], (float)gc.dx[1], (float)gc.dx[2]);
+      const float rayDxLevel = lA - (ccRel - 0.5f * cdx);
+      const float tTmp = (sel3(ax, sgx, sgy, sgz) * cdx - rayDxLevel) * sel3(ax, ix, iy, iz) * N::LEN_SCALE;
+      if (ax == 0) d.tx = w.t + tTmp; else if (ax == 1) d.ty = w.t + tTmp; else d.tz = w.t + tTmp;
+      // coarse cell, strides and tDelta of level 0
+      const int k0 = min(max(map_to_coarser(c0, gf.rr[0]) - gc.lo[0], 0), gc.n[0] - 1);
+      const int k1 = min(max(map_to_coarser(c1, gf.rr[1]) - gc.lo[1], 0), gc.n[1] - 1);
+      const int k2 = min(max(map_to_coarser(c2, gf.rr[2]) - gc.lo[2], 0), gc.n[2] - 1);
+      sy = gc.n[0]; sz = gc.n[0] * gc.n[1];
+      stx = stx > 0 ? 1 : -1; sty = sty > 0 ? sy : -sy; stz = stz > 0 ? sz : -sz;
+      ddx = fabsf(ix) * (float)gc.dx[0] * N::LEN_SCALE; ddy = fabsf(iy) * (float)gc.dx[1] * N::LEN_SCALE;
+      ddz = fabsf(iz) * (float)gc.dx[2] * N::LEN_SCALE;
+      d.idx = k0 + sy * k1 + sz * k2;
+      cur = static_cast<const RecT*>(gc.rec);
+      onFine = false;
+      const Rec8 r = ldrec(cur + d.idx);
+      q.k = fabsf(r.k); q.s = r.s;
+      q.A = fmaf(-q.k, w.t, q.tau);
+      if (!is_wall(r.k)) continue;                   // keep marching on the coarse level
+    }
+    // wall (fine or coarse): (q.k, q.s) = record of the non-flow cell entered
+    const float eps = q.k > 1.0f ? 1.0f : q.k;                 // Ray.cc:2594-2598
+    sum = fmaf(eps * q.s, q.ePrev, sum);                       // 2602: NOT multiplied by fs
+    const float intensity = q.ePrev * fs;
+    if (!allowReflect || !(intensity > threshold)) break;      // 2607-2609, 2621
+    fs *= (1.0f - q.k);
+    if (skipZero && fs == 0.0f) break;
+    // reflect (RMCRTCommon.cc:581-602): previous cell on the CURRENT level, flip the stepping axis
+    d.idx -= sel3(ax, stx, sty, stz);
+    const float lHit = fmaf((w.t - sel3(ax, tbx, tby, tbz)) * LN2, sel3(ax, dvx, dvy, dvz), sel3(ax, lbx, lby, lbz));
+    if (ax == 0) { stx = -stx; sgx = -sgx; dvx = -dvx; lbx = lHit; tbx = w.t; }
+    else if (ax == 1) { sty = -sty; sgy = -sgy; dvy = -dvy; lby = lHit; tby = w.t; }
+    else { stz = -stz; sgz = -sgz; dvz = -dvz; lbz = lHit; tbz = w.t; }
+    const Rec8 r = ldrec(cur + d.idx);
+    q.k = fabsf(r.k); q.s = r.s;
+    q.A = fmaf(-q.k, w.t, q.tau);
+  }
+  nSteps += (unsigned)q.nsteps;
+  return sum;
+}
+
 template <class Real, class RecT, int MAXL, bool RECORD>
 __device__ __forceinline__ Real march_multi_level(const OnionGeom<MAXL>& G, int ci, int cj, int ck,
                                                   Real dx, Real dy, Real dz, Real rx, Real ry, Real rz,

@@ -71,7 +71,8 @@ struct TraceArgs {
   unsigned long long* counters;   // [0] divQ steps [1] flux steps [2] divQ cells [3] flux cells
   const unsigned* lstat;          // per-level device status words [MAXL][LSTAT_WORDS] (see finalize_kernel)
   int firstLevel;                 // levels [firstLevel, maxLevels) take part in this trace
-  int recBytes;                   // sizeof(record); a kernel PARAMETER on purpose (see RM_LD8 in march.cuh)
+  int recBytes;                   // sizeof(record)
+  RoiBox roi;                     // Data-Onion fast path: shell-wrapped copy of the fine level's ROI (rec == nullptr: generic march)
   // flux items
   const int* items;       // compacted item ids: face * nCells + patch-linear cell
   const int* nItems;      // device count
@@ -228,6 +229,14 @@ __device__ __forceinline__ Real trace_one(const TraceArgs& a, bool skipZero, int
                                    nz<float, D>(dir[0]), nz<float, D>(dir[1]), nz<float, D>(dir[2]), (float)rayDx[0], (float)rayDx[1],
                                    (float)rayDx[2], (float)g.dx[0], (float)g.dx[1], (float)g.dx[2], (float)a.threshold,
                                    a.allowReflect != 0, skipZero, steps, a.recBytes);
+  } else if constexpr (FAST && ML && !RECORD && std::is_same<Real, float>::value) {
+    if (a.roi.rec)   // 2-level Data Onion on the per-patch ROI copy
+      return UNSCALE * march_onion2_fast<RecT, MAXL>(a.G, a.roi, i, j, k, nz<float, D>(dir[0]), nz<float, D>(dir[1]), nz<float, D>(dir[2]),
+                                                     (float)rayDx[0], (float)rayDx[1], (float)rayDx[2], (float)a.threshold,
+                                                     a.allowReflect != 0, skipZero, steps, a.recBytes);
+    return UNSCALE * march_multi_level<Real, RecT, MAXL, RECORD>(a.G, i, j, k, nz<Real, D>(dir[0]), nz<Real, D>(dir[1]), nz<Real, D>(dir[2]),
+                                                       (Real)rayDx[0], (Real)rayDx[1], (Real)rayDx[2], (Real)a.threshold,
+                                                       a.allowReflect != 0, skipZero, steps, path);
   } else
   if (ML) {
     return UNSCALE * march_multi_level<Real, RecT, MAXL, RECORD>(a.G, i, j, k, nz<Real, D>(dir[0]), nz<Real, D>(dir[1]), nz<Real, D>(dir[2]),
@@ -257,7 +266,7 @@ template <class Real, class RecT, bool ML, bool FAST = false>
 #ifndef RMCRT_FAST_MIN_BLOCKS
 #define RMCRT_FAST_MIN_BLOCKS 8
 #endif
-__global__ void __launch_bounds__(256, (FAST ? RMCRT_FAST_MIN_BLOCKS : 4)) divq_kernel(const __grid_constant__ TraceArgs a) {
+__global__ void __launch_bounds__(256, ((FAST && !ML) ? RMCRT_FAST_MIN_BLOCKS : 4)) divq_kernel(const __grid_constant__ TraceArgs a) {
   extern __shared__ double red[];     // [W][32]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
   const int F = a.G.maxLevels - 1;
@@ -629,6 +638,30 @@ __global__ void assemble_kernel(const unsigned char* __restrict__ gathered, size
 }
 
 
+// Data-Onion fast path: copy of the fine level over [roiLo, roiHi) wrapped in a one-cell shell (and the guard records
+// around the box) of marker records {wall flag, abskg = inf}; replaces the reference's per-patch getRegion(ROI) (Ray.cc:1060-1075)
+template <class RecT>
+__global__ void roi_copy_kernel(const RecT* __restrict__ fine, Box fb, RecT* __restrict__ dst /* incl. guards */, long long guard,
+                                Box shellBox, Box roiBox) {
+  const long long nBox = box_cells(shellBox), n = nBox + 2 * guard;
+  const RecT marker = make_rec<RecT, float>(-INFINITY, 0.0f);
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const long long u = t - guard;
+    RecT v = marker;
+    if (u >= 0 && u < nBox) {
+      const long long row = u / shellBox.n[0];
+      const int i = shellBox.lo[0] + (int)(u - row * shellBox.n[0]);
+      const int kk = (int)(row / shellBox.n[1]);
+      const int j = shellBox.lo[1] + (int)(row - (long long)kk * shellBox.n[1]);
+      const int k = shellBox.lo[2] + kk;
+      const bool in = i >= roiBox.lo[0] && i < roiBox.lo[0] + roiBox.n[0] && j >= roiBox.lo[1] && j < roiBox.lo[1] + roiBox.n[1] &&
+                      k >= roiBox.lo[2] && k < roiBox.lo[2] + roiBox.n[2];
+      if (in) v = fine[(long long)(i - fb.lo[0]) + (long long)fb.n[0] * ((long long)(j - fb.lo[1]) + (long long)fb.n[1] * (long long)(k - fb.lo[2]))];
+    }
+    dst[t] = v;
+  }
+}
+
 // ---- roofline denominators ----
 __global__ void bw_stream_kernel(const uint4* __restrict__ buf, long long n16, int inner, unsigned* sink) {
   unsigned acc = 0;
@@ -700,7 +733,7 @@ struct rmcrt_ctx {
   int* d_nItems = nullptr;
   DevBuf stage[3];      // upload staging
   DevBuf outDivQ, outVolq, outFlux;   // host-API output staging
-  DevBuf fluxFlags, fluxItems, cubTemp, dbg[6], misc;
+  DevBuf fluxFlags, fluxItems, cubTemp, dbg[6], misc, roiBuf;
   std::string err;
   void* persistedStreamFor = nullptr;
 };
@@ -952,7 +985,26 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
     // grid-stride loop over ~7 tiles per block left a ~10 % tail at 128^3)
     const long long cap = ctx->p.maxBlocksPerSM > 0 ? (long long)ctx->smCount * ctx->p.maxBlocksPerSM : (1LL << 22);
     if (grid > cap) grid = cap;
-    if (ML) divq_kernel<Real, RecT, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
+    if (ML && std::is_same<Real, float>::value && !ctx->p.genericMarch && a.G.maxLevels == 2) {
+      // 2-level Data Onion fast path: per-patch ROI copy with a marker shell, then the tuned leg loop on both levels
+      const LevelState& fl = ctx->lv[1];
+      Box roiBox, shell;
+      long long cellsB = 1;
+      for (int d = 0; d < 3; ++d) {
+        roiBox.lo[d] = a.G.roiLo[d]; roiBox.n[d] = a.G.roiHi[d] - a.G.roiLo[d];
+        shell.lo[d] = roiBox.lo[d] - 1; shell.n[d] = roiBox.n[d] + 2;
+        cellsB *= shell.n[d];
+      }
+      const long long guard = (long long)shell.n[0] * shell.n[1] + shell.n[0] + 1;
+      if (cellsB + 2 * guard >= (1LL << 31)) return fail(ctx, RMCRT_ERR_INVALID, "ROI too large");
+      if (ctx->roiBuf.ensure((size_t)(cellsB + 2 * guard) * sizeof(RecT))) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc ROI buffer");
+      roi_copy_kernel<RecT><<<grid_for(cellsB + 2 * guard, 256, ctx->smCount), 256, 0, st>>>(
+          static_cast<const RecT*>(fl.rec), mkbox(fl.d.lo, fl.d.hi), static_cast<RecT*>(ctx->roiBuf.p), guard, shell, roiBox);
+      CK(cudaGetLastError());
+      a.roi.rec = static_cast<RecT*>(ctx->roiBuf.p) + guard;
+      for (int d = 0; d < 3; ++d) { a.roi.lo[d] = shell.lo[d]; a.roi.n[d] = shell.n[d]; }
+      divq_kernel<Real, RecT, true, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
+    } else if (ML) divq_kernel<Real, RecT, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
     else if (std::is_same<Real, float>::value && (!ctx->p.genericMarch || std::is_same<RecT, Rec4>::value))
       divq_kernel<Real, RecT, false, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
     else    divq_kernel<Real, RecT, false><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
@@ -1096,7 +1148,7 @@ void rmcrt_destroy(rmcrt_ctx* ctx) {
   if (ctx->d_nItems) cudaFree(ctx->d_nItems);
   for (auto& b : ctx->stage) b.release();
   ctx->outDivQ.release(); ctx->outVolq.release(); ctx->outFlux.release();
-  ctx->fluxFlags.release(); ctx->fluxItems.release(); ctx->cubTemp.release(); ctx->misc.release();
+  ctx->fluxFlags.release(); ctx->fluxItems.release(); ctx->cubTemp.release(); ctx->misc.release(); ctx->roiBuf.release();
   for (auto& b : ctx->dbg) b.release();
   delete ctx;
 }
