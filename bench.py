@@ -49,6 +49,17 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+def profiled_traffic(n, rays, rec_bytes):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one divq_kernel launch, from the committed ncu --set full capture of
+    the same workload (profiles/traffic.json names the report it was read from); None when this workload was not profiled"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        e = t.get(f"divq_{n}cubed_{rays}rays_rec{rec_bytes}")
+        return (float(e["dram_bytes_per_launch"]), e["source"]) if e else (None, None)
+    except Exception:
+        return None, None
+
+
 # --------------------------------------------------------------------------------------------------- synthetic fields
 def burns_christon_fields(shape_cells, lo, hi, dtype=np.float32):
     """Burns & Christon benchmark field (RMCRT_Test.cc:676-679 generalised to a box of `shape_cells` cells with
@@ -165,8 +176,7 @@ def run_reference(args):
         "divq_cells_per_s": cells * len(times) / total,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"Burns-Christon single level {shape[0]}x{shape[1]}x{shape[2]}, {rays} rays/cell, float properties "
-                               f"(BASELINE configs[{1 if world == 1 else 2}])",
+        "config": {"workload": workload_name(n, shape, rays, world),
                    "sample_per_step": sample, "semantics": "reference (allowReflect default true: zero-weight legs marched)"},
         "cpu_baseline": {"value": value, "unit": "ray-cell steps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "ray-cell steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -180,6 +190,14 @@ def run_reference(args):
 def patch_grid(n_gpus):
     from uintah_b200.partition import patch_grid as pg
     return pg(n_gpus)
+
+
+def workload_name(P, shape, rays, world):
+    """same string in both arms (the driver compares the arms on `config.workload`)"""
+    if world == 1:
+        return f"Burns-Christon single level {P}^3, {rays} rays/cell, float properties, 1 B200 (BASELINE configs[1])"
+    return (f"Burns-Christon single level {shape[0]}x{shape[1]}x{shape[2]}, {rays} rays/cell, one {P}^3 patch per GPU, "
+            f"packed-record all-gather per solve (BASELINE configs[2] at 8 GPUs)")
 
 
 def run_ours(args):
@@ -372,8 +390,9 @@ def run_ours(args):
     alg_bytes = ALG_BYTES_PER_STEP * per_rank_steps + ALG_BYTES_PER_CELL * per_rank_cells
     kern_s = (t_trace_total / args.steps)
     achieved = alg_bytes / kern_s / 1e9
+    traffic, traffic_src = profiled_traffic(P, rays, rec_bytes) if world == 1 else (None, None)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": None, "kernel": "divq_kernel<float,Rec8,false>", "kernel_ms": 1e3 * kern_s,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": "divq_kernel<float,Rec8,false>", "kernel_ms": 1e3 * kern_s,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "note": "12 B per executed ray-cell step + 28 B per divQ cell; the property records are L2-resident, so the "
                         "binding roofline is L2 (see roofline_l2), HBM peak shown because MEASURED_PEAKS.json has no L2 figure"}
@@ -407,10 +426,7 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step_total / args.steps,
         "trace_ms_per_step": 1e3 * t_trace_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": (f"Burns-Christon single level {P}^3, {rays} rays/cell, float properties, 1 B200 (BASELINE configs[1])"
-                                if world == 1 else
-                                f"Burns-Christon single level {shape[0]}x{shape[1]}x{shape[2]}, {rays} rays/cell, one {P}^3 patch per GPU, "
-                                f"packed-record all-gather per solve (BASELINE configs[2] at 8 GPUs)"),
+        "config": {"workload": workload_name(P, shape, rays, world),
                    "executed_steps_per_ray": all_steps / (all_cells * rays),
                    "zero_weight_legs": "marched (reference semantics)" if not skip else "skipped (exact: cold black walls, fs==0)",
                    "ray_coherence": {0: "independent per cell", 1: "warp-shared direction", 2: "warp-shared direction and in-cell offset"}[args.coherence],
@@ -430,7 +446,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=128, help="cells per side of the per-GPU patch")
