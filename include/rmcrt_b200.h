@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RMCRT_ABI_VERSION 1
+#define RMCRT_ABI_VERSION 2
 #define RMCRT_MAX_LEVELS 8
 
 typedef struct rmcrt_ctx rmcrt_ctx;
@@ -78,8 +78,21 @@ typedef struct rmcrt_params {
                                   single-level fast path (A/B measurements, debugging); results agree to FP32 round-off */
   int32_t  maxBlocksPerSM;     /* 0 = one tile per block (hardware balances the tail); > 0 caps the divQ grid at this many
                                   blocks per SM and grid-strides over the tiles (A/B measurements) */
-  int32_t  reserved[2];
+  int32_t  rayDirSampleAlgo;   /* <rayDirSampleAlgo> 0 naive (default), 1 LatinHyperCube (Ray.cc:174-179, 1398-1460) */
+  int32_t  reserved;
+  double   maxRayLength;       /* <ROI_extents type="boundedRayLength"><length> (Ray.cc:243, RMCRTCommon.cc:680,684);
+                                  <= 0 or >= 1e300: unbounded (DBL_MAX, RMCRTCommon.cc:117).  Single-level solves only, like
+                                  the reference (updateSumI_ML has no length test) */
 } rmcrt_params;
+
+/* One <Radiometer> block after Radiometer::problemSetup (Radiometer.cc:96-271; struct radiometer, Radiometer.h:117-127) */
+typedef struct rmcrt_radiometer {
+  int32_t cellLo[3], cellHi[3];   /* level->getCellIndex(locationsMin / locationsMax) (Radiometer.cc:448-449) */
+  int32_t nRays;                  /* <nRays> */
+  int32_t pad;
+  double  solidAngle, theta_viewAngle, range;    /* Radiometer.cc:258-260 */
+  double  phi_rotate, theta_rotate, xi_rotate;   /* Radiometer.cc:238-254 */
+} rmcrt_radiometer;
 
 /* geometry of one level (Level.cc:473-477, 1285-1307) */
 typedef struct rmcrt_level_desc {
@@ -95,12 +108,13 @@ typedef struct rmcrt_counters {
   uint64_t nFluxRaySteps;    /* executed boundary-flux steps  (Ray.cc:1262)               */
   uint64_t nDivQCells;       /* flow cells that received a divQ                           */
   uint64_t nFluxCells;       /* cells with boundFlux.p == 1                               */
+  uint64_t nRadiometerSteps; /* executed virtual-radiometer ray-cell steps                */
 } rmcrt_counters;
 
 /* ------------------------------------------------------------------ life cycle */
 int  rmcrt_abi_version(void);
-/* sizeof of the ABI structs as compiled (0 rmcrt_params, 1 rmcrt_level_desc, 2 rmcrt_counters): lets a foreign-language
- * binding verify its struct layout at load time */
+/* sizeof of the ABI structs as compiled (0 rmcrt_params, 1 rmcrt_level_desc, 2 rmcrt_counters, 3 rmcrt_radiometer): lets a
+ * foreign-language binding verify its struct layout at load time */
 size_t rmcrt_struct_size(int which);
 void rmcrt_default_params(rmcrt_params* p);
 /* replaces the per-process Ray instance state; device = CUDA ordinal (patch->GPU map of
@@ -167,6 +181,28 @@ int rmcrt_trace_dataonion(rmcrt_ctx* ctx, int maxLevels, const int32_t patchLo[3
                           double* divQ, double* radiationVolq, double* boundFlux,
                           const int32_t outLo[3], const int32_t outHi[3],
                           int zeroInit, uint64_t timestep, void* stream);
+
+/* ------------------------------------------------------------------ virtual radiometer
+ * Radiometer::problemSetup's angle derivation (Radiometer.cc:118-120, 214-260): viewAngle in degrees, vec = <unitNormalVector>
+ * (isNormalVector 0) or <normalVector> (1: normalised first).  Fills the six angle members of *r; cell box and nRays are the
+ * caller's.  Returns RMCRT_ERR_INVALID for viewAngle > 360 (Radiometer.cc:203-207). */
+int rmcrt_radiometer_setup(double viewAngle, const double vec[3], int isNormalVector, rmcrt_radiometer* r);
+/* Body of Radiometer::radiometerFlux<T> for one patch (Radiometer.cc:428-500; ray directions rayDirection_VR 505-560):
+ * for every cell of (radiometer box n patch) nRays cell-centred rays inside the view cone,
+ *   VRFlux = (T)sumProjI * solidAngle / nRays,  VRIntensity = (T)sumProjI / nRays   (Radiometer.cc:492-493).
+ * VRFlux / VRIntensity are arrays of T (isFloat) x-fastest over [outLo,outHi); cells outside the radiometer boxes are left
+ * untouched (modifiesFlux) or zeroed first (zeroInit, Radiometer.cc:443-446).  Single level L. */
+int rmcrt_trace_radiometer_device(rmcrt_ctx* ctx, int L, const rmcrt_radiometer* rads, int nRads,
+                                  const int32_t patchLo[3], const int32_t patchHi[3],
+                                  void* d_VRFlux, void* d_VRIntensity, int isFloat,
+                                  const int32_t outLo[3], const int32_t outHi[3],
+                                  int zeroInit, uint64_t timestep, void* stream);
+/* same with host output buffers (blocking) */
+int rmcrt_trace_radiometer(rmcrt_ctx* ctx, int L, const rmcrt_radiometer* rads, int nRads,
+                           const int32_t patchLo[3], const int32_t patchHi[3],
+                           void* VRFlux, void* VRIntensity, int isFloat,
+                           const int32_t outLo[3], const int32_t outHi[3],
+                           int zeroInit, uint64_t timestep, void* stream);
 
 /* Ray::computeExtents (patch_based) on the host, exported so callers/tests see the same boxes. */
 int rmcrt_compute_extents(rmcrt_ctx* ctx, int maxLevels, const int32_t patchLo[3], const int32_t patchHi[3],

@@ -31,7 +31,14 @@ class Params(C.Structure):
     _fields_ = [("nDivQRays", C.c_int), ("nFluxRays", C.c_int), ("threshold", C.c_double),
                 ("allowReflect", C.c_int), ("CCRays", C.c_int), ("isSeedRandom", C.c_int),
                 ("solveDivQ", C.c_int), ("solveBoundaryFlux", C.c_int), ("fixedRandom", C.c_int),
-                ("flowCell", C.c_int), ("dataOnionFluxFlowGuard", C.c_int)]
+                ("flowCell", C.c_int), ("dataOnionFluxFlowGuard", C.c_int), ("rayDirSampleAlgo", C.c_int),
+                ("maxRayLength", C.c_double)]
+
+
+class CRadiometer(C.Structure):
+    _fields_ = [("cellLo", C.c_int * 3), ("cellHi", C.c_int * 3), ("nRays", C.c_int), ("solidAngle", C.c_double),
+                ("theta_viewAngle", C.c_double), ("range", C.c_double), ("phi_rotate", C.c_double),
+                ("theta_rotate", C.c_double), ("xi_rotate", C.c_double)]
 
 
 class CLevel(C.Structure):
@@ -213,6 +220,36 @@ def update_sumI_ML(p: Params, levels, roi_lo, roi_hi, region_lo, region_hi, dire
                                C.byref(sumI), C.byref(n), path.ctypes.data_as(C.c_void_p) if max_path else None,
                                max_path, C.byref(npath))
     return sumI.value, n.value, path[:min(npath.value, max_path)]
+
+
+# ---------------------------------------------------------------- radiometer / LHC
+def radiometer(view_angle, vec, cell_lo, cell_hi, n_rays, is_normal_vector=False) -> CRadiometer:
+    """one <Radiometer> block: angles per Radiometer::problemSetup, cell box = getCellIndex(locationsMin/Max)"""
+    r = CRadiometer()
+    lib().oracle_radiometer_setup(C.c_double(view_angle), _d3(vec), 1 if is_normal_vector else 0, C.byref(r))
+    r.cellLo = _i3(cell_lo); r.cellHi = _i3(cell_hi); r.nRays = int(n_rays)
+    return r
+
+
+def radiometer_flux(p: Params, lv: Level, rads, patch_lo=None, patch_hi=None, seed=1):
+    """Radiometer::radiometerFlux over one patch; returns (VRFlux, VRIntensity, steps) over the level window, dtype of lv"""
+    patch_lo = lv.interior_lo if patch_lo is None else tuple(patch_lo)
+    patch_hi = lv.interior_hi if patch_hi is None else tuple(patch_hi)
+    flux = np.zeros(lv.abskg.shape, lv.abskg.dtype)
+    inten = np.zeros(lv.abskg.shape, lv.abskg.dtype)
+    arr = (CRadiometer * len(rads))(*rads)
+    cl = lv.c()
+    n = C.c_uint64(0)
+    lib().oracle_radiometerFlux(C.byref(p), C.byref(cl), arr, len(rads), _i3(patch_lo), _i3(patch_hi), C.c_uint32(seed),
+                                flux.ctypes.data_as(C.c_void_p), inten.ctypes.data_as(C.c_void_p), _i3(lv.lo), _i3(lv.hi),
+                                C.byref(n))
+    return flux, inten, n.value
+
+
+def rand_vector(p: Params, cell, n, seed=1):
+    out = np.zeros(n, np.int32)
+    lib().oracle_randVector(C.byref(p), C.c_uint32(seed), _i3(cell), n, out.ctypes.data_as(C.c_void_p))
+    return out
 
 
 # ---------------------------------------------------------------- patch solves

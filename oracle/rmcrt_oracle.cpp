@@ -41,6 +41,15 @@ class MT {
     y ^= (y << 15) & 0xefc60000u;
     return y ^ (y >> 18);
   }
+  // integer in [0,n]  (MersenneTwister.h:233-250)
+  uint32_t randInt(uint32_t n) {
+    uint32_t used = n;
+    used |= used >> 1; used |= used >> 2; used |= used >> 4; used |= used >> 8; used |= used >> 16;
+    uint32_t i;
+    do i = u32() & used; while (i > n);
+    return i;
+  }
+  bool fixed() const { return fixed_; }
   // real in [0,1]
   double rand() { return fixed_ ? 0.3 : double(u32()) * (1.0 / 4294967295.0); }
   // real in (0,1)
@@ -150,7 +159,7 @@ struct PathRec {
 const double FUZZ = 1e-12;  // RMCRT/RMCRTCommon.cc:49
 
 //----------------------------------------------------------------------------------------
-// RMCRTCommon::updateSumI<T>  (RMCRT/RMCRTCommon.cc:607-904), no RAY_SCATTER, maxRayLength = DBL_MAX
+// RMCRTCommon::updateSumI<T>  (RMCRT/RMCRTCommon.cc:607-904), no RAY_SCATTER
 //----------------------------------------------------------------------------------------
 template <class T>
 void updateSumI(const oracle_params& P, const LevelT<T>& lv, double dir[3], const double rayOrigin[3],
@@ -174,10 +183,11 @@ void updateSumI(const oracle_params& P, const LevelT<T>& lv, double dir[3], cons
   bool inDomain = true;
   double tMaxPrev = 0, intensity = 1.0, fs = 1.0;
   double tau = 0, expPrev = 1.0;
+  double rayLength = 0.0;            // 666
 
-  while (intensity > P.threshold) {  // 683
+  while (intensity > P.threshold && rayLength < P.maxRayLength) {  // 680
     int ax = -9;
-    while (inDomain) {  // 687
+    while (inDomain && rayLength < P.maxRayLength) {  // 684
       prev[0] = cur[0]; prev[1] = cur[1]; prev[2] = cur[2];
       const T kPrev = lv.abskg(prev);      // 690
       const T sPrev = lv.sigmaT4(prev);    // 691
@@ -187,6 +197,7 @@ void updateSumI(const oracle_params& P, const LevelT<T>& lv, double dir[3], cons
       tMaxPrev = tMax[ax];
       tMax[ax] += tDelta[ax];
       if (ds > -FUZZ && ds < FUZZ) ds += FUZZ;  // 717-720
+      rayLength += ds;                     // 723
       inDomain = (lv.cellType(cur) == P.flowCell);   // 729
       tau += kPrev * ds;                   // 731
       ++nSteps;                            // 733
@@ -330,6 +341,29 @@ inline void findRayDirection(MT& mt, const oracle_params& P, const int origin[3]
   dir[2] = pm1;
 }
 
+// RMCRTCommon::randVector (RMCRTCommon.cc:998-1024): modern Fisher-Yates with randInt(i); FIXED_RANDOM_NUM: 0.3*i
+inline void randVector(std::vector<int>& a, MT& mt, const oracle_params& P, const int cell[3]) {
+  const int max = (int)a.size();
+  for (int i = 0; i < max; ++i) a[i] = i;
+  if (!P.isSeedRandom) mt.seed((uint32_t)(cell[0] + cell[1] + cell[2]));   // 1011-1013
+  for (int i = max - 1; i > 0; --i) {
+    const int r = mt.fixed() ? (int)(0.3 * i) : (int)mt.randInt((uint32_t)i);
+    std::swap(a[i], a[r]);
+  }
+}
+
+// Ray::findRayDirectionHyperCube (Ray.cc:1438-1460)
+inline void findRayDirectionHyperCube(MT& mt, const oracle_params& P, const int origin[3], int iRay, int bin_i, int bin_j,
+                                      double dir[3]) {
+  if (!P.isSeedRandom) mt.seed((uint32_t)((origin[0] + origin[1] + origin[2]) * iRay + 1));
+  const double pm1 = 2.0 * (mt.randDblExc() + (double)bin_i) / P.nDivQRays - 1.0;
+  const double r = std::sqrt(1.0 - pm1 * pm1);
+  const double phi = 2.0 * M_PI * (mt.randDblExc() + (double)bin_j) / P.nDivQRays;
+  dir[0] = r * std::cos(phi);
+  dir[1] = r * std::sin(phi);
+  dir[2] = pm1;
+}
+
 // RMCRTCommon::ray_Origin (RMCRTCommon.cc:544-576); draws in x,y,z order
 inline void rayOriginInCell(MT& mt, const double cc[3], const double dx[3], bool ccRays, double o[3]) {
   if (!ccRays) {
@@ -375,6 +409,18 @@ inline void rayDirectionCellFace(MT& mt, const oracle_params& P, const int origi
   for (int d = 0; d < 3; ++d) dir[d] = tmp[kDirIndexOrder[face][d]] * kDirSignSwap[face][d];
 }
 
+// Ray::rayDirectionHyperCube_cellFace (Ray.cc:1398-1432)
+inline void rayDirectionHyperCubeCellFace(MT& mt, const oracle_params& P, const int origin[3], int face, int iRay,
+                                          double dir[3], double& cosTheta, int bin_i, int bin_j) {
+  if (!P.isSeedRandom) mt.seed((uint32_t)((origin[0] + origin[1] + origin[2]) * iRay + 1));
+  cosTheta = (mt.randDblExc() + (double)bin_i) / P.nFluxRays;
+  const double theta = std::acos(cosTheta);
+  const double phi = 2.0 * M_PI * (mt.randDblExc() + (double)bin_j) / P.nFluxRays;
+  cosTheta = std::cos(theta);
+  double tmp[3] = {std::sin(theta) * std::cos(phi), std::sin(theta) * std::sin(phi), cosTheta};
+  for (int d = 0; d < 3; ++d) dir[d] = tmp[kDirIndexOrder[face][d]] * kDirSignSwap[face][d];
+}
+
 // Ray::rayLocation_cellFace (Ray.cc:1465-1513)
 inline void rayLocationCellFace(MT& mt, int face, const double dx[3], const double cc[3], double o[3]) {
   const double c0[3] = {cc[0] - 0.5 * dx[0], cc[1] - 0.5 * dx[1], cc[2] - 0.5 * dx[2]};
@@ -402,7 +448,9 @@ void rayTracePatch(const oracle_params& P, const LevelT<T>& lv, const int pLo[3]
   MT mt(P.fixedRandom != 0);
   mt.seed(mtSeed);  // stands in for MTRand() = seed(hash(time,clock)), Ray.cc:539
 
+  const bool lhc = P.rayDirSampleAlgo == 1;
   if (P.solveBoundaryFlux) {  // 645-730
+    std::vector<int> rand_i(lhc ? P.nFluxRays : 0);     // 649
     for (int k = pLo[2]; k < pHi[2]; ++k) for (int j = pLo[1]; j < pHi[1]; ++j) for (int i = pLo[0]; i < pHi[0]; ++i) {
       const int origin[3] = {i, j, k};
       if (lv.cellType(origin) != P.flowCell) continue;  // 654-656
@@ -415,9 +463,11 @@ void rayTracePatch(const oracle_params& P, const LevelT<T>& lv, const int pLo[3]
       for (int f = 0; f < nf; ++f) {
         const int rayFace = faces[f];
         double sumI = 0, sumProjI = 0, sumIprev = 0, sumCos = 0;
+        if (lhc) randVector(rand_i, mt, P, origin);      // 679-681
         for (int iRay = 0; iRay < P.nFluxRays; ++iRay) {
           double dir[3], o[3], cosT;
-          rayDirectionCellFace(mt, P, origin, rayFace, iRay, dir, cosT);
+          if (lhc) rayDirectionHyperCubeCellFace(mt, P, origin, rayFace, iRay, dir, cosT, rand_i[iRay], iRay);   // 692-695
+          else rayDirectionCellFace(mt, P, origin, rayFace, iRay, dir, cosT);
           rayLocationCellFace(mt, rayFace, lv.dx, cc, o);
           updateSumI<T>(P, lv, dir, o, origin, nFluxSteps, sumI, nullptr);
           sumProjI += cosT * (sumI - sumIprev);  // 704
@@ -431,20 +481,82 @@ void rayTracePatch(const oracle_params& P, const LevelT<T>& lv, const int pLo[3]
   }
 
   if (P.solveDivQ) {  // 742-788
+    std::vector<int> rand_i(lhc ? P.nDivQRays : 0);     // 740
     for (int k = pLo[2]; k < pHi[2]; ++k) for (int j = pLo[1]; j < pHi[1]; ++j) for (int i = pLo[0]; i < pHi[0]; ++i) {
       const int origin[3] = {i, j, k};
       if (lv.cellType(origin) != P.flowCell) continue;
       double sumI = 0, cc[3];
       lv.cellPosition(origin, cc);
+      if (lhc) randVector(rand_i, mt, P, origin);        // 750-752
       for (int iRay = 0; iRay < P.nDivQRays; ++iRay) {
         double dir[3], o[3];
-        findRayDirection(mt, P, origin, iRay, dir);
+        if (lhc) findRayDirectionHyperCube(mt, P, origin, iRay, rand_i[iRay], iRay, dir);   // 760-761
+        else findRayDirection(mt, P, origin, iRay, dir);
         rayOriginInCell(mt, cc, lv.dx, P.CCRays != 0, o);
         updateSumI<T>(P, lv, dir, o, origin, nSteps, sumI, nullptr);
       }
       const int64_t q = ow.idx(origin);
       divQ[q] = -4.0 * M_PI * lv.abskg(origin) * (lv.sigmaT4(origin) - (sumI / P.nDivQRays));  // 775
       volq[q] = 4.0 * M_PI * (sumI / P.nDivQRays);                                            // 778
+    }
+  }
+}
+
+// Radiometer::rayDirection_VR (Radiometer.cc:505-560)
+inline void rayDirectionVR(MT& mt, const oracle_params& P, const int origin[3], int iRay, const oracle_radiometer& rad,
+                           double dir[3], double& cosThetaRay) {
+  if (!P.isSeedRandom) mt.seed((uint32_t)((origin[0] + origin[1] + origin[2]) * iRay + 1));   // 512-514
+  const double theta_rotate = rad.theta_rotate, theta_viewAngle = rad.theta_viewAngle, xi_rotate = rad.xi_rotate,
+               phi_rotate = rad.phi_rotate, range = rad.range;
+  const double R1 = mt.randDblExc();
+  const double R2 = mt.randDblExc();
+  const double phi_ray = 2 * M_PI * R1;                                        // 526
+  const double theta_ray = std::acos(std::cos(theta_viewAngle) + range * R2);  // 530
+  cosThetaRay = std::cos(theta_ray);
+  const double x = std::sin(theta_ray) * std::cos(phi_ray);                    // 534-536
+  const double y = std::sin(theta_ray) * std::sin(phi_ray);
+  const double z = cosThetaRay;
+  dir[0] = x * std::cos(theta_rotate) * std::cos(xi_rotate) +                  // 539-552
+           y * (-std::cos(phi_rotate) * std::sin(xi_rotate) + std::sin(phi_rotate) * std::sin(theta_rotate) * std::cos(xi_rotate)) +
+           z * (std::sin(phi_rotate) * std::sin(xi_rotate) + std::cos(phi_rotate) * std::sin(theta_rotate) * std::cos(xi_rotate));
+  dir[1] = x * std::cos(theta_rotate) * std::sin(xi_rotate) +
+           y * (std::cos(phi_rotate) * std::cos(xi_rotate) + std::sin(phi_rotate) * std::sin(theta_rotate) * std::sin(xi_rotate)) +
+           z * (-std::sin(phi_rotate) * std::cos(xi_rotate) + std::cos(phi_rotate) * std::sin(theta_rotate) * std::sin(xi_rotate));
+  dir[2] = x * -std::sin(theta_rotate) + y * std::sin(phi_rotate) * std::cos(theta_rotate) + z * std::cos(phi_rotate) * std::cos(theta_rotate);
+}
+
+// Radiometer::radiometerFlux<T> (Radiometer.cc:428-500)
+template <class T>
+void radiometerPatch(const oracle_params& P, const LevelT<T>& lv, const oracle_radiometer* rads, int nRads, const int pLo[3],
+                     const int pHi[3], uint32_t mtSeed, T* VRFlux, T* VRIntensity, const OutWin& ow, uint64_t& nSteps) {
+  MT mt(P.fixedRandom != 0);
+  mt.seed(mtSeed);
+  for (int r = 0; r < nRads; ++r) {
+    const oracle_radiometer& rad = rads[r];
+    int lo[3], hi[3];
+    bool hit = true;
+    for (int d = 0; d < 3; ++d) {                      // doesIntersect + Max/Min (451-454)
+      lo[d] = std::max(pLo[d], rad.cellLo[d]);
+      hi[d] = std::min(pHi[d], rad.cellHi[d]);
+      hit = hit && lo[d] < hi[d];
+    }
+    if (!hit) continue;
+    for (int k = lo[2]; k < hi[2]; ++k) for (int j = lo[1]; j < hi[1]; ++j) for (int i = lo[0]; i < hi[0]; ++i) {
+      const int c[3] = {i, j, k};
+      double sumI = 0, sumProjI = 0, sumIprev = 0, cc[3];
+      lv.cellPosition(c, cc);
+      const int nRays = rad.nRays;
+      for (int iRay = 0; iRay < nRays; ++iRay) {
+        double o[3], dir[3], cosVR;
+        rayOriginInCell(mt, cc, lv.dx, true, o);        // useCCRays = true (472-473)
+        rayDirectionVR(mt, P, c, iRay, rad, dir, cosVR);
+        updateSumI<T>(P, lv, dir, o, c, nSteps, sumI, nullptr);
+        sumProjI += cosVR * (sumI - sumIprev);          // 483
+        sumIprev = sumI;
+      }
+      const int64_t q = ow.idx(c);
+      VRFlux[q] = (T)sumProjI * rad.solidAngle / nRays;   // 492: the cast binds to sumProjI
+      VRIntensity[q] = (T)sumProjI / nRays;               // 493
     }
   }
 }
@@ -460,6 +572,47 @@ void oracle_default_params(oracle_params* p) {
   p->nDivQRays = 10; p->nFluxRays = 1; p->threshold = 0.01; p->allowReflect = 1; p->CCRays = 0;
   p->isSeedRandom = 1; p->solveDivQ = 1; p->solveBoundaryFlux = 0; p->fixedRandom = 0; p->flowCell = -1;
   p->dataOnionFluxFlowGuard = 0;
+  p->rayDirSampleAlgo = 0;
+  p->maxRayLength = DBL_MAX;   // RMCRTCommon.cc:117
+}
+
+// Radiometer::problemSetup (Radiometer.cc:214-260)
+void oracle_radiometer_setup(double viewAngle, const double vec[3], int isNormalVector, oracle_radiometer* r) {
+  double n[3] = {vec[0], vec[1], vec[2]};
+  if (isNormalVector) {                                                         // 118-120: unitNormalVec = normalVec/normalVec.length()
+    const double l = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    for (int d = 0; d < 3; ++d) n[d] = n[d] / l;
+  }
+  for (int d = 0; d < 3; ++d) if (n[d] == 0) n[d] = 1e-16;                      // 216-220
+  const double len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+  r->phi_rotate = 0;                                                            // 238
+  r->theta_rotate = std::acos(n[2] / len);                                      // 240
+  double xi = std::acos(n[0] / std::sqrt(n[0] * n[0] + n[1] * n[1]));           // 242
+  if (n[0] < 0 && n[1] < 0) xi = (M_PI / 2 + xi);                               // 246-248
+  if (n[0] > 0 && n[1] < 0) xi = (2 * M_PI - xi);                               // 249-251
+  r->xi_rotate = xi;
+  r->theta_viewAngle = viewAngle / 360 * M_PI;                                  // 258
+  r->range = 1 - std::cos(r->theta_viewAngle);                                  // 259
+  r->solidAngle = 2 * M_PI * r->range;                                          // 260
+}
+
+void oracle_radiometerFlux(const oracle_params* p, const oracle_level* lv, const oracle_radiometer* rads, int nRads,
+                           const int patchLo[3], const int patchHi[3], uint32_t mtSeed, void* VRFlux, void* VRIntensity,
+                           const int outLo[3], const int outHi[3], uint64_t* nRaySteps) {
+  OutWin ow;
+  for (int d = 0; d < 3; ++d) { ow.lo[d] = outLo[d]; ow.n[d] = outHi[d] - outLo[d]; }
+  uint64_t n = 0;
+  if (lv->isFloat) { LevelT<float> L(*lv); radiometerPatch<float>(*p, L, rads, nRads, patchLo, patchHi, mtSeed, (float*)VRFlux, (float*)VRIntensity, ow, n); }
+  else             { LevelT<double> L(*lv); radiometerPatch<double>(*p, L, rads, nRads, patchLo, patchHi, mtSeed, (double*)VRFlux, (double*)VRIntensity, ow, n); }
+  if (nRaySteps) *nRaySteps = n;
+}
+
+void oracle_randVector(const oracle_params* p, uint32_t mtSeed, const int cell[3], int n, int* out) {
+  MT mt(p->fixedRandom != 0);
+  mt.seed(mtSeed);
+  std::vector<int> a(n);
+  randVector(a, mt, *p, cell);
+  for (int i = 0; i < n; ++i) out[i] = a[i];
 }
 
 void oracle_mt_u32(uint32_t seed, int n, uint32_t* out) { MT m; m.seed(seed); for (int i = 0; i < n; ++i) out[i] = m.u32(); }
@@ -546,7 +699,9 @@ void dataOnionPatch(const oracle_params& P, const oracle_level* levels, int maxL
   MT mt(P.fixedRandom != 0);
   mt.seed(mtSeed);  // Ray.cc:979 / 1041-1043
 
+  const bool lhc = P.rayDirSampleAlgo == 1;
   if (P.solveBoundaryFlux) {  // 1091-1170, no flow-cell guard
+    std::vector<int> rand_i(lhc ? P.nFluxRays : 0);     // 1096
     for (int k = pLo[2]; k < pHi[2]; ++k) for (int j = pLo[1]; j < pHi[1]; ++j) for (int i = pLo[0]; i < pHi[0]; ++i) {
       int origin[3] = {i, j, k};
       if (P.dataOnionFluxFlowGuard && lv[F].cellType(origin) != P.flowCell) continue;
@@ -559,9 +714,11 @@ void dataOnionPatch(const oracle_params& P, const oracle_level* levels, int maxL
       for (int f = 0; f < nf; ++f) {
         const int rayFace = faces[f];
         double sumI = 0, sumProjI = 0, sumIprev = 0, sumCos = 0;
+        if (lhc) randVector(rand_i, mt, P, origin);      // 1122-1124
         for (int iRay = 0; iRay < P.nFluxRays; ++iRay) {
           double dir[3], o[3], cosT;
-          rayDirectionCellFace(mt, P, origin, rayFace, iRay, dir, cosT);
+          if (lhc) rayDirectionHyperCubeCellFace(mt, P, origin, rayFace, iRay, dir, cosT, rand_i[iRay], iRay);   // 1134-1136
+          else rayDirectionCellFace(mt, P, origin, rayFace, iRay, dir, cosT);
           rayLocationCellFace(mt, rayFace, lv[F].dx, cc, o);
           updateSumI_ML<T>(P, lv, maxLevels, bbMin, bbMax, roiLo, roiHi, regLo.data(), regHi.data(), dir, o, origin,
                            nFluxSteps, sumI, nullptr);
@@ -576,14 +733,17 @@ void dataOnionPatch(const oracle_params& P, const oracle_level* levels, int maxL
   }
 
   if (P.solveDivQ) {  // 1177-1241
+    std::vector<int> rand_i(lhc ? P.nDivQRays : 0);     // 1183
     for (int k = pLo[2]; k < pHi[2]; ++k) for (int j = pLo[1]; j < pHi[1]; ++j) for (int i = pLo[0]; i < pHi[0]; ++i) {
       int origin[3] = {i, j, k};
       if (lv[F].cellType(origin) != P.flowCell) continue;
       double cc[3], sumI = 0;
       lv[F].cellPosition(origin, cc);
+      if (lhc) randVector(rand_i, mt, P, origin);        // 1196-1198
       for (int iRay = 0; iRay < P.nDivQRays; ++iRay) {
         double dir[3], o[3];
-        findRayDirection(mt, P, origin, iRay, dir);
+        if (lhc) findRayDirectionHyperCube(mt, P, origin, iRay, rand_i[iRay], iRay, dir);   // 1207-1208
+        else findRayDirection(mt, P, origin, iRay, dir);
         rayOriginInCell(mt, cc, lv[F].dx, P.CCRays != 0, o);
         updateSumI_ML<T>(P, lv, maxLevels, bbMin, bbMax, roiLo, roiHi, regLo.data(), regHi.data(), dir, o, origin,
                          nSteps, sumI, nullptr);

@@ -41,7 +41,17 @@ typedef struct oracle_params {
   int    fixedRandom;        /* MersenneTwister.h:93 FIXED_RANDOM_NUM: every draw == 0.3 */
   int    flowCell;           /* RMCRTCommon.cc:116, hard-wired -1 */
   int    dataOnionFluxFlowGuard; /* 0 = reference (Ray.cc:1098-1107 has no flow-cell guard) */
+  int    rayDirSampleAlgo;   /* Ray.cc:174-179: 0 NAIVE, 1 LATIN_HYPER_CUBE */
+  double maxRayLength;       /* RMCRTCommon.cc:117 DBL_MAX; <ROI_extents type="boundedRayLength"><length> (Ray.cc:243) */
 } oracle_params;
+
+/* one <Radiometer> block after Radiometer::problemSetup (Radiometer.cc:96-271, Radiometer.h:117-127) */
+typedef struct oracle_radiometer {
+  int    cellLo[3], cellHi[3];   /* level->getCellIndex(locationsMin/Max) (Radiometer.cc:448-449) */
+  int    nRays;
+  double solidAngle, theta_viewAngle, range;       /* 258-260 */
+  double phi_rotate, theta_rotate, xi_rotate;      /* 240-254 */
+} oracle_radiometer;
 
 /* one level's property arrays: x-fastest Array3 window [lo,hi) (Array3Data.h:93,212-220) */
 typedef struct oracle_level {
@@ -87,6 +97,17 @@ void oracle_rayTrace(const oracle_params* p, const oracle_level* lv,
                      double* divQ, double* radiationVolq, double* boundFlux,
                      const int outLo[3], const int outHi[3],
                      uint64_t* nRaySteps, uint64_t* nFluxRaySteps);
+
+/* ---- Radiometer::problemSetup angle derivation (Radiometer.cc:118-120,214-260) from viewAngle [deg] and <unitNormalVector>
+ * (isNormalVector = 0) or <normalVector> (1, normalised first); fills the angle members of *r only */
+void oracle_radiometer_setup(double viewAngle, const double vec[3], int isNormalVector, oracle_radiometer* r);
+/* ---- Radiometer::radiometerFlux<T> for one patch (Radiometer.cc:428-500) + rayDirection_VR (505-560).
+ * VRFlux / VRIntensity: arrays of T (lv->isFloat) over [outLo,outHi); only cells of (radiometer box ∩ patch) are written. */
+void oracle_radiometerFlux(const oracle_params* p, const oracle_level* lv, const oracle_radiometer* rads, int nRads,
+                           const int patchLo[3], const int patchHi[3], uint32_t mtSeed,
+                           void* VRFlux, void* VRIntensity, const int outLo[3], const int outHi[3], uint64_t* nRaySteps);
+/* ---- RMCRTCommon::randVector (RMCRTCommon.cc:998-1024): Fisher-Yates shuffle of 0..n-1 */
+void oracle_randVector(const oracle_params* p, uint32_t mtSeed, const int cell[3], int n, int* out);
 
 /* ---- Ray::computeExtents, patch_based ROI (Ray.cc:1279-1358) ---- */
 void oracle_computeExtents(const oracle_level* levels, int maxLevels,

@@ -25,7 +25,8 @@ static void rayDxOf(const HsLevel& g, const int c[3], const double* o, double r[
 
 // single level: kind 0 = fp32/Rec8, 1 = fp64/Rec16
 void hs_trace_1L(const HsLevel* g, int kind, int n, const int* cells, const double* dirs, const double* orgs, double threshold,
-                 int allowReflect, int skipZero, double* sumI, unsigned* steps, int* path, int maxPath) {
+                 int allowReflect, int skipZero, double* sumI, unsigned* steps, int* path, int maxPath, double maxRayLength) {
+  const double maxLen = (maxRayLength > 0 && maxRayLength < 1e300) ? maxRayLength : INFINITY;
   const int nx = g->hi[0] - g->lo[0], ny = g->hi[1] - g->lo[1];
   for (int t = 0; t < n; ++t) {
     const int* c = cells + 3 * t;
@@ -38,10 +39,12 @@ void hs_trace_1L(const HsLevel* g, int kind, int n, const int* cells, const doub
     if (kind == 0)
       sumI[t] = march_single_level<float, Rec8, true>(static_cast<const Rec8*>(g->rec), idx, nx, nx * ny, (float)d[0], (float)d[1], (float)d[2],
                   (float)r[0], (float)r[1], (float)r[2], (float)g->dx[0], (float)g->dx[1], (float)g->dx[2], (float)threshold,
-                  allowReflect != 0, skipZero != 0, s, path ? &sink : nullptr, c[0], c[1], c[2]);
+                  allowReflect != 0, skipZero != 0, s, path ? &sink : nullptr, c[0], c[1], c[2],
+                  (float)(maxLen * (double)Num<float>::LEN_SCALE));
     else
       sumI[t] = march_single_level<double, Rec16, true>(static_cast<const Rec16*>(g->rec), idx, nx, nx * ny, d[0], d[1], d[2], r[0], r[1], r[2],
-                  g->dx[0], g->dx[1], g->dx[2], threshold, allowReflect != 0, skipZero != 0, s, path ? &sink : nullptr, c[0], c[1], c[2]);
+                  g->dx[0], g->dx[1], g->dx[2], threshold, allowReflect != 0, skipZero != 0, s, path ? &sink : nullptr, c[0], c[1], c[2],
+                  maxLen);
     steps[t] = s;
   }
 }
@@ -146,6 +149,10 @@ void hs_trace_DO2_fast(const HsLevel* lv, const int* roiLo, const int* roiHi, co
 void hs_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
   const u32x4 r = philox4x32_10(u32x4{ctr[0], ctr[1], ctr[2], ctr[3]}, key[0], key[1]);
   out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+void hs_keyed_permutation(uint32_t n, const uint32_t key[4], uint32_t* out) {
+  const u32x4 k{key[0], key[1], key[2], key[3]};
+  for (uint32_t x = 0; x < n; ++x) out[x] = keyed_permutation(x, n, k);
 }
 void hs_mt_first5(uint32_t seed, uint32_t out[5]) { mt19937_first<5>(seed, out); }
 void hs_mt_first4(uint32_t seed, uint32_t out[4]) { mt19937_first<4>(seed, out); }

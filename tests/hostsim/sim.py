@@ -50,15 +50,21 @@ def _vp(a):
     return np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)
 
 
-def trace_1L(lv, kind, cells, dirs, org, thr, refl, skip=0, max_path=4000):
+def trace_1L(lv, kind, cells, dirs, org, thr, refl, skip=0, max_path=4000, max_ray_length=0.0):
     rec = pack(lv, kind)
     h = hslevel(lv, rec)
     n = len(cells)
     sumI = np.zeros(n); steps = np.zeros(n, np.uint32); path = np.zeros((n, max_path, 4), np.int32)
     cells = np.ascontiguousarray(cells, np.int32); dirs = np.ascontiguousarray(dirs); org = np.ascontiguousarray(org)
     lib().hs_trace_1L(C.byref(h), kind, n, _vp(cells), _vp(dirs), _vp(org), C.c_double(thr), refl, skip, _vp(sumI), _vp(steps),
-                      path.ctypes.data_as(C.c_void_p), max_path)
+                      path.ctypes.data_as(C.c_void_p), max_path, C.c_double(max_ray_length))
     return sumI, steps, path
+
+
+def keyed_permutation(n, key):
+    out = np.zeros(n, np.uint32)
+    lib().hs_keyed_permutation(C.c_uint32(n), (C.c_uint32 * 4)(*key), _vp(out))
+    return out
 
 
 def trace_1L_fast(lv, cells, dirs, org, thr, refl, skip=0):

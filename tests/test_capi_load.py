@@ -1,6 +1,7 @@
 """C-ABI surface checks that need no GPU: the library builds for sm_100a, loads, exports every symbol the header
 declares, reports the reference's .ups defaults, and refuses to work (loudly) without a CUDA device."""
 import ctypes as C
+import math
 import os
 import re
 import subprocess
@@ -31,7 +32,7 @@ def test_header_and_binding_agree(lib):
 def test_library_exports_every_declared_symbol(lib):
     for s in _header_symbols():
         assert hasattr(lib, s), s
-    assert lib.rmcrt_abi_version() == 1
+    assert lib.rmcrt_abi_version() == 2
 
 
 def test_library_is_sm100a_and_has_no_torch_dependency():
@@ -52,6 +53,21 @@ def test_default_params_are_the_ups_defaults(lib):
     assert lib.rmcrt_struct_size(0) == C.sizeof(capi.Params)
     assert lib.rmcrt_struct_size(1) == C.sizeof(capi.LevelDesc)
     assert lib.rmcrt_struct_size(2) == C.sizeof(capi.Counters)
+    assert lib.rmcrt_struct_size(3) == C.sizeof(capi.Radiometer)
+    assert p.rayDirSampleAlgo == 0 and p.maxRayLength == 0.0      # "naive" (Ray.cc:174), unbounded (RMCRTCommon.cc:117)
+
+
+def test_radiometer_setup_is_host_only(lib):
+    """Radiometer::problemSetup's angle derivation (Radiometer.cc:214-260) needs no device"""
+    from uintah_b200 import capi
+    r = capi.Radiometer()
+    v = (C.c_double * 3)(0.0, 0.0, 1.0)
+    assert lib.rmcrt_radiometer_setup(30.0, v, 0, C.byref(r)) == 0
+    assert r.theta_viewAngle == pytest.approx(math.radians(15.0))
+    assert r.solidAngle == pytest.approx(2 * math.pi * (1 - math.cos(math.radians(15.0))))
+    assert r.theta_rotate == 0.0 and r.phi_rotate == 0.0
+    assert r.xi_rotate == pytest.approx(math.pi / 4)      # the reference's 1e-16 zero guard: acos(1e-16 / (sqrt(2) 1e-16))
+    assert lib.rmcrt_radiometer_setup(361.0, v, 0, C.byref(r)) != 0
 
 
 def test_no_cpu_fallback(lib):

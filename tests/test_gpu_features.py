@@ -1,0 +1,184 @@
+"""GPU parity tests of the RMCRT features beside the plain divQ solve: Latin-Hyper-Cube sampling,
+boundedRayLength ROI, the virtual radiometer.  Same bars as test_gpu_parity.py: integer outputs and step counts bit-exact,
+deterministic mode (<randomSeed> false, FP64 march) to round-off, production mode within the Monte-Carlo tolerance."""
+import numpy as np
+import pytest
+
+from util import random_rays
+
+pytestmark = pytest.mark.gpu
+
+
+def make(gpu_lib, **kw):
+    from uintah_b200 import RMCRT
+    return RMCRT(device=0, **kw)
+
+
+# ------------------------------------------------------------------------------------------------ Latin Hyper Cube
+@pytest.mark.parametrize("flux", [False, True])
+def test_lhc_deterministic_matches_oracle(gpu_lib, po, flux):
+    """<rayDirSampleAlgo> LatinHyperCube with <randomSeed> false: randVector's MT19937 Fisher-Yates permutation per
+    (i+j+k) (RMCRTCommon.cc:998-1024) + per-ray reseed -- reproduced to round-off, identical step counts"""
+    lv = po.parallel_plates(12) if flux else po.burns_christon(14)
+    kw = dict(nDivQRays=12, nFluxRays=9, threshold=0.01, isSeedRandom=0, rayDirSampleAlgo=1, solveBoundaryFlux=1 if flux else 0)
+    ref = po.ray_trace(po.default_params(**kw), lv)
+    g = make(gpu_lib, marchPrecision=1, skipZeroWeightLegs=0, **kw)
+    g.upload_level(0, lv)
+    out = g.trace_divq(0)
+    c = g.counters()
+    assert c.nRaySteps == ref["steps"] and c.nFluxRaySteps == ref["fluxSteps"]
+    scale = np.abs(ref["divQ"]).max()
+    assert np.abs(out["divQ"] - ref["divQ"]).max() <= 1e-10 * scale
+    if flux:
+        assert np.array_equal(out["boundFlux"][..., 6], ref["boundFlux"][..., 6])
+        assert np.array_equal(out["boundFlux"] != 0, ref["boundFlux"] != 0)
+        np.testing.assert_allclose(out["boundFlux"], ref["boundFlux"], rtol=1e-10, atol=1e-10 * np.abs(ref["boundFlux"]).max())
+    # differs from the naive sampler on the same deck
+    kw0 = dict(kw, rayDirSampleAlgo=0)
+    g0 = make(gpu_lib, marchPrecision=1, skipZeroWeightLegs=0, **kw0)
+    g0.upload_level(0, lv)
+    assert np.abs(g0.trace_divq(0)["divQ"] - out["divQ"]).max() > 1e-6 * scale
+
+
+def test_lhc_fixed_random_matches_oracle(gpu_lib, po):
+    """FIXED_RANDOM_NUM build: rand_int = 0.3*i in the shuffle (RMCRTCommon.cc:1017-1019) and every draw 0.3"""
+    lv = po.burns_christon(10)
+    kw = dict(nDivQRays=7, threshold=0.05, fixedRandom=1, rayDirSampleAlgo=1)
+    ref = po.ray_trace(po.default_params(**kw), lv)
+    g = make(gpu_lib, marchPrecision=1, skipZeroWeightLegs=0, **kw)
+    g.upload_level(0, lv)
+    out = g.trace_divq(0)
+    assert g.counters().nRaySteps == ref["steps"]
+    assert np.abs(out["divQ"] - ref["divQ"]).max() <= 1e-10 * np.abs(ref["divQ"]).max()
+
+
+@pytest.mark.parametrize("coherence", [0, 1])
+def test_lhc_production_is_unbiased_and_stratified(gpu_lib, po, coherence):
+    """production LHC (Philox + keyed permutation): same mean as the oracle's LHC runs, and a smaller seed-to-seed
+    spread than the production naive sampler at the same ray count"""
+    lv = po.burns_christon(17)
+    K = 6
+    ref = np.mean([po.ray_trace(po.default_params(nDivQRays=64, threshold=0.05, rayDirSampleAlgo=1), lv, seed=50 + k)["divQ"]
+                   for k in range(K)], 0)
+    runs = {}
+    for algo in (0, 1):
+        g = make(gpu_lib, nDivQRays=64, threshold=0.05, rayDirSampleAlgo=algo, rayCoherence=coherence)
+        g.upload_level(0, lv)
+        runs[algo] = [g.trace_divq(0, timestep=10 + k)["divQ"] for k in range(K)]
+    inner = (slice(1, -1),) * 3
+    mu = np.mean(runs[1], 0)
+    assert np.linalg.norm((mu - ref)[inner]) / np.linalg.norm(ref[inner]) < 0.02
+    assert abs(mu[inner].mean() - ref[inner].mean()) < 0.005 * abs(ref[inner].mean())
+    s_naive = np.std(runs[0], 0)[inner].mean()
+    s_lhc = np.std(runs[1], 0)[inner].mean()
+    assert s_lhc < 0.9 * s_naive
+
+
+# ------------------------------------------------------------------------------------------------ bounded ray length
+@pytest.mark.parametrize("max_len", [0.08, 0.3])
+def test_bounded_ray_length_debug_rays(gpu_lib, po, max_len):
+    lv = po.parallel_plates(16)
+    rng = np.random.default_rng(21)
+    cells, dirs, org = random_rays(lv, 300, rng)
+    p = po.default_params(threshold=0.001, allowReflect=1, maxRayLength=max_len)
+    ref = [po.update_sumI(p, lv, dirs[t], org[t], cells[t], max_path=3000) for t in range(len(cells))]
+    ref_s = np.array([r[0] for r in ref]); ref_n = np.array([r[1] for r in ref])
+    g = make(gpu_lib, threshold=0.001, allowReflect=1, marchPrecision=1, skipZeroWeightLegs=0, maxRayLength=max_len)
+    g.upload_level(0, lv)
+    s64, n64, p64 = g.debug_trace_rays(cells, dirs, org, max_path=3000)
+    assert np.array_equal(n64, ref_n)
+    for t in range(len(cells)):
+        assert np.array_equal(p64[t, :ref_n[t], :3], ref[t][2]), t
+    np.testing.assert_allclose(s64, ref_s, rtol=1e-11)
+    g32 = make(gpu_lib, threshold=0.001, allowReflect=1, skipZeroWeightLegs=0, maxRayLength=max_len)
+    g32.upload_level(0, lv)
+    s32, n32, _ = g32.debug_trace_rays(cells, dirs, org)
+    assert (n32 == ref_n).mean() > 0.97
+    same = n32 == ref_n
+    np.testing.assert_allclose(s32[same], ref_s[same], rtol=5e-4, atol=1e-6 * np.abs(ref_s).max())
+
+
+@pytest.mark.parametrize("half", [False, True])
+def test_bounded_ray_length_solve(gpu_lib, po, half):
+    """RMCRT_bm1_1L_bounded.ups pattern: whole solve with <ROI_extents type="boundedRayLength">, deterministic mode to
+    round-off (FP64 march) and the FP32 production kernels (float and half-packed records) on the same rays"""
+    lv = po.burns_christon(16, dtype=np.float32)
+    kw = dict(nDivQRays=6, nFluxRays=4, threshold=0.05, isSeedRandom=0, maxRayLength=0.25, solveBoundaryFlux=1)
+    ref = po.ray_trace(po.default_params(**kw), lv)
+    full = po.ray_trace(po.default_params(**dict(kw, maxRayLength=1e308)), lv)
+    assert ref["steps"] < 0.8 * full["steps"]
+    scale = np.abs(ref["divQ"]).max()
+    if not half:
+        g = make(gpu_lib, marchPrecision=1, skipZeroWeightLegs=0, **kw)
+        g.upload_level(0, lv)
+        out = g.trace_divq(0)
+        c = g.counters()
+        assert c.nRaySteps == ref["steps"] and c.nFluxRaySteps == ref["fluxSteps"]
+        assert np.abs(out["divQ"] - ref["divQ"]).max() <= 1e-10 * scale
+        np.testing.assert_allclose(out["boundFlux"], ref["boundFlux"], rtol=1e-10, atol=1e-10 * np.abs(ref["boundFlux"]).max())
+    g32 = make(gpu_lib, skipZeroWeightLegs=0, half_records=half, **kw)
+    g32.upload_level(0, lv)
+    o32 = g32.trace_divq(0)
+    tol = 5e-3 if half else 3e-4          # fp16 properties vs fp32
+    assert np.abs(o32["divQ"] - ref["divQ"]).max() <= tol * scale
+    assert abs(int(g32.counters().nRaySteps) - ref["steps"]) <= 2e-3 * ref["steps"]
+
+
+def test_bounded_ray_length_refused_for_data_onion(gpu_lib, po):
+    from uintah_b200 import RmcrtError
+    fine = po.burns_christon(16)
+    fine.rr = (4, 4, 4)
+    coarse = po.coarsen_level(fine, (4, 4, 4))
+    g = make(gpu_lib, nDivQRays=2, maxRayLength=0.2, haloCells=(2, 2, 2))
+    g.upload_level(0, coarse)
+    g.upload_level(1, fine)
+    with pytest.raises(RmcrtError, match="single-level"):
+        g.trace_dataonion(2)
+
+
+# ------------------------------------------------------------------------------------------------ virtual radiometer
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_radiometer_deterministic_matches_oracle(gpu_lib, po, dtype):
+    """Radiometer::radiometerFlux (Radiometer.cc:428-560), <randomSeed> false: per-ray reseed (i+j+k)*iRay+1, 2 draws"""
+    lv = po.parallel_plates(14, dtype=dtype)
+    lv.sigmaT4[:, :, -1] *= 0.25                      # an x+ wall that differs, so the orientation matters
+    p = po.default_params(threshold=0.001, isSeedRandom=0)
+    specs = [(30.0, (0, 0, 1), False, (6, 6, 6), (8, 7, 7), 50), (120.0, (1, -2, 0.5), True, (2, 3, 4), (3, 5, 5), 33),
+             (60.0, (-1, 1, 0), False, (10, 10, 0), (12, 11, 1), 40)]
+    g = make(gpu_lib, threshold=0.001, isSeedRandom=0, marchPrecision=1, skipZeroWeightLegs=0)
+    g.upload_level(0, lv)
+    rads_o = [po.radiometer(v, n, lo, hi, nr, is_normal_vector=nv) for v, n, nv, lo, hi, nr in specs]
+    rads_g = [g.radiometer(v, n, lo, hi, nr, is_normal_vector=nv) for v, n, nv, lo, hi, nr in specs]
+    for a, b in zip(rads_o, rads_g):                  # the angle derivation itself (Radiometer.cc:214-260)
+        for f in ("solidAngle", "theta_viewAngle", "range", "phi_rotate", "theta_rotate", "xi_rotate"):
+            assert getattr(a, f) == pytest.approx(getattr(b, f), rel=1e-15, abs=1e-300)
+    fo, io, steps = po.radiometer_flux(p, lv, rads_o)
+    fg, ig = g.trace_radiometer(rads_g, dtype=dtype)
+    assert g.counters().nRadiometerSteps == steps
+    assert np.array_equal(fg != 0, fo != 0) and np.count_nonzero(fo) == 2 + 2 + 2
+    tol = 1e-10 if dtype == np.float64 else 3e-7
+    np.testing.assert_allclose(fg, fo, rtol=tol)
+    np.testing.assert_allclose(ig, io, rtol=tol)
+    # patch restriction: only the cells of (radiometer box n patch) are written, the others keep their values
+    keepF = np.full(fo.shape, 7.0, dtype); keepI = np.full(fo.shape, 9.0, dtype)
+    g.trace_radiometer(rads_g, patch_lo=(0, 0, 0), patch_hi=(7, 14, 14), dtype=dtype, zero_init=False, outputs=(keepF, keepI))
+    sel = np.zeros(fo.shape, bool)
+    sel[7, 7, 7] = True            # cell (6,6,6) of radiometer 0
+    sel[5:6, 4:6, 3] = True        # radiometer 1: x 2, y 3..4, z 4
+    assert np.array_equal(keepF != 7.0, sel)
+    np.testing.assert_allclose(keepF[sel], fo[sel], rtol=tol)
+
+
+def test_radiometer_production_closed_form(gpu_lib, po):
+    """Philox rays, FP32 march: isothermal black enclosure => VRIntensity = I (1 + cos(viewAngle/2)) / 2"""
+    lv = po.parallel_plates(16, dtype=np.float32, T_gas=1000.0, T_wall=1000.0, mirror_faces=())
+    I = float(lv.sigmaT4[5, 5, 5])
+    for half in (False, True):
+        g = make(gpu_lib, threshold=0.0001, allowReflect=0, half_records=half)
+        g.upload_level(0, lv)
+        for view, vec in ((40.0, (0, 1, 0)), (150.0, (1, 1, 1))):
+            r = g.radiometer(view, vec, (8, 8, 8), (9, 9, 9), 20000, is_normal_vector=True)
+            flux, inten = g.trace_radiometer([r], dtype=np.float32)
+            hv = np.radians(view / 2)
+            assert inten[9, 9, 9] == pytest.approx(I * (1 + np.cos(hv)) / 2, rel=(2e-3 if half else 5e-4))
+            assert flux[9, 9, 9] == pytest.approx(inten[9, 9, 9] * 2 * np.pi * (1 - np.cos(hv)), rel=1e-6)

@@ -84,3 +84,39 @@ def test_mt_first_outputs_match_full_generator(po):
         full = [int(x) for x in po.mt_u32(seed, 5)]
         assert sim.mt_first(seed, 5) == full
         assert sim.mt_first(seed, 4) == full[:4]
+
+
+@pytest.mark.parametrize("max_len", [0.05, 0.2, 0.6])
+def test_single_level_bounded_ray_length(po, max_len):
+    """<ROI_extents type="boundedRayLength">: inner and outer loops also stop on rayLength >= d_maxRayLength
+    (RMCRTCommon.cc:680,684) and the cell the ray stops in is added like a wall (846-854)"""
+    lv = po.parallel_plates(16)
+    rng = np.random.default_rng(11)
+    cells, dirs, org = random_rays(lv, 150, rng)
+    p = po.default_params(threshold=0.001, allowReflect=1, maxRayLength=max_len)
+    s64, n64, p64 = sim.trace_1L(lv, 1, cells, dirs, org, 0.001, 1, max_ray_length=max_len)
+    s32, n32, _ = sim.trace_1L(lv, 0, cells, dirs, org, 0.001, 1, max_ray_length=max_len)
+    unbounded = sim.trace_1L(lv, 1, cells, dirs, org, 0.001, 1)[1]
+    assert (n64 < unbounded).any()            # the bound really cut rays short
+    for t in range(len(cells)):
+        s, ns, path = po.update_sumI(p, lv, dirs[t], org[t], cells[t], max_path=4000)
+        assert ns == n64[t]
+        assert np.array_equal(path, p64[t, :ns, :3])
+        assert s == pytest.approx(s64[t], rel=1e-13, abs=1e-300)
+        if ns == n32[t]:
+            assert s == pytest.approx(s32[t], rel=5e-4, abs=1e-6 * max(1.0, abs(s)))
+    assert (n32 == n64).mean() > 0.97
+
+
+def test_keyed_permutation_is_a_bijection():
+    """Latin-Hyper-Cube strata with <randomSeed> true: every n, every key must give a permutation of [0,n)"""
+    rng = np.random.default_rng(3)
+    seen = set()
+    for n in (1, 2, 3, 5, 10, 16, 17, 100, 127, 128, 1000, 4097):
+        for _ in range(4):
+            key = [int(x) for x in rng.integers(0, 2 ** 32, 4)]
+            perm = sim.keyed_permutation(n, key)
+            assert np.array_equal(np.sort(perm), np.arange(n))
+            if n == 100:
+                seen.add(tuple(perm))
+    assert len(seen) == 4                     # different keys, different permutations

@@ -182,3 +182,79 @@ def test_extents_patch_based(po):
     assert roiLo == (12, -1, -1) and roiHi == (33, 20, 20)           # clamped to the level incl. extra cells
     assert tuple(regLo[1]) == (13, 0, 0) and tuple(regHi[1]) == (32, 19, 19)
     assert tuple(regLo[0]) == (0, 0, 0) and tuple(regHi[0]) == (8, 8, 8)
+
+
+def test_randVector_is_the_reference_fisher_yates(po):
+    """RMCRTCommon::randVector (RMCRTCommon.cc:998-1024) restated independently in python on the pinned MT19937 stream:
+    seed(i+j+k), then for i = n-1..1 swap a[i] with a[randInt(i)] (randInt(n) = rejection on the masked word)"""
+    def rand_int(stream, n):
+        used = n
+        for s in (1, 2, 4, 8, 16):
+            used |= used >> s
+        while True:
+            v = int(next(stream)) & used
+            if v <= n:
+                return v
+    p = po.default_params(isSeedRandom=0)
+    for cell, n in (((1, 2, 3), 10), ((0, 0, 0), 7), ((20, 3, 40), 100), ((5, 5, 5), 600)):
+        words = iter(po.mt_u32(sum(cell), 4 * n + 64))
+        a = list(range(n))
+        for i in range(n - 1, 0, -1):
+            r = rand_int(words, i)
+            a[i], a[r] = a[r], a[i]
+        assert list(po.rand_vector(p, cell, n)) == a
+    fixed = po.default_params(fixedRandom=1)
+    a = list(range(10))
+    for i in range(9, 0, -1):
+        r = int(0.3 * i)
+        a[i], a[r] = a[r], a[i]
+    assert list(po.rand_vector(fixed, (1, 1, 1), 10)) == a
+
+
+def test_latin_hyper_cube_lowers_the_variance(po):
+    """LHC stratifies cos(theta) and phi (Ray.cc:1438-1460): same mean, smaller seed-to-seed spread than naive sampling"""
+    lv = po.burns_christon(11)
+    runs = {0: [], 1: []}
+    for algo in (0, 1):
+        for seed in range(6):
+            p = po.default_params(nDivQRays=64, threshold=0.05, rayDirSampleAlgo=algo)
+            runs[algo].append(po.ray_trace(p, lv, seed=100 + seed)["divQ"][1:-1, 1:-1, 1:-1])
+    m0, m1 = np.mean(runs[0], 0), np.mean(runs[1], 0)
+    s0, s1 = np.std(runs[0], 0).mean(), np.std(runs[1], 0).mean()
+    assert abs(m0.mean() - m1.mean()) < 0.02 * abs(m0.mean())
+    assert s1 < 0.9 * s0
+
+
+def test_radiometer_isothermal_enclosure(po):
+    """closed form: in an isothermal black enclosure every ray returns sigmaT4/pi, so
+    VRIntensity = I * mean(cos theta) and VRFlux = VRIntensity * solidAngle (Radiometer.cc:483-493);
+    for the uniform-in-cos(theta) cone sampling (530) mean(cos theta) = (1 + cos(viewAngle/2)) / 2"""
+    lv = po.parallel_plates(12, T_gas=1000.0, T_wall=1000.0, mirror_faces=())
+    I = float(lv.sigmaT4[5, 5, 5])
+    p = po.default_params(threshold=0.0001, allowReflect=0)      # (with reflections the un-weighted wall term, SURVEY Q1, adds to I)
+    for view, vec in ((30.0, (0, 0, 1)), (120.0, (1, 1, 0)), (60.0, (-1, -2, 0.5))):
+        r = po.radiometer(view, vec, (5, 5, 5), (7, 6, 6), 4000, is_normal_vector=True)
+        flux, inten, steps = po.radiometer_flux(p, lv, [r], seed=3)
+        half = np.radians(view / 2)
+        expect = I * (1 + np.cos(half)) / 2
+        for c in ((6, 6, 6), (6, 6, 7)):          # [z][y][x] with lo = -1
+            assert inten[c] == pytest.approx(expect, rel=0.01)
+            assert flux[c] == pytest.approx(inten[c] * 2 * np.pi * (1 - np.cos(half)), rel=1e-12)
+        assert np.count_nonzero(flux) == 2 and steps > 0
+
+
+def test_radiometer_direction_cone(po):
+    """every rayDirection_VR direction lies inside the view cone around the requested normal (Radiometer.cc:505-560).
+    The rotation (theta about y, then xi about z) is exact for normals in quadrants 1, 2 and 4 of the x-y plane."""
+    lv = po.parallel_plates(8, T_gas=1000.0, T_wall=1000.0, mirror_faces=())
+    # a cold black wall on x+ only: the radiometer sees less when it looks at it
+    lv.sigmaT4[:, :, -1] = 0.0
+    p = po.default_params(threshold=0.0001, allowReflect=0)
+    I = float(lv.sigmaT4[4, 4, 4])
+    towards = po.radiometer(20.0, (1, 0, 0), (4, 4, 4), (5, 5, 5), 3000)
+    away = po.radiometer(20.0, (-1, 0, 0), (4, 4, 4), (5, 5, 5), 3000)
+    f1, i1, _ = po.radiometer_flux(p, lv, [towards])
+    f2, i2, _ = po.radiometer_flux(p, lv, [away])
+    # looking at the cold wall: only the gas column (kappa 1, ~0.44 m) emits; looking away: full black-body intensity
+    assert i1[5, 5, 5] < 0.5 * i2[5, 5, 5]
+    assert i2[5, 5, 5] == pytest.approx(I * (1 + np.cos(np.radians(10))) / 2, rel=0.01)

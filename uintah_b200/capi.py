@@ -22,6 +22,7 @@ SYMBOLS = [
     "rmcrt_trace_dataonion_device", "rmcrt_trace_dataonion", "rmcrt_compute_extents", "rmcrt_reset_counters",
     "rmcrt_get_counters", "rmcrt_sigmaT4_device", "rmcrt_sigmaT4", "rmcrt_coarsen_level_device", "rmcrt_set_level_extra_cells",
     "rmcrt_pack_box_device", "rmcrt_assemble_level", "rmcrt_allgather_records", "rmcrt_measure_read_bandwidth", "rmcrt_debug_trace_rays",
+    "rmcrt_radiometer_setup", "rmcrt_trace_radiometer_device", "rmcrt_trace_radiometer",
 ]
 
 
@@ -39,7 +40,16 @@ class Params(C.Structure):
         ("haloCells", C.c_int32 * 3), ("cellTypeCoarsenLogic", C.c_int32), ("seed", C.c_uint64),
         ("marchPrecision", C.c_int32), ("rayCoherence", C.c_int32), ("skipZeroWeightLegs", C.c_int32),
         ("fixedRandom", C.c_int32), ("l2Persist", C.c_int32), ("warpsPerTile", C.c_int32),
-        ("genericMarch", C.c_int32), ("maxBlocksPerSM", C.c_int32), ("reserved", C.c_int32 * 2),
+        ("genericMarch", C.c_int32), ("maxBlocksPerSM", C.c_int32), ("rayDirSampleAlgo", C.c_int32), ("reserved", C.c_int32),
+        ("maxRayLength", C.c_double),
+    ]
+
+
+class Radiometer(C.Structure):
+    _fields_ = [
+        ("cellLo", C.c_int32 * 3), ("cellHi", C.c_int32 * 3), ("nRays", C.c_int32), ("pad", C.c_int32),
+        ("solidAngle", C.c_double), ("theta_viewAngle", C.c_double), ("range", C.c_double),
+        ("phi_rotate", C.c_double), ("theta_rotate", C.c_double), ("xi_rotate", C.c_double),
     ]
 
 
@@ -52,7 +62,7 @@ class LevelDesc(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [("nRaySteps", C.c_uint64), ("nFluxRaySteps", C.c_uint64), ("nDivQCells", C.c_uint64),
-                ("nFluxCells", C.c_uint64)]
+                ("nFluxCells", C.c_uint64), ("nRadiometerSteps", C.c_uint64)]
 
 
 _lib = None
@@ -73,7 +83,7 @@ def load_library(path: str | None = None):
     lib.rmcrt_abi_version.restype = C.c_int
     lib.rmcrt_struct_size.argtypes = [C.c_int]
     lib.rmcrt_struct_size.restype = C.c_size_t
-    for which, cls in ((0, Params), (1, LevelDesc), (2, Counters)):
+    for which, cls in ((0, Params), (1, LevelDesc), (2, Counters), (3, Radiometer)):
         if lib.rmcrt_struct_size(which) != C.sizeof(cls):
             raise RmcrtError(-1, f"ABI struct layout mismatch for {cls.__name__}: library {lib.rmcrt_struct_size(which)} B, binding {C.sizeof(cls)} B")
     lib.rmcrt_default_params.argtypes = [C.POINTER(Params)]
@@ -92,6 +102,10 @@ def load_library(path: str | None = None):
     lib.rmcrt_level_records.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     for name in ("rmcrt_trace_divq_device", "rmcrt_trace_divq", "rmcrt_trace_dataonion_device", "rmcrt_trace_dataonion"):
         getattr(lib, name).argtypes = [vp, C.c_int, i3, i3, vp, vp, vp, i3, i3, C.c_int, C.c_uint64, vp]
+    lib.rmcrt_radiometer_setup.argtypes = [C.c_double, C.POINTER(C.c_double), C.c_int, C.POINTER(Radiometer)]
+    for name in ("rmcrt_trace_radiometer_device", "rmcrt_trace_radiometer"):
+        getattr(lib, name).argtypes = [vp, C.c_int, C.POINTER(Radiometer), C.c_int, i3, i3, vp, vp, C.c_int, i3, i3, C.c_int,
+                                       C.c_uint64, vp]
     lib.rmcrt_compute_extents.argtypes = [vp, C.c_int, i3, i3, i3, i3, i3, i3]
     lib.rmcrt_reset_counters.argtypes = [vp, vp]
     lib.rmcrt_get_counters.argtypes = [vp, C.POINTER(Counters), vp]

@@ -72,6 +72,7 @@ template <> struct Num<float> {
   static __device__ __forceinline__ float add(float a, float b) { return a + b; }
   static __device__ __forceinline__ float rcp(float a) { return __frcp_rn(a); }
   static __device__ __forceinline__ float fuzz(float ds) { return ds; }
+  static __device__ __forceinline__ float wall_product(float eps, float s, bool) { return eps * s; }
 };
 template <> struct Num<double> {
   static constexpr double LEN_SCALE = 1.0;
@@ -82,6 +83,11 @@ template <> struct Num<double> {
   static __device__ __forceinline__ double rcp(double a) { return __ddiv_rn(1.0, a); }
   // RMCRTCommon.cc:717-720 (FUZZ = 1e-12); single level only
   static __device__ __forceinline__ double fuzz(double ds) { return (ds > -1e-12 && ds < 1e-12) ? ds + 1e-12 : ds; }
+  // `wallEmissivity * sigmaT4OverPi[cur]` is a T*T product in the reference (RMCRTCommon.cc:854, Ray.cc:2602): evaluated in
+  // float when the properties are float, before the double `* intensity`
+  static __device__ __forceinline__ double wall_product(double eps, double s, bool floatProps) {
+    return floatProps ? (double)((float)eps * (float)s) : __dmul_rn(eps, s);
+  }
 };
 
 template <class Real> __device__ __forceinline__ Real absr(Real v);
@@ -106,9 +112,11 @@ __device__ __forceinline__ Real march_single_level(const RecT* __restrict__ recs
                                                    Real dx, Real dy, Real dz, Real rx, Real ry, Real rz,
                                                    Real cx, Real cy, Real cz,   // cell size
                                                    Real threshold, bool allowReflect, bool skipZero,
-                                                   unsigned& nSteps, PathSink* path, int pi, int pj, int pk) {
+                                                   unsigned& nSteps, PathSink* path, int pi, int pj, int pk,
+                                                   Real maxLen = Real(INFINITY),     // d_maxRayLength * LEN_SCALE
+                                                   bool floatProps = false) {        // FP64 march of a float deck
   typedef Num<Real> N;
-  if (!(Real(1) > threshold)) return Real(0);   // while (intensity > d_threshold), RMCRTCommon.cc:683
+  if (!(Real(1) > threshold) || !(Real(0) < maxLen)) return Real(0);   // while (intensity > d_threshold && rayLength < d_maxRayLength), RMCRTCommon.cc:680
 
   // raySignStep (RMCRTCommon.cc:482-494): +1 / -1 by the sign BIT of the direction
   const bool posx = !sign_bit(dx), posy = !sign_bit(dy), posz = !sign_bit(dz);
@@ -123,6 +131,7 @@ __device__ __forceinline__ Real march_single_level(const RecT* __restrict__ recs
   const Real ddz = N::mul(N::mul(absr(iz), cz), N::LEN_SCALE);
 
   Real tPrev = 0, tau = 0, ePrev = 1, sum = 0, fs = 1;
+  Real len = 0;                    // rayLength (723), only compared when the ROI is boundedRayLength
   typename RecInfo<RecT>::decoded r = ldrec(recs + idx);
   Real k = absr(r.k), s = r.s;
   unsigned steps = 0;
@@ -150,6 +159,7 @@ __device__ __forceinline__ Real march_single_level(const RecT* __restrict__ recs
       ty = py ? N::add(ty, ddy) : ty;
       tz = (px || py) ? tz : N::add(tz, ddz);
       ds = N::fuzz(ds);
+      len = N::add(len, ds);                 // rayLength += disMin   (723)
       tau = N::add(tau, N::mul(k, ds));      // optical_thickness += abskg[prev]*disMin   (731)
       ++steps;
       e = N::attenuation(tau);               // 782
@@ -161,14 +171,15 @@ __device__ __forceinline__ Real march_single_level(const RecT* __restrict__ recs
         int32_t* q = path->buf + 4 * path->n; q[0] = ci; q[1] = cj; q[2] = ck; q[3] = 0;
       }
       if (RECORD && path) path->n++;
-    } while (!is_wall(r.k));                 // in_domain = (celltype[cur] == d_flowCell)  (729)
+    } while (!is_wall(r.k) && len < maxLen); // in_domain = (celltype[cur] == d_flowCell) (729) && rayLength < d_maxRayLength (684)
 
-    // wall: r = record of the non-flow cell entered
+    // wall: r = record of the non-flow cell entered -- or, when the ray ran out of length, of the FLOW cell it stopped in:
+    // the reference then adds that cell's abskg*sigmaT4/pi like a wall emission (846-854) and ends the ray (680)
     const Real eps = k > Real(1) ? Real(1) : k;          // 846-850
     Real intensity = e;                                   // exp(-optical_thickness), same argument as the last step
-    sum = N::add(sum, N::mul(N::mul(eps, s), intensity)); // 854: NOT multiplied by fs
+    sum = N::add(sum, N::mul(N::wall_product(eps, s, floatProps), intensity)); // 854: NOT multiplied by fs
     intensity = N::mul(intensity, fs);                    // 856
-    if (!allowReflect || !(intensity > threshold)) break; // 884, 898, 683
+    if (!allowReflect || !(intensity > threshold) || !(len < maxLen)) break; // 884, 898, 680
     // RMCRTCommon::reflect (581-602)
     fs = N::mul(fs, N::add(Real(1), -k));
     idx = idxPrev;
@@ -567,7 +578,7 @@ template <class Real, class RecT, int MAXL, bool RECORD>
 __device__ __forceinline__ Real march_multi_level(const OnionGeom<MAXL>& G, int ci, int cj, int ck,
                                                   Real dx, Real dy, Real dz, Real rx, Real ry, Real rz,
                                                   Real threshold, bool allowReflect, bool skipZero,
-                                                  unsigned& nSteps, PathSink* path) {
+                                                  unsigned& nSteps, PathSink* path, bool floatProps = false) {
   typedef Num<Real> N;
   if (!(Real(1) > threshold)) return Real(0);
   int L = G.maxLevels - 1;
@@ -679,7 +690,7 @@ __device__ __forceinline__ Real march_multi_level(const OnionGeom<MAXL>& G, int 
 
     const Real eps = k > Real(1) ? Real(1) : k;          // 2594-2598
     Real intensity = e;
-    sum = N::add(sum, N::mul(N::mul(eps, s), intensity)); // 2602
+    sum = N::add(sum, N::mul(N::wall_product(eps, s, floatProps), intensity)); // 2602
     intensity = N::mul(intensity, fs);
     if (!allowReflect || !(intensity > threshold)) break; // 2607-2609, 2621
     fs = N::mul(fs, N::add(Real(1), -k));                // reflect(); cur = prevCell with L unchanged

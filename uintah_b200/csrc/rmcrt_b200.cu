@@ -39,6 +39,7 @@ constexpr int MAXL = 4;   // levels supported by the Data-Onion kernels (referen
 //   [3] valid: set by finalize_kernel's last block, cleared by every kernel that modifies the level
 //   [4] ticket for "last block"      [5] non-finite inputs seen by the pack kernels
 constexpr int LSTAT_WORDS = 8;
+constexpr int NCOUNTERS = 5;    // [0] divQ steps [1] flux steps [2] divQ cells [3] flux cells [4] radiometer steps
 
 //======================================================================================================
 // device-side helpers
@@ -50,6 +51,11 @@ struct RayGen {
   int fixedRandom;        // every draw 0.3
   int ccRays;
   int coherent;           // direction shared by the warp's 32 origin cells
+  int lhc;                // rayDirSampleAlgo == LATIN_HYPER_CUBE (Ray.cc:174-179)
+  // LHC, regression modes: the Fisher-Yates permutations of RMCRTCommon::randVector (RMCRTCommon.cc:998-1024) depend only on
+  // i+j+k (MT19937 reseeded with it) or on nothing (FIXED_RANDOM_NUM); the host tabulates them: perm[(i+j+k) - sumLo][nRays]
+  const int* lhcPerm;
+  int lhcSumLo, lhcRows;
 };
 
 struct TraceArgs {
@@ -73,6 +79,8 @@ struct TraceArgs {
   int firstLevel;                 // levels [firstLevel, maxLevels) take part in this trace
   int recBytes;                   // sizeof(record)
   RoiBox roi;                     // Data-Onion fast path: shell-wrapped copy of the fine level's ROI (rec == nullptr: generic march)
+  double maxRayLength;            // boundedRayLength ROI (RMCRTCommon.cc:680,684); +inf when unbounded
+  int floatProps;                 // the level was packed from float arrays: the FP64 parity march rounds T*T products to float
   // flux items
   const int* items;       // compacted item ids: face * nCells + patch-linear cell
   const int* nItems;      // device count
@@ -90,9 +98,26 @@ __device__ __forceinline__ long long level_index(const LevelGeom& g, int i, int 
   return (long long)(i - g.lo[0]) + (long long)g.n[0] * ((long long)(j - g.lo[1]) + (long long)g.n[1] * (long long)(k - g.lo[2]));
 }
 
+// Latin-Hyper-Cube stratum of ray `ray` (RMCRTCommon::randVector + Ray.cc:750-752,760-761): a permutation of [0,nRays).
+//  * regression modes: row (i+j+k) of the host-built table (exactly the reference's Fisher-Yates shuffle);
+//  * <randomSeed> true: a keyed pseudo-random bijection of [0,nRays) (rng.cuh: keyed_permutation), evaluated statelessly per
+//    ray; key = one Philox block per (cell or tile, timestep).  Any bijection gives a valid Latin hyper cube; the key
+//    makes it differ from cell to cell.
+__device__ __forceinline__ int lhc_bin(const RayGen& rg, int i, int j, int k, int ray, int nRays, unsigned long long permId,
+                                       uint32_t stream) {
+  if (rg.fixedRandom || !rg.isSeedRandom) {
+    int row = rg.fixedRandom ? 0 : (i + j + k) - rg.lhcSumLo;
+    row = min(max(row, 0), rg.lhcRows - 1);
+    return rg.lhcPerm[(long long)row * nRays + ray];
+  }
+  const u32x4 key = philox4x32_10(u32x4{(uint32_t)permId, 0xFFFFFFFFu, rg.timestep, ((uint32_t)(permId >> 32) << 8) | stream},
+                                  rg.key0, rg.key1);
+  return (int)keyed_permutation((uint32_t)ray, (uint32_t)nRays, key);
+}
+
 // RMCRTCommon::findRayDirection (RMCRTCommon.cc:499-538) + ray_Origin (544-576), FP64 like the reference.
 // cellId / dirId : Philox counters (the cell itself; the warp tile's first cell when coherent).
-__device__ __forceinline__ void gen_divq_ray(const RayGen& rg, const LevelGeom& g, int i, int j, int k, int ray,
+__device__ __forceinline__ void gen_divq_ray(const RayGen& rg, const LevelGeom& g, int i, int j, int k, int ray, int nRays,
                                              unsigned long long cellId, unsigned long long dirId,
                                              double dir[3], double rayDx[3]) {
   double u1, u2, o0, o1, o2;
@@ -112,9 +137,16 @@ __device__ __forceinline__ void gen_divq_ray(const RayGen& rg, const LevelGeom& 
     u1 = u01_open(a.x); u2 = u01_open(a.y);
     o0 = u01_closed(b.x); o1 = u01_closed(b.y); o2 = u01_closed(b.z);
   }
-  const double pm1 = 2.0 * u1 - 1.0 + DBL_EPSILON;
+  double pm1, theta;
+  if (rg.lhc) {      // Ray::findRayDirectionHyperCube (Ray.cc:1438-1460): bin_i = rand_i[iRay], bin_j = iRay
+    const int bin_i = lhc_bin(rg, i, j, k, ray, nRays, dirId, STREAM_LHC_DIVQ);
+    pm1 = 2.0 * (u1 + (double)bin_i) / nRays - 1.0;
+    theta = 2.0 * M_PI * (u2 + (double)ray) / nRays;
+  } else {
+    pm1 = 2.0 * u1 - 1.0 + DBL_EPSILON;
+    theta = 2.0 * M_PI * u2;
+  }
   const double r = sqrt(1.0 - pm1 * pm1);
-  const double theta = 2.0 * M_PI * u2;
   double sn, cs;
   sincos(theta, &sn, &cs);
   dir[0] = r * cs; dir[1] = r * sn; dir[2] = pm1;
@@ -154,15 +186,17 @@ __device__ __forceinline__ void gen_divq_ray_f32(const RayGen& rg, const LevelGe
 // Ray::rayDirection_cellFace (Ray.cc:1362-1390) + rayLocation_cellFace (1465-1513).
 // face in push order of has_a_boundary: 0 W(-x) 1 E(+x) 2 S(-y) 3 N(+y) 4 B(-z) 5 T(+z) == Stencil7 slot.
 __device__ __forceinline__ void gen_flux_ray(const RayGen& rg, const LevelGeom& g, int i, int j, int k, int face, int ray,
-                                             unsigned long long cellId, unsigned long long dirId,
+                                             int nRays, unsigned long long cellId, unsigned long long dirId,
                                              double dir[3], double rayDx[3], double& cosTheta) {
   double u1, u2, p0, p1;
+  double e1 = 0.3, e2 = 0.3;     // the (0,1) conversions of the same two words: the LHC variant draws randDblExc() (Ray.cc:1413,1416)
   if (rg.fixedRandom) {
     u1 = u2 = p0 = p1 = 0.3;
   } else if (!rg.isSeedRandom) {
     uint32_t v[4];
     mt19937_first<4>((uint32_t)((i + j + k) * ray + 1), v);      // Ray.cc:1371-1373
     u1 = u01_closed(v[0]); u2 = u01_closed(v[1]); p0 = u01_closed(v[2]); p1 = u01_closed(v[3]);
+    e1 = u01_open(v[0]); e2 = u01_open(v[1]);
   } else {
     const uint32_t rw = (uint32_t)ray | ((uint32_t)face << 28);
     const u32x4 a = philox4x32_10(u32x4{(uint32_t)dirId, rw, rg.timestep,
@@ -170,9 +204,17 @@ __device__ __forceinline__ void gen_flux_ray(const RayGen& rg, const LevelGeom& 
     const u32x4 b = philox4x32_10(u32x4{(uint32_t)cellId, rw, rg.timestep,
                                         ((uint32_t)(cellId >> 32) << 8) | STREAM_FLUX_ORIGIN}, rg.key0, rg.key1);
     u1 = u01_closed(a.x); u2 = u01_closed(a.y); p0 = u01_closed(b.x); p1 = u01_closed(b.y);
+    e1 = u01_open(a.x); e2 = u01_open(a.y);
   }
-  const double phi = 2 * M_PI * u1;
-  const double theta = acos(u2);
+  double phi, theta;
+  if (rg.lhc) {      // Ray::rayDirectionHyperCube_cellFace (Ray.cc:1398-1432): cosTheta stratum first, then phi
+    const int bin_i = lhc_bin(rg, i, j, k, ray, nRays, dirId * 8ull + (unsigned long long)face, STREAM_LHC_FLUX);
+    theta = acos((e1 + (double)bin_i) / nRays);
+    phi = 2.0 * M_PI * (e2 + (double)ray) / nRays;
+  } else {
+    phi = 2 * M_PI * u1;
+    theta = acos(u2);
+  }
   cosTheta = cos(theta);
   double sp, cp;
   sincos(phi, &sp, &cp);
@@ -236,18 +278,19 @@ __device__ __forceinline__ Real trace_one(const TraceArgs& a, bool skipZero, int
                                                      a.allowReflect != 0, skipZero, steps, a.recBytes);
     return UNSCALE * march_multi_level<Real, RecT, MAXL, RECORD>(a.G, i, j, k, nz<Real, D>(dir[0]), nz<Real, D>(dir[1]), nz<Real, D>(dir[2]),
                                                        (Real)rayDx[0], (Real)rayDx[1], (Real)rayDx[2], (Real)a.threshold,
-                                                       a.allowReflect != 0, skipZero, steps, path);
+                                                       a.allowReflect != 0, skipZero, steps, path, a.floatProps != 0);
   } else
   if (ML) {
     return UNSCALE * march_multi_level<Real, RecT, MAXL, RECORD>(a.G, i, j, k, nz<Real, D>(dir[0]), nz<Real, D>(dir[1]), nz<Real, D>(dir[2]),
                                                        (Real)rayDx[0], (Real)rayDx[1], (Real)rayDx[2], (Real)a.threshold,
-                                                       a.allowReflect != 0, skipZero, steps, path);
+                                                       a.allowReflect != 0, skipZero, steps, path, a.floatProps != 0);
   } else {
     return UNSCALE * march_single_level<Real, RecT, RECORD>(static_cast<const RecT*>(g.rec), level_index(g, i, j, k), g.n[0],
                                                   g.n[0] * g.n[1], nz<Real, D>(dir[0]), nz<Real, D>(dir[1]), nz<Real, D>(dir[2]),
                                                   (Real)rayDx[0], (Real)rayDx[1], (Real)rayDx[2], (Real)g.dx[0],
                                                   (Real)g.dx[1], (Real)g.dx[2], (Real)a.threshold, a.allowReflect != 0,
-                                                  skipZero, steps, path, i, j, k);
+                                                  skipZero, steps, path, i, j, k,
+                                                  (Real)(a.maxRayLength * (double)Num<Real>::LEN_SCALE), a.floatProps != 0);
   }
 }
 
@@ -258,7 +301,10 @@ __device__ __forceinline__ Real trace_one(const TraceArgs& a, bool skipZero, int
 // Per-lane sums are combined across the W warps through shared memory in a fixed order (deterministic),
 // then lane = cell writes divQ / radiationVolq fully coalesced.
 //======================================================================================================
-template <class Real, class RecT, bool ML, bool FAST = false>
+// F32GEN: production ray set-up only (Philox draws, FP32 direction/origin); false: the FP64 set-up that also serves the
+// regression modes (MT19937 reseed, FIXED_RANDOM_NUM), Latin-Hyper-Cube sampling and the FP64 march.  Two instantiations
+// rather than a branch so the hot kernel carries no FP64 sincos / table code in its 32-register budget.
+template <class Real, class RecT, bool ML, bool FAST = false, bool F32GEN = false>
 // Register budget: the tuned single-level kernel is built for 32 registers/thread (8 x 256-thread blocks per SM = 64
 // resident warps).  Measured at 128^3 x 100 rays: 96 regs 5.5e11, 80 regs 6.5e11, 64 regs 8.0e11, 48 regs 8.5e11,
 // 40 regs 8.8e11, 32 regs 9.3e11 steps/s -- latency hiding by occupancy beats the spills, which sit in the per-ray
@@ -298,7 +344,7 @@ __global__ void __launch_bounds__(256, ((FAST && !ML) ? RMCRT_FAST_MIN_BLOCKS : 
     double acc = 0;
     unsigned steps = 0;
     if (flow) {
-      if (std::is_same<Real, float>::value && a.rng.isSeedRandom && !a.rng.fixedRandom) {
+      if constexpr (F32GEN && std::is_same<Real, float>::value) {
         for (int ray = warp; ray < a.nRays; ray += W) {      // production: Philox draws, FP32 ray set-up
           float dir[3], rayDx[3];
           gen_divq_ray_f32(a.rng, g, ray, cellId, dirId, dir, rayDx);
@@ -307,7 +353,7 @@ __global__ void __launch_bounds__(256, ((FAST && !ML) ? RMCRT_FAST_MIN_BLOCKS : 
       } else {
         for (int ray = warp; ray < a.nRays; ray += W) {      // regression modes (MT19937 reseed, FIXED_RANDOM_NUM) and the FP64 march
           double dir[3], rayDx[3];
-          gen_divq_ray(a.rng, g, i, j, k, ray, cellId, dirId, dir, rayDx);
+          gen_divq_ray(a.rng, g, i, j, k, ray, a.nRays, cellId, dirId, dir, rayDx);
           acc += (double)trace_one<Real, RecT, ML, false, FAST>(a, skipZero, i, j, k, dir, rayDx, steps, nullptr);
         }
       }
@@ -381,7 +427,7 @@ __global__ void flux_mask_kernel(const __grid_constant__ TraceArgs a, unsigned c
 }
 
 // lane = one (face, cell) item; consecutive items are neighbouring cells on the same face.
-template <class Real, class RecT, bool ML>
+template <class Real, class RecT, bool ML, bool FAST = true>
 __global__ void __launch_bounds__(256) flux_trace_kernel(const __grid_constant__ TraceArgs a) {
   extern __shared__ double red[];     // [W][32][2]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
@@ -415,8 +461,8 @@ __global__ void __launch_bounds__(256) flux_trace_kernel(const __grid_constant__
     if (valid) {
       for (int ray = warp; ray < a.nRays; ray += W) {
         double dir[3], rayDx[3], cosT;
-        gen_flux_ray(a.rng, g, i, j, k, face, ray, cellId, dirId, dir, rayDx, cosT);
-        const double dI = (double)trace_one<Real, RecT, ML, false, true>(a, skipZero, i, j, k, dir, rayDx, steps, nullptr);
+        gen_flux_ray(a.rng, g, i, j, k, face, ray, a.nRays, cellId, dirId, dir, rayDx, cosT);
+        const double dI = (double)trace_one<Real, RecT, ML, false, FAST>(a, skipZero, i, j, k, dir, rayDx, steps, nullptr);
         sumProj += cosT * dI;      // sumProjI += cosTheta * (sumI - sumI_prev)   (Ray.cc:704)
         sumCos += cosT;
       }
@@ -437,6 +483,92 @@ __global__ void __launch_bounds__(256) flux_trace_kernel(const __grid_constant__
   }
   for (int o = 16; o > 0; o >>= 1) stepsTotal += __shfl_down_sync(0xffffffffu, stepsTotal, o);
   if (lane == 0 && stepsTotal) atomicAdd(a.counters + 1, stepsTotal);
+}
+
+//======================================================================================================
+// virtual radiometer (Radiometer.cc:428-560).  A radiometer is a handful of cells with thousands of rays each, so the
+// parallel axis is the ray: one block per radiometer cell, thread t marches rays t, t+B, ...; per-thread FP64 partial sums
+// are combined in a fixed order (deterministic).
+//======================================================================================================
+struct RadArgs {
+  rmcrt_radiometer rad;
+  int lo[3], n[3];        // cells of (radiometer box n patch)
+  void* flux;
+  void* intensity;
+  int isFloat;
+};
+
+template <class Real, class RecT>
+__global__ void __launch_bounds__(256) radiometer_kernel(const __grid_constant__ TraceArgs a, const __grid_constant__ RadArgs ra) {
+  __shared__ double red[256];
+  __shared__ unsigned long long redSteps[256];
+  const int F = a.G.maxLevels - 1;
+  const LevelGeom& g = a.G.lev[F];
+  const bool skipZero = skip_allowed(a);
+  const long long nCells = (long long)ra.n[0] * ra.n[1] * ra.n[2];
+  const rmcrt_radiometer& rad = ra.rad;
+  // rotation matrix of Radiometer.cc:539-552 (phi_rotate is always 0, kept for fidelity)
+  const double cth = cos(rad.theta_rotate), sth = sin(rad.theta_rotate), cxi = cos(rad.xi_rotate), sxi = sin(rad.xi_rotate),
+               cph = cos(rad.phi_rotate), sph = sin(rad.phi_rotate);
+  const double cosView = cos(rad.theta_viewAngle);
+  for (long long cell = blockIdx.x; cell < nCells; cell += gridDim.x) {
+    const int ci = (int)(cell % ra.n[0]), cj = (int)((cell / ra.n[0]) % ra.n[1]), ck = (int)(cell / ((long long)ra.n[0] * ra.n[1]));
+    const int i = ra.lo[0] + ci, j = ra.lo[1] + cj, k = ra.lo[2] + ck;
+    const unsigned long long cellId = (unsigned long long)level_index(g, i, j, k);
+    double sumProj = 0;
+    unsigned steps = 0;
+    for (int ray = threadIdx.x; ray < rad.nRays; ray += blockDim.x) {
+      double R1, R2;
+      if (a.rng.fixedRandom) R1 = R2 = 0.3;
+      else if (!a.rng.isSeedRandom) {
+        uint32_t v[2];
+        mt19937_first<2>((uint32_t)((i + j + k) * ray + 1), v);      // Radiometer.cc:512-514
+        R1 = u01_open(v[0]); R2 = u01_open(v[1]);
+      } else {
+        const u32x4 w = philox4x32_10(u32x4{(uint32_t)cellId, (uint32_t)ray, a.rng.timestep,
+                                            ((uint32_t)(cellId >> 32) << 8) | STREAM_RADIOMETER}, a.rng.key0, a.rng.key1);
+        R1 = u01_open(w.x); R2 = u01_open(w.y);
+      }
+      const double phiRay = 2 * M_PI * R1;                        // 526
+      const double thetaRay = acos(cosView + rad.range * R2);     // 530
+      const double cosT = cos(thetaRay);
+      const double x = sin(thetaRay) * cos(phiRay), y = sin(thetaRay) * sin(phiRay), z = cosT;   // 534-536
+      double dir[3];
+      dir[0] = x * cth * cxi + y * (-cph * sxi + sph * sth * cxi) + z * (sph * sxi + cph * sth * cxi);
+      dir[1] = x * cth * sxi + y * (cph * cxi + sph * sth * sxi) + z * (-sph * cxi + cph * sth * sxi);
+      dir[2] = x * -sth + y * sph * cth + z * cph * cth;
+      double rayDx[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {                               // ray_Origin with useCCRays = true (Radiometer.cc:472-473)
+        const int c = d == 0 ? i : (d == 1 ? j : k);
+        const double cc = g.anchor[d] + g.dx[d] * c + g.dx[d] * 0.5;
+        rayDx[d] = cc - (cc - 0.5 * g.dx[d]);
+      }
+      const double dI = (double)trace_one<Real, RecT, false, false, false>(a, skipZero, i, j, k, dir, rayDx, steps, nullptr);
+      sumProj += cosT * dI;                                       // 483
+    }
+    red[threadIdx.x] = sumProj;
+    redSteps[threadIdx.x] = steps;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {               // fixed-order tree: deterministic
+      if ((int)threadIdx.x < o) { red[threadIdx.x] += red[threadIdx.x + o]; redSteps[threadIdx.x] += redSteps[threadIdx.x + o]; }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      const long long q = (long long)(i - a.outLo[0]) +
+                          (long long)a.outN[0] * ((long long)(j - a.outLo[1]) + (long long)a.outN[1] * (long long)(k - a.outLo[2]));
+      const double sp = red[0];
+      if (ra.isFloat) {     // `(T) sumProjI * solidAngle/nRays`: the cast binds to sumProjI (Radiometer.cc:492-493)
+        static_cast<float*>(ra.flux)[q] = (float)((double)(float)sp * rad.solidAngle / rad.nRays);
+        static_cast<float*>(ra.intensity)[q] = (float)((float)sp / rad.nRays);
+      } else {
+        static_cast<double*>(ra.flux)[q] = sp * rad.solidAngle / rad.nRays;
+        static_cast<double*>(ra.intensity)[q] = sp / rad.nRays;
+      }
+      if (redSteps[0]) atomicAdd(a.counters + 4, redSteps[0]);
+    }
+    __syncthreads();
+  }
 }
 
 //======================================================================================================
@@ -707,6 +839,7 @@ struct LevelState {
   void* recFull = nullptr;   // recordKind 2: float records of the same cells (epilogue of the divQ kernel)
   long long nCells = 0;
   size_t recBytes = 8;
+  bool propsFloat = false;   // the last pack read float property arrays
 };
 
 struct DevBuf {
@@ -728,12 +861,16 @@ struct rmcrt_ctx {
   int smCount = 148;
   rmcrt_params p{};
   LevelState lv[RMCRT_MAX_LEVELS];
-  unsigned long long* d_counters = nullptr;   // 4
+  unsigned long long* d_counters = nullptr;   // NCOUNTERS
   unsigned* d_lstat = nullptr;                // [RMCRT_MAX_LEVELS][LSTAT_WORDS]
   int* d_nItems = nullptr;
   DevBuf stage[3];      // upload staging
   DevBuf outDivQ, outVolq, outFlux;   // host-API output staging
   DevBuf fluxFlags, fluxItems, cubTemp, dbg[6], misc, roiBuf;
+  DevBuf lhcDivQ, lhcFlux;            // LHC permutation tables of the regression modes
+  int lhcKeyDivQ[4] = {0, 0, 0, 0};   // (nRays, sumLo, rows, mode) the tables were built for
+  int lhcKeyFlux[4] = {0, 0, 0, 0};
+  DevBuf outVR[2];                    // host-API radiometer output staging
   std::string err;
   void* persistedStreamFor = nullptr;
 };
@@ -784,6 +921,8 @@ int validate_params(rmcrt_ctx* ctx, const rmcrt_params* p) {
   if (p->nFluxRays >= (1 << 28)) return fail(ctx, RMCRT_ERR_INVALID, "nFluxRays too large");
   if (!(p->threshold >= 0)) return fail(ctx, RMCRT_ERR_INVALID, "Threshold must be >= 0");
   if (p->marchPrecision != 0 && p->marchPrecision != 1) return fail(ctx, RMCRT_ERR_INVALID, "marchPrecision must be 0 (fp32) or 1 (fp64)");
+  if (p->rayDirSampleAlgo != 0 && p->rayDirSampleAlgo != 1) return fail(ctx, RMCRT_ERR_INVALID, "rayDirSampleAlgo must be 0 (naive) or 1 (LatinHyperCube)");
+  if (p->maxRayLength != p->maxRayLength) return fail(ctx, RMCRT_ERR_INVALID, "maxRayLength is NaN");
   return 0;
 }
 
@@ -899,6 +1038,65 @@ int do_pack(rmcrt_ctx* ctx, int recordKind, int isFloat, const void* a, const vo
                  : launch_pack<double, Rec16>(ctx, a, s, ct, src, region, dst, dstBox, status, nullptr, fullBox, st);
 }
 
+// MT19937 exactly as MTRand (Core/Math/MersenneTwister.h:217-258,339-368): the regression modes of the LHC sampler shuffle
+// with randInt(n), which draws an unbounded number of words, so the stateless mt19937_first<> does not cover it.
+struct HostMT {
+  uint32_t st[624];
+  int next = 624;
+  void seed(uint32_t s) {
+    st[0] = s;
+    for (int i = 1; i < 624; ++i) st[i] = 1812433253u * (st[i - 1] ^ (st[i - 1] >> 30)) + (uint32_t)i;
+    reload();
+  }
+  static uint32_t tw(uint32_t m, uint32_t s0, uint32_t s1) {
+    return m ^ (((s0 & 0x80000000u) | (s1 & 0x7fffffffu)) >> 1) ^ ((s1 & 1u) ? 0x9908b0dfu : 0u);
+  }
+  void reload() {
+    int k = 0;
+    for (; k < 624 - 397; ++k) st[k] = tw(st[k + 397], st[k], st[k + 1]);
+    for (; k < 623; ++k) st[k] = tw(st[k + 397 - 624], st[k], st[k + 1]);
+    st[623] = tw(st[396], st[623], st[0]);
+    next = 0;
+  }
+  uint32_t u32() {
+    if (next >= 624) reload();
+    uint32_t y = st[next++];
+    y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u;
+    return y ^ (y >> 18);
+  }
+  uint32_t randInt(uint32_t n) {     // MersenneTwister.h:233-250
+    uint32_t used = n;
+    used |= used >> 1; used |= used >> 2; used |= used >> 4; used |= used >> 8; used |= used >> 16;
+    uint32_t i;
+    do i = u32() & used; while (i > n);
+    return i;
+  }
+};
+
+// RMCRTCommon::randVector (RMCRTCommon.cc:998-1024) for every value of i+j+k on the level (regression modes only)
+int ensure_lhc_table(rmcrt_ctx* ctx, DevBuf& buf, int key[4], int nRays, const rmcrt_level_desc& f, cudaStream_t st) {
+  const int mode = ctx->p.fixedRandom ? 2 : 1;
+  const int sumLo = f.lo[0] + f.lo[1] + f.lo[2];
+  const int rows = ctx->p.fixedRandom ? 1 : (f.hi[0] + f.hi[1] + f.hi[2] - 3) - sumLo + 1;
+  if (buf.p && key[0] == nRays && key[1] == sumLo && key[2] == rows && key[3] == mode) return 0;
+  std::vector<int> tab((size_t)rows * nRays);
+  HostMT mt;
+  for (int r = 0; r < rows; ++r) {
+    int* a = tab.data() + (size_t)r * nRays;
+    for (int i = 0; i < nRays; ++i) a[i] = i;
+    if (mode == 1) mt.seed((uint32_t)(sumLo + r));                   // mTwister.seed(cell.x()+cell.y()+cell.z())
+    for (int i = nRays - 1; i > 0; --i) {
+      const int ri = mode == 2 ? (int)(0.3 * i) : (int)mt.randInt((uint32_t)i);
+      std::swap(a[i], a[ri]);
+    }
+  }
+  if (buf.ensure(tab.size() * sizeof(int))) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc LHC table");
+  CK(cudaMemcpyAsync(buf.p, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));      // `tab` is pageable and goes out of scope
+  key[0] = nRays; key[1] = sumLo; key[2] = rows; key[3] = mode;
+  return 0;
+}
+
 int build_args(rmcrt_ctx* ctx, int maxLevels, bool multiLevel, const int32_t pLo[3], const int32_t pHi[3], const int32_t oLo[3],
                const int32_t oHi[3], uint64_t timestep, TraceArgs& a) {
   memset(&a, 0, sizeof a);
@@ -946,12 +1144,21 @@ int build_args(rmcrt_ctx* ctx, int maxLevels, bool multiLevel, const int32_t pLo
   a.rng.fixedRandom = ctx->p.fixedRandom;
   a.rng.ccRays = ctx->p.CCRays;
   a.rng.coherent = ctx->p.rayCoherence;
+  a.rng.lhc = ctx->p.rayDirSampleAlgo == 1 ? 1 : 0;
   a.counters = ctx->d_counters;
+  const bool bounded = ctx->p.maxRayLength > 0 && ctx->p.maxRayLength < 1e300;
+  if (bounded && multiLevel)
+    return fail(ctx, RMCRT_ERR_INVALID, "maxRayLength (boundedRayLength ROI) applies to single-level solves only (Ray.cc:2349-2627 has no length test)");
+  a.maxRayLength = bounded ? ctx->p.maxRayLength : (double)INFINITY;
+  a.floatProps = ctx->lv[F].propsFloat ? 1 : 0;
   return 0;
 }
 
 template <class Real, class RecT>
 int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
+  const bool bounded = a.maxRayLength < 1e300;       // boundedRayLength ROI: the generic march carries the length test
+  const bool lhcTable = a.rng.lhc && (!a.rng.isSeedRandom || a.rng.fixedRandom);
+  const bool f32gen = std::is_same<Real, float>::value && a.rng.isSeedRandom && !a.rng.fixedRandom && !a.rng.lhc;
   // ---- boundary flux first, like the task body (Ray.cc:645 before 742)
   if (ctx->p.solveBoundaryFlux) {
     if (!a.bflux) return fail(ctx, RMCRT_ERR_INVALID, "solveBoundaryFlux needs a boundFlux buffer");
@@ -970,14 +1177,27 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
     f.items = static_cast<const int*>(ctx->fluxItems.p);
     f.nItems = ctx->d_nItems;
     f.nRays = ctx->p.nFluxRays;
+    if (lhcTable) {
+      int rc = ensure_lhc_table(ctx, ctx->lhcFlux, ctx->lhcKeyFlux, f.nRays, ctx->lv[a.G.maxLevels - 1].d, st);
+      if (rc) return rc;
+      f.rng.lhcPerm = static_cast<const int*>(ctx->lhcFlux.p);
+      f.rng.lhcSumLo = ctx->lhcKeyFlux[1]; f.rng.lhcRows = ctx->lhcKeyFlux[2];
+    }
     const int W = ctx->p.warpsPerTile > 0 ? std::min(ctx->p.warpsPerTile, 8) : (ctx->p.nFluxRays >= 8 ? 8 : 1);
     const int grid = ctx->smCount * 8;
     if (ML) flux_trace_kernel<Real, RecT, true><<<grid, 32 * W, W * 64 * sizeof(double), st>>>(f);
+    else if (bounded) flux_trace_kernel<Real, RecT, false, false><<<grid, 32 * W, W * 64 * sizeof(double), st>>>(f);
     else    flux_trace_kernel<Real, RecT, false><<<grid, 32 * W, W * 64 * sizeof(double), st>>>(f);
     CK(cudaGetLastError());
   }
   if (ctx->p.solveDivQ) {
     a.nRays = ctx->p.nDivQRays;
+    if (lhcTable) {
+      int rc = ensure_lhc_table(ctx, ctx->lhcDivQ, ctx->lhcKeyDivQ, a.nRays, ctx->lv[a.G.maxLevels - 1].d, st);
+      if (rc) return rc;
+      a.rng.lhcPerm = static_cast<const int*>(ctx->lhcDivQ.p);
+      a.rng.lhcSumLo = ctx->lhcKeyDivQ[1]; a.rng.lhcRows = ctx->lhcKeyDivQ[2];
+    }
     int W = pick_warps(ctx, a.nTiles);
     if (W > a.nRays) W = 1;
     long long grid = a.nTiles;
@@ -1003,11 +1223,18 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
       CK(cudaGetLastError());
       a.roi.rec = static_cast<RecT*>(ctx->roiBuf.p) + guard;
       for (int d = 0; d < 3; ++d) { a.roi.lo[d] = shell.lo[d]; a.roi.n[d] = shell.n[d]; }
-      divq_kernel<Real, RecT, true, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
-    } else if (ML) divq_kernel<Real, RecT, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
-    else if (std::is_same<Real, float>::value && (!ctx->p.genericMarch || std::is_same<RecT, Rec4>::value))
-      divq_kernel<Real, RecT, false, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
-    else    divq_kernel<Real, RecT, false><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
+      if (f32gen) divq_kernel<Real, RecT, true, true, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
+      else        divq_kernel<Real, RecT, true, true, false><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
+    } else if (ML) {
+      if (f32gen) divq_kernel<Real, RecT, true, false, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
+      else        divq_kernel<Real, RecT, true, false, false><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
+    } else if (std::is_same<Real, float>::value && !bounded && (!ctx->p.genericMarch || std::is_same<RecT, Rec4>::value)) {
+      if (f32gen) divq_kernel<Real, RecT, false, true, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
+      else        divq_kernel<Real, RecT, false, true, false><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
+    } else {
+      if (f32gen) divq_kernel<Real, RecT, false, false, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
+      else        divq_kernel<Real, RecT, false, false, false><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
+    }
     CK(cudaGetLastError());
   }
   return 0;
@@ -1067,6 +1294,51 @@ int trace_host(rmcrt_ctx* ctx, int maxLevels, bool ML, const int32_t pLo[3], con
   return 0;
 }
 
+template <class Real, class RecT>
+int launch_radiometer(rmcrt_ctx* ctx, const TraceArgs& a, const RadArgs& ra, cudaStream_t st) {
+  const long long nCells = (long long)ra.n[0] * ra.n[1] * ra.n[2];
+  const int grid = (int)std::min<long long>(nCells, (long long)ctx->smCount * 8);
+  radiometer_kernel<Real, RecT><<<grid, 256, 0, st>>>(a, ra);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int radiometer_common(rmcrt_ctx* ctx, int L, const rmcrt_radiometer* rads, int nRads, const int32_t pLo[3], const int32_t pHi[3],
+                      void* dFlux, void* dInt, int isFloat, const int32_t oLo[3], const int32_t oHi[3], int zeroInit,
+                      uint64_t timestep, cudaStream_t st) {
+  if (!rads && nRads > 0) return fail(ctx, RMCRT_ERR_INVALID, "null radiometer array");
+  if (!dFlux || !dInt) return fail(ctx, RMCRT_ERR_INVALID, "VRFlux and VRIntensity buffers are required");
+  TraceArgs a;
+  int rc = build_args(ctx, L + 1, false, pLo, pHi, oLo, oHi, timestep, a);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  const size_t nOut = (size_t)a.outN[0] * a.outN[1] * a.outN[2];
+  const size_t esz = isFloat ? 4 : 8;
+  if (zeroInit) {     // Radiometer.cc:443-446
+    CK(cudaMemsetAsync(dFlux, 0, nOut * esz, st));
+    CK(cudaMemsetAsync(dInt, 0, nOut * esz, st));
+  }
+  for (int r = 0; r < nRads; ++r) {
+    RadArgs ra;
+    memset(&ra, 0, sizeof ra);
+    ra.rad = rads[r];
+    if (ra.rad.nRays < 1) return fail(ctx, RMCRT_ERR_INVALID, "radiometer %d: nRays must be >= 1", r);
+    bool hit = true;
+    for (int d = 0; d < 3; ++d) {     // doesIntersect + Max/Min (Radiometer.cc:451-454)
+      const int lo = std::max(pLo[d], ra.rad.cellLo[d]), hi = std::min(pHi[d], ra.rad.cellHi[d]);
+      ra.lo[d] = lo; ra.n[d] = hi - lo;
+      hit = hit && hi > lo;
+    }
+    if (!hit) continue;
+    ra.flux = dFlux; ra.intensity = dInt; ra.isFloat = isFloat;
+    if (ctx->p.marchPrecision == 1) rc = launch_radiometer<double, Rec16>(ctx, a, ra, st);
+    else if (ctx->lv[L].recordKind == 2) rc = launch_radiometer<float, Rec4>(ctx, a, ra, st);
+    else rc = launch_radiometer<float, Rec8>(ctx, a, ra, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 }  // namespace
 
 //======================================================================================================
@@ -1081,6 +1353,7 @@ size_t rmcrt_struct_size(int which) {
     case 0: return sizeof(rmcrt_params);
     case 1: return sizeof(rmcrt_level_desc);
     case 2: return sizeof(rmcrt_counters);
+    case 3: return sizeof(rmcrt_radiometer);
     default: return 0;
   }
 }
@@ -1095,6 +1368,8 @@ void rmcrt_default_params(rmcrt_params* p) {
   p->seed = 0x9E3779B97F4A7C15ull;
   p->marchPrecision = 0; p->rayCoherence = 1; p->skipZeroWeightLegs = 1; p->fixedRandom = 0; p->l2Persist = 1;
   p->warpsPerTile = 0;
+  p->rayDirSampleAlgo = 0;     // "naive", Ray.cc:174
+  p->maxRayLength = 0.0;       // unbounded (DBL_MAX, RMCRTCommon.cc:117)
 }
 
 const char* rmcrt_last_error(const rmcrt_ctx* ctx) {
@@ -1120,10 +1395,10 @@ int rmcrt_create(int device, const rmcrt_params* p, rmcrt_ctx** out) {
   auto bail = [&](const char* what) { std::string m = what; rmcrt_destroy(ctx); return fail(nullptr, RMCRT_ERR_CUDA, "%s", m.c_str()); };
   if (cudaSetDevice(device) != cudaSuccess) return bail("cudaSetDevice failed");
   cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, device);
-  if (cudaMalloc(&ctx->d_counters, 4 * sizeof(unsigned long long)) != cudaSuccess) return bail("cudaMalloc counters");
+  if (cudaMalloc(&ctx->d_counters, NCOUNTERS * sizeof(unsigned long long)) != cudaSuccess) return bail("cudaMalloc counters");
   if (cudaMalloc(&ctx->d_lstat, RMCRT_MAX_LEVELS * LSTAT_WORDS * sizeof(unsigned)) != cudaSuccess) return bail("cudaMalloc status");
   if (cudaMalloc(&ctx->d_nItems, sizeof(int)) != cudaSuccess) return bail("cudaMalloc nItems");
-  cudaMemset(ctx->d_counters, 0, 4 * sizeof(unsigned long long));
+  cudaMemset(ctx->d_counters, 0, NCOUNTERS * sizeof(unsigned long long));
   cudaMemset(ctx->d_lstat, 0, RMCRT_MAX_LEVELS * LSTAT_WORDS * sizeof(unsigned));
   cudaMemset(ctx->d_nItems, 0, sizeof(int));
   *out = ctx;
@@ -1149,6 +1424,7 @@ void rmcrt_destroy(rmcrt_ctx* ctx) {
   for (auto& b : ctx->stage) b.release();
   ctx->outDivQ.release(); ctx->outVolq.release(); ctx->outFlux.release();
   ctx->fluxFlags.release(); ctx->fluxItems.release(); ctx->cubTemp.release(); ctx->misc.release(); ctx->roiBuf.release();
+  ctx->lhcDivQ.release(); ctx->lhcFlux.release(); ctx->outVR[0].release(); ctx->outVR[1].release();
   for (auto& b : ctx->dbg) b.release();
   delete ctx;
 }
@@ -1216,6 +1492,7 @@ int rmcrt_pack_level_device(rmcrt_ctx* ctx, int L, const void* a, const void* s,
   }
   int rci = invalidate_level(ctx, L, (cudaStream_t)stream);
   if (rci) return rci;
+  lv.propsFloat = isFloat != 0;
   return do_pack(ctx, lv.recordKind, isFloat, a, s, ct, src, region, lv.rec, dst, lstat_of(ctx, L), lv.recFull, dst, (cudaStream_t)stream);
 }
 
@@ -1316,6 +1593,62 @@ int rmcrt_trace_dataonion(rmcrt_ctx* ctx, int maxLevels, const int32_t pLo[3], c
   return trace_host(ctx, maxLevels, true, pLo, pHi, dq, vq, bf, oLo, oHi, zeroInit, timestep, (cudaStream_t)stream);
 }
 
+// Radiometer::problemSetup (Radiometer.cc:118-120, 203-260)
+int rmcrt_radiometer_setup(double viewAngle, const double vec[3], int isNormalVector, rmcrt_radiometer* r) {
+  if (!vec || !r) return RMCRT_ERR_INVALID;
+  if (viewAngle > 360) return fail(nullptr, RMCRT_ERR_INVALID, "VRViewAngle (%g) exceeds the maximum acceptable value of 360 degrees", viewAngle);
+  double n[3] = {vec[0], vec[1], vec[2]};
+  if (isNormalVector) {
+    const double l = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    for (int d = 0; d < 3; ++d) n[d] = n[d] / l;
+  }
+  for (int d = 0; d < 3; ++d) if (n[d] == 0) n[d] = 1e-16;       // 216-220 (the reference's divide-by-zero guard)
+  const double len = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+  r->phi_rotate = 0;                                              // 238: never a rotation about x
+  r->theta_rotate = acos(n[2] / len);                             // 240
+  double xi = acos(n[0] / sqrt(n[0] * n[0] + n[1] * n[1]));       // 242
+  if (n[0] < 0 && n[1] < 0) xi = (M_PI / 2 + xi);                 // 246-248 (quadrant 3, as coded in the reference)
+  if (n[0] > 0 && n[1] < 0) xi = (2 * M_PI - xi);                 // 249-251 (quadrant 4)
+  r->xi_rotate = xi;
+  r->theta_viewAngle = viewAngle / 360 * M_PI;                    // 258
+  r->range = 1 - cos(r->theta_viewAngle);                         // 259
+  r->solidAngle = 2 * M_PI * r->range;                            // 260
+  return 0;
+}
+
+int rmcrt_trace_radiometer_device(rmcrt_ctx* ctx, int L, const rmcrt_radiometer* rads, int nRads, const int32_t pLo[3],
+                                  const int32_t pHi[3], void* dFlux, void* dInt, int isFloat, const int32_t oLo[3],
+                                  const int32_t oHi[3], int zeroInit, uint64_t timestep, void* stream) {
+  if (!ctx) return RMCRT_ERR_INVALID;
+  return radiometer_common(ctx, L, rads, nRads, pLo, pHi, dFlux, dInt, isFloat, oLo, oHi, zeroInit, timestep, (cudaStream_t)stream);
+}
+
+int rmcrt_trace_radiometer(rmcrt_ctx* ctx, int L, const rmcrt_radiometer* rads, int nRads, const int32_t pLo[3], const int32_t pHi[3],
+                           void* flux, void* inten, int isFloat, const int32_t oLo[3], const int32_t oHi[3], int zeroInit,
+                           uint64_t timestep, void* stream) {
+  if (!ctx) return RMCRT_ERR_INVALID;
+  if (!flux || !inten) return fail(ctx, RMCRT_ERR_INVALID, "VRFlux and VRIntensity buffers are required");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t nOut = 1;
+  for (int d = 0; d < 3; ++d) {
+    if (oHi[d] <= oLo[d]) return fail(ctx, RMCRT_ERR_INVALID, "empty output window");
+    nOut *= (size_t)(oHi[d] - oLo[d]);
+  }
+  const size_t bytes = nOut * (isFloat ? 4 : 8);
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->outVR[0].ensure(bytes) || ctx->outVR[1].ensure(bytes)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc radiometer outputs");
+  if (!zeroInit) {     // modifiesFlux: start from the caller's values
+    CK(cudaMemcpyAsync(ctx->outVR[0].p, flux, bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->outVR[1].p, inten, bytes, cudaMemcpyHostToDevice, st));
+  }
+  int rc = radiometer_common(ctx, L, rads, nRads, pLo, pHi, ctx->outVR[0].p, ctx->outVR[1].p, isFloat, oLo, oHi, zeroInit, timestep, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(flux, ctx->outVR[0].p, bytes, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(inten, ctx->outVR[1].p, bytes, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
 int rmcrt_compute_extents(rmcrt_ctx* ctx, int maxLevels, const int32_t pLo[3], const int32_t pHi[3], int32_t roiLo[3],
                           int32_t roiHi[3], int32_t* regionLo, int32_t* regionHi) {
   if (!ctx) return RMCRT_ERR_INVALID;
@@ -1328,17 +1661,17 @@ int rmcrt_compute_extents(rmcrt_ctx* ctx, int maxLevels, const int32_t pLo[3], c
 int rmcrt_reset_counters(rmcrt_ctx* ctx, void* stream) {
   if (!ctx) return RMCRT_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
-  CK(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), (cudaStream_t)stream));
+  CK(cudaMemsetAsync(ctx->d_counters, 0, NCOUNTERS * sizeof(unsigned long long), (cudaStream_t)stream));
   return 0;
 }
 
 int rmcrt_get_counters(rmcrt_ctx* ctx, rmcrt_counters* out, void* stream) {
   if (!ctx || !out) return RMCRT_ERR_INVALID;
   CK(cudaSetDevice(ctx->device));
-  unsigned long long h[4];
+  unsigned long long h[NCOUNTERS];
   CK(cudaMemcpyAsync(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CK(cudaStreamSynchronize((cudaStream_t)stream));
-  out->nRaySteps = h[0]; out->nFluxRaySteps = h[1]; out->nDivQCells = h[2]; out->nFluxCells = h[3];
+  out->nRaySteps = h[0]; out->nFluxRaySteps = h[1]; out->nDivQCells = h[2]; out->nFluxCells = h[3]; out->nRadiometerSteps = h[4];
   return 0;
 }
 
@@ -1376,6 +1709,7 @@ int rmcrt_coarsen_level_device(rmcrt_ctx* ctx, int fineL, int coarseL, void* str
   LevelState& f = ctx->lv[fineL];
   LevelState& c = ctx->lv[coarseL];
   if (f.recordKind != c.recordKind) return fail(ctx, RMCRT_ERR_INVALID, "recordKind mismatch between levels");
+  c.propsFloat = f.propsFloat;
   const int* rr = f.d.refineRatio;
   for (int d = 0; d < 3; ++d) {
     if (rr[d] < 1) return fail(ctx, RMCRT_ERR_INVALID, "fine level refineRatio must be >= 1");
@@ -1424,6 +1758,7 @@ int rmcrt_pack_box_device(rmcrt_ctx* ctx, int L, const void* a, const void* s, c
   for (int d = 0; d < 3; ++d)
     if (boxLo[d] < srcLo[d] || boxHi[d] > srcHi[d] || boxHi[d] <= boxLo[d]) return fail(ctx, RMCRT_ERR_INVALID, "box must lie inside the source window");
   CK(cudaSetDevice(ctx->device));
+  ctx->lv[L].propsFloat = isFloat != 0;
   Box src = mkbox(srcLo, srcHi), box = mkbox(boxLo, boxHi);
   // half-packed levels: the float copy of the rank's own cells goes straight into the level (only origin cells need it)
   return do_pack(ctx, ctx->lv[L].recordKind, isFloat, a, s, ct, src, box, d_send, box, lstat_of(ctx, L), ctx->lv[L].recFull,

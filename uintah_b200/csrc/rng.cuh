@@ -36,12 +36,34 @@ __host__ __device__ __forceinline__ u32x4 philox4x32_10(u32x4 c, uint32_t k0, ui
 }
 
 // streams (low byte of counter word 3)
-enum : uint32_t { STREAM_DIR = 1, STREAM_ORIGIN = 2, STREAM_FLUX_DIR = 3, STREAM_FLUX_ORIGIN = 4 };
+enum : uint32_t { STREAM_DIR = 1, STREAM_ORIGIN = 2, STREAM_FLUX_DIR = 3, STREAM_FLUX_ORIGIN = 4, STREAM_LHC_DIVQ = 5, STREAM_LHC_FLUX = 6,
+                  STREAM_RADIOMETER = 7 };
 
 // (0,1) from 32 random bits, MTRand::randDblExc() formula (MersenneTwister.h:190-197)
 __host__ __device__ __forceinline__ double u01_open(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0); }
 // [0,1], MTRand::rand() formula (MersenneTwister.h:172-179)
 __host__ __device__ __forceinline__ double u01_closed(uint32_t x) { return (double)x * (1.0 / 4294967295.0); }
+
+// Keyed pseudo-random bijection of [0,n): position x of a permutation chosen by `key` (Latin-Hyper-Cube strata when
+// <randomSeed> true; stands in for the Fisher-Yates shuffle RMCRTCommon::randVector draws from the task's MTRand stream,
+// RMCRTCommon.cc:998-1024).  Add / multiply-by-odd / xor-shift-right are bijections mod 2^b; values >= n are cycle-walked.
+__host__ __device__ __forceinline__ uint32_t keyed_permutation(uint32_t x, uint32_t n, const u32x4& key) {
+  if (n <= 1u) return 0u;
+  int bits = 0;
+  for (uint32_t v = n - 1u; v; v >>= 1) ++bits;
+  const uint32_t m = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u);
+  const int sh = bits > 1 ? (bits + 1) / 2 : 1;
+  do {
+    x = (x + key.x) & m;
+    x = (x * (key.y | 1u)) & m;
+    x ^= x >> sh;
+    x = (x * (key.z | 1u)) & m;
+    x = (x + key.w) & m;
+    x ^= x >> sh;
+    x = (x * 0x9E3779B1u) & m;
+  } while (x >= n);
+  return x;
+}
 
 constexpr int MT_MAXOUT = 5;
 

@@ -86,6 +86,19 @@ class Vector {
   double v_[3];
 };
 typedef Vector Point;
+// Core/Geometry/BBox.h: axis-aligned box grown by extend()
+class BBox {
+ public:
+  void extend(const Point& p) {
+    if (!valid_) { min_ = max_ = p; valid_ = true; return; }
+    for (int d = 0; d < 3; ++d) { min_[d] = std::min(min_[d], p[d]); max_[d] = std::max(max_[d], p[d]); }
+  }
+  Point min() const { return min_; }
+  Point max() const { return max_; }
+ private:
+  Point min_, max_;
+  bool valid_ = false;
+};
 inline std::ostream& operator<<(std::ostream& o, const Vector& v) { return o << "[" << v.x() << "," << v.y() << "," << v.z() << "]"; }
 
 //----------------------------------------------------------------------------------------------------- type tags, labels
@@ -97,16 +110,34 @@ namespace Ghost {
 enum GhostType { None, AroundCells };
 }
 
+// VarLabel.cc:56-122: labels are unique per name and reference counted -- create() of an existing name returns the same
+// object (Ray and Radiometer both construct an RMCRTCommon and must see the same "sigmaT4" label), destroy() drops a reference.
 class VarLabel {
  public:
-  static VarLabel* create(const std::string& name, TypeDescription::Type type) { return new VarLabel(name, type); }
-  static void destroy(const VarLabel* l) { delete l; }
+  static VarLabel* create(const std::string& name, TypeDescription::Type type) {
+    auto& reg = registry();
+    auto it = reg.find(name);
+    if (it != reg.end()) { ++it->second->refs_; return it->second; }
+    VarLabel* l = new VarLabel(name, type);
+    reg[name] = l;
+    return l;
+  }
+  static void destroy(const VarLabel* l) {
+    if (!l) return;
+    VarLabel* m = const_cast<VarLabel*>(l);
+    if (--m->refs_ > 0) return;
+    registry().erase(m->name_);
+    delete m;
+  }
   const std::string& getName() const { return name_; }
   TypeDescription::Type typeDescription() const { return type_; }
+  bool equals(const VarLabel* o) const { return this == o; }
  private:
   VarLabel(const std::string& n, TypeDescription::Type t) : name_(n), type_(t) {}
+  static std::map<std::string, VarLabel*>& registry() { static std::map<std::string, VarLabel*> r; return r; }
   std::string name_;
   TypeDescription::Type type_;
+  int refs_ = 1;
 };
 
 struct Stencil7 {   // Stencil7.h:38-76: AoS of 7 doubles; RMCRTboundFlux uses w,e,s,n,b,t for the faces and p as the "has a boundary" mark
@@ -243,6 +274,17 @@ class Level {
   Point getCellPosition(const IntVector& c) const {
     return Point(anchor_.x() + dcell_.x() * (c.x() + 0.5), anchor_.y() + dcell_.y() * (c.y() + 0.5), anchor_.z() + dcell_.z() * (c.z() + 0.5));
   }
+  // Level.cc:480-485: RoundDown((p - anchor) / dcell)
+  IntVector getCellIndex(const Point& p) const {
+    return IntVector((int)std::floor((p.x() - anchor_.x()) / dcell_.x()), (int)std::floor((p.y() - anchor_.y()) / dcell_.y()),
+                     (int)std::floor((p.z() - anchor_.z()) / dcell_.z()));
+  }
+  // Level.cc getSpatialRange: the boxes of all patches, extra cells included
+  void getSpatialRange(BBox& b) const {
+    const IntVector lo = lo_ - extra_, hi = hi_ + extra_;
+    b.extend(Point(anchor_.x() + dcell_.x() * lo.x(), anchor_.y() + dcell_.y() * lo.y(), anchor_.z() + dcell_.z() * lo.z()));
+    b.extend(Point(anchor_.x() + dcell_.x() * hi.x(), anchor_.y() + dcell_.y() * hi.y(), anchor_.z() + dcell_.z() * hi.z()));
+  }
   void findCellIndexRange(IntVector& lo, IntVector& hi) const { lo = lo_ - extra_; hi = hi_ + extra_; }
   void findInteriorCellIndexRange(IntVector& lo, IntVector& hi) const { lo = lo_; hi = hi_; }
   // Level.cc:1285-1307: truncating division, negative indices shifted by (int)fmod(idx, ratio)
@@ -283,6 +325,7 @@ struct BCEntry { std::string var; double value = 0; };
 class Grid {
  public:
   int numLevels() const { return (int)levels_.size(); }
+  void getSpatialRange(BBox& b) const { for (auto& l : levels_) l->getSpatialRange(b); }   // Grid.cc:726-732
   const LevelP& getLevel(int i) const { return levels_[i]; }
   void addLevel(const LevelP& l) { levels_.push_back(l); }
   // face in Patch::FaceType order; returns false when the deck has no BCType for (face, label)
@@ -425,6 +468,9 @@ class Task {
   }
   void computesVar(const VarLabel* l) { deps_.push_back({Dependency::Computes, NewDW, l, Ghost::None, 0, NormalDomain, 0}); }
   void modifiesVar(const VarLabel* l) { deps_.push_back({Dependency::Modifies, NewDW, l, Ghost::None, 0, NormalDomain, 0}); }
+  enum TaskType { Normal, Spatial };                 // Task.h: Spatial = scheduled on a subset of the level's patches
+  void setType(TaskType t) { type_ = t; }
+  TaskType getType() const { return type_; }
   void usesDevice(bool on, int streams = 1) { usesDevice_ = on; deviceStreams_ = streams; }
   bool usesDevice() const { return usesDevice_; }
   int deviceStreams() const { return deviceStreams_; }
@@ -436,6 +482,7 @@ class Task {
   std::vector<Dependency> deps_;
   bool usesDevice_ = false;
   int deviceStreams_ = 1;
+  TaskType type_ = Normal;
 };
 
 inline DataWarehouse* DataWarehouse::getOtherDataWarehouse(int whichDW) { return whichDW == Task::OldDW ? old_ : new_; }
@@ -452,7 +499,10 @@ class Scheduler {
     entries_.push_back(Entry{std::unique_ptr<Task>(t), patches, matls, tg});
   }
   const std::vector<Entry>& tasks() const { return entries_; }
-  void clearTasks() { entries_.clear(); }
+  void clearTasks() { entries_.clear(); ownedSets_.clear(); }
+  // spatial tasks build their own PatchSet (Radiometer::sched_radiometer); the real scheduler reference-counts it, the
+  // shim takes a copy that lives as long as the task list
+  const PatchSet* adopt(const PatchSet& ps) { ownedSets_.push_back(std::make_unique<PatchSet>(ps)); return ownedSets_.back().get(); }
   DataWarehouse* get_dw(int which) { return which == Task::OldDW ? old_.get() : new_.get(); }
   // OldDW <- NewDW, fresh NewDW
   void advanceDataWarehouse(int timestep) {
@@ -479,6 +529,7 @@ class Scheduler {
   }
  private:
   std::vector<Entry> entries_;
+  std::vector<std::unique_ptr<PatchSet>> ownedSets_;
   std::shared_ptr<DataWarehouse> old_, new_;
   int nGraphs_ = 1;
   int generation_ = 0;

@@ -15,7 +15,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import capi
-from .capi import Counters, LevelDesc, Params, RmcrtError, check, i3
+from .capi import Counters, LevelDesc, Params, Radiometer, RmcrtError, check, i3
 
 
 @dataclass
@@ -243,6 +243,37 @@ class RMCRT:
                                                               volq.data_ptr(), None if bflux is None else bflux.data_ptr(),
                                                               i3(out_lo), i3(out_hi), 1 if zero_init else 0,
                                                               C.c_uint64(timestep), _stream_handle(stream)))
+
+    # ------------------------------------------------------------------ virtual radiometer
+    def radiometer(self, view_angle, vec, cell_lo, cell_hi, n_rays, is_normal_vector=False) -> Radiometer:
+        """one <Radiometer> block (Radiometer::problemSetup): angles from the library, cell box and nRays from the caller"""
+        r = Radiometer()
+        v = (C.c_double * 3)(*[float(x) for x in vec])
+        rc = self.lib.rmcrt_radiometer_setup(float(view_angle), v, 1 if is_normal_vector else 0, C.byref(r))
+        if rc != 0:
+            msg = self.lib.rmcrt_last_error(None)
+            raise RmcrtError(rc, msg.decode() if msg else "")
+        r.cellLo = i3(cell_lo); r.cellHi = i3(cell_hi); r.nRays = int(n_rays)
+        return r
+
+    def trace_radiometer(self, rads, L=0, patch_lo=None, patch_hi=None, out_lo=None, out_hi=None, dtype=np.float64, timestep=1,
+                         zero_init=True, outputs=None, stream=None):
+        """Radiometer::radiometerFlux for one patch, host buffers; returns (VRFlux, VRIntensity) over the output window"""
+        lv = self.levels[L]
+        patch_lo = lv.interior_lo if patch_lo is None else tuple(patch_lo)
+        patch_hi = lv.interior_hi if patch_hi is None else tuple(patch_hi)
+        out_lo, out_hi = self._window(L, out_lo, out_hi)
+        shape = (out_hi[2] - out_lo[2], out_hi[1] - out_lo[1], out_hi[0] - out_lo[0])
+        if outputs is None:
+            flux = np.zeros(shape, dtype); inten = np.zeros(shape, dtype)
+        else:
+            flux, inten = outputs
+        arr = (Radiometer * max(len(rads), 1))(*rads)
+        check(self.ctx, self.lib.rmcrt_trace_radiometer(self.ctx, L, arr, len(rads), i3(patch_lo), i3(patch_hi), flux.ctypes.data,
+                                                        inten.ctypes.data, 1 if flux.dtype == np.float32 else 0, i3(out_lo),
+                                                        i3(out_hi), 1 if zero_init else 0, C.c_uint64(timestep),
+                                                        _stream_handle(stream)))
+        return flux, inten
 
     def compute_extents(self, max_levels, patch_lo, patch_hi):
         roiLo = (C.c_int32 * 3)(); roiHi = (C.c_int32 * 3)()
