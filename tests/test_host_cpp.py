@@ -190,3 +190,96 @@ def test_bm2_boundary_flux_and_reflections(exe, po, tmp_path, gpu_lib):
     assert out["report"]["nRaySteps"] == ref["steps"] and out["report"]["nFluxRaySteps"] == ref["fluxSteps"]
     np.testing.assert_allclose(S, R, rtol=1e-9, atol=0)
     np.testing.assert_allclose(out["divQ"], ref["divQ"], rtol=1e-9, atol=1e-9 * np.abs(ref["divQ"]).max())
+
+
+# ------------------------------------------------------------------------------------------------ SURVEY 8f-4 features through the plugin
+def edit_deck(tmp_path, deck, *edits):
+    src = open(os.path.join(DECKS, deck)).read()
+    for old, new in edits:
+        assert old in src, old
+        src = src.replace(old, new, 1)
+    out = tmp_path / "edited.ups"
+    out.write_text(src)
+    return str(out)
+
+
+BOUNDED = ("<CCRays>             false      </CCRays>",
+           "<CCRays> false </CCRays>\n<algorithm type='singleLevel'> <ROI_extents type='boundedRayLength'> <length> 0.25 </length> </ROI_extents> </algorithm>")
+LHC = ("<rayDirSampleAlgo>   naive      </rayDirSampleAlgo>", "<rayDirSampleAlgo> LatinHyperCube </rayDirSampleAlgo>")
+
+
+def test_radiometer_schedule_matches_reference_surface(exe):
+    """Radiometer::sched_radiometer (Radiometer.cc:346-398): initialize_VRFlux on every patch, the spatial radiometerTask only
+    on the patches that hold radiometer cells, whole-level requires, modifies VRFlux / VRIntensity; RMCRT_Test's
+    radiometerOnly graph (RMCRT_Test.cc:559-583) computes no divQ"""
+    r = run(exe, "radiometer_only.ups", "--parse-only")
+    t = tasks_of(r.stdout)
+    names = [x["name"] for x in t]
+    assert names == ["RMCRT_Test::initialize", "Radiometer::initialize_VRFlux", "RMCRT_Test::initProperties",
+                     "RMCRTCommon::carryForward_VarLabels", "RMCRTCommon::sigmaT4", "Ray::setBoundaryConditions",
+                     "Radiometer::initialize_VRFlux", "Radiometer::radiometerTask"]
+    rt = t[-1]
+    assert rt["patches"] == "3" and rt["tg"] == "1" and rt["device"] == "1"      # 4 patches, one holds no radiometer cell
+    assert [(d[1], d[3]) for d in rt["deps"] if d[0] == "requires"] == [("abskg", "ghost=32767"), ("sigmaT4", "ghost=32767"), ("cellType", "ghost=32767")]
+    assert [d[1] for d in rt["deps"] if d[0] == "modifies"] == ["VRFlux", "VRIntensity"]
+    assert {d[1] for d in t[3]["deps"]} == {"sigmaT4", "VRFlux", "VRIntensity"} and t[3]["tg"] == "0"
+    assert "lower cell [7,8,14] upper cell [9,9,16]" in r.stdout
+
+
+@pytest.mark.parametrize("edit,needle", [
+    (("<locationsMax>      [0.13,0.07,0.07]           </locationsMax>", "<locationsMax> [1.3,0.07,0.07] </locationsMax>"), "outside of the computational domain"),
+    (("<locationsMax>      [0.13,0.07,0.07]           </locationsMax>", "<locationsMax> [0.13,0.0,0.07] </locationsMax>"), "same starting and ending points"),
+    (("<viewAngle>         30                         </viewAngle>", "<viewAngle> 400 </viewAngle>"), "exceeds the maximum acceptable value of 360"),
+    (("<unitNormalVector>  [0.57735,0.57735,0.57735]  </unitNormalVector>", ""), "<unitNormalVector> or <normalVector>"),
+    (("<nRays>             40                         </nRays>", ""), "<nRays>"),
+])
+def test_radiometer_input_errors(exe, tmp_path, edit, needle):
+    r = subprocess.run([exe, edit_deck(tmp_path, "radiometer_only.ups", edit), "--parse-only"], capture_output=True, text=True)
+    assert r.returncode == 1 and "ProblemSetupException" in r.stderr and needle in r.stderr, r.stderr
+
+
+def test_bounded_ray_length_and_lhc_are_accepted(exe, tmp_path):
+    """Ray.cc:455-475: ghost cells = ceil(|length/Dx|) for boundedRayLength; Ray.cc:175-180 LatinHyperCube"""
+    r = subprocess.run([exe, edit_deck(tmp_path, "bm1_1L_double.ups", BOUNDED, LHC), "--parse-only"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Using Latin Hyper Cube method" in r.stdout and "bounded ray length has been set to: (0.25)" in r.stdout
+    rt = [x for x in tasks_of(r.stdout) if x["name"] == "Ray::rayTrace"][0]
+    n = int(np.ceil(np.sqrt(3) * 0.25 * 21))
+    assert [d[3] for d in rt["deps"] if d[0] == "requires"] == [f"ghost={n}"] * 3
+
+
+@pytest.mark.gpu
+def test_radiometer_only_deck(exe, po, tmp_path, gpu_lib):
+    """radiometerOnly through the plugin: VRFlux / VRIntensity of both radiometers against Radiometer::radiometerFlux's restatement"""
+    out = load_dump(run(exe, "radiometer_only.ups", "--dump", str(tmp_path), "--knob", "skipZeroWeightLegs=0").args[3])
+    assert "divQ" not in out
+    lv = po.burns_christon(16)
+    p = po.default_params(threshold=0.05, isSeedRandom=0, allowReflect=0)
+    rads = [po.radiometer(30.0, (0.57735, 0.57735, 0.57735), (0, 0, 0), (2, 1, 1), 40),
+            po.radiometer(90.0, (0.5, 0.5, -0.5), (7, 8, 14), (9, 9, 16), 25, is_normal_vector=True)]
+    fo, io, _ = po.radiometer_flux(p, lv, rads)
+    assert np.count_nonzero(fo) == 2 + 4
+    assert np.array_equal(out["VRFlux"] != 0, fo != 0)
+    np.testing.assert_allclose(out["VRFlux"], fo, rtol=1e-10)
+    np.testing.assert_allclose(out["VRIntensity"], io, rtol=1e-10)
+
+
+@pytest.mark.gpu
+def test_single_level_with_radiometer_bounded_lhc(exe, po, tmp_path, gpu_lib):
+    """singleLevel + <Radiometer> + boundedRayLength + LatinHyperCube in one deck (RMCRT_bm1_1L_bounded / RMCRT_VR patterns)"""
+    rad = ("</RMCRT>", "<Radiometer> <viewAngle> 60 </viewAngle> <normalVector> [0,0,2] </normalVector> <locationsMin> [0.4,0.4,0.0] </locationsMin>"
+                       " <locationsMax> [0.5,0.5,0.06] </locationsMax> <nRays> 30 </nRays> </Radiometer>\n</RMCRT>")
+    deck = edit_deck(tmp_path, "bm1_1L_double.ups", BOUNDED, LHC, rad)
+    r = subprocess.run([exe, deck, "--dump", str(tmp_path / "d"), "--knob", "skipZeroWeightLegs=0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = load_dump(str(tmp_path / "d"))
+    lv = po.burns_christon(21)
+    kw = dict(nDivQRays=3, threshold=0.05, isSeedRandom=0, rayDirSampleAlgo=1, maxRayLength=0.25)
+    ref = po.ray_trace(po.default_params(**kw), lv)
+    assert out["report"]["nRaySteps"] == ref["steps"]
+    np.testing.assert_allclose(out["divQ"], ref["divQ"], rtol=1e-9, atol=1e-10 * np.abs(ref["divQ"]).max())
+    lo = (int(np.floor(0.4 * 21)), int(np.floor(0.4 * 21)), 0)
+    hi = (int(np.floor(0.5 * 21)), int(np.floor(0.5 * 21)), int(np.floor(0.06 * 21)))
+    rads = [po.radiometer(60.0, (0, 0, 2), lo, hi, 30, is_normal_vector=True)]
+    fo, io, _ = po.radiometer_flux(po.default_params(**kw), lv, rads)
+    np.testing.assert_allclose(out["VRFlux"], fo, rtol=1e-10)

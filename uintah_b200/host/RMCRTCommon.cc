@@ -108,6 +108,7 @@ void RMCRTCommon::fillParams(rmcrt_params& p) const {
 }
 
 std::vector<RMCRTCommon::Device>& RMCRTCommon::devices() {
+  if (d_backend != this) return d_backend->devices();
   std::lock_guard<std::mutex> lock(d_deviceMutex);
   if (d_devices.empty()) {
     int n = 0;
@@ -128,6 +129,54 @@ std::vector<RMCRTCommon::Device>& RMCRTCommon::devices() {
   }
   return d_devices;
 }
+
+rmcrt_level_desc RMCRTCommon::describe(const Level* level) {
+  rmcrt_level_desc d;
+  IntVector lo, hi, ilo, ihi;
+  level->findCellIndexRange(lo, hi);
+  level->findInteriorCellIndexRange(ilo, ihi);
+  const Vector dx = level->dCell();
+  const Point anchor = level->getAnchor();
+  const IntVector rr = level->hasCoarserLevel() ? level->getRefinementRatio() : IntVector(1, 1, 1);
+  for (int k = 0; k < 3; ++k) {
+    d.lo[k] = lo[k]; d.hi[k] = hi[k];
+    d.interiorLo[k] = ilo[k]; d.interiorHi[k] = ihi[k];
+    d.dx[k] = dx[k]; d.anchor[k] = anchor[k];
+    d.refineRatio[k] = rr[k];
+  }
+  return d;
+}
+
+// the three whole-level gathers of Ray.cc:549-553 followed by the H2D + pack that replaces the GPU DataWarehouse staging
+template <class T>
+void RMCRTCommon::uploadLevel(const Level* level, DataWarehouse* abskg_dw, DataWarehouse* sigmaT4_dw, DataWarehouse* celltype_dw, long long stamp) {
+  if (d_backend != this) { d_backend->uploadLevel<T>(level, abskg_dw, sigmaT4_dw, celltype_dw, stamp); return; }
+  const int L = level->getIndex();
+  auto& devs = devices();
+  bool needed = false;
+  for (auto& dev : devs) {
+    auto it = dev.levelStamp.find(L);
+    if (it == dev.levelStamp.end() || it->second != stamp) needed = true;
+  }
+  if (!needed) return;
+  constCCVariable<T> abskg, sigmaT4OverPi;
+  constCCVariable<int> celltype;
+  abskg_dw->getLevel(abskg, d_abskgLabel, d_matl, level);
+  sigmaT4_dw->getLevel(sigmaT4OverPi, d_sigmaT4Label, d_matl, level);
+  celltype_dw->getLevel(celltype, d_cellTypeLabel, d_matl, level);
+  const rmcrt_level_desc desc = describe(level);
+  rmcrt_params p;
+  fillParams(p);
+  for (auto& dev : devs) {
+    check(dev.ctx, rmcrt_set_params(dev.ctx, &p), "rmcrt_set_params");
+    check(dev.ctx, rmcrt_define_level(dev.ctx, L, &desc, recordKind(p)), "rmcrt_define_level");
+    check(dev.ctx, rmcrt_upload_level(dev.ctx, L, abskg.getPointer(), sigmaT4OverPi.getPointer(), celltype.getPointer(),
+                                      sizeof(T) == 4 ? 1 : 0, desc.lo, desc.hi, nullptr), "rmcrt_upload_level");
+    dev.levelStamp[L] = stamp;
+  }
+}
+template void RMCRTCommon::uploadLevel<double>(const Level*, DataWarehouse*, DataWarehouse*, DataWarehouse*, long long);
+template void RMCRTCommon::uploadLevel<float>(const Level*, DataWarehouse*, DataWarehouse*, DataWarehouse*, long long);
 
 void RMCRTCommon::releaseDevices() {
   std::lock_guard<std::mutex> lock(d_deviceMutex);

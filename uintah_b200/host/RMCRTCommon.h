@@ -25,7 +25,7 @@ namespace Uintah {
 class RMCRTCommon {
  public:
   explicit RMCRTCommon(TypeDescription::Type FLT_DBL);
-  ~RMCRTCommon();
+  virtual ~RMCRTCommon();
 
   /** map the component VarLabels to RMCRT class VarLabels (RMCRTCommon.cc:157-203) */
   void registerVariables(int matl, const VarLabel* abskg, const VarLabel* temperature, const VarLabel* celltype,
@@ -114,18 +114,30 @@ class RMCRTCommon {
     std::map<int, long long> levelStamp;   // level index -> DataWarehouse generation its records were packed from
   };
   std::vector<Device>& devices();
+  /** use the device contexts (and the level records already packed there) of another RMCRTCommon: the Radiometer that a
+      Ray owns traces through the Ray's records instead of uploading the level a second time */
+  void shareDevicesOf(RMCRTCommon* owner) { d_backend = owner ? owner : this; }
   /** limit the number of devices used (0 = all visible); call before the first solve */
   static void setMaxDevices(int n) { s_maxDevices = n; }
   /** throws InternalError / ProblemSetupException with rmcrt_last_error() */
   static void check(rmcrt_ctx* ctx, int rc, const char* what);
 
+  /** getLevel() the three property arrays of `level` (the whole-level gathers of Ray.cc:549-553 / Radiometer.cc:411-417) and
+      pack them on every device, once per DataWarehouse generation `stamp` */
+  template <class T>
+  void uploadLevel(const Level* level, DataWarehouse* abskg_dw, DataWarehouse* sigmaT4_dw, DataWarehouse* celltype_dw, long long stamp);
+  static rmcrt_level_desc describe(const Level* level);
+
  protected:
   virtual void fillParams(rmcrt_params& p) const;   // Ray adds its members
+  /** 0 float records, 1 double records (FP64 parity march), 2 half-packed records */
+  virtual int recordKind(const rmcrt_params& p) const { return p.marchPrecision == 1 ? 1 : 0; }
   void releaseDevices();
   std::mutex d_deviceMutex;
 
  private:
   std::vector<Device> d_devices;
+  RMCRTCommon* d_backend{this};
   static int s_maxDevices;
 };
 

@@ -164,6 +164,7 @@ class RMCRT_Test {
     int ray_algo = RMCRTCommon::singleLevel;
     if (d_whichAlgo == dataOnion || d_whichAlgo == dataOnionSlim) ray_algo = RMCRTCommon::dataOnion;
     else if (d_whichAlgo == coarseLevel) ray_algo = RMCRTCommon::coarseLevel;
+    else if (d_whichAlgo == radiometerOnly) ray_algo = RMCRTCommon::radiometerOnly;
     d_RMCRT->registerVariables(0, d_compAbskgLabel, d_colorLabel, d_cellTypeLabel, d_divQLabel, ray_algo);
     d_RMCRT->problemSetup(prob_spec, rmcrt_ps, grid);
     d_RMCRT->BC_bulletproofing(rmcrt_ps, true, true);
@@ -186,6 +187,7 @@ class RMCRT_Test {
     task->computesVar(d_compAbskgLabel);
     task->computesVar(d_cellTypeLabel);
     sched->addTask(task, level->eachPatch(), RMCRTCommon::d_matlSet);
+    if (Radiometer* radiometer = d_RMCRT->getRadiometer()) radiometer->sched_initialize_VRFlux(level, sched);   // 337-340
   }
 
   //______________________________________________________________________ RMCRT_Test.cc:365-600
@@ -200,6 +202,7 @@ class RMCRT_Test {
                                                        RMCRTCommon::d_radiationVolqLabel, RMCRTCommon::d_sigmaT4Label};
     const bool includeExtraCells = true;
     Task::WhichDW notUsed = Task::None;
+    Radiometer* radiometer = d_RMCRT->getRadiometer();                    // 384
 
     if (d_whichAlgo == dataOnion || d_whichAlgo == dataOnionSlim) {      // 385-460
       Task::WhichDW temp_dw = Task::NewDW, sigmaT4_dw = Task::NewDW, celltype_dw = Task::NewDW;
@@ -229,8 +232,23 @@ class RMCRT_Test {
       d_RMCRT->sched_sigmaT4(level, sched, temp_dw, includeExtraCells);
       d_RMCRT->sched_setBoundaryConditions(level, sched, temp_dw, backoutTemp);
       d_RMCRT->sched_rayTrace(level, sched, notUsed, sigmaT4_dw, celltype_dw, modifies_divQ);
+      if (radiometer) {                                                   // 549-553
+        d_RMCRT->sched_CarryForward_Var(level, sched, radiometer->d_VRFluxLabel, RMCRTCommon::TG_CARRY_FORWARD);
+        radiometer->sched_radiometer(level, sched, notUsed, sigmaT4_dw, celltype_dw);
+      }
     }
-    if (d_whichAlgo == coarseLevel || d_whichAlgo == radiometerOnly)
+    if (d_whichAlgo == radiometerOnly) {                                  // 559-583: no other calculations
+      if (!radiometer) throw ProblemSetupException("RMCRT_Test: algorithm radiometerOnly needs a <Radiometer> block", __FILE__, __LINE__);
+      Task::WhichDW temp_dw = Task::NewDW, sigmaT4_dw = Task::NewDW, celltype_dw = Task::NewDW;
+      const bool backoutTemp = true;
+      d_RMCRT->set_abskg_dw_perLevel(level, Task::NewDW);
+      d_RMCRT->sched_carryForward_VarLabels(level, sched, {RMCRTCommon::d_sigmaT4Label, radiometer->d_VRFluxLabel, radiometer->d_VRIntensityLabel});
+      d_RMCRT->sched_DoubleToFloat(level, sched, notUsed);
+      d_RMCRT->sched_sigmaT4(level, sched, temp_dw, includeExtraCells);
+      d_RMCRT->sched_setBoundaryConditions(level, sched, temp_dw, backoutTemp);
+      radiometer->sched_radiometer(level, sched, notUsed, sigmaT4_dw, celltype_dw);
+    }
+    if (d_whichAlgo == coarseLevel)
       throw ProblemSetupException("rmcrt_test: algorithm not supported by the B200 back end", __FILE__, __LINE__);
   }
 
@@ -399,7 +417,8 @@ int main(int argc, char** argv) {
 
     const Level* fine = grid->getLevel(grid->numLevels() - 1).get();
     DataWarehouse* dw = sched->get_dw(Task::NewDW);
-    {   // centre line of divQ along x (what RMCRT.m / lineextract look at)
+    const bool haveDivQ = dw->exists(app.d_divQLabel, 0, fine->getPatch(0));   // radiometerOnly computes no divQ
+    if (haveDivQ) {   // centre line of divQ along x (what RMCRT.m / lineextract look at)
       constCCVariable<double> divQ;
       dw->getLevel(divQ, app.d_divQLabel, 0, fine);
       IntVector lo, hi;
@@ -415,9 +434,20 @@ int main(int argc, char** argv) {
       std::ofstream meta(dumpDir + "/meta.json");
       meta << "{\n";
       bool first = true;
-      dumpVar<double>(dumpDir, "divQ", "f8", 1, dw, app.d_divQLabel, fine, meta, first);
-      dumpVar<double>(dumpDir, "radiationVolq", "f8", 1, dw, RMCRTCommon::d_radiationVolqLabel, fine, meta, first);
-      dumpVar<Stencil7>(dumpDir, "RMCRTboundFlux", "f8", 7, dw, RMCRTCommon::d_boundFluxLabel, fine, meta, first);
+      if (haveDivQ) {
+        dumpVar<double>(dumpDir, "divQ", "f8", 1, dw, app.d_divQLabel, fine, meta, first);
+        dumpVar<double>(dumpDir, "radiationVolq", "f8", 1, dw, RMCRTCommon::d_radiationVolqLabel, fine, meta, first);
+        dumpVar<Stencil7>(dumpDir, "RMCRTboundFlux", "f8", 7, dw, RMCRTCommon::d_boundFluxLabel, fine, meta, first);
+      }
+      if (Radiometer* radiometer = app.d_RMCRT->getRadiometer()) {
+        if (radiometer->d_VRFluxLabel->typeDescription() == TypeDescription::float_type) {
+          dumpVar<float>(dumpDir, "VRFlux", "f4", 1, dw, radiometer->d_VRFluxLabel, fine, meta, first);
+          dumpVar<float>(dumpDir, "VRIntensity", "f4", 1, dw, radiometer->d_VRIntensityLabel, fine, meta, first);
+        } else {
+          dumpVar<double>(dumpDir, "VRFlux", "f8", 1, dw, radiometer->d_VRFluxLabel, fine, meta, first);
+          dumpVar<double>(dumpDir, "VRIntensity", "f8", 1, dw, radiometer->d_VRIntensityLabel, fine, meta, first);
+        }
+      }
       dumpVar<double>(dumpDir, "abskg", "f8", 1, dw, app.d_compAbskgLabel, fine, meta, first);
       dumpVar<int>(dumpDir, "cellType", "i4", 1, dw, app.d_cellTypeLabel, fine, meta, first);
       if (RMCRTCommon::d_sigmaT4Label->typeDescription() == TypeDescription::float_type)

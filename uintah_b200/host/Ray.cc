@@ -25,6 +25,7 @@ Ray::Ray(TypeDescription::Type FLT_DBL) : RMCRTCommon(FLT_DBL) {
 }
 
 Ray::~Ray() {
+  delete d_radiometer;   // Ray.cc:145-147
   VarLabel::destroy(m_timeStepLabel);
   VarLabel::destroy(d_mag_grad_abskgLabel);
   VarLabel::destroy(d_mag_grad_sigmaT4Label);
@@ -54,10 +55,16 @@ void Ray::problemSetup(const ProblemSpecP& prob_spec, const ProblemSpecP& rmcrtp
   rmcrt_ps->getWithDefault("applyFilter", d_applyFilter, false);
   rmcrt_ps->getWithDefault("rayDirSampleAlgo", rayDirSampleAlgo, "naive");
 
-  if (rayDirSampleAlgo == "LatinHyperCube")
-    throw ProblemSetupException("RMCRT (B200 back end): rayDirSampleAlgo LatinHyperCube is not implemented; use naive", __FILE__, __LINE__);
-  if (rmcrt_ps->findBlock("Radiometer"))
-    throw ProblemSetupException("RMCRT (B200 back end): the <Radiometer> is not implemented", __FILE__, __LINE__);
+  if (rayDirSampleAlgo == "LatinHyperCube") {                       // Ray.cc:175-180
+    d_rayDirSampleAlgo = LATIN_HYPER_CUBE;
+    std::cout << "  - Using Latin Hyper Cube method for selecting ray directions.\n";
+  } else {
+    std::cout << "  - Using traditional Monte-Carlo method for selecting ray directions.\n";
+  }
+  if (rmcrt_ps->findBlock("Radiometer")) {                          // Ray.cc:183-188
+    d_radiometer = new Radiometer(d_FLT_DBL, this);
+    d_radiometer->problemSetup(prob_spec, rmcrtps, grid);
+  }
 
   // the reference refuses sigmaScat > 0 unless it was configured with --enable-ray-scatter (Ray.cc:193-201)
   if (d_sigmaScat > 0) {
@@ -89,7 +96,7 @@ void Ray::problemSetup(const ProblemSpecP& prob_spec, const ProblemSpecP& rmcrtp
         ROI_ps->getAttribute("type", type);
         ROI_ps->get("length", d_maxRayLength);
         d_ROI_algo = boundedRayLength;
-        throw ProblemSetupException("RMCRT (B200 back end): singleLevel with ROI_extents boundedRayLength is not implemented", __FILE__, __LINE__);
+        std::cout << "  RMCRT: The bounded ray length has been set to: (" << d_maxRayLength << ")\n";
       }
     } else if (type == "dataOnion") {
       isMultilevel = true;
@@ -189,6 +196,8 @@ void Ray::fillParams(rmcrt_params& p) const {
   for (int d = 0; d < 3; ++d) p.haloCells[d] = d_haloCells[d] > 0 ? d_haloCells[d] : 10;
   p.cellTypeCoarsenLogic = d_cellTypeCoarsenLogic == ROUNDDOWN ? 1 : 0;
   p.seed = d_seed;
+  p.rayDirSampleAlgo = d_rayDirSampleAlgo == LATIN_HYPER_CUBE ? 1 : 0;
+  p.maxRayLength = d_maxRayLength;
   for (auto& kv : d_knobs) {
     if (kv.first == "rayCoherence") p.rayCoherence = kv.second;
     else if (kv.first == "skipZeroWeightLegs") p.skipZeroWeightLegs = kv.second;
@@ -217,6 +226,22 @@ void Ray::sched_rayTrace(const LevelP& level, SchedulerP& sched, Task::WhichDW /
   // an "infinite" number of ghost cells: the whole level is needed around every patch (449-481)
   Ghost::GhostType gac = Ghost::AroundCells;
   int n_ghostCells = SHRT_MAX;
+  if (d_ROI_algo == boundedRayLength) {                             // Ray.cc:455-475
+    const Vector Dx = level->dCell();
+    const Vector nCells = Vector(d_maxRayLength) / Dx;
+    n_ghostCells = (int)std::ceil(nCells.length());
+    IntVector lo, hi;
+    level->findCellIndexRange(lo, hi);
+    const IntVector diff = hi - lo;
+    const int nCellsLevel = Max(diff.x(), diff.y(), diff.z());
+    if (n_ghostCells > SHRT_MAX || n_ghostCells > nCellsLevel) {
+      std::cout << "\n  WARNING  RMCRT:sched_rayTrace Clamping the number of ghostCells to SHRT_MAX, (n_ghostCells: " << n_ghostCells
+                << ") max cells in any direction on a Levels: " << nCellsLevel << "\n\n";
+      n_ghostCells = SHRT_MAX;
+      d_ROI_algo = entireDomain;
+    }
+    d_haloCells = IntVector(n_ghostCells, n_ghostCells, n_ghostCells);
+  }
   tsk->requiresVar(abskg_dw, d_abskgLabel, gac, n_ghostCells);
   tsk->requiresVar(sigma_dw, d_sigmaT4Label, gac, n_ghostCells);
   tsk->requiresVar(celltype_dw, d_cellTypeLabel, gac, n_ghostCells);
@@ -282,51 +307,6 @@ int Ray::recordKind(const rmcrt_params& p) const {
   if (p.marchPrecision == 1) return 1;
   auto it = d_knobs.find("halfRecords");
   return (it != d_knobs.end() && it->second) ? 2 : 0;
-}
-
-rmcrt_level_desc Ray::describe(const Level* level) {
-  rmcrt_level_desc d;
-  IntVector lo, hi, ilo, ihi;
-  level->findCellIndexRange(lo, hi);
-  level->findInteriorCellIndexRange(ilo, ihi);
-  const Vector dx = level->dCell();
-  const Point anchor = level->getAnchor();
-  const IntVector rr = level->hasCoarserLevel() ? level->getRefinementRatio() : IntVector(1, 1, 1);
-  for (int k = 0; k < 3; ++k) {
-    d.lo[k] = lo[k]; d.hi[k] = hi[k];
-    d.interiorLo[k] = ilo[k]; d.interiorHi[k] = ihi[k];
-    d.dx[k] = dx[k]; d.anchor[k] = anchor[k];
-    d.refineRatio[k] = rr[k];
-  }
-  return d;
-}
-
-// the three whole-level gathers of Ray.cc:549-553 followed by the H2D + pack that replaces the GPU DataWarehouse staging
-template <class T>
-void Ray::uploadLevel(const Level* level, DataWarehouse* abskg_dw, DataWarehouse* sigmaT4_dw, DataWarehouse* celltype_dw, long long stamp) {
-  const int L = level->getIndex();
-  auto& devs = devices();
-  bool needed = false;
-  for (auto& dev : devs) {
-    auto it = dev.levelStamp.find(L);
-    if (it == dev.levelStamp.end() || it->second != stamp) needed = true;
-  }
-  if (!needed) return;
-  constCCVariable<T> abskg, sigmaT4OverPi;
-  constCCVariable<int> celltype;
-  abskg_dw->getLevel(abskg, d_abskgLabel, d_matl, level);
-  sigmaT4_dw->getLevel(sigmaT4OverPi, d_sigmaT4Label, d_matl, level);
-  celltype_dw->getLevel(celltype, d_cellTypeLabel, d_matl, level);
-  const rmcrt_level_desc desc = describe(level);
-  rmcrt_params p;
-  fillParams(p);
-  for (auto& dev : devs) {
-    check(dev.ctx, rmcrt_set_params(dev.ctx, &p), "rmcrt_set_params");
-    check(dev.ctx, rmcrt_define_level(dev.ctx, L, &desc, recordKind(p)), "rmcrt_define_level");
-    check(dev.ctx, rmcrt_upload_level(dev.ctx, L, abskg.getPointer(), sigmaT4OverPi.getPointer(), celltype.getPointer(),
-                                      sizeof(T) == 4 ? 1 : 0, desc.lo, desc.hi, nullptr), "rmcrt_upload_level");
-    dev.levelStamp[L] = stamp;
-  }
 }
 
 void Ray::forEachPatchOnDevices(const PatchSubset* patches, const std::function<void(Device&, int)>& fn) {
@@ -426,6 +406,8 @@ void Ray::rayTrace(const ProcessorGroup*, const PatchSubset* patches, const Mate
   DataWarehouse* sigmaT4_dw = new_dw->getOtherDataWarehouse(which_sigmaT4_dw);
   DataWarehouse* celltype_dw = new_dw->getOtherDataWarehouse(which_celltype_dw);
   uploadLevel<T>(level, abskg_dw, sigmaT4_dw, celltype_dw, new_dw->getID());
+  if (d_radiometer)                                                 // Ray.cc:638-640
+    for (int p = 0; p < patches->size(); ++p) d_radiometer->radiometerFlux<T>(patches->get(p), level, new_dw, modifies_divQ);
   traceCommon<T>(false, patches, new_dw, modifies_divQ);
 }
 

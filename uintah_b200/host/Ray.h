@@ -7,6 +7,7 @@
 // rmcrt_upload_level / rmcrt_trace_divq / rmcrt_trace_dataonion; no ray is traced on the host.
 #pragma once
 #include "RMCRTCommon.h"
+#include "Radiometer.h"
 
 #include <cfloat>
 
@@ -43,7 +44,7 @@ class Ray : public RMCRTCommon {
   void sched_computeCellType(const LevelP& coarseLevel, SchedulerP& sched, const Ray::modifiesComputes which);
   void sched_ROI_Extents(const LevelP& level, SchedulerP& scheduler);
 
-  void* getRadiometer() { return nullptr; }   // the radiometer is not part of the B200 hot path
+  Radiometer* getRadiometer() { return d_radiometer; }   // Ray.h:151-153
 
   bool d_coarsenExtraCells{false};
 
@@ -78,6 +79,7 @@ class Ray : public RMCRTCommon {
   bool d_onOff_SetBCs{true};
   bool d_applyFilter{false};
   int d_rayDirSampleAlgo{NAIVE};
+  Radiometer* d_radiometer{nullptr};
   int d_cellTypeCoarsenLogic{ROUNDUP};
   ROI_algo d_ROI_algo{entireDomain};
   Point d_ROI_minPt, d_ROI_maxPt;
@@ -112,11 +114,7 @@ class Ray : public RMCRTCommon {
   void coarsenAll(const ProcessorGroup*, const PatchSubset* patches, const MaterialSubset*, DataWarehouse*, DataWarehouse* new_dw);
 
   //__________________________________ helpers
-  static rmcrt_level_desc describe(const Level* level);
-  int recordKind(const rmcrt_params& p) const;
-  /** getLevel() the three property arrays of `level` and pack them on every device, once per DataWarehouse generation */
-  template <class T>
-  void uploadLevel(const Level* level, DataWarehouse* abskg_dw, DataWarehouse* sigmaT4_dw, DataWarehouse* celltype_dw, long long stamp);
+  int recordKind(const rmcrt_params& p) const override;
   /** run `fn(device, patchIndex)` for every patch, patches dealt round-robin to the devices, one host thread per device */
   void forEachPatchOnDevices(const PatchSubset* patches, const std::function<void(Device&, int)>& fn);
   template <class T>

@@ -516,7 +516,7 @@ class Scheduler {
   void execute(int tg) {
     ProcessorGroup pg;
     for (auto& e : entries_) {
-      if (e.tg != ALL_GRAPHS && e.tg != tg) continue;
+      if (tg != ALL_GRAPHS && e.tg != ALL_GRAPHS && e.tg != tg) continue;   // execute(ALL_GRAPHS): the initialisation graph runs everything
       for (const auto& d : e.task->dependencies())
         if (d.kind == Task::Dependency::Requires && d.domain == Task::NormalDomain) {
           DataWarehouse* dw = get_dw(d.dw);
