@@ -183,6 +183,90 @@ def parallel_plates(N, dtype=np.float64, T_gas=1500.0, T_wall=1000.0, kappa=1.0,
                  interior_lo=(0, 0, 0), interior_hi=(N, N, N))
 
 
+def benchmark_level(bm, N, pDir=0, dtype=np.float64, wall_type=8) -> Level:
+    """RMCRT_Test::initialize benchmark fields (Examples/RMCRT_Test.cc:653-779) on the unit cube at N^3 with cold black
+    walls (abskg 1, T 0: the Dirichlet values of RMCRT_bm1_1L.ups / RMCRT_bm3.ups).  bm: 1 Burns & Christon; 2 abskg==1;
+    3 Burns & Christon abskg with T = 1000*abskg; 6 sinusoidal T; 7 exponential abskg, linear T^4; 8 hot and cold clouds."""
+    base = burns_christon(N, np.float64, wall_type=wall_type)
+    flow = base.cellType == -1
+    c = (np.arange(-1, N + 1) + 0.5) / N              # Level::getCellPosition (Level.cc:473-477), anchor 0
+    z, y, x = np.meshgrid(c, c, c, indexing="ij")
+    p = (x, y, z)[pDir]
+    ab = base.abskg.copy()
+    T = np.full(ab.shape, 64.804)
+    if bm == 1:
+        pass
+    elif bm == 2:
+        ab[:] = 1.0                                                      # 683-685
+    elif bm == 3:
+        T = 1000.0 * ab                                                  # 687-692
+    elif bm == 6:
+        ab[:] = 5.0                                                      # 710-731
+        T = (1e7 * (1.0 + np.sin(4.5 * 2 * np.pi * p))) ** 0.25
+    elif bm == 7:
+        ab = 5.0 * np.exp(-2 * p - 0.1)                                  # 736-756
+        T = (1.0e7 * (2.0 * p + 1.0)) ** 0.25
+    elif bm == 8:                                                        # 759-779
+        pi, mx = np.pi, np.maximum
+        ab = (mx(np.sin(x * 5 * pi) * np.abs(np.sin(z * 3 * pi + pi) + np.sin(y * 3 * pi)), 0.0)
+              + mx(np.sin(x * 5.0 * pi + pi), 0.0) * mx(np.sin(z * 3 * pi + pi) + np.sin(y * 3 * pi + pi), 0.0)) * 5.0
+        T = (mx(np.sin(x * 5.0 * pi) * mx(np.sin(z * 3.0 * pi) + np.sin(y * 3.0 * pi), 0.0), 0.0)
+             + mx(np.sin(x * 5.0 * pi), 0.0) * mx(np.sin(z * 3.0 * pi + pi) + np.sin(y * 3.0 * pi + pi), 0.0)) * 1000.0
+    else:
+        raise ValueError(f"benchmark {bm}: not initialised here (4 and 5 are the RAY_SCATTER problems)")
+    ab = np.where(flow, ab, 1.0)
+    T = np.where(flow, T, 0.0)
+    return Level(ab.astype(dtype), sigmaT4(T, dtype), base.cellType, base.lo, base.hi, base.dx,
+                 interior_lo=(0, 0, 0), interior_hi=(N, N, N))
+
+
+def centreline_box(N, axis):
+    """origin cells RMCRT.m:387-398 extracts with lineextract: the centre line along `axis` (0 x, 1 y, 2 z)"""
+    m = N // 2
+    lo, hi = [m, m, m], [m + 1, m + 1, m + 1]
+    lo[axis], hi[axis] = 0, N
+    return tuple(lo), tuple(hi)
+
+
+def centreline_of(field_level, N, axis):
+    """the same line out of an (N+2)^3 level window [z][y][x]"""
+    m = N // 2
+    sl = [m + 1, m + 1, m + 1]
+    sl[2 - axis] = slice(1, N + 1)
+    return field_level[tuple(sl)]
+
+
+_GOLDEN = None
+
+
+def golden_benchmarks():
+    """tests/golden/rmcrt_benchmarks.json (made from the reference's postProcessTools tables by make_benchmark_golden.py)"""
+    global _GOLDEN
+    if _GOLDEN is None:
+        import json
+        with open(os.path.join(os.path.dirname(_HERE), "tests", "golden", "rmcrt_benchmarks.json")) as f:
+            _GOLDEN = json.load(f)
+    return _GOLDEN
+
+
+def benchmark_exact(bm, N, axis):
+    """exact divQ at the N cell centres of the centre line, in Ray.cc:775's sign, for the problem benchmark_level builds.
+    bm 3: RMCRT.m:100-135 (243-point table, sub-sampled for 81/27/9/3, pchip otherwise); bm 7/8: RMCRT.m:202-277 (pchip)."""
+    from scipy.interpolate import PchipInterpolator
+    g = golden_benchmarks()
+    xc = (np.arange(N) + 0.5) / N
+    if bm == 3:
+        ex = -np.array(g["bench3"]["values"])
+        sub = {243: ex}
+        sub[81] = sub[243][1:242:3]; sub[27] = sub[81][1:80:3]; sub[9] = sub[27][1:26:3]; sub[3] = sub[9][1:8:3]
+        if N in sub:
+            return sub[N]
+        return PchipInterpolator((np.arange(243) + 0.5) / 243, ex)(xc)
+    name, scale = {7: ("kexp", g["kexp"]["scale_to_code_problem"]), 8: ("clouds", 1.0)}[bm]
+    t = g[name]["xyz"[axis]]
+    return scale * PchipInterpolator(np.array(t["x"]), np.array(t["divQ"]))(xc)
+
+
 # ---------------------------------------------------------------- single rays
 def update_sumI(p: Params, lv: Level, direction, ray_origin, origin_cell, max_path=0):
     cl = lv.c()

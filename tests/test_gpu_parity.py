@@ -548,3 +548,26 @@ def test_full_size_isothermal_enclosure_and_linearity(gpu_lib, po):
     g.upload_level(0, lv2); d2 = g.trace_divq(0)["divQ"]
     assert np.array_equal(2 * d1, d2)
     assert n1 > 0
+
+
+@pytest.mark.parametrize("bm,N,axis,rays,tol,dtype", [
+    (3, 243, 2, 4096, 0.004, np.float32),   # bench3Exact.txt at its native 243 cells, no interpolation (RMCRT.m:108)
+    (3, 81, 2, 4096, 0.004, np.float32),
+    (7, 128, 0, 4096, 0.02, np.float32),    # kexpDivQx.dat on a BASELINE-size level
+    (7, 41, 1, 4096, 0.03, np.float64),
+    (8, 128, 0, 4096, 0.03, np.float32),    # cloudsDivQx.dat
+    (8, 128, 1, 4096, 0.02, np.float32),    # cloudsDivQy.dat
+])
+def test_reference_exact_tables(gpu_lib, po, bm, N, axis, rays, tol, dtype):
+    """The CUDA path against the exact-solution tables the reference keeps for RMCRT_Test benchmarks 3, 7, 8
+    (tests/golden/rmcrt_benchmarks.json): centre-line divQ, production march (Philox rays, FP32, warp-coherent)."""
+    lv = po.benchmark_level(bm, N, pDir=0, dtype=dtype)
+    lo, hi = po.centreline_box(N, axis)
+    g = make(gpu_lib, nDivQRays=rays, threshold=0.001, seed=99)
+    g.upload_level(0, lv)
+    d = g.trace_divq(0, patch_lo=lo, patch_hi=hi)["divQ"]
+    line = po.centreline_of(d, N, axis)
+    ex = po.benchmark_exact(bm, N, axis)
+    rel = np.linalg.norm(line - ex) / np.linalg.norm(ex)
+    assert rel < tol, rel
+    assert g.counters().nDivQCells == N

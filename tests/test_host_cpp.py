@@ -283,3 +283,44 @@ def test_single_level_with_radiometer_bounded_lhc(exe, po, tmp_path, gpu_lib):
     rads = [po.radiometer(60.0, (0, 0, 2), lo, hi, 30, is_normal_vector=True)]
     fo, io, _ = po.radiometer_flux(po.default_params(**kw), lv, rads)
     np.testing.assert_allclose(out["VRFlux"], fo, rtol=1e-10)
+
+
+# ------------------------------------------------------------------------------------------------ RMCRT_Test benchmarks 6-8 and <Intrusion>
+BM7 = ("<benchmark>      1      </benchmark>", '<benchmark dir="1"> 7 </benchmark>')
+CYL = ("</Uintah_specification>", "<Intrusion> <geom_object> <cylinder> <bottom>[0,.5,.5]</bottom> <top>[1,.5,.5]</top> <radius>.1</radius>"
+                                  " </cylinder> </geom_object> </Intrusion>\n</Uintah_specification>")
+
+
+def test_benchmark_direction_is_required(exe, tmp_path):
+    """RMCRT_Test.cc:146-151"""
+    deck = edit_deck(tmp_path, "bm1_1L_double.ups", ("<benchmark>      1      </benchmark>", "<benchmark> 6 </benchmark>"))
+    r = subprocess.run([exe, deck, "--parse-only"], capture_output=True, text=True)
+    assert r.returncode == 1 and "requires the attribute 'dir'" in r.stderr
+    deck = edit_deck(tmp_path, "bm1_1L_double.ups", ("<benchmark>      1      </benchmark>", "<benchmark> 4 </benchmark>"))
+    r = subprocess.run([exe, deck, "--parse-only"], capture_output=True, text=True)
+    assert r.returncode == 1 and "isotropic scattering" in r.stderr
+
+
+@pytest.mark.gpu
+def test_benchmark7_with_cylinder_intrusion(exe, po, tmp_path, gpu_lib):
+    """RMCRT_Test benchmark 7 along y (RMCRT_Test.cc:736-756) with the cylinder intrusion of RMCRT_test_1L_wIntrusion.ups:115-123:
+    the driver's fields equal the oracle's restatement and the deterministic solve agrees to round-off (rays stop at the intrusion)"""
+    deck = edit_deck(tmp_path, "bm1_1L_double.ups", BM7, CYL)
+    r = subprocess.run([exe, deck, "--dump", str(tmp_path / "d"), "--knob", "skipZeroWeightLegs=0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = load_dump(str(tmp_path / "d"))
+    N = 21
+    lv = po.benchmark_level(7, N, pDir=1)
+    c = (np.arange(-1, N + 1) + 0.5) / N
+    z, y, x = np.meshgrid(c, c, c, indexing="ij")
+    inside = (x >= 0) & (x <= 1) & ((y - 0.5) ** 2 + (z - 0.5) ** 2 <= 0.01)
+    lv.cellType[inside] = 8
+    assert inside[1:-1, 1:-1, 1:-1].sum() > 100
+    assert np.array_equal(out["cellType"], lv.cellType)
+    np.testing.assert_allclose(out["abskg"], lv.abskg, rtol=1e-15)
+    np.testing.assert_allclose(out["sigmaT4"], lv.sigmaT4, rtol=1e-13)
+    lv.abskg[...] = out["abskg"]; lv.sigmaT4[...] = out["sigmaT4"]
+    ref = po.ray_trace(po.default_params(nDivQRays=3, threshold=0.05, isSeedRandom=0), lv)
+    assert out["report"]["nRaySteps"] == ref["steps"] and out["report"]["nDivQCells"] == int((lv.cellType == -1).sum())
+    np.testing.assert_allclose(out["divQ"], ref["divQ"], rtol=1e-9, atol=1e-10 * np.abs(ref["divQ"]).max())
+    assert not out["divQ"][lv.cellType != -1].any()

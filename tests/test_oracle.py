@@ -258,3 +258,38 @@ def test_radiometer_direction_cone(po):
     # looking at the cold wall: only the gas column (kappa 1, ~0.44 m) emits; looking away: full black-body intensity
     assert i1[5, 5, 5] < 0.5 * i2[5, 5, 5]
     assert i2[5, 5, 5] == pytest.approx(I * (1 + np.cos(np.radians(10))) / 2, rel=0.01)
+
+
+# ---------------------------------------------------------------- the reference's own exact-solution tables (postProcessTools)
+@pytest.mark.parametrize("bm,N,axis,rays,tol", [
+    (3, 27, 2, 2000, 0.006),     # bench3Exact.txt sub-sampled exactly like RMCRT.m:113-131 (Exact27)
+    (3, 81, 2, 500, 0.006),      # Exact81
+    (7, 41, 0, 1000, 0.03),      # kexpDivQx.dat (pchip to 41 cells)
+    (7, 41, 1, 1000, 0.03),
+    (7, 41, 2, 1000, 0.03),
+    (8, 41, 0, 1000, 0.06),      # cloudsDivQx.dat
+    (8, 41, 1, 1000, 0.03),      # cloudsDivQy.dat
+])
+def test_oracle_matches_reference_exact_tables(po, bm, N, axis, rays, tol):
+    """Known answers the reference keeps for this path besides Burns & Christon: the oracle's centre-line divQ of
+    RMCRT_Test benchmarks 3, 7 and 8 against tests/golden/rmcrt_benchmarks.json (made from bench3Exact.txt, kexpDivQ*.dat,
+    cloudsDivQ*.dat).  Measured here: 0.0016-0.0023 (bm 3), 0.010-0.015 (bm 7), 0.010 / 0.038 (bm 8 y / x at 41 cells)."""
+    lv = po.benchmark_level(bm, N, pDir=0)
+    lo, hi = po.centreline_box(N, axis)
+    r = po.ray_trace(po.default_params(nDivQRays=rays, threshold=0.001, isSeedRandom=1), lv, patch_lo=lo, patch_hi=hi, seed=5)
+    line = po.centreline_of(r["divQ"], N, axis)
+    ex = po.benchmark_exact(bm, N, axis)
+    rel = np.linalg.norm(line - ex) / np.linalg.norm(ex)
+    assert rel < tol, rel
+    # only the centre line was traced
+    assert np.count_nonzero(r["divQ"]) <= N
+
+
+def test_benchmark_golden_fixture_shape(po):
+    g = po.golden_benchmarks()
+    assert g["bench3"]["n"] == 243 and len(g["bench3"]["values"]) == 243
+    assert sorted(g["kexp"].keys()) == ["scale_to_code_problem", "x", "y", "z"]
+    assert len(g["clouds"]["x"]["x"]) == len(g["clouds"]["x"]["divQ"]) == 247
+    # the 243-point table is symmetric about the mid plane to its own Monte-Carlo noise (it is itself a computed solution)
+    v = np.array(g["bench3"]["values"])
+    assert np.linalg.norm(v - v[::-1]) / np.linalg.norm(v) < 5e-3

@@ -135,8 +135,29 @@ class RMCRT_Test {
       warn << "RMCRT:ERROR:  Benchmark (" << d_benchmark << ") only valid options are 1-7\n";
       throw ProblemSetupException(warn.str(), __FILE__, __LINE__);
     }
-    if (d_benchmark > 3)
-      throw ProblemSetupException("rmcrt_test: only benchmarks 0-3 are initialised by this driver", __FILE__, __LINE__);
+    if (ProblemSpecP bm_ps = prob_spec->findBlock("benchmark")) {        // 134-137: <benchmark dir="0|1|2">
+      std::string dir;
+      if (bm_ps->getAttribute("dir", dir)) d_pDir = std::stoi(dir);
+    }
+    if ((d_benchmark == 6 || d_benchmark == 7) && (d_pDir > 2 || d_pDir < 0)) {
+      std::ostringstream warn;
+      warn << "RMCRT:ERROR:  Benchmark (" << d_benchmark << ") requires the attribute 'dir' to be specified (0,1,2)\n";
+      throw ProblemSetupException(warn.str(), __FILE__, __LINE__);
+    }
+    if (d_benchmark == 4 || d_benchmark == 5)     // Siegel isotropic scattering: needs a RAY_SCATTER build (Ray.cc:196-201)
+      throw ProblemSetupException("rmcrt_test: benchmarks 4 and 5 need isotropic scattering, which this build does not have", __FILE__, __LINE__);
+    // <Intrusion><geom_object> box | cylinder | sphere (221-225; GeometryPieceFactory::create)
+    if (ProblemSpecP intr = prob_spec->findBlock("Intrusion"))
+      if (ProblemSpecP go = intr->findBlock("geom_object"))
+        for (const auto& c : go->children()) {
+          Intrusion g;
+          const std::string& nm = c->getNodeName();
+          if (nm == "box") { g.kind = 0; c->require("min", g.a); c->require("max", g.b); }
+          else if (nm == "cylinder") { g.kind = 1; c->require("bottom", g.a); c->require("top", g.b); c->require("radius", g.r); }
+          else if (nm == "sphere") { g.kind = 2; c->require("origin", g.a); c->require("radius", g.r); }
+          else throw ProblemSetupException("rmcrt_test: <Intrusion> geometry piece <" + nm + "> is not supported (box, cylinder, sphere)", __FILE__, __LINE__);
+          d_intrusions.push_back(g);
+        }
 
     ProblemSpecP rmcrt_ps = prob_spec->findBlock("RMCRT");
     if (!rmcrt_ps) throw ProblemSetupException("no <RMCRT> block", __FILE__, __LINE__);
@@ -304,8 +325,43 @@ class RMCRT_Test {
           for (int j = lo.y(); j < hi.y(); ++j)
             for (int i = lo.x(); i < hi.x(); ++i) { const IntVector c(i, j, k); color[c] = 1000 * abskg[c]; }
 
-      // cellType: flow everywhere, then the boundary conditions on the extra cells (776-786)
+      if (d_benchmark == 6 || d_benchmark == 7 || d_benchmark == 8) {      // 710-779: fields given at the cell centres
+        const double twoPI = 2 * M_PI;
+        if (d_benchmark == 6) abskg.initialize(5.0);
+        for (int k = lo.z(); k < hi.z(); ++k)
+          for (int j = lo.y(); j < hi.y(); ++j)
+            for (int i = lo.x(); i < hi.x(); ++i) {
+              const IntVector c(i, j, k);
+              const Point p = level->getCellPosition(c);
+              if (d_benchmark == 6) {             // sinusoidal temperature, abskg = 5
+                color[c] = std::pow(1e7 * (1.0 + std::sin(4.5 * twoPI * p[d_pDir])), 0.25);
+              } else if (d_benchmark == 7) {      // abskg = 5 exp(-2x-0.1), T^4 linear in x
+                const double x = p[d_pDir];
+                abskg[c] = 5.0 * std::exp(-2 * x - 0.1);
+                color[c] = std::pow(1.0e7 * (2.0 * x + 1.0), 0.25);
+              } else {                            // hot and cold clouds
+                const double x = p[0], y = p[1], z = p[2];
+                abskg[c] = (std::max(std::sin(x * 5 * M_PI) * std::abs((std::sin(z * 3 * M_PI + M_PI)) + (std::sin(y * 3 * M_PI))), 0.0)
+                            + std::max(std::sin(x * 5.0 * M_PI + M_PI), 0.0) * std::max(std::sin(z * 3 * M_PI + M_PI) + std::sin(y * 3 * M_PI + M_PI), 0.0)) * 5.0;
+                color[c] = (std::max(std::sin(x * 5.0 * M_PI) * std::max(std::sin(z * 3.0 * M_PI) + std::sin(y * 3.0 * M_PI), 0.0), 0.0)
+                            + std::max(std::sin(x * 5.0 * M_PI), 0.0) * std::max(std::sin(z * 3.0 * M_PI + M_PI) + std::sin(y * 3.0 * M_PI + M_PI), 0.0)) * 1000.0;
+              }
+            }
+      }
+
+      // cellType: flow everywhere, intrusions (788-811: cellType only, abskg and temperature keep their values), then the
+      // boundary conditions on the extra cells (776-786, 813)
       cellType.initialize(d_RMCRT->d_flowCell);
+      if (!d_intrusions.empty()) {
+        const IntVector elo = patch->getExtraCellLowIndex(), ehi = patch->getExtraCellHighIndex();
+        for (const Intrusion& g : d_intrusions)
+          for (int k = elo.z(); k < ehi.z(); ++k)
+            for (int j = elo.y(); j < ehi.y(); ++j)
+              for (int i = elo.x(); i < ehi.x(); ++i) {
+                const IntVector c(i, j, k);
+                if (g.inside(level->getCellPosition(c))) cellType[c] = d_wall_cell;
+              }
+      }
       d_RMCRT->setBC<int, int>(cellType, d_cellTypeLabel->getName(), patch, matl);
       d_RMCRT->setBC<double, double>(color, d_colorLabel->getName(), patch, matl);
       d_RMCRT->setBC<double, double>(abskg, d_compAbskgLabel->getName(), patch, matl);
@@ -320,6 +376,26 @@ class RMCRT_Test {
   GridP d_grid;
   double d_initColor = 0, d_initAbskg = 0;
   int d_radCalc_freq = 1, d_benchmark = 0, d_whichAlgo = singleLevel;
+  int d_pDir = -9;                 // RMCRT_Test.cc:82
+  static constexpr int d_wall_cell = 8;   // RMCRT_Test.cc:80
+  // the three GeometryPiece kinds the RMCRT decks use; inside() follows Core/GeometryPiece/{Box,Cylinder,Sphere}GeometryPiece.cc
+  struct Intrusion {
+    int kind = 0; Vector a, b; double r = 0;
+    bool inside(const Point& p) const {
+      if (kind == 0) { for (int d = 0; d < 3; ++d) if (p[d] < a[d] || p[d] > b[d]) return false; return true; }   // Box:91-100
+      if (kind == 1) {                                                                                          // Cylinder:126-143
+        const double ax[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, tb[3] = {p[0] - a[0], p[1] - a[1], p[2] - a[2]};
+        const double h2 = ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2];
+        const double h = tb[0] * ax[0] + tb[1] * ax[1] + tb[2] * ax[2];
+        if (h < 0.0 || h > h2) return false;
+        const double cx = ax[1] * tb[2] - ax[2] * tb[1], cy = ax[2] * tb[0] - ax[0] * tb[2], cz = ax[0] * tb[1] - ax[1] * tb[0];
+        return (cx * cx + cy * cy + cz * cz) / h2 <= r * r;
+      }
+      const double dx = p[0] - a[0], dy = p[1] - a[1], dz = p[2] - a[2];                                         // Sphere:83-92
+      return dx * dx + dy * dy + dz * dz <= r * r;
+    }
+  };
+  std::vector<Intrusion> d_intrusions;
 };
 
 template <class T>
