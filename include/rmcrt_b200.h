@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RMCRT_ABI_VERSION 2
+#define RMCRT_ABI_VERSION 3
 #define RMCRT_MAX_LEVELS 8
 
 typedef struct rmcrt_ctx rmcrt_ctx;
@@ -227,6 +227,49 @@ int rmcrt_coarsen_level_device(rmcrt_ctx* ctx, int fineL, int coarseL, void* str
  * x-,x+,y-,y+,z-,z+: abskg[6], sigmaT4OverPi[6], cellType[6]. */
 int rmcrt_set_level_extra_cells(rmcrt_ctx* ctx, int L, const double abskg[6], const double sigmaT4OverPi[6],
                                 const int32_t cellType[6], void* stream);
+
+/* ------------------------------------------------------------------ callers either side of the path
+ * Ray::refine_Q (Ray.cc:1872-1945), the last task of <algorithm type="RMCRT_coarseLevel">: interpolate one coarse-level field
+ * (divQ, radiationVolq) to the interior cells [fl,fh) of one fine patch with selectInterpolator (Core/Grid/AMR.h:708-745):
+ * order 0 piecewise constant, 1 linear, 2 quadratic.  coarseQ is x-fastest over [cLo,cHi) -- the getRegion box, which must
+ * cover the mapped cells +- 1 for order > 0 (getCoarseLevelRange with one ghost cell, AMR.cc:90-135); gridLo/gridHi =
+ * coarseLevel->findCellIndexRange() incl. extra cells; rr = the fine level's refinement ratio.  fineQ is x-fastest over
+ * [outLo,outHi) (the fine patch's allocateAndPut window); zeroInit reproduces `divQ_fine.initialize(0.0)` (Ray.cc:1899).
+ * FP64 in the reference's operation order: results are bit-identical to the CPU interpolators. */
+int rmcrt_refine_Q_device(rmcrt_ctx* ctx, const double* d_coarseQ, const int32_t cLo[3], const int32_t cHi[3],
+                          const int32_t gridLo[3], const int32_t gridHi[3], const int32_t rr[3], int order,
+                          const int32_t fl[3], const int32_t fh[3], double* d_fineQ,
+                          const int32_t outLo[3], const int32_t outHi[3], int zeroInit, void* stream);
+/* same with host buffers (blocking); the fine window is zero-initialised first, like the task */
+int rmcrt_refine_Q(rmcrt_ctx* ctx, const double* coarseQ, const int32_t cLo[3], const int32_t cHi[3],
+                   const int32_t gridLo[3], const int32_t gridHi[3], const int32_t rr[3], int order,
+                   const int32_t fl[3], const int32_t fh[3], double* fineQ,
+                   const int32_t outLo[3], const int32_t outHi[3], void* stream);
+
+/* The three property tasks of the Arches caller, RMCRT_Radiation (CCA/Components/Arches/SourceTerms/RMCRT.cc), over one patch.
+ * partGas arrays: [0] = gas phase (radiation_temperature / gas absk), [1..] = particle size classes; nPartGas <= 16.
+ *   sigmaT4  (RMCRT.cc:939-1016): doPartRadiation == 0 -> (sigma/pi) T_gas^4; else the absk-weighted mean of T^4 over gas and
+ *            particles in cells with gasVolFrac > 1e-16 and (sigma/pi) T_gas^4 in walls / intrusions.  n cells, T = isFloat.
+ *   sumAbsk  (RMCRT.cc:1062-1130): sum of the gas and particle absorption coefficients in interior gas cells, 1 in solid cells
+ *            and on the boundary faces (hard-wired in the reference).  Arrays x-fastest over [lo,hi), interior [intLo,intHi).
+ *   stencilToDBLs (RMCRT.cc:1389-1423): RMCRTboundFlux Stencil7 {w,e,s,n,b,t,p} -> radiationFlux{E,W,N,S,T,B}. */
+int rmcrt_arches_sigmaT4_device(rmcrt_ctx* ctx, const double* d_gasVolFrac, const double* const* d_partGas_absk,
+                                const double* const* d_partGas_temp, int nPartGas, int doPartRadiation,
+                                void* d_sigmaT4OverPi, int isFloat, int64_t n, void* stream);
+int rmcrt_arches_sumAbsk_device(rmcrt_ctx* ctx, const double* d_gasVolFrac, const double* const* d_partGas_absk, int nPartGas,
+                                const int32_t lo[3], const int32_t hi[3], const int32_t intLo[3], const int32_t intHi[3],
+                                void* d_sumAbsk, int isFloat, void* stream);
+int rmcrt_stencil_to_dbls_device(rmcrt_ctx* ctx, const double* d_boundFlux, int64_t n, double* d_E, double* d_W, double* d_N,
+                                 double* d_S, double* d_T, double* d_B, void* stream);
+/* host-buffer forms (H2D, kernel, D2H; blocking) */
+int rmcrt_arches_sigmaT4(rmcrt_ctx* ctx, const double* gasVolFrac, const double* const* partGas_absk,
+                         const double* const* partGas_temp, int nPartGas, int doPartRadiation,
+                         void* sigmaT4OverPi, int isFloat, int64_t n, void* stream);
+int rmcrt_arches_sumAbsk(rmcrt_ctx* ctx, const double* gasVolFrac, const double* const* partGas_absk, int nPartGas,
+                         const int32_t lo[3], const int32_t hi[3], const int32_t intLo[3], const int32_t intHi[3],
+                         void* sumAbsk, int isFloat, void* stream);
+int rmcrt_stencil_to_dbls(rmcrt_ctx* ctx, const double* boundFlux, int64_t n, double* E, double* W, double* N, double* S,
+                          double* T, double* B, void* stream);
 
 /* ------------------------------------------------------------------ multi-GPU replication
  * Each rank packs the cells it owns, box [lo,hi) of level L, into its slot of an all-gather send buffer

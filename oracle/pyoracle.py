@@ -457,6 +457,46 @@ def coarsen_level(fine: Level, rr=(4, 4, 4), logic=0, wall_abskg=None, wall_sigm
     return Level(ab, s4, ct, clo, chi, cdx, fine.anchor, (1, 1, 1), cil, cih)
 
 
+# ---------------------------------------------------------------- RMCRT_coarseLevel: Ray::refine_Q; Arches property tasks
+def refine_Q(coarseQ, c_lo, c_hi, grid_lo, grid_hi, rr, order, fl, fh, out_lo, out_hi):
+    q = np.ascontiguousarray(coarseQ, np.float64)
+    assert q.shape == (c_hi[2] - c_lo[2], c_hi[1] - c_lo[1], c_hi[0] - c_lo[0])
+    out = np.zeros((out_hi[2] - out_lo[2], out_hi[1] - out_lo[1], out_hi[0] - out_lo[0]), np.float64)
+    lib().oracle_refine_Q(q.ctypes.data_as(C.c_void_p), _i3(c_lo), _i3(c_hi), _i3(grid_lo), _i3(grid_hi), _i3(rr), int(order),
+                          _i3(fl), _i3(fh), out.ctypes.data_as(C.c_void_p), _i3(out_lo), _i3(out_hi))
+    return out
+
+
+def _pp(arrays):
+    return (C.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
+
+
+def arches_sigmaT4(gasVolFrac, absk, temp, do_part_radiation, dtype=np.float64, sigma=SIGMA):
+    temp = [np.ascontiguousarray(t, np.float64) for t in temp]
+    absk = [np.ascontiguousarray(a, np.float64) for a in (absk if absk is not None else temp)]
+    gv = np.ascontiguousarray(gasVolFrac if gasVolFrac is not None else np.ones_like(temp[0]), np.float64)
+    out = np.empty(temp[0].shape, dtype)
+    lib().oracle_arches_sigmaT4(gv.ctypes.data_as(C.c_void_p), _pp(absk), _pp(temp), len(temp), 1 if do_part_radiation else 0,
+                                out.ctypes.data_as(C.c_void_p), 1 if dtype == np.float32 else 0, C.c_int64(out.size), C.c_double(sigma))
+    return out
+
+
+def arches_sumAbsk(gasVolFrac, absk, lo, hi, int_lo, int_hi, dtype=np.float64):
+    absk = [np.ascontiguousarray(a, np.float64) for a in absk]
+    gv = np.ascontiguousarray(gasVolFrac, np.float64)
+    out = np.empty(gv.shape, dtype)
+    lib().oracle_arches_sumAbsk(gv.ctypes.data_as(C.c_void_p), _pp(absk), len(absk), _i3(lo), _i3(hi), _i3(int_lo), _i3(int_hi),
+                                out.ctypes.data_as(C.c_void_p), 1 if dtype == np.float32 else 0)
+    return out
+
+
+def arches_stencilToDBLs(boundFlux):
+    bf = np.ascontiguousarray(boundFlux, np.float64)
+    outs = [np.empty(bf.shape[:-1], np.float64) for _ in range(6)]
+    lib().oracle_arches_stencilToDBLs(bf.ctypes.data_as(C.c_void_p), C.c_int64(outs[0].size), *[o.ctypes.data_as(C.c_void_p) for o in outs])
+    return dict(zip(("E", "W", "N", "S", "T", "B"), outs))
+
+
 # ---------------------------------------------------------------- golden: Burns & Christon centre line
 # parametricStudies/postProcessTools/RMCRT.m:22-35 (x = 0:1/40:1, symmetric about 0.5)
 _BC_HALF = [3.07561, 2.94305, 2.81667, 2.69362, 2.57196, 2.45069, 2.32896, 2.20616, 2.08181, 1.95549, 1.82691,

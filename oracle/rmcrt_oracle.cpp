@@ -875,4 +875,140 @@ void oracle_computeCellType(const int32_t* fine, const int fLo[3], const int fHi
   }
 }
 
+//______________________________________________________________________ SURVEY 8f-4: RMCRT_coarseLevel, Ray::refine_Q
+// normalizedDistance_CC (Core/Grid/AMR.cc:207-235)
+static void normalizedDistance_CC(int rr, std::vector<double>& nd) {
+  for (int i = 0; i < rr; i++) nd[i] = 0.0;
+  if (rr > 1) {
+    const int half = rr / 2;
+    const double hdx = 0.5 * (1.0 / rr);
+    int count = rr - 1;
+    for (int i = 0; i < half; i++) { nd[i] = -count * hdx; count -= 2; }
+    count = half - 1;
+    for (int i = half; i < rr; i++) { nd[i] = std::fabs(nd[count]); count -= 1; }
+  }
+}
+static inline int signOf(double d) { return d < 0 ? -1 : 1; }                 // Core/Math/MiscMath.h:63-66
+static inline int roundUp(double d) {                                         // MiscMath.h:195-207 (d >= 0 here)
+  return ((d - (int)d) == 0) ? (int)d : (int)(d + 1);
+}
+
+// Ray::refine_Q for one scalar field of one fine patch (Ray.cc:1916-1934): selectInterpolator (Core/Grid/AMR.h:708-745) over fine
+// cells [fl,fh) = the patch's interior cells (getCoarseLevelRange, AMR.cc:132-133).
+//   order 0: piecewiseConstantInterpolation (AMR.h:49-61); 1: linearInterpolation (106-167); 2: quadraticInterpolation (341-431).
+// qC is x-fastest over the coarse window [cLo,cHi) (the getRegion box: coarse range of the patch +- 1 cell); gridLo/gridHi =
+// coarseLevel->findCellIndexRange() incl. extra cells.  qF is x-fastest over [oLo,oHi) and only [fl,fh) is written.
+void oracle_refine_Q(const double* qC, const int cLo[3], const int cHi[3], const int gridLo[3], const int gridHi_[3],
+                     const int rr[3], int order, const int fl[3], const int fh[3], double* qF, const int oLo[3], const int oHi[3]) {
+  const int64_t cnx = cHi[0] - cLo[0], cny = cHi[1] - cLo[1];
+  const int64_t onx = oHi[0] - oLo[0], ony = oHi[1] - oLo[1];
+  auto C = [&](int i, int j, int k) -> double { return qC[(i - cLo[0]) + cnx * ((j - cLo[1]) + cny * (int64_t)(k - cLo[2]))]; };
+  std::vector<double> ndx(rr[0]), ndy(rr[1]), ndz(rr[2]);
+  normalizedDistance_CC(rr[0], ndx); normalizedDistance_CC(rr[1], ndy); normalizedDistance_CC(rr[2], ndz);
+  const int gridHi[3] = {gridHi_[0] - 1, gridHi_[1] - 1, gridHi_[2] - 1};      // AMR.h:353
+  for (int kf = fl[2]; kf < fh[2]; ++kf) for (int jf = fl[1]; jf < fh[1]; ++jf) for (int i_f = fl[0]; i_f < fh[0]; ++i_f) {
+    const int f[3] = {i_f, jf, kf};
+    int c[3];
+    mapToCoarser(f, rr, c);
+    double out;
+    if (order == 0) {
+      out = C(c[0], c[1], c[2]);
+    } else if (order == 1) {
+      const int rel[3] = {f[0] - c[0] * rr[0], f[1] - c[1] * rr[1], f[2] - c[2] * rr[2]};
+      const double dist[3] = {ndx[rel[0]], ndy[rel[1]], ndz[rel[2]]};
+      int i = signOf(dist[0]), j = signOf(dist[1]), k = signOf(dist[2]);
+      i *= roundUp(std::fabs(dist[0])); j *= roundUp(std::fabs(dist[1])); k *= roundUp(std::fabs(dist[2]));
+      const double x = std::fabs(dist[0]), y = std::fabs(dist[1]), z = std::fabs(dist[2]);
+      const double w0 = (1.0 - x) * (1.0 - y), w1 = x * (1.0 - y), w2 = y * (1.0 - x), w3 = x * y;
+      const double p1 = w0 * C(c[0], c[1], c[2]) + w1 * C(c[0] + i, c[1], c[2]) + w2 * C(c[0], c[1] + j, c[2]) + w3 * C(c[0] + i, c[1] + j, c[2]);
+      const double p2 = w0 * C(c[0], c[1], c[2] + k) + w1 * C(c[0] + i, c[1], c[2] + k) + w2 * C(c[0], c[1] + j, c[2] + k) + w3 * C(c[0] + i, c[1] + j, c[2] + k);
+      out = (1.0 - z) * p1 + z * p2;
+    } else {
+      int b[3], rel[3];
+      for (int d = 0; d < 3; ++d) {
+        int shift = 0;
+        if ((c[d] - gridLo[d]) == 0) shift = 1;
+        if ((gridHi[d] - c[d]) == 0) shift = -1;
+        b[d] = c[d] + shift;
+        // AMR.h:386 takes f - baseCell*rr; with a shifted base cell that leaves [0,rr) and the reference reads its distance table out
+        // of range.  Unreachable from refine_Q (interior fine cells never map to a coarse extra cell); keep the in-range index.
+        rel[d] = shift ? f[d] - c[d] * rr[d] : f[d] - b[d] * rr[d];
+      }
+      const double x = ndx[rel[0]], y = ndy[rel[1]], z = ndz[rel[2]];
+      const double wx[3] = {0.5 * x * (x - 1.0), -(x + 1.0) * (x - 1.0), 0.5 * x * (x + 1.0)};
+      const double wy[3] = {0.5 * y * (y - 1.0), -(y + 1.0) * (y - 1.0), 0.5 * y * (y + 1.0)};
+      const double wz[3] = {0.5 * z * (z - 1.0), -(z + 1.0) * (z - 1.0), 0.5 * z * (z + 1.0)};
+      double plane[3];
+      for (int pz = 0; pz < 3; ++pz) {
+        const int k = pz - 1;
+        double acc = (wx[0] * wy[0]) * C(b[0] - 1, b[1] - 1, b[2] + k);
+        acc += (wx[1] * wy[0]) * C(b[0], b[1] - 1, b[2] + k);
+        acc += (wx[2] * wy[0]) * C(b[0] + 1, b[1] - 1, b[2] + k);
+        acc += (wx[0] * wy[1]) * C(b[0] - 1, b[1], b[2] + k);
+        acc += (wx[1] * wy[1]) * C(b[0], b[1], b[2] + k);
+        acc += (wx[2] * wy[1]) * C(b[0] + 1, b[1], b[2] + k);
+        acc += (wx[0] * wy[2]) * C(b[0] - 1, b[1] + 1, b[2] + k);
+        acc += (wx[1] * wy[2]) * C(b[0], b[1] + 1, b[2] + k);
+        acc += (wx[2] * wy[2]) * C(b[0] + 1, b[1] + 1, b[2] + k);
+        plane[pz] = acc;
+      }
+      out = wz[0] * plane[0] + wz[1] * plane[1] + wz[2] * plane[2];
+    }
+    qF[(f[0] - oLo[0]) + onx * ((f[1] - oLo[1]) + ony * (int64_t)(f[2] - oLo[2]))] = out;
+  }
+}
+
+//______________________________________________________________________ SURVEY 8f-2: the Arches caller's property tasks
+// RMCRT_Radiation::sigmaT4<T> (Arches/SourceTerms/RMCRT.cc:939-1016) over n cells (the patch incl. extra cells).
+// partGas_absk / partGas_temp: nPartGas arrays; [0] is the gas phase (radiation_temperature).
+void oracle_arches_sigmaT4(const double* gasVolFrac, const double* const* partGas_absk, const double* const* partGas_temp,
+                           int nPartGas, int doPartRadiation, void* out, int isFloat, int64_t n, double sigma) {
+  const double sigma_over_pi = sigma / M_PI;
+  for (int64_t c = 0; c < n; ++c) {
+    double v;
+    if (!doPartRadiation || !(gasVolFrac[c] > 1e-16)) {
+      const double T_sqrd = partGas_temp[0][c] * partGas_temp[0][c];
+      v = sigma_over_pi * T_sqrd * T_sqrd;
+    } else {
+      double sumT = 0.0, sumAbsk = 0.0;
+      for (int i = 0; i < nPartGas; i++) {
+        const double T_sqrd = partGas_temp[i][c] * partGas_temp[i][c];
+        sumT += T_sqrd * T_sqrd * partGas_absk[i][c];
+        sumAbsk += partGas_absk[i][c];
+      }
+      v = 0.0;
+      if (sumAbsk > 1e-16) v = sigma_over_pi * sumT / sumAbsk;
+    }
+    if (isFloat) static_cast<float*>(out)[c] = (float)v; else static_cast<double*>(out)[c] = v;
+  }
+}
+
+// RMCRT_Radiation::sumAbsk<T> (RMCRT.cc:1062-1130): arrays x-fastest over the patch window [lo,hi) incl. extra cells; interior
+// cells [intLo,intHi); every cell outside the interior is a boundary-face cell (ExtraPlusEdgeCells) and gets the hard-wired 1.
+void oracle_arches_sumAbsk(const double* gasVolFrac, const double* const* partGas_absk, int nPartGas, const int lo[3],
+                           const int hi[3], const int intLo[3], const int intHi[3], void* out, int isFloat) {
+  const int64_t nx = hi[0] - lo[0], ny = hi[1] - lo[1];
+  for (int k = lo[2]; k < hi[2]; ++k) for (int j = lo[1]; j < hi[1]; ++j) for (int i = lo[0]; i < hi[0]; ++i) {
+    const int64_t c = (i - lo[0]) + nx * ((j - lo[1]) + ny * (int64_t)(k - lo[2]));
+    const bool interior = i >= intLo[0] && i < intHi[0] && j >= intLo[1] && j < intHi[1] && k >= intLo[2] && k < intHi[2];
+    double v = 0.0;
+    if (interior) {
+      for (int p = 0; p < nPartGas; p++) {
+        if (gasVolFrac[c] > 1e-16) v += partGas_absk[p][c]; else v = 1.0;
+      }
+    } else {
+      v = 1.0;
+    }
+    if (isFloat) static_cast<float*>(out)[c] = (float)v; else static_cast<double*>(out)[c] = v;
+  }
+}
+
+// RMCRT_Radiation::stencilToDBLs (RMCRT.cc:1389-1423): Stencil7 {w,e,s,n,b,t,p} -> radiationFlux{E,W,N,S,T,B}
+void oracle_arches_stencilToDBLs(const double* boundFlux7, int64_t n, double* E, double* W, double* N, double* S, double* T, double* B) {
+  for (int64_t c = 0; c < n; ++c) {
+    const double* me = boundFlux7 + 7 * c;
+    E[c] = me[1]; W[c] = me[0]; N[c] = me[3]; S[c] = me[2]; T[c] = me[5]; B[c] = me[4];
+  }
+}
+
 }  // extern "C"

@@ -142,6 +142,17 @@ void oracle_computeCellType(const int32_t* fine, const int fLo[3], const int fHi
 /* Level::mapCellToCoarser including its negative-index behaviour (Level.cc:1285-1307) */
 void oracle_mapCellToCoarser(const int idx[3], const int rr[3], int out[3]);
 
+/* ---- Ray::refine_Q (Ray.cc:1872-1945) = selectInterpolator (Core/Grid/AMR.h:708-745), order 0|1|2 ---- */
+void oracle_refine_Q(const double* qC, const int cLo[3], const int cHi[3], const int gridLo[3], const int gridHi[3],
+                     const int rr[3], int order, const int fl[3], const int fh[3], double* qF, const int oLo[3], const int oHi[3]);
+
+/* ---- Arches RMCRT_Radiation property tasks (Arches/SourceTerms/RMCRT.cc) ---- */
+void oracle_arches_sigmaT4(const double* gasVolFrac, const double* const* partGas_absk, const double* const* partGas_temp,
+                           int nPartGas, int doPartRadiation, void* out, int isFloat, int64_t n, double sigma);
+void oracle_arches_sumAbsk(const double* gasVolFrac, const double* const* partGas_absk, int nPartGas, const int lo[3],
+                           const int hi[3], const int intLo[3], const int intHi[3], void* out, int isFloat);
+void oracle_arches_stencilToDBLs(const double* boundFlux7, int64_t n, double* E, double* W, double* N, double* S, double* T, double* B);
+
 #ifdef __cplusplus
 }
 #endif

@@ -182,3 +182,87 @@ def test_radiometer_production_closed_form(gpu_lib, po):
             hv = np.radians(view / 2)
             assert inten[9, 9, 9] == pytest.approx(I * (1 + np.cos(hv)) / 2, rel=(2e-3 if half else 5e-4))
             assert flux[9, 9, 9] == pytest.approx(inten[9, 9, 9] * 2 * np.pi * (1 - np.cos(hv)), rel=1e-6)
+
+
+# ---------------------------------------------------------------- RMCRT_coarseLevel: Ray::refine_Q on the device
+@pytest.mark.parametrize("order", [0, 1, 2])
+@pytest.mark.parametrize("rr", [(2, 2, 2), (4, 4, 4), (2, 4, 1)])
+def test_refine_Q_bit_exact(gpu_lib, po, order, rr):
+    """selectInterpolator (Core/Grid/AMR.h) on the device: FP64, the reference's operation order -> identical bits"""
+    from test_oracle import _refine_case
+    q, glo, ghi, fl, fh, olo, ohi = _refine_case(rr)
+    g = make(gpu_lib)
+    ref = po.refine_Q(q, glo, ghi, glo, ghi, rr, order, fl, fh, olo, ohi)
+    out = g.refine_Q(q, glo, ghi, glo, ghi, rr, order, fl, fh, olo, ohi)
+    assert np.array_equal(out, ref)
+    # a coarse window cut down to what the interpolation reads (the getRegion box of getCoarseLevelRange) gives the same result
+    reach = 0 if order == 0 else 1
+    clo = tuple(fl[d] // rr[d] - reach for d in range(3)); chi = tuple((fh[d] - 1) // rr[d] + 1 + reach for d in range(3))
+    sub = q[clo[2] + 1:chi[2] + 1, clo[1] + 1:chi[1] + 1, clo[0] + 1:chi[0] + 1]
+    assert np.array_equal(g.refine_Q(sub, clo, chi, glo, ghi, rr, order, fl, fh, olo, ohi), ref)
+
+
+def test_refine_Q_errors(gpu_lib, po):
+    from test_oracle import _refine_case
+    from uintah_b200 import RmcrtError
+    q, glo, ghi, fl, fh, olo, ohi = _refine_case((2, 2, 2))
+    g = make(gpu_lib)
+    with pytest.raises(RmcrtError, match="orderOfInterpolation"):
+        g.refine_Q(q, glo, ghi, glo, ghi, (2, 2, 2), 3, fl, fh, olo, ohi)
+    with pytest.raises(RmcrtError, match="does not cover"):
+        g.refine_Q(q[1:], (-1, -1, 0), ghi, glo, ghi, (2, 2, 2), 1, (0, 0, 0), (4, 4, 4), (0, 0, 0), (4, 4, 4))
+
+
+def test_coarse_level_solve_then_refine(gpu_lib, po):
+    """<algorithm type="RMCRT_coarseLevel"> (RMCRT_Test.cc:464-519): coarsen the fine properties, ray trace the coarse level,
+    interpolate divQ back to the fine level -- every stage against the oracle in deterministic mode"""
+    N, RR = 32, 4
+    fine = po.burns_christon(N)
+    fine.rr = (RR,) * 3
+    coarse = po.coarsen_level(fine, (RR,) * 3)
+    p = po.default_params(nDivQRays=5, threshold=0.05, isSeedRandom=0)
+    ref_c = po.ray_trace(p, coarse)["divQ"]
+    g = make(gpu_lib, nDivQRays=5, threshold=0.05, isSeedRandom=0, marchPrecision=1, skipZeroWeightLegs=0)
+    g.upload_level(0, coarse)
+    dq_c = g.trace_divq(0)["divQ"]
+    np.testing.assert_allclose(dq_c, ref_c, rtol=1e-9, atol=1e-10 * np.abs(ref_c).max())
+    n = N // RR
+    for order in (1, 2):
+        ref_f = po.refine_Q(ref_c, coarse.lo, coarse.hi, coarse.lo, coarse.hi, (RR,) * 3, order, (0,) * 3, (N,) * 3, fine.lo, fine.hi)
+        out_f = g.refine_Q(ref_c, coarse.lo, coarse.hi, coarse.lo, coarse.hi, (RR,) * 3, order, (0,) * 3, (N,) * 3, fine.lo, fine.hi)
+        assert np.array_equal(out_f, ref_f)
+        # the interpolated coarse solve approximates the fine-level solve (same physics, 64x fewer ray origins)
+        assert out_f.shape == fine.abskg.shape
+    fine_ref = po.ray_trace(po.default_params(nDivQRays=20, threshold=0.05), fine, seed=9, patches=(1, 1, 8), threads=8)["divQ"]
+    inner = (slice(1 + RR, -1 - RR),) * 3
+    assert np.linalg.norm(out_f[inner] - fine_ref[inner]) / np.linalg.norm(fine_ref[inner]) < 0.25
+    assert n == coarse.interior_hi[0]
+
+
+# ---------------------------------------------------------------- the Arches caller's property tasks on the device
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_arches_property_tasks_match_oracle(gpu_lib, po, dtype):
+    """RMCRT_Radiation::sigmaT4 (gas only and gas + 3 particle classes), sumAbsk and stencilToDBLs: bit-exact"""
+    rng = np.random.default_rng(11)
+    shp = (12, 11, 13)                      # a 10x9x11-cell patch with its extra cells
+    lo, hi, ilo, ihi = (-1, -1, -1), (12, 10, 11), (0, 0, 0), (11, 9, 10)
+    gv = (rng.uniform(size=shp) > 0.1).astype(np.float64)       # 10 % solid cells
+    temp = [rng.uniform(300, 2000, shp) for _ in range(4)]
+    absk = [rng.uniform(0, 2, shp) * (rng.uniform(size=shp) > 0.2) for _ in range(4)]
+    zero = rng.uniform(size=shp) < 0.05
+    for a in absk:
+        a[zero] = 0.0                       # cells with sumAbsk == 0 -> sigmaT4 = 0 (RMCRT.cc:1000-1003)
+    g = make(gpu_lib)
+    for part in (False, True):
+        ref = po.arches_sigmaT4(gv, absk, temp, part, dtype)
+        out = g.arches_sigmaT4(gv, absk, temp, part, dtype)
+        assert np.array_equal(out, ref) and out.dtype == dtype
+    assert (po.arches_sigmaT4(gv, absk, temp, True, dtype) == 0).sum() >= int((zero & (gv > 0)).sum()) > 0
+    ref = po.arches_sumAbsk(gv, absk, lo, hi, ilo, ihi, dtype)
+    out = g.arches_sumAbsk(gv, absk, lo, hi, ilo, ihi, dtype)
+    assert np.array_equal(out, ref) and (out[0] == 1).all() and (out[:, :, -1] == 1).all()
+    bf = rng.normal(size=shp + (7,))
+    r6, o6 = po.arches_stencilToDBLs(bf), g.stencil_to_dbls(bf)
+    for k in "EWNSTB":
+        assert np.array_equal(o6[k], r6[k])
+    assert np.array_equal(o6["E"], bf[..., 1]) and np.array_equal(o6["B"], bf[..., 4])

@@ -324,3 +324,49 @@ def test_benchmark7_with_cylinder_intrusion(exe, po, tmp_path, gpu_lib):
     assert out["report"]["nRaySteps"] == ref["steps"] and out["report"]["nDivQCells"] == int((lv.cellType == -1).sum())
     np.testing.assert_allclose(out["divQ"], ref["divQ"], rtol=1e-9, atol=1e-10 * np.abs(ref["divQ"]).max())
     assert not out["divQ"][lv.cellType != -1].any()
+
+
+# ------------------------------------------------------------------------------------------------ <algorithm type="RMCRT_coarseLevel">
+def coarse_level_deck(tmp_path, order=1):
+    return edit_deck(tmp_path, "bm1_DO.ups", ('''<algorithm type="dataOnion">
+      <haloCells>        [4,4,4]    </haloCells>
+      <ROI_extents type="patch_based"/>
+    </algorithm>''', f'<algorithm type="RMCRT_coarseLevel"> <orderOfInterpolation> {order} </orderOfInterpolation> </algorithm>'))
+
+
+def test_coarse_level_schedule_matches_reference_surface(exe, tmp_path):
+    """RMCRT_Test.cc:464-519: CoarsenAll + BCs on the coarse level, Ray::rayTrace on the COARSE level, Ray::refine_Q on the fine one
+    with the dependencies of Ray::sched_Refine_Q (Ray.cc:1841-1867)"""
+    t = tasks_of(run(exe, coarse_level_deck(tmp_path), "--parse-only").stdout)
+    names = [(x["name"], x["level"]) for x in t]
+    assert ("Ray::rayTrace", "0") in names and ("Ray::rayTrace", "1") not in names
+    assert names.index(("Ray::coarsenAll", "0")) < names.index(("Ray::setBoundaryConditions", "0")) < names.index(("Ray::rayTrace", "0")) \
+        < names.index(("Ray::refine_Q", "1"))
+    rq = [x for x in t if x["name"] == "Ray::refine_Q"][0]
+    assert rq["patches"] == "8" and rq["tg"] == "1"
+    assert [(d[1], d[3], d[4], d[5]) for d in rq["deps"] if d[0] == "requires"] == \
+        [(n, "ghost=1", "domain=coarse", "offset=1") for n in ("divQ", "RMCRTboundFlux", "radiationVolq")]
+    assert [d[1] for d in rq["deps"] if d[0] == "computes"] == ["divQ", "RMCRTboundFlux", "radiationVolq"]
+    r = subprocess.run([exe, edit_deck(tmp_path, "bm1_DO.ups", ('<haloCells>        [4,4,4]    </haloCells>', ''),
+                                       ('type="dataOnion"', 'type="RMCRT_coarseLevel"')), "--parse-only"], capture_output=True, text=True)
+    assert r.returncode == 1 and "orderOfInterpolation" in r.stderr      # alg_ps->require (Ray.cc:314)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", [1, 2])
+def test_coarse_level_deck(exe, po, tmp_path, gpu_lib, order):
+    """RMCRT_ML.ups pattern through the plugin: coarse 8^3 solve == the oracle's Ray::rayTrace on the coarsened level, fine 32^3
+    divQ == the oracle's refine_Q of it, bit for bit"""
+    r = subprocess.run([exe, coarse_level_deck(tmp_path, order), "--dump", str(tmp_path / "d"), "--knob", "skipZeroWeightLegs=0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = load_dump(str(tmp_path / "d"))
+    fine = po.burns_christon(32)
+    fine.rr = (4, 4, 4)
+    coarse = po.coarsen_level(fine, (4, 4, 4))
+    ref_c = po.ray_trace(po.default_params(nDivQRays=3, threshold=0.05, isSeedRandom=0), coarse)
+    assert out["report"]["nRaySteps"] == ref_c["steps"] and out["report"]["nDivQCells"] == 8 ** 3
+    np.testing.assert_allclose(out["divQ_L0"], ref_c["divQ"], rtol=1e-9, atol=1e-10 * np.abs(ref_c["divQ"]).max())
+    ref_f = po.refine_Q(out["divQ_L0"], coarse.lo, coarse.hi, coarse.lo, coarse.hi, (4, 4, 4), order, (0,) * 3, (32,) * 3, fine.lo, fine.hi)
+    assert np.array_equal(out["divQ"], ref_f)
+    assert not out["RMCRTboundFlux"].any()

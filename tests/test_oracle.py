@@ -293,3 +293,56 @@ def test_benchmark_golden_fixture_shape(po):
     # the 243-point table is symmetric about the mid plane to its own Monte-Carlo noise (it is itself a computed solution)
     v = np.array(g["bench3"]["values"])
     assert np.linalg.norm(v - v[::-1]) / np.linalg.norm(v) < 5e-3
+
+
+# ---------------------------------------------------------------- RMCRT_coarseLevel: Ray::refine_Q (selectInterpolator, AMR.h)
+def _refine_case(rr, n_coarse=6, seed=3):
+    """one coarse level of n_coarse^3 interior cells (+1 extra layer), fine patch = a sub-box of the rr-times finer level"""
+    rng = np.random.default_rng(seed)
+    glo, ghi = (-1, -1, -1), (n_coarse + 1,) * 3
+    q = rng.normal(size=(n_coarse + 2,) * 3)
+    fl, fh = (rr[0] * 1, rr[1] * 0, rr[2] * 2), (rr[0] * 4, rr[1] * 3, rr[2] * n_coarse)      # touches y-, z+ domain faces
+    olo, ohi = (fl[0], fl[1] - 1, fl[2]), (fh[0], fh[1], fh[2] + 1)                           # patch window incl. its extra cells
+    return q, glo, ghi, fl, fh, olo, ohi
+
+
+@pytest.mark.parametrize("rr", [(2, 2, 2), (4, 4, 4), (2, 4, 1)])
+def test_refine_Q_reproduces_polynomials(po, rr):
+    """order 0 copies the parent, order 1 is exact for tri-linear fields, order 2 for tri-quadratic ones (cell-centred)"""
+    q, glo, ghi, fl, fh, olo, ohi = _refine_case(rr)
+    n = q.shape[0] - 2
+    cc = np.arange(-1, n + 1) + 0.5                                    # coarse cell centres in coarse-cell units
+    Z, Y, X = np.meshgrid(cc, cc, cc, indexing="ij")
+    fx = [(np.arange(olo[d], ohi[d]) + 0.5) / rr[d] for d in range(3)]
+    FZ, FY, FX = np.meshgrid(fx[2], fx[1], fx[0], indexing="ij")
+    sl = tuple(slice(fl[d] - olo[d], fh[d] - olo[d]) for d in (2, 1, 0))
+    lin = lambda x, y, z: 1.5 + 0.25 * x - 0.5 * y + 2 * z + 0.125 * x * y * z
+    quad = lambda x, y, z: lin(x, y, z) + 0.5 * x * x - 0.25 * y * y + z * z * x
+    for order, fn, tol in ((1, lin, 1e-13), (2, quad, 1e-12)):
+        out = po.refine_Q(fn(X, Y, Z), glo, ghi, glo, ghi, rr, order, fl, fh, olo, ohi)
+        np.testing.assert_allclose(out[sl], fn(FX, FY, FZ)[sl], rtol=tol, atol=tol)
+        mask = np.ones(out.shape, bool); mask[sl] = False
+        assert not out[mask].any()                                         # only [fl,fh) is written (Ray.cc:1899-1934)
+    out0 = po.refine_Q(q, glo, ghi, glo, ghi, rr, 0, fl, fh, olo, ohi)
+    k, j, i = np.meshgrid(*[np.arange(fl[d], fh[d]) // rr[d] + 1 for d in (2, 1, 0)], indexing="ij")
+    assert np.array_equal(out0[sl], q[k, j, i])
+
+
+def test_arches_property_tasks_known_answers(po):
+    """RMCRT_Radiation::sigmaT4 / sumAbsk / stencilToDBLs restatements on hand-checkable inputs"""
+    T = np.array([[[1000.0, 500.0, 300.0]]]); Tp = np.array([[[2000.0, 500.0, 900.0]]])
+    ak = np.array([[[1.0, 0.0, 0.3]]]); akp = np.array([[[3.0, 0.0, 0.1]]])
+    gv = np.array([[[1.0, 1.0, 0.0]]])
+    s = po.arches_sigmaT4(gv, [ak, akp], [T, Tp], True)
+    sop = po.SIGMA / np.pi
+    np.testing.assert_allclose(s[0, 0], [sop * (1e12 * 1 + 16e12 * 3) / 4, 0.0, sop * 300.0 ** 4], rtol=1e-15)
+    np.testing.assert_allclose(po.arches_sigmaT4(gv, None, [T], False)[0, 0], sop * T[0, 0] ** 4, rtol=1e-15)
+    # sumAbsk: 3x3x3 window with a 1-cell extra layer around one interior cell
+    gvw = np.ones((3, 3, 3)); a1 = np.full((3, 3, 3), 0.25); a2 = np.full((3, 3, 3), 0.5)
+    out = po.arches_sumAbsk(gvw, [a1, a2], (-1,) * 3, (2,) * 3, (0,) * 3, (1,) * 3)
+    assert out[1, 1, 1] == 0.75 and (np.delete(out.ravel(), 13) == 1.0).all()
+    gvw[1, 1, 1] = 0.0
+    assert po.arches_sumAbsk(gvw, [a1, a2], (-1,) * 3, (2,) * 3, (0,) * 3, (1,) * 3)[1, 1, 1] == 1.0
+    bf = np.arange(14.0).reshape(2, 7)
+    d = po.arches_stencilToDBLs(bf)
+    assert [d[k][0] for k in "EWNSTB"] == [1, 0, 3, 2, 5, 4] and d["T"][1] == 12

@@ -23,6 +23,8 @@ SYMBOLS = [
     "rmcrt_get_counters", "rmcrt_sigmaT4_device", "rmcrt_sigmaT4", "rmcrt_coarsen_level_device", "rmcrt_set_level_extra_cells",
     "rmcrt_pack_box_device", "rmcrt_assemble_level", "rmcrt_allgather_records", "rmcrt_measure_read_bandwidth", "rmcrt_debug_trace_rays",
     "rmcrt_radiometer_setup", "rmcrt_trace_radiometer_device", "rmcrt_trace_radiometer",
+    "rmcrt_refine_Q_device", "rmcrt_refine_Q", "rmcrt_arches_sigmaT4_device", "rmcrt_arches_sumAbsk_device",
+    "rmcrt_stencil_to_dbls_device", "rmcrt_arches_sigmaT4", "rmcrt_arches_sumAbsk", "rmcrt_stencil_to_dbls",
 ]
 
 
@@ -119,6 +121,15 @@ def load_library(path: str | None = None):
     lib.rmcrt_measure_read_bandwidth.argtypes = [vp, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.rmcrt_debug_trace_rays.argtypes = [vp, C.c_int, C.c_int, i3, i3, C.c_int, i3, C.POINTER(C.c_double),
                                            C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint32), i3, C.c_int]
+    lib.rmcrt_refine_Q_device.argtypes = [vp, vp, i3, i3, i3, i3, i3, C.c_int, i3, i3, vp, i3, i3, C.c_int, vp]
+    lib.rmcrt_refine_Q.argtypes = [vp, vp, i3, i3, i3, i3, i3, C.c_int, i3, i3, vp, i3, i3, vp]
+    pp = C.POINTER(vp)
+    for name in ("rmcrt_arches_sigmaT4_device", "rmcrt_arches_sigmaT4"):
+        getattr(lib, name).argtypes = [vp, vp, pp, pp, C.c_int, C.c_int, vp, C.c_int, C.c_int64, vp]
+    for name in ("rmcrt_arches_sumAbsk_device", "rmcrt_arches_sumAbsk"):
+        getattr(lib, name).argtypes = [vp, vp, pp, C.c_int, i3, i3, i3, i3, vp, C.c_int, vp]
+    for name in ("rmcrt_stencil_to_dbls_device", "rmcrt_stencil_to_dbls"):
+        getattr(lib, name).argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp]
     if path is None:
         _lib = lib
     return lib

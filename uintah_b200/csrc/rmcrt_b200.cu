@@ -794,6 +794,155 @@ __global__ void roi_copy_kernel(const RecT* __restrict__ fine, Box fb, RecT* __r
   }
 }
 
+// ---- callers either side of the path: streaming kernels, HBM bound ----
+// Ray::refine_Q (Ray.cc:1872-1945) = selectInterpolator (Core/Grid/AMR.h:708-745) for one scalar of one fine patch.
+// FP64 without FMA contraction and in the reference's operation order, so the result equals the CPU's bit for bit.
+struct RefineArgs {
+  Box cw;            // window of the coarse array (getRegion box)
+  Box fr;            // fine cells to fill [fl,fh)
+  Box ow;            // window of the fine array
+  int gridLo[3], gridHiM1[3];   // coarseLevel->findCellIndexRange(), high - 1 (AMR.h:351-353)
+  int rr[3];
+  int order;
+};
+// normalizedDistance_CC (Core/Grid/AMR.cc:207-235) for one fine index inside its coarse cell
+__device__ __forceinline__ double norm_dist_cc(int rel, int rr) {
+  if (rr <= 1) return 0.0;
+  const int half = rr / 2;
+  const double hdx = __dmul_rn(0.5, 1.0 / (double)rr);
+  if (rel < half) return __dmul_rn((double)(-(rr - 1 - 2 * rel)), hdx);
+  if (rel >= rr) return 0.0;
+  const int m = half - 1 - (rel - half);          // mirror copy; odd ratios keep 0 for the last index
+  return m >= 0 ? fabs(__dmul_rn((double)(-(rr - 1 - 2 * m)), hdx)) : 0.0;
+}
+__device__ __forceinline__ int map_coarser_dev(int i, int rr) {     // Level::mapCellToCoarser (Level.cc:1285-1307)
+  int q = i / rr;
+  if (i < 0 && rr > 1) q += (int)fmod((double)i, (double)rr);
+  return q;
+}
+__global__ void refine_kernel(const double* __restrict__ qC, double* __restrict__ qF, const __grid_constant__ RefineArgs a) {
+  const long long n = box_cells(a.fr);
+  const long long cnx = a.cw.n[0], cny = a.cw.n[1];
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const long long row = t / a.fr.n[0];
+    const int kk = (int)(row / a.fr.n[1]);
+    const int f[3] = {a.fr.lo[0] + (int)(t - row * a.fr.n[0]), a.fr.lo[1] + (int)(row - (long long)kk * a.fr.n[1]), a.fr.lo[2] + kk};
+    int c[3];
+    for (int d = 0; d < 3; ++d) c[d] = map_coarser_dev(f[d], a.rr[d]);
+    auto C = [&](int i, int j, int k) -> double {
+      return __ldg(qC + ((i - a.cw.lo[0]) + cnx * ((j - a.cw.lo[1]) + cny * (long long)(k - a.cw.lo[2]))));
+    };
+    double out;
+    if (a.order == 0) {
+      out = C(c[0], c[1], c[2]);
+    } else if (a.order == 1) {
+      double dist[3];
+      int off[3];
+      for (int d = 0; d < 3; ++d) {
+        dist[d] = norm_dist_cc(f[d] - c[d] * a.rr[d], a.rr[d]);
+        const double ad = fabs(dist[d]);
+        off[d] = (dist[d] < 0 ? -1 : 1) * (((ad - (int)ad) == 0) ? (int)ad : (int)(ad + 1));
+        dist[d] = ad;
+      }
+      const double x = dist[0], y = dist[1], z = dist[2];
+      const double w0 = __dmul_rn(1.0 - x, 1.0 - y), w1 = __dmul_rn(x, 1.0 - y), w2 = __dmul_rn(y, 1.0 - x), w3 = __dmul_rn(x, y);
+      const int i = off[0], j = off[1], k = off[2];
+      const double p1 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(w0, C(c[0], c[1], c[2])), __dmul_rn(w1, C(c[0] + i, c[1], c[2]))),
+                                            __dmul_rn(w2, C(c[0], c[1] + j, c[2]))), __dmul_rn(w3, C(c[0] + i, c[1] + j, c[2])));
+      const double p2 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(w0, C(c[0], c[1], c[2] + k)), __dmul_rn(w1, C(c[0] + i, c[1], c[2] + k))),
+                                            __dmul_rn(w2, C(c[0], c[1] + j, c[2] + k))), __dmul_rn(w3, C(c[0] + i, c[1] + j, c[2] + k)));
+      out = __dadd_rn(__dmul_rn(1.0 - z, p1), __dmul_rn(z, p2));
+    } else {
+      int b[3];
+      double w[3][3];
+      for (int d = 0; d < 3; ++d) {
+        int shift = 0;
+        if ((c[d] - a.gridLo[d]) == 0) shift = 1;
+        if ((a.gridHiM1[d] - c[d]) == 0) shift = -1;
+        b[d] = c[d] + shift;
+        const int rel = f[d] - b[d] * a.rr[d];
+        // a shifted base cell puts the fine cell outside [0,rr): the reference then indexes its table out of range; such cells
+        // (coarse cell == an extra cell) never occur for interior fine cells, keep the in-range distance of the unshifted cell
+        const double x = norm_dist_cc(shift ? f[d] - c[d] * a.rr[d] : rel, a.rr[d]);
+        w[d][0] = __dmul_rn(__dmul_rn(0.5, x), x - 1.0);
+        w[d][1] = __dmul_rn(-(x + 1.0), x - 1.0);
+        w[d][2] = __dmul_rn(__dmul_rn(0.5, x), x + 1.0);
+      }
+      double plane[3];
+#pragma unroll
+      for (int pz = 0; pz < 3; ++pz) {
+        const int k = b[2] + pz - 1;
+        double acc = __dmul_rn(__dmul_rn(w[0][0], w[1][0]), C(b[0] - 1, b[1] - 1, k));
+        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(w[0][1], w[1][0]), C(b[0], b[1] - 1, k)));
+        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(w[0][2], w[1][0]), C(b[0] + 1, b[1] - 1, k)));
+        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(w[0][0], w[1][1]), C(b[0] - 1, b[1], k)));
+        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(w[0][1], w[1][1]), C(b[0], b[1], k)));
+        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(w[0][2], w[1][1]), C(b[0] + 1, b[1], k)));
+        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(w[0][0], w[1][2]), C(b[0] - 1, b[1] + 1, k)));
+        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(w[0][1], w[1][2]), C(b[0], b[1] + 1, k)));
+        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(w[0][2], w[1][2]), C(b[0] + 1, b[1] + 1, k)));
+        plane[pz] = acc;
+      }
+      out = __dadd_rn(__dadd_rn(__dmul_rn(w[2][0], plane[0]), __dmul_rn(w[2][1], plane[1])), __dmul_rn(w[2][2], plane[2]));
+    }
+    qF[(f[0] - a.ow.lo[0]) + (long long)a.ow.n[0] * ((f[1] - a.ow.lo[1]) + (long long)a.ow.n[1] * (long long)(f[2] - a.ow.lo[2]))] = out;
+  }
+}
+
+// Arches RMCRT_Radiation::sigmaT4<T> (Arches/SourceTerms/RMCRT.cc:939-1016): gas-only or absk-weighted gas + particle emission
+#define RMCRT_MAX_PARTGAS 16
+struct PartGasPtrs { const double* absk[RMCRT_MAX_PARTGAS]; const double* temp[RMCRT_MAX_PARTGAS]; int n; };
+template <class T>
+__global__ void arches_sigmaT4_kernel(const double* __restrict__ gasVolFrac, const __grid_constant__ PartGasPtrs pg, int doPart,
+                                      T* __restrict__ out, long long n, double sigma_over_pi) {
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+    double v;
+    if (!doPart || !(gasVolFrac[c] > 1e-16)) {          // gas only, or a wall / intrusion cell (1005-1009)
+      const double T2 = __dmul_rn(pg.temp[0][c], pg.temp[0][c]);
+      v = __dmul_rn(__dmul_rn(sigma_over_pi, T2), T2);
+    } else {                                            // 985-1003
+      double sumT = 0.0, sumAbsk = 0.0;
+      for (int i = 0; i < pg.n; ++i) {
+        const double T2 = __dmul_rn(pg.temp[i][c], pg.temp[i][c]);
+        const double ak = pg.absk[i][c];
+        sumT = __dadd_rn(sumT, __dmul_rn(__dmul_rn(T2, T2), ak));
+        sumAbsk = __dadd_rn(sumAbsk, ak);
+      }
+      v = 0.0;
+      if (sumAbsk > 1e-16) v = __ddiv_rn(__dmul_rn(sigma_over_pi, sumT), sumAbsk);
+    }
+    out[c] = (T)v;
+  }
+}
+// RMCRT_Radiation::sumAbsk<T> (RMCRT.cc:1062-1130)
+template <class T>
+__global__ void arches_sumAbsk_kernel(const double* __restrict__ gasVolFrac, const __grid_constant__ PartGasPtrs pg, Box w, Box interior,
+                                      T* __restrict__ out) {
+  const long long n = box_cells(w);
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+    const long long row = c / w.n[0];
+    const int kk = (int)(row / w.n[1]);
+    const int idx[3] = {w.lo[0] + (int)(c - row * w.n[0]), w.lo[1] + (int)(row - (long long)kk * w.n[1]), w.lo[2] + kk};
+    bool in = true;
+    for (int d = 0; d < 3; ++d) in = in && idx[d] >= interior.lo[d] && idx[d] < interior.lo[d] + interior.n[d];
+    double v = 1.0;                                     // boundary faces, ExtraPlusEdgeCells: hard-wired 1 (1108-1120)
+    if (in) {
+      v = 0.0;
+      const bool gas = gasVolFrac[c] > 1e-16;
+      for (int i = 0; i < pg.n; ++i) v = gas ? __dadd_rn(v, pg.absk[i][c]) : 1.0;   // 1093-1104
+    }
+    out[c] = (T)v;
+  }
+}
+// RMCRT_Radiation::stencilToDBLs (RMCRT.cc:1389-1423): Stencil7 {w,e,s,n,b,t,p} AoS -> six double fields
+struct SixPtrs { double* p[6]; };   // E W N S T B
+__global__ void stencil_to_dbls_kernel(const double* __restrict__ bf7, long long n, const __grid_constant__ SixPtrs o) {
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
+    const double* me = bf7 + 7 * c;
+    o.p[0][c] = me[1]; o.p[1][c] = me[0]; o.p[2][c] = me[3]; o.p[3][c] = me[2]; o.p[4][c] = me[5]; o.p[5][c] = me[4];
+  }
+}
+
 // ---- roofline denominators ----
 __global__ void bw_stream_kernel(const uint4* __restrict__ buf, long long n16, int inner, unsigned* sink) {
   unsigned acc = 0;
@@ -1747,6 +1896,200 @@ int rmcrt_set_level_extra_cells(rmcrt_ctx* ctx, int L, const double abskg[6], co
   else                         extra_cells_kernel<Rec16><<<grid_for(lv.nCells, 256, ctx->smCount), 256, 0, st>>>(static_cast<Rec16*>(lv.rec), b, in, static_cast<const double*>(ctx->misc.p), dT, ctx->p.flowCell, nullptr);
   CK(cudaGetLastError());
   return invalidate_level(ctx, L, st);
+}
+
+//------------------------------------------------------------------ callers either side of the path
+static int refine_args(rmcrt_ctx* ctx, const int32_t cLo[3], const int32_t cHi[3], const int32_t gLo[3], const int32_t gHi[3],
+                       const int32_t rr[3], int order, const int32_t fl[3], const int32_t fh[3], const int32_t oLo[3],
+                       const int32_t oHi[3], RefineArgs& a) {
+  if (order < 0 || order > 2)      // selectInterpolator's InternalError (AMR.h:735-737)
+    return fail(ctx, RMCRT_ERR_INVALID, "ERROR:AMR: You're trying to use an interpolator that doesn't exist.  <orderOfInterpolation> must be 0,1,2");
+  a.cw = mkbox(cLo, cHi); a.fr = mkbox(fl, fh); a.ow = mkbox(oLo, oHi);
+  a.order = order;
+  const int reach = order == 0 ? 0 : 1;
+  for (int d = 0; d < 3; ++d) {
+    if (rr[d] < 1) return fail(ctx, RMCRT_ERR_INVALID, "refinement ratio must be >= 1");
+    if (fh[d] < fl[d] || oHi[d] <= oLo[d] || cHi[d] <= cLo[d]) return fail(ctx, RMCRT_ERR_INVALID, "empty window");
+    if (fl[d] < oLo[d] || fh[d] > oHi[d]) return fail(ctx, RMCRT_ERR_INVALID, "fine region outside of the fine window on axis %d", d);
+    a.rr[d] = rr[d]; a.gridLo[d] = gLo[d]; a.gridHiM1[d] = gHi[d] - 1;
+    if (fh[d] > fl[d]) {
+      const int c0 = map_coarser_host(fl[d], rr[d]) - reach, c1 = map_coarser_host(fh[d] - 1, rr[d]) + reach;
+      if (c0 < cLo[d] || c1 >= cHi[d])
+        return fail(ctx, RMCRT_ERR_INVALID, "coarse window [%d,%d) does not cover the cells [%d,%d] the interpolation reads on axis %d", cLo[d], cHi[d], c0, c1, d);
+    }
+  }
+  return 0;
+}
+
+int rmcrt_refine_Q_device(rmcrt_ctx* ctx, const double* d_coarseQ, const int32_t cLo[3], const int32_t cHi[3], const int32_t gLo[3],
+                          const int32_t gHi[3], const int32_t rr[3], int order, const int32_t fl[3], const int32_t fh[3],
+                          double* d_fineQ, const int32_t oLo[3], const int32_t oHi[3], int zeroInit, void* stream) {
+  if (!ctx) return RMCRT_ERR_INVALID;
+  if (!d_coarseQ || !d_fineQ) return fail(ctx, RMCRT_ERR_INVALID, "null field pointer");
+  RefineArgs a;
+  int rc = refine_args(ctx, cLo, cHi, gLo, gHi, rr, order, fl, fh, oLo, oHi, a);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (zeroInit) CK(cudaMemsetAsync(d_fineQ, 0, (size_t)box_cells(a.ow) * sizeof(double), st));   // Ray.cc:1899-1900
+  const long long n = box_cells(a.fr);
+  if (n == 0) return 0;
+  refine_kernel<<<grid_for(n, 256, ctx->smCount), 256, 0, st>>>(d_coarseQ, d_fineQ, a);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int rmcrt_refine_Q(rmcrt_ctx* ctx, const double* coarseQ, const int32_t cLo[3], const int32_t cHi[3], const int32_t gLo[3],
+                   const int32_t gHi[3], const int32_t rr[3], int order, const int32_t fl[3], const int32_t fh[3], double* fineQ,
+                   const int32_t oLo[3], const int32_t oHi[3], void* stream) {
+  if (!ctx) return RMCRT_ERR_INVALID;
+  if (!coarseQ || !fineQ) return fail(ctx, RMCRT_ERR_INVALID, "null field pointer");
+  RefineArgs a;
+  int rc = refine_args(ctx, cLo, cHi, gLo, gHi, rr, order, fl, fh, oLo, oHi, a);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t cb = (size_t)box_cells(a.cw) * sizeof(double), fb = (size_t)box_cells(a.ow) * sizeof(double);
+  if (ctx->stage[0].ensure(cb) || ctx->stage[1].ensure(fb)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc staging failed");
+  CK(cudaMemcpyAsync(ctx->stage[0].p, coarseQ, cb, cudaMemcpyHostToDevice, st));
+  rc = rmcrt_refine_Q_device(ctx, static_cast<const double*>(ctx->stage[0].p), cLo, cHi, gLo, gHi, rr, order, fl, fh,
+                             static_cast<double*>(ctx->stage[1].p), oLo, oHi, 1, stream);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(fineQ, ctx->stage[1].p, fb, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+static int partgas_ptrs(rmcrt_ctx* ctx, const double* const* absk, const double* const* temp, int nPartGas, PartGasPtrs& pg) {
+  if (nPartGas < 1 || nPartGas > RMCRT_MAX_PARTGAS) return fail(ctx, RMCRT_ERR_INVALID, "nPartGas must be in [1,%d]", RMCRT_MAX_PARTGAS);
+  pg.n = nPartGas;
+  for (int i = 0; i < RMCRT_MAX_PARTGAS; ++i) {
+    pg.absk[i] = (absk && i < nPartGas) ? absk[i] : nullptr;
+    pg.temp[i] = (temp && i < nPartGas) ? temp[i] : nullptr;
+    if (i < nPartGas && ((absk && !absk[i]) || (temp && !temp[i]))) return fail(ctx, RMCRT_ERR_INVALID, "null gas/particle field %d", i);
+  }
+  return 0;
+}
+
+int rmcrt_arches_sigmaT4_device(rmcrt_ctx* ctx, const double* d_gasVolFrac, const double* const* d_absk, const double* const* d_temp,
+                                int nPartGas, int doPartRadiation, void* d_out, int isFloat, int64_t n, void* stream) {
+  if (!ctx) return RMCRT_ERR_INVALID;
+  if (!d_temp || !d_out || n < 0 || (doPartRadiation && (!d_gasVolFrac || !d_absk))) return fail(ctx, RMCRT_ERR_INVALID, "null field pointer");
+  PartGasPtrs pg;
+  int rc = partgas_ptrs(ctx, doPartRadiation ? d_absk : nullptr, d_temp, nPartGas, pg);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  if (n == 0) return 0;
+  const double sop = ctx->p.sigma / M_PI;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (isFloat) arches_sigmaT4_kernel<float><<<grid_for(n, 256, ctx->smCount), 256, 0, st>>>(d_gasVolFrac, pg, doPartRadiation, static_cast<float*>(d_out), n, sop);
+  else         arches_sigmaT4_kernel<double><<<grid_for(n, 256, ctx->smCount), 256, 0, st>>>(d_gasVolFrac, pg, doPartRadiation, static_cast<double*>(d_out), n, sop);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int rmcrt_arches_sumAbsk_device(rmcrt_ctx* ctx, const double* d_gasVolFrac, const double* const* d_absk, int nPartGas,
+                                const int32_t lo[3], const int32_t hi[3], const int32_t intLo[3], const int32_t intHi[3],
+                                void* d_out, int isFloat, void* stream) {
+  if (!ctx) return RMCRT_ERR_INVALID;
+  if (!d_gasVolFrac || !d_absk || !d_out) return fail(ctx, RMCRT_ERR_INVALID, "null field pointer");
+  PartGasPtrs pg;
+  int rc = partgas_ptrs(ctx, d_absk, nullptr, nPartGas, pg);
+  if (rc) return rc;
+  for (int d = 0; d < 3; ++d) if (hi[d] <= lo[d]) return fail(ctx, RMCRT_ERR_INVALID, "empty window");
+  CK(cudaSetDevice(ctx->device));
+  Box w = mkbox(lo, hi), in = mkbox(intLo, intHi);
+  const long long n = box_cells(w);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (isFloat) arches_sumAbsk_kernel<float><<<grid_for(n, 256, ctx->smCount), 256, 0, st>>>(d_gasVolFrac, pg, w, in, static_cast<float*>(d_out));
+  else         arches_sumAbsk_kernel<double><<<grid_for(n, 256, ctx->smCount), 256, 0, st>>>(d_gasVolFrac, pg, w, in, static_cast<double*>(d_out));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int rmcrt_stencil_to_dbls_device(rmcrt_ctx* ctx, const double* d_boundFlux, int64_t n, double* d_E, double* d_W, double* d_N,
+                                 double* d_S, double* d_T, double* d_B, void* stream) {
+  if (!ctx) return RMCRT_ERR_INVALID;
+  if (!d_boundFlux || !d_E || !d_W || !d_N || !d_S || !d_T || !d_B || n < 0) return fail(ctx, RMCRT_ERR_INVALID, "null field pointer");
+  CK(cudaSetDevice(ctx->device));
+  if (n == 0) return 0;
+  SixPtrs o{{d_E, d_W, d_N, d_S, d_T, d_B}};
+  stencil_to_dbls_kernel<<<grid_for(n, 256, ctx->smCount), 256, 0, (cudaStream_t)stream>>>(d_boundFlux, n, o);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// host-buffer forms of the three Arches tasks (H2D, kernel, D2H; blocking) -- what the C++ RMCRT_Radiation mirror calls
+int rmcrt_arches_sigmaT4(rmcrt_ctx* ctx, const double* gasVolFrac, const double* const* absk, const double* const* temp, int nPartGas,
+                         int doPartRadiation, void* out, int isFloat, int64_t n, void* stream) {
+  if (!ctx) return RMCRT_ERR_INVALID;
+  if (!temp || !out || n < 0 || (doPartRadiation && (!gasVolFrac || !absk))) return fail(ctx, RMCRT_ERR_INVALID, "null field pointer");
+  if (nPartGas < 1 || nPartGas > RMCRT_MAX_PARTGAS) return fail(ctx, RMCRT_ERR_INVALID, "nPartGas must be in [1,%d]", RMCRT_MAX_PARTGAS);
+  if (n == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t fb = (size_t)n * sizeof(double);
+  const int nIn = 1 + 2 * nPartGas;
+  if (ctx->stage[0].ensure(fb * nIn) || ctx->stage[1].ensure((size_t)n * (isFloat ? 4 : 8))) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc staging failed");
+  double* base = static_cast<double*>(ctx->stage[0].p);
+  const double* dA[RMCRT_MAX_PARTGAS]; const double* dT[RMCRT_MAX_PARTGAS];
+  if (gasVolFrac) CK(cudaMemcpyAsync(base, gasVolFrac, fb, cudaMemcpyHostToDevice, st));
+  for (int i = 0; i < nPartGas; ++i) {
+    dA[i] = base + (size_t)n * (1 + i); dT[i] = base + (size_t)n * (1 + nPartGas + i);
+    if (!temp[i] || (doPartRadiation && !absk[i])) return fail(ctx, RMCRT_ERR_INVALID, "null gas/particle field %d", i);
+    if (doPartRadiation) CK(cudaMemcpyAsync(const_cast<double*>(dA[i]), absk[i], fb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(const_cast<double*>(dT[i]), temp[i], fb, cudaMemcpyHostToDevice, st));
+  }
+  int rc = rmcrt_arches_sigmaT4_device(ctx, base, dA, dT, nPartGas, doPartRadiation, ctx->stage[1].p, isFloat, n, stream);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(out, ctx->stage[1].p, (size_t)n * (isFloat ? 4 : 8), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int rmcrt_arches_sumAbsk(rmcrt_ctx* ctx, const double* gasVolFrac, const double* const* absk, int nPartGas, const int32_t lo[3],
+                         const int32_t hi[3], const int32_t intLo[3], const int32_t intHi[3], void* out, int isFloat, void* stream) {
+  if (!ctx) return RMCRT_ERR_INVALID;
+  if (!gasVolFrac || !absk || !out) return fail(ctx, RMCRT_ERR_INVALID, "null field pointer");
+  if (nPartGas < 1 || nPartGas > RMCRT_MAX_PARTGAS) return fail(ctx, RMCRT_ERR_INVALID, "nPartGas must be in [1,%d]", RMCRT_MAX_PARTGAS);
+  size_t n = 1;
+  for (int d = 0; d < 3; ++d) { if (hi[d] <= lo[d]) return fail(ctx, RMCRT_ERR_INVALID, "empty window"); n *= (size_t)(hi[d] - lo[d]); }
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t fb = n * sizeof(double);
+  if (ctx->stage[0].ensure(fb * (1 + nPartGas)) || ctx->stage[1].ensure(n * (isFloat ? 4 : 8))) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc staging failed");
+  double* base = static_cast<double*>(ctx->stage[0].p);
+  const double* dA[RMCRT_MAX_PARTGAS];
+  CK(cudaMemcpyAsync(base, gasVolFrac, fb, cudaMemcpyHostToDevice, st));
+  for (int i = 0; i < nPartGas; ++i) {
+    if (!absk[i]) return fail(ctx, RMCRT_ERR_INVALID, "null gas/particle field %d", i);
+    dA[i] = base + n * (1 + i);
+    CK(cudaMemcpyAsync(const_cast<double*>(dA[i]), absk[i], fb, cudaMemcpyHostToDevice, st));
+  }
+  int rc = rmcrt_arches_sumAbsk_device(ctx, base, dA, nPartGas, lo, hi, intLo, intHi, ctx->stage[1].p, isFloat, stream);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(out, ctx->stage[1].p, n * (isFloat ? 4 : 8), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int rmcrt_stencil_to_dbls(rmcrt_ctx* ctx, const double* boundFlux, int64_t n, double* E, double* W, double* N, double* S, double* T,
+                          double* B, void* stream) {
+  if (!ctx) return RMCRT_ERR_INVALID;
+  if (!boundFlux || !E || !W || !N || !S || !T || !B || n < 0) return fail(ctx, RMCRT_ERR_INVALID, "null field pointer");
+  if (n == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t fb = (size_t)n * sizeof(double);
+  if (ctx->stage[0].ensure(fb * 7) || ctx->stage[1].ensure(fb * 6)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc staging failed");
+  CK(cudaMemcpyAsync(ctx->stage[0].p, boundFlux, fb * 7, cudaMemcpyHostToDevice, st));
+  double* o = static_cast<double*>(ctx->stage[1].p);
+  int rc = rmcrt_stencil_to_dbls_device(ctx, static_cast<const double*>(ctx->stage[0].p), n, o, o + n, o + 2 * n, o + 3 * n, o + 4 * n, o + 5 * n, stream);
+  if (rc) return rc;
+  double* host[6] = {E, W, N, S, T, B};
+  for (int i = 0; i < 6; ++i) CK(cudaMemcpyAsync(host[i], o + (size_t)i * n, fb, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
 }
 
 int rmcrt_pack_box_device(rmcrt_ctx* ctx, int L, const void* a, const void* s, const int32_t* ct, int isFloat,

@@ -9,6 +9,7 @@
 // It reads the same .ups decks (the <Grid>, <Temperature>/<abskg>/<benchmark>/<calc_frequency> keys and the <RMCRT> block),
 // builds the grid, runs the time loop with the two task graphs (TG_CARRY_FORWARD / TG_RMCRT) and, with --dump, writes the
 // finest level's divQ / radiationVolq / RMCRTboundFlux / abskg / sigmaT4 / cellType as raw arrays for the parity tests.
+#include "DriverCommon.h"
 #include "Ray.h"
 
 #include <sys/stat.h>
@@ -21,15 +22,6 @@
 
 using namespace Uintah;
 
-namespace Uintah {
-ProblemSpecP ProblemSpec::parseFile(const std::string& path) {
-  std::ifstream in(path);
-  if (!in) throw ProblemSetupException("cannot open input deck " + path, __FILE__, __LINE__);
-  std::stringstream ss;
-  ss << in.rdbuf();
-  return parseString(ss.str());
-}
-}  // namespace Uintah
 
 namespace {
 
@@ -49,77 +41,6 @@ class RMCRT_Test {
     VarLabel::destroy(d_compAbskgLabel);
     VarLabel::destroy(d_divQLabel);
     VarLabel::destroy(d_cellTypeLabel);
-  }
-
-  //______________________________________________________________________ <Grid>
-  static GridP buildGrid(const ProblemSpecP& root) {
-    ProblemSpecP grid_ps = root->findBlock("Grid");
-    if (!grid_ps) throw ProblemSetupException("no <Grid> block", __FILE__, __LINE__);
-    auto grid = std::make_shared<Grid>();
-    static const char* sides[6] = {"x-", "x+", "y-", "y+", "z-", "z+"};
-    if (ProblemSpecP bc_ps = grid_ps->findBlock("BoundaryConditions")) {
-      for (ProblemSpecP face = bc_ps->findBlock("Face"); face; face = face->findNextBlock("Face")) {
-        std::string side;
-        if (!face->getAttribute("side", side)) throw ProblemSetupException("<Face> without side (only side= faces are supported)", __FILE__, __LINE__);
-        int f = -1;
-        for (int i = 0; i < 6; ++i) if (side == sides[i]) f = i;
-        if (f < 0) throw ProblemSetupException("unknown face side " + side, __FILE__, __LINE__);
-        for (ProblemSpecP bc = face->findBlock("BCType"); bc; bc = bc->findNextBlock("BCType")) {
-          BCEntry e;
-          std::string label;
-          bc->getAttribute("label", label);
-          bc->getAttribute("var", e.var);
-          bc->get("value", e.value);
-          grid->setBC(f, label, e);
-        }
-      }
-    }
-    int index = 0;
-    IntVector prevRes(0, 0, 0);
-    for (ProblemSpecP level_ps = grid_ps->findBlock("Level"); level_ps; level_ps = level_ps->findNextBlock("Level"), ++index) {
-      ProblemSpecP box = level_ps->findBlock("Box");
-      if (!box) throw ProblemSetupException("<Level> without <Box>", __FILE__, __LINE__);
-      if (box->findNextBlock("Box")) throw ProblemSetupException("multi-box levels are not supported by this driver", __FILE__, __LINE__);
-      Vector lower, upper;
-      IntVector res, patches(1, 1, 1), extra(0, 0, 0);
-      box->require("lower", lower);
-      box->require("upper", upper);
-      box->require("resolution", res);
-      box->getWithDefault("patches", patches, IntVector(1, 1, 1));
-      box->getWithDefault("extraCells", extra, IntVector(0, 0, 0));
-      Vector periodic(0, 0, 0);
-      level_ps->getWithDefault("periodic", periodic, Vector(0, 0, 0));
-      grid->periodic = IntVector((int)periodic.x(), (int)periodic.y(), (int)periodic.z());
-      const Vector dx((upper.x() - lower.x()) / res.x(), (upper.y() - lower.y()) / res.y(), (upper.z() - lower.z()) / res.z());
-      IntVector rr(1, 1, 1);
-      if (index > 0) {
-        for (int d = 0; d < 3; ++d) {
-          if (res[d] % prevRes[d] != 0) throw ProblemSetupException("level resolution is not a multiple of the coarser level's", __FILE__, __LINE__);
-          rr[d] = res[d] / prevRes[d];
-        }
-      }
-      auto level = std::make_shared<Level>(grid.get(), index, lower, dx, extra, rr);
-      level->setInterior(IntVector(0, 0, 0), res);
-      int id = index * 100000;
-      for (int pk = 0; pk < patches.z(); ++pk)
-        for (int pj = 0; pj < patches.y(); ++pj)
-          for (int pi = 0; pi < patches.x(); ++pi) {
-            const IntVector pidx(pi, pj, pk);
-            IntVector lo, hi, exLo, exHi;
-            for (int d = 0; d < 3; ++d) {
-              if (res[d] % patches[d] != 0) throw ProblemSetupException("resolution is not divisible by patches", __FILE__, __LINE__);
-              const int n = res[d] / patches[d];
-              lo[d] = pidx[d] * n; hi[d] = lo[d] + n;
-              exLo[d] = lo[d] - (pidx[d] == 0 ? extra[d] : 0);
-              exHi[d] = hi[d] + (pidx[d] == patches[d] - 1 ? extra[d] : 0);
-            }
-            level->addPatch(std::unique_ptr<Patch>(new Patch(id++, level.get(), lo, hi, exLo, exHi)));
-          }
-      grid->addLevel(level);
-      prevRes = res;
-    }
-    if (grid->numLevels() == 0) throw ProblemSetupException("no <Level> in <Grid>", __FILE__, __LINE__);
-    return grid;
   }
 
   //______________________________________________________________________ RMCRT_Test.cc:111-260
@@ -269,8 +190,31 @@ class RMCRT_Test {
       d_RMCRT->sched_setBoundaryConditions(level, sched, temp_dw, backoutTemp);
       radiometer->sched_radiometer(level, sched, notUsed, sigmaT4_dw, celltype_dw);
     }
-    if (d_whichAlgo == coarseLevel)
-      throw ProblemSetupException("rmcrt_test: algorithm not supported by the B200 back end", __FILE__, __LINE__);
+    if (d_whichAlgo == coarseLevel) {                                     // 464-519: RMCRT on the coarse level, divQ interpolated to the fine one
+      Task::WhichDW temp_dw = Task::NewDW, sigmaT4_dw = Task::NewDW, celltype_dw = Task::NewDW;
+      const bool modifies_divQ = false, backoutTemp = true, modifies_abskg = false, modifies_sigmaT4 = false;
+      // coarse levels: sigmaT4 / abskg live on the device only (Ray::coarsenAll), so only the results are carried forward there
+      for (int l = 0; l < maxLevels; l++)
+        d_RMCRT->sched_carryForward_VarLabels(grid->getLevel(l), sched, l == maxLevels - 1 ? fineLevelVarLabels
+                                              : std::vector<const VarLabel*>{RMCRTCommon::d_divQLabel, RMCRTCommon::d_boundFluxLabel, RMCRTCommon::d_radiationVolqLabel});
+      const LevelP& fineLevel = finestLevel;
+      d_RMCRT->set_abskg_dw_perLevel(fineLevel, Task::NewDW);
+      d_RMCRT->sched_DoubleToFloat(fineLevel, sched, notUsed);
+      d_RMCRT->sched_sigmaT4(fineLevel, sched, temp_dw, includeExtraCells);
+      // the reference leaves the fine level's extra cells as initialised (no setBoundaryConditions there); they are never read:
+      // coarsen_Q averages interior cells only
+      for (int l = maxLevels - 2; l >= 0; l--) {                          // coarsest last: each level is coarsened from the next finer one
+        const LevelP& lev = grid->getLevel(l);
+        d_RMCRT->sched_CoarsenAll(lev, sched, modifies_abskg, modifies_sigmaT4);
+        if (d_RMCRT->d_coarsenExtraCells == false) d_RMCRT->sched_setBoundaryConditions(lev, sched, temp_dw, backoutTemp);
+      }
+      for (int l = 0; l < maxLevels - 1; l++)
+        d_RMCRT->sched_rayTrace(grid->getLevel(l), sched, notUsed, sigmaT4_dw, celltype_dw, modifies_divQ);
+      for (int l = 1; l < maxLevels; l++) {                               // 512-518
+        const LevelP& lev = grid->getLevel(l);
+        d_RMCRT->sched_Refine_Q(sched, lev->eachPatch(), RMCRTCommon::d_matlSet);
+      }
+    }
   }
 
   // RMCRT_Test.cc:944-958: carry abskg, color, cellType Old -> New to mimic what a component would compute
@@ -398,20 +342,6 @@ class RMCRT_Test {
   std::vector<Intrusion> d_intrusions;
 };
 
-template <class T>
-void dumpVar(const std::string& dir, const std::string& name, const char* dtype, int comps, DataWarehouse* dw, const VarLabel* label,
-             const Level* level, std::ostream& meta, bool& first) {
-  constCCVariable<T> v;
-  dw->getLevel(v, label, 0, level);
-  const std::string file = name + ".bin";
-  std::ofstream out(dir + "/" + file, std::ios::binary);
-  out.write(reinterpret_cast<const char*>(v.getPointer()), (std::streamsize)(v.cells() * sizeof(T)));
-  const IntVector lo = v.getLowIndex(), hi = v.getHighIndex();
-  meta << (first ? "" : ",\n") << "  \"" << name << "\": {\"file\": \"" << file << "\", \"dtype\": \"" << dtype << "\", \"components\": " << comps
-       << ", \"lo\": [" << lo.x() << "," << lo.y() << "," << lo.z() << "], \"hi\": [" << hi.x() << "," << hi.y() << "," << hi.z() << "]}";
-  first = false;
-}
-
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -451,7 +381,7 @@ int main(int argc, char** argv) {
     if (timesteps > 0) maxTimesteps = timesteps;
 
     RMCRTCommon::setMaxDevices(devices);
-    GridP grid = RMCRT_Test::buildGrid(ups);
+    GridP grid = buildGrid(ups);
     SchedulerP sched = std::make_shared<Scheduler>();
     RMCRT_Test app;
     app.problemSetup(ups, grid, sched);
@@ -514,6 +444,11 @@ int main(int argc, char** argv) {
         dumpVar<double>(dumpDir, "divQ", "f8", 1, dw, app.d_divQLabel, fine, meta, first);
         dumpVar<double>(dumpDir, "radiationVolq", "f8", 1, dw, RMCRTCommon::d_radiationVolqLabel, fine, meta, first);
         dumpVar<Stencil7>(dumpDir, "RMCRTboundFlux", "f8", 7, dw, RMCRTCommon::d_boundFluxLabel, fine, meta, first);
+        for (int l = 0; l + 1 < grid->numLevels(); ++l) {      // RMCRT_coarseLevel: the coarse-level solve the fine divQ was interpolated from
+          const Level* lev = grid->getLevel(l).get();
+          if (dw->exists(app.d_divQLabel, 0, lev->getPatch(0)))
+            dumpVar<double>(dumpDir, "divQ_L" + std::to_string(l), "f8", 1, dw, app.d_divQLabel, lev, meta, first);
+        }
       }
       if (Radiometer* radiometer = app.d_RMCRT->getRadiometer()) {
         if (radiometer->d_VRFluxLabel->typeDescription() == TypeDescription::float_type) {

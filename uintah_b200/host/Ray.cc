@@ -124,7 +124,6 @@ void Ray::problemSetup(const ProblemSpecP& prob_spec, const ProblemSpecP& rmcrtp
       d_ROI_algo = entireDomain;
       alg_ps->require("orderOfInterpolation", d_orderOfInterpolation);
       alg_ps->get("coarsenExtraCells", d_coarsenExtraCells);
-      throw ProblemSetupException("RMCRT (B200 back end): algorithm RMCRT_coarseLevel (refine_Q) is not implemented", __FILE__, __LINE__);
     }
   }
 
@@ -242,9 +241,11 @@ void Ray::sched_rayTrace(const LevelP& level, SchedulerP& sched, Task::WhichDW /
     }
     d_haloCells = IntVector(n_ghostCells, n_ghostCells, n_ghostCells);
   }
-  tsk->requiresVar(abskg_dw, d_abskgLabel, gac, n_ghostCells);
-  tsk->requiresVar(sigma_dw, d_sigmaT4Label, gac, n_ghostCells);
-  tsk->requiresVar(celltype_dw, d_cellTypeLabel, gac, n_ghostCells);
+  if (!isDeviceLevel(level.get())) {
+    tsk->requiresVar(abskg_dw, d_abskgLabel, gac, n_ghostCells);
+    tsk->requiresVar(sigma_dw, d_sigmaT4Label, gac, n_ghostCells);
+    tsk->requiresVar(celltype_dw, d_cellTypeLabel, gac, n_ghostCells);
+  }   // else (RMCRT_coarseLevel): the coarse level's records were derived on the device by Ray::coarsenAll, scheduled before this task
   if (modifies_divQ) {
     tsk->modifiesVar(d_divQLabel);
     tsk->modifiesVar(d_boundFluxLabel);
@@ -405,7 +406,13 @@ void Ray::rayTrace(const ProcessorGroup*, const PatchSubset* patches, const Mate
   DataWarehouse* abskg_dw = new_dw->getOtherDataWarehouse(which_abskg_dw);
   DataWarehouse* sigmaT4_dw = new_dw->getOtherDataWarehouse(which_sigmaT4_dw);
   DataWarehouse* celltype_dw = new_dw->getOtherDataWarehouse(which_celltype_dw);
-  uploadLevel<T>(level, abskg_dw, sigmaT4_dw, celltype_dw, new_dw->getID());
+  if (isDeviceLevel(level)) {                                       // RMCRT_coarseLevel: trace the level Ray::coarsenAll derived
+    auto it = d_deviceCoarsened.find(level->getIndex());
+    if (it == d_deviceCoarsened.end() || it->second != new_dw->getID())
+      throw InternalError("Ray::rayTrace: level " + std::to_string(level->getIndex()) + " was not coarsened this time step (sched_CoarsenAll missing)", __FILE__, __LINE__);
+  } else {
+    uploadLevel<T>(level, abskg_dw, sigmaT4_dw, celltype_dw, new_dw->getID());
+  }
   if (d_radiometer)                                                 // Ray.cc:638-640
     for (int p = 0; p < patches->size(); ++p) d_radiometer->radiometerFlux<T>(patches->get(p), level, new_dw, modifies_divQ);
   traceCommon<T>(false, patches, new_dw, modifies_divQ);
@@ -481,8 +488,71 @@ void Ray::sched_ROI_Extents(const LevelP&, SchedulerP&) {
     throw ProblemSetupException("GPU:RMCRT:ERROR: At this time only ROI_extents type=\"patch_based\" work on the GPU", __FILE__, __LINE__);
 }
 
-void Ray::sched_Refine_Q(SchedulerP&, const PatchSet*, const MaterialSet*) {
-  throw ProblemSetupException("RMCRT (B200 back end): refine_Q (algorithm RMCRT_coarseLevel) is not implemented", __FILE__, __LINE__);
+// a level whose property records exist only on the device: every level below the finest one of a multi-level algorithm
+bool Ray::isDeviceLevel(const Level* level) const {
+  return level->hasFinerLevel() && (d_whichAlgo == dataOnion || d_whichAlgo == coarseLevel);
+}
+
+//______________________________________________________________________
+// Ray.cc:1841-1867: same task name and dependencies (coarse-level divQ / boundFlux / radiationVolq with one ghost cell)
+void Ray::sched_Refine_Q(SchedulerP& sched, const PatchSet* patches, const MaterialSet* matls) {
+  const Level* fineLevel = getLevel(patches);
+  const int L_indx = fineLevel->getIndex();
+  if (L_indx > 0) {
+    Task* task = new Task("Ray::refine_Q", this, &Ray::refine_Q);
+    Task::DomainSpec ND = Task::NormalDomain;
+    Ghost::GhostType gac = Ghost::AroundCells;
+    task->requiresVar(Task::NewDW, d_divQLabel, nullptr, Task::CoarseLevel, 1, nullptr, ND, gac, 1);
+    task->requiresVar(Task::NewDW, d_boundFluxLabel, nullptr, Task::CoarseLevel, 1, nullptr, ND, gac, 1);
+    task->requiresVar(Task::NewDW, d_radiationVolqLabel, nullptr, Task::CoarseLevel, 1, nullptr, ND, gac, 1);
+    task->computesVar(d_divQLabel);
+    task->computesVar(d_boundFluxLabel);
+    task->computesVar(d_radiationVolqLabel);
+    task->usesDevice(true);
+    sched->addTask(task, patches, matls, RMCRTCommon::TG_RMCRT);
+  }
+}
+
+//______________________________________________________________________
+// Ray.cc:1872-1945.  The interpolation (selectInterpolator, Core/Grid/AMR.h:708-745) runs in refine_kernel through rmcrt_refine_Q;
+// like the reference, the Stencil7 boundary flux is only zero-initialised on the fine level (its interpolation is "#if 0"-ed out).
+void Ray::refine_Q(const ProcessorGroup*, const PatchSubset* patches, const MaterialSubset*, DataWarehouse*, DataWarehouse* new_dw) {
+  const Level* fineLevel = getLevel(patches);
+  const Level* coarseLevel = fineLevel->getCoarserLevel();
+  Device& dev = devices()[0];
+  IntVector gridLo, gridHi;
+  coarseLevel->findCellIndexRange(gridLo, gridHi);
+  const IntVector refineRatio = fineLevel->getRefinementRatio();
+  for (int p = 0; p < patches->size(); p++) {
+    const Patch* finePatch = patches->get(p);
+    CCVariable<double> divQ_fine, radVolQ_fine;
+    CCVariable<Stencil7> boundFlux_fine;
+    new_dw->allocateAndPut(divQ_fine, d_divQLabel, d_matl, finePatch);
+    new_dw->allocateAndPut(radVolQ_fine, d_radiationVolqLabel, d_matl, finePatch);
+    new_dw->allocateAndPut(boundFlux_fine, d_boundFluxLabel, d_matl, finePatch);
+    Stencil7 zero; zero.initialize(0.0);
+    boundFlux_fine.initialize(zero);
+    // getCoarseLevelRange (Core/Grid/AMR.cc:90-135) with one ghost cell, exclusive range: the coarse cells under the patch incl. its
+    // extra cells and one more layer, clamped to the coarse level; the fine region is the patch interior
+    const IntVector fl = finePatch->getCellLowIndex(), fh = finePatch->getCellHighIndex();
+    const IntVector el = finePatch->getExtraCellLowIndex() - IntVector(1, 1, 1), eh = finePatch->getExtraCellHighIndex() + IntVector(1, 1, 1);
+    IntVector cl = fineLevel->mapCellToCoarser(el), ch = fineLevel->mapCellToCoarser(eh);
+    for (int d = 0; d < 3; ++d) {
+      if (ch[d] != eh[d]) ch[d] += 1;
+      cl[d] = std::max(cl[d], gridLo[d]);
+      ch[d] = std::min(ch[d], gridHi[d]);
+    }
+    const IntVector olo = divQ_fine.getLowIndex(), ohi = divQ_fine.getHighIndex();
+    constCCVariable<double> divQ_coarse, radVolQ_coarse;
+    new_dw->getRegion(divQ_coarse, d_divQLabel, d_matl, coarseLevel, cl, ch);
+    new_dw->getRegion(radVolQ_coarse, d_radiationVolqLabel, d_matl, coarseLevel, cl, ch);
+    check(dev.ctx, rmcrt_refine_Q(dev.ctx, divQ_coarse.getPointer(), cl.get_pointer(), ch.get_pointer(), gridLo.get_pointer(), gridHi.get_pointer(),
+                                  refineRatio.get_pointer(), d_orderOfInterpolation, fl.get_pointer(), fh.get_pointer(), divQ_fine.getPointer(),
+                                  olo.get_pointer(), ohi.get_pointer(), nullptr), "rmcrt_refine_Q");
+    check(dev.ctx, rmcrt_refine_Q(dev.ctx, radVolQ_coarse.getPointer(), cl.get_pointer(), ch.get_pointer(), gridLo.get_pointer(), gridHi.get_pointer(),
+                                  refineRatio.get_pointer(), d_orderOfInterpolation, fl.get_pointer(), fh.get_pointer(), radVolQ_fine.getPointer(),
+                                  olo.get_pointer(), ohi.get_pointer(), nullptr), "rmcrt_refine_Q");
+  }
 }
 
 //______________________________________________________________________
@@ -492,7 +562,7 @@ void Ray::sched_setBoundaryConditions(const LevelP& level, SchedulerP& sched, Ta
   Task* tsk = nullptr;
   if (d_FLT_DBL == TypeDescription::double_type) tsk = new Task(taskname, this, &Ray::setBoundaryConditions<double>, temp_dw, backoutTemp);
   else                                           tsk = new Task(taskname, this, &Ray::setBoundaryConditions<float>, temp_dw, backoutTemp);
-  const bool deviceLevel = level->hasFinerLevel() && d_whichAlgo == dataOnion;   // coarse Data-Onion level: records live on the device
+  const bool deviceLevel = isDeviceLevel(level.get());   // coarse Data-Onion / RMCRT_coarseLevel level: records live on the device
   if (!deviceLevel) {
     if (!backoutTemp) tsk->requiresVar(temp_dw, d_compTempLabel, Ghost::None, 0);
     tsk->modifiesVar(d_sigmaT4Label);
@@ -511,7 +581,7 @@ void Ray::setBoundaryConditions(const ProcessorGroup*, const PatchSubset* patche
   const Level* level = getLevel(patches);
   const double sigma_over_pi = d_sigma / M_PI;
 
-  if (level->hasFinerLevel() && d_whichAlgo == dataOnion) {
+  if (isDeviceLevel(level)) {
     double abskg[6], sig[6];
     int32_t types[6];
     for (int f = 0; f < 6; ++f) {

@@ -112,6 +112,8 @@ class Ray : public RMCRTCommon {
                              DataWarehouse* new_dw, Task::WhichDW temp_dw, const bool backoutTemp);
   template <class T>
   void coarsenAll(const ProcessorGroup*, const PatchSubset* patches, const MaterialSubset*, DataWarehouse*, DataWarehouse* new_dw);
+  void refine_Q(const ProcessorGroup*, const PatchSubset* patches, const MaterialSubset* matls, DataWarehouse* old_dw, DataWarehouse* new_dw);   // Ray.h:307-311
+  bool isDeviceLevel(const Level* level) const;
 
   //__________________________________ helpers
   int recordKind(const rmcrt_params& p) const override;

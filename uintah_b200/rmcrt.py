@@ -281,6 +281,54 @@ class RMCRT:
         check(self.ctx, self.lib.rmcrt_compute_extents(self.ctx, max_levels, i3(patch_lo), i3(patch_hi), roiLo, roiHi, regLo, regHi))
         return (tuple(roiLo), tuple(roiHi), np.array(regLo).reshape(max_levels, 3), np.array(regHi).reshape(max_levels, 3))
 
+    # ------------------------------------------------------------------ callers either side of the path
+    def refine_Q(self, coarseQ, c_lo, c_hi, grid_lo, grid_hi, rr, order, fl, fh, out_lo, out_hi, stream=None):
+        """Ray::refine_Q for one scalar of one fine patch, host buffers; returns the fine window (zero outside [fl,fh))"""
+        q = np.ascontiguousarray(coarseQ, np.float64)
+        assert q.shape == (c_hi[2] - c_lo[2], c_hi[1] - c_lo[1], c_hi[0] - c_lo[0])
+        out = np.empty((out_hi[2] - out_lo[2], out_hi[1] - out_lo[1], out_hi[0] - out_lo[0]), np.float64)
+        check(self.ctx, self.lib.rmcrt_refine_Q(self.ctx, q.ctypes.data, i3(c_lo), i3(c_hi), i3(grid_lo), i3(grid_hi), i3(rr), int(order),
+                                                i3(fl), i3(fh), out.ctypes.data, i3(out_lo), i3(out_hi), _stream_handle(stream)))
+        return out
+
+    def refine_Q_device(self, coarseQ, c_lo, c_hi, grid_lo, grid_hi, rr, order, fl, fh, fineQ, out_lo, out_hi, zero_init=True,
+                        stream=None):
+        check(self.ctx, self.lib.rmcrt_refine_Q_device(self.ctx, coarseQ.data_ptr(), i3(c_lo), i3(c_hi), i3(grid_lo), i3(grid_hi),
+                                                       i3(rr), int(order), i3(fl), i3(fh), fineQ.data_ptr(), i3(out_lo), i3(out_hi),
+                                                       1 if zero_init else 0, _stream_handle(stream)))
+
+    @staticmethod
+    def _ptr_array(arrays):
+        return (C.c_void_p * len(arrays))(*[_ptr(a) for a in arrays])
+
+    def arches_sigmaT4(self, gasVolFrac, absk, temp, do_part_radiation, dtype=np.float64, stream=None):
+        """RMCRT_Radiation::sigmaT4<T> over one patch (host numpy arrays of equal shape); absk/temp: lists, [0] = gas"""
+        temp = [np.ascontiguousarray(t, np.float64) for t in temp]
+        absk = [np.ascontiguousarray(a, np.float64) for a in absk] if absk is not None else None
+        gv = np.ascontiguousarray(gasVolFrac, np.float64) if gasVolFrac is not None else None
+        out = np.empty(temp[0].shape, dtype)
+        check(self.ctx, self.lib.rmcrt_arches_sigmaT4(self.ctx, _ptr(gv), self._ptr_array(absk) if absk else None, self._ptr_array(temp),
+                                                      len(temp), 1 if do_part_radiation else 0, out.ctypes.data,
+                                                      1 if dtype == np.float32 else 0, out.size, _stream_handle(stream)))
+        return out
+
+    def arches_sumAbsk(self, gasVolFrac, absk, lo, hi, int_lo, int_hi, dtype=np.float64, stream=None):
+        absk = [np.ascontiguousarray(a, np.float64) for a in absk]
+        gv = np.ascontiguousarray(gasVolFrac, np.float64)
+        out = np.empty(gv.shape, dtype)
+        check(self.ctx, self.lib.rmcrt_arches_sumAbsk(self.ctx, gv.ctypes.data, self._ptr_array(absk), len(absk), i3(lo), i3(hi), i3(int_lo),
+                                                      i3(int_hi), out.ctypes.data, 1 if dtype == np.float32 else 0, _stream_handle(stream)))
+        return out
+
+    def stencil_to_dbls(self, boundFlux, stream=None):
+        """RMCRT_Radiation::stencilToDBLs: Stencil7 AoS [...,7] -> dict of the six radiationFlux fields"""
+        bf = np.ascontiguousarray(boundFlux, np.float64)
+        assert bf.shape[-1] == 7
+        outs = [np.empty(bf.shape[:-1], np.float64) for _ in range(6)]
+        check(self.ctx, self.lib.rmcrt_stencil_to_dbls(self.ctx, bf.ctypes.data, outs[0].size, *[o.ctypes.data for o in outs],
+                                                       _stream_handle(stream)))
+        return dict(zip(("E", "W", "N", "S", "T", "B"), outs))
+
     # ------------------------------------------------------------------ counters / debug
     def reset_counters(self, stream=None):
         check(self.ctx, self.lib.rmcrt_reset_counters(self.ctx, _stream_handle(stream)))
