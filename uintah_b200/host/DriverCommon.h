@@ -68,15 +68,17 @@ inline GridP buildGrid(const ProblemSpecP& root) {
     auto level = std::make_shared<Level>(grid.get(), index, lower, dx, extra, rr);
     level->setInterior(IntVector(0, 0, 0), res);
     int id = index * 100000;
-    for (int pk = 0; pk < patches.z(); ++pk)
+    // patch ids in the order sus assigns them: x slowest, z fastest; uneven splits like sus' (50 cells in 3 patches: 16, 17, 17 --
+    // inputs/Examples/restartUda_RT.uda/t01000/timestep.xml)
+    for (int pi = 0; pi < patches.x(); ++pi)
       for (int pj = 0; pj < patches.y(); ++pj)
-        for (int pi = 0; pi < patches.x(); ++pi) {
+        for (int pk = 0; pk < patches.z(); ++pk) {
           const IntVector pidx(pi, pj, pk);
           IntVector lo, hi, exLo, exHi;
           for (int d = 0; d < 3; ++d) {
-            if (res[d] % patches[d] != 0) throw ProblemSetupException("resolution is not divisible by patches", __FILE__, __LINE__);
-            const int n = res[d] / patches[d];
-            lo[d] = pidx[d] * n; hi[d] = lo[d] + n;
+            if (patches[d] < 1 || patches[d] > res[d]) throw ProblemSetupException("<patches> must be between 1 and the resolution", __FILE__, __LINE__);
+            lo[d] = (res[d] * pidx[d]) / patches[d];
+            hi[d] = (res[d] * (pidx[d] + 1)) / patches[d];
             exLo[d] = lo[d] - (pidx[d] == 0 ? extra[d] : 0);
             exHi[d] = hi[d] + (pidx[d] == patches[d] - 1 ? extra[d] : 0);
           }

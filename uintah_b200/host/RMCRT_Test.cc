@@ -9,6 +9,7 @@
 // It reads the same .ups decks (the <Grid>, <Temperature>/<abskg>/<benchmark>/<calc_frequency> keys and the <RMCRT> block),
 // builds the grid, runs the time loop with the two task graphs (TG_CARRY_FORWARD / TG_RMCRT) and, with --dump, writes the
 // finest level's divQ / radiationVolq / RMCRTboundFlux / abskg / sigmaT4 / cellType as raw arrays for the parity tests.
+#include "DataArchive.h"
 #include "DriverCommon.h"
 #include "Ray.h"
 
@@ -80,6 +81,46 @@ class RMCRT_Test {
           d_intrusions.push_back(g);
         }
 
+    // <initalizeUsingUda> (sic; 211-219) + its bullet proofing (253-310)
+    if (ProblemSpecP uda_ps = prob_spec->findBlock("initalizeUsingUda")) {
+      d_old_uda.reset(new useOldUdaData());
+      uda_ps->get("uda_name", d_old_uda->udaName);
+      uda_ps->get("timestep", d_old_uda->timestep);
+      uda_ps->get("abskg_varName", d_old_uda->abskgName);
+      uda_ps->get("temperature_varName", d_old_uda->temperatureName);
+      uda_ps->getWithDefault("matl_index", d_old_uda->matl, 0);
+      uda_ps->getWithDefault("cellType_varName", d_old_uda->cellTypeName, "NONE");
+      if (!d_udaDirOverride.empty()) d_old_uda->udaName = d_udaDirOverride;
+      DataArchive archive(d_old_uda->udaName);
+      std::vector<int> index;
+      std::vector<double> times;
+      archive.queryTimesteps(index, times);
+      d_old_uda->timeIndex = -9;
+      for (unsigned int i = 0; i < index.size(); i++)
+        if (d_old_uda->timestep == index[i]) d_old_uda->timeIndex = (int)i;
+      if (d_old_uda->timeIndex < 0) {
+        std::ostringstream warn;
+        warn << "The timestep (" << d_old_uda->timestep << ") was not found in the uda\nThere are " << index.size() << " timesteps\n";
+        throw ProblemSetupException(warn.str(), __FILE__, __LINE__);
+      }
+      areGridsEqual(archive.queryGrid(d_old_uda->timeIndex), grid);
+      std::vector<std::string> vars;
+      std::vector<int> num_matls;
+      std::vector<TypeDescription::Type> types;
+      archive.queryVariables(vars, num_matls, types);
+      int vars_found = 0;
+      for (unsigned int i = 0; i < vars.size(); i++) {
+        if (d_old_uda->abskgName == vars[i]) { vars_found += 1; d_old_uda->subType = types[i]; }
+        else if (d_old_uda->temperatureName == vars[i]) { vars_found += 1; d_old_uda->subType = types[i]; }
+      }
+      if (vars_found != 2 && vars_found != 3) {
+        std::ostringstream warn;
+        warn << "The variables (" << d_old_uda->abskgName << "), (" << d_old_uda->temperatureName << "), or optional variale cellType: ("
+             << d_old_uda->cellTypeName << ") was not found in the uda";
+        throw ProblemSetupException(warn.str(), __FILE__, __LINE__);
+      }
+    }
+
     ProblemSpecP rmcrt_ps = prob_spec->findBlock("RMCRT");
     if (!rmcrt_ps) throw ProblemSetupException("no <RMCRT> block", __FILE__, __LINE__);
     std::map<std::string, std::string> type;
@@ -124,7 +165,8 @@ class RMCRT_Test {
 
   //______________________________________________________________________ RMCRT_Test.cc:317-341
   void scheduleInitialize(const LevelP& level, SchedulerP& sched) {
-    Task* task = new Task("RMCRT_Test::initialize", this, &RMCRT_Test::initialize);
+    Task* task = !d_old_uda ? new Task("RMCRT_Test::initialize", this, &RMCRT_Test::initialize)
+                            : new Task("RMCRT_Test::initializeWithUda", this, &RMCRT_Test::initializeWithUda);   // 321-328
     task->computesVar(d_colorLabel);
     task->computesVar(d_compAbskgLabel);
     task->computesVar(d_cellTypeLabel);
@@ -312,6 +354,72 @@ class RMCRT_Test {
     }
   }
 
+  //______________________________________________________________________ RMCRT_Test.cc:824-940
+  // initialise abskg / temperature (/ cellType) from a previously written uda; the archive may hold floats or doubles
+  void initializeWithUda(const ProcessorGroup*, const PatchSubset* patches, const MaterialSubset*, DataWarehouse*, DataWarehouse* new_dw) {
+    DataArchive archive(d_old_uda->udaName);
+    const int timeIndex = d_old_uda->timeIndex;
+    GridP uda_grid = archive.queryGrid(timeIndex);
+    const Level* uda_level = uda_grid->getLevel(0).get();   // there's only one level in these problems
+    const int uda_matl = d_old_uda->matl, matl = 0;
+    for (int p = 0; p < patches->size(); p++) {
+      const Patch* patch = patches->get(p);
+      const IntVector low = patch->getExtraCellLowIndex(), high = patch->getExtraCellHighIndex();
+      CCVariable<int> cellType, uda_cellType;
+      new_dw->allocateAndPut(cellType, d_cellTypeLabel, matl, patch);
+      cellType.initialize(d_RMCRT->d_flowCell);
+      if (d_old_uda->cellTypeName != "NONE") {
+        archive.queryRegion(uda_cellType, d_old_uda->cellTypeName, uda_matl, uda_level, timeIndex, low, high);
+        cellType.copyData(uda_cellType);
+      }
+      CCVariable<double> color, abskg;
+      new_dw->allocateAndPut(color, d_colorLabel, matl, patch);
+      new_dw->allocateAndPut(abskg, d_compAbskgLabel, matl, patch);
+      if (d_old_uda->subType == TypeDescription::double_type) {
+        CCVariable<double> uda_temp, uda_abskg;
+        archive.queryRegion(uda_temp, d_old_uda->temperatureName, uda_matl, uda_level, timeIndex, low, high);
+        archive.queryRegion(uda_abskg, d_old_uda->abskgName, uda_matl, uda_level, timeIndex, low, high);
+        for (size_t i = 0; i < color.cells(); ++i) { color.getPointer()[i] = uda_temp.getPointer()[i]; abskg.getPointer()[i] = uda_abskg.getPointer()[i]; }
+      } else {
+        CCVariable<float> uda_temp, uda_abskg;
+        archive.queryRegion(uda_temp, d_old_uda->temperatureName, uda_matl, uda_level, timeIndex, low, high);
+        archive.queryRegion(uda_abskg, d_old_uda->abskgName, uda_matl, uda_level, timeIndex, low, high);
+        for (size_t i = 0; i < color.cells(); ++i) { color.getPointer()[i] = uda_temp.getPointer()[i]; abskg.getPointer()[i] = uda_abskg.getPointer()[i]; }
+      }
+      d_RMCRT->setBC<double, double>(color, d_colorLabel->getName(), patch, matl);
+      d_RMCRT->setBC<double, double>(abskg, d_compAbskgLabel->getName(), patch, matl);
+    }
+  }
+
+  // RMCRT_Test.cc:1001-1043: the finest level of the input file against the (single) level of the initialisation uda
+  static void areGridsEqual(const GridP& uda_grid, const GridP& grid) {
+    bool areEqual = true;
+    const LevelP level = grid->getLevel(grid->numLevels() - 1);
+    const LevelP otherlevel = uda_grid->getLevel(0);
+    if (level->numPatches() != otherlevel->numPatches()) areEqual = false;
+    for (int p = 0; areEqual && p < level->numPatches(); ++p) {
+      const Patch* patch = level->getPatch(p);
+      const Patch* otherpatch = otherlevel->getPatch(p);
+      const IntVector lo = patch->getCellLowIndex(), hi = patch->getCellHighIndex();
+      const IntVector o_lo = otherpatch->getCellLowIndex(), o_hi = otherpatch->getCellHighIndex();
+      if (lo != o_lo || hi != o_hi) areEqual = false;
+      const Point a = level->getCellPosition(lo), b = otherlevel->getCellPosition(o_lo), c = level->getCellPosition(hi), d = otherlevel->getCellPosition(o_hi);
+      for (int k = 0; k < 3; ++k)
+        if (std::fabs(a[k] - b[k]) > 1e-12 * (1 + std::fabs(a[k])) || std::fabs(c[k] - d[k]) > 1e-12 * (1 + std::fabs(c[k]))) areEqual = false;
+    }
+    if (!areEqual)
+      throw ProblemSetupException("\n\nERROR initalizeUsingUda: The grid defined in the input file is not equal to the initialization uda's grid\n"
+                                  " For the Data Onion algorithm the finest level in the input file must be equal", __FILE__, __LINE__);
+  }
+
+  struct useOldUdaData {   // RMCRT_Test.h:174-183
+    std::string udaName, cellTypeName, abskgName, temperatureName;
+    int timestep = 0, matl = 0, timeIndex = -9;
+    TypeDescription::Type subType = TypeDescription::double_type;
+  };
+  std::unique_ptr<useOldUdaData> d_old_uda;
+  std::string d_udaDirOverride;     // --init-uda DIR: use this archive instead of <uda_name> (fixtures live at test-time paths)
+
   // RMCRT_Test.cc:989-994 decides the task graph of the NEXT step; equivalently, for step ts:
   int taskGraphFor(int ts) const { return (ts % d_radCalc_freq == 0 || ts == 1) ? RMCRTCommon::TG_RMCRT : RMCRTCommon::TG_CARRY_FORWARD; }
 
@@ -345,7 +453,7 @@ class RMCRT_Test {
 }  // namespace
 
 int main(int argc, char** argv) {
-  std::string deck, dumpDir;
+  std::string deck, dumpDir, udaOut, initUda;
   int timesteps = -1, devices = 0;
   unsigned long long seed = 0;
   bool haveSeed = false, parseOnly = false;
@@ -355,6 +463,8 @@ int main(int argc, char** argv) {
     auto next = [&]() -> std::string { if (i + 1 >= argc) { std::cerr << "missing value after " << a << "\n"; std::exit(2); } return argv[++i]; };
     if (a == "--parse-only") parseOnly = true;
     else if (a == "--dump") dumpDir = next();
+    else if (a == "--uda") udaOut = next();
+    else if (a == "--init-uda") initUda = next();
     else if (a == "--timesteps") timesteps = std::atoi(next().c_str());
     else if (a == "--devices") devices = std::atoi(next().c_str());
     else if (a == "--seed") { seed = std::strtoull(next().c_str(), nullptr, 0); haveSeed = true; }
@@ -367,7 +477,7 @@ int main(int argc, char** argv) {
     else deck = a;
   }
   if (deck.empty()) {
-    std::cerr << "usage: rmcrt_test <deck.ups> [--dump DIR] [--timesteps N] [--devices N] [--seed S] [--knob name=value]...\n";
+    std::cerr << "usage: rmcrt_test <deck.ups> [--dump DIR] [--uda DIR] [--init-uda DIR] [--timesteps N] [--devices N] [--seed S] [--knob name=value]...\n";
     return 2;
   }
   try {
@@ -384,6 +494,7 @@ int main(int argc, char** argv) {
     GridP grid = buildGrid(ups);
     SchedulerP sched = std::make_shared<Scheduler>();
     RMCRT_Test app;
+    app.d_udaDirOverride = initUda;
     app.problemSetup(ups, grid, sched);
     if (haveSeed) app.d_RMCRT->setSeed(seed);
     for (auto& kv : knobs) app.d_RMCRT->setKnob(kv.first, kv.second);
@@ -434,6 +545,26 @@ int main(int argc, char** argv) {
       const int stride = std::max(1, (hi.x() - lo.x()) / 8);
       for (int i = lo.x(); i < hi.x(); i += stride) std::cout << " " << divQ[IntVector(i, j, k)];
       std::cout << std::endl;
+    }
+    if (!udaOut.empty()) {     // <DataArchiver>: the saved labels of the last time step, every level they exist on
+      DataArchiver out(udaOut, grid.get());
+      out.beginTimestep(maxTimesteps, (double)maxTimesteps, 1.0);
+      auto saveOn = [&](const VarLabel* l, const Level* lev) {
+        if (!ups->isLabelSaved(l->getName()) || !dw->exists(l, 0, lev->getPatch(0))) return;
+        for (int p = 0; p < lev->numPatches(); ++p) {
+          const Patch* patch = lev->getPatch(p);
+          if (l == RMCRTCommon::d_boundFluxLabel) { constCCVariable<Stencil7> v; dw->get(v, l, 0, patch); out.save(l->getName(), 0, patch, v); }
+          else if (l->typeDescription() == TypeDescription::int_type) { constCCVariable<int> v; dw->get(v, l, 0, patch); out.save(l->getName(), 0, patch, v); }
+          else if (l->typeDescription() == TypeDescription::float_type) { constCCVariable<float> v; dw->get(v, l, 0, patch); out.save(l->getName(), 0, patch, v); }
+          else { constCCVariable<double> v; dw->get(v, l, 0, patch); out.save(l->getName(), 0, patch, v); }
+        }
+      };
+      for (int l = 0; l < grid->numLevels(); ++l)
+        for (const VarLabel* lab : {app.d_divQLabel, RMCRTCommon::d_radiationVolqLabel, RMCRTCommon::d_boundFluxLabel, RMCRTCommon::d_sigmaT4Label,
+                                    app.d_compAbskgLabel, app.d_colorLabel, app.d_cellTypeLabel})
+          saveOn(lab, grid->getLevel(l).get());
+      out.endTimestep();
+      std::cout << "rmcrt_test: wrote " << udaOut << std::endl;
     }
     if (!dumpDir.empty()) {
       mkdir(dumpDir.c_str(), 0755);
