@@ -189,7 +189,8 @@ def benchmark_level(bm, N, pDir=0, dtype=np.float64, wall_type=8) -> Level:
     3 Burns & Christon abskg with T = 1000*abskg; 6 sinusoidal T; 7 exponential abskg, linear T^4; 8 hot and cold clouds."""
     base = burns_christon(N, np.float64, wall_type=wall_type)
     flow = base.cellType == -1
-    c = (np.arange(-1, N + 1) + 0.5) / N              # Level::getCellPosition (Level.cc:473-477), anchor 0
+    dx = 1.0 / N
+    c = 0.0 + dx * np.arange(-1, N + 1) + dx * 0.5    # Level::getCellPosition (Level.cc:473-477): anchor + dcell*v + dcell*0.5
     z, y, x = np.meshgrid(c, c, c, indexing="ij")
     p = (x, y, z)[pDir]
     ab = base.abskg.copy()
@@ -304,6 +305,49 @@ def update_sumI_ML(p: Params, levels, roi_lo, roi_hi, region_lo, region_hi, dire
                                C.byref(sumI), C.byref(n), path.ctypes.data_as(C.c_void_p) if max_path else None,
                                max_path, C.byref(npath))
     return sumI.value, n.value, path[:min(npath.value, max_path)]
+
+
+# ---------------------------------------------------------------- the reference's own per-ray routines (oracle/_ref/libref_rmcrt.so)
+_REF_LIB_PATH = os.path.join(_HERE, "_ref", "libref_rmcrt.so")
+_ref = None
+
+
+def ref_lib():
+    """the reference's updateSumI / updateSumI_ML / findRayDirection / ray_Origin compiled from the reference tree by `make -C oracle ref`
+    (oracle/extract_ref.py + ref_rmcrt_shim.cpp); None when it was never built (no reference tree at build time)"""
+    global _ref
+    if _ref is None and os.path.exists(_REF_LIB_PATH):
+        _ref = C.CDLL(_REF_LIB_PATH)
+    return _ref
+
+
+def ref_update_sumI(p: Params, lv: Level, direction, ray_origin, origin_cell):
+    cl = lv.c()
+    sumI = C.c_double(0)
+    n = C.c_uint64(0)
+    rc = ref_lib().ref_updateSumI(C.byref(p), C.byref(cl), _d3(direction), _d3(ray_origin), _i3(origin_cell), C.byref(sumI), C.byref(n))
+    return sumI.value, n.value, rc
+
+
+def ref_update_sumI_ML(p: Params, levels, roi_lo, roi_hi, region_lo, region_hi, direction, ray_origin, origin_cell):
+    nl = len(levels)
+    arr = (CLevel * nl)(*[l.c() for l in levels])
+    regLo = np.ascontiguousarray(region_lo, np.int32)
+    regHi = np.ascontiguousarray(region_hi, np.int32)
+    sumI = C.c_double(0)
+    n = C.c_uint64(0)
+    rc = ref_lib().ref_updateSumI_ML(C.byref(p), arr, nl, _i3(roi_lo), _i3(roi_hi), regLo.ctypes.data_as(C.c_void_p), regHi.ctypes.data_as(C.c_void_p),
+                                     _d3(direction), _d3(ray_origin), _i3(origin_cell), C.byref(sumI), C.byref(n))
+    return sumI.value, n.value, rc
+
+
+def generate_rays(p: Params, lv: Level, cell, n_rays, seed=1, reference=False):
+    """(dirs, origins) of rays 0..n_rays-1 of one cell as the divQ loop draws them (Ray.cc:752-760); reference=True: the reference's own code"""
+    cl = lv.c()
+    dirs = np.zeros((n_rays, 3)); orgs = np.zeros((n_rays, 3))
+    fn = ref_lib().ref_generate_rays if reference else lib().oracle_generate_rays
+    fn(C.byref(p), C.byref(cl), _i3(cell), int(n_rays), C.c_uint32(seed), dirs.ctypes.data_as(C.c_void_p), orgs.ctypes.data_as(C.c_void_p))
+    return dirs, orgs
 
 
 # ---------------------------------------------------------------- radiometer / LHC

@@ -1,0 +1,285 @@
+// ref_rmcrt_shim.cpp -- TEST INFRASTRUCTURE: compiles the reference's OWN per-ray routines
+//   RMCRTCommon::raySignStep / findRayDirection / ray_Origin / reflect / updateSumI<T>   (RMCRT/RMCRTCommon.cc:482-904)
+//   Ray::containsCell / Ray::updateSumI_ML<T>                                            (RMCRT/Ray.cc:1578-1586, 2349-2627)
+// cut out of the reference tree at build time by oracle/extract_ref.py into oracle/_ref/ref_rmcrt_extracted.inc, together with the
+// reference's own Core/Math/MersenneTwister.h (-I/root/reference/src), into oracle/_ref/libref_rmcrt.so (git-ignored, travels to the
+// GPU box).  tests/test_oracle_ref.py compares the oracle's restatement with these bit for bit.
+//
+// What is NOT the reference's here: the value types below.  The reference's functions use a handful of members of IntVector, Vector,
+// Point, BBox, Level, constCCVariable and InternalError; the real classes pull in the whole Core library (and MPI through the grid),
+// so this file supplies look-alikes with exactly those members.  Their arithmetic is component-wise double arithmetic
+// (Core/Geometry/Vector.h: operator/ and operator* of two Vectors are component-wise, Abs() is fabs per component), cell position is
+// Level.cc:473-477 (anchor + dcell*v + dcell*0.5, in that order), mapCellToCoarser is Level.cc:1285-1307, BBox::inside is BBox.h:96 -- the same restatements the oracle makes, so a
+// bit-level agreement pins every line of the marching routines themselves.
+#include <Core/Math/MersenneTwister.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <iostream>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace Uintah {
+
+class IntVector {
+ public:
+  IntVector() : v_{0, 0, 0} {}
+  IntVector(int x, int y, int z) : v_{x, y, z} {}
+  int x() const { return v_[0]; }
+  int y() const { return v_[1]; }
+  int z() const { return v_[2]; }
+  int& operator[](int i) { return v_[i]; }
+  int operator[](int i) const { return v_[i]; }
+ private:
+  int v_[3];
+};
+inline std::ostream& operator<<(std::ostream& o, const IntVector& v) { return o << "[int " << v.x() << ", " << v.y() << ", " << v.z() << "]"; }
+
+class Vector {
+ public:
+  Vector() : v_{0, 0, 0} {}
+  explicit Vector(double a) : v_{a, a, a} {}
+  Vector(double x, double y, double z) : v_{x, y, z} {}
+  double x() const { return v_[0]; }
+  double y() const { return v_[1]; }
+  double z() const { return v_[2]; }
+  void x(double a) { v_[0] = a; }
+  void y(double a) { v_[1] = a; }
+  void z(double a) { v_[2] = a; }
+  double& operator[](int i) { return v_[i]; }
+  double operator[](int i) const { return v_[i]; }
+  Vector operator/(const Vector& o) const { return Vector(v_[0] / o.v_[0], v_[1] / o.v_[1], v_[2] / o.v_[2]); }   // Vector.h: component-wise
+  Vector operator*(const Vector& o) const { return Vector(v_[0] * o.v_[0], v_[1] * o.v_[1], v_[2] * o.v_[2]); }
+ private:
+  double v_[3];
+};
+inline Vector Abs(const Vector& v) { return Vector(std::fabs(v.x()), std::fabs(v.y()), std::fabs(v.z())); }
+inline std::ostream& operator<<(std::ostream& o, const Vector& v) { return o << "[" << v.x() << ", " << v.y() << ", " << v.z() << "]"; }
+
+class Point {
+ public:
+  Point() : v_{0, 0, 0} {}
+  Point(double x, double y, double z) : v_{x, y, z} {}
+  double x() const { return v_[0]; }
+  double y() const { return v_[1]; }
+  double z() const { return v_[2]; }
+  double operator()(int i) const { return v_[i]; }
+ private:
+  double v_[3];
+};
+
+class BBox {      // Core/Geometry/BBox.h:96
+ public:
+  BBox(const Point& lo, const Point& hi) : cmin(lo), cmax(hi) {}
+  bool inside(const Point& p) const {
+    return (p.x() >= cmin.x() && p.y() >= cmin.y() && p.z() >= cmin.z() && p.x() <= cmax.x() && p.y() <= cmax.y() && p.z() <= cmax.z());
+  }
+ private:
+  Point cmin, cmax;
+};
+
+class Level;
+struct LevelHandle {     // Handle<Level>::get_rep()
+  const Level* p;
+  const Level* get_rep() const { return p; }
+};
+class Level {
+ public:
+  int index = 0;
+  double anchor[3] = {0, 0, 0}, dcell[3] = {1, 1, 1};
+  int rr[3] = {1, 1, 1};
+  const Level* coarser = nullptr;
+  int getIndex() const { return index; }
+  Point getCellPosition(const IntVector& c) const {           // Level.cc:473-477: m_anchor + m_dcell * v + m_dcell * 0.5
+    return Point(anchor[0] + dcell[0] * c.x() + dcell[0] * 0.5, anchor[1] + dcell[1] * c.y() + dcell[1] * 0.5, anchor[2] + dcell[2] * c.z() + dcell[2] * 0.5);
+  }
+  IntVector mapCellToCoarser(const IntVector& idx) const {    // Level.cc:1285-1307 (level_offset 1)
+    IntVector r;
+    for (int d = 0; d < 3; ++d) {
+      int ratio = idx[d] / rr[d];
+      int offset = 0;
+      if (idx[d] < 0 && rr[d] > 1) offset = (int)fmod((double)idx[d], (double)rr[d]);
+      r[d] = ratio + offset;
+    }
+    return r;
+  }
+  LevelHandle getCoarserLevel() const { return LevelHandle{coarser}; }
+};
+
+template <class T>
+class constCCVariable {      // Array3<T>::operator[](IntVector): x-fastest over the window (Array3.h, Array3Data.h:93,212-220)
+ public:
+  const T* data = nullptr;
+  int lo[3] = {0, 0, 0}, n[3] = {0, 0, 0};
+  const T& operator[](const IntVector& c) const {
+    return data[(int64_t)(c.x() - lo[0]) + (int64_t)n[0] * ((c.y() - lo[1]) + (int64_t)n[1] * (c.z() - lo[2]))];
+  }
+};
+
+class InternalError : public std::runtime_error {
+ public:
+  InternalError(const std::string& m, const char*, int) : std::runtime_error(m) {}
+};
+
+// the members the extracted definitions touch (RMCRTCommon.h:65-315, Ray.h:162-330)
+class RMCRTCommon {
+ public:
+  enum DIR { X = 0, Y = 1, Z = 2, NONE = -9 };
+  void raySignStep(double sign[], int cellStep[], const Vector& inv_direction_vector);
+  Vector findRayDirection(MTRand& mTwister, const IntVector& origin, const int iRay = -9);
+  void ray_Origin(MTRand& mTwister, const Point CC_pos, const Vector dx, const bool useCCRays, Vector& rayOrigin);
+  void reflect(double& fs, IntVector& cur, IntVector& prevCell, const double abskg, bool& in_domain, int& step, double& sign, double& ray_direction);
+  template <class T>
+  void updateSumI(const Level* level, Vector& ray_direction, Vector& ray_origin, const IntVector& origin, const Vector& Dx,
+                  constCCVariable<T>& sigmaT4OverPi, constCCVariable<T>& abskg, constCCVariable<int>& celltype, unsigned long int& nRaySteps,
+                  double& sumI, MTRand& mTwister);
+  bool isDbgCell(IntVector) { return false; }
+  int d_flowCell{-1};
+  static double d_threshold, d_sigmaScat, d_maxRayLength;
+  static bool d_isSeedRandom, d_allowReflect;
+};
+double RMCRTCommon::d_threshold = 0.01, RMCRTCommon::d_sigmaScat = 0, RMCRTCommon::d_maxRayLength = DBL_MAX;
+bool RMCRTCommon::d_isSeedRandom = true, RMCRTCommon::d_allowReflect = true;
+
+class Ray : public RMCRTCommon {
+ public:
+  inline bool containsCell(const IntVector& low, const IntVector& high, const IntVector& cell, const int& dir);
+  template <class T>
+  void updateSumI_ML(Vector& ray_direction, Vector& ray_origin, const IntVector& origin, const std::vector<Vector>& Dx, const BBox& domain_BB,
+                     const int maxLevels, const Level* fineLevel, const IntVector& fineLevel_ROI_Lo1, const IntVector& fineLevel_ROI_Hi1,
+                     std::vector<IntVector>& regionLo, std::vector<IntVector>& regionHi, std::vector<constCCVariable<T>>& sigmaT4OverPi,
+                     std::vector<constCCVariable<T>>& abskg, std::vector<constCCVariable<int>>& cellType, unsigned long int& nRaySteps,
+                     double& sumI, MTRand& mTwister);
+  bool m_use_virtual_ROI{false};
+  IntVector m_virtual_ROI{IntVector(0, 0, 0)};
+  IntVector d_haloCells{IntVector(-9, -9, -9)};
+};
+
+using std::vector;
+using std::cout;
+using std::endl;
+
+#include "_ref/ref_rmcrt_extracted.inc"      // the reference's definitions, verbatim
+
+}  // namespace Uintah
+
+//______________________________________________________________________ C interface (same level / parameter structs as the oracle)
+#include "rmcrt_oracle.h"
+
+using namespace Uintah;
+
+namespace {
+void setStatics(const oracle_params* p) {
+  RMCRTCommon::d_threshold = p->threshold;
+  RMCRTCommon::d_allowReflect = p->allowReflect != 0;
+  RMCRTCommon::d_isSeedRandom = p->isSeedRandom != 0;
+  RMCRTCommon::d_maxRayLength = (p->maxRayLength > 0 && p->maxRayLength < 1e300) ? p->maxRayLength : DBL_MAX;
+}
+void fillLevel(const oracle_level& s, int index, Level& L) {
+  L.index = index;
+  for (int d = 0; d < 3; ++d) { L.anchor[d] = s.anchor[d]; L.dcell[d] = s.dx[d]; L.rr[d] = s.refineRatio[d] > 0 ? s.refineRatio[d] : 1; }
+}
+template <class T> void fillVar(const oracle_level& s, const void* ptr, constCCVariable<T>& v) {
+  v.data = static_cast<const T*>(ptr);
+  for (int d = 0; d < 3; ++d) { v.lo[d] = s.lo[d]; v.n[d] = s.hi[d] - s.lo[d]; }
+}
+template <class T>
+void updateSumI_T(const oracle_params* p, const oracle_level* lv, const double dir[3], const double rayOrigin[3], const int cell[3], double* sumI,
+                  uint64_t* nSteps) {
+  Ray ray;
+  ray.d_flowCell = p->flowCell;
+  Level L;
+  fillLevel(*lv, 0, L);
+  constCCVariable<T> abskg, sig;
+  constCCVariable<int> ct;
+  fillVar<T>(*lv, lv->abskg, abskg);
+  fillVar<T>(*lv, lv->sigmaT4, sig);
+  fillVar<int>(*lv, lv->cellType, ct);
+  Vector d(dir[0], dir[1], dir[2]), o(rayOrigin[0], rayOrigin[1], rayOrigin[2]);
+  const Vector Dx(lv->dx[0], lv->dx[1], lv->dx[2]);
+  unsigned long int n = 0;
+  double s = 0;
+  MTRand mt;
+  ray.updateSumI<T>(&L, d, o, IntVector(cell[0], cell[1], cell[2]), Dx, sig, abskg, ct, n, s, mt);
+  *sumI = s; *nSteps = n;
+}
+template <class T>
+void updateSumI_ML_T(const oracle_params* p, const oracle_level* lv, int maxLevels, const int roiLo[3], const int roiHi[3], const int* regLo,
+                     const int* regHi, const double dir[3], const double rayOrigin[3], const int cell[3], double* sumI, uint64_t* nSteps) {
+  Ray ray;
+  ray.d_flowCell = p->flowCell;
+  std::vector<Level> levels(maxLevels);
+  std::vector<Vector> Dx(maxLevels);
+  std::vector<constCCVariable<T>> abskg(maxLevels), sig(maxLevels);
+  std::vector<constCCVariable<int>> ct(maxLevels);
+  std::vector<IntVector> regionLo(maxLevels), regionHi(maxLevels);
+  for (int l = 0; l < maxLevels; ++l) {
+    fillLevel(lv[l], l, levels[l]);
+    levels[l].coarser = l > 0 ? &levels[l - 1] : nullptr;
+    Dx[l] = Vector(lv[l].dx[0], lv[l].dx[1], lv[l].dx[2]);
+    fillVar<T>(lv[l], lv[l].abskg, abskg[l]);
+    fillVar<T>(lv[l], lv[l].sigmaT4, sig[l]);
+    fillVar<int>(lv[l], lv[l].cellType, ct[l]);
+    regionLo[l] = IntVector(regLo[3 * l], regLo[3 * l + 1], regLo[3 * l + 2]);
+    regionHi[l] = IntVector(regHi[3 * l], regHi[3 * l + 1], regHi[3 * l + 2]);
+  }
+  // Ray.cc:1033-1034: level_0->getInteriorSpatialRange(domain_BB)
+  const BBox bb(Point(lv[0].anchor[0] + lv[0].dx[0] * lv[0].interiorLo[0], lv[0].anchor[1] + lv[0].dx[1] * lv[0].interiorLo[1], lv[0].anchor[2] + lv[0].dx[2] * lv[0].interiorLo[2]),
+                Point(lv[0].anchor[0] + lv[0].dx[0] * lv[0].interiorHi[0], lv[0].anchor[1] + lv[0].dx[1] * lv[0].interiorHi[1], lv[0].anchor[2] + lv[0].dx[2] * lv[0].interiorHi[2]));
+  Vector d(dir[0], dir[1], dir[2]), o(rayOrigin[0], rayOrigin[1], rayOrigin[2]);
+  unsigned long int n = 0;
+  double s = 0;
+  MTRand mt;
+  ray.updateSumI_ML<T>(d, o, IntVector(cell[0], cell[1], cell[2]), Dx, bb, maxLevels, &levels[maxLevels - 1], IntVector(roiLo[0], roiLo[1], roiLo[2]),
+                       IntVector(roiHi[0], roiHi[1], roiHi[2]), regionLo, regionHi, sig, abskg, ct, n, s, mt);
+  *sumI = s; *nSteps = n;
+}
+}  // namespace
+
+extern "C" {
+
+// returns 0, or 1 when the reference threw InternalError (non-physical ray length)
+int ref_updateSumI(const oracle_params* p, const oracle_level* lv, const double dir[3], const double rayOrigin[3], const int originCell[3],
+                   double* sumI, uint64_t* nRaySteps) {
+  setStatics(p);
+  try {
+    if (lv->isFloat) updateSumI_T<float>(p, lv, dir, rayOrigin, originCell, sumI, nRaySteps);
+    else             updateSumI_T<double>(p, lv, dir, rayOrigin, originCell, sumI, nRaySteps);
+  } catch (const InternalError&) { return 1; }
+  return 0;
+}
+
+int ref_updateSumI_ML(const oracle_params* p, const oracle_level* levels, int maxLevels, const int roiLo[3], const int roiHi[3], const int* regionLo,
+                      const int* regionHi, const double dir[3], const double rayOrigin[3], const int originCell[3], double* sumI, uint64_t* nRaySteps) {
+  setStatics(p);
+  try {
+    if (levels[0].isFloat) updateSumI_ML_T<float>(p, levels, maxLevels, roiLo, roiHi, regionLo, regionHi, dir, rayOrigin, originCell, sumI, nRaySteps);
+    else                   updateSumI_ML_T<double>(p, levels, maxLevels, roiLo, roiHi, regionLo, regionHi, dir, rayOrigin, originCell, sumI, nRaySteps);
+  } catch (const InternalError&) { return 1; }
+  return 0;
+}
+
+// the ray generation of the divQ loop (Ray.cc:752-760): findRayDirection(mTwister, origin, iRay) then ray_Origin(mTwister, CC_pos, Dx, CCRays, ..)
+// for rays iRay = 0..nRays-1 of one cell on one MTRand seeded with mtSeed; dirs / origins: [nRays][3]
+void ref_generate_rays(const oracle_params* p, const oracle_level* lv, const int cell[3], int nRays, uint32_t mtSeed, double* dirs, double* origins) {
+  setStatics(p);
+  Ray ray;
+  Level L;
+  fillLevel(*lv, 0, L);
+  MTRand mt(mtSeed);
+  const IntVector c(cell[0], cell[1], cell[2]);
+  const Vector Dx(lv->dx[0], lv->dx[1], lv->dx[2]);
+  for (int i = 0; i < nRays; ++i) {
+    Vector d = ray.findRayDirection(mt, c, i);
+    Vector o;
+    ray.ray_Origin(mt, L.getCellPosition(c), Dx, p->CCRays != 0, o);
+    for (int k = 0; k < 3; ++k) { dirs[3 * i + k] = d[k]; origins[3 * i + k] = o[k]; }
+  }
+}
+
+}  // extern "C"

@@ -214,7 +214,7 @@ void updateSumI(const oracle_params& P, const LevelT<T>& lv, double dir[3], cons
     if (!P.allowReflect) intensity = 0;    // 884
     if (intensity > P.threshold && P.allowReflect) {  // 898
       // RMCRTCommon::reflect (581-602)
-      fs = fs * (1 - lv.abskg(cur));
+      fs = fs * (1 - (double)lv.abskg(cur));   // reflect() takes `const double abskg` (581-588): the subtraction is in double also for T = float
       cur[0] = prev[0]; cur[1] = prev[1]; cur[2] = prev[2];
       inDomain = true;
       step[ax] *= -1;
@@ -320,7 +320,7 @@ void updateSumI_ML(const oracle_params& P, const std::vector<LevelT<T>>& lv, int
     intensity = intensity * fs;
     if (!P.allowReflect) intensity = 0;  // 2607-2609
     if (intensity > P.threshold && P.allowReflect) {  // 2621-2624; L is left unchanged
-      fs = fs * (1 - lv[L].abskg(cur));
+      fs = fs * (1 - (double)lv[L].abskg(cur));   // reflect(..., const double abskg, ...): double arithmetic also for T = float
       cur[0] = prev[0]; cur[1] = prev[1]; cur[2] = prev[2];
       inDomain = true;
       step[ax] *= -1;
@@ -1008,6 +1008,19 @@ void oracle_arches_stencilToDBLs(const double* boundFlux7, int64_t n, double* E,
   for (int64_t c = 0; c < n; ++c) {
     const double* me = boundFlux7 + 7 * c;
     E[c] = me[1]; W[c] = me[0]; N[c] = me[3]; S[c] = me[2]; T[c] = me[5]; B[c] = me[4];
+  }
+}
+
+// the ray generation of the divQ loop (Ray.cc:752-760), exposed so it can be compared with the reference's own findRayDirection / ray_Origin
+// (oracle/_ref/libref_rmcrt.so): rays iRay = 0..nRays-1 of one cell on one MT seeded with mtSeed; dirs / origins: [nRays][3]
+void oracle_generate_rays(const oracle_params* p, const oracle_level* lv, const int cell[3], int nRays, uint32_t mtSeed, double* dirs, double* origins) {
+  MT mt(p->fixedRandom != 0);
+  mt.seed(mtSeed);
+  double cc[3];
+  for (int d = 0; d < 3; ++d) cc[d] = lv->anchor[d] + lv->dx[d] * cell[d] + lv->dx[d] * 0.5;     // Level.cc:473-477
+  for (int i = 0; i < nRays; ++i) {
+    findRayDirection(mt, *p, cell, i, dirs + 3 * i);
+    rayOriginInCell(mt, cc, lv->dx, p->CCRays != 0, origins + 3 * i);
   }
 }
 

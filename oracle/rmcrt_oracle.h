@@ -16,8 +16,13 @@
  *     generated from it.
  *   - Burns & Christon exact centre line (parametricStudies/postProcessTools/RMCRT.m:22-38).
  *   - Modest parallel-plate closed form (RMCRT.m:44-94).
- *   The bit-level results of Ray.cc itself are NOT pinned in the reference tree
- *   (gold-standard UDAs live outside the repo) and sus cannot be built here.
+ *   - The reference's OWN per-ray routines (raySignStep, findRayDirection, ray_Origin, reflect, updateSumI<T>,
+ *     containsCell, updateSumI_ML<T>), cut out of RMCRTCommon.cc / Ray.cc at build time (oracle/extract_ref.py) and
+ *     compiled into oracle/_ref/libref_rmcrt.so (oracle/ref_rmcrt_shim.cpp): sumI and step counts of random rays agree
+ *     bit for bit (tests/test_oracle_ref.py).
+ *   - The exact-solution tables of parametricStudies/postProcessTools (tests/golden/rmcrt_benchmarks.json).
+ *   sus itself cannot be built here and the gold-standard UDAs live outside the repo, so whole-deck outputs
+ *   of the reference executable are not available; the task-level loops around the per-ray routines are restatements.
  */
 #ifndef RMCRT_ORACLE_H
 #define RMCRT_ORACLE_H
@@ -152,6 +157,10 @@ void oracle_arches_sigmaT4(const double* gasVolFrac, const double* const* partGa
 void oracle_arches_sumAbsk(const double* gasVolFrac, const double* const* partGas_absk, int nPartGas, const int lo[3],
                            const int hi[3], const int intLo[3], const int intHi[3], void* out, int isFloat);
 void oracle_arches_stencilToDBLs(const double* boundFlux7, int64_t n, double* E, double* W, double* N, double* S, double* T, double* B);
+
+/* ---- ray generation of the divQ loop (Ray.cc:752-760): findRayDirection + ray_Origin for rays 0..nRays-1 of one cell ---- */
+void oracle_generate_rays(const oracle_params* p, const oracle_level* lv, const int cell[3], int nRays, uint32_t mtSeed,
+                          double* dirs /*[nRays][3]*/, double* origins);
 
 #ifdef __cplusplus
 }

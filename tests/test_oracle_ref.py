@@ -1,0 +1,98 @@
+"""The oracle against the REFERENCE'S OWN per-ray code.
+
+`make -C oracle ref` (run by __graft_entry__.build() where /root/reference exists) cuts RMCRTCommon::raySignStep / findRayDirection /
+ray_Origin / reflect / updateSumI<T> and Ray::containsCell / updateSumI_ML<T> out of the reference's RMCRTCommon.cc and Ray.cc
+(oracle/extract_ref.py) and compiles them, unmodified, with the reference's own MersenneTwister.h into oracle/_ref/libref_rmcrt.so
+(oracle/ref_rmcrt_shim.cpp; git-ignored, travels to the GPU box).  These tests feed the same rays through that library and through the
+oracle's restatement: sumI must agree BIT FOR BIT and the step counts exactly -- which pins every line of the marching routines the CUDA
+path is checked against.
+"""
+import numpy as np
+import pytest
+
+from util import add_random_walls, random_rays
+
+
+@pytest.fixture(scope="module")
+def ref(po):
+    if po.ref_lib() is None:
+        pytest.skip("oracle/_ref/libref_rmcrt.so was not built (no reference tree at build time)")
+    return po.ref_lib()
+
+
+def cases(po, dtype):
+    rng = np.random.default_rng(7)
+    bc = po.burns_christon(24, dtype=dtype)
+    add_random_walls(bc, 0.02, rng, abskg=0.6, sigmaT4=0.2)
+    pl = po.parallel_plates(20, dtype=dtype, mirror_faces=("x-", "y-", "z+"))
+    add_random_walls(pl, 0.01, rng, abskg=0.3, sigmaT4=5000.0)
+    M = 18
+    rnd = po.Level(rng.uniform(0.05, 3.0, (M, M, M)).astype(dtype), rng.uniform(0, 2, (M, M, M)).astype(dtype), np.full((M, M, M), -1, np.int32),
+                   (-1,) * 3, (M - 1,) * 3, (0.07, 0.05, 0.11), anchor=(-0.3, 0.2, 1.0), interior_lo=(0,) * 3, interior_hi=(M - 2,) * 3)
+    for ax in range(3):
+        for idx in (0, M - 1):
+            sl = [slice(None)] * 3; sl[ax] = idx
+            rnd.cellType[tuple(sl)] = 8
+    rnd.abskg[rnd.cellType != -1] = rng.uniform(0, 1.4, int((rnd.cellType != -1).sum())).astype(dtype)     # emissivities above 1 get clamped
+    return {"burns_christon+intrusions": bc, "plates+mirrors": pl, "anisotropic_random": rnd}
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("kw", [dict(threshold=0.05), dict(threshold=0.001, allowReflect=0), dict(threshold=0.01, maxRayLength=0.35)])
+def test_updateSumI_bit_exact(po, ref, dtype, kw):
+    """RMCRTCommon::updateSumI<T> (RMCRTCommon.cc:607-904): 1500 random rays per field, thresholds / reflections / bounded length"""
+    rng = np.random.default_rng(11)
+    p = po.default_params(**kw)
+    total = 0
+    for name, lv in cases(po, dtype).items():
+        cells, dirs, orgs = random_rays(lv, 1500, rng)
+        for c, d, o in zip(cells, dirs, orgs):
+            if lv.cellType[c[2] - lv.lo[2], c[1] - lv.lo[1], c[0] - lv.lo[0]] != -1:
+                continue
+            s_ref, n_ref, rc = po.ref_update_sumI(p, lv, d, o, c)
+            s, n, _ = po.update_sumI(p, lv, d, o, c)
+            assert rc == 0
+            assert n == n_ref, (name, c, d)
+            assert s == s_ref or (np.isnan(s) and np.isnan(s_ref)), (name, c, d, s, s_ref)      # bit for bit
+            total += n
+    assert total > 30000
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_updateSumI_ML_bit_exact(po, ref, dtype):
+    """Ray::updateSumI_ML<T> (Ray.cc:2349-2627) on a 3-level Data Onion: level jumps, region boxes, reflections on every level"""
+    rng = np.random.default_rng(13)
+    fine = po.parallel_plates(32, dtype=dtype, mirror_faces=("x+", "z-"))
+    fine.abskg[1:-1, 1:-1, 1:-1] = rng.uniform(0.05, 1.5, (32, 32, 32)).astype(dtype)
+    fine.sigmaT4[1:-1, 1:-1, 1:-1] = rng.uniform(0, 1e4, (32, 32, 32)).astype(dtype)
+    walls = fine.cellType != -1
+    fine.abskg[walls] = rng.uniform(0, 1.3, int(walls.sum())).astype(dtype)     # grey walls: fs = fs (1 - abskg) matters, > 1 gets clamped
+    fine.rr = (2, 2, 2)
+    mid = po.coarsen_level(fine, (2, 2, 2))
+    mid.rr = (4, 4, 4)
+    coarse = po.coarsen_level(mid, (4, 4, 4))
+    levels = [coarse, mid, fine]
+    for thr in (0.05, 0.002):
+        p = po.default_params(threshold=thr)
+        for patch_lo, patch_hi in (((0, 0, 0), (16, 16, 16)), ((16, 8, 16), (32, 24, 32))):
+            roi_lo, roi_hi, reg_lo, reg_hi = po.compute_extents(levels, patch_lo, patch_hi, (3, 3, 3))
+            cells, dirs, orgs = random_rays(fine, 600, rng, lo=patch_lo, hi=patch_hi)
+            for c, d, o in zip(cells, dirs, orgs):
+                s_ref, n_ref, rc = po.ref_update_sumI_ML(p, levels, roi_lo, roi_hi, reg_lo, reg_hi, d, o, c)
+                s, n, _ = po.update_sumI_ML(p, levels, roi_lo, roi_hi, reg_lo, reg_hi, d, o, c)
+                assert rc == 0 and n == n_ref and s == s_ref, (thr, c, d, n, n_ref, s, s_ref)
+
+
+@pytest.mark.parametrize("kw", [dict(isSeedRandom=1), dict(isSeedRandom=0), dict(isSeedRandom=1, CCRays=1)])
+def test_ray_generation_bit_exact(po, ref, kw):
+    """findRayDirection + ray_Origin as the divQ loop calls them (Ray.cc:752-760; RMCRTCommon.cc:499-576), random and per-ray re-seeded"""
+    lv = po.burns_christon(12)
+    lv2 = po.Level(lv.abskg, lv.sigmaT4, lv.cellType, lv.lo, lv.hi, (0.07, 0.05, 0.11), anchor=(-0.3, 0.2, 1.0), interior_lo=(0,) * 3, interior_hi=(12,) * 3)
+    p = po.default_params(**kw)
+    for level in (lv, lv2):
+        for cell in ((0, 0, 0), (3, 7, 11), (11, 11, 11)):
+            for seed in (1, 12345):
+                d0, o0 = po.generate_rays(p, level, cell, 300, seed, reference=True)
+                d1, o1 = po.generate_rays(p, level, cell, 300, seed)
+                assert np.array_equal(d0, d1) and np.array_equal(o0, o1)
+    np.testing.assert_allclose(np.linalg.norm(d0, axis=1), 1.0, rtol=1e-12)

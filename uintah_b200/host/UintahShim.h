@@ -272,7 +272,8 @@ class Level {
   IntVector getRefinementRatio() const { return rr_; }     // to the next coarser level
   // Level.cc:473-477
   Point getCellPosition(const IntVector& c) const {
-    return Point(anchor_.x() + dcell_.x() * (c.x() + 0.5), anchor_.y() + dcell_.y() * (c.y() + 0.5), anchor_.z() + dcell_.z() * (c.z() + 0.5));
+    return Point(anchor_.x() + dcell_.x() * c.x() + dcell_.x() * 0.5, anchor_.y() + dcell_.y() * c.y() + dcell_.y() * 0.5,
+                 anchor_.z() + dcell_.z() * c.z() + dcell_.z() * 0.5);   // m_anchor + m_dcell * v + m_dcell * 0.5, in that order
   }
   // Level.cc:480-485: RoundDown((p - anchor) / dcell)
   IntVector getCellIndex(const Point& p) const {
