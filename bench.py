@@ -134,6 +134,13 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------- reference arm
+CPU_KIND_NOTE = {
+    "reference": "; the reference's own RMCRTCommon::findRayDirection / ray_Origin / updateSumI<T> compiled from its tree (oracle/_ref/libref_rmcrt.so) "
+                 "under the Ray::rayTrace divQ cell loop",
+    "port": "; oracle restatement of Ray::rayTrace (oracle/_ref/libref_rmcrt.so absent)",
+}
+
+
 def cpu_reference_sample(n_cells_side, rays, shape_cells, slab_cells, threads, repeats=1, warm=0):
     """Time the oracle's Ray::rayTrace restatement on a z-slab of `slab_cells` planes in the middle of the level,
     split into `threads` patch tasks run on `threads` host threads (reference partitioning: one task per patch)."""
@@ -147,9 +154,13 @@ def cpu_reference_sample(n_cells_side, rays, shape_cells, slab_cells, threads, r
     z0 = shape_cells[2] // 2 - slab_cells // 2
     plo, phi = (0, 0, z0), (shape_cells[0], shape_cells[1], z0 + slab_cells)
     times, steps = [], 0
+    # the reference's own findRayDirection / ray_Origin / updateSumI<T> (oracle/_ref/libref_rmcrt.so, built from the reference tree by
+    # `make -C oracle ref`) under the Ray::rayTrace cell loop when that library is there, else the oracle's restatement of the same
+    trace = po.ref_ray_trace if po.ref_lib() is not None else po.ray_trace
+    cpu_reference_sample.kind = "reference" if po.ref_lib() is not None else "port"
     for it in range(warm + repeats):
         t0 = time.perf_counter()
-        r = po.ray_trace(p, lv, plo, phi, seed=1 + it, patches=(1, threads, slab_cells), threads=threads)
+        r = trace(p, lv, plo, phi, seed=1 + it, patches=(1, threads, slab_cells), threads=threads)
         dt = time.perf_counter() - t0
         if it >= warm:
             times.append(dt)
@@ -178,7 +189,8 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(n, shape, rays, world),
                    "sample_per_step": sample, "semantics": "reference (allowReflect default true: zero-weight legs marched)"},
-        "cpu_baseline": {"value": value, "unit": "ray-cell steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "ray-cell steps/s", "cores": threads, "kind": cpu_reference_sample.kind,
+                         "sample": sample + CPU_KIND_NOTE[cpu_reference_sample.kind]},
         "e2e": {"value": value, "unit": "ray-cell steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -414,10 +426,10 @@ def run_ours(args):
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        slab = max(1, int(round(4 * threads / 8)))
+        slab = max(1, int(round(12 * threads / 8)))          # ~10-15 s of CPU work
         times, csteps, ccells, sample = cpu_reference_sample(P, rays, shape, slab, threads, repeats=1, warm=0)
-        cpu_baseline = {"value": csteps / times[0], "unit": "ray-cell steps/s", "cores": threads, "kind": "port",
-                        "sample": sample + f"; {times[0]:.1f} s wall; {threads} patch tasks on {threads} threads",
+        cpu_baseline = {"value": csteps / times[0], "unit": "ray-cell steps/s", "cores": threads, "kind": cpu_reference_sample.kind,
+                        "sample": sample + f"; {times[0]:.1f} s wall; {threads} patch tasks on {threads} threads" + CPU_KIND_NOTE[cpu_reference_sample.kind],
                         "divq_cells_per_s": ccells / times[0], "steps_per_ray": csteps / (ccells * rays)}
 
     line = {

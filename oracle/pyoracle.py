@@ -341,6 +341,34 @@ def ref_update_sumI_ML(p: Params, levels, roi_lo, roi_hi, region_lo, region_hi, 
     return sumI.value, n.value, rc
 
 
+def ref_ray_trace(p: Params, lv: Level, patch_lo=None, patch_hi=None, seed=1, patches=(1, 1, 1), threads=1):
+    """the divQ part of Ray::rayTrace with the reference's own per-ray routines (ref_rayTrace_divQ); same task split / seeds as ray_trace"""
+    patch_lo = lv.interior_lo if patch_lo is None else tuple(patch_lo)
+    patch_hi = lv.interior_hi if patch_hi is None else tuple(patch_hi)
+    shape = lv.abskg.shape
+    divQ = np.zeros(shape, np.float64)
+    volq = np.zeros(shape, np.float64)
+    cl = lv.c()
+    tasks = _split(patch_lo, patch_hi, patches)
+    steps = [0] * len(tasks)
+
+    def run(t):
+        lo, hi = tasks[t]
+        n = C.c_uint64(0)
+        rc = ref_lib().ref_rayTrace_divQ(C.byref(p), C.byref(cl), _i3(lo), _i3(hi), C.c_uint32(seed + t), divQ.ctypes.data_as(C.c_void_p),
+                                         volq.ctypes.data_as(C.c_void_p), _i3(lv.lo), _i3(lv.hi), C.byref(n))
+        assert rc == 0
+        steps[t] = n.value
+
+    if threads > 1 and len(tasks) > 1:
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            list(ex.map(run, range(len(tasks))))
+    else:
+        for t in range(len(tasks)):
+            run(t)
+    return dict(divQ=divQ, radiationVolq=volq, steps=sum(steps))
+
+
 def generate_rays(p: Params, lv: Level, cell, n_rays, seed=1, reference=False):
     """(dirs, origins) of rays 0..n_rays-1 of one cell as the divQ loop draws them (Ray.cc:752-760); reference=True: the reference's own code"""
     cl = lv.c()

@@ -283,3 +283,52 @@ void ref_generate_rays(const oracle_params* p, const oracle_level* lv, const int
 }
 
 }  // extern "C"
+
+// The divQ loop of Ray::rayTrace<T> (Ray.cc:742-779, naive sampling) over cells [patchLo,patchHi), with every per-ray routine it calls
+// (findRayDirection, ray_Origin, updateSumI<T>) being the reference's own code above; only the loop shell and the two assignment lines
+// 775/778 are restated here.  One MTRand per call, seeded with mtSeed (the per-task generator of Ray.cc:539).  This is what bench.py
+// times as the CPU baseline ("kind": "reference") and what tests/test_oracle_ref.py compares oracle_rayTrace with.
+template <class T>
+static void rayTrace_divQ_T(const oracle_params* p, const oracle_level* lv, const int pLo[3], const int pHi[3], uint32_t mtSeed, double* divQ,
+                            double* volq, const int oLo[3], const int oHi[3], uint64_t* nSteps) {
+  Ray ray;
+  ray.d_flowCell = p->flowCell;
+  Level L;
+  fillLevel(*lv, 0, L);
+  constCCVariable<T> abskg, sig;
+  constCCVariable<int> ct;
+  fillVar<T>(*lv, lv->abskg, abskg);
+  fillVar<T>(*lv, lv->sigmaT4, sig);
+  fillVar<int>(*lv, lv->cellType, ct);
+  const Vector Dx(lv->dx[0], lv->dx[1], lv->dx[2]);
+  MTRand mTwister(mtSeed);
+  unsigned long int size = 0;
+  const int64_t onx = oHi[0] - oLo[0], ony = oHi[1] - oLo[1];
+  const int d_nDivQRays = p->nDivQRays;
+  for (int k = pLo[2]; k < pHi[2]; ++k) for (int j = pLo[1]; j < pHi[1]; ++j) for (int i = pLo[0]; i < pHi[0]; ++i) {   // CellIterator: x fastest
+    const IntVector origin(i, j, k);
+    if (ct[origin] != ray.d_flowCell) continue;
+    double sumI = 0;
+    Point CC_pos = L.getCellPosition(origin);
+    for (int iRay = 0; iRay < d_nDivQRays; iRay++) {
+      Vector direction_vector = ray.findRayDirection(mTwister, origin, iRay);
+      Vector rayOrigin;
+      ray.ray_Origin(mTwister, CC_pos, Dx, p->CCRays != 0, rayOrigin);
+      ray.updateSumI<T>(&L, direction_vector, rayOrigin, origin, Dx, sig, abskg, ct, size, sumI, mTwister);
+    }
+    const int64_t q = (i - oLo[0]) + onx * ((j - oLo[1]) + ony * (int64_t)(k - oLo[2]));
+    divQ[q] = -4.0 * M_PI * abskg[origin] * (sig[origin] - (sumI / d_nDivQRays));
+    volq[q] = 4.0 * M_PI * (sumI / d_nDivQRays);
+  }
+  *nSteps = size;
+}
+
+extern "C" int ref_rayTrace_divQ(const oracle_params* p, const oracle_level* lv, const int patchLo[3], const int patchHi[3], uint32_t mtSeed,
+                                 double* divQ, double* radiationVolq, const int outLo[3], const int outHi[3], uint64_t* nRaySteps) {
+  setStatics(p);
+  try {
+    if (lv->isFloat) rayTrace_divQ_T<float>(p, lv, patchLo, patchHi, mtSeed, divQ, radiationVolq, outLo, outHi, nRaySteps);
+    else             rayTrace_divQ_T<double>(p, lv, patchLo, patchHi, mtSeed, divQ, radiationVolq, outLo, outHi, nRaySteps);
+  } catch (const InternalError&) { return 1; }
+  return 0;
+}

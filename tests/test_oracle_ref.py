@@ -96,3 +96,17 @@ def test_ray_generation_bit_exact(po, ref, kw):
                 d1, o1 = po.generate_rays(p, level, cell, 300, seed)
                 assert np.array_equal(d0, d1) and np.array_equal(o0, o1)
     np.testing.assert_allclose(np.linalg.norm(d0, axis=1), 1.0, rtol=1e-12)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("seed_random", [1, 0])
+def test_divQ_loop_bit_exact(po, ref, dtype, seed_random):
+    """the divQ loop of Ray::rayTrace<T> (Ray.cc:742-779) driven by the reference's own per-ray routines == oracle_rayTrace, bit for bit,
+    including the MT19937 stream shared by all cells of a task and the task split / seeds"""
+    lv = po.burns_christon(14, dtype=dtype)
+    add_random_walls(lv, 0.03, np.random.default_rng(3), abskg=0.5, sigmaT4=0.1)
+    p = po.default_params(nDivQRays=7, threshold=0.02, isSeedRandom=seed_random)
+    a = po.ref_ray_trace(p, lv, seed=5, patches=(1, 2, 2), threads=4)
+    b = po.ray_trace(p, lv, seed=5, patches=(1, 2, 2), threads=4)
+    assert a["steps"] == b["steps"] and a["steps"] > 1e5
+    assert np.array_equal(a["divQ"], b["divQ"]) and np.array_equal(a["radiationVolq"], b["radiationVolq"])
