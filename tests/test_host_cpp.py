@@ -37,8 +37,8 @@ def tasks_of(stdout):
     tasks, cur = [], None
     for line in stdout.splitlines():
         if line.startswith("TASK "):
-            f = line.split()
-            cur = {"name": f[1], **{k: v for k, v in (x.split("=") for x in f[2:])}, "deps": []}
+            name, rest = line[5:].split(" level=", 1)            # task names may hold blanks ("RadiationSource: setup bndflux")
+            cur = {"name": name, **{k: v for k, v in (x.split("=") for x in ("level=" + rest).split())}, "deps": []}
             tasks.append(cur)
         elif line.startswith("  ") and cur is not None:
             f = line.split()
@@ -370,3 +370,34 @@ def test_coarse_level_deck(exe, po, tmp_path, gpu_lib, order):
     ref_f = po.refine_Q(out["divQ_L0"], coarse.lo, coarse.hi, coarse.lo, coarse.hi, (4, 4, 4), order, (0,) * 3, (32,) * 3, fine.lo, fine.hi)
     assert np.array_equal(out["divQ"], ref_f)
     assert not out["RMCRTboundFlux"].any()
+
+
+# ------------------------------------------------------------------------------------------------ the Wasatch consumer (modifies_divQ = true)
+def test_wasatch_schedule_matches_reference_surface(exe):
+    """RadiationSource::schedule_ray_tracing (Wasatch/Expressions/RadiationSource.cc:141-172): setup bndflux, sigmaT4, BCs from the
+    temperature field (backoutTemp false), Ray::rayTrace scheduled with MODIFIES on divQ / RMCRTboundFlux / radiationVolq"""
+    t = tasks_of(run(exe, "bm2_1L_flux_reflect.ups", "--caller", "wasatch", "--parse-only").stdout)
+    names = [x["name"] for x in t]
+    assert names.index("RMCRTCommon::carryForward_VarLabels") < names.index("RMCRTCommon::sigmaT4") < names.index("Ray::setBoundaryConditions") \
+        < names.index("Ray::rayTrace")
+    rt = t[-1]
+    assert rt["name"] == "Ray::rayTrace" and [d[1] for d in rt["deps"] if d[0] == "modifies"] == ["divQ", "RMCRTboundFlux", "radiationVolq"]
+    assert not [d for d in rt["deps"] if d[0] == "computes"]
+    bc = [x for x in t if x["name"] == "Ray::setBoundaryConditions"][0]
+    assert ("requires", "color", "dw=NewDW", "ghost=0", "domain=normal", "offset=0") in bc["deps"]      # backoutTemp == false (Ray.cc:1604-1606)
+
+
+@pytest.mark.gpu
+def test_wasatch_caller_modifies_divQ(exe, po, tmp_path, gpu_lib):
+    """modifies_divQ = true end to end: cells the trace does not compute keep what the caller put there (the expression tree's field),
+    everything else equals the oracle; the boundary temperature comes from the temperature field, not from sigmaT4"""
+    out = load_dump(run(exe, "bm2_1L_flux_reflect.ups", "--caller", "wasatch", "--dump", str(tmp_path), "--knob", "skipZeroWeightLegs=0").args[5])
+    lv = po.parallel_plates(16, mirror_faces=("x-", "y-"))
+    np.testing.assert_allclose(out["sigmaT4"], lv.sigmaT4, rtol=1e-14, atol=0)
+    p = po.default_params(nDivQRays=4, nFluxRays=4, threshold=0.001, isSeedRandom=0, solveBoundaryFlux=1, allowReflect=1)
+    ref = po.ray_trace(p, lv)
+    flow = lv.cellType == -1
+    np.testing.assert_allclose(out["divQ"][flow], ref["divQ"][flow], rtol=1e-9, atol=1e-9 * np.abs(ref["divQ"]).max())
+    assert (out["divQ"][~flow] == 123.0).all() and (out["radiationVolq"][~flow] == -7.0).all()      # untouched (Ray.cc:573-580)
+    np.testing.assert_allclose(out["RMCRTboundFlux"], ref["boundFlux"], rtol=1e-9, atol=0)
+    assert out["report"]["nRaySteps"] == ref["steps"] and out["report"]["nFluxRaySteps"] == ref["fluxSteps"]

@@ -278,8 +278,10 @@ struct LegOut {
 #if defined(__CUDA_ARCH__)
 // record-type specific pieces: request the record of slot J / decode slot C into a<C> = |abskg|, s<C> (k<C> keeps the raw word
 // whose bit 31 is the wall flag for both layouts)
-// (%20 = record size in a REGISTER: with an immediate ptxas turns the address into two ALU-pipe LEAs; with a register it
-// is one IMAD.WIDE on the FMA pipe, and the ALU pipe is the one that saturates)
+// Address arithmetic, measured alternatives (sm_100a SASS, session 8): `mad.wide.s32 ad, i, 8, base` becomes LEA + LEA.HI.X (2 ALU
+// ops, what ships); a REGISTER record size (%20, unused) makes it IMAD.WIDE + IADD3 + IMAD.X (3 ops); 32-bit low-word addressing with a
+// constant high word costs two MOVs per step to rebuild the register pair the load clobbers (no gain at the 32-register budget);
+// a 32-bit offset from a uniform base has no single-instruction LDG form (IADD3 + IMAD.X).
 #define RM_LD8(J)  "mad.wide.s32 ad, i" #J ", 8, %13;\n\t" "ld.global.nc.v2.f32 {k" #J ", s" #J "}, [ad];\n\t"
 #define RM_LD4(J)  "mad.wide.s32 ad, i" #J ", 4, %13;\n\t" "ld.global.nc.b32 k" #J ", [ad];\n\t"
 #define RM_DEC8(C) "abs.f32 a" #C ", k" #C ";\n\t"

@@ -12,6 +12,7 @@
 #include "DataArchive.h"
 #include "DriverCommon.h"
 #include "Ray.h"
+#include "WasatchRadiationSource.h"
 
 #include <sys/stat.h>
 
@@ -37,6 +38,7 @@ class RMCRT_Test {
     d_cellTypeLabel = VarLabel::create("cellType", TypeDescription::int_type);
   }
   ~RMCRT_Test() {
+    d_wasatch.reset();
     d_RMCRT.reset();
     VarLabel::destroy(d_colorLabel);
     VarLabel::destroy(d_compAbskgLabel);
@@ -148,9 +150,14 @@ class RMCRT_Test {
     if (d_whichAlgo == dataOnion || d_whichAlgo == dataOnionSlim) ray_algo = RMCRTCommon::dataOnion;
     else if (d_whichAlgo == coarseLevel) ray_algo = RMCRTCommon::coarseLevel;
     else if (d_whichAlgo == radiometerOnly) ray_algo = RMCRTCommon::radiometerOnly;
-    d_RMCRT->registerVariables(0, d_compAbskgLabel, d_colorLabel, d_cellTypeLabel, d_divQLabel, ray_algo);
-    d_RMCRT->problemSetup(prob_spec, rmcrt_ps, grid);
-    d_RMCRT->BC_bulletproofing(rmcrt_ps, true, true);
+    if (d_wasatchCaller) {   // the Wasatch consumer: RadiationSource's constructor registers the variables and runs problemSetup itself
+      if (d_whichAlgo != singleLevel) throw ProblemSetupException("rmcrt_test --caller wasatch: Wasatch drives RMCRT on a single level", __FILE__, __LINE__);
+      d_wasatch.reset(new WasatchCore::RadiationSource("divQ", "color", "abskg", "cellType", d_RMCRT.get(), rmcrt_ps, grid));
+    } else {
+      d_RMCRT->registerVariables(0, d_compAbskgLabel, d_colorLabel, d_cellTypeLabel, d_divQLabel, ray_algo);
+      d_RMCRT->problemSetup(prob_spec, rmcrt_ps, grid);
+      d_RMCRT->BC_bulletproofing(rmcrt_ps, true, true);
+    }
 
     // one extra cell (or periodicity) in each direction (RMCRT_Test.cc:238-251)
     const IntVector extraCells = grid->getLevel(0)->getExtraCells();
@@ -187,6 +194,17 @@ class RMCRT_Test {
     const bool includeExtraCells = true;
     Task::WhichDW notUsed = Task::None;
     Radiometer* radiometer = d_RMCRT->getRadiometer();                    // 384
+
+    if (d_wasatchCaller) {     // RadiationSource::schedule_ray_tracing (Wasatch/Expressions/RadiationSource.cc:141-172): modifies_divQ = true
+      // stands in for the expression tree, which owns the divQ field: allocate it (and radiationVolq) filled with a sentinel so the test
+      // can see that the trace leaves every cell it does not compute untouched
+      Task* alloc = new Task("Wasatch::allocate_fields", this, &RMCRT_Test::wasatchAllocate);
+      alloc->computesVar(d_divQLabel);
+      alloc->computesVar(RMCRTCommon::d_radiationVolqLabel);
+      sched->addTask(alloc, level->eachPatch(), RMCRTCommon::d_matlSet, RMCRTCommon::TG_RMCRT);
+      d_wasatch->schedule_ray_tracing(level, sched, RMCRTCommon::d_matlSet, 0);
+      return;
+    }
 
     if (d_whichAlgo == dataOnion || d_whichAlgo == dataOnionSlim) {      // 385-460
       Task::WhichDW temp_dw = Task::NewDW, sigmaT4_dw = Task::NewDW, celltype_dw = Task::NewDW;
@@ -412,6 +430,18 @@ class RMCRT_Test {
                                   " For the Data Onion algorithm the finest level in the input file must be equal", __FILE__, __LINE__);
   }
 
+  void wasatchAllocate(const ProcessorGroup*, const PatchSubset* patches, const MaterialSubset*, DataWarehouse*, DataWarehouse* new_dw) {
+    for (int p = 0; p < patches->size(); p++) {
+      CCVariable<double> divQ, volq;
+      new_dw->allocateAndPut(divQ, d_divQLabel, 0, patches->get(p));
+      new_dw->allocateAndPut(volq, RMCRTCommon::d_radiationVolqLabel, 0, patches->get(p));
+      divQ.initialize(123.0);
+      volq.initialize(-7.0);
+    }
+  }
+  bool d_wasatchCaller = false;      // --caller wasatch
+  std::unique_ptr<WasatchCore::RadiationSource> d_wasatch;
+
   struct useOldUdaData {   // RMCRT_Test.h:174-183
     std::string udaName, cellTypeName, abskgName, temperatureName;
     int timestep = 0, matl = 0, timeIndex = -9;
@@ -453,7 +483,7 @@ class RMCRT_Test {
 }  // namespace
 
 int main(int argc, char** argv) {
-  std::string deck, dumpDir, udaOut, initUda;
+  std::string deck, dumpDir, udaOut, initUda, caller = "rmcrt_test";
   int timesteps = -1, devices = 0;
   unsigned long long seed = 0;
   bool haveSeed = false, parseOnly = false;
@@ -465,6 +495,7 @@ int main(int argc, char** argv) {
     else if (a == "--dump") dumpDir = next();
     else if (a == "--uda") udaOut = next();
     else if (a == "--init-uda") initUda = next();
+    else if (a == "--caller") caller = next();
     else if (a == "--timesteps") timesteps = std::atoi(next().c_str());
     else if (a == "--devices") devices = std::atoi(next().c_str());
     else if (a == "--seed") { seed = std::strtoull(next().c_str(), nullptr, 0); haveSeed = true; }
@@ -477,7 +508,7 @@ int main(int argc, char** argv) {
     else deck = a;
   }
   if (deck.empty()) {
-    std::cerr << "usage: rmcrt_test <deck.ups> [--dump DIR] [--uda DIR] [--init-uda DIR] [--timesteps N] [--devices N] [--seed S] [--knob name=value]...\n";
+    std::cerr << "usage: rmcrt_test <deck.ups> [--dump DIR] [--uda DIR] [--init-uda DIR] [--caller rmcrt_test|wasatch] [--timesteps N] [--devices N] [--seed S] [--knob name=value]...\n";
     return 2;
   }
   try {
@@ -495,6 +526,8 @@ int main(int argc, char** argv) {
     SchedulerP sched = std::make_shared<Scheduler>();
     RMCRT_Test app;
     app.d_udaDirOverride = initUda;
+    if (caller == "wasatch") app.d_wasatchCaller = true;
+    else if (caller != "rmcrt_test") { std::cerr << "--caller must be rmcrt_test or wasatch\n"; return 2; }
     app.problemSetup(ups, grid, sched);
     if (haveSeed) app.d_RMCRT->setSeed(seed);
     for (auto& kv : knobs) app.d_RMCRT->setKnob(kv.first, kv.second);
