@@ -32,7 +32,7 @@ class Params(C.Structure):
                 ("allowReflect", C.c_int), ("CCRays", C.c_int), ("isSeedRandom", C.c_int),
                 ("solveDivQ", C.c_int), ("solveBoundaryFlux", C.c_int), ("fixedRandom", C.c_int),
                 ("flowCell", C.c_int), ("dataOnionFluxFlowGuard", C.c_int), ("rayDirSampleAlgo", C.c_int),
-                ("maxRayLength", C.c_double)]
+                ("maxRayLength", C.c_double), ("sigmaScat", C.c_double)]
 
 
 class CRadiometer(C.Structure):
@@ -321,6 +321,28 @@ def ref_lib():
     return _ref
 
 
+_ref_scatter = None
+
+
+def ref_scatter_lib():
+    """the same routines compiled with -DRAY_SCATTER (the reference's --enable-ray-scatter build)"""
+    global _ref_scatter
+    path = os.path.join(_HERE, "_ref", "libref_rmcrt_scatter.so")
+    if _ref_scatter is None and os.path.exists(path):
+        _ref_scatter = C.CDLL(path)
+    return _ref_scatter
+
+
+def update_sumI_seeded(p: Params, lv: Level, direction, ray_origin, origin_cell, seed, reference=None):
+    """one ray with the task generator seeded (scattering draws from it inside the march); reference = a ref_lib() handle or None = oracle"""
+    cl = lv.c()
+    sumI = C.c_double(0)
+    n = C.c_uint64(0)
+    fn = lib().oracle_updateSumI_seeded if reference is None else reference.ref_updateSumI_seeded
+    fn(C.byref(p), C.byref(cl), _d3(direction), _d3(ray_origin), _i3(origin_cell), C.c_uint32(seed), C.byref(sumI), C.byref(n))
+    return sumI.value, n.value
+
+
 def ref_update_sumI(p: Params, lv: Level, direction, ray_origin, origin_cell):
     cl = lv.c()
     sumI = C.c_double(0)
@@ -341,7 +363,7 @@ def ref_update_sumI_ML(p: Params, levels, roi_lo, roi_hi, region_lo, region_hi, 
     return sumI.value, n.value, rc
 
 
-def ref_ray_trace(p: Params, lv: Level, patch_lo=None, patch_hi=None, seed=1, patches=(1, 1, 1), threads=1):
+def ref_ray_trace(p: Params, lv: Level, patch_lo=None, patch_hi=None, seed=1, patches=(1, 1, 1), threads=1, library=None):
     """the divQ part of Ray::rayTrace with the reference's own per-ray routines (ref_rayTrace_divQ); same task split / seeds as ray_trace"""
     patch_lo = lv.interior_lo if patch_lo is None else tuple(patch_lo)
     patch_hi = lv.interior_hi if patch_hi is None else tuple(patch_hi)
@@ -355,7 +377,7 @@ def ref_ray_trace(p: Params, lv: Level, patch_lo=None, patch_hi=None, seed=1, pa
     def run(t):
         lo, hi = tasks[t]
         n = C.c_uint64(0)
-        rc = ref_lib().ref_rayTrace_divQ(C.byref(p), C.byref(cl), _i3(lo), _i3(hi), C.c_uint32(seed + t), divQ.ctypes.data_as(C.c_void_p),
+        rc = (library or ref_lib()).ref_rayTrace_divQ(C.byref(p), C.byref(cl), _i3(lo), _i3(hi), C.c_uint32(seed + t), divQ.ctypes.data_as(C.c_void_p),
                                          volq.ctypes.data_as(C.c_void_p), _i3(lv.lo), _i3(lv.hi), C.byref(n))
         assert rc == 0
         steps[t] = n.value

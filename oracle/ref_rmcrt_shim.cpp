@@ -3,7 +3,7 @@
 //   Ray::containsCell / Ray::updateSumI_ML<T>                                            (RMCRT/Ray.cc:1578-1586, 2349-2627)
 // cut out of the reference tree at build time by oracle/extract_ref.py into oracle/_ref/ref_rmcrt_extracted.inc, together with the
 // reference's own Core/Math/MersenneTwister.h (-I/root/reference/src), into oracle/_ref/libref_rmcrt.so (git-ignored, travels to the
-// GPU box).  tests/test_oracle_ref.py compares the oracle's restatement with these bit for bit.
+// GPU box) and, with -DRAY_SCATTER (the reference's --enable-ray-scatter configuration), into oracle/_ref/libref_rmcrt_scatter.so.  tests/test_oracle_ref.py compares the oracle's restatement with these bit for bit.
 //
 // What is NOT the reference's here: the value types below.  The reference's functions use a handful of members of IntVector, Vector,
 // Point, BBox, Level, constCCVariable and InternalError; the real classes pull in the whole Core library (and MPI through the grid),
@@ -179,6 +179,7 @@ void setStatics(const oracle_params* p) {
   RMCRTCommon::d_allowReflect = p->allowReflect != 0;
   RMCRTCommon::d_isSeedRandom = p->isSeedRandom != 0;
   RMCRTCommon::d_maxRayLength = (p->maxRayLength > 0 && p->maxRayLength < 1e300) ? p->maxRayLength : DBL_MAX;
+  RMCRTCommon::d_sigmaScat = p->sigmaScat;
 }
 void fillLevel(const oracle_level& s, int index, Level& L) {
   L.index = index;
@@ -190,7 +191,7 @@ template <class T> void fillVar(const oracle_level& s, const void* ptr, constCCV
 }
 template <class T>
 void updateSumI_T(const oracle_params* p, const oracle_level* lv, const double dir[3], const double rayOrigin[3], const int cell[3], double* sumI,
-                  uint64_t* nSteps) {
+                  uint64_t* nSteps, uint32_t mtSeed = 5489u) {
   Ray ray;
   ray.d_flowCell = p->flowCell;
   Level L;
@@ -204,7 +205,7 @@ void updateSumI_T(const oracle_params* p, const oracle_level* lv, const double d
   const Vector Dx(lv->dx[0], lv->dx[1], lv->dx[2]);
   unsigned long int n = 0;
   double s = 0;
-  MTRand mt;
+  MTRand mt(mtSeed);
   ray.updateSumI<T>(&L, d, o, IntVector(cell[0], cell[1], cell[2]), Dx, sig, abskg, ct, n, s, mt);
   *sumI = s; *nSteps = n;
 }
@@ -252,6 +253,25 @@ int ref_updateSumI(const oracle_params* p, const oracle_level* lv, const double 
     else             updateSumI_T<double>(p, lv, dir, rayOrigin, originCell, sumI, nRaySteps);
   } catch (const InternalError&) { return 1; }
   return 0;
+}
+
+// the same with the generator seeded (scatter builds draw from it inside the march)
+int ref_updateSumI_seeded(const oracle_params* p, const oracle_level* lv, const double dir[3], const double rayOrigin[3], const int originCell[3],
+                          uint32_t mtSeed, double* sumI, uint64_t* nRaySteps) {
+  setStatics(p);
+  try {
+    if (lv->isFloat) updateSumI_T<float>(p, lv, dir, rayOrigin, originCell, sumI, nRaySteps, mtSeed);
+    else             updateSumI_T<double>(p, lv, dir, rayOrigin, originCell, sumI, nRaySteps, mtSeed);
+  } catch (const InternalError&) { return 1; }
+  return 0;
+}
+// 1 when this library was compiled with -DRAY_SCATTER (the reference's --enable-ray-scatter build)
+int ref_has_ray_scatter(void) {
+#ifdef RAY_SCATTER
+  return 1;
+#else
+  return 0;
+#endif
 }
 
 int ref_updateSumI_ML(const oracle_params* p, const oracle_level* levels, int maxLevels, const int roiLo[3], const int roiHi[3], const int* regionLo,

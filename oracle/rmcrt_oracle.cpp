@@ -161,9 +161,12 @@ const double FUZZ = 1e-12;  // RMCRT/RMCRTCommon.cc:49
 //----------------------------------------------------------------------------------------
 // RMCRTCommon::updateSumI<T>  (RMCRT/RMCRTCommon.cc:607-904), no RAY_SCATTER
 //----------------------------------------------------------------------------------------
+inline void findRayDirection(MT& mt, const oracle_params& P, const int origin[3], int iRay, double dir[3]);
+
+// mt: the task's generator; only used by the RAY_SCATTER code (P.sigmaScat > 0), which draws from it inside the march
 template <class T>
 void updateSumI(const oracle_params& P, const LevelT<T>& lv, double dir[3], const double rayOrigin[3],
-                const int origin[3], uint64_t& nSteps, double& sumI, PathRec* rec) {
+                const int origin[3], uint64_t& nSteps, double& sumI, PathRec* rec, MT* mt = nullptr) {
   int cur[3] = {origin[0], origin[1], origin[2]};
   int prev[3] = {cur[0], cur[1], cur[2]};
   int step[3];
@@ -184,6 +187,12 @@ void updateSumI(const oracle_params& P, const LevelT<T>& lv, double dir[3], cons
   double tMaxPrev = 0, intensity = 1.0, fs = 1.0;
   double tau = 0, expPrev = 1.0;
   double rayLength = 0.0;            // 666
+  // RAY_SCATTER (670-676): the free path to the first scattering event
+  const bool scatter = P.sigmaScat > 0 && mt != nullptr;
+  double rayLengthScatter = 0.0;     // 665
+  double loc[3] = {rayOrigin[0], rayOrigin[1], rayOrigin[2]};   // ray_location (667)
+  const double scatCoeff = std::max(P.sigmaScat, 1e-99);
+  double scatLength = scatter ? -std::log(mt->randDblExc()) / scatCoeff : 0.0;
 
   while (intensity > P.threshold && rayLength < P.maxRayLength) {  // 680
     int ax = -9;
@@ -198,6 +207,8 @@ void updateSumI(const oracle_params& P, const LevelT<T>& lv, double dir[3], cons
       tMax[ax] += tDelta[ax];
       if (ds > -FUZZ && ds < FUZZ) ds += FUZZ;  // 717-720
       rayLength += ds;                     // 723
+      rayLengthScatter += ds;              // 724
+      for (int d = 0; d < 3; ++d) loc[d] = loc[d] + (ds * dir[d]);   // 726-728
       inDomain = (lv.cellType(cur) == P.flowCell);   // 729
       tau += kPrev * ds;                   // 731
       ++nSteps;                            // 733
@@ -205,6 +216,23 @@ void updateSumI(const oracle_params& P, const LevelT<T>& lv, double dir[3], cons
       const double e = std::exp(-tau);     // 782
       sumI += sPrev * (expPrev - e) * fs;  // 786
       expPrev = e;
+      if (scatter && rayLengthScatter > scatLength && inDomain) {        // 790-836
+        scatLength = -std::log(mt->randDblExc()) / scatCoeff;            // a new free path for every event
+        findRayDirection(*mt, P, cur, -9, dir);                          // findRayDirection(mTwister, cur): iRay defaults to -9
+        for (int d = 0; d < 3; ++d) inv[d] = 1.0 / dir[d];
+        const int stepOld = step[ax];
+        signStep(dir, sign, step);
+        if (step[ax] * stepOld < 0) { cur[0] = prev[0]; cur[1] = prev[1]; cur[2] = prev[2]; }   // back scattering: return to prevCell
+        double ccs[3];
+        lv.cellPosition(cur, ccs);
+        for (int d = 0; d < 3; ++d) {
+          const double rayDx = loc[d] - (ccs[d] - 0.5 * lv.dx[d]);
+          tMax[d] = (sign[d] * lv.dx[d] - rayDx) * inv[d];
+          tDelta[d] = std::fabs(inv[d]) * lv.dx[d];
+        }
+        tMaxPrev = 0;
+        rayLengthScatter = 0;              // allow for multiple scattering events per ray
+      }
     }
     T wallEps = lv.abskg(cur);             // 846
     if (wallEps > 1.0) wallEps = 1.0;
@@ -469,7 +497,7 @@ void rayTracePatch(const oracle_params& P, const LevelT<T>& lv, const int pLo[3]
           if (lhc) rayDirectionHyperCubeCellFace(mt, P, origin, rayFace, iRay, dir, cosT, rand_i[iRay], iRay);   // 692-695
           else rayDirectionCellFace(mt, P, origin, rayFace, iRay, dir, cosT);
           rayLocationCellFace(mt, rayFace, lv.dx, cc, o);
-          updateSumI<T>(P, lv, dir, o, origin, nFluxSteps, sumI, nullptr);
+          updateSumI<T>(P, lv, dir, o, origin, nFluxSteps, sumI, nullptr, &mt);
           sumProjI += cosT * (sumI - sumIprev);  // 704
           sumCos += cosT;
           sumIprev = sumI;
@@ -493,7 +521,7 @@ void rayTracePatch(const oracle_params& P, const LevelT<T>& lv, const int pLo[3]
         if (lhc) findRayDirectionHyperCube(mt, P, origin, iRay, rand_i[iRay], iRay, dir);   // 760-761
         else findRayDirection(mt, P, origin, iRay, dir);
         rayOriginInCell(mt, cc, lv.dx, P.CCRays != 0, o);
-        updateSumI<T>(P, lv, dir, o, origin, nSteps, sumI, nullptr);
+        updateSumI<T>(P, lv, dir, o, origin, nSteps, sumI, nullptr, &mt);
       }
       const int64_t q = ow.idx(origin);
       divQ[q] = -4.0 * M_PI * lv.abskg(origin) * (lv.sigmaT4(origin) - (sumI / P.nDivQRays));  // 775
@@ -550,7 +578,7 @@ void radiometerPatch(const oracle_params& P, const LevelT<T>& lv, const oracle_r
         double o[3], dir[3], cosVR;
         rayOriginInCell(mt, cc, lv.dx, true, o);        // useCCRays = true (472-473)
         rayDirectionVR(mt, P, c, iRay, rad, dir, cosVR);
-        updateSumI<T>(P, lv, dir, o, c, nSteps, sumI, nullptr);
+        updateSumI<T>(P, lv, dir, o, c, nSteps, sumI, nullptr, &mt);
         sumProjI += cosVR * (sumI - sumIprev);          // 483
         sumIprev = sumI;
       }
@@ -574,6 +602,7 @@ void oracle_default_params(oracle_params* p) {
   p->dataOnionFluxFlowGuard = 0;
   p->rayDirSampleAlgo = 0;
   p->maxRayLength = DBL_MAX;   // RMCRTCommon.cc:117
+  p->sigmaScat = 0;
 }
 
 // Radiometer::problemSetup (Radiometer.cc:214-260)
@@ -1022,6 +1051,19 @@ void oracle_generate_rays(const oracle_params* p, const oracle_level* lv, const 
     findRayDirection(mt, *p, cell, i, dirs + 3 * i);
     rayOriginInCell(mt, cc, lv->dx, p->CCRays != 0, origins + 3 * i);
   }
+}
+
+// one ray with the task generator in a known state (RAY_SCATTER draws from it inside the march): MT seeded with mtSeed
+void oracle_updateSumI_seeded(const oracle_params* p, const oracle_level* lv, const double dir[3], const double rayOrigin[3],
+                              const int originCell[3], uint32_t mtSeed, double* sumI, uint64_t* nRaySteps) {
+  double d[3] = {dir[0], dir[1], dir[2]};
+  uint64_t n = 0;
+  double s = 0;
+  MT mt(p->fixedRandom != 0);
+  mt.seed(mtSeed);
+  if (lv->isFloat) { LevelT<float> L(*lv); updateSumI<float>(*p, L, d, rayOrigin, originCell, n, s, nullptr, &mt); }
+  else             { LevelT<double> L(*lv); updateSumI<double>(*p, L, d, rayOrigin, originCell, n, s, nullptr, &mt); }
+  *sumI = s; *nRaySteps = n;
 }
 
 }  // extern "C"

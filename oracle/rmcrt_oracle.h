@@ -48,6 +48,8 @@ typedef struct oracle_params {
   int    dataOnionFluxFlowGuard; /* 0 = reference (Ray.cc:1098-1107 has no flow-cell guard) */
   int    rayDirSampleAlgo;   /* Ray.cc:174-179: 0 NAIVE, 1 LATIN_HYPER_CUBE */
   double maxRayLength;       /* RMCRTCommon.cc:117 DBL_MAX; <ROI_extents type="boundedRayLength"><length> (Ray.cc:243) */
+  double sigmaScat;          /* <sigmaScat> (Ray.cc:169): > 0 = a RAY_SCATTER build with isotropic scattering (RMCRTCommon.cc:670-676,
+                                790-836); 0 = the stock build (no scattering code, no extra random draws) */
 } oracle_params;
 
 /* one <Radiometer> block after Radiometer::problemSetup (Radiometer.cc:96-271, Radiometer.h:117-127) */
@@ -161,6 +163,10 @@ void oracle_arches_stencilToDBLs(const double* boundFlux7, int64_t n, double* E,
 /* ---- ray generation of the divQ loop (Ray.cc:752-760): findRayDirection + ray_Origin for rays 0..nRays-1 of one cell ---- */
 void oracle_generate_rays(const oracle_params* p, const oracle_level* lv, const int cell[3], int nRays, uint32_t mtSeed,
                           double* dirs /*[nRays][3]*/, double* origins);
+
+/* one ray with the generator seeded with mtSeed (the RAY_SCATTER code of updateSumI draws from it inside the march) */
+void oracle_updateSumI_seeded(const oracle_params* p, const oracle_level* lv, const double dir[3], const double rayOrigin[3],
+                              const int originCell[3], uint32_t mtSeed, double* sumI, uint64_t* nRaySteps);
 
 #ifdef __cplusplus
 }

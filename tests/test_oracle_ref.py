@@ -110,3 +110,48 @@ def test_divQ_loop_bit_exact(po, ref, dtype, seed_random):
     b = po.ray_trace(p, lv, seed=5, patches=(1, 2, 2), threads=4)
     assert a["steps"] == b["steps"] and a["steps"] > 1e5
     assert np.array_equal(a["divQ"], b["divQ"]) and np.array_equal(a["radiationVolq"], b["radiationVolq"])
+
+
+# ---------------------------------------------------------------- isotropic scattering: the reference's --enable-ray-scatter build
+@pytest.fixture(scope="module")
+def ref_scatter(po):
+    lib = po.ref_scatter_lib()
+    if lib is None:
+        pytest.skip("oracle/_ref/libref_rmcrt_scatter.so was not built (no reference tree at build time)")
+    assert lib.ref_has_ray_scatter() == 1 and po.ref_lib().ref_has_ray_scatter() == 0
+    return lib
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("kw", [dict(sigmaScat=1.0, threshold=0.05), dict(sigmaScat=8.0, threshold=0.01, isSeedRandom=0),
+                                dict(sigmaScat=3.0, threshold=0.02, allowReflect=0), dict(sigmaScat=25.0, threshold=0.01, maxRayLength=0.6)])
+def test_scattering_rays_bit_exact(po, ref_scatter, dtype, kw):
+    """RMCRTCommon::updateSumI<T> compiled with RAY_SCATTER (RMCRTCommon.cc:670-676, 790-836): free-path draws, re-direction (with the
+    per-event MT reseed (i+j+k)*(-9)+1 of the regression mode), back scattering into prevCell, tMax rebuilt from the ray location"""
+    rng = np.random.default_rng(17)
+    p = po.default_params(**kw)
+    scattered = 0
+    for name, lv in cases(po, dtype).items():
+        cells, dirs, orgs = random_rays(lv, 400, rng)
+        for n_, (c, d, o) in enumerate(zip(cells, dirs, orgs)):
+            if lv.cellType[c[2] - lv.lo[2], c[1] - lv.lo[1], c[0] - lv.lo[0]] != -1:
+                continue
+            s_ref, n_ref = po.update_sumI_seeded(p, lv, d, o, c, 100 + n_, reference=ref_scatter)
+            s, n = po.update_sumI_seeded(p, lv, d, o, c, 100 + n_)
+            assert n == n_ref and s == s_ref, (name, c, d, n, n_ref, s, s_ref)
+            p0 = po.default_params(**{**kw, "sigmaScat": 0.0})
+            scattered += (po.update_sumI(p0, lv, d, o, c)[1] != n)
+    assert scattered > 200          # scattering really changed the paths
+
+
+@pytest.mark.parametrize("seed_random", [1, 0])
+def test_scattering_divQ_loop_bit_exact(po, ref_scatter, seed_random):
+    """RMCRT_isoScat.ups pattern (benchmark 1, sigmaScat 1): whole-patch divQ with the reference's scatter build == the oracle"""
+    lv = po.burns_christon(13)
+    p = po.default_params(nDivQRays=5, threshold=0.05, isSeedRandom=seed_random, sigmaScat=1.0)
+    a = po.ref_ray_trace(p, lv, seed=9, patches=(1, 1, 2), threads=2, library=ref_scatter)
+    b = po.ray_trace(p, lv, seed=9, patches=(1, 1, 2), threads=2)
+    assert a["steps"] == b["steps"]
+    assert np.array_equal(a["divQ"], b["divQ"]) and np.array_equal(a["radiationVolq"], b["radiationVolq"])
+    c = po.ray_trace(po.default_params(nDivQRays=5, threshold=0.05, isSeedRandom=seed_random), lv, seed=9, patches=(1, 1, 2), threads=2)
+    assert c["steps"] != b["steps"]
