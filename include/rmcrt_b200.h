@@ -83,6 +83,11 @@ typedef struct rmcrt_params {
   double   maxRayLength;       /* <ROI_extents type="boundedRayLength"><length> (Ray.cc:243, RMCRTCommon.cc:680,684);
                                   <= 0 or >= 1e300: unbounded (DBL_MAX, RMCRTCommon.cc:117).  Single-level solves only, like
                                   the reference (updateSumI_ML has no length test) */
+  double   sigmaScat;          /* <sigmaScat> 0 (Ray.cc:169).  > 0: isotropic scattering, the code the reference compiles with
+                                  --enable-ray-scatter (RAY_SCATTER; RMCRTCommon.cc:670-676, 790-836): exponentially distributed free
+                                  paths, a new isotropic direction per event.  Single-level divQ and boundary-flux rays; runs through
+                                  the generic march kernels.  Multi-level solves ignore it like the reference (no scattering code in
+                                  Ray::updateSumI_ML). */
 } rmcrt_params;
 
 /* One <Radiometer> block after Radiometer::problemSetup (Radiometer.cc:96-271; struct radiometer, Radiometer.h:117-127) */

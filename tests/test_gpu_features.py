@@ -266,3 +266,70 @@ def test_arches_property_tasks_match_oracle(gpu_lib, po, dtype):
     for k in "EWNSTB":
         assert np.array_equal(o6[k], r6[k])
     assert np.array_equal(o6["E"], bf[..., 1]) and np.array_equal(o6["B"], bf[..., 4])
+
+
+# ---------------------------------------------------------------- isotropic scattering (<sigmaScat> > 0; RMCRT_isoScat.ups)
+@pytest.mark.parametrize("mode", ["reseed", "fixed", "reseed_float_lhc"])
+def test_scattering_deterministic_matches_oracle(gpu_lib, po, mode):
+    """RMCRT_isoScat.ups / RMCRT_isoScat_LHC pattern in the regression modes: divQ and boundary fluxes of the FP64 scattering march against
+    the oracle (itself bit-exact against the reference's --enable-ray-scatter build, tests/test_oracle_ref.py)"""
+    dtype = np.float32 if "float" in mode else np.float64
+    lv = po.burns_christon(15, dtype=dtype)
+    add = dict(fixedRandom=1) if mode == "fixed" else {}
+    lhc = dict(rayDirSampleAlgo=1) if "lhc" in mode else {}
+    kw = dict(nDivQRays=4, nFluxRays=6, threshold=0.05, isSeedRandom=0, solveBoundaryFlux=1, sigmaScat=2.0, **add, **lhc)
+    ref = po.ray_trace(po.default_params(**kw), lv)
+    g = make(gpu_lib, marchPrecision=1, skipZeroWeightLegs=0, **kw)
+    g.upload_level(0, lv)
+    out = g.trace_divq(0)
+    c = g.counters()
+    # libm vs CUDA log / sincos differ in the last bits: a DDA tie can flip for a few rays out of 2e4
+    assert abs(int(c.nRaySteps) - ref["steps"]) <= 2e-4 * ref["steps"], (c.nRaySteps, ref["steps"])
+    assert abs(int(c.nFluxRaySteps) - ref["fluxSteps"]) <= 2e-4 * ref["fluxSteps"]
+    scale = np.abs(ref["divQ"]).max()
+    bad = np.abs(out["divQ"] - ref["divQ"]) > 1e-9 * scale
+    assert bad.mean() < 2e-3, bad.mean()
+    assert np.array_equal(out["boundFlux"][..., 6], ref["boundFlux"][..., 6])
+    fb = np.abs(out["boundFlux"][..., :6] - ref["boundFlux"][..., :6]) > 1e-9 * np.abs(ref["boundFlux"][..., :6]).max()
+    assert fb.mean() < 2e-3
+    # scattering really happened: the same solve without it marches a different number of steps
+    p0 = po.default_params(**{**kw, "sigmaScat": 0.0})
+    assert po.ray_trace(p0, lv)["steps"] != ref["steps"]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_scattering_production_properties(gpu_lib, po, dtype):
+    """Philox rays: (i) isotropic scattering cannot change the radiation field of an isothermal black enclosure: divQ == 0 to round-off
+    whatever sigmaScat is; (ii) Burns & Christon with scattering agrees with the oracle's scattering solve within Monte-Carlo error and
+    differs from the non-scattering solution"""
+    N = 24
+    rng = np.random.default_rng(4)
+    M = N + 2
+    ab = rng.uniform(0.1, 2.0, (M, M, M)).astype(dtype)
+    s4 = np.full((M, M, M), 0.6, dtype)
+    ct = np.full((M, M, M), -1, np.int32)
+    for ax in range(3):
+        for idx in (0, M - 1):
+            sl = [slice(None)] * 3; sl[ax] = idx
+            ct[tuple(sl)] = 8; ab[tuple(sl)] = 1.0
+    iso = po.Level(ab, s4, ct, (-1,) * 3, (N + 1,) * 3, (1.0 / N,) * 3, interior_lo=(0,) * 3, interior_hi=(N,) * 3)
+    g = make(gpu_lib, nDivQRays=8, threshold=0.001, seed=5, allowReflect=0, sigmaScat=6.0)
+    g.upload_level(0, iso)
+    out = g.trace_divq(0)
+    assert np.abs(out["divQ"]).max() < 2e-5 * 4 * np.pi * 2.0 * 0.6          # FP32 production march whatever the property type
+    n_scat = g.counters().nRaySteps
+    g0 = make(gpu_lib, nDivQRays=8, threshold=0.001, seed=5, allowReflect=0)
+    g0.upload_level(0, iso); g0.trace_divq(0)
+    assert n_scat != g0.counters().nRaySteps
+    # Burns & Christon, sigmaScat = 3
+    lv = po.burns_christon(21, dtype=dtype)
+    p = po.default_params(nDivQRays=60, threshold=0.01, sigmaScat=3.0)
+    runs = [po.ray_trace(p, lv, seed=10 * s, patches=(1, 1, 7), threads=7)["divQ"] for s in range(1, 5)]
+    mu = np.mean(runs, 0)
+    spread = max(np.linalg.norm(r - mu) / np.linalg.norm(mu) for r in runs)
+    gs = make(gpu_lib, nDivQRays=60, threshold=0.01, seed=8, sigmaScat=3.0, rayCoherence=0)
+    gs.upload_level(0, lv)
+    d = gs.trace_divq(0)["divQ"]
+    assert np.linalg.norm(d - mu) / np.linalg.norm(mu) < 1.5 * spread, (np.linalg.norm(d - mu) / np.linalg.norm(mu), spread)
+    noscat = po.ray_trace(po.default_params(nDivQRays=60, threshold=0.01), lv, seed=3, patches=(1, 1, 7), threads=7)["divQ"]
+    assert np.linalg.norm(noscat - mu) / np.linalg.norm(mu) > 2 * spread          # scattering is a visible effect at this optical thickness

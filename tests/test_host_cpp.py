@@ -86,7 +86,6 @@ def test_data_onion_schedule(exe):
 
 
 @pytest.mark.parametrize("edit,needle", [
-    (("<nDivQRays>          3          </nDivQRays>", "<nDivQRays> 3 </nDivQRays> <sigmaScat> 0.5 </sigmaScat>"), "--enable-ray-scatter"),
     (("<periodic> [0,0,0] </periodic>", "<periodic> [1,0,0] </periodic>"), "Periodic boundary conditions are not allowed"),
     (("<extraCells> [1,1,1]   </extraCells>", "<extraCells> [0,0,0] </extraCells>"), "one extraCell"),
     (('<BCType id="0" label="abskg"    var="Dirichlet"> <value> 1.0 </value> </BCType>', ""), "boundary condition for (abskg)"),
@@ -401,3 +400,22 @@ def test_wasatch_caller_modifies_divQ(exe, po, tmp_path, gpu_lib):
     assert (out["divQ"][~flow] == 123.0).all() and (out["radiationVolq"][~flow] == -7.0).all()      # untouched (Ray.cc:573-580)
     np.testing.assert_allclose(out["RMCRTboundFlux"], ref["boundFlux"], rtol=1e-9, atol=0)
     assert out["report"]["nRaySteps"] == ref["steps"] and out["report"]["nFluxRaySteps"] == ref["fluxSteps"]
+
+
+@pytest.mark.gpu
+def test_isotropic_scattering_deck(exe, po, tmp_path, gpu_lib):
+    """RMCRT_isoScat.ups pattern through the plugin: <sigmaScat> 1, boundary fluxes, <randomSeed> false.  The stock reference needs a
+    --enable-ray-scatter build for this deck; here the scattering march is selected at run time"""
+    deck = edit_deck(tmp_path, "bm1_1L_double.ups",
+                     ("<nDivQRays>          3          </nDivQRays>", "<nDivQRays> 3 </nDivQRays> <sigmaScat> 1 </sigmaScat> <nFluxRays> 5 </nFluxRays>"),
+                     ("<solveBoundaryFlux>  false      </solveBoundaryFlux>", "<solveBoundaryFlux> true </solveBoundaryFlux>"))
+    r = subprocess.run([exe, deck, "--dump", str(tmp_path / "d"), "--knob", "skipZeroWeightLegs=0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "Ray scattering is enabled" in r.stdout
+    out = load_dump(str(tmp_path / "d"))
+    lv = po.burns_christon(21)
+    ref = po.ray_trace(po.default_params(nDivQRays=3, nFluxRays=5, threshold=0.05, isSeedRandom=0, solveBoundaryFlux=1, sigmaScat=1.0), lv)
+    assert abs(out["report"]["nRaySteps"] - ref["steps"]) <= 2e-4 * ref["steps"]
+    bad = np.abs(out["divQ"] - ref["divQ"]) > 1e-9 * np.abs(ref["divQ"]).max()
+    assert bad.mean() < 2e-3
+    assert np.array_equal(out["RMCRTboundFlux"][..., 6], ref["boundFlux"][..., 6])

@@ -13,6 +13,8 @@
 #pragma once
 #include <cstdint>
 #include <cmath>
+#include <cfloat>
+#include "rng.cuh"
 #if defined(__CUDACC__)
 #include <cuda_fp16.h>
 #endif
@@ -186,6 +188,118 @@ __device__ __forceinline__ Real march_single_level(const RecT* __restrict__ recs
     if (px) stx = -stx; else if (py) sty = -sty; else stz = -stz;
     if (RECORD) { if (px) ci += (stx > 0 ? 1 : -1); else if (py) cj += (sty > 0 ? 1 : -1); else ck += (stz > 0 ? 1 : -1); }
     if (skipZero && fs == Real(0)) break;                 // exact: every later term carries fs==0 or a zero wall emission
+    r = ldrec(recs + idx);
+    k = absr(r.k);
+    s = r.s;
+  }
+  nSteps += steps;
+  return sum;
+}
+
+//------------------------------------------------------------------------------------------------------
+// single level with isotropic scattering: RMCRTCommon::updateSumI<T> as compiled with RAY_SCATTER (--enable-ray-scatter),
+// RMCRTCommon.cc:670-676 and 790-836 on top of the march above.  Absorption still uses abskg only; a scattering event re-draws the
+// direction, puts the ray back into the previous cell if the stepping axis flipped, and rebuilds tMax / tDelta from the ray's
+// ABSOLUTE location in the (new) current cell -- which is why this variant tracks cell indices and the location like the reference
+// does.  Lengths are physical here (tMax carries LEN_SCALE only where it multiplies abskg).  Generic template, not the PTX fast path.
+//   org : absolute ray origin;  anchor/cdx : Level::getCellPosition data;  sigmaScat > 0
+template <class Real, class RecT>
+__device__ __forceinline__ Real march_single_level_scatter(const RecT* __restrict__ recs, long long idx, int sy, int sz, int ci, int cj, int ck,
+                                                           const double dir0[3], const double org[3], const double anchor[3],
+                                                           const double cdx[3], Real threshold, bool allowReflect, unsigned& nSteps,
+                                                           Real maxLen, bool floatProps, double sigmaScat, ScatRng& rng) {
+  typedef Num<Real> N;
+  typedef Num<double> D;
+  if (!(Real(1) > threshold) || !(Real(0) < maxLen)) return Real(0);
+  const Real LS = N::LEN_SCALE;
+  double dir[3] = {dir0[0], dir0[1], dir0[2]};
+  double loc[3] = {org[0], org[1], org[2]};                       // ray_location (667)
+  int c[3] = {ci, cj, ck};
+  int st[3];
+  double sgn[3];
+  Real t[3], dd[3];
+  // tMax / tDelta from the location inside cell c (643-655 at the start, 812-822 after an event); geometry in FP64 like the reference
+  auto setup = [&]() {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const bool pos = !sign_bit(dir[d]);
+      st[d] = pos ? 1 : -1;
+      sgn[d] = pos ? 1.0 : 0.0;
+      const double inv = D::rcp(dir[d]);
+      const double cc = D::add(D::add(anchor[d], D::mul(cdx[d], (double)c[d])), D::mul(cdx[d], 0.5));   // Level.cc:473-477
+      const double rayDx = D::add(loc[d], -D::add(cc, -D::mul(0.5, cdx[d])));
+      t[d] = (Real)D::mul(D::add(D::mul(sgn[d], cdx[d]), -rayDx), inv) * LS;
+      dd[d] = (Real)D::mul(fabs(inv), cdx[d]) * LS;
+    }
+  };
+  setup();
+  const double scatCoeff = sigmaScat > 1e-99 ? sigmaScat : 1e-99;
+  double scatLength = -log(rng.open01()) / scatCoeff;            // 675
+  double lenScatter = 0.0;
+  Real tPrev = 0, tau = 0, ePrev = 1, sum = 0, fs = 1, len = 0;
+  typename RecInfo<RecT>::decoded r = ldrec(recs + idx);
+  Real k = absr(r.k), s = r.s;
+  unsigned steps = 0;
+  for (;;) {
+    long long idxPrev;
+    int ax, cPrev;
+    Real e;
+    do {
+      idxPrev = idx;
+      ax = (t[0] < t[1]) ? ((t[0] < t[2]) ? 0 : 2) : ((t[1] < t[2]) ? 1 : 2);        // 696-708
+      const Real tNext = ax == 0 ? t[0] : (ax == 1 ? t[1] : t[2]);
+      cPrev = ax == 0 ? c[0] : (ax == 1 ? c[1] : c[2]);
+      if (ax == 0) { c[0] += st[0]; idx += st[0]; } else if (ax == 1) { c[1] += st[1]; idx += st[1] * (long long)sy; } else { c[2] += st[2]; idx += st[2] * (long long)sz; }
+      r = ldrec(recs + idx);
+      Real ds = N::add(tNext, -tPrev);
+      tPrev = tNext;
+      if (ax == 0) t[0] = N::add(t[0], dd[0]); else if (ax == 1) t[1] = N::add(t[1], dd[1]); else t[2] = N::add(t[2], dd[2]);
+      ds = N::fuzz(ds);
+      len = N::add(len, ds);
+      const double dsPhys = (double)ds / (double)LS;
+      lenScatter = D::add(lenScatter, dsPhys);                     // 724
+#pragma unroll
+      for (int d = 0; d < 3; ++d) loc[d] = D::add(loc[d], D::mul(dsPhys, dir[d]));    // 726-728
+      tau = N::add(tau, N::mul(k, ds));
+      ++steps;
+      e = N::attenuation(tau);
+      sum = N::add(sum, N::mul(N::mul(s, N::add(ePrev, -e)), fs));
+      ePrev = e;
+      k = absr(r.k);
+      s = r.s;
+      if (lenScatter > scatLength && !is_wall(r.k)) {              // 790: a scattering event inside the flow cell just entered
+        scatLength = -log(rng.open01()) / scatCoeff;
+        rng.reseedAt(c[0], c[1], c[2]);
+        const double pm1 = 2.0 * rng.open01() - 1.0 + DBL_EPSILON;  // findRayDirection (517-530)
+        const double rr = sqrt(1.0 - pm1 * pm1);
+        const double theta = 2.0 * M_PI * rng.open01();
+        double sn, cs;
+        sincos(theta, &sn, &cs);
+        const int stepOld = ax == 0 ? st[0] : (ax == 1 ? st[1] : st[2]);
+        dir[0] = rr * cs; dir[1] = rr * sn; dir[2] = pm1;
+        const bool posA = !sign_bit(ax == 0 ? dir[0] : (ax == 1 ? dir[1] : dir[2]));
+        if ((posA ? 1 : -1) * stepOld < 0) {                       // 803-807: back scattering, the ray returns to prevCell
+          if (ax == 0) c[0] = cPrev; else if (ax == 1) c[1] = cPrev; else c[2] = cPrev;
+          idx = idxPrev;
+          r = ldrec(recs + idx);
+          k = absr(r.k);
+          s = r.s;
+        }
+        setup();
+        tPrev = 0;                                                 // 833
+        lenScatter = 0.0;                                          // 834
+      }
+    } while (!is_wall(r.k) && len < maxLen);
+    const Real eps = k > Real(1) ? Real(1) : k;
+    Real intensity = e;
+    sum = N::add(sum, N::mul(N::wall_product(eps, s, floatProps), intensity));
+    intensity = N::mul(intensity, fs);
+    if (!allowReflect || !(intensity > threshold) || !(len < maxLen)) break;
+    fs = N::mul(fs, N::add(Real(1), -k));                          // reflect (581-602)
+    idx = idxPrev;
+    if (ax == 0) { c[0] = cPrev; st[0] = -st[0]; sgn[0] = -sgn[0]; dir[0] = -dir[0]; }
+    else if (ax == 1) { c[1] = cPrev; st[1] = -st[1]; sgn[1] = -sgn[1]; dir[1] = -dir[1]; }
+    else { c[2] = cPrev; st[2] = -st[2]; sgn[2] = -sgn[2]; dir[2] = -dir[2]; }
     r = ldrec(recs + idx);
     k = absr(r.k);
     s = r.s;

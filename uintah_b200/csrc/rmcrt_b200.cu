@@ -73,6 +73,7 @@ struct TraceArgs {
   int allowReflect;
   int skipZero;
   int fluxFlowGuard;      // 1L: only flow cells get boundary fluxes (Ray.cc:654-656); DO: no guard (Q3)
+  double sigmaScat;       // <sigmaScat>: > 0 = isotropic scattering in the single-level march (generic kernels)
   RayGen rng;
   unsigned long long* counters;   // [0] divQ steps [1] flux steps [2] divQ cells [3] flux cells
   const unsigned* lstat;          // per-level device status words [MAXL][LSTAT_WORDS] (see finalize_kernel)
@@ -119,7 +120,7 @@ __device__ __forceinline__ int lhc_bin(const RayGen& rg, int i, int j, int k, in
 // cellId / dirId : Philox counters (the cell itself; the warp tile's first cell when coherent).
 __device__ __forceinline__ void gen_divq_ray(const RayGen& rg, const LevelGeom& g, int i, int j, int k, int ray, int nRays,
                                              unsigned long long cellId, unsigned long long dirId,
-                                             double dir[3], double rayDx[3]) {
+                                             double dir[3], double rayDx[3], double* org = nullptr) {
   double u1, u2, o0, o1, o2;
   if (rg.fixedRandom) {
     u1 = u2 = o0 = o1 = o2 = 0.3;
@@ -158,6 +159,7 @@ __device__ __forceinline__ void gen_divq_ray(const RayGen& rg, const LevelGeom& 
     const double cc = g.anchor[d] + g.dx[d] * c[d] + g.dx[d] * 0.5;
     const double o = rg.ccRays ? cc : (cc - 0.5 * g.dx[d] + off[d] * g.dx[d]);
     rayDx[d] = o - (cc - 0.5 * g.dx[d]);
+    if (org) org[d] = o;        // absolute ray origin (RMCRTCommon.cc:565-567), needed by the scattering march
   }
 }
 
@@ -187,7 +189,7 @@ __device__ __forceinline__ void gen_divq_ray_f32(const RayGen& rg, const LevelGe
 // face in push order of has_a_boundary: 0 W(-x) 1 E(+x) 2 S(-y) 3 N(+y) 4 B(-z) 5 T(+z) == Stencil7 slot.
 __device__ __forceinline__ void gen_flux_ray(const RayGen& rg, const LevelGeom& g, int i, int j, int k, int face, int ray,
                                              int nRays, unsigned long long cellId, unsigned long long dirId,
-                                             double dir[3], double rayDx[3], double& cosTheta) {
+                                             double dir[3], double rayDx[3], double& cosTheta, double* org = nullptr) {
   double u1, u2, p0, p1;
   double e1 = 0.3, e2 = 0.3;     // the (0,1) conversions of the same two words: the LHC variant draws randDblExc() (Ray.cc:1413,1416)
   if (rg.fixedRandom) {
@@ -241,7 +243,23 @@ __device__ __forceinline__ void gen_flux_ray(const RayGen& rg, const LevelGeom& 
     if (d == axisN) o = hiFace ? (c0 + g.dx[d]) : c0;
     else o = c0 + q[qi++] * g.dx[d];
     rayDx[d] = o - (cc - 0.5 * g.dx[d]);
+    if (org) org[d] = o;
   }
+}
+
+// the generator state a ray's scattering events start from (rng.cuh: ScatRng).  mtPos = MT19937 outputs the ray's own set-up has
+// consumed since its reseed (divQ: 2 direction + 3 origin draws, 2 with CCRays; boundary flux: 2 + 2); tag separates the
+// Philox counters of divQ rays (0) from the six flux faces.
+__device__ __forceinline__ ScatRng scat_rng(const RayGen& rg, int i, int j, int k, int ray, unsigned long long cellId, int mtPos, uint32_t tag) {
+  ScatRng r;
+  r.mode = rg.fixedRandom ? 2 : (rg.isSeedRandom ? 0 : 1);
+  r.key0 = rg.key0; r.key1 = rg.key1;
+  r.c0 = (uint32_t)cellId; r.c2 = rg.timestep; r.c3 = ((uint32_t)(cellId >> 32) << 8) | STREAM_SCATTER;
+  r.ray = (uint32_t)ray | tag;
+  r.draw = 0;
+  r.mtSeed = (uint32_t)((i + j + k) * ray + 1);
+  r.mtPos = mtPos;
+  return r;
 }
 
 // zero-weight legs may be skipped only when every level in play has been finalized and none of its non-flow cells emits
@@ -262,7 +280,7 @@ __device__ __forceinline__ Real nz(D v) {   // direction component as Real, neve
 
 template <class Real, class RecT, bool ML, bool RECORD, bool FAST = false, class D = double>
 __device__ __forceinline__ Real trace_one(const TraceArgs& a, bool skipZero, int i, int j, int k, const D dir[3], const D rayDx[3],
-                                          unsigned& steps, PathSink* path) {
+                                          unsigned& steps, PathSink* path, ScatRng* srng = nullptr, const double* org = nullptr) {
   const int F = a.G.maxLevels - 1;
   const LevelGeom& g = a.G.lev[F];
   constexpr Real UNSCALE = (Real)RecInfo<RecT>::unscale;   // half-packed records carry sigmaT4/pi scaled by a power of two
@@ -285,6 +303,13 @@ __device__ __forceinline__ Real trace_one(const TraceArgs& a, bool skipZero, int
                                                        (Real)rayDx[0], (Real)rayDx[1], (Real)rayDx[2], (Real)a.threshold,
                                                        a.allowReflect != 0, skipZero, steps, path, a.floatProps != 0);
   } else {
+    if constexpr (std::is_same<D, double>::value) {
+      if (srng)     // <sigmaScat> > 0: isotropic scattering (the reference's RAY_SCATTER build), generic march only
+        return UNSCALE * march_single_level_scatter<Real, RecT>(static_cast<const RecT*>(g.rec), level_index(g, i, j, k), g.n[0], g.n[0] * g.n[1],
+                                                                i, j, k, dir, org, g.anchor, g.dx, (Real)a.threshold, a.allowReflect != 0, steps,
+                                                                (Real)(a.maxRayLength * (double)Num<Real>::LEN_SCALE), a.floatProps != 0,
+                                                                a.sigmaScat, *srng);
+    }
     return UNSCALE * march_single_level<Real, RecT, RECORD>(static_cast<const RecT*>(g.rec), level_index(g, i, j, k), g.n[0],
                                                   g.n[0] * g.n[1], nz<Real, D>(dir[0]), nz<Real, D>(dir[1]), nz<Real, D>(dir[2]),
                                                   (Real)rayDx[0], (Real)rayDx[1], (Real)rayDx[2], (Real)g.dx[0],
@@ -353,6 +378,15 @@ __global__ void __launch_bounds__(256, ((FAST && !ML) ? RMCRT_FAST_MIN_BLOCKS : 
       } else {
         for (int ray = warp; ray < a.nRays; ray += W) {      // regression modes (MT19937 reseed, FIXED_RANDOM_NUM) and the FP64 march
           double dir[3], rayDx[3];
+          if constexpr (!FAST && !ML) {
+            if (a.sigmaScat > 0) {
+              double org[3];
+              gen_divq_ray(a.rng, g, i, j, k, ray, a.nRays, cellId, dirId, dir, rayDx, org);
+              ScatRng srng = scat_rng(a.rng, i, j, k, ray, cellId, a.rng.ccRays ? 2 : 5, 0u);
+              acc += (double)trace_one<Real, RecT, ML, false, FAST>(a, skipZero, i, j, k, dir, rayDx, steps, nullptr, &srng, org);
+              continue;
+            }
+          }
           gen_divq_ray(a.rng, g, i, j, k, ray, a.nRays, cellId, dirId, dir, rayDx);
           acc += (double)trace_one<Real, RecT, ML, false, FAST>(a, skipZero, i, j, k, dir, rayDx, steps, nullptr);
         }
@@ -460,9 +494,21 @@ __global__ void __launch_bounds__(256) flux_trace_kernel(const __grid_constant__
     unsigned steps = 0;
     if (valid) {
       for (int ray = warp; ray < a.nRays; ray += W) {
-        double dir[3], rayDx[3], cosT;
-        gen_flux_ray(a.rng, g, i, j, k, face, ray, a.nRays, cellId, dirId, dir, rayDx, cosT);
-        const double dI = (double)trace_one<Real, RecT, ML, false, FAST>(a, skipZero, i, j, k, dir, rayDx, steps, nullptr);
+        double dir[3], rayDx[3], cosT, dI;
+        bool done = false;
+        if constexpr (!FAST && !ML) {
+          if (a.sigmaScat > 0) {
+            double org[3];
+            gen_flux_ray(a.rng, g, i, j, k, face, ray, a.nRays, cellId, dirId, dir, rayDx, cosT, org);
+            ScatRng srng = scat_rng(a.rng, i, j, k, ray, cellId, 4, (uint32_t)(face + 1) << 28);
+            dI = (double)trace_one<Real, RecT, ML, false, FAST>(a, skipZero, i, j, k, dir, rayDx, steps, nullptr, &srng, org);
+            done = true;
+          }
+        }
+        if (!done) {
+          gen_flux_ray(a.rng, g, i, j, k, face, ray, a.nRays, cellId, dirId, dir, rayDx, cosT);
+          dI = (double)trace_one<Real, RecT, ML, false, FAST>(a, skipZero, i, j, k, dir, rayDx, steps, nullptr);
+        }
         sumProj += cosT * dI;      // sumProjI += cosTheta * (sumI - sumI_prev)   (Ray.cc:704)
         sumCos += cosT;
       }
@@ -1072,6 +1118,7 @@ int validate_params(rmcrt_ctx* ctx, const rmcrt_params* p) {
   if (p->marchPrecision != 0 && p->marchPrecision != 1) return fail(ctx, RMCRT_ERR_INVALID, "marchPrecision must be 0 (fp32) or 1 (fp64)");
   if (p->rayDirSampleAlgo != 0 && p->rayDirSampleAlgo != 1) return fail(ctx, RMCRT_ERR_INVALID, "rayDirSampleAlgo must be 0 (naive) or 1 (LatinHyperCube)");
   if (p->maxRayLength != p->maxRayLength) return fail(ctx, RMCRT_ERR_INVALID, "maxRayLength is NaN");
+  if (!(p->sigmaScat >= 0)) return fail(ctx, RMCRT_ERR_INVALID, "sigmaScat must be >= 0");
   return 0;
 }
 
@@ -1300,14 +1347,19 @@ int build_args(rmcrt_ctx* ctx, int maxLevels, bool multiLevel, const int32_t pLo
     return fail(ctx, RMCRT_ERR_INVALID, "maxRayLength (boundedRayLength ROI) applies to single-level solves only (Ray.cc:2349-2627 has no length test)");
   a.maxRayLength = bounded ? ctx->p.maxRayLength : (double)INFINITY;
   a.floatProps = ctx->lv[F].propsFloat ? 1 : 0;
+  // isotropic scattering lives in RMCRTCommon::updateSumI only (RMCRTCommon.cc:670-676, 790-836): the Data-Onion march
+  // (Ray::updateSumI_ML) has no scattering code, so multi-level solves ignore <sigmaScat> exactly like the reference
+  a.sigmaScat = (!multiLevel && ctx->p.sigmaScat > 0) ? ctx->p.sigmaScat : 0.0;
   return 0;
 }
 
 template <class Real, class RecT>
 int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
-  const bool bounded = a.maxRayLength < 1e300;       // boundedRayLength ROI: the generic march carries the length test
+  // boundedRayLength ROI and scattering: the generic march carries the length test / the scattering events
+  const bool bounded = a.maxRayLength < 1e300 || a.sigmaScat > 0;
   const bool lhcTable = a.rng.lhc && (!a.rng.isSeedRandom || a.rng.fixedRandom);
-  const bool f32gen = std::is_same<Real, float>::value && a.rng.isSeedRandom && !a.rng.fixedRandom && !a.rng.lhc;
+  // (the scattering march needs the absolute ray origin, which only the FP64 ray set-up provides)
+  const bool f32gen = std::is_same<Real, float>::value && a.rng.isSeedRandom && !a.rng.fixedRandom && !a.rng.lhc && !(a.sigmaScat > 0);
   // ---- boundary flux first, like the task body (Ray.cc:645 before 742)
   if (ctx->p.solveBoundaryFlux) {
     if (!a.bflux) return fail(ctx, RMCRT_ERR_INVALID, "solveBoundaryFlux needs a boundFlux buffer");
@@ -1519,6 +1571,7 @@ void rmcrt_default_params(rmcrt_params* p) {
   p->warpsPerTile = 0;
   p->rayDirSampleAlgo = 0;     // "naive", Ray.cc:174
   p->maxRayLength = 0.0;       // unbounded (DBL_MAX, RMCRTCommon.cc:117)
+  p->sigmaScat = 0.0;          // Ray.cc:169
 }
 
 const char* rmcrt_last_error(const rmcrt_ctx* ctx) {

@@ -37,7 +37,7 @@ __host__ __device__ __forceinline__ u32x4 philox4x32_10(u32x4 c, uint32_t k0, ui
 
 // streams (low byte of counter word 3)
 enum : uint32_t { STREAM_DIR = 1, STREAM_ORIGIN = 2, STREAM_FLUX_DIR = 3, STREAM_FLUX_ORIGIN = 4, STREAM_LHC_DIVQ = 5, STREAM_LHC_FLUX = 6,
-                  STREAM_RADIOMETER = 7 };
+                  STREAM_RADIOMETER = 7, STREAM_SCATTER = 8 };
 
 // (0,1) from 32 random bits, MTRand::randDblExc() formula (MersenneTwister.h:190-197)
 __host__ __device__ __forceinline__ double u01_open(uint32_t x) { return ((double)x + 0.5) * (1.0 / 4294967296.0); }
@@ -65,9 +65,9 @@ __host__ __device__ __forceinline__ uint32_t keyed_permutation(uint32_t x, uint3
   return x;
 }
 
-constexpr int MT_MAXOUT = 5;
+constexpr int MT_MAXOUT = 8;    // 5 for a ray's direction + origin; scattering draws up to 2 more before the next reseed
 
-// out[i] = i-th randInt() after MTRand::seed(seed), i < NOUT <= 5
+// out[i] = i-th randInt() after MTRand::seed(seed), i < NOUT <= MT_MAXOUT
 template <int NOUT>
 __host__ __device__ __forceinline__ void mt19937_first(uint32_t seed, uint32_t out[NOUT]) {
   static_assert(NOUT >= 1 && NOUT <= MT_MAXOUT, "NOUT");
@@ -92,5 +92,38 @@ __host__ __device__ __forceinline__ void mt19937_first(uint32_t seed, uint32_t o
     out[i] = v ^ (v >> 18);
   }
 }
+
+// Random numbers of the scattering events of ONE ray (RAY_SCATTER code of RMCRTCommon::updateSumI, RMCRTCommon.cc:670-676, 790-836).
+// The reference draws them from the task's MTRand inside the march: one randDblExc() for the first free path, then per event one for
+// the next free path and two for the new direction (findRayDirection, which in the regression mode re-seeds the generator with
+// (i+j+k)*iRay+1, iRay = -9, of the cell the event happens in).
+//   mode 0  <randomSeed> true : Philox4x32-10, counter (cell or tile id, ray | draw index, timestep, STREAM_SCATTER)
+//   mode 1  <randomSeed> false: the MT19937 stream the reference would be on -- the ray's own seed, `mtPos` outputs consumed
+//   mode 2  FIXED_RANDOM_NUM  : every draw 0.3
+struct ScatRng {
+  int mode;
+  uint32_t key0, key1, c0, c2, c3, ray;
+  uint32_t draw;
+  uint32_t mtSeed;
+  int mtPos;
+  __host__ __device__ __forceinline__ double open01() {
+    if (mode == 2) return 0.3;
+    if (mode == 1) {
+      uint32_t v[MT_MAXOUT];
+      mt19937_first<MT_MAXOUT>(mtSeed, v);
+      const int q = mtPos < MT_MAXOUT ? mtPos : MT_MAXOUT - 1;
+      ++mtPos;
+      return u01_open(v[q]);
+    }
+    const u32x4 b = philox4x32_10(u32x4{c0, ray + ((draw >> 2) << 20), c2, c3}, key0, key1);
+    const uint32_t w = (draw & 3u) == 0u ? b.x : ((draw & 3u) == 1u ? b.y : ((draw & 3u) == 2u ? b.z : b.w));
+    ++draw;
+    return u01_open(w);
+  }
+  // findRayDirection(mTwister, cur) with the default iRay = -9 (RMCRTCommon.cc:504-506)
+  __host__ __device__ __forceinline__ void reseedAt(int i, int j, int k) {
+    if (mode == 1) { mtSeed = (uint32_t)((i + j + k) * (-9) + 1); mtPos = 0; }
+  }
+};
 
 }  // namespace rmcrt

@@ -66,13 +66,13 @@ void Ray::problemSetup(const ProblemSpecP& prob_spec, const ProblemSpecP& rmcrtp
     d_radiometer->problemSetup(prob_spec, rmcrtps, grid);
   }
 
-  // the reference refuses sigmaScat > 0 unless it was configured with --enable-ray-scatter (Ray.cc:193-201)
+  // Ray.cc:192-211.  The stock reference refuses sigmaScat > 0 unless it was configured with --enable-ray-scatter; this back end always
+  // carries the scattering march (the RAY_SCATTER code of updateSumI), selected at run time, so a scattering deck just runs
+  std::cout << "    - sigmaScat: " << d_sigmaScat << "\n";
   if (d_sigmaScat > 0) {
-    std::ostringstream warn;
-    warn << " ERROR:  To run a scattering case, you must use the following in your configure line...\n"
-         << "                 --enable-ray-scatter\n"
-         << "         To run a non-scattering case, please remove the line containing <sigmaScat> from your input file.\n";
-    throw ProblemSetupException(warn.str(), __FILE__, __LINE__);
+    std::cout << "  - Ray scattering is enabled.\n";
+    if (d_radiometer)   // Radiometer::radiometerFlux calls updateSumI as well; its kernel has no scattering variant
+      throw ProblemSetupException("RMCRT (B200 back end): <sigmaScat> > 0 together with a <Radiometer> is not supported", __FILE__, __LINE__);
   }
   if (d_nDivQRays == 1) {
     std::cout << "    WARNING: You have specified only 1 ray to compute the radiative flux divergence.\n"
@@ -197,6 +197,7 @@ void Ray::fillParams(rmcrt_params& p) const {
   p.seed = d_seed;
   p.rayDirSampleAlgo = d_rayDirSampleAlgo == LATIN_HYPER_CUBE ? 1 : 0;
   p.maxRayLength = d_maxRayLength;
+  p.sigmaScat = d_sigmaScat;
   for (auto& kv : d_knobs) {
     if (kv.first == "rayCoherence") p.rayCoherence = kv.second;
     else if (kv.first == "skipZeroWeightLegs") p.skipZeroWeightLegs = kv.second;
