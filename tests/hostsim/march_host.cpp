@@ -156,4 +156,27 @@ void hs_keyed_permutation(uint32_t n, const uint32_t key[4], uint32_t* out) {
 }
 void hs_mt_first5(uint32_t seed, uint32_t out[5]) { mt19937_first<5>(seed, out); }
 void hs_mt_first4(uint32_t seed, uint32_t out[4]) { mt19937_first<4>(seed, out); }
+
+// isotropic scattering march (march_single_level_scatter) with the regression-mode generator: MT19937 seeded with `seeds[t]`, no output
+// consumed yet -- the state oracle_updateSumI_seeded starts from.  kind 0 = fp32/Rec8, 1 = fp64/Rec16
+void hs_trace_1L_scatter(const HsLevel* g, int kind, int n, const int* cells, const double* dirs, const double* orgs, const unsigned* seeds,
+                         double threshold, int allowReflect, double sigmaScat, double maxRayLength, int floatProps, double* sumI, unsigned* steps) {
+  const double maxLen = (maxRayLength > 0 && maxRayLength < 1e300) ? maxRayLength : INFINITY;
+  const int nx = g->hi[0] - g->lo[0], ny = g->hi[1] - g->lo[1];
+  for (int t = 0; t < n; ++t) {
+    const int* c = cells + 3 * t;
+    const long long idx = (long long)(c[0] - g->lo[0]) + (long long)nx * ((c[1] - g->lo[1]) + (long long)ny * (c[2] - g->lo[2]));
+    ScatRng rng;
+    rng.mode = 1; rng.key0 = rng.key1 = rng.c0 = rng.c2 = rng.c3 = rng.ray = rng.draw = 0;
+    rng.mtSeed = seeds[t]; rng.mtPos = 0;
+    unsigned s = 0;
+    if (kind == 0)
+      sumI[t] = march_single_level_scatter<float, Rec8>(static_cast<const Rec8*>(g->rec), idx, nx, nx * ny, c[0], c[1], c[2], dirs + 3 * t, orgs + 3 * t,
+                  g->anchor, g->dx, (float)threshold, allowReflect != 0, s, (float)(maxLen * (double)Num<float>::LEN_SCALE), false, sigmaScat, rng);
+    else
+      sumI[t] = march_single_level_scatter<double, Rec16>(static_cast<const Rec16*>(g->rec), idx, nx, nx * ny, c[0], c[1], c[2], dirs + 3 * t, orgs + 3 * t,
+                  g->anchor, g->dx, threshold, allowReflect != 0, s, maxLen, floatProps != 0, sigmaScat, rng);
+    steps[t] = s;
+  }
+}
 }

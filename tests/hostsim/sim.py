@@ -113,3 +113,16 @@ def mt_first(seed, n):
     out = (C.c_uint32 * n)()
     getattr(lib(), f"hs_mt_first{n}")(C.c_uint32(seed), out)
     return [int(x) for x in out]
+
+
+def trace_1L_scatter(lv, kind, cells, dirs, org, seeds, thr, refl, sigma_scat, max_ray_length=0.0):
+    """march_single_level_scatter on the host with the regression-mode MT19937 stream seeded per ray"""
+    rec = pack(lv, kind)
+    h = hslevel(lv, rec)
+    n = len(cells)
+    sumI = np.zeros(n); steps = np.zeros(n, np.uint32)
+    cells = np.ascontiguousarray(cells, np.int32); dirs = np.ascontiguousarray(dirs); org = np.ascontiguousarray(org)
+    seeds = np.ascontiguousarray(seeds, np.uint32)
+    lib().hs_trace_1L_scatter(C.byref(h), kind, n, _vp(cells), _vp(dirs), _vp(org), _vp(seeds), C.c_double(thr), refl, C.c_double(sigma_scat),
+                              C.c_double(max_ray_length), 1 if lv.is_float else 0, _vp(sumI), _vp(steps))
+    return sumI, steps

@@ -120,3 +120,35 @@ def test_keyed_permutation_is_a_bijection():
             if n == 100:
                 seen.add(tuple(perm))
     assert len(seen) == 4                     # different keys, different permutations
+
+
+@pytest.mark.parametrize("case", ["bc", "plates_float", "bounded"])
+def test_scattering_march_is_the_oracle_bit_for_bit(po, case):
+    """march_single_level_scatter (the device code of <sigmaScat> > 0) compiled for the host, where it shares glibc's log / sincos with
+    the oracle: FP64 instantiation == oracle (== the reference's RAY_SCATTER build, test_oracle_ref.py) BIT FOR BIT, the FP32
+    instantiation to round-off"""
+    rng = np.random.default_rng(21)
+    kw = dict(threshold=0.02, isSeedRandom=0, sigmaScat=4.0)
+    if case == "bc":
+        lv = po.burns_christon(17)
+    elif case == "plates_float":
+        lv = po.parallel_plates(14, dtype=np.float32, mirror_faces=("x-", "z+"))
+        lv.abskg[lv.cellType != -1] = rng.uniform(0, 1.2, int((lv.cellType != -1).sum())).astype(np.float32)
+        kw.update(threshold=0.005, sigmaScat=9.0)
+    else:
+        lv = po.burns_christon(17)
+        kw.update(maxRayLength=0.4, sigmaScat=12.0)
+    n = 300
+    cells, dirs, org = random_rays(lv, n, rng)
+    seeds = rng.integers(1, 2 ** 31, n).astype(np.uint32)
+    p = po.default_params(**kw)
+    ref = [po.update_sumI_seeded(p, lv, dirs[t], org[t], cells[t], int(seeds[t])) for t in range(n)]
+    s64, n64 = sim.trace_1L_scatter(lv, 1, cells, dirs, org, seeds, kw["threshold"], 1, kw["sigmaScat"], kw.get("maxRayLength", 0.0))
+    assert np.array_equal(n64, np.array([r[1] for r in ref], np.uint32))
+    assert np.array_equal(s64, np.array([r[0] for r in ref]))
+    s32, n32 = sim.trace_1L_scatter(lv, 0, cells, dirs, org, seeds, kw["threshold"], 1, kw["sigmaScat"], kw.get("maxRayLength", 0.0))
+    same = n32 == n64
+    assert same.mean() > 0.9
+    np.testing.assert_allclose(s32[same], s64[same], rtol=2e-3, atol=1e-6 * np.abs(s64).max())
+    p0 = po.default_params(**{**kw, "sigmaScat": 0.0})
+    assert sum(po.update_sumI(p0, lv, dirs[t], org[t], cells[t])[1] != ref[t][1] for t in range(n)) > 100
