@@ -419,3 +419,41 @@ def test_isotropic_scattering_deck(exe, po, tmp_path, gpu_lib):
     bad = np.abs(out["divQ"] - ref["divQ"]) > 1e-9 * np.abs(ref["divQ"]).max()
     assert bad.mean() < 2e-3
     assert np.array_equal(out["RMCRTboundFlux"][..., 6], ref["boundFlux"][..., 6])
+
+
+# ------------------------------------------------------------------------------------------------ non-rectangular levels (RMCRT_+Domain*.ups)
+def test_plus_domain_grid(exe):
+    """a level made of seven <Box>es: 13 patches, extra cells only on patch faces that no other patch covers"""
+    t = tasks_of(run(exe, "plus_domain_1L.ups", "--parse-only").stdout)
+    rt = [x for x in t if x["name"] == "Ray::rayTrace"][0]
+    assert rt["patches"] == "13" and rt["level"] == "0"
+
+
+@pytest.mark.gpu
+def test_plus_domain_deck(exe, po, tmp_path, gpu_lib):
+    """RMCRT_+Domain.ups pattern: the whole-level gather covers the bounding box of the plus, the cells no patch owns are not flow cells
+    (a ray meets the legs' extra cells first) -- fields and the deterministic solve against the oracle on the same arrays"""
+    out = load_dump(run(exe, "plus_domain_1L.ups", "--dump", str(tmp_path), "--knob", "skipZeroWeightLegs=0").args[3])
+    N = 40
+    ct = out["cellType"]
+    assert ct.shape == (N + 2,) * 3
+    idx = np.arange(-1, N + 1)
+    k, j, i = np.meshgrid(idx, idx, idx, indexing="ij")
+    mid = lambda a: (a >= 16) & (a < 24)
+    inr = lambda a: (a >= 0) & (a < N)
+    flow = (mid(j) & mid(k) & inr(i)) | (mid(i) & mid(k) & inr(j)) | (mid(i) & mid(j) & inr(k))
+    assert np.array_equal(ct == -1, flow) and flow.sum() == 8 * 8 * (3 * 40 - 2 * 8)
+    assert set(np.unique(ct)) == {-1, 0, 8}                      # flow, not owned by any patch, wall
+    # walls: exactly the cells one step outside the flow region along an axis (no extra cells on the internal box interfaces)
+    sh = lambda a, ax, d: np.roll(a, d, axis=ax)
+    touching = np.zeros_like(flow)
+    for ax in range(3):
+        for d in (1, -1):
+            touching |= sh(flow, ax, d)
+    assert (ct[touching & ~flow] == 8).all()
+    ab = 0.9 * (1 - 2 * np.abs((i - (N - 1.0) / 2) / N)) * (1 - 2 * np.abs((j - (N - 1.0) / 2) / N)) * (1 - 2 * np.abs((k - (N - 1.0) / 2) / N)) + 0.1
+    np.testing.assert_allclose(out["abskg"][flow], ab[flow], rtol=1e-13)
+    lv = po.Level(out["abskg"], out["sigmaT4"], ct, (-1,) * 3, (N + 1,) * 3, (1.0 / N,) * 3, interior_lo=(0,) * 3, interior_hi=(N,) * 3)
+    ref = po.ray_trace(po.default_params(nDivQRays=3, threshold=0.05, isSeedRandom=0), lv, patches=(1, 1, 8), threads=8)
+    assert out["report"]["nRaySteps"] == ref["steps"] and out["report"]["nDivQCells"] == int(flow.sum())
+    np.testing.assert_allclose(out["divQ"], ref["divQ"], rtol=1e-9, atol=1e-10 * np.abs(ref["divQ"]).max())
