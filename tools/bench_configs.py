@@ -7,6 +7,7 @@
       solveBoundaryFlux + allowReflect, nDivQRays = nFluxRays = 100, Threshold 0.001
 
     python tools/bench_configs.py [--n 256] [--rays 100] [--steps 2] [--config C4 C5]
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/bench_configs.py --config C4     # C4 across 8 GPUs
 
 One JSON line per config: executed ray-cell steps/s, divQ cells/s, ms per solve (CUDA events on the launching stream,
 property records re-packed every solve, L2 flushed between solves).
@@ -40,6 +41,83 @@ def plates_fields(n, dtype=np.float32, T_gas=1500.0, T_wall=1000.0, mirrors=("x-
         ab[tuple(sl)] = 0.0 if name in mirrors else 1.0
     s4 = 5.67051e-8 / np.pi * T ** 4
     return ab.astype(dtype), s4.astype(dtype), ct
+
+
+def c4_multi_gpu(args, N, half, world):
+    """BASELINE configs[3]: the Data Onion across `world` GPUs of one box (torchrun, one rank per GPU).  The fine level is sharded by
+    patch: every rank packs the records of the cells it owns, ONE all-gather replicates the packed fine level (the halo and the
+    coarsening both need neighbours' cells), each rank derives the coarse level on its own device and traces its own fine patch.
+    Weak-scaling unit = one (N/2)^3 fine patch per GPU, like the single-level headline."""
+    import torch
+    import torch.distributed as dist
+    from bench import burns_christon_fields
+    from uintah_b200 import RMCRT, LevelData, partition
+    rank, local = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.current_stream()
+    pg = partition.patch_grid(world)
+    P = N // 2
+    shape = tuple(P * g for g in pg)                       # fine interior: 8 ranks -> (N, N, N)
+    lo, hi = (-1,) * 3, tuple(s + 1 for s in shape)
+    dxf = tuple(1.0 / s for s in shape)
+    plo, phi = partition.rank_patch(rank, pg, P)
+    blo, bhi = partition.owner_box(plo, phi, shape)
+    ab, s4, ct = burns_christon_fields(shape, blo, bhi, np.float32)
+    d_ab, d_s4, d_ct = (torch.from_numpy(x).to(dev) for x in (ab, s4, ct))
+    boxes_lo, boxes_hi = partition.all_owner_boxes(world, pg, P, shape)
+    rec_bytes = 4 if half else 8
+    slot = partition.slot_bytes(boxes_lo, boxes_hi, rec_bytes)
+    send = torch.zeros(slot, dtype=torch.uint8, device=dev)
+    gathered = torch.zeros(slot * world, dtype=torch.uint8, device=dev)
+    g = RMCRT(device=local, nDivQRays=args.rays, threshold=0.05, haloCells=(4, 4, 4), seed=99, half_records=bool(half))
+    fine = LevelData(None, None, None, lo, hi, dxf, rr=(4, 4, 4), interior_lo=(0,) * 3, interior_hi=shape)
+    cshape = tuple(s // 4 for s in shape)
+    coarse = LevelData(None, None, None, lo, tuple(c + 1 for c in cshape), tuple(4.0 / s for s in shape), interior_lo=(0,) * 3, interior_hi=cshape)
+    g.define_level(0, coarse.desc()); g.levels[0] = coarse
+    g.define_level(1, fine.desc()); g.levels[1] = fine
+    oshape = (bhi[2] - blo[2], bhi[1] - blo[1], bhi[0] - blo[0])
+    d_divQ = torch.empty(oshape, dtype=torch.float64, device=dev)
+    d_volq = torch.empty_like(d_divQ)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def solve(ts):
+        g.pack_box_device(1, d_ab, d_s4, d_ct, blo, bhi, blo, bhi, send, stream=stream)
+        dist.all_gather_into_tensor(gathered, send)
+        g.assemble_level(1, gathered, slot, boxes_lo, boxes_hi, stream=stream)
+        g.coarsen_level_device(1, 0, stream=stream)
+        g.set_level_extra_cells(0, [1.0] * 6, [0.0] * 6, [8] * 6, stream=stream)
+        g.finalize_level_async(1, stream)
+        g.finalize_level_async(0, stream)
+        g.trace_dataonion_device(2, plo, phi, d_divQ, d_volq, None, blo, bhi, timestep=ts, zero_init=True, stream=stream)
+
+    for w in range(3):
+        solve(w + 1)
+    dist.barrier(); torch.cuda.synchronize()
+    g.reset_counters(stream)
+    ev = []
+    for k in range(args.steps):
+        flush.fill_(k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream); solve(100 + k); e1.record(stream)
+        ev.append((e0, e1))
+    dist.barrier(); torch.cuda.synchronize()
+    c = g.counters(stream)
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) * 1e-3], dtype=torch.float64, device=dev)
+    wk = torch.tensor([float(c.nRaySteps), float(c.nDivQCells)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(wk, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        sec = float(t.item())
+        print(json.dumps({"config": "C4", "n_gpus": world,
+                          "workload": f"Data Onion fine {shape[0]}x{shape[1]}x{shape[2]} ({world} patches of {P}^3, one per GPU) / coarse {cshape[0]}x{cshape[1]}x{cshape[2]}, RR 4, "
+                                      f"halo 4, {args.rays} rays/cell; packed fine level all-gathered per solve, coarse level derived on every GPU",
+                          "ray_cell_steps_per_s": float(wk[0]) / sec, "divq_cells_per_s": float(wk[1]) / sec, "ms_per_solve": 1e3 * sec / args.steps,
+                          "steps_per_ray": float(wk[0]) / (float(wk[1]) * args.rays), "record_bytes": rec_bytes, "solves": args.steps,
+                          "timing": "CUDA events per rank, max over ranks"}))
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 def main():
@@ -85,6 +163,11 @@ def main():
     oshape = (N + 2, N + 2, N + 2)
     d_divQ = torch.empty(oshape, dtype=torch.float64, device=dev)
     d_volq = torch.empty_like(d_divQ)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if "C4" in args.config and world > 1:
+        c4_multi_gpu(args, N, half, world)
+        return
 
     if "C4" in args.config:
         ab, s4, ct = burns_christon_fields((N,) * 3, lo, hi, np.float32)
