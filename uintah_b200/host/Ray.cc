@@ -335,7 +335,7 @@ void Ray::traceCommon(bool dataOnion, const PatchSubset* patches, DataWarehouse*
   const int L = level->getIndex();
   const int maxLevels = level->getGrid()->numLevels();
   auto& devs = devices();
-  const auto t0 = std::chrono::steady_clock::now();
+  const auto tTask = std::chrono::steady_clock::now();
 
   for (auto& dev : devs) {
     check(dev.ctx, rmcrt_finalize_level(dev.ctx, L, nullptr), "rmcrt_finalize_level");   // non-finite abskg etc. -> InternalError
@@ -365,6 +365,8 @@ void Ray::traceCommon(bool dataOnion, const PatchSubset* patches, DataWarehouse*
     }
   }
   const uint64_t timestep = (uint64_t)new_dw->getTimeStep();
+  // the reference starts its timer after the outputs are allocated and initialised (Ray.cc:590 `timer.start()` follows 573-588)
+  const auto t0 = std::chrono::steady_clock::now();
 
   forEachPatchOnDevices(patches, [&](Device& dev, int p) {
     const Patch* patch = patches->get(p);
@@ -390,10 +392,12 @@ void Ray::traceCommon(bool dataOnion, const PatchSubset* patches, DataWarehouse*
   }
   d_report.devicesUsed = (int)std::min<size_t>(devs.size(), (size_t)patches->size());
   d_report.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  const double taskSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - tTask).count();
   // Ray.cc:803-812 prints this for patch 0
   const unsigned long long size = d_report.nRaySteps + d_report.nFluxRaySteps;
   std::cout << "\n RMCRT REPORT: Patch " << patches->get(0)->getID() << " +" << patches->size() - 1 << " more on " << d_report.devicesUsed
-            << " GPU(s)\n Used " << d_report.seconds * 1000 << " milliseconds of wall time (trace kernels + D2H of divQ / radiationVolq / boundFlux)\n"
+            << " GPU(s)\n Used " << d_report.seconds * 1000 << " milliseconds of wall time (trace kernels + D2H of divQ / radiationVolq / boundFlux; "
+            << taskSeconds * 1000 << " ms for the whole task incl. level validation and allocateAndPut of the outputs)\n"
             << " Size: " << size << " ray-cell steps\n Efficiency: " << size / d_report.seconds << " steps per sec\n" << std::endl;
 }
 
