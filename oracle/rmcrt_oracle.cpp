@@ -914,7 +914,7 @@ static void normalizedDistance_CC(int rr, std::vector<double>& nd) {
     int count = rr - 1;
     for (int i = 0; i < half; i++) { nd[i] = -count * hdx; count -= 2; }
     count = half - 1;
-    for (int i = half; i < rr; i++) { nd[i] = std::fabs(nd[count]); count -= 1; }
+    for (int i = half; i < rr; i++) { nd[i] = count >= 0 ? std::fabs(nd[count]) : 0.0; count -= 1; }   // odd ratios index nd[-1] in the reference (AMR.cc:230-233); 0 here
   }
 }
 static inline int signOf(double d) { return d < 0 ? -1 : 1; }                 // Core/Math/MiscMath.h:63-66
