@@ -49,12 +49,12 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
-def profiled_traffic(n, rays, rec_bytes):
+def profiled_traffic(n, rays, rec_bytes, kernel="divq"):
     """dram__bytes_read.sum + dram__bytes_write.sum of one divq_kernel launch, from the committed ncu --set full capture of
     the same workload (profiles/traffic.json names the report it was read from); None when this workload was not profiled"""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        e = t.get(f"divq_{n}cubed_{rays}rays_rec{rec_bytes}")
+        e = t.get(f"{kernel}_{n}cubed_{rays}rays_rec{rec_bytes}")
         return (float(e["dram_bytes_per_launch"]), e["source"]) if e else (None, None)
     except Exception:
         return None, None
@@ -239,7 +239,7 @@ def run_ours(args):
         args.half_records = 1 if int(np.prod([h - l for l, h in zip(lo, hi)])) * 8 > 64e6 else 0
     skip = 0 if args.reference_semantics else 1
     g = RMCRT(device=local, nDivQRays=rays, threshold=0.05, seed=1234, skipZeroWeightLegs=skip,
-              rayCoherence=args.coherence, l2Persist=args.l2persist, warpsPerTile=args.warps,
+              rayCoherence=args.coherence, l2Persist=args.l2persist, warpsPerTile=args.warps, cellsPerLane=args.cells_per_lane,
               genericMarch=args.generic_march, maxBlocksPerSM=args.max_blocks_per_sm, half_records=bool(args.half_records))
     stream = torch.cuda.current_stream()
     desc = LevelData(None, None, None, lo, hi, dx, interior_lo=(0, 0, 0), interior_hi=shape).desc()
@@ -402,9 +402,10 @@ def run_ours(args):
     alg_bytes = ALG_BYTES_PER_STEP * per_rank_steps + ALG_BYTES_PER_CELL * per_rank_cells
     kern_s = (t_trace_total / args.steps)
     achieved = alg_bytes / kern_s / 1e9
-    traffic, traffic_src = profiled_traffic(P, rays, rec_bytes) if world == 1 else (None, None)
+    traffic, traffic_src = (profiled_traffic(P, rays, rec_bytes, "divq_dual" if (args.cells_per_lane == 2 and args.coherence >= 1) else "divq")
+                            if world == 1 else (None, None))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": traffic, "traffic_source": traffic_src, "kernel": "divq_kernel<float,Rec8,false>", "kernel_ms": 1e3 * kern_s,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": ("divq_dual_kernel" if (args.cells_per_lane == 2 and args.coherence >= 1) else "divq_kernel") + ("<Rec4>" if args.half_records else "<Rec8>"), "kernel_ms": 1e3 * kern_s,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "note": "12 B per executed ray-cell step + 28 B per divQ cell; the property records are L2-resident, so the "
                         "binding roofline is L2 (see roofline_l2), HBM peak shown because MEASURED_PEAKS.json has no L2 figure"}
@@ -442,6 +443,7 @@ def run_ours(args):
                    "executed_steps_per_ray": all_steps / (all_cells * rays),
                    "zero_weight_legs": "marched (reference semantics)" if not skip else "skipped (exact: cold black walls, fs==0)",
                    "ray_coherence": {0: "independent per cell", 1: "warp-shared direction", 2: "warp-shared direction and in-cell offset"}[args.coherence],
+                   "cells_per_lane": args.cells_per_lane if args.coherence >= 1 else 1,
                    "l2": "flushed between steps (256 MiB fill); level records (%.1f MB, %d B/cell) re-packed every step" % (np.prod([h - l for l, h in zip(lo, hi)]) * rec_bytes / 1e6, rec_bytes),
                    "timing": "CUDA events on the launching stream per step, max over ranks"},
         "roofline": roofline, "roofline_l2": roofline_l2, "cpu_baseline": cpu_baseline, "e2e": e2e,
@@ -466,6 +468,7 @@ def main():
     ap.add_argument("--coherence", type=int, default=1)
     ap.add_argument("--l2persist", type=int, default=1)
     ap.add_argument("--warps", type=int, default=0)
+    ap.add_argument("--cells-per-lane", type=int, default=2, help="2 (library default): a lane marches two cells with one DDA; 1: one cell per lane (A/B)")
     ap.add_argument("--half-records", type=int, default=-1,
                     help="1: 4-B half-packed level records (fp16 abskg|wall, fp16 sigmaT4/pi); 0: 8-B float records; "
                          "-1 (default): half-packed when the float records of the level would exceed 64 MB (beyond the L2)")

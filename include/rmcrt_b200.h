@@ -79,7 +79,11 @@ typedef struct rmcrt_params {
   int32_t  maxBlocksPerSM;     /* 0 = one tile per block (hardware balances the tail); > 0 caps the divQ grid at this many
                                   blocks per SM and grid-strides over the tiles (A/B measurements) */
   int32_t  rayDirSampleAlgo;   /* <rayDirSampleAlgo> 0 naive (default), 1 LatinHyperCube (Ray.cc:174-179, 1398-1460) */
-  int32_t  reserved;
+  int32_t  cellsPerLane;       /* 2 (default): with rayCoherence >= 1 a lane owns cells (i,j,k) and (i,j+1,k); their rays share the direction AND
+                                  the in-cell origin, so they are exact translates and ONE DDA drives both (divq_dual_kernel: the DDA
+                                  instructions are paid once per two ray-cell steps).  Per-ray arithmetic identical to the one-cell kernel.
+                                  1: one cell per lane (every cell its own in-cell origin when rayCoherence == 1).
+                                  Applies to the production FP32 / Philox single-level solve; all other modes use one cell per lane. */
   double   maxRayLength;       /* <ROI_extents type="boundedRayLength"><length> (Ray.cc:243, RMCRTCommon.cc:680,684);
                                   <= 0 or >= 1e300: unbounded (DBL_MAX, RMCRTCommon.cc:117).  Single-level solves only, like
                                   the reference (updateSumI_ML has no length test) */

@@ -152,3 +152,38 @@ def test_scattering_march_is_the_oracle_bit_for_bit(po, case):
     np.testing.assert_allclose(s32[same], s64[same], rtol=2e-3, atol=1e-6 * np.abs(s64).max())
     p0 = po.default_params(**{**kw, "sigmaScat": 0.0})
     assert sum(po.update_sumI(p0, lv, dirs[t], org[t], cells[t])[1] != ref[t][1] for t in range(n)) > 100
+
+
+@pytest.mark.parametrize("case", ["bc_walls", "plates_mirrors", "bc_refsem"])
+def test_two_cells_per_lane_march_equals_two_single_marches(po, case):
+    """march_single_level_dual (one DDA drives the rays of cells (i,j,k) and (i,j+1,k), which are exact translates) == the single-ray
+    production march run twice: same sums and step counts, including when the two rays meet walls at different steps, reflect off
+    mirrors (they separate at the first wall) or one of them starts next to an intrusion"""
+    rng = np.random.default_rng(31)
+    if case == "plates_mirrors":
+        lv = po.parallel_plates(18, dtype=np.float32, mirror_faces=("x-", "y+"))
+        thr, refl, skip = 0.001, 1, 0
+    else:
+        lv = po.burns_christon(20, dtype=np.float32)
+        from util import add_random_walls
+        add_random_walls(lv, 0.03, rng, abskg=0.8, sigmaT4=0.05)
+        thr, refl, skip = 0.05, 1, (1 if case == "bc_walls" else 0)
+    n = 400
+    cells, dirs, org = random_rays(lv, n, rng)
+    N = lv.interior_hi[1]
+    ct = lv.cellType
+    keep = [t for t in range(n) if cells[t][1] + 1 < N and ct[cells[t][2] + 1, cells[t][1] + 1, cells[t][0] + 1] == -1
+            and ct[cells[t][2] + 1, cells[t][1] + 2, cells[t][0] + 1] == -1]
+    cells, dirs, org = cells[keep], dirs[keep], org[keep]
+    assert len(cells) > 250
+    cellsB = cells + np.array([0, 1, 0], np.int32)
+    orgB = org + np.array([0.0, lv.dx[1], 0.0])
+    sa, sb, na, nb = sim.trace_1L_dual(lv, cells, dirs, org, thr, refl, skip)
+    ra, nra = sim.trace_1L_fast(lv, cells, dirs, org, thr, refl, skip)
+    rb, nrb = sim.trace_1L_fast(lv, cellsB, dirs, orgB, thr, refl, skip)
+    # the in-cell offset of B's origin is rebuilt from an absolute position in the single march: allow FP32 round-off, not more
+    assert (na == nra).mean() > 0.99 and (nb == nrb).mean() > 0.97
+    same = (na == nra) & (nb == nrb)
+    np.testing.assert_allclose(sa[same], ra[same], rtol=1e-5, atol=1e-6 * np.abs(ra).max())
+    np.testing.assert_allclose(sb[same], rb[same], rtol=2e-4, atol=1e-5 * np.abs(rb).max())
+    assert (na != nb).mean() > 0.2          # the two rays of a lane really end at different steps often

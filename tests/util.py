@@ -72,3 +72,18 @@ def candidate_stats(x, runs, sel=None):
     else:
         z = np.abs(x - mu) / (sd * np.sqrt(1 + 1 / K) + 1e-300)
     return float((z <= 3.0).mean()), float((z <= 5.0).mean()), float(np.linalg.norm(x - mu) / np.linalg.norm(mu))
+
+
+def centreline_rms(po, solve, N=41, timesteps=(1, 2, 3)):
+    """RMS over the x, y and z centre lines of several solves of sqrt(mean((divQ - exact)^2)) against the Burns & Christon exact
+    solution (RMCRT.m:368-413).  With ray batching the cells of one centre line share their ray directions, so the error along ONE line
+    is a handful of draws rather than N: same expectation as for independent rays, much wider spread -- hence the average.
+    solve(ts) -> divQ over the (N+2)^3 window"""
+    sq = []
+    mid = N // 2 + 1
+    for ts in timesteps:
+        d = solve(ts)
+        ex = po.centreline_L2(d, N)[2]
+        for ln in (d[mid, mid, 1:N + 1], d[mid, 1:N + 1, mid], d[1:N + 1, mid, mid]):
+            sq.append(np.mean((ln - ex) ** 2))
+    return float(np.sqrt(np.mean(sq)))

@@ -554,6 +554,104 @@ __device__ __forceinline__ float march_single_level_fast(const RecT* __restrict_
 }
 
 //------------------------------------------------------------------------------------------------------
+// single level, TWO cells per lane (rayCoherence == 2, cellsPerLane == 2).  With a shared direction AND a shared in-cell origin the
+// rays of neighbouring cells are exact translates: tMax, the stepping axis and tDelta are identical, and the record a ray enters is
+// its neighbour's plus a constant stride.  One DDA therefore drives the rays of cell A and of cell B = A + (0,1,0) of the same lane:
+// 12 DDA instructions are shared by two loads / integrals per step.  The joint leg ends at the first step where either ray enters a
+// non-flow cell; from there each ray finishes on its own with the single-ray leg loop (they have different histories once one of them
+// met a wall).  Same arithmetic per ray as march_single_level_fast, so the result of each ray is identical to the single-cell kernel's.
+//------------------------------------------------------------------------------------------------------
+struct RayState {
+  Dda d;
+  Integ q;
+  float sum, fs;
+  int stx, sty, stz;
+};
+// the ray just entered a non-flow cell (q.k, q.s = its record) at w: wall emission, threshold test, reflection (RMCRTCommon.cc:846-902).
+// Returns true when the ray goes on (reflected into the cell it came from).
+template <class RecT>
+__device__ __forceinline__ bool ray_wall(RayState& r, const LegOut& w, const RecT* __restrict__ recs, float threshold, bool allowReflect,
+                                         bool skipZero) {
+  Integ& q = r.q;
+  r.sum = fmaf(q.leg, r.fs, r.sum);
+  q.leg = 0.0f;
+  const float eps = q.k > 1.0f ? 1.0f : q.k;
+  r.sum = fmaf(eps * q.s, q.ePrev, r.sum);
+  const float intensity = q.ePrev * r.fs;
+  if (!allowReflect || !(intensity > threshold)) return false;
+  r.fs *= (1.0f - q.k);
+  if (skipZero && r.fs == 0.0f) return false;
+  r.d.idx -= w.axis == 0 ? r.stx : (w.axis == 1 ? r.sty : r.stz);
+  if (w.axis == 0) r.stx = -r.stx; else if (w.axis == 1) r.sty = -r.sty; else r.stz = -r.stz;
+  const Rec8 rec = ldrec(recs + r.d.idx);
+  q.k = fabsf(rec.k); q.s = rec.s;
+  q.A = fmaf(-q.k, w.t, q.tau);
+  return true;
+}
+template <class RecT>
+__device__ __forceinline__ void ray_finish(RayState& r, const RecT* __restrict__ recs, float ddx, float ddy, float ddz, float threshold,
+                                           bool allowReflect, bool skipZero, int recBytes) {
+  for (;;) {
+    const LegOut w = march_leg(r.d, r.q, recs, ddx, ddy, ddz, r.stx, r.sty, r.stz, recBytes);
+    if (!ray_wall(r, w, recs, threshold, allowReflect, skipZero)) break;
+  }
+}
+
+template <class RecT>
+__device__ __forceinline__ void march_single_level_dual(const RecT* __restrict__ recs, int idxA, int sy, int sz, float dx, float dy, float dz,
+                                                        float rx, float ry, float rz, float cx, float cy, float cz, float threshold,
+                                                        bool allowReflect, bool skipZero, unsigned& stepsA, unsigned& stepsB, int recBytes,
+                                                        float& sumA, float& sumB) {
+  typedef Num<float> N;
+  sumA = sumB = 0.0f;
+  if (!(1.0f > threshold)) return;
+  const bool posx = !sign_bit(dx), posy = !sign_bit(dy), posz = !sign_bit(dz);
+  const int stx = posx ? 1 : -1, sty = posy ? sy : -sy, stz = posz ? sz : -sz;
+  const float ix = N::rcp(dx), iy = N::rcp(dy), iz = N::rcp(dz);
+  Dda d;
+  d.tx = ((posx ? cx : 0.0f) - rx) * ix * N::LEN_SCALE;
+  d.ty = ((posy ? cy : 0.0f) - ry) * iy * N::LEN_SCALE;
+  d.tz = ((posz ? cz : 0.0f) - rz) * iz * N::LEN_SCALE;
+  const float ddx = fabsf(ix) * cx * N::LEN_SCALE, ddy = fabsf(iy) * cy * N::LEN_SCALE, ddz = fabsf(iz) * cz * N::LEN_SCALE;
+  d.idx = idxA;
+  const RecT* __restrict__ recsB = recs + sy;          // cell B = cell A + one row
+  Integ qa, qb;
+  {
+    const Rec8 ra = ldrec(recs + idxA), rb = ldrec(recsB + idxA);
+    qa.k = fabsf(ra.k); qa.s = ra.s;
+    qb.k = fabsf(rb.k); qb.s = rb.s;
+  }
+  qa.A = qb.A = 0.0f; qa.ePrev = qb.ePrev = 1.0f; qa.nsteps = qb.nsteps = 0.0f; qa.tau = qb.tau = 0.0f; qa.leg = qb.leg = 0.0f;
+  // ---- joint leg: pipelined like march_leg (the records of step n+1 are requested before the wall tests of step n)
+  Peek p1 = dda_peek(d, stx, sty, stz), p2, w;
+  Rec8 a1 = ldrec(recs + p1.idx), b1 = ldrec(recsB + p1.idx), a2, b2;
+  bool wa, wb;
+  for (;;) {
+    dda_commit(d, p1, ddx, ddy, ddz);
+    p2 = dda_peek(d, stx, sty, stz);
+    a2 = ldrec(recs + p2.idx); b2 = ldrec(recsB + p2.idx);
+    integ_cross(qa, p1.t, a1); integ_cross(qb, p1.t, b1);
+    wa = is_wall(a1.k); wb = is_wall(b1.k);
+    if (wa || wb) { w = p1; break; }
+    dda_commit(d, p2, ddx, ddy, ddz);
+    p1 = dda_peek(d, stx, sty, stz);
+    a1 = ldrec(recs + p1.idx); b1 = ldrec(recsB + p1.idx);
+    integ_cross(qa, p2.t, a2); integ_cross(qb, p2.t, b2);
+    wa = is_wall(a2.k); wb = is_wall(b2.k);
+    if (wa || wb) { w = p2; break; }
+  }
+  const LegOut lw{w.t, w.px ? 0 : (w.py ? 1 : 2)};
+  // ---- each ray on its own from here
+  RayState A{d, qa, 0.0f, 1.0f, stx, sty, stz};
+  if (!wa || ray_wall(A, lw, recs, threshold, allowReflect, skipZero)) ray_finish(A, recs, ddx, ddy, ddz, threshold, allowReflect, skipZero, recBytes);
+  RayState B{d, qb, 0.0f, 1.0f, stx, sty, stz};
+  if (!wb || ray_wall(B, lw, recsB, threshold, allowReflect, skipZero)) ray_finish(B, recsB, ddx, ddy, ddz, threshold, allowReflect, skipZero, recBytes);
+  sumA = A.sum; sumB = B.sum;
+  stepsA += (unsigned)A.q.nsteps;
+  stepsB += (unsigned)B.q.nsteps;
+}
+
+//------------------------------------------------------------------------------------------------------
 // multi level (Data Onion)
 //------------------------------------------------------------------------------------------------------
 struct LevelGeom {

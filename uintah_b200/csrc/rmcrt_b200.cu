@@ -425,6 +425,101 @@ __global__ void __launch_bounds__(256, ((FAST && !ML) ? RMCRT_FAST_MIN_BLOCKS : 
 }
 
 //======================================================================================================
+// Two cells per lane (rayCoherence == 2 and cellsPerLane == 2): one block = a tile of 32 x-consecutive cells x 2 rows; lane = the pair
+// of cells (i, j) and (i, j+1); all 64 cells share the direction and the in-cell origin of ray r, so one DDA per lane drives both
+// rays (march_single_level_dual).  Production ray set-up only (Philox, FP32), single level.
+//======================================================================================================
+template <class RecT>
+__global__ void __launch_bounds__(256, 4) divq_dual_kernel(const __grid_constant__ TraceArgs a, int nxc, int njp) {
+  extern __shared__ double red[];     // [W][64]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+  const int F = a.G.maxLevels - 1;
+  const LevelGeom& g = a.G.lev[F];
+  const RecT* recs = static_cast<const RecT*>(g.rec);
+  const bool skipZero = skip_allowed(a);
+  constexpr float UNSCALE = RecInfo<RecT>::unscale;
+  const int sy = g.n[0], sz = g.n[0] * g.n[1];
+  unsigned long long stepsTotal = 0, cellsTotal = 0;
+  const long long nTiles = (long long)nxc * njp * a.patchN[2];
+  for (long long tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+    const int xc = (int)(tile % nxc);
+    const long long rest = tile / nxc;
+    const int jp = (int)(rest % njp), kz = (int)(rest / njp);
+    const int i = a.patchLo[0] + xc * 32 + lane, jA = a.patchLo[1] + 2 * jp, k = a.patchLo[2] + kz;
+    const bool validA = (xc * 32 + lane) < a.patchN[0], validB = validA && (2 * jp + 1) < a.patchN[1];
+    Rec8 rA{0, 0}, rB{0, 0};
+    long long idA = 0;
+    bool flowA = false, flowB = false;
+    if (validA) {
+      idA = level_index(g, i, jA, k);
+      if constexpr (std::is_same<RecT, Rec4>::value) rA = ldrec(static_cast<const Rec8*>(g.recFull) + idA); else rA = ldrec(recs + idA);
+      flowA = !is_wall(rA.k);
+    }
+    if (validB) {
+      if constexpr (std::is_same<RecT, Rec4>::value) rB = ldrec(static_cast<const Rec8*>(g.recFull) + idA + sy); else rB = ldrec(recs + idA + sy);
+      flowB = !is_wall(rB.k);
+    }
+    const unsigned long long dirId = (unsigned long long)level_index(g, a.patchLo[0] + xc * 32, jA, k);
+    double accA = 0, accB = 0;
+    unsigned stA = 0, stB = 0;
+    if (flowA || flowB) {
+      const float cx = (float)g.dx[0], cy = (float)g.dx[1], cz = (float)g.dx[2];
+      for (int ray = warp; ray < a.nRays; ray += W) {
+        float dir[3], rayDx[3];
+        // direction: shared by the tile (dirId); in-cell origin: shared by the tile (rayCoherence 2) or by the lane's two cells only (1)
+        gen_divq_ray_f32(a.rng, g, ray, (unsigned long long)idA, dirId, dir, rayDx);
+        const float d0 = nz<float, float>(dir[0]), d1 = nz<float, float>(dir[1]), d2 = nz<float, float>(dir[2]);
+        if (flowA && flowB) {
+          float sA, sB;
+          march_single_level_dual(recs, (int)idA, sy, sz, d0, d1, d2, rayDx[0], rayDx[1], rayDx[2], cx, cy, cz, (float)a.threshold,
+                                  a.allowReflect != 0, skipZero, stA, stB, a.recBytes, sA, sB);
+          accA += (double)(UNSCALE * sA); accB += (double)(UNSCALE * sB);
+        } else if (flowA) {
+          accA += (double)(UNSCALE * march_single_level_fast(recs, (int)idA, sy, sz, d0, d1, d2, rayDx[0], rayDx[1], rayDx[2], cx, cy, cz,
+                                                             (float)a.threshold, a.allowReflect != 0, skipZero, stA, a.recBytes));
+        } else {
+          accB += (double)(UNSCALE * march_single_level_fast(recs, (int)idA + sy, sy, sz, d0, d1, d2, rayDx[0], rayDx[1], rayDx[2], cx, cy, cz,
+                                                             (float)a.threshold, a.allowReflect != 0, skipZero, stB, a.recBytes));
+        }
+      }
+    }
+    red[warp * 64 + lane] = accA;
+    red[warp * 64 + 32 + lane] = accB;
+    __syncthreads();
+    if (warp < 2) {           // warp 0 writes row A, warp 1 row B
+      const bool valid = warp == 0 ? validA : validB;
+      if (valid) {
+        double sumI = 0;
+        for (int w = 0; w < W; ++w) sumI += red[w * 64 + warp * 32 + lane];
+        const int j = jA + warp;
+        const long long q = (long long)(i - a.outLo[0]) +
+                            (long long)a.outN[0] * ((long long)(j - a.outLo[1]) + (long long)a.outN[1] * (long long)(k - a.outLo[2]));
+        const Rec8 r0 = warp == 0 ? rA : rB;
+        if (warp == 0 ? flowA : flowB) {
+          const double mean = sumI / a.nRays;
+          a.divQ[q] = -4.0 * M_PI * (double)r0.k * ((double)r0.s - mean);
+          a.volq[q] = 4.0 * M_PI * mean;
+          ++cellsTotal;
+        } else {
+          a.divQ[q] = 0.0;
+          a.volq[q] = 0.0;
+        }
+      }
+    }
+    __syncthreads();
+    stepsTotal += (unsigned long long)stA + stB;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    stepsTotal += __shfl_down_sync(0xffffffffu, stepsTotal, o);
+    cellsTotal += __shfl_down_sync(0xffffffffu, cellsTotal, o);
+  }
+  if (lane == 0) {
+    if (stepsTotal) atomicAdd(a.counters + 0, stepsTotal);
+    if (cellsTotal) atomicAdd(a.counters + 2, cellsTotal);
+  }
+}
+
+//======================================================================================================
 // boundary flux
 //======================================================================================================
 // Ray::has_a_boundary (Ray.cc:1517-1572): `celltype[adj]+1 != 0`  <=>  adj is not a flow cell  <=>  record sign bit.
@@ -1429,6 +1524,15 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
     } else if (ML) {
       if (f32gen) divq_kernel<Real, RecT, true, false, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
       else        divq_kernel<Real, RecT, true, false, false><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
+    } else if (std::is_same<Real, float>::value && !bounded && f32gen && ctx->p.rayCoherence >= 1 && ctx->p.cellsPerLane == 2 && !ctx->p.genericMarch) {
+      if constexpr (std::is_same<Real, float>::value && !std::is_same<RecT, Rec16>::value) {
+        const int nxc = (a.patchN[0] + 31) / 32, njp = (a.patchN[1] + 1) / 2;
+        long long g2 = (long long)nxc * njp * a.patchN[2];
+        if (g2 > cap) g2 = cap;
+        int W2 = ctx->p.warpsPerTile > 0 ? std::min(ctx->p.warpsPerTile, 8) : 4;
+        if (W2 < 2) W2 = 2;        // rows A and B are written by warps 0 and 1
+        divq_dual_kernel<RecT><<<(int)g2, 32 * W2, W2 * 64 * sizeof(double), st>>>(a, nxc, njp);
+      }
     } else if (std::is_same<Real, float>::value && !bounded && (!ctx->p.genericMarch || std::is_same<RecT, Rec4>::value)) {
       if (f32gen) divq_kernel<Real, RecT, false, true, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
       else        divq_kernel<Real, RecT, false, true, false><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
@@ -1572,6 +1676,7 @@ void rmcrt_default_params(rmcrt_params* p) {
   p->rayDirSampleAlgo = 0;     // "naive", Ray.cc:174
   p->maxRayLength = 0.0;       // unbounded (DBL_MAX, RMCRTCommon.cc:117)
   p->sigmaScat = 0.0;          // Ray.cc:169
+  p->cellsPerLane = 2;         // production: two cells per lane share one DDA (divq_dual_kernel); 1 = one cell per lane
 }
 
 const char* rmcrt_last_error(const rmcrt_ctx* ctx) {
