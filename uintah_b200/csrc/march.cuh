@@ -597,6 +597,151 @@ __device__ __forceinline__ void ray_finish(RayState& r, const RecT* __restrict__
   }
 }
 
+// The joint leg of two translate rays, PTX on the device like march_leg: three-slot rotation, the records of step n+1 of BOTH rays
+// requested before the wall tests of step n, one DDA (peek / commit) per step for the pair.  Ends at the first step where either ray
+// enters a non-flow cell.  Returns axis | 4*(ray A hit a wall) | 8*(ray B hit a wall) in LegOut::axis.
+#if defined(__CUDA_ARCH__)
+// (%20 = byte distance of ray B's record from ray A's: the second address is one 64-bit add, not a second multiply-add)
+#define RJ_LD8(J)                                                                                   \
+  "mad.wide.s32 ad, i" #J ", 8, %19;\n\t" "ld.global.nc.v2.f32 {ka" #J ", sa" #J "}, [ad];\n\t"     \
+  "add.s64 ad, ad, %20;\n\t" "ld.global.nc.v2.f32 {kb" #J ", sb" #J "}, [ad];\n\t"
+#define RJ_LD4(J)                                                                                   \
+  "mad.wide.s32 ad, i" #J ", 4, %19;\n\t" "ld.global.nc.b32 ka" #J ", [ad];\n\t"                    \
+  "add.s64 ad, ad, %20;\n\t" "ld.global.nc.b32 kb" #J ", [ad];\n\t"
+#define RJ_DEC8(C) "abs.f32 aa" #C ", ka" #C ";\n\t" "abs.f32 ab" #C ", kb" #C ";\n\t"
+#define RJ_DEC4(C)                                                                                  \
+  "mov.b32 {hl, hh}, ka" #C ";\n\t" "cvt.f32.f16 sa" #C ", hl;\n\t" "cvt.f32.f16 aa" #C ", hh;\n\t" "abs.f32 aa" #C ", aa" #C ";\n\t" \
+  "mov.b32 {hl, hh}, kb" #C ";\n\t" "cvt.f32.f16 sb" #C ", hl;\n\t" "cvt.f32.f16 ab" #C ", hh;\n\t" "abs.f32 ab" #C ", ab" #C ";\n\t"
+#define RJ_PEEK(J, IB, LD)                                  \
+  "min.f32 t" #J ", %0, %1, %2;\n\t"                        \
+  "setp.neu.f32 n" #J ", t" #J ", %2;\n\t"                  \
+  "setp.lt.and.f32 x" #J ", %0, %1, n" #J ";\n\t"           \
+  "setp.ge.and.f32 y" #J ", %0, %1, n" #J ";\n\t"           \
+  "selp.s32 i" #J ", %24, %26, x" #J ";\n\t"                \
+  "@y" #J " mov.s32 i" #J ", %25;\n\t"                      \
+  "add.s32 i" #J ", i" #J ", " IB ";\n\t"                   \
+  LD(J)
+#define RJ_COMMIT(J)                                        \
+  "@x" #J " add.f32 %0, %0, %21;\n\t"                       \
+  "@y" #J " add.f32 %1, %1, %22;\n\t"                       \
+  "@!n" #J " add.f32 %2, %2, %23;\n\t"
+#define RJ_INTEG(P, C, DEC)                                 \
+  "fma.rn.f32 taa, aa" #P ", t" #C ", %4;\n\t"              \
+  "fma.rn.f32 tab, ab" #P ", t" #C ", %9;\n\t"              \
+  "neg.f32 d, taa;\n\t"                                     \
+  "ex2.approx.ftz.f32 ea" #C ", d;\n\t"                     \
+  "neg.f32 d, tab;\n\t"                                     \
+  "ex2.approx.ftz.f32 eb" #C ", d;\n\t"                     \
+  "sub.f32 d, ea" #P ", ea" #C ";\n\t"                      \
+  "fma.rn.f32 %8, sa" #P ", d, %8;\n\t"                     \
+  "sub.f32 d, eb" #P ", eb" #C ";\n\t"                      \
+  "fma.rn.f32 %13, sb" #P ", d, %13;\n\t"                   \
+  "add.f32 %14, %14, 0f3F800000;\n\t"                       \
+  DEC(C)                                                    \
+  "neg.f32 d, aa" #C ";\n\t"                                \
+  "fma.rn.f32 %4, d, t" #C ", taa;\n\t"                     \
+  "neg.f32 d, ab" #C ";\n\t"                                \
+  "fma.rn.f32 %9, d, t" #C ", tab;\n\t"                     \
+  "or.b32 wz, ka" #C ", kb" #C ";\n\t"                      \
+  "setp.lt.s32 w, wz, 0;\n\t"                               \
+  "@w bra EXIT" #C ";\n\t"
+#define RJ_EXIT(C)                                          \
+  "EXIT" #C ":\n\t"                                         \
+  "mov.s32 %3, i" #C ";\n\t"                                \
+  "mov.f32 %15, t" #C ";\n\t"                               \
+  "selp.s32 %16, 1, 2, y" #C ";\n\t"                        \
+  "@x" #C " mov.s32 %16, 0;\n\t"                            \
+  "setp.lt.s32 w, ka" #C ", 0;\n\t"                         \
+  "@w add.s32 %16, %16, 4;\n\t"                             \
+  "setp.lt.s32 w, kb" #C ", 0;\n\t"                         \
+  "@w add.s32 %16, %16, 8;\n\t"                             \
+  "mov.f32 %5, aa" #C ";\n\t"                               \
+  "mov.f32 %6, sa" #C ";\n\t"                               \
+  "mov.f32 %7, ea" #C ";\n\t"                               \
+  "mov.f32 %10, ab" #C ";\n\t"                              \
+  "mov.f32 %11, sb" #C ";\n\t"                              \
+  "mov.f32 %12, eb" #C ";\n\t"                              \
+  "bra DONE;\n\t"
+#define RJ_ASM(LD, DEC)                                                                                              \
+  asm volatile(                                                                                                      \
+      "{\n\t"                                                                                                        \
+      ".reg .pred x0, y0, n0, x1, y1, n1, x2, y2, n2, w;\n\t"                                                        \
+      ".reg .f32 d, taa, tab, t0, t1, t2, sa0, sa1, sa2, sb0, sb1, sb2, ea0, ea1, ea2, eb0, eb1, eb2;\n\t"           \
+      ".reg .f32 aa0, aa1, aa2, ab0, ab1, ab2;\n\t"                                                                  \
+      ".reg .b32 ka0, ka1, ka2, kb0, kb1, kb2, wz;\n\t"                                                              \
+      ".reg .b16 hl, hh;\n\t"                                                                                        \
+      ".reg .s32 i0, i1, i2;\n\t"                                                                                    \
+      ".reg .s64 ad;\n\t"                                                                                            \
+      /* slot 2 = the cells the leg starts in */                                                                     \
+      "mov.f32 aa2, %5;\n\t" "mov.f32 sa2, %6;\n\t" "mov.f32 ea2, %7;\n\t"                                           \
+      "mov.f32 ab2, %10;\n\t" "mov.f32 sb2, %11;\n\t" "mov.f32 eb2, %12;\n\t"                                        \
+      "mov.f32 taa, %4;\n\t" "mov.f32 tab, %9;\n\t"                                                                  \
+      RJ_PEEK(0, "%3", LD)                                                                                           \
+      "LOOP:\n\t"                                                                                                    \
+      RJ_COMMIT(0) RJ_PEEK(1, "i0", LD) RJ_INTEG(2, 0, DEC)                                                          \
+      RJ_COMMIT(1) RJ_PEEK(2, "i1", LD) RJ_INTEG(0, 1, DEC)                                                          \
+      RJ_COMMIT(2) RJ_PEEK(0, "i2", LD) RJ_INTEG(1, 2, DEC)                                                          \
+      "bra LOOP;\n\t"                                                                                                \
+      RJ_EXIT(0) RJ_EXIT(1) RJ_EXIT(2)                                                                               \
+      "DONE:\n\t"                                                                                                    \
+      "mov.f32 %17, taa;\n\t"                                                                                        \
+      "mov.f32 %18, tab;\n\t"                                                                                        \
+      "}"                                                                                                            \
+      : "+f"(d.tx), "+f"(d.ty), "+f"(d.tz), "+r"(d.idx), "+f"(qa.A), "+f"(qa.k), "+f"(qa.s), "+f"(qa.ePrev), "+f"(qa.leg), \
+        "+f"(qb.A), "+f"(qb.k), "+f"(qb.s), "+f"(qb.ePrev), "+f"(qb.leg), "+f"(nsteps), "=f"(o.t), "=r"(o.axis), "=f"(qa.tau), "=f"(qb.tau) \
+      : "l"(recs), "l"(offB), "f"(ddx), "f"(ddy), "f"(ddz), "r"(stx), "r"(sty), "r"(stz)                              \
+      : "memory")
+
+__device__ __forceinline__ LegOut march_leg_pair(Dda& d, Integ& qa, Integ& qb, float& nsteps, const Rec8* __restrict__ recs,
+                                                 const Rec8* __restrict__ recsB, float ddx, float ddy, float ddz, int stx, int sty, int stz) {
+  LegOut o;
+  const long long offB = (long long)(reinterpret_cast<const char*>(recsB) - reinterpret_cast<const char*>(recs));
+  RJ_ASM(RJ_LD8, RJ_DEC8);
+  return o;
+}
+__device__ __forceinline__ LegOut march_leg_pair(Dda& d, Integ& qa, Integ& qb, float& nsteps, const Rec4* __restrict__ recs,
+                                                 const Rec4* __restrict__ recsB, float ddx, float ddy, float ddz, int stx, int sty, int stz) {
+  LegOut o;
+  const long long offB = (long long)(reinterpret_cast<const char*>(recsB) - reinterpret_cast<const char*>(recs));
+  RJ_ASM(RJ_LD4, RJ_DEC4);
+  return o;
+}
+#undef RJ_ASM
+#undef RJ_PEEK
+#undef RJ_COMMIT
+#undef RJ_INTEG
+#undef RJ_EXIT
+#undef RJ_LD8
+#undef RJ_LD4
+#undef RJ_DEC8
+#undef RJ_DEC4
+#else
+// host build (tests/hostsim): the same algorithm statement by statement
+template <class RecT>
+__device__ __forceinline__ LegOut march_leg_pair(Dda& d, Integ& qa, Integ& qb, float& nsteps, const RecT* __restrict__ recs,
+                                                 const RecT* __restrict__ recsB, float ddx, float ddy, float ddz, int stx, int sty, int stz) {
+  Peek p1 = dda_peek(d, stx, sty, stz), p2;
+  Rec8 a1 = ldrec(recs + p1.idx), b1 = ldrec(recsB + p1.idx), a2, b2;
+  const float n0 = qa.nsteps, n1 = qb.nsteps;
+  LegOut o;
+  for (;;) {
+    dda_commit(d, p1, ddx, ddy, ddz);
+    p2 = dda_peek(d, stx, sty, stz);
+    a2 = ldrec(recs + p2.idx); b2 = ldrec(recsB + p2.idx);
+    integ_cross(qa, p1.t, a1); integ_cross(qb, p1.t, b1);
+    if (is_wall(a1.k) || is_wall(b1.k)) { o = LegOut{p1.t, (p1.px ? 0 : (p1.py ? 1 : 2)) | (is_wall(a1.k) ? 4 : 0) | (is_wall(b1.k) ? 8 : 0)}; break; }
+    dda_commit(d, p2, ddx, ddy, ddz);
+    p1 = dda_peek(d, stx, sty, stz);
+    a1 = ldrec(recs + p1.idx); b1 = ldrec(recsB + p1.idx);
+    integ_cross(qa, p2.t, a2); integ_cross(qb, p2.t, b2);
+    if (is_wall(a2.k) || is_wall(b2.k)) { o = LegOut{p2.t, (p2.px ? 0 : (p2.py ? 1 : 2)) | (is_wall(a2.k) ? 4 : 0) | (is_wall(b2.k) ? 8 : 0)}; break; }
+  }
+  nsteps += qa.nsteps - n0;
+  qa.nsteps = n0; qb.nsteps = n1;
+  return o;
+}
+#endif
+
 template <class RecT>
 __device__ __forceinline__ void march_single_level_dual(const RecT* __restrict__ recs, int idxA, int sy, int sz, float dx, float dy, float dz,
                                                         float rx, float ry, float rz, float cx, float cy, float cz, float threshold,
@@ -622,25 +767,12 @@ __device__ __forceinline__ void march_single_level_dual(const RecT* __restrict__
     qb.k = fabsf(rb.k); qb.s = rb.s;
   }
   qa.A = qb.A = 0.0f; qa.ePrev = qb.ePrev = 1.0f; qa.nsteps = qb.nsteps = 0.0f; qa.tau = qb.tau = 0.0f; qa.leg = qb.leg = 0.0f;
-  // ---- joint leg: pipelined like march_leg (the records of step n+1 are requested before the wall tests of step n)
-  Peek p1 = dda_peek(d, stx, sty, stz), p2, w;
-  Rec8 a1 = ldrec(recs + p1.idx), b1 = ldrec(recsB + p1.idx), a2, b2;
-  bool wa, wb;
-  for (;;) {
-    dda_commit(d, p1, ddx, ddy, ddz);
-    p2 = dda_peek(d, stx, sty, stz);
-    a2 = ldrec(recs + p2.idx); b2 = ldrec(recsB + p2.idx);
-    integ_cross(qa, p1.t, a1); integ_cross(qb, p1.t, b1);
-    wa = is_wall(a1.k); wb = is_wall(b1.k);
-    if (wa || wb) { w = p1; break; }
-    dda_commit(d, p2, ddx, ddy, ddz);
-    p1 = dda_peek(d, stx, sty, stz);
-    a1 = ldrec(recs + p1.idx); b1 = ldrec(recsB + p1.idx);
-    integ_cross(qa, p2.t, a2); integ_cross(qb, p2.t, b2);
-    wa = is_wall(a2.k); wb = is_wall(b2.k);
-    if (wa || wb) { w = p2; break; }
-  }
-  const LegOut lw{w.t, w.px ? 0 : (w.py ? 1 : 2)};
+  // ---- joint leg (march_leg_pair): both rays take the same steps until either enters a non-flow cell
+  float joint = 0.0f;
+  const LegOut jw = march_leg_pair(d, qa, qb, joint, recs, recsB, ddx, ddy, ddz, stx, sty, stz);
+  qa.nsteps += joint; qb.nsteps += joint;
+  const bool wa = (jw.axis & 4) != 0, wb = (jw.axis & 8) != 0;
+  const LegOut lw{jw.t, jw.axis & 3};
   // ---- each ray on its own from here
   RayState A{d, qa, 0.0f, 1.0f, stx, sty, stz};
   if (!wa || ray_wall(A, lw, recs, threshold, allowReflect, skipZero)) ray_finish(A, recs, ddx, ddy, ddz, threshold, allowReflect, skipZero, recBytes);
