@@ -279,7 +279,10 @@ def run_ours(args):
     # one validated set-up solve
     replicate()
     g.finalize_level(0, stream)
-    kernels_per_step = 3 if world == 1 else 3 + world         # pack + finalize + divq (+ assemble per rank box)
+    dual = args.cells_per_lane == 2 and args.coherence >= 1
+    # pack + finalize + divq (+ assemble per rank box); the two-cells-per-lane solve launches the pair kernel AND the gated one-cell
+    # kernel, of which one returns at once (launch_gate)
+    kernels_per_step = (3 if world == 1 else 3 + world) + (1 if dual else 0)
 
     def barrier():
         if world > 1:

@@ -615,3 +615,27 @@ def test_two_cells_per_lane_kernel(gpu_lib, po):
     g = make(gpu_lib, nDivQRays=8, threshold=0.001, seed=5, allowReflect=0)
     g.upload_level(0, iso)
     assert np.abs(g.trace_divq(0)["divQ"]).max() < 2e-5 * 4 * np.pi * 2.0 * 0.6
+
+
+def test_kernel_choice_follows_the_walls(gpu_lib, po):
+    """launch_gate: with reflective walls (mirrors) and allowReflect the production solve runs on the one-cell-per-lane kernel -- bit
+    identical to cellsPerLane=1; with black walls, or allowReflect off, the two-cells-per-lane kernel does the work (different rays)"""
+    pl = po.parallel_plates(24, dtype=np.float32, mirror_faces=("x-", "y-"))
+    bc = po.burns_christon(24, dtype=np.float32)
+
+    def solve(lv, **kw):
+        g = make(gpu_lib, nDivQRays=12, threshold=0.01, seed=6, **kw)
+        g.upload_level(0, lv)
+        d = g.trace_divq(0, timestep=4)["divQ"]
+        return d, int(g.counters().nRaySteps), int(g.counters().nDivQCells)
+
+    d2, n2, c2 = solve(pl)
+    d1, n1, c1 = solve(pl, cellsPerLane=1)
+    assert np.array_equal(d1, d2) and n1 == n2 and c1 == c2 == 24 ** 3          # mirrors: the one-cell kernel ran in both
+    e2, m2, _ = solve(pl, allowReflect=0)
+    e1, m1, _ = solve(pl, allowReflect=0, cellsPerLane=1)
+    assert not np.array_equal(e1, e2) and abs(m1 - m2) < 0.01 * m1                  # rays end at the first wall: the pair kernel ran
+    b2, k2, cb2 = solve(bc)
+    b1, k1, cb1 = solve(bc, cellsPerLane=1)
+    assert not np.array_equal(b1, b2) and cb1 == cb2 == 24 ** 3 and abs(k1 - k2) < 0.01 * k1
+    assert np.linalg.norm(b1 - b2) / np.linalg.norm(b1) < 0.08                      # same physics, other random draws

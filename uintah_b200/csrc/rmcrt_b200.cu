@@ -38,6 +38,7 @@ constexpr int MAXL = 4;   // levels supported by the Data-Onion kernels (referen
 //   [0] non-finite records  [1] flow cells on the outer layer  [2] non-flow cells that can emit (k*s != 0)
 //   [3] valid: set by finalize_kernel's last block, cleared by every kernel that modifies the level
 //   [4] ticket for "last block"      [5] non-finite inputs seen by the pack kernels
+//   [6] reflective non-flow cells (abskg < 1): rays can go on after their first wall (chooses between the one- and two-cells-per-lane kernels)
 constexpr int LSTAT_WORDS = 8;
 constexpr int NCOUNTERS = 5;    // [0] divQ steps [1] flux steps [2] divQ cells [3] flux cells [4] radiometer steps
 
@@ -74,6 +75,8 @@ struct TraceArgs {
   int skipZero;
   int fluxFlowGuard;      // 1L: only flow cells get boundary fluxes (Ray.cc:654-656); DO: no guard (Q3)
   double sigmaScat;       // <sigmaScat>: > 0 = isotropic scattering in the single-level march (generic kernels)
+  int gate;               // 0: the kernel always runs; 1: only when rays END at their first wall (no reflective wall on the level, or
+                          // allowReflect off); 2: only when they can go on -- see launch_gate()
   RayGen rng;
   unsigned long long* counters;   // [0] divQ steps [1] flux steps [2] divQ cells [3] flux cells
   const unsigned* lstat;          // per-level device status words [MAXL][LSTAT_WORDS] (see finalize_kernel)
@@ -262,6 +265,17 @@ __device__ __forceinline__ ScatRng scat_rng(const RayGen& rg, int i, int j, int 
   return r;
 }
 
+// The production solve is launched as TWO kernels of which exactly one does the work, chosen on the device from the level's
+// finalize status (no host round trip): the two-cells-per-lane kernel wins when every ray ends at its first wall (its joint leg is the
+// whole ray), the one-cell kernel (32 registers, twice the occupancy) when reflective walls send rays on for several more legs
+// (C5: 1.01e12 vs 0.94e12 steps/s).  Both are correct for any input; an unfinalized level counts as reflective.
+__device__ __forceinline__ bool launch_gate(const TraceArgs& a) {
+  if (a.gate == 0) return true;
+  const unsigned* ls = a.lstat + (a.G.maxLevels - 1) * LSTAT_WORDS;
+  const bool raysGoOn = a.allowReflect != 0 && (ls[3] == 0u || ls[6] != 0u);
+  return (a.gate == 2) == raysGoOn;
+}
+
 // zero-weight legs may be skipped only when every level in play has been finalized and none of its non-flow cells emits
 __device__ __forceinline__ bool skip_allowed(const TraceArgs& a) {
   if (!a.skipZero) return false;
@@ -339,6 +353,7 @@ template <class Real, class RecT, bool ML, bool FAST = false, bool F32GEN = fals
 #endif
 __global__ void __launch_bounds__(256, ((FAST && !ML) ? RMCRT_FAST_MIN_BLOCKS : 4)) divq_kernel(const __grid_constant__ TraceArgs a) {
   extern __shared__ double red[];     // [W][32]
+  if (!launch_gate(a)) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
   const int F = a.G.maxLevels - 1;
   const LevelGeom& g = a.G.lev[F];
@@ -432,6 +447,7 @@ __global__ void __launch_bounds__(256, ((FAST && !ML) ? RMCRT_FAST_MIN_BLOCKS : 
 template <class RecT>
 __global__ void __launch_bounds__(256, 4) divq_dual_kernel(const __grid_constant__ TraceArgs a, int nxc, int njp) {
   extern __shared__ double red[];     // [W][64]
+  if (!launch_gate(a)) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
   const int F = a.G.maxLevels - 1;
   const LevelGeom& g = a.G.lev[F];
@@ -792,7 +808,7 @@ __global__ void pack_kernel(const T* __restrict__ abskg, const T* __restrict__ s
 template <class RecT>
 __global__ void finalize_kernel(const RecT* __restrict__ recs, Box b, unsigned* __restrict__ status) {
   const long long n = box_cells(b);
-  unsigned open = 0, emit = 0, bad = 0;
+  unsigned open = 0, emit = 0, bad = 0, refl = 0;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
     const long long row = t / b.n[0];
     const int i = (int)(t - row * b.n[0]);
@@ -803,11 +819,13 @@ __global__ void finalize_kernel(const RecT* __restrict__ recs, Box b, unsigned* 
     const bool outer = (i == 0 || j == 0 || k == 0 || i == b.n[0] - 1 || j == b.n[1] - 1 || k == b.n[2] - 1);
     if (outer && !wall) ++open;
     if (wall && (r.k != 0) && (r.s != 0)) ++emit;
+    if (wall && fabs((double)r.k) < 1.0) ++refl;        // fs = fs (1 - abskg) stays > 0 after this wall (RMCRTCommon.cc:588)
     if (!isfinite((double)r.k) || !isfinite((double)r.s)) ++bad;
   }
   if (bad) atomicAdd(status + 0, bad);
   if (open) atomicAdd(status + 1, open);
   if (emit) atomicAdd(status + 2, emit);
+  if (refl) atomicAdd(status + 6, refl);
   // the last block to finish publishes the result (words 0..2 were zeroed before the launch)
   __threadfence();
   __syncthreads();
@@ -1531,7 +1549,11 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
         if (g2 > cap) g2 = cap;
         int W2 = ctx->p.warpsPerTile > 0 ? std::min(ctx->p.warpsPerTile, 8) : 4;
         if (W2 < 2) W2 = 2;        // rows A and B are written by warps 0 and 1
-        divq_dual_kernel<RecT><<<(int)g2, 32 * W2, W2 * 64 * sizeof(double), st>>>(a, nxc, njp);
+        TraceArgs a2 = a;
+        a2.gate = 1;
+        divq_dual_kernel<RecT><<<(int)g2, 32 * W2, W2 * 64 * sizeof(double), st>>>(a2, nxc, njp);
+        a2.gate = 2;      // the same solve on the one-cell kernel when reflective walls keep the rays going (launch_gate)
+        divq_kernel<Real, RecT, false, true, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a2);
       }
     } else if (std::is_same<Real, float>::value && !bounded && (!ctx->p.genericMarch || std::is_same<RecT, Rec4>::value)) {
       if (f32gen) divq_kernel<Real, RecT, false, true, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
@@ -1829,6 +1851,7 @@ static int finalize_launch(rmcrt_ctx* ctx, int L, cudaStream_t st) {
   LevelState& lv = ctx->lv[L];
   unsigned* ls = lstat_of(ctx, L);
   CK(cudaMemsetAsync(ls, 0, 5 * sizeof(unsigned), st));      // words 0..4; word 5 (pack-time input check) survives
+  CK(cudaMemsetAsync(ls + 6, 0, sizeof(unsigned), st));
   Box b = mkbox(lv.d.lo, lv.d.hi);
   if (lv.recordKind == 0)      finalize_kernel<Rec8><<<grid_for(lv.nCells, 256, ctx->smCount), 256, 0, st>>>(static_cast<const Rec8*>(lv.rec), b, ls);
   else if (lv.recordKind == 2) finalize_kernel<Rec4><<<grid_for(lv.nCells, 256, ctx->smCount), 256, 0, st>>>(static_cast<const Rec4*>(lv.rec), b, ls);
