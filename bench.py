@@ -279,7 +279,7 @@ def run_ours(args):
     # one validated set-up solve
     replicate()
     g.finalize_level(0, stream)
-    dual = args.cells_per_lane == 2 and args.coherence >= 1
+    dual = args.cells_per_lane in (2, 4) and args.coherence >= 1
     # pack + finalize + divq (+ assemble per rank box); the two-cells-per-lane solve launches the pair kernel AND the gated one-cell
     # kernel, of which one returns at once (launch_gate)
     kernels_per_step = (3 if world == 1 else 3 + world) + (1 if dual else 0)
@@ -405,10 +405,10 @@ def run_ours(args):
     alg_bytes = ALG_BYTES_PER_STEP * per_rank_steps + ALG_BYTES_PER_CELL * per_rank_cells
     kern_s = (t_trace_total / args.steps)
     achieved = alg_bytes / kern_s / 1e9
-    traffic, traffic_src = (profiled_traffic(P, rays, rec_bytes, "divq_dual" if (args.cells_per_lane == 2 and args.coherence >= 1) else "divq")
+    traffic, traffic_src = (profiled_traffic(P, rays, rec_bytes, {2: "divq_dual", 4: "divq_quad"}.get(args.cells_per_lane if args.coherence >= 1 else 1, "divq"))
                             if world == 1 else (None, None))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": traffic, "traffic_source": traffic_src, "kernel": ("divq_dual_kernel" if (args.cells_per_lane == 2 and args.coherence >= 1) else "divq_kernel") + ("<Rec4>" if args.half_records else "<Rec8>"), "kernel_ms": 1e3 * kern_s,
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": {2: "divq_dual_kernel", 4: "divq_quad_kernel"}.get(args.cells_per_lane if args.coherence >= 1 else 1, "divq_kernel") + ("<Rec4>" if args.half_records else "<Rec8>"), "kernel_ms": 1e3 * kern_s,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "note": "12 B per executed ray-cell step + 28 B per divQ cell; the property records are L2-resident, so the "
                         "binding roofline is L2 (see roofline_l2), HBM peak shown because MEASURED_PEAKS.json has no L2 figure"}
@@ -468,10 +468,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=128, help="cells per side of the per-GPU patch")
     ap.add_argument("--rays", type=int, default=100)
-    ap.add_argument("--coherence", type=int, default=1)
+    ap.add_argument("--coherence", type=int, default=2, help="rayCoherence (library default 2)")
     ap.add_argument("--l2persist", type=int, default=1)
     ap.add_argument("--warps", type=int, default=0)
-    ap.add_argument("--cells-per-lane", type=int, default=2, help="2 (library default): a lane marches two cells with one DDA; 1: one cell per lane (A/B)")
+    ap.add_argument("--cells-per-lane", type=int, default=4, help="4 (library default): a lane marches 2 x 2 cells with one DDA; 2: a pair; 1: one cell per lane (A/B)")
     ap.add_argument("--half-records", type=int, default=-1,
                     help="1: 4-B half-packed level records (fp16 abskg|wall, fp16 sigmaT4/pi); 0: 8-B float records; "
                          "-1 (default): half-packed when the float records of the level would exceed 64 MB (beyond the L2)")

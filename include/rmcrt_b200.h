@@ -65,10 +65,10 @@ typedef struct rmcrt_params {
   uint64_t seed;               /* mixed into the Philox key (randomSeed=true) */
   /* ---- implementation knobs (no counterpart in the reference) ---- */
   int32_t  marchPrecision;     /* 0 = FP32 march (production), 1 = FP64 march (parity debugging) */
-  int32_t  rayCoherence;       /* 1 = the 32 origin cells of a warp share one direction per ray index
-                                  (warp-coherent batching); 0 = independent direction per (cell, ray);
-                                  2 = they also share the in-cell origin offset, so the 32 rays are exact translates
-                                  of each other and march in lockstep (divQ rays only) */
+  int32_t  rayCoherence;       /* 2 (default) = the origin cells of a tile share one direction AND one in-cell origin offset per
+                                  ray index, so the rays of a warp are exact translates of each other and march in lockstep
+                                  (divQ rays only; every cell still sees nDivQRays independent isotropic rays);
+                                  1 = shared direction, every lane its own in-cell origin; 0 = independent rays per (cell, ray) */
   int32_t  skipZeroWeightLegs; /* 1 = end a ray once fs==0 and no non-flow cell can emit (exact);
                                   0 = march every leg the reference marches */
   int32_t  fixedRandom;        /* FIXED_RANDOM_NUM (MersenneTwister.h:93): every draw = 0.3 */
@@ -79,10 +79,11 @@ typedef struct rmcrt_params {
   int32_t  maxBlocksPerSM;     /* 0 = one tile per block (hardware balances the tail); > 0 caps the divQ grid at this many
                                   blocks per SM and grid-strides over the tiles (A/B measurements) */
   int32_t  rayDirSampleAlgo;   /* <rayDirSampleAlgo> 0 naive (default), 1 LatinHyperCube (Ray.cc:174-179, 1398-1460) */
-  int32_t  cellsPerLane;       /* 2 (default): with rayCoherence >= 1 a lane owns cells (i,j,k) and (i,j+1,k); their rays share the direction AND
-                                  the in-cell origin, so they are exact translates and ONE DDA drives both (divq_dual_kernel: the DDA
-                                  instructions are paid once per two ray-cell steps).  Per-ray arithmetic identical to the one-cell kernel.
-                                  1: one cell per lane (every cell its own in-cell origin when rayCoherence == 1).
+  int32_t  cellsPerLane;       /* 4 (default): with rayCoherence >= 1 a lane owns the 2 x 2 cells (i, j..j+1, k..k+1); their rays share the
+                                  direction AND the in-cell origin, so they are exact translates and ONE DDA drives all four
+                                  (divq_quad_kernel: the DDA instructions are paid once per four ray-cell steps).
+                                  2: the pair (i,j,k), (i,j+1,k) (divq_dual_kernel).  1: one cell per lane.
+                                  Per-ray arithmetic is identical in all three (bit-identical divQ for cells that trace the same rays).
                                   Applies to the production FP32 / Philox single-level solve; all other modes use one cell per lane. */
   double   maxRayLength;       /* <ROI_extents type="boundedRayLength"><length> (Ray.cc:243, RMCRTCommon.cc:680,684);
                                   <= 0 or >= 1e300: unbounded (DBL_MAX, RMCRTCommon.cc:117).  Single-level solves only, like

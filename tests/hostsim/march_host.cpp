@@ -198,4 +198,24 @@ void hs_trace_1L_dual(const HsLevel* g, int n, const int* cells, const double* d
     sumA[t] = a; sumB[t] = b; stepsA[t] = sa; stepsB[t] = sb;
   }
 }
+// four cells per lane (march_single_level_quad): the rays of the 2 x 2 cells c, c + (0,1,0), c + (0,0,1), c + (0,1,1) with the SAME direction
+// and in-cell origin; steps = the sum over the four rays (what the kernel counts)
+void hs_trace_1L_quad(const HsLevel* g, int n, const int* cells, const double* dirs, const double* orgs, double threshold, int allowReflect,
+                      int skipZero, double* sums /* [n][4] */, unsigned* steps /* [n] */) {
+  const int nx = g->hi[0] - g->lo[0], ny = g->hi[1] - g->lo[1];
+  for (int t = 0; t < n; ++t) {
+    const int* c = cells + 3 * t;
+    double r[3];
+    rayDxOf(*g, c, orgs + 3 * t, r);
+    const int idx = (c[0] - g->lo[0]) + nx * ((c[1] - g->lo[1]) + ny * (c[2] - g->lo[2]));
+    unsigned st = 0;
+    float sm[4];
+    const double* d = dirs + 3 * t;
+    march_single_level_quad(static_cast<const Rec8*>(g->rec), idx, nx, nx * ny, (float)d[0], (float)d[1], (float)d[2], (float)r[0], (float)r[1],
+                            (float)r[2], (float)g->dx[0], (float)g->dx[1], (float)g->dx[2], (float)threshold, allowReflect != 0, skipZero != 0,
+                            st, 8, sm);
+    for (int q = 0; q < 4; ++q) sums[4 * t + q] = sm[q];
+    steps[t] = st;
+  }
+}
 }

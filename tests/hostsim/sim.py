@@ -137,3 +137,15 @@ def trace_1L_dual(lv, cells, dirs, org, thr, refl, skip=0):
     cells = np.ascontiguousarray(cells, np.int32); dirs = np.ascontiguousarray(dirs); org = np.ascontiguousarray(org)
     lib().hs_trace_1L_dual(C.byref(h), n, _vp(cells), _vp(dirs), _vp(org), C.c_double(thr), refl, skip, _vp(sa), _vp(sb), _vp(na), _vp(nb))
     return sa, sb, na, nb
+
+
+def trace_1L_quad(lv, cells, dirs, org, thr, refl, skip=0):
+    """march_single_level_quad: rays of the 2 x 2 cells c, c+(0,1,0), c+(0,0,1), c+(0,1,1) sharing direction and in-cell origin;
+    returns sums [n, 4] and the step total of the four rays [n]"""
+    rec = pack(lv, 0)
+    h = hslevel(lv, rec)
+    n = len(cells)
+    sm = np.zeros((n, 4)); st = np.zeros(n, np.uint32)
+    cells = np.ascontiguousarray(cells, np.int32); dirs = np.ascontiguousarray(dirs); org = np.ascontiguousarray(org)
+    lib().hs_trace_1L_quad(C.byref(h), n, _vp(cells), _vp(dirs), _vp(org), C.c_double(thr), refl, skip, _vp(sm), _vp(st))
+    return sm, st

@@ -211,7 +211,7 @@ def bc41_stats(po):
     return lv, runs
 
 
-@pytest.mark.parametrize("coherent,cpl", [(1, 2), (1, 1), (0, 1), (2, 2), (2, 1)])
+@pytest.mark.parametrize("coherent,cpl", [(2, 4), (1, 4), (1, 2), (1, 1), (0, 1), (2, 2), (2, 1)])
 def test_burns_christon_monte_carlo_tolerance(gpu_lib, po, bc41_stats, coherent, cpl):
     """BASELINE config 1 (RMCRT_bm1_1L, 41^3, 100 rays/cell): SURVEY 8c acceptance (i)-(iii)"""
     lv, runs = bc41_stats
@@ -639,3 +639,60 @@ def test_kernel_choice_follows_the_walls(gpu_lib, po):
     b1, k1, cb1 = solve(bc, cellsPerLane=1)
     assert not np.array_equal(b1, b2) and cb1 == cb2 == 24 ** 3 and abs(k1 - k2) < 0.01 * k1
     assert np.linalg.norm(b1 - b2) / np.linalg.norm(b1) < 0.08                      # same physics, other random draws
+
+
+def test_four_cells_per_lane_kernel(gpu_lib, po):
+    """divq_quad_kernel (the production default, cellsPerLane = 4).
+    (a) With rayCoherence = 2 a cell's rays are keyed on the first cell of its tile only, so the cells with (j - lo, k - lo) both even trace
+        IDENTICAL rays in the 1-, 2- and 4-cells-per-lane kernels when a row of the patch is one 32-cell tile: divQ must agree BIT FOR BIT
+        (same per-ray arithmetic in the PTX joint legs, same accumulation order), for float and half-packed records.
+    (b) odd patch sizes and offsets (partial 32-cell chunks, unpaired last row and last plane), intrusions inside a 2 x 2 block: same
+        cells written and counted as the one-cell kernel, steps per ray within 1 %, per-cell agreement within Monte-Carlo error.
+    (c) exactly zero divQ in an isothermal black enclosure with intrusions."""
+    rng = np.random.default_rng(11)
+    lv = po.burns_christon(37, dtype=np.float32)
+    add_random_walls(lv, 0.02, rng, abskg=1.0, sigmaT4=0.1)
+    lo, hi = (3, 5, 2), (35, 30, 13)
+    for half in (False, True):
+        res = {}
+        for cpl in (1, 2, 4):
+            g = make(gpu_lib, nDivQRays=32, threshold=0.05, seed=3, rayCoherence=2, warpsPerTile=4, cellsPerLane=cpl, half_records=half)
+            g.upload_level(0, lv)
+            res[cpl] = (g.trace_divq(0, patch_lo=lo, patch_hi=hi, timestep=3)["divQ"], int(g.counters().nRaySteps), int(g.counters().nDivQCells))
+        rows = (slice(lo[2] + 1, hi[2] + 1, 2), slice(lo[1] + 1, hi[1] + 1, 2), slice(lo[0] + 1, hi[0] + 1))
+        assert (res[1][0][rows] != 0).sum() > 2000
+        assert np.array_equal(res[1][0][rows], res[4][0][rows]) and np.array_equal(res[1][0][rows], res[2][0][rows])
+        assert res[1][2] == res[2][2] == res[4][2]
+        assert np.array_equal(res[1][0] != 0, res[4][0] != 0)
+    # (b)
+    res = {}
+    for cpl in (1, 4):
+        g = make(gpu_lib, nDivQRays=200, threshold=0.05, seed=3, cellsPerLane=cpl)
+        g.upload_level(0, lv)
+        d = g.trace_divq(0, patch_lo=(3, 5, 2), patch_hi=(36, 30, 11))["divQ"]
+        res[cpl] = (d, int(g.counters().nDivQCells), int(g.counters().nRaySteps))
+    (d1, n1, s1), (d4, n4, s4) = res[1], res[4]
+    flow = lv.cellType == -1
+    box = np.zeros(flow.shape, bool); box[3:12, 6:31, 4:37] = True
+    assert n1 == n4 == int((flow & box).sum())
+    assert np.array_equal(d1 != 0, d4 != 0) and not d4[~(flow & box)].any()
+    assert abs(s1 - s4) < 0.01 * s1
+    sel = d1 != 0
+    g = make(gpu_lib, nDivQRays=200, threshold=0.05, seed=3, cellsPerLane=1)
+    g.upload_level(0, lv)
+    d1b = g.trace_divq(0, patch_lo=(3, 5, 2), patch_hi=(36, 30, 11), timestep=2)["divQ"]
+    l2 = lambda x, y: np.linalg.norm(x[sel] - y[sel]) / np.linalg.norm(x[sel])
+    assert l2(d1, d4) < 1.25 * l2(d1, d1b), (l2(d1, d4), l2(d1, d1b))
+    # (c)
+    M = 27
+    ab = rng.uniform(0.1, 2.0, (M, M, M)).astype(np.float32); s4_ = np.full((M, M, M), 0.6, np.float32); ct = np.full((M, M, M), -1, np.int32)
+    for ax in range(3):
+        for idx in (0, M - 1):
+            sl = [slice(None)] * 3; sl[ax] = idx; ct[tuple(sl)] = 8; ab[tuple(sl)] = 1.0
+    walls = (rng.uniform(size=(M, M, M)) < 0.03) & (ct == -1); ct[walls] = 8; ab[walls] = 1.0
+    iso = po.Level(ab, s4_, ct, (-1,) * 3, (M - 1,) * 3, (1.0 / 25,) * 3, interior_lo=(0,) * 3, interior_hi=(25,) * 3)
+    for coh in (1, 2):
+        g = make(gpu_lib, nDivQRays=8, threshold=0.001, seed=5, allowReflect=0, cellsPerLane=4, rayCoherence=coh)
+        g.upload_level(0, iso)
+        assert np.abs(g.trace_divq(0)["divQ"]).max() < 2e-5 * 4 * np.pi * 2.0 * 0.6
+        assert int(g.counters().nDivQCells) == int((ct == -1).sum())

@@ -187,3 +187,41 @@ def test_two_cells_per_lane_march_equals_two_single_marches(po, case):
     np.testing.assert_allclose(sa[same], ra[same], rtol=1e-5, atol=1e-6 * np.abs(ra).max())
     np.testing.assert_allclose(sb[same], rb[same], rtol=2e-4, atol=1e-5 * np.abs(rb).max())
     assert (na != nb).mean() > 0.2          # the two rays of a lane really end at different steps often
+
+
+@pytest.mark.parametrize("case", ["bc_walls", "plates_mirrors", "bc_refsem"])
+def test_four_cells_per_lane_march_equals_four_single_marches(po, case):
+    """march_single_level_quad (one DDA drives the rays of the 2 x 2 cells (i, j..j+1, k..k+1), exact translates of each other) == the
+    single-ray production march run four times: same sums and the same step total, including when the rays meet walls at different
+    steps, reflect off mirrors or start next to an intrusion"""
+    rng = np.random.default_rng(37)
+    if case == "plates_mirrors":
+        lv = po.parallel_plates(18, dtype=np.float32, mirror_faces=("x-", "z+"))
+        thr, refl, skip = 0.001, 1, 0
+    else:
+        lv = po.burns_christon(20, dtype=np.float32)
+        from util import add_random_walls
+        add_random_walls(lv, 0.03, rng, abskg=0.8, sigmaT4=0.05)
+        thr, refl, skip = 0.05, 1, (1 if case == "bc_walls" else 0)
+    n = 500
+    cells, dirs, org = random_rays(lv, n, rng)
+    N = lv.interior_hi
+    ct = lv.cellType
+    offs = [(0, 0, 0), (0, 1, 0), (0, 0, 1), (0, 1, 1)]
+    keep = [t for t in range(n) if cells[t][1] + 1 < N[1] and cells[t][2] + 1 < N[2]
+            and all(ct[cells[t][2] + 1 + o[2], cells[t][1] + 1 + o[1], cells[t][0] + 1] == -1 for o in offs)]
+    cells, dirs, org = cells[keep], dirs[keep], org[keep]
+    assert len(cells) > 250
+    sm, st = sim.trace_1L_quad(lv, cells, dirs, org, thr, refl, skip)
+    tot = np.zeros(len(cells), np.int64)
+    ok = np.ones(len(cells), bool)
+    singles = []
+    for o in offs:
+        r, nr = sim.trace_1L_fast(lv, cells + np.array(o, np.int32), dirs, org + np.array(o) * np.array(lv.dx), thr, refl, skip)
+        singles.append(r); tot += nr
+    # the in-cell offset of the translated origins is rebuilt from an absolute position in the single march: allow FP32 round-off
+    same = st.astype(np.int64) == tot
+    assert same.mean() > 0.95, same.mean()
+    np.testing.assert_allclose(sm[same, 0], singles[0][same], rtol=1e-5, atol=1e-6 * np.abs(singles[0]).max())
+    for q in (1, 2, 3):
+        np.testing.assert_allclose(sm[same, q], singles[q][same], rtol=2e-4, atol=1e-5 * np.abs(singles[q]).max())

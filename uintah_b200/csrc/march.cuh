@@ -645,8 +645,8 @@ __device__ __forceinline__ void ray_finish(RayState& r, const RecT* __restrict__
   "or.b32 wz, ka" #C ", kb" #C ";\n\t"                      \
   "setp.lt.s32 w, wz, 0;\n\t"                               \
   "@w bra EXIT" #C ";\n\t"
-#define RJ_EXIT(C)                                          \
-  "EXIT" #C ":\n\t"                                         \
+#define RJ_EXIT(L, C)                                       \
+  "EXIT" #L ":\n\t"                                         \
   "mov.s32 %3, i" #C ";\n\t"                                \
   "mov.f32 %15, t" #C ";\n\t"                               \
   "selp.s32 %16, 1, 2, y" #C ";\n\t"                        \
@@ -662,16 +662,27 @@ __device__ __forceinline__ void ray_finish(RayState& r, const RecT* __restrict__
   "mov.f32 %11, sb" #C ";\n\t"                              \
   "mov.f32 %12, eb" #C ";\n\t"                              \
   "bra DONE;\n\t"
+#ifndef RMCRT_PAIR_DEPTH
+#define RMCRT_PAIR_DEPTH 1      // steps the pair's record requests run ahead of the wall test (1: three-slot rotation, 2: four-slot)
+#endif
+#define RJ_REGS(SLOTS)                                                                                               \
+      ".reg .pred x0, y0, n0, x1, y1, n1, x2, y2, n2, x3, y3, n3, w;\n\t"                                            \
+      ".reg .f32 d, taa, tab, t0, t1, t2, t3, sa0, sa1, sa2, sa3, sb0, sb1, sb2, sb3;\n\t"                           \
+      ".reg .f32 ea0, ea1, ea2, ea3, eb0, eb1, eb2, eb3, aa0, aa1, aa2, aa3, ab0, ab1, ab2, ab3;\n\t"                \
+      ".reg .b32 ka0, ka1, ka2, ka3, kb0, kb1, kb2, kb3, wz;\n\t"                                                    \
+      ".reg .b16 hl, hh;\n\t"                                                                                        \
+      ".reg .s32 i0, i1, i2, i3;\n\t"                                                                                \
+      ".reg .s64 ad;\n\t"
+#define RJ_OPERANDS                                                                                                  \
+      : "+f"(d.tx), "+f"(d.ty), "+f"(d.tz), "+r"(d.idx), "+f"(qa.A), "+f"(qa.k), "+f"(qa.s), "+f"(qa.ePrev), "+f"(qa.leg), \
+        "+f"(qb.A), "+f"(qb.k), "+f"(qb.s), "+f"(qb.ePrev), "+f"(qb.leg), "+f"(nsteps), "=f"(o.t), "=r"(o.axis), "=f"(qa.tau), "=f"(qb.tau) \
+      : "l"(recs), "l"(offB), "f"(ddx), "f"(ddy), "f"(ddz), "r"(stx), "r"(sty), "r"(stz)                              \
+      : "memory"
+#if RMCRT_PAIR_DEPTH == 1
 #define RJ_ASM(LD, DEC)                                                                                              \
   asm volatile(                                                                                                      \
       "{\n\t"                                                                                                        \
-      ".reg .pred x0, y0, n0, x1, y1, n1, x2, y2, n2, w;\n\t"                                                        \
-      ".reg .f32 d, taa, tab, t0, t1, t2, sa0, sa1, sa2, sb0, sb1, sb2, ea0, ea1, ea2, eb0, eb1, eb2;\n\t"           \
-      ".reg .f32 aa0, aa1, aa2, ab0, ab1, ab2;\n\t"                                                                  \
-      ".reg .b32 ka0, ka1, ka2, kb0, kb1, kb2, wz;\n\t"                                                              \
-      ".reg .b16 hl, hh;\n\t"                                                                                        \
-      ".reg .s32 i0, i1, i2;\n\t"                                                                                    \
-      ".reg .s64 ad;\n\t"                                                                                            \
+      RJ_REGS(3)                                                                                                     \
       /* slot 2 = the cells the leg starts in */                                                                     \
       "mov.f32 aa2, %5;\n\t" "mov.f32 sa2, %6;\n\t" "mov.f32 ea2, %7;\n\t"                                           \
       "mov.f32 ab2, %10;\n\t" "mov.f32 sb2, %11;\n\t" "mov.f32 eb2, %12;\n\t"                                        \
@@ -682,15 +693,68 @@ __device__ __forceinline__ void ray_finish(RayState& r, const RecT* __restrict__
       RJ_COMMIT(1) RJ_PEEK(2, "i1", LD) RJ_INTEG(0, 1, DEC)                                                          \
       RJ_COMMIT(2) RJ_PEEK(0, "i2", LD) RJ_INTEG(1, 2, DEC)                                                          \
       "bra LOOP;\n\t"                                                                                                \
-      RJ_EXIT(0) RJ_EXIT(1) RJ_EXIT(2)                                                                               \
+      RJ_EXIT(0, 0) RJ_EXIT(1, 1) RJ_EXIT(2, 2)                                                                            \
       "DONE:\n\t"                                                                                                    \
       "mov.f32 %17, taa;\n\t"                                                                                        \
       "mov.f32 %18, tab;\n\t"                                                                                        \
       "}"                                                                                                            \
-      : "+f"(d.tx), "+f"(d.ty), "+f"(d.tz), "+r"(d.idx), "+f"(qa.A), "+f"(qa.k), "+f"(qa.s), "+f"(qa.ePrev), "+f"(qa.leg), \
-        "+f"(qb.A), "+f"(qb.k), "+f"(qb.s), "+f"(qb.ePrev), "+f"(qb.leg), "+f"(nsteps), "=f"(o.t), "=r"(o.axis), "=f"(qa.tau), "=f"(qb.tau) \
-      : "l"(recs), "l"(offB), "f"(ddx), "f"(ddy), "f"(ddz), "r"(stx), "r"(sty), "r"(stz)                              \
-      : "memory")
+      RJ_OPERANDS)
+#else
+// Depth 2: the requests of steps n+1 AND n+2 are in flight when the wall test of step n resolves (four-slot rotation), which covers an
+// L2 round trip with 32 resident warps per SM.  The DDA is then committed through step n+1 at that test; leaving at step n rolls the one
+// extra commit back EXACTLY: the tMax that step n+1 advanced was the minimum t<n+1> itself (min returns one of its inputs bit for bit).
+// Speculative requests reach two cells past a non-flow cell: rmcrt_define_level / the ROI copy size the guard records for that.
+// (which axis a step took is read off the index difference at the exit, so no predicate of the steps n and n+1 stays live in the loop)
+#define RJ_EXIT2(C, R, PM)                                  \
+  "EXIT" #C ":\n\t"                                         \
+  "sub.s32 wz, i" #R ", i" #C ";\n\t"                       \
+  "setp.eq.s32 w, wz, %24;\n\t"                             \
+  "@w mov.f32 %0, t" #R ";\n\t"                             \
+  "setp.eq.s32 w, wz, %25;\n\t"                             \
+  "@w mov.f32 %1, t" #R ";\n\t"                             \
+  "setp.eq.s32 w, wz, %26;\n\t"                             \
+  "@w mov.f32 %2, t" #R ";\n\t"                             \
+  "sub.s32 wz, i" #C ", i" #PM ";\n\t"                      \
+  "setp.eq.s32 w, wz, %25;\n\t"                             \
+  "selp.s32 %16, 1, 2, w;\n\t"                              \
+  "setp.eq.s32 w, wz, %24;\n\t"                             \
+  "@w mov.s32 %16, 0;\n\t"                                  \
+  "mov.s32 %3, i" #C ";\n\t"                                \
+  "mov.f32 %15, t" #C ";\n\t"                               \
+  "setp.lt.s32 w, ka" #C ", 0;\n\t"                         \
+  "@w add.s32 %16, %16, 4;\n\t"                             \
+  "setp.lt.s32 w, kb" #C ", 0;\n\t"                         \
+  "@w add.s32 %16, %16, 8;\n\t"                             \
+  "mov.f32 %5, aa" #C ";\n\t"                               \
+  "mov.f32 %6, sa" #C ";\n\t"                               \
+  "mov.f32 %7, ea" #C ";\n\t"                               \
+  "mov.f32 %10, ab" #C ";\n\t"                              \
+  "mov.f32 %11, sb" #C ";\n\t"                              \
+  "mov.f32 %12, eb" #C ";\n\t"                              \
+  "bra DONE;\n\t"
+#define RJ_ASM(LD, DEC)                                                                                              \
+  asm volatile(                                                                                                      \
+      "{\n\t"                                                                                                        \
+      RJ_REGS(4)                                                                                                     \
+      /* slot 3 = the cells the leg starts in */                                                                     \
+      "mov.f32 aa3, %5;\n\t" "mov.f32 sa3, %6;\n\t" "mov.f32 ea3, %7;\n\t"                                           \
+      "mov.f32 ab3, %10;\n\t" "mov.f32 sb3, %11;\n\t" "mov.f32 eb3, %12;\n\t"                                        \
+      "mov.f32 taa, %4;\n\t" "mov.f32 tab, %9;\n\t" "mov.s32 i3, %3;\n\t"                                            \
+      RJ_PEEK(0, "%3", LD)                                                                                           \
+      RJ_COMMIT(0) RJ_PEEK(1, "i0", LD)                                                                              \
+      "LOOP:\n\t"                                                                                                    \
+      RJ_COMMIT(1) RJ_PEEK(2, "i1", LD) RJ_INTEG(3, 0, DEC)                                                          \
+      RJ_COMMIT(2) RJ_PEEK(3, "i2", LD) RJ_INTEG(0, 1, DEC)                                                          \
+      RJ_COMMIT(3) RJ_PEEK(0, "i3", LD) RJ_INTEG(1, 2, DEC)                                                          \
+      RJ_COMMIT(0) RJ_PEEK(1, "i0", LD) RJ_INTEG(2, 3, DEC)                                                          \
+      "bra LOOP;\n\t"                                                                                                \
+      RJ_EXIT2(0, 1, 3) RJ_EXIT2(1, 2, 0) RJ_EXIT2(2, 3, 1) RJ_EXIT2(3, 0, 2)                                        \
+      "DONE:\n\t"                                                                                                    \
+      "mov.f32 %17, taa;\n\t"                                                                                        \
+      "mov.f32 %18, tab;\n\t"                                                                                        \
+      "}"                                                                                                            \
+      RJ_OPERANDS)
+#endif
 
 __device__ __forceinline__ LegOut march_leg_pair(Dda& d, Integ& qa, Integ& qb, float& nsteps, const Rec8* __restrict__ recs,
                                                  const Rec8* __restrict__ recsB, float ddx, float ddy, float ddz, int stx, int sty, int stz) {
@@ -711,6 +775,9 @@ __device__ __forceinline__ LegOut march_leg_pair(Dda& d, Integ& qa, Integ& qb, f
 #undef RJ_COMMIT
 #undef RJ_INTEG
 #undef RJ_EXIT
+#undef RJ_EXIT2
+#undef RJ_REGS
+#undef RJ_OPERANDS
 #undef RJ_LD8
 #undef RJ_LD4
 #undef RJ_DEC8
@@ -781,6 +848,216 @@ __device__ __forceinline__ void march_single_level_dual(const RecT* __restrict__
   sumA = A.sum; sumB = B.sum;
   stepsA += (unsigned)A.q.nsteps;
   stepsB += (unsigned)B.q.nsteps;
+}
+
+//------------------------------------------------------------------------------------------------------
+// single level, FOUR cells per lane (cellsPerLane == 4): the 2 x 2 block of cells (i,j,k), (i,j+1,k), (i,j,k+1), (i,j+1,k+1) of a lane
+// traces four exact translates of one ray, so the 16 instructions of a step that do not depend on the ray (DDA peek / commit, index,
+// first address, step counter, loop control) are paid once per FOUR ray-cell steps: ~11 SASS instructions per ray-cell step instead of
+// ~15 for the pair.  Same structure as the pair: a joint leg (march_leg_quad, PTX, three-slot rotation, the four records of step n+1 in
+// flight) until any of the four rays enters a non-flow cell, then every ray finishes on its own with the single-ray leg loop.  Per-ray
+// arithmetic is that of march_single_level_fast, statement by statement.
+//------------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+// operands: %0-%2 tMax, %3 idx; ray a %4 A %5 k %6 s %7 ePrev %8 leg; ray b %9-%13; ray c %14-%18; ray d %19-%23; %24 nsteps;
+// %25 o.t, %26 o.axis, %27-%30 tau a..d; %31 recs, %32-%34 record offsets of rays b, c, d; %35-%37 tDelta; %38-%40 index strides
+#define RQ_LD8(J)                                                                                   \
+  "mad.wide.s32 pa, i" #J ", 8, %31;\n\t"  "ld.global.nc.v2.f32 {ka" #J ", sa" #J "}, [pa];\n\t"    \
+  "add.s64 pb, pa, %32;\n\t"             "ld.global.nc.v2.f32 {kb" #J ", sb" #J "}, [pb];\n\t"    \
+  "add.s64 pb, pa, %33;\n\t"             "ld.global.nc.v2.f32 {kc" #J ", sc" #J "}, [pb];\n\t"    \
+  "add.s64 pb, pa, %34;\n\t"             "ld.global.nc.v2.f32 {kd" #J ", sd" #J "}, [pb];\n\t"
+#define RQ_LD4(J)                                                                                   \
+  "mad.wide.s32 pa, i" #J ", 4, %31;\n\t"  "ld.global.nc.b32 ka" #J ", [pa];\n\t"                   \
+  "add.s64 pb, pa, %32;\n\t"             "ld.global.nc.b32 kb" #J ", [pb];\n\t"                   \
+  "add.s64 pb, pa, %33;\n\t"             "ld.global.nc.b32 kc" #J ", [pb];\n\t"                   \
+  "add.s64 pb, pa, %34;\n\t"             "ld.global.nc.b32 kd" #J ", [pb];\n\t"
+#define RQ_DEC8_1(R, C) "abs.f32 a" #R #C ", k" #R #C ";\n\t"
+#define RQ_DEC4_1(R, C) "mov.b32 {hl, hh}, k" #R #C ";\n\t" "cvt.f32.f16 s" #R #C ", hl;\n\t" "cvt.f32.f16 a" #R #C ", hh;\n\t" "abs.f32 a" #R #C ", a" #R #C ";\n\t"
+#define RQ_PEEK(J, IB, LD)                                  \
+  "min.f32 t" #J ", %0, %1, %2;\n\t"                        \
+  "setp.neu.f32 n" #J ", t" #J ", %2;\n\t"                  \
+  "setp.lt.and.f32 x" #J ", %0, %1, n" #J ";\n\t"           \
+  "setp.ge.and.f32 y" #J ", %0, %1, n" #J ";\n\t"           \
+  "selp.s32 i" #J ", %38, %40, x" #J ";\n\t"                \
+  "@y" #J " mov.s32 i" #J ", %39;\n\t"                      \
+  "add.s32 i" #J ", i" #J ", " IB ";\n\t"                   \
+  LD(J)
+#define RQ_COMMIT(J)                                        \
+  "@x" #J " add.f32 %0, %0, %35;\n\t"                       \
+  "@y" #J " add.f32 %1, %1, %36;\n\t"                       \
+  "@!n" #J " add.f32 %2, %2, %37;\n\t"
+// one ray: leave the cell in slot P at t<C> (A = operand of the tau offset, LEG = operand of the leg integral)
+#define RQ_INT1(R, P, C, A, LEG)                            \
+  "fma.rn.f32 t" #R ", a" #R #P ", t" #C ", " A ";\n\t"     \
+  "neg.f32 d, t" #R ";\n\t"                                 \
+  "ex2.approx.ftz.f32 e" #R #C ", d;\n\t"                   \
+  "sub.f32 d, e" #R #P ", e" #R #C ";\n\t"                  \
+  "fma.rn.f32 " LEG ", s" #R #P ", d, " LEG ";\n\t"
+// one ray: enter the cell in slot C (re-base the tau offset)
+#define RQ_ENT1(R, C, A)                                    \
+  "neg.f32 d, a" #R #C ";\n\t"                              \
+  "fma.rn.f32 " A ", d, t" #C ", t" #R ";\n\t"
+#define RQ_INTEG(P, C, DEC1)                                \
+  RQ_INT1(a, P, C, "%4", "%8") RQ_INT1(b, P, C, "%9", "%13") RQ_INT1(c, P, C, "%14", "%18") RQ_INT1(d, P, C, "%19", "%23") \
+  "add.f32 %24, %24, 0f3F800000;\n\t"                       \
+  DEC1(a, C) DEC1(b, C) DEC1(c, C) DEC1(d, C)               \
+  RQ_ENT1(a, C, "%4") RQ_ENT1(b, C, "%9") RQ_ENT1(c, C, "%14") RQ_ENT1(d, C, "%19") \
+  "or.b32 wz, ka" #C ", kb" #C ";\n\t"                      \
+  "or.b32 wy, kc" #C ", kd" #C ";\n\t"                      \
+  "or.b32 wz, wz, wy;\n\t"                                  \
+  "setp.lt.s32 w, wz, 0;\n\t"                               \
+  "@w bra EXIT" #C ";\n\t"
+#define RQ_OUT1(R, C, K, S, E)                              \
+  "mov.f32 " K ", a" #R #C ";\n\t"                          \
+  "mov.f32 " S ", s" #R #C ";\n\t"                          \
+  "mov.f32 " E ", e" #R #C ";\n\t"
+#define RQ_FLAG1(R, C, BIT)                                 \
+  "setp.lt.s32 w, k" #R #C ", 0;\n\t"                       \
+  "@w add.s32 %26, %26, " #BIT ";\n\t"
+#define RQ_EXIT(C)                                          \
+  "EXIT" #C ":\n\t"                                         \
+  "mov.s32 %3, i" #C ";\n\t"                                \
+  "mov.f32 %25, t" #C ";\n\t"                               \
+  "selp.s32 %26, 1, 2, y" #C ";\n\t"                        \
+  "@x" #C " mov.s32 %26, 0;\n\t"                            \
+  RQ_FLAG1(a, C, 4) RQ_FLAG1(b, C, 8) RQ_FLAG1(c, C, 16) RQ_FLAG1(d, C, 32) \
+  RQ_OUT1(a, C, "%5", "%6", "%7") RQ_OUT1(b, C, "%10", "%11", "%12") RQ_OUT1(c, C, "%15", "%16", "%17") RQ_OUT1(d, C, "%20", "%21", "%22") \
+  "bra DONE;\n\t"
+#define RQ_START1(R, K, S, E) "mov.f32 a" #R "2, " K ";\n\t" "mov.f32 s" #R "2, " S ";\n\t" "mov.f32 e" #R "2, " E ";\n\t"
+#define RQ_ASM(LD, DEC1)                                                                                             \
+  asm volatile(                                                                                                      \
+      "{\n\t"                                                                                                        \
+      ".reg .pred x0, y0, n0, x1, y1, n1, x2, y2, n2, w;\n\t"                                                        \
+      ".reg .f32 d, ta, tb, tc, td, t0, t1, t2;\n\t"                                                                 \
+      ".reg .f32 sa0, sa1, sa2, sb0, sb1, sb2, sc0, sc1, sc2, sd0, sd1, sd2;\n\t"                                    \
+      ".reg .f32 ea0, ea1, ea2, eb0, eb1, eb2, ec0, ec1, ec2, ed0, ed1, ed2;\n\t"                                    \
+      ".reg .f32 aa0, aa1, aa2, ab0, ab1, ab2, ac0, ac1, ac2, ad0, ad1, ad2;\n\t"                                    \
+      ".reg .b32 ka0, ka1, ka2, kb0, kb1, kb2, kc0, kc1, kc2, kd0, kd1, kd2, wz, wy;\n\t"                            \
+      ".reg .b16 hl, hh;\n\t"                                                                                        \
+      ".reg .s32 i0, i1, i2;\n\t"                                                                                    \
+      ".reg .s64 pa, pb;\n\t"                                                                                        \
+      /* slot 2 = the cells the leg starts in */                                                                     \
+      RQ_START1(a, "%5", "%6", "%7") RQ_START1(b, "%10", "%11", "%12") RQ_START1(c, "%15", "%16", "%17") RQ_START1(d, "%20", "%21", "%22") \
+      "mov.f32 ta, %4;\n\t" "mov.f32 tb, %9;\n\t" "mov.f32 tc, %14;\n\t" "mov.f32 td, %19;\n\t"                      \
+      RQ_PEEK(0, "%3", LD)                                                                                           \
+      "LOOP:\n\t"                                                                                                    \
+      RQ_COMMIT(0) RQ_PEEK(1, "i0", LD) RQ_INTEG(2, 0, DEC1)                                                         \
+      RQ_COMMIT(1) RQ_PEEK(2, "i1", LD) RQ_INTEG(0, 1, DEC1)                                                         \
+      RQ_COMMIT(2) RQ_PEEK(0, "i2", LD) RQ_INTEG(1, 2, DEC1)                                                         \
+      "bra LOOP;\n\t"                                                                                                \
+      RQ_EXIT(0) RQ_EXIT(1) RQ_EXIT(2)                                                                               \
+      "DONE:\n\t"                                                                                                    \
+      "mov.f32 %27, ta;\n\t" "mov.f32 %28, tb;\n\t" "mov.f32 %29, tc;\n\t" "mov.f32 %30, td;\n\t"                    \
+      "}"                                                                                                            \
+      : "+f"(d.tx), "+f"(d.ty), "+f"(d.tz), "+r"(d.idx),                                                             \
+        "+f"(q[0].A), "+f"(q[0].k), "+f"(q[0].s), "+f"(q[0].ePrev), "+f"(q[0].leg),                                  \
+        "+f"(q[1].A), "+f"(q[1].k), "+f"(q[1].s), "+f"(q[1].ePrev), "+f"(q[1].leg),                                  \
+        "+f"(q[2].A), "+f"(q[2].k), "+f"(q[2].s), "+f"(q[2].ePrev), "+f"(q[2].leg),                                  \
+        "+f"(q[3].A), "+f"(q[3].k), "+f"(q[3].s), "+f"(q[3].ePrev), "+f"(q[3].leg),                                  \
+        "+f"(nsteps), "=f"(o.t), "=r"(o.axis), "=f"(q[0].tau), "=f"(q[1].tau), "=f"(q[2].tau), "=f"(q[3].tau)         \
+      : "l"(recs), "l"(bB), "l"(bC), "l"(bD), "f"(ddx), "f"(ddy), "f"(ddz), "r"(stx), "r"(sty), "r"(stz)       \
+      : "memory")
+
+// Returns axis | 4 << r for every ray r that entered a non-flow cell in LegOut::axis.
+__device__ __forceinline__ LegOut march_leg_quad(Dda& d, Integ (&q)[4], float& nsteps, const Rec8* __restrict__ recs, int offB, int offC,
+                                                 int offD, float ddx, float ddy, float ddz, int stx, int sty, int stz) {
+  LegOut o;
+  const long long bB = (long long)offB * 8, bC = (long long)offC * 8, bD = (long long)offD * 8;     // byte offsets of rays b, c, d
+  RQ_ASM(RQ_LD8, RQ_DEC8_1);
+  return o;
+}
+__device__ __forceinline__ LegOut march_leg_quad(Dda& d, Integ (&q)[4], float& nsteps, const Rec4* __restrict__ recs, int offB, int offC,
+                                                 int offD, float ddx, float ddy, float ddz, int stx, int sty, int stz) {
+  LegOut o;
+  const long long bB = (long long)offB * 4, bC = (long long)offC * 4, bD = (long long)offD * 4;
+  RQ_ASM(RQ_LD4, RQ_DEC4_1);
+  return o;
+}
+#undef RQ_ASM
+#undef RQ_START1
+#undef RQ_EXIT
+#undef RQ_FLAG1
+#undef RQ_OUT1
+#undef RQ_INTEG
+#undef RQ_ENT1
+#undef RQ_INT1
+#undef RQ_COMMIT
+#undef RQ_PEEK
+#undef RQ_DEC4_1
+#undef RQ_DEC8_1
+#undef RQ_LD4
+#undef RQ_LD8
+#else
+// host build (tests/hostsim): the same algorithm statement by statement
+template <class RecT>
+__device__ __forceinline__ LegOut march_leg_quad(Dda& d, Integ (&q)[4], float& nsteps, const RecT* __restrict__ recs, int offB, int offC,
+                                                 int offD, float ddx, float ddy, float ddz, int stx, int sty, int stz) {
+  const int off[4] = {0, offB, offC, offD};
+  float n0[4];
+  for (int r = 0; r < 4; ++r) n0[r] = q[r].nsteps;
+  Peek p = dda_peek(d, stx, sty, stz);
+  Rec8 rec[4];
+  for (int r = 0; r < 4; ++r) rec[r] = ldrec(recs + off[r] + p.idx);
+  LegOut o;
+  for (;;) {
+    dda_commit(d, p, ddx, ddy, ddz);
+    const Peek pn = dda_peek(d, stx, sty, stz);
+    Rec8 nxt[4];
+    for (int r = 0; r < 4; ++r) nxt[r] = ldrec(recs + off[r] + pn.idx);      // speculative, like the device loop
+    int walls = 0;
+    for (int r = 0; r < 4; ++r) {
+      integ_cross(q[r], p.t, rec[r]);
+      if (is_wall(rec[r].k)) walls |= 4 << r;
+    }
+    if (walls) { o = LegOut{p.t, (p.px ? 0 : (p.py ? 1 : 2)) | walls}; break; }
+    p = pn;
+    for (int r = 0; r < 4; ++r) rec[r] = nxt[r];
+  }
+  nsteps += q[0].nsteps - n0[0];
+  for (int r = 0; r < 4; ++r) q[r].nsteps = n0[r];
+  return o;
+}
+#endif
+
+// cells: A = idxA, B = A + one row, C = A + one plane, D = A + one row + one plane
+template <class RecT>
+__device__ __forceinline__ void march_single_level_quad(const RecT* __restrict__ recs, int idxA, int sy, int sz, float dx, float dy, float dz,
+                                                        float rx, float ry, float rz, float cx, float cy, float cz, float threshold,
+                                                        bool allowReflect, bool skipZero, unsigned& steps, int recBytes, float (&sum)[4]) {
+  typedef Num<float> N;
+  sum[0] = sum[1] = sum[2] = sum[3] = 0.0f;
+  if (!(1.0f > threshold)) return;
+  const bool posx = !sign_bit(dx), posy = !sign_bit(dy), posz = !sign_bit(dz);
+  const int stx = posx ? 1 : -1, sty = posy ? sy : -sy, stz = posz ? sz : -sz;
+  const float ix = N::rcp(dx), iy = N::rcp(dy), iz = N::rcp(dz);
+  Dda d;
+  d.tx = ((posx ? cx : 0.0f) - rx) * ix * N::LEN_SCALE;
+  d.ty = ((posy ? cy : 0.0f) - ry) * iy * N::LEN_SCALE;
+  d.tz = ((posz ? cz : 0.0f) - rz) * iz * N::LEN_SCALE;
+  const float ddx = fabsf(ix) * cx * N::LEN_SCALE, ddy = fabsf(iy) * cy * N::LEN_SCALE, ddz = fabsf(iz) * cz * N::LEN_SCALE;
+  d.idx = idxA;
+  const int off[4] = {0, sy, sz, sy + sz};
+  Integ q[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const Rec8 rec = ldrec(recs + off[r] + idxA);
+    q[r].k = fabsf(rec.k); q[r].s = rec.s;
+    q[r].A = 0.0f; q[r].ePrev = 1.0f; q[r].nsteps = 0.0f; q[r].tau = 0.0f; q[r].leg = 0.0f;
+  }
+  float joint = 0.0f;
+  const LegOut jw = march_leg_quad(d, q, joint, recs, off[1], off[2], off[3], ddx, ddy, ddz, stx, sty, stz);
+  const LegOut lw{jw.t, jw.axis & 3};
+  // ---- each ray on its own from here
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    q[r].nsteps += joint;
+    RayState R{d, q[r], 0.0f, 1.0f, stx, sty, stz};
+    const RecT* __restrict__ rr = recs + off[r];
+    if (!(jw.axis & (4 << r)) || ray_wall(R, lw, rr, threshold, allowReflect, skipZero))
+      ray_finish(R, rr, ddx, ddy, ddz, threshold, allowReflect, skipZero, recBytes);
+    sum[r] = R.sum;
+    steps += (unsigned)R.q.nsteps;
+  }
 }
 
 //------------------------------------------------------------------------------------------------------

@@ -536,6 +536,113 @@ __global__ void __launch_bounds__(256, 4) divq_dual_kernel(const __grid_constant
 }
 
 //======================================================================================================
+// Four cells per lane (cellsPerLane == 4): one block = a tile of 32 x-consecutive cells x 2 rows x 2 planes; lane = the 2 x 2 block of
+// cells (i, j..j+1, k..k+1); the four rays of ray index r are exact translates (shared direction and in-cell origin), so one DDA per
+// lane drives all four (march_single_level_quad).  Production ray set-up only (Philox, FP32), single level.
+//======================================================================================================
+#ifndef RMCRT_QUAD_BLOCKS
+#define RMCRT_QUAD_BLOCKS 6       // resident blocks per SM the register budget is cut for (80 registers; measured 4: 1.28e12, 5: 1.36e12, 6: 1.46e12, 7: 1.46e12, 8: 1.44e12 steps/s)
+#endif
+template <class RecT>
+__global__ void __launch_bounds__(128, RMCRT_QUAD_BLOCKS) divq_quad_kernel(const __grid_constant__ TraceArgs a, int nxc, int njp, int nkp) {
+  extern __shared__ double red[];     // [W][128]
+  if (!launch_gate(a)) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+  const int F = a.G.maxLevels - 1;
+  const LevelGeom& g = a.G.lev[F];
+  const RecT* recs = static_cast<const RecT*>(g.rec);
+  const bool skipZero = skip_allowed(a);
+  constexpr float UNSCALE = RecInfo<RecT>::unscale;
+  const int sy = g.n[0], sz = g.n[0] * g.n[1];
+  unsigned long long stepsTotal = 0, cellsTotal = 0;
+  const long long nTiles = (long long)nxc * njp * nkp;
+  for (long long tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+    const int xc = (int)(tile % nxc);
+    const long long rest = tile / nxc;
+    const int jp = (int)(rest % njp), kp = (int)(rest / njp);
+    const int i = a.patchLo[0] + xc * 32 + lane, jA = a.patchLo[1] + 2 * jp, kA = a.patchLo[2] + 2 * kp;
+    const bool vx = (xc * 32 + lane) < a.patchN[0], vj = (2 * jp + 1) < a.patchN[1], vk = (2 * kp + 1) < a.patchN[2];
+    const bool valid[4] = {vx, vx && vj, vx && vk, vx && vj && vk};
+    const int off[4] = {0, sy, sz, sy + sz};
+    bool flow[4];
+    const long long idA = level_index(g, vx ? i : a.patchLo[0], jA, kA);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      flow[c] = valid[c] && !is_wall(ldrec(recs + idA + off[c]).k);
+    }
+    const unsigned long long dirId = (unsigned long long)level_index(g, a.patchLo[0] + xc * 32, jA, kA);
+    double acc[4] = {0, 0, 0, 0};
+    unsigned st = 0;          // ray-cell steps of the lane's four cells
+    const bool all4 = flow[0] && flow[1] && flow[2] && flow[3];
+    if (flow[0] || flow[1] || flow[2] || flow[3]) {
+      const float cx = (float)g.dx[0], cy = (float)g.dx[1], cz = (float)g.dx[2];
+      for (int ray = warp; ray < a.nRays; ray += W) {
+        float dir[3], rayDx[3];
+        // direction: shared by the tile (dirId); in-cell origin: shared by the tile (rayCoherence 2) or by the lane's four cells only (1)
+        gen_divq_ray_f32(a.rng, g, ray, (unsigned long long)idA, dirId, dir, rayDx);
+        const float d0 = nz<float, float>(dir[0]), d1 = nz<float, float>(dir[1]), d2 = nz<float, float>(dir[2]);
+        if (all4) {
+          float sm[4];
+          march_single_level_quad(recs, (int)idA, sy, sz, d0, d1, d2, rayDx[0], rayDx[1], rayDx[2], cx, cy, cz, (float)a.threshold,
+                                  a.allowReflect != 0, skipZero, st, a.recBytes, sm);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[c] += (double)(UNSCALE * sm[c]);
+        } else {
+          // a wall inside the 2 x 2 block (or a partial block at the patch edge): every flow cell of it marches alone, same ray
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            if (!flow[c]) continue;
+            unsigned s1 = 0;
+            const float v = march_single_level_fast(recs, (int)idA + off[c], sy, sz, d0, d1, d2, rayDx[0], rayDx[1], rayDx[2], cx, cy, cz,
+                                                    (float)a.threshold, a.allowReflect != 0, skipZero, s1, a.recBytes);
+            st += s1;
+            if (c == 0) acc[0] += (double)(UNSCALE * v);
+            else if (c == 1) acc[1] += (double)(UNSCALE * v);
+            else if (c == 2) acc[2] += (double)(UNSCALE * v);
+            else acc[3] += (double)(UNSCALE * v);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) red[warp * 128 + c * 32 + lane] = acc[c];
+    __syncthreads();
+    for (int c = warp; c < 4; c += W) {           // warp c writes the row of cell c
+      const bool v = c == 0 ? valid[0] : (c == 1 ? valid[1] : (c == 2 ? valid[2] : valid[3]));
+      if (!v) continue;
+      double sumI = 0;
+      for (int w = 0; w < W; ++w) sumI += red[w * 128 + c * 32 + lane];
+      const int j = jA + (c & 1), k = kA + (c >> 1);
+      const long long q = (long long)(i - a.outLo[0]) +
+                          (long long)a.outN[0] * ((long long)(j - a.outLo[1]) + (long long)a.outN[1] * (long long)(k - a.outLo[2]));
+      const long long idc = idA + (c & 1 ? sy : 0) + (c & 2 ? sz : 0);
+      Rec8 rc;       // the cell's own record at full precision for the epilogue
+      if constexpr (std::is_same<RecT, Rec4>::value) rc = ldrec(static_cast<const Rec8*>(g.recFull) + idc); else rc = ldrec(recs + idc);
+      const bool fl = c == 0 ? flow[0] : (c == 1 ? flow[1] : (c == 2 ? flow[2] : flow[3]));
+      if (fl) {
+        const double mean = sumI / a.nRays;
+        a.divQ[q] = -4.0 * M_PI * (double)rc.k * ((double)rc.s - mean);      // Ray.cc:775,778
+        a.volq[q] = 4.0 * M_PI * mean;
+        ++cellsTotal;
+      } else {
+        a.divQ[q] = 0.0;
+        a.volq[q] = 0.0;
+      }
+    }
+    __syncthreads();
+    stepsTotal += st;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    stepsTotal += __shfl_down_sync(0xffffffffu, stepsTotal, o);
+    cellsTotal += __shfl_down_sync(0xffffffffu, cellsTotal, o);
+  }
+  if (lane == 0) {
+    if (stepsTotal) atomicAdd(a.counters + 0, stepsTotal);
+    if (cellsTotal) atomicAdd(a.counters + 2, cellsTotal);
+  }
+}
+
+//======================================================================================================
 // boundary flux
 //======================================================================================================
 // Ray::has_a_boundary (Ray.cc:1517-1572): `celltype[adj]+1 != 0`  <=>  adj is not a flow cell  <=>  record sign bit.
@@ -1542,6 +1649,18 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
     } else if (ML) {
       if (f32gen) divq_kernel<Real, RecT, true, false, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
       else        divq_kernel<Real, RecT, true, false, false><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
+    } else if (std::is_same<Real, float>::value && !bounded && f32gen && ctx->p.rayCoherence >= 1 && ctx->p.cellsPerLane == 4 && !ctx->p.genericMarch) {
+      if constexpr (std::is_same<Real, float>::value && !std::is_same<RecT, Rec16>::value) {
+        const int nxc = (a.patchN[0] + 31) / 32, njp = (a.patchN[1] + 1) / 2, nkp = (a.patchN[2] + 1) / 2;
+        long long g4 = (long long)nxc * njp * nkp;
+        if (g4 > cap) g4 = cap;
+        int W4 = ctx->p.warpsPerTile > 0 ? std::min(ctx->p.warpsPerTile, 4) : 4;
+        TraceArgs a2 = a;
+        a2.gate = 1;
+        divq_quad_kernel<RecT><<<(int)g4, 32 * W4, W4 * 128 * sizeof(double), st>>>(a2, nxc, njp, nkp);
+        a2.gate = 2;      // the same solve on the one-cell kernel when reflective walls keep the rays going (launch_gate)
+        divq_kernel<Real, RecT, false, true, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a2);
+      }
     } else if (std::is_same<Real, float>::value && !bounded && f32gen && ctx->p.rayCoherence >= 1 && ctx->p.cellsPerLane == 2 && !ctx->p.genericMarch) {
       if constexpr (std::is_same<Real, float>::value && !std::is_same<RecT, Rec16>::value) {
         const int nxc = (a.patchN[0] + 31) / 32, njp = (a.patchN[1] + 1) / 2;
@@ -1693,12 +1812,12 @@ void rmcrt_default_params(rmcrt_params* p) {
   p->haloCells[0] = p->haloCells[1] = p->haloCells[2] = 10;   // Ray.cc:254
   p->cellTypeCoarsenLogic = 0;
   p->seed = 0x9E3779B97F4A7C15ull;
-  p->marchPrecision = 0; p->rayCoherence = 1; p->skipZeroWeightLegs = 1; p->fixedRandom = 0; p->l2Persist = 1;
+  p->marchPrecision = 0; p->rayCoherence = 2; p->skipZeroWeightLegs = 1; p->fixedRandom = 0; p->l2Persist = 1;
   p->warpsPerTile = 0;
   p->rayDirSampleAlgo = 0;     // "naive", Ray.cc:174
   p->maxRayLength = 0.0;       // unbounded (DBL_MAX, RMCRTCommon.cc:117)
   p->sigmaScat = 0.0;          // Ray.cc:169
-  p->cellsPerLane = 2;         // production: two cells per lane share one DDA (divq_dual_kernel); 1 = one cell per lane
+  p->cellsPerLane = 4;         // production: the 2 x 2 cells of a lane share one DDA (divq_quad_kernel); 2 = a pair (divq_dual_kernel); 1 = one cell per lane
 }
 
 const char* rmcrt_last_error(const rmcrt_ctx* ctx) {
@@ -1787,8 +1906,8 @@ int rmcrt_define_level(rmcrt_ctx* ctx, int L, const rmcrt_level_desc* d, int rec
   s.recBytes = recordKind == 0 ? sizeof(Rec8) : (recordKind == 1 ? sizeof(Rec16) : sizeof(Rec4));
   s.nCells = n;
   // guard records on both ends (flagged "not a flow cell") so neighbour / speculative loads issued from any cell of
-  // the level stay inside the allocation
-  const long long guard = (long long)(d->hi[0] - d->lo[0]) * (d->hi[1] - d->lo[1]) + (d->hi[0] - d->lo[0]) + 1;
+  // the level stay inside the allocation; the pair march requests records up to TWO steps past the cell whose wall test is pending
+  const long long guard = 2 * ((long long)(d->hi[0] - d->lo[0]) * (d->hi[1] - d->lo[1]) + (d->hi[0] - d->lo[0]) + 1);
   void* base = nullptr;
   CK(cudaMalloc(&base, (size_t)(n + 2 * guard) * s.recBytes));
   CK(cudaMemset(base, 0xFF, (size_t)(n + 2 * guard) * s.recBytes));   // 0xFF.. = negative NaN: wall flag set, caught by finalize if left
