@@ -239,7 +239,7 @@ def run_ours(args):
         args.half_records = 1 if int(np.prod([h - l for l, h in zip(lo, hi)])) * 8 > 64e6 else 0
     skip = 0 if args.reference_semantics else 1
     g = RMCRT(device=local, nDivQRays=rays, threshold=0.05, seed=1234, skipZeroWeightLegs=skip,
-              rayCoherence=args.coherence, l2Persist=args.l2persist, warpsPerTile=args.warps, cellsPerLane=args.cells_per_lane,
+              rayCoherence=args.coherence, l2Persist=args.l2persist, warpsPerTile=args.warps, tileX=args.tile_x, cellsPerLane=args.cells_per_lane,
               genericMarch=args.generic_march, maxBlocksPerSM=args.max_blocks_per_sm, half_records=bool(args.half_records))
     stream = torch.cuda.current_stream()
     desc = LevelData(None, None, None, lo, hi, dx, interior_lo=(0, 0, 0), interior_hi=shape).desc()
@@ -471,6 +471,7 @@ def main():
     ap.add_argument("--coherence", type=int, default=2, help="rayCoherence (library default 2)")
     ap.add_argument("--l2persist", type=int, default=1)
     ap.add_argument("--warps", type=int, default=0)
+    ap.add_argument("--tile-x", type=int, default=0, help="cellsPerLane 4: origin cells of a warp in x (32, 16, 8; 0 = library default)")
     ap.add_argument("--cells-per-lane", type=int, default=4, help="4 (library default): a lane marches 2 x 2 cells with one DDA; 2: a pair; 1: one cell per lane (A/B)")
     ap.add_argument("--half-records", type=int, default=-1,
                     help="1: 4-B half-packed level records (fp16 abskg|wall, fp16 sigmaT4/pi); 0: 8-B float records; "

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RMCRT_ABI_VERSION 3
+#define RMCRT_ABI_VERSION 4
 #define RMCRT_MAX_LEVELS 8
 
 typedef struct rmcrt_ctx rmcrt_ctx;
@@ -93,6 +93,11 @@ typedef struct rmcrt_params {
                                   paths, a new isotropic direction per event.  Single-level divQ and boundary-flux rays; runs through
                                   the generic march kernels.  Multi-level solves ignore it like the reference (no scattering code in
                                   Ray::updateSumI_ML). */
+  int32_t  tileX;              /* implementation knob, cellsPerLane == 4: origin cells of a warp in x (32, 16 or 8; 0 = default 16).  The
+                                  32 lanes cover tileX x (32 / tileX) blocks of 2 x 2 cells; a squarer footprint makes the lockstep rays
+                                  of a warp reach a wall within fewer steps of each other (fewer idle lanes) at the same number of
+                                  sectors per request.  The rays of a cell depend on the tile it falls in, not on the arithmetic. */
+  int32_t  reserved0;
 } rmcrt_params;
 
 /* One <Radiometer> block after Radiometer::problemSetup (Radiometer.cc:96-271; struct radiometer, Radiometer.h:117-127) */

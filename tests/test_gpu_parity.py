@@ -644,9 +644,9 @@ def test_kernel_choice_follows_the_walls(gpu_lib, po):
 def test_four_cells_per_lane_kernel(gpu_lib, po):
     """divq_quad_kernel (the production default, cellsPerLane = 4).
     (a) With rayCoherence = 2 a cell's rays are keyed on the first cell of its tile only, so the cells with (j - lo, k - lo) both even trace
-        IDENTICAL rays in the 1-, 2- and 4-cells-per-lane kernels when a row of the patch is one 32-cell tile: divQ must agree BIT FOR BIT
+        IDENTICAL rays in the 1-, 2- and 4-cells-per-lane kernels when a row of the patch is one 32-cell tile (tileX = 32): divQ must agree BIT FOR BIT
         (same per-ray arithmetic in the PTX joint legs, same accumulation order), for float and half-packed records.
-    (b) odd patch sizes and offsets (partial 32-cell chunks, unpaired last row and last plane), intrusions inside a 2 x 2 block: same
+    (b) default warp footprint (16 x 2 blocks), odd patch sizes and offsets (partial chunks, unpaired last row and last plane), intrusions inside a 2 x 2 block: same
         cells written and counted as the one-cell kernel, steps per ray within 1 %, per-cell agreement within Monte-Carlo error.
     (c) exactly zero divQ in an isothermal black enclosure with intrusions."""
     rng = np.random.default_rng(11)
@@ -656,7 +656,7 @@ def test_four_cells_per_lane_kernel(gpu_lib, po):
     for half in (False, True):
         res = {}
         for cpl in (1, 2, 4):
-            g = make(gpu_lib, nDivQRays=32, threshold=0.05, seed=3, rayCoherence=2, warpsPerTile=4, cellsPerLane=cpl, half_records=half)
+            g = make(gpu_lib, nDivQRays=32, threshold=0.05, seed=3, rayCoherence=2, warpsPerTile=4, cellsPerLane=cpl, tileX=32, half_records=half)
             g.upload_level(0, lv)
             res[cpl] = (g.trace_divq(0, patch_lo=lo, patch_hi=hi, timestep=3)["divQ"], int(g.counters().nRaySteps), int(g.counters().nDivQCells))
         rows = (slice(lo[2] + 1, hi[2] + 1, 2), slice(lo[1] + 1, hi[1] + 1, 2), slice(lo[0] + 1, hi[0] + 1))

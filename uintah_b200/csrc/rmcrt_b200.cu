@@ -540,11 +540,14 @@ __global__ void __launch_bounds__(256, 4) divq_dual_kernel(const __grid_constant
 // cells (i, j..j+1, k..k+1); the four rays of ray index r are exact translates (shared direction and in-cell origin), so one DDA per
 // lane drives all four (march_single_level_quad).  Production ray set-up only (Philox, FP32), single level.
 //======================================================================================================
+#ifndef RMCRT_QUAD_TILE_X
+#define RMCRT_QUAD_TILE_X 16      // default origin cells of a warp in x (rmcrt_params.tileX = 0): measured 32: 1.655e12, 16: 1.712e12, 8: 1.686e12 steps/s at 128^3
+#endif
 #ifndef RMCRT_QUAD_BLOCKS
 #define RMCRT_QUAD_BLOCKS 6       // resident blocks per SM the register budget is cut for (80 registers; measured 4: 1.28e12, 5: 1.36e12, 6: 1.46e12, 7: 1.46e12, 8: 1.44e12 steps/s)
 #endif
 template <class RecT>
-__global__ void __launch_bounds__(128, RMCRT_QUAD_BLOCKS) divq_quad_kernel(const __grid_constant__ TraceArgs a, int nxc, int njp, int nkp) {
+__global__ void __launch_bounds__(128, RMCRT_QUAD_BLOCKS) divq_quad_kernel(const __grid_constant__ TraceArgs a, int nxc, int njp, int nkp, int lxBits) {
   extern __shared__ double red[];     // [W][128]
   if (!launch_gate(a)) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
@@ -560,17 +563,20 @@ __global__ void __launch_bounds__(128, RMCRT_QUAD_BLOCKS) divq_quad_kernel(const
     const int xc = (int)(tile % nxc);
     const long long rest = tile / nxc;
     const int jp = (int)(rest % njp), kp = (int)(rest / njp);
-    const int i = a.patchLo[0] + xc * 32 + lane, jA = a.patchLo[1] + 2 * jp, kA = a.patchLo[2] + 2 * kp;
-    const bool vx = (xc * 32 + lane) < a.patchN[0], vj = (2 * jp + 1) < a.patchN[1], vk = (2 * kp + 1) < a.patchN[2];
+    // lane -> 2 x 2 block: lx of the tile's TX = 1 << lxBits blocks in x, ly of its 32 / TX block rows in y
+    const int TX = 1 << lxBits, lx = lane & (TX - 1), ly = lane >> lxBits, RY = 2 * (32 >> lxBits);
+    const int i = a.patchLo[0] + xc * TX + lx, jA = a.patchLo[1] + RY * jp + 2 * ly, kA = a.patchLo[2] + 2 * kp;
+    const bool vx = (xc * TX + lx) < a.patchN[0] && (RY * jp + 2 * ly) < a.patchN[1];
+    const bool vj = (RY * jp + 2 * ly + 1) < a.patchN[1], vk = (2 * kp + 1) < a.patchN[2];
     const bool valid[4] = {vx, vx && vj, vx && vk, vx && vj && vk};
     const int off[4] = {0, sy, sz, sy + sz};
     bool flow[4];
-    const long long idA = level_index(g, vx ? i : a.patchLo[0], jA, kA);
+    const long long idA = vx ? level_index(g, i, jA, kA) : level_index(g, a.patchLo[0], a.patchLo[1], kA);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       flow[c] = valid[c] && !is_wall(ldrec(recs + idA + off[c]).k);
     }
-    const unsigned long long dirId = (unsigned long long)level_index(g, a.patchLo[0] + xc * 32, jA, kA);
+    const unsigned long long dirId = (unsigned long long)level_index(g, a.patchLo[0] + xc * TX, a.patchLo[1] + RY * jp, kA);
     double acc[4] = {0, 0, 0, 0};
     unsigned st = 0;          // ray-cell steps of the lane's four cells
     const bool all4 = flow[0] && flow[1] && flow[2] && flow[3];
@@ -1651,13 +1657,15 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
       else        divq_kernel<Real, RecT, true, false, false><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
     } else if (std::is_same<Real, float>::value && !bounded && f32gen && ctx->p.rayCoherence >= 1 && ctx->p.cellsPerLane == 4 && !ctx->p.genericMarch) {
       if constexpr (std::is_same<Real, float>::value && !std::is_same<RecT, Rec16>::value) {
-        const int nxc = (a.patchN[0] + 31) / 32, njp = (a.patchN[1] + 1) / 2, nkp = (a.patchN[2] + 1) / 2;
+        const int tx = ctx->p.tileX == 8 || ctx->p.tileX == 16 || ctx->p.tileX == 32 ? ctx->p.tileX : RMCRT_QUAD_TILE_X;
+        const int lxBits = tx == 8 ? 3 : (tx == 16 ? 4 : 5), ry = 2 * (32 / tx);
+        const int nxc = (a.patchN[0] + tx - 1) / tx, njp = (a.patchN[1] + ry - 1) / ry, nkp = (a.patchN[2] + 1) / 2;
         long long g4 = (long long)nxc * njp * nkp;
         if (g4 > cap) g4 = cap;
         int W4 = ctx->p.warpsPerTile > 0 ? std::min(ctx->p.warpsPerTile, 4) : 4;
         TraceArgs a2 = a;
         a2.gate = 1;
-        divq_quad_kernel<RecT><<<(int)g4, 32 * W4, W4 * 128 * sizeof(double), st>>>(a2, nxc, njp, nkp);
+        divq_quad_kernel<RecT><<<(int)g4, 32 * W4, W4 * 128 * sizeof(double), st>>>(a2, nxc, njp, nkp, lxBits);
         a2.gate = 2;      // the same solve on the one-cell kernel when reflective walls keep the rays going (launch_gate)
         divq_kernel<Real, RecT, false, true, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a2);
       }
@@ -1817,6 +1825,7 @@ void rmcrt_default_params(rmcrt_params* p) {
   p->rayDirSampleAlgo = 0;     // "naive", Ray.cc:174
   p->maxRayLength = 0.0;       // unbounded (DBL_MAX, RMCRTCommon.cc:117)
   p->sigmaScat = 0.0;          // Ray.cc:169
+  p->tileX = 0; p->reserved0 = 0;
   p->cellsPerLane = 4;         // production: the 2 x 2 cells of a lane share one DDA (divq_quad_kernel); 2 = a pair (divq_dual_kernel); 1 = one cell per lane
 }
 

@@ -179,7 +179,7 @@ void Ray::BC_bulletproofing(const ProblemSpecP& rmcrtps, const bool chk_temp, co
 
 //______________________________________________________________________
 void Ray::setKnob(const std::string& name, int value) {
-  static const char* known[] = {"rayCoherence", "skipZeroWeightLegs", "l2Persist", "genericMarch", "marchPrecision", "warpsPerTile", "fixedRandom", "halfRecords", "cellsPerLane"};
+  static const char* known[] = {"rayCoherence", "skipZeroWeightLegs", "l2Persist", "genericMarch", "marchPrecision", "warpsPerTile", "fixedRandom", "halfRecords", "cellsPerLane", "tileX"};
   for (auto k : known)
     if (name == k) { d_knobs[name] = value; return; }
   throw ProblemSetupException("RMCRT (B200 back end): unknown knob " + name, __FILE__, __LINE__);
@@ -207,6 +207,7 @@ void Ray::fillParams(rmcrt_params& p) const {
     else if (kv.first == "warpsPerTile") p.warpsPerTile = kv.second;
     else if (kv.first == "fixedRandom") p.fixedRandom = kv.second;
     else if (kv.first == "cellsPerLane") p.cellsPerLane = kv.second;
+    else if (kv.first == "tileX") p.tileX = kv.second;
   }
 }
 
