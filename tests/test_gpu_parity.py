@@ -644,8 +644,9 @@ def test_kernel_choice_follows_the_walls(gpu_lib, po):
 def test_four_cells_per_lane_kernel(gpu_lib, po):
     """divq_quad_kernel (the production default, cellsPerLane = 4).
     (a) With rayCoherence = 2 a cell's rays are keyed on the first cell of its tile only, so the cells with (j - lo, k - lo) both even trace
-        IDENTICAL rays in the 1-, 2- and 4-cells-per-lane kernels when a row of the patch is one 32-cell tile (tileX = 32): divQ must agree BIT FOR BIT
-        (same per-ray arithmetic in the PTX joint legs, same accumulation order), for float and half-packed records.
+        IDENTICAL rays in the 1-, 2- and 4-cells-per-lane kernels when a row of the patch is one 32-cell tile (tileX = 32): divQ of the 1- and
+        2-cell kernels must agree BIT FOR BIT (same per-ray arithmetic, same accumulation order), the 4-cell kernel's to FP32 round-off
+        (its joint leg accumulates tau differently), for float and half-packed records.
     (b) default warp footprint (16 x 2 blocks), odd patch sizes and offsets (partial chunks, unpaired last row and last plane), intrusions inside a 2 x 2 block: same
         cells written and counted as the one-cell kernel, steps per ray within 1 %, per-cell agreement within Monte-Carlo error.
     (c) exactly zero divQ in an isothermal black enclosure with intrusions."""
@@ -661,7 +662,11 @@ def test_four_cells_per_lane_kernel(gpu_lib, po):
             res[cpl] = (g.trace_divq(0, patch_lo=lo, patch_hi=hi, timestep=3)["divQ"], int(g.counters().nRaySteps), int(g.counters().nDivQCells))
         rows = (slice(lo[2] + 1, hi[2] + 1, 2), slice(lo[1] + 1, hi[1] + 1, 2), slice(lo[0] + 1, hi[0] + 1))
         assert (res[1][0][rows] != 0).sum() > 2000
-        assert np.array_equal(res[1][0][rows], res[4][0][rows]) and np.array_equal(res[1][0][rows], res[2][0][rows])
+        assert np.array_equal(res[1][0][rows], res[2][0][rows])
+        # the quad leg carries tau itself (tau += k dt, one FFMA per ray and step) instead of the offset form of the single-ray legs:
+        # same rays, same steps, FP32 round-off in the integral
+        scale = np.abs(res[1][0][rows]).max()
+        assert np.abs(res[1][0][rows] - res[4][0][rows]).max() <= 2e-5 * scale, np.abs(res[1][0][rows] - res[4][0][rows]).max() / scale
         assert res[1][2] == res[2][2] == res[4][2]
         assert np.array_equal(res[1][0] != 0, res[4][0] != 0)
     # (b)

@@ -886,28 +886,27 @@ __device__ __forceinline__ void march_single_level_dual(const RecT* __restrict__
   "@x" #J " add.f32 %0, %0, %35;\n\t"                       \
   "@y" #J " add.f32 %1, %1, %36;\n\t"                       \
   "@!n" #J " add.f32 %2, %2, %37;\n\t"
-// one ray: leave the cell in slot P at t<C> (A = operand of the tau offset, LEG = operand of the leg integral)
-#define RQ_INT1(R, P, C, A, LEG)                            \
-  "fma.rn.f32 t" #R ", a" #R #P ", t" #C ", " A ";\n\t"     \
+// one ray: leave the cell in slot P after the path dt inside it (LEG = operand of the leg integral).  The quad leg starts at the ray
+// origin (t = 0), so it can carry tau itself instead of the offset form of the single-ray legs: tau += |k_P| dt with ONE dt = t<C> - t<P>
+// for the four rays -- one FFMA per ray and step instead of two.  (Same quantity, other FP32 rounding: a cell's divQ differs from the
+// single-ray kernels' by round-off, ~1e-6 relative.)
+#define RQ_INT1(R, P, C, LEG)                               \
+  "fma.rn.f32 t" #R ", a" #R #P ", dt, t" #R ";\n\t"        \
   "neg.f32 d, t" #R ";\n\t"                                 \
   "ex2.approx.ftz.f32 e" #R #C ", d;\n\t"                   \
   "sub.f32 d, e" #R #P ", e" #R #C ";\n\t"                  \
   "fma.rn.f32 " LEG ", s" #R #P ", d, " LEG ";\n\t"
-// one ray: enter the cell in slot C (re-base the tau offset)
-#define RQ_ENT1(R, C, A)                                    \
-  "neg.f32 d, a" #R #C ";\n\t"                              \
-  "fma.rn.f32 " A ", d, t" #C ", t" #R ";\n\t"
 #define RQ_INTEG(P, C, DEC1)                                \
-  RQ_INT1(a, P, C, "%4", "%8") RQ_INT1(b, P, C, "%9", "%13") RQ_INT1(c, P, C, "%14", "%18") RQ_INT1(d, P, C, "%19", "%23") \
+  "sub.f32 dt, t" #C ", t" #P ";\n\t"                       \
+  RQ_INT1(a, P, C, "%8") RQ_INT1(b, P, C, "%13") RQ_INT1(c, P, C, "%18") RQ_INT1(d, P, C, "%23") \
   "add.f32 %24, %24, 0f3F800000;\n\t"                       \
   DEC1(a, C) DEC1(b, C) DEC1(c, C) DEC1(d, C)               \
-  RQ_ENT1(a, C, "%4") RQ_ENT1(b, C, "%9") RQ_ENT1(c, C, "%14") RQ_ENT1(d, C, "%19") \
-  "or.b32 wz, ka" #C ", kb" #C ";\n\t"                      \
-  "or.b32 wy, kc" #C ", kd" #C ";\n\t"                      \
-  "or.b32 wz, wz, wy;\n\t"                                  \
-  "setp.lt.s32 w, wz, 0;\n\t"                               \
+  "lop3.b32 wz, ka" #C ", kb" #C ", kc" #C ", 0xFE;\n\t"      \
+  "lop3.or.b32 wy|w, wz, kd" #C ", 0x80000000, 0xA8, pf;\n\t" \
   "@w bra EXIT" #C ";\n\t"
-#define RQ_OUT1(R, C, K, S, E)                              \
+#define RQ_OUT1(R, C, A, K, S, E)                           \
+  "neg.f32 d, a" #R #C ";\n\t"                              \
+  "fma.rn.f32 " A ", d, t" #C ", t" #R ";\n\t"              \
   "mov.f32 " K ", a" #R #C ";\n\t"                          \
   "mov.f32 " S ", s" #R #C ";\n\t"                          \
   "mov.f32 " E ", e" #R #C ";\n\t"
@@ -921,14 +920,14 @@ __device__ __forceinline__ void march_single_level_dual(const RecT* __restrict__
   "selp.s32 %26, 1, 2, y" #C ";\n\t"                        \
   "@x" #C " mov.s32 %26, 0;\n\t"                            \
   RQ_FLAG1(a, C, 4) RQ_FLAG1(b, C, 8) RQ_FLAG1(c, C, 16) RQ_FLAG1(d, C, 32) \
-  RQ_OUT1(a, C, "%5", "%6", "%7") RQ_OUT1(b, C, "%10", "%11", "%12") RQ_OUT1(c, C, "%15", "%16", "%17") RQ_OUT1(d, C, "%20", "%21", "%22") \
+  RQ_OUT1(a, C, "%4", "%5", "%6", "%7") RQ_OUT1(b, C, "%9", "%10", "%11", "%12") RQ_OUT1(c, C, "%14", "%15", "%16", "%17") RQ_OUT1(d, C, "%19", "%20", "%21", "%22") \
   "bra DONE;\n\t"
 #define RQ_START1(R, K, S, E) "mov.f32 a" #R "2, " K ";\n\t" "mov.f32 s" #R "2, " S ";\n\t" "mov.f32 e" #R "2, " E ";\n\t"
 #define RQ_ASM(LD, DEC1)                                                                                             \
   asm volatile(                                                                                                      \
       "{\n\t"                                                                                                        \
-      ".reg .pred x0, y0, n0, x1, y1, n1, x2, y2, n2, w;\n\t"                                                        \
-      ".reg .f32 d, ta, tb, tc, td, t0, t1, t2;\n\t"                                                                 \
+      ".reg .pred x0, y0, n0, x1, y1, n1, x2, y2, n2, w, pf;\n\t"                                                    \
+      ".reg .f32 d, dt, ta, tb, tc, td, t0, t1, t2;\n\t"                                                                 \
       ".reg .f32 sa0, sa1, sa2, sb0, sb1, sb2, sc0, sc1, sc2, sd0, sd1, sd2;\n\t"                                    \
       ".reg .f32 ea0, ea1, ea2, eb0, eb1, eb2, ec0, ec1, ec2, ed0, ed1, ed2;\n\t"                                    \
       ".reg .f32 aa0, aa1, aa2, ab0, ab1, ab2, ac0, ac1, ac2, ad0, ad1, ad2;\n\t"                                    \
@@ -939,6 +938,7 @@ __device__ __forceinline__ void march_single_level_dual(const RecT* __restrict__
       /* slot 2 = the cells the leg starts in */                                                                     \
       RQ_START1(a, "%5", "%6", "%7") RQ_START1(b, "%10", "%11", "%12") RQ_START1(c, "%15", "%16", "%17") RQ_START1(d, "%20", "%21", "%22") \
       "mov.f32 ta, %4;\n\t" "mov.f32 tb, %9;\n\t" "mov.f32 tc, %14;\n\t" "mov.f32 td, %19;\n\t"                      \
+      "setp.ne.s32 pf, 0, 0;\n\t" "mov.f32 t2, 0f00000000;\n\t" /* the leg starts at t = 0 with tau = A */                                                                                   \
       RQ_PEEK(0, "%3", LD)                                                                                           \
       "LOOP:\n\t"                                                                                                    \
       RQ_COMMIT(0) RQ_PEEK(1, "i0", LD) RQ_INTEG(2, 0, DEC1)                                                         \
@@ -979,7 +979,6 @@ __device__ __forceinline__ LegOut march_leg_quad(Dda& d, Integ (&q)[4], float& n
 #undef RQ_FLAG1
 #undef RQ_OUT1
 #undef RQ_INTEG
-#undef RQ_ENT1
 #undef RQ_INT1
 #undef RQ_COMMIT
 #undef RQ_PEEK
@@ -993,28 +992,33 @@ template <class RecT>
 __device__ __forceinline__ LegOut march_leg_quad(Dda& d, Integ (&q)[4], float& nsteps, const RecT* __restrict__ recs, int offB, int offC,
                                                  int offD, float ddx, float ddy, float ddz, int stx, int sty, int stz) {
   const int off[4] = {0, offB, offC, offD};
-  float n0[4];
-  for (int r = 0; r < 4; ++r) n0[r] = q[r].nsteps;
   Peek p = dda_peek(d, stx, sty, stz);
   Rec8 rec[4];
-  for (int r = 0; r < 4; ++r) rec[r] = ldrec(recs + off[r] + p.idx);
+  float tau[4], tPrev = 0.0f;                 // the leg starts at the ray origin: t = 0, tau = A
+  for (int r = 0; r < 4; ++r) { rec[r] = ldrec(recs + off[r] + p.idx); tau[r] = q[r].A; }
   LegOut o;
   for (;;) {
     dda_commit(d, p, ddx, ddy, ddz);
     const Peek pn = dda_peek(d, stx, sty, stz);
     Rec8 nxt[4];
     for (int r = 0; r < 4; ++r) nxt[r] = ldrec(recs + off[r] + pn.idx);      // speculative, like the device loop
+    const float dt = p.t - tPrev;
     int walls = 0;
     for (int r = 0; r < 4; ++r) {
-      integ_cross(q[r], p.t, rec[r]);
+      tau[r] = fmaf(q[r].k, dt, tau[r]);
+      const float e = Num<float>::attenuation(tau[r]);
+      q[r].leg = fmaf(q[r].s, q[r].ePrev - e, q[r].leg);
+      q[r].ePrev = e;
+      q[r].k = fabsf(rec[r].k); q[r].s = rec[r].s;
       if (is_wall(rec[r].k)) walls |= 4 << r;
     }
+    nsteps += 1.0f;
+    tPrev = p.t;
     if (walls) { o = LegOut{p.t, (p.px ? 0 : (p.py ? 1 : 2)) | walls}; break; }
     p = pn;
     for (int r = 0; r < 4; ++r) rec[r] = nxt[r];
   }
-  nsteps += q[0].nsteps - n0[0];
-  for (int r = 0; r < 4; ++r) q[r].nsteps = n0[r];
+  for (int r = 0; r < 4; ++r) { q[r].tau = tau[r]; q[r].A = fmaf(-q[r].k, o.t, tau[r]); }      // offset form for the legs that follow
   return o;
 }
 #endif
