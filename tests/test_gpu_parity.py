@@ -401,7 +401,7 @@ def test_data_onion_fast_path_matches_generic_march(gpu_lib, po, case):
     coarse = po.coarsen_level(fine, (4, 4, 4))
     res = {}
     for gm in (0, 1):
-        g = make(gpu_lib, nDivQRays=16, threshold=thr, haloCells=(4, 4, 4), seed=17, genericMarch=gm)
+        g = make(gpu_lib, nDivQRays=16, threshold=thr, haloCells=(4, 4, 4), seed=17, genericMarch=gm, cellsPerLane=1)   # the same Philox rays per cell
         g.upload_level(0, coarse)
         g.upload_level(1, fine)
         divQ = np.zeros(fine.abskg.shape); vol = np.zeros_like(divQ)
@@ -414,6 +414,40 @@ def test_data_onion_fast_path_matches_generic_march(gpu_lib, po, case):
     scale = np.abs(b).max()
     diff = np.abs(a - b)
     assert np.percentile(diff, 99.9) <= 2e-4 * scale and diff.max() <= 2e-2 * scale, (np.percentile(diff, 99.9) / scale, diff.max() / scale)
+
+
+@pytest.mark.parametrize("case", ["bc", "bc_walls_noreflect"])
+def test_data_onion_four_cells_per_lane(gpu_lib, po, case):
+    """2-level Data Onion, production default: the 2 x 2 cells of a lane march the ROI with one DDA (divq_quad_kernel<ONION>), then each
+    ray leaves the ROI / finishes on its own.  With rayCoherence 2 and 32-cell patch rows the cells with even (j, k) trace the same rays
+    as the one-cell-per-lane fast path: agreement to FP32 round-off; same cells written, step totals within 1 %."""
+    rng = np.random.default_rng(23)
+    fine = po.burns_christon(64, dtype=np.float32)
+    kw = {}
+    if case == "bc_walls_noreflect":
+        add_random_walls(fine, 0.01, rng, abskg=0.7, sigmaT4=0.2)
+        kw = {"allowReflect": 0}
+    fine.rr = (4, 4, 4)
+    coarse = po.coarsen_level(fine, (4, 4, 4))
+    res = {}
+    for cpl in (1, 4):
+        g = make(gpu_lib, nDivQRays=12, threshold=0.05, haloCells=(4, 4, 4), seed=19, cellsPerLane=cpl, tileX=32, warpsPerTile=4, **kw)
+        g.upload_level(0, coarse)
+        g.upload_level(1, fine)
+        divQ = np.zeros(fine.abskg.shape); vol = np.zeros_like(divQ)
+        for plo, phi in po._split((0, 0, 0), (64, 64, 64), (2, 2, 2)):
+            g.trace_dataonion(2, plo, phi, zero_init=False, outputs=(divQ, vol, None), timestep=4)
+        res[cpl] = (divQ, int(g.counters().nRaySteps), int(g.counters().nDivQCells))
+    (d1, n1, c1), (d4, n4, c4) = res[1], res[4]
+    assert c1 == c4 == int((fine.cellType[1:-1, 1:-1, 1:-1] == -1).sum())
+    assert np.array_equal(d1 == 0, d4 == 0)
+    assert abs(n1 - n4) < 0.01 * n1
+    rows = (slice(1, -1, 2), slice(1, -1, 2), slice(1, -1))
+    scale = np.abs(d1).max()
+    diff = np.abs(d1[rows] - d4[rows])
+    assert np.percentile(diff, 99.9) <= 2e-5 * scale and diff.max() <= 2e-3 * scale, (np.percentile(diff, 99.9) / scale, diff.max() / scale)
+    assert not np.array_equal(d1, d4)
+    assert np.linalg.norm(d1 - d4) / np.linalg.norm(d1) < 0.3
 
 
 def test_data_onion_statistical(gpu_lib, po):

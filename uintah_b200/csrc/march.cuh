@@ -1118,7 +1118,10 @@ __device__ __forceinline__ int sel3(int ax, int a, int b, int c) { return ax == 
 template <class RecT, int MAXL>
 __device__ __forceinline__ float march_onion2_fast(const OnionGeom<MAXL>& G, const RoiBox& roi, int ci, int cj, int ck,
                                                    float dx, float dy, float dz, float rx, float ry, float rz, float threshold,
-                                                   bool allowReflect, bool skipZero, unsigned& nSteps, int recBytes) {
+                                                   bool allowReflect, bool skipZero, unsigned& nSteps, int recBytes,
+                                                   const Dda* d0 = nullptr, const Integ* q0 = nullptr, const LegOut* w0 = nullptr) {
+  // d0 / q0 / w0: continue a ray that march_onion2_quad marched through the ROI together with three translates -- the DDA and integral
+  // state after their joint leg, and (w0) the non-flow / shell cell this ray entered at its last step, if it did
   typedef Num<float> N;
   if (!(1.0f > threshold)) return 0.0f;
   const LevelGeom& gf = G.lev[1];
@@ -1143,14 +1146,17 @@ __device__ __forceinline__ float march_onion2_fast(const OnionGeom<MAXL>& G, con
     const Rec8 r = ldrec(cur + d.idx);
     q.k = fabsf(r.k); q.s = r.s;
   }
-  q.A = 0.0f; q.ePrev = 1.0f; q.nsteps = 0.0f; q.tau = 0.0f;
+  q.A = 0.0f; q.ePrev = 1.0f; q.nsteps = 0.0f; q.tau = 0.0f; q.leg = 0.0f;
+  if (d0) { d = *d0; q = *q0; }
+  bool first = d0 != nullptr;
   // position along each axis relative to the origin cell's low corner: l(t) = lb + (t - tb) ln2 * dir   (t is scaled by log2 e)
   float lbx = rx, lby = ry, lbz = rz, tbx = 0.0f, tby = 0.0f, tbz = 0.0f, dvx = dx, dvy = dy, dvz = dz;
   bool onFine = true;
   float sum = 0.0f, fs = 1.0f;
   for (;;) {
-    q.leg = 0.0f;
-    const LegOut w = march_leg(d, q, cur, ddx, ddy, ddz, stx, sty, stz, recBytes);
+    if (!first) q.leg = 0.0f;                          // (a continued ray keeps the integral of its joint leg)
+    const LegOut w = (first && w0) ? *w0 : march_leg(d, q, cur, ddx, ddy, ddz, stx, sty, stz, recBytes);
+    first = false;
     sum = fmaf(q.leg, fs, sum);
     const int ax = w.axis;
     if (onFine && q.k > 3.0e38f) {                   // stepped into the shell: leave the ROI (Ray.cc:2489-2527)
@@ -1203,6 +1209,52 @@ __device__ __forceinline__ float march_onion2_fast(const OnionGeom<MAXL>& G, con
   nSteps += (unsigned)q.nsteps;
   return sum;
 }
+
+// 2-level Data Onion, four cells per lane: the rays of the 2 x 2 cells (ci, cj..cj+1, ck..ck+1) are exact translates inside the ROI copy
+// (one array, one cell size), so ONE DDA marches all four there (march_leg_quad) until any of them enters a non-flow cell or the shell;
+// from that step on every ray continues on its own through march_onion2_fast (ROI exit, coarse level, reflections).
+template <class RecT, int MAXL>
+__device__ __forceinline__ void march_onion2_quad(const OnionGeom<MAXL>& G, const RoiBox& roi, int ci, int cj, int ck, float dx, float dy,
+                                                  float dz, float rx, float ry, float rz, float threshold, bool allowReflect, bool skipZero,
+                                                  unsigned& steps, int recBytes, float (&sum)[4]) {
+  typedef Num<float> N;
+  sum[0] = sum[1] = sum[2] = sum[3] = 0.0f;
+  if (!(1.0f > threshold)) return;
+  const LevelGeom& gf = G.lev[1];
+  const bool posx = !sign_bit(dx), posy = !sign_bit(dy), posz = !sign_bit(dz);
+  const int sy = roi.n[0], sz = roi.n[0] * roi.n[1];
+  const int stx = posx ? 1 : -1, sty = posy ? sy : -sy, stz = posz ? sz : -sz;
+  const float sgx = posx ? 1.0f : 0.0f, sgy = posy ? 1.0f : 0.0f, sgz = posz ? 1.0f : 0.0f;
+  const float ix = N::rcp(dx), iy = N::rcp(dy), iz = N::rcp(dz);
+  const float fx = (float)gf.dx[0], fy = (float)gf.dx[1], fz = (float)gf.dx[2];
+  Dda d;
+  d.tx = (sgx * fx - rx) * ix * N::LEN_SCALE;
+  d.ty = (sgy * fy - ry) * iy * N::LEN_SCALE;
+  d.tz = (sgz * fz - rz) * iz * N::LEN_SCALE;
+  const float ddx = fabsf(ix) * fx * N::LEN_SCALE, ddy = fabsf(iy) * fy * N::LEN_SCALE, ddz = fabsf(iz) * fz * N::LEN_SCALE;
+  d.idx = (ci - roi.lo[0]) + sy * (cj - roi.lo[1]) + sz * (ck - roi.lo[2]);
+  const RecT* cur = static_cast<const RecT*>(roi.rec);
+  const int off[4] = {0, sy, sz, sy + sz};
+  Integ q[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const Rec8 rec = ldrec(cur + off[r] + d.idx);
+    q[r].k = fabsf(rec.k); q[r].s = rec.s;
+    q[r].A = 0.0f; q[r].ePrev = 1.0f; q[r].nsteps = 0.0f; q[r].tau = 0.0f; q[r].leg = 0.0f;
+  }
+  float joint = 0.0f;
+  const LegOut jw = march_leg_quad(d, q, joint, cur, off[1], off[2], off[3], ddx, ddy, ddz, stx, sty, stz);
+  const LegOut lw{jw.t, jw.axis & 3};
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    q[r].nsteps += joint;
+    Dda dr = d;
+    dr.idx += off[r];
+    sum[r] = march_onion2_fast<RecT, MAXL>(G, roi, ci, cj + (r & 1), ck + (r >> 1), dx, dy, dz, rx, ry, rz, threshold, allowReflect, skipZero,
+                                           steps, recBytes, &dr, &q[r], (jw.axis & (4 << r)) ? &lw : nullptr);
+  }
+}
+
 
 template <class Real, class RecT, int MAXL, bool RECORD>
 __device__ __forceinline__ Real march_multi_level(const OnionGeom<MAXL>& G, int ci, int cj, int ck,

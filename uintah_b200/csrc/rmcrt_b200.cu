@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(256, 4) divq_dual_kernel(const __grid_constant
 #ifndef RMCRT_QUAD_BLOCKS
 #define RMCRT_QUAD_BLOCKS 6       // resident blocks per SM the register budget is cut for (80 registers; measured 4: 1.28e12, 5: 1.36e12, 6: 1.46e12, 7: 1.46e12, 8: 1.44e12 steps/s)
 #endif
-template <class RecT>
+template <class RecT, bool ONION>
 __global__ void __launch_bounds__(128, RMCRT_QUAD_BLOCKS) divq_quad_kernel(const __grid_constant__ TraceArgs a, int nxc, int njp, int nkp, int lxBits) {
   extern __shared__ double red[];     // [W][128]
   if (!launch_gate(a)) return;
@@ -589,8 +589,12 @@ __global__ void __launch_bounds__(128, RMCRT_QUAD_BLOCKS) divq_quad_kernel(const
         const float d0 = nz<float, float>(dir[0]), d1 = nz<float, float>(dir[1]), d2 = nz<float, float>(dir[2]);
         if (all4) {
           float sm[4];
-          march_single_level_quad(recs, (int)idA, sy, sz, d0, d1, d2, rayDx[0], rayDx[1], rayDx[2], cx, cy, cz, (float)a.threshold,
-                                  a.allowReflect != 0, skipZero, st, a.recBytes, sm);
+          if constexpr (ONION)    // 2-level Data Onion: joint leg inside the per-patch ROI copy
+            march_onion2_quad<RecT, MAXL>(a.G, a.roi, i, jA, kA, d0, d1, d2, rayDx[0], rayDx[1], rayDx[2], (float)a.threshold,
+                                          a.allowReflect != 0, skipZero, st, a.recBytes, sm);
+          else
+            march_single_level_quad(recs, (int)idA, sy, sz, d0, d1, d2, rayDx[0], rayDx[1], rayDx[2], cx, cy, cz, (float)a.threshold,
+                                    a.allowReflect != 0, skipZero, st, a.recBytes, sm);
 #pragma unroll
           for (int c = 0; c < 4; ++c) acc[c] += (double)(UNSCALE * sm[c]);
         } else {
@@ -599,8 +603,13 @@ __global__ void __launch_bounds__(128, RMCRT_QUAD_BLOCKS) divq_quad_kernel(const
           for (int c = 0; c < 4; ++c) {
             if (!flow[c]) continue;
             unsigned s1 = 0;
-            const float v = march_single_level_fast(recs, (int)idA + off[c], sy, sz, d0, d1, d2, rayDx[0], rayDx[1], rayDx[2], cx, cy, cz,
-                                                    (float)a.threshold, a.allowReflect != 0, skipZero, s1, a.recBytes);
+            float v;
+            if constexpr (ONION)
+              v = march_onion2_fast<RecT, MAXL>(a.G, a.roi, i, jA + (c & 1), kA + (c >> 1), d0, d1, d2, rayDx[0], rayDx[1], rayDx[2],
+                                                (float)a.threshold, a.allowReflect != 0, skipZero, s1, a.recBytes);
+            else
+              v = march_single_level_fast(recs, (int)idA + off[c], sy, sz, d0, d1, d2, rayDx[0], rayDx[1], rayDx[2], cx, cy, cz,
+                                          (float)a.threshold, a.allowReflect != 0, skipZero, s1, a.recBytes);
             st += s1;
             if (c == 0) acc[0] += (double)(UNSCALE * v);
             else if (c == 1) acc[1] += (double)(UNSCALE * v);
@@ -1650,7 +1659,22 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
       CK(cudaGetLastError());
       a.roi.rec = static_cast<RecT*>(ctx->roiBuf.p) + guard;
       for (int d = 0; d < 3; ++d) { a.roi.lo[d] = shell.lo[d]; a.roi.n[d] = shell.n[d]; }
-      if (f32gen) divq_kernel<Real, RecT, true, true, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
+      if (f32gen && ctx->p.rayCoherence >= 1 && ctx->p.cellsPerLane == 4) {
+        // four cells per lane inside the ROI (divq_quad_kernel<ONION>); with reflective walls the one-cell kernel (launch_gate)
+        if constexpr (std::is_same<Real, float>::value && !std::is_same<RecT, Rec16>::value) {
+          const int tx = ctx->p.tileX == 8 || ctx->p.tileX == 16 || ctx->p.tileX == 32 ? ctx->p.tileX : RMCRT_QUAD_TILE_X;
+          const int lxBits = tx == 8 ? 3 : (tx == 16 ? 4 : 5), ry = 2 * (32 / tx);
+          const int nxc = (a.patchN[0] + tx - 1) / tx, njp = (a.patchN[1] + ry - 1) / ry, nkp = (a.patchN[2] + 1) / 2;
+          long long g4 = (long long)nxc * njp * nkp;
+          if (g4 > cap) g4 = cap;
+          const int W4 = ctx->p.warpsPerTile > 0 ? std::min(ctx->p.warpsPerTile, 4) : 4;
+          TraceArgs a2 = a;
+          a2.gate = 1;
+          divq_quad_kernel<RecT, true><<<(int)g4, 32 * W4, W4 * 128 * sizeof(double), st>>>(a2, nxc, njp, nkp, lxBits);
+          a2.gate = 2;
+          divq_kernel<Real, RecT, true, true, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a2);
+        }
+      } else if (f32gen) divq_kernel<Real, RecT, true, true, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
       else        divq_kernel<Real, RecT, true, true, false><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
     } else if (ML) {
       if (f32gen) divq_kernel<Real, RecT, true, false, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
@@ -1665,7 +1689,7 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
         int W4 = ctx->p.warpsPerTile > 0 ? std::min(ctx->p.warpsPerTile, 4) : 4;
         TraceArgs a2 = a;
         a2.gate = 1;
-        divq_quad_kernel<RecT><<<(int)g4, 32 * W4, W4 * 128 * sizeof(double), st>>>(a2, nxc, njp, nkp, lxBits);
+        divq_quad_kernel<RecT, false><<<(int)g4, 32 * W4, W4 * 128 * sizeof(double), st>>>(a2, nxc, njp, nkp, lxBits);
         a2.gate = 2;      // the same solve on the one-cell kernel when reflective walls keep the rays going (launch_gate)
         divq_kernel<Real, RecT, false, true, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a2);
       }
