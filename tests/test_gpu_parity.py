@@ -735,3 +735,27 @@ def test_four_cells_per_lane_kernel(gpu_lib, po):
         g.upload_level(0, iso)
         assert np.abs(g.trace_divq(0)["divQ"]).max() < 2e-5 * 4 * np.pi * 2.0 * 0.6
         assert int(g.counters().nDivQCells) == int((ct == -1).sum())
+
+
+@pytest.mark.parametrize("flux", [0, 1])
+def test_pinned_outputs_are_written_in_place(gpu_lib, po, flux):
+    """rmcrt_trace_divq with page-locked divQ / radiationVolq buffers: the kernels write the mapped host memory directly (no device
+    staging buffer, no D2H copy after the solve) and only the part of the window outside the patch is zero-filled.  Same bits as the
+    staged path pageable buffers take, whatever the buffers held before."""
+    import torch
+    rng = np.random.default_rng(5)
+    lv = po.burns_christon(37, dtype=np.float32)
+    add_random_walls(lv, 0.03, rng, abskg=0.9, sigmaT4=0.15)
+    g = make(gpu_lib, nDivQRays=16, nFluxRays=4, threshold=0.05, seed=9, solveBoundaryFlux=flux)
+    g.upload_level(0, lv)
+    kw = dict(patch_lo=(3, 5, 2), patch_hi=(36, 30, 11), timestep=5)
+    ref = g.trace_divq(0, **kw)
+    shape = ref["divQ"].shape
+    tq = torch.full(shape, float("nan"), dtype=torch.float64).pin_memory()
+    tv = torch.full(shape, float("nan"), dtype=torch.float64).pin_memory()
+    bf = np.full(shape + (7,), np.nan) if flux else None
+    g.trace_divq(0, outputs=(tq.numpy(), tv.numpy(), bf), **kw)
+    assert np.array_equal(tq.numpy(), ref["divQ"]) and np.array_equal(tv.numpy(), ref["radiationVolq"])
+    assert (ref["divQ"] != 0).sum() > 5000
+    if flux:
+        assert np.array_equal(bf, ref["boundFlux"])

@@ -1718,6 +1718,19 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
   return 0;
 }
 
+// zero the cells of the output window that lie outside the traced patch (the trace kernels write every cell inside it)
+__global__ void zero_border_kernel(double* __restrict__ q0, double* __restrict__ q1, int ox, int oy, int oz, int lx, int ly, int lz,
+                                   int nx, int ny, int nz_) {
+  const long long n = (long long)ox * oy * oz;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(t % ox);
+    const long long r = t / ox;
+    const int y = (int)(r % oy), z = (int)(r / oy);
+    const bool inside = x >= lx && x < lx + nx && y >= ly && y < ly + ny && z >= lz && z < lz + nz_;
+    if (!inside) { q0[t] = 0.0; q1[t] = 0.0; }
+  }
+}
+
 int trace_common(rmcrt_ctx* ctx, int maxLevels, bool ML, const int32_t pLo[3], const int32_t pHi[3], double* dDivQ, double* dVolq,
                  double* dFlux, const int32_t oLo[3], const int32_t oHi[3], int zeroInit, uint64_t timestep, cudaStream_t st) {
   TraceArgs a;
@@ -1727,7 +1740,14 @@ int trace_common(rmcrt_ctx* ctx, int maxLevels, bool ML, const int32_t pLo[3], c
   a.divQ = dDivQ; a.volq = dVolq; a.bflux = dFlux;
   const size_t nOut = (size_t)a.outN[0] * a.outN[1] * a.outN[2];
   CK(cudaSetDevice(ctx->device));
-  if (zeroInit) {   // Ray.cc:577-587
+  if (zeroInit == 2 && ctx->p.solveDivQ) {
+    // outputs written straight into mapped host memory (trace_host): every cell of the patch is written by the divQ kernel, so only the
+    // rest of the window is zeroed -- nothing crosses the bus twice
+    zero_border_kernel<<<grid_for((long long)nOut, 256, ctx->smCount), 256, 0, st>>>(dDivQ, dVolq, a.outN[0], a.outN[1], a.outN[2],
+        a.patchLo[0] - a.outLo[0], a.patchLo[1] - a.outLo[1], a.patchLo[2] - a.outLo[2], a.patchN[0], a.patchN[1], a.patchN[2]);
+    CK(cudaGetLastError());
+    if (dFlux) CK(cudaMemsetAsync(dFlux, 0, nOut * 7 * sizeof(double), st));
+  } else if (zeroInit) {   // Ray.cc:577-587
     CK(cudaMemsetAsync(dDivQ, 0, nOut * sizeof(double), st));
     CK(cudaMemsetAsync(dVolq, 0, nOut * sizeof(double), st));
     if (dFlux) CK(cudaMemsetAsync(dFlux, 0, nOut * 7 * sizeof(double), st));
@@ -1751,8 +1771,29 @@ int trace_host(rmcrt_ctx* ctx, int maxLevels, bool ML, const int32_t pLo[3], con
     nOut *= (size_t)(oHi[d] - oLo[d]);
   }
   CK(cudaSetDevice(ctx->device));
-  if (ctx->outDivQ.ensure(nOut * 8) || ctx->outVolq.ensure(nOut * 8)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc outputs");
   double* dFlux = nullptr;
+  // Pinned (page-locked, device-mapped) divQ / radiationVolq buffers are written by the kernels directly: the two f64 rows a tile
+  // produces go over the bus while the other tiles are still marching, instead of a device buffer + a D2H copy after the solve.
+  // Pageable buffers (a CCVariable of the stand-in DataWarehouse) take the staged path below.
+  if (zeroInit && ctx->p.solveDivQ) {
+    cudaPointerAttributes aq, av;
+    const bool mq = cudaPointerGetAttributes(&aq, divQ) == cudaSuccess && aq.type == cudaMemoryTypeHost && aq.devicePointer;
+    const bool mv = cudaPointerGetAttributes(&av, volq) == cudaSuccess && av.type == cudaMemoryTypeHost && av.devicePointer;
+    cudaGetLastError();      // an unregistered host pointer is not an error here
+    if (mq && mv) {
+      if (flux) {
+        if (ctx->outFlux.ensure(nOut * 56)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc boundFlux");
+        dFlux = static_cast<double*>(ctx->outFlux.p);
+      }
+      int rc = trace_common(ctx, maxLevels, ML, pLo, pHi, static_cast<double*>(aq.devicePointer), static_cast<double*>(av.devicePointer),
+                            dFlux, oLo, oHi, 2, timestep, st);
+      if (rc) return rc;
+      if (flux) CK(cudaMemcpyAsync(flux, dFlux, nOut * 56, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      return 0;
+    }
+  }
+  if (ctx->outDivQ.ensure(nOut * 8) || ctx->outVolq.ensure(nOut * 8)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc outputs");
   if (flux) {
     if (ctx->outFlux.ensure(nOut * 56)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc boundFlux");
     dFlux = static_cast<double*>(ctx->outFlux.p);
