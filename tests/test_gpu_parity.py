@@ -416,7 +416,7 @@ def test_data_onion_fast_path_matches_generic_march(gpu_lib, po, case):
     assert np.percentile(diff, 99.9) <= 2e-4 * scale and diff.max() <= 2e-2 * scale, (np.percentile(diff, 99.9) / scale, diff.max() / scale)
 
 
-@pytest.mark.parametrize("case", ["bc", "bc_walls_noreflect"])
+@pytest.mark.parametrize("case", ["bc", "bc_walls_noreflect", "bc_half"])
 def test_data_onion_four_cells_per_lane(gpu_lib, po, case):
     """2-level Data Onion, production default: the 2 x 2 cells of a lane march the ROI with one DDA (divq_quad_kernel<ONION>), then each
     ray leaves the ROI / finishes on its own.  With rayCoherence 2 and 32-cell patch rows the cells with even (j, k) trace the same rays
@@ -431,7 +431,8 @@ def test_data_onion_four_cells_per_lane(gpu_lib, po, case):
     coarse = po.coarsen_level(fine, (4, 4, 4))
     res = {}
     for cpl in (1, 4):
-        g = make(gpu_lib, nDivQRays=12, threshold=0.05, haloCells=(4, 4, 4), seed=19, cellsPerLane=cpl, tileX=32, warpsPerTile=4, **kw)
+        g = make(gpu_lib, nDivQRays=12, threshold=0.05, haloCells=(4, 4, 4), seed=19, cellsPerLane=cpl, tileX=32, warpsPerTile=4,
+                 half_records=(case == "bc_half"), **kw)
         g.upload_level(0, coarse)
         g.upload_level(1, fine)
         divQ = np.zeros(fine.abskg.shape); vol = np.zeros_like(divQ)
@@ -705,17 +706,19 @@ def test_four_cells_per_lane_kernel(gpu_lib, po):
         assert np.array_equal(res[1][0] != 0, res[4][0] != 0)
     # (b)
     res = {}
-    for cpl in (1, 4):
-        g = make(gpu_lib, nDivQRays=200, threshold=0.05, seed=3, cellsPerLane=cpl)
+    for cpl, tx in ((1, 0), (4, 0), (4, 8), (4, 32)):
+        g = make(gpu_lib, nDivQRays=200, threshold=0.05, seed=3, cellsPerLane=cpl, tileX=tx)
         g.upload_level(0, lv)
         d = g.trace_divq(0, patch_lo=(3, 5, 2), patch_hi=(36, 30, 11))["divQ"]
-        res[cpl] = (d, int(g.counters().nDivQCells), int(g.counters().nRaySteps))
-    (d1, n1, s1), (d4, n4, s4) = res[1], res[4]
+        res[(cpl, tx)] = (d, int(g.counters().nDivQCells), int(g.counters().nRaySteps))
+    (d1, n1, s1), (d4, n4, s4) = res[(1, 0)], res[(4, 0)]
     flow = lv.cellType == -1
     box = np.zeros(flow.shape, bool); box[3:12, 6:31, 4:37] = True
-    assert n1 == n4 == int((flow & box).sum())
-    assert np.array_equal(d1 != 0, d4 != 0) and not d4[~(flow & box)].any()
-    assert abs(s1 - s4) < 0.01 * s1
+    for key in ((4, 0), (4, 8), (4, 32)):          # every warp footprint: same cells written and counted, same work
+        dk, nk, sk = res[key]
+        assert n1 == nk == int((flow & box).sum())
+        assert np.array_equal(d1 != 0, dk != 0) and not dk[~(flow & box)].any()
+        assert abs(s1 - sk) < 0.01 * s1
     sel = d1 != 0
     g = make(gpu_lib, nDivQRays=200, threshold=0.05, seed=3, cellsPerLane=1)
     g.upload_level(0, lv)
