@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(256, 4) divq_dual_kernel(const __grid_constant
 #define RMCRT_QUAD_TILE_X 16      // default origin cells of a warp in x (rmcrt_params.tileX = 0): measured 32: 1.655e12, 16: 1.712e12, 8: 1.686e12 steps/s at 128^3
 #endif
 #ifndef RMCRT_QUAD_BLOCKS
-#define RMCRT_QUAD_BLOCKS 6       // resident blocks per SM the register budget is cut for (80 registers; measured 4: 1.28e12, 5: 1.36e12, 6: 1.46e12, 7: 1.46e12, 8: 1.44e12 steps/s)
+#define RMCRT_QUAD_BLOCKS 7       // resident blocks per SM the register budget is cut for (72 registers).  Measured, first quad loop: 4: 1.28e12, 5: 1.36e12, 6: 1.46e12, 7: 1.46e12, 8: 1.44e12 steps/s; shipped loop: 6: 1.79e12, 7: 1.83e12
 #endif
 template <class RecT, bool ONION>
 __global__ void __launch_bounds__(128, RMCRT_QUAD_BLOCKS) divq_quad_kernel(const __grid_constant__ TraceArgs a, int nxc, int njp, int nkp, int lxBits) {
