@@ -174,9 +174,14 @@ __device__ __forceinline__ void gen_divq_ray_f32(const RayGen& rg, const LevelGe
                                                  unsigned long long dirId, float dir[3], float rayDx[3]) {
   const u32x4 a = philox4x32_10(u32x4{(uint32_t)dirId, (uint32_t)ray, rg.timestep,
                                       ((uint32_t)(dirId >> 32) << 8) | STREAM_DIR}, rg.key0, rg.key1);
-  const unsigned long long orgId = rg.coherent == 2 ? dirId : cellId;
-  const u32x4 b = philox4x32_10(u32x4{(uint32_t)orgId, (uint32_t)ray, rg.timestep,
-                                      ((uint32_t)(orgId >> 32) << 8) | STREAM_ORIGIN}, rg.key0, rg.key1);
+  // in-cell origin: rayCoherence 2 keys it on the tile like the direction, so the two spare words of the direction draw serve (24 bits
+  // for x, 16 bits each for y and z: one Philox call per ray instead of two); otherwise a draw of its own keyed on the cell
+  u32x4 b;
+  if (rg.coherent == 2) {
+    b = u32x4{a.z, a.w & 0xFFFF0000u, a.w << 16, 0u};
+  } else {
+    b = philox4x32_10(u32x4{(uint32_t)cellId, (uint32_t)ray, rg.timestep, ((uint32_t)(cellId >> 32) << 8) | STREAM_ORIGIN}, rg.key0, rg.key1);
+  }
   const float S = 1.0f / 16777216.0f;                     // 2^-24
   const float z = fmaf((float)(a.x >> 8) + 0.5f, 2.0f * S, -1.0f);      // (-1,1), never +-1
   const float r = sqrtf(fmaxf(0.0f, fmaf(-z, z, 1.0f)));
@@ -544,10 +549,10 @@ __global__ void __launch_bounds__(256, 4) divq_dual_kernel(const __grid_constant
 #define RMCRT_QUAD_TILE_X 16      // default origin cells of a warp in x (rmcrt_params.tileX = 0): measured 32: 1.655e12, 16: 1.712e12, 8: 1.686e12 steps/s at 128^3
 #endif
 #ifndef RMCRT_QUAD_BLOCKS
-#define RMCRT_QUAD_BLOCKS 7       // resident blocks per SM the register budget is cut for (72 registers).  Measured, first quad loop: 4: 1.28e12, 5: 1.36e12, 6: 1.46e12, 7: 1.46e12, 8: 1.44e12 steps/s; shipped loop: 6: 1.79e12, 7: 1.83e12
+#define RMCRT_QUAD_BLOCKS 7       // resident blocks per SM the register budget is cut for (72 registers).  Measured, first quad loop: 4: 1.28e12, 5: 1.36e12, 6: 1.46e12, 7: 1.46e12, 8: 1.44e12 steps/s; shipped loop: 6: 1.79e12, 7: 1.83e12, 8: 1.89e12 at 128^3 (float records); 256^3 (half records) 7: 1.947e12, 8: 1.937e12 -- hence one block more for the float-record single-level kernel
 #endif
 template <class RecT, bool ONION>
-__global__ void __launch_bounds__(128, RMCRT_QUAD_BLOCKS) divq_quad_kernel(const __grid_constant__ TraceArgs a, int nxc, int njp, int nkp, int lxBits) {
+__global__ void __launch_bounds__(128, (!ONION && std::is_same<RecT, Rec8>::value) ? RMCRT_QUAD_BLOCKS + 1 : RMCRT_QUAD_BLOCKS) divq_quad_kernel(const __grid_constant__ TraceArgs a, int nxc, int njp, int nkp, int lxBits) {
   extern __shared__ double red[];     // [W][128]
   if (!launch_gate(a)) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
