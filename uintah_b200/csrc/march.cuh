@@ -899,7 +899,6 @@ __device__ __forceinline__ void march_single_level_dual(const RecT* __restrict__
 #define RQ_INTEG(P, C, DEC1)                                \
   "sub.f32 dt, t" #C ", t" #P ";\n\t"                       \
   RQ_INT1(a, P, C, "%8") RQ_INT1(b, P, C, "%13") RQ_INT1(c, P, C, "%18") RQ_INT1(d, P, C, "%23") \
-  "add.f32 %24, %24, 0f3F800000;\n\t"                       \
   DEC1(a, C) DEC1(b, C) DEC1(c, C) DEC1(d, C)               \
   "lop3.b32 wz, ka" #C ", kb" #C ", kc" #C ", 0xFE;\n\t"      \
   "lop3.or.b32 wy|w, wz, kd" #C ", 0x80000000, 0xA8, pf;\n\t" \
@@ -913,8 +912,10 @@ __device__ __forceinline__ void march_single_level_dual(const RecT* __restrict__
 #define RQ_FLAG1(R, C, BIT)                                 \
   "setp.lt.s32 w, k" #R #C ", 0;\n\t"                       \
   "@w add.s32 %26, %26, " #BIT ";\n\t"
-#define RQ_EXIT(C)                                          \
+// (steps are counted once per loop iteration of three; an exit adds the steps of the iteration it leaves: NS = C + 1 as a float)
+#define RQ_EXIT(C, NS)                                      \
   "EXIT" #C ":\n\t"                                         \
+  "add.f32 %24, %24, " NS ";\n\t"                           \
   "mov.s32 %3, i" #C ";\n\t"                                \
   "mov.f32 %25, t" #C ";\n\t"                               \
   "selp.s32 %26, 1, 2, y" #C ";\n\t"                        \
@@ -944,8 +945,9 @@ __device__ __forceinline__ void march_single_level_dual(const RecT* __restrict__
       RQ_COMMIT(0) RQ_PEEK(1, "i0", LD) RQ_INTEG(2, 0, DEC1)                                                         \
       RQ_COMMIT(1) RQ_PEEK(2, "i1", LD) RQ_INTEG(0, 1, DEC1)                                                         \
       RQ_COMMIT(2) RQ_PEEK(0, "i2", LD) RQ_INTEG(1, 2, DEC1)                                                         \
+      "add.f32 %24, %24, 0f40400000;\n\t"                                                                            \
       "bra LOOP;\n\t"                                                                                                \
-      RQ_EXIT(0) RQ_EXIT(1) RQ_EXIT(2)                                                                               \
+      RQ_EXIT(0, "0f3F800000") RQ_EXIT(1, "0f40000000") RQ_EXIT(2, "0f40400000")                                                                             \
       "DONE:\n\t"                                                                                                    \
       "mov.f32 %27, ta;\n\t" "mov.f32 %28, tb;\n\t" "mov.f32 %29, tc;\n\t" "mov.f32 %30, td;\n\t"                    \
       "}"                                                                                                            \
