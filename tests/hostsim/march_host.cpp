@@ -182,7 +182,7 @@ void hs_trace_1L_scatter(const HsLevel* g, int kind, int n, const int* cells, co
 
 // two cells per lane (march_single_level_dual): the rays of cell c and of cell c + (0,1,0) with the SAME direction and in-cell origin
 void hs_trace_1L_dual(const HsLevel* g, int n, const int* cells, const double* dirs, const double* orgs, double threshold, int allowReflect,
-                      int skipZero, double* sumA, double* sumB, unsigned* stepsA, unsigned* stepsB) {
+                      int skipZero, int rejoin, int pairK, double* sumA, double* sumB, unsigned* stepsA, unsigned* stepsB) {
   const int nx = g->hi[0] - g->lo[0], ny = g->hi[1] - g->lo[1];
   for (int t = 0; t < n; ++t) {
     const int* c = cells + 3 * t;
@@ -192,9 +192,15 @@ void hs_trace_1L_dual(const HsLevel* g, int n, const int* cells, const double* d
     unsigned sa = 0, sb = 0;
     float a, b;
     const double* d = dirs + 3 * t;
-    march_single_level_dual(static_cast<const Rec8*>(g->rec), idx, nx, nx * ny, (float)d[0], (float)d[1], (float)d[2], (float)r[0], (float)r[1],
-                            (float)r[2], (float)g->dx[0], (float)g->dx[1], (float)g->dx[2], (float)threshold, allowReflect != 0, skipZero != 0,
-                            sa, sb, 8, a, b);
+    const int offB = pairK ? nx * ny : nx;
+    if (rejoin)
+      march_single_level_dual<true>(static_cast<const Rec8*>(g->rec), idx, offB, nx, nx * ny, (float)d[0], (float)d[1], (float)d[2], (float)r[0],
+                                    (float)r[1], (float)r[2], (float)g->dx[0], (float)g->dx[1], (float)g->dx[2], (float)threshold,
+                                    allowReflect != 0, skipZero != 0, sa, sb, 8, a, b);
+    else
+      march_single_level_dual<false>(static_cast<const Rec8*>(g->rec), idx, offB, nx, nx * ny, (float)d[0], (float)d[1], (float)d[2], (float)r[0],
+                                     (float)r[1], (float)r[2], (float)g->dx[0], (float)g->dx[1], (float)g->dx[2], (float)threshold,
+                                     allowReflect != 0, skipZero != 0, sa, sb, 8, a, b);
     sumA[t] = a; sumB[t] = b; stepsA[t] = sa; stepsB[t] = sb;
   }
 }

@@ -128,14 +128,14 @@ def trace_1L_scatter(lv, kind, cells, dirs, org, seeds, thr, refl, sigma_scat, m
     return sumI, steps
 
 
-def trace_1L_dual(lv, cells, dirs, org, thr, refl, skip=0):
+def trace_1L_dual(lv, cells, dirs, org, thr, refl, skip=0, rejoin=0, pair_k=0):
     """march_single_level_dual: rays of cell c (A) and c + (0,1,0) (B) sharing direction and in-cell origin"""
     rec = pack(lv, 0)
     h = hslevel(lv, rec)
     n = len(cells)
     sa = np.zeros(n); sb = np.zeros(n); na = np.zeros(n, np.uint32); nb = np.zeros(n, np.uint32)
     cells = np.ascontiguousarray(cells, np.int32); dirs = np.ascontiguousarray(dirs); org = np.ascontiguousarray(org)
-    lib().hs_trace_1L_dual(C.byref(h), n, _vp(cells), _vp(dirs), _vp(org), C.c_double(thr), refl, skip, _vp(sa), _vp(sb), _vp(na), _vp(nb))
+    lib().hs_trace_1L_dual(C.byref(h), n, _vp(cells), _vp(dirs), _vp(org), C.c_double(thr), refl, skip, rejoin, pair_k, _vp(sa), _vp(sb), _vp(na), _vp(nb))
     return sa, sb, na, nb
 
 

@@ -653,27 +653,39 @@ def test_two_cells_per_lane_kernel(gpu_lib, po):
 
 
 def test_kernel_choice_follows_the_walls(gpu_lib, po):
-    """launch_gate: with reflective walls (mirrors) and allowReflect the production solve runs on the one-cell-per-lane kernel -- bit
-    identical to cellsPerLane=1; with black walls, or allowReflect off, the two-cells-per-lane kernel does the work (different rays)"""
-    pl = po.parallel_plates(24, dtype=np.float32, mirror_faces=("x-", "y-"))
-    bc = po.burns_christon(24, dtype=np.float32)
+    """launch_gate, decided on the device from the level's status words.  Reflective walls (mirrors) + allowReflect: the production solve
+    runs on the pair kernel with the pairs stacked in z and a joint leg that survives every wall both rays reach at the same step
+    (divq_dual_kernel<REJOIN>), whatever cellsPerLane (2 or 4) says; black walls, or allowReflect off: on the four- / two-cell kernels.
+    Either way the first cell of every lane traces the same rays as the one-cell-per-lane kernel (rayCoherence 2, a row of the level =
+    one 32-cell tile) and must agree with it -- bit for bit for the pair kernels (reflections included), to round-off for the quad."""
+    pl = po.parallel_plates(32, dtype=np.float32, mirror_faces=("x-", "y-"))
+    bc = po.burns_christon(32, dtype=np.float32)
+    even_k = (slice(1, -1, 2), slice(1, -1), slice(1, -1))
+    even_jk = (slice(1, -1, 2), slice(1, -1, 2), slice(1, -1))
 
     def solve(lv, **kw):
-        g = make(gpu_lib, nDivQRays=12, threshold=0.01, seed=6, **kw)
+        g = make(gpu_lib, nDivQRays=12, seed=6, warpsPerTile=4, tileX=32, **kw)
         g.upload_level(0, lv)
         d = g.trace_divq(0, timestep=4)["divQ"]
         return d, int(g.counters().nRaySteps), int(g.counters().nDivQCells)
 
-    d2, n2, c2 = solve(pl)
-    d1, n1, c1 = solve(pl, cellsPerLane=1)
-    assert np.array_equal(d1, d2) and n1 == n2 and c1 == c2 == 24 ** 3          # mirrors: the one-cell kernel ran in both
-    e2, m2, _ = solve(pl, allowReflect=0)
-    e1, m1, _ = solve(pl, allowReflect=0, cellsPerLane=1)
-    assert not np.array_equal(e1, e2) and abs(m1 - m2) < 0.01 * m1                  # rays end at the first wall: the pair kernel ran
-    b2, k2, cb2 = solve(bc)
-    b1, k1, cb1 = solve(bc, cellsPerLane=1)
-    assert not np.array_equal(b1, b2) and cb1 == cb2 == 24 ** 3 and abs(k1 - k2) < 0.01 * k1
-    assert np.linalg.norm(b1 - b2) / np.linalg.norm(b1) < 0.08                      # same physics, other random draws
+    for thr in (0.01, 0.0005):                      # mirrors: several reflections per ray
+        d4, n4, c4 = solve(pl, threshold=thr)
+        d2, n2, c2 = solve(pl, threshold=thr, cellsPerLane=2)
+        d1, n1, c1 = solve(pl, threshold=thr, cellsPerLane=1)
+        assert c1 == c2 == c4 == 32 ** 3
+        assert np.array_equal(d4, d2) and n4 == n2                      # the same kernel ran for both
+        assert np.array_equal(d1[even_k], d4[even_k]) and not np.array_equal(d1, d4)
+        assert abs(n1 - n4) < 0.04 * n1
+        assert np.linalg.norm(d1 - d4) / np.linalg.norm(d1) < 0.35      # same physics, 12 rays per cell
+    for lv, kw in ((pl, {"allowReflect": 0}), (bc, {})):               # rays end at the first wall: quad / pair-in-y kernels
+        d4, n4, c4 = solve(lv, threshold=0.01, **kw)
+        d2, n2, c2 = solve(lv, threshold=0.01, cellsPerLane=2, **kw)
+        d1, n1, c1 = solve(lv, threshold=0.01, cellsPerLane=1, **kw)
+        assert c1 == c2 == c4 == 32 ** 3 and not np.array_equal(d4, d2)
+        assert np.array_equal(d1[even_jk], d2[even_jk])
+        assert np.abs(d1[even_jk] - d4[even_jk]).max() <= 2e-5 * np.abs(d1).max()
+        assert abs(n1 - n4) < 0.04 * n1 and abs(n1 - n2) < 0.04 * n1
 
 
 def test_four_cells_per_lane_kernel(gpu_lib, po):

@@ -225,3 +225,40 @@ def test_four_cells_per_lane_march_equals_four_single_marches(po, case):
     np.testing.assert_allclose(sm[same, 0], singles[0][same], rtol=1e-5, atol=1e-6 * np.abs(singles[0]).max())
     for q in (1, 2, 3):
         np.testing.assert_allclose(sm[same, q], singles[q][same], rtol=2e-4, atol=1e-5 * np.abs(singles[q]).max())
+
+
+@pytest.mark.parametrize("pair_k", [0, 1])
+@pytest.mark.parametrize("case", ["plates_mirrors_xy", "plates_mirrors_xz", "bc_walls"])
+def test_pair_march_rejoins_after_a_wall_both_rays_hit_at_once(po, case, pair_k):
+    """march_single_level_dual<REJOIN> (the variant used when walls reflect): when both rays of the pair enter a non-flow cell at the
+    same step and are reflected, the joint leg goes on.  Pairs stacked in y (pair_k = 0) or in z (1): equal to two single marches --
+    same sums, same step counts -- through several mirror reflections, staggered hits on the walls normal to the pair's axis and
+    intrusions"""
+    rng = np.random.default_rng(41 + pair_k)
+    if case.startswith("plates"):
+        lv = po.parallel_plates(18, dtype=np.float32, mirror_faces=("x-", "y-") if case.endswith("xy") else ("x-", "z+"))
+        thr, refl, skip = 0.001, 1, 0
+    else:
+        lv = po.burns_christon(20, dtype=np.float32)
+        from util import add_random_walls
+        add_random_walls(lv, 0.03, rng, abskg=0.8, sigmaT4=0.05)
+        thr, refl, skip = 0.05, 1, 0
+    n = 500
+    cells, dirs, org = random_rays(lv, n, rng)
+    N = lv.interior_hi
+    ct = lv.cellType
+    o = np.array([0, 0, 1] if pair_k else [0, 1, 0], np.int32)
+    keep = [t for t in range(n) if cells[t][1] + o[1] < N[1] and cells[t][2] + o[2] < N[2]
+            and ct[cells[t][2] + 1, cells[t][1] + 1, cells[t][0] + 1] == -1
+            and ct[cells[t][2] + 1 + o[2], cells[t][1] + 1 + o[1], cells[t][0] + 1] == -1]
+    cells, dirs, org = cells[keep], dirs[keep], org[keep]
+    assert len(cells) > 250
+    sa, sb, na, nb = sim.trace_1L_dual(lv, cells, dirs, org, thr, refl, skip, rejoin=1, pair_k=pair_k)
+    ra, nra = sim.trace_1L_fast(lv, cells, dirs, org, thr, refl, skip)
+    rb, nrb = sim.trace_1L_fast(lv, cells + o, dirs, org + o * np.array(lv.dx), thr, refl, skip)
+    assert (na == nra).mean() > 0.99 and (nb == nrb).mean() > 0.95, ((na == nra).mean(), (nb == nrb).mean())
+    same = (na == nra) & (nb == nrb)
+    np.testing.assert_allclose(sa[same], ra[same], rtol=1e-5, atol=1e-6 * np.abs(ra).max())
+    np.testing.assert_allclose(sb[same], rb[same], rtol=2e-4, atol=1e-5 * np.abs(rb).max())
+    if case.startswith("plates"):
+        assert na.mean() > 25          # 18 cells across: two to three legs per ray, the rejoin path is what is being exercised

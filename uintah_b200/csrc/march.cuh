@@ -809,16 +809,21 @@ __device__ __forceinline__ LegOut march_leg_pair(Dda& d, Integ& qa, Integ& qb, f
 }
 #endif
 
-template <class RecT>
-__device__ __forceinline__ void march_single_level_dual(const RecT* __restrict__ recs, int idxA, int sy, int sz, float dx, float dy, float dz,
-                                                        float rx, float ry, float rz, float cx, float cy, float cz, float threshold,
+// offB = record offset of cell B from cell A (one row, or one plane).
+// REJOIN: when both rays enter a non-flow cell at the SAME step -- a planar wall not normal to the pair's axis, e.g. the x- and y-
+// mirrors of RMCRT_1L_perf.ups for a pair stacked in z -- and both are reflected, the reflected rays are again exact translates
+// (RMCRTCommon::reflect flips the same axis for both and tMax is never recomputed): the joint leg goes on instead of handing over to
+// two single marches.  Same per-ray arithmetic either way.
+template <bool REJOIN, class RecT>
+__device__ __forceinline__ void march_single_level_dual(const RecT* __restrict__ recs, int idxA, int offB, int sy, int sz, float dx, float dy,
+                                                        float dz, float rx, float ry, float rz, float cx, float cy, float cz, float threshold,
                                                         bool allowReflect, bool skipZero, unsigned& stepsA, unsigned& stepsB, int recBytes,
                                                         float& sumA, float& sumB) {
   typedef Num<float> N;
   sumA = sumB = 0.0f;
   if (!(1.0f > threshold)) return;
   const bool posx = !sign_bit(dx), posy = !sign_bit(dy), posz = !sign_bit(dz);
-  const int stx = posx ? 1 : -1, sty = posy ? sy : -sy, stz = posz ? sz : -sz;
+  int stx = posx ? 1 : -1, sty = posy ? sy : -sy, stz = posz ? sz : -sz;
   const float ix = N::rcp(dx), iy = N::rcp(dy), iz = N::rcp(dz);
   Dda d;
   d.tx = ((posx ? cx : 0.0f) - rx) * ix * N::LEN_SCALE;
@@ -826,7 +831,7 @@ __device__ __forceinline__ void march_single_level_dual(const RecT* __restrict__
   d.tz = ((posz ? cz : 0.0f) - rz) * iz * N::LEN_SCALE;
   const float ddx = fabsf(ix) * cx * N::LEN_SCALE, ddy = fabsf(iy) * cy * N::LEN_SCALE, ddz = fabsf(iz) * cz * N::LEN_SCALE;
   d.idx = idxA;
-  const RecT* __restrict__ recsB = recs + sy;          // cell B = cell A + one row
+  const RecT* __restrict__ recsB = recs + offB;
   Integ qa, qb;
   {
     const Rec8 ra = ldrec(recs + idxA), rb = ldrec(recsB + idxA);
@@ -834,20 +839,57 @@ __device__ __forceinline__ void march_single_level_dual(const RecT* __restrict__
     qb.k = fabsf(rb.k); qb.s = rb.s;
   }
   qa.A = qb.A = 0.0f; qa.ePrev = qb.ePrev = 1.0f; qa.nsteps = qb.nsteps = 0.0f; qa.tau = qb.tau = 0.0f; qa.leg = qb.leg = 0.0f;
-  // ---- joint leg (march_leg_pair): both rays take the same steps until either enters a non-flow cell
-  float joint = 0.0f;
-  const LegOut jw = march_leg_pair(d, qa, qb, joint, recs, recsB, ddx, ddy, ddz, stx, sty, stz);
+  float joint = 0.0f, fsA = 1.0f, fsB = 1.0f;
+  bool goA = true, goB = true;     // the ray still marches
+  bool wa, wb;                     // the ray has a pending wall (lw) that has not been dealt with yet
+  LegOut lw;
+  for (;;) {
+    // ---- joint leg (march_leg_pair): both rays take the same steps until either enters a non-flow cell
+    const LegOut jw = march_leg_pair(d, qa, qb, joint, recs, recsB, ddx, ddy, ddz, stx, sty, stz);
+    wa = (jw.axis & 4) != 0; wb = (jw.axis & 8) != 0;
+    lw = LegOut{jw.t, jw.axis & 3};
+    if (!REJOIN || !(wa && wb) || !allowReflect) break;
+    // a wall for both at once: wall emission and threshold test per ray (RMCRTCommon.cc:846-898), as in ray_wall
+    {
+      sumA = fmaf(qa.leg, fsA, sumA); qa.leg = 0.0f;
+      const float eps = qa.k > 1.0f ? 1.0f : qa.k;
+      sumA = fmaf(eps * qa.s, qa.ePrev, sumA);
+      goA = qa.ePrev * fsA > threshold;
+      if (goA) { fsA *= (1.0f - qa.k); if (skipZero && fsA == 0.0f) goA = false; }
+    }
+    {
+      sumB = fmaf(qb.leg, fsB, sumB); qb.leg = 0.0f;
+      const float eps = qb.k > 1.0f ? 1.0f : qb.k;
+      sumB = fmaf(eps * qb.s, qb.ePrev, sumB);
+      goB = qb.ePrev * fsB > threshold;
+      if (goB) { fsB *= (1.0f - qb.k); if (skipZero && fsB == 0.0f) goB = false; }
+    }
+    wa = wb = false;               // the wall has been dealt with for both
+    if (!goA && !goB) break;
+    // RMCRTCommon::reflect (581-602), once for the shared DDA: back to the cells the rays came from, flip the stepping axis
+    d.idx -= lw.axis == 0 ? stx : (lw.axis == 1 ? sty : stz);
+    if (lw.axis == 0) stx = -stx; else if (lw.axis == 1) sty = -sty; else stz = -stz;
+    {
+      const Rec8 ra = ldrec(recs + d.idx), rb = ldrec(recsB + d.idx);
+      qa.k = fabsf(ra.k); qa.s = ra.s; qa.A = fmaf(-qa.k, lw.t, qa.tau);
+      qb.k = fabsf(rb.k); qb.s = rb.s; qb.A = fmaf(-qb.k, lw.t, qb.tau);
+    }
+    if (!(goA && goB)) break;      // one ray ended here: the other finishes on its own (already reflected)
+  }
   qa.nsteps += joint; qb.nsteps += joint;
-  const bool wa = (jw.axis & 4) != 0, wb = (jw.axis & 8) != 0;
-  const LegOut lw{jw.t, jw.axis & 3};
-  // ---- each ray on its own from here
-  RayState A{d, qa, 0.0f, 1.0f, stx, sty, stz};
-  if (!wa || ray_wall(A, lw, recs, threshold, allowReflect, skipZero)) ray_finish(A, recs, ddx, ddy, ddz, threshold, allowReflect, skipZero, recBytes);
-  RayState B{d, qb, 0.0f, 1.0f, stx, sty, stz};
-  if (!wb || ray_wall(B, lw, recsB, threshold, allowReflect, skipZero)) ray_finish(B, recsB, ddx, ddy, ddz, threshold, allowReflect, skipZero, recBytes);
-  sumA = A.sum; sumB = B.sum;
-  stepsA += (unsigned)A.q.nsteps;
-  stepsB += (unsigned)B.q.nsteps;
+  // ---- each ray that still marches on its own from here
+  if (goA) {
+    RayState A{d, qa, sumA, fsA, stx, sty, stz};
+    if (!wa || ray_wall(A, lw, recs, threshold, allowReflect, skipZero)) ray_finish(A, recs, ddx, ddy, ddz, threshold, allowReflect, skipZero, recBytes);
+    sumA = A.sum; qa.nsteps = A.q.nsteps;
+  }
+  if (goB) {
+    RayState B{d, qb, sumB, fsB, stx, sty, stz};
+    if (!wb || ray_wall(B, lw, recsB, threshold, allowReflect, skipZero)) ray_finish(B, recsB, ddx, ddy, ddz, threshold, allowReflect, skipZero, recBytes);
+    sumB = B.sum; qb.nsteps = B.q.nsteps;
+  }
+  stepsA += (unsigned)qa.nsteps;
+  stepsB += (unsigned)qb.nsteps;
 }
 
 //------------------------------------------------------------------------------------------------------

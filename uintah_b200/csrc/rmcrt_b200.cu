@@ -449,8 +449,10 @@ __global__ void __launch_bounds__(256, ((FAST && !ML) ? RMCRT_FAST_MIN_BLOCKS : 
 // of cells (i, j) and (i, j+1); all 64 cells share the direction and the in-cell origin of ray r, so one DDA per lane drives both
 // rays (march_single_level_dual).  Production ray set-up only (Philox, FP32), single level.
 //======================================================================================================
-template <class RecT>
-__global__ void __launch_bounds__(256, 4) divq_dual_kernel(const __grid_constant__ TraceArgs a, int nxc, int njp) {
+// pairK: the pair is stacked in z, cells (i,j,k) and (i,j,k+1), instead of in y -- for REJOIN (see march_single_level_dual): which walls
+// the two rays reach at the same step depends on the pair's axis, and the reference's mirror decks put their mirrors on x- and y-.
+template <class RecT, bool REJOIN>
+__global__ void __launch_bounds__(256, 4) divq_dual_kernel(const __grid_constant__ TraceArgs a, int nxc, int njp, int pairK) {
   extern __shared__ double red[];     // [W][64]
   if (!launch_gate(a)) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
@@ -461,13 +463,17 @@ __global__ void __launch_bounds__(256, 4) divq_dual_kernel(const __grid_constant
   constexpr float UNSCALE = RecInfo<RecT>::unscale;
   const int sy = g.n[0], sz = g.n[0] * g.n[1];
   unsigned long long stepsTotal = 0, cellsTotal = 0;
-  const long long nTiles = (long long)nxc * njp * a.patchN[2];
+  // njp = rows of pairs in y: (patchN[1] + 1) / 2 pairs stacked in y, or patchN[1] single rows when the pairs are stacked in z
+  const int nkp = pairK ? (a.patchN[2] + 1) / 2 : a.patchN[2];
+  const int offB = pairK ? sz : sy;
+  const long long nTiles = (long long)nxc * njp * nkp;
   for (long long tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
     const int xc = (int)(tile % nxc);
     const long long rest = tile / nxc;
     const int jp = (int)(rest % njp), kz = (int)(rest / njp);
-    const int i = a.patchLo[0] + xc * 32 + lane, jA = a.patchLo[1] + 2 * jp, k = a.patchLo[2] + kz;
-    const bool validA = (xc * 32 + lane) < a.patchN[0], validB = validA && (2 * jp + 1) < a.patchN[1];
+    const int i = a.patchLo[0] + xc * 32 + lane, jA = a.patchLo[1] + (pairK ? jp : 2 * jp), k = a.patchLo[2] + (pairK ? 2 * kz : kz);
+    const bool validA = (xc * 32 + lane) < a.patchN[0];
+    const bool validB = validA && (pairK ? (2 * kz + 1) < a.patchN[2] : (2 * jp + 1) < a.patchN[1]);
     Rec8 rA{0, 0}, rB{0, 0};
     long long idA = 0;
     bool flowA = false, flowB = false;
@@ -477,7 +483,7 @@ __global__ void __launch_bounds__(256, 4) divq_dual_kernel(const __grid_constant
       flowA = !is_wall(rA.k);
     }
     if (validB) {
-      if constexpr (std::is_same<RecT, Rec4>::value) rB = ldrec(static_cast<const Rec8*>(g.recFull) + idA + sy); else rB = ldrec(recs + idA + sy);
+      if constexpr (std::is_same<RecT, Rec4>::value) rB = ldrec(static_cast<const Rec8*>(g.recFull) + idA + offB); else rB = ldrec(recs + idA + offB);
       flowB = !is_wall(rB.k);
     }
     const unsigned long long dirId = (unsigned long long)level_index(g, a.patchLo[0] + xc * 32, jA, k);
@@ -492,14 +498,14 @@ __global__ void __launch_bounds__(256, 4) divq_dual_kernel(const __grid_constant
         const float d0 = nz<float, float>(dir[0]), d1 = nz<float, float>(dir[1]), d2 = nz<float, float>(dir[2]);
         if (flowA && flowB) {
           float sA, sB;
-          march_single_level_dual(recs, (int)idA, sy, sz, d0, d1, d2, rayDx[0], rayDx[1], rayDx[2], cx, cy, cz, (float)a.threshold,
+          march_single_level_dual<REJOIN>(recs, (int)idA, offB, sy, sz, d0, d1, d2, rayDx[0], rayDx[1], rayDx[2], cx, cy, cz, (float)a.threshold,
                                   a.allowReflect != 0, skipZero, stA, stB, a.recBytes, sA, sB);
           accA += (double)(UNSCALE * sA); accB += (double)(UNSCALE * sB);
         } else if (flowA) {
           accA += (double)(UNSCALE * march_single_level_fast(recs, (int)idA, sy, sz, d0, d1, d2, rayDx[0], rayDx[1], rayDx[2], cx, cy, cz,
                                                              (float)a.threshold, a.allowReflect != 0, skipZero, stA, a.recBytes));
         } else {
-          accB += (double)(UNSCALE * march_single_level_fast(recs, (int)idA + sy, sy, sz, d0, d1, d2, rayDx[0], rayDx[1], rayDx[2], cx, cy, cz,
+          accB += (double)(UNSCALE * march_single_level_fast(recs, (int)idA + offB, sy, sz, d0, d1, d2, rayDx[0], rayDx[1], rayDx[2], cx, cy, cz,
                                                              (float)a.threshold, a.allowReflect != 0, skipZero, stB, a.recBytes));
         }
       }
@@ -512,9 +518,9 @@ __global__ void __launch_bounds__(256, 4) divq_dual_kernel(const __grid_constant
       if (valid) {
         double sumI = 0;
         for (int w = 0; w < W; ++w) sumI += red[w * 64 + warp * 32 + lane];
-        const int j = jA + warp;
+        const int j = jA + (pairK ? 0 : warp), kc = k + (pairK ? warp : 0);
         const long long q = (long long)(i - a.outLo[0]) +
-                            (long long)a.outN[0] * ((long long)(j - a.outLo[1]) + (long long)a.outN[1] * (long long)(k - a.outLo[2]));
+                            (long long)a.outN[0] * ((long long)(j - a.outLo[1]) + (long long)a.outN[1] * (long long)(kc - a.outLo[2]));
         const Rec8 r0 = warp == 0 ? rA : rB;
         if (warp == 0 ? flowA : flowB) {
           const double mean = sumI / a.nRays;
@@ -1593,6 +1599,22 @@ int build_args(rmcrt_ctx* ctx, int maxLevels, bool multiLevel, const int32_t pLo
   return 0;
 }
 
+// The same single-level production solve when reflective walls keep the rays going (launch_gate 2): translates separate at the first
+// wall they do not reach at the same step and stay apart, so the four-cell kernel loses its point.  Pairs stacked in z reach every wall
+// normal to x or y together and go on jointly after the reflection (REJOIN); a black or z wall ends the joint march.
+template <class RecT>
+void launch_reflective_pairs(rmcrt_ctx* ctx, TraceArgs a2, long long cap, cudaStream_t st) {
+  if constexpr (!std::is_same<RecT, Rec16>::value) {
+    const int nxc = (a2.patchN[0] + 31) / 32;
+    long long g2 = (long long)nxc * a2.patchN[1] * ((a2.patchN[2] + 1) / 2);
+    if (g2 > cap) g2 = cap;
+    int W2 = ctx->p.warpsPerTile > 0 ? std::min(ctx->p.warpsPerTile, 8) : 4;
+    if (W2 < 2) W2 = 2;        // cells A and B are written by warps 0 and 1
+    a2.gate = 2;
+    divq_dual_kernel<RecT, true><<<(int)g2, 32 * W2, W2 * 64 * sizeof(double), st>>>(a2, nxc, a2.patchN[1], 1);
+  }
+}
+
 template <class Real, class RecT>
 int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
   // boundedRayLength ROI and scattering: the generic march carries the length test / the scattering events
@@ -1695,8 +1717,7 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
         TraceArgs a2 = a;
         a2.gate = 1;
         divq_quad_kernel<RecT, false><<<(int)g4, 32 * W4, W4 * 128 * sizeof(double), st>>>(a2, nxc, njp, nkp, lxBits);
-        a2.gate = 2;      // the same solve on the one-cell kernel when reflective walls keep the rays going (launch_gate)
-        divq_kernel<Real, RecT, false, true, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a2);
+        launch_reflective_pairs<RecT>(ctx, a2, cap, st);
       }
     } else if (std::is_same<Real, float>::value && !bounded && f32gen && ctx->p.rayCoherence >= 1 && ctx->p.cellsPerLane == 2 && !ctx->p.genericMarch) {
       if constexpr (std::is_same<Real, float>::value && !std::is_same<RecT, Rec16>::value) {
@@ -1707,9 +1728,8 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
         if (W2 < 2) W2 = 2;        // rows A and B are written by warps 0 and 1
         TraceArgs a2 = a;
         a2.gate = 1;
-        divq_dual_kernel<RecT><<<(int)g2, 32 * W2, W2 * 64 * sizeof(double), st>>>(a2, nxc, njp);
-        a2.gate = 2;      // the same solve on the one-cell kernel when reflective walls keep the rays going (launch_gate)
-        divq_kernel<Real, RecT, false, true, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a2);
+        divq_dual_kernel<RecT, false><<<(int)g2, 32 * W2, W2 * 64 * sizeof(double), st>>>(a2, nxc, njp, 0);
+        launch_reflective_pairs<RecT>(ctx, a2, cap, st);
       }
     } else if (std::is_same<Real, float>::value && !bounded && (!ctx->p.genericMarch || std::is_same<RecT, Rec4>::value)) {
       if (f32gen) divq_kernel<Real, RecT, false, true, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
