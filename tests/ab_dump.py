@@ -53,7 +53,9 @@ def main(out):
     pl = po.parallel_plates(24, dtype=np.float32, mirror_faces=("x-", "y-"))
     add_random_walls(pl, 0.02, rng, abskg=0.5, sigmaT4=0.2)
     run("plates_noreflect", pl, None, nDivQRays=32, threshold=0.01, seed=6, allowReflect=0)
-    run("plates_reflect_cpl2", pl, None, nDivQRays=16, threshold=0.01, seed=6)
+    run("plates_reflect_cpl2", pl, None, nDivQRays=16, threshold=0.01, seed=6, cellsPerLane=2)
+    run("plates_reflect_default", pl, None, nDivQRays=16, threshold=0.001, seed=7)
+    run("bc64_cpl2", lv, None, nDivQRays=16, threshold=0.05, seed=4, cellsPerLane=2)
     np.savez_compressed(out, **res)
     print("wrote", out, {k: v.tolist() for k, v in res.items() if k.endswith("_n")})
 

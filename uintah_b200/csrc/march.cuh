@@ -636,17 +636,17 @@ __device__ __forceinline__ void ray_finish(RayState& r, const RecT* __restrict__
   "fma.rn.f32 %8, sa" #P ", d, %8;\n\t"                     \
   "sub.f32 d, eb" #P ", eb" #C ";\n\t"                      \
   "fma.rn.f32 %13, sb" #P ", d, %13;\n\t"                   \
-  "add.f32 %14, %14, 0f3F800000;\n\t"                       \
   DEC(C)                                                    \
   "neg.f32 d, aa" #C ";\n\t"                                \
   "fma.rn.f32 %4, d, t" #C ", taa;\n\t"                     \
   "neg.f32 d, ab" #C ";\n\t"                                \
   "fma.rn.f32 %9, d, t" #C ", tab;\n\t"                     \
-  "or.b32 wz, ka" #C ", kb" #C ";\n\t"                      \
-  "setp.lt.s32 w, wz, 0;\n\t"                               \
+  "lop3.or.b32 wz|w, ka" #C ", kb" #C ", 0x80000000, 0xA8, pf;\n\t" \
   "@w bra EXIT" #C ";\n\t"
-#define RJ_EXIT(L, C)                                       \
+// (steps are counted once per loop iteration of three; an exit adds the steps of the iteration it leaves: NS = C + 1 as a float)
+#define RJ_EXIT(L, C, NS)                                   \
   "EXIT" #L ":\n\t"                                         \
+  "add.f32 %14, %14, " NS ";\n\t"                           \
   "mov.s32 %3, i" #C ";\n\t"                                \
   "mov.f32 %15, t" #C ";\n\t"                               \
   "selp.s32 %16, 1, 2, y" #C ";\n\t"                        \
@@ -662,23 +662,19 @@ __device__ __forceinline__ void ray_finish(RayState& r, const RecT* __restrict__
   "mov.f32 %11, sb" #C ";\n\t"                              \
   "mov.f32 %12, eb" #C ";\n\t"                              \
   "bra DONE;\n\t"
-#ifndef RMCRT_PAIR_DEPTH
-#define RMCRT_PAIR_DEPTH 1      // steps the pair's record requests run ahead of the wall test (1: three-slot rotation, 2: four-slot)
-#endif
 #define RJ_REGS(SLOTS)                                                                                               \
-      ".reg .pred x0, y0, n0, x1, y1, n1, x2, y2, n2, x3, y3, n3, w;\n\t"                                            \
-      ".reg .f32 d, taa, tab, t0, t1, t2, t3, sa0, sa1, sa2, sa3, sb0, sb1, sb2, sb3;\n\t"                           \
-      ".reg .f32 ea0, ea1, ea2, ea3, eb0, eb1, eb2, eb3, aa0, aa1, aa2, aa3, ab0, ab1, ab2, ab3;\n\t"                \
-      ".reg .b32 ka0, ka1, ka2, ka3, kb0, kb1, kb2, kb3, wz;\n\t"                                                    \
+      ".reg .pred x0, y0, n0, x1, y1, n1, x2, y2, n2, w, pf;\n\t"                                                    \
+      ".reg .f32 d, taa, tab, t0, t1, t2, sa0, sa1, sa2, sb0, sb1, sb2;\n\t"                                         \
+      ".reg .f32 ea0, ea1, ea2, eb0, eb1, eb2, aa0, aa1, aa2, ab0, ab1, ab2;\n\t"                                    \
+      ".reg .b32 ka0, ka1, ka2, kb0, kb1, kb2, wz;\n\t"                                                              \
       ".reg .b16 hl, hh;\n\t"                                                                                        \
-      ".reg .s32 i0, i1, i2, i3;\n\t"                                                                                \
+      ".reg .s32 i0, i1, i2;\n\t"                                                                                    \
       ".reg .s64 ad;\n\t"
 #define RJ_OPERANDS                                                                                                  \
       : "+f"(d.tx), "+f"(d.ty), "+f"(d.tz), "+r"(d.idx), "+f"(qa.A), "+f"(qa.k), "+f"(qa.s), "+f"(qa.ePrev), "+f"(qa.leg), \
         "+f"(qb.A), "+f"(qb.k), "+f"(qb.s), "+f"(qb.ePrev), "+f"(qb.leg), "+f"(nsteps), "=f"(o.t), "=r"(o.axis), "=f"(qa.tau), "=f"(qb.tau) \
       : "l"(recs), "l"(offB), "f"(ddx), "f"(ddy), "f"(ddz), "r"(stx), "r"(sty), "r"(stz)                              \
       : "memory"
-#if RMCRT_PAIR_DEPTH == 1
 #define RJ_ASM(LD, DEC)                                                                                              \
   asm volatile(                                                                                                      \
       "{\n\t"                                                                                                        \
@@ -686,75 +682,23 @@ __device__ __forceinline__ void ray_finish(RayState& r, const RecT* __restrict__
       /* slot 2 = the cells the leg starts in */                                                                     \
       "mov.f32 aa2, %5;\n\t" "mov.f32 sa2, %6;\n\t" "mov.f32 ea2, %7;\n\t"                                           \
       "mov.f32 ab2, %10;\n\t" "mov.f32 sb2, %11;\n\t" "mov.f32 eb2, %12;\n\t"                                        \
-      "mov.f32 taa, %4;\n\t" "mov.f32 tab, %9;\n\t"                                                                  \
+      "mov.f32 taa, %4;\n\t" "mov.f32 tab, %9;\n\t" "setp.ne.s32 pf, 0, 0;\n\t"                                      \
       RJ_PEEK(0, "%3", LD)                                                                                           \
       "LOOP:\n\t"                                                                                                    \
       RJ_COMMIT(0) RJ_PEEK(1, "i0", LD) RJ_INTEG(2, 0, DEC)                                                          \
       RJ_COMMIT(1) RJ_PEEK(2, "i1", LD) RJ_INTEG(0, 1, DEC)                                                          \
       RJ_COMMIT(2) RJ_PEEK(0, "i2", LD) RJ_INTEG(1, 2, DEC)                                                          \
+      "add.f32 %14, %14, 0f40400000;\n\t"                                                                            \
       "bra LOOP;\n\t"                                                                                                \
-      RJ_EXIT(0, 0) RJ_EXIT(1, 1) RJ_EXIT(2, 2)                                                                            \
+      RJ_EXIT(0, 0, "0f3F800000") RJ_EXIT(1, 1, "0f40000000") RJ_EXIT(2, 2, "0f40400000")                                                                            \
       "DONE:\n\t"                                                                                                    \
       "mov.f32 %17, taa;\n\t"                                                                                        \
       "mov.f32 %18, tab;\n\t"                                                                                        \
       "}"                                                                                                            \
       RJ_OPERANDS)
-#else
-// Depth 2: the requests of steps n+1 AND n+2 are in flight when the wall test of step n resolves (four-slot rotation), which covers an
-// L2 round trip with 32 resident warps per SM.  The DDA is then committed through step n+1 at that test; leaving at step n rolls the one
-// extra commit back EXACTLY: the tMax that step n+1 advanced was the minimum t<n+1> itself (min returns one of its inputs bit for bit).
-// Speculative requests reach two cells past a non-flow cell: rmcrt_define_level / the ROI copy size the guard records for that.
-// (which axis a step took is read off the index difference at the exit, so no predicate of the steps n and n+1 stays live in the loop)
-#define RJ_EXIT2(C, R, PM)                                  \
-  "EXIT" #C ":\n\t"                                         \
-  "sub.s32 wz, i" #R ", i" #C ";\n\t"                       \
-  "setp.eq.s32 w, wz, %24;\n\t"                             \
-  "@w mov.f32 %0, t" #R ";\n\t"                             \
-  "setp.eq.s32 w, wz, %25;\n\t"                             \
-  "@w mov.f32 %1, t" #R ";\n\t"                             \
-  "setp.eq.s32 w, wz, %26;\n\t"                             \
-  "@w mov.f32 %2, t" #R ";\n\t"                             \
-  "sub.s32 wz, i" #C ", i" #PM ";\n\t"                      \
-  "setp.eq.s32 w, wz, %25;\n\t"                             \
-  "selp.s32 %16, 1, 2, w;\n\t"                              \
-  "setp.eq.s32 w, wz, %24;\n\t"                             \
-  "@w mov.s32 %16, 0;\n\t"                                  \
-  "mov.s32 %3, i" #C ";\n\t"                                \
-  "mov.f32 %15, t" #C ";\n\t"                               \
-  "setp.lt.s32 w, ka" #C ", 0;\n\t"                         \
-  "@w add.s32 %16, %16, 4;\n\t"                             \
-  "setp.lt.s32 w, kb" #C ", 0;\n\t"                         \
-  "@w add.s32 %16, %16, 8;\n\t"                             \
-  "mov.f32 %5, aa" #C ";\n\t"                               \
-  "mov.f32 %6, sa" #C ";\n\t"                               \
-  "mov.f32 %7, ea" #C ";\n\t"                               \
-  "mov.f32 %10, ab" #C ";\n\t"                              \
-  "mov.f32 %11, sb" #C ";\n\t"                              \
-  "mov.f32 %12, eb" #C ";\n\t"                              \
-  "bra DONE;\n\t"
-#define RJ_ASM(LD, DEC)                                                                                              \
-  asm volatile(                                                                                                      \
-      "{\n\t"                                                                                                        \
-      RJ_REGS(4)                                                                                                     \
-      /* slot 3 = the cells the leg starts in */                                                                     \
-      "mov.f32 aa3, %5;\n\t" "mov.f32 sa3, %6;\n\t" "mov.f32 ea3, %7;\n\t"                                           \
-      "mov.f32 ab3, %10;\n\t" "mov.f32 sb3, %11;\n\t" "mov.f32 eb3, %12;\n\t"                                        \
-      "mov.f32 taa, %4;\n\t" "mov.f32 tab, %9;\n\t" "mov.s32 i3, %3;\n\t"                                            \
-      RJ_PEEK(0, "%3", LD)                                                                                           \
-      RJ_COMMIT(0) RJ_PEEK(1, "i0", LD)                                                                              \
-      "LOOP:\n\t"                                                                                                    \
-      RJ_COMMIT(1) RJ_PEEK(2, "i1", LD) RJ_INTEG(3, 0, DEC)                                                          \
-      RJ_COMMIT(2) RJ_PEEK(3, "i2", LD) RJ_INTEG(0, 1, DEC)                                                          \
-      RJ_COMMIT(3) RJ_PEEK(0, "i3", LD) RJ_INTEG(1, 2, DEC)                                                          \
-      RJ_COMMIT(0) RJ_PEEK(1, "i0", LD) RJ_INTEG(2, 3, DEC)                                                          \
-      "bra LOOP;\n\t"                                                                                                \
-      RJ_EXIT2(0, 1, 3) RJ_EXIT2(1, 2, 0) RJ_EXIT2(2, 3, 1) RJ_EXIT2(3, 0, 2)                                        \
-      "DONE:\n\t"                                                                                                    \
-      "mov.f32 %17, taa;\n\t"                                                                                        \
-      "mov.f32 %18, tab;\n\t"                                                                                        \
-      "}"                                                                                                            \
-      RJ_OPERANDS)
-#endif
+// (Measured and dropped in session 9: a four-slot rotation with the requests of steps n+1 AND n+2 in flight at the wall test of step n --
+// bit-identical results, but ptxas turned the predicated commits into FFMA + FSEL: +12 % instructions, -7 % throughput,
+// profiles/r01s9_ab_pair_depth.log.)
 
 __device__ __forceinline__ LegOut march_leg_pair(Dda& d, Integ& qa, Integ& qb, float& nsteps, const Rec8* __restrict__ recs,
                                                  const Rec8* __restrict__ recsB, float ddx, float ddy, float ddz, int stx, int sty, int stz) {
@@ -775,7 +719,6 @@ __device__ __forceinline__ LegOut march_leg_pair(Dda& d, Integ& qa, Integ& qb, f
 #undef RJ_COMMIT
 #undef RJ_INTEG
 #undef RJ_EXIT
-#undef RJ_EXIT2
 #undef RJ_REGS
 #undef RJ_OPERANDS
 #undef RJ_LD8

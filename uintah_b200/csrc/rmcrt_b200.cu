@@ -2005,7 +2005,7 @@ int rmcrt_define_level(rmcrt_ctx* ctx, int L, const rmcrt_level_desc* d, int rec
   s.recBytes = recordKind == 0 ? sizeof(Rec8) : (recordKind == 1 ? sizeof(Rec16) : sizeof(Rec4));
   s.nCells = n;
   // guard records on both ends (flagged "not a flow cell") so neighbour / speculative loads issued from any cell of
-  // the level stay inside the allocation; the pair march requests records up to TWO steps past the cell whose wall test is pending
+  // the level stay inside the allocation (one speculative step past the cell whose wall test is pending; sized for two)
   const long long guard = 2 * ((long long)(d->hi[0] - d->lo[0]) * (d->hi[1] - d->lo[1]) + (d->hi[0] - d->lo[0]) + 1);
   void* base = nullptr;
   CK(cudaMalloc(&base, (size_t)(n + 2 * guard) * s.recBytes));
