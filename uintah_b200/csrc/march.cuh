@@ -10,6 +10,14 @@
 // vectorised read-only load (LDG.E.64/.128.CONSTANT) that yields both the stop flag of the cell just entered
 // and the properties integrated on the next step.  The FP32 march keeps all lengths pre-multiplied by
 // log2(e) so the attenuation is one ex2.approx per step.
+//
+// Leg loops (PTX on the device, the same algorithm in C++ for tests/hostsim):
+//   march_leg       one ray                                  ~22 SASS instructions per ray-cell step
+//   march_leg_pair  two translates of one ray (one DDA)      ~15
+//   march_leg_quad  four translates of one ray (one DDA)     ~10.5   <- production single-level and Data-Onion ROI march
+// Translates = rays of neighbouring cells with the same direction and in-cell origin: identical tMax sequence, records a constant
+// stride apart.  A joint leg ends at the first step where any of its rays enters a non-flow cell; the rays then finish one by one with
+// march_leg (march_single_level_quad / _dual, march_onion2_quad).
 #pragma once
 #include <cstdint>
 #include <cmath>
