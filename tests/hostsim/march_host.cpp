@@ -23,6 +23,45 @@ static void rayDxOf(const HsLevel& g, const int c[3], const double* o, double r[
   for (int d = 0; d < 3; ++d) { const double cc = g.anchor[d] + g.dx[d] * c[d] + g.dx[d] * 0.5; r[d] = o[d] - (cc - 0.5 * g.dx[d]); }
 }
 
+namespace {
+struct Do2Setup {
+  OnionGeom<4> G;
+  RoiBox roi;
+  std::vector<Rec8> buf;
+};
+// the shell-wrapped ROI copy of roi_copy_kernel + the two-level geometry
+void do2_setup(const HsLevel* lv, const int* roiLo, const int* roiHi, const int* regLo, const int* regHi, Do2Setup& S) {
+  OnionGeom<4>& G = S.G;
+  RoiBox& roi = S.roi;
+  std::memset(&G, 0, sizeof G);
+  G.maxLevels = 2;
+  for (int L = 0; L < 2; ++L) {
+    LevelGeom& g = G.lev[L];
+    g.rec = lv[L].rec;
+    for (int d = 0; d < 3; ++d) {
+      g.lo[d] = lv[L].lo[d]; g.n[d] = lv[L].hi[d] - lv[L].lo[d]; g.intLo[d] = lv[L].intLo[d]; g.intHi[d] = lv[L].intHi[d];
+      g.rr[d] = lv[L].rr[d]; g.regLo[d] = regLo[3 * L + d]; g.regHi[d] = regHi[3 * L + d]; g.dx[d] = lv[L].dx[d];
+      g.anchor[d] = lv[L].anchor[d]; g.off[d] = lv[L].anchor[d] - lv[1].anchor[d];
+    }
+  }
+  long long cellsB = 1;
+  for (int d = 0; d < 3; ++d) { roi.lo[d] = roiLo[d] - 1; roi.n[d] = roiHi[d] - roiLo[d] + 2; cellsB *= roi.n[d]; }
+  const long long guard = (long long)roi.n[0] * roi.n[1] + roi.n[0] + 1;
+  S.buf.assign((size_t)(cellsB + 2 * guard), Rec8{-INFINITY, 0.0f});
+  Rec8* base = S.buf.data() + guard;
+  const LevelGeom& gf = G.lev[1];
+  const Rec8* fine = static_cast<const Rec8*>(gf.rec);
+  for (int k = roiLo[2]; k < roiHi[2]; ++k)
+    for (int j = roiLo[1]; j < roiHi[1]; ++j)
+      for (int i = roiLo[0]; i < roiHi[0]; ++i) {
+        const long long src = (long long)(i - gf.lo[0]) + (long long)gf.n[0] * ((j - gf.lo[1]) + (long long)gf.n[1] * (k - gf.lo[2]));
+        const long long dst = (long long)(i - roi.lo[0]) + (long long)roi.n[0] * ((j - roi.lo[1]) + (long long)roi.n[1] * (k - roi.lo[2]));
+        base[dst] = fine[src];
+      }
+  roi.rec = base;
+}
+}  // namespace
+
 // single level: kind 0 = fp32/Rec8, 1 = fp64/Rec16
 void hs_trace_1L(const HsLevel* g, int kind, int n, const int* cells, const double* dirs, const double* orgs, double threshold,
                  int allowReflect, int skipZero, double* sumI, unsigned* steps, int* path, int maxPath, double maxRayLength) {
@@ -106,34 +145,10 @@ void hs_trace_ML(const HsLevel* lv, int maxLevels, const int* roiLo, const int* 
 void hs_trace_DO2_fast(const HsLevel* lv, const int* roiLo, const int* roiHi, const int* regLo, const int* regHi, int n,
                        const int* cells, const double* dirs, const double* orgs, double threshold, int allowReflect, int skipZero,
                        double* sumI, unsigned* steps) {
-  OnionGeom<4> G;
-  std::memset(&G, 0, sizeof G);
-  G.maxLevels = 2;
-  for (int L = 0; L < 2; ++L) {
-    LevelGeom& g = G.lev[L];
-    g.rec = lv[L].rec;
-    for (int d = 0; d < 3; ++d) {
-      g.lo[d] = lv[L].lo[d]; g.n[d] = lv[L].hi[d] - lv[L].lo[d]; g.intLo[d] = lv[L].intLo[d]; g.intHi[d] = lv[L].intHi[d];
-      g.rr[d] = lv[L].rr[d]; g.regLo[d] = regLo[3 * L + d]; g.regHi[d] = regHi[3 * L + d]; g.dx[d] = lv[L].dx[d];
-      g.anchor[d] = lv[L].anchor[d]; g.off[d] = lv[L].anchor[d] - lv[1].anchor[d];
-    }
-  }
-  RoiBox roi;
-  long long cellsB = 1;
-  for (int d = 0; d < 3; ++d) { roi.lo[d] = roiLo[d] - 1; roi.n[d] = roiHi[d] - roiLo[d] + 2; cellsB *= roi.n[d]; }
-  const long long guard = (long long)roi.n[0] * roi.n[1] + roi.n[0] + 1;
-  std::vector<Rec8> buf((size_t)(cellsB + 2 * guard), Rec8{-INFINITY, 0.0f});
-  Rec8* base = buf.data() + guard;
-  const LevelGeom& gf = G.lev[1];
-  const Rec8* fine = static_cast<const Rec8*>(gf.rec);
-  for (int k = roiLo[2]; k < roiHi[2]; ++k)
-    for (int j = roiLo[1]; j < roiHi[1]; ++j)
-      for (int i = roiLo[0]; i < roiHi[0]; ++i) {
-        const long long src = (long long)(i - gf.lo[0]) + (long long)gf.n[0] * ((j - gf.lo[1]) + (long long)gf.n[1] * (k - gf.lo[2]));
-        const long long dst = (long long)(i - roi.lo[0]) + (long long)roi.n[0] * ((j - roi.lo[1]) + (long long)roi.n[1] * (k - roi.lo[2]));
-        base[dst] = fine[src];
-      }
-  roi.rec = base;
+  Do2Setup S;
+  do2_setup(lv, roiLo, roiHi, regLo, regHi, S);
+  const OnionGeom<4>& G = S.G;
+  const RoiBox& roi = S.roi;
   for (int t = 0; t < n; ++t) {
     const int* c = cells + 3 * t;
     double r[3];
@@ -220,6 +235,26 @@ void hs_trace_1L_quad(const HsLevel* g, int n, const int* cells, const double* d
     march_single_level_quad(static_cast<const Rec8*>(g->rec), idx, nx, nx * ny, (float)d[0], (float)d[1], (float)d[2], (float)r[0], (float)r[1],
                             (float)r[2], (float)g->dx[0], (float)g->dx[1], (float)g->dx[2], (float)threshold, allowReflect != 0, skipZero != 0,
                             st, 8, sm);
+    for (int q = 0; q < 4; ++q) sums[4 * t + q] = sm[q];
+    steps[t] = st;
+  }
+}
+// 2-level Data Onion, four cells per lane (march_onion2_quad): the rays of the 2 x 2 cells c, c+(0,1,0), c+(0,0,1), c+(0,1,1) with the SAME
+// direction and in-cell origin; sums [n][4], steps = total of the four rays
+void hs_trace_DO2_quad(const HsLevel* lv, const int* roiLo, const int* roiHi, const int* regLo, const int* regHi, int n,
+                       const int* cells, const double* dirs, const double* orgs, double threshold, int allowReflect, int skipZero,
+                       double* sums, unsigned* steps) {
+  Do2Setup S;
+  do2_setup(lv, roiLo, roiHi, regLo, regHi, S);
+  for (int t = 0; t < n; ++t) {
+    const int* c = cells + 3 * t;
+    double r[3];
+    rayDxOf(lv[1], c, orgs + 3 * t, r);
+    unsigned st = 0;
+    float sm[4];
+    const double* d = dirs + 3 * t;
+    march_onion2_quad<Rec8, 4>(S.G, S.roi, c[0], c[1], c[2], (float)d[0], (float)d[1], (float)d[2], (float)r[0], (float)r[1], (float)r[2],
+                               (float)threshold, allowReflect != 0, skipZero != 0, st, 8, sm);
     for (int q = 0; q < 4; ++q) sums[4 * t + q] = sm[q];
     steps[t] = st;
   }

@@ -103,6 +103,21 @@ def trace_DO2_fast(levels, roi, reg, cells, dirs, org, thr, refl, skip=0):
     return sumI, steps
 
 
+def trace_DO2_quad(levels, roi, reg, cells, dirs, org, thr, refl, skip=0):
+    """march_onion2_quad: the 2 x 2 cells c, c+(0,1,0), c+(0,0,1), c+(0,1,1) of the fine level share direction and in-cell origin;
+    returns sums [n, 4] and the step total of the four rays [n]"""
+    assert len(levels) == 2
+    recs = [pack(l, 0) for l in levels]
+    arr = (HsLevel * 2)(*[hslevel(l, r) for l, r in zip(levels, recs)])
+    n = len(cells)
+    sm = np.zeros((n, 4)); st = np.zeros(n, np.uint32)
+    cells = np.ascontiguousarray(cells, np.int32); dirs = np.ascontiguousarray(dirs); org = np.ascontiguousarray(org)
+    regLo = np.ascontiguousarray(reg[0], np.int32); regHi = np.ascontiguousarray(reg[1], np.int32)
+    lib().hs_trace_DO2_quad(arr, (C.c_int * 3)(*roi[0]), (C.c_int * 3)(*roi[1]), _vp(regLo), _vp(regHi), n, _vp(cells), _vp(dirs),
+                            _vp(org), C.c_double(thr), refl, skip, _vp(sm), _vp(st))
+    return sm, st
+
+
 def philox(ctr, key):
     out = (C.c_uint32 * 4)()
     lib().hs_philox((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), out)

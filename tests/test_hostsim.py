@@ -262,3 +262,33 @@ def test_pair_march_rejoins_after_a_wall_both_rays_hit_at_once(po, case, pair_k)
     np.testing.assert_allclose(sb[same], rb[same], rtol=2e-4, atol=1e-5 * np.abs(rb).max())
     if case.startswith("plates"):
         assert na.mean() > 25          # 18 cells across: two to three legs per ray, the rejoin path is what is being exercised
+
+
+@pytest.mark.parametrize("case", ["bc", "plates_mirrors"])
+def test_data_onion_quad_march_equals_four_single_marches(po, case):
+    """march_onion2_quad (2-level Data Onion, four cells per lane: one DDA marches the four translates through the ROI copy, then each
+    ray leaves the ROI / finishes on the coarse level through march_onion2_fast's continuation) == march_onion2_fast run four times"""
+    rng = np.random.default_rng(53)
+    fine = po.burns_christon(32, dtype=np.float32) if case == "bc" else po.parallel_plates(32, dtype=np.float32, mirror_faces=("x-", "y-"))
+    thr = 0.05 if case == "bc" else 0.001
+    fine.rr = (4, 4, 4)
+    coarse = po.coarsen_level(fine, (4, 4, 4))
+    levels = [coarse, fine]
+    offs = [(0, 0, 0), (0, 1, 0), (0, 0, 1), (0, 1, 1)]
+    for plo, phi in (((0, 0, 0), (16, 16, 16)), ((16, 16, 0), (32, 32, 16)), ((8, 8, 8), (24, 24, 24))):
+        roiLo, roiHi, regLo, regHi = po.compute_extents(levels, plo, phi, (4, 4, 4))
+        cells, dirs, org = random_rays(fine, 150, rng, plo, (phi[0], phi[1] - 1, phi[2] - 1))      # the whole 2 x 2 block inside the patch
+        sm, st = sim.trace_DO2_quad(levels, (roiLo, roiHi), (regLo, regHi), cells, dirs, org, thr, 1)
+        tot = np.zeros(len(cells), np.int64)
+        singles = []
+        for o in offs:
+            s1, n1 = sim.trace_DO2_fast(levels, (roiLo, roiHi), (regLo, regHi), cells + np.array(o, np.int32), dirs,
+                                        org + np.array(o) * np.array(fine.dx), thr, 1)
+            singles.append(s1); tot += n1
+        # the in-cell offset of a translated origin is rebuilt from an absolute position in the single march: FP32 round-off can move a
+        # ray across a cell face, rarely
+        same = st.astype(np.int64) == tot
+        assert same.mean() > 0.9, same.mean()
+        np.testing.assert_allclose(sm[same, 0], singles[0][same], rtol=2e-5, atol=2e-6 * np.abs(singles[0]).max())
+        for q in (1, 2, 3):
+            np.testing.assert_allclose(sm[same, q], singles[q][same], rtol=5e-4, atol=2e-5 * np.abs(singles[q]).max())
