@@ -8,7 +8,11 @@ A "step" is one radiation solve (one pass of the hot path) over synthetic Burns 
   N>1   one 128^3 patch of origin cells per GPU on a (128*px, 128*py, 128*pz) level (N=8: configs[2], 256^3);
         every step each rank packs its own patch, the packed records are all-gathered over NCCL, assembled into the
         replicated level and the rank traces its own patch ("scaling": "weak": origin cells per GPU are fixed).
-`value`  = executed ray-cell steps of all ranks / max-over-ranks device time, inputs resident in HBM.
+`value`  = executed ray-cell steps of all ranks / max-over-ranks device time, inputs resident in HBM, LIBRARY DEFAULTS: rayCoherence 0 =
+           the reference's sampling (independent Philox rays per (cell, ray, timestep)).  `by_coherence` repeats the measurement for the
+           opt-in batched modes (1: warp-shared direction, 2: lockstep translates, four cells per lane) so the price of the conformant
+           keying is visible; `configs` (N=1) adds driver-timed records for 256^3 on one GPU, C4 (Data Onion) and C5 (boundary flux +
+           reflections); at N>1 `configs.c4` times the Data Onion across the ranks.
 `e2e`    = the same metric through the host-buffer C-ABI calls (rmcrt_upload_level + rmcrt_finalize_level +
            rmcrt_trace_divq): pinned host arrays in, host arrays out, H2D/D2H inside the timed region.
 --impl reference times the CPU restatement of the reference's own Ray::rayTrace (oracle/) on the host cores.
@@ -141,9 +145,10 @@ CPU_KIND_NOTE = {
 }
 
 
-def cpu_reference_sample(n_cells_side, rays, shape_cells, slab_cells, threads, repeats=1, warm=0):
-    """Time the oracle's Ray::rayTrace restatement on a z-slab of `slab_cells` planes in the middle of the level,
-    split into `threads` patch tasks run on `threads` host threads (reference partitioning: one task per patch)."""
+def cpu_reference_sample(n_cells_side, rays, shape_cells, n_planes, threads, repeats=1, warm=0):
+    """Time the reference's Ray::rayTrace divQ loop on `n_planes` xy-planes of origin cells spread evenly over z (so that rays per cell
+    and steps per ray are representative of the whole level), each plane split into patch tasks run on `threads` host threads
+    (reference partitioning: one task per patch)."""
     from oracle import pyoracle as po
     po.build()
     lo = (-1, -1, -1)
@@ -151,22 +156,31 @@ def cpu_reference_sample(n_cells_side, rays, shape_cells, slab_cells, threads, r
     ab, s4, ct = burns_christon_fields(shape_cells, lo, hi, np.float32)
     lv = po.Level(ab, s4, ct, lo, hi, tuple(1.0 / s for s in shape_cells), interior_lo=(0, 0, 0), interior_hi=tuple(shape_cells))
     p = po.default_params(nDivQRays=rays, threshold=0.05, isSeedRandom=1)      # reference semantics: allowReflect default
-    z0 = shape_cells[2] // 2 - slab_cells // 2
-    plo, phi = (0, 0, z0), (shape_cells[0], shape_cells[1], z0 + slab_cells)
+    nz = shape_cells[2]
+    n_planes = max(1, min(n_planes, nz))
+    planes = sorted({min(nz - 1, int((2 * i + 1) * nz / (2 * n_planes))) for i in range(n_planes)})
     times, steps = [], 0
     # the reference's own findRayDirection / ray_Origin / updateSumI<T> (oracle/_ref/libref_rmcrt.so, built from the reference tree by
     # `make -C oracle ref`) under the Ray::rayTrace cell loop when that library is there, else the oracle's restatement of the same
     trace = po.ref_ray_trace if po.ref_lib() is not None else po.ray_trace
     cpu_reference_sample.kind = "reference" if po.ref_lib() is not None else "port"
+    from concurrent.futures import ThreadPoolExecutor
+    per_plane = max(1, threads // len(planes))
     for it in range(warm + repeats):
         t0 = time.perf_counter()
-        r = trace(p, lv, plo, phi, seed=1 + it, patches=(1, threads, slab_cells), threads=threads)
+
+        def one(z):
+            return trace(p, lv, (0, 0, z), (shape_cells[0], shape_cells[1], z + 1), seed=1 + it + 1000 * z, patches=(1, per_plane, 1),
+                         threads=per_plane)["steps"]
+        with ThreadPoolExecutor(max_workers=max(1, min(len(planes), threads // per_plane))) as ex:
+            st = sum(ex.map(one, planes))
         dt = time.perf_counter() - t0
         if it >= warm:
             times.append(dt)
-            steps = r["steps"]
-    cells = shape_cells[0] * shape_cells[1] * slab_cells
-    return times, steps, cells, f"z-slab [{z0},{z0 + slab_cells}) of the {shape_cells} level = {cells} origin cells x {rays} rays"
+            steps = st
+    cells = shape_cells[0] * shape_cells[1] * len(planes)
+    return times, steps, cells, (f"xy-planes z in {planes} of the {shape_cells} level = {cells} origin cells x {rays} rays, "
+                                 f"{len(planes) * per_plane} patch tasks on {threads} threads")
 
 
 def run_reference(args):
@@ -178,8 +192,8 @@ def run_reference(args):
     world = max(env_int("WORLD_SIZE", 1), args.gpus)
     shape = tuple(n * g for g in patch_grid(world))
     rays = args.rays
-    # ~1/128 of the level per step: one xy plane of origin cells
-    times, steps, cells, sample = cpu_reference_sample(n, rays, shape, 1, threads, repeats=args.steps, warm=args.warmup)
+    # four xy-planes of origin cells spread over z per step (1/32 of a 128^3 level, ~2 s on 16 threads)
+    times, steps, cells, sample = cpu_reference_sample(n, rays, shape, 4, threads, repeats=args.steps, warm=min(args.warmup, 1))
     total = sum(times)
     value = steps * len(times) / total
     line = {
@@ -188,7 +202,10 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(n, shape, rays, world),
-                   "sample_per_step": sample, "semantics": "reference (allowReflect default true: zero-weight legs marched)"},
+                   "sample_per_step": sample, "semantics": "reference (allowReflect default true: zero-weight legs marched)",
+                   "executed_steps_per_ray": steps / (cells * rays),
+                   "note": "the reference marches its zero-weight second legs (SURVEY 3.5-Q2), so it executes ~2.2x the ray-cell steps per "
+                           "divQ cell of the GPU arm, which skips them exactly; divq_cells_per_s compares like with like"},
         "cpu_baseline": {"value": value, "unit": "ray-cell steps/s", "cores": threads, "kind": cpu_reference_sample.kind,
                          "sample": sample + CPU_KIND_NOTE[cpu_reference_sample.kind]},
         "e2e": {"value": value, "unit": "ray-cell steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -212,10 +229,195 @@ def workload_name(P, shape, rays, world):
             f"packed-record all-gather per solve (BASELINE configs[2] at 8 GPUs)")
 
 
+KERNEL_OF = {0: "divq_kernel<float,{r},ML=0,FAST,F32GEN> (one cell per lane, independent rays)",
+             1: "divq_quad_kernel<{r}> (warp-shared direction)", 2: "divq_quad_kernel<{r}> (lockstep translates)"}
+COHERENCE_NAME = {0: "independent per (cell, ray, timestep) -- the reference's sampling", 1: "warp-shared direction",
+                  2: "warp-shared direction and in-cell offset (lockstep translates)"}
+
+
+class SingleLevelSolve:
+    """one rank's share of a single-level solve: pack own box -> (all-gather) -> assemble -> finalize -> trace own patch"""
+
+    def __init__(self, args, P, rays, coherence, cells_per_lane, half, world, rank, local, torch, dist):
+        from uintah_b200 import RMCRT, LevelData, partition
+        self.torch, self.dist, self.world = torch, dist, world
+        dev = self.dev = torch.device(f"cuda:{local}")
+        pg = patch_grid(world)
+        self.shape = shape = tuple(P * g for g in pg)
+        self.lo, self.hi = lo, hi = (-1, -1, -1), tuple(s + 1 for s in shape)
+        dx = tuple(1.0 / s for s in shape)       # unit-cube domain like every Burns & Christon deck
+        self.plo, self.phi = partition.rank_patch(rank, pg, P)
+        if half < 0:     # policy: keep the replicated level L2-resident
+            half = 1 if int(np.prod([h - l for l, h in zip(lo, hi)])) * 8 > 64e6 else 0
+        self.rec_bytes = 4 if half else 8
+        kw = {} if coherence < 0 else {"rayCoherence": coherence}
+        skip = 0 if args.reference_semantics else 1
+        self.g = g = RMCRT(device=local, nDivQRays=rays, threshold=0.05, seed=1234, skipZeroWeightLegs=skip, l2Persist=args.l2persist,
+                           warpsPerTile=args.warps, tileX=args.tile_x, cellsPerLane=cells_per_lane, genericMarch=args.generic_march,
+                           maxBlocksPerSM=args.max_blocks_per_sm, half_records=bool(half), **kw)
+        self.coherence = int(g.params.rayCoherence)
+        self.stream = stream = torch.cuda.current_stream()
+        lvl = LevelData(None, None, None, lo, hi, dx, interior_lo=(0, 0, 0), interior_hi=shape)
+        g.define_level(0, lvl.desc())
+        g.levels[0] = lvl
+        # the rank's own property box (its patch plus the extra cells it touches), resident on the device
+        self.blo, self.bhi = blo, bhi = partition.owner_box(self.plo, self.phi, shape)
+        self.fields = burns_christon_fields(shape, blo, bhi, np.float32)
+        self.d_props = [tuple(torch.from_numpy(x).to(dev) for x in self.fields)]
+        self.boxes_lo, self.boxes_hi = partition.all_owner_boxes(world, pg, P, shape)
+        self.slot = partition.slot_bytes(self.boxes_lo, self.boxes_hi, self.rec_bytes)
+        self.send = torch.zeros(self.slot, dtype=torch.uint8, device=dev)
+        self.gathered = torch.zeros(self.slot * world, dtype=torch.uint8, device=dev) if world > 1 else None
+        self.oshape = (bhi[2] - blo[2], bhi[1] - blo[1], bhi[0] - blo[0])      # allocateAndPut window of the patch incl. its extra cells
+        self.d_divQ = torch.empty(self.oshape, dtype=torch.float64, device=dev)
+        self.d_volq = torch.empty_like(self.d_divQ)
+        dual = self.coherence >= 1 and cells_per_lane in (2, 4)
+        # pack + finalize + divq (+ assemble per rank box); the batched solves launch a second, gated kernel that returns at once
+        self.kernels_per_step = (3 if world == 1 else 3 + world) + (1 if dual else 0)
+        self.kernel_name = KERNEL_OF[self.coherence if cells_per_lane == 4 or self.coherence == 0 else 0].format(r="Rec4" if half else "Rec8")
+        if self.coherence >= 1 and cells_per_lane == 2:
+            self.kernel_name = f"divq_dual_kernel<{'Rec4' if half else 'Rec8'}>"
+        if self.coherence >= 1 and cells_per_lane == 1:
+            self.kernel_name = KERNEL_OF[0].format(r="Rec4" if half else "Rec8").replace("independent rays", "warp-shared direction")
+
+    def replicate(self, props=None):
+        g, st = self.g, self.stream
+        d_ab, d_s4, d_ct = props or self.d_props[0]
+        if self.world == 1:
+            g.pack_level_device(0, d_ab, d_s4, d_ct, self.blo, self.bhi, stream=st)
+        else:
+            g.pack_box_device(0, d_ab, d_s4, d_ct, self.blo, self.bhi, self.blo, self.bhi, self.send, stream=st)
+            self.dist.all_gather_into_tensor(self.gathered, self.send)
+            g.assemble_level(0, self.gathered, self.slot, self.boxes_lo, self.boxes_hi, stream=st)
+        g.finalize_level_async(0, st)     # device-side validation scan; no host round trip
+
+    def trace(self, ts, divQ=None, volq=None, zero_init=True):
+        self.g.trace_divq_device(0, self.plo, self.phi, self.d_divQ if divQ is None else divQ, self.d_volq if volq is None else volq, None,
+                                 self.blo, self.bhi, timestep=ts, zero_init=zero_init, stream=self.stream)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, steps, warmup, flush, sampler=None):
+        """K steps, each bracketed by CUDA events on the launching stream, L2 flushed between steps; returns per-rank sums"""
+        torch, st = self.torch, self.stream
+        self.replicate()
+        self.g.finalize_level(0, st)      # one validated set-up solve
+        for w in range(warmup):
+            self.replicate(); self.trace(w + 1)
+        self.barrier()
+        self.g.reset_counters(st)
+        if sampler:
+            sampler.start()
+        ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(steps)]
+        self.barrier()
+        t0 = time.perf_counter()
+        for k in range(steps):
+            flush.fill_(k & 0xFF)
+            e0, e1, e2 = ev[k]
+            e0.record(st)
+            self.replicate()
+            e1.record(st)
+            self.trace(100 + k)
+            e2.record(st)
+        self.barrier()
+        wall = time.perf_counter() - t0
+        c = self.g.counters(st)
+        return (sum(e[0].elapsed_time(e[2]) for e in ev) * 1e-3, sum(e[1].elapsed_time(e[2]) for e in ev) * 1e-3,
+                int(c.nRaySteps), int(c.nDivQCells), wall)
+
+    def reduce(self, t_step, t_trace, steps, cells):
+        torch, dist = self.torch, self.dist
+        t_total = torch.tensor([t_step, t_trace], dtype=torch.float64, device=self.dev)
+        work = torch.tensor([steps, cells], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
+            dist.all_reduce(work, op=dist.ReduceOp.SUM)
+        return tuple(float(x) for x in t_total.cpu()) + tuple(float(x) for x in work.cpu())
+
+    def e2e(self, n_steps):
+        """the same metric through host buffers: page-locked property arrays in, page-locked divQ / radiationVolq out, every step.
+        N=1: the reference-facing C-ABI calls rmcrt_upload_level + rmcrt_finalize_level + rmcrt_trace_divq.  N>1: per rank the H2D of the
+        next step's property box runs on a copy stream while this step traces (two device buffers), and the kernels write the mapped
+        page-locked outputs in place (no staging buffer, no D2H after the solve)."""
+        import ctypes as C
+        from uintah_b200.capi import check, i3
+        torch, g, st = self.torch, self.g, self.stream
+        ab, s4, ct = self.fields
+        h_props = tuple(torch.from_numpy(x).pin_memory() for x in (ab, s4, ct))
+        h_divQ = torch.empty(self.oshape, dtype=torch.float64).pin_memory()
+        h_volq = torch.empty(self.oshape, dtype=torch.float64).pin_memory()
+        h2d = sum(x.numel() * 4 for x in h_props)
+        d2h = (h_divQ.numel() + h_volq.numel()) * 8
+        if self.world == 1:
+            def step(ts):
+                check(g.ctx, g.lib.rmcrt_upload_level(g.ctx, 0, h_props[0].data_ptr(), h_props[1].data_ptr(), h_props[2].data_ptr(), 1,
+                                                      i3(self.blo), i3(self.bhi), st.cuda_stream))
+                g.finalize_level(0, st)
+                check(g.ctx, g.lib.rmcrt_trace_divq(g.ctx, 0, i3(self.plo), i3(self.phi), h_divQ.data_ptr(), h_volq.data_ptr(), None,
+                                                    i3(self.blo), i3(self.bhi), 1, C.c_uint64(ts), st.cuda_stream))
+            step(1)
+            api = "rmcrt_upload_level + rmcrt_finalize_level + rmcrt_trace_divq (pinned host buffers, outputs written in place)"
+        else:
+            copy = torch.cuda.Stream()
+            if len(self.d_props) == 1:
+                self.d_props.append(tuple(torch.empty_like(x) for x in self.d_props[0]))
+            ready = [torch.cuda.Event(), torch.cuda.Event()]      # H2D of buffer b complete
+            freed = [torch.cuda.Event(), torch.cuda.Event()]      # pack of buffer b complete (it may be overwritten)
+
+            def upload(b):
+                with torch.cuda.stream(copy):
+                    copy.wait_event(freed[b])
+                    for d, h in zip(self.d_props[b], h_props):
+                        d.copy_(h, non_blocking=True)
+                    ready[b].record(copy)
+            for b in (0, 1):
+                freed[b].record(st)
+            upload(0)
+            self._k = 0
+
+            def step(ts):
+                b = self._k & 1
+                upload(b ^ 1)                      # next step's inputs cross the bus while this step packs / gathers / traces
+                st.wait_event(ready[b])
+                self.replicate(self.d_props[b])
+                freed[b].record(st)
+                self.trace(ts, h_divQ, h_volq, zero_init=2)      # mapped page-locked outputs, border-only zero fill
+                st.synchronize()                   # the caller owns the results of step k before step k+1 starts
+                self._k += 1
+            step(1)
+            api = ("pinned host property box -> H2D on a copy stream (double-buffered) -> pack / all-gather / assemble / trace -> "
+                   "divQ, radiationVolq written in place into mapped pinned host buffers, per rank")
+        g.reset_counters(st)
+        self.barrier()
+        es, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        es.record(st)
+        for k in range(n_steps):
+            step(200 + k)
+        ee.record(st)
+        self.barrier()
+        c = g.counters(st)
+        sec, _, steps, cells = self.reduce(es.elapsed_time(ee) * 1e-3, 0.0, float(c.nRaySteps), float(c.nDivQCells))
+        return {"value": steps / sec, "unit": "ray-cell steps/s", "h2d_bytes_per_step": int(h2d) * self.world,
+                "d2h_bytes_per_step": int(d2h) * self.world, "steps": n_steps, "ms_per_step": 1e3 * sec / n_steps,
+                "divq_cells_per_s": cells / sec, "api": api}
+
+
+def issue_model(kernel_key):
+    """warp instructions per ray-cell step of the committed ncu capture of this kernel (profiles/traffic.json), for the issue-rate roofline"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        e = t.get(kernel_key)
+        return e if e and "warp_instructions_per_launch" in e else None
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from uintah_b200 import RMCRT, LevelData
 
     world = env_int("WORLD_SIZE", 1)
     rank = env_int("RANK", 0)
@@ -226,171 +428,63 @@ def run_ours(args):
     dev = torch.device(f"cuda:{local}")
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    P = args.n                                # patch edge = origin cells per GPU per axis
-    pg = patch_grid(world)
-    shape = tuple(P * g for g in pg)          # level interior
-    lo, hi = (-1, -1, -1), tuple(s + 1 for s in shape)
-    dx = tuple(1.0 / s for s in shape)       # unit-cube domain like every Burns & Christon deck
-    from uintah_b200 import partition
-    plo, phi = partition.rank_patch(rank, pg, P)
-    rays = args.rays
-
-    if args.half_records < 0:     # policy: keep the replicated level L2-resident
-        args.half_records = 1 if int(np.prod([h - l for l, h in zip(lo, hi)])) * 8 > 64e6 else 0
-    skip = 0 if args.reference_semantics else 1
-    g = RMCRT(device=local, nDivQRays=rays, threshold=0.05, seed=1234, skipZeroWeightLegs=skip,
-              rayCoherence=args.coherence, l2Persist=args.l2persist, warpsPerTile=args.warps, tileX=args.tile_x, cellsPerLane=args.cells_per_lane,
-              genericMarch=args.generic_march, maxBlocksPerSM=args.max_blocks_per_sm, half_records=bool(args.half_records))
-    stream = torch.cuda.current_stream()
-    desc = LevelData(None, None, None, lo, hi, dx, interior_lo=(0, 0, 0), interior_hi=shape).desc()
-    g.define_level(0, desc)
-    g.levels[0] = LevelData(None, None, None, lo, hi, dx, interior_lo=(0, 0, 0), interior_hi=shape)
-
-    # ---- the rank's own property box (its patch plus the extra cells it touches), resident on the device
-    blo, bhi = partition.owner_box(plo, phi, shape)
-    ab, s4, ct = burns_christon_fields(shape, blo, bhi, np.float32)
-    d_ab, d_s4, d_ct = (torch.from_numpy(x).to(dev) for x in (ab, s4, ct))
-    boxes_lo, boxes_hi = partition.all_owner_boxes(world, pg, P, shape)
-    rec_bytes = 4 if args.half_records else 8
-    slot = partition.slot_bytes(boxes_lo, boxes_hi, rec_bytes)
-    send = torch.zeros(slot, dtype=torch.uint8, device=dev)
-    gathered = torch.zeros(slot * world, dtype=torch.uint8, device=dev) if world > 1 else None
-
-    out_lo, out_hi = blo, bhi                 # allocateAndPut window of the patch incl. its extra cells
-    oshape = (out_hi[2] - out_lo[2], out_hi[1] - out_lo[1], out_hi[0] - out_lo[0])
-    d_divQ = torch.empty(oshape, dtype=torch.float64, device=dev)
-    d_volq = torch.empty_like(d_divQ)
+    P, rays = args.n, args.rays
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
-    def replicate():
-        """pack own box -> (all-gather) -> assemble the replicated level"""
-        if world == 1:
-            g.pack_level_device(0, d_ab, d_s4, d_ct, blo, bhi, stream=stream)
-        else:
-            g.pack_box_device(0, d_ab, d_s4, d_ct, blo, bhi, blo, bhi, send, stream=stream)
-            dist.all_gather_into_tensor(gathered, send)
-            g.assemble_level(0, gathered, slot, boxes_lo, boxes_hi, stream=stream)
-        g.finalize_level_async(0, stream)     # device-side validation scan; no host round trip
-
-    def device_step(ts):
-        replicate()
-        g.trace_divq_device(0, plo, phi, d_divQ, d_volq, None, out_lo, out_hi, timestep=ts, zero_init=True, stream=stream)
-
-    # one validated set-up solve
-    replicate()
-    g.finalize_level(0, stream)
-    dual = args.cells_per_lane in (2, 4) and args.coherence >= 1
-    # pack + finalize + divq (+ assemble per rank box); the two-cells-per-lane solve launches the pair kernel AND the gated one-cell
-    # kernel, of which one returns at once (launch_gate)
-    kernels_per_step = (3 if world == 1 else 3 + world) + (1 if dual else 0)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for w in range(args.warmup):
-        device_step(w + 1)
-    barrier()
-    g.reset_counters(stream)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    # ---- timed: K steps, each bracketed by events on the launching stream; L2 flushed between steps
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
-    barrier()
-    t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush.fill_(k & 0xFF)
-        e0, e1, e2 = ev[k]
-        e0.record(stream)
-        replicate()
-        e1.record(stream)
-        g.trace_divq_device(0, plo, phi, d_divQ, d_volq, None, out_lo, out_hi, timestep=100 + k, zero_init=True, stream=stream)
-        e2.record(stream)
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    step_ms = [e[0].elapsed_time(e[2]) for e in ev]
-    trace_ms = [e[1].elapsed_time(e[2]) for e in ev]
-    c = g.counters(stream)
-    steps_exec, cells_exec = int(c.nRaySteps), int(c.nDivQCells)
+    S = SingleLevelSolve(args, P, rays, args.coherence, args.cells_per_lane, args.half_records, world, rank, local, torch, dist)
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_step, t_trace, n_steps, n_cells, t_wall = S.timed(args.steps, args.warmup, flush, sampler)
     clocks = sampler.stop() if rank == 0 else None
-
-    t_total = torch.tensor([sum(step_ms) * 1e-3, sum(trace_ms) * 1e-3], dtype=torch.float64, device=dev)
-    work = torch.tensor([steps_exec, cells_exec], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
-        dist.all_reduce(work, op=dist.ReduceOp.SUM)
-    t_step_total, t_trace_total = (float(x) for x in t_total.cpu())
-    all_steps, all_cells = (float(x) for x in work.cpu())
+    t_step_total, t_trace_total, all_steps, all_cells = S.reduce(t_step, t_trace, n_steps, n_cells)
     value = all_steps / t_step_total
+    e2e = S.e2e(max(1, min(args.steps, 5)))
+    g, shape, rec_bytes = S.g, S.shape, S.rec_bytes
 
-    # ---- e2e: host buffers through the reference-facing C-ABI calls, H2D and D2H inside the timed region
-    lv_lo, lv_hi = lo, hi
-    if world == 1:
-        h_ab, h_s4, h_ct = (torch.from_numpy(x).pin_memory() for x in (ab, s4, ct))
-        h_divQ = torch.empty(oshape, dtype=torch.float64).pin_memory()
-        h_volq = torch.empty(oshape, dtype=torch.float64).pin_memory()
-        import ctypes as C
-        from uintah_b200.capi import check, i3
-
-        def e2e_step(ts):
-            check(g.ctx, g.lib.rmcrt_upload_level(g.ctx, 0, h_ab.data_ptr(), h_s4.data_ptr(), h_ct.data_ptr(), 1, i3(blo), i3(bhi),
-                                                  stream.cuda_stream))
-            g.finalize_level(0, stream)
-            check(g.ctx, g.lib.rmcrt_trace_divq(g.ctx, 0, i3(plo), i3(phi), h_divQ.data_ptr(), h_volq.data_ptr(), None, i3(out_lo),
-                                                i3(out_hi), 1, C.c_uint64(ts), stream.cuda_stream))
-        h2d = (h_ab.numel() + h_s4.numel()) * 4 + h_ct.numel() * 4
-        d2h = (h_divQ.numel() + h_volq.numel()) * 8
-        e2e_step(1)
-        g.reset_counters(stream)
-        e2e_n = max(1, min(args.steps, 5))
-        es, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        es.record(stream)
-        for k in range(e2e_n):
-            e2e_step(200 + k)
-        ee.record(stream)
-        torch.cuda.synchronize()
-        e2e_s = es.elapsed_time(ee) * 1e-3
-        c2 = g.counters(stream)
-        e2e_val = int(c2.nRaySteps) / e2e_s
-        e2e = {"value": e2e_val, "unit": "ray-cell steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "steps": e2e_n, "ms_per_step": 1e3 * e2e_s / e2e_n, "divq_cells_per_s": int(c2.nDivQCells) / e2e_s,
-               "api": "rmcrt_upload_level + rmcrt_finalize_level + rmcrt_trace_divq (pinned host buffers)"}
-    else:
-        # per rank: host property box in, host divQ/radiationVolq of the patch out, every step
-        h_ab, h_s4, h_ct = (torch.from_numpy(x).pin_memory() for x in (ab, s4, ct))
-        h_divQ = torch.empty(oshape, dtype=torch.float64).pin_memory()
-        h_volq = torch.empty(oshape, dtype=torch.float64).pin_memory()
-
-        def e2e_step(ts):
-            d_ab.copy_(h_ab, non_blocking=True); d_s4.copy_(h_s4, non_blocking=True); d_ct.copy_(h_ct, non_blocking=True)
-            device_step(ts)
-            h_divQ.copy_(d_divQ, non_blocking=True); h_volq.copy_(d_volq, non_blocking=True)
-            stream.synchronize()
-        h2d = (h_ab.numel() + h_s4.numel() + h_ct.numel()) * 4
-        d2h = (h_divQ.numel() + h_volq.numel()) * 8
-        e2e_step(1)
-        g.reset_counters(stream)
-        e2e_n = max(1, min(args.steps, 5))
-        barrier()
-        es, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        es.record(stream)
-        for k in range(e2e_n):
-            e2e_step(200 + k)
-        ee.record(stream)
-        barrier()
-        tt = torch.tensor([es.elapsed_time(ee) * 1e-3], dtype=torch.float64, device=dev)
-        ww = torch.tensor([float(g.counters(stream).nRaySteps), float(g.counters(stream).nDivQCells)], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dist.all_reduce(ww, op=dist.ReduceOp.SUM)
-        e2e_s = float(tt.item())
-        e2e = {"value": float(ww[0].item()) / e2e_s, "unit": "ray-cell steps/s", "h2d_bytes_per_step": int(h2d) * world,
-               "d2h_bytes_per_step": int(d2h) * world, "steps": e2e_n, "ms_per_step": 1e3 * e2e_s / e2e_n,
-               "divq_cells_per_s": float(ww[1].item()) / e2e_s,
-               "api": "pinned host property box -> pack/all-gather/assemble/trace -> pinned host divQ, per rank"}
+    # ---- the opt-in batched modes on the same workload (and 256^3 / C4 / C5 at N=1; C4 across the ranks at N>1)
+    by_coherence, configs = {}, {}
+    sub_steps, sub_warm = max(1, min(args.steps, 5)), 3
+    if not args.no_sweeps:
+        for coh in (0, 1, 2):
+            if coh == S.coherence and args.cells_per_lane == 4:
+                by_coherence[str(coh)] = {"ray_cell_steps_per_s": value, "ms_per_step": 1e3 * t_step_total / args.steps,
+                                          "kernel": S.kernel_name, "sampling": COHERENCE_NAME[coh], "is_default": coh == 0}
+                continue
+            S2 = SingleLevelSolve(args, P, rays, coh, 4, args.half_records, world, rank, local, torch, dist)
+            a, b, c, d, _ = S2.timed(sub_steps, sub_warm, flush)
+            ts, tt, st_, ce = S2.reduce(a, b, c, d)
+            by_coherence[str(coh)] = {"ray_cell_steps_per_s": st_ / ts, "ms_per_step": 1e3 * ts / sub_steps, "divq_cells_per_s": ce / ts,
+                                      "kernel": S2.kernel_name, "sampling": COHERENCE_NAME[coh], "is_default": coh == 0}
+            S2.g.close()
+            del S2
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_configs as bc
+        if world == 1:
+            cfg_steps = max(1, min(args.steps, 2))
+            CN = args.configs_n
+            for coh in (0, 2):
+                S3 = SingleLevelSolve(args, CN, rays, coh, 4, -1, 1, 0, local, torch, dist)
+                a, b, c, d, _ = S3.timed(cfg_steps, 1, flush)
+                configs[f"single_level_{CN}_1gpu_coherence{coh}"] = {
+                    "workload": f"Burns-Christon single level {CN}^3, {rays} rays/cell, 1 B200 (north_star target; BASELINE configs[2] on one GPU)",
+                    "ray_cell_steps_per_s": c / a, "divq_cells_per_s": d / a, "ms_per_solve": 1e3 * a / cfg_steps, "trace_ms": 1e3 * b / cfg_steps,
+                    "steps_per_ray": c / (d * rays), "record_bytes": S3.rec_bytes, "kernel": S3.kernel_name, "ray_coherence": coh}
+                S3.g.close()
+                del S3
+                torch.cuda.empty_cache()
+            for coh in (0, 2):
+                configs[f"c4_dataonion_{CN}_{CN // 4}_coherence{coh}"] = bc.c4_single_gpu(CN, rays, cfg_steps, -1, coh, 4, warm=1, flush=flush)
+                torch.cuda.empty_cache()
+            for coh in (0, 2):
+                configs[f"c5_flux_reflect_{CN}_coherence{coh}"] = bc.c5_single_gpu(CN, rays, cfg_steps, -1, coh, 4, warm=1, flush=flush)
+                torch.cuda.empty_cache()
+        elif world in (2, 4, 8):
+            class A:      # the Data Onion sharded by fine patch over the ranks (BASELINE configs[3] at 8 GPUs)
+                pass
+            a_ = A(); a_.rays = rays; a_.steps = max(1, min(args.steps, 3))
+            for coh in (0, 2):
+                rec = bc.c4_multi_gpu(a_, 2 * P, 1 if (2 * P + 2) ** 3 * 8 > 64e6 else 0, world, own_pg=False, coherence=coh)
+                if rank == 0:
+                    configs[f"c4_dataonion_coherence{coh}"] = rec
 
     if rank != 0:
         if world > 1:
@@ -398,44 +492,65 @@ def run_ours(args):
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (divq_kernel): algorithmic bytes / CUDA-event duration of the launch
+    # ---- roofline of the dominant kernel: algorithmic bytes / CUDA-event duration of the launch
     peaks, peak_src = measured_peaks()
     per_rank_steps = all_steps / world / args.steps
     per_rank_cells = all_cells / world / args.steps
     alg_bytes = ALG_BYTES_PER_STEP * per_rank_steps + ALG_BYTES_PER_CELL * per_rank_cells
     kern_s = (t_trace_total / args.steps)
     achieved = alg_bytes / kern_s / 1e9
-    traffic, traffic_src = (profiled_traffic(P, rays, rec_bytes, {2: "divq_dual", 4: "divq_quad"}.get(args.cells_per_lane if args.coherence >= 1 else 1, "divq"))
-                            if world == 1 else (None, None))
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": traffic, "traffic_source": traffic_src, "kernel": {2: "divq_dual_kernel", 4: "divq_quad_kernel"}.get(args.cells_per_lane if args.coherence >= 1 else 1, "divq_kernel") + ("<Rec4>" if args.half_records else "<Rec8>"), "kernel_ms": 1e3 * kern_s,
-                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "note": "12 B per executed ray-cell step + 28 B per divQ cell; the property records are L2-resident, so the "
-                        "binding roofline is L2 (see roofline_l2), HBM peak shown because MEASURED_PEAKS.json has no L2 figure"}
-    # L2 denominators measured live with the library's microbenchmarks (16 MiB scratch, L2-resident)
+    cpl_eff = args.cells_per_lane if S.coherence >= 1 else 1
+    kkey = {2: "divq_dual", 4: "divq_quad"}.get(cpl_eff, "divq_indep" if S.coherence == 0 else "divq") + f"_{P}cubed_{rays}rays_rec{rec_bytes}"
+    prof = issue_model(kkey) or {}
+    # L2 denominators measured live with the library's microbenchmarks (L2-resident scratch buffers)
     try:
         l2_stream, _ = g.measure_read_bandwidth(16 << 20, repeats=10, pattern=0)
+        l2_cg, _ = g.measure_read_bandwidth(32 << 20, repeats=10, pattern=2)
         l2_gather, l2_gacc = g.measure_read_bandwidth(16 << 20, repeats=20, pattern=1)
         hbm_stream, _ = g.measure_read_bandwidth(2 << 30, repeats=5, pattern=0)
-        roofline_l2 = {"bound": "l2", "achieved": achieved, "peak": l2_stream, "unit": "GB/s", "frac": achieved / l2_stream,
-                       "l2_sector_gather_gbs": l2_gather, "l2_gathers_per_s": l2_gacc * 1e9,
-                       "steps_per_s_vs_gather_rate": (per_rank_steps / kern_s) / (l2_gacc * 1e9),
-                       "hbm_read_gbs_live": hbm_stream,
-                       "how": "rmcrt_measure_read_bandwidth: 16 MiB buffer, coalesced 16-B loads (peak) and per-lane hashed 8-B "
-                              "gathers counted as 32-B sectors (incoherent-ray ceiling)"}
+        l2_peak = max(l2_stream, l2_cg, l2_gather)
+        l2_live = {"l2_stream_ldg128_gbs": l2_stream, "l2_stream_ldcg_8deep_gbs": l2_cg, "l2_sector_gather_gbs": l2_gather,
+                   "l2_gathers_per_s": l2_gacc * 1e9, "hbm_read_gbs_live": hbm_stream,
+                   "how": "rmcrt_measure_read_bandwidth on L2-resident scratch: coalesced 16-B loads, eight-deep L2-only 16-B loads, and "
+                          "per-lane hashed 8-B gathers counted as 32-B sectors; peak = the largest of the three"}
     except Exception as ex:      # noqa: BLE001
-        roofline_l2 = {"error": str(ex)}
+        l2_peak, l2_live = None, {"error": str(ex)}
+    sm_hz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    sm_hz *= 1e6
+    if S.coherence == 0 and l2_peak:
+        # independent rays: a dependent 32-B sector gather per ray-cell step; the L1 -> L2 request path (one miss request per clock per SM)
+        # and the L2 -> SM bandwidth bind (ncu: l1tex__m_l1tex2xbar_req_cycles_active 96 %, lts__throughput 77 %)
+        roofline = {"bound": "l2", "achieved": achieved, "peak": l2_peak, "unit": "GB/s", "frac": achieved / l2_peak,
+                    "traffic": prof.get("dram_bytes_per_launch"), "l2_traffic": prof.get("l2_bytes_per_launch"),
+                    "frac_of_l2_peak_by_actual_sector_traffic": (prof["l2_bytes_per_launch"] / kern_s / 1e9 / l2_peak) if prof.get("l2_bytes_per_launch") else None,
+                    "sector_gathers_per_s_vs_measured_gather_rate": (per_rank_steps / kern_s) / (l2_gacc * 1e9),
+                    "peak_source": "measured live (rmcrt_measure_read_bandwidth, see l2_live); MEASURED_PEAKS.json has no L2 figure"}
+    else:
+        # batched rays: neither HBM (records are read once) nor L2 (25 %) binds; the SM issue rate does
+        ipl = prof.get("warp_instructions_per_launch")
+        spl = prof.get("steps_per_launch")
+        ips = (ipl / spl) if ipl and spl else None
+        issue_peak = 148 * 4 * sm_hz
+        roofline = {"bound": "issue", "achieved": (ips * per_rank_steps / kern_s / 1e9) if ips else None, "peak": issue_peak / 1e9,
+                    "unit": "G warp-instructions/s", "frac": (ips * per_rank_steps / kern_s / issue_peak) if ips else None,
+                    "warp_instructions_per_step": ips, "traffic": prof.get("dram_bytes_per_launch"),
+                    "algorithmic_GBps": achieved, "algorithmic_over_hbm_peak": achieved / peaks["hbm_gbs"],
+                    "peak_source": "148 SMs x 4 schedulers x SM clock sampled during the run; instructions per step from the committed ncu capture"}
+    roofline.update({"kernel": S.kernel_name, "kernel_ms": 1e3 * kern_s, "algorithmic_bytes_per_launch": alg_bytes,
+                     "traffic_source": prof.get("source"), "hbm_peak_gbs": peaks["hbm_gbs"], "hbm_peak_source": peak_src,
+                     "note": "algorithmic bytes = 12 B per executed ray-cell step + 28 B per divQ cell (SURVEY 8d)"})
 
-    # ---- CPU baseline: the oracle restatement of Ray::rayTrace on the host cores, bounded sample (rank 0, N=1 only)
+    # ---- CPU baseline: the reference's Ray::rayTrace divQ loop on the host cores, bounded sample (rank 0, N=1 only)
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        slab = max(1, int(round(12 * threads / 8)))          # ~10-15 s of CPU work
-        times, csteps, ccells, sample = cpu_reference_sample(P, rays, shape, slab, threads, repeats=1, warm=0)
+        planes = max(1, int(round(12 * threads / 8)))          # ~10-15 s of CPU work
+        times, csteps, ccells, sample = cpu_reference_sample(P, rays, shape, planes, threads, repeats=1, warm=0)
         cpu_baseline = {"value": csteps / times[0], "unit": "ray-cell steps/s", "cores": threads, "kind": cpu_reference_sample.kind,
-                        "sample": sample + f"; {times[0]:.1f} s wall; {threads} patch tasks on {threads} threads" + CPU_KIND_NOTE[cpu_reference_sample.kind],
+                        "sample": sample + f"; {times[0]:.1f} s wall" + CPU_KIND_NOTE[cpu_reference_sample.kind],
                         "divq_cells_per_s": ccells / times[0], "steps_per_ray": csteps / (ccells * rays)}
 
+    launches = S.kernels_per_step * args.steps
     line = {
         "metric": "rmcrt_ray_cell_steps_per_s", "value": value, "unit": "ray-cell steps/s",
         "divq_cells_per_s": all_cells / t_step_total,
@@ -444,13 +559,14 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(P, shape, rays, world),
                    "executed_steps_per_ray": all_steps / (all_cells * rays),
-                   "zero_weight_legs": "marched (reference semantics)" if not skip else "skipped (exact: cold black walls, fs==0)",
-                   "ray_coherence": {0: "independent per cell", 1: "warp-shared direction", 2: "warp-shared direction and in-cell offset"}[args.coherence],
-                   "cells_per_lane": args.cells_per_lane if args.coherence >= 1 else 1,
-                   "l2": "flushed between steps (256 MiB fill); level records (%.1f MB, %d B/cell) re-packed every step" % (np.prod([h - l for l, h in zip(lo, hi)]) * rec_bytes / 1e6, rec_bytes),
+                   "zero_weight_legs": "marched (reference semantics)" if args.reference_semantics else "skipped (exact: cold black walls, fs==0)",
+                   "ray_coherence": S.coherence, "sampling": COHERENCE_NAME[S.coherence],
+                   "cells_per_lane": cpl_eff,
+                   "l2": "flushed between steps (256 MiB fill); level records (%.1f MB, %d B/cell) re-packed every step" % (np.prod([h - l for l, h in zip(S.lo, S.hi)]) * rec_bytes / 1e6, rec_bytes),
                    "timing": "CUDA events on the launching stream per step, max over ranks"},
-        "roofline": roofline, "roofline_l2": roofline_l2, "cpu_baseline": cpu_baseline, "e2e": e2e,
-        "gpu_launches": kernels_per_step * args.steps, "clocks": clocks,
+        "roofline": roofline, "l2_live": l2_live, "by_coherence": by_coherence, "configs": configs,
+        "cpu_baseline": cpu_baseline, "e2e": e2e,
+        "gpu_launches": launches, "clocks": clocks,
         "wall_s_timed_region": t_wall,
     }
     print(json.dumps(line))
@@ -468,7 +584,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=128, help="cells per side of the per-GPU patch")
     ap.add_argument("--rays", type=int, default=100)
-    ap.add_argument("--coherence", type=int, default=2, help="rayCoherence (library default 2)")
+    ap.add_argument("--coherence", type=int, default=-1, help="rayCoherence; -1 (default) = the library default 0, the reference's sampling")
     ap.add_argument("--l2persist", type=int, default=1)
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--tile-x", type=int, default=0, help="cellsPerLane 4: origin cells of a warp in x (32, 16, 8; 0 = library default)")
@@ -480,6 +596,8 @@ def main():
     ap.add_argument("--generic-march", type=int, default=0, help="1: generic march template instead of the tuned fast path (A/B)")
     ap.add_argument("--reference-semantics", action="store_true", help="march the zero-weight reflected legs like the reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--configs-n", type=int, default=256, help="cells per side of the configs sub-records (256^3 single level, C4, C5)")
+    ap.add_argument("--no-sweeps", action="store_true", help="skip by_coherence and the configs sub-records (A/B runs, profiling)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

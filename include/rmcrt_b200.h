@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RMCRT_ABI_VERSION 4
+#define RMCRT_ABI_VERSION 5
 #define RMCRT_MAX_LEVELS 8
 
 typedef struct rmcrt_ctx rmcrt_ctx;
@@ -65,10 +65,17 @@ typedef struct rmcrt_params {
   uint64_t seed;               /* mixed into the Philox key (randomSeed=true) */
   /* ---- implementation knobs (no counterpart in the reference) ---- */
   int32_t  marchPrecision;     /* 0 = FP32 march (production), 1 = FP64 march (parity debugging) */
-  int32_t  rayCoherence;       /* 2 (default) = the origin cells of a tile share one direction AND one in-cell origin offset per
-                                  ray index, so the rays of a warp are exact translates of each other and march in lockstep
-                                  (divQ rays only; every cell still sees nDivQRays independent isotropic rays);
-                                  1 = shared direction, every lane its own in-cell origin; 0 = independent rays per (cell, ray) */
+  int32_t  rayCoherence;       /* ray batching of the divQ rays.
+                                  0 (DEFAULT) = the reference's sampling: every (cell, ray) draws its own direction and in-cell origin,
+                                      Philox4x32-10 keyed on (cell, ray, timestep) -- independent rays per cell like the task-local MTRand
+                                      stream of Ray.cc:539,757-771; errors of neighbouring cells are uncorrelated.
+                                  1 = the origin cells of a warp tile share one DIRECTION per ray index (own in-cell origins);
+                                  2 = they share direction AND in-cell origin, so the rays of a tile are exact translates marching in
+                                      lockstep (with cellsPerLane 4: the fastest kernel, 5.7x the default at 128^3).
+                                  1 and 2 keep every cell's estimate unbiased with the same per-cell variance, but the errors of the
+                                  cells of a tile become (almost fully) correlated: the mean over a 128-cell tile is no better than one
+                                  cell (variance 100x the independent-ray value, tests/test_gpu_atsize.py::test_error_correlation).
+                                  Opt-in for callers that post-filter or only need per-cell statistics; .ups: <rayCoherence>. */
   int32_t  skipZeroWeightLegs; /* 1 = end a ray once fs==0 and no non-flow cell can emit (exact);
                                   0 = march every leg the reference marches */
   int32_t  fixedRandom;        /* FIXED_RANDOM_NUM (MersenneTwister.h:93): every draw = 0.3 */
@@ -79,7 +86,7 @@ typedef struct rmcrt_params {
   int32_t  maxBlocksPerSM;     /* 0 = one tile per block (hardware balances the tail); > 0 caps the divQ grid at this many
                                   blocks per SM and grid-strides over the tiles (A/B measurements) */
   int32_t  rayDirSampleAlgo;   /* <rayDirSampleAlgo> 0 naive (default), 1 LatinHyperCube (Ray.cc:174-179, 1398-1460) */
-  int32_t  cellsPerLane;       /* 4 (default): with rayCoherence >= 1 a lane owns the 2 x 2 cells (i, j..j+1, k..k+1); their rays share the
+  int32_t  cellsPerLane;       /* (rayCoherence >= 1 only) 4 (default): a lane owns the 2 x 2 cells (i, j..j+1, k..k+1); their rays share the
                                   direction AND the in-cell origin, so they are exact translates and ONE DDA drives all four
                                   (divq_quad_kernel: the DDA instructions are paid once per four ray-cell steps).
                                   2: the pair (i,j,k), (i,j+1,k) (divq_dual_kernel).  1: one cell per lane.
@@ -97,7 +104,8 @@ typedef struct rmcrt_params {
                                   32 lanes cover tileX x (32 / tileX) blocks of 2 x 2 cells; a squarer footprint makes the lockstep rays
                                   of a warp reach a wall within fewer steps of each other (fewer idle lanes) at the same number of
                                   sectors per request.  The rays of a cell depend on the tile it falls in, not on the arithmetic. */
-  int32_t  reserved0;
+  int32_t  nonFlowCellType;    /* integer cell type the coarsening assumes for non-flow fine cells when it rebuilds the type sum of
+                                  Ray::computeCellType (Ray.cc:2285-2342) from the packed records: 8 (default; RMCRT_Test.cc:80, Arches walls) */
 } rmcrt_params;
 
 /* One <Radiometer> block after Radiometer::problemSetup (Radiometer.cc:96-271; struct radiometer, Radiometer.h:117-127) */
@@ -173,7 +181,10 @@ int rmcrt_level_records(rmcrt_ctx* ctx, int L, void** d_records, size_t* bytes, 
  * boundary flux (if solveBoundaryFlux) then divQ (if solveDivQ) for cells [patchLo,patchHi) of level L.
  * Outputs are x-fastest over [outLo,outHi) (the patch's allocateAndPut window incl. extra cells):
  *   divQ, radiationVolq : double per cell;  boundFlux : Stencil7 {w,e,s,n,b,t,p} = 7 doubles per cell.
- * zeroInit != 0 reproduces `modifies_divQ == false` (Ray.cc:577-587): the whole window is zeroed first.
+ * zeroInit != 0 reproduces `modifies_divQ == false` (Ray.cc:577-587): the whole window is zeroed first (1), or -- same result,
+ * less traffic when the outputs live in mapped page-locked host memory -- only the part of the window outside the patch (2; the
+ * kernels write every cell of the patch).  zeroInit == 0 (`modifies_divQ`): cells the trace does not compute, non-flow cells of the
+ * patch included, keep the caller's values (Ray.cc:746-748).
  * boundFlux may be NULL when solveBoundaryFlux is off.  timestep enters the Philox counter. */
 int rmcrt_trace_divq_device(rmcrt_ctx* ctx, int L, const int32_t patchLo[3], const int32_t patchHi[3],
                             double* d_divQ, double* d_radiationVolq, double* d_boundFlux,
@@ -307,7 +318,9 @@ int rmcrt_allgather_records(rmcrt_ctx* ctx, const void* d_sendSlot, void* d_gath
  * Measures device read bandwidth on a scratch buffer of `bytes` (L2-resident when well below the L2 size, HBM when far
  * above it), `repeats` passes, CUDA-event timed.  pattern 0: coalesced 16-B loads (streaming);
  * pattern 1: one dependent-free 8-B gather per lane at a hashed record index -- every lane touches its own 32-B sector,
- * the access shape of an incoherent ray step; *gbps counts 32 B per gather (sector traffic), *gaccess the gathers/s. */
+ * the access shape of an incoherent ray step; *gbps counts 32 B per gather (sector traffic), *gaccess the gathers/s;
+ * pattern 2: eight independent 16-B L2-only loads (ld.global.cg) in flight per thread, whole lines per warp request -- the L2 -> SM
+ * bandwidth the L2 roofline is quoted against. */
 int rmcrt_measure_read_bandwidth(rmcrt_ctx* ctx, size_t bytes, int repeats, int pattern, double* gbps, double* gaccess);
 
 /* ------------------------------------------------------------------ debugging (cf. isDbgCell, RMCRTCommon.cc:38,632-635)

@@ -480,6 +480,33 @@ def ray_trace(p: Params, lv: Level, patch_lo=None, patch_hi=None, seed=1, patche
     return dict(divQ=divQ, radiationVolq=volq, boundFlux=bflux, steps=sum(steps), fluxSteps=sum(fsteps))
 
 
+def ray_trace_data_onion_sub(p: Params, levels, halo, patch_lo, patch_hi, sub_lo, sub_hi, seed=1, parts=(1, 1, 1), threads=1):
+    """Ray::rayTrace_dataOnion of ONE fine patch [patch_lo,patch_hi) (ROI and region extents of that patch), restricted to the origin
+    cells of [sub_lo,sub_hi); the sub-box is split into `parts` pieces run on `threads` threads (piece t: MT seed `seed + t`)."""
+    fine = levels[-1]
+    nl = len(levels)
+    arr = (CLevel * nl)(*[l.c() for l in levels])
+    shape = fine.abskg.shape
+    divQ = np.zeros(shape, np.float64)
+    volq = np.zeros(shape, np.float64)
+    bflux = np.zeros(shape + (7,), np.float64) if p.solveBoundaryFlux else np.zeros((1, 7), np.float64)
+    tasks = _split(tuple(sub_lo), tuple(sub_hi), parts)
+    steps = [0] * len(tasks)
+
+    def run(t):
+        lo, hi = tasks[t]
+        n = C.c_uint64(0)
+        nf = C.c_uint64(0)
+        lib().oracle_rayTrace_dataOnion_sub(C.byref(p), arr, nl, _i3(patch_lo), _i3(patch_hi), _i3(halo), _i3(lo), _i3(hi), C.c_uint32(seed + t),
+                                            divQ.ctypes.data_as(C.c_void_p), volq.ctypes.data_as(C.c_void_p),
+                                            bflux.ctypes.data_as(C.c_void_p), _i3(fine.lo), _i3(fine.hi), C.byref(n), C.byref(nf))
+        steps[t] = n.value
+
+    with ThreadPoolExecutor(max_workers=max(threads, 1)) as ex:
+        list(ex.map(run, range(len(tasks))))
+    return dict(divQ=divQ, radiationVolq=volq, boundFlux=bflux if p.solveBoundaryFlux else None, steps=sum(steps))
+
+
 def ray_trace_data_onion(p: Params, levels, halo, patch_lo=None, patch_hi=None, seed=1, patches=(1, 1, 1), threads=1):
     """Ray::rayTrace_dataOnion over the fine level's interior split into `patches` fine patches."""
     fine = levels[-1]

@@ -707,8 +707,9 @@ namespace {
 template <class T>
 void dataOnionPatch(const oracle_params& P, const oracle_level* levels, int maxLevels, const int pLo[3], const int pHi[3],
                     const int halo[3], uint32_t mtSeed, double* divQ, double* volq, double* bflux, const OutWin& ow,
-                    uint64_t& nSteps, uint64_t& nFluxSteps, const int* dbgRay, double* dbgOut) {
-  (void)dbgRay; (void)dbgOut;
+                    uint64_t& nSteps, uint64_t& nFluxSteps, const int* subLo, const int* subHi) {
+  // subLo/subHi (test sampling only): the ROI / region extents come from the PATCH [pLo,pHi) as in the task, but only the origin
+  // cells of [subLo,subHi) inside it are traced -- a slab of a production-size patch in seconds instead of the whole patch
   std::vector<LevelT<T>> lv;
   lv.reserve(maxLevels);
   for (int l = 0; l < maxLevels; ++l) lv.emplace_back(levels[l]);
@@ -727,6 +728,7 @@ void dataOnionPatch(const oracle_params& P, const oracle_level* levels, int maxL
 
   MT mt(P.fixedRandom != 0);
   mt.seed(mtSeed);  // Ray.cc:979 / 1041-1043
+  if (subLo && subHi) { pLo = subLo; pHi = subHi; }     // extents are computed: from here on [pLo,pHi) is only the cell loop
 
   const bool lhc = P.rayDirSampleAlgo == 1;
   if (P.solveBoundaryFlux) {  // 1091-1170, no flow-cell guard
@@ -820,6 +822,20 @@ void oracle_rayTrace_dataOnion(const oracle_params* p, const oracle_level* level
   uint64_t n = 0, nf = 0;
   if (levels[0].isFloat) dataOnionPatch<float>(*p, levels, maxLevels, patchLo, patchHi, haloCells, mtSeed, divQ, radiationVolq, boundFlux, ow, n, nf, nullptr, nullptr);
   else                   dataOnionPatch<double>(*p, levels, maxLevels, patchLo, patchHi, haloCells, mtSeed, divQ, radiationVolq, boundFlux, ow, n, nf, nullptr, nullptr);
+  if (nRaySteps) *nRaySteps = n;
+  if (nFluxRaySteps) *nFluxRaySteps = nf;
+}
+
+// the same task body restricted to the origin cells of [subLo,subHi) of the patch (at-size parity sampling, tests/golden/make_atsize_golden.py)
+void oracle_rayTrace_dataOnion_sub(const oracle_params* p, const oracle_level* levels, int maxLevels, const int patchLo[3],
+                                   const int patchHi[3], const int haloCells[3], const int subLo[3], const int subHi[3], uint32_t mtSeed,
+                                   double* divQ, double* radiationVolq, double* boundFlux, const int outLo[3], const int outHi[3],
+                                   uint64_t* nRaySteps, uint64_t* nFluxRaySteps) {
+  OutWin ow;
+  for (int d = 0; d < 3; ++d) { ow.lo[d] = outLo[d]; ow.n[d] = outHi[d] - outLo[d]; }
+  uint64_t n = 0, nf = 0;
+  if (levels[0].isFloat) dataOnionPatch<float>(*p, levels, maxLevels, patchLo, patchHi, haloCells, mtSeed, divQ, radiationVolq, boundFlux, ow, n, nf, subLo, subHi);
+  else                   dataOnionPatch<double>(*p, levels, maxLevels, patchLo, patchHi, haloCells, mtSeed, divQ, radiationVolq, boundFlux, ow, n, nf, subLo, subHi);
   if (nRaySteps) *nRaySteps = n;
   if (nFluxRaySteps) *nFluxRaySteps = nf;
 }

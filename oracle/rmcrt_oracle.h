@@ -129,6 +129,14 @@ void oracle_rayTrace_dataOnion(const oracle_params* p, const oracle_level* level
                                double* divQ, double* radiationVolq, double* boundFlux,
                                const int outLo[3], const int outHi[3],
                                uint64_t* nRaySteps, uint64_t* nFluxRaySteps);
+/* the same task body with the ROI / region extents of the PATCH but only the origin cells of [subLo,subHi) traced
+ * (sampling a production-size patch for the at-size parity fixtures) */
+void oracle_rayTrace_dataOnion_sub(const oracle_params* p, const oracle_level* levels, int maxLevels,
+                                   const int patchLo[3], const int patchHi[3], const int haloCells[3],
+                                   const int subLo[3], const int subHi[3], uint32_t mtSeed,
+                                   double* divQ, double* radiationVolq, double* boundFlux,
+                                   const int outLo[3], const int outHi[3],
+                                   uint64_t* nRaySteps, uint64_t* nFluxRaySteps);
 
 /* ---- property preparation ---- */
 /* RMCRTCommon::sigmaT4<T> (RMCRTCommon.cc:304-343): out = (sigma/pi) T^2 T^2 */

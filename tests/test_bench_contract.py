@@ -40,14 +40,22 @@ def test_no_gpu_fails_loudly():
 
 @pytest.mark.gpu
 def test_our_arm_line(gpu_lib):
-    d = run_bench("--n", "48", "--rays", "16", "--steps", "3", "--warmup", "3")
+    d = run_bench("--n", "48", "--rays", "16", "--steps", "3", "--warmup", "3", "--configs-n", "64")
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
               "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
         assert k in d, k
     assert d["metric"] == "rmcrt_ray_cell_steps_per_s" and d["scaling"] == "weak" and d["dtype"] == "f32" and d["vs_baseline"] is None
-    assert d["steps"] == 3 and d["warmup"] == 3 and d["gpu_launches"] == 12 and d["value"] > 1e9
+    assert d["steps"] == 3 and d["warmup"] == 3 and d["gpu_launches"] == 9 and d["value"] > 1e9
+    assert d["config"]["ray_coherence"] == 0            # the headline is the library default: the reference's sampling
     r = d["roofline"]
-    assert r["bound"] in ("hbm", "tensor") and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["bound"] == "l2" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    bc = d["by_coherence"]
+    assert set(bc) == {"0", "1", "2"} and bc["0"]["is_default"] and bc["0"]["ray_cell_steps_per_s"] == d["value"]
+    assert all(v["ray_cell_steps_per_s"] > 1e9 for v in bc.values())
+    cf = d["configs"]
+    assert {"single_level_64_1gpu_coherence0", "single_level_64_1gpu_coherence2", "c4_dataonion_64_16_coherence0", "c4_dataonion_64_16_coherence2",
+            "c5_flux_reflect_64_coherence0", "c5_flux_reflect_64_coherence2"} <= set(cf)
+    assert all(v["ray_cell_steps_per_s"] > 1e9 and v["ms_per_solve"] > 0 for v in cf.values())
     e = d["e2e"]
     assert 0 < e["value"] <= d["value"] * 1.05 and e["h2d_bytes_per_step"] == 3 * 4 * 50 ** 3 and e["d2h_bytes_per_step"] == 2 * 8 * 50 ** 3
     assert d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port")

@@ -32,7 +32,7 @@ def test_header_and_binding_agree(lib):
 def test_library_exports_every_declared_symbol(lib):
     for s in _header_symbols():
         assert hasattr(lib, s), s
-    assert lib.rmcrt_abi_version() == 4
+    assert lib.rmcrt_abi_version() == 5
 
 
 def test_library_is_sm100a_and_has_no_torch_dependency():

@@ -431,7 +431,7 @@ def test_data_onion_four_cells_per_lane(gpu_lib, po, case):
     coarse = po.coarsen_level(fine, (4, 4, 4))
     res = {}
     for cpl in (1, 4):
-        g = make(gpu_lib, nDivQRays=12, threshold=0.05, haloCells=(4, 4, 4), seed=19, cellsPerLane=cpl, tileX=32, warpsPerTile=4,
+        g = make(gpu_lib, nDivQRays=12, threshold=0.05, haloCells=(4, 4, 4), seed=19, rayCoherence=2, cellsPerLane=cpl, tileX=32, warpsPerTile=4,
                  half_records=(case == "bc_half"), **kw)
         g.upload_level(0, coarse)
         g.upload_level(1, fine)
@@ -621,7 +621,7 @@ def test_two_cells_per_lane_kernel(gpu_lib, po):
     add_random_walls(lv, 0.05, rng, abskg=1.0, sigmaT4=float(lv.sigmaT4[5, 5, 5]))
     res = {}
     for cpl in (1, 2):
-        g = make(gpu_lib, nDivQRays=200, threshold=0.05, seed=3, cellsPerLane=cpl)
+        g = make(gpu_lib, nDivQRays=200, threshold=0.05, seed=3, rayCoherence=2, cellsPerLane=cpl)
         g.upload_level(0, lv)
         d = g.trace_divq(0, patch_lo=(3, 5, 2), patch_hi=(36, 30, 11))["divQ"]
         c = g.counters()
@@ -634,7 +634,7 @@ def test_two_cells_per_lane_kernel(gpu_lib, po):
     assert abs(s1 - s2) < 0.01 * s1
     sel = d1 != 0
     # control: the one-cell kernel against itself with other Philox draws (another time step), under the same statistics
-    g = make(gpu_lib, nDivQRays=200, threshold=0.05, seed=3, cellsPerLane=1)
+    g = make(gpu_lib, nDivQRays=200, threshold=0.05, seed=3, rayCoherence=2, cellsPerLane=1)
     g.upload_level(0, lv)
     d1b = g.trace_divq(0, patch_lo=(3, 5, 2), patch_hi=(36, 30, 11), timestep=2)["divQ"]
     l2 = lambda x, y: np.linalg.norm(x[sel] - y[sel]) / np.linalg.norm(x[sel])
@@ -647,7 +647,7 @@ def test_two_cells_per_lane_kernel(gpu_lib, po):
             sl = [slice(None)] * 3; sl[ax] = idx; ct[tuple(sl)] = 8; ab[tuple(sl)] = 1.0
     walls = (rng.uniform(size=(M, M, M)) < 0.03) & (ct == -1); ct[walls] = 8; ab[walls] = 1.0
     iso = po.Level(ab, s4, ct, (-1,) * 3, (M - 1,) * 3, (1.0 / 24,) * 3, interior_lo=(0,) * 3, interior_hi=(24,) * 3)
-    g = make(gpu_lib, nDivQRays=8, threshold=0.001, seed=5, allowReflect=0)
+    g = make(gpu_lib, nDivQRays=8, threshold=0.001, seed=5, allowReflect=0, rayCoherence=2)
     g.upload_level(0, iso)
     assert np.abs(g.trace_divq(0)["divQ"]).max() < 2e-5 * 4 * np.pi * 2.0 * 0.6
 
@@ -664,7 +664,7 @@ def test_kernel_choice_follows_the_walls(gpu_lib, po):
     even_jk = (slice(1, -1, 2), slice(1, -1, 2), slice(1, -1))
 
     def solve(lv, **kw):
-        g = make(gpu_lib, nDivQRays=12, seed=6, warpsPerTile=4, tileX=32, **kw)
+        g = make(gpu_lib, nDivQRays=12, seed=6, rayCoherence=2, warpsPerTile=4, tileX=32, **kw)
         g.upload_level(0, lv)
         d = g.trace_divq(0, timestep=4)["divQ"]
         return d, int(g.counters().nRaySteps), int(g.counters().nDivQCells)
@@ -719,7 +719,7 @@ def test_four_cells_per_lane_kernel(gpu_lib, po):
     # (b)
     res = {}
     for cpl, tx in ((1, 0), (4, 0), (4, 8), (4, 32)):
-        g = make(gpu_lib, nDivQRays=200, threshold=0.05, seed=3, cellsPerLane=cpl, tileX=tx)
+        g = make(gpu_lib, nDivQRays=200, threshold=0.05, seed=3, rayCoherence=2, cellsPerLane=cpl, tileX=tx)
         g.upload_level(0, lv)
         d = g.trace_divq(0, patch_lo=(3, 5, 2), patch_hi=(36, 30, 11))["divQ"]
         res[(cpl, tx)] = (d, int(g.counters().nDivQCells), int(g.counters().nRaySteps))
@@ -732,7 +732,7 @@ def test_four_cells_per_lane_kernel(gpu_lib, po):
         assert np.array_equal(d1 != 0, dk != 0) and not dk[~(flow & box)].any()
         assert abs(s1 - sk) < 0.01 * s1
     sel = d1 != 0
-    g = make(gpu_lib, nDivQRays=200, threshold=0.05, seed=3, cellsPerLane=1)
+    g = make(gpu_lib, nDivQRays=200, threshold=0.05, seed=3, rayCoherence=2, cellsPerLane=1)
     g.upload_level(0, lv)
     d1b = g.trace_divq(0, patch_lo=(3, 5, 2), patch_hi=(36, 30, 11), timestep=2)["divQ"]
     l2 = lambda x, y: np.linalg.norm(x[sel] - y[sel]) / np.linalg.norm(x[sel])

@@ -43,7 +43,7 @@ def plates_fields(n, dtype=np.float32, T_gas=1500.0, T_wall=1000.0, mirrors=("x-
     return ab.astype(dtype), s4.astype(dtype), ct
 
 
-def c4_multi_gpu(args, N, half, world):
+def c4_multi_gpu(args, N, half, world, own_pg=True, coherence=-1, cells_per_lane=4):
     """BASELINE configs[3]: the Data Onion across `world` GPUs of one box (torchrun, one rank per GPU).  The fine level is sharded by
     patch: every rank packs the records of the cells it owns, ONE all-gather replicates the packed fine level (the halo and the
     coarsening both need neighbours' cells), each rank derives the coarse level on its own device and traces its own fine patch.
@@ -55,7 +55,8 @@ def c4_multi_gpu(args, N, half, world):
     rank, local = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
-    dist.init_process_group("nccl", device_id=dev)
+    if own_pg:
+        dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.current_stream()
     pg = partition.patch_grid(world)
     P = N // 2
@@ -71,7 +72,8 @@ def c4_multi_gpu(args, N, half, world):
     slot = partition.slot_bytes(boxes_lo, boxes_hi, rec_bytes)
     send = torch.zeros(slot, dtype=torch.uint8, device=dev)
     gathered = torch.zeros(slot * world, dtype=torch.uint8, device=dev)
-    g = RMCRT(device=local, nDivQRays=args.rays, threshold=0.05, haloCells=(4, 4, 4), seed=99, half_records=bool(half))
+    kw = {} if coherence < 0 else {"rayCoherence": coherence, "cellsPerLane": cells_per_lane}
+    g = RMCRT(device=local, nDivQRays=args.rays, threshold=0.05, haloCells=(4, 4, 4), seed=99, half_records=bool(half), **kw)
     fine = LevelData(None, None, None, lo, hi, dxf, rr=(4, 4, 4), interior_lo=(0,) * 3, interior_hi=shape)
     cshape = tuple(s // 4 for s in shape)
     coarse = LevelData(None, None, None, lo, tuple(c + 1 for c in cshape), tuple(4.0 / s for s in shape), interior_lo=(0,) * 3, interior_hi=cshape)
@@ -108,16 +110,124 @@ def c4_multi_gpu(args, N, half, world):
     wk = torch.tensor([float(c.nRaySteps), float(c.nDivQCells)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(wk, op=dist.ReduceOp.SUM)
+    rec = None
     if rank == 0:
         sec = float(t.item())
-        print(json.dumps({"config": "C4", "n_gpus": world,
+        rec = ({"config": "C4", "n_gpus": world, "ray_coherence": int(g.params.rayCoherence),
                           "workload": f"Data Onion fine {shape[0]}x{shape[1]}x{shape[2]} ({world} patches of {P}^3, one per GPU) / coarse {cshape[0]}x{cshape[1]}x{cshape[2]}, RR 4, "
                                       f"halo 4, {args.rays} rays/cell; packed fine level all-gathered per solve, coarse level derived on every GPU",
                           "ray_cell_steps_per_s": float(wk[0]) / sec, "divq_cells_per_s": float(wk[1]) / sec, "ms_per_solve": 1e3 * sec / args.steps,
                           "steps_per_ray": float(wk[0]) / (float(wk[1]) * args.rays), "record_bytes": rec_bytes, "solves": args.steps,
-                          "timing": "CUDA events per rank, max over ranks"}))
+                          "timing": "CUDA events per rank, max over ranks"})
+    g.close()
     dist.barrier()
-    dist.destroy_process_group()
+    if own_pg:
+        if rec is not None:
+            print(json.dumps(rec))
+        dist.destroy_process_group()
+    return rec
+
+
+def _timed(torch, stream, flush, solve, g, steps, warm=2):
+    for w in range(warm):
+        solve(w + 1)
+    torch.cuda.synchronize()
+    g.reset_counters(stream)
+    ev = []
+    for k in range(steps):
+        flush.fill_(k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        solve(100 + k)
+        e1.record(stream)
+        ev.append((e0, e1))
+    torch.cuda.synchronize()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    return sum(ms) * 1e-3, g.counters(stream)
+
+
+def _half_policy(N, half):
+    return half if half >= 0 else (1 if (N + 2) ** 3 * 8 > 64e6 else 0)
+
+
+def c4_single_gpu(N=256, rays=100, steps=2, half=-1, coherence=-1, cells_per_lane=4, warm=2, flush=None):
+    """BASELINE configs[3] on ONE B200: all eight (N/2)^3 fine patches, coarse level derived on the device every solve"""
+    import torch
+    from bench import burns_christon_fields
+    from uintah_b200 import RMCRT, LevelData
+    dev = torch.device("cuda", torch.cuda.current_device())
+    stream = torch.cuda.current_stream()
+    half = _half_policy(N, half)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if flush is None else flush
+    lo, hi = (-1,) * 3, (N + 1,) * 3
+    P = N // 2
+    patches = [((a * P, b * P, c * P), ((a + 1) * P, (b + 1) * P, (c + 1) * P)) for c in range(2) for b in range(2) for a in range(2)]
+    oshape = (N + 2, N + 2, N + 2)
+    d_divQ = torch.empty(oshape, dtype=torch.float64, device=dev)
+    d_volq = torch.empty_like(d_divQ)
+    ab, s4, ct = burns_christon_fields((N,) * 3, lo, hi, np.float32)
+    d_ab, d_s4, d_ct = (torch.from_numpy(x).to(dev) for x in (ab, s4, ct))
+    kw = {} if coherence < 0 else {"rayCoherence": coherence, "cellsPerLane": cells_per_lane}
+    g = RMCRT(device=dev.index, nDivQRays=rays, threshold=0.05, haloCells=(4, 4, 4), seed=99, half_records=bool(half), **kw)
+    fine = LevelData(None, None, None, lo, hi, (1.0 / N,) * 3, rr=(4, 4, 4), interior_lo=(0,) * 3, interior_hi=(N,) * 3)
+    C = N // 4
+    coarse = LevelData(None, None, None, lo, (C + 1,) * 3, (4.0 / N,) * 3, interior_lo=(0,) * 3, interior_hi=(C,) * 3)
+    g.define_level(0, coarse.desc()); g.levels[0] = coarse
+    g.define_level(1, fine.desc()); g.levels[1] = fine
+
+    def solve(ts):
+        g.pack_level_device(1, d_ab, d_s4, d_ct, lo, hi, stream=stream)
+        g.coarsen_level_device(1, 0, stream=stream)
+        g.set_level_extra_cells(0, [1.0] * 6, [0.0] * 6, [8] * 6, stream=stream)
+        g.finalize_level_async(1, stream)
+        g.finalize_level_async(0, stream)
+        for i, (plo, phi) in enumerate(patches):
+            g.trace_dataonion_device(2, plo, phi, d_divQ, d_volq, None, lo, hi, timestep=ts, zero_init=(i == 0), stream=stream)
+    sec, c = _timed(torch, stream, flush, solve, g, steps, warm)
+    rec = {"config": "C4", "workload": f"Data Onion fine {N}^3 (8 patches of {P}^3) / coarse {C}^3, RR 4, halo 4, {rays} rays/cell, 1 B200",
+           "ray_coherence": int(g.params.rayCoherence),
+           "ray_cell_steps_per_s": c.nRaySteps / sec, "divq_cells_per_s": c.nDivQCells / sec, "ms_per_solve": 1e3 * sec / steps,
+           "steps_per_ray": c.nRaySteps / (c.nDivQCells * rays), "record_bytes": 4 if half else 8, "solves": steps,
+           "kernels_per_solve": 5 + 8 * 3}
+    g.close()
+    return rec
+
+
+def c5_single_gpu(N=256, rays=100, steps=2, half=-1, coherence=-1, cells_per_lane=4, warm=2, flush=None):
+    """BASELINE configs[4] on ONE B200"""
+    import torch
+    from uintah_b200 import RMCRT, LevelData
+    dev = torch.device("cuda", torch.cuda.current_device())
+    stream = torch.cuda.current_stream()
+    half = _half_policy(N, half)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if flush is None else flush
+    lo, hi = (-1,) * 3, (N + 1,) * 3
+    oshape = (N + 2, N + 2, N + 2)
+    d_divQ = torch.empty(oshape, dtype=torch.float64, device=dev)
+    d_volq = torch.empty_like(d_divQ)
+    ab, s4, ct = plates_fields(N)
+    d_ab, d_s4, d_ct = (torch.from_numpy(x).to(dev) for x in (ab, s4, ct))
+    kw = {} if coherence < 0 else {"rayCoherence": coherence, "cellsPerLane": cells_per_lane}
+    g = RMCRT(device=dev.index, nDivQRays=rays, nFluxRays=rays, threshold=0.001, solveBoundaryFlux=1, allowReflect=1, seed=99,
+              half_records=bool(half), **kw)
+    lvl = LevelData(None, None, None, lo, hi, (1.0 / N,) * 3, interior_lo=(0,) * 3, interior_hi=(N,) * 3)
+    g.define_level(0, lvl.desc()); g.levels[0] = lvl
+    d_flux = torch.empty(oshape + (7,), dtype=torch.float64, device=dev)
+
+    def solve(ts):
+        g.pack_level_device(0, d_ab, d_s4, d_ct, lo, hi, stream=stream)
+        g.finalize_level_async(0, stream)
+        g.trace_divq_device(0, (0,) * 3, (N,) * 3, d_divQ, d_volq, d_flux, lo, hi, timestep=ts, zero_init=True, stream=stream)
+    sec, c = _timed(torch, stream, flush, solve, g, steps, warm)
+    tot = c.nRaySteps + c.nFluxRaySteps
+    rec = {"config": "C5", "workload": f"single level {N}^3, benchmark 2, walls 1000 K with x-/y- mirrors, solveBoundaryFlux + allowReflect, "
+                                       f"{rays} divQ + {rays} flux rays, Threshold 0.001, 1 B200",
+           "ray_coherence": int(g.params.rayCoherence),
+           "ray_cell_steps_per_s": tot / sec, "divq_cells_per_s": c.nDivQCells / sec, "ms_per_solve": 1e3 * sec / steps,
+           "divq_steps_per_ray": c.nRaySteps / (c.nDivQCells * rays), "flux_cells": c.nFluxCells / steps,
+           "flux_steps_share": c.nFluxRaySteps / tot, "record_bytes": 4 if half else 8, "solves": steps}
+    g.close()
+    return rec
 
 
 def main():
@@ -127,93 +237,21 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--config", nargs="+", default=["C4", "C5"])
     ap.add_argument("--half-records", type=int, default=-1)
+    ap.add_argument("--coherence", type=int, default=-1, help="rayCoherence (-1: library default = 0, the reference's sampling)")
+    ap.add_argument("--cells-per-lane", type=int, default=4)
     args = ap.parse_args()
 
     import torch
-    from bench import burns_christon_fields
-    from uintah_b200 import RMCRT, LevelData
     assert torch.cuda.is_available(), "needs a GPU (no CPU fallback)"
-    dev = torch.device("cuda:0")
-    stream = torch.cuda.current_stream()
     N = args.n
-    half = args.half_records if args.half_records >= 0 else (1 if (N + 2) ** 3 * 8 > 64e6 else 0)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    lo, hi = (-1,) * 3, (N + 1,) * 3
-    P = N // 2
-    patches = [((a * P, b * P, c * P), ((a + 1) * P, (b + 1) * P, (c + 1) * P)) for c in range(2) for b in range(2) for a in range(2)]
-
-    def timed(solve, g):
-        for w in range(2):
-            solve(w + 1)
-        torch.cuda.synchronize()
-        g.reset_counters(stream)
-        ev = []
-        for k in range(args.steps):
-            flush.fill_(k)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            solve(100 + k)
-            e1.record(stream)
-            ev.append((e0, e1))
-        torch.cuda.synchronize()
-        ms = [a.elapsed_time(b) for a, b in ev]
-        return sum(ms) * 1e-3, g.counters(stream)
-
-    out_lo, out_hi = lo, hi
-    oshape = (N + 2, N + 2, N + 2)
-    d_divQ = torch.empty(oshape, dtype=torch.float64, device=dev)
-    d_volq = torch.empty_like(d_divQ)
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if "C4" in args.config and world > 1:
-        c4_multi_gpu(args, N, half, world)
+        c4_multi_gpu(args, N, _half_policy(N, args.half_records), world, coherence=args.coherence, cells_per_lane=args.cells_per_lane)
         return
-
     if "C4" in args.config:
-        ab, s4, ct = burns_christon_fields((N,) * 3, lo, hi, np.float32)
-        d_ab, d_s4, d_ct = (torch.from_numpy(x).to(dev) for x in (ab, s4, ct))
-        g = RMCRT(device=0, nDivQRays=args.rays, threshold=0.05, haloCells=(4, 4, 4), seed=99, half_records=bool(half))
-        fine = LevelData(None, None, None, lo, hi, (1.0 / N,) * 3, rr=(4, 4, 4), interior_lo=(0,) * 3, interior_hi=(N,) * 3)
-        C = N // 4
-        coarse = LevelData(None, None, None, lo, (C + 1,) * 3, (4.0 / N,) * 3, interior_lo=(0,) * 3, interior_hi=(C,) * 3)
-        g.define_level(0, coarse.desc()); g.levels[0] = coarse
-        g.define_level(1, fine.desc()); g.levels[1] = fine
-
-        def solve(ts):
-            g.pack_level_device(1, d_ab, d_s4, d_ct, lo, hi, stream=stream)
-            g.coarsen_level_device(1, 0, stream=stream)
-            g.set_level_extra_cells(0, [1.0] * 6, [0.0] * 6, [8] * 6, stream=stream)
-            g.finalize_level_async(1, stream)
-            g.finalize_level_async(0, stream)
-            for i, (plo, phi) in enumerate(patches):
-                g.trace_dataonion_device(2, plo, phi, d_divQ, d_volq, None, out_lo, out_hi, timestep=ts, zero_init=(i == 0), stream=stream)
-        sec, c = timed(solve, g)
-        print(json.dumps({"config": "C4", "workload": f"Data Onion fine {N}^3 (8 patches of {P}^3) / coarse {C}^3, RR 4, halo 4, {args.rays} rays/cell, 1 B200",
-                          "ray_cell_steps_per_s": c.nRaySteps / sec, "divq_cells_per_s": c.nDivQCells / sec, "ms_per_solve": 1e3 * sec / args.steps,
-                          "steps_per_ray": c.nRaySteps / (c.nDivQCells * args.rays), "record_bytes": 4 if half else 8, "solves": args.steps}))
-        g.close()
-
+        print(json.dumps(c4_single_gpu(N, args.rays, args.steps, args.half_records, args.coherence, args.cells_per_lane)))
     if "C5" in args.config:
-        ab, s4, ct = plates_fields(N)
-        d_ab, d_s4, d_ct = (torch.from_numpy(x).to(dev) for x in (ab, s4, ct))
-        g = RMCRT(device=0, nDivQRays=args.rays, nFluxRays=args.rays, threshold=0.001, solveBoundaryFlux=1, allowReflect=1, seed=99,
-                  half_records=bool(half))
-        lvl = LevelData(None, None, None, lo, hi, (1.0 / N,) * 3, interior_lo=(0,) * 3, interior_hi=(N,) * 3)
-        g.define_level(0, lvl.desc()); g.levels[0] = lvl
-        d_flux = torch.empty(oshape + (7,), dtype=torch.float64, device=dev)
-
-        def solve(ts):
-            g.pack_level_device(0, d_ab, d_s4, d_ct, lo, hi, stream=stream)
-            g.finalize_level_async(0, stream)
-            g.trace_divq_device(0, (0,) * 3, (N,) * 3, d_divQ, d_volq, d_flux, out_lo, out_hi, timestep=ts, zero_init=True, stream=stream)
-        sec, c = timed(solve, g)
-        tot = c.nRaySteps + c.nFluxRaySteps
-        print(json.dumps({"config": "C5", "workload": f"single level {N}^3, benchmark 2, walls 1000 K with x-/y- mirrors, solveBoundaryFlux + allowReflect, "
-                                                      f"{args.rays} divQ + {args.rays} flux rays, Threshold 0.001, 1 B200",
-                          "ray_cell_steps_per_s": tot / sec, "divq_cells_per_s": c.nDivQCells / sec, "ms_per_solve": 1e3 * sec / args.steps,
-                          "divq_steps_per_ray": c.nRaySteps / (c.nDivQCells * args.rays), "flux_cells": c.nFluxCells / args.steps,
-                          "flux_steps_share": c.nFluxRaySteps / tot, "record_bytes": 4 if half else 8, "solves": args.steps}))
-        g.close()
+        print(json.dumps(c5_single_gpu(N, args.rays, args.steps, args.half_records, args.coherence, args.cells_per_lane)))
 
 
 if __name__ == "__main__":

@@ -43,7 +43,7 @@ class Params(C.Structure):
         ("marchPrecision", C.c_int32), ("rayCoherence", C.c_int32), ("skipZeroWeightLegs", C.c_int32),
         ("fixedRandom", C.c_int32), ("l2Persist", C.c_int32), ("warpsPerTile", C.c_int32),
         ("genericMarch", C.c_int32), ("maxBlocksPerSM", C.c_int32), ("rayDirSampleAlgo", C.c_int32), ("cellsPerLane", C.c_int32),
-        ("maxRayLength", C.c_double), ("sigmaScat", C.c_double), ("tileX", C.c_int32), ("reserved0", C.c_int32),
+        ("maxRayLength", C.c_double), ("sigmaScat", C.c_double), ("tileX", C.c_int32), ("nonFlowCellType", C.c_int32),
     ]
 
 

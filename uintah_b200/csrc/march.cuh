@@ -93,7 +93,7 @@ template <> struct Num<double> {
   static __device__ __forceinline__ double rcp(double a) { return __ddiv_rn(1.0, a); }
   // RMCRTCommon.cc:717-720 (FUZZ = 1e-12); single level only
   static __device__ __forceinline__ double fuzz(double ds) { return (ds > -1e-12 && ds < 1e-12) ? ds + 1e-12 : ds; }
-  // `wallEmissivity * sigmaT4OverPi[cur]` is a T*T product in the reference (RMCRTCommon.cc:854, Ray.cc:2602): evaluated in
+  // `wallEmissivity * sigmaT4OverPi[cur]` is a T*T product in the reference (RMCRTCommon.cc:846-854; NOT in Ray::updateSumI_ML, whose wallEmissivity is a double): evaluated in
   // float when the properties are float, before the double `* intensity`
   static __device__ __forceinline__ double wall_product(double eps, double s, bool floatProps) {
     return floatProps ? (double)((float)eps * (float)s) : __dmul_rn(eps, s);
@@ -1367,7 +1367,9 @@ __device__ __forceinline__ Real march_multi_level(const OnionGeom<MAXL>& G, int 
 
     const Real eps = k > Real(1) ? Real(1) : k;          // 2594-2598
     Real intensity = e;
-    sum = N::add(sum, N::mul(N::wall_product(eps, s, floatProps), intensity)); // 2602
+    // Ray.cc:2595,2602: here `double wallEmissivity = abskg[L][cur]`, so the product with sigmaT4OverPi is evaluated in double even for
+    // T = float (only the single-level updateSumI keeps `T wallEmissivity`, RMCRTCommon.cc:846-854)
+    sum = N::add(sum, N::mul(N::wall_product(eps, s, false), intensity));
     intensity = N::mul(intensity, fs);
     if (!allowReflect || !(intensity > threshold)) break; // 2607-2609, 2621
     fs = N::mul(fs, N::add(Real(1), -k));                // reflect(); cur = prevCell with L unchanged

@@ -85,6 +85,8 @@ struct TraceArgs {
   RoiBox roi;                     // Data-Onion fast path: shell-wrapped copy of the fine level's ROI (rec == nullptr: generic march)
   double maxRayLength;            // boundedRayLength ROI (RMCRTCommon.cc:680,684); +inf when unbounded
   int floatProps;                 // the level was packed from float arrays: the FP64 parity march rounds T*T products to float
+  int zeroNonFlow;                // write 0 into the non-flow cells of the patch (zeroInit != 0).  With zeroInit == 0 (modifies_divQ:
+                                  // getModifiable, Ray.cc:573-588) the reference `continue`s over them and their values survive (746-748)
   // flux items
   const int* items;       // compacted item ids: face * nCells + patch-linear cell
   const int* nItems;      // device count
@@ -425,7 +427,7 @@ __global__ void __launch_bounds__(256, ((FAST && !ML) ? RMCRT_FAST_MIN_BLOCKS : 
         a.divQ[q] = -4.0 * M_PI * (double)r0.k * ((double)r0.s - mean);
         a.volq[q] = 4.0 * M_PI * mean;
         ++cellsTotal;
-      } else {
+      } else if (a.zeroNonFlow) {
         a.divQ[q] = 0.0;   // non-flow cells keep their initial 0 (Ray.cc:581-582,746-748)
         a.volq[q] = 0.0;
       }
@@ -527,7 +529,7 @@ __global__ void __launch_bounds__(256, 4) divq_dual_kernel(const __grid_constant
           a.divQ[q] = -4.0 * M_PI * (double)r0.k * ((double)r0.s - mean);
           a.volq[q] = 4.0 * M_PI * mean;
           ++cellsTotal;
-        } else {
+        } else if (a.zeroNonFlow) {
           a.divQ[q] = 0.0;
           a.volq[q] = 0.0;
         }
@@ -650,7 +652,7 @@ __global__ void __launch_bounds__(128, (!ONION && std::is_same<RecT, Rec8>::valu
         a.divQ[q] = -4.0 * M_PI * (double)rc.k * ((double)rc.s - mean);      // Ray.cc:775,778
         a.volq[q] = 4.0 * M_PI * mean;
         ++cellsTotal;
-      } else {
+      } else if (a.zeroNonFlow) {
         a.divQ[q] = 0.0;
         a.volq[q] = 0.0;
       }
@@ -977,14 +979,15 @@ __global__ void sigmaT4_kernel(const double* __restrict__ temp, T* __restrict__ 
 }
 
 // Ray::coarsen_Q (Ray.cc:2103-2145; AMR_CoarsenRefine.cc:42-86) + Ray::computeCellType (2272-2345), interior coarse cells.
-// cellType enters only as flow / not-flow: the integer sum of the reference equals -nFlow + sum(types of non-flow cells);
-// with the record's 1-bit cell type we reproduce the decision for the cases where every non-flow fine cell has a
-// positive type (true for every RMCRT deck and for Arches): ROUNDUP -> non-flow iff any fine cell is non-flow with
-// |avg|/10 >= 1/RR; ROUNDDOWN -> flow unless |avg|/10 > 1 - 1/RR.  We store the fine non-flow TYPE-free decision:
-//   all flow -> flow;  otherwise ROUNDUP -> intrusion, ROUNDDOWN -> flow unless all RR cells are non-flow.
+// computeCellType sums the INTEGER cell types of the RR fine cells (flow = -1) and decides on tmp = sum / RR:
+//   tmp == -1 -> flow;  ROUNDUP: intrusion iff |tmp|/10 >= 1/RR (i.e. |sum| >= 10);  ROUNDDOWN: flow iff |tmp|/10 <= 1 - 1/RR.
+// The packed record keeps one bit of the cell type, so the sum is rebuilt as -nFlow + wallType * nNonFlow with
+// wallType = rmcrt_params.nonFlowCellType (8: the wall / intrusion id of RMCRT_Test.cc:80 and of Arches' walls) and the reference's two
+// floating-point tests are then applied verbatim -- e.g. RR = 8 with ONE non-flow fine cell gives sum = 1: the coarse cell stays a flow
+// cell under ROUNDUP, as in the reference.  Exact whenever the non-flow cells of a level share one type.
 template <class RecT>
 __global__ void coarsen_kernel(const RecT* __restrict__ fine, Box fb, RecT* __restrict__ coarse, Box cb, Box cint,
-                               int rr0, int rr1, int rr2, int logic, Rec8* __restrict__ coarseFull) {
+                               int rr0, int rr1, int rr2, int logic, int wallType, Rec8* __restrict__ coarseFull) {
   typedef typename RecTraits<RecT>::real R;
   const long long n = box_cells(cint);
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
@@ -1008,10 +1011,12 @@ __global__ void coarsen_kernel(const RecT* __restrict__ fine, Box fb, RecT* __re
     const double invRR = 1.0 / ((double)(rr0 * rr1 * rr2));
     R kc = (R)(ak * invRR), sc = (R)(as * invRR);
     const int RR = rr0 * rr1 * rr2;
-    bool wall;
-    if (nWall == 0) wall = false;
-    else if (logic == 0) wall = true;           // ROUNDUP: any partial cell becomes an intrusion
-    else wall = (nWall == RR);                  // ROUNDDOWN: any partial cell becomes a flow cell
+    const double tmp = (double)(-(RR - nWall) + wallType * nWall) * invRR;      // Ray.cc:2320
+    bool wall = false;
+    if (tmp != -1.0) {                                                          // 2324
+      if (logic == 1) wall = !(fabs(tmp) / 10.0 <= (1.0 - invRR));              // ROUNDDOWN, 2327-2333
+      else            wall = fabs(tmp) / 10.0 >= invRR;                         // ROUNDUP, 2336-2342
+    }
     const long long d = (long long)(i - cb.lo[0]) + (long long)cb.n[0] * ((long long)(j - cb.lo[1]) + (long long)cb.n[1] * (long long)(k - cb.lo[2]));
     coarse[d] = make_rec<RecT, R>(wall ? -kc : kc, sc);
     if (coarseFull) coarseFull[d] = Rec8{(float)(wall ? -kc : kc), (float)sc};
@@ -1247,6 +1252,28 @@ __global__ void bw_stream_kernel(const uint4* __restrict__ buf, long long n16, i
       if (u >= n16) u -= n16 * (u / n16);
       const uint4 v = __ldg(buf + u);
       acc ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
+  }
+  if (acc == 0x12345677u) *sink = acc;
+}
+// pattern 2: L2 -> SM bandwidth proper.  Eight independent 16-B loads in flight per thread, cached in L2 only (ld.global.cg), every warp
+// request four whole 128-B lines, consecutive sweeps rotated so nothing is served from L1: what the L2 slices and the crossbar deliver
+// when the SMs ask as hard as they can (the denominator of the L2 roofline; B300_MICROARCH.md quotes ~6300 B/clk for the chip)
+__global__ void bw_stream_cg_kernel(const uint4* __restrict__ buf, long long n16, int inner, unsigned* sink) {
+  unsigned acc = 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (int it = 0; it < inner; ++it) {
+    const long long shift = (long long)it * 7919 * blockDim.x;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n16; t += 8 * stride) {
+      uint4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        long long w = t + u * stride + shift;
+        if (w >= n16) w -= n16 * (w / n16);
+        v[u] = __ldcg(buf + w);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc ^= v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
     }
   }
   if (acc == 0x12345677u) *sink = acc;
@@ -1763,6 +1790,7 @@ int trace_common(rmcrt_ctx* ctx, int maxLevels, bool ML, const int32_t pLo[3], c
   if (rc) return rc;
   if (!dDivQ || !dVolq) return fail(ctx, RMCRT_ERR_INVALID, "divQ and radiationVolq buffers are required");
   a.divQ = dDivQ; a.volq = dVolq; a.bflux = dFlux;
+  a.zeroNonFlow = zeroInit ? 1 : 0;
   const size_t nOut = (size_t)a.outN[0] * a.outN[1] * a.outN[2];
   CK(cudaSetDevice(ctx->device));
   if (zeroInit == 2 && ctx->p.solveDivQ) {
@@ -1910,12 +1938,12 @@ void rmcrt_default_params(rmcrt_params* p) {
   p->haloCells[0] = p->haloCells[1] = p->haloCells[2] = 10;   // Ray.cc:254
   p->cellTypeCoarsenLogic = 0;
   p->seed = 0x9E3779B97F4A7C15ull;
-  p->marchPrecision = 0; p->rayCoherence = 2; p->skipZeroWeightLegs = 1; p->fixedRandom = 0; p->l2Persist = 1;
+  p->marchPrecision = 0; p->rayCoherence = 0; p->skipZeroWeightLegs = 1; p->fixedRandom = 0; p->l2Persist = 1;
   p->warpsPerTile = 0;
   p->rayDirSampleAlgo = 0;     // "naive", Ray.cc:174
   p->maxRayLength = 0.0;       // unbounded (DBL_MAX, RMCRTCommon.cc:117)
   p->sigmaScat = 0.0;          // Ray.cc:169
-  p->tileX = 0; p->reserved0 = 0;
+  p->tileX = 0; p->nonFlowCellType = 8;
   p->cellsPerLane = 4;         // production: the 2 x 2 cells of a lane share one DDA (divq_quad_kernel); 2 = a pair (divq_dual_kernel); 1 = one cell per lane
 }
 
@@ -2269,9 +2297,9 @@ int rmcrt_coarsen_level_device(rmcrt_ctx* ctx, int fineL, int coarseL, void* str
   Box fb = mkbox(f.d.lo, f.d.hi), cb = mkbox(c.d.lo, c.d.hi), ci = mkbox(c.d.interiorLo, c.d.interiorHi);
   const long long n = box_cells(ci);
   cudaStream_t st = (cudaStream_t)stream;
-  if (f.recordKind == 0)      coarsen_kernel<Rec8><<<grid_for(n, 128, ctx->smCount), 128, 0, st>>>(static_cast<const Rec8*>(f.rec), fb, static_cast<Rec8*>(c.rec), cb, ci, rr[0], rr[1], rr[2], ctx->p.cellTypeCoarsenLogic, nullptr);
-  else if (f.recordKind == 2) coarsen_kernel<Rec4><<<grid_for(n, 128, ctx->smCount), 128, 0, st>>>(static_cast<const Rec4*>(f.rec), fb, static_cast<Rec4*>(c.rec), cb, ci, rr[0], rr[1], rr[2], ctx->p.cellTypeCoarsenLogic, static_cast<Rec8*>(c.recFull));
-  else                        coarsen_kernel<Rec16><<<grid_for(n, 128, ctx->smCount), 128, 0, st>>>(static_cast<const Rec16*>(f.rec), fb, static_cast<Rec16*>(c.rec), cb, ci, rr[0], rr[1], rr[2], ctx->p.cellTypeCoarsenLogic, nullptr);
+  if (f.recordKind == 0)      coarsen_kernel<Rec8><<<grid_for(n, 128, ctx->smCount), 128, 0, st>>>(static_cast<const Rec8*>(f.rec), fb, static_cast<Rec8*>(c.rec), cb, ci, rr[0], rr[1], rr[2], ctx->p.cellTypeCoarsenLogic, ctx->p.nonFlowCellType, nullptr);
+  else if (f.recordKind == 2) coarsen_kernel<Rec4><<<grid_for(n, 128, ctx->smCount), 128, 0, st>>>(static_cast<const Rec4*>(f.rec), fb, static_cast<Rec4*>(c.rec), cb, ci, rr[0], rr[1], rr[2], ctx->p.cellTypeCoarsenLogic, ctx->p.nonFlowCellType, static_cast<Rec8*>(c.recFull));
+  else                        coarsen_kernel<Rec16><<<grid_for(n, 128, ctx->smCount), 128, 0, st>>>(static_cast<const Rec16*>(f.rec), fb, static_cast<Rec16*>(c.rec), cb, ci, rr[0], rr[1], rr[2], ctx->p.cellTypeCoarsenLogic, ctx->p.nonFlowCellType, nullptr);
   CK(cudaGetLastError());
   return invalidate_level(ctx, coarseL, st);
 }
@@ -2567,6 +2595,7 @@ int rmcrt_measure_read_bandwidth(rmcrt_ctx* ctx, size_t bytes, int repeats, int 
   const int inner = bytes <= (64u << 20) ? 64 : 1;
   auto pass = [&]() {
     if (pattern == 0) bw_stream_kernel<<<grid, block>>>(static_cast<const uint4*>(buf), n16, inner, sink);
+    else if (pattern == 2) bw_stream_cg_kernel<<<ctx->smCount * 4, 512>>>(static_cast<const uint4*>(buf), n16, inner, sink);
     else bw_gather_kernel<<<grid, block>>>(static_cast<const float2*>(buf), nRec, perThread, sink);
   };
   for (int i = 0; i < 3; ++i) pass();     // warm-up (and L2 fill for small buffers)
@@ -2578,7 +2607,12 @@ int rmcrt_measure_read_bandwidth(rmcrt_ctx* ctx, size_t bytes, int repeats, int 
   CK(cudaEventElapsedTime(&ms, e0, e1));
   CK(cudaGetLastError());
   const double sec = ms * 1e-3;
-  if (pattern == 0) {
+  if (pattern == 2) {      // every thread issues whole groups of eight loads (indices wrap around the buffer)
+    const long long per = 8LL * ctx->smCount * 4 * 512;
+    const double loads = (double)((n16 + per - 1) / per * per);
+    if (gbps) *gbps = loads * 16.0 * repeats * inner / sec / 1e9;
+    if (gaccess) *gaccess = loads * repeats * inner / sec / 1e9;
+  } else if (pattern == 0) {
     if (gbps) *gbps = (double)n16 * 16.0 * repeats * inner / sec / 1e9;
     if (gaccess) *gaccess = (double)n16 * repeats * inner / sec / 1e9;
   } else {

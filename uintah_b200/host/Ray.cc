@@ -54,6 +54,22 @@ void Ray::problemSetup(const ProblemSpecP& prob_spec, const ProblemSpecP& rmcrtp
   rmcrt_ps->getWithDefault("solveDivQ", d_solveDivQ, true);
   rmcrt_ps->getWithDefault("applyFilter", d_applyFilter, false);
   rmcrt_ps->getWithDefault("rayDirSampleAlgo", rayDirSampleAlgo, "naive");
+  // back-end keys (no counterpart in the reference; absent from a stock deck => the reference's sampling):
+  //   <rayCoherence> 0 (default) independent rays per (cell, ray, timestep); 1 / 2 opt into warp-batched directions (rmcrt_b200.h)
+  //   <cellsPerLane> 1 | 2 | 4 cells of a lane sharing one DDA when rayCoherence >= 1
+  int rayCoherence = 0, cellsPerLane = 4;
+  rmcrt_ps->getWithDefault("rayCoherence", rayCoherence, 0);
+  rmcrt_ps->getWithDefault("cellsPerLane", cellsPerLane, 4);
+  if (rayCoherence < 0 || rayCoherence > 2)
+    throw ProblemSetupException("RMCRT (B200 back end): <rayCoherence> must be 0, 1 or 2", __FILE__, __LINE__);
+  if (cellsPerLane != 1 && cellsPerLane != 2 && cellsPerLane != 4)
+    throw ProblemSetupException("RMCRT (B200 back end): <cellsPerLane> must be 1, 2 or 4", __FILE__, __LINE__);
+  if (rayCoherence != 0) {
+    d_knobs["rayCoherence"] = rayCoherence;
+    std::cout << "  - B200 back end: rayCoherence " << rayCoherence << " (ray directions shared by the origin cells of a warp tile; errors of\n"
+              << "    neighbouring cells are correlated -- not the reference's sampling)\n";
+  }
+  if (cellsPerLane != 4) d_knobs["cellsPerLane"] = cellsPerLane;
 
   if (rayDirSampleAlgo == "LatinHyperCube") {                       // Ray.cc:175-180
     d_rayDirSampleAlgo = LATIN_HYPER_CUBE;

@@ -232,16 +232,18 @@ class RMCRT:
 
     def trace_divq_device(self, L, patch_lo, patch_hi, divQ, volq, bflux, out_lo, out_hi, timestep=1, zero_init=True,
                           stream=None):
+        """zero_init: True / 1 = the whole window is zeroed first; 2 = only the part of the window outside the patch (the kernels write
+        every cell of the patch: for output buffers in mapped page-locked host memory); False / 0 = modifies_divQ"""
         check(self.ctx, self.lib.rmcrt_trace_divq_device(self.ctx, L, i3(patch_lo), i3(patch_hi), divQ.data_ptr(),
                                                          volq.data_ptr(), None if bflux is None else bflux.data_ptr(),
-                                                         i3(out_lo), i3(out_hi), 1 if zero_init else 0,
+                                                         i3(out_lo), i3(out_hi), int(zero_init),
                                                          C.c_uint64(timestep), _stream_handle(stream)))
 
     def trace_dataonion_device(self, max_levels, patch_lo, patch_hi, divQ, volq, bflux, out_lo, out_hi, timestep=1,
                                zero_init=True, stream=None):
         check(self.ctx, self.lib.rmcrt_trace_dataonion_device(self.ctx, max_levels, i3(patch_lo), i3(patch_hi), divQ.data_ptr(),
                                                               volq.data_ptr(), None if bflux is None else bflux.data_ptr(),
-                                                              i3(out_lo), i3(out_hi), 1 if zero_init else 0,
+                                                              i3(out_lo), i3(out_hi), int(zero_init),
                                                               C.c_uint64(timestep), _stream_handle(stream)))
 
     # ------------------------------------------------------------------ virtual radiometer
