@@ -229,7 +229,7 @@ def workload_name(P, shape, rays, world):
             f"packed-record all-gather per solve (BASELINE configs[2] at 8 GPUs)")
 
 
-KERNEL_OF = {0: "divq_kernel<float,{r},ML=0,FAST,F32GEN> (one cell per lane, independent rays)",
+KERNEL_OF = {0: "divq_indep_kernel<{r}> (independent rays, blocked half-packed records, per-lane refill)",
              1: "divq_quad_kernel<{r}> (warp-shared direction)", 2: "divq_quad_kernel<{r}> (lockstep translates)"}
 COHERENCE_NAME = {0: "independent per (cell, ray, timestep) -- the reference's sampling", 1: "warp-shared direction",
                   2: "warp-shared direction and in-cell offset (lockstep translates)"}
@@ -254,7 +254,8 @@ class SingleLevelSolve:
         skip = 0 if args.reference_semantics else 1
         self.g = g = RMCRT(device=local, nDivQRays=rays, threshold=0.05, seed=1234, skipZeroWeightLegs=skip, l2Persist=args.l2persist,
                            warpsPerTile=args.warps, tileX=args.tile_x, cellsPerLane=cells_per_lane, genericMarch=args.generic_march,
-                           maxBlocksPerSM=args.max_blocks_per_sm, half_records=bool(half), **kw)
+                           maxBlocksPerSM=args.max_blocks_per_sm, half_records=bool(half), blockedMarch=args.blocked_march,
+                           refillLanes=args.refill_lanes, **kw)
         self.coherence = int(g.params.rayCoherence)
         self.stream = stream = torch.cuda.current_stream()
         lvl = LevelData(None, None, None, lo, hi, dx, interior_lo=(0, 0, 0), interior_hi=shape)
@@ -277,8 +278,10 @@ class SingleLevelSolve:
         self.kernel_name = KERNEL_OF[self.coherence if cells_per_lane == 4 or self.coherence == 0 else 0].format(r="Rec4" if half else "Rec8")
         if self.coherence >= 1 and cells_per_lane == 2:
             self.kernel_name = f"divq_dual_kernel<{'Rec4' if half else 'Rec8'}>"
-        if self.coherence >= 1 and cells_per_lane == 1:
-            self.kernel_name = KERNEL_OF[0].format(r="Rec4" if half else "Rec8").replace("independent rays", "warp-shared direction")
+        if (self.coherence >= 1 and cells_per_lane == 1) or (self.coherence == 0 and not args.blocked_march):
+            self.kernel_name = f"divq_kernel<float,{'Rec4' if half else 'Rec8'},ML=0,FAST,F32GEN> (one cell per lane)"
+        if self.coherence == 0 and args.blocked_march:
+            self.kernels_per_step += 1          # blk_build_kernel: the blocked copy is rebuilt after every re-pack
 
     def replicate(self, props=None):
         g, st = self.g, self.stream
@@ -595,6 +598,8 @@ def main():
     ap.add_argument("--max-blocks-per-sm", type=int, default=0, help="cap the divQ grid (0: one tile per block)")
     ap.add_argument("--generic-march", type=int, default=0, help="1: generic march template instead of the tuned fast path (A/B)")
     ap.add_argument("--reference-semantics", action="store_true", help="march the zero-weight reflected legs like the reference")
+    ap.add_argument("--blocked-march", type=int, default=1, help="rayCoherence 0: 1 = divq_indep_kernel on the blocked half-packed copy (library default), 0 = one-cell kernel (A/B)")
+    ap.add_argument("--refill-lanes", type=int, default=0, help="divq_indep_kernel: waiting lanes that trigger ray set-up (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--configs-n", type=int, default=256, help="cells per side of the configs sub-records (256^3 single level, C4, C5)")
     ap.add_argument("--no-sweeps", action="store_true", help="skip by_coherence and the configs sub-records (A/B runs, profiling)")

@@ -33,8 +33,10 @@ def make(**kw):
     return RMCRT(device=0, **kw)
 
 
-def accept(d, mu, sd, K, ctl, what, flow=None):
-    """criteria (i), (ii), (iv); returns the numbers for the report"""
+def accept(d, mu, sd, K, ctl, what, flow=None, draws_per_cell=1.0):
+    """criteria (i), (ii), (iv); returns the numbers for the report.  draws_per_cell < 1 (opt-in batched modes only): the cells of a warp
+    tile share their rays, so the fractions of (i) are estimated from cells * draws_per_cell independent draws -- three binomial standard
+    deviations of that smaller sample are allowed; the default sampling is held to the reference's own minimum without any allowance."""
     mu = mu.astype(np.float64); sd = sd.astype(np.float64)
     sel = np.ones(mu.shape, bool) if flow is None else flow
     z = np.abs(d[sel] - mu[sel]) / (sd[sel] * np.sqrt(1 + 1 / K) + 1e-300)
@@ -45,9 +47,12 @@ def accept(d, mu, sd, K, ctl, what, flow=None):
     rep = dict(what=what, f3=f3, f3_ref_min=min(ctl["loo_f3"]), f5=f5, f5_ref_min=min(ctl["loo_f5"]), l2=l2, l2_ref_max=max(ctl["loo_l2"]),
                bias_in_se=bias / se)
     print(json.dumps(rep))
-    assert f3 >= min(ctl["loo_f3"]), rep
-    assert f5 >= min(ctl["loo_f5"]), rep
-    assert l2 <= max(ctl["loo_l2"]), rep
+    n_eff = sel.sum() * draws_per_cell
+    a3 = 0.0 if draws_per_cell >= 1 else 3 * np.sqrt(0.975 * 0.025 / n_eff)
+    a5 = 0.0 if draws_per_cell >= 1 else 3 * np.sqrt(0.998 * 0.002 / n_eff)
+    assert f3 >= min(ctl["loo_f3"]) - a3, rep
+    assert f5 >= min(ctl["loo_f5"]) - a5, rep
+    assert l2 <= max(ctl["loo_l2"]) * (1.0 if draws_per_cell >= 1 else 1.0 + 3 / np.sqrt(2 * n_eff)), rep
     return rep
 
 
@@ -70,7 +75,8 @@ def test_single_level_at_size(gpu_lib, po, case, half, coh):
         out = g.trace_divq(0, (0, 0, z0), (N, N, z1), out_lo=(0, 0, z0), out_hi=(N, N, z1), timestep=7)
         d = out["divQ"]
         assert np.all(d != 0) and np.all(out["radiationVolq"] > 0)
-        rep = accept(d, fx[f"mu{si}"], fx[f"sd{si}"], K, meta[f"control{si}"], f"{case} half={half} coh={coh} slab [{z0},{z1})")
+        rep = accept(d, fx[f"mu{si}"], fx[f"sd{si}"], K, meta[f"control{si}"], f"{case} half={half} coh={coh} slab [{z0},{z1})",
+                     draws_per_cell=1.0 if coh == 0 else 1.0 / 128)
         assert abs(rep["bias_in_se"]) <= (4 if coh == 0 else 4 * np.sqrt(128)), rep     # batched modes: one tile = one draw
         if z0 <= N // 2 < z1 and coh == 0:       # (iii): both centre lines of the plane through cell N/2
             ref = np.array(meta["centreline_L2"])

@@ -1,0 +1,115 @@
+"""divq_indep_kernel (indep.cuh): the production kernel of the default sampling (rayCoherence 0) -- blocked half-packed records, one
+256-bit load per 2 x 2 x 2 block, per-lane ray refill -- against the one-cell-per-lane kernel (blockedMarch = 0) on the SAME Philox rays
+(both key direction and origin on (cell, ray, timestep)), and against the oracle."""
+import numpy as np
+import pytest
+
+from util import add_random_walls
+
+pytestmark = pytest.mark.gpu
+
+
+def make(**kw):
+    from uintah_b200 import RMCRT
+    return RMCRT(device=0, **kw)
+
+
+def solve(lv, patch=None, **kw):
+    g = make(**kw)
+    g.upload_level(0, lv)
+    plo, phi = patch if patch else (None, None)
+    out = g.trace_divq(0, patch_lo=plo, patch_hi=phi, timestep=6)
+    c = g.counters()
+    g.close()
+    return out["divQ"], out["radiationVolq"], int(c.nRaySteps), int(c.nDivQCells)
+
+
+@pytest.mark.parametrize("case", ["bc_walls_odd_patch", "plates_mirrors", "bc_refsem"])
+def test_blocked_march_matches_one_cell_kernel(gpu_lib, po, case):
+    """same rays, same fp16 properties (half-packed level records for the one-cell kernel): divQ to FP32 round-off, executed steps and
+    written cells equal (ties of the axis choice aside)"""
+    rng = np.random.default_rng(4)
+    kw = dict(nDivQRays=24, threshold=0.05, seed=13, half_records=True)
+    patch = None
+    if case == "bc_walls_odd_patch":
+        lv = po.burns_christon(37, dtype=np.float32)
+        add_random_walls(lv, 0.03, rng, abskg=0.8, sigmaT4=0.25)
+        patch = ((3, 5, 2), (36, 30, 11))                  # partial 32 x 2 x 2 blocks on every side, odd offsets
+    elif case == "plates_mirrors":                         # several reflections per ray, hot black walls
+        lv = po.parallel_plates(24, dtype=np.float32, mirror_faces=("x-", "y-"))
+        kw["threshold"] = 0.001
+    else:                                                  # the reference's zero-weight second legs are marched
+        lv = po.burns_christon(24, dtype=np.float32)
+        kw["skipZeroWeightLegs"] = 0
+    d1, v1, n1, c1 = solve(lv, patch, blockedMarch=0, **kw)
+    d2, v2, n2, c2 = solve(lv, patch, blockedMarch=1, **kw)
+    assert c1 == c2 and c1 > 0
+    assert np.array_equal(d1 == 0, d2 == 0) and np.array_equal(v1 == 0, v2 == 0)
+    assert abs(n1 - n2) <= 3e-4 * n1, (n1, n2)
+    # the ray sums (radiationVolq = 4 pi sumI / N) agree to FP32 round-off; divQ additionally differs by the fp16 rounding of the origin
+    # cell's own sigmaT4/pi, which the blocked kernel's epilogue uses on purpose (<= 2^-11 relative on the emission term)
+    scale = np.abs(v1).max()
+    diff = np.abs(v1 - v2)
+    assert np.percentile(diff, 99.9) <= 1e-4 * scale and diff.max() <= 2e-2 * scale, (np.percentile(diff, 99.9) / scale, diff.max() / scale)
+    assert np.linalg.norm(v1 - v2) / np.linalg.norm(v1) < 3e-4
+    assert np.abs(d1 - d2).max() <= 2e-2 * np.abs(d1).max() and np.linalg.norm(d1 - d2) / np.linalg.norm(d1) < 1.5e-3
+
+
+def test_blocked_march_on_float_records(gpu_lib, po):
+    """float (8-B) level records: the blocked copy is their fp16 rounding -- divQ within the fp16 rounding of the properties along the
+    rays of the one-cell kernel marching the float records, same masks"""
+    rng = np.random.default_rng(5)
+    lv = po.burns_christon(32, dtype=np.float32)
+    add_random_walls(lv, 0.01, rng)
+    kw = dict(nDivQRays=32, threshold=0.05, seed=21)
+    d1, _, n1, c1 = solve(lv, None, blockedMarch=0, **kw)
+    d2, _, n2, c2 = solve(lv, None, blockedMarch=1, **kw)
+    assert c1 == c2 and np.array_equal(d1 == 0, d2 == 0)
+    assert abs(n1 - n2) <= 5e-4 * n1
+    scale = np.abs(d1).max()
+    diff = np.abs(d1 - d2)[d1 != 0]
+    assert np.percentile(diff, 99.5) < 1.5e-3 * scale and np.linalg.norm(d1 - d2) / np.linalg.norm(d1) < 1e-3
+
+
+def test_isothermal_enclosure_is_exact(gpu_lib, po):
+    """sigmaT4/pi = 0.6 is NOT exact in fp16: the epilogue uses the same fp16 value the rays integrate, so divQ == 0 to FP32 round-off"""
+    rng = np.random.default_rng(6)
+    M = 27
+    ab = rng.uniform(0.1, 2.0, (M, M, M)).astype(np.float32); s4 = np.full((M, M, M), 0.6, np.float32); ct = np.full((M, M, M), -1, np.int32)
+    for ax in range(3):
+        for idx in (0, M - 1):
+            sl = [slice(None)] * 3; sl[ax] = idx; ct[tuple(sl)] = 8; ab[tuple(sl)] = 1.0
+    walls = (rng.uniform(size=(M, M, M)) < 0.03) & (ct == -1); ct[walls] = 8; ab[walls] = 1.0
+    iso = po.Level(ab, s4, ct, (-1,) * 3, (M - 1,) * 3, (1.0 / 25,) * 3, interior_lo=(0,) * 3, interior_hi=(25,) * 3)
+    for half in (False, True):
+        d, _, _, c = solve(iso, None, nDivQRays=8, threshold=0.001, seed=5, allowReflect=0, half_records=half)
+        assert np.abs(d).max() < 2e-5 * 4 * np.pi * 2.0 * 0.6
+        assert c == int((ct == -1).sum())
+
+
+def test_refill_threshold_does_not_change_results(gpu_lib, po):
+    """the rays of a cell and their order are fixed by (cell, ray index): any refill batching gives bit-identical divQ"""
+    lv = po.burns_christon(20, dtype=np.float32)
+    ref = None
+    for rl in (1, 8, 32):
+        d, _, n, _ = solve(lv, None, nDivQRays=10, threshold=0.05, seed=2, refillLanes=rl)
+        if ref is None:
+            ref = (d, n)
+        assert np.array_equal(d, ref[0]) and n == ref[1]
+
+
+def test_monte_carlo_tolerance_41(gpu_lib, po):
+    """BASELINE config 1 through the default kernel: SURVEY 8c (i)-(iii) against 8 oracle seeds, unrelaxed"""
+    from util import candidate_stats, loo_control
+    lv = po.burns_christon(41)
+    p = po.default_params(nDivQRays=100, threshold=0.05, isSeedRandom=1)
+    runs = [po.ray_trace(p, lv, seed=100 * s, patches=(1, 1, 8), threads=8)["divQ"] for s in range(1, 9)]
+    g = make(nDivQRays=100, threshold=0.05, seed=2024)
+    g.upload_level(0, lv)
+    d = g.trace_divq(0)["divQ"]
+    inner = (slice(1, -1),) * 3
+    c3, c5, cl2 = loo_control(runs, inner)
+    f3, f5, l2 = candidate_stats(d, runs, inner)
+    assert f3 >= min(c3) and f5 >= min(c5) and l2 <= max(cl2), (f3, c3, f5, c5, l2, cl2)
+    L2_ref = [po.centreline_L2(r, 41)[0] for r in runs]
+    assert po.centreline_L2(d, 41)[0] <= max(L2_ref), (po.centreline_L2(d, 41)[0], L2_ref)

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "librmcrt_b200.so")
 SOURCES = ["rmcrt_b200.cu"]
-HEADERS = ["march.cuh", "rng.cuh", os.path.join("..", "..", "include", "rmcrt_b200.h")]
+HEADERS = ["march.cuh", "rng.cuh", "indep.cuh", os.path.join("..", "..", "include", "rmcrt_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-ldl"]

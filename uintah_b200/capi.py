@@ -44,6 +44,7 @@ class Params(C.Structure):
         ("fixedRandom", C.c_int32), ("l2Persist", C.c_int32), ("warpsPerTile", C.c_int32),
         ("genericMarch", C.c_int32), ("maxBlocksPerSM", C.c_int32), ("rayDirSampleAlgo", C.c_int32), ("cellsPerLane", C.c_int32),
         ("maxRayLength", C.c_double), ("sigmaScat", C.c_double), ("tileX", C.c_int32), ("nonFlowCellType", C.c_int32),
+        ("blockedMarch", C.c_int32), ("refillLanes", C.c_int32),
     ]
 
 

@@ -1,0 +1,141 @@
+// indep.cuh -- the production march of the DEFAULT sampling (rayCoherence 0): every (cell, ray) has its own direction and in-cell origin
+// (Philox keyed on (cell, ray, timestep), the reference's independent rays: Ray.cc:539,757-771), so the 32 lanes of a warp gather from 32
+// unrelated places and nothing of the lockstep machinery of march_leg_pair / _quad applies.
+//
+// What binds such a march on B200 (ncu, profiles/r02v1_divq_coh0_128_ncu.md): every ray-cell step of the one-cell-per-lane kernel is one
+// 32-B sector request from L1 to L2 -- the SM's miss-request path (one request per clock, 96 % busy) and the L2 -> SM bandwidth (77 %) --
+// issued by warps whose lanes finish at very different steps (13.4 of 32 lanes active).  Two things are done about it here:
+//
+//  * BLOCKED HALF-PACKED RECORDS.  The level is kept a second time as 2 x 2 x 2 cell blocks of 4-B half-packed records (the Rec4 word of
+//    march.cuh): one block = one 32-B sector.  A lane fetches the whole block it enters with ONE 256-bit load (LDG.E.256) into its private
+//    slot of shared memory and takes the records of the cells it visits inside the block from there.  A ray visits two cells per block on
+//    average (mean chord of a 2-cube over the mean chord of a cell), so the global sector requests per ray-cell step halve.
+//  * PER-LANE RAY REFILL.  A lane owns one origin cell and walks through ITS rays on its own: when a ray ends the lane starts its next one
+//    (in batches: ray set-up runs when at least REFILL lanes of the warp wait, so its ~100 instructions are shared), instead of idling until
+//    the longest ray of the warp's batch ends.  The work of a lane is the sum over all its rays (relative spread 7 % at 100 rays) rather
+//    than the maximum over the warp of single ray lengths (relative spread 70 %).
+//
+// Per-ray arithmetic is that of march_single_level_fast (offset-form tau, one ex2 per step, integral per leg scaled by fs at the wall,
+// reflections without recomputing tMax -- RMCRTCommon.cc:607-904), on the fp16 properties of the blocked copy.
+#pragma once
+#include "march.cuh"
+
+namespace rmcrt {
+
+struct BlkGeom {
+  const uint32_t* blk;   // [block][8]: word (x&1) | (y&1)<<1 | (z&1)<<2 of block (x>>1, y>>1, z>>1), x-fastest block order; 32-B aligned
+  int bx, bxy;           // blocks per row, per plane (one guard block of wall records on every side of the level)
+  int lo[3];             // cell index of block-local coordinate 0 (= level lo - 2)
+};
+
+#if defined(__CUDACC__)
+// A lane's slot in shared memory: two 16-B chunks, chunk c of thread t at byte (c * 128 + t) * 16 of the block's slot array (128 threads).
+// The position of a cell inside its 2 x 2 x 2 block is kept directly as the byte offset of its word in the slot:
+constexpr unsigned OX = 4u, OY = 8u, OZ = 2048u;     // x&1 -> +4 B, y&1 -> +8 B, z&1 -> the second chunk
+constexpr int ONEG = 12;                             // bits (OX|OY|OZ) << ONEG of the same word: the direction is negative on that axis
+
+// one 2 x 2 x 2 block (32 B, one sector) -> the calling thread's slot (slot = 32-bit shared-window address of its first chunk)
+__device__ __forceinline__ void blk_fetch(const uint32_t* __restrict__ blk, int B, uint32_t slot) {
+  uint32_t v0, v1, v2, v3, v4, v5, v6, v7;
+  const uint32_t* p = blk + (size_t)B * 8;
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3), "=r"(v4), "=r"(v5), "=r"(v6), "=r"(v7) : "l"(p));
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(slot), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
+  asm volatile("st.shared.v4.b32 [%0+2048], {%1,%2,%3,%4};" :: "r"(slot), "r"(v4), "r"(v5), "r"(v6), "r"(v7) : "memory");
+}
+__device__ __forceinline__ uint32_t blk_word(uint32_t slot, unsigned o) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(slot + (o & (OX | OY | OZ))) : "memory");
+  return v;
+}
+
+// state of one lane's current ray
+struct IndepRay {
+  float tx, ty, tz;          // tMax, scaled by log2(e)
+  float ddx, ddy, ddz;       // tDelta
+  int B;                     // block index of the current cell
+  int sbx, sby, sbz;         // signed block strides of the three axes (flip on reflection)
+  unsigned o;                // OX|OY|OZ bits: position of the current cell inside its block; the same bits << ONEG: direction negative
+  float A, k, s, ePrev, leg, tau;
+  float fs, sum, nsteps;
+};
+
+// step into the neighbour cell across the face of axis `obit` (OX, OY or OZ) in the ray's direction; returns the raw record word
+__device__ __forceinline__ uint32_t indep_enter(IndepRay& r, unsigned obit, int stepB, const uint32_t* __restrict__ blk, uint32_t slot) {
+  r.o ^= obit;
+  // the block changes when a positive step wraps the position bit to 0 or a negative step wraps it to 1
+  if (((r.o ^ (r.o >> ONEG)) & obit) == 0u) {
+    r.B += stepB;
+    blk_fetch(blk, r.B, slot);
+  }
+  return blk_word(slot, r.o);
+}
+
+__device__ __forceinline__ void indep_decode(IndepRay& r, uint32_t word) {
+  r.k = fabsf(__half2float(__ushort_as_half((unsigned short)(word >> 16))));
+  r.s = __half2float(__ushort_as_half((unsigned short)(word & 0xFFFFu)));
+}
+
+// one DDA step of a live ray.  Returns false when the ray has ended (its contribution is then in r.sum, its steps in r.nsteps).
+__device__ __forceinline__ bool indep_step(IndepRay& r, const uint32_t* __restrict__ blk, uint32_t slot, float threshold,
+                                           bool allowReflect, bool skipZero) {
+  // axis with the smallest tMax, strict '<' tie order of RMCRTCommon.cc:696-708 (dda_peek)
+  const bool a = r.tx < r.ty;
+  const float m = fminf(r.tx, r.ty);
+  const bool nz_ = m < r.tz;
+  const bool px = a && nz_, py = !a && nz_;
+  const float t = fminf(m, r.tz);
+  r.tx = px ? r.tx + r.ddx : r.tx;
+  r.ty = py ? r.ty + r.ddy : r.ty;
+  r.tz = nz_ ? r.tz : r.tz + r.ddz;
+  const unsigned obit = px ? OX : (py ? OY : OZ);
+  const int stepB = px ? r.sbx : (py ? r.sby : r.sbz);
+  uint32_t word = indep_enter(r, obit, stepB, blk, slot);
+  // integ_cross
+  r.tau = fmaf(r.k, t, r.A);
+  const float e = Num<float>::attenuation(r.tau);
+  r.leg = fmaf(r.s, r.ePrev - e, r.leg);
+  r.ePrev = e;
+  r.nsteps += 1.0f;
+  indep_decode(r, word);
+  r.A = fmaf(-r.k, t, r.tau);
+  if ((int)word >= 0) return true;                         // still in a flow cell
+  // ---- a non-flow cell was entered: wall emission, threshold test, reflection (RMCRTCommon.cc:846-902; march_single_level_fast)
+  r.sum = fmaf(r.leg, r.fs, r.sum);
+  r.leg = 0.0f;
+  const float eps = r.k > 1.0f ? 1.0f : r.k;
+  r.sum = fmaf(eps * r.s, r.ePrev, r.sum);                 // not weighted by fs
+  const float intensity = r.ePrev * r.fs;
+  if (!allowReflect || !(intensity > threshold)) return false;
+  r.fs *= (1.0f - r.k);
+  if (skipZero && r.fs == 0.0f) return false;
+  // reflect: back into the cell the ray came from, stepping direction of that axis flipped, tMax NOT recomputed
+  r.o ^= obit << ONEG;
+  if (px) r.sbx = -r.sbx; else if (py) r.sby = -r.sby; else r.sbz = -r.sbz;
+  word = indep_enter(r, obit, -stepB, blk, slot);
+  indep_decode(r, word);
+  r.A = fmaf(-r.k, t, r.tau);
+  return true;
+}
+
+// start a ray in the origin cell (block B0, position o0): dir never exactly zero (nz<>), rayDx = origin offset from the cell's low corner
+__device__ __forceinline__ void indep_start(IndepRay& r, int B0, unsigned o0, float dx, float dy, float dz, float rx, float ry, float rz,
+                                            float cx, float cy, float cz, const BlkGeom& g, uint32_t slot) {
+  typedef Num<float> N;
+  const bool posx = !sign_bit(dx), posy = !sign_bit(dy), posz = !sign_bit(dz);
+  const float ix = N::rcp(dx), iy = N::rcp(dy), iz = N::rcp(dz);
+  r.tx = ((posx ? cx : 0.0f) - rx) * ix * N::LEN_SCALE;
+  r.ty = ((posy ? cy : 0.0f) - ry) * iy * N::LEN_SCALE;
+  r.tz = ((posz ? cz : 0.0f) - rz) * iz * N::LEN_SCALE;
+  r.ddx = fabsf(ix) * cx * N::LEN_SCALE; r.ddy = fabsf(iy) * cy * N::LEN_SCALE; r.ddz = fabsf(iz) * cz * N::LEN_SCALE;
+  r.sbx = posx ? 1 : -1; r.sby = posy ? g.bx : -g.bx; r.sbz = posz ? g.bxy : -g.bxy;
+  r.o = o0 | (posx ? 0u : OX << ONEG) | (posy ? 0u : OY << ONEG) | (posz ? 0u : OZ << ONEG);
+  r.B = B0;
+  blk_fetch(g.blk, B0, slot);
+  indep_decode(r, blk_word(slot, o0));
+  r.A = 0.0f; r.ePrev = 1.0f; r.leg = 0.0f; r.tau = 0.0f;
+  r.fs = 1.0f; r.sum = 0.0f; r.nsteps = 0.0f;
+}
+#endif
+
+}  // namespace rmcrt

@@ -13,6 +13,7 @@
 #include "../../include/rmcrt_b200.h"
 #include "march.cuh"
 #include "rng.cuh"
+#include "indep.cuh"
 
 #include <cuda_runtime.h>
 #include <cub/device/device_select.cuh>
@@ -671,6 +672,117 @@ __global__ void __launch_bounds__(128, (!ONION && std::is_same<RecT, Rec8>::valu
 }
 
 //======================================================================================================
+// The production kernel of the DEFAULT sampling (rayCoherence 0, independent rays per (cell, ray, timestep)): indep.cuh.
+// One WARP = one tile of 8 x 2 x 2 origin cells, lane = cell; a lane traces ALL nDivQRays rays of its cell one after the other (per-lane
+// refill), so nothing is reduced across warps and there is no barrier; a block is four independent warps (32 x 2 x 2 cells).  The
+// records come from the blocked half-packed copy of the level (BlkGeom), one 256-bit load per 2 x 2 x 2 block entered.
+//======================================================================================================
+#ifndef RMCRT_INDEP_BLOCKS
+#define RMCRT_INDEP_BLOCKS 8       // resident 128-thread blocks per SM the register budget is cut for
+#endif
+#ifndef RMCRT_INDEP_REFILL
+#define RMCRT_INDEP_REFILL 8       // ray set-up runs when this many lanes of the warp wait for a new ray (or nothing else is left to do)
+#endif
+#ifndef RMCRT_INDEP_BURST
+#define RMCRT_INDEP_BURST 8        // DDA steps between two looks at the warp's refill state
+#endif
+template <class RecT>
+__global__ void __launch_bounds__(128, RMCRT_INDEP_BLOCKS) divq_indep_kernel(const __grid_constant__ TraceArgs a, const BlkGeom bg, int nxc, int njp, int nkp,
+                                                                             int refill) {
+  __shared__ __align__(16) uint32_t slots[2 * 128 * 4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int F = a.G.maxLevels - 1;
+  const LevelGeom& g = a.G.lev[F];
+  const bool skipZero = skip_allowed(a);
+  constexpr float UNSCALE = 1.0f / HALF_S_SCALE;
+  // block -> (xc, jp, kp): 32 x 2 x 2 cells; warp -> its 8 x 2 x 2 tile; lane -> cell
+  const long long tile = blockIdx.x;
+  const int xc = (int)(tile % nxc);
+  const long long rest = tile / nxc;
+  const int jp = (int)(rest % njp), kp = (int)(rest / njp);
+  const int li = xc * 32 + warp * 8 + (lane & 7), lj = 2 * jp + ((lane >> 3) & 1), lk = 2 * kp + (lane >> 4);
+  const bool valid = li < a.patchN[0] && lj < a.patchN[1] && lk < a.patchN[2];
+  const int i = a.patchLo[0] + li, j = a.patchLo[1] + lj, k = a.patchLo[2] + lk;
+  unsigned long long cellId = 0;
+  Rec8 r0{0, 0};
+  bool flow = false;
+  if (valid) {
+    cellId = (unsigned long long)level_index(g, i, j, k);
+    // epilogue properties of the origin cell at full precision
+    if constexpr (std::is_same<RecT, Rec4>::value) r0 = ldrec(static_cast<const Rec8*>(g.recFull) + cellId);
+    else r0 = ldrec(static_cast<const Rec8*>(g.rec) + cellId);
+    flow = !is_wall(r0.k);
+  }
+  const int ux = i - bg.lo[0], uy = j - bg.lo[1], uz = k - bg.lo[2];
+  const int B0 = (ux >> 1) + bg.bx * (uy >> 1) + bg.bxy * (uz >> 1);
+  const unsigned o0 = ((ux & 1) ? OX : 0u) | ((uy & 1) ? OY : 0u) | ((uz & 1) ? OZ : 0u);
+  const uint32_t slot = (uint32_t)__cvta_generic_to_shared(slots) + (uint32_t)tid * 16u;
+  const uint32_t* __restrict__ blk = bg.blk;
+  const float cx = (float)g.dx[0], cy = (float)g.dx[1], cz = (float)g.dx[2];
+  const float thr = (float)a.threshold;
+  const bool reflect = a.allowReflect != 0;
+
+  IndepRay r;
+  double acc = 0;
+  unsigned long long steps = 0;
+  int next = 0;              // next ray index of this lane
+  bool alive = false;
+  const int nRays = (flow && 1.0f > thr) ? a.nRays : 0;      // `while (intensity > d_threshold)`, RMCRTCommon.cc:680
+  for (;;) {
+    const bool want = !alive && next < nRays;
+    const unsigned needm = __ballot_sync(0xffffffffu, want);
+    const unsigned livem = __ballot_sync(0xffffffffu, alive);
+    if ((needm | livem) == 0u) break;
+    if (needm != 0u && (__popc(needm) >= refill || livem == 0u)) {
+      if (want) {
+        float dir[3], rayDx[3];
+        gen_divq_ray_f32(a.rng, g, next, cellId, cellId, dir, rayDx);
+        ++next;
+        indep_start(r, B0, o0, nz<float, float>(dir[0]), nz<float, float>(dir[1]), nz<float, float>(dir[2]), rayDx[0], rayDx[1], rayDx[2],
+                    cx, cy, cz, bg, slot);
+        alive = true;
+      }
+    }
+#pragma unroll 1
+    for (int m = 0; m < RMCRT_INDEP_BURST; ++m) {
+      if (alive) {
+        if (!indep_step(r, blk, slot, thr, reflect, skipZero)) {
+          alive = false;
+          acc += (double)(UNSCALE * r.sum);
+          steps += (unsigned long long)r.nsteps;
+        }
+      }
+    }
+  }
+  unsigned long long cells = 0;
+  if (valid) {
+    const long long q = (long long)(i - a.outLo[0]) +
+                        (long long)a.outN[0] * ((long long)(j - a.outLo[1]) + (long long)a.outN[1] * (long long)(k - a.outLo[2]));
+    if (flow) {
+      const double mean = acc / a.nRays;
+      // emission of the origin cell with the SAME fp16 sigmaT4/pi its rays integrate, so that an isothermal enclosure gives divQ == 0
+      // whatever the rounding (abskg multiplies both terms: full precision)
+      const uint32_t w0 = __ldg(blk + (size_t)B0 * 8 + (((o0 & OX) ? 1 : 0) | ((o0 & OY) ? 2 : 0) | ((o0 & OZ) ? 4 : 0)));
+      const double s0 = (double)(UNSCALE * __half2float(__ushort_as_half((unsigned short)(w0 & 0xFFFFu))));
+      a.divQ[q] = -4.0 * M_PI * (double)r0.k * (s0 - mean);      // Ray.cc:775,778
+      a.volq[q] = 4.0 * M_PI * mean;
+      cells = 1;
+    } else if (a.zeroNonFlow) {
+      a.divQ[q] = 0.0;
+      a.volq[q] = 0.0;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    steps += __shfl_down_sync(0xffffffffu, steps, o);
+    cells += __shfl_down_sync(0xffffffffu, cells, o);
+  }
+  if (lane == 0) {
+    if (steps) atomicAdd(a.counters + 0, steps);
+    if (cells) atomicAdd(a.counters + 2, cells);
+  }
+}
+
+//======================================================================================================
 // boundary flux
 //======================================================================================================
 // Ray::has_a_boundary (Ray.cc:1517-1572): `celltype[adj]+1 != 0`  <=>  adj is not a flow cell  <=>  record sign bit.
@@ -967,6 +1079,33 @@ __global__ void finalize_kernel(const RecT* __restrict__ recs, Box b, unsigned* 
   if (threadIdx.x == 0) {
     const unsigned t = atomicAdd(status + 4, 1u);
     if (t == gridDim.x - 1) { __threadfence(); atomicExch(status + 3, 1u); }
+  }
+}
+
+// blocked half-packed copy of a level (indep.cuh): thread = one 2 x 2 x 2 block of the guard-padded block grid
+template <class RecT>
+__global__ void blk_build_kernel(const RecT* __restrict__ recs, Box lb, uint32_t* __restrict__ blk, int bx, int by, int bz) {
+  const long long n = (long long)bx * by * bz;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const int b0 = (int)(t % bx);
+    const long long rest = t / bx;
+    const int b1 = (int)(rest % by), b2 = (int)(rest / by);
+    uint32_t w[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      // block-local coordinate 0 = cell lb.lo - 2
+      const int x = 2 * b0 + (c & 1) - 2, y = 2 * b1 + ((c >> 1) & 1) - 2, z = 2 * b2 + (c >> 2) - 2;
+      uint32_t v = 0x80000000u;                     // guard: a wall with abskg 0, sigmaT4 0
+      if (x >= 0 && x < lb.n[0] && y >= 0 && y < lb.n[1] && z >= 0 && z < lb.n[2]) {
+        const long long f = (long long)x + (long long)lb.n[0] * ((long long)y + (long long)lb.n[1] * (long long)z);
+        if constexpr (std::is_same<RecT, Rec4>::value) v = recs[f].w;
+        else { const Rec8 r = ldrec(recs + f); v = encode_rec4(r.k, r.s).w; }
+      }
+      w[c] = v;
+    }
+    uint4* o = reinterpret_cast<uint4*>(blk + t * 8);
+    o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    o[1] = make_uint4(w[4], w[5], w[6], w[7]);
   }
 }
 
@@ -1308,6 +1447,11 @@ struct LevelState {
   long long nCells = 0;
   size_t recBytes = 8;
   bool propsFloat = false;   // the last pack read float property arrays
+  // blocked half-packed copy for the independent-ray march (indep.cuh), built on demand after the level last changed
+  void* blk = nullptr;
+  size_t blkCap = 0;
+  bool blkValid = false;
+  int blkDims[3] = {0, 0, 0};
 };
 
 struct DevBuf {
@@ -1446,6 +1590,7 @@ unsigned* lstat_of(const rmcrt_ctx* ctx, int L) { return ctx->d_lstat + (size_t)
 // every modification of a level clears its device-side "valid" word (stream-ordered)
 int invalidate_level(rmcrt_ctx* ctx, int L, cudaStream_t st) {
   ctx->lv[L].finalized = false;
+  ctx->lv[L].blkValid = false;
   CK(cudaMemsetAsync(lstat_of(ctx, L) + 3, 0, sizeof(unsigned), st));
   return 0;
 }
@@ -1626,6 +1771,36 @@ int build_args(rmcrt_ctx* ctx, int maxLevels, bool multiLevel, const int32_t pLo
   return 0;
 }
 
+// blocked half-packed copy of level L (indep.cuh), rebuilt when the level changed since the last build (stream-ordered)
+template <class RecT>
+int ensure_blocked_level(rmcrt_ctx* ctx, int L, BlkGeom& bg, cudaStream_t st) {
+  LevelState& s = ctx->lv[L];
+  int nb[3];
+  for (int d = 0; d < 3; ++d) nb[d] = (s.d.hi[d] - s.d.lo[d] + 4 + 1) / 2;        // cells [lo - 2, hi + 2) in 2-cell blocks
+  const size_t bytes = (size_t)nb[0] * nb[1] * nb[2] * 32;
+  if ((long long)nb[0] * nb[1] * nb[2] >= (1LL << 31)) return fail(ctx, RMCRT_ERR_INVALID, "level too large for the blocked march");
+  if (bytes > s.blkCap) {
+    if (s.blk) cudaFree(s.blk);
+    s.blk = nullptr; s.blkCap = 0;
+    CK(cudaMalloc(&s.blk, bytes));
+    s.blkCap = bytes;
+    s.blkValid = false;
+  }
+  if (!s.blkValid || s.blkDims[0] != nb[0] || s.blkDims[1] != nb[1] || s.blkDims[2] != nb[2]) {
+    if constexpr (!std::is_same<RecT, Rec16>::value) {
+      blk_build_kernel<RecT><<<grid_for((long long)nb[0] * nb[1] * nb[2], 256, ctx->smCount), 256, 0, st>>>(
+          static_cast<const RecT*>(s.rec), mkbox(s.d.lo, s.d.hi), static_cast<uint32_t*>(s.blk), nb[0], nb[1], nb[2]);
+      CK(cudaGetLastError());
+    }
+    s.blkDims[0] = nb[0]; s.blkDims[1] = nb[1]; s.blkDims[2] = nb[2];
+    s.blkValid = true;
+  }
+  bg.blk = static_cast<const uint32_t*>(s.blk);
+  bg.bx = nb[0]; bg.bxy = nb[0] * nb[1];
+  for (int d = 0; d < 3; ++d) bg.lo[d] = s.d.lo[d] - 2;
+  return 0;
+}
+
 // The same single-level production solve when reflective walls keep the rays going (launch_gate 2): translates separate at the first
 // wall they do not reach at the same step and stay apart, so the four-cell kernel loses its point.  Pairs stacked in z reach every wall
 // normal to x or y together and go on jointly after the reflection (REJOIN); a black or z wall ends the joint march.
@@ -1757,6 +1932,18 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
         a2.gate = 1;
         divq_dual_kernel<RecT, false><<<(int)g2, 32 * W2, W2 * 64 * sizeof(double), st>>>(a2, nxc, njp, 0);
         launch_reflective_pairs<RecT>(ctx, a2, cap, st);
+      }
+    } else if (std::is_same<Real, float>::value && !bounded && f32gen && ctx->p.rayCoherence == 0 && ctx->p.blockedMarch && !ctx->p.genericMarch) {
+      // DEFAULT: independent rays per (cell, ray, timestep) on the blocked half-packed copy of the level (indep.cuh)
+      if constexpr (std::is_same<Real, float>::value && !std::is_same<RecT, Rec16>::value) {
+        BlkGeom bg;
+        int rc = ensure_blocked_level<RecT>(ctx, a.G.maxLevels - 1, bg, st);
+        if (rc) return rc;
+        const int nxc = (a.patchN[0] + 31) / 32, njp = (a.patchN[1] + 1) / 2, nkp = (a.patchN[2] + 1) / 2;
+        const long long gi = (long long)nxc * njp * nkp;
+        if (gi >= (1LL << 31)) return fail(ctx, RMCRT_ERR_INVALID, "patch too large");
+        const int refill = ctx->p.refillLanes > 0 ? std::min(ctx->p.refillLanes, 32) : RMCRT_INDEP_REFILL;
+        divq_indep_kernel<RecT><<<(int)gi, 128, 0, st>>>(a, bg, nxc, njp, nkp, refill);
       }
     } else if (std::is_same<Real, float>::value && !bounded && (!ctx->p.genericMarch || std::is_same<RecT, Rec4>::value)) {
       if (f32gen) divq_kernel<Real, RecT, false, true, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
@@ -1944,6 +2131,7 @@ void rmcrt_default_params(rmcrt_params* p) {
   p->maxRayLength = 0.0;       // unbounded (DBL_MAX, RMCRTCommon.cc:117)
   p->sigmaScat = 0.0;          // Ray.cc:169
   p->tileX = 0; p->nonFlowCellType = 8;
+  p->blockedMarch = 1; p->refillLanes = 0;
   p->cellsPerLane = 4;         // production: the 2 x 2 cells of a lane share one DDA (divq_quad_kernel); 2 = a pair (divq_dual_kernel); 1 = one cell per lane
 }
 
@@ -1992,7 +2180,7 @@ int rmcrt_set_params(rmcrt_ctx* ctx, const rmcrt_params* p) {
 void rmcrt_destroy(rmcrt_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  for (auto& l : ctx->lv) { if (l.base) cudaFree(l.base); if (l.recFull) cudaFree(l.recFull); }
+  for (auto& l : ctx->lv) { if (l.base) cudaFree(l.base); if (l.recFull) cudaFree(l.recFull); if (l.blk) cudaFree(l.blk); }
   if (ctx->d_counters) cudaFree(ctx->d_counters);
   if (ctx->d_lstat) cudaFree(ctx->d_lstat);
   if (ctx->d_nItems) cudaFree(ctx->d_nItems);
@@ -2023,11 +2211,13 @@ int rmcrt_define_level(rmcrt_ctx* ctx, int L, const rmcrt_level_desc* d, int rec
       memcmp(s.d.hi, d->hi, sizeof d->hi) == 0) {
     s.d = *d;              // same shape: keep the allocation (a new radiation solve re-packs into it)
     s.finalized = false;
+    s.blkValid = false;
     CK(cudaMemset(lstat_of(ctx, L), 0, LSTAT_WORDS * sizeof(unsigned)));
     return 0;
   }
   if (s.base) { cudaFree(s.base); s.base = nullptr; s.rec = nullptr; }
   if (s.recFull) { cudaFree(s.recFull); s.recFull = nullptr; }
+  s.blkValid = false;
   s.d = *d;
   s.recordKind = recordKind;
   s.recBytes = recordKind == 0 ? sizeof(Rec8) : (recordKind == 1 ? sizeof(Rec16) : sizeof(Rec4));
