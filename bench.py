@@ -229,7 +229,7 @@ def workload_name(P, shape, rays, world):
             f"packed-record all-gather per solve (BASELINE configs[2] at 8 GPUs)")
 
 
-KERNEL_OF = {0: "divq_indep_kernel<{r}> (independent rays, blocked half-packed records, per-lane refill)",
+KERNEL_OF = {0: "divq_kernel<float,{r},ML=0,FAST,F32GEN> (one cell per lane, independent rays)",
              1: "divq_quad_kernel<{r}> (warp-shared direction)", 2: "divq_quad_kernel<{r}> (lockstep translates)"}
 COHERENCE_NAME = {0: "independent per (cell, ray, timestep) -- the reference's sampling", 1: "warp-shared direction",
                   2: "warp-shared direction and in-cell offset (lockstep translates)"}
@@ -278,9 +278,10 @@ class SingleLevelSolve:
         self.kernel_name = KERNEL_OF[self.coherence if cells_per_lane == 4 or self.coherence == 0 else 0].format(r="Rec4" if half else "Rec8")
         if self.coherence >= 1 and cells_per_lane == 2:
             self.kernel_name = f"divq_dual_kernel<{'Rec4' if half else 'Rec8'}>"
-        if (self.coherence >= 1 and cells_per_lane == 1) or (self.coherence == 0 and not args.blocked_march):
-            self.kernel_name = f"divq_kernel<float,{'Rec4' if half else 'Rec8'},ML=0,FAST,F32GEN> (one cell per lane)"
+        if self.coherence >= 1 and cells_per_lane == 1:
+            self.kernel_name = f"divq_kernel<float,{'Rec4' if half else 'Rec8'},ML=0,FAST,F32GEN> (one cell per lane, warp-shared direction)"
         if self.coherence == 0 and args.blocked_march:
+            self.kernel_name = f"divq_indep_kernel<{'Rec4' if half else 'Rec8'}> (independent rays, blocked half-packed records, per-lane refill)"
             self.kernels_per_step += 1          # blk_build_kernel: the blocked copy is rebuilt after every re-pack
 
     def replicate(self, props=None):
@@ -598,7 +599,7 @@ def main():
     ap.add_argument("--max-blocks-per-sm", type=int, default=0, help="cap the divQ grid (0: one tile per block)")
     ap.add_argument("--generic-march", type=int, default=0, help="1: generic march template instead of the tuned fast path (A/B)")
     ap.add_argument("--reference-semantics", action="store_true", help="march the zero-weight reflected legs like the reference")
-    ap.add_argument("--blocked-march", type=int, default=1, help="rayCoherence 0: 1 = divq_indep_kernel on the blocked half-packed copy (library default), 0 = one-cell kernel (A/B)")
+    ap.add_argument("--blocked-march", type=int, default=0, help="rayCoherence 0: 0 = one-cell-per-lane kernel (library default), 1 = divq_indep_kernel on a blocked half-packed copy (A/B)")
     ap.add_argument("--refill-lanes", type=int, default=0, help="divq_indep_kernel: waiting lanes that trigger ray set-up (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--configs-n", type=int, default=256, help="cells per side of the configs sub-records (256^3 single level, C4, C5)")

@@ -106,10 +106,11 @@ typedef struct rmcrt_params {
                                   sectors per request.  The rays of a cell depend on the tile it falls in, not on the arithmetic. */
   int32_t  nonFlowCellType;    /* integer cell type the coarsening assumes for non-flow fine cells when it rebuilds the type sum of
                                   Ray::computeCellType (Ray.cc:2285-2342) from the packed records: 8 (default; RMCRT_Test.cc:80, Arches walls) */
-  int32_t  blockedMarch;       /* 1 (default): the default sampling (rayCoherence 0) marches a blocked half-packed copy of the level --
-                                  2 x 2 x 2 cells per 32-B sector, one 256-bit load per block entered, fp16 properties (as recordKind 2) --
-                                  with per-lane ray refill (divq_indep_kernel).  0: the one-cell-per-lane kernel on the level's own
-                                  records (A/B measurements; the same Philox rays, divQ equal to fp16 rounding of the properties). */
+  int32_t  blockedMarch;       /* 0 (default): the default sampling (rayCoherence 0) runs on the one-cell-per-lane kernel over the level's own
+                                  records.  1: experimental divq_indep_kernel -- a blocked half-packed copy of the level (2 x 2 x 2 cells per
+                                  32-B sector, one 256-bit load per block entered, fp16 properties as recordKind 2) with per-lane ray
+                                  refill; same Philox rays, divQ equal to the fp16 rounding of the properties.  Measured slower on B200
+                                  (DESIGN.md section 3), kept for A/B measurements. */
   int32_t  refillLanes;        /* implementation knob of divq_indep_kernel: lanes of a warp that must wait for a new ray before ray
                                   set-up runs (0 = default 8) */
 } rmcrt_params;

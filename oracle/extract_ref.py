@@ -22,6 +22,11 @@ WANT = [
     (RMCRT + "RMCRTCommon.cc", r"^RMCRTCommon::updateSumI \("),
     (RMCRT + "Ray.cc", r"^Ray::containsCell\("),
     (RMCRT + "Ray.cc", r"^\s*void Ray::updateSumI_ML \("),
+    # the shells around the per-ray routines: boundary-flux helpers and the Data-Onion extents
+    (RMCRT + "Ray.cc", r"^Ray::computeExtents\("),
+    (RMCRT + "Ray.cc", r"^void Ray::rayDirection_cellFace\("),
+    (RMCRT + "Ray.cc", r"^void Ray::rayLocation_cellFace\("),
+    (RMCRT + "Ray.cc", r"^Ray::has_a_boundary\("),
 ]
 MACROS = ["DEBUG", "FIXED_RAY_DIR", "SIGN", "FUZZ"]
 
@@ -80,6 +85,10 @@ def main(ref, out):
         lines = cache[rel]
         a, b = cut(lines, pat)
         chunks.append(f"// ---- {rel}:{a + 1}-{b + 1}\n" + "\n".join(lines[a:b + 1]) + "\n")
+    # the face tables the constructor fills (Ray.cc:112-125), as the body of a member function of the look-alike class
+    tables = [l for l in cache[RMCRT + "Ray.cc"] if re.match(r"\s*d_dir(IndexOrder|SignSwap)\[\w+\]\s*=", l)]
+    assert len(tables) == 12, tables
+    chunks.append("// ---- " + RMCRT + "Ray.cc: d_dirIndexOrder / d_dirSignSwap assignments of Ray::Ray\nvoid Ray::initFaceTables()\n{\n" + "\n".join(tables) + "\n}\n")
     macros = []
     for l in cache[RMCRT + "RMCRTCommon.cc"]:
         m = re.match(r"#define (\w+)\s", l)

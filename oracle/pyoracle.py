@@ -391,6 +391,36 @@ def ref_ray_trace(p: Params, lv: Level, patch_lo=None, patch_hi=None, seed=1, pa
     return dict(divQ=divQ, radiationVolq=volq, steps=sum(steps))
 
 
+def ref_ray_trace_boundflux(p: Params, lv: Level, patch_lo=None, patch_hi=None, seed=1):
+    """the boundary-flux part of Ray::rayTrace (Ray.cc:645-730) with the reference's OWN has_a_boundary / rayDirection_cellFace /
+    rayLocation_cellFace / updateSumI and face tables (ref_rayTrace_boundFlux); one task, MT seed `seed`.  Returns (boundFlux, steps)."""
+    patch_lo = lv.interior_lo if patch_lo is None else tuple(patch_lo)
+    patch_hi = lv.interior_hi if patch_hi is None else tuple(patch_hi)
+    bflux = np.zeros(lv.abskg.shape + (7,), np.float64)
+    cl = lv.c()
+    n = C.c_uint64(0)
+    rc = ref_lib().ref_rayTrace_boundFlux(C.byref(p), C.byref(cl), _i3(patch_lo), _i3(patch_hi), C.c_uint32(seed), bflux.ctypes.data_as(C.c_void_p),
+                                          _i3(lv.lo), _i3(lv.hi), C.byref(n))
+    assert rc == 0
+    return bflux, n.value
+
+
+def ref_compute_extents(levels, patch_lo, patch_hi, halo, roi_algo="patch_based", roi_min=None, roi_max=None):
+    """Ray::computeExtents, the reference's own code (Ray.cc:1279-1358).  roi_algo: 'fixed' (roi_min / roi_max physical points),
+    'dynamic' (roi_min / roi_max = the ROI_loCell / ROI_hiCell reduction values) or 'patch_based'.  Returns the tuple of
+    compute_extents, or None when the reference throws (fixed ROI outside the fine level)."""
+    nl = len(levels)
+    arr = (CLevel * nl)(*[l.c() for l in levels])
+    roiLo = (C.c_int * 3)(); roiHi = (C.c_int * 3)()
+    regLo = (C.c_int * (3 * nl))(); regHi = (C.c_int * (3 * nl))()
+    algo = {"fixed": 0, "dynamic": 1, "patch_based": 2}[roi_algo]
+    rc = ref_lib().ref_computeExtents(arr, nl, _i3(patch_lo), _i3(patch_hi), _i3(halo), algo, _d3(roi_min) if roi_min is not None else None,
+                                      _d3(roi_max) if roi_max is not None else None, roiLo, roiHi, regLo, regHi)
+    if rc != 0:
+        return None
+    return (tuple(roiLo), tuple(roiHi), np.array(regLo).reshape(nl, 3).copy(), np.array(regHi).reshape(nl, 3).copy())
+
+
 def generate_rays(p: Params, lv: Level, cell, n_rays, seed=1, reference=False):
     """(dirs, origins) of rays 0..n_rays-1 of one cell as the divQ loop draws them (Ray.cc:752-760); reference=True: the reference's own code"""
     cl = lv.c()

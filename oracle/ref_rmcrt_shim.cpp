@@ -19,6 +19,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <iostream>
+#include <map>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -39,6 +40,10 @@ class IntVector {
   int v_[3];
 };
 inline std::ostream& operator<<(std::ostream& o, const IntVector& v) { return o << "[int " << v.x() << ", " << v.y() << ", " << v.z() << "]"; }
+inline IntVector operator+(const IntVector& a, const IntVector& b) { return IntVector(a.x() + b.x(), a.y() + b.y(), a.z() + b.z()); }
+inline IntVector operator-(const IntVector& a, const IntVector& b) { return IntVector(a.x() - b.x(), a.y() - b.y(), a.z() - b.z()); }
+inline IntVector Max(const IntVector& a, const IntVector& b) { return IntVector(std::max(a.x(), b.x()), std::max(a.y(), b.y()), std::max(a.z(), b.z())); }
+inline IntVector Min(const IntVector& a, const IntVector& b) { return IntVector(std::min(a.x(), b.x()), std::min(a.y(), b.y()), std::min(a.z(), b.z())); }
 
 class Vector {
  public:
@@ -87,10 +92,19 @@ class Level;
 struct LevelHandle {     // Handle<Level>::get_rep()
   const Level* p;
   const Level* get_rep() const { return p; }
+  const Level* operator->() const { return p; }
 };
+typedef LevelHandle LevelP;
 class Level {
  public:
   int index = 0;
+  int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}, intLo[3] = {0, 0, 0}, intHi[3] = {0, 0, 0};   // findCellIndexRange / findInteriorCellIndexRange
+  void findCellIndexRange(IntVector& l, IntVector& h) const { l = IntVector(lo[0], lo[1], lo[2]); h = IntVector(hi[0], hi[1], hi[2]); }
+  void findInteriorCellIndexRange(IntVector& l, IntVector& h) const { l = IntVector(intLo[0], intLo[1], intLo[2]); h = IntVector(intHi[0], intHi[1], intHi[2]); }
+  IntVector getExtraCells() const { return IntVector(intLo[0] - lo[0], intLo[1] - lo[1], intLo[2] - lo[2]); }
+  bool hasCoarserLevel() const { return coarser != nullptr; }
+  bool containsCell(const IntVector& c) const { return c.x() >= lo[0] && c.y() >= lo[1] && c.z() >= lo[2] && c.x() < hi[0] && c.y() < hi[1] && c.z() < hi[2]; }
+  IntVector getCellIndex(const Point& pt) const;       // Level.cc:553-557: floor((p - anchor) / dcell)
   double anchor[3] = {0, 0, 0}, dcell[3] = {1, 1, 1};
   int rr[3] = {1, 1, 1};
   const Level* coarser = nullptr;
@@ -111,6 +125,43 @@ class Level {
   LevelHandle getCoarserLevel() const { return LevelHandle{coarser}; }
 };
 
+inline IntVector Level::getCellIndex(const Point& pt) const {
+  return IntVector((int)std::floor((pt.x() - anchor[0]) / dcell[0]), (int)std::floor((pt.y() - anchor[1]) / dcell[1]), (int)std::floor((pt.z() - anchor[2]) / dcell[2]));
+}
+inline std::ostream& operator<<(std::ostream& o, const Point& v) { return o << "[" << v.x() << ", " << v.y() << ", " << v.z() << "]"; }
+
+// what Ray::computeExtents touches of the framework (Ray.cc:1279-1358): a patch's cell range, the grid's levels, two reduction variables
+class Patch {
+ public:
+  IntVector lo, hi;
+  IntVector getCellLowIndex() const { return lo; }
+  IntVector getCellHighIndex() const { return hi; }
+  int getID() const { return 0; }
+};
+struct VarLabel {};
+struct minvec_vartype { Vector v; operator Vector() const { return v; } };
+struct maxvec_vartype { Vector v; operator Vector() const { return v; } };
+inline IntVector roundNearest(const Vector& v) { return IntVector((int)std::lround(v.x()), (int)std::lround(v.y()), (int)std::lround(v.z())); }
+class Grid {
+ public:
+  std::vector<const Level*> levels;
+  LevelP getLevel(int L) const { return LevelP{levels[L]}; }
+};
+class DataWarehouse {
+ public:
+  const Grid* grid = nullptr;
+  Vector roiLo, roiHi;
+  const Grid* getGrid() const { return grid; }
+  void get(minvec_vartype& v, const VarLabel*) const { v.v = roiLo; }
+  void get(maxvec_vartype& v, const VarLabel*) const { v.v = roiHi; }
+};
+class ProblemSetupException : public std::runtime_error {
+ public:
+  ProblemSetupException(const std::string& m, const char*, int) : std::runtime_error(m) {}
+};
+#define DOUT(cond, msg)
+static const bool g_ray_dbg = false;
+
 template <class T>
 class constCCVariable {      // Array3<T>::operator[](IntVector): x-fastest over the window (Array3.h, Array3Data.h:93,212-220)
  public:
@@ -130,6 +181,7 @@ class InternalError : public std::runtime_error {
 class RMCRTCommon {
  public:
   enum DIR { X = 0, Y = 1, Z = 2, NONE = -9 };
+  enum FACE { EAST = 0, WEST = 1, NORTH = 2, SOUTH = 3, TOP = 4, BOT = 5, nFACES = 6 };      // RMCRTCommon.h:261
   void raySignStep(double sign[], int cellStep[], const Vector& inv_direction_vector);
   Vector findRayDirection(MTRand& mTwister, const IntVector& origin, const int iRay = -9);
   void ray_Origin(MTRand& mTwister, const Point CC_pos, const Vector dx, const bool useCCRays, Vector& rayOrigin);
@@ -158,6 +210,20 @@ class Ray : public RMCRTCommon {
   bool m_use_virtual_ROI{false};
   IntVector m_virtual_ROI{IntVector(0, 0, 0)};
   IntVector d_haloCells{IntVector(-9, -9, -9)};
+  // the shells (Ray.h:187-214, 262-330)
+  enum ROI_algo { fixed, dynamic, patch_based, boundedRayLength, entireDomain };
+  ROI_algo d_ROI_algo{entireDomain};
+  Point d_ROI_minPt, d_ROI_maxPt;
+  const VarLabel* d_ROI_LoCellLabel{nullptr};
+  const VarLabel* d_ROI_HiCellLabel{nullptr};
+  std::map<int, IntVector> d_dirIndexOrder, d_dirSignSwap;
+  void initFaceTables();
+  void computeExtents(LevelP level_0, const Level* fineLevel, const Patch* patch, const int maxLevels, DataWarehouse* new_dw,
+                      IntVector& fineLevel_ROI_Lo, IntVector& fineLevel_ROI_Hi, std::vector<IntVector>& regionLo, std::vector<IntVector>& regionHi);
+  void rayDirection_cellFace(MTRand& mTwister, const IntVector& origin, const IntVector& indexOrder, const IntVector& signOrder, const int iRay,
+                             Vector& directionVector, double& cosTheta);
+  void rayLocation_cellFace(MTRand& mTwister, const int face, const Vector Dx, const Point CC_pos, Vector& rayOrigin);
+  bool has_a_boundary(const IntVector& c, constCCVariable<int>& celltype, std::vector<int>& boundaryFaces);
 };
 
 using std::vector;
@@ -183,7 +249,10 @@ void setStatics(const oracle_params* p) {
 }
 void fillLevel(const oracle_level& s, int index, Level& L) {
   L.index = index;
-  for (int d = 0; d < 3; ++d) { L.anchor[d] = s.anchor[d]; L.dcell[d] = s.dx[d]; L.rr[d] = s.refineRatio[d] > 0 ? s.refineRatio[d] : 1; }
+  for (int d = 0; d < 3; ++d) {
+    L.anchor[d] = s.anchor[d]; L.dcell[d] = s.dx[d]; L.rr[d] = s.refineRatio[d] > 0 ? s.refineRatio[d] : 1;
+    L.lo[d] = s.lo[d]; L.hi[d] = s.hi[d]; L.intLo[d] = s.interiorLo[d]; L.intHi[d] = s.interiorHi[d];
+  }
 }
 template <class T> void fillVar(const oracle_level& s, const void* ptr, constCCVariable<T>& v) {
   v.data = static_cast<const T*>(ptr);
@@ -350,5 +419,99 @@ extern "C" int ref_rayTrace_divQ(const oracle_params* p, const oracle_level* lv,
     if (lv->isFloat) rayTrace_divQ_T<float>(p, lv, patchLo, patchHi, mtSeed, divQ, radiationVolq, outLo, outHi, nRaySteps);
     else             rayTrace_divQ_T<double>(p, lv, patchLo, patchHi, mtSeed, divQ, radiationVolq, outLo, outHi, nRaySteps);
   } catch (const InternalError&) { return 1; }
+  return 0;
+}
+
+
+// The boundary-flux loop of Ray::rayTrace<T> (Ray.cc:645-730, naive sampling) with every routine it calls being the reference's own
+// code: has_a_boundary, rayDirection_cellFace, rayLocation_cellFace (and the face tables of the constructor), updateSumI<T>.  Only the
+// loop shell and the two flux lines (712, 716-717) are restated.  boundFlux: Stencil7 AoS (w,e,s,n,b,t,p), p written as 1.0 / 0.0.
+template <class T>
+static void rayTrace_boundFlux_T(const oracle_params* p, const oracle_level* lv, const int pLo[3], const int pHi[3], uint32_t mtSeed, double* bflux,
+                                 const int oLo[3], const int oHi[3], uint64_t* nSteps) {
+  Ray ray;
+  ray.d_flowCell = p->flowCell;
+  ray.initFaceTables();
+  Level L;
+  fillLevel(*lv, 0, L);
+  constCCVariable<T> abskg, sig;
+  constCCVariable<int> ct;
+  fillVar<T>(*lv, lv->abskg, abskg);
+  fillVar<T>(*lv, lv->sigmaT4, sig);
+  fillVar<int>(*lv, lv->cellType, ct);
+  const Vector Dx(lv->dx[0], lv->dx[1], lv->dx[2]);
+  MTRand mTwister(mtSeed);
+  unsigned long int size = 0;
+  const int64_t onx = oHi[0] - oLo[0], ony = oHi[1] - oLo[1];
+  const int d_nFluxRays = p->nFluxRays;
+  for (int k = pLo[2]; k < pHi[2]; ++k) for (int j = pLo[1]; j < pHi[1]; ++j) for (int i = pLo[0]; i < pHi[0]; ++i) {
+    const IntVector origin(i, j, k);
+    if (ct[origin] != ray.d_flowCell) continue;
+    std::vector<int> boundaryFaces;
+    double* S = bflux + 7 * ((i - oLo[0]) + onx * ((j - oLo[1]) + ony * (int64_t)(k - oLo[2])));
+    S[6] = ray.has_a_boundary(origin, ct, boundaryFaces);
+    Point CC_pos = L.getCellPosition(origin);
+    for (std::vector<int>::iterator it = boundaryFaces.begin(); it < boundaryFaces.end(); it++) {
+      int RayFace = *it;
+      int UintahFace[6] = {Ray::WEST, Ray::EAST, Ray::SOUTH, Ray::NORTH, Ray::BOT, Ray::TOP};
+      double sumI = 0, sumProjI = 0, sumI_prev = 0, sumCosTheta = 0;
+      for (int iRay = 0; iRay < d_nFluxRays; iRay++) {
+        Vector direction_vector, rayOrigin;
+        double cosTheta;
+        ray.rayDirection_cellFace(mTwister, origin, ray.d_dirIndexOrder[RayFace], ray.d_dirSignSwap[RayFace], iRay, direction_vector, cosTheta);
+        ray.rayLocation_cellFace(mTwister, RayFace, Dx, CC_pos, rayOrigin);
+        ray.updateSumI<T>(&L, direction_vector, rayOrigin, origin, Dx, sig, abskg, ct, size, sumI, mTwister);
+        sumProjI += cosTheta * (sumI - sumI_prev);
+        sumCosTheta += cosTheta;
+        sumI_prev = sumI;
+      }
+      sumProjI = sumProjI * (double)d_nFluxRays / sumCosTheta / 2.0;
+      int face = UintahFace[RayFace];
+      S[face] = sumProjI * 2 * M_PI / (double)d_nFluxRays;      // Stencil7::operator[]: w e s n b t p (Stencil7.h:38-76)
+    }
+  }
+  *nSteps = size;
+}
+
+extern "C" int ref_rayTrace_boundFlux(const oracle_params* p, const oracle_level* lv, const int patchLo[3], const int patchHi[3], uint32_t mtSeed,
+                                      double* boundFlux, const int outLo[3], const int outHi[3], uint64_t* nFluxRaySteps) {
+  setStatics(p);
+  try {
+    if (lv->isFloat) rayTrace_boundFlux_T<float>(p, lv, patchLo, patchHi, mtSeed, boundFlux, outLo, outHi, nFluxRaySteps);
+    else             rayTrace_boundFlux_T<double>(p, lv, patchLo, patchHi, mtSeed, boundFlux, outLo, outHi, nFluxRaySteps);
+  } catch (const InternalError&) { return 1; }
+  return 0;
+}
+
+// Ray::computeExtents (Ray.cc:1279-1358), the reference's own code: roiAlgo 0 fixed (roiMin / roiMax points), 1 dynamic (ROI_loCell /
+// ROI_hiCell reduction values), 2 patch_based.  returns 0, or 2 when the reference threw ProblemSetupException (fixed ROI off the level)
+extern "C" int ref_computeExtents(const oracle_level* levels, int maxLevels, const int patchLo[3], const int patchHi[3], const int haloCells[3],
+                                  int roiAlgo, const double roiMin[3], const double roiMax[3], int roiLo[3], int roiHi[3], int* regionLo,
+                                  int* regionHi) {
+  Ray ray;
+  std::vector<Level> lv(maxLevels);
+  Grid grid;
+  for (int l = 0; l < maxLevels; ++l) {
+    fillLevel(levels[l], l, lv[l]);
+    lv[l].coarser = l > 0 ? &lv[l - 1] : nullptr;
+    grid.levels.push_back(&lv[l]);
+  }
+  DataWarehouse dw;
+  dw.grid = &grid;
+  if (roiMin && roiMax) {
+    dw.roiLo = Vector(roiMin[0], roiMin[1], roiMin[2]); dw.roiHi = Vector(roiMax[0], roiMax[1], roiMax[2]);
+    ray.d_ROI_minPt = Point(roiMin[0], roiMin[1], roiMin[2]); ray.d_ROI_maxPt = Point(roiMax[0], roiMax[1], roiMax[2]);
+  }
+  ray.d_ROI_algo = roiAlgo == 0 ? Ray::fixed : (roiAlgo == 1 ? Ray::dynamic : Ray::patch_based);
+  ray.d_haloCells = IntVector(haloCells[0], haloCells[1], haloCells[2]);
+  Patch patch;
+  patch.lo = IntVector(patchLo[0], patchLo[1], patchLo[2]); patch.hi = IntVector(patchHi[0], patchHi[1], patchHi[2]);
+  IntVector rl, rh;
+  std::vector<IntVector> regLo(maxLevels), regHi(maxLevels);
+  try {
+    ray.computeExtents(LevelP{&lv[0]}, &lv[maxLevels - 1], &patch, maxLevels, &dw, rl, rh, regLo, regHi);
+  } catch (const ProblemSetupException&) { return 2; }
+  for (int d = 0; d < 3; ++d) { roiLo[d] = rl[d]; roiHi[d] = rh[d]; }
+  for (int l = 0; l < maxLevels; ++l) for (int d = 0; d < 3; ++d) { regionLo[3 * l + d] = regLo[l][d]; regionHi[3 * l + d] = regHi[l][d]; }
   return 0;
 }

@@ -55,7 +55,8 @@ def centre_lines(d, N, z_index):
     return [float(np.sqrt(np.mean((lx - ex) ** 2))), float(np.sqrt(np.mean((ly - ex) ** 2)))]
 
 
-def single_level_case(name, N, slabs, level, params, tracer, centre=None):
+def single_level_case(name, N, slabs, level, params, tracer, centre=None, ny=None):
+    """ny: only rows y < ny of every plane are traced and kept (the statistics must not see untraced cells)"""
     out, meta = {}, dict(name=name, N=N, K=K, slabs=[list(s) for s in slabs], seeds=[], steps=[], centreline_L2=[])
     for si, (z0, z1) in enumerate(slabs):
         runs, fruns = [], []
@@ -63,10 +64,10 @@ def single_level_case(name, N, slabs, level, params, tracer, centre=None):
             seed = 1000 * (k + 1) + 17 * si
             t0 = time.time()
             r = tracer(params, level, (0, 0, z0), (N, N, z1), seed=seed, patches=(1, THREADS, 1), threads=THREADS)
-            d = r["divQ"][z0 + 1:z1 + 1, 1:N + 1, 1:N + 1].copy()
+            d = r["divQ"][z0 + 1:z1 + 1, 1:(ny or N) + 1, 1:N + 1].copy()
             runs.append(d)
             if params.solveBoundaryFlux:
-                fruns.append(r["boundFlux"][z0 + 1:z1 + 1, 1:N + 1, 1:N + 1, :].copy())
+                fruns.append(r["boundFlux"][z0 + 1:z1 + 1, 1:(ny or N) + 1, 1:N + 1, :].copy())
             meta["seeds"].append(seed); meta["steps"].append(int(r["steps"]))
             if centre is not None and z0 <= centre < z1:
                 meta["centreline_L2"].append(centre_lines(d, N, centre - z0))
@@ -99,10 +100,8 @@ def case_c5():
 
     def tracer(p_, lv_, lo, hi, seed, patches, threads):     # half planes: the mirror corner (x-, y-) and the z- wall
         return po.ray_trace(p_, lv_, lo, (hi[0], N // 2, hi[2]), seed=seed, patches=patches, threads=threads)
-    out, meta = single_level_case("c5_256", N, [(0, 2), (128, 130)], lv, p, tracer)
+    out, meta = single_level_case("c5_256", N, [(0, 2), (128, 130)], lv, p, tracer, ny=N // 2)
     meta["y_range"] = [0, N // 2]
-    for k in list(out):
-        out[k] = np.ascontiguousarray(out[k][:, :N // 2])
     return out, meta
 
 

@@ -1,6 +1,6 @@
-"""divq_indep_kernel (indep.cuh): the production kernel of the default sampling (rayCoherence 0) -- blocked half-packed records, one
-256-bit load per 2 x 2 x 2 block, per-lane ray refill -- against the one-cell-per-lane kernel (blockedMarch = 0) on the SAME Philox rays
-(both key direction and origin on (cell, ray, timestep)), and against the oracle."""
+"""divq_indep_kernel (indep.cuh, rmcrt_params.blockedMarch = 1): the alternative kernel of the default sampling (rayCoherence 0) --
+blocked half-packed records, one 256-bit load per 2 x 2 x 2 block, per-lane ray refill -- against the production one-cell-per-lane
+kernel (blockedMarch = 0) on the SAME Philox rays (both key direction and origin on (cell, ray, timestep)), and against the oracle."""
 import numpy as np
 import pytest
 
@@ -82,7 +82,7 @@ def test_isothermal_enclosure_is_exact(gpu_lib, po):
     walls = (rng.uniform(size=(M, M, M)) < 0.03) & (ct == -1); ct[walls] = 8; ab[walls] = 1.0
     iso = po.Level(ab, s4, ct, (-1,) * 3, (M - 1,) * 3, (1.0 / 25,) * 3, interior_lo=(0,) * 3, interior_hi=(25,) * 3)
     for half in (False, True):
-        d, _, _, c = solve(iso, None, nDivQRays=8, threshold=0.001, seed=5, allowReflect=0, half_records=half)
+        d, _, _, c = solve(iso, None, nDivQRays=8, threshold=0.001, seed=5, allowReflect=0, half_records=half, blockedMarch=1)
         assert np.abs(d).max() < 2e-5 * 4 * np.pi * 2.0 * 0.6
         assert c == int((ct == -1).sum())
 
@@ -92,19 +92,19 @@ def test_refill_threshold_does_not_change_results(gpu_lib, po):
     lv = po.burns_christon(20, dtype=np.float32)
     ref = None
     for rl in (1, 8, 32):
-        d, _, n, _ = solve(lv, None, nDivQRays=10, threshold=0.05, seed=2, refillLanes=rl)
+        d, _, n, _ = solve(lv, None, nDivQRays=10, threshold=0.05, seed=2, refillLanes=rl, blockedMarch=1)
         if ref is None:
             ref = (d, n)
         assert np.array_equal(d, ref[0]) and n == ref[1]
 
 
 def test_monte_carlo_tolerance_41(gpu_lib, po):
-    """BASELINE config 1 through the default kernel: SURVEY 8c (i)-(iii) against 8 oracle seeds, unrelaxed"""
+    """BASELINE config 1 through the blocked kernel: SURVEY 8c (i)-(iii) against 8 oracle seeds, unrelaxed"""
     from util import candidate_stats, loo_control
     lv = po.burns_christon(41)
     p = po.default_params(nDivQRays=100, threshold=0.05, isSeedRandom=1)
     runs = [po.ray_trace(p, lv, seed=100 * s, patches=(1, 1, 8), threads=8)["divQ"] for s in range(1, 9)]
-    g = make(nDivQRays=100, threshold=0.05, seed=2024)
+    g = make(nDivQRays=100, threshold=0.05, seed=2024, blockedMarch=1)
     g.upload_level(0, lv)
     d = g.trace_divq(0)["divQ"]
     inner = (slice(1, -1),) * 3

@@ -155,3 +155,40 @@ def test_scattering_divQ_loop_bit_exact(po, ref_scatter, seed_random):
     assert np.array_equal(a["divQ"], b["divQ"]) and np.array_equal(a["radiationVolq"], b["radiationVolq"])
     c = po.ray_trace(po.default_params(nDivQRays=5, threshold=0.05, isSeedRandom=seed_random), lv, seed=9, patches=(1, 1, 2), threads=2)
     assert c["steps"] != b["steps"]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("seeded", [1, 0])
+def test_boundary_flux_loop_bit_exact(po, ref, dtype, seeded):
+    """Ray::has_a_boundary, rayDirection_cellFace, rayLocation_cellFace and the d_dirIndexOrder / d_dirSignSwap tables (Ray.cc:112-125,
+    1362-1390, 1465-1572), the reference's own code, under the boundary-flux loop of Ray::rayTrace: the whole Stencil7 field -- face
+    selection, boundFlux.p and every flux -- equals the oracle's restatement bit for bit, and so do the executed steps"""
+    rng = np.random.default_rng(17)
+    for name, lv in cases(po, dtype).items():
+        if name == "anisotropic_random":
+            add_random_walls(lv, 0.03, rng, abskg=0.5, sigmaT4=0.7)
+        p = po.default_params(nDivQRays=1, nFluxRays=7, threshold=0.01, isSeedRandom=seeded, solveBoundaryFlux=1, solveDivQ=0)
+        R, nR = po.ref_ray_trace_boundflux(p, lv, seed=31)
+        O = po.ray_trace(p, lv, seed=31)
+        assert nR == O["fluxSteps"], name
+        assert (R[..., 6] == 1).sum() > 100
+        assert np.array_equal(R, O["boundFlux"]), (name, np.abs(R - O["boundFlux"]).max())
+
+
+def test_computeExtents_is_the_reference(po, ref):
+    """Ray::computeExtents (Ray.cc:1279-1358), the reference's own code, against the oracle's restatement: patch_based ROI for two- and
+    three-level stacks, patches in corners / on faces / inside, several halos; mapCellToCoarser of negative indices included"""
+    fine = po.burns_christon(64, dtype=np.float32); fine.rr = (2, 2, 2)
+    mid = po.coarsen_level(fine, (2, 2, 2)); mid.rr = (4, 4, 4)
+    coarse = po.coarsen_level(mid, (4, 4, 4))
+    f2 = po.burns_christon(32, dtype=np.float32); f2.rr = (4, 4, 4)
+    c2 = po.coarsen_level(f2, (4, 4, 4))
+    n = 0
+    for levels, N in (([coarse, mid, fine], 64), ([c2, f2], 32)):
+        for halo in ((4, 4, 4), (1, 2, 3), (10, 10, 10), (0, 0, 0)):
+            for lo, hi in (((0, 0, 0), (N // 2,) * 3), ((N // 2,) * 3, (N,) * 3), ((N // 4, 0, N // 2), (N // 2, N // 4, N)), ((3, 5, 7), (11, 9, 8))):
+                a = po.ref_compute_extents(levels, lo, hi, halo)
+                b = po.compute_extents(levels, lo, hi, halo)
+                assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3]), (N, halo, lo, hi, a, b)
+                n += 1
+    assert n == 32

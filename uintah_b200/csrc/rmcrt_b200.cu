@@ -672,7 +672,10 @@ __global__ void __launch_bounds__(128, (!ONION && std::is_same<RecT, Rec8>::valu
 }
 
 //======================================================================================================
-// The production kernel of the DEFAULT sampling (rayCoherence 0, independent rays per (cell, ray, timestep)): indep.cuh.
+// An alternative kernel for the DEFAULT sampling (rayCoherence 0, independent rays per (cell, ray, timestep)): indep.cuh; opt-in
+// (rmcrt_params.blockedMarch = 1) because it measured SLOWER than the one-cell-per-lane divq_kernel (70 vs 53 ms at 128^3 x 100 rays,
+// profiles/r02v3_divq_indep_128cubed_ncu.md): it halves the global sector requests as designed, but the per-lane slot traffic puts as
+// many wavefronts on the L1 data pipe as it saves, and the block bookkeeping doubles the instructions per step.
 // One WARP = one tile of 8 x 2 x 2 origin cells, lane = cell; a lane traces ALL nDivQRays rays of its cell one after the other (per-lane
 // refill), so nothing is reduced across warps and there is no barrier; a block is four independent warps (32 x 2 x 2 cells).  The
 // records come from the blocked half-packed copy of the level (BlkGeom), one 256-bit load per 2 x 2 x 2 block entered.
@@ -1934,7 +1937,7 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
         launch_reflective_pairs<RecT>(ctx, a2, cap, st);
       }
     } else if (std::is_same<Real, float>::value && !bounded && f32gen && ctx->p.rayCoherence == 0 && ctx->p.blockedMarch && !ctx->p.genericMarch) {
-      // DEFAULT: independent rays per (cell, ray, timestep) on the blocked half-packed copy of the level (indep.cuh)
+      // opt-in: independent rays per (cell, ray, timestep) on the blocked half-packed copy of the level (indep.cuh)
       if constexpr (std::is_same<Real, float>::value && !std::is_same<RecT, Rec16>::value) {
         BlkGeom bg;
         int rc = ensure_blocked_level<RecT>(ctx, a.G.maxLevels - 1, bg, st);
@@ -2131,7 +2134,7 @@ void rmcrt_default_params(rmcrt_params* p) {
   p->maxRayLength = 0.0;       // unbounded (DBL_MAX, RMCRTCommon.cc:117)
   p->sigmaScat = 0.0;          // Ray.cc:169
   p->tileX = 0; p->nonFlowCellType = 8;
-  p->blockedMarch = 1; p->refillLanes = 0;
+  p->blockedMarch = 0; p->refillLanes = 0;
   p->cellsPerLane = 4;         // production: the 2 x 2 cells of a lane share one DDA (divq_quad_kernel); 2 = a pair (divq_dual_kernel); 1 = one cell per lane
 }
 
