@@ -113,6 +113,13 @@ typedef struct rmcrt_params {
                                   (DESIGN.md section 3), kept for A/B measurements. */
   int32_t  refillLanes;        /* implementation knob of divq_indep_kernel: lanes of a warp that must wait for a new ray before ray
                                   set-up runs (0 = default 8) */
+  int32_t  coarsenExtraCells;  /* <coarsenExtraCells> (Ray.cc:256,315; default false): rmcrt_coarsen_level_device also fills the coarse level's
+                                  extra cells on the domain faces with the tangential average of the fine level's extra cells (Ray::coarsen_Q,
+                                  Ray.cc:2148-2245) instead of leaving them to rmcrt_set_level_extra_cells (setBoundaryConditions) */
+  int32_t  roiFixed;           /* <ROI_extents type="fixed"> (Ray.cc:265-271, 1303-1314): 1 = the Data-Onion fine-level region of interest is the
+                                  cell box [roiFixedLo, roiFixedHi) = fineLevel->getCellIndex(min / max point), the same for every patch,
+                                  instead of patch +- haloCells (0, patch_based).  Clamped to the fine level like the reference. */
+  int32_t  roiFixedLo[3], roiFixedHi[3];
 } rmcrt_params;
 
 /* One <Radiometer> block after Radiometer::problemSetup (Radiometer.cc:96-271; struct radiometer, Radiometer.h:117-127) */

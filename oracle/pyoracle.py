@@ -32,7 +32,8 @@ class Params(C.Structure):
                 ("allowReflect", C.c_int), ("CCRays", C.c_int), ("isSeedRandom", C.c_int),
                 ("solveDivQ", C.c_int), ("solveBoundaryFlux", C.c_int), ("fixedRandom", C.c_int),
                 ("flowCell", C.c_int), ("dataOnionFluxFlowGuard", C.c_int), ("rayDirSampleAlgo", C.c_int),
-                ("maxRayLength", C.c_double), ("sigmaScat", C.c_double)]
+                ("maxRayLength", C.c_double), ("sigmaScat", C.c_double),
+                ("roiFixed", C.c_int), ("roiFixedLo", C.c_int * 3), ("roiFixedHi", C.c_int * 3)]
 
 
 class CRadiometer(C.Structure):
@@ -63,7 +64,7 @@ def default_params(**kw) -> Params:
     for k, v in kw.items():
         if not hasattr(p, k):
             raise AttributeError(k)
-        setattr(p, k, v)
+        setattr(p, k, (C.c_int * 3)(*[int(x) for x in v]) if k in ("roiFixedLo", "roiFixedHi") else v)
     return p
 
 
@@ -281,12 +282,14 @@ def update_sumI(p: Params, lv: Level, direction, ray_origin, origin_cell, max_pa
     return sumI.value, n.value, path[:min(npath.value, max_path)]
 
 
-def compute_extents(levels, patch_lo, patch_hi, halo):
+def compute_extents(levels, patch_lo, patch_hi, halo, fixed_lo=None, fixed_hi=None):
+    """Ray::computeExtents: patch_based ROI (patch +- halo), or the fixed cell box [fixed_lo, fixed_hi)"""
     nl = len(levels)
     arr = (CLevel * nl)(*[l.c() for l in levels])
     roiLo = (C.c_int * 3)(); roiHi = (C.c_int * 3)()
     regLo = (C.c_int * (3 * nl))(); regHi = (C.c_int * (3 * nl))()
-    lib().oracle_computeExtents(arr, nl, _i3(patch_lo), _i3(patch_hi), _i3(halo), roiLo, roiHi, regLo, regHi)
+    lib().oracle_computeExtents_roi(arr, nl, _i3(patch_lo), _i3(patch_hi), _i3(halo), _i3(fixed_lo) if fixed_lo is not None else None,
+                                    _i3(fixed_hi) if fixed_hi is not None else None, roiLo, roiHi, regLo, regHi)
     return (tuple(roiLo), tuple(roiHi), np.array(regLo).reshape(nl, 3).copy(), np.array(regHi).reshape(nl, 3).copy())
 
 
@@ -572,10 +575,12 @@ def ray_trace_data_onion(p: Params, levels, halo, patch_lo=None, patch_hi=None, 
     return dict(divQ=divQ, radiationVolq=volq, boundFlux=bflux, steps=sum(steps), fluxSteps=sum(fsteps))
 
 
-def coarsen_level(fine: Level, rr=(4, 4, 4), logic=0, wall_abskg=None, wall_sigmaT4=None, wall_type=None) -> Level:
+def coarsen_level(fine: Level, rr=(4, 4, 4), logic=0, wall_abskg=None, wall_sigmaT4=None, wall_type=None, coarsen_extra_cells=False) -> Level:
     """Build the coarse level the Data-Onion needs: Ray::coarsen_Q interior average of abskg and sigmaT4 and
     Ray::computeCellType; coarse extra cells are then filled the way sched_setBoundaryConditions does for
-    Dirichlet walls (taken from the fine level's extra-cell corner value unless given)."""
+    Dirichlet walls (taken from the fine level's extra-cell corner value unless given) -- or, with coarsen_extra_cells
+    (<coarsenExtraCells> true, Ray.cc:2148-2245), with the average of the fine extra cells each coarse face cell covers (ratio 1 along
+    the face normal; faces without edges, edge / corner extra cells stay 0; accumulation in T, scaled by the double 1/RR)."""
     fl, fh = fine.interior_lo, fine.interior_hi
     cil = tuple(fl[d] // rr[d] for d in range(3))
     cih = tuple(fh[d] // rr[d] for d in range(3))
@@ -601,9 +606,26 @@ def coarsen_level(fine: Level, rr=(4, 4, 4), logic=0, wall_abskg=None, wall_sigm
             fsl = [1, 1, 1]
             fsl[axis] = fidx
             dst[tuple(sl)] = src[tuple(fsl)] if override is None else override
-    face_fill(ab, fine.abskg, wall_abskg)
-    face_fill(s4, fine.sigmaT4, wall_sigmaT4)
     face_fill(ct, fine.cellType, wall_type)
+    if coarsen_extra_cells:
+        for src, dst in ((fine.abskg, ab), (fine.sigmaT4, s4)):
+            for a in range(3):                      # array axis 0 = z, 1 = y, 2 = x
+                t1, t2 = [x for x in range(3) if x != a]
+                r1, r2 = rr[2 - t1], rr[2 - t2]
+                for cidx, fidx in ((0, 0), (dst.shape[a] - 1, src.shape[a] - 1)):
+                    fsl = [slice(1, -1)] * 3; fsl[a] = fidx
+                    face = src[tuple(fsl)]                                  # fine extra cells of the face without its edges, 2-D
+                    n1, n2 = face.shape[0] // r1, face.shape[1] // r2
+                    acc = np.zeros((n1, n2), dt)
+                    for i1 in range(r1):            # the reference's CellIterator runs x fastest: same summation order per coarse cell
+                        for i2 in range(r2):
+                            acc = (acc + face[i1::r1, i2::r2][:n1, :n2]).astype(dt)
+                    val = (acc.astype(np.float64) * (1.0 / float(r1 * r2))).astype(dt)
+                    csl = [slice(1, -1)] * 3; csl[a] = cidx
+                    dst[tuple(csl)] = val
+    else:
+        face_fill(ab, fine.abskg, wall_abskg)
+        face_fill(s4, fine.sigmaT4, wall_sigmaT4)
     cdx = tuple(fine.dx[d] * rr[d] for d in range(3))
     return Level(ab, s4, ct, clo, chi, cdx, fine.anchor, (1, 1, 1), cil, cih)
 

@@ -603,6 +603,8 @@ void oracle_default_params(oracle_params* p) {
   p->rayDirSampleAlgo = 0;
   p->maxRayLength = DBL_MAX;   // RMCRTCommon.cc:117
   p->sigmaScat = 0;
+  p->roiFixed = 0;
+  for (int d = 0; d < 3; ++d) { p->roiFixedLo[d] = 0; p->roiFixedHi[d] = 0; }
 }
 
 // Radiometer::problemSetup (Radiometer.cc:214-260)
@@ -679,10 +681,18 @@ void oracle_rayTrace(const oracle_params* p, const oracle_level* lv, const int p
 // NOTE: for the fine level pass lo/hi = the whole fine level's index range here, not an ROI window.
 void oracle_computeExtents(const oracle_level* levels, int maxLevels, const int patchLo[3], const int patchHi[3],
                            const int haloCells[3], int roiLo[3], int roiHi[3], int* regionLo, int* regionHi) {
+  oracle_computeExtents_roi(levels, maxLevels, patchLo, patchHi, haloCells, nullptr, nullptr, roiLo, roiHi, regionLo, regionHi);
+}
+
+void oracle_computeExtents_roi(const oracle_level* levels, int maxLevels, const int patchLo[3], const int patchHi[3],
+                               const int haloCells[3], const int fixedLo[3], const int fixedHi[3], int roiLo[3], int roiHi[3],
+                               int* regionLo, int* regionHi) {
   const int F = maxLevels - 1;
   for (int d = 0; d < 3; ++d) {
-    roiLo[d] = std::max(patchLo[d] - haloCells[d], levels[F].lo[d]);   // 1316-1328
-    roiHi[d] = std::min(patchHi[d] + haloCells[d], levels[F].hi[d]);
+    const int lo = fixedLo ? fixedLo[d] : patchLo[d] - haloCells[d];   // fixed: 1303-1306; patch_based: 1316-1320
+    const int hi = fixedHi ? fixedHi[d] : patchHi[d] + haloCells[d];
+    roiLo[d] = std::max(lo, levels[F].lo[d]);                          // 1327-1328
+    roiHi[d] = std::min(hi, levels[F].hi[d]);
     const int ec = levels[F].interiorLo[d] - levels[F].lo[d];          // fineLevel->getExtraCells()
     regionLo[3 * F + d] = roiLo[d] + ec;                               // 1333-1335
     regionHi[3 * F + d] = roiHi[d] - ec;
@@ -717,7 +727,8 @@ void dataOnionPatch(const oracle_params& P, const oracle_level* levels, int maxL
 
   int roiLo[3], roiHi[3];
   std::vector<int> regLo(3 * maxLevels), regHi(3 * maxLevels);
-  oracle_computeExtents(levels, maxLevels, pLo, pHi, halo, roiLo, roiHi, regLo.data(), regHi.data());
+  oracle_computeExtents_roi(levels, maxLevels, pLo, pHi, halo, P.roiFixed ? P.roiFixedLo : nullptr, P.roiFixed ? P.roiFixedHi : nullptr,
+                            roiLo, roiHi, regLo.data(), regHi.data());
 
   // level_0->getInteriorSpatialRange (Ray.cc:1023-1024)
   double bbMin[3], bbMax[3];

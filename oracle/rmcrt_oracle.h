@@ -50,6 +50,8 @@ typedef struct oracle_params {
   double maxRayLength;       /* RMCRTCommon.cc:117 DBL_MAX; <ROI_extents type="boundedRayLength"><length> (Ray.cc:243) */
   double sigmaScat;          /* <sigmaScat> (Ray.cc:169): > 0 = a RAY_SCATTER build with isotropic scattering (RMCRTCommon.cc:670-676,
                                 790-836); 0 = the stock build (no scattering code, no extra random draws) */
+  int    roiFixed;           /* <ROI_extents type="fixed"> (Ray.cc:1303-1314): the Data-Onion ROI is the cell box below for every patch */
+  int    roiFixedLo[3], roiFixedHi[3];   /* fineLevel->getCellIndex(d_ROI_minPt / d_ROI_maxPt) */
 } oracle_params;
 
 /* one <Radiometer> block after Radiometer::problemSetup (Radiometer.cc:96-271, Radiometer.h:117-127) */
@@ -120,6 +122,11 @@ void oracle_randVector(const oracle_params* p, uint32_t mtSeed, const int cell[3
 void oracle_computeExtents(const oracle_level* levels, int maxLevels,
                            const int patchLo[3], const int patchHi[3], const int haloCells[3],
                            int roiLo[3], int roiHi[3], int* regionLo, int* regionHi);
+/* the same with a fixed ROI box instead of patch +- halo (Ray.cc:1303-1314); fixedLo == NULL: patch_based */
+void oracle_computeExtents_roi(const oracle_level* levels, int maxLevels,
+                               const int patchLo[3], const int patchHi[3], const int haloCells[3],
+                               const int fixedLo[3], const int fixedHi[3],
+                               int roiLo[3], int roiHi[3], int* regionLo, int* regionHi);
 
 /* ---- Ray::rayTrace_dataOnion<T> for one fine patch (Ray.cc:943-1274) ----
  * levels[maxLevels-1] is the fine level; its arrays must cover at least the ROI. */

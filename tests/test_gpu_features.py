@@ -333,3 +333,114 @@ def test_scattering_production_properties(gpu_lib, po, dtype):
     assert np.linalg.norm(d - mu) / np.linalg.norm(mu) < 1.5 * spread, (np.linalg.norm(d - mu) / np.linalg.norm(mu), spread)
     noscat = po.ray_trace(po.default_params(nDivQRays=60, threshold=0.01), lv, seed=3, patches=(1, 1, 7), threads=7)["divQ"]
     assert np.linalg.norm(noscat - mu) / np.linalg.norm(mu) > 2 * spread          # scattering is a visible effect at this optical thickness
+
+
+# ------------------------------------------------------------------------------------------------ coarsening (Ray::coarsen_Q, computeCellType)
+def _device_coarse_level(g, fine, coarse_like, dtype):
+    """coarsen level 1 (uploaded from `fine`) into level 0 on the device and read its records back: (abskg, sigmaT4, nonFlow)"""
+    from uintah_b200 import LevelData
+    g.upload_level(1, fine)
+    g.define_level(0, LevelData.of(coarse_like).desc())
+    g.levels[0] = LevelData.of(coarse_like)
+    g.coarsen_level_device(1, 0)
+    rec, rb = g.level_records(0)
+    raw = rec.cpu().numpy()
+    a = raw.view(np.float64 if rb == 16 else np.float32).reshape(coarse_like.abskg.shape + (2,))
+    k, s = a[..., 0], a[..., 1]
+    return np.abs(k), s, np.signbit(k)
+
+
+@pytest.mark.parametrize("rr,logic", [((2, 2, 2), 0), ((4, 4, 4), 0), ((2, 2, 2), 1), ((4, 4, 4), 1), ((2, 4, 1), 0)])
+def test_coarsened_cell_type_follows_the_integer_sum(gpu_lib, po, rr, logic):
+    """Ray::computeCellType (Ray.cc:2272-2345) sums the INTEGER cell types of the fine cells (flow -1, RMCRT_Test walls 8): with RR = 8 and
+    ONE non-flow fine cell the sum is 1 and ROUNDUP keeps the coarse cell a FLOW cell (|sum| < 10); RR = 64 with five or six likewise.
+    Partial intrusions of every fill level against the oracle's restatement of the reference logic."""
+    rng = np.random.default_rng(12)
+    N = 32
+    fine = po.burns_christon(N, dtype=np.float64)
+    fine.rr = rr
+    ct = fine.cellType
+    RR = rr[0] * rr[1] * rr[2]
+    # every coarse cell gets a random number 0..RR of non-flow fine cells
+    for kc in range(N // rr[2]):
+        for jc in range(N // rr[1]):
+            for ic in range(N // rr[0]):
+                nw = int(rng.integers(0, RR + 1)) if rng.uniform() < 0.5 else 0
+                if nw:
+                    idx = rng.choice(RR, nw, replace=False)
+                    for q in idx:
+                        a, b, c = q % rr[0], (q // rr[0]) % rr[1], q // (rr[0] * rr[1])
+                        ct[1 + kc * rr[2] + c, 1 + jc * rr[1] + b, 1 + ic * rr[0] + a] = 8
+    ref = po.coarsen_level(fine, rr, logic=logic)
+    g = make(gpu_lib, marchPrecision=1, cellTypeCoarsenLogic=logic)
+    k, s, wall = _device_coarse_level(g, fine, ref, np.float64)
+    inner = (slice(1, -1),) * 3
+    assert np.array_equal(wall[inner], ref.cellType[inner] != -1)
+    assert 0 < (ref.cellType[inner] != -1).sum() < ref.cellType[inner].size
+    np.testing.assert_allclose(k[inner], ref.abskg[inner], rtol=1e-13)
+    np.testing.assert_allclose(s[inner], ref.sigmaT4[inner], rtol=1e-13)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_coarsen_extra_cells(gpu_lib, po, dtype):
+    """<coarsenExtraCells> true (Ray::coarsen_Q, Ray.cc:2148-2245): coarse extra cells on the domain faces = tangential average of the fine
+    extra cells (ratio 1 along the normal), edges / corners 0, all of them non-flow; then the Data-Onion solve on the device-derived
+    coarse level equals the oracle's on the oracle-built one"""
+    rng = np.random.default_rng(14)
+    fine = po.parallel_plates(32, dtype=dtype, mirror_faces=())
+    fine.rr = (4, 4, 4)
+    wall = fine.cellType != -1
+    fine.abskg[wall] = rng.uniform(0.2, 1.0, int(wall.sum())).astype(dtype)          # walls that vary along the faces
+    fine.sigmaT4[wall] = (fine.sigmaT4[wall] * rng.uniform(0.5, 1.5, int(wall.sum()))).astype(dtype)
+    ref = po.coarsen_level(fine, (4, 4, 4), coarsen_extra_cells=True)
+    prec = 1 if dtype == np.float64 else 0
+    g = make(gpu_lib, marchPrecision=prec, coarsenExtraCells=1, haloCells=(4, 4, 4), nDivQRays=3, threshold=0.01, isSeedRandom=0, skipZeroWeightLegs=0)
+    k, s, nonflow = _device_coarse_level(g, fine, ref, dtype)
+    M = ref.abskg.shape[0]
+    ext = np.ones(ref.abskg.shape, bool); ext[1:-1, 1:-1, 1:-1] = False
+    assert nonflow[ext].all()
+    tol = dict(rtol=1e-13) if dtype == np.float64 else dict(rtol=2e-7)
+    np.testing.assert_allclose(k[ext], ref.abskg[ext], **tol)
+    np.testing.assert_allclose(s[ext], ref.sigmaT4[ext], **tol)
+    edges = ext.copy()
+    for a in range(3):
+        sl = [slice(1, -1)] * 3
+        for idx in (0, M - 1):
+            sl[a] = idx; edges[tuple(sl)] = False
+    assert np.all(k[edges] == 0) and np.all(s[edges] == 0) and (k[ext & ~edges] > 0).all()
+    if dtype == np.float64:          # the solve itself (deterministic regression mode) on the device-derived coarse level
+        g.finalize_level(0)
+        kw = dict(nDivQRays=3, threshold=0.01, isSeedRandom=0)
+        want = po.ray_trace_data_onion(po.default_params(**kw), [ref, fine], (4, 4, 4), patches=(2, 2, 2), threads=8)
+        divQ = np.zeros_like(want["divQ"]); vol = np.zeros_like(divQ)
+        for plo, phi in po._split((0, 0, 0), (32, 32, 32), (2, 2, 2)):
+            g.trace_dataonion(2, plo, phi, zero_init=False, outputs=(divQ, vol, None))
+        assert g.counters().nRaySteps == want["steps"]
+        np.testing.assert_allclose(divQ, want["divQ"], rtol=1e-9, atol=1e-10 * np.abs(want["divQ"]).max())
+
+
+@pytest.mark.parametrize("prec", [1, 0])
+def test_data_onion_fixed_roi(gpu_lib, po, prec):
+    """<ROI_extents type="fixed">: one ROI box for every fine patch (Ray.cc:1303-1314) -- patches inside it (ROI-copy fast path in FP32),
+    straddling it and outside it (their rays start on the fine level and leave it at the first step); extents equal the oracle's,
+    deterministic solve to round-off (FP64) / FP32 round-off"""
+    fine = po.burns_christon(32, dtype=np.float64 if prec else np.float32)
+    fine.rr = (4, 4, 4)
+    coarse = po.coarsen_level(fine, (4, 4, 4))
+    rlo, rhi = (6, 4, 8), (26, 30, 24)
+    kw = dict(nDivQRays=3, threshold=0.05, isSeedRandom=0)
+    want = po.ray_trace_data_onion(po.default_params(roiFixed=1, roiFixedLo=rlo, roiFixedHi=rhi, **kw), [coarse, fine], (4, 4, 4), patches=(2, 2, 2), threads=8)
+    g = make(gpu_lib, marchPrecision=prec, skipZeroWeightLegs=0, haloCells=(4, 4, 4), roiFixed=1, roiFixedLo=rlo, roiFixedHi=rhi, **kw)
+    g.upload_level(0, coarse)
+    g.upload_level(1, fine)
+    for plo, phi in (((0, 0, 0), (16, 16, 16)), ((8, 8, 8), (24, 24, 24))):
+        a = g.compute_extents(2, plo, phi)
+        b = po.compute_extents([coarse, fine], plo, phi, (4, 4, 4), rlo, rhi)
+        assert a[0] == b[0] == rlo and a[1] == b[1] == rhi and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    divQ = np.zeros_like(want["divQ"]); vol = np.zeros_like(divQ)
+    for plo, phi in list(po._split((0, 0, 0), (32, 32, 32), (2, 2, 2))) + [((8, 8, 8), (24, 24, 24))]:      # the last patch lies inside the ROI
+        g.trace_dataonion(2, plo, phi, zero_init=False, outputs=(divQ, vol, None))
+    if prec:
+        np.testing.assert_allclose(divQ, want["divQ"], rtol=1e-9, atol=1e-10 * np.abs(want["divQ"]).max())
+    else:
+        assert np.abs(divQ - want["divQ"]).max() <= 2e-4 * np.abs(want["divQ"]).max()

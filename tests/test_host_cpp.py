@@ -106,7 +106,22 @@ def test_data_onion_needs_patch_based_roi(exe, tmp_path):
     deck = tmp_path / "bad.ups"
     deck.write_text(src.replace('<ROI_extents type="patch_based"/>', '<ROI_extents type="dynamic"> <abskgd_threshold> 0.1 </abskgd_threshold> </ROI_extents>'))
     r = subprocess.run([exe, str(deck), "--parse-only"], capture_output=True, text=True)
-    assert r.returncode == 1 and 'only ROI_extents type="patch_based" work on the GPU' in r.stderr
+    assert r.returncode == 1 and 'only ROI_extents type="patch_based" and type="fixed" work on the GPU' in r.stderr
+
+
+def test_fixed_roi_and_coarsen_extra_cells_are_accepted(exe, tmp_path):
+    """<ROI_extents type="fixed"> (Ray.cc:265-271) and <coarsenExtraCells> (Ray.cc:256): parsed and scheduled; with coarsenExtraCells the
+    coarse level gets no setBoundaryConditions task (RMCRT_Test.cc:441-443); a fixed ROI off the fine level is refused like the reference
+    does in computeExtents (Ray.cc:1308-1313)"""
+    src = open(os.path.join(DECKS, "bm1_DO.ups")).read()
+    deck = tmp_path / "fixed.ups"
+    deck.write_text(src.replace('<ROI_extents type="patch_based"/>', '<ROI_extents type="fixed"> <min> [0.25,0.25,0.25] </min> <max> [0.75,0.75,0.75] </max> </ROI_extents>\n<coarsenExtraCells> true </coarsenExtraCells>'))
+    r = subprocess.run([exe, str(deck), "--parse-only"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    t = tasks_of(r.stdout)
+    assert [x["level"] for x in t if x["name"] == "Ray::setBoundaryConditions"] == ["1"]      # fine level only
+    base = tasks_of(run(exe, "bm1_DO.ups", "--parse-only").stdout)
+    assert sorted(x["level"] for x in base if x["name"] == "Ray::setBoundaryConditions") == ["0", "1"]
 
 
 def test_no_gpu_fails_loudly(exe):

@@ -192,3 +192,25 @@ def test_computeExtents_is_the_reference(po, ref):
                 assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3]), (N, halo, lo, hi, a, b)
                 n += 1
     assert n == 32
+
+
+def test_computeExtents_fixed_roi_is_the_reference(po, ref):
+    """the fixed branch of Ray::computeExtents (Ray.cc:1303-1314): ROI = fineLevel->getCellIndex(min / max point), clamped to the level,
+    the same for every patch; points off the fine level make the reference throw"""
+    fine = po.burns_christon(64, dtype=np.float32); fine.rr = (2, 2, 2)
+    mid = po.coarsen_level(fine, (2, 2, 2)); mid.rr = (4, 4, 4)
+    coarse = po.coarsen_level(mid, (4, 4, 4))
+    levels = [coarse, mid, fine]
+    dx = 1.0 / 64
+    n = 0
+    for pmin, pmax in (((0.25, 0.25, 0.25), (0.75, 0.75, 0.75)), ((0.0, 0.1, 0.3), (0.999, 0.6, 0.31)), ((-0.01, -0.01, -0.01), (1.01, 1.01, 1.01))):
+        lo = tuple(int(np.floor(x / dx)) for x in pmin)
+        hi = tuple(int(np.floor(x / dx)) for x in pmax)
+        for plo, phi in (((0, 0, 0), (32, 32, 32)), ((32, 32, 32), (64, 64, 64))):
+            a = po.ref_compute_extents(levels, plo, phi, (4, 4, 4), "fixed", pmin, pmax)
+            b = po.compute_extents(levels, plo, phi, (4, 4, 4), lo, hi)
+            assert a is not None
+            assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3]), (pmin, pmax, a, b)
+            n += 1
+    assert n == 6
+    assert po.ref_compute_extents(levels, (0, 0, 0), (32, 32, 32), (4, 4, 4), "fixed", (0.2, 0.2, 0.2), (1.5, 0.5, 0.5)) is None

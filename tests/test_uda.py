@@ -62,6 +62,27 @@ def test_cpp_reader_agrees_with_python_across_layouts(tools, tmp_path):
     assert all(v == (0.0, 0.0, 0.0, 125000) for v in rows.values()) and len(rows) == 3
 
 
+@pytest.mark.parametrize("nprocs,gridxml", [(1, False), (3, False), (4, True)])
+def test_files_are_named_after_the_writing_rank(tools, tmp_path, nprocs, gridxml):
+    """lL/p<rank>.{xml,data} hold every patch a rank owned (DataArchive.cc:2310-2314): archives written by fewer ranks than patches --
+    1 rank / 10 patches (everything in p00000), 3 ranks, 4 ranks with <Grid> in grid.xml (newer archives, DataArchive.cc:431-457)"""
+    fields = {n: np.ascontiguousarray(U.read_level_var(FIXTURE, n)[0]) for n in ("abskg", "temperature", "cellType")}
+    lev = U.read_grid(FIXTURE, "t01000")[0]
+    other = str(tmp_path / f"ranks{nprocs}.uda")
+    U.write_uda(other, fields, (-1,) * 3, (51,) * 3, (0,) * 3, (50,) * 3, (2, 5, 1), lev["anchor"], lev["dx"], timestep=1000,
+                time=0.0011495386101984409, gzip=True, nprocs=nprocs)
+    assert sorted(os.listdir(os.path.join(other, "t01000", "l0"))) == sorted(f"p{r:05d}.{e}" for r in range(nprocs) for e in ("xml", "data"))
+    if gridxml:       # move <Grid> out of timestep.xml
+        tsx = os.path.join(other, "t01000", "timestep.xml")
+        x = open(tsx).read()
+        a, b = x.index("  <Grid>"), x.index("</Grid>") + len("</Grid>\n")
+        open(os.path.join(other, "t01000", "grid.xml"), "w").write('<?xml version="1.0" encoding="UTF-8"?>\n<Grid>' + x[a + len("  <Grid>"):b])
+        open(tsx, "w").write(x[:a] + x[b:])
+    r, rows = lnorm(FIXTURE, other)
+    assert r.returncode == 0, r.stderr
+    assert all(v == (0.0, 0.0, 0.0, 125000) for v in rows.values()) and len(rows) == 3
+
+
 def test_lnorm_known_answer(tools, tmp_path):
     """L1 = sum|d|/n, L2 = sqrt(sum d^2/n), Linf = max|d| over interior cells (compute_Lnorm_udas.cc:208-214, 332-335)"""
     rng = np.random.default_rng(5)

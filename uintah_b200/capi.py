@@ -44,7 +44,8 @@ class Params(C.Structure):
         ("fixedRandom", C.c_int32), ("l2Persist", C.c_int32), ("warpsPerTile", C.c_int32),
         ("genericMarch", C.c_int32), ("maxBlocksPerSM", C.c_int32), ("rayDirSampleAlgo", C.c_int32), ("cellsPerLane", C.c_int32),
         ("maxRayLength", C.c_double), ("sigmaScat", C.c_double), ("tileX", C.c_int32), ("nonFlowCellType", C.c_int32),
-        ("blockedMarch", C.c_int32), ("refillLanes", C.c_int32),
+        ("blockedMarch", C.c_int32), ("refillLanes", C.c_int32), ("coarsenExtraCells", C.c_int32), ("roiFixed", C.c_int32),
+        ("roiFixedLo", C.c_int32 * 3), ("roiFixedHi", C.c_int32 * 3),
     ]
 
 
@@ -142,8 +143,8 @@ def default_params(**overrides) -> Params:
     for k, v in overrides.items():
         if not hasattr(p, k):
             raise AttributeError(f"rmcrt_params has no field {k!r}")
-        if k == "haloCells":
-            p.haloCells = (C.c_int32 * 3)(*[int(x) for x in v])
+        if k in ("haloCells", "roiFixedLo", "roiFixedHi"):
+            setattr(p, k, (C.c_int32 * 3)(*[int(x) for x in v]))
         else:
             setattr(p, k, v)
     return p

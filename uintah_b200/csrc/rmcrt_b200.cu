@@ -1165,6 +1165,50 @@ __global__ void coarsen_kernel(const RecT* __restrict__ fine, Box fb, RecT* __re
   }
 }
 
+// <coarsenExtraCells> true (Ray::coarsen_Q, Ray.cc:2148-2245): the coarse level's extra cells on the faces of the computational domain take
+// the average of the fine level's extra cells they cover -- refinement ratio 1 along the face normal (one layer of extra cells on both
+// levels), the full ratio in the two tangential directions, faces WITHOUT their edges (Patch::ExtraMinusEdgeCells); accumulated in T and
+// scaled by the double 1/RR like the reference.  Edge and corner extra cells keep the 0 of Q_coarse.initialize(0.0); no ray can enter
+// them.  The cell type of coarse extra cells is not touched by computeCellType (it loops over interior cells): they stay the non-flow
+// cells the caller initialised, i.e. the wall flag is set.
+template <class RecT>
+__global__ void coarsen_extra_kernel(const RecT* __restrict__ fine, Box fb, Box fint, RecT* __restrict__ coarse, Box cb, Box cint,
+                                     int rr0, int rr1, int rr2, Rec8* __restrict__ coarseFull) {
+  typedef typename RecTraits<RecT>::real R;
+  const long long n = box_cells(cb);
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const long long row = t / cb.n[0];
+    const int c[3] = {cb.lo[0] + (int)(t - row * cb.n[0]), cb.lo[1] + (int)(row % cb.n[1]), cb.lo[2] + (int)(row / cb.n[1])};
+    int nOut = 0, axis = -1;
+    bool high = false;
+    for (int d = 0; d < 3; ++d) {
+      if (c[d] < cint.lo[d]) { ++nOut; axis = d; high = false; }
+      else if (c[d] >= cint.lo[d] + cint.n[d]) { ++nOut; axis = d; high = true; }
+    }
+    if (nOut == 0) continue;                      // interior: coarsen_kernel
+    R kc = 0, sc = 0;
+    if (nOut == 1) {
+      const int rr[3] = {rr0, rr1, rr2};
+      int f0[3], cnt[3];
+      for (int d = 0; d < 3; ++d) {
+        if (d == axis) { f0[d] = high ? fint.lo[d] + fint.n[d] : fint.lo[d] - 1; cnt[d] = 1; }     // the fine extra-cell layer of that face
+        else { f0[d] = c[d] * rr[d]; cnt[d] = rr[d]; }
+      }
+      R ak = 0, as = 0;
+      for (int z = 0; z < cnt[2]; ++z) for (int y = 0; y < cnt[1]; ++y) for (int x = 0; x < cnt[0]; ++x) {
+        const long long f = (long long)(f0[0] + x - fb.lo[0]) + (long long)fb.n[0] * ((long long)(f0[1] + y - fb.lo[1]) + (long long)fb.n[1] * (long long)(f0[2] + z - fb.lo[2]));
+        const auto r = load_true(fine + f);
+        ak += (r.k < R(0) || is_wall(r.k)) ? -r.k : r.k;
+        as += r.s;
+      }
+      const double invRR = 1.0 / ((double)(cnt[0] * cnt[1] * cnt[2]));
+      kc = (R)(ak * invRR); sc = (R)(as * invRR);
+    }
+    coarse[t] = make_rec<RecT, R>(-kc, sc);       // wall flag set (also for abskg == 0: -0.0)
+    if (coarseFull) coarseFull[t] = Rec8{(float)(-kc), (float)sc};
+  }
+}
+
 template <class RecT>
 __global__ void extra_cells_kernel(RecT* __restrict__ recs, Box b, Box interior, const double* __restrict__ vals /*[3][6]*/,
                                    const int* __restrict__ types, int flowCell, Rec8* __restrict__ full) {
@@ -1564,14 +1608,16 @@ int map_coarser_host(int i, int rr) {
   return q;
 }
 
-// Ray::computeExtents, patch_based (Ray.cc:1312-1357)
+// Ray::computeExtents, patch_based and fixed ROI (Ray.cc:1303-1357)
 void compute_extents(const rmcrt_ctx* ctx, int maxLevels, const int32_t pLo[3], const int32_t pHi[3], int32_t roiLo[3],
                      int32_t roiHi[3], int32_t* regLo, int32_t* regHi) {
   const int F = maxLevels - 1;
   const rmcrt_level_desc& f = ctx->lv[F].d;
   for (int d = 0; d < 3; ++d) {
-    roiLo[d] = std::max(pLo[d] - ctx->p.haloCells[d], f.lo[d]);
-    roiHi[d] = std::min(pHi[d] + ctx->p.haloCells[d], f.hi[d]);
+    const int lo = ctx->p.roiFixed ? ctx->p.roiFixedLo[d] : pLo[d] - ctx->p.haloCells[d];
+    const int hi = ctx->p.roiFixed ? ctx->p.roiFixedHi[d] : pHi[d] + ctx->p.haloCells[d];
+    roiLo[d] = std::max(lo, f.lo[d]);
+    roiHi[d] = std::min(hi, f.hi[d]);
     const int ec = f.interiorLo[d] - f.lo[d];
     regLo[3 * F + d] = roiLo[d] + ec;
     regHi[3 * F + d] = roiHi[d] - ec;
@@ -1873,7 +1919,9 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
     // grid-stride loop over ~7 tiles per block left a ~10 % tail at 128^3)
     const long long cap = ctx->p.maxBlocksPerSM > 0 ? (long long)ctx->smCount * ctx->p.maxBlocksPerSM : (1LL << 22);
     if (grid > cap) grid = cap;
-    if (ML && std::is_same<Real, float>::value && !ctx->p.genericMarch && a.G.maxLevels == 2) {
+    bool patchInRoi = true;       // a fixed ROI need not contain the patch; the ROI-copy fast path starts every ray inside the copy
+    for (int d = 0; d < 3 && ML; ++d) patchInRoi = patchInRoi && a.G.roiLo[d] <= a.patchLo[d] && a.patchLo[d] + a.patchN[d] <= a.G.roiHi[d];
+    if (ML && std::is_same<Real, float>::value && !ctx->p.genericMarch && a.G.maxLevels == 2 && patchInRoi) {
       // 2-level Data Onion fast path: per-patch ROI copy with a marker shell, then the tuned leg loop on both levels
       const LevelState& fl = ctx->lv[1];
       Box roiBox, shell;
@@ -2135,6 +2183,8 @@ void rmcrt_default_params(rmcrt_params* p) {
   p->sigmaScat = 0.0;          // Ray.cc:169
   p->tileX = 0; p->nonFlowCellType = 8;
   p->blockedMarch = 0; p->refillLanes = 0;
+  p->coarsenExtraCells = 0; p->roiFixed = 0;
+  for (int d = 0; d < 3; ++d) { p->roiFixedLo[d] = 0; p->roiFixedHi[d] = 0; }
   p->cellsPerLane = 4;         // production: the 2 x 2 cells of a lane share one DDA (divq_quad_kernel); 2 = a pair (divq_dual_kernel); 1 = one cell per lane
 }
 
@@ -2494,6 +2544,17 @@ int rmcrt_coarsen_level_device(rmcrt_ctx* ctx, int fineL, int coarseL, void* str
   else if (f.recordKind == 2) coarsen_kernel<Rec4><<<grid_for(n, 128, ctx->smCount), 128, 0, st>>>(static_cast<const Rec4*>(f.rec), fb, static_cast<Rec4*>(c.rec), cb, ci, rr[0], rr[1], rr[2], ctx->p.cellTypeCoarsenLogic, ctx->p.nonFlowCellType, static_cast<Rec8*>(c.recFull));
   else                        coarsen_kernel<Rec16><<<grid_for(n, 128, ctx->smCount), 128, 0, st>>>(static_cast<const Rec16*>(f.rec), fb, static_cast<Rec16*>(c.rec), cb, ci, rr[0], rr[1], rr[2], ctx->p.cellTypeCoarsenLogic, ctx->p.nonFlowCellType, nullptr);
   CK(cudaGetLastError());
+  if (ctx->p.coarsenExtraCells) {
+    for (int d = 0; d < 3; ++d)
+      if (f.d.interiorLo[d] - f.d.lo[d] != 1 || f.d.hi[d] - f.d.interiorHi[d] != 1 || c.d.interiorLo[d] - c.d.lo[d] != 1 || c.d.hi[d] - c.d.interiorHi[d] != 1)
+        return fail(ctx, RMCRT_ERR_INVALID, "coarsenExtraCells needs one layer of extra cells on both levels");
+    Box fi = mkbox(f.d.interiorLo, f.d.interiorHi);
+    const long long nc = box_cells(cb);
+    if (f.recordKind == 0)      coarsen_extra_kernel<Rec8><<<grid_for(nc, 128, ctx->smCount), 128, 0, st>>>(static_cast<const Rec8*>(f.rec), fb, fi, static_cast<Rec8*>(c.rec), cb, ci, rr[0], rr[1], rr[2], nullptr);
+    else if (f.recordKind == 2) coarsen_extra_kernel<Rec4><<<grid_for(nc, 128, ctx->smCount), 128, 0, st>>>(static_cast<const Rec4*>(f.rec), fb, fi, static_cast<Rec4*>(c.rec), cb, ci, rr[0], rr[1], rr[2], static_cast<Rec8*>(c.recFull));
+    else                        coarsen_extra_kernel<Rec16><<<grid_for(nc, 128, ctx->smCount), 128, 0, st>>>(static_cast<const Rec16*>(f.rec), fb, fi, static_cast<Rec16*>(c.rec), cb, ci, rr[0], rr[1], rr[2], nullptr);
+    CK(cudaGetLastError());
+  }
   return invalidate_level(ctx, coarseL, st);
 }
 

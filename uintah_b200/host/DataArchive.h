@@ -107,9 +107,25 @@ class DataArchive {
   GridP queryGrid(int timeIndex) {
     checkIndex(timeIndex);
     if (grids_.count(timeIndex)) return grids_[timeIndex];
-    ProblemSpecP ts = ProblemSpec::parseString(uda_detail::readFile(base_ + "/" + tsHref_[timeIndex]));
-    ProblemSpecP grid_ps = ts->findBlock("Grid");
-    if (!grid_ps) throw InternalError("DataArchive: no <Grid> in " + tsHref_[timeIndex], __FILE__, __LINE__);
+    // newer archives keep <Grid> in tNNNNN/grid.xml, older ones inside timestep.xml (DataArchive.cc:431-457)
+    const std::string tsPath = base_ + "/" + tsHref_[timeIndex];
+    const std::string gridPath = tsPath.substr(0, tsPath.find_last_of('/') + 1) + "grid.xml";
+    ProblemSpecP grid_ps;
+    {
+      std::ifstream gx(gridPath, std::ios::binary);
+      if (gx) {
+        const std::string text = uda_detail::readFile(gridPath);
+        if (text.find("<Grid") == std::string::npos)
+          throw InternalError("DataArchive: " + gridPath + " is a binary grid file (GRID_MAGIC_NUMBER); only the xml form is read", __FILE__, __LINE__);
+        ProblemSpecP doc = ProblemSpec::parseString(text);
+        grid_ps = doc->getNodeName() == "Grid" ? doc : doc->findBlock("Grid");
+      }
+    }
+    if (!grid_ps) {
+      ProblemSpecP ts = ProblemSpec::parseString(uda_detail::readFile(tsPath));
+      grid_ps = ts->findBlock("Grid");
+    }
+    if (!grid_ps) throw InternalError("DataArchive: no <Grid> in " + tsHref_[timeIndex] + " (nor a grid.xml next to it)", __FILE__, __LINE__);
     auto grid = std::make_shared<Grid>();
     int L = 0;
     Vector prevDx(0, 0, 0);
@@ -124,8 +140,10 @@ class DataArchive {
       auto level = std::make_shared<Level>(grid.get(), L, anchor, dx, extra, rr);
       IntVector ilo(INT_MAX, INT_MAX, INT_MAX), ihi(INT_MIN, INT_MIN, INT_MIN);
       for (ProblemSpecP p = lev->findBlock("Patch"); p; p = p->findNextBlock("Patch")) {
-        int id = 0;
+        int id = 0, proc = -1;
         p->require("id", id);
+        p->get("proc", proc);             // the rank that wrote the patch: its data is in lL/p<proc>.{xml,data} (DataArchive.cc:2310-2314)
+        procOf_[timeIndex][id] = proc;
         IntVector lo, hi;
         p->require("lowIndex", lo);
         p->require("highIndex", hi);
@@ -149,7 +167,25 @@ class DataArchive {
     if (typeName(name) != want) throw InternalError("DataArchive::query: " + name + " is a " + typeName(name) + ", not a " + want, __FILE__, __LINE__);
     const std::string tdir = base_ + "/" + tsHref_[timeIndex].substr(0, tsHref_[timeIndex].find_last_of('/'));
     const std::string ldir = tdir + "/l" + std::to_string(patch->getLevel()->getIndex());
-    const std::string pxml = ldir + "/p" + uda_detail::pad5(patch->getID()) + ".xml";
+    // Output files are named after the RANK that wrote them, not after the patch: lL/p<proc>.xml lists the variables of every patch that
+    // rank owned (DataArchive.cc:2310-2314).  Archives without <proc> (old format): guess the file of the same index, then scan the
+    // level's files (2330-2347).
+    if (!grids_.count(timeIndex)) queryGrid(timeIndex);
+    std::vector<std::string> candidates;
+    const auto pit = procOf_[timeIndex].find(patch->getID());
+    if (pit != procOf_[timeIndex].end() && pit->second >= 0) candidates.push_back(ldir + "/p" + uda_detail::pad5(pit->second) + ".xml");
+    else {
+      candidates.push_back(ldir + "/p" + uda_detail::pad5(patch->getID()) + ".xml");
+      for (int r = 0; r < 100000; ++r) {
+        const std::string f = ldir + "/p" + uda_detail::pad5(r) + ".xml";
+        if (!std::ifstream(f)) { if (r > patch->getLevel()->numPatches()) break; else continue; }
+        if (r != patch->getID()) candidates.push_back(f);
+      }
+    }
+    std::string pxml;
+    for (const std::string& cand : candidates) {
+    if (!std::ifstream(cand)) continue;
+    pxml = cand;
     ProblemSpecP out = ProblemSpec::parseString(uda_detail::readFile(pxml));
     for (auto& v : out->children()) {
       if (v->getNodeName() != "Variable") continue;
@@ -190,7 +226,9 @@ class DataArchive {
       }
       return;
     }
-    throw InternalError("DataArchive::query: " + name + " (matl " + std::to_string(matl) + ") is not in " + pxml, __FILE__, __LINE__);
+    }
+    throw InternalError("DataArchive::query: " + name + " (matl " + std::to_string(matl) + ", patch " + std::to_string(patch->getID()) + ") is not in " +
+                        (pxml.empty() ? ldir + "/p*.xml (no such file)" : pxml), __FILE__, __LINE__);
   }
 
   // DataArchive::queryRegion: gather [low,high) of a level from every patch that overlaps it
@@ -226,6 +264,7 @@ class DataArchive {
   std::vector<int> tsIndex_;
   std::vector<double> tsTime_;
   std::map<int, GridP> grids_;
+  std::map<int, std::map<int, int>> procOf_;      // time index -> patch id -> rank whose files hold the patch (-1: not recorded)
 };
 
 //______________________________________________________________________ writer: what <DataArchiver> produces for the saved labels
@@ -249,7 +288,8 @@ class DataArchiver {
     bool known = false;
     for (auto& v : vars_) known = known || v.first == name;
     if (!known) vars_.emplace_back(name, type);
-    const std::string key = "l" + std::to_string(patch->getLevel()->getIndex()) + "/p" + uda_detail::pad5(patch->getID());
+    // this writer is ONE rank (rank 0): like sus it keeps one file pair per level and rank, lL/p00000.{xml,data}, holding all its patches
+    const std::string key = "l" + std::to_string(patch->getLevel()->getIndex()) + "/p" + uda_detail::pad5(0);
     const std::string data = base_ + "/" + tdir_ + "/" + key + ".data";
     size_t& off = offsets_[key];
     std::ofstream out(data, off == 0 ? (std::ios::binary | std::ios::trunc) : (std::ios::binary | std::ios::app));
@@ -270,7 +310,7 @@ class DataArchiver {
     std::ostringstream x;
     x << "  <Variable type=\"" << uda_detail::encodeEntities(type) << "\">\n    <variable>" << name << "</variable>\n    <index>" << matl << "</index>\n    <patch>"
       << patch->getID() << "</patch>\n    <start>" << off << "</start>\n" << (gzip_ ? "    <compression>gzip</compression>\n" : "") << "    <end>" << off + written
-      << "</end>\n    <filename>p" << uda_detail::pad5(patch->getID()) << ".data</filename>\n  </Variable>\n";
+      << "</end>\n    <filename>p" << uda_detail::pad5(0) << ".data</filename>\n  </Variable>\n";
     patchXml_[key] += x.str();
     off += written;
   }
@@ -302,7 +342,9 @@ class DataArchiver {
       }
       t << "    </Level>\n";
     }
-    t << "  </Grid>\n</Uintah_timestep>\n";
+    t << "  </Grid>\n  <Data>\n";
+    for (auto& kv : patchXml_) t << "    <Datafile href=\"" << kv.first << ".xml\" proc=\"0\"/>\n";
+    t << "  </Data>\n</Uintah_timestep>\n";
     steps_.emplace_back(ts_, time_, delt_);
     writeIndex();
   }

@@ -151,15 +151,15 @@ void Ray::problemSetup(const ProblemSpecP& prob_spec, const ProblemSpecP& rmcrtp
     if (tmp == "ROUNDUP") d_cellTypeCoarsenLogic = ROUNDUP;
   }
 
-  //__________________________________ bulletproofing: this IS the device build (Ray.cc:338-345)
-  if (algorithm == dataOnion && d_ROI_algo != patch_based) {
+  //__________________________________ bulletproofing (Ray.cc:338-345): the reference's own device build refuses everything but patch_based;
+  // this back end also takes the fixed ROI (the whole fine level is resident on the device, so the ROI is only a box test).  The
+  // dynamic ROI needs the abskg / sigmaT4 gradient reduction tasks (Ray.cc:1950-2044), which are not part of this path.
+  if (algorithm == dataOnion && d_ROI_algo == dynamic) {
     std::ostringstream warn;
     warn << "GPU:RMCRT:ERROR: ";
-    warn << "At this time only ROI_extents type=\"patch_based\" work on the GPU";
+    warn << "At this time only ROI_extents type=\"patch_based\" and type=\"fixed\" work on the GPU";
     throw ProblemSetupException(warn.str(), __FILE__, __LINE__);
   }
-  if (d_coarsenExtraCells)
-    throw ProblemSetupException("RMCRT (B200 back end): coarsenExtraCells=true is not implemented; coarse-level extra cells are set from the boundary conditions", __FILE__, __LINE__);
   d_sigma_over_pi = d_sigma / M_PI;
 }
 
@@ -214,6 +214,19 @@ void Ray::fillParams(rmcrt_params& p) const {
   p.rayDirSampleAlgo = d_rayDirSampleAlgo == LATIN_HYPER_CUBE ? 1 : 0;
   p.maxRayLength = d_maxRayLength;
   p.sigmaScat = d_sigmaScat;
+  p.roiFixed = 0;
+  if (d_ROI_algo == fixed && d_grid) {                      // Ray::computeExtents, fixed branch (Ray.cc:1303-1314)
+    const Level* fineLevel = d_grid->getLevel(d_grid->numLevels() - 1).get();
+    const IntVector lo = fineLevel->getCellIndex(d_ROI_minPt), hi = fineLevel->getCellIndex(d_ROI_maxPt);
+    if (!fineLevel->containsCell(lo) || !fineLevel->containsCell(hi)) {
+      std::ostringstream warn;
+      warn << "ERROR:  the fixed ROI extents " << d_ROI_minPt << " " << d_ROI_maxPt << " are not contained on the fine level.\n";
+      throw ProblemSetupException(warn.str(), __FILE__, __LINE__);
+    }
+    p.roiFixed = 1;
+    for (int d = 0; d < 3; ++d) { p.roiFixedLo[d] = lo[d]; p.roiFixedHi[d] = hi[d]; }
+  }
+  p.coarsenExtraCells = d_coarsenExtraCells ? 1 : 0;     // Ray::coarsen_Q's domain-face branch (Ray.cc:2148-2245) runs inside rmcrt_coarsen_level_device
   for (auto& kv : d_knobs) {
     if (kv.first == "rayCoherence") p.rayCoherence = kv.second;
     else if (kv.first == "skipZeroWeightLegs") p.skipZeroWeightLegs = kv.second;
@@ -505,10 +518,11 @@ void Ray::sched_computeCellType(const LevelP&, SchedulerP&, const Ray::modifiesC
   // fused into the device coarsening kernel (ROUNDUP / ROUNDDOWN, Ray.cc:2315-2342); nothing to schedule
 }
 
-// Ray.cc:1950-2043: only the dynamic ROI needs this task; the B200 back end supports patch_based (see problemSetup)
+// Ray.cc:1950-2043: only the dynamic ROI needs this task (it returns at once otherwise, 1957-1959); the B200 back end supports
+// patch_based and fixed (see problemSetup)
 void Ray::sched_ROI_Extents(const LevelP&, SchedulerP&) {
-  if (d_ROI_algo != patch_based && d_ROI_algo != entireDomain)
-    throw ProblemSetupException("GPU:RMCRT:ERROR: At this time only ROI_extents type=\"patch_based\" work on the GPU", __FILE__, __LINE__);
+  if (d_ROI_algo == dynamic)
+    throw ProblemSetupException("GPU:RMCRT:ERROR: At this time only ROI_extents type=\"patch_based\" and type=\"fixed\" work on the GPU", __FILE__, __LINE__);
 }
 
 // a level whose property records exist only on the device: every level below the finest one of a multi-level algorithm

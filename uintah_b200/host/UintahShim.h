@@ -287,6 +287,11 @@ class Level {
     b.extend(Point(anchor_.x() + dcell_.x() * hi.x(), anchor_.y() + dcell_.y() * hi.y(), anchor_.z() + dcell_.z() * hi.z()));
   }
   void findCellIndexRange(IntVector& lo, IntVector& hi) const { lo = lo_ - extra_; hi = hi_ + extra_; }
+  // Level::containsCell: any cell of the level, extra cells included
+  bool containsCell(const IntVector& c) const {
+    const IntVector lo = lo_ - extra_, hi = hi_ + extra_;
+    return c.x() >= lo.x() && c.y() >= lo.y() && c.z() >= lo.z() && c.x() < hi.x() && c.y() < hi.y() && c.z() < hi.z();
+  }
   void findInteriorCellIndexRange(IntVector& lo, IntVector& hi) const { lo = lo_; hi = hi_; }
   // Level.cc:1285-1307: truncating division, negative indices shifted by (int)fmod(idx, ratio)
   IntVector mapCellToCoarser(const IntVector& c) const {

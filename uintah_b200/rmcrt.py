@@ -113,8 +113,8 @@ class RMCRT:
         for k, v in kw.items():
             if not hasattr(self.params, k):
                 raise AttributeError(k)
-            if k == "haloCells":
-                self.params.haloCells = i3(v)
+            if k in ("haloCells", "roiFixedLo", "roiFixedHi"):
+                setattr(self.params, k, i3(v))
             else:
                 setattr(self.params, k, v)
         check(self.ctx, self.lib.rmcrt_set_params(self.ctx, C.byref(self.params)))
