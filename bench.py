@@ -481,6 +481,25 @@ def run_ours(args):
             for coh in (0, 2):
                 configs[f"c5_flux_reflect_{CN}_coherence{coh}"] = bc.c5_single_gpu(CN, rays, cfg_steps, -1, coh, 4, warm=1, flush=flush)
                 torch.cuda.empty_cache()
+            # the same solve through the C++ plugin: deck -> DataWarehouse -> Ray::rayTrace<float> task on 8 patches of 64^3 -> C ABI
+            exe = os.path.join(ROOT, "uintah_b200", "host", "rmcrt_test")
+            deck = os.path.join(ROOT, "tests", "decks", "bm1_1L_float_128_perf.ups")
+            if os.path.exists(exe) and os.path.exists(deck) and P == 128 and rays == 100:
+                try:
+                    import re
+                    r = subprocess.run([exe, deck, "--timesteps", "3"], capture_output=True, text=True, timeout=300)
+                    used = [float(x) for x in re.findall(r"Used ([0-9.eE+-]+) milliseconds", r.stdout)]
+                    whole = [float(x) for x in re.findall(r"; ([0-9.eE+-]+) ms for the whole task", r.stdout)]
+                    size = [float(x) for x in re.findall(r"Size: ([0-9.eE+-]+) ray-cell steps", r.stdout)]
+                    if used and size:
+                        configs["cpp_plugin_128"] = {
+                            "workload": "tests/decks/bm1_1L_float_128_perf.ups through rmcrt_test: Ray::rayTrace<float> task, 8 patches of 64^3, "
+                                        "DataWarehouse grid variables in pooled page-locked memory (rmcrt_host_alloc)",
+                            "trace_ms_per_solve": used[-1], "task_ms_per_solve": whole[-1] if whole else None,
+                            "ray_cell_steps_per_s": size[-1] / (used[-1] * 1e-3), "solves": len(used),
+                            "timing": "the task's own RMCRT REPORT (host clock around the trace calls, results in the DataWarehouse when it stops)"}
+                except Exception as ex:      # noqa: BLE001
+                    configs["cpp_plugin_128"] = {"error": str(ex)}
         elif world in (2, 4, 8):
             class A:      # the Data Onion sharded by fine patch over the ranks (BASELINE configs[3] at 8 GPUs)
                 pass

@@ -328,6 +328,27 @@ int rmcrt_assemble_level(rmcrt_ctx* ctx, int L, const void* d_gathered, size_t s
 int rmcrt_allgather_records(rmcrt_ctx* ctx, const void* d_sendSlot, void* d_gathered, size_t slotBytes,
                             void* ncclComm, void* stream);
 
+/* ------------------------------------------------------------------ one process driving several devices
+ * rmcrt_replicate_level: what n calls of rmcrt_upload_level (one per context / device) achieve -- level L of every context holds the
+ * packed records of the host arrays -- with 1/n of the PCIe traffic: device d uploads and packs only its z-slab of the level and ONE
+ * ncclAllGather (single-process communicators, created on first use) replicates the packed records over NVLink; then every device
+ * assembles the level (Ray.cc:479-481: every patch needs the whole level).  Arrays must cover the whole level window.
+ * Falls back to plain per-device uploads when NCCL is not loadable, for n == 1 and for half-packed levels.  Blocking on the host only
+ * as far as the CUDA calls are; all work is queued on each device's default stream. */
+int rmcrt_replicate_level(rmcrt_ctx** ctxs, int n, int L, const void* abskg, const void* sigmaT4, const int32_t* cellType, int isFloat,
+                          const int32_t srcLo[3], const int32_t srcHi[3]);
+
+/* ------------------------------------------------------------------ page-locked host memory for the DataWarehouse side
+ * The host entry points (rmcrt_upload_level, rmcrt_trace_divq, rmcrt_trace_dataonion) are fastest when the caller's grid variables live
+ * in page-locked, device-mapped memory: property arrays upload at full PCIe rate and divQ / radiationVolq are written by the kernels in
+ * place (no staging buffer, no D2H copy after the solve).  These two functions are an allocator for such memory with a size-bucketed
+ * free list (page-locking costs ~0.3 ms per MB, so blocks are recycled, not returned to the driver): the hook for the framework's
+ * Array3Data allocation (Array3Data.h:93-125; the stand-in DataWarehouse installs it in Ray::devices()).  Thread safe.
+ * rmcrt_host_alloc returns NULL without a CUDA device; rmcrt_host_free(NULL) is a no-op; rmcrt_host_pool_trim releases the free list. */
+void* rmcrt_host_alloc(size_t bytes);
+void  rmcrt_host_free(void* p);
+void  rmcrt_host_pool_trim(void);
+
 /* ------------------------------------------------------------------ roofline denominators
  * Measures device read bandwidth on a scratch buffer of `bytes` (L2-resident when well below the L2 size, HBM when far
  * above it), `repeats` passes, CUDA-event timed.  pattern 0: coalesced 16-B loads (streaming);

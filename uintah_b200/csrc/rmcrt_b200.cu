@@ -24,6 +24,7 @@
 #include <cstdio>
 #include <cstring>
 #include <dlfcn.h>
+#include <map>
 #include <mutex>
 #include <string>
 #include <type_traits>
@@ -1530,6 +1531,7 @@ struct rmcrt_ctx {
   int lhcKeyDivQ[4] = {0, 0, 0, 0};   // (nRays, sumLo, rows, mode) the tables were built for
   int lhcKeyFlux[4] = {0, 0, 0, 0};
   DevBuf outVR[2];                    // host-API radiometer output staging
+  DevBuf replSend, replGathered;      // rmcrt_replicate_level: this device's packed slab / the gathered slabs of all devices
   std::string err;
   void* persistedStreamFor = nullptr;
 };
@@ -2242,6 +2244,7 @@ void rmcrt_destroy(rmcrt_ctx* ctx) {
   ctx->fluxFlags.release(); ctx->fluxItems.release(); ctx->cubTemp.release(); ctx->misc.release(); ctx->roiBuf.release();
   ctx->lhcDivQ.release(); ctx->lhcFlux.release(); ctx->outVR[0].release(); ctx->outVR[1].release();
   for (auto& b : ctx->dbg) b.release();
+  ctx->replSend.release(); ctx->replGathered.release();
   delete ctx;
 }
 
@@ -2828,6 +2831,169 @@ int rmcrt_allgather_records(rmcrt_ctx* ctx, const void* d_send, void* d_gathered
   const int r = fn(d_send, d_gathered, slotBytes, ncclInt8, comm, (cudaStream_t)stream);
   if (r != 0) return fail(ctx, RMCRT_ERR_NCCL, "ncclAllGather failed with code %d", r);
   return 0;
+}
+
+//------------------------------------------------------------------------------------------------------ one process, several devices
+// Replication of a level over the devices of ONE process (the C++ host path: one rmcrt_ctx per visible device, patches dealt round robin,
+// GPUGridVariableInfo.cc:610-632).  Instead of uploading the whole level to every device (n x the level over PCIe), device d uploads and
+// packs only its z-slab (1/n of the level) and the packed records are replicated with ONE ncclAllGather over NVLink, the collective
+// SURVEY 8e prescribes for the "all-to-all" ghost requirement of Ray.cc:479-481; then every device assembles the level.
+namespace {
+struct NcclApi {
+  int (*commInitAll)(void**, int, const int*) = nullptr;
+  int (*groupStart)() = nullptr;
+  int (*groupEnd)() = nullptr;
+  int (*allGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*commDestroy)(void*) = nullptr;
+  bool ok = false;
+  bool tried = false;
+} g_nccl;
+std::mutex g_ncclMu;
+std::map<std::vector<int>, std::vector<void*>> g_ncclComms;      // device list -> communicators
+
+bool load_nccl() {
+  if (g_nccl.tried) return g_nccl.ok;
+  g_nccl.tried = true;
+  void* h = nullptr;
+  auto sym = [&](const char* n) -> void* {
+    void* p = dlsym(RTLD_DEFAULT, n);
+    if (!p) {
+      if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+      if (h) p = dlsym(h, n);
+    }
+    return p;
+  };
+  g_nccl.commInitAll = (int (*)(void**, int, const int*))sym("ncclCommInitAll");
+  g_nccl.groupStart = (int (*)())sym("ncclGroupStart");
+  g_nccl.groupEnd = (int (*)())sym("ncclGroupEnd");
+  g_nccl.allGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))sym("ncclAllGather");
+  g_nccl.commDestroy = (int (*)(void*))sym("ncclCommDestroy");
+  g_nccl.ok = g_nccl.commInitAll && g_nccl.groupStart && g_nccl.groupEnd && g_nccl.allGather;
+  return g_nccl.ok;
+}
+}  // namespace
+
+int rmcrt_replicate_level(rmcrt_ctx** ctxs, int n, int L, const void* a, const void* s, const int32_t* ct, int isFloat,
+                          const int32_t srcLo[3], const int32_t srcHi[3]) {
+  if (!ctxs || n < 1 || !ctxs[0]) return RMCRT_ERR_INVALID;
+  rmcrt_ctx* ctx = ctxs[0];
+  if (!a || !s || !ct) return fail(ctx, RMCRT_ERR_INVALID, "null property pointer");
+  for (int d = 0; d < n; ++d) { int rc = check_level(ctxs[d], L); if (rc) return rc; }
+  const LevelState& l0 = ctx->lv[L];
+  for (int d = 0; d < 3; ++d)
+    if (srcLo[d] != l0.d.lo[d] || srcHi[d] != l0.d.hi[d]) return fail(ctx, RMCRT_ERR_INVALID, "rmcrt_replicate_level needs arrays over the whole level window");
+  const int nz = srcHi[2] - srcLo[2];
+  // half-packed levels keep a float copy of the cells a device ORIGINATES rays from, which pack_box only writes for the packed box:
+  // a device traces patches anywhere in the level here, so those levels (and single devices, short levels) take the plain upload
+  bool plain = n == 1 || nz < n || l0.recordKind == 2;
+  std::lock_guard<std::mutex> lock(g_ncclMu);
+  if (!plain && !load_nccl()) plain = true;
+  std::vector<void*>* comms = nullptr;
+  if (!plain) {
+    std::vector<int> devs(n);
+    for (int d = 0; d < n; ++d) devs[d] = ctxs[d]->device;
+    auto it = g_ncclComms.find(devs);
+    if (it == g_ncclComms.end()) {
+      std::vector<void*> c(n, nullptr);
+      if (g_nccl.commInitAll(c.data(), n, devs.data()) != 0) plain = true;
+      else it = g_ncclComms.emplace(devs, c).first;
+    }
+    if (!plain) comms = &it->second;
+  }
+  if (plain) {
+    for (int d = 0; d < n; ++d) {
+      int rc = rmcrt_upload_level(ctxs[d], L, a, s, ct, isFloat, srcLo, srcHi, nullptr);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+  // z-slabs: contiguous chunks of the x-fastest arrays
+  const size_t plane = (size_t)(srcHi[0] - srcLo[0]) * (srcHi[1] - srcLo[1]);
+  const size_t eb = isFloat ? 4 : 8;
+  std::vector<int32_t> blo(3 * n), bhi(3 * n);
+  size_t slot = 0;
+  for (int d = 0; d < n; ++d) {
+    const int z0 = srcLo[2] + (int)((long long)nz * d / n), z1 = srcLo[2] + (int)((long long)nz * (d + 1) / n);
+    blo[3 * d] = srcLo[0]; blo[3 * d + 1] = srcLo[1]; blo[3 * d + 2] = z0;
+    bhi[3 * d] = srcHi[0]; bhi[3 * d + 1] = srcHi[1]; bhi[3 * d + 2] = z1;
+    slot = std::max(slot, plane * (size_t)(z1 - z0) * l0.recBytes);
+  }
+  slot = (slot + 255) / 256 * 256;
+  for (int d = 0; d < n; ++d) {
+    rmcrt_ctx* c = ctxs[d];
+    CK(cudaSetDevice(c->device));
+    const size_t cells = plane * (size_t)(bhi[3 * d + 2] - blo[3 * d + 2]);
+    if (c->stage[0].ensure(cells * eb) || c->stage[1].ensure(cells * eb) || c->stage[2].ensure(cells * 4) || c->replSend.ensure(slot) ||
+        c->replGathered.ensure(slot * n))
+      return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc replication buffers failed");
+    const size_t off = plane * (size_t)(blo[3 * d + 2] - srcLo[2]);
+    CK(cudaMemcpyAsync(c->stage[0].p, static_cast<const char*>(a) + off * eb, cells * eb, cudaMemcpyHostToDevice, 0));
+    CK(cudaMemcpyAsync(c->stage[1].p, static_cast<const char*>(s) + off * eb, cells * eb, cudaMemcpyHostToDevice, 0));
+    CK(cudaMemcpyAsync(c->stage[2].p, ct + off, cells * 4, cudaMemcpyHostToDevice, 0));
+    int rc = rmcrt_pack_box_device(c, L, c->stage[0].p, c->stage[1].p, static_cast<const int32_t*>(c->stage[2].p), isFloat, &blo[3 * d], &bhi[3 * d],
+                                   &blo[3 * d], &bhi[3 * d], c->replSend.p, nullptr);
+    if (rc) { if (c != ctx) ctx->err = c->err; return rc; }
+  }
+  g_nccl.groupStart();
+  int nrc = 0;
+  for (int d = 0; d < n; ++d) {
+    cudaSetDevice(ctxs[d]->device);
+    nrc |= g_nccl.allGather(ctxs[d]->replSend.p, ctxs[d]->replGathered.p, slot, 0 /* ncclInt8 */, (*comms)[d], 0);
+  }
+  nrc |= g_nccl.groupEnd();
+  if (nrc != 0) return fail(ctx, RMCRT_ERR_NCCL, "ncclAllGather (group of %d devices) failed with code %d", n, nrc);
+  for (int d = 0; d < n; ++d) {
+    int rc = rmcrt_assemble_level(ctxs[d], L, ctxs[d]->replGathered.p, slot, n, blo.data(), bhi.data(), nullptr);
+    if (rc) { if (ctxs[d] != ctx) ctx->err = ctxs[d]->err; return rc; }
+  }
+  return 0;
+}
+
+//------------------------------------------------------------------------------------------------------ pinned host pool
+namespace {
+struct HostPool {
+  std::mutex mu;
+  std::map<void*, size_t> live;                    // block -> capacity
+  std::multimap<size_t, void*> freeList;           // capacity -> block
+} g_hostPool;
+size_t pool_bucket(size_t bytes) {                 // 64-KiB granularity: windows of neighbouring patches differ by a few cells
+  const size_t g = 64u << 10;
+  return ((bytes ? bytes : 1) + g - 1) / g * g;
+}
+}  // namespace
+
+void* rmcrt_host_alloc(size_t bytes) {
+  const size_t cap = pool_bucket(bytes);
+  {
+    std::lock_guard<std::mutex> l(g_hostPool.mu);
+    auto it = g_hostPool.freeList.find(cap);
+    if (it != g_hostPool.freeList.end()) {
+      void* p = it->second;
+      g_hostPool.freeList.erase(it);
+      g_hostPool.live[p] = cap;
+      return p;
+    }
+  }
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, cap, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  std::lock_guard<std::mutex> l(g_hostPool.mu);
+  g_hostPool.live[p] = cap;
+  return p;
+}
+
+void rmcrt_host_free(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> l(g_hostPool.mu);
+  auto it = g_hostPool.live.find(p);
+  if (it == g_hostPool.live.end()) return;         // not ours
+  g_hostPool.freeList.emplace(it->second, p);
+  g_hostPool.live.erase(it);
+}
+
+void rmcrt_host_pool_trim(void) {
+  std::lock_guard<std::mutex> l(g_hostPool.mu);
+  for (auto& kv : g_hostPool.freeList) cudaFreeHost(kv.second);
+  g_hostPool.freeList.clear();
 }
 
 int rmcrt_measure_read_bandwidth(rmcrt_ctx* ctx, size_t bytes, int repeats, int pattern, double* gbps, double* gaccess) {

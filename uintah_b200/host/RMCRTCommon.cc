@@ -1,5 +1,6 @@
 // RMCRTCommon.cc -- see RMCRTCommon.h.  Reference behaviour followed: RMCRT/RMCRTCommon.cc (line ranges cited per method).
 #include "RMCRTCommon.h"
+#include <cstdlib>
 
 #include <cuda_runtime_api.h>
 
@@ -44,6 +45,12 @@ RMCRTCommon::RMCRTCommon(TypeDescription::Type FLT_DBL) : d_FLT_DBL(FLT_DBL) {
   d_radiationVolqLabel = VarLabel::create("radiationVolq", TypeDescription::double_type);
   d_flowCell = -1;
   d_destructorCount = 0;
+  // grid variables allocated from here on live in page-locked, device-mapped, pooled host memory (include/rmcrt_b200.h: rmcrt_host_alloc);
+  // without a CUDA device the allocator returns NULL and the stand-in Array3 falls back to the heap (parse-only runs)
+  if (!std::getenv("RMCRT_PAGEABLE_HOST")) {      // A/B switch: the staged path through pageable CCVariable buffers
+    HostAllocator::get().alloc = rmcrt_host_alloc;
+    HostAllocator::get().release = rmcrt_host_free;
+  }
 }
 
 // RMCRTCommon.cc:128-152: Ray and Radiometer share the statics, so only the first destructor frees them
@@ -167,13 +174,16 @@ void RMCRTCommon::uploadLevel(const Level* level, DataWarehouse* abskg_dw, DataW
   const rmcrt_level_desc desc = describe(level);
   rmcrt_params p;
   fillParams(p);
+  std::vector<rmcrt_ctx*> ctxs;
   for (auto& dev : devs) {
     check(dev.ctx, rmcrt_set_params(dev.ctx, &p), "rmcrt_set_params");
     check(dev.ctx, rmcrt_define_level(dev.ctx, L, &desc, recordKind(p)), "rmcrt_define_level");
-    check(dev.ctx, rmcrt_upload_level(dev.ctx, L, abskg.getPointer(), sigmaT4OverPi.getPointer(), celltype.getPointer(),
-                                      sizeof(T) == 4 ? 1 : 0, desc.lo, desc.hi, nullptr), "rmcrt_upload_level");
-    dev.levelStamp[L] = stamp;
+    ctxs.push_back(dev.ctx);
   }
+  // every device needs the whole level (Ray.cc:479-481): each uploads and packs its z-slab, one NCCL all-gather replicates the records
+  check(ctxs[0], rmcrt_replicate_level(ctxs.data(), (int)ctxs.size(), L, abskg.getPointer(), sigmaT4OverPi.getPointer(), celltype.getPointer(),
+                                       sizeof(T) == 4 ? 1 : 0, desc.lo, desc.hi), "rmcrt_replicate_level");
+  for (auto& dev : devs) dev.levelStamp[L] = stamp;
 }
 template void RMCRTCommon::uploadLevel<double>(const Level*, DataWarehouse*, DataWarehouse*, DataWarehouse*, long long);
 template void RMCRTCommon::uploadLevel<float>(const Level*, DataWarehouse*, DataWarehouse*, DataWarehouse*, long long);

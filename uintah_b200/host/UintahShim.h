@@ -149,6 +149,40 @@ struct Stencil7 {   // Stencil7.h:38-76: AoS of 7 doubles; RMCRTboundFlux uses w
 
 //----------------------------------------------------------------------------------------------------- Array3 / CCVariable
 // x-fastest storage over the index window [lo,hi); copies share the data (ref-counted like Array3Data).
+// Where grid-variable storage comes from (Array3Data's allocation, Array3Data.h:93-125).  Default: the C++ heap.  A back end may install
+// its own pair -- the RMCRT back end installs rmcrt_host_alloc / rmcrt_host_free (page-locked, device-mapped, pooled) so that uploads run
+// at full PCIe rate and the trace kernels write divQ / radiationVolq in place; in a real Uintah tree the same two calls go where
+// Array3Data allocates.
+struct HostAllocator {
+  void* (*alloc)(size_t) = nullptr;
+  void (*release)(void*) = nullptr;
+  static HostAllocator& get() { static HostAllocator a; return a; }
+};
+template <class T>
+struct HookAlloc {
+  typedef T value_type;
+  HookAlloc() {}
+  template <class U> HookAlloc(const HookAlloc<U>&) {}
+  T* allocate(size_t n) {
+    HostAllocator& h = HostAllocator::get();
+    if (h.alloc) {
+      // a 16-byte header remembers which release function belongs to the block (the hook may be installed after older blocks were made)
+      char* raw = static_cast<char*>(h.alloc(n * sizeof(T) + 16));
+      if (raw) { *reinterpret_cast<void (**)(void*)>(raw) = h.release; return reinterpret_cast<T*>(raw + 16); }
+    }
+    char* raw = static_cast<char*>(::operator new(n * sizeof(T) + 16));
+    *reinterpret_cast<void (**)(void*)>(raw) = nullptr;
+    return reinterpret_cast<T*>(raw + 16);
+  }
+  void deallocate(T* p, size_t) {
+    char* raw = reinterpret_cast<char*>(p) - 16;
+    void (*rel)(void*) = *reinterpret_cast<void (**)(void*)>(raw);
+    if (rel) rel(raw); else ::operator delete(raw);
+  }
+  template <class U> bool operator==(const HookAlloc<U>&) const { return true; }
+  template <class U> bool operator!=(const HookAlloc<U>&) const { return false; }
+};
+
 template <class T>
 class Array3 {
  public:
@@ -156,7 +190,7 @@ class Array3 {
   void resize(const IntVector& lo, const IntVector& hi) {
     lo_ = lo; hi_ = hi;
     const IntVector n = hi - lo;
-    data_ = std::make_shared<std::vector<T>>((size_t)std::max(n.x(), 0) * std::max(n.y(), 0) * std::max(n.z(), 0));
+    data_ = std::make_shared<std::vector<T, HookAlloc<T>>>((size_t)std::max(n.x(), 0) * std::max(n.y(), 0) * std::max(n.z(), 0));
   }
   IntVector getLowIndex() const { return lo_; }
   IntVector getHighIndex() const { return hi_; }
@@ -186,7 +220,7 @@ class Array3 {
   void copyData(const Array3<T>& src) { copyRegion(src); }
  protected:
   IntVector lo_, hi_;
-  std::shared_ptr<std::vector<T>> data_;
+  std::shared_ptr<std::vector<T, HookAlloc<T>>> data_;
 };
 template <class T> class CCVariable : public Array3<T> {};
 template <class T> class constCCVariable : public Array3<T> {
