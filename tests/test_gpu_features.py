@@ -350,8 +350,8 @@ def _device_coarse_level(g, fine, coarse_like, dtype):
     return np.abs(k), s, np.signbit(k)
 
 
-@pytest.mark.parametrize("rr,logic", [((2, 2, 2), 0), ((4, 4, 4), 0), ((2, 2, 2), 1), ((4, 4, 4), 1), ((2, 4, 1), 0)])
-def test_coarsened_cell_type_follows_the_integer_sum(gpu_lib, po, rr, logic):
+@pytest.mark.parametrize("rr,logic,wtype", [((2, 2, 2), 0, 8), ((4, 4, 4), 0, 8), ((2, 2, 2), 1, 8), ((4, 4, 4), 1, 10), ((2, 4, 1), 0, 8), ((2, 2, 2), 1, 10)])
+def test_coarsened_cell_type_follows_the_integer_sum(gpu_lib, po, rr, logic, wtype):
     """Ray::computeCellType (Ray.cc:2272-2345) sums the INTEGER cell types of the fine cells (flow -1, RMCRT_Test walls 8): with RR = 8 and
     ONE non-flow fine cell the sum is 1 and ROUNDUP keeps the coarse cell a FLOW cell (|sum| < 10); RR = 64 with five or six likewise.
     Partial intrusions of every fill level against the oracle's restatement of the reference logic."""
@@ -365,21 +365,23 @@ def test_coarsened_cell_type_follows_the_integer_sum(gpu_lib, po, rr, logic):
     for kc in range(N // rr[2]):
         for jc in range(N // rr[1]):
             for ic in range(N // rr[0]):
-                nw = int(rng.integers(0, RR + 1)) if rng.uniform() < 0.5 else 0
+                u = rng.uniform()
+                nw = RR if u < 0.1 else (int(rng.integers(0, RR + 1)) if u < 0.55 else 0)
                 if nw:
                     idx = rng.choice(RR, nw, replace=False)
                     for q in idx:
                         a, b, c = q % rr[0], (q // rr[0]) % rr[1], q // (rr[0] * rr[1])
-                        ct[1 + kc * rr[2] + c, 1 + jc * rr[1] + b, 1 + ic * rr[0] + a] = 8
+                        ct[1 + kc * rr[2] + c, 1 + jc * rr[1] + b, 1 + ic * rr[0] + a] = wtype
     ref = po.coarsen_level(fine, rr, logic=logic)
-    g = make(gpu_lib, marchPrecision=1, cellTypeCoarsenLogic=logic)
+    g = make(gpu_lib, marchPrecision=1, cellTypeCoarsenLogic=logic, nonFlowCellType=wtype)
     k, s, wall = _device_coarse_level(g, fine, ref, np.float64)
     inner = (slice(1, -1),) * 3
     assert np.array_equal(wall[inner], ref.cellType[inner] != -1)
     nwall = int((ref.cellType[inner] != -1).sum())
     assert nwall < ref.cellType[inner].size
-    if logic == 0 or RR > 8:      # ROUNDDOWN with RR = 8 and type-8 walls can never reach |sum| > 10 (RR - 1): every coarse cell stays a flow cell
-        assert nwall > 0
+    # ROUNDDOWN needs |sum| > 10 (RR - 1): out of reach for the wall id 8 of RMCRT_Test (every coarse cell stays a flow cell, in the
+    # reference too), reached by completely filled cells of the intrusion id 10
+    assert (nwall > 0) == (logic == 0 or wtype == 10)
     np.testing.assert_allclose(k[inner], ref.abskg[inner], rtol=1e-13)
     np.testing.assert_allclose(s[inner], ref.sigmaT4[inner], rtol=1e-13)
 
