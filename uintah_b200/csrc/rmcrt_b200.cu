@@ -16,8 +16,6 @@
 #include "indep.cuh"
 
 #include <cuda_runtime.h>
-#include <cub/device/device_select.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
 
 #include <cfloat>
 #include <cstdarg>
@@ -822,6 +820,57 @@ __global__ void flux_mask_kernel(const __grid_constant__ TraceArgs a, unsigned c
   if ((threadIdx.x & 31) == 0 && nb) atomicAdd(a.counters + 3, nb);
 }
 
+// Ordered stream compaction of the (face, cell) flags into item ids (replaces cub::DeviceSelect::Flagged: no library kernel on the path).
+// Three small launches: per-chunk counts, one-block exclusive scan of the counts, scatter with an in-chunk ballot scan.  The order of the
+// items is that of the flags (face-major, cells x-fastest), so consecutive items are neighbouring cells of one face -- deterministic.
+constexpr int COMPACT_CHUNK = 4096;      // flags per block (256 threads x 16)
+__global__ void __launch_bounds__(256) compact_count_kernel(const unsigned char* __restrict__ flags, int n, int* __restrict__ chunkCount) {
+  __shared__ int wsum[8];
+  const int base = blockIdx.x * COMPACT_CHUNK;
+  int c = 0;
+  for (int t = threadIdx.x; t < COMPACT_CHUNK; t += 256) { const int q = base + t; c += (q < n && flags[q]) ? 1 : 0; }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) { int s = 0; for (int w = 0; w < 8; ++w) s += wsum[w]; chunkCount[blockIdx.x] = s; }
+}
+__global__ void __launch_bounds__(1024) compact_scan_kernel(int* __restrict__ chunkCount, int nChunks, int* __restrict__ nItems) {
+  __shared__ int part[1024];
+  // thread t owns a contiguous run of chunks; exclusive scan in place
+  const int per = (nChunks + 1023) / 1024;
+  const int lo = min(threadIdx.x * per, nChunks), hi = min(lo + per, nChunks);
+  int s = 0;
+  for (int q = lo; q < hi; ++q) s += chunkCount[q];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { int run = 0; for (int t = 0; t < 1024; ++t) { const int v = part[t]; part[t] = run; run += v; } *nItems = run; }
+  __syncthreads();
+  int run = part[threadIdx.x];
+  for (int q = lo; q < hi; ++q) { const int v = chunkCount[q]; chunkCount[q] = run; run += v; }
+}
+__global__ void __launch_bounds__(256) compact_scatter_kernel(const unsigned char* __restrict__ flags, int n, const int* __restrict__ chunkOffset,
+                                                              int* __restrict__ items) {
+  __shared__ int wbase[8];
+  __shared__ int carry;
+  const int base = blockIdx.x * COMPACT_CHUNK;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = chunkOffset[blockIdx.x];
+  __syncthreads();
+  for (int r = 0; r < COMPACT_CHUNK / 256; ++r) {      // rounds of 256 consecutive flags keep the order
+    const int q = base + r * 256 + threadIdx.x;
+    const bool f = q < n && flags[q];
+    const unsigned m = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) wbase[warp] = __popc(m);
+    __syncthreads();
+    int off = carry;
+    for (int w = 0; w < warp; ++w) off += wbase[w];
+    if (f) items[off + __popc(m & ((1u << lane) - 1u))] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) { int s = 0; for (int w = 0; w < 8; ++w) s += wbase[w]; carry += s; }
+    __syncthreads();
+  }
+}
+
 // lane = one (face, cell) item; consecutive items are neighbouring cells on the same face.
 template <class Real, class RecT, bool ML, bool FAST = true>
 __global__ void __launch_bounds__(256) flux_trace_kernel(const __grid_constant__ TraceArgs a) {
@@ -1526,7 +1575,7 @@ struct rmcrt_ctx {
   int* d_nItems = nullptr;
   DevBuf stage[3];      // upload staging
   DevBuf outDivQ, outVolq, outFlux;   // host-API output staging
-  DevBuf fluxFlags, fluxItems, cubTemp, dbg[6], misc, roiBuf;
+  DevBuf fluxFlags, fluxItems, compactTmp, dbg[6], misc, roiBuf;
   DevBuf lhcDivQ, lhcFlux;            // LHC permutation tables of the regression modes
   int lhcKeyDivQ[4] = {0, 0, 0, 0};   // (nRays, sumLo, rows, mode) the tables were built for
   int lhcKeyFlux[4] = {0, 0, 0, 0};
@@ -1883,12 +1932,14 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
     unsigned char* flags = static_cast<unsigned char*>(ctx->fluxFlags.p);
     flux_mask_kernel<RecT><<<grid_for(a.nCells, 256, ctx->smCount), 256, 0, st>>>(a, flags);
     CK(cudaGetLastError());
-    cub::CountingInputIterator<int> ids(0);
-    size_t tmpBytes = 0;
     const int nFlag = (int)(a.nCells * 6);
-    CK(cub::DeviceSelect::Flagged(nullptr, tmpBytes, ids, flags, static_cast<int*>(ctx->fluxItems.p), ctx->d_nItems, nFlag, st));
-    if (ctx->cubTemp.ensure(tmpBytes + 16)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc cub temp");
-    CK(cub::DeviceSelect::Flagged(ctx->cubTemp.p, tmpBytes, ids, flags, static_cast<int*>(ctx->fluxItems.p), ctx->d_nItems, nFlag, st));
+    const int nChunks = (nFlag + COMPACT_CHUNK - 1) / COMPACT_CHUNK;
+    if (ctx->compactTmp.ensure((size_t)nChunks * sizeof(int))) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc compaction counts");
+    int* chunk = static_cast<int*>(ctx->compactTmp.p);
+    compact_count_kernel<<<nChunks, 256, 0, st>>>(flags, nFlag, chunk);
+    compact_scan_kernel<<<1, 1024, 0, st>>>(chunk, nChunks, ctx->d_nItems);
+    compact_scatter_kernel<<<nChunks, 256, 0, st>>>(flags, nFlag, chunk, static_cast<int*>(ctx->fluxItems.p));
+    CK(cudaGetLastError());
     TraceArgs f = a;
     f.items = static_cast<const int*>(ctx->fluxItems.p);
     f.nItems = ctx->d_nItems;
@@ -2241,7 +2292,7 @@ void rmcrt_destroy(rmcrt_ctx* ctx) {
   if (ctx->d_nItems) cudaFree(ctx->d_nItems);
   for (auto& b : ctx->stage) b.release();
   ctx->outDivQ.release(); ctx->outVolq.release(); ctx->outFlux.release();
-  ctx->fluxFlags.release(); ctx->fluxItems.release(); ctx->cubTemp.release(); ctx->misc.release(); ctx->roiBuf.release();
+  ctx->fluxFlags.release(); ctx->fluxItems.release(); ctx->compactTmp.release(); ctx->misc.release(); ctx->roiBuf.release();
   ctx->lhcDivQ.release(); ctx->lhcFlux.release(); ctx->outVR[0].release(); ctx->outVR[1].release();
   for (auto& b : ctx->dbg) b.release();
   ctx->replSend.release(); ctx->replGathered.release();
