@@ -18,7 +18,9 @@
  *   - "host" entry points take host pointers and do the H2D/D2H copies themselves;
  *     "_device" entry points take device pointers of the context's device.
  *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  Calls are
- *     asynchronous with respect to the host unless stated otherwise.
+ *     asynchronous with respect to the host unless stated otherwise -- but a HOST pointer
+ *     passed to an entry point is never read or written after that call has returned
+ *     (the DataWarehouse may free or recycle the buffer at once).
  *   - the library never falls back to a CPU path: without a CUDA device every call fails.
  */
 #ifndef RMCRT_B200_H

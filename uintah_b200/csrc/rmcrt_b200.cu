@@ -2368,6 +2368,16 @@ int rmcrt_pack_level_device(rmcrt_ctx* ctx, int L, const void* a, const void* s,
   return do_pack(ctx, lv.recordKind, isFloat, a, s, ct, src, region, lv.rec, dst, lstat_of(ctx, L), lv.recFull, dst, (cudaStream_t)stream);
 }
 
+static int wait_for_copies(rmcrt_ctx* ctx, cudaStream_t st) {
+  cudaEvent_t ev;
+  CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  cudaError_t e = cudaEventRecord(ev, st);
+  if (e == cudaSuccess) e = cudaEventSynchronize(ev);
+  cudaEventDestroy(ev);
+  if (e != cudaSuccess) return fail(ctx, RMCRT_ERR_CUDA, "waiting for the host-to-device copies failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 int rmcrt_upload_level(rmcrt_ctx* ctx, int L, const void* a, const void* s, const int32_t* ct, int isFloat,
                        const int32_t srcLo[3], const int32_t srcHi[3], void* stream) {
   int rc = check_level(ctx, L);
@@ -2386,6 +2396,10 @@ int rmcrt_upload_level(rmcrt_ctx* ctx, int L, const void* a, const void* s, cons
   CK(cudaMemcpyAsync(ctx->stage[0].p, a, n * eb, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->stage[1].p, s, n * eb, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->stage[2].p, ct, n * 4, cudaMemcpyHostToDevice, st));
+  // The caller's arrays are not read after this call returns (the DataWarehouse frees or recycles getLevel temporaries at once): from
+  // page-locked memory the copies above are truly asynchronous, so wait for THEM -- not for the pack kernel queued behind them
+  int rc = wait_for_copies(ctx, st);
+  if (rc) return rc;
   return rmcrt_pack_level_device(ctx, L, ctx->stage[0].p, ctx->stage[1].p, static_cast<const int32_t*>(ctx->stage[2].p), isFloat,
                                  srcLo, srcHi, stream);
 }
@@ -2970,6 +2984,7 @@ int rmcrt_replicate_level(rmcrt_ctx** ctxs, int n, int L, const void* a, const v
     slot = std::max(slot, plane * (size_t)(z1 - z0) * l0.recBytes);
   }
   slot = (slot + 255) / 256 * 256;
+  std::vector<cudaEvent_t> copyEvents(n, nullptr);
   for (int d = 0; d < n; ++d) {
     rmcrt_ctx* c = ctxs[d];
     CK(cudaSetDevice(c->device));
@@ -2981,10 +2996,15 @@ int rmcrt_replicate_level(rmcrt_ctx** ctxs, int n, int L, const void* a, const v
     CK(cudaMemcpyAsync(c->stage[0].p, static_cast<const char*>(a) + off * eb, cells * eb, cudaMemcpyHostToDevice, 0));
     CK(cudaMemcpyAsync(c->stage[1].p, static_cast<const char*>(s) + off * eb, cells * eb, cudaMemcpyHostToDevice, 0));
     CK(cudaMemcpyAsync(c->stage[2].p, ct + off, cells * 4, cudaMemcpyHostToDevice, 0));
+    copyEvents[d] = nullptr;
+    if (cudaEventCreateWithFlags(&copyEvents[d], cudaEventDisableTiming) == cudaSuccess) cudaEventRecord(copyEvents[d], 0);
     int rc = rmcrt_pack_box_device(c, L, c->stage[0].p, c->stage[1].p, static_cast<const int32_t*>(c->stage[2].p), isFloat, &blo[3 * d], &bhi[3 * d],
                                    &blo[3 * d], &bhi[3 * d], c->replSend.p, nullptr);
     if (rc) { if (c != ctx) ctx->err = c->err; return rc; }
   }
+  // the caller's arrays are not read after return: wait for every device's slab copy (they ran concurrently), not for the kernels
+  for (int d = 0; d < n; ++d)
+    if (copyEvents[d]) { cudaSetDevice(ctxs[d]->device); cudaEventSynchronize(copyEvents[d]); cudaEventDestroy(copyEvents[d]); }
   g_nccl.groupStart();
   int nrc = 0;
   for (int d = 0; d < n; ++d) {
