@@ -2398,7 +2398,7 @@ int rmcrt_upload_level(rmcrt_ctx* ctx, int L, const void* a, const void* s, cons
   CK(cudaMemcpyAsync(ctx->stage[2].p, ct, n * 4, cudaMemcpyHostToDevice, st));
   // The caller's arrays are not read after this call returns (the DataWarehouse frees or recycles getLevel temporaries at once): from
   // page-locked memory the copies above are truly asynchronous, so wait for THEM -- not for the pack kernel queued behind them
-  int rc = wait_for_copies(ctx, st);
+  rc = wait_for_copies(ctx, st);
   if (rc) return rc;
   return rmcrt_pack_level_device(ctx, L, ctx->stage[0].p, ctx->stage[1].p, static_cast<const int32_t*>(ctx->stage[2].p), isFloat,
                                  srcLo, srcHi, stream);
