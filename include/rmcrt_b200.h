@@ -330,6 +330,18 @@ int rmcrt_assemble_level(rmcrt_ctx* ctx, int L, const void* d_gathered, size_t s
 int rmcrt_allgather_records(rmcrt_ctx* ctx, const void* d_sendSlot, void* d_gathered, size_t slotBytes,
                             void* ncclComm, void* stream);
 
+/* ------------------------------------------------------------------ dynamic ROI (Ray::ROI_Extents, Ray.cc:1984-2043)
+ * For one fine patch [patchLo,patchHi) of level L (records already on the device): |grad abskg| and |grad sigmaT4/pi| by first-order
+ * central differences (compute_Mag_gradient, Core/Grid/AMR.cc:464-483, in the precision of the level's records) and the flag
+ * `mag_grad_abskg > abskgThreshold || mag_grad_sigmaT4 > sigmaT4Threshold` per cell.  *anyFlagged = 1 when a cell of the patch is
+ * flagged: the caller then extends the ROI by the patch's extra-cell box (Ray.cc:2032-2038) and, after all patches, hands the box to
+ * the solve as rmcrt_params.roiFixed* (Ray::computeExtents, dynamic branch, Ray.cc:1291-1300: the same box for every patch).
+ * Optional host outputs (all three or none) over [outLo,outHi), zero outside the patch: the reference's mag_grad_abskg /
+ * mag_grad_sigmaT4 (float or double as the records) / flaggedCells (int) visualisation variables.  Blocking. */
+int rmcrt_roi_extents(rmcrt_ctx* ctx, int L, const int32_t patchLo[3], const int32_t patchHi[3], double abskgThreshold,
+                      double sigmaT4Threshold, void* magGradAbskg, void* magGradSigmaT4, int32_t* flaggedCells, int isFloat,
+                      const int32_t outLo[3], const int32_t outHi[3], int32_t* anyFlagged, void* stream);
+
 /* ------------------------------------------------------------------ one process driving several devices
  * rmcrt_replicate_level: what n calls of rmcrt_upload_level (one per context / device) achieve -- level L of every context holds the
  * packed records of the host arrays -- with 1/n of the PCIe traffic: device d uploads and packs only its z-slab of the level and ONE

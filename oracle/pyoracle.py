@@ -575,6 +575,40 @@ def ray_trace_data_onion(p: Params, levels, halo, patch_lo=None, patch_hi=None, 
     return dict(divQ=divQ, radiationVolq=volq, boundFlux=bflux, steps=sum(steps), fluxSteps=sum(fsteps))
 
 
+def roi_extents(lv: Level, patches, abskg_thld, sigmaT4_thld):
+    """Ray::ROI_Extents (Ray.cc:1984-2043) with compute_Mag_gradient (Core/Grid/AMR.cc:464-483): for every patch (lo, hi, extraLo, extraHi)
+    the first-order central-difference gradient magnitudes of abskg and sigmaT4 (T inv_dx = (T)0.5/dx, differences and product in T,
+    Vector::length() in double, stored as T), the flags mag > threshold, and the ROI_loCell / ROI_hiCell reduction = the union of the
+    extra-cell boxes of the patches that hold a flagged cell (SHRT_MAX / -SHRT_MAX when there is none).
+    Returns (mag_grad_abskg, mag_grad_sigmaT4, flaggedCells) over the level window (zero outside the patches) and (roi_lo, roi_hi)."""
+    T = lv.abskg.dtype.type
+    mags = []
+    for q in (lv.abskg, lv.sigmaT4):
+        g2 = np.zeros(q[1:-1, 1:-1, 1:-1].shape, np.float64)
+        for axis, d in ((2, 0), (1, 1), (0, 2)):          # array axis 2 = x
+            inv = T(np.float64(0.5) / np.float64(lv.dx[d]))      # (T)0.5 / dx: a double division, rounded to T
+            r = [slice(1, -1)] * 3; l = [slice(1, -1)] * 3
+            r[axis] = slice(2, None); l[axis] = slice(0, -2)
+            g = ((q[tuple(r)] - q[tuple(l)]).astype(T) * inv).astype(T).astype(np.float64)
+            g2 = g2 + g * g if d == 0 else (g2 + g * g)
+        m = np.zeros(q.shape, T)
+        m[1:-1, 1:-1, 1:-1] = np.sqrt(g2).astype(T)
+        mags.append(m)
+    # (x*x + y*y) + z*z in that order, like Vector::length()
+    flagged = np.zeros(lv.abskg.shape, np.int32)
+    roi_lo, roi_hi = [32767] * 3, [-32767] * 3
+    outA, outS = np.zeros_like(mags[0]), np.zeros_like(mags[1])
+    for lo, hi, elo, ehi in patches:
+        sl = tuple(slice(lo[d] - lv.lo[d], hi[d] - lv.lo[d]) for d in (2, 1, 0))
+        outA[sl] = mags[0][sl]; outS[sl] = mags[1][sl]
+        f = (mags[0][sl].astype(np.float64) > abskg_thld) | (mags[1][sl].astype(np.float64) > sigmaT4_thld)
+        flagged[sl] = f
+        if f.any():
+            roi_lo = [min(a, b) for a, b in zip(roi_lo, elo)]
+            roi_hi = [max(a, b) for a, b in zip(roi_hi, ehi)]
+    return outA, outS, flagged, (tuple(roi_lo), tuple(roi_hi))
+
+
 def coarsen_level(fine: Level, rr=(4, 4, 4), logic=0, wall_abskg=None, wall_sigmaT4=None, wall_type=None, coarsen_extra_cells=False) -> Level:
     """Build the coarse level the Data-Onion needs: Ray::coarsen_Q interior average of abskg and sigmaT4 and
     Ray::computeCellType; coarse extra cells are then filled the way sched_setBoundaryConditions does for

@@ -449,3 +449,50 @@ def test_data_onion_fixed_roi(gpu_lib, po, prec):
         np.testing.assert_allclose(divQ, want["divQ"], rtol=1e-9, atol=1e-10 * np.abs(want["divQ"]).max())
     else:
         assert np.abs(divQ - want["divQ"]).max() <= 2e-4 * np.abs(want["divQ"]).max()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_dynamic_roi_extents(gpu_lib, po, dtype):
+    """Ray::ROI_Extents (Ray.cc:1984-2043): gradient magnitudes, flags and the ROI_loCell / ROI_hiCell reduction bit for bit against the
+    numpy restatement (float records for float decks, double records for the FP64 march); then the Data-Onion solve with that ROI"""
+    rng = np.random.default_rng(21)
+    fine = po.burns_christon(32, dtype=dtype)
+    fine.rr = (4, 4, 4)
+    # a hot, optically thick blob in one corner region: only the patches it touches get flagged
+    z, y, x = np.meshgrid(*[np.arange(-1, 33)] * 3, indexing="ij")
+    blob = np.exp(-((x - 9.0) ** 2 + (y - 8.0) ** 2 + (z - 10.0) ** 2) / 18.0)
+    flow = fine.cellType == -1
+    fine.abskg[flow] = (fine.abskg[flow] * 0.2 + 3.0 * blob[flow]).astype(dtype)
+    fine.sigmaT4[flow] = (fine.sigmaT4[flow] * (1 + 4.0 * blob[flow])).astype(dtype)
+    coarse = po.coarsen_level(fine, (4, 4, 4))
+    patches = [(lo, hi, tuple(l - (1 if l == 0 else 0) for l in lo), tuple(h + (1 if h == 32 else 0) for h in hi))
+               for lo, hi in po._split((0, 0, 0), (32, 32, 32), (2, 2, 2))]
+    thrA, thrS = 6.0, 2.5
+    wantA, wantS, wantF, (rlo, rhi) = po.roi_extents(fine, patches, thrA, thrS)
+    prec = 1 if dtype == np.float64 else 0
+    kw = dict(nDivQRays=3, threshold=0.05, isSeedRandom=0)
+    g = make(gpu_lib, marchPrecision=prec, skipZeroWeightLegs=0, haloCells=(4, 4, 4), **kw)
+    g.upload_level(0, coarse)
+    g.upload_level(1, fine)
+    gotA = np.zeros_like(wantA); gotS = np.zeros_like(wantS); gotF = np.zeros_like(wantF)
+    lo_, hi_ = [32767] * 3, [-32767] * 3
+    for lo, hi, elo, ehi in patches:
+        a, s_, f, any_ = g.roi_extents(1, lo, hi, thrA, thrS, dtype=dtype)
+        gotA += a; gotS += s_; gotF += f
+        assert any_ == bool(f.any())
+        if any_:
+            lo_ = [min(p, q) for p, q in zip(lo_, elo)]; hi_ = [max(p, q) for p, q in zip(hi_, ehi)]
+    assert np.array_equal(gotF, wantF) and 0 < wantF.sum() < 32 ** 3
+    assert np.array_equal(gotA, wantA) and np.array_equal(gotS, wantS)
+    assert (tuple(lo_), tuple(hi_)) == (rlo, rhi)
+    assert rhi != (33, 33, 33) or rlo != (-1, -1, -1)            # not every patch is flagged
+    # the solve with the dynamic ROI = the fixed-ROI solve with that box (Ray::computeExtents: one box for every patch)
+    want = po.ray_trace_data_onion(po.default_params(roiFixed=1, roiFixedLo=rlo, roiFixedHi=rhi, **kw), [coarse, fine], (4, 4, 4), patches=(2, 2, 2), threads=8)
+    g.set_params(roiFixed=1, roiFixedLo=rlo, roiFixedHi=rhi)
+    divQ = np.zeros_like(want["divQ"]); vol = np.zeros_like(divQ)
+    for lo, hi, _, _ in patches:
+        g.trace_dataonion(2, lo, hi, zero_init=False, outputs=(divQ, vol, None))
+    if prec:
+        np.testing.assert_allclose(divQ, want["divQ"], rtol=1e-9, atol=1e-10 * np.abs(want["divQ"]).max())
+    else:
+        assert np.abs(divQ - want["divQ"]).max() <= 3e-4 * np.abs(want["divQ"]).max()

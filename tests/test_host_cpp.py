@@ -100,13 +100,22 @@ def test_input_errors_raise_problem_setup_exception(exe, tmp_path, edit, needle)
     assert r.returncode == 1 and "ProblemSetupException" in r.stderr and needle in r.stderr, r.stderr
 
 
-def test_data_onion_needs_patch_based_roi(exe, tmp_path):
-    """GPU bullet proofing of Ray::problemSetup (Ray.cc:338-345)"""
+def test_dynamic_roi_schedules_roi_extents(exe, tmp_path):
+    """<ROI_extents type="dynamic">: Ray::sched_ROI_Extents (Ray.cc:1947-1978) adds the Ray::ROI_Extents task on the finest level, before the
+    trace, computing mag_grad_abskg / mag_grad_sigmaT4 / flaggedCells and the ROI_loCell / ROI_hiCell reduction (the reference's own
+    device build refuses this ROI, Ray.cc:338-345; patch_based decks get no such task)"""
     src = open(os.path.join(DECKS, "bm1_DO.ups")).read()
-    deck = tmp_path / "bad.ups"
+    deck = tmp_path / "dyn.ups"
     deck.write_text(src.replace('<ROI_extents type="patch_based"/>', '<ROI_extents type="dynamic"> <abskgd_threshold> 0.1 </abskgd_threshold> </ROI_extents>'))
     r = subprocess.run([exe, str(deck), "--parse-only"], capture_output=True, text=True)
-    assert r.returncode == 1 and 'only ROI_extents type="patch_based" and type="fixed" work on the GPU' in r.stderr
+    assert r.returncode == 0, r.stderr
+    t = tasks_of(r.stdout)
+    names = [x["name"] for x in t]
+    assert names.count("Ray::ROI_Extents") == 1 and names.index("Ray::ROI_Extents") < names.index("Ray::rayTrace_dataOnion")
+    roi = [x for x in t if x["name"] == "Ray::ROI_Extents"][0]
+    assert roi["level"] == "1" and [d[1] for d in roi["deps"] if d[0] == "computes"] == ["mag_grad_abskg", "mag_grad_sigmaT4", "flaggedCells", "ROI_loCell", "ROI_hiCell"]
+    assert [d[3] for d in roi["deps"] if d[0] == "requires"] == ["ghost=1", "ghost=1"]
+    assert "Ray::ROI_Extents" not in [x["name"] for x in tasks_of(run(exe, "bm1_DO.ups", "--parse-only").stdout)]
 
 
 def test_fixed_roi_and_coarsen_extra_cells_are_accepted(exe, tmp_path):
@@ -185,6 +194,26 @@ def test_bm1_data_onion_deterministic(exe, po, tmp_path, gpu_lib):
     coarse = po.coarsen_level(fine, (4, 4, 4))
     ref = po.ray_trace_data_onion(po.default_params(nDivQRays=3, threshold=0.05, isSeedRandom=0), [coarse, fine], (4, 4, 4),
                                   patches=(2, 2, 2), threads=8)
+    assert out["report"]["nRaySteps"] == ref["steps"]
+    np.testing.assert_allclose(out["divQ"], ref["divQ"], rtol=1e-9, atol=1e-10 * np.abs(ref["divQ"]).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("roi,box", [
+    ('<ROI_extents type="dynamic"> <abskgd_threshold> 0.5 </abskgd_threshold> </ROI_extents>', ((-1,) * 3, (33,) * 3)),          # every patch flagged
+    ('<ROI_extents type="dynamic"> <abskgd_threshold> 1e9 </abskgd_threshold> </ROI_extents>', ((32767,) * 3, (-32767,) * 3)),   # none: empty ROI
+    ('<ROI_extents type="fixed"> <min> [0.25,0.2,0.3] </min> <max> [0.8,0.75,0.7] </max> </ROI_extents>', ((8, 6, 9), (25, 24, 22))),
+])
+def test_data_onion_dynamic_and_fixed_roi_decks(exe, po, tmp_path, gpu_lib, roi, box):
+    """bm1_DO.ups with the two other ROI types end to end through the plugin: Ray::ROI_Extents on the device (dynamic), getCellIndex of
+    the two points (fixed), the same box for every patch in the trace; deterministic regression mode against the oracle"""
+    deck = edit_deck(tmp_path, "bm1_DO.ups", ('<ROI_extents type="patch_based"/>', roi))
+    out = load_dump(run(exe, deck, "--dump", str(tmp_path / "d"), "--knob", "skipZeroWeightLegs=0").args[3])
+    fine = po.burns_christon(32)
+    fine.rr = (4, 4, 4)
+    coarse = po.coarsen_level(fine, (4, 4, 4))
+    p = po.default_params(nDivQRays=3, threshold=0.05, isSeedRandom=0, roiFixed=1, roiFixedLo=box[0], roiFixedHi=box[1])
+    ref = po.ray_trace_data_onion(p, [coarse, fine], (4, 4, 4), patches=(2, 2, 2), threads=8)
     assert out["report"]["nRaySteps"] == ref["steps"]
     np.testing.assert_allclose(out["divQ"], ref["divQ"], rtol=1e-9, atol=1e-10 * np.abs(ref["divQ"]).max())
 

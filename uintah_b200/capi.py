@@ -25,7 +25,7 @@ SYMBOLS = [
     "rmcrt_radiometer_setup", "rmcrt_trace_radiometer_device", "rmcrt_trace_radiometer",
     "rmcrt_refine_Q_device", "rmcrt_refine_Q", "rmcrt_arches_sigmaT4_device", "rmcrt_arches_sumAbsk_device",
     "rmcrt_stencil_to_dbls_device", "rmcrt_arches_sigmaT4", "rmcrt_arches_sumAbsk", "rmcrt_stencil_to_dbls",
-    "rmcrt_host_alloc", "rmcrt_host_free", "rmcrt_host_pool_trim", "rmcrt_replicate_level",
+    "rmcrt_host_alloc", "rmcrt_host_free", "rmcrt_host_pool_trim", "rmcrt_replicate_level", "rmcrt_roi_extents",
 ]
 
 

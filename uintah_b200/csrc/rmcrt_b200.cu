@@ -1135,6 +1135,40 @@ __global__ void finalize_kernel(const RecT* __restrict__ recs, Box b, unsigned* 
   }
 }
 
+// Ray::ROI_Extents (Ray.cc:1984-2043) for one patch: magnitude of the first-order central-difference gradient of abskg and sigmaT4/pi
+// (compute_Mag_gradient, Core/Grid/AMR.cc:464-483: T inv_dx = (T)0.5 / dx; (q[r] - q[l]) * inv_dx in T; Vector::length() in double; stored
+// as T) and the flag `mag_grad_abskg > abskg_threshold || mag_grad_sigmaT4 > sigmaT4_threshold`.  Optional outputs over the out window.
+template <class RecT, class T>
+__global__ void roi_extents_kernel(const RecT* __restrict__ recs, Box lb, Box patch, double dx0, double dx1, double dx2, double thrA, double thrS,
+                                   T* __restrict__ magA, T* __restrict__ magS, int* __restrict__ flagged, Box out, unsigned* __restrict__ any) {
+  const long long n = box_cells(patch);
+  const T inv[3] = {(T)((T)0.5 / dx0), (T)((T)0.5 / dx1), (T)((T)0.5 / dx2)};
+  const long long st[3] = {1, lb.n[0], (long long)lb.n[0] * lb.n[1]};
+  unsigned mine = 0;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const long long row = t / patch.n[0];
+    const int i = patch.lo[0] + (int)(t - row * patch.n[0]), j = patch.lo[1] + (int)(row % patch.n[1]), k = patch.lo[2] + (int)(row / patch.n[1]);
+    const long long c = (long long)(i - lb.lo[0]) + st[1] * (long long)(j - lb.lo[1]) + st[2] * (long long)(k - lb.lo[2]);
+    double ga[3], gs[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const auto r = load_true(recs + c + st[d]), l = load_true(recs + c - st[d]);
+      const T ar = (T)fabs((double)r.k), al = (T)fabs((double)l.k);       // abskg = |k| (the sign bit is the wall flag)
+      ga[d] = (double)(T)((T)(ar - al) * inv[d]);
+      gs[d] = (double)(T)((T)((T)r.s - (T)l.s) * inv[d]);
+    }
+    const T ma = (T)sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ga[0], ga[0]), __dmul_rn(ga[1], ga[1])), __dmul_rn(ga[2], ga[2])));
+    const T ms = (T)sqrt(__dadd_rn(__dadd_rn(__dmul_rn(gs[0], gs[0]), __dmul_rn(gs[1], gs[1])), __dmul_rn(gs[2], gs[2])));
+    const bool f = (double)ma > thrA || (double)ms > thrS;
+    mine |= f ? 1u : 0u;
+    if (magA) {
+      const long long q = (long long)(i - out.lo[0]) + (long long)out.n[0] * ((long long)(j - out.lo[1]) + (long long)out.n[1] * (long long)(k - out.lo[2]));
+      magA[q] = ma; magS[q] = ms; flagged[q] = f ? 1 : 0;
+    }
+  }
+  if (__any_sync(0xffffffffu, mine != 0u) && (threadIdx.x & 31) == 0) atomicOr(any, 1u);
+}
+
 // blocked half-packed copy of a level (indep.cuh): thread = one 2 x 2 x 2 block of the guard-padded block grid
 template <class RecT>
 __global__ void blk_build_kernel(const RecT* __restrict__ recs, Box lb, uint32_t* __restrict__ blk, int bx, int by, int bz) {
@@ -2533,6 +2567,57 @@ int rmcrt_trace_radiometer(rmcrt_ctx* ctx, int L, const rmcrt_radiometer* rads, 
   CK(cudaMemcpyAsync(flux, ctx->outVR[0].p, bytes, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(inten, ctx->outVR[1].p, bytes, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int rmcrt_roi_extents(rmcrt_ctx* ctx, int L, const int32_t pLo[3], const int32_t pHi[3], double abskgThreshold, double sigmaT4Threshold,
+                      void* magGradAbskg, void* magGradSigmaT4, int32_t* flaggedCells, int isFloat, const int32_t oLo[3], const int32_t oHi[3],
+                      int32_t* anyFlagged, void* stream) {
+  int rc = check_level(ctx, L);
+  if (rc) return rc;
+  if (!anyFlagged) return fail(ctx, RMCRT_ERR_INVALID, "anyFlagged is required");
+  const bool outs = magGradAbskg || magGradSigmaT4 || flaggedCells;
+  if (outs && !(magGradAbskg && magGradSigmaT4 && flaggedCells && oLo && oHi))
+    return fail(ctx, RMCRT_ERR_INVALID, "mag_grad_abskg, mag_grad_sigmaT4 and flaggedCells are given together or not at all");
+  const LevelState& lv = ctx->lv[L];
+  if ((lv.recordKind == 1) == (isFloat != 0) && outs) return fail(ctx, RMCRT_ERR_INVALID, "isFloat must match the level's records (double records <=> double outputs)");
+  for (int d = 0; d < 3; ++d)
+    if (pLo[d] < lv.d.interiorLo[d] || pHi[d] > lv.d.interiorHi[d] || pHi[d] <= pLo[d]) return fail(ctx, RMCRT_ERR_INVALID, "patch outside the level interior");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  Box lb = mkbox(lv.d.lo, lv.d.hi), pb = mkbox(pLo, pHi), ob = outs ? mkbox(oLo, oHi) : pb;
+  const size_t nOut = outs ? (size_t)box_cells(ob) : 0;
+  const size_t eb = isFloat ? 4 : 8;
+  if (ctx->misc.ensure(64)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc");
+  unsigned* dAny = static_cast<unsigned*>(ctx->misc.p);
+  CK(cudaMemsetAsync(dAny, 0, sizeof(unsigned), st));
+  void *dA = nullptr, *dS = nullptr; int* dF = nullptr;
+  if (outs) {
+    if (ctx->stage[0].ensure(nOut * eb) || ctx->stage[1].ensure(nOut * eb) || ctx->stage[2].ensure(nOut * 4)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc staging failed");
+    dA = ctx->stage[0].p; dS = ctx->stage[1].p; dF = static_cast<int*>(ctx->stage[2].p);
+    CK(cudaMemsetAsync(dA, 0, nOut * eb, st)); CK(cudaMemsetAsync(dS, 0, nOut * eb, st)); CK(cudaMemsetAsync(dF, 0, nOut * 4, st));   // Ray.cc:2010-2012
+  }
+  const int grid = grid_for(box_cells(pb), 256, ctx->smCount);
+  const double* dx = lv.d.dx;
+  if (lv.recordKind == 1)
+    roi_extents_kernel<Rec16, double><<<grid, 256, 0, st>>>(static_cast<const Rec16*>(lv.rec), lb, pb, dx[0], dx[1], dx[2], abskgThreshold, sigmaT4Threshold,
+                                                           static_cast<double*>(dA), static_cast<double*>(dS), dF, ob, dAny);
+  else if (lv.recordKind == 2)
+    roi_extents_kernel<Rec4, float><<<grid, 256, 0, st>>>(static_cast<const Rec4*>(lv.rec), lb, pb, dx[0], dx[1], dx[2], abskgThreshold, sigmaT4Threshold,
+                                                         static_cast<float*>(dA), static_cast<float*>(dS), dF, ob, dAny);
+  else
+    roi_extents_kernel<Rec8, float><<<grid, 256, 0, st>>>(static_cast<const Rec8*>(lv.rec), lb, pb, dx[0], dx[1], dx[2], abskgThreshold, sigmaT4Threshold,
+                                                         static_cast<float*>(dA), static_cast<float*>(dS), dF, ob, dAny);
+  CK(cudaGetLastError());
+  unsigned h = 0;
+  CK(cudaMemcpyAsync(&h, dAny, sizeof h, cudaMemcpyDeviceToHost, st));
+  if (outs) {
+    CK(cudaMemcpyAsync(magGradAbskg, dA, nOut * eb, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(magGradSigmaT4, dS, nOut * eb, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(flaggedCells, dF, nOut * 4, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  *anyFlagged = h ? 1 : 0;
   return 0;
 }
 

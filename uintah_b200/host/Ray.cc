@@ -151,15 +151,9 @@ void Ray::problemSetup(const ProblemSpecP& prob_spec, const ProblemSpecP& rmcrtp
     if (tmp == "ROUNDUP") d_cellTypeCoarsenLogic = ROUNDUP;
   }
 
-  //__________________________________ bulletproofing (Ray.cc:338-345): the reference's own device build refuses everything but patch_based;
-  // this back end also takes the fixed ROI (the whole fine level is resident on the device, so the ROI is only a box test).  The
-  // dynamic ROI needs the abskg / sigmaT4 gradient reduction tasks (Ray.cc:1950-2044), which are not part of this path.
-  if (algorithm == dataOnion && d_ROI_algo == dynamic) {
-    std::ostringstream warn;
-    warn << "GPU:RMCRT:ERROR: ";
-    warn << "At this time only ROI_extents type=\"patch_based\" and type=\"fixed\" work on the GPU";
-    throw ProblemSetupException(warn.str(), __FILE__, __LINE__);
-  }
+  //__________________________________ bulletproofing (Ray.cc:338-345): the reference's own device build refuses every ROI but patch_based.
+  // This back end takes all three Data-Onion ROI types: the whole fine level is resident on the device, so the ROI is only a box test
+  // in the march; fixed and dynamic ROIs are one box for every patch (Ray.cc:1291-1314).
   d_sigma_over_pi = d_sigma / M_PI;
 }
 
@@ -225,6 +219,10 @@ void Ray::fillParams(rmcrt_params& p) const {
     }
     p.roiFixed = 1;
     for (int d = 0; d < 3; ++d) { p.roiFixedLo[d] = lo[d]; p.roiFixedHi[d] = hi[d]; }
+  }
+  if (d_ROI_algo == dynamic) {                              // Ray::computeExtents, dynamic branch (Ray.cc:1291-1300): one box for every patch
+    p.roiFixed = 1;
+    for (int d = 0; d < 3; ++d) { p.roiFixedLo[d] = d_dynROI_lo[d]; p.roiFixedHi[d] = d_dynROI_hi[d]; }
   }
   p.coarsenExtraCells = d_coarsenExtraCells ? 1 : 0;     // Ray::coarsen_Q's domain-face branch (Ray.cc:2148-2245) runs inside rmcrt_coarsen_level_device
   for (auto& kv : d_knobs) {
@@ -368,6 +366,13 @@ void Ray::traceCommon(bool dataOnion, const PatchSubset* patches, DataWarehouse*
   auto& devs = devices();
   const auto tTask = std::chrono::steady_clock::now();
 
+  if (dataOnion && d_ROI_algo == dynamic) {     // this solve's ROI_loCell / ROI_hiCell (Ray::ROI_Extents ran after the level was uploaded)
+    if (d_dynROI_stamp != new_dw->getID())
+      throw InternalError("Ray::rayTrace_dataOnion: dynamic ROI without Ray::ROI_Extents this time step (sched_ROI_Extents missing)", __FILE__, __LINE__);
+    rmcrt_params p;
+    fillParams(p);
+    for (auto& dev : devs) check(dev.ctx, rmcrt_set_params(dev.ctx, &p), "rmcrt_set_params");
+  }
   for (auto& dev : devs) {
     check(dev.ctx, rmcrt_finalize_level(dev.ctx, L, nullptr), "rmcrt_finalize_level");   // non-finite abskg etc. -> InternalError
     if (dataOnion)
@@ -518,12 +523,73 @@ void Ray::sched_computeCellType(const LevelP&, SchedulerP&, const Ray::modifiesC
   // fused into the device coarsening kernel (ROUNDUP / ROUNDDOWN, Ray.cc:2315-2342); nothing to schedule
 }
 
-// Ray.cc:1950-2043: only the dynamic ROI needs this task (it returns at once otherwise, 1957-1959); the B200 back end supports
-// patch_based and fixed (see problemSetup)
-void Ray::sched_ROI_Extents(const LevelP&, SchedulerP&) {
-  if (d_ROI_algo == dynamic)
-    throw ProblemSetupException("GPU:RMCRT:ERROR: At this time only ROI_extents type=\"patch_based\" and type=\"fixed\" work on the GPU", __FILE__, __LINE__);
+// Ray.cc:1947-1978: only on the finest level and only for the dynamic ROI
+void Ray::sched_ROI_Extents(const LevelP& level, SchedulerP& scheduler) {
+  const int maxLevels = level->getGrid()->numLevels() - 1;
+  if (level->getIndex() != maxLevels || d_ROI_algo != dynamic) return;
+  Task* tsk = nullptr;
+  if (d_FLT_DBL == TypeDescription::double_type) tsk = new Task("Ray::ROI_Extents", this, &Ray::ROI_Extents<double>);
+  else                                           tsk = new Task("Ray::ROI_Extents", this, &Ray::ROI_Extents<float>);
+  Ghost::GhostType gac = Ghost::AroundCells;
+  tsk->requiresVar(Task::NewDW, d_abskgLabel, gac, 1);
+  tsk->requiresVar(Task::NewDW, d_sigmaT4Label, gac, 1);
+  tsk->computesVar(d_mag_grad_abskgLabel);
+  tsk->computesVar(d_mag_grad_sigmaT4Label);
+  tsk->computesVar(d_flaggedCellsLabel);
+  tsk->computesVar(d_ROI_LoCellLabel);
+  tsk->computesVar(d_ROI_HiCellLabel);
+  tsk->usesDevice(true);
+  scheduler->addTask(tsk, level->eachPatch(), d_matlSet, RMCRTCommon::TG_RMCRT);
 }
+
+// Ray.cc:1984-2043.  The gradient magnitudes and the flags are computed on the device from the level's packed records
+// (rmcrt_roi_extents: compute_Mag_gradient + the threshold test); the union of the flagged patches' extra-cell boxes is the
+// ROI_loCell / ROI_hiCell reduction, kept in d_dynROI_* (the stand-in DataWarehouse has no reduction variables).
+template <class T>
+void Ray::ROI_Extents(const ProcessorGroup*, const PatchSubset* patches, const MaterialSubset*, DataWarehouse*, DataWarehouse* new_dw) {
+  const Level* level = getLevel(patches);
+  const int L = level->getIndex();
+  DataWarehouse* abskg_dw = get_abskg_dw(L, d_abskgLabel, new_dw);
+  uploadLevel<T>(level, abskg_dw, new_dw, new_dw, new_dw->getID());
+  if (d_dynROI_stamp != new_dw->getID()) {      // a new radiation solve: restart the min / max reduction
+    d_dynROI_lo = IntVector(SHRT_MAX, SHRT_MAX, SHRT_MAX);
+    d_dynROI_hi = IntVector(-SHRT_MAX, -SHRT_MAX, -SHRT_MAX);
+    d_dynROI_stamp = new_dw->getID();
+  }
+  Device& dev = devices()[0];
+  for (int p = 0; p < patches->size(); ++p) {
+    const Patch* patch = patches->get(p);
+    CCVariable<T> mag_grad_abskg, mag_grad_sigmaT4;
+    CCVariable<int> flaggedCells;
+    new_dw->allocateAndPut(mag_grad_abskg, d_mag_grad_abskgLabel, 0, patch);
+    new_dw->allocateAndPut(mag_grad_sigmaT4, d_mag_grad_sigmaT4Label, 0, patch);
+    new_dw->allocateAndPut(flaggedCells, d_flaggedCellsLabel, 0, patch);
+    const IntVector lo = patch->getCellLowIndex(), hi = patch->getCellHighIndex();
+    const IntVector olo = mag_grad_abskg.getLowIndex(), ohi = mag_grad_abskg.getHighIndex();
+    rmcrt_params prm;
+    fillParams(prm);
+    const bool doubleRecords = recordKind(prm) == 1;      // FP64 records <=> the gradients come back as double
+    int32_t flaggedPatch = 0;
+    if (doubleRecords == (sizeof(T) == 8)) {
+      check(dev.ctx, rmcrt_roi_extents(dev.ctx, L, lo.get_pointer(), hi.get_pointer(), d_abskg_thld, d_sigmaT4_thld, mag_grad_abskg.getPointer(),
+                                       mag_grad_sigmaT4.getPointer(), flaggedCells.getPointer(), sizeof(T) == 4 ? 1 : 0, olo.get_pointer(),
+                                       ohi.get_pointer(), &flaggedPatch, nullptr), "rmcrt_roi_extents");
+    } else {      // double deck marched in FP32: float records, the visualisation variables are widened on the host
+      CCVariable<float> ga, gs;
+      ga.resize(olo, ohi); gs.resize(olo, ohi);
+      check(dev.ctx, rmcrt_roi_extents(dev.ctx, L, lo.get_pointer(), hi.get_pointer(), d_abskg_thld, d_sigmaT4_thld, ga.getPointer(), gs.getPointer(),
+                                       flaggedCells.getPointer(), 1, olo.get_pointer(), ohi.get_pointer(), &flaggedPatch, nullptr), "rmcrt_roi_extents");
+      mag_grad_abskg.copyRegion(ga);
+      mag_grad_sigmaT4.copyRegion(gs);
+    }
+    if (flaggedPatch) {                                   // Ray.cc:2032-2038: include BCs
+      d_dynROI_lo = Min(d_dynROI_lo, patch->getExtraCellLowIndex());
+      d_dynROI_hi = Max(d_dynROI_hi, patch->getExtraCellHighIndex());
+    }
+  }
+}
+template void Ray::ROI_Extents<double>(const ProcessorGroup*, const PatchSubset*, const MaterialSubset*, DataWarehouse*, DataWarehouse*);
+template void Ray::ROI_Extents<float>(const ProcessorGroup*, const PatchSubset*, const MaterialSubset*, DataWarehouse*, DataWarehouse*);
 
 // a level whose property records exist only on the device: every level below the finest one of a multi-level algorithm
 bool Ray::isDeviceLevel(const Level* level) const {

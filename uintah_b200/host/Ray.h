@@ -6,6 +6,7 @@
 // obtain the same DataWarehouse variables the reference obtains and hand their raw x-fastest buffers to
 // rmcrt_upload_level / rmcrt_trace_divq / rmcrt_trace_dataonion; no ray is traced on the host.
 #pragma once
+#include <climits>
 #include "RMCRTCommon.h"
 #include "Radiometer.h"
 
@@ -96,6 +97,9 @@ class Ray : public RMCRTCommon {
   std::map<std::string, int> d_knobs;
   Report d_report;
   std::map<int, long long> d_deviceCoarsened;   // coarse level index -> DataWarehouse generation it was derived in
+  // dynamic ROI: the ROI_loCell / ROI_hiCell reduction of Ray::ROI_Extents (Ray.cc:1990-1991, 2041-2042) and the generation it belongs to
+  IntVector d_dynROI_lo{IntVector(SHRT_MAX, SHRT_MAX, SHRT_MAX)}, d_dynROI_hi{IntVector(-SHRT_MAX, -SHRT_MAX, -SHRT_MAX)};
+  long long d_dynROI_stamp{-1};
   GridP d_grid;
 
   //__________________________________ task bodies
@@ -112,6 +116,8 @@ class Ray : public RMCRTCommon {
                              DataWarehouse* new_dw, Task::WhichDW temp_dw, const bool backoutTemp);
   template <class T>
   void coarsenAll(const ProcessorGroup*, const PatchSubset* patches, const MaterialSubset*, DataWarehouse*, DataWarehouse* new_dw);
+  template <class T>
+  void ROI_Extents(const ProcessorGroup*, const PatchSubset* patches, const MaterialSubset*, DataWarehouse*, DataWarehouse* new_dw);   // Ray.h:283-288
   void refine_Q(const ProcessorGroup*, const PatchSubset* patches, const MaterialSubset* matls, DataWarehouse* old_dw, DataWarehouse* new_dw);   // Ray.h:307-311
   bool isDeviceLevel(const Level* level) const;
 

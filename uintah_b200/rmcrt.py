@@ -283,6 +283,19 @@ class RMCRT:
         check(self.ctx, self.lib.rmcrt_compute_extents(self.ctx, max_levels, i3(patch_lo), i3(patch_hi), roiLo, roiHi, regLo, regHi))
         return (tuple(roiLo), tuple(roiHi), np.array(regLo).reshape(max_levels, 3), np.array(regHi).reshape(max_levels, 3))
 
+    def roi_extents(self, L, patch_lo, patch_hi, abskg_thld, sigmaT4_thld, out_lo=None, out_hi=None, dtype=np.float32, stream=None):
+        """Ray::ROI_Extents for one patch: (mag_grad_abskg, mag_grad_sigmaT4, flaggedCells, anyFlagged) over the output window"""
+        out_lo, out_hi = self._window(L, out_lo, out_hi)
+        shape = (out_hi[2] - out_lo[2], out_hi[1] - out_lo[1], out_hi[0] - out_lo[0])
+        ga = np.zeros(shape, dtype); gs = np.zeros(shape, dtype); fl = np.zeros(shape, np.int32)
+        flag = C.c_int32(0)
+        self.lib.rmcrt_roi_extents.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_double, C.c_double, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p]
+        check(self.ctx, self.lib.rmcrt_roi_extents(self.ctx, L, i3(patch_lo), i3(patch_hi), float(abskg_thld), float(sigmaT4_thld), ga.ctypes.data,
+                                                   gs.ctypes.data, fl.ctypes.data, 1 if dtype == np.float32 else 0, i3(out_lo), i3(out_hi),
+                                                   C.byref(flag), _stream_handle(stream)))
+        return ga, gs, fl, bool(flag.value)
+
     # ------------------------------------------------------------------ callers either side of the path (SURVEY 8f-2, 8f-4)
     def refine_Q(self, coarseQ, c_lo, c_hi, grid_lo, grid_hi, rr, order, fl, fh, out_lo, out_hi, stream=None):
         """Ray::refine_Q for one scalar of one fine patch, host buffers; returns the fine window (zero outside [fl,fh))"""
