@@ -458,16 +458,19 @@ def test_dynamic_roi_extents(gpu_lib, po, dtype):
     rng = np.random.default_rng(21)
     fine = po.burns_christon(32, dtype=dtype)
     fine.rr = (4, 4, 4)
-    # a hot, optically thick blob in one corner region: only the patches it touches get flagged
+    # a flat medium with a hot, optically thick blob inside the first octant: only the patch it lies in gets flagged (the walls are given
+    # the medium's sigmaT4 and nearly its abskg so that they do not flag every patch)
     z, y, x = np.meshgrid(*[np.arange(-1, 33)] * 3, indexing="ij")
     blob = np.exp(-((x - 9.0) ** 2 + (y - 8.0) ** 2 + (z - 10.0) ** 2) / 18.0)
-    flow = fine.cellType == -1
-    fine.abskg[flow] = (fine.abskg[flow] * 0.2 + 3.0 * blob[flow]).astype(dtype)
-    fine.sigmaT4[flow] = (fine.sigmaT4[flow] * (1 + 4.0 * blob[flow])).astype(dtype)
+    base_s = float(fine.sigmaT4[5, 5, 5])
+    fine.abskg[...] = (0.9 + 3.0 * blob).astype(dtype)
+    fine.abskg[fine.cellType != -1] = 1.0
+    fine.sigmaT4[...] = (base_s * (1 + 4.0 * blob)).astype(dtype)
+    fine.sigmaT4[fine.cellType != -1] = base_s
     coarse = po.coarsen_level(fine, (4, 4, 4))
     patches = [(lo, hi, tuple(l - (1 if l == 0 else 0) for l in lo), tuple(h + (1 if h == 32 else 0) for h in hi))
                for lo, hi in po._split((0, 0, 0), (32, 32, 32), (2, 2, 2))]
-    thrA, thrS = 6.0, 2.5
+    thrA, thrS = 8.0, 1.0e9
     wantA, wantS, wantF, (rlo, rhi) = po.roi_extents(fine, patches, thrA, thrS)
     prec = 1 if dtype == np.float64 else 0
     kw = dict(nDivQRays=3, threshold=0.05, isSeedRandom=0)
@@ -485,7 +488,7 @@ def test_dynamic_roi_extents(gpu_lib, po, dtype):
     assert np.array_equal(gotF, wantF) and 0 < wantF.sum() < 32 ** 3
     assert np.array_equal(gotA, wantA) and np.array_equal(gotS, wantS)
     assert (tuple(lo_), tuple(hi_)) == (rlo, rhi)
-    assert rhi != (33, 33, 33) or rlo != (-1, -1, -1)            # not every patch is flagged
+    assert (rlo, rhi) == ((-1, -1, -1), (16, 16, 33))             # the two patches the blob reaches (of eight)
     # the solve with the dynamic ROI = the fixed-ROI solve with that box (Ray::computeExtents: one box for every patch)
     want = po.ray_trace_data_onion(po.default_params(roiFixed=1, roiFixedLo=rlo, roiFixedHi=rhi, **kw), [coarse, fine], (4, 4, 4), patches=(2, 2, 2), threads=8)
     g.set_params(roiFixed=1, roiFixedLo=rlo, roiFixedHi=rhi)
