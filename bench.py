@@ -255,7 +255,7 @@ class SingleLevelSolve:
         self.g = g = RMCRT(device=local, nDivQRays=rays, threshold=0.05, seed=1234, skipZeroWeightLegs=skip, l2Persist=args.l2persist,
                            warpsPerTile=args.warps, tileX=args.tile_x, cellsPerLane=cells_per_lane, genericMarch=args.generic_march,
                            maxBlocksPerSM=args.max_blocks_per_sm, half_records=bool(half), blockedMarch=args.blocked_march,
-                           refillLanes=args.refill_lanes, **kw)
+                           refillLanes=args.refill_lanes, originBrickHalo=args.origin_brick_halo, **kw)
         self.coherence = int(g.params.rayCoherence)
         self.stream = stream = torch.cuda.current_stream()
         lvl = LevelData(None, None, None, lo, hi, dx, interior_lo=(0, 0, 0), interior_hi=shape)
@@ -620,6 +620,7 @@ def main():
     ap.add_argument("--reference-semantics", action="store_true", help="march the zero-weight reflected legs like the reference")
     ap.add_argument("--blocked-march", type=int, default=0, help="rayCoherence 0: 0 = one-cell-per-lane kernel (library default), 1 = divq_indep_kernel on a blocked half-packed copy (A/B)")
     ap.add_argument("--refill-lanes", type=int, default=0, help="divq_indep_kernel: waiting lanes that trigger ray set-up (0 = library default)")
+    ap.add_argument("--origin-brick-halo", type=int, default=0, help="with --generic-march 1: stage the origin tile + halo in shared memory (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--configs-n", type=int, default=256, help="cells per side of the configs sub-records (256^3 single level, C4, C5)")
     ap.add_argument("--no-sweeps", action="store_true", help="skip by_coherence and the configs sub-records (A/B runs, profiling)")

@@ -122,6 +122,10 @@ typedef struct rmcrt_params {
                                   cell box [roiFixedLo, roiFixedHi) = fineLevel->getCellIndex(min / max point), the same for every patch,
                                   instead of patch +- haloCells (0, patch_based).  Clamped to the fine level like the reference. */
   int32_t  roiFixedLo[3], roiFixedHi[3];
+  int32_t  originBrickHalo;    /* A/B knob (0 = off): with genericMarch = 1 and rayCoherence 0 the block stages its origin tile + this many
+                                  cells on every side in shared memory and the march reads records inside that brick from there
+                                  (divq_brick_kernel; north_star's "shared-memory staging of the per-patch origin block") */
+  int32_t  reserved2;
 } rmcrt_params;
 
 /* One <Radiometer> block after Radiometer::problemSetup (Radiometer.cc:96-271; struct radiometer, Radiometer.h:117-127) */

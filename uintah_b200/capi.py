@@ -46,7 +46,7 @@ class Params(C.Structure):
         ("genericMarch", C.c_int32), ("maxBlocksPerSM", C.c_int32), ("rayDirSampleAlgo", C.c_int32), ("cellsPerLane", C.c_int32),
         ("maxRayLength", C.c_double), ("sigmaScat", C.c_double), ("tileX", C.c_int32), ("nonFlowCellType", C.c_int32),
         ("blockedMarch", C.c_int32), ("refillLanes", C.c_int32), ("coarsenExtraCells", C.c_int32), ("roiFixed", C.c_int32),
-        ("roiFixedLo", C.c_int32 * 3), ("roiFixedHi", C.c_int32 * 3),
+        ("roiFixedLo", C.c_int32 * 3), ("roiFixedHi", C.c_int32 * 3), ("originBrickHalo", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 

@@ -113,19 +113,36 @@ struct PathSink {       // debug only
 //------------------------------------------------------------------------------------------------------
 // single level
 //------------------------------------------------------------------------------------------------------
+// A box of level records a block has staged in shared memory (origin tile + halo): north_star's "shared-memory staging of the per-patch
+// origin block", built for the A/B measurement of DESIGN.md section 3 (rmcrt_params.originBrickHalo; default off).
+struct Brick {
+  const Rec8* sm;        // [n[2]][n[1]][n[0]], x fastest
+  int lo[3], n[3];       // the cell window it covers
+};
+
 // recs  : level records, x-fastest, strides (1, sy, sz)
 // idx   : record index of the origin cell
 // d*    : ray direction;  r* : rayDx = distance of the ray origin from the cell's low corner (RMCRTCommon.cc:643-646)
 // returns the ray's contribution to sumI
-template <class Real, class RecT, bool RECORD>
+template <class Real, class RecT, bool RECORD, bool BRICK = false>
 __device__ __forceinline__ Real march_single_level(const RecT* __restrict__ recs, long long idx, int sy, int sz,
                                                    Real dx, Real dy, Real dz, Real rx, Real ry, Real rz,
                                                    Real cx, Real cy, Real cz,   // cell size
                                                    Real threshold, bool allowReflect, bool skipZero,
                                                    unsigned& nSteps, PathSink* path, int pi, int pj, int pk,
                                                    Real maxLen = Real(INFINITY),     // d_maxRayLength * LEN_SCALE
-                                                   bool floatProps = false) {        // FP64 march of a float deck
+                                                   bool floatProps = false,          // FP64 march of a float deck
+                                                   const Brick* brick = nullptr) {   // BRICK: records inside this box come from shared memory
   typedef Num<Real> N;
+  // the record of cell (i, j, k) = recs[index]: from the staged brick when the cell lies inside it
+  auto fetch = [&](long long index, int i, int j, int k) -> typename RecInfo<RecT>::decoded {
+    if constexpr (BRICK) {
+      const unsigned x = (unsigned)(i - brick->lo[0]), y = (unsigned)(j - brick->lo[1]), z = (unsigned)(k - brick->lo[2]);
+      if (x < (unsigned)brick->n[0] && y < (unsigned)brick->n[1] && z < (unsigned)brick->n[2])
+        return brick->sm[x + (unsigned)brick->n[0] * (y + (unsigned)brick->n[1] * z)];
+    }
+    return ldrec(recs + index);
+  };
   if (!(Real(1) > threshold) || !(Real(0) < maxLen)) return Real(0);   // while (intensity > d_threshold && rayLength < d_maxRayLength), RMCRTCommon.cc:680
 
   // raySignStep (RMCRTCommon.cc:482-494): +1 / -1 by the sign BIT of the direction
@@ -142,7 +159,7 @@ __device__ __forceinline__ Real march_single_level(const RecT* __restrict__ recs
 
   Real tPrev = 0, tau = 0, ePrev = 1, sum = 0, fs = 1;
   Real len = 0;                    // rayLength (723), only compared when the ROI is boundedRayLength
-  typename RecInfo<RecT>::decoded r = ldrec(recs + idx);
+  typename RecInfo<RecT>::decoded r = fetch(idx, pi, pj, pk);
   Real k = absr(r.k), s = r.s;
   unsigned steps = 0;
   int ci = pi, cj = pj, ck = pk;   // only maintained when RECORD
@@ -159,10 +176,10 @@ __device__ __forceinline__ Real march_single_level(const RecT* __restrict__ recs
       py = !xy && (ty < tz);
       const Real tNext = px ? tx : (py ? ty : tz);
       idx += px ? stx : (py ? sty : stz);
-      if (RECORD) {
+      if (RECORD || BRICK) {
         if (px) ci += (stx > 0 ? 1 : -1); else if (py) cj += (sty > 0 ? 1 : -1); else ck += (stz > 0 ? 1 : -1);
       }
-      r = ldrec(recs + idx);                 // the one load of this step
+      r = fetch(idx, ci, cj, ck);            // the one load of this step
       Real ds = N::add(tNext, -tPrev);
       tPrev = tNext;
       tx = px ? N::add(tx, ddx) : tx;
@@ -194,9 +211,9 @@ __device__ __forceinline__ Real march_single_level(const RecT* __restrict__ recs
     fs = N::mul(fs, N::add(Real(1), -k));
     idx = idxPrev;
     if (px) stx = -stx; else if (py) sty = -sty; else stz = -stz;
-    if (RECORD) { if (px) ci += (stx > 0 ? 1 : -1); else if (py) cj += (sty > 0 ? 1 : -1); else ck += (stz > 0 ? 1 : -1); }
+    if (RECORD || BRICK) { if (px) ci += (stx > 0 ? 1 : -1); else if (py) cj += (sty > 0 ? 1 : -1); else ck += (stz > 0 ? 1 : -1); }
     if (skipZero && fs == Real(0)) break;                 // exact: every later term carries fs==0 or a zero wall emission
-    r = ldrec(recs + idx);
+    r = fetch(idx, ci, cj, ck);
     k = absr(r.k);
     s = r.s;
   }

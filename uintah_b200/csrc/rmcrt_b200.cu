@@ -671,6 +671,98 @@ __global__ void __launch_bounds__(128, (!ONION && std::is_same<RecT, Rec8>::valu
 }
 
 //======================================================================================================
+// A/B kernel for north_star's "shared-memory staging of the per-patch origin block" (rmcrt_params.originBrickHalo > 0 together with
+// genericMarch; default off): the block of W warps that shares a tile of 32 x-consecutive origin cells first copies the tile's
+// neighbourhood -- the tile plus `halo` cells on every side, clipped to the level -- into shared memory; the generic march then takes
+// every record inside that brick from shared memory and only the rest from global memory.  Same rays, same arithmetic, same results as
+// divq_kernel<float, Rec8, false, false, true>; measured in DESIGN.md section 3.
+//======================================================================================================
+__global__ void __launch_bounds__(256) divq_brick_kernel(const __grid_constant__ TraceArgs a, int halo) {
+  extern __shared__ double red[];     // [W][32] doubles, then the brick records
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+  const int F = a.G.maxLevels - 1;
+  const LevelGeom& g = a.G.lev[F];
+  const Rec8* recs = static_cast<const Rec8*>(g.rec);
+  Rec8* bsm = reinterpret_cast<Rec8*>(red + W * 32);
+  const bool skipZero = skip_allowed(a);
+  unsigned long long stepsTotal = 0, cellsTotal = 0;
+  for (long long tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
+    const long long t = tile * 32 + lane;
+    const bool valid = t < a.nCells;
+    int i = 0, j = 0, k = 0;
+    bool flow = false;
+    Rec8 r0{0, 0};
+    unsigned long long cellId = 0;
+    if (valid) {
+      patch_cell(a, t, i, j, k);
+      cellId = (unsigned long long)level_index(g, i, j, k);
+      r0 = ldrec(recs + cellId);
+      flow = !is_wall(r0.k);
+    }
+    // brick = bounding box of the tile's cells (a tile may wrap over patch rows) + halo, clipped to the level window
+    int i0, j0, k0, i1, j1, k1;
+    patch_cell(a, tile * 32, i0, j0, k0);
+    patch_cell(a, min(tile * 32 + 31, a.nCells - 1), i1, j1, k1);
+    Brick br;
+    const int tlo[3] = {(j0 == j1 && k0 == k1) ? i0 : a.patchLo[0], (k0 == k1) ? min(j0, j1) : a.patchLo[1], k0};
+    const int thi[3] = {(j0 == j1 && k0 == k1) ? i1 : a.patchLo[0] + a.patchN[0] - 1, (k0 == k1) ? max(j0, j1) : a.patchLo[1] + a.patchN[1] - 1, k1};
+    long long nb = 1;
+    for (int d = 0; d < 3; ++d) {
+      br.lo[d] = max(tlo[d] - halo, g.lo[d]);
+      br.n[d] = min(thi[d] + halo + 1, g.lo[d] + g.n[d]) - br.lo[d];
+      nb *= br.n[d];
+    }
+    br.sm = bsm;
+    for (long long q = threadIdx.x; q < nb; q += blockDim.x) {
+      const int x = (int)(q % br.n[0]);
+      const long long rest = q / br.n[0];
+      const int y = (int)(rest % br.n[1]), z = (int)(rest / br.n[1]);
+      bsm[q] = ldrec(recs + level_index(g, br.lo[0] + x, br.lo[1] + y, br.lo[2] + z));
+    }
+    __syncthreads();
+    double acc = 0;
+    unsigned steps = 0;
+    if (flow) {
+      for (int ray = warp; ray < a.nRays; ray += W) {
+        float dir[3], rayDx[3];
+        gen_divq_ray_f32(a.rng, g, ray, cellId, cellId, dir, rayDx);
+        acc += (double)march_single_level<float, Rec8, false, true>(recs, (long long)cellId, g.n[0], g.n[0] * g.n[1], nz<float, float>(dir[0]),
+                                                                    nz<float, float>(dir[1]), nz<float, float>(dir[2]), rayDx[0], rayDx[1], rayDx[2],
+                                                                    (float)g.dx[0], (float)g.dx[1], (float)g.dx[2], (float)a.threshold,
+                                                                    a.allowReflect != 0, skipZero, steps, nullptr, i, j, k, INFINITY, false, &br);
+      }
+    }
+    red[warp * 32 + lane] = acc;
+    __syncthreads();
+    if (warp == 0 && valid) {
+      double sumI = 0;
+      for (int w = 0; w < W; ++w) sumI += red[w * 32 + lane];
+      const long long q = (long long)(i - a.outLo[0]) +
+                          (long long)a.outN[0] * ((long long)(j - a.outLo[1]) + (long long)a.outN[1] * (long long)(k - a.outLo[2]));
+      if (flow) {
+        const double mean = sumI / a.nRays;
+        a.divQ[q] = -4.0 * M_PI * (double)r0.k * ((double)r0.s - mean);
+        a.volq[q] = 4.0 * M_PI * mean;
+        ++cellsTotal;
+      } else if (a.zeroNonFlow) {
+        a.divQ[q] = 0.0;
+        a.volq[q] = 0.0;
+      }
+    }
+    __syncthreads();
+    stepsTotal += steps;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    stepsTotal += __shfl_down_sync(0xffffffffu, stepsTotal, o);
+    cellsTotal += __shfl_down_sync(0xffffffffu, cellsTotal, o);
+  }
+  if (lane == 0) {
+    if (stepsTotal) atomicAdd(a.counters + 0, stepsTotal);
+    if (cellsTotal) atomicAdd(a.counters + 2, cellsTotal);
+  }
+}
+
+//======================================================================================================
 // An alternative kernel for the DEFAULT sampling (rayCoherence 0, independent rays per (cell, ray, timestep)): indep.cuh; opt-in
 // (rmcrt_params.blockedMarch = 1) because it measured SLOWER than the one-cell-per-lane divq_kernel (70 vs 53 ms at 128^3 x 100 rays,
 // profiles/r02v3_divq_indep_128cubed_ncu.md): it halves the global sector requests as designed, but the per-lane slot traffic puts as
@@ -2086,6 +2178,20 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
     } else if (std::is_same<Real, float>::value && !bounded && (!ctx->p.genericMarch || std::is_same<RecT, Rec4>::value)) {
       if (f32gen) divq_kernel<Real, RecT, false, true, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
       else        divq_kernel<Real, RecT, false, true, false><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
+    } else if (std::is_same<Real, float>::value && std::is_same<RecT, Rec8>::value && !bounded && f32gen && ctx->p.rayCoherence == 0 &&
+               ctx->p.originBrickHalo > 0 && ctx->p.originBrickHalo <= 16) {
+      // A/B: the generic march with the origin tile's neighbourhood staged in shared memory (divq_brick_kernel)
+      if constexpr (std::is_same<Real, float>::value && std::is_same<RecT, Rec8>::value) {
+        const int h = ctx->p.originBrickHalo;
+        // an A/B kernel: tiles must not wrap over patch rows, so that a tile's brick is (32 + 2h) x (2h + 1) x (2h + 1) at most
+        if (a.patchN[0] % 32 != 0) return fail(ctx, RMCRT_ERR_INVALID, "originBrickHalo needs patch rows that are a multiple of 32 cells");
+        const long long bx = std::min<long long>(32 + 2 * h, a.G.lev[a.G.maxLevels - 1].n[0]);
+        const long long by = 2 * h + 1, bz = 2 * h + 1;
+        const size_t smem = (size_t)W * 32 * sizeof(double) + (size_t)(bx * by * bz) * sizeof(Rec8);
+        if (smem > 200 * 1024) return fail(ctx, RMCRT_ERR_INVALID, "originBrickHalo %d needs %zu bytes of shared memory", h, smem);
+        CK(cudaFuncSetAttribute(divq_brick_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        divq_brick_kernel<<<(int)grid, 32 * W, smem, st>>>(a, h);
+      }
     } else {
       if (f32gen) divq_kernel<Real, RecT, false, false, true><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
       else        divq_kernel<Real, RecT, false, false, false><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a);
@@ -2270,7 +2376,7 @@ void rmcrt_default_params(rmcrt_params* p) {
   p->sigmaScat = 0.0;          // Ray.cc:169
   p->tileX = 0; p->nonFlowCellType = 8;
   p->blockedMarch = 0; p->refillLanes = 0;
-  p->coarsenExtraCells = 0; p->roiFixed = 0;
+  p->coarsenExtraCells = 0; p->roiFixed = 0; p->originBrickHalo = 0; p->reserved2 = 0;
   for (int d = 0; d < 3; ++d) { p->roiFixedLo[d] = 0; p->roiFixedHi[d] = 0; }
   p->cellsPerLane = 4;         // production: the 2 x 2 cells of a lane share one DDA (divq_quad_kernel); 2 = a pair (divq_dual_kernel); 1 = one cell per lane
 }
