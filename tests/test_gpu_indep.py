@@ -24,8 +24,9 @@ def solve(lv, patch=None, **kw):
     return out["divQ"], out["radiationVolq"], int(c.nRaySteps), int(c.nDivQCells)
 
 
+@pytest.mark.parametrize("bm", [1, 2, 3])
 @pytest.mark.parametrize("case", ["bc_walls_odd_patch", "plates_mirrors", "bc_refsem"])
-def test_blocked_march_matches_one_cell_kernel(gpu_lib, po, case):
+def test_blocked_march_matches_one_cell_kernel(gpu_lib, po, case, bm):
     """same rays, same fp16 properties (half-packed level records for the one-cell kernel): divQ to FP32 round-off, executed steps and
     written cells equal (ties of the axis choice aside)"""
     rng = np.random.default_rng(4)
@@ -42,8 +43,12 @@ def test_blocked_march_matches_one_cell_kernel(gpu_lib, po, case):
         lv = po.burns_christon(24, dtype=np.float32)
         kw["skipZeroWeightLegs"] = 0
     d1, v1, n1, c1 = solve(lv, patch, blockedMarch=0, **kw)
-    d2, v2, n2, c2 = solve(lv, patch, blockedMarch=1, **kw)
+    d2, v2, n2, c2 = solve(lv, patch, blockedMarch=bm, **kw)
     assert c1 == c2 and c1 > 0
+    if bm == 2:      # the same PTX leg loop on the same fp16 words: ray sums and step counts bit for bit
+        assert n1 == n2 and np.array_equal(v1, v2)
+    if bm == 3:      # the same rays again, added per cell in ray order instead of per warp: FP64 round-off
+        assert n1 == n2 and np.allclose(v1, v2, rtol=1e-12, atol=0)
     assert np.array_equal(d1 == 0, d2 == 0) and np.array_equal(v1 == 0, v2 == 0)
     assert abs(n1 - n2) <= 3e-4 * n1, (n1, n2)
     # the ray sums (radiationVolq = 4 pi sumI / N) agree to FP32 round-off; divQ additionally differs by the fp16 rounding of the origin
@@ -55,7 +60,8 @@ def test_blocked_march_matches_one_cell_kernel(gpu_lib, po, case):
     assert np.abs(d1 - d2).max() <= 2e-2 * np.abs(d1).max() and np.linalg.norm(d1 - d2) / np.linalg.norm(d1) < 1.5e-3
 
 
-def test_blocked_march_on_float_records(gpu_lib, po):
+@pytest.mark.parametrize("bm", [1, 2, 3])
+def test_blocked_march_on_float_records(gpu_lib, po, bm):
     """float (8-B) level records: the blocked copy is their fp16 rounding -- divQ within the fp16 rounding of the properties along the
     rays of the one-cell kernel marching the float records, same masks"""
     rng = np.random.default_rng(5)
@@ -63,7 +69,7 @@ def test_blocked_march_on_float_records(gpu_lib, po):
     add_random_walls(lv, 0.01, rng)
     kw = dict(nDivQRays=32, threshold=0.05, seed=21)
     d1, _, n1, c1 = solve(lv, None, blockedMarch=0, **kw)
-    d2, _, n2, c2 = solve(lv, None, blockedMarch=1, **kw)
+    d2, _, n2, c2 = solve(lv, None, blockedMarch=bm, **kw)
     assert c1 == c2 and np.array_equal(d1 == 0, d2 == 0)
     assert abs(n1 - n2) <= 5e-4 * n1
     scale = np.abs(d1).max()
@@ -71,7 +77,8 @@ def test_blocked_march_on_float_records(gpu_lib, po):
     assert np.percentile(diff, 99.5) < 1.5e-3 * scale and np.linalg.norm(d1 - d2) / np.linalg.norm(d1) < 1e-3
 
 
-def test_isothermal_enclosure_is_exact(gpu_lib, po):
+@pytest.mark.parametrize("bm", [1, 2, 3])
+def test_isothermal_enclosure_is_exact(gpu_lib, po, bm):
     """sigmaT4/pi = 0.6 is NOT exact in fp16: the epilogue uses the same fp16 value the rays integrate, so divQ == 0 to FP32 round-off"""
     rng = np.random.default_rng(6)
     M = 27
@@ -82,7 +89,7 @@ def test_isothermal_enclosure_is_exact(gpu_lib, po):
     walls = (rng.uniform(size=(M, M, M)) < 0.03) & (ct == -1); ct[walls] = 8; ab[walls] = 1.0
     iso = po.Level(ab, s4, ct, (-1,) * 3, (M - 1,) * 3, (1.0 / 25,) * 3, interior_lo=(0,) * 3, interior_hi=(25,) * 3)
     for half in (False, True):
-        d, _, _, c = solve(iso, None, nDivQRays=8, threshold=0.001, seed=5, allowReflect=0, half_records=half, blockedMarch=1)
+        d, _, _, c = solve(iso, None, nDivQRays=8, threshold=0.001, seed=5, allowReflect=0, half_records=half, blockedMarch=bm)
         assert np.abs(d).max() < 2e-5 * 4 * np.pi * 2.0 * 0.6
         assert c == int((ct == -1).sum())
 
@@ -98,13 +105,14 @@ def test_refill_threshold_does_not_change_results(gpu_lib, po):
         assert np.array_equal(d, ref[0]) and n == ref[1]
 
 
-def test_monte_carlo_tolerance_41(gpu_lib, po):
+@pytest.mark.parametrize("bm", [1, 2, 3])
+def test_monte_carlo_tolerance_41(gpu_lib, po, bm):
     """BASELINE config 1 through the blocked kernel: SURVEY 8c (i)-(iii) against 8 oracle seeds, unrelaxed"""
     from util import candidate_stats, loo_control
     lv = po.burns_christon(41)
     p = po.default_params(nDivQRays=100, threshold=0.05, isSeedRandom=1)
     runs = [po.ray_trace(p, lv, seed=100 * s, patches=(1, 1, 8), threads=8)["divQ"] for s in range(1, 9)]
-    g = make(nDivQRays=100, threshold=0.05, seed=2024, blockedMarch=1)
+    g = make(nDivQRays=100, threshold=0.05, seed=2024, blockedMarch=bm)
     g.upload_level(0, lv)
     d = g.trace_divq(0)["divQ"]
     inner = (slice(1, -1),) * 3
@@ -133,3 +141,23 @@ def test_origin_brick_staging_is_bit_identical(gpu_lib, po, halo):
     a = solve(pl, None, **kw)
     b = solve(pl, None, originBrickHalo=halo, **kw)
     assert a[2] == b[2] and np.array_equal(a[0], b[0])
+
+
+def test_sorted_kernel_is_independent_of_the_launch_shape(gpu_lib, po):
+    """divq_sorted_kernel (blockedMarch = 3) adds the rays of a cell in ray order whatever the sort, the chunk hand-out and the pass
+    length did: bit-identical divQ for any rays-per-pass (refillLanes doubles as that A/B knob), any patch decomposition, run to run"""
+    rng = np.random.default_rng(9)
+    lv = po.burns_christon(30, dtype=np.float32)
+    add_random_walls(lv, 0.02, rng, abskg=0.7, sigmaT4=0.3)
+    kw = dict(nDivQRays=37, threshold=0.05, seed=4, blockedMarch=3)
+    d0, v0, n0, c0 = solve(lv, None, **kw)
+    for rp in (5, 16, 37):
+        d1, v1, n1, c1 = solve(lv, None, refillLanes=rp, **kw)
+        assert n0 == n1 and c0 == c1 and np.array_equal(d0, d1) and np.array_equal(v0, v1), rp
+    # two patches (tiles of 32 cells start elsewhere): every cell keeps its rays and their order
+    g = make(**kw)
+    g.upload_level(0, lv)
+    a = g.trace_divq(0, patch_lo=(0, 0, 0), patch_hi=(30, 30, 13), timestep=6)["divQ"]
+    b = g.trace_divq(0, patch_lo=(0, 0, 13), patch_hi=(30, 30, 30), timestep=6)["divQ"]
+    g.close()
+    assert np.array_equal(a + b, d0)

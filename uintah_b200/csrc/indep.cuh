@@ -136,6 +136,152 @@ __device__ __forceinline__ void indep_start(IndepRay& r, int B0, unsigned o0, fl
   r.A = 0.0f; r.ePrev = 1.0f; r.leg = 0.0f; r.tau = 0.0f;
   r.fs = 1.0f; r.sum = 0.0f; r.nsteps = 0.0f;
 }
+
+//------------------------------------------------------------------------------------------------------
+// blockedMarch = 2: the one-cell-per-lane PTX leg loop of march.cuh (march_leg) on the blocked copy, with PLAIN 4-byte loads.
+// Nothing is cached per lane: the second cell a ray visits inside a 2 x 2 x 2 block (one 32-B sector) is an L1 hit on the sector its
+// first visit fetched, so the L1 -> L2 miss requests per ray-cell step halve while the per-step instruction count grows by three.
+//
+// Blocked addressing without coordinates: the word index of a cell is 8 * block + (x&1 | (y&1)<<1 | (z&1)<<2).  Along one axis the
+// index changes alternately by a and b (x: 1 / 7, y: 2 / 8 nbx - 2, z: 4 / 8 nbx nby - 4; negated for a negative direction), so every axis
+// carries its CURRENT signed delta, and a step on that axis toggles it with one XOR: (a ^ b) == ((-a) ^ (-b)) for these pairs, a constant
+// of the level (6, tgy, tgz).  A reflection steps back by the previous delta d and goes on with d - sign(d) (a + b).
+//------------------------------------------------------------------------------------------------------
+struct BlkStride {
+  int dlx, dly, dlz;     // current signed word-index deltas of the three axes
+};
+#if defined(__CUDA_ARCH__)
+#define RB_PEEK(J, IB)                                      \
+  "min.f32 t" #J ", %0, %1, %2;\n\t"                        \
+  "setp.neu.f32 n" #J ", t" #J ", %2;\n\t"                  \
+  "setp.lt.and.f32 x" #J ", %0, %1, n" #J ";\n\t"           \
+  "setp.ge.and.f32 y" #J ", %0, %1, n" #J ";\n\t"           \
+  "selp.s32 i" #J ", %13, %15, x" #J ";\n\t"                \
+  "@y" #J " mov.s32 i" #J ", %14;\n\t"                      \
+  "add.s32 i" #J ", i" #J ", " IB ";\n\t"                   \
+  "mad.wide.s32 ad, i" #J ", 4, %16;\n\t" "ld.global.nc.b32 k" #J ", [ad];\n\t"
+#define RB_COMMIT(J)                                        \
+  "@x" #J " add.f32 %0, %0, %17;\n\t"                       \
+  "@x" #J " xor.b32 %13, %13, 6;\n\t"                       \
+  "@y" #J " add.f32 %1, %1, %18;\n\t"                       \
+  "@y" #J " xor.b32 %14, %14, %20;\n\t"                     \
+  "@!n" #J " add.f32 %2, %2, %19;\n\t"                      \
+  "@!n" #J " xor.b32 %15, %15, %21;\n\t"
+#define RB_INTEG(P, C)                                      \
+  "fma.rn.f32 ta, a" #P ", t" #C ", %4;\n\t"                \
+  "neg.f32 d, ta;\n\t"                                      \
+  "ex2.approx.ftz.f32 e" #C ", d;\n\t"                      \
+  "sub.f32 d, e" #P ", e" #C ";\n\t"                        \
+  "fma.rn.f32 %8, s" #P ", d, %8;\n\t"                      \
+  "add.f32 %9, %9, 0f3F800000;\n\t"                         \
+  "mov.b32 {hl, hh}, k" #C ";\n\t" "cvt.f32.f16 s" #C ", hl;\n\t" "cvt.f32.f16 a" #C ", hh;\n\t" "abs.f32 a" #C ", a" #C ";\n\t" \
+  "neg.f32 d, a" #C ";\n\t"                                 \
+  "fma.rn.f32 %4, d, t" #C ", ta;\n\t"                      \
+  "setp.lt.s32 w, k" #C ", 0;\n\t"                          \
+  "@w bra EXIT" #C ";\n\t"
+#define RB_EXIT(C)                                          \
+  "EXIT" #C ":\n\t"                                         \
+  "mov.s32 %3, i" #C ";\n\t"                                \
+  "mov.f32 %10, t" #C ";\n\t"                               \
+  "selp.s32 %11, 1, 2, y" #C ";\n\t"                        \
+  "@x" #C " mov.s32 %11, 0;\n\t"                            \
+  "mov.f32 %5, a" #C ";\n\t"                                \
+  "mov.f32 %6, s" #C ";\n\t"                                \
+  "mov.f32 %7, e" #C ";\n\t"                                \
+  "bra DONE;\n\t"
+// same three-slot rotation as march_leg; the speculative request of step n+1 uses the deltas as they are after the commit of step n
+__device__ __forceinline__ LegOut march_leg_blk(Dda& d, Integ& q, BlkStride& b, const uint32_t* __restrict__ blk, float ddx, float ddy,
+                                                float ddz, int tgy, int tgz) {
+  LegOut o;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred x0, y0, n0, x1, y1, n1, x2, y2, n2, w;\n\t"
+      ".reg .f32 d, ta, t0, t1, t2, s0, s1, s2, e0, e1, e2, a0, a1, a2;\n\t"
+      ".reg .b32 k0, k1, k2;\n\t"
+      ".reg .b16 hl, hh;\n\t"
+      ".reg .s32 i0, i1, i2;\n\t"
+      ".reg .s64 ad;\n\t"
+      "mov.f32 a2, %5;\n\t"
+      "mov.f32 s2, %6;\n\t"
+      "mov.f32 e2, %7;\n\t"
+      RB_PEEK(0, "%3")
+      "LOOP:\n\t"
+      RB_COMMIT(0) RB_PEEK(1, "i0") RB_INTEG(2, 0)
+      RB_COMMIT(1) RB_PEEK(2, "i1") RB_INTEG(0, 1)
+      RB_COMMIT(2) RB_PEEK(0, "i2") RB_INTEG(1, 2)
+      "bra LOOP;\n\t"
+      RB_EXIT(0) RB_EXIT(1) RB_EXIT(2)
+      "DONE:\n\t"
+      "mov.f32 %12, ta;\n\t"
+      "}"
+      : "+f"(d.tx), "+f"(d.ty), "+f"(d.tz), "+r"(d.idx), "+f"(q.A), "+f"(q.k), "+f"(q.s), "+f"(q.ePrev), "+f"(q.leg),
+        "+f"(q.nsteps), "=f"(o.t), "=r"(o.axis), "=f"(q.tau), "+r"(b.dlx), "+r"(b.dly), "+r"(b.dlz)
+      : "l"(blk), "f"(ddx), "f"(ddy), "f"(ddz), "r"(tgy), "r"(tgz)
+      : "memory");
+  return o;
+}
+#undef RB_PEEK
+#undef RB_COMMIT
+#undef RB_INTEG
+#undef RB_EXIT
+#else
+__device__ __forceinline__ LegOut march_leg_blk(Dda&, Integ&, BlkStride&, const uint32_t*, float, float, float, int, int) { return LegOut{0.0f, 0}; }
+#endif
+
+__device__ __forceinline__ void blk_decode(Integ& q, uint32_t word) {
+  q.k = fabsf(__half2float(__ushort_as_half((unsigned short)(word >> 16))));
+  q.s = __half2float(__ushort_as_half((unsigned short)(word & 0xFFFFu)));
+}
+
+// march_single_level_fast (RMCRTCommon.cc:607-904) on the blocked copy.  w0 = word index of the origin cell, par = its position bits
+// (x&1 | (y&1)<<1 | (z&1)<<2), sy8 = 8 * blocks per row, sz8 = 8 * blocks per plane.  Result in the scaled units of the half-packed records.
+__device__ __forceinline__ float march_single_level_blk(const uint32_t* __restrict__ blk, int w0, unsigned par, int sy8, int sz8,
+                                                        float dx, float dy, float dz, float rx, float ry, float rz,
+                                                        float cx, float cy, float cz, float threshold, bool allowReflect,
+                                                        bool skipZero, unsigned& nSteps) {
+  typedef Num<float> N;
+  if (!(1.0f > threshold)) return 0.0f;
+  const bool posx = !sign_bit(dx), posy = !sign_bit(dy), posz = !sign_bit(dz);
+  const int tgy = 2 ^ (sy8 - 2), tgz = 4 ^ (sz8 - 4);
+  BlkStride b;
+  // positive direction: a on an even position, b = S - a on an odd one; negative: -a on an odd position, -b on an even one
+  b.dlx = posx ? ((par & 1u) ? 7 : 1) : ((par & 1u) ? -1 : -7);
+  b.dly = posy ? ((par & 2u) ? sy8 - 2 : 2) : ((par & 2u) ? -2 : 2 - sy8);
+  b.dlz = posz ? ((par & 4u) ? sz8 - 4 : 4) : ((par & 4u) ? -4 : 4 - sz8);
+  const float ix = N::rcp(dx), iy = N::rcp(dy), iz = N::rcp(dz);
+  Dda d;
+  d.tx = ((posx ? cx : 0.0f) - rx) * ix * N::LEN_SCALE;
+  d.ty = ((posy ? cy : 0.0f) - ry) * iy * N::LEN_SCALE;
+  d.tz = ((posz ? cz : 0.0f) - rz) * iz * N::LEN_SCALE;
+  const float ddx = fabsf(ix) * cx * N::LEN_SCALE, ddy = fabsf(iy) * cy * N::LEN_SCALE, ddz = fabsf(iz) * cz * N::LEN_SCALE;
+  d.idx = w0;
+  Integ q;
+  blk_decode(q, __ldg(blk + w0));
+  q.A = 0.0f; q.ePrev = 1.0f; q.nsteps = 0.0f; q.tau = 0.0f;
+  float sum = 0.0f, fs = 1.0f;
+  for (;;) {
+    q.leg = 0.0f;
+    const LegOut w = march_leg_blk(d, q, b, blk, ddx, ddy, ddz, tgy, tgz);
+    sum = fmaf(q.leg, fs, sum);
+    const float eps = q.k > 1.0f ? 1.0f : q.k;                 // 846-850
+    sum = fmaf(eps * q.s, q.ePrev, sum);                       // 854: NOT multiplied by fs
+    const float intensity = q.ePrev * fs;                      // 856
+    if (!allowReflect || !(intensity > threshold)) break;      // 884, 898, 683
+    fs *= (1.0f - q.k);
+    if (skipZero && fs == 0.0f) break;
+    // RMCRTCommon::reflect (581-602): back into the cell the ray came from (the delta of that step is the current one toggled back),
+    // stepping direction of that axis flipped; tMax is NOT recomputed (reference behaviour)
+    int dprev;
+    if (w.axis == 0)      { dprev = b.dlx ^ 6;   b.dlx = dprev > 0 ? dprev - 8 : dprev + 8; }
+    else if (w.axis == 1) { dprev = b.dly ^ tgy; b.dly = dprev > 0 ? dprev - sy8 : dprev + sy8; }
+    else                  { dprev = b.dlz ^ tgz; b.dlz = dprev > 0 ? dprev - sz8 : dprev + sz8; }
+    d.idx -= dprev;
+    blk_decode(q, __ldg(blk + d.idx));
+    q.A = fmaf(-q.k, w.t, q.tau);
+  }
+  nSteps += (unsigned)q.nsteps;
+  return sum;
+}
 #endif
 
 }  // namespace rmcrt

@@ -877,6 +877,281 @@ __global__ void __launch_bounds__(128, RMCRT_INDEP_BLOCKS) divq_indep_kernel(con
 }
 
 //======================================================================================================
+// blockedMarch = 2: the tile / warp layout of divq_kernel (32 x-consecutive origin cells per tile, lane = cell, warp w traces rays w, w + W,
+// ... of its cells, fixed-order cross-warp sum) with march_single_level_blk: the PTX leg loop on the 2 x 2 x 2 blocked half-packed copy
+// of the level, plain 4-byte loads (indep.cuh).  Same rays as divq_kernel (Philox keyed on (cell, ray, timestep)).
+//======================================================================================================
+template <class RecT>
+__global__ void __launch_bounds__(256, RMCRT_FAST_MIN_BLOCKS) divq_blk_kernel(const __grid_constant__ TraceArgs a, const BlkGeom bg) {
+  extern __shared__ double red[];     // [W][32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+  const int F = a.G.maxLevels - 1;
+  const LevelGeom& g = a.G.lev[F];
+  const bool skipZero = skip_allowed(a);
+  constexpr float UNSCALE = 1.0f / HALF_S_SCALE;
+  const uint32_t* __restrict__ blk = bg.blk;
+  const int sy8 = 8 * bg.bx, sz8 = 8 * bg.bxy;
+  const float cx = (float)g.dx[0], cy = (float)g.dx[1], cz = (float)g.dx[2];
+  unsigned long long stepsTotal = 0, cellsTotal = 0;
+
+  for (long long tile = blockIdx.x; tile < a.nTiles; tile += gridDim.x) {
+    const long long t = tile * 32 + lane;
+    const bool valid = t < a.nCells;
+    int i = 0, j = 0, k = 0;
+    bool flow = false;
+    Rec8 r0{0, 0};
+    unsigned long long cellId = 0;
+    int w0 = 0;
+    unsigned par = 0;
+    if (valid) {
+      patch_cell(a, t, i, j, k);
+      cellId = (unsigned long long)level_index(g, i, j, k);
+      if constexpr (std::is_same<RecT, Rec4>::value) r0 = ldrec(static_cast<const Rec8*>(g.recFull) + cellId);
+      else r0 = ldrec(static_cast<const Rec8*>(g.rec) + cellId);
+      flow = !is_wall(r0.k);
+      const int ux = i - bg.lo[0], uy = j - bg.lo[1], uz = k - bg.lo[2];
+      par = (unsigned)((ux & 1) | ((uy & 1) << 1) | ((uz & 1) << 2));
+      w0 = 8 * ((ux >> 1) + bg.bx * (uy >> 1) + bg.bxy * (uz >> 1)) + (int)par;
+    }
+    double acc = 0;
+    unsigned steps = 0;
+    if (flow) {
+      for (int ray = warp; ray < a.nRays; ray += W) {
+        float dir[3], rayDx[3];
+        gen_divq_ray_f32(a.rng, g, ray, cellId, cellId, dir, rayDx);
+        acc += (double)(UNSCALE * march_single_level_blk(blk, w0, par, sy8, sz8, nz<float, float>(dir[0]), nz<float, float>(dir[1]),
+                                                         nz<float, float>(dir[2]), rayDx[0], rayDx[1], rayDx[2], cx, cy, cz,
+                                                         (float)a.threshold, a.allowReflect != 0, skipZero, steps));
+      }
+    }
+    red[warp * 32 + lane] = acc;
+    __syncthreads();
+    if (warp == 0 && valid) {
+      double sumI = 0;
+      for (int w = 0; w < W; ++w) sumI += red[w * 32 + lane];
+      const long long q = (long long)(i - a.outLo[0]) +
+                          (long long)a.outN[0] * ((long long)(j - a.outLo[1]) + (long long)a.outN[1] * (long long)(k - a.outLo[2]));
+      if (flow) {
+        const double mean = sumI / a.nRays;
+        // emission of the origin cell with the SAME fp16 sigmaT4/pi its rays integrate (isothermal enclosure => divQ == 0 whatever the
+        // rounding); abskg multiplies both terms: full precision.  Ray.cc:775,778
+        const uint32_t ww = __ldg(blk + w0);
+        const double s0 = (double)(UNSCALE * __half2float(__ushort_as_half((unsigned short)(ww & 0xFFFFu))));
+        a.divQ[q] = -4.0 * M_PI * (double)r0.k * (s0 - mean);
+        a.volq[q] = 4.0 * M_PI * mean;
+        ++cellsTotal;
+      } else if (a.zeroNonFlow) {
+        a.divQ[q] = 0.0;
+        a.volq[q] = 0.0;
+      }
+    }
+    __syncthreads();
+    stepsTotal += steps;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    stepsTotal += __shfl_down_sync(0xffffffffu, stepsTotal, o);
+    cellsTotal += __shfl_down_sync(0xffffffffu, cellsTotal, o);
+  }
+  if (lane == 0) {
+    if (stepsTotal) atomicAdd(a.counters + 0, stepsTotal);
+    if (cellsTotal) atomicAdd(a.counters + 2, cellsTotal);
+  }
+}
+
+//======================================================================================================
+// blockedMarch = 3: LENGTH-SORTED independent rays on the blocked copy.  Same rays as divq_kernel / divq_blk_kernel (Philox keyed on
+// (cell, ray, timestep)), but the lanes of a warp no longer trace ray r of 32 neighbouring cells -- whose lengths differ by the full
+// range (13.4 of 32 lanes active, ncu) -- they trace 32 rays of the tile that are expected to END TOGETHER:
+//   1. every (cell, ray) of the tile's 32 cells x RP rays gets an 8-bit key = the number of DDA steps to the far side of the level along
+//      its direction (closed form from the direction and the cell index, ~15 FP instructions; walls inside the domain and the intensity
+//      threshold make it an estimate -- correctness never depends on it);
+//   2. a counting sort in shared memory (histogram, scan, scatter) orders the rays by key, longest first;
+//   3. warps take chunks of 32 consecutive rays off that list (dynamic hand-out: longest chunks first, so the warps of a block end
+//      together), regenerate each ray from its Philox counter and march it (march_single_level_blk);
+//   4. each ray's sum is written to res[ray][cell] in shared memory and the rays of a cell are added in RAY ORDER in FP64 -- the result
+//      does not depend on the sort, the hand-out or the number of warps, bit for bit.
+//======================================================================================================
+#ifndef RMCRT_SORTED_BLOCKS
+#define RMCRT_SORTED_BLOCKS 4
+#endif
+constexpr int SORT_BINS = 256;
+// per-block scratch in GLOBAL memory (L2-resident, accessed with .cg so it never takes L1 lines from the records): res[RP][32] f32 |
+// ids[RP * 32] u16 | keys[RP * 32] u8.  Shared memory would do, but every KB of it comes out of the SM's L1, and the march lives on the
+// L1 keeping a sector until the ray's next step (23 KB per block = 187 KB per SM measured: L1 hit rate 46 % -> 8 %, solve 47 -> 59 ms).
+__host__ __device__ inline size_t sorted_scratch_bytes(int RP) { return (((size_t)RP * 32 * 7) + 127) / 128 * 128; }
+template <class RecT>
+__global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(const __grid_constant__ TraceArgs a, const BlkGeom bg, int RP,
+                                                                               unsigned char* __restrict__ scratch, int* __restrict__ tileCounter) {
+  // 2.9 KB of shared memory per block: eight resident blocks stay inside the 32-KB carve-out, the rest of the SM's 256 KB is L1
+  __shared__ double part[8 * 32];
+  __shared__ unsigned long long cellIds[32];
+  int* hist = reinterpret_cast<int*>(part);      // [SORT_BINS], dead when phase 4 writes part
+  __shared__ int w0s[32];            // word index of the cell, -1: not traced
+  __shared__ int ijk[96];
+  __shared__ int ctl[4];             // [0] next chunk [1] list length [2] tile
+  __shared__ int warpTot[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int W = 8;
+  unsigned char* my = scratch + (size_t)blockIdx.x * sorted_scratch_bytes(RP);
+  float* res = reinterpret_cast<float*>(my);                                           // [RP][32]
+  unsigned short* ids = reinterpret_cast<unsigned short*>(my + (size_t)RP * 128);      // [RP * 32]
+  unsigned char* keys = my + (size_t)RP * 192;                                         // [RP * 32]
+  const int F = a.G.maxLevels - 1;
+  const LevelGeom& g = a.G.lev[F];
+  const bool skipZero = skip_allowed(a);
+  constexpr float UNSCALE = 1.0f / HALF_S_SCALE;
+  const uint32_t* __restrict__ blk = bg.blk;
+  const int sy8 = 8 * bg.bx, sz8 = 8 * bg.bxy;
+  const float cx = (float)g.dx[0], cy = (float)g.dx[1], cz = (float)g.dx[2];
+  const float icx = 1.0f / cx, icy = 1.0f / cy, icz = 1.0f / cz;
+  // a ray crosses at most n[0] + n[1] + n[2] cells of the level before it leaves it
+  const float keyScale = (float)(SORT_BINS - 1) / (float)(g.n[0] + g.n[1] + g.n[2]);
+  unsigned long long stepsTotal = 0, cellsTotal = 0;
+
+  for (;;) {
+    // tiles are handed out dynamically (rays near the centre of the domain are several times longer than those in its corners)
+    if (tid == 0) ctl[2] = atomicAdd(tileCounter, 1);
+    __syncthreads();
+    const long long tile = ctl[2];
+    if (tile >= a.nTiles) break;
+    // ---- phase 0: the tile's cells (warp 0, lane = cell)
+    int i = 0, j = 0, k = 0;
+    bool valid = false, flow = false;
+    Rec8 r0{0, 0};
+    int w0 = -1;
+    if (warp == 0) {
+      const long long t = tile * 32 + lane;
+      valid = t < a.nCells;
+      unsigned long long cellId = 0;
+      if (valid) {
+        patch_cell(a, t, i, j, k);
+        cellId = (unsigned long long)level_index(g, i, j, k);
+        if constexpr (std::is_same<RecT, Rec4>::value) r0 = ldrec(static_cast<const Rec8*>(g.recFull) + cellId);
+        else r0 = ldrec(static_cast<const Rec8*>(g.rec) + cellId);
+        flow = !is_wall(r0.k);
+        const int ux = i - bg.lo[0], uy = j - bg.lo[1], uz = k - bg.lo[2];
+        if (flow) w0 = 8 * ((ux >> 1) + bg.bx * (uy >> 1) + bg.bxy * (uz >> 1)) + ((ux & 1) | ((uy & 1) << 1) | ((uz & 1) << 2));
+      }
+      cellIds[lane] = cellId;
+      w0s[lane] = w0;
+      ijk[lane * 3 + 0] = i - g.lo[0]; ijk[lane * 3 + 1] = j - g.lo[1]; ijk[lane * 3 + 2] = k - g.lo[2];
+    }
+    double acc = 0;       // warp 0: running sum over the passes
+    unsigned steps = 0;
+    for (int ray0 = 0; ray0 < a.nRays; ray0 += RP) {
+      const int nr = min(RP, a.nRays - ray0);
+      hist[tid] = 0;                    // blockDim.x == SORT_BINS
+      if (tid == 0) ctl[0] = 0;
+      __syncthreads();
+      // ---- phase 1: keys + histogram (thread -> cell = lane, rays warp, warp + W, ...)
+      const int cw0 = w0s[lane];
+      {
+        const unsigned long long cid = cellIds[lane];
+        const float ci = (float)ijk[lane * 3 + 0], cj = (float)ijk[lane * 3 + 1], ck = (float)ijk[lane * 3 + 2];
+        if (cw0 >= 0)
+          for (int r = warp; r < nr; r += W) {
+            float dir[3], rayDx[3];
+            gen_divq_ray_f32(a.rng, g, ray0 + r, cid, cid, dir, rayDx);
+            // cell faces to the outer layer of the level along each axis, from the cell centre
+            const float ax = fabsf(dir[0]) * icx + 1e-30f, ay = fabsf(dir[1]) * icy + 1e-30f, az = fabsf(dir[2]) * icz + 1e-30f;
+            const float nx_ = (dir[0] >= 0.0f ? (float)(g.n[0] - 1) - ci : ci) - 0.5f;
+            const float ny_ = (dir[1] >= 0.0f ? (float)(g.n[1] - 1) - cj : cj) - 0.5f;
+            const float nz_ = (dir[2] >= 0.0f ? (float)(g.n[2] - 1) - ck : ck) - 0.5f;
+            const float tExit = fminf(fminf(nx_ / ax, ny_ / ay), nz_ / az);
+            const float est = tExit * (ax + ay + az);
+            const int key = min(SORT_BINS - 1, max(0, (int)(est * keyScale + 0.5f)));
+            atomicAdd(&hist[key], 1);
+            __stcg(keys + r * 32 + lane, (unsigned char)key);
+          }
+      }
+      __syncthreads();
+      // ---- phase 2: exclusive scan over the bins in DESCENDING key order (thread t owns bin 255 - t), then scatter
+      {
+        const int h = hist[SORT_BINS - 1 - tid];
+        int incl = h;
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        if (lane == 31) warpTot[warp] = incl;
+        __syncthreads();
+        int base = 0;
+        for (int w = 0; w < warp; ++w) base += warpTot[w];
+        hist[SORT_BINS - 1 - tid] = base + incl - h;          // start of the bin in the sorted list
+        if (tid == SORT_BINS - 1) ctl[1] = base + incl;       // list length = rays of flow cells
+        __syncthreads();
+        if (cw0 >= 0)
+          for (int r = warp; r < nr; r += W) {
+            const int pos = atomicAdd(&hist[__ldcg(keys + r * 32 + lane)], 1);
+            __stcg(ids + pos, (unsigned short)(r * 32 + lane));
+          }
+      }
+      __syncthreads();
+      // ---- phase 3: march chunks of 32 rays, longest first
+      {
+        const int nList = ctl[1];
+        for (;;) {
+          int chunk = 0;
+          if (lane == 0) chunk = atomicAdd(&ctl[0], 1);
+          chunk = __shfl_sync(0xffffffffu, chunk, 0);
+          if (chunk * 32 >= nList) break;
+          const int p = chunk * 32 + lane;
+          if (p < nList) {
+            const int id = __ldcg(ids + p);
+            const int c = id & 31, r = id >> 5;
+            const int rw0 = w0s[c];
+            const unsigned long long cid = cellIds[c];
+            float dir[3], rayDx[3];
+            gen_divq_ray_f32(a.rng, g, ray0 + r, cid, cid, dir, rayDx);
+            __stcg(res + id, UNSCALE * march_single_level_blk(blk, rw0, (unsigned)(rw0 & 7), sy8, sz8, nz<float, float>(dir[0]),
+                                                              nz<float, float>(dir[1]), nz<float, float>(dir[2]), rayDx[0], rayDx[1],
+                                                              rayDx[2], cx, cy, cz, (float)a.threshold, a.allowReflect != 0, skipZero, steps));
+          }
+        }
+      }
+      __syncthreads();
+      // ---- phase 4: rays of a cell added in ray order (warp w: its contiguous share, then the shares in warp order)
+      {
+        const int per = (nr + W - 1) / W;
+        double s = 0;
+        if (cw0 >= 0)
+          for (int r = warp * per; r < min(nr, (warp + 1) * per); ++r) s += (double)__ldcg(res + r * 32 + lane);
+        part[warp * 32 + lane] = s;
+        __syncthreads();
+        if (warp == 0)
+          for (int w = 0; w < W; ++w) acc += part[w * 32 + lane];
+        __syncthreads();       // hist aliases part
+      }
+    }
+    if (warp == 0 && valid) {
+      const long long q = (long long)(i - a.outLo[0]) +
+                          (long long)a.outN[0] * ((long long)(j - a.outLo[1]) + (long long)a.outN[1] * (long long)(k - a.outLo[2]));
+      if (flow) {
+        const double mean = acc / a.nRays;
+        const uint32_t ww = __ldg(blk + w0);      // the fp16 sigmaT4/pi the rays integrate (see divq_blk_kernel); Ray.cc:775,778
+        const double s0 = (double)(UNSCALE * __half2float(__ushort_as_half((unsigned short)(ww & 0xFFFFu))));
+        a.divQ[q] = -4.0 * M_PI * (double)r0.k * (s0 - mean);
+        a.volq[q] = 4.0 * M_PI * mean;
+        ++cellsTotal;
+      } else if (a.zeroNonFlow) {
+        a.divQ[q] = 0.0;
+        a.volq[q] = 0.0;
+      }
+    }
+    stepsTotal += steps;
+    __syncthreads();      // ctl[2] / part / w0s are rewritten for the next tile
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    stepsTotal += __shfl_down_sync(0xffffffffu, stepsTotal, o);
+    cellsTotal += __shfl_down_sync(0xffffffffu, cellsTotal, o);
+  }
+  if (lane == 0) {
+    if (stepsTotal) atomicAdd(a.counters + 0, stepsTotal);
+    if (cellsTotal) atomicAdd(a.counters + 2, cellsTotal);
+  }
+}
+
+//======================================================================================================
 // boundary flux
 //======================================================================================================
 // Ray::has_a_boundary (Ray.cc:1517-1572): `celltype[adj]+1 != 0`  <=>  adj is not a flow cell  <=>  record sign bit.
@@ -1706,6 +1981,7 @@ struct rmcrt_ctx {
   int lhcKeyDivQ[4] = {0, 0, 0, 0};   // (nRays, sumLo, rows, mode) the tables were built for
   int lhcKeyFlux[4] = {0, 0, 0, 0};
   DevBuf outVR[2];                    // host-API radiometer output staging
+  DevBuf sortScratch;                 // divq_sorted_kernel: tile counter + per-block res / ids / keys
   DevBuf replSend, replGathered;      // rmcrt_replicate_level: this device's packed slab / the gathered slabs of all devices
   std::string err;
   void* persistedStreamFor = nullptr;
@@ -2004,7 +2280,7 @@ int ensure_blocked_level(rmcrt_ctx* ctx, int L, BlkGeom& bg, cudaStream_t st) {
   int nb[3];
   for (int d = 0; d < 3; ++d) nb[d] = (s.d.hi[d] - s.d.lo[d] + 4 + 1) / 2;        // cells [lo - 2, hi + 2) in 2-cell blocks
   const size_t bytes = (size_t)nb[0] * nb[1] * nb[2] * 32;
-  if ((long long)nb[0] * nb[1] * nb[2] >= (1LL << 31)) return fail(ctx, RMCRT_ERR_INVALID, "level too large for the blocked march");
+  if ((long long)nb[0] * nb[1] * nb[2] >= (1LL << 28)) return fail(ctx, RMCRT_ERR_INVALID, "level too large for the blocked march");   // 32-bit word index
   if (bytes > s.blkCap) {
     if (s.blk) cudaFree(s.blk);
     s.blk = nullptr; s.blkCap = 0;
@@ -2162,6 +2438,29 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
         a2.gate = 1;
         divq_dual_kernel<RecT, false><<<(int)g2, 32 * W2, W2 * 64 * sizeof(double), st>>>(a2, nxc, njp, 0);
         launch_reflective_pairs<RecT>(ctx, a2, cap, st);
+      }
+    } else if (std::is_same<Real, float>::value && !bounded && f32gen && ctx->p.rayCoherence == 0 && ctx->p.blockedMarch == 3 && !ctx->p.genericMarch) {
+      // independent rays per (cell, ray, timestep), sorted by expected length inside a tile, on the blocked copy (divq_sorted_kernel)
+      if constexpr (std::is_same<Real, float>::value && !std::is_same<RecT, Rec16>::value) {
+        BlkGeom bg;
+        int rc = ensure_blocked_level<RecT>(ctx, a.G.maxLevels - 1, bg, st);
+        if (rc) return rc;
+        const int RP = std::min(a.nRays, ctx->p.refillLanes > 0 ? ctx->p.refillLanes : 256);      // rays per pass (A/B: refillLanes)
+        // persistent blocks (their scratch is per block), tiles handed out through a counter
+        const int nb = (int)std::min<long long>(a.nTiles, (long long)ctx->smCount * (ctx->p.maxBlocksPerSM > 0 ? ctx->p.maxBlocksPerSM : RMCRT_SORTED_BLOCKS));
+        if (ctx->sortScratch.ensure((size_t)nb * sorted_scratch_bytes(RP) + 256)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc sort scratch");
+        unsigned char* base = static_cast<unsigned char*>(ctx->sortScratch.p);
+        int* tileCounter = reinterpret_cast<int*>(base);
+        CK(cudaMemsetAsync(tileCounter, 0, sizeof(int), st));
+        divq_sorted_kernel<RecT><<<nb, 256, 0, st>>>(a, bg, RP, base + 256, tileCounter);
+      }
+    } else if (std::is_same<Real, float>::value && !bounded && f32gen && ctx->p.rayCoherence == 0 && ctx->p.blockedMarch == 2 && !ctx->p.genericMarch) {
+      // independent rays per (cell, ray, timestep) on the blocked half-packed copy of the level, plain loads (divq_blk_kernel)
+      if constexpr (std::is_same<Real, float>::value && !std::is_same<RecT, Rec16>::value) {
+        BlkGeom bg;
+        int rc = ensure_blocked_level<RecT>(ctx, a.G.maxLevels - 1, bg, st);
+        if (rc) return rc;
+        divq_blk_kernel<RecT><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a, bg);
       }
     } else if (std::is_same<Real, float>::value && !bounded && f32gen && ctx->p.rayCoherence == 0 && ctx->p.blockedMarch && !ctx->p.genericMarch) {
       // opt-in: independent rays per (cell, ray, timestep) on the blocked half-packed copy of the level (indep.cuh)
@@ -2435,7 +2734,7 @@ void rmcrt_destroy(rmcrt_ctx* ctx) {
   ctx->fluxFlags.release(); ctx->fluxItems.release(); ctx->compactTmp.release(); ctx->misc.release(); ctx->roiBuf.release();
   ctx->lhcDivQ.release(); ctx->lhcFlux.release(); ctx->outVR[0].release(); ctx->outVR[1].release();
   for (auto& b : ctx->dbg) b.release();
-  ctx->replSend.release(); ctx->replGathered.release();
+  ctx->replSend.release(); ctx->replGathered.release(); ctx->sortScratch.release();
   delete ctx;
 }
 
