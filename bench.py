@@ -251,10 +251,12 @@ class SingleLevelSolve:
             half = 1 if int(np.prod([h - l for l, h in zip(lo, hi)])) * 8 > 64e6 else 0
         self.rec_bytes = 4 if half else 8
         kw = {} if coherence < 0 else {"rayCoherence": coherence}
+        if args.blocked_march >= 0:
+            kw["blockedMarch"] = args.blocked_march
         skip = 0 if args.reference_semantics else 1
         self.g = g = RMCRT(device=local, nDivQRays=rays, threshold=0.05, seed=1234, skipZeroWeightLegs=skip, l2Persist=args.l2persist,
                            warpsPerTile=args.warps, tileX=args.tile_x, cellsPerLane=cells_per_lane, genericMarch=args.generic_march,
-                           maxBlocksPerSM=args.max_blocks_per_sm, half_records=bool(half), blockedMarch=args.blocked_march,
+                           maxBlocksPerSM=args.max_blocks_per_sm, half_records=bool(half),
                            refillLanes=args.refill_lanes, originBrickHalo=args.origin_brick_halo, **kw)
         self.coherence = int(g.params.rayCoherence)
         self.stream = stream = torch.cuda.current_stream()
@@ -280,8 +282,12 @@ class SingleLevelSolve:
             self.kernel_name = f"divq_dual_kernel<{'Rec4' if half else 'Rec8'}>"
         if self.coherence >= 1 and cells_per_lane == 1:
             self.kernel_name = f"divq_kernel<float,{'Rec4' if half else 'Rec8'},ML=0,FAST,F32GEN> (one cell per lane, warp-shared direction)"
-        if self.coherence == 0 and args.blocked_march:
-            self.kernel_name = f"divq_indep_kernel<{'Rec4' if half else 'Rec8'}> (independent rays, blocked half-packed records, per-lane refill)"
+        self.blocked = int(g.params.blockedMarch) if self.coherence == 0 and not args.generic_march else 0
+        if self.blocked:
+            r = "Rec4" if half else "Rec8"
+            self.kernel_name = {1: f"divq_indep_kernel<{r}> (independent rays, blocked half-packed records, per-lane refill)",
+                                2: f"divq_blk_kernel<{r}> (independent rays, blocked half-packed records, one cell per lane)",
+                                3: f"divq_sorted_kernel<{r}> (independent rays sorted by length per 32-cell tile, blocked half-packed records)"}[self.blocked]
             self.kernels_per_step += 1          # blk_build_kernel: the blocked copy is rebuilt after every re-pack
 
     def replicate(self, props=None):
@@ -523,7 +529,10 @@ def run_ours(args):
     kern_s = (t_trace_total / args.steps)
     achieved = alg_bytes / kern_s / 1e9
     cpl_eff = args.cells_per_lane if S.coherence >= 1 else 1
-    kkey = {2: "divq_dual", 4: "divq_quad"}.get(cpl_eff, "divq_indep" if S.coherence == 0 else "divq") + f"_{P}cubed_{rays}rays_rec{rec_bytes}"
+    kname = {2: "divq_dual", 4: "divq_quad"}.get(cpl_eff, "divq_indep" if S.coherence == 0 else "divq")
+    if S.coherence == 0 and S.blocked:
+        kname = {1: "divq_indepblk", 2: "divq_blk", 3: "divq_sorted"}[S.blocked]
+    kkey = kname + f"_{P}cubed_{rays}rays_rec{rec_bytes}"
     prof = issue_model(kkey) or {}
     # L2 denominators measured live with the library's microbenchmarks (L2-resident scratch buffers)
     try:
@@ -585,7 +594,10 @@ def run_ours(args):
                    "zero_weight_legs": "marched (reference semantics)" if args.reference_semantics else "skipped (exact: cold black walls, fs==0)",
                    "ray_coherence": S.coherence, "sampling": COHERENCE_NAME[S.coherence],
                    "cells_per_lane": cpl_eff,
-                   "l2": "flushed between steps (256 MiB fill); level records (%.1f MB, %d B/cell) re-packed every step" % (np.prod([h - l for l, h in zip(S.lo, S.hi)]) * rec_bytes / 1e6, rec_bytes),
+                   "l2": "flushed between steps (256 MiB fill); level records (%.1f MB, %d B/cell) re-packed every step%s" % (
+                       np.prod([h - l for l, h in zip(S.lo, S.hi)]) * rec_bytes / 1e6, rec_bytes,
+                       " and their blocked half-packed copy (4 B/cell, 2 x 2 x 2 cells per sector) rebuilt" if S.blocked else ""),
+                   "blocked_march": S.blocked,
                    "timing": "CUDA events on the launching stream per step, max over ranks"},
         "roofline": roofline, "l2_live": l2_live, "by_coherence": by_coherence, "configs": configs,
         "cpu_baseline": cpu_baseline, "e2e": e2e,
@@ -618,7 +630,7 @@ def main():
     ap.add_argument("--max-blocks-per-sm", type=int, default=0, help="cap the divQ grid (0: one tile per block)")
     ap.add_argument("--generic-march", type=int, default=0, help="1: generic march template instead of the tuned fast path (A/B)")
     ap.add_argument("--reference-semantics", action="store_true", help="march the zero-weight reflected legs like the reference")
-    ap.add_argument("--blocked-march", type=int, default=0, help="rayCoherence 0: 0 = one-cell-per-lane kernel (library default), 1 = divq_indep_kernel on a blocked half-packed copy (A/B)")
+    ap.add_argument("--blocked-march", type=int, default=-1, help="rayCoherence 0: -1 = library default (3: divq_sorted_kernel); 0 = one-cell-per-lane kernel on the level's own records; 1 = divq_indep_kernel; 2 = divq_blk_kernel (A/B)")
     ap.add_argument("--refill-lanes", type=int, default=0, help="divq_indep_kernel: waiting lanes that trigger ray set-up (0 = library default)")
     ap.add_argument("--origin-brick-halo", type=int, default=0, help="with --generic-march 1: stage the origin tile + halo in shared memory (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -108,13 +108,20 @@ typedef struct rmcrt_params {
                                   sectors per request.  The rays of a cell depend on the tile it falls in, not on the arithmetic. */
   int32_t  nonFlowCellType;    /* integer cell type the coarsening assumes for non-flow fine cells when it rebuilds the type sum of
                                   Ray::computeCellType (Ray.cc:2285-2342) from the packed records: 8 (default; RMCRT_Test.cc:80, Arches walls) */
-  int32_t  blockedMarch;       /* 0 (default): the default sampling (rayCoherence 0) runs on the one-cell-per-lane kernel over the level's own
-                                  records.  1: experimental divq_indep_kernel -- a blocked half-packed copy of the level (2 x 2 x 2 cells per
-                                  32-B sector, one 256-bit load per block entered, fp16 properties as recordKind 2) with per-lane ray
-                                  refill; same Philox rays, divQ equal to the fp16 rounding of the properties.  Measured slower on B200
-                                  (DESIGN.md section 3), kept for A/B measurements. */
-  int32_t  refillLanes;        /* implementation knob of divq_indep_kernel: lanes of a warp that must wait for a new ray before ray
-                                  set-up runs (0 = default 8) */
+  int32_t  blockedMarch;       /* kernel of the default sampling (rayCoherence 0; production FP32 / Philox single-level divQ rays).  All four
+                                  trace the SAME rays (Philox keyed on (cell, ray, timestep)):
+                                  3 (DEFAULT): divq_sorted_kernel -- the march runs on a blocked half-packed copy of the level (2 x 2 x 2 cells
+                                     per 32-B sector, fp16 abskg / sigmaT4 like recordKind 2, rebuilt when the level changes) and the rays of
+                                     a 32-cell tile are sorted by their expected number of steps, so the 32 lanes of a warp end together
+                                     (30.6 instead of 13.4 active lanes) and the second visit to a sector is an L1 hit; per cell the rays are
+                                     added in ray order in FP64, so divQ does not depend on the sort, the launch shape or the patch layout.
+                                  2: divq_blk_kernel -- the blocked copy with the tile / warp layout of the one-cell kernel (no sort).
+                                  1: divq_indep_kernel -- the blocked copy, one 256-bit load per block entered, per-lane ray refill (A/B).
+                                  0: divq_kernel on the level's own records (float or half-packed), one cell per lane.
+                                  Levels too large for a 32-bit blocked index, and every other mode (FP64 march, regression generators,
+                                  Latin hyper cube, scattering, bounded rays, Data Onion), march the level's own records. */
+  int32_t  refillLanes;        /* implementation knob.  blockedMarch 1: lanes of a warp that must wait for a new ray before ray set-up runs
+                                  (0 = default 8).  blockedMarch 3: rays of a cell sorted per pass (0 = default min(nDivQRays, 256)). */
   int32_t  coarsenExtraCells;  /* <coarsenExtraCells> (Ray.cc:256,315; default false): rmcrt_coarsen_level_device also fills the coarse level's
                                   extra cells on the domain faces with the tangential average of the fine level's extra cells (Ray::coarsen_Q,
                                   Ray.cc:2148-2245) instead of leaving them to rmcrt_set_level_extra_cells (setBoundaryConditions) */

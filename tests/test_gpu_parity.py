@@ -278,7 +278,8 @@ def test_tuned_march_matches_generic_march(gpu_lib, po, case):
         kw["skipZeroWeightLegs"] = 0
     out = {}
     for gm in (0, 1):
-        g = make(gpu_lib, genericMarch=gm, cellsPerLane=1, **kw)     # one cell per lane: the same Philox rays per cell as the generic kernel
+        # the level's own float records, one cell per lane: the same Philox rays per cell as the generic kernel
+        g = make(gpu_lib, genericMarch=gm, cellsPerLane=1, blockedMarch=0, **kw)
         g.upload_level(0, lv)
         out[gm] = (g.trace_divq(0, timestep=5)["divQ"], g.counters().nRaySteps)
     (a, na), (b, nb) = out[0], out[1]
@@ -579,7 +580,8 @@ def test_full_size_isothermal_enclosure_and_linearity(gpu_lib, po):
     assert np.abs(out["divQ"]).max() < 2e-5 * scale
     np.testing.assert_allclose(out["radiationVolq"][ct == -1], 4 * np.pi * 0.75, rtol=2e-5)
     # linearity on a non-trivial temperature field
-    s4b = rng.uniform(0.0, 1.0, (M, M, M)).astype(np.float32)
+    # (>= 0.01: the default kernel marches fp16 sigmaT4/pi * 2^-5, and rounding commutes with the factor 2 in fp16's normal range only)
+    s4b = rng.uniform(0.01, 1.0, (M, M, M)).astype(np.float32)
     lv1 = po.Level(ab, s4b, ct, (-1,) * 3, (N + 1,) * 3, (1.0 / N,) * 3, interior_lo=(0,) * 3, interior_hi=(N,) * 3)
     lv2 = po.Level(ab, 2 * s4b, ct, (-1,) * 3, (N + 1,) * 3, (1.0 / N,) * 3, interior_lo=(0,) * 3, interior_hi=(N,) * 3)
     g.upload_level(0, lv1); d1 = g.trace_divq(0)["divQ"]; n1 = g.counters().nRaySteps

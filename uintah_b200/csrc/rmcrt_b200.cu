@@ -1985,6 +1985,7 @@ struct rmcrt_ctx {
   DevBuf replSend, replGathered;      // rmcrt_replicate_level: this device's packed slab / the gathered slabs of all devices
   std::string err;
   void* persistedStreamFor = nullptr;
+  void* persistedPtr = nullptr;
 };
 
 namespace {
@@ -2110,25 +2111,30 @@ int pick_warps(const rmcrt_ctx* ctx, long long nTiles) {
   return w;
 }
 
-void apply_l2_window(rmcrt_ctx* ctx, int L, cudaStream_t st) {
+void apply_l2_window_raw(rmcrt_ctx* ctx, void* base, size_t bytes, cudaStream_t st) {
   if (!ctx->p.l2Persist) return;
-  const LevelState& s = ctx->lv[L];
   int maxWin = 0, maxPersist = 0;
   cudaDeviceGetAttribute(&maxWin, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
   cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
   if (maxWin <= 0 || maxPersist <= 0) return;
-  const size_t bytes = (size_t)s.nCells * s.recBytes;
   const size_t win = std::min(bytes, (size_t)maxWin);
   cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(win, (size_t)maxPersist));
   cudaStreamAttrValue attr;
   memset(&attr, 0, sizeof attr);
-  attr.accessPolicyWindow.base_ptr = s.rec;
+  attr.accessPolicyWindow.base_ptr = base;
   attr.accessPolicyWindow.num_bytes = win;
   attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)maxPersist / (double)win);
   attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
   attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
   cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
   cudaGetLastError();
+}
+// the persisting window follows the buffer the march reads: the level's records, or its blocked copy (one window per stream)
+void persist_in_l2(rmcrt_ctx* ctx, void* base, size_t bytes, cudaStream_t st) {
+  if (!ctx->p.l2Persist || (ctx->persistedStreamFor == (void*)st && ctx->persistedPtr == base)) return;
+  apply_l2_window_raw(ctx, base, bytes, st);
+  ctx->persistedStreamFor = (void*)st;
+  ctx->persistedPtr = base;
 }
 
 template <class T, class RecT>
@@ -2273,6 +2279,18 @@ int build_args(rmcrt_ctx* ctx, int maxLevels, bool multiLevel, const int32_t pLo
   return 0;
 }
 
+// does this solve run on the blocked copy of its level (blockedMarch 1..3: divq_indep / divq_blk / divq_sorted_kernel)?  Production
+// FP32 / Philox single-level divQ rays with the default sampling; everything else marches the level's own records.
+bool blocked_default(const rmcrt_ctx* ctx, const TraceArgs& a, bool ML) {
+  if (ML || !ctx->p.solveDivQ || ctx->p.marchPrecision != 0 || ctx->p.rayCoherence != 0 || ctx->p.blockedMarch <= 0 || ctx->p.genericMarch) return false;
+  if (!ctx->p.isSeedRandom || ctx->p.fixedRandom || ctx->p.rayDirSampleAlgo != 0) return false;       // f32gen
+  if (a.maxRayLength < 1e300 || a.sigmaScat > 0) return false;                                        // the generic march
+  const rmcrt_level_desc& d = ctx->lv[a.G.maxLevels - 1].d;
+  long long nb = 1;
+  for (int k = 0; k < 3; ++k) nb *= (d.hi[k] - d.lo[k] + 4 + 1) / 2;
+  return nb < (1LL << 28);      // 32-bit word index
+}
+
 // blocked half-packed copy of level L (indep.cuh), rebuilt when the level changed since the last build (stream-ordered)
 template <class RecT>
 int ensure_blocked_level(rmcrt_ctx* ctx, int L, BlkGeom& bg, cudaStream_t st) {
@@ -2297,6 +2315,7 @@ int ensure_blocked_level(rmcrt_ctx* ctx, int L, BlkGeom& bg, cudaStream_t st) {
     s.blkDims[0] = nb[0]; s.blkDims[1] = nb[1]; s.blkDims[2] = nb[2];
     s.blkValid = true;
   }
+  persist_in_l2(ctx, s.blk, bytes, st);
   bg.blk = static_cast<const uint32_t*>(s.blk);
   bg.bx = nb[0]; bg.bxy = nb[0] * nb[1];
   for (int d = 0; d < 3; ++d) bg.lo[d] = s.d.lo[d] - 2;
@@ -2439,7 +2458,7 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
         divq_dual_kernel<RecT, false><<<(int)g2, 32 * W2, W2 * 64 * sizeof(double), st>>>(a2, nxc, njp, 0);
         launch_reflective_pairs<RecT>(ctx, a2, cap, st);
       }
-    } else if (std::is_same<Real, float>::value && !bounded && f32gen && ctx->p.rayCoherence == 0 && ctx->p.blockedMarch == 3 && !ctx->p.genericMarch) {
+    } else if (ctx->p.blockedMarch == 3 && blocked_default(ctx, a, ML)) {
       // independent rays per (cell, ray, timestep), sorted by expected length inside a tile, on the blocked copy (divq_sorted_kernel)
       if constexpr (std::is_same<Real, float>::value && !std::is_same<RecT, Rec16>::value) {
         BlkGeom bg;
@@ -2454,7 +2473,7 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
         CK(cudaMemsetAsync(tileCounter, 0, sizeof(int), st));
         divq_sorted_kernel<RecT><<<nb, 256, 0, st>>>(a, bg, RP, base + 256, tileCounter);
       }
-    } else if (std::is_same<Real, float>::value && !bounded && f32gen && ctx->p.rayCoherence == 0 && ctx->p.blockedMarch == 2 && !ctx->p.genericMarch) {
+    } else if (ctx->p.blockedMarch == 2 && blocked_default(ctx, a, ML)) {
       // independent rays per (cell, ray, timestep) on the blocked half-packed copy of the level, plain loads (divq_blk_kernel)
       if constexpr (std::is_same<Real, float>::value && !std::is_same<RecT, Rec16>::value) {
         BlkGeom bg;
@@ -2462,7 +2481,7 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
         if (rc) return rc;
         divq_blk_kernel<RecT><<<(int)grid, 32 * W, W * 32 * sizeof(double), st>>>(a, bg);
       }
-    } else if (std::is_same<Real, float>::value && !bounded && f32gen && ctx->p.rayCoherence == 0 && ctx->p.blockedMarch && !ctx->p.genericMarch) {
+    } else if (ctx->p.blockedMarch == 1 && blocked_default(ctx, a, ML)) {
       // opt-in: independent rays per (cell, ray, timestep) on the blocked half-packed copy of the level (indep.cuh)
       if constexpr (std::is_same<Real, float>::value && !std::is_same<RecT, Rec16>::value) {
         BlkGeom bg;
@@ -2535,9 +2554,9 @@ int trace_common(rmcrt_ctx* ctx, int maxLevels, bool ML, const int32_t pLo[3], c
     CK(cudaMemsetAsync(dVolq, 0, nOut * sizeof(double), st));
     if (dFlux) CK(cudaMemsetAsync(dFlux, 0, nOut * 7 * sizeof(double), st));
   }
-  if (ctx->p.l2Persist && ctx->persistedStreamFor != (void*)st) {
-    apply_l2_window(ctx, maxLevels - 1, st);
-    ctx->persistedStreamFor = (void*)st;
+  if (!blocked_default(ctx, a, ML)) {
+    const LevelState& ls = ctx->lv[maxLevels - 1];
+    persist_in_l2(ctx, ls.rec, (size_t)ls.nCells * ls.recBytes, st);
   }
   if (ctx->p.marchPrecision == 1) return launch_trace<double, Rec16>(ctx, a, ML, st);
   if (ctx->lv[maxLevels - 1].recordKind == 2) return launch_trace<float, Rec4>(ctx, a, ML, st);
@@ -2674,7 +2693,7 @@ void rmcrt_default_params(rmcrt_params* p) {
   p->maxRayLength = 0.0;       // unbounded (DBL_MAX, RMCRTCommon.cc:117)
   p->sigmaScat = 0.0;          // Ray.cc:169
   p->tileX = 0; p->nonFlowCellType = 8;
-  p->blockedMarch = 0; p->refillLanes = 0;
+  p->blockedMarch = 3; p->refillLanes = 0;      // production: divq_sorted_kernel on the blocked half-packed copy
   p->coarsenExtraCells = 0; p->roiFixed = 0; p->originBrickHalo = 0; p->reserved2 = 0;
   for (int d = 0; d < 3; ++d) { p->roiFixedLo[d] = 0; p->roiFixedHi[d] = 0; }
   p->cellsPerLane = 4;         // production: the 2 x 2 cells of a lane share one DDA (divq_quad_kernel); 2 = a pair (divq_dual_kernel); 1 = one cell per lane
