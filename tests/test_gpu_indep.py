@@ -161,3 +161,37 @@ def test_sorted_kernel_is_independent_of_the_launch_shape(gpu_lib, po):
     b = g.trace_divq(0, patch_lo=(0, 0, 13), patch_hi=(30, 30, 30), timestep=6)["divQ"]
     g.close()
     assert np.array_equal(a + b, d0)
+
+
+@pytest.mark.parametrize("case", ["bc", "bc_walls", "plates_mirrors"])
+def test_sorted_data_onion_matches_roi_copy_path(gpu_lib, po, case):
+    """2-level Data Onion, library default (divq_sorted_kernel<ONION>: blocked copies of the patch's ROI and of level 0, march_onion2_blk)
+    against the linear ROI-copy path (blockedMarch 0, march_onion2_fast) on half-packed levels: the same Philox rays through the same fp16
+    words with the same leg arithmetic -- executed steps equal, ray sums equal up to the order they are added in (FP64 round-off)"""
+    rng = np.random.default_rng(31)
+    kw = dict(nDivQRays=20, haloCells=(4, 4, 4), seed=17, half_records=True)
+    if case == "plates_mirrors":
+        fine, kw["threshold"] = po.parallel_plates(32, dtype=np.float32, mirror_faces=("x-", "y-")), 0.001
+    else:
+        fine, kw["threshold"] = po.burns_christon(32, dtype=np.float32), 0.05
+        if case == "bc_walls":
+            add_random_walls(fine, 0.02, rng, abskg=0.7, sigmaT4=0.3)
+    fine.rr = (4, 4, 4)
+    coarse = po.coarsen_level(fine, (4, 4, 4))
+    res = {}
+    for bm in (0, 3):
+        g = make(blockedMarch=bm, **kw)
+        g.upload_level(0, coarse)
+        g.upload_level(1, fine)
+        divQ = np.zeros(fine.abskg.shape); vol = np.zeros_like(divQ)
+        for plo, phi in po._split((0, 0, 0), (32, 32, 32), (2, 2, 1)):
+            g.trace_dataonion(2, plo, phi, zero_init=False, outputs=(divQ, vol, None), timestep=4)
+        c = g.counters()
+        res[bm] = (divQ, vol, int(c.nRaySteps), int(c.nDivQCells))
+        g.close()
+    (d0, v0, n0, c0), (d3, v3, n3, c3) = res[0], res[3]
+    assert c0 == c3 and c0 > 0 and n0 == n3
+    assert np.array_equal(v0 == 0, v3 == 0)
+    assert np.allclose(v0, v3, rtol=1e-12, atol=0)
+    # divQ: the default kernel's epilogue takes the origin cell's sigmaT4/pi from the fp16 word its rays integrate
+    assert np.abs(d0 - d3).max() <= 2e-3 * np.abs(d0).max()

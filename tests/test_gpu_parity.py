@@ -402,7 +402,8 @@ def test_data_onion_fast_path_matches_generic_march(gpu_lib, po, case):
     coarse = po.coarsen_level(fine, (4, 4, 4))
     res = {}
     for gm in (0, 1):
-        g = make(gpu_lib, nDivQRays=16, threshold=thr, haloCells=(4, 4, 4), seed=17, genericMarch=gm, cellsPerLane=1)   # the same Philox rays per cell
+        # the same Philox rays per cell, on the level's own float records
+        g = make(gpu_lib, nDivQRays=16, threshold=thr, haloCells=(4, 4, 4), seed=17, genericMarch=gm, cellsPerLane=1, blockedMarch=0)
         g.upload_level(0, coarse)
         g.upload_level(1, fine)
         divQ = np.zeros(fine.abskg.shape); vol = np.zeros_like(divQ)

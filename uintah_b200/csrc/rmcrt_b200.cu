@@ -39,6 +39,8 @@ constexpr int MAXL = 4;   // levels supported by the Data-Onion kernels (referen
 //   [3] valid: set by finalize_kernel's last block, cleared by every kernel that modifies the level
 //   [4] ticket for "last block"      [5] non-finite inputs seen by the pack kernels
 //   [6] reflective non-flow cells (abskg < 1): rays can go on after their first wall (chooses between the one- and two-cells-per-lane kernels)
+//   [7] bit f: the outer layer of face f (0 x- 1 x+ 2 y- 3 y+ 4 z- 5 z+) has an absorbing cell (abskg >= 0.5); a face without is a mirror
+//       for the ray-length estimate of divq_sorted_kernel
 constexpr int LSTAT_WORDS = 8;
 constexpr int NCOUNTERS = 5;    // [0] divQ steps [1] flux steps [2] divQ cells [3] flux cells [4] radiometer steps
 
@@ -979,8 +981,11 @@ constexpr int SORT_BINS = 256;
 // ids[RP * 32] u16 | keys[RP * 32] u8.  Shared memory would do, but every KB of it comes out of the SM's L1, and the march lives on the
 // L1 keeping a sector until the ray's next step (23 KB per block = 187 KB per SM measured: L1 hit rate 46 % -> 8 %, solve 47 -> 59 ms).
 __host__ __device__ inline size_t sorted_scratch_bytes(int RP) { return (((size_t)RP * 32 * 7) + 127) / 128 * 128; }
-template <class RecT>
-__global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(const __grid_constant__ TraceArgs a, const BlkGeom bg, int RP,
+// ONION: the 2-level Data Onion (Ray::rayTrace_dataOnion with two levels): origin cells on the fine level, rays march the blocked copy of
+// the patch's region of interest and go on in the blocked copy of level 0 (march_onion2_blk); bg = the ROI box, ob = both boxes.
+template <class RecT, bool ONION>
+__global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(const __grid_constant__ TraceArgs a, const BlkGeom bg,
+                                                                               const __grid_constant__ OnionBlk ob, int RP,
                                                                                unsigned char* __restrict__ scratch, int* __restrict__ tileCounter) {
   // 2.9 KB of shared memory per block: eight resident blocks stay inside the 32-KB carve-out, the rest of the SM's 256 KB is L1
   __shared__ double part[8 * 32];
@@ -1005,7 +1010,21 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
   const float cx = (float)g.dx[0], cy = (float)g.dx[1], cz = (float)g.dx[2];
   const float icx = 1.0f / cx, icy = 1.0f / cy, icz = 1.0f / cz;
   // a ray crosses at most n[0] + n[1] + n[2] cells of the level before it leaves it
-  const float keyScale = (float)(SORT_BINS - 1) / (float)(g.n[0] + g.n[1] + g.n[2]);
+  // faces that do not end a ray: allowReflect and no absorbing cell on the face (finalize_kernel); an unfinalized level has none
+  const unsigned* ls = a.lstat + (ONION ? 0 : F) * LSTAT_WORDS;      // (Data Onion: rays end on level 0)
+  const unsigned mirrors = (a.allowReflect && ls[3] != 0u && ls[6] != 0u) ? (~ls[7] & 63u) : 0u;
+  const float logThr = a.threshold > 0 ? (float)log(1.0 / a.threshold) : 1e30f;
+  // legs followed by the length estimate: 0 = rays end at their first wall
+  const int bounces = (a.allowReflect && !ONION && (mirrors != 0u || !skipZero)) ? 6 : 0;
+  float keyScale = (float)(SORT_BINS - 1) / ((bounces ? 3.0f : 1.0f) * (float)(g.n[0] + g.n[1] + g.n[2]));
+  // Data Onion: a ray crosses at most the ROI on the fine level and then level 0
+  float rrx = 1.0f, rry = 1.0f, rrz = 1.0f;
+  if constexpr (ONION) {
+    const LevelGeom& gc = a.G.lev[0];
+    rrx = (float)g.rr[0]; rry = (float)g.rr[1]; rrz = (float)g.rr[2];
+    const float nRoi = (float)((a.G.roiHi[0] - a.G.roiLo[0]) + (a.G.roiHi[1] - a.G.roiLo[1]) + (a.G.roiHi[2] - a.G.roiLo[2]));
+    keyScale = (float)(SORT_BINS - 1) / (nRoi + (float)(gc.n[0] + gc.n[1] + gc.n[2]));
+  }
   unsigned long long stepsTotal = 0, cellsTotal = 0;
 
   for (;;) {
@@ -1048,17 +1067,59 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
       {
         const unsigned long long cid = cellIds[lane];
         const float ci = (float)ijk[lane * 3 + 0], cj = (float)ijk[lane * 3 + 1], ck = (float)ijk[lane * 3 + 2];
+        // ... or the intensity threshold ends it first: optical depth ln(1 / threshold) at the origin cell's abskg (RMCRTCommon.cc:680)
+        float tThr = 1e30f;
+        if (cw0 >= 0) {
+          const float k0 = fabsf(__half2float(__ushort_as_half((unsigned short)(__ldg(blk + cw0) >> 16))));
+          tThr = logThr / fmaxf(k0, 1e-20f);
+        }
         if (cw0 >= 0)
           for (int r = warp; r < nr; r += W) {
             float dir[3], rayDx[3];
             gen_divq_ray_f32(a.rng, g, ray0 + r, cid, cid, dir, rayDx);
             // cell faces to the outer layer of the level along each axis, from the cell centre
             const float ax = fabsf(dir[0]) * icx + 1e-30f, ay = fabsf(dir[1]) * icy + 1e-30f, az = fabsf(dir[2]) * icz + 1e-30f;
-            const float nx_ = (dir[0] >= 0.0f ? (float)(g.n[0] - 1) - ci : ci) - 0.5f;
-            const float ny_ = (dir[1] >= 0.0f ? (float)(g.n[1] - 1) - cj : cj) - 0.5f;
-            const float nz_ = (dir[2] >= 0.0f ? (float)(g.n[2] - 1) - ck : ck) - 0.5f;
-            const float tExit = fminf(fminf(nx_ / ax, ny_ / ay), nz_ / az);
-            const float est = tExit * (ax + ay + az);
+            const bool px = dir[0] >= 0.0f, py = dir[1] >= 0.0f, pz = dir[2] >= 0.0f;
+            float tExit;
+            if (bounces == 0) {
+              const float nx_ = (px ? (float)(g.n[0] - 1) - ci : ci) - 0.5f;
+              const float ny_ = (py ? (float)(g.n[1] - 1) - cj : cj) - 0.5f;
+              const float nz_ = (pz ? (float)(g.n[2] - 1) - ck : ck) - 0.5f;
+              tExit = fminf(fminf(nx_ / ax, ny_ / ay), nz_ / az);
+            } else {
+              // rays that go on after a wall (RMCRTCommon.cc:846-902): follow the bounces through the empty box.  A mirror face (no
+              // absorbing cell, finalize_kernel) keeps the weight; an absorbing one zeroes it, after which the ray still runs to its
+              // NEXT wall unless zero-weight legs are skipped
+              float p0 = ci + 0.5f, p1 = cj + 0.5f, p2 = ck + 0.5f;        // position in cells from the level's low corner
+              bool s0 = px, s1 = py, s2 = pz, dead = false;
+              tExit = 0.0f;
+              for (int bnc = 0; bnc < bounces; ++bnc) {
+                const float t0 = (s0 ? (float)(g.n[0] - 1) - p0 : p0 - 1.0f) / ax;
+                const float t1 = (s1 ? (float)(g.n[1] - 1) - p1 : p1 - 1.0f) / ay;
+                const float t2 = (s2 ? (float)(g.n[2] - 1) - p2 : p2 - 1.0f) / az;
+                const float t = fmaxf(fminf(fminf(t0, t1), t2), 0.0f);
+                const int axh = (t0 <= t1 && t0 <= t2) ? 0 : (t1 <= t2 ? 1 : 2);
+                tExit += t;
+                p0 += (s0 ? t : -t) * ax; p1 += (s1 ? t : -t) * ay; p2 += (s2 ? t : -t) * az;
+                const unsigned face = 2u * axh + ((axh == 0 ? s0 : (axh == 1 ? s1 : s2)) ? 1u : 0u);
+                if (dead) break;                      // a weightless ray ends at the next wall of any kind (intensity 0)
+                if (!((mirrors >> face) & 1u)) {
+                  if (skipZero) break;
+                  dead = true;
+                }
+                if (axh == 0) s0 = !s0; else if (axh == 1) s1 = !s1; else s2 = !s2;
+              }
+            }
+            tExit = fminf(tExit, tThr);
+            float est = fminf(tExit * (ax + ay + az), 1e9f);
+            if constexpr (ONION) {
+              // fine steps up to the ROI face, coarse steps (cells rr times larger) from there to the end
+              const float rx_ = (px ? (float)(a.G.roiHi[0] - g.lo[0]) - ci : ci - (float)(a.G.roiLo[0] - g.lo[0]) + 1.0f) - 0.5f;
+              const float ry_ = (py ? (float)(a.G.roiHi[1] - g.lo[1]) - cj : cj - (float)(a.G.roiLo[1] - g.lo[1]) + 1.0f) - 0.5f;
+              const float rz_ = (pz ? (float)(a.G.roiHi[2] - g.lo[2]) - ck : ck - (float)(a.G.roiLo[2] - g.lo[2]) + 1.0f) - 0.5f;
+              const float tRoi = fminf(fminf(fminf(rx_ / ax, ry_ / ay), rz_ / az), tExit);
+              est = fminf(tRoi * (ax + ay + az) + (tExit - tRoi) * (ax / rrx + ay / rry + az / rrz), 1e9f);
+            }
             const int key = min(SORT_BINS - 1, max(0, (int)(est * keyScale + 0.5f)));
             atomicAdd(&hist[key], 1);
             __stcg(keys + r * 32 + lane, (unsigned char)key);
@@ -1103,9 +1164,16 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
             const unsigned long long cid = cellIds[c];
             float dir[3], rayDx[3];
             gen_divq_ray_f32(a.rng, g, ray0 + r, cid, cid, dir, rayDx);
-            __stcg(res + id, UNSCALE * march_single_level_blk(blk, rw0, (unsigned)(rw0 & 7), sy8, sz8, nz<float, float>(dir[0]),
-                                                              nz<float, float>(dir[1]), nz<float, float>(dir[2]), rayDx[0], rayDx[1],
-                                                              rayDx[2], cx, cy, cz, (float)a.threshold, a.allowReflect != 0, skipZero, steps));
+            float sumI;
+            if constexpr (ONION)
+              sumI = march_onion2_blk<MAXL>(a.G, ob, ijk[c * 3 + 0] + g.lo[0], ijk[c * 3 + 1] + g.lo[1], ijk[c * 3 + 2] + g.lo[2], rw0,
+                                            nz<float, float>(dir[0]), nz<float, float>(dir[1]), nz<float, float>(dir[2]), rayDx[0], rayDx[1],
+                                            rayDx[2], (float)a.threshold, a.allowReflect != 0, skipZero, steps);
+            else
+              sumI = march_single_level_blk(blk, rw0, (unsigned)(rw0 & 7), sy8, sz8, nz<float, float>(dir[0]), nz<float, float>(dir[1]),
+                                            nz<float, float>(dir[2]), rayDx[0], rayDx[1], rayDx[2], cx, cy, cz, (float)a.threshold,
+                                            a.allowReflect != 0, skipZero, steps);
+            __stcg(res + id, UNSCALE * sumI);
           }
         }
       }
@@ -1475,7 +1543,7 @@ __global__ void pack_kernel(const T* __restrict__ abskg, const T* __restrict__ s
 template <class RecT>
 __global__ void finalize_kernel(const RecT* __restrict__ recs, Box b, unsigned* __restrict__ status) {
   const long long n = box_cells(b);
-  unsigned open = 0, emit = 0, bad = 0, refl = 0;
+  unsigned open = 0, emit = 0, bad = 0, refl = 0, absorbing = 0;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
     const long long row = t / b.n[0];
     const int i = (int)(t - row * b.n[0]);
@@ -1488,7 +1556,13 @@ __global__ void finalize_kernel(const RecT* __restrict__ recs, Box b, unsigned* 
     if (wall && (r.k != 0) && (r.s != 0)) ++emit;
     if (wall && fabs((double)r.k) < 1.0) ++refl;        // fs = fs (1 - abskg) stays > 0 after this wall (RMCRTCommon.cc:588)
     if (!isfinite((double)r.k) || !isfinite((double)r.s)) ++bad;
+    // faces of the level whose outer layer absorbs (abskg >= 0.5; edges and corners aside): the others send most of a ray's weight on
+    const int nOuter = (i == 0) + (j == 0) + (k == 0) + (i == b.n[0] - 1) + (j == b.n[1] - 1) + (k == b.n[2] - 1);
+    if (nOuter == 1 && !(wall && fabs((double)r.k) < 0.5))
+      absorbing |= i == 0 ? 1u : (i == b.n[0] - 1 ? 2u : (j == 0 ? 4u : (j == b.n[1] - 1 ? 8u : (k == 0 ? 16u : 32u))));
   }
+  absorbing = __reduce_or_sync(0xffffffffu, absorbing);
+  if (absorbing && (threadIdx.x & 31) == 0) atomicOr(status + 7, absorbing);
   if (bad) atomicAdd(status + 0, bad);
   if (open) atomicAdd(status + 1, open);
   if (emit) atomicAdd(status + 2, emit);
@@ -1554,6 +1628,35 @@ __global__ void blk_build_kernel(const RecT* __restrict__ recs, Box lb, uint32_t
         const long long f = (long long)x + (long long)lb.n[0] * ((long long)y + (long long)lb.n[1] * (long long)z);
         if constexpr (std::is_same<RecT, Rec4>::value) v = recs[f].w;
         else { const Rec8 r = ldrec(recs + f); v = encode_rec4(r.k, r.s).w; }
+      }
+      w[c] = v;
+    }
+    uint4* o = reinterpret_cast<uint4*>(blk + t * 8);
+    o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
+// blocked half-packed copy of the fine level's region of interest for the Data-Onion march (march_onion2_blk): thread = one 2 x 2 x 2 block
+// of the box [lo, lo + 2 nb); cells inside roi = the fine level's records, every other cell a marker {wall flag, abskg = inf} -- the
+// one-cell shell that ends the ROI leg, and the guard blocks the speculative load past it may touch
+template <class RecT>
+__global__ void roi_blk_build_kernel(const RecT* __restrict__ fine, Box fb, uint32_t* __restrict__ blk, int bx, int by, int bz, int lo0, int lo1,
+                                     int lo2, Box roi) {
+  const long long n = (long long)bx * by * bz;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const int b0 = (int)(t % bx);
+    const long long rest = t / bx;
+    const int b1 = (int)(rest % by), b2 = (int)(rest / by);
+    uint32_t w[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int x = lo0 + 2 * b0 + (c & 1), y = lo1 + 2 * b1 + ((c >> 1) & 1), z = lo2 + 2 * b2 + (c >> 2);
+      uint32_t v = 0xFC000000u;                     // fp16 -inf | 0
+      if (x >= roi.lo[0] && x < roi.lo[0] + roi.n[0] && y >= roi.lo[1] && y < roi.lo[1] + roi.n[1] && z >= roi.lo[2] && z < roi.lo[2] + roi.n[2]) {
+        const long long f = (long long)(x - fb.lo[0]) + (long long)fb.n[0] * ((long long)(y - fb.lo[1]) + (long long)fb.n[1] * (long long)(z - fb.lo[2]));
+        if constexpr (std::is_same<RecT, Rec4>::value) v = fine[f].w;
+        else { const Rec8 r = ldrec(fine + f); v = encode_rec4(r.k, r.s).w; }
       }
       w[c] = v;
     }
@@ -2291,9 +2394,19 @@ bool blocked_default(const rmcrt_ctx* ctx, const TraceArgs& a, bool ML) {
   return nb < (1LL << 28);      // 32-bit word index
 }
 
+// ... and the 2-level Data Onion: the same kernel on blocked copies of the patch's ROI and of level 0 (divq_sorted_kernel<ONION>)
+bool onion_blocked_default(const rmcrt_ctx* ctx, const TraceArgs& a, bool ML) {
+  if (!ML || a.G.maxLevels != 2 || !ctx->p.solveDivQ || ctx->p.marchPrecision != 0 || ctx->p.rayCoherence != 0 || ctx->p.blockedMarch != 3 ||
+      ctx->p.genericMarch) return false;
+  if (!ctx->p.isSeedRandom || ctx->p.fixedRandom || ctx->p.rayDirSampleAlgo != 0) return false;
+  for (int d = 0; d < 3; ++d)      // the patch lies inside the ROI (a fixed / dynamic ROI need not contain it)
+    if (!(a.G.roiLo[d] <= a.patchLo[d] && a.patchLo[d] + a.patchN[d] <= a.G.roiHi[d])) return false;
+  return true;
+}
+
 // blocked half-packed copy of level L (indep.cuh), rebuilt when the level changed since the last build (stream-ordered)
 template <class RecT>
-int ensure_blocked_level(rmcrt_ctx* ctx, int L, BlkGeom& bg, cudaStream_t st) {
+int ensure_blocked_level(rmcrt_ctx* ctx, int L, BlkGeom& bg, cudaStream_t st, bool persist = true) {
   LevelState& s = ctx->lv[L];
   int nb[3];
   for (int d = 0; d < 3; ++d) nb[d] = (s.d.hi[d] - s.d.lo[d] + 4 + 1) / 2;        // cells [lo - 2, hi + 2) in 2-cell blocks
@@ -2315,7 +2428,7 @@ int ensure_blocked_level(rmcrt_ctx* ctx, int L, BlkGeom& bg, cudaStream_t st) {
     s.blkDims[0] = nb[0]; s.blkDims[1] = nb[1]; s.blkDims[2] = nb[2];
     s.blkValid = true;
   }
-  persist_in_l2(ctx, s.blk, bytes, st);
+  if (persist) persist_in_l2(ctx, s.blk, bytes, st);
   bg.blk = static_cast<const uint32_t*>(s.blk);
   bg.bx = nb[0]; bg.bxy = nb[0] * nb[1];
   for (int d = 0; d < 3; ++d) bg.lo[d] = s.d.lo[d] - 2;
@@ -2395,7 +2508,44 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
     if (grid > cap) grid = cap;
     bool patchInRoi = true;       // a fixed ROI need not contain the patch; the ROI-copy fast path starts every ray inside the copy
     for (int d = 0; d < 3 && ML; ++d) patchInRoi = patchInRoi && a.G.roiLo[d] <= a.patchLo[d] && a.patchLo[d] + a.patchN[d] <= a.G.roiHi[d];
-    if (ML && std::is_same<Real, float>::value && !ctx->p.genericMarch && a.G.maxLevels == 2 && patchInRoi) {
+    if (onion_blocked_default(ctx, a, ML)) {
+      // 2-level Data Onion, default sampling: length-sorted rays on blocked copies of the patch's ROI (marker shell) and of level 0
+      if constexpr (std::is_same<Real, float>::value && !std::is_same<RecT, Rec16>::value) {
+        const LevelState& fl = ctx->lv[1];
+        Box roiBox;
+        int nbk[3], rlo[3];
+        long long nBlocks = 1;
+        for (int d = 0; d < 3; ++d) {
+          roiBox.lo[d] = a.G.roiLo[d]; roiBox.n[d] = a.G.roiHi[d] - a.G.roiLo[d];
+          rlo[d] = roiBox.lo[d] - 1 - 2;                       // shell, then one guard block
+          nbk[d] = (roiBox.n[d] + 2 + 4 + 1) / 2;
+          nBlocks *= nbk[d];
+        }
+        if (nBlocks >= (1LL << 28)) return fail(ctx, RMCRT_ERR_INVALID, "ROI too large");
+        if (ctx->roiBuf.ensure((size_t)nBlocks * 32)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc ROI buffer");
+        roi_blk_build_kernel<RecT><<<grid_for(nBlocks, 256, ctx->smCount), 256, 0, st>>>(
+            static_cast<const RecT*>(fl.rec), mkbox(fl.d.lo, fl.d.hi), static_cast<uint32_t*>(ctx->roiBuf.p), nbk[0], nbk[1], nbk[2], rlo[0], rlo[1],
+            rlo[2], roiBox);
+        CK(cudaGetLastError());
+        BlkGeom bgC;
+        int rc = ensure_blocked_level<RecT>(ctx, 0, bgC, st, false);
+        if (rc) return rc;
+        persist_in_l2(ctx, ctx->roiBuf.p, (size_t)nBlocks * 32, st);
+        BlkGeom bg;
+        bg.blk = static_cast<const uint32_t*>(ctx->roiBuf.p); bg.bx = nbk[0]; bg.bxy = nbk[0] * nbk[1];
+        OnionBlk ob;
+        ob.roi = bg.blk; ob.rbx = bg.bx; ob.rbxy = bg.bxy;
+        ob.coarse = bgC.blk; ob.cbx = bgC.bx; ob.cbxy = bgC.bxy;
+        for (int d = 0; d < 3; ++d) { bg.lo[d] = rlo[d]; ob.rlo[d] = rlo[d]; ob.clo[d] = bgC.lo[d]; }
+        const int RP = std::min(a.nRays, ctx->p.refillLanes > 0 ? ctx->p.refillLanes : 256);
+        const int nb = (int)std::min<long long>(a.nTiles, (long long)ctx->smCount * (ctx->p.maxBlocksPerSM > 0 ? ctx->p.maxBlocksPerSM : RMCRT_SORTED_BLOCKS));
+        if (ctx->sortScratch.ensure((size_t)nb * sorted_scratch_bytes(RP) + 256)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc sort scratch");
+        unsigned char* base = static_cast<unsigned char*>(ctx->sortScratch.p);
+        int* tileCounter = reinterpret_cast<int*>(base);
+        CK(cudaMemsetAsync(tileCounter, 0, sizeof(int), st));
+        divq_sorted_kernel<RecT, true><<<nb, 256, 0, st>>>(a, bg, ob, RP, base + 256, tileCounter);
+      }
+    } else if (ML && std::is_same<Real, float>::value && !ctx->p.genericMarch && a.G.maxLevels == 2 && patchInRoi) {
       // 2-level Data Onion fast path: per-patch ROI copy with a marker shell, then the tuned leg loop on both levels
       const LevelState& fl = ctx->lv[1];
       Box roiBox, shell;
@@ -2471,7 +2621,7 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
         unsigned char* base = static_cast<unsigned char*>(ctx->sortScratch.p);
         int* tileCounter = reinterpret_cast<int*>(base);
         CK(cudaMemsetAsync(tileCounter, 0, sizeof(int), st));
-        divq_sorted_kernel<RecT><<<nb, 256, 0, st>>>(a, bg, RP, base + 256, tileCounter);
+        divq_sorted_kernel<RecT, false><<<nb, 256, 0, st>>>(a, bg, OnionBlk{}, RP, base + 256, tileCounter);
       }
     } else if (ctx->p.blockedMarch == 2 && blocked_default(ctx, a, ML)) {
       // independent rays per (cell, ray, timestep) on the blocked half-packed copy of the level, plain loads (divq_blk_kernel)
@@ -2554,7 +2704,7 @@ int trace_common(rmcrt_ctx* ctx, int maxLevels, bool ML, const int32_t pLo[3], c
     CK(cudaMemsetAsync(dVolq, 0, nOut * sizeof(double), st));
     if (dFlux) CK(cudaMemsetAsync(dFlux, 0, nOut * 7 * sizeof(double), st));
   }
-  if (!blocked_default(ctx, a, ML)) {
+  if (!blocked_default(ctx, a, ML) && !onion_blocked_default(ctx, a, ML)) {
     const LevelState& ls = ctx->lv[maxLevels - 1];
     persist_in_l2(ctx, ls.rec, (size_t)ls.nCells * ls.recBytes, st);
   }
@@ -2866,7 +3016,7 @@ static int finalize_launch(rmcrt_ctx* ctx, int L, cudaStream_t st) {
   LevelState& lv = ctx->lv[L];
   unsigned* ls = lstat_of(ctx, L);
   CK(cudaMemsetAsync(ls, 0, 5 * sizeof(unsigned), st));      // words 0..4; word 5 (pack-time input check) survives
-  CK(cudaMemsetAsync(ls + 6, 0, sizeof(unsigned), st));
+  CK(cudaMemsetAsync(ls + 6, 0, 2 * sizeof(unsigned), st));
   Box b = mkbox(lv.d.lo, lv.d.hi);
   if (lv.recordKind == 0)      finalize_kernel<Rec8><<<grid_for(lv.nCells, 256, ctx->smCount), 256, 0, st>>>(static_cast<const Rec8*>(lv.rec), b, ls);
   else if (lv.recordKind == 2) finalize_kernel<Rec4><<<grid_for(lv.nCells, 256, ctx->smCount), 256, 0, st>>>(static_cast<const Rec4*>(lv.rec), b, ls);
