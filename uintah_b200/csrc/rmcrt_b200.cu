@@ -976,21 +976,22 @@ __global__ void __launch_bounds__(256, RMCRT_FAST_MIN_BLOCKS) divq_blk_kernel(co
 #ifndef RMCRT_SORTED_BLOCKS
 #define RMCRT_SORTED_BLOCKS 4
 #endif
-constexpr int SORT_BINS = 256;
+constexpr int SORT_BINS = 512;       // 9-bit keys: one length, or two lengths (first leg: 5 bits | rest: 4 bits)
 // per-block scratch in GLOBAL memory (L2-resident, accessed with .cg so it never takes L1 lines from the records): res[RP][32] f32 |
-// ids[RP * 32] u16 | keys[RP * 32] u8.  Shared memory would do, but every KB of it comes out of the SM's L1, and the march lives on the
+// ids[RP * 32] u16 | keys[RP * 32] u16.  Shared memory would do, but every KB of it comes out of the SM's L1, and the march lives on the
 // L1 keeping a sector until the ray's next step (23 KB per block = 187 KB per SM measured: L1 hit rate 46 % -> 8 %, solve 47 -> 59 ms).
-__host__ __device__ inline size_t sorted_scratch_bytes(int RP) { return (((size_t)RP * 32 * 7) + 127) / 128 * 128; }
+__host__ __device__ inline size_t sorted_scratch_bytes(int RP) { return (((size_t)RP * 32 * 8) + 127) / 128 * 128; }
 // ONION: the 2-level Data Onion (Ray::rayTrace_dataOnion with two levels): origin cells on the fine level, rays march the blocked copy of
 // the patch's region of interest and go on in the blocked copy of level 0 (march_onion2_blk); bg = the ROI box, ob = both boxes.
 template <class RecT, bool ONION>
 __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(const __grid_constant__ TraceArgs a, const BlkGeom bg,
                                                                                const __grid_constant__ OnionBlk ob, int RP,
                                                                                unsigned char* __restrict__ scratch, int* __restrict__ tileCounter) {
-  // 2.9 KB of shared memory per block: eight resident blocks stay inside the 32-KB carve-out, the rest of the SM's 256 KB is L1
-  __shared__ double part[8 * 32];
+  // 2.9 KB of shared memory per block: four resident blocks stay inside the 16-KB carve-out, the rest of the SM's 256 KB is L1
+  // (1024 bins = 4.9 KB per block move the carve-out to 32 KB: 3 % slower at 128^3)
+  __shared__ int hist[SORT_BINS];
   __shared__ unsigned long long cellIds[32];
-  int* hist = reinterpret_cast<int*>(part);      // [SORT_BINS], dead when phase 4 writes part
+  double* part = reinterpret_cast<double*>(hist);      // [8][32] = 2 KB, written in phase 4 when hist is dead
   __shared__ int w0s[32];            // word index of the cell, -1: not traced
   __shared__ int ijk[96];
   __shared__ int ctl[4];             // [0] next chunk [1] list length [2] tile
@@ -1000,7 +1001,7 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
   unsigned char* my = scratch + (size_t)blockIdx.x * sorted_scratch_bytes(RP);
   float* res = reinterpret_cast<float*>(my);                                           // [RP][32]
   unsigned short* ids = reinterpret_cast<unsigned short*>(my + (size_t)RP * 128);      // [RP * 32]
-  unsigned char* keys = my + (size_t)RP * 192;                                         // [RP * 32]
+  unsigned short* keys = reinterpret_cast<unsigned short*>(my + (size_t)RP * 192);     // [RP * 32]
   const int F = a.G.maxLevels - 1;
   const LevelGeom& g = a.G.lev[F];
   const bool skipZero = skip_allowed(a);
@@ -1014,16 +1015,21 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
   const unsigned* ls = a.lstat + (ONION ? 0 : F) * LSTAT_WORDS;      // (Data Onion: rays end on level 0)
   const unsigned mirrors = (a.allowReflect && ls[3] != 0u && ls[6] != 0u) ? (~ls[7] & 63u) : 0u;
   const float logThr = a.threshold > 0 ? (float)log(1.0 / a.threshold) : 1e30f;
-  // legs followed by the length estimate: 0 = rays end at their first wall
+  // Sort key.  The lanes of a warp wait for each other at the end of every LEG (a wall, the ROI exit), so rays that are to run together
+  // must agree leg by leg, not just in total: when a ray has more than one leg the key is (first leg: 5 bits | rest: 4 bits);
+  // rays that end at their first wall get one 9-bit length.
+  // legs followed by the estimate: 0 = rays end at their first wall
   const int bounces = (a.allowReflect && !ONION && (mirrors != 0u || !skipZero)) ? 6 : 0;
-  float keyScale = (float)(SORT_BINS - 1) / ((bounces ? 3.0f : 1.0f) * (float)(g.n[0] + g.n[1] + g.n[2]));
-  // Data Onion: a ray crosses at most the ROI on the fine level and then level 0
+  const bool twoPart = ONION || bounces != 0;
+  float scale1 = (float)(SORT_BINS - 1) / (float)(g.n[0] + g.n[1] + g.n[2]), scale2 = 0.0f;
+  if (bounces) { scale1 = 31.0f / (0.6f * (float)(g.n[0] + g.n[1] + g.n[2])); scale2 = 15.0f / (1.2f * (float)(g.n[0] + g.n[1] + g.n[2])); }
   float rrx = 1.0f, rry = 1.0f, rrz = 1.0f;
-  if constexpr (ONION) {
+  if constexpr (ONION) {     // fine steps inside the ROI | coarse steps on level 0
     const LevelGeom& gc = a.G.lev[0];
     rrx = (float)g.rr[0]; rry = (float)g.rr[1]; rrz = (float)g.rr[2];
     const float nRoi = (float)((a.G.roiHi[0] - a.G.roiLo[0]) + (a.G.roiHi[1] - a.G.roiLo[1]) + (a.G.roiHi[2] - a.G.roiLo[2]));
-    keyScale = (float)(SORT_BINS - 1) / (nRoi + (float)(gc.n[0] + gc.n[1] + gc.n[2]));
+    scale1 = 31.0f / (0.6f * nRoi);
+    scale2 = 15.0f / (0.6f * (float)(gc.n[0] + gc.n[1] + gc.n[2]));
   }
   unsigned long long stepsTotal = 0, cellsTotal = 0;
 
@@ -1059,7 +1065,7 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
     unsigned steps = 0;
     for (int ray0 = 0; ray0 < a.nRays; ray0 += RP) {
       const int nr = min(RP, a.nRays - ray0);
-      hist[tid] = 0;                    // blockDim.x == SORT_BINS
+      for (int q4 = tid; q4 < SORT_BINS; q4 += 256) hist[q4] = 0;
       if (tid == 0) ctl[0] = 0;
       __syncthreads();
       // ---- phase 1: keys + histogram (thread -> cell = lane, rays warp, warp + W, ...)
@@ -1080,26 +1086,39 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
             // cell faces to the outer layer of the level along each axis, from the cell centre
             const float ax = fabsf(dir[0]) * icx + 1e-30f, ay = fabsf(dir[1]) * icy + 1e-30f, az = fabsf(dir[2]) * icz + 1e-30f;
             const bool px = dir[0] >= 0.0f, py = dir[1] >= 0.0f, pz = dir[2] >= 0.0f;
-            float tExit;
+            const float rate = ax + ay + az;             // cell faces crossed per unit length
+            float e1, e2 = 0.0f;                         // steps of the first leg, of the rest
             if (bounces == 0) {
               const float nx_ = (px ? (float)(g.n[0] - 1) - ci : ci) - 0.5f;
               const float ny_ = (py ? (float)(g.n[1] - 1) - cj : cj) - 0.5f;
               const float nz_ = (pz ? (float)(g.n[2] - 1) - ck : ck) - 0.5f;
-              tExit = fminf(fminf(nx_ / ax, ny_ / ay), nz_ / az);
+              const float tExit = fminf(fminf(fminf(nx_ / ax, ny_ / ay), nz_ / az), tThr);
+              e1 = tExit * rate;
+              if constexpr (ONION) {
+                // fine steps up to the ROI face, coarse steps (cells rr times larger) from there to the end
+                const float rx_ = (px ? (float)(a.G.roiHi[0] - g.lo[0]) - ci : ci - (float)(a.G.roiLo[0] - g.lo[0]) + 1.0f) - 0.5f;
+                const float ry_ = (py ? (float)(a.G.roiHi[1] - g.lo[1]) - cj : cj - (float)(a.G.roiLo[1] - g.lo[1]) + 1.0f) - 0.5f;
+                const float rz_ = (pz ? (float)(a.G.roiHi[2] - g.lo[2]) - ck : ck - (float)(a.G.roiLo[2] - g.lo[2]) + 1.0f) - 0.5f;
+                const float tRoi = fminf(fminf(fminf(rx_ / ax, ry_ / ay), rz_ / az), tExit);
+                e1 = tRoi * rate;
+                e2 = (tExit - tRoi) * (ax / rrx + ay / rry + az / rrz);
+              }
             } else {
               // rays that go on after a wall (RMCRTCommon.cc:846-902): follow the bounces through the empty box.  A mirror face (no
               // absorbing cell, finalize_kernel) keeps the weight; an absorbing one zeroes it, after which the ray still runs to its
               // NEXT wall unless zero-weight legs are skipped
               float p0 = ci + 0.5f, p1 = cj + 0.5f, p2 = ck + 0.5f;        // position in cells from the level's low corner
               bool s0 = px, s1 = py, s2 = pz, dead = false;
-              tExit = 0.0f;
+              float tTot = 0.0f, tFirst = 0.0f;
               for (int bnc = 0; bnc < bounces; ++bnc) {
                 const float t0 = (s0 ? (float)(g.n[0] - 1) - p0 : p0 - 1.0f) / ax;
                 const float t1 = (s1 ? (float)(g.n[1] - 1) - p1 : p1 - 1.0f) / ay;
                 const float t2 = (s2 ? (float)(g.n[2] - 1) - p2 : p2 - 1.0f) / az;
                 const float t = fmaxf(fminf(fminf(t0, t1), t2), 0.0f);
                 const int axh = (t0 <= t1 && t0 <= t2) ? 0 : (t1 <= t2 ? 1 : 2);
-                tExit += t;
+                tTot += t;
+                if (bnc == 0) tFirst = tTot;
+                if (tTot >= tThr) break;
                 p0 += (s0 ? t : -t) * ax; p1 += (s1 ? t : -t) * ay; p2 += (s2 ? t : -t) * az;
                 const unsigned face = 2u * axh + ((axh == 0 ? s0 : (axh == 1 ? s1 : s2)) ? 1u : 0u);
                 if (dead) break;                      // a weightless ray ends at the next wall of any kind (intensity 0)
@@ -1109,26 +1128,25 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
                 }
                 if (axh == 0) s0 = !s0; else if (axh == 1) s1 = !s1; else s2 = !s2;
               }
+              tTot = fminf(tTot, tThr); tFirst = fminf(tFirst, tThr);
+              e1 = tFirst * rate;
+              e2 = (tTot - tFirst) * rate;
             }
-            tExit = fminf(tExit, tThr);
-            float est = fminf(tExit * (ax + ay + az), 1e9f);
-            if constexpr (ONION) {
-              // fine steps up to the ROI face, coarse steps (cells rr times larger) from there to the end
-              const float rx_ = (px ? (float)(a.G.roiHi[0] - g.lo[0]) - ci : ci - (float)(a.G.roiLo[0] - g.lo[0]) + 1.0f) - 0.5f;
-              const float ry_ = (py ? (float)(a.G.roiHi[1] - g.lo[1]) - cj : cj - (float)(a.G.roiLo[1] - g.lo[1]) + 1.0f) - 0.5f;
-              const float rz_ = (pz ? (float)(a.G.roiHi[2] - g.lo[2]) - ck : ck - (float)(a.G.roiLo[2] - g.lo[2]) + 1.0f) - 0.5f;
-              const float tRoi = fminf(fminf(fminf(rx_ / ax, ry_ / ay), rz_ / az), tExit);
-              est = fminf(tRoi * (ax + ay + az) + (tExit - tRoi) * (ax / rrx + ay / rry + az / rrz), 1e9f);
-            }
-            const int key = min(SORT_BINS - 1, max(0, (int)(est * keyScale + 0.5f)));
+            int key;
+            if (twoPart) key = (min(31, (int)(e1 * scale1 + 0.5f)) << 4) | min(15, (int)(e2 * scale2 + 0.5f));
+            else key = min(SORT_BINS - 1, (int)(e1 * scale1 + 0.5f));
             atomicAdd(&hist[key], 1);
-            __stcg(keys + r * 32 + lane, (unsigned char)key);
+            __stcg(keys + r * 32 + lane, (unsigned short)key);
           }
       }
       __syncthreads();
       // ---- phase 2: exclusive scan over the bins in DESCENDING key order (thread t owns bin 255 - t), then scatter
       {
-        const int h = hist[SORT_BINS - 1 - tid];
+        // thread t owns PER consecutive bins, descending keys
+        constexpr int PER = SORT_BINS / 256;
+        int hq[PER], h = 0;
+#pragma unroll
+        for (int u = 0; u < PER; ++u) { hq[u] = hist[SORT_BINS - 1 - (tid * PER + u)]; h += hq[u]; }
         int incl = h;
         for (int o = 1; o < 32; o <<= 1) {
           const int v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -1138,8 +1156,10 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
         __syncthreads();
         int base = 0;
         for (int w = 0; w < warp; ++w) base += warpTot[w];
-        hist[SORT_BINS - 1 - tid] = base + incl - h;          // start of the bin in the sorted list
-        if (tid == SORT_BINS - 1) ctl[1] = base + incl;       // list length = rays of flow cells
+        int start = base + incl - h;                           // start of the thread's first bin in the sorted list
+#pragma unroll
+        for (int u = 0; u < PER; ++u) { hist[SORT_BINS - 1 - (tid * PER + u)] = start; start += hq[u]; }
+        if (tid == 255) ctl[1] = base + incl;                  // list length = rays of flow cells
         __syncthreads();
         if (cw0 >= 0)
           for (int r = warp; r < nr; r += W) {
