@@ -55,6 +55,8 @@ def test_default_params_are_the_ups_defaults(lib):
     assert lib.rmcrt_struct_size(2) == C.sizeof(capi.Counters)
     assert lib.rmcrt_struct_size(3) == C.sizeof(capi.Radiometer)
     assert p.rayDirSampleAlgo == 0 and p.maxRayLength == 0.0      # "naive" (Ray.cc:174), unbounded (RMCRTCommon.cc:117)
+    # implementation knobs: the reference's sampling (independent rays per cell) on the length-sorted blocked kernel
+    assert p.rayCoherence == 0 and p.blockedMarch == 3
 
 
 def test_radiometer_setup_is_host_only(lib):

@@ -62,20 +62,23 @@ def centre_lines(po, d, N, zi):
     return [float(np.sqrt(np.mean((d[zi, mid, :] - ex) ** 2))), float(np.sqrt(np.mean((d[zi, :, mid] - ex) ** 2)))]
 
 
-@pytest.mark.parametrize("case,half,coh", [("c2", False, 0), ("c2", True, 0), ("c3", True, 0), ("c3", False, 0), ("c2", False, 2), ("c3", True, 2)])
-def test_single_level_at_size(gpu_lib, po, case, half, coh):
-    """C2 (128^3) and C3 (256^3) Burns & Christon, 100 rays / cell, float properties; float (8-B) and half-packed (4-B) level records"""
+@pytest.mark.parametrize("case,half,coh,bm", [("c2", False, 0, 3), ("c3", True, 0, 3), ("c3", False, 0, 3), ("c2", False, 0, 0), ("c2", True, 0, 0),
+                                              ("c3", True, 0, 0), ("c2", False, 0, 2), ("c2", False, 2, 3), ("c3", True, 2, 3)])
+def test_single_level_at_size(gpu_lib, po, case, half, coh, bm):
+    """C2 (128^3) and C3 (256^3) Burns & Christon, 100 rays / cell, float properties; float (8-B) and half-packed (4-B) level records.
+    bm = blockedMarch: 3 = the library default (divq_sorted_kernel on the blocked fp16 copy of either record kind), 0 = the one-cell
+    kernel on the level's own records (float: no fp16 anywhere), 2 = the blocked copy without the sort"""
     fx, meta = load(case)
     N, K = meta["N"], meta["K"]
     lv = po.burns_christon(N, dtype=np.float32)
-    g = make(nDivQRays=100, threshold=0.05, seed=20261018, half_records=half, rayCoherence=coh)
+    g = make(nDivQRays=100, threshold=0.05, seed=20261018, half_records=half, rayCoherence=coh, blockedMarch=bm)
     g.upload_level(0, lv)
     reps = []
     for si, (z0, z1) in enumerate(meta["slabs"]):
         out = g.trace_divq(0, (0, 0, z0), (N, N, z1), out_lo=(0, 0, z0), out_hi=(N, N, z1), timestep=7)
         d = out["divQ"]
         assert np.all(d != 0) and np.all(out["radiationVolq"] > 0)
-        rep = accept(d, fx[f"mu{si}"], fx[f"sd{si}"], K, meta[f"control{si}"], f"{case} half={half} coh={coh} slab [{z0},{z1})",
+        rep = accept(d, fx[f"mu{si}"], fx[f"sd{si}"], K, meta[f"control{si}"], f"{case} half={half} coh={coh} bm={bm} slab [{z0},{z1})",
                      draws_per_cell=1.0 if coh == 0 else 1.0 / 128)
         assert abs(rep["bias_in_se"]) <= (4 if coh == 0 else 4 * np.sqrt(128)), rep     # batched modes: one tile = one draw
         if z0 <= N // 2 < z1 and coh == 0:       # (iii): both centre lines of the plane through cell N/2

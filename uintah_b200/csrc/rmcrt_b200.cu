@@ -976,7 +976,7 @@ __global__ void __launch_bounds__(256, RMCRT_FAST_MIN_BLOCKS) divq_blk_kernel(co
 #ifndef RMCRT_SORTED_BLOCKS
 #define RMCRT_SORTED_BLOCKS 4
 #endif
-constexpr int SORT_BINS = 512;       // 9-bit keys: one length, or two lengths (first leg: 5 bits | rest: 4 bits)
+constexpr int SORT_BINS = 512;       // 9-bit keys: one length, or two lengths (first leg: 4 bits | rest: 5 bits)
 // per-block scratch in GLOBAL memory (L2-resident, accessed with .cg so it never takes L1 lines from the records): res[RP][32] f32 |
 // ids[RP * 32] u16 | keys[RP * 32] u16.  Shared memory would do, but every KB of it comes out of the SM's L1, and the march lives on the
 // L1 keeping a sector until the ray's next step (23 KB per block = 187 KB per SM measured: L1 hit rate 46 % -> 8 %, solve 47 -> 59 ms).
@@ -1016,20 +1016,21 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
   const unsigned mirrors = (a.allowReflect && ls[3] != 0u && ls[6] != 0u) ? (~ls[7] & 63u) : 0u;
   const float logThr = a.threshold > 0 ? (float)log(1.0 / a.threshold) : 1e30f;
   // Sort key.  The lanes of a warp wait for each other at the end of every LEG (a wall, the ROI exit), so rays that are to run together
-  // must agree leg by leg, not just in total: when a ray has more than one leg the key is (first leg: 5 bits | rest: 4 bits);
+  // must agree leg by leg, not just in total: when a ray has more than one leg the key is (first leg: 4 bits | rest: 5 bits) -- a chunk of 32 out of a
+  // tile's ~3200 rays then spans about a sixteenth of the range of the first part and a sixth of the second;
   // rays that end at their first wall get one 9-bit length.
   // legs followed by the estimate: 0 = rays end at their first wall
   const int bounces = (a.allowReflect && !ONION && (mirrors != 0u || !skipZero)) ? 6 : 0;
   const bool twoPart = ONION || bounces != 0;
   float scale1 = (float)(SORT_BINS - 1) / (float)(g.n[0] + g.n[1] + g.n[2]), scale2 = 0.0f;
-  if (bounces) { scale1 = 31.0f / (0.6f * (float)(g.n[0] + g.n[1] + g.n[2])); scale2 = 15.0f / (1.2f * (float)(g.n[0] + g.n[1] + g.n[2])); }
+  if (bounces) { scale1 = 15.0f / (0.6f * (float)(g.n[0] + g.n[1] + g.n[2])); scale2 = 31.0f / (1.2f * (float)(g.n[0] + g.n[1] + g.n[2])); }
   float rrx = 1.0f, rry = 1.0f, rrz = 1.0f;
   if constexpr (ONION) {     // fine steps inside the ROI | coarse steps on level 0
     const LevelGeom& gc = a.G.lev[0];
     rrx = (float)g.rr[0]; rry = (float)g.rr[1]; rrz = (float)g.rr[2];
     const float nRoi = (float)((a.G.roiHi[0] - a.G.roiLo[0]) + (a.G.roiHi[1] - a.G.roiLo[1]) + (a.G.roiHi[2] - a.G.roiLo[2]));
-    scale1 = 31.0f / (0.6f * nRoi);
-    scale2 = 15.0f / (0.6f * (float)(gc.n[0] + gc.n[1] + gc.n[2]));
+    scale1 = 15.0f / (0.6f * nRoi);
+    scale2 = 31.0f / (0.6f * (float)(gc.n[0] + gc.n[1] + gc.n[2]));
   }
   unsigned long long stepsTotal = 0, cellsTotal = 0;
 
@@ -1133,7 +1134,7 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
               e2 = (tTot - tFirst) * rate;
             }
             int key;
-            if (twoPart) key = (min(31, (int)(e1 * scale1 + 0.5f)) << 4) | min(15, (int)(e2 * scale2 + 0.5f));
+            if (twoPart) key = (min(15, (int)(e1 * scale1 + 0.5f)) << 5) | min(31, (int)(e2 * scale2 + 0.5f));
             else key = min(SORT_BINS - 1, (int)(e1 * scale1 + 0.5f));
             atomicAdd(&hist[key], 1);
             __stcg(keys + r * 32 + lane, (unsigned short)key);
