@@ -1018,11 +1018,12 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
   // Sort key.  The lanes of a warp wait for each other at the end of every LEG (a wall, the ROI exit), so rays that are to run together
   // must agree leg by leg, not just in total: when a ray has more than one leg the key is (first leg: 4 bits | rest: 5 bits) -- a chunk of 32 out of a
   // tile's ~3200 rays then spans about a sixteenth of the range of the first part and a sixth of the second;
-  // rays that end at their first wall get one 9-bit length.
+  // rays that end at their first wall get (length: 6 bits | octant of the direction: 3 bits), so the 32 rays of a chunk also head the same
+  // way (measured: +0.8 % at 128^3 over a 9-bit length, profiles/r02v22).
   // legs followed by the estimate: 0 = rays end at their first wall
   const int bounces = (a.allowReflect && !ONION && (mirrors != 0u || !skipZero)) ? 6 : 0;
   const bool twoPart = ONION || bounces != 0;
-  float scale1 = (float)(SORT_BINS - 1) / (float)(g.n[0] + g.n[1] + g.n[2]), scale2 = 0.0f;
+  float scale1 = 63.0f / (float)(g.n[0] + g.n[1] + g.n[2]), scale2 = 0.0f;
   if (bounces) { scale1 = 15.0f / (0.6f * (float)(g.n[0] + g.n[1] + g.n[2])); scale2 = 31.0f / (1.2f * (float)(g.n[0] + g.n[1] + g.n[2])); }
   float rrx = 1.0f, rry = 1.0f, rrz = 1.0f;
   if constexpr (ONION) {     // fine steps inside the ROI | coarse steps on level 0
@@ -1135,7 +1136,7 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
             }
             int key;
             if (twoPart) key = (min(15, (int)(e1 * scale1 + 0.5f)) << 5) | min(31, (int)(e2 * scale2 + 0.5f));
-            else key = min(SORT_BINS - 1, (int)(e1 * scale1 + 0.5f));
+            else key = (min(63, (int)(e1 * scale1 + 0.5f)) << 3) | (px ? 1 : 0) | (py ? 2 : 0) | (pz ? 4 : 0);
             atomicAdd(&hist[key], 1);
             __stcg(keys + r * 32 + lane, (unsigned short)key);
           }
