@@ -243,51 +243,74 @@ __device__ __forceinline__ void blk_decode(Integ& q, uint32_t word) {
   q.s = __half2float(__ushort_as_half((unsigned short)(word & 0xFFFFu)));
 }
 
-// march_single_level_fast (RMCRTCommon.cc:607-904) on the blocked copy.  w0 = word index of the origin cell, par = its position bits
-// (x&1 | (y&1)<<1 | (z&1)<<2), sy8 = 8 * blocks per row, sz8 = 8 * blocks per plane.  Result in the scaled units of the half-packed records.
+// One ray of the single-level march on the blocked copy, as a resumable state: blk_ray_start + blk_ray_legs(all legs) is
+// march_single_level_fast (RMCRTCommon.cc:607-904); divq_sorted_kernel marches the first leg, parks the rays that go on after their wall
+// (48 B of state each) and finishes them in a second, re-sorted pass.
+struct BlkRay {
+  Dda d;                 // tMax (scaled by log2 e), word index of the current cell
+  BlkStride b;
+  Integ q;
+  float sum, fs;
+};
+// w0 = word index of the origin cell, par = its position bits (x&1 | (y&1)<<1 | (z&1)<<2), sy8 = 8 * blocks per row, sz8 = 8 * blocks per
+// plane; tDelta returned in ddx, ddy, ddz
+__device__ __forceinline__ void blk_ray_start(BlkRay& r, const uint32_t* __restrict__ blk, int w0, unsigned par, int sy8, int sz8, float dx,
+                                              float dy, float dz, float rx, float ry, float rz, float cx, float cy, float cz, float& ddx,
+                                              float& ddy, float& ddz) {
+  typedef Num<float> N;
+  const bool posx = !sign_bit(dx), posy = !sign_bit(dy), posz = !sign_bit(dz);
+  r.b = blk_stride_init(par, posx, posy, posz, sy8, sz8);
+  const float ix = N::rcp(dx), iy = N::rcp(dy), iz = N::rcp(dz);
+  r.d.tx = ((posx ? cx : 0.0f) - rx) * ix * N::LEN_SCALE;
+  r.d.ty = ((posy ? cy : 0.0f) - ry) * iy * N::LEN_SCALE;
+  r.d.tz = ((posz ? cz : 0.0f) - rz) * iz * N::LEN_SCALE;
+  ddx = fabsf(ix) * cx * N::LEN_SCALE; ddy = fabsf(iy) * cy * N::LEN_SCALE; ddz = fabsf(iz) * cz * N::LEN_SCALE;
+  r.d.idx = w0;
+  blk_decode(r.q, __ldg(blk + w0));
+  r.q.A = 0.0f; r.q.ePrev = 1.0f; r.q.nsteps = 0.0f; r.q.tau = 0.0f; r.q.leg = 0.0f;
+  r.sum = 0.0f; r.fs = 1.0f;
+}
+// march up to maxLegs legs; true = the ray has ended (its result is r.sum, its steps r.q.nsteps), false = it stands reflected in the cell
+// it came from, ready for its next leg
+__device__ __forceinline__ bool blk_ray_legs(BlkRay& r, const uint32_t* __restrict__ blk, float ddx, float ddy, float ddz, int sy8, int sz8,
+                                             float threshold, bool allowReflect, bool skipZero, int maxLegs) {
+  const int tgy = 2 ^ (sy8 - 2), tgz = 4 ^ (sz8 - 4);
+  Integ& q = r.q;
+  for (int leg = 1;; ++leg) {
+    q.leg = 0.0f;
+    const LegOut w = march_leg_blk(r.d, q, r.b, blk, ddx, ddy, ddz, tgy, tgz);
+    r.sum = fmaf(q.leg, r.fs, r.sum);
+    const float eps = q.k > 1.0f ? 1.0f : q.k;                 // 846-850
+    r.sum = fmaf(eps * q.s, q.ePrev, r.sum);                   // 854: NOT multiplied by fs
+    const float intensity = q.ePrev * r.fs;                    // 856
+    if (!allowReflect || !(intensity > threshold)) return true;      // 884, 898, 683
+    r.fs *= (1.0f - q.k);
+    if (skipZero && r.fs == 0.0f) return true;
+    // RMCRTCommon::reflect (581-602): back into the cell the ray came from (the delta of that step is the current one toggled back),
+    // stepping direction of that axis flipped; tMax is NOT recomputed (reference behaviour)
+    int dprev;
+    if (w.axis == 0)      { dprev = r.b.dlx ^ 6;   r.b.dlx = dprev > 0 ? dprev - 8 : dprev + 8; }
+    else if (w.axis == 1) { dprev = r.b.dly ^ tgy; r.b.dly = dprev > 0 ? dprev - sy8 : dprev + sy8; }
+    else                  { dprev = r.b.dlz ^ tgz; r.b.dlz = dprev > 0 ? dprev - sz8 : dprev + sz8; }
+    r.d.idx -= dprev;
+    blk_decode(q, __ldg(blk + r.d.idx));
+    q.A = fmaf(-q.k, w.t, q.tau);
+    if (leg >= maxLegs) return false;
+  }
+}
+
+// the whole ray.  Result in the scaled units of the half-packed records.
 __device__ __forceinline__ float march_single_level_blk(const uint32_t* __restrict__ blk, int w0, unsigned par, int sy8, int sz8,
                                                         float dx, float dy, float dz, float rx, float ry, float rz,
                                                         float cx, float cy, float cz, float threshold, bool allowReflect,
                                                         bool skipZero, unsigned& nSteps) {
-  typedef Num<float> N;
   if (!(1.0f > threshold)) return 0.0f;
-  const bool posx = !sign_bit(dx), posy = !sign_bit(dy), posz = !sign_bit(dz);
-  const int tgy = 2 ^ (sy8 - 2), tgz = 4 ^ (sz8 - 4);
-  const BlkStride b0 = blk_stride_init(par, posx, posy, posz, sy8, sz8);
-  BlkStride b = b0;
-  const float ix = N::rcp(dx), iy = N::rcp(dy), iz = N::rcp(dz);
-  Dda d;
-  d.tx = ((posx ? cx : 0.0f) - rx) * ix * N::LEN_SCALE;
-  d.ty = ((posy ? cy : 0.0f) - ry) * iy * N::LEN_SCALE;
-  d.tz = ((posz ? cz : 0.0f) - rz) * iz * N::LEN_SCALE;
-  const float ddx = fabsf(ix) * cx * N::LEN_SCALE, ddy = fabsf(iy) * cy * N::LEN_SCALE, ddz = fabsf(iz) * cz * N::LEN_SCALE;
-  d.idx = w0;
-  Integ q;
-  blk_decode(q, __ldg(blk + w0));
-  q.A = 0.0f; q.ePrev = 1.0f; q.nsteps = 0.0f; q.tau = 0.0f;
-  float sum = 0.0f, fs = 1.0f;
-  for (;;) {
-    q.leg = 0.0f;
-    const LegOut w = march_leg_blk(d, q, b, blk, ddx, ddy, ddz, tgy, tgz);
-    sum = fmaf(q.leg, fs, sum);
-    const float eps = q.k > 1.0f ? 1.0f : q.k;                 // 846-850
-    sum = fmaf(eps * q.s, q.ePrev, sum);                       // 854: NOT multiplied by fs
-    const float intensity = q.ePrev * fs;                      // 856
-    if (!allowReflect || !(intensity > threshold)) break;      // 884, 898, 683
-    fs *= (1.0f - q.k);
-    if (skipZero && fs == 0.0f) break;
-    // RMCRTCommon::reflect (581-602): back into the cell the ray came from (the delta of that step is the current one toggled back),
-    // stepping direction of that axis flipped; tMax is NOT recomputed (reference behaviour)
-    int dprev;
-    if (w.axis == 0)      { dprev = b.dlx ^ 6;   b.dlx = dprev > 0 ? dprev - 8 : dprev + 8; }
-    else if (w.axis == 1) { dprev = b.dly ^ tgy; b.dly = dprev > 0 ? dprev - sy8 : dprev + sy8; }
-    else                  { dprev = b.dlz ^ tgz; b.dlz = dprev > 0 ? dprev - sz8 : dprev + sz8; }
-    d.idx -= dprev;
-    blk_decode(q, __ldg(blk + d.idx));
-    q.A = fmaf(-q.k, w.t, q.tau);
-  }
-  nSteps += (unsigned)q.nsteps;
-  return sum;
+  BlkRay r;
+  float ddx, ddy, ddz;
+  blk_ray_start(r, blk, w0, par, sy8, sz8, dx, dy, dz, rx, ry, rz, cx, cy, cz, ddx, ddy, ddz);
+  blk_ray_legs(r, blk, ddx, ddy, ddz, sy8, sz8, threshold, allowReflect, skipZero, 0x7fffffff);
+  nSteps += (unsigned)r.q.nsteps;
+  return r.sum;
 }
 
 //------------------------------------------------------------------------------------------------------

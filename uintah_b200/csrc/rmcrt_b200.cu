@@ -980,10 +980,17 @@ constexpr int SORT_BINS = 512;       // 9-bit keys: one length, or two lengths (
 // per-block scratch in GLOBAL memory (L2-resident, accessed with .cg so it never takes L1 lines from the records): res[RP][32] f32 |
 // ids[RP * 32] u16 | keys[RP * 32] u16.  Shared memory would do, but every KB of it comes out of the SM's L1, and the march lives on the
 // L1 keeping a sector until the ray's next step (23 KB per block = 187 KB per SM measured: L1 hit rate 46 % -> 8 %, solve 47 -> 59 ms).
-__host__ __device__ inline size_t sorted_scratch_bytes(int RP) { return (((size_t)RP * 32 * 8) + 127) / 128 * 128; }
+// RESORT adds state[RP * 32] x 48 B: the rays parked after their first leg.
+__host__ __device__ inline size_t sorted_scratch_bytes(int RP, bool resort) { return (size_t)RP * 32 * (resort ? 56 : 8); }
 // ONION: the 2-level Data Onion (Ray::rayTrace_dataOnion with two levels): origin cells on the fine level, rays march the blocked copy of
 // the patch's region of interest and go on in the blocked copy of level 0 (march_onion2_blk); bg = the ROI box, ob = both boxes.
-template <class RecT, bool ONION>
+// RESORT (single level, rays that go on after their first wall: reflective walls, or hot black ones whose zero-weight second leg the
+// reference marches): the lanes of a warp wait for each other at the end of every leg, so a sort by whole-ray length does not keep them
+// busy (C5 at 256^3: 18 of 32 lanes).  Here the FIRST legs are sorted and marched as usual; a ray that goes on parks its state (48 B) and
+// gets a new key from where it stands -- a weightless ray ends at its next wall, so its one remaining leg sorts exactly -- and the parked
+// rays are sorted and finished in a second pass over the tile.  The two instantiations are launched back to back and the level's status
+// words decide on the device which one does the work (a.gate: 1 = rays end at their first wall, 2 = they can go on).
+template <class RecT, bool ONION, bool RESORT = false>
 __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(const __grid_constant__ TraceArgs a, const BlkGeom bg,
                                                                                const __grid_constant__ OnionBlk ob, int RP,
                                                                                unsigned char* __restrict__ scratch, int* __restrict__ tileCounter) {
@@ -998,7 +1005,8 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
   __shared__ int warpTot[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int W = 8;
-  unsigned char* my = scratch + (size_t)blockIdx.x * sorted_scratch_bytes(RP);
+  unsigned char* my = scratch + (size_t)blockIdx.x * sorted_scratch_bytes(RP, RESORT);
+  uint4* parked = reinterpret_cast<uint4*>(my + (size_t)RP * 256);                     // RESORT: [RP * 32][3]
   float* res = reinterpret_cast<float*>(my);                                           // [RP][32]
   unsigned short* ids = reinterpret_cast<unsigned short*>(my + (size_t)RP * 128);      // [RP * 32]
   unsigned short* keys = reinterpret_cast<unsigned short*>(my + (size_t)RP * 192);     // [RP * 32]
@@ -1016,15 +1024,16 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
   const unsigned mirrors = (a.allowReflect && ls[3] != 0u && ls[6] != 0u) ? (~ls[7] & 63u) : 0u;
   const float logThr = a.threshold > 0 ? (float)log(1.0 / a.threshold) : 1e30f;
   // Sort key.  The lanes of a warp wait for each other at the end of every LEG (a wall, the ROI exit), so rays that are to run together
-  // must agree leg by leg, not just in total: when a ray has more than one leg the key is (first leg: 4 bits | rest: 5 bits) -- a chunk of 32 out of a
-  // tile's ~3200 rays then spans about a sixteenth of the range of the first part and a sixth of the second;
-  // rays that end at their first wall get (length: 6 bits | octant of the direction: 3 bits), so the 32 rays of a chunk also head the same
-  // way (measured: +0.8 % at 128^3 over a 9-bit length, profiles/r02v22).
-  // legs followed by the estimate: 0 = rays end at their first wall
-  const int bounces = (a.allowReflect && !ONION && (mirrors != 0u || !skipZero)) ? 6 : 0;
-  const bool twoPart = ONION || bounces != 0;
-  float scale1 = 63.0f / (float)(g.n[0] + g.n[1] + g.n[2]), scale2 = 0.0f;
-  if (bounces) { scale1 = 15.0f / (0.6f * (float)(g.n[0] + g.n[1] + g.n[2])); scale2 = 31.0f / (1.2f * (float)(g.n[0] + g.n[1] + g.n[2])); }
+  // must agree leg by leg, not just in total.  Single level: the key is that of the FIRST leg, (length: 6 bits | octant of the direction:
+  // 3 bits) -- the 32 rays of a chunk also head the same way (+0.8 % at 128^3 over a 9-bit length, profiles/r02v22) -- and rays that go on
+  // are sorted again where they stand (RESORT).  Data Onion: (fine steps inside the ROI: 4 bits | coarse steps: 5 bits) -- a chunk of 32
+  // out of a tile's ~3200 rays then spans about a sixteenth of the range of the first part and a sixth of the second.
+  // goOn: bounces the estimate follows for a ray that goes on after a wall; 0 = rays end at their first wall
+  const int goOn = (a.allowReflect && !ONION && (mirrors != 0u || !skipZero)) ? 6 : 0;
+  if (a.gate != 0 && (a.gate == 2) != (goOn != 0)) return;
+  const bool twoPart = ONION;
+  const float nSum = (float)(g.n[0] + g.n[1] + g.n[2]);
+  float scale1 = 63.0f / nSum, scale2 = 0.0f;
   float rrx = 1.0f, rry = 1.0f, rrz = 1.0f;
   if constexpr (ONION) {     // fine steps inside the ROI | coarse steps on level 0
     const LevelGeom& gc = a.G.lev[0];
@@ -1033,6 +1042,28 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
     scale1 = 15.0f / (0.6f * nRoi);
     scale2 = 31.0f / (0.6f * (float)(gc.n[0] + gc.n[1] + gc.n[2]));
   }
+  // exclusive scan over the bins in DESCENDING key order (thread t owns PER consecutive bins): hist[bin] = start of the bin in the
+  // sorted list, ctl[1] = list length.  All threads; hist must be complete (a barrier before), is ready after the call.
+  auto scan_bins = [&]() {
+    constexpr int PER = SORT_BINS / 256;
+    int hq[PER], h = 0;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) { hq[u] = hist[SORT_BINS - 1 - (tid * PER + u)]; h += hq[u]; }
+    int incl = h;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) warpTot[warp] = incl;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < warp; ++w) base += warpTot[w];
+    int start = base + incl - h;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) { hist[SORT_BINS - 1 - (tid * PER + u)] = start; start += hq[u]; }
+    if (tid == 255) ctl[1] = base + incl;
+    __syncthreads();
+  };
   unsigned long long stepsTotal = 0, cellsTotal = 0;
 
   for (;;) {
@@ -1089,50 +1120,20 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
             const float ax = fabsf(dir[0]) * icx + 1e-30f, ay = fabsf(dir[1]) * icy + 1e-30f, az = fabsf(dir[2]) * icz + 1e-30f;
             const bool px = dir[0] >= 0.0f, py = dir[1] >= 0.0f, pz = dir[2] >= 0.0f;
             const float rate = ax + ay + az;             // cell faces crossed per unit length
-            float e1, e2 = 0.0f;                         // steps of the first leg, of the rest
-            if (bounces == 0) {
-              const float nx_ = (px ? (float)(g.n[0] - 1) - ci : ci) - 0.5f;
-              const float ny_ = (py ? (float)(g.n[1] - 1) - cj : cj) - 0.5f;
-              const float nz_ = (pz ? (float)(g.n[2] - 1) - ck : ck) - 0.5f;
-              const float tExit = fminf(fminf(fminf(nx_ / ax, ny_ / ay), nz_ / az), tThr);
-              e1 = tExit * rate;
-              if constexpr (ONION) {
-                // fine steps up to the ROI face, coarse steps (cells rr times larger) from there to the end
-                const float rx_ = (px ? (float)(a.G.roiHi[0] - g.lo[0]) - ci : ci - (float)(a.G.roiLo[0] - g.lo[0]) + 1.0f) - 0.5f;
-                const float ry_ = (py ? (float)(a.G.roiHi[1] - g.lo[1]) - cj : cj - (float)(a.G.roiLo[1] - g.lo[1]) + 1.0f) - 0.5f;
-                const float rz_ = (pz ? (float)(a.G.roiHi[2] - g.lo[2]) - ck : ck - (float)(a.G.roiLo[2] - g.lo[2]) + 1.0f) - 0.5f;
-                const float tRoi = fminf(fminf(fminf(rx_ / ax, ry_ / ay), rz_ / az), tExit);
-                e1 = tRoi * rate;
-                e2 = (tExit - tRoi) * (ax / rrx + ay / rry + az / rrz);
-              }
-            } else {
-              // rays that go on after a wall (RMCRTCommon.cc:846-902): follow the bounces through the empty box.  A mirror face (no
-              // absorbing cell, finalize_kernel) keeps the weight; an absorbing one zeroes it, after which the ray still runs to its
-              // NEXT wall unless zero-weight legs are skipped
-              float p0 = ci + 0.5f, p1 = cj + 0.5f, p2 = ck + 0.5f;        // position in cells from the level's low corner
-              bool s0 = px, s1 = py, s2 = pz, dead = false;
-              float tTot = 0.0f, tFirst = 0.0f;
-              for (int bnc = 0; bnc < bounces; ++bnc) {
-                const float t0 = (s0 ? (float)(g.n[0] - 1) - p0 : p0 - 1.0f) / ax;
-                const float t1 = (s1 ? (float)(g.n[1] - 1) - p1 : p1 - 1.0f) / ay;
-                const float t2 = (s2 ? (float)(g.n[2] - 1) - p2 : p2 - 1.0f) / az;
-                const float t = fmaxf(fminf(fminf(t0, t1), t2), 0.0f);
-                const int axh = (t0 <= t1 && t0 <= t2) ? 0 : (t1 <= t2 ? 1 : 2);
-                tTot += t;
-                if (bnc == 0) tFirst = tTot;
-                if (tTot >= tThr) break;
-                p0 += (s0 ? t : -t) * ax; p1 += (s1 ? t : -t) * ay; p2 += (s2 ? t : -t) * az;
-                const unsigned face = 2u * axh + ((axh == 0 ? s0 : (axh == 1 ? s1 : s2)) ? 1u : 0u);
-                if (dead) break;                      // a weightless ray ends at the next wall of any kind (intensity 0)
-                if (!((mirrors >> face) & 1u)) {
-                  if (skipZero) break;
-                  dead = true;
-                }
-                if (axh == 0) s0 = !s0; else if (axh == 1) s1 = !s1; else s2 = !s2;
-              }
-              tTot = fminf(tTot, tThr); tFirst = fminf(tFirst, tThr);
-              e1 = tFirst * rate;
-              e2 = (tTot - tFirst) * rate;
+            float e1, e2 = 0.0f;                         // steps of the first leg (Data Onion: inside the ROI), of the rest
+            const float nx_ = (px ? (float)(g.n[0] - 1) - ci : ci) - 0.5f;
+            const float ny_ = (py ? (float)(g.n[1] - 1) - cj : cj) - 0.5f;
+            const float nz_ = (pz ? (float)(g.n[2] - 1) - ck : ck) - 0.5f;
+            const float tExit = fminf(fminf(fminf(nx_ / ax, ny_ / ay), nz_ / az), tThr);
+            e1 = tExit * rate;
+            if constexpr (ONION) {
+              // fine steps up to the ROI face, coarse steps (cells rr times larger) from there to the end
+              const float rx_ = (px ? (float)(a.G.roiHi[0] - g.lo[0]) - ci : ci - (float)(a.G.roiLo[0] - g.lo[0]) + 1.0f) - 0.5f;
+              const float ry_ = (py ? (float)(a.G.roiHi[1] - g.lo[1]) - cj : cj - (float)(a.G.roiLo[1] - g.lo[1]) + 1.0f) - 0.5f;
+              const float rz_ = (pz ? (float)(a.G.roiHi[2] - g.lo[2]) - ck : ck - (float)(a.G.roiLo[2] - g.lo[2]) + 1.0f) - 0.5f;
+              const float tRoi = fminf(fminf(fminf(rx_ / ax, ry_ / ay), rz_ / az), tExit);
+              e1 = tRoi * rate;
+              e2 = (tExit - tRoi) * (ax / rrx + ay / rry + az / rrz);
             }
             int key;
             if (twoPart) key = (min(15, (int)(e1 * scale1 + 0.5f)) << 5) | min(31, (int)(e2 * scale2 + 0.5f));
@@ -1142,27 +1143,9 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
           }
       }
       __syncthreads();
-      // ---- phase 2: exclusive scan over the bins in DESCENDING key order (thread t owns bin 255 - t), then scatter
+      // ---- phase 2: start of every bin in the sorted list (descending keys), then scatter
       {
-        // thread t owns PER consecutive bins, descending keys
-        constexpr int PER = SORT_BINS / 256;
-        int hq[PER], h = 0;
-#pragma unroll
-        for (int u = 0; u < PER; ++u) { hq[u] = hist[SORT_BINS - 1 - (tid * PER + u)]; h += hq[u]; }
-        int incl = h;
-        for (int o = 1; o < 32; o <<= 1) {
-          const int v = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += v;
-        }
-        if (lane == 31) warpTot[warp] = incl;
-        __syncthreads();
-        int base = 0;
-        for (int w = 0; w < warp; ++w) base += warpTot[w];
-        int start = base + incl - h;                           // start of the thread's first bin in the sorted list
-#pragma unroll
-        for (int u = 0; u < PER; ++u) { hist[SORT_BINS - 1 - (tid * PER + u)] = start; start += hq[u]; }
-        if (tid == 255) ctl[1] = base + incl;                  // list length = rays of flow cells
-        __syncthreads();
+        scan_bins();
         if (cw0 >= 0)
           for (int r = warp; r < nr; r += W) {
             const int pos = atomicAdd(&hist[__ldcg(keys + r * 32 + lane)], 1);
@@ -1170,6 +1153,126 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
           }
       }
       __syncthreads();
+      if constexpr (RESORT) {
+        // ---- phase 3a: FIRST legs, longest first; rays that go on are parked with a key for what is left of them
+        for (int q4 = tid; q4 < SORT_BINS; q4 += 256) hist[q4] = 0;
+        __syncthreads();
+        const int nList = ctl[1];
+        const float thr = (float)a.threshold;
+        for (;;) {
+          int chunk = 0;
+          if (lane == 0) chunk = atomicAdd(&ctl[0], 1);
+          chunk = __shfl_sync(0xffffffffu, chunk, 0);
+          if (chunk * 32 >= nList) break;
+          const int p = chunk * 32 + lane;
+          if (p < nList) {
+            const int id = __ldcg(ids + p);
+            const int c = id & 31, r = id >> 5;
+            const int rw0 = w0s[c];
+            const unsigned long long cid = cellIds[c];
+            float dir[3], rayDx[3];
+            gen_divq_ray_f32(a.rng, g, ray0 + r, cid, cid, dir, rayDx);
+            unsigned short key2 = 0xFFFFu;
+            float out = 0.0f;
+            if (1.0f > thr) {
+              BlkRay ry;
+              float ddx, ddy, ddz;
+              blk_ray_start(ry, blk, rw0, (unsigned)(rw0 & 7), sy8, sz8, nz<float, float>(dir[0]), nz<float, float>(dir[1]),
+                            nz<float, float>(dir[2]), rayDx[0], rayDx[1], rayDx[2], cx, cy, cz, ddx, ddy, ddz);
+              if (blk_ray_legs(ry, blk, ddx, ddy, ddz, sy8, sz8, thr, a.allowReflect != 0, skipZero, 1)) {
+                out = UNSCALE * ry.sum;
+                steps += (unsigned)ry.q.nsteps;
+              } else {
+                parked[id * 3 + 0] = make_uint4(__float_as_uint(ry.d.tx), __float_as_uint(ry.d.ty), __float_as_uint(ry.d.tz), (unsigned)ry.d.idx);
+                parked[id * 3 + 1] = make_uint4((unsigned)ry.b.dlx, (unsigned)ry.b.dly, (unsigned)ry.b.dlz, __float_as_uint(ry.q.A));
+                parked[id * 3 + 2] = make_uint4(__float_as_uint(ry.q.ePrev), __float_as_uint(ry.q.nsteps), __float_as_uint(ry.sum), __float_as_uint(ry.fs));
+                // what is left: follow the bounces from the cell the ray stands in (decoded from its word index)
+                int B = ry.d.idx >> 3;
+                const int bz_ = B / bg.bxy; B -= bz_ * bg.bxy;
+                const int by_ = B / bg.bx, bx_ = B - by_ * bg.bx;
+                float p0 = (float)(2 * bx_ + (ry.d.idx & 1) + bg.lo[0] - g.lo[0]) + 0.5f;
+                float p1 = (float)(2 * by_ + ((ry.d.idx >> 1) & 1) + bg.lo[1] - g.lo[1]) + 0.5f;
+                float p2 = (float)(2 * bz_ + ((ry.d.idx >> 2) & 1) + bg.lo[2] - g.lo[2]) + 0.5f;
+                const float ax = fabsf(dir[0]) * icx + 1e-30f, ay = fabsf(dir[1]) * icy + 1e-30f, az = fabsf(dir[2]) * icz + 1e-30f;
+                bool s0 = ry.b.dlx > 0, s1 = ry.b.dly > 0, s2 = ry.b.dlz > 0, dead = ry.fs == 0.0f;
+                const bool deadAtStart = dead;
+                float tTot = 0.0f, tFirst = 0.0f;
+                for (int bnc = 0; bnc < goOn; ++bnc) {
+                  const float t0 = (s0 ? (float)(g.n[0] - 1) - p0 : p0 - 1.0f) / ax;
+                  const float t1 = (s1 ? (float)(g.n[1] - 1) - p1 : p1 - 1.0f) / ay;
+                  const float t2 = (s2 ? (float)(g.n[2] - 1) - p2 : p2 - 1.0f) / az;
+                  const float t = fmaxf(fminf(fminf(t0, t1), t2), 0.0f);
+                  const int axh = (t0 <= t1 && t0 <= t2) ? 0 : (t1 <= t2 ? 1 : 2);
+                  tTot += t;
+                  if (bnc == 0) tFirst = tTot;
+                  p0 += (s0 ? t : -t) * ax; p1 += (s1 ? t : -t) * ay; p2 += (s2 ? t : -t) * az;
+                  const unsigned face = 2u * axh + ((axh == 0 ? s0 : (axh == 1 ? s1 : s2)) ? 1u : 0u);
+                  if (dead) break;                      // a weightless ray ends at its next wall of any kind (intensity 0)
+                  if (!((mirrors >> face) & 1u)) {
+                    if (skipZero) break;
+                    dead = true;
+                  }
+                  if (axh == 0) s0 = !s0; else if (axh == 1) s1 = !s1; else s2 = !s2;
+                }
+                const float rate = ax + ay + az;
+                // weightless rays: one leg, 8 bits of length, upper half of the key space; the others (leg: 3 bits | rest: 5 bits)
+                if (deadAtStart) key2 = (unsigned short)(256 + min(255, (int)(tTot * rate * (255.0f / nSum) + 0.5f)));
+                else key2 = (unsigned short)((min(7, (int)(tFirst * rate * (7.0f / (0.6f * nSum)) + 0.5f)) << 5) |
+                                             min(31, (int)((tTot - tFirst) * rate * (31.0f / (1.2f * nSum)) + 0.5f)));
+                atomicAdd(&hist[key2], 1);
+              }
+            }
+            __stcg(keys + id, key2);
+            __stcg(res + id, out);
+          }
+        }
+        __syncthreads();
+        // ---- phase 3b: the parked rays, sorted again, to their end
+        scan_bins();
+        const int nParked = ctl[1];
+        if (tid == 0) ctl[0] = 0;
+        if (nParked > 0) {
+          if (cw0 >= 0)
+            for (int r = warp; r < nr; r += W) {
+              const unsigned short k2 = __ldcg(keys + r * 32 + lane);
+              if (k2 != 0xFFFFu) {
+                const int pos = atomicAdd(&hist[k2], 1);
+                __stcg(ids + pos, (unsigned short)(r * 32 + lane));
+              }
+            }
+          __syncthreads();
+          for (;;) {
+            int chunk = 0;
+            if (lane == 0) chunk = atomicAdd(&ctl[0], 1);
+            chunk = __shfl_sync(0xffffffffu, chunk, 0);
+            if (chunk * 32 >= nParked) break;
+            const int p = chunk * 32 + lane;
+            if (p < nParked) {
+              const int id = __ldcg(ids + p);
+              const int c = id & 31, r = id >> 5;
+              const unsigned long long cid = cellIds[c];
+              float dir[3], rayDx[3];
+              gen_divq_ray_f32(a.rng, g, ray0 + r, cid, cid, dir, rayDx);
+              typedef Num<float> N;
+              const float ddx = fabsf(N::rcp(nz<float, float>(dir[0]))) * cx * N::LEN_SCALE;
+              const float ddy = fabsf(N::rcp(nz<float, float>(dir[1]))) * cy * N::LEN_SCALE;
+              const float ddz = fabsf(N::rcp(nz<float, float>(dir[2]))) * cz * N::LEN_SCALE;
+              const uint4 v0 = __ldcg(parked + id * 3 + 0), v1 = __ldcg(parked + id * 3 + 1), v2 = __ldcg(parked + id * 3 + 2);
+              BlkRay ry;
+              ry.d.tx = __uint_as_float(v0.x); ry.d.ty = __uint_as_float(v0.y); ry.d.tz = __uint_as_float(v0.z); ry.d.idx = (int)v0.w;
+              ry.b.dlx = (int)v1.x; ry.b.dly = (int)v1.y; ry.b.dlz = (int)v1.z;
+              blk_decode(ry.q, __ldg(blk + ry.d.idx));
+              ry.q.A = __uint_as_float(v1.w); ry.q.ePrev = __uint_as_float(v2.x); ry.q.nsteps = __uint_as_float(v2.y);
+              ry.q.tau = 0.0f; ry.q.leg = 0.0f;
+              ry.sum = __uint_as_float(v2.z); ry.fs = __uint_as_float(v2.w);
+              blk_ray_legs(ry, blk, ddx, ddy, ddz, sy8, sz8, thr, a.allowReflect != 0, skipZero, 0x7fffffff);
+              steps += (unsigned)ry.q.nsteps;
+              __stcg(res + id, UNSCALE * ry.sum);
+            }
+          }
+        }
+        __syncthreads();
+      } else {
       // ---- phase 3: march chunks of 32 rays, longest first
       {
         const int nList = ctl[1];
@@ -1200,6 +1303,7 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
         }
       }
       __syncthreads();
+      }
       // ---- phase 4: rays of a cell added in ray order (warp w: its contiguous share, then the shares in warp order)
       {
         const int per = (nr + W - 1) / W;
@@ -2561,11 +2665,11 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
         for (int d = 0; d < 3; ++d) { bg.lo[d] = rlo[d]; ob.rlo[d] = rlo[d]; ob.clo[d] = bgC.lo[d]; }
         const int RP = std::min(a.nRays, ctx->p.refillLanes > 0 ? ctx->p.refillLanes : 256);
         const int nb = (int)std::min<long long>(a.nTiles, (long long)ctx->smCount * (ctx->p.maxBlocksPerSM > 0 ? ctx->p.maxBlocksPerSM : RMCRT_SORTED_BLOCKS));
-        if (ctx->sortScratch.ensure((size_t)nb * sorted_scratch_bytes(RP) + 256)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc sort scratch");
+        if (ctx->sortScratch.ensure((size_t)nb * sorted_scratch_bytes(RP, false) + 256)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc sort scratch");
         unsigned char* base = static_cast<unsigned char*>(ctx->sortScratch.p);
         int* tileCounter = reinterpret_cast<int*>(base);
         CK(cudaMemsetAsync(tileCounter, 0, sizeof(int), st));
-        divq_sorted_kernel<RecT, true><<<nb, 256, 0, st>>>(a, bg, ob, RP, base + 256, tileCounter);
+        divq_sorted_kernel<RecT, true, false><<<nb, 256, 0, st>>>(a, bg, ob, RP, base + 256, tileCounter);
       }
     } else if (ML && std::is_same<Real, float>::value && !ctx->p.genericMarch && a.G.maxLevels == 2 && patchInRoi) {
       // 2-level Data Onion fast path: per-patch ROI copy with a marker shell, then the tuned leg loop on both levels
@@ -2639,11 +2743,19 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
         const int RP = std::min(a.nRays, ctx->p.refillLanes > 0 ? ctx->p.refillLanes : 256);      // rays per pass (A/B: refillLanes)
         // persistent blocks (their scratch is per block), tiles handed out through a counter
         const int nb = (int)std::min<long long>(a.nTiles, (long long)ctx->smCount * (ctx->p.maxBlocksPerSM > 0 ? ctx->p.maxBlocksPerSM : RMCRT_SORTED_BLOCKS));
-        if (ctx->sortScratch.ensure((size_t)nb * sorted_scratch_bytes(RP) + 256)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc sort scratch");
+        const bool mayGoOn = a.allowReflect != 0;      // ... whether rays DO go on after a wall is known on the device only (level status)
+        if (ctx->sortScratch.ensure((size_t)nb * sorted_scratch_bytes(RP, mayGoOn) + 256)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc sort scratch");
         unsigned char* base = static_cast<unsigned char*>(ctx->sortScratch.p);
         int* tileCounter = reinterpret_cast<int*>(base);
+        TraceArgs a2 = a;
+        a2.gate = mayGoOn ? 1 : 0;
         CK(cudaMemsetAsync(tileCounter, 0, sizeof(int), st));
-        divq_sorted_kernel<RecT, false><<<nb, 256, 0, st>>>(a, bg, OnionBlk{}, RP, base + 256, tileCounter);
+        divq_sorted_kernel<RecT, false, false><<<nb, 256, 0, st>>>(a2, bg, OnionBlk{}, RP, base + 256, tileCounter);
+        if (mayGoOn) {
+          a2.gate = 2;
+          CK(cudaMemsetAsync(tileCounter, 0, sizeof(int), st));
+          divq_sorted_kernel<RecT, false, true><<<nb, 256, 0, st>>>(a2, bg, OnionBlk{}, RP, base + 256, tileCounter);
+        }
       }
     } else if (ctx->p.blockedMarch == 2 && blocked_default(ctx, a, ML)) {
       // independent rays per (cell, ray, timestep) on the blocked half-packed copy of the level, plain loads (divq_blk_kernel)
