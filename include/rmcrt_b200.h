@@ -73,7 +73,7 @@ typedef struct rmcrt_params {
                                       stream of Ray.cc:539,757-771; errors of neighbouring cells are uncorrelated.
                                   1 = the origin cells of a warp tile share one DIRECTION per ray index (own in-cell origins);
                                   2 = they share direction AND in-cell origin, so the rays of a tile are exact translates marching in
-                                      lockstep (with cellsPerLane 4: the fastest kernel, 5.7x the default at 128^3).
+                                      lockstep (with cellsPerLane 4: the fastest kernel, 3.3x the default at 128^3).
                                   1 and 2 keep every cell's estimate unbiased with the same per-cell variance, but the errors of the
                                   cells of a tile become (almost fully) correlated: the mean over a 128-cell tile is no better than one
                                   cell (variance 100x the independent-ray value, tests/test_gpu_atsize.py::test_error_correlation).

@@ -1,19 +1,20 @@
-// indep.cuh -- the production march of the DEFAULT sampling (rayCoherence 0): every (cell, ray) has its own direction and in-cell origin
-// (Philox keyed on (cell, ray, timestep), the reference's independent rays: Ray.cc:539,757-771), so the 32 lanes of a warp gather from 32
-// unrelated places and nothing of the lockstep machinery of march_leg_pair / _quad applies.
+// indep.cuh -- the march of the DEFAULT sampling (rayCoherence 0): every (cell, ray) has its own direction and in-cell origin (Philox keyed
+// on (cell, ray, timestep), the reference's independent rays: Ray.cc:539,757-771), so the 32 lanes of a warp gather from 32 unrelated
+// places and nothing of the lockstep machinery of march_leg_pair / _quad applies.
 //
-// What binds such a march on B200 (ncu, profiles/r02v1_divq_coh0_128_ncu.md): every ray-cell step of the one-cell-per-lane kernel is one
-// 32-B sector request from L1 to L2 -- the SM's miss-request path (one request per clock, 96 % busy) and the L2 -> SM bandwidth (77 %) --
-// issued by warps whose lanes finish at very different steps (13.4 of 32 lanes active).  Two things are done about it here:
+// What binds such a march on B200 (ncu): on the level's linear records every ray-cell step is one 32-B sector
+// request from L1 to L2 -- the SM's miss-request path (one request per clock) is 96 % busy -- issued by warps whose lanes finish at very
+// different steps (13.4 of 32 lanes active).  What is done about it:
 //
-//  * BLOCKED HALF-PACKED RECORDS.  The level is kept a second time as 2 x 2 x 2 cell blocks of 4-B half-packed records (the Rec4 word of
-//    march.cuh): one block = one 32-B sector.  A lane fetches the whole block it enters with ONE 256-bit load (LDG.E.256) into its private
-//    slot of shared memory and takes the records of the cells it visits inside the block from there.  A ray visits two cells per block on
-//    average (mean chord of a 2-cube over the mean chord of a cell), so the global sector requests per ray-cell step halve.
-//  * PER-LANE RAY REFILL.  A lane owns one origin cell and walks through ITS rays on its own: when a ray ends the lane starts its next one
-//    (in batches: ray set-up runs when at least REFILL lanes of the warp wait, so its ~100 instructions are shared), instead of idling until
-//    the longest ray of the warp's batch ends.  The work of a lane is the sum over all its rays (relative spread 7 % at 100 rays) rather
-//    than the maximum over the warp of single ray lengths (relative spread 70 %).
+//  * BLOCKED HALF-PACKED RECORDS (BlkGeom).  The level is kept a second time as 2 x 2 x 2 cell blocks of 4-B half-packed records (the
+//    Rec4 word of march.cuh): one block = one 32-B sector.  A ray visits two cells per block on average (mean chord of a 2-cube over the
+//    mean chord of a cell), so the second visit is an L1 hit on the sector the first one fetched.
+//      - march_leg_blk / BlkRay / march_single_level_blk / march_onion2_blk (PRODUCTION, blockedMarch 2 and 3): the PTX leg loop of
+//        march.cuh with plain 4-byte loads and coordinate-free blocked addressing (one XOR per step toggles the stepped axis' delta);
+//        divq_sorted_kernel (rmcrt_b200.cu) sorts the rays of a tile by expected length so that the lanes of a warp end together.
+//      - blk_fetch / IndepRay / indep_step (blockedMarch 1, measured slower, kept for A/B): one 256-bit load per block entered into a
+//        per-lane slot of shared memory, and PER-LANE RAY REFILL -- a lane walks through the rays of its cell on its own and starts the
+//        next one when one ends (ray set-up batched over >= REFILL waiting lanes).
 //
 // Per-ray arithmetic is that of march_single_level_fast (offset-form tau, one ex2 per step, integral per leg scaled by fs at the wall,
 // reflections without recomputing tMax -- RMCRTCommon.cc:607-904), on the fp16 properties of the blocked copy.

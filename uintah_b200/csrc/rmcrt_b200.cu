@@ -5,7 +5,13 @@
 // Kernel inventory
 //   pack_kernel<T,RecT>        abskg/sigmaT4/cellType (Array3 windows) -> packed cell records   (HBM streaming)
 //   finalize_kernel<RecT>      validation + "can any non-flow cell emit?" reduction             (HBM streaming)
-//   divq_kernel<Real,RecT,ML>  THE hot kernel: ray generation + DDA march + divQ epilogue        (L2/L1 gather bound)
+//   divq_sorted_kernel<RecT,ONION,RESORT>  THE hot kernel (library default): independent Philox rays of a 32-cell tile sorted by expected
+//                              length, marched on the blocked half-packed copy of the level (indep.cuh), per-cell sums in ray order
+//                              (L1 miss path / L1 data pipe / L2 -> SM bandwidth bound at 30.6 of 32 lanes)
+//   blk_build_kernel / roi_blk_build_kernel  the blocked copies (level; Data-Onion region of interest with its marker shell)
+//   divq_kernel<Real,RecT,ML>  one cell per lane on the level's own records: FP64 parity march, regression generators, Latin hyper cube,
+//                              scattering, bounded rays, 3+ levels, blockedMarch 0          (L2/L1 gather bound)
+//   divq_quad / divq_dual_kernel  opt-in lockstep sampling (rayCoherence 1 / 2)                 (issue bound)
 //   flux_mask_kernel<RecT>     Ray::has_a_boundary face masks, boundFlux.p                        (streaming)
 //   flux_trace_kernel<...>     boundary-flux rays for the compacted (face, cell) items            (gather bound)
 //   debug_rays_kernel<...>     caller-specified rays through the production march code

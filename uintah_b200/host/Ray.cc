@@ -189,7 +189,7 @@ void Ray::BC_bulletproofing(const ProblemSpecP& rmcrtps, const bool chk_temp, co
 
 //______________________________________________________________________
 void Ray::setKnob(const std::string& name, int value) {
-  static const char* known[] = {"rayCoherence", "skipZeroWeightLegs", "l2Persist", "genericMarch", "marchPrecision", "warpsPerTile", "fixedRandom", "halfRecords", "cellsPerLane", "tileX"};
+  static const char* known[] = {"rayCoherence", "skipZeroWeightLegs", "l2Persist", "genericMarch", "marchPrecision", "warpsPerTile", "fixedRandom", "halfRecords", "cellsPerLane", "tileX", "blockedMarch"};
   for (auto k : known)
     if (name == k) { d_knobs[name] = value; return; }
   throw ProblemSetupException("RMCRT (B200 back end): unknown knob " + name, __FILE__, __LINE__);
@@ -235,6 +235,7 @@ void Ray::fillParams(rmcrt_params& p) const {
     else if (kv.first == "fixedRandom") p.fixedRandom = kv.second;
     else if (kv.first == "cellsPerLane") p.cellsPerLane = kv.second;
     else if (kv.first == "tileX") p.tileX = kv.second;
+    else if (kv.first == "blockedMarch") p.blockedMarch = kv.second;
   }
 }
 
