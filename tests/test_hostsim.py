@@ -292,3 +292,46 @@ def test_data_onion_quad_march_equals_four_single_marches(po, case):
         np.testing.assert_allclose(sm[same, 0], singles[0][same], rtol=2e-5, atol=2e-6 * np.abs(singles[0]).max())
         for q in (1, 2, 3):
             np.testing.assert_allclose(sm[same, q], singles[q][same], rtol=5e-4, atol=2e-5 * np.abs(singles[q]).max())
+
+
+def test_blocked_addressing_algebra():
+    """indep.cuh, march_leg_blk: the word index of a cell in the blocked copy is 8 * block + (x&1 | (y&1)<<1 | (z&1)<<2); a ray keeps one
+    signed delta per axis, a step on an axis adds it and toggles it with ONE XOR by a constant of the level (6, 2 ^ (8 nbx - 2),
+    4 ^ (8 nbx nby - 4) -- the same for both directions), a reflection steps back by the previous delta d and goes on with d - sign(d) S.
+    Walks random paths with reflections and checks every index against the closed form (integer arithmetic as the device does it)."""
+    rng = np.random.default_rng(0)
+
+    def i32(v):
+        return ((int(v) + 2 ** 31) % 2 ** 32) - 2 ** 31
+
+    for nbx, nby, nbz in ((7, 5, 6), (66, 66, 66), (131, 131, 131)):
+        M = nbx * nby
+        dims = (2 * nbx, 2 * nby, 2 * nbz)
+
+        def widx(x, y, z):
+            return 8 * ((z >> 1) * M + (y >> 1) * nbx + (x >> 1)) + ((x & 1) | ((y & 1) << 1) | ((z & 1) << 2))
+
+        A, S = (1, 2, 4), (8, 8 * nbx, 8 * M)
+        T = (6, 2 ^ (8 * nbx - 2), 4 ^ (8 * M - 4))
+        for trial in range(300):
+            p = [int(rng.integers(2, d - 2)) for d in dims]
+            sg = [int(rng.choice([-1, 1])) for _ in range(3)]
+            # blk_stride_init
+            dl = [(A[a] if not (p[a] & 1) else S[a] - A[a]) if sg[a] > 0 else (-A[a] if (p[a] & 1) else A[a] - S[a]) for a in range(3)]
+            w = widx(*p)
+            for step in range(40):
+                a = int(rng.integers(3))
+                q = list(p); q[a] += sg[a]
+                if not (0 <= q[a] < dims[a]):
+                    continue
+                w2 = i32(w + dl[a]); dl[a] = i32(dl[a] ^ T[a])           # RB_PEEK / RB_COMMIT
+                assert w2 == widx(*q)
+                if rng.random() < 0.25:                                   # the cell entered is a wall: reflect (blk_ray_legs)
+                    dprev = i32(dl[a] ^ T[a])
+                    w2 = i32(w2 - dprev)
+                    dl[a] = dprev - S[a] if dprev > 0 else dprev + S[a]
+                    sg[a] = -sg[a]
+                    assert w2 == widx(*p)
+                else:
+                    p = q
+                w = w2
