@@ -390,11 +390,13 @@ def test_data_onion_deterministic(gpu_lib, po):
     np.testing.assert_allclose(divQ2, divQ, rtol=1e-12, atol=0)
 
 
-@pytest.mark.parametrize("case", ["bc", "plates_mirrors"])
+@pytest.mark.parametrize("case", ["bc", "bc_refsem", "plates_mirrors"])
 def test_data_onion_fast_path_matches_generic_march(gpu_lib, po, case):
     """2-level Data Onion: the production path (per-patch ROI copy with a marker shell + the tuned leg loop on both levels)
-    against the generic multi-level march on the same Philox rays."""
-    if case == "bc":
+    against the generic multi-level march on the same Philox rays.  bc_refsem: the zero-weight legs behind the black walls are marched
+    like the reference does, so WHERE a ray reflects (fine or coarse level) shows in the step count."""
+    kw = {"skipZeroWeightLegs": 0} if case == "bc_refsem" else {}
+    if case in ("bc", "bc_refsem"):
         fine, thr = po.burns_christon(32, dtype=np.float32), 0.05
     else:
         fine, thr = po.parallel_plates(32, dtype=np.float32, mirror_faces=("x-", "y-")), 0.001
@@ -403,11 +405,13 @@ def test_data_onion_fast_path_matches_generic_march(gpu_lib, po, case):
     res = {}
     for gm in (0, 1):
         # the same Philox rays per cell, on the level's own float records
-        g = make(gpu_lib, nDivQRays=16, threshold=thr, haloCells=(4, 4, 4), seed=17, genericMarch=gm, cellsPerLane=1, blockedMarch=0)
+        g = make(gpu_lib, nDivQRays=16, threshold=thr, haloCells=(4, 4, 4), seed=17, genericMarch=gm, cellsPerLane=1, blockedMarch=0, **kw)
         g.upload_level(0, coarse)
         g.upload_level(1, fine)
         divQ = np.zeros(fine.abskg.shape); vol = np.zeros_like(divQ)
-        for plo, phi in po._split((0, 0, 0), (32, 32, 32), (2, 2, 2)):
+        # (the last patch: halo 4 around [4, 12) -- its ROI ends exactly at the interior's edge, where the cell beyond is a wall of the fine
+        # level and not a level jump: `inDomain`, Ray.cc:2486-2493)
+        for plo, phi in po._split((0, 0, 0), (32, 32, 32), (2, 2, 2)) + [((4, 4, 4), (12, 12, 12))]:
             g.trace_dataonion(2, plo, phi, zero_init=False, outputs=(divQ, vol, None), timestep=4)
         res[gm] = (divQ, g.counters().nRaySteps)
     (a, na), (b, nb) = res[0], res[1]

@@ -315,91 +315,95 @@ __device__ __forceinline__ float march_single_level_blk(const uint32_t* __restri
 }
 
 //------------------------------------------------------------------------------------------------------
-// 2-level Data Onion on blocked copies: march_onion2_fast (march.cuh; Ray::updateSumI_ML, Ray.cc:2349-2627, for two levels) with
-// march_leg_blk.  The fine level's region of interest is a blocked half-packed box wrapped in marker cells {wall flag, abskg = inf}
-// (roi_blk_build_kernel); entering a marker ends the leg like a wall and identifies the ROI exit of Ray.cc:2489-2527: the fine cell is
-// decoded from the word index, mapped to the coarse level, tMax of the stepping axis re-anchored as the reference does, and
-// the march goes on in the blocked copy of level 0.
+// Data Onion on blocked copies, any number of levels: Ray::updateSumI_ML (Ray.cc:2349-2627) with march_leg_blk -- march_onion2_fast
+// (march.cuh) generalised.  Every level above 0 is a blocked half-packed box: the fine level's region of interest (Ray.cc:2489), a coarser
+// level's region (2490), each wrapped in marker cells {wall flag, abskg = inf} wherever the cell next to the box is an interior cell of the
+// level (where the box ends at the domain boundary the level's own extra cells are copied, so a ray meets its wall on that level).  Entering
+// a marker ends the leg like a wall and identifies the level jump of Ray.cc:2492-2527: the cell is decoded from the word index, mapped to
+// the next coarser level (mapCellToCoarser), tMax of the stepping axis re-anchored as the reference does and the march goes on
+// in that level's box; level 0 is the blocked copy of the whole level.  (The reference tests the stepped axis only; a box test is the same
+// as long as the ray is inside the box before the step, which the host guarantees: every region contains the mapped region above it.)
 //------------------------------------------------------------------------------------------------------
+constexpr int ONION_MAXL = 4;
 struct OnionBlk {
-  const uint32_t* roi;   // blocked ROI box incl. marker shell and guard blocks
-  int rbx, rbxy;         // blocks per row / plane
-  int rlo[3];            // fine cell index of block-local coordinate 0
-  const uint32_t* coarse;
-  int cbx, cbxy;
-  int clo[3];
+  const uint32_t* blk[ONION_MAXL];   // per level: blocked box incl. marker shell and guard blocks (level 0: the whole level)
+  int bx[ONION_MAXL], bxy[ONION_MAXL];   // blocks per row / plane
+  int lo[ONION_MAXL][3];             // cell index (on that level) of block-local coordinate 0
 };
 
 template <int MAXL>
-__device__ __forceinline__ float march_onion2_blk(const OnionGeom<MAXL>& G, const OnionBlk& ob, int ci, int cj, int ck, int w0,
-                                                  float dx, float dy, float dz, float rx, float ry, float rz, float threshold,
-                                                  bool allowReflect, bool skipZero, unsigned& nSteps) {
+__device__ __forceinline__ float march_onion_blk(const OnionGeom<MAXL>& G, const OnionBlk& ob, int ci, int cj, int ck, int w0,
+                                                 float dx, float dy, float dz, float rx, float ry, float rz, float threshold,
+                                                 bool allowReflect, bool skipZero, unsigned& nSteps) {
   typedef Num<float> N;
   if (!(1.0f > threshold)) return 0.0f;
-  const LevelGeom& gf = G.lev[1];
-  const LevelGeom& gc = G.lev[0];
+  const int F = G.maxLevels - 1;
+  int L = F;
   const float LN2 = 0.6931471805599453f;
   const bool posx = !sign_bit(dx), posy = !sign_bit(dy), posz = !sign_bit(dz);
-  int sy8 = 8 * ob.rbx, sz8 = 8 * ob.rbxy;
+  int sy8 = 8 * ob.bx[L], sz8 = 8 * ob.bxy[L];
   int tgy = 2 ^ (sy8 - 2), tgz = 4 ^ (sz8 - 4);
   BlkStride b = blk_stride_init((unsigned)(w0 & 7), posx, posy, posz, sy8, sz8);
   // sign[] of the reference: 1/0, after a reflection along that axis -1/-0 (RMCRTCommon.cc:599)
   float sgx = posx ? 1.0f : 0.0f, sgy = posy ? 1.0f : 0.0f, sgz = posz ? 1.0f : 0.0f;
   const float ix = N::rcp(dx), iy = N::rcp(dy), iz = N::rcp(dz);     // never refreshed on reflection (Ray.cc:2395)
-  const float fx = (float)gf.dx[0], fy = (float)gf.dx[1], fz = (float)gf.dx[2];
+  const float fx = (float)G.lev[F].dx[0], fy = (float)G.lev[F].dx[1], fz = (float)G.lev[F].dx[2];
   Dda d;
   d.tx = (sgx * fx - rx) * ix * N::LEN_SCALE;
   d.ty = (sgy * fy - ry) * iy * N::LEN_SCALE;
   d.tz = (sgz * fz - rz) * iz * N::LEN_SCALE;
   float ddx = fabsf(ix) * fx * N::LEN_SCALE, ddy = fabsf(iy) * fy * N::LEN_SCALE, ddz = fabsf(iz) * fz * N::LEN_SCALE;
   d.idx = w0;
-  const uint32_t* cur = ob.roi;
+  const uint32_t* cur = ob.blk[L];
   Integ q;
   blk_decode(q, __ldg(cur + w0));
   q.A = 0.0f; q.ePrev = 1.0f; q.nsteps = 0.0f; q.tau = 0.0f; q.leg = 0.0f;
   // position along each axis relative to the origin cell's low corner: l(t) = lb + (t - tb) ln2 * dir   (t is scaled by log2 e)
   float lbx = rx, lby = ry, lbz = rz, tbx = 0.0f, tby = 0.0f, tbz = 0.0f, dvx = dx, dvy = dy, dvz = dz;
-  bool onFine = true;
   float sum = 0.0f, fs = 1.0f;
   for (;;) {
     q.leg = 0.0f;
     const LegOut w = march_leg_blk(d, q, b, cur, ddx, ddy, ddz, tgy, tgz);
     sum = fmaf(q.leg, fs, sum);
     const int ax = w.axis;
-    if (onFine && q.k > 3.0e38f) {                   // stepped into the marker shell: leave the ROI (Ray.cc:2489-2527)
+    if (L > 0 && q.k > 3.0e38f) {                    // stepped into the marker shell: leave this level's box (Ray.cc:2489-2527)
+      const LevelGeom& gp = G.lev[L];                // the level being left
+      const LevelGeom& gc = G.lev[L - 1];
       int B = d.idx >> 3;
       const int par = d.idx & 7;
-      const int bk = B / ob.rbxy; B -= bk * ob.rbxy;
-      const int bj = B / ob.rbx;
-      const int bi = B - bj * ob.rbx;
-      const int c0 = ob.rlo[0] + 2 * bi + (par & 1), c1 = ob.rlo[1] + 2 * bj + ((par >> 1) & 1), c2 = ob.rlo[2] + 2 * bk + (par >> 2);
-      // re-anchor tMax of the stepping axis from the ray position and the centre of that fine cell (Ray.cc:2486,2534-2550)
-      const float fA = sel3(ax, fx, fy, fz);
-      const float ccRel = fA * ((float)sel3(ax, c0, c1, c2) + 0.5f) - fA * (float)sel3(ax, ci, cj, ck);
+      const int bk = B / ob.bxy[L]; B -= bk * ob.bxy[L];
+      const int bj = B / ob.bx[L];
+      const int bi = B - bj * ob.bx[L];
+      const int c0 = ob.lo[L][0] + 2 * bi + (par & 1), c1 = ob.lo[L][1] + 2 * bj + ((par >> 1) & 1), c2 = ob.lo[L][2] + 2 * bk + (par >> 2);
+      // re-anchor tMax of the stepping axis from the ray position and the centre of the cell entered, on the level being left
+      // (Ray.cc:2486,2534-2550), relative to the origin cell's low corner
+      const float pA = sel3(ax, (float)gp.dx[0], (float)gp.dx[1], (float)gp.dx[2]);
+      const float ccRel = (sel3(ax, (float)gp.off[0], (float)gp.off[1], (float)gp.off[2]) + pA * ((float)sel3(ax, c0, c1, c2) + 0.5f)) -
+                          sel3(ax, fx, fy, fz) * (float)sel3(ax, ci, cj, ck);
       const float lA = fmaf((w.t - sel3(ax, tbx, tby, tbz)) * LN2, sel3(ax, dvx, dvy, dvz), sel3(ax, lbx, lby, lbz));
-      const float cdx = (float)sel3(ax, (float)gc.dx[0], (float)gc.dx[1], (float)gc.dx[2]);
+      const float cdx = sel3(ax, (float)gc.dx[0], (float)gc.dx[1], (float)gc.dx[2]);
       const float rayDxLevel = lA - (ccRel - 0.5f * cdx);
       const float tTmp = (sel3(ax, sgx, sgy, sgz) * cdx - rayDxLevel) * sel3(ax, ix, iy, iz) * N::LEN_SCALE;
       if (ax == 0) d.tx = w.t + tTmp; else if (ax == 1) d.ty = w.t + tTmp; else d.tz = w.t + tTmp;
-      // coarse cell, blocked strides and tDelta of level 0 (the stepping directions are those of the current deltas)
-      const int k0 = min(max(map_to_coarser(c0, gf.rr[0]) - gc.lo[0], 0), gc.n[0] - 1) + gc.lo[0] - ob.clo[0];
-      const int k1 = min(max(map_to_coarser(c1, gf.rr[1]) - gc.lo[1], 0), gc.n[1] - 1) + gc.lo[1] - ob.clo[1];
-      const int k2 = min(max(map_to_coarser(c2, gf.rr[2]) - gc.lo[2], 0), gc.n[2] - 1) + gc.lo[2] - ob.clo[2];
-      sy8 = 8 * ob.cbx; sz8 = 8 * ob.cbxy;
+      // the coarser cell, blocked strides and tDelta of its level (the stepping directions are those of the current deltas)
+      --L;
+      const int k0 = min(max(map_to_coarser(c0, gp.rr[0]) - gc.lo[0], 0), gc.n[0] - 1) + gc.lo[0] - ob.lo[L][0];
+      const int k1 = min(max(map_to_coarser(c1, gp.rr[1]) - gc.lo[1], 0), gc.n[1] - 1) + gc.lo[1] - ob.lo[L][1];
+      const int k2 = min(max(map_to_coarser(c2, gp.rr[2]) - gc.lo[2], 0), gc.n[2] - 1) + gc.lo[2] - ob.lo[L][2];
+      sy8 = 8 * ob.bx[L]; sz8 = 8 * ob.bxy[L];
       tgy = 2 ^ (sy8 - 2); tgz = 4 ^ (sz8 - 4);
       const unsigned parC = (unsigned)((k0 & 1) | ((k1 & 1) << 1) | ((k2 & 1) << 2));
       b = blk_stride_init(parC, b.dlx > 0, b.dly > 0, b.dlz > 0, sy8, sz8);
       ddx = fabsf(ix) * (float)gc.dx[0] * N::LEN_SCALE; ddy = fabsf(iy) * (float)gc.dx[1] * N::LEN_SCALE;
       ddz = fabsf(iz) * (float)gc.dx[2] * N::LEN_SCALE;
-      d.idx = 8 * ((k0 >> 1) + ob.cbx * (k1 >> 1) + ob.cbxy * (k2 >> 1)) + (int)parC;
-      cur = ob.coarse;
-      onFine = false;
+      d.idx = 8 * ((k0 >> 1) + ob.bx[L] * (k1 >> 1) + ob.bxy[L] * (k2 >> 1)) + (int)parC;
+      cur = ob.blk[L];
       const uint32_t word = __ldg(cur + d.idx);
       blk_decode(q, word);
       q.A = fmaf(-q.k, w.t, q.tau);
-      if ((int)word >= 0) continue;                  // keep marching on the coarse level
+      if ((int)word >= 0) continue;                  // keep marching on the coarser level
     }
-    // wall (fine or coarse): (q.k, q.s) = record of the non-flow cell entered
+    // wall (on whatever level): (q.k, q.s) = record of the non-flow cell entered
     const float eps = q.k > 1.0f ? 1.0f : q.k;                 // Ray.cc:2594-2598
     sum = fmaf(eps * q.s, q.ePrev, sum);                       // 2602: NOT multiplied by fs
     const float intensity = q.ePrev * fs;

@@ -988,8 +988,9 @@ constexpr int SORT_BINS = 512;       // 9-bit keys: one length, or two lengths (
 // L1 keeping a sector until the ray's next step (23 KB per block = 187 KB per SM measured: L1 hit rate 46 % -> 8 %, solve 47 -> 59 ms).
 // RESORT adds state[RP * 32] x 48 B: the rays parked after their first leg.
 __host__ __device__ inline size_t sorted_scratch_bytes(int RP, bool resort) { return (size_t)RP * 32 * (resort ? 56 : 8); }
-// ONION: the 2-level Data Onion (Ray::rayTrace_dataOnion with two levels): origin cells on the fine level, rays march the blocked copy of
-// the patch's region of interest and go on in the blocked copy of level 0 (march_onion2_blk); bg = the ROI box, ob = both boxes.
+// ONION: the Data Onion (Ray::rayTrace_dataOnion, 2 to 4 levels): origin cells on the fine level, rays march the blocked copy of the
+// patch's region of interest and go on, level by level, in the blocked region boxes of the coarser levels (march_onion_blk); bg = the
+// ROI box, ob = all boxes.
 // RESORT (single level, rays that go on after their first wall: reflective walls, or hot black ones whose zero-weight second leg the
 // reference marches): the lanes of a warp wait for each other at the end of every leg, so a sort by whole-ray length does not keep them
 // busy (C5 at 256^3: 18 of 32 lanes).  Here the FIRST legs are sorted and marched as usual; a ray that goes on parks its state (48 B) and
@@ -1040,13 +1041,13 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
   const bool twoPart = ONION;
   const float nSum = (float)(g.n[0] + g.n[1] + g.n[2]);
   float scale1 = 63.0f / nSum, scale2 = 0.0f;
-  float rrx = 1.0f, rry = 1.0f, rrz = 1.0f;
-  if constexpr (ONION) {     // fine steps inside the ROI | coarse steps on level 0
-    const LevelGeom& gc = a.G.lev[0];
-    rrx = (float)g.rr[0]; rry = (float)g.rr[1]; rrz = (float)g.rr[2];
+  if constexpr (ONION) {     // fine steps inside the ROI | steps on the coarser levels
+    float nCoarse = 0.0f;
+    for (int l = 0; l < F; ++l) nCoarse += (float)((a.G.lev[l].regHi[0] - a.G.lev[l].regLo[0]) + (a.G.lev[l].regHi[1] - a.G.lev[l].regLo[1]) +
+                                                   (a.G.lev[l].regHi[2] - a.G.lev[l].regLo[2]) + 6);
     const float nRoi = (float)((a.G.roiHi[0] - a.G.roiLo[0]) + (a.G.roiHi[1] - a.G.roiLo[1]) + (a.G.roiHi[2] - a.G.roiLo[2]));
     scale1 = 15.0f / (0.6f * nRoi);
-    scale2 = 31.0f / (0.6f * (float)(gc.n[0] + gc.n[1] + gc.n[2]));
+    scale2 = 31.0f / (0.6f * nCoarse);
   }
   // exclusive scan over the bins in DESCENDING key order (thread t owns PER consecutive bins): hist[bin] = start of the bin in the
   // sorted list, ctl[1] = list length.  All threads; hist must be complete (a barrier before), is ready after the call.
@@ -1133,13 +1134,28 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
             const float tExit = fminf(fminf(fminf(nx_ / ax, ny_ / ay), nz_ / az), tThr);
             e1 = tExit * rate;
             if constexpr (ONION) {
-              // fine steps up to the ROI face, coarse steps (cells rr times larger) from there to the end
+              // fine steps up to the ROI face, then level by level to the face of that level's region (cells R times larger; level 0:
+              // to the wall)
               const float rx_ = (px ? (float)(a.G.roiHi[0] - g.lo[0]) - ci : ci - (float)(a.G.roiLo[0] - g.lo[0]) + 1.0f) - 0.5f;
               const float ry_ = (py ? (float)(a.G.roiHi[1] - g.lo[1]) - cj : cj - (float)(a.G.roiLo[1] - g.lo[1]) + 1.0f) - 0.5f;
               const float rz_ = (pz ? (float)(a.G.roiHi[2] - g.lo[2]) - ck : ck - (float)(a.G.roiLo[2] - g.lo[2]) + 1.0f) - 0.5f;
-              const float tRoi = fminf(fminf(fminf(rx_ / ax, ry_ / ay), rz_ / az), tExit);
-              e1 = tRoi * rate;
-              e2 = (tExit - tRoi) * (ax / rrx + ay / rry + az / rrz);
+              float tPrev = fminf(fminf(fminf(rx_ / ax, ry_ / ay), rz_ / az), tExit);
+              e1 = tPrev * rate;
+              float R0 = 1.0f, R1 = 1.0f, R2 = 1.0f;       // fine cells per cell of level l
+              for (int l = F - 1; l >= 0; --l) {
+                const LevelGeom& gu = a.G.lev[l + 1];
+                const LevelGeom& gl = a.G.lev[l];
+                R0 *= (float)gu.rr[0]; R1 *= (float)gu.rr[1]; R2 *= (float)gu.rr[2];
+                float tl = tExit;
+                if (l > 0) {      // faces of the region of level l, in fine cells from the fine level's low corner (same anchor)
+                  const float q0 = px ? (float)gl.regHi[0] * R0 - (float)g.lo[0] - (ci + 0.5f) : (ci + 0.5f) - ((float)gl.regLo[0] * R0 - (float)g.lo[0]);
+                  const float q1 = py ? (float)gl.regHi[1] * R1 - (float)g.lo[1] - (cj + 0.5f) : (cj + 0.5f) - ((float)gl.regLo[1] * R1 - (float)g.lo[1]);
+                  const float q2 = pz ? (float)gl.regHi[2] * R2 - (float)g.lo[2] - (ck + 0.5f) : (ck + 0.5f) - ((float)gl.regLo[2] * R2 - (float)g.lo[2]);
+                  tl = fminf(fminf(fminf(q0 / ax, q1 / ay), q2 / az), tExit);
+                }
+                e2 += fmaxf(tl - tPrev, 0.0f) * (ax / R0 + ay / R1 + az / R2);
+                tPrev = fmaxf(tPrev, tl);
+              }
             }
             int key;
             if (twoPart) key = (min(15, (int)(e1 * scale1 + 0.5f)) << 5) | min(31, (int)(e2 * scale2 + 0.5f));
@@ -1297,7 +1313,7 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
             gen_divq_ray_f32(a.rng, g, ray0 + r, cid, cid, dir, rayDx);
             float sumI;
             if constexpr (ONION)
-              sumI = march_onion2_blk<MAXL>(a.G, ob, ijk[c * 3 + 0] + g.lo[0], ijk[c * 3 + 1] + g.lo[1], ijk[c * 3 + 2] + g.lo[2], rw0,
+              sumI = march_onion_blk<MAXL>(a.G, ob, ijk[c * 3 + 0] + g.lo[0], ijk[c * 3 + 1] + g.lo[1], ijk[c * 3 + 2] + g.lo[2], rw0,
                                             nz<float, float>(dir[0]), nz<float, float>(dir[1]), nz<float, float>(dir[2]), rayDx[0], rayDx[1],
                                             rayDx[2], (float)a.threshold, a.allowReflect != 0, skipZero, steps);
             else
@@ -2216,6 +2232,7 @@ struct rmcrt_ctx {
   int lhcKeyDivQ[4] = {0, 0, 0, 0};   // (nRays, sumLo, rows, mode) the tables were built for
   int lhcKeyFlux[4] = {0, 0, 0, 0};
   DevBuf outVR[2];                    // host-API radiometer output staging
+  DevBuf regionBuf[MAXL];             // Data Onion: blocked region boxes of the levels between 0 and the fine one
   DevBuf sortScratch;                 // divq_sorted_kernel: tile counter + per-block res / ids / keys
   DevBuf replSend, replGathered;      // rmcrt_replicate_level: this device's packed slab / the gathered slabs of all devices
   std::string err;
@@ -2527,12 +2544,37 @@ bool blocked_default(const rmcrt_ctx* ctx, const TraceArgs& a, bool ML) {
 }
 
 // ... and the 2-level Data Onion: the same kernel on blocked copies of the patch's ROI and of level 0 (divq_sorted_kernel<ONION>)
+// Boxes of the levels above 0 that the Data-Onion march copies verbatim: the fine level's ROI, a coarser level's region, each with the
+// level's extra cells where it ends at the domain boundary.
+void onion_copy_box(const rmcrt_ctx* ctx, const TraceArgs& a, int L, int lo[3], int hi[3]) {
+  const int F = a.G.maxLevels - 1;
+  const rmcrt_level_desc& d = ctx->lv[L].d;
+  for (int k = 0; k < 3; ++k) {
+    // (a cell outside the box but not inside the domain is a wall of THIS level, not a jump: `inDomain`, Ray.cc:2486-2493)
+    const int rlo = L == F ? a.G.roiLo[k] : a.G.lev[L].regLo[k], rhi = L == F ? a.G.roiHi[k] : a.G.lev[L].regHi[k];
+    lo[k] = rlo <= d.interiorLo[k] ? d.lo[k] : rlo;
+    hi[k] = rhi >= d.interiorHi[k] ? d.hi[k] : rhi;
+  }
+}
 bool onion_blocked_default(const rmcrt_ctx* ctx, const TraceArgs& a, bool ML) {
-  if (!ML || a.G.maxLevels != 2 || !ctx->p.solveDivQ || ctx->p.marchPrecision != 0 || ctx->p.rayCoherence != 0 || ctx->p.blockedMarch != 3 ||
-      ctx->p.genericMarch) return false;
+  if (!ML || a.G.maxLevels < 2 || a.G.maxLevels > ONION_MAXL || !ctx->p.solveDivQ || ctx->p.marchPrecision != 0 || ctx->p.rayCoherence != 0 ||
+      ctx->p.blockedMarch != 3 || ctx->p.genericMarch) return false;
   if (!ctx->p.isSeedRandom || ctx->p.fixedRandom || ctx->p.rayDirSampleAlgo != 0) return false;
   for (int d = 0; d < 3; ++d)      // the patch lies inside the ROI (a fixed / dynamic ROI need not contain it)
     if (!(a.G.roiLo[d] <= a.patchLo[d] && a.patchLo[d] + a.patchN[d] <= a.G.roiHi[d])) return false;
+  // a ray that leaves the box of level L through an interior cell must land INSIDE the box of level L - 1 (the march tests "marker cell",
+  // the reference the stepped axis only: the same thing as long as every jump ends inside the next box)
+  for (int L = a.G.maxLevels - 1; L >= 2; --L) {
+    int lo[3], hi[3], clo[3], chi[3];
+    onion_copy_box(ctx, a, L, lo, hi);
+    onion_copy_box(ctx, a, L - 1, clo, chi);
+    const rmcrt_level_desc& d = ctx->lv[L].d;
+    for (int k = 0; k < 3; ++k) {
+      const int rr = d.refineRatio[k] > 0 ? d.refineRatio[k] : 1;
+      if (lo[k] - 1 >= d.interiorLo[k] && map_coarser_host(lo[k] - 1, rr) < clo[k]) return false;
+      if (hi[k] < d.interiorHi[k] && map_coarser_host(hi[k], rr) >= chi[k]) return false;
+    }
+  }
   return true;
 }
 
@@ -2641,34 +2683,44 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
     bool patchInRoi = true;       // a fixed ROI need not contain the patch; the ROI-copy fast path starts every ray inside the copy
     for (int d = 0; d < 3 && ML; ++d) patchInRoi = patchInRoi && a.G.roiLo[d] <= a.patchLo[d] && a.patchLo[d] + a.patchN[d] <= a.G.roiHi[d];
     if (onion_blocked_default(ctx, a, ML)) {
-      // 2-level Data Onion, default sampling: length-sorted rays on blocked copies of the patch's ROI (marker shell) and of level 0
+      // Data Onion, default sampling: length-sorted rays on blocked copies -- level 0 whole, every level above it the box the rays can
+      // visit (ROI / region) wrapped in marker cells
       if constexpr (std::is_same<Real, float>::value && !std::is_same<RecT, Rec16>::value) {
-        const LevelState& fl = ctx->lv[1];
-        Box roiBox;
-        int nbk[3], rlo[3];
-        long long nBlocks = 1;
-        for (int d = 0; d < 3; ++d) {
-          roiBox.lo[d] = a.G.roiLo[d]; roiBox.n[d] = a.G.roiHi[d] - a.G.roiLo[d];
-          rlo[d] = roiBox.lo[d] - 1 - 2;                       // shell, then one guard block
-          nbk[d] = (roiBox.n[d] + 2 + 4 + 1) / 2;
-          nBlocks *= nbk[d];
+        const int F = a.G.maxLevels - 1;
+        OnionBlk ob;
+        memset(&ob, 0, sizeof ob);
+        size_t fineBytes = 0;
+        for (int L = F; L >= 1; --L) {
+          const LevelState& ls = ctx->lv[L];
+          int lo[3], hi[3], nbk[3];
+          onion_copy_box(ctx, a, L, lo, hi);
+          Box box;
+          long long nBlocks = 1;
+          for (int d = 0; d < 3; ++d) {
+            box.lo[d] = lo[d]; box.n[d] = hi[d] - lo[d];
+            ob.lo[L][d] = lo[d] - 1 - 2;                         // marker shell, then one guard block
+            nbk[d] = (box.n[d] + 2 + 4 + 1) / 2;
+            nBlocks *= nbk[d];
+          }
+          if (nBlocks >= (1LL << 28)) return fail(ctx, RMCRT_ERR_INVALID, "ROI too large");
+          DevBuf& buf = L == F ? ctx->roiBuf : ctx->regionBuf[L];
+          if (buf.ensure((size_t)nBlocks * 32)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc ROI buffer");
+          roi_blk_build_kernel<RecT><<<grid_for(nBlocks, 256, ctx->smCount), 256, 0, st>>>(
+              static_cast<const RecT*>(ls.rec), mkbox(ls.d.lo, ls.d.hi), static_cast<uint32_t*>(buf.p), nbk[0], nbk[1], nbk[2], ob.lo[L][0],
+              ob.lo[L][1], ob.lo[L][2], box);
+          CK(cudaGetLastError());
+          ob.blk[L] = static_cast<const uint32_t*>(buf.p); ob.bx[L] = nbk[0]; ob.bxy[L] = nbk[0] * nbk[1];
+          if (L == F) fineBytes = (size_t)nBlocks * 32;
         }
-        if (nBlocks >= (1LL << 28)) return fail(ctx, RMCRT_ERR_INVALID, "ROI too large");
-        if (ctx->roiBuf.ensure((size_t)nBlocks * 32)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc ROI buffer");
-        roi_blk_build_kernel<RecT><<<grid_for(nBlocks, 256, ctx->smCount), 256, 0, st>>>(
-            static_cast<const RecT*>(fl.rec), mkbox(fl.d.lo, fl.d.hi), static_cast<uint32_t*>(ctx->roiBuf.p), nbk[0], nbk[1], nbk[2], rlo[0], rlo[1],
-            rlo[2], roiBox);
-        CK(cudaGetLastError());
         BlkGeom bgC;
         int rc = ensure_blocked_level<RecT>(ctx, 0, bgC, st, false);
         if (rc) return rc;
-        persist_in_l2(ctx, ctx->roiBuf.p, (size_t)nBlocks * 32, st);
-        BlkGeom bg;
-        bg.blk = static_cast<const uint32_t*>(ctx->roiBuf.p); bg.bx = nbk[0]; bg.bxy = nbk[0] * nbk[1];
-        OnionBlk ob;
-        ob.roi = bg.blk; ob.rbx = bg.bx; ob.rbxy = bg.bxy;
-        ob.coarse = bgC.blk; ob.cbx = bgC.bx; ob.cbxy = bgC.bxy;
-        for (int d = 0; d < 3; ++d) { bg.lo[d] = rlo[d]; ob.rlo[d] = rlo[d]; ob.clo[d] = bgC.lo[d]; }
+        ob.blk[0] = bgC.blk; ob.bx[0] = bgC.bx; ob.bxy[0] = bgC.bxy;
+        for (int d = 0; d < 3; ++d) ob.lo[0][d] = bgC.lo[d];
+        persist_in_l2(ctx, ctx->roiBuf.p, fineBytes, st);
+        BlkGeom bg;      // the box of the origin cells
+        bg.blk = ob.blk[F]; bg.bx = ob.bx[F]; bg.bxy = ob.bxy[F];
+        for (int d = 0; d < 3; ++d) bg.lo[d] = ob.lo[F][d];
         const int RP = std::min(a.nRays, ctx->p.refillLanes > 0 ? ctx->p.refillLanes : 256);
         const int nb = (int)std::min<long long>(a.nTiles, (long long)ctx->smCount * (ctx->p.maxBlocksPerSM > 0 ? ctx->p.maxBlocksPerSM : RMCRT_SORTED_BLOCKS));
         if (ctx->sortScratch.ensure((size_t)nb * sorted_scratch_bytes(RP, false) + 256)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc sort scratch");
@@ -2682,8 +2734,10 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
       const LevelState& fl = ctx->lv[1];
       Box roiBox, shell;
       long long cellsB = 1;
+      int cbLo[3], cbHi[3];
+      onion_copy_box(ctx, a, 1, cbLo, cbHi);      // the ROI plus the level's extra cells where it ends at the domain boundary
       for (int d = 0; d < 3; ++d) {
-        roiBox.lo[d] = a.G.roiLo[d]; roiBox.n[d] = a.G.roiHi[d] - a.G.roiLo[d];
+        roiBox.lo[d] = cbLo[d]; roiBox.n[d] = cbHi[d] - cbLo[d];
         shell.lo[d] = roiBox.lo[d] - 1; shell.n[d] = roiBox.n[d] + 2;
         cellsB *= shell.n[d];
       }
@@ -2756,11 +2810,13 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
         TraceArgs a2 = a;
         a2.gate = mayGoOn ? 1 : 0;
         CK(cudaMemsetAsync(tileCounter, 0, sizeof(int), st));
-        divq_sorted_kernel<RecT, false, false><<<nb, 256, 0, st>>>(a2, bg, OnionBlk{}, RP, base + 256, tileCounter);
+        OnionBlk none;
+        memset(&none, 0, sizeof none);
+        divq_sorted_kernel<RecT, false, false><<<nb, 256, 0, st>>>(a2, bg, none, RP, base + 256, tileCounter);
         if (mayGoOn) {
           a2.gate = 2;
           CK(cudaMemsetAsync(tileCounter, 0, sizeof(int), st));
-          divq_sorted_kernel<RecT, false, true><<<nb, 256, 0, st>>>(a2, bg, OnionBlk{}, RP, base + 256, tileCounter);
+          divq_sorted_kernel<RecT, false, true><<<nb, 256, 0, st>>>(a2, bg, none, RP, base + 256, tileCounter);
         }
       }
     } else if (ctx->p.blockedMarch == 2 && blocked_default(ctx, a, ML)) {
@@ -3044,6 +3100,7 @@ void rmcrt_destroy(rmcrt_ctx* ctx) {
   ctx->lhcDivQ.release(); ctx->lhcFlux.release(); ctx->outVR[0].release(); ctx->outVR[1].release();
   for (auto& b : ctx->dbg) b.release();
   ctx->replSend.release(); ctx->replGathered.release(); ctx->sortScratch.release();
+  for (auto& b : ctx->regionBuf) b.release();
   delete ctx;
 }
 
