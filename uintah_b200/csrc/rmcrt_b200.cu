@@ -967,21 +967,26 @@ __global__ void __launch_bounds__(256, RMCRT_FAST_MIN_BLOCKS) divq_blk_kernel(co
 }
 
 //======================================================================================================
-// blockedMarch = 3: LENGTH-SORTED independent rays on the blocked copy.  Same rays as divq_kernel / divq_blk_kernel (Philox keyed on
-// (cell, ray, timestep)), but the lanes of a warp no longer trace ray r of 32 neighbouring cells -- whose lengths differ by the full
-// range (13.4 of 32 lanes active, ncu) -- they trace 32 rays of the tile that are expected to END TOGETHER:
-//   1. every (cell, ray) of the tile's 32 cells x RP rays gets an 8-bit key = the number of DDA steps to the far side of the level along
+// blockedMarch = 3 (the library default): LENGTH-SORTED independent rays on the blocked copy.  Same rays as divq_kernel / divq_blk_kernel
+// (Philox keyed on (cell, ray, timestep)), but the lanes of a warp no longer trace ray r of 32 neighbouring cells -- whose lengths differ
+// by the full range (13.4 of 32 lanes active, ncu) -- they trace 32 rays of the tile that are expected to END TOGETHER:
+//   0. persistent blocks of 8 warps take tiles of 32 x-consecutive origin cells off a counter;
+//   1. every (cell, ray) of the tile's 32 cells x RP rays gets a 9-bit key from the number of DDA steps to the far side of the level along
 //      its direction (closed form from the direction and the cell index, ~15 FP instructions; walls inside the domain and the intensity
 //      threshold make it an estimate -- correctness never depends on it);
-//   2. a counting sort in shared memory (histogram, scan, scatter) orders the rays by key, longest first;
+//   2. a counting sort (histogram in shared memory, scan, scatter of the ray ids into global scratch) orders the rays, longest first;
 //   3. warps take chunks of 32 consecutive rays off that list (dynamic hand-out: longest chunks first, so the warps of a block end
-//      together), regenerate each ray from its Philox counter and march it (march_single_level_blk);
-//   4. each ray's sum is written to res[ray][cell] in shared memory and the rays of a cell are added in RAY ORDER in FP64 -- the result
-//      does not depend on the sort, the hand-out or the number of warps, bit for bit.
+//      together), regenerate each ray from its Philox counter and march it (march_single_level_blk / march_onion_blk);
+//   4. each ray's sum is written to res[ray][cell] (global scratch) and the rays of a cell are added in RAY ORDER in FP64 -- the result
+//      does not depend on the sort, the hand-out, the rays per pass or the patch layout, bit for bit.
 //======================================================================================================
 #ifndef RMCRT_SORTED_BLOCKS
 #define RMCRT_SORTED_BLOCKS 4
 #endif
+#ifndef RMCRT_RESORT_ROUNDS
+#define RMCRT_RESORT_ROUNDS 4      // RESORT: rounds of one leg each before whatever is left runs to its end
+#endif
+constexpr int RESORT_ROUNDS = RMCRT_RESORT_ROUNDS;
 constexpr int SORT_BINS = 512;       // 9-bit keys: one length, or two lengths (first leg: 4 bits | rest: 5 bits)
 // per-block scratch in GLOBAL memory (L2-resident, accessed with .cg so it never takes L1 lines from the records): res[RP][32] f32 |
 // ids[RP * 32] u16 | keys[RP * 32] u16.  Shared memory would do, but every KB of it comes out of the SM's L1, and the march lives on the
@@ -1025,7 +1030,6 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
   const int sy8 = 8 * bg.bx, sz8 = 8 * bg.bxy;
   const float cx = (float)g.dx[0], cy = (float)g.dx[1], cz = (float)g.dx[2];
   const float icx = 1.0f / cx, icy = 1.0f / cy, icz = 1.0f / cz;
-  // a ray crosses at most n[0] + n[1] + n[2] cells of the level before it leaves it
   // faces that do not end a ray: allowReflect and no absorbing cell on the face (finalize_kernel); an unfinalized level has none
   const unsigned* ls = a.lstat + (ONION ? 0 : F) * LSTAT_WORDS;      // (Data Onion: rays end on level 0)
   const unsigned mirrors = (a.allowReflect && ls[3] != 0u && ls[6] != 0u) ? (~ls[7] & 63u) : 0u;
@@ -1176,84 +1180,110 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
       }
       __syncthreads();
       if constexpr (RESORT) {
-        // ---- phase 3a: FIRST legs, longest first; rays that go on are parked with a key for what is left of them
-        for (int q4 = tid; q4 < SORT_BINS; q4 += 256) hist[q4] = 0;
-        __syncthreads();
-        const int nList = ctl[1];
+        // ---- phase 3, in ROUNDS of one leg: round 0 marches the first legs (the list phase 2 sorted); a ray that goes on is parked with a
+        // key for what is left of it; the parked rays are sorted and marched for their next leg, and so on until none is left (a weightless
+        // ray ends at its next wall; with mirrors a few per cent of the rays see a fourth round)
         const float thr = (float)a.threshold;
-        for (;;) {
-          int chunk = 0;
-          if (lane == 0) chunk = atomicAdd(&ctl[0], 1);
-          chunk = __shfl_sync(0xffffffffu, chunk, 0);
-          if (chunk * 32 >= nList) break;
-          const int p = chunk * 32 + lane;
-          if (p < nList) {
-            const int id = __ldcg(ids + p);
-            const int c = id & 31, r = id >> 5;
-            const int rw0 = w0s[c];
-            const unsigned long long cid = cellIds[c];
-            float dir[3], rayDx[3];
-            gen_divq_ray_f32(a.rng, g, ray0 + r, cid, cid, dir, rayDx);
-            unsigned short key2 = 0xFFFFu;
-            float out = 0.0f;
-            if (1.0f > thr) {
+        typedef Num<float> N;
+        // park: state of a ray standing reflected in d.idx + the key of its remaining legs, followed through the empty box from the cell
+        // it stands in (decoded from its word index)
+        auto park = [&](const BlkRay& ry, int id, const float (&dir)[3]) {
+          parked[id * 3 + 0] = make_uint4(__float_as_uint(ry.d.tx), __float_as_uint(ry.d.ty), __float_as_uint(ry.d.tz), (unsigned)ry.d.idx);
+          parked[id * 3 + 1] = make_uint4((unsigned)ry.b.dlx, (unsigned)ry.b.dly, (unsigned)ry.b.dlz, __float_as_uint(ry.q.A));
+          parked[id * 3 + 2] = make_uint4(__float_as_uint(ry.q.ePrev), __float_as_uint(ry.q.nsteps), __float_as_uint(ry.sum), __float_as_uint(ry.fs));
+          int B = ry.d.idx >> 3;
+          const int bz_ = B / bg.bxy; B -= bz_ * bg.bxy;
+          const int by_ = B / bg.bx, bx_ = B - by_ * bg.bx;
+          float p0 = (float)(2 * bx_ + (ry.d.idx & 1) + bg.lo[0] - g.lo[0]) + 0.5f;
+          float p1 = (float)(2 * by_ + ((ry.d.idx >> 1) & 1) + bg.lo[1] - g.lo[1]) + 0.5f;
+          float p2 = (float)(2 * bz_ + ((ry.d.idx >> 2) & 1) + bg.lo[2] - g.lo[2]) + 0.5f;
+          const float ax = fabsf(dir[0]) * icx + 1e-30f, ay = fabsf(dir[1]) * icy + 1e-30f, az = fabsf(dir[2]) * icz + 1e-30f;
+          bool s0 = ry.b.dlx > 0, s1 = ry.b.dly > 0, s2 = ry.b.dlz > 0, dead = ry.fs == 0.0f;
+          const bool deadAtStart = dead;
+          float tTot = 0.0f, tFirst = 0.0f;
+          for (int bnc = 0; bnc < goOn; ++bnc) {
+            const float t0 = (s0 ? (float)(g.n[0] - 1) - p0 : p0 - 1.0f) / ax;
+            const float t1 = (s1 ? (float)(g.n[1] - 1) - p1 : p1 - 1.0f) / ay;
+            const float t2 = (s2 ? (float)(g.n[2] - 1) - p2 : p2 - 1.0f) / az;
+            const float t = fmaxf(fminf(fminf(t0, t1), t2), 0.0f);
+            const int axh = (t0 <= t1 && t0 <= t2) ? 0 : (t1 <= t2 ? 1 : 2);
+            tTot += t;
+            if (bnc == 0) tFirst = tTot;
+            p0 += (s0 ? t : -t) * ax; p1 += (s1 ? t : -t) * ay; p2 += (s2 ? t : -t) * az;
+            const unsigned face = 2u * axh + ((axh == 0 ? s0 : (axh == 1 ? s1 : s2)) ? 1u : 0u);
+            if (dead) break;                      // a weightless ray ends at its next wall of any kind (intensity 0)
+            if (!((mirrors >> face) & 1u)) {      // an absorbing face: the weight is gone, the ray is not
+              if (skipZero) break;
+              dead = true;
+            }
+            if (axh == 0) s0 = !s0; else if (axh == 1) s1 = !s1; else s2 = !s2;
+          }
+          const float rate = ax + ay + az;
+          // weightless rays: ONE leg, 8 bits of length, upper half of the key space; the others (next leg: 3 bits | rest: 5 bits)
+          unsigned short key2;
+          if (deadAtStart) key2 = (unsigned short)(256 + min(255, (int)(tTot * rate * (255.0f / nSum) + 0.5f)));
+          else key2 = (unsigned short)((min(7, (int)(tFirst * rate * (7.0f / (0.6f * nSum)) + 0.5f)) << 5) |
+                                       min(31, (int)((tTot - tFirst) * rate * (31.0f / (1.2f * nSum)) + 0.5f)));
+          atomicAdd(&hist[key2], 1);
+          __stcg(keys + id, key2);
+        };
+        for (int round = 0;; ++round) {
+          // (hist: the bin positions of the list being marched are no longer needed; it collects the keys of the rays parked in this round)
+          const int nList = ctl[1];
+          __syncthreads();
+          for (int q4 = tid; q4 < SORT_BINS; q4 += 256) hist[q4] = 0;
+          __syncthreads();
+          for (;;) {
+            int chunk = 0;
+            if (lane == 0) chunk = atomicAdd(&ctl[0], 1);
+            chunk = __shfl_sync(0xffffffffu, chunk, 0);
+            if (chunk * 32 >= nList) break;
+            const int p = chunk * 32 + lane;
+            if (p < nList) {
+              const int id = __ldcg(ids + p);
+              const int c = id & 31, r = id >> 5;
+              const unsigned long long cid = cellIds[c];
+              float dir[3], rayDx[3];
+              gen_divq_ray_f32(a.rng, g, ray0 + r, cid, cid, dir, rayDx);
               BlkRay ry;
               float ddx, ddy, ddz;
-              blk_ray_start(ry, blk, rw0, (unsigned)(rw0 & 7), sy8, sz8, nz<float, float>(dir[0]), nz<float, float>(dir[1]),
-                            nz<float, float>(dir[2]), rayDx[0], rayDx[1], rayDx[2], cx, cy, cz, ddx, ddy, ddz);
-              if (blk_ray_legs(ry, blk, ddx, ddy, ddz, sy8, sz8, thr, a.allowReflect != 0, skipZero, 1)) {
-                out = UNSCALE * ry.sum;
-                steps += (unsigned)ry.q.nsteps;
-              } else {
-                parked[id * 3 + 0] = make_uint4(__float_as_uint(ry.d.tx), __float_as_uint(ry.d.ty), __float_as_uint(ry.d.tz), (unsigned)ry.d.idx);
-                parked[id * 3 + 1] = make_uint4((unsigned)ry.b.dlx, (unsigned)ry.b.dly, (unsigned)ry.b.dlz, __float_as_uint(ry.q.A));
-                parked[id * 3 + 2] = make_uint4(__float_as_uint(ry.q.ePrev), __float_as_uint(ry.q.nsteps), __float_as_uint(ry.sum), __float_as_uint(ry.fs));
-                // what is left: follow the bounces from the cell the ray stands in (decoded from its word index)
-                int B = ry.d.idx >> 3;
-                const int bz_ = B / bg.bxy; B -= bz_ * bg.bxy;
-                const int by_ = B / bg.bx, bx_ = B - by_ * bg.bx;
-                float p0 = (float)(2 * bx_ + (ry.d.idx & 1) + bg.lo[0] - g.lo[0]) + 0.5f;
-                float p1 = (float)(2 * by_ + ((ry.d.idx >> 1) & 1) + bg.lo[1] - g.lo[1]) + 0.5f;
-                float p2 = (float)(2 * bz_ + ((ry.d.idx >> 2) & 1) + bg.lo[2] - g.lo[2]) + 0.5f;
-                const float ax = fabsf(dir[0]) * icx + 1e-30f, ay = fabsf(dir[1]) * icy + 1e-30f, az = fabsf(dir[2]) * icz + 1e-30f;
-                bool s0 = ry.b.dlx > 0, s1 = ry.b.dly > 0, s2 = ry.b.dlz > 0, dead = ry.fs == 0.0f;
-                const bool deadAtStart = dead;
-                float tTot = 0.0f, tFirst = 0.0f;
-                for (int bnc = 0; bnc < goOn; ++bnc) {
-                  const float t0 = (s0 ? (float)(g.n[0] - 1) - p0 : p0 - 1.0f) / ax;
-                  const float t1 = (s1 ? (float)(g.n[1] - 1) - p1 : p1 - 1.0f) / ay;
-                  const float t2 = (s2 ? (float)(g.n[2] - 1) - p2 : p2 - 1.0f) / az;
-                  const float t = fmaxf(fminf(fminf(t0, t1), t2), 0.0f);
-                  const int axh = (t0 <= t1 && t0 <= t2) ? 0 : (t1 <= t2 ? 1 : 2);
-                  tTot += t;
-                  if (bnc == 0) tFirst = tTot;
-                  p0 += (s0 ? t : -t) * ax; p1 += (s1 ? t : -t) * ay; p2 += (s2 ? t : -t) * az;
-                  const unsigned face = 2u * axh + ((axh == 0 ? s0 : (axh == 1 ? s1 : s2)) ? 1u : 0u);
-                  if (dead) break;                      // a weightless ray ends at its next wall of any kind (intensity 0)
-                  if (!((mirrors >> face) & 1u)) {
-                    if (skipZero) break;
-                    dead = true;
-                  }
-                  if (axh == 0) s0 = !s0; else if (axh == 1) s1 = !s1; else s2 = !s2;
+              bool done = true;
+              ry.sum = 0.0f; ry.q.nsteps = 0.0f;
+              if (round == 0) {
+                if (1.0f > thr) {
+                  const int rw0 = w0s[c];
+                  blk_ray_start(ry, blk, rw0, (unsigned)(rw0 & 7), sy8, sz8, nz<float, float>(dir[0]), nz<float, float>(dir[1]),
+                                nz<float, float>(dir[2]), rayDx[0], rayDx[1], rayDx[2], cx, cy, cz, ddx, ddy, ddz);
+                  done = blk_ray_legs(ry, blk, ddx, ddy, ddz, sy8, sz8, thr, a.allowReflect != 0, skipZero, 1);
                 }
-                const float rate = ax + ay + az;
-                // weightless rays: one leg, 8 bits of length, upper half of the key space; the others (leg: 3 bits | rest: 5 bits)
-                if (deadAtStart) key2 = (unsigned short)(256 + min(255, (int)(tTot * rate * (255.0f / nSum) + 0.5f)));
-                else key2 = (unsigned short)((min(7, (int)(tFirst * rate * (7.0f / (0.6f * nSum)) + 0.5f)) << 5) |
-                                             min(31, (int)((tTot - tFirst) * rate * (31.0f / (1.2f * nSum)) + 0.5f)));
-                atomicAdd(&hist[key2], 1);
+              } else {
+                ddx = fabsf(N::rcp(nz<float, float>(dir[0]))) * cx * N::LEN_SCALE;
+                ddy = fabsf(N::rcp(nz<float, float>(dir[1]))) * cy * N::LEN_SCALE;
+                ddz = fabsf(N::rcp(nz<float, float>(dir[2]))) * cz * N::LEN_SCALE;
+                const uint4 v0 = __ldcg(parked + id * 3 + 0), v1 = __ldcg(parked + id * 3 + 1), v2 = __ldcg(parked + id * 3 + 2);
+                ry.d.tx = __uint_as_float(v0.x); ry.d.ty = __uint_as_float(v0.y); ry.d.tz = __uint_as_float(v0.z); ry.d.idx = (int)v0.w;
+                ry.b.dlx = (int)v1.x; ry.b.dly = (int)v1.y; ry.b.dlz = (int)v1.z;
+                blk_decode(ry.q, __ldg(blk + ry.d.idx));
+                ry.q.A = __uint_as_float(v1.w); ry.q.ePrev = __uint_as_float(v2.x); ry.q.nsteps = __uint_as_float(v2.y);
+                ry.q.tau = 0.0f; ry.q.leg = 0.0f;
+                ry.sum = __uint_as_float(v2.z); ry.fs = __uint_as_float(v2.w);
+                // (after RESORT_ROUNDS rounds whatever is left runs to its end in the company it has)
+                done = blk_ray_legs(ry, blk, ddx, ddy, ddz, sy8, sz8, thr, a.allowReflect != 0, skipZero, round < RESORT_ROUNDS ? 1 : 0x7fffffff);
+              }
+              if (done) {
+                steps += (unsigned)ry.q.nsteps;
+                __stcg(res + id, UNSCALE * ry.sum);
+                __stcg(keys + id, (unsigned short)0xFFFFu);
+              } else {
+                park(ry, id, dir);
               }
             }
-            __stcg(keys + id, key2);
-            __stcg(res + id, out);
           }
-        }
-        __syncthreads();
-        // ---- phase 3b: the parked rays, sorted again, to their end
-        scan_bins();
-        const int nParked = ctl[1];
-        if (tid == 0) ctl[0] = 0;
-        if (nParked > 0) {
+          __syncthreads();
+          // the rays parked in this round -> the next round's sorted list
+          scan_bins();
+          if (tid == 0) ctl[0] = 0;
+          if (ctl[1] == 0) break;
           if (cw0 >= 0)
             for (int r = warp; r < nr; r += W) {
               const unsigned short k2 = __ldcg(keys + r * 32 + lane);
@@ -1263,35 +1293,6 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
               }
             }
           __syncthreads();
-          for (;;) {
-            int chunk = 0;
-            if (lane == 0) chunk = atomicAdd(&ctl[0], 1);
-            chunk = __shfl_sync(0xffffffffu, chunk, 0);
-            if (chunk * 32 >= nParked) break;
-            const int p = chunk * 32 + lane;
-            if (p < nParked) {
-              const int id = __ldcg(ids + p);
-              const int c = id & 31, r = id >> 5;
-              const unsigned long long cid = cellIds[c];
-              float dir[3], rayDx[3];
-              gen_divq_ray_f32(a.rng, g, ray0 + r, cid, cid, dir, rayDx);
-              typedef Num<float> N;
-              const float ddx = fabsf(N::rcp(nz<float, float>(dir[0]))) * cx * N::LEN_SCALE;
-              const float ddy = fabsf(N::rcp(nz<float, float>(dir[1]))) * cy * N::LEN_SCALE;
-              const float ddz = fabsf(N::rcp(nz<float, float>(dir[2]))) * cz * N::LEN_SCALE;
-              const uint4 v0 = __ldcg(parked + id * 3 + 0), v1 = __ldcg(parked + id * 3 + 1), v2 = __ldcg(parked + id * 3 + 2);
-              BlkRay ry;
-              ry.d.tx = __uint_as_float(v0.x); ry.d.ty = __uint_as_float(v0.y); ry.d.tz = __uint_as_float(v0.z); ry.d.idx = (int)v0.w;
-              ry.b.dlx = (int)v1.x; ry.b.dly = (int)v1.y; ry.b.dlz = (int)v1.z;
-              blk_decode(ry.q, __ldg(blk + ry.d.idx));
-              ry.q.A = __uint_as_float(v1.w); ry.q.ePrev = __uint_as_float(v2.x); ry.q.nsteps = __uint_as_float(v2.y);
-              ry.q.tau = 0.0f; ry.q.leg = 0.0f;
-              ry.sum = __uint_as_float(v2.z); ry.fs = __uint_as_float(v2.w);
-              blk_ray_legs(ry, blk, ddx, ddy, ddz, sy8, sz8, thr, a.allowReflect != 0, skipZero, 0x7fffffff);
-              steps += (unsigned)ry.q.nsteps;
-              __stcg(res + id, UNSCALE * ry.sum);
-            }
-          }
         }
         __syncthreads();
       } else {
