@@ -22,3 +22,36 @@ inline float __frcp_rn(float a) { return 1.0f / a; }
 inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
 using std::min;
 using std::max;
+// fp16 <-> fp32 (IEEE binary16, round to nearest even) for the half-packed words of the blocked march
+inline float half_bits_to_float(unsigned short h) {
+  const unsigned sign = (unsigned)(h >> 15) << 31, ex = (h >> 10) & 31u, man = h & 1023u;
+  unsigned u;
+  if (ex == 0) {
+    if (man == 0) u = sign;
+    else { int e = -1; unsigned m = man; do { ++e; m <<= 1; } while (!(m & 1024u)); u = sign | ((unsigned)(127 - 15 - e) << 23) | ((m & 1023u) << 13); }
+  } else if (ex == 31) u = sign | 0x7F800000u | (man << 13);
+  else u = sign | ((ex + 112u) << 23) | (man << 13);
+  float f; std::memcpy(&f, &u, 4); return f;
+}
+inline unsigned short float_to_half_bits(float f) {
+  unsigned u; std::memcpy(&u, &f, 4);
+  const unsigned sign = (u >> 16) & 0x8000u;
+  const int ex = (int)((u >> 23) & 255u) - 127 + 15;
+  unsigned man = u & 0x7FFFFFu;
+  if (((u >> 23) & 255u) == 255u) return (unsigned short)(sign | 0x7C00u | (man ? 0x200u : 0u));
+  if (ex >= 31) return (unsigned short)(sign | 0x7C00u);
+  if (ex <= 0) {
+    if (ex < -10) return (unsigned short)sign;
+    man |= 0x800000u;
+    const int shift = 14 - ex;
+    unsigned r = man >> shift;
+    const unsigned rem = man & ((1u << shift) - 1u), half = 1u << (shift - 1);
+    if (rem > half || (rem == half && (r & 1u))) ++r;
+    return (unsigned short)(sign | r);
+  }
+  unsigned r = ((unsigned)ex << 10) | (man >> 13);
+  const unsigned rem = man & 0x1FFFu;
+  if (rem > 0x1000u || (rem == 0x1000u && (r & 1u))) ++r;
+  return (unsigned short)(sign | r);
+}
+inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }

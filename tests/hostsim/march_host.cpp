@@ -3,6 +3,7 @@
 #include <vector>
 #include "../../uintah_b200/csrc/march.cuh"
 #include "../../uintah_b200/csrc/rng.cuh"
+#include "../../uintah_b200/csrc/indep.cuh"
 using namespace rmcrt;
 
 extern "C" {
@@ -257,6 +258,135 @@ void hs_trace_DO2_quad(const HsLevel* lv, const int* roiLo, const int* roiHi, co
                                (float)threshold, allowReflect != 0, skipZero != 0, st, 8, sm);
     for (int q = 0; q < 4; ++q) sums[4 * t + q] = sm[q];
     steps[t] = st;
+  }
+}
+
+// ---- the default solve's march: blocked half-packed copy (blk_build_kernel) + march_leg_blk / BlkRay (indep.cuh)
+static void blk_build_host(const HsLevel& g, std::vector<uint32_t>& blk, BlkGeom& bg) {
+  const Rec8* recs = static_cast<const Rec8*>(g.rec);
+  int n[3], nb[3];
+  for (int d = 0; d < 3; ++d) { n[d] = g.hi[d] - g.lo[d]; nb[d] = (n[d] + 4 + 1) / 2; bg.lo[d] = g.lo[d] - 2; }
+  blk.assign((size_t)nb[0] * nb[1] * nb[2] * 8, 0x80000000u);      // guard: a wall with abskg 0, sigmaT4 0
+  for (int b2 = 0; b2 < nb[2]; ++b2) for (int b1 = 0; b1 < nb[1]; ++b1) for (int b0 = 0; b0 < nb[0]; ++b0)
+    for (int c = 0; c < 8; ++c) {
+      const int x = 2 * b0 + (c & 1) - 2, y = 2 * b1 + ((c >> 1) & 1) - 2, z = 2 * b2 + (c >> 2) - 2;
+      if (x < 0 || x >= n[0] || y < 0 || y >= n[1] || z < 0 || z >= n[2]) continue;
+      const Rec8 r = recs[(long long)x + (long long)n[0] * (y + (long long)n[1] * z)];
+      blk[((size_t)b0 + (size_t)nb[0] * (b1 + (size_t)nb[1] * b2)) * 8 + c] =
+          ((uint32_t)float_to_half_bits(r.k) << 16) | float_to_half_bits(r.s * HALF_S_SCALE);
+    }
+  bg.blk = blk.data(); bg.bx = nb[0]; bg.bxy = nb[0] * nb[1];
+}
+
+// legsPerCall 0: march_single_level_blk (the whole ray); k > 0: blk_ray_legs(k) again and again, the ray's state going through the 12
+// words divq_sorted_kernel<RESORT> parks between two calls
+void hs_trace_1L_blk(const HsLevel* g, int n, const int* cells, const double* dirs, const double* orgs, double threshold, int allowReflect,
+                     int skipZero, int legsPerCall, double* sumI, unsigned* steps) {
+  std::vector<uint32_t> store;
+  BlkGeom bg;
+  blk_build_host(*g, store, bg);
+  const int sy8 = 8 * bg.bx, sz8 = 8 * bg.bxy;
+  const float cx = (float)g->dx[0], cy = (float)g->dx[1], cz = (float)g->dx[2];
+  for (int t = 0; t < n; ++t) {
+    const int* c = cells + 3 * t;
+    double r[3];
+    rayDxOf(*g, c, orgs + 3 * t, r);
+    const int ux = c[0] - bg.lo[0], uy = c[1] - bg.lo[1], uz = c[2] - bg.lo[2];
+    const unsigned par = (unsigned)((ux & 1) | ((uy & 1) << 1) | ((uz & 1) << 2));
+    const int w0 = 8 * ((ux >> 1) + bg.bx * (uy >> 1) + bg.bxy * (uz >> 1)) + (int)par;
+    const double* d = dirs + 3 * t;
+    unsigned s = 0;
+    if (legsPerCall <= 0) {
+      sumI[t] = (1.0f / HALF_S_SCALE) * march_single_level_blk(bg.blk, w0, par, sy8, sz8, (float)d[0], (float)d[1], (float)d[2], (float)r[0],
+                                                               (float)r[1], (float)r[2], cx, cy, cz, (float)threshold, allowReflect != 0,
+                                                               skipZero != 0, s);
+    } else if (!(1.0f > (float)threshold)) {
+      sumI[t] = 0.0;
+    } else {
+      BlkRay ry;
+      float ddx, ddy, ddz;
+      blk_ray_start(ry, bg.blk, w0, par, sy8, sz8, (float)d[0], (float)d[1], (float)d[2], (float)r[0], (float)r[1], (float)r[2], cx, cy, cz,
+                    ddx, ddy, ddz);
+      while (!blk_ray_legs(ry, bg.blk, ddx, ddy, ddz, sy8, sz8, (float)threshold, allowReflect != 0, skipZero != 0, legsPerCall)) {
+        // park and resume: tMax, word index | deltas, tau offset | exp(-tau), steps, sum, weight
+        const unsigned w[12] = {__float_as_uint(ry.d.tx), __float_as_uint(ry.d.ty), __float_as_uint(ry.d.tz), (unsigned)ry.d.idx,
+                                (unsigned)ry.b.dlx, (unsigned)ry.b.dly, (unsigned)ry.b.dlz, __float_as_uint(ry.q.A),
+                                __float_as_uint(ry.q.ePrev), __float_as_uint(ry.q.nsteps), __float_as_uint(ry.sum), __float_as_uint(ry.fs)};
+        BlkRay z;
+        z.d.tx = __uint_as_float(w[0]); z.d.ty = __uint_as_float(w[1]); z.d.tz = __uint_as_float(w[2]); z.d.idx = (int)w[3];
+        z.b.dlx = (int)w[4]; z.b.dly = (int)w[5]; z.b.dlz = (int)w[6];
+        blk_decode(z.q, bg.blk[z.d.idx]);
+        z.q.A = __uint_as_float(w[7]); z.q.ePrev = __uint_as_float(w[8]); z.q.nsteps = __uint_as_float(w[9]);
+        z.q.tau = 0.0f; z.q.leg = 0.0f;
+        z.sum = __uint_as_float(w[10]); z.fs = __uint_as_float(w[11]);
+        ry = z;
+      }
+      s = (unsigned)ry.q.nsteps;
+      sumI[t] = (1.0f / HALF_S_SCALE) * ry.sum;
+    }
+    steps[t] = s;
+  }
+}
+
+// ---- Data Onion on blocked boxes (march_onion_blk): level 0 whole, every level above it the box of onion_copy_box (rmcrt_b200.cu) --
+// the ROI / region plus the level's extra cells where it ends at the domain boundary -- wrapped in markers (roi_blk_build_kernel)
+void hs_trace_DO_blk(const HsLevel* lv, int maxLevels, const int* roiLo, const int* roiHi, const int* regLo, const int* regHi, int n,
+                     const int* cells, const double* dirs, const double* orgs, double threshold, int allowReflect, int skipZero,
+                     double* sumI, unsigned* steps) {
+  OnionGeom<4> G;
+  std::memset(&G, 0, sizeof G);
+  G.maxLevels = maxLevels;
+  const int F = maxLevels - 1;
+  for (int L = 0; L < maxLevels; ++L) {
+    LevelGeom& g = G.lev[L];
+    g.rec = lv[L].rec;
+    for (int d = 0; d < 3; ++d) {
+      g.lo[d] = lv[L].lo[d]; g.n[d] = lv[L].hi[d] - lv[L].lo[d]; g.intLo[d] = lv[L].intLo[d]; g.intHi[d] = lv[L].intHi[d];
+      g.rr[d] = lv[L].rr[d]; g.regLo[d] = regLo[3 * L + d]; g.regHi[d] = regHi[3 * L + d]; g.dx[d] = lv[L].dx[d];
+      g.anchor[d] = lv[L].anchor[d]; g.off[d] = lv[L].anchor[d] - lv[F].anchor[d];
+    }
+  }
+  for (int d = 0; d < 3; ++d) { G.roiLo[d] = roiLo[d]; G.roiHi[d] = roiHi[d]; }
+  OnionBlk ob;
+  std::memset(&ob, 0, sizeof ob);
+  std::vector<uint32_t> store[4];
+  {
+    BlkGeom bg0;
+    blk_build_host(lv[0], store[0], bg0);
+    ob.blk[0] = bg0.blk; ob.bx[0] = bg0.bx; ob.bxy[0] = bg0.bxy;
+    for (int d = 0; d < 3; ++d) ob.lo[0][d] = bg0.lo[d];
+  }
+  for (int L = 1; L <= F; ++L) {
+    const LevelGeom& g = G.lev[L];
+    const Rec8* recs = static_cast<const Rec8*>(g.rec);
+    int lo[3], hi[3], nb[3];
+    for (int d = 0; d < 3; ++d) {
+      const int rlo = L == F ? roiLo[d] : g.regLo[d], rhi = L == F ? roiHi[d] : g.regHi[d];
+      lo[d] = rlo <= g.intLo[d] ? g.lo[d] : rlo;
+      hi[d] = rhi >= g.intHi[d] ? g.lo[d] + g.n[d] : rhi;
+      ob.lo[L][d] = lo[d] - 1 - 2;
+      nb[d] = (hi[d] - lo[d] + 2 + 4 + 1) / 2;
+    }
+    store[L].assign((size_t)nb[0] * nb[1] * nb[2] * 8, 0xFC000000u);      // marker: wall flag, abskg = inf
+    for (int z = lo[2]; z < hi[2]; ++z) for (int y = lo[1]; y < hi[1]; ++y) for (int x = lo[0]; x < hi[0]; ++x) {
+      const Rec8 r = recs[(long long)(x - g.lo[0]) + (long long)g.n[0] * ((y - g.lo[1]) + (long long)g.n[1] * (z - g.lo[2]))];
+      const int ux = x - ob.lo[L][0], uy = y - ob.lo[L][1], uz = z - ob.lo[L][2];
+      store[L][((size_t)(ux >> 1) + (size_t)nb[0] * ((uy >> 1) + (size_t)nb[1] * (uz >> 1))) * 8 + ((ux & 1) | ((uy & 1) << 1) | ((uz & 1) << 2))] =
+          ((uint32_t)float_to_half_bits(r.k) << 16) | float_to_half_bits(r.s * HALF_S_SCALE);
+    }
+    ob.blk[L] = store[L].data(); ob.bx[L] = nb[0]; ob.bxy[L] = nb[0] * nb[1];
+  }
+  for (int t = 0; t < n; ++t) {
+    const int* c = cells + 3 * t;
+    double r[3];
+    rayDxOf(lv[F], c, orgs + 3 * t, r);
+    const int ux = c[0] - ob.lo[F][0], uy = c[1] - ob.lo[F][1], uz = c[2] - ob.lo[F][2];
+    const int w0 = 8 * ((ux >> 1) + ob.bx[F] * (uy >> 1) + ob.bxy[F] * (uz >> 1)) + ((ux & 1) | ((uy & 1) << 1) | ((uz & 1) << 2));
+    const double* d = dirs + 3 * t;
+    unsigned s = 0;
+    sumI[t] = (1.0f / HALF_S_SCALE) * march_onion_blk<4>(G, ob, c[0], c[1], c[2], w0, (float)d[0], (float)d[1], (float)d[2], (float)r[0],
+                                                         (float)r[1], (float)r[2], (float)threshold, allowReflect != 0, skipZero != 0, s);
+    steps[t] = s;
   }
 }
 }

@@ -20,7 +20,8 @@ def lib():
     if _lib is None:
         srcs = [os.path.join(HERE, "march_host.cpp"), os.path.join(HERE, "cuda_shim.h"),
                 os.path.join(HERE, "..", "..", "uintah_b200", "csrc", "march.cuh"),
-                os.path.join(HERE, "..", "..", "uintah_b200", "csrc", "rng.cuh")]
+                os.path.join(HERE, "..", "..", "uintah_b200", "csrc", "rng.cuh"),
+                os.path.join(HERE, "..", "..", "uintah_b200", "csrc", "indep.cuh")]
         if (not os.path.exists(SO)) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
             subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", SO, srcs[0]], check=True)
         _lib = C.CDLL(SO)
@@ -77,6 +78,17 @@ def trace_1L_fast(lv, cells, dirs, org, thr, refl, skip=0):
     return sumI, steps
 
 
+def trace_1L_blk(lv, cells, dirs, org, thr, refl, skip=0, legs_per_call=0):
+    """the default solve's march (indep.cuh): blocked half-packed copy of the level, march_leg_blk; legs_per_call > 0: resumed leg by leg"""
+    rec = pack(lv, 0)
+    h = hslevel(lv, rec)
+    n = len(cells)
+    sumI = np.zeros(n); steps = np.zeros(n, np.uint32)
+    cells = np.ascontiguousarray(cells, np.int32); dirs = np.ascontiguousarray(dirs); org = np.ascontiguousarray(org)
+    lib().hs_trace_1L_blk(C.byref(h), n, _vp(cells), _vp(dirs), _vp(org), C.c_double(thr), refl, skip, legs_per_call, _vp(sumI), _vp(steps))
+    return sumI, steps
+
+
 def trace_ML(levels, kind, roi, reg, cells, dirs, org, thr, refl, skip=0, max_path=4000):
     recs = [pack(l, kind) for l in levels]
     nl = len(levels)
@@ -88,6 +100,20 @@ def trace_ML(levels, kind, roi, reg, cells, dirs, org, thr, refl, skip=0, max_pa
     lib().hs_trace_ML(arr, nl, (C.c_int * 3)(*roi[0]), (C.c_int * 3)(*roi[1]), _vp(regLo), _vp(regHi), kind, n, _vp(cells),
                       _vp(dirs), _vp(org), C.c_double(thr), refl, skip, _vp(sumI), _vp(steps), path.ctypes.data_as(C.c_void_p), max_path)
     return sumI, steps, path
+
+
+def trace_DO_blk(levels, roi, reg, cells, dirs, org, thr, refl, skip=0):
+    """the default Data-Onion march (indep.cuh, march_onion_blk): one blocked half-packed box per level, 2 to 4 levels"""
+    recs = [pack(l, 0) for l in levels]
+    nl = len(levels)
+    arr = (HsLevel * nl)(*[hslevel(l, r) for l, r in zip(levels, recs)])
+    n = len(cells)
+    sumI = np.zeros(n); steps = np.zeros(n, np.uint32)
+    cells = np.ascontiguousarray(cells, np.int32); dirs = np.ascontiguousarray(dirs); org = np.ascontiguousarray(org)
+    regLo = np.ascontiguousarray(reg[0], np.int32); regHi = np.ascontiguousarray(reg[1], np.int32)
+    lib().hs_trace_DO_blk(arr, nl, (C.c_int * 3)(*roi[0]), (C.c_int * 3)(*roi[1]), _vp(regLo), _vp(regHi), n, _vp(cells), _vp(dirs), _vp(org),
+                          C.c_double(thr), refl, skip, _vp(sumI), _vp(steps))
+    return sumI, steps
 
 
 def trace_DO2_fast(levels, roi, reg, cells, dirs, org, thr, refl, skip=0):

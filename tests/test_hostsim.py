@@ -335,3 +335,85 @@ def test_blocked_addressing_algebra():
                 else:
                     p = q
                 w = w2
+
+
+def _fp16_level(po, lv):
+    """the level as the blocked copy sees it: abskg and sigmaT4/pi * 2^-5 rounded to fp16 (exactly representable in float)"""
+    import copy
+    q = copy.copy(lv)
+    q.abskg = lv.abskg.astype(np.float16).astype(lv.abskg.dtype)
+    q.sigmaT4 = ((lv.sigmaT4 / 32).astype(np.float16).astype(lv.sigmaT4.dtype)) * 32
+    return q
+
+
+@pytest.mark.parametrize("case", ["bc", "bc_walls", "plates_mirrors", "bc_refsem"])
+def test_blocked_march_equals_the_fast_march_and_the_oracle(po, case):
+    """march_single_level_blk (indep.cuh: the default solve's march on the 2 x 2 x 2 blocked half-packed copy, coordinate-free addressing)
+    against march_single_level_fast on the same fp16-rounded properties -- same cells, same arithmetic: equal step counts, sums to FP32
+    round-off -- against the oracle on those properties, and resumed leg by leg through the 12 words divq_sorted_kernel<RESORT> parks:
+    bit-identical to the uninterrupted march."""
+    rng = np.random.default_rng(41)
+    if case == "plates_mirrors":
+        lv = po.parallel_plates(17, dtype=np.float32, mirror_faces=("x-", "y+"))
+        thr, refl, skip = 0.001, 1, 0
+    else:
+        lv = po.burns_christon(19, dtype=np.float32)       # odd sizes: partial blocks at the high faces
+        if case == "bc_walls":
+            from util import add_random_walls
+            add_random_walls(lv, 0.03, rng, abskg=0.8, sigmaT4=0.05)
+        thr, refl, skip = 0.05, 1, (0 if case == "bc_refsem" else 1)
+    n = 300
+    cells, dirs, org = random_rays(lv, n, rng)
+    lv16 = _fp16_level(po, lv)
+    sb, nb = sim.trace_1L_blk(lv, cells, dirs, org, thr, refl, skip)
+    sf, nf = sim.trace_1L_fast(lv16, cells, dirs, org, thr, refl, skip)
+    assert np.array_equal(nb, nf)
+    np.testing.assert_allclose(sb, sf, rtol=1e-6, atol=1e-7 * np.abs(sf).max())
+    # resumed after every leg / every second leg
+    for legs in (1, 2):
+        sr, nr = sim.trace_1L_blk(lv, cells, dirs, org, thr, refl, skip, legs_per_call=legs)
+        assert np.array_equal(nr, nb) and np.array_equal(sr, sb)
+    if skip == 0:      # the oracle marches every leg the reference marches
+        p = po.default_params(threshold=thr, allowReflect=refl)
+        ref = [po.update_sumI(p, lv16, dirs[t], org[t], cells[t]) for t in range(n)]
+        rs = np.array([r[0] for r in ref]); rn = np.array([r[1] for r in ref])
+        assert (rn == nb).mean() > 0.97
+        same = rn == nb
+        np.testing.assert_allclose(sb[same], rs[same], rtol=5e-4, atol=1e-6 * max(1.0, np.abs(rs).max()))
+
+
+@pytest.mark.parametrize("case", ["bc2", "plates2", "bc3", "plates3"])
+def test_blocked_data_onion_march(po, case):
+    """march_onion_blk (the default Data-Onion march: one blocked half-packed box per level, marker shell = level jump, the level's own
+    extra cells where a box ends at the domain boundary) with two and three levels against the oracle's updateSumI_ML (pinned bit for
+    bit on the reference's own routine) on the same fp16-rounded properties: same executed steps up to FP32 ties, sums to FP32
+    round-off.  Patches at the boundary, inside, and with an ROI that ends exactly at the interior's edge; zero-weight legs marched."""
+    rng = np.random.default_rng(43)
+    three = case.endswith("3")
+    N = 48 if three else 32
+    fine = po.burns_christon(N, dtype=np.float32) if case.startswith("bc") else po.parallel_plates(N, dtype=np.float32, mirror_faces=("x-", "y-"))
+    thr = 0.05 if case.startswith("bc") else 0.001
+    if three:
+        fine.rr = (2, 2, 2)
+        mid = po.coarsen_level(fine, (2, 2, 2)); mid.rr = (2, 2, 2)
+        levels = [po.coarsen_level(mid, (2, 2, 2)), mid, fine]
+        halo, patches = (2, 2, 2), (((0, 0, 0), (16, 16, 16)), ((16, 16, 16), (32, 32, 32)), ((2, 32, 20), (18, 48, 36)))
+    else:
+        fine.rr = (4, 4, 4)
+        levels = [po.coarsen_level(fine, (4, 4, 4)), fine]
+        halo, patches = (4, 4, 4), (((0, 0, 0), (16, 16, 16)), ((8, 8, 8), (24, 24, 24)), ((4, 4, 4), (12, 12, 12)))
+    levels16 = [_fp16_level(po, l) for l in levels]
+    for l16, l in zip(levels16, levels):
+        l16.rr = getattr(l, "rr", (1, 1, 1))
+    p = po.default_params(threshold=thr, allowReflect=1)
+    for plo, phi in patches:
+        roiLo, roiHi, regLo, regHi = po.compute_extents(levels, plo, phi, halo)
+        cells, dirs, org = random_rays(fine, 100, rng, plo, phi)
+        sb, nb = sim.trace_DO_blk(levels, (roiLo, roiHi), (regLo, regHi), cells, dirs, org, thr, 1)
+        same = 0
+        for t in range(len(cells)):
+            s, ns, _ = po.update_sumI_ML(p, levels16, roiLo, roiHi, regLo, regHi, dirs[t], org[t], cells[t], max_path=0)
+            if ns == nb[t]:
+                same += 1
+                assert s == pytest.approx(sb[t], rel=1e-3, abs=1e-6 * max(1.0, abs(s))), (plo, t)
+        assert same >= 0.96 * len(cells), (plo, same)

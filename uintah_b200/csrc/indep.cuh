@@ -137,6 +137,7 @@ __device__ __forceinline__ void indep_start(IndepRay& r, int B0, unsigned o0, fl
   r.A = 0.0f; r.ePrev = 1.0f; r.leg = 0.0f; r.tau = 0.0f;
   r.fs = 1.0f; r.sum = 0.0f; r.nsteps = 0.0f;
 }
+#endif   // __CUDACC__ (the slot march)
 
 //------------------------------------------------------------------------------------------------------
 // blockedMarch = 2: the one-cell-per-lane PTX leg loop of march.cuh (march_leg) on the blocked copy, with PLAIN 4-byte loads.
@@ -226,7 +227,30 @@ __device__ __forceinline__ LegOut march_leg_blk(Dda& d, Integ& q, BlkStride& b, 
 #undef RB_INTEG
 #undef RB_EXIT
 #else
-__device__ __forceinline__ LegOut march_leg_blk(Dda&, Integ&, BlkStride&, const uint32_t*, float, float, float, int, int) { return LegOut{0.0f, 0}; }
+// the same leg statement by statement in C++ (what tests/hostsim steps against the oracle; the device loop additionally requests the
+// word of step n + 1 before the wall test of step n)
+__device__ __forceinline__ void blk_decode(Integ& q, uint32_t word);
+__device__ __forceinline__ LegOut march_leg_blk(Dda& d, Integ& q, BlkStride& b, const uint32_t* __restrict__ blk, float ddx, float ddy,
+                                                float ddz, int tgy, int tgz) {
+  for (;;) {
+    const bool a = d.tx < d.ty;
+    const float m = fminf(d.tx, d.ty);
+    const bool nz_ = m < d.tz;                 // false: z is the stepping axis (strict '<' tie order of RMCRTCommon.cc:696-708)
+    const bool px = a && nz_, py = !a && nz_;
+    const float t = fminf(m, d.tz);
+    d.idx += px ? b.dlx : (py ? b.dly : b.dlz);
+    if (px) { d.tx += ddx; b.dlx ^= 6; } else if (py) { d.ty += ddy; b.dly ^= tgy; } else { d.tz += ddz; b.dlz ^= tgz; }
+    const uint32_t word = blk[d.idx];
+    q.tau = fmaf(q.k, t, q.A);
+    const float e = Num<float>::attenuation(q.tau);
+    q.leg = fmaf(q.s, q.ePrev - e, q.leg);
+    q.ePrev = e;
+    q.nsteps += 1.0f;
+    blk_decode(q, word);
+    q.A = fmaf(-q.k, t, q.tau);
+    if ((int)word < 0) return LegOut{t, px ? 0 : (py ? 1 : 2)};
+  }
+}
 #endif
 
 // deltas of a ray standing on position bits `par` with the given direction signs: positive direction: a on an even position, b = S - a on
@@ -240,8 +264,8 @@ __device__ __forceinline__ BlkStride blk_stride_init(unsigned par, bool posx, bo
 }
 
 __device__ __forceinline__ void blk_decode(Integ& q, uint32_t word) {
-  q.k = fabsf(__half2float(__ushort_as_half((unsigned short)(word >> 16))));
-  q.s = __half2float(__ushort_as_half((unsigned short)(word & 0xFFFFu)));
+  q.k = fabsf(half_bits_to_float((unsigned short)(word >> 16)));
+  q.s = half_bits_to_float((unsigned short)(word & 0xFFFFu));
 }
 
 // One ray of the single-level march on the blocked copy, as a resumable state: blk_ray_start + blk_ray_legs(all legs) is
@@ -423,6 +447,5 @@ __device__ __forceinline__ float march_onion_blk(const OnionGeom<MAXL>& G, const
   nSteps += (unsigned)q.nsteps;
   return sum;
 }
-#endif
 
 }  // namespace rmcrt

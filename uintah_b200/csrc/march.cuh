@@ -59,6 +59,10 @@ __device__ __forceinline__ Rec4 encode_rec4(float kSigned, float s) {
   return Rec4{(hk << 16) | hs};
 }
 #endif
+// fp16 bits -> float (the half-packed words; on the host, tests/hostsim/cuda_shim.h supplies the conversion)
+#if defined(__CUDACC__)
+__device__ __forceinline__ float half_bits_to_float(unsigned short h) { return __half2float(__ushort_as_half(h)); }
+#endif
 __device__ __forceinline__ bool sign_bit(float v)  { return (__float_as_uint(v) >> 31) != 0u; }
 __device__ __forceinline__ bool sign_bit(double v) { return (__double2hiint(v) < 0); }
 // a record whose abskg carries the sign bit is "not a flow cell" (cellType != d_flowCell)
