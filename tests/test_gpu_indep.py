@@ -236,3 +236,28 @@ def test_sorted_data_onion_three_levels(gpu_lib, po, case):
     diff = np.abs(v0 - v3)
     assert np.percentile(diff, 99.9) <= 2e-4 * scale and diff.max() <= 2e-2 * scale, (np.percentile(diff, 99.9) / scale, diff.max() / scale)
     assert np.abs(d0 - d3).max() <= 2e-2 * np.abs(d0).max() and np.linalg.norm(d0 - d3) / np.linalg.norm(d0) < 2e-3
+
+
+@pytest.mark.parametrize("rays,ccrays", [(1, 0), (3, 0), (7, 1), (300, 0)])
+def test_sorted_kernel_odd_shapes(gpu_lib, po, rays, ccrays):
+    """fewer rays than warps, more rays than one pass sorts (256), cell-centred rays, a level of 5 x 4 x 3 cells and a patch smaller than a
+    tile: the default kernel against the one-cell kernel on the same rays (half-packed level)"""
+    rng = np.random.default_rng(51)
+    for shape_case in ("tiny_level", "small_patch"):
+        if shape_case == "tiny_level":
+            M = (3 + 2, 4 + 2, 5 + 2)            # (z, y, x) incl. extra cells
+            ab = rng.uniform(0.2, 1.5, M).astype(np.float32); s4 = rng.uniform(0.1, 1.0, M).astype(np.float32); ct = np.full(M, -1, np.int32)
+            for ax in range(3):
+                for idx in (0, M[ax] - 1):
+                    sl = [slice(None)] * 3; sl[ax] = idx; ct[tuple(sl)] = 8; ab[tuple(sl)] = 1.0
+            lv = po.Level(ab, s4, ct, (-1,) * 3, (5 + 1, 4 + 1, 3 + 1), (0.2, 0.25, 1.0 / 3), interior_lo=(0,) * 3, interior_hi=(5, 4, 3))
+            patch = None
+        else:
+            lv = po.burns_christon(21, dtype=np.float32)
+            add_random_walls(lv, 0.05, rng, abskg=0.6, sigmaT4=0.2)
+            patch = ((7, 9, 11), (12, 11, 13))
+        kw = dict(nDivQRays=rays, threshold=0.01, seed=3, half_records=True, CCRays=ccrays)
+        d0, v0, n0, c0 = solve(lv, patch, blockedMarch=0, **kw)
+        d3, v3, n3, c3 = solve(lv, patch, blockedMarch=3, **kw)
+        assert c0 == c3 and c0 > 0 and n0 == n3, (shape_case, c0, c3, n0, n3)
+        assert np.array_equal(v0 == 0, v3 == 0) and np.allclose(v0, v3, rtol=1e-12, atol=0), shape_case
