@@ -558,6 +558,12 @@ def run_ours(args):
                     "traffic": prof.get("dram_bytes_per_launch"), "l2_traffic": prof.get("l2_bytes_per_launch"),
                     "frac_of_l2_peak_by_actual_sector_traffic": (prof["l2_bytes_per_launch"] / kern_s / 1e9 / l2_peak) if prof.get("l2_bytes_per_launch") else None,
                     "sector_gathers_per_s_vs_measured_gather_rate": (per_rank_steps / kern_s) / (l2_gacc * 1e9),
+                    # the resource that binds: L1 -> L2 miss requests (one 32-B sector per request, one request per clock per SM).  Requests
+                    # per step from the committed capture x steps/s, against the request rate the gather microbenchmark reaches live
+                    "l1_miss_requests_per_step": (prof["l2_bytes_per_launch"] / 32.0 / prof["steps_per_launch"])
+                                                 if prof.get("l2_bytes_per_launch") and prof.get("steps_per_launch") else None,
+                    "frac_of_measured_miss_request_rate": ((prof["l2_bytes_per_launch"] / 32.0 / prof["steps_per_launch"]) * (per_rank_steps / kern_s)
+                                                           / (l2_gacc * 1e9)) if prof.get("l2_bytes_per_launch") and prof.get("steps_per_launch") else None,
                     "peak_source": "measured live (rmcrt_measure_read_bandwidth, see l2_live); MEASURED_PEAKS.json has no L2 figure"}
     else:
         # batched rays: neither HBM (records are read once) nor L2 (25 %) binds; the SM issue rate does

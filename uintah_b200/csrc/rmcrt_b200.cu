@@ -983,6 +983,12 @@ __global__ void __launch_bounds__(256, RMCRT_FAST_MIN_BLOCKS) divq_blk_kernel(co
 #ifndef RMCRT_SORTED_BLOCKS
 #define RMCRT_SORTED_BLOCKS 4
 #endif
+#ifndef RMCRT_SORT_MIN_RAYS
+// below this many rays per cell a tile has too few 32-ray chunks for its eight warps (a block is as slow as its longest chunk) and the
+// default runs the unsorted kernel on the same blocked copy: 128^3 x 3 / 5 / 10 / 25 rays: sorted 1.3 / 2.1 / 3.6 / 5.4e11 steps/s,
+// unsorted 3.2 / 3.5 / 3.6 / 3.7e11 (profiles/r02v32_few_rays.txt)
+#define RMCRT_SORT_MIN_RAYS 12
+#endif
 #ifndef RMCRT_RESORT_ROUNDS
 #define RMCRT_RESORT_ROUNDS 4      // RESORT: rounds of one leg each before whatever is left runs to its end
 #endif
@@ -2795,7 +2801,7 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
         divq_dual_kernel<RecT, false><<<(int)g2, 32 * W2, W2 * 64 * sizeof(double), st>>>(a2, nxc, njp, 0);
         launch_reflective_pairs<RecT>(ctx, a2, cap, st);
       }
-    } else if (ctx->p.blockedMarch == 3 && blocked_default(ctx, a, ML)) {
+    } else if (ctx->p.blockedMarch == 3 && blocked_default(ctx, a, ML) && a.nRays >= RMCRT_SORT_MIN_RAYS) {
       // independent rays per (cell, ray, timestep), sorted by expected length inside a tile, on the blocked copy (divq_sorted_kernel)
       if constexpr (std::is_same<Real, float>::value && !std::is_same<RecT, Rec16>::value) {
         BlkGeom bg;
@@ -2820,7 +2826,8 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
           divq_sorted_kernel<RecT, false, true><<<nb, 256, 0, st>>>(a2, bg, none, RP, base + 256, tileCounter);
         }
       }
-    } else if (ctx->p.blockedMarch == 2 && blocked_default(ctx, a, ML)) {
+    } else if ((ctx->p.blockedMarch == 2 || ctx->p.blockedMarch == 3) && blocked_default(ctx, a, ML)) {
+      // (also the default's choice below RMCRT_SORT_MIN_RAYS rays per cell)
       // independent rays per (cell, ray, timestep) on the blocked half-packed copy of the level, plain loads (divq_blk_kernel)
       if constexpr (std::is_same<Real, float>::value && !std::is_same<RecT, Rec16>::value) {
         BlkGeom bg;
