@@ -39,6 +39,12 @@ using namespace rmcrt;
 namespace {
 
 constexpr int MAXL = 4;   // levels supported by the Data-Onion kernels (reference decks use 2-3)
+#ifndef RMCRT_SORT_MIN_RAYS
+// below this many rays per cell a tile has too few 32-ray chunks for its eight warps (a block is as slow as its longest chunk) and the
+// default runs the unsorted kernel on the same blocked copy: 128^3 x 3 / 5 / 10 / 25 rays: sorted 1.3 / 2.1 / 3.6 / 5.4e11 steps/s,
+// unsorted 3.2 / 3.5 / 3.6 / 3.7e11 (profiles/r02v32_few_rays.txt)
+#define RMCRT_SORT_MIN_RAYS 12
+#endif
 
 // per-level status words living on the device, so that a radiation solve needs no host round trip:
 //   [0] non-finite records  [1] flow cells on the outer layer  [2] non-flow cells that can emit (k*s != 0)
@@ -983,12 +989,6 @@ __global__ void __launch_bounds__(256, RMCRT_FAST_MIN_BLOCKS) divq_blk_kernel(co
 #ifndef RMCRT_SORTED_BLOCKS
 #define RMCRT_SORTED_BLOCKS 4
 #endif
-#ifndef RMCRT_SORT_MIN_RAYS
-// below this many rays per cell a tile has too few 32-ray chunks for its eight warps (a block is as slow as its longest chunk) and the
-// default runs the unsorted kernel on the same blocked copy: 128^3 x 3 / 5 / 10 / 25 rays: sorted 1.3 / 2.1 / 3.6 / 5.4e11 steps/s,
-// unsorted 3.2 / 3.5 / 3.6 / 3.7e11 (profiles/r02v32_few_rays.txt)
-#define RMCRT_SORT_MIN_RAYS 12
-#endif
 #ifndef RMCRT_RESORT_ROUNDS
 #define RMCRT_RESORT_ROUNDS 4      // RESORT: rounds of one leg each before whatever is left runs to its end
 #endif
@@ -1082,6 +1082,9 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
     __syncthreads();
   };
   unsigned long long stepsTotal = 0, cellsTotal = 0;
+#ifdef RMCRT_PHASE_CLOCKS
+  long long tMarch = 0, tAll = clock64(), tMark = 0;
+#endif
 
   for (;;) {
     // tiles are handed out dynamically (rays near the centre of the domain are several times longer than those in its corners)
@@ -1304,6 +1307,9 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
       } else {
       // ---- phase 3: march chunks of 32 rays, longest first
       {
+#ifdef RMCRT_PHASE_CLOCKS
+        tMark = clock64();
+#endif
         const int nList = ctl[1];
         for (;;) {
           int chunk = 0;
@@ -1330,6 +1336,9 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
             __stcg(res + id, UNSCALE * sumI);
           }
         }
+#ifdef RMCRT_PHASE_CLOCKS
+        tMarch += clock64() - tMark;      // this warp's time inside the chunk loop (the barrier wait after it counts as "outside")
+#endif
       }
       __syncthreads();
       }
@@ -1364,6 +1373,11 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
     stepsTotal += steps;
     __syncthreads();      // ctl[2] / part / w0s are rewritten for the next tile
   }
+#ifdef RMCRT_PHASE_CLOCKS
+  if (!RESORT && lane == 0 && (blockIdx.x % 97) == 0)
+    printf("block %d warp %d: %.1f %% of %lld cycles inside the chunk loop\n", blockIdx.x, warp, 100.0 * (double)tMarch / (double)(clock64() - tAll),
+           clock64() - tAll);
+#endif
   for (int o = 16; o > 0; o >>= 1) {
     stepsTotal += __shfl_down_sync(0xffffffffu, stepsTotal, o);
     cellsTotal += __shfl_down_sync(0xffffffffu, cellsTotal, o);
@@ -2567,6 +2581,7 @@ bool onion_blocked_default(const rmcrt_ctx* ctx, const TraceArgs& a, bool ML) {
   if (!ML || a.G.maxLevels < 2 || a.G.maxLevels > ONION_MAXL || !ctx->p.solveDivQ || ctx->p.marchPrecision != 0 || ctx->p.rayCoherence != 0 ||
       ctx->p.blockedMarch != 3 || ctx->p.genericMarch) return false;
   if (!ctx->p.isSeedRandom || ctx->p.fixedRandom || ctx->p.rayDirSampleAlgo != 0) return false;
+  if (ctx->p.nDivQRays < RMCRT_SORT_MIN_RAYS) return false;      // too few rays per tile to sort: the one-cell kernels
   for (int d = 0; d < 3; ++d)      // the patch lies inside the ROI (a fixed / dynamic ROI need not contain it)
     if (!(a.G.roiLo[d] <= a.patchLo[d] && a.patchLo[d] + a.patchN[d] <= a.G.roiHi[d])) return false;
   // a ray that leaves the box of level L through an interior cell must land INSIDE the box of level L - 1 (the march tests "marker cell",
