@@ -208,8 +208,6 @@ def c5_single_gpu(N=256, rays=100, steps=2, half=-1, coherence=-1, cells_per_lan
     ab, s4, ct = plates_fields(N)
     d_ab, d_s4, d_ct = (torch.from_numpy(x).to(dev) for x in (ab, s4, ct))
     kw = {} if coherence < 0 else {"rayCoherence": coherence, "cellsPerLane": cells_per_lane}
-    if os.environ.get("RMCRT_AB_TILEX"):
-        kw["tileX"] = int(os.environ["RMCRT_AB_TILEX"])
     g = RMCRT(device=dev.index, nDivQRays=rays, nFluxRays=rays, threshold=0.001, solveBoundaryFlux=1, allowReflect=1, seed=99,
               half_records=bool(half), **kw)
     lvl = LevelData(None, None, None, lo, hi, (1.0 / N,) * 3, interior_lo=(0,) * 3, interior_hi=(N,) * 3)
