@@ -1104,8 +1104,10 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
       if (valid) {
         patch_cell(a, t, i, j, k);
         cellId = (unsigned long long)level_index(g, i, j, k);
-        if constexpr (std::is_same<RecT, Rec4>::value) r0 = ldrec(static_cast<const Rec8*>(g.recFull) + cellId);
-        else r0 = ldrec(static_cast<const Rec8*>(g.rec) + cellId);
+        {      // (read once per cell: streaming, so that 8 B per cell of float records do not push the blocked copy out of the L2)
+          const float2 v = __ldcs(reinterpret_cast<const float2*>(std::is_same<RecT, Rec4>::value ? g.recFull : g.rec) + cellId);
+          r0 = Rec8{v.x, v.y};
+        }
         flow = !is_wall(r0.k);
         const int ux = i - bg.lo[0], uy = j - bg.lo[1], uz = k - bg.lo[2];
         if (flow) w0 = 8 * ((ux >> 1) + bg.bx * (uy >> 1) + bg.bxy * (uz >> 1)) + ((ux & 1) | ((uy & 1) << 1) | ((uz & 1) << 2));
@@ -1362,12 +1364,12 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
         const double mean = acc / a.nRays;
         const uint32_t ww = __ldg(blk + w0);      // the fp16 sigmaT4/pi the rays integrate (see divq_blk_kernel); Ray.cc:775,778
         const double s0 = (double)(UNSCALE * __half2float(__ushort_as_half((unsigned short)(ww & 0xFFFFu))));
-        a.divQ[q] = -4.0 * M_PI * (double)r0.k * (s0 - mean);
-        a.volq[q] = 4.0 * M_PI * mean;
+        __stcs(a.divQ + q, -4.0 * M_PI * (double)r0.k * (s0 - mean));      // streaming stores: the outputs are not read again
+        __stcs(a.volq + q, 4.0 * M_PI * mean);
         ++cellsTotal;
       } else if (a.zeroNonFlow) {
-        a.divQ[q] = 0.0;
-        a.volq[q] = 0.0;
+        __stcs(a.divQ + q, 0.0);
+        __stcs(a.volq + q, 0.0);
       }
     }
     stepsTotal += steps;
