@@ -102,6 +102,8 @@ struct TraceArgs {
   int zeroNonFlow;                // write 0 into the non-flow cells of the patch (zeroInit != 0).  With zeroInit == 0 (modifies_divQ:
                                   // getModifiable, Ray.cc:573-588) the reference `continue`s over them and their values survive (746-748)
   // flux items
+  const uint32_t* fluxBlk;   // blocked half-packed copy of the level for the boundary-flux rays (nullptr: the level's own records)
+  int fluxBx, fluxBxy, fluxLo[3];
   const int* items;       // compacted item ids: face * nCells + patch-linear cell
   const int* nItems;      // device count
 };
@@ -1524,7 +1526,20 @@ __global__ void __launch_bounds__(256) flux_trace_kernel(const __grid_constant__
         }
         if (!done) {
           gen_flux_ray(a.rng, g, i, j, k, face, ray, a.nRays, cellId, dirId, dir, rayDx, cosT);
-          dI = (double)trace_one<Real, RecT, ML, false, FAST>(a, skipZero, i, j, k, dir, rayDx, steps, nullptr);
+          bool blocked = false;
+          if constexpr (FAST && !ML && std::is_same<Real, float>::value) {
+            if (a.fluxBlk) {      // the production solve: the same blocked half-packed copy the divQ rays march (indep.cuh)
+              const int ux = i - a.fluxLo[0], uy = j - a.fluxLo[1], uz = k - a.fluxLo[2];
+              const unsigned par = (unsigned)((ux & 1) | ((uy & 1) << 1) | ((uz & 1) << 2));
+              const int w0 = 8 * ((ux >> 1) + a.fluxBx * (uy >> 1) + a.fluxBxy * (uz >> 1)) + (int)par;
+              dI = (double)((1.0f / HALF_S_SCALE) *
+                            march_single_level_blk(a.fluxBlk, w0, par, 8 * a.fluxBx, 8 * a.fluxBxy, nz<float, double>(dir[0]), nz<float, double>(dir[1]),
+                                                   nz<float, double>(dir[2]), (float)rayDx[0], (float)rayDx[1], (float)rayDx[2], (float)g.dx[0],
+                                                   (float)g.dx[1], (float)g.dx[2], (float)a.threshold, a.allowReflect != 0, skipZero, steps));
+              blocked = true;
+            }
+          }
+          if (!blocked) dI = (double)trace_one<Real, RecT, ML, false, FAST>(a, skipZero, i, j, k, dir, rayDx, steps, nullptr);
         }
         sumProj += cosT * dI;      // sumProjI += cosTheta * (sumI - sumI_prev)   (Ray.cc:704)
         sumCos += cosT;
@@ -2556,8 +2571,8 @@ int build_args(rmcrt_ctx* ctx, int maxLevels, bool multiLevel, const int32_t pLo
 
 // does this solve run on the blocked copy of its level (blockedMarch 1..3: divq_indep / divq_blk / divq_sorted_kernel)?  Production
 // FP32 / Philox single-level divQ rays with the default sampling; everything else marches the level's own records.
-bool blocked_default(const rmcrt_ctx* ctx, const TraceArgs& a, bool ML) {
-  if (ML || !ctx->p.solveDivQ || ctx->p.marchPrecision != 0 || ctx->p.rayCoherence != 0 || ctx->p.blockedMarch <= 0 || ctx->p.genericMarch) return false;
+bool blocked_default(const rmcrt_ctx* ctx, const TraceArgs& a, bool ML, bool divQ = true) {
+  if (ML || (divQ && !ctx->p.solveDivQ) || ctx->p.marchPrecision != 0 || ctx->p.rayCoherence != 0 || ctx->p.blockedMarch <= 0 || ctx->p.genericMarch) return false;
   if (!ctx->p.isSeedRandom || ctx->p.fixedRandom || ctx->p.rayDirSampleAlgo != 0) return false;       // f32gen
   if (a.maxRayLength < 1e300 || a.sigmaScat > 0) return false;                                        // the generic march
   const rmcrt_level_desc& d = ctx->lv[a.G.maxLevels - 1].d;
@@ -2673,6 +2688,15 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
     compact_scatter_kernel<<<nChunks, 256, 0, st>>>(flags, nFlag, chunk, static_cast<int*>(ctx->fluxItems.p));
     CK(cudaGetLastError());
     TraceArgs f = a;
+    if (!bounded && blocked_default(ctx, a, ML, false)) {      // boundary-flux rays of the production solve: the blocked copy too
+      if constexpr (std::is_same<Real, float>::value && !std::is_same<RecT, Rec16>::value) {
+        BlkGeom bgF;
+        int rc = ensure_blocked_level<RecT>(ctx, a.G.maxLevels - 1, bgF, st);
+        if (rc) return rc;
+        f.fluxBlk = bgF.blk; f.fluxBx = bgF.bx; f.fluxBxy = bgF.bxy;
+        for (int d = 0; d < 3; ++d) f.fluxLo[d] = bgF.lo[d];
+      }
+    }
     f.items = static_cast<const int*>(ctx->fluxItems.p);
     f.nItems = ctx->d_nItems;
     f.nRays = ctx->p.nFluxRays;
