@@ -115,7 +115,7 @@ typedef struct rmcrt_params {
                                      a 32-cell tile are sorted by their expected number of steps, so the 32 lanes of a warp end together
                                      (30.6 instead of 13.4 active lanes) and the second visit to a sector is an L1 hit; per cell the rays are
                                      added in ray order in FP64, so divQ does not depend on the sort, the launch shape or the patch layout.
-                                     (Below 12 rays per cell a tile has too few rays to sort: the default then runs kernel 2.)
+                                     (With 3 ... 16 rays per cell up to eight tiles are sorted together; below 3 the default runs kernel 2.)
                                   2: divq_blk_kernel -- the blocked copy with the tile / warp layout of the one-cell kernel (no sort).
                                   1: divq_indep_kernel -- the blocked copy, one 256-bit load per block entered, per-lane ray refill (A/B).
                                   0: divq_kernel on the level's own records (float or half-packed), one cell per lane.

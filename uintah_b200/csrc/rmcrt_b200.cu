@@ -40,10 +40,9 @@ namespace {
 
 constexpr int MAXL = 4;   // levels supported by the Data-Onion kernels (reference decks use 2-3)
 #ifndef RMCRT_SORT_MIN_RAYS
-// below this many rays per cell a tile has too few 32-ray chunks for its eight warps (a block is as slow as its longest chunk) and the
-// default runs the unsorted kernel on the same blocked copy: 128^3 x 3 / 5 / 10 / 25 rays: sorted 1.3 / 2.1 / 3.6 / 5.4e11 steps/s,
-// unsorted 3.2 / 3.5 / 3.6 / 3.7e11 (profiles/r02v32_few_rays.txt)
-#define RMCRT_SORT_MIN_RAYS 12
+// below this many rays per cell the default runs the unsorted kernel on the same blocked copy (nothing to sort); from here to 16 rays
+// divq_sorted_kernel sorts up to eight tiles together (launch_trace, profiles/r02v40_few_rays.txt)
+#define RMCRT_SORT_MIN_RAYS 3
 #endif
 
 // per-level status words living on the device, so that a radiation solve needs no host round trip:
@@ -1001,6 +1000,8 @@ constexpr int SORT_BINS = 512;       // 9-bit keys: one length, or two lengths (
 // L1 keeping a sector until the ray's next step (23 KB per block = 187 KB per SM measured: L1 hit rate 46 % -> 8 %, solve 47 -> 59 ms).
 // RESORT adds state[RP * 32] x 48 B: the rays parked after their first leg.
 __host__ __device__ inline size_t sorted_scratch_bytes(int RP, bool resort) { return (size_t)RP * 32 * (resort ? 56 : 8); }
+// dynamic shared memory: Philox counter (8 B), word index, threshold length (4 B each) and cell index (12 B) of the 32 cells of each of G tiles
+inline size_t sorted_cell_smem(int G) { return (size_t)G * 32 * 28; }
 // ONION: the Data Onion (Ray::rayTrace_dataOnion, 2 to 4 levels): origin cells on the fine level, rays march the blocked copy of the
 // patch's region of interest and go on, level by level, in the blocked region boxes of the coarser levels (march_onion_blk); bg = the
 // ROI box, ob = all boxes.
@@ -1010,18 +1011,25 @@ __host__ __device__ inline size_t sorted_scratch_bytes(int RP, bool resort) { re
 // gets a new key from where it stands -- a weightless ray ends at its next wall, so its one remaining leg sorts exactly -- and the parked
 // rays are sorted and finished in a second pass over the tile.  The two instantiations are launched back to back and the level's status
 // words decide on the device which one does the work (a.gate: 1 = rays end at their first wall, 2 = they can go on).
-template <class RecT, bool ONION, bool RESORT = false>
+// MULTI: G > 1 tiles per block (few rays per cell); otherwise G is the constant 1 and the group arithmetic folds away
+template <class RecT, bool ONION, bool RESORT = false, bool MULTI = false>
 __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(const __grid_constant__ TraceArgs a, const BlkGeom bg,
-                                                                               const __grid_constant__ OnionBlk ob, int RP,
+                                                                               const __grid_constant__ OnionBlk ob, int RP, int Garg,
                                                                                unsigned char* __restrict__ scratch, int* __restrict__ tileCounter) {
-  // 2.9 KB of shared memory per block: four resident blocks stay inside the 16-KB carve-out, the rest of the SM's 256 KB is L1
+  const int G = MULTI ? Garg : 1;
+  // G: 32-cell tiles sorted and marched TOGETHER (1 at the BASELINE's 100 rays per cell; up to 8 when a cell has few rays, so that a
+  // block still has a few dozen 32-ray chunks for its eight warps -- a block is as slow as its longest chunk).  RP = capacity of a pass in
+  // (tile, ray) pairs per lane: the "virtual rays" v = group * nr + ray of the lists below.
+  // 2.9 KB of shared memory per block at G = 1: four resident blocks stay inside the 16-KB carve-out, the rest of the SM's 256 KB is L1
   // (1024 bins = 4.9 KB per block move the carve-out to 32 KB: 3 % slower at 128^3)
   __shared__ int hist[SORT_BINS];
-  __shared__ unsigned long long cellIds[32];
   double* part = reinterpret_cast<double*>(hist);      // [8][32] = 2 KB, written in phase 4 when hist is dead
-  __shared__ int w0s[32];            // word index of the cell, -1: not traced
-  __shared__ int ijk[96];
-  __shared__ int ctl[4];             // [0] next chunk [1] list length [2] tile
+  extern __shared__ __align__(16) unsigned char cellSmem[];      // per group of 32 cells:
+  unsigned long long* cellIds = reinterpret_cast<unsigned long long*>(cellSmem);        // [G * 32] Philox counter of the cell
+  int* w0s = reinterpret_cast<int*>(cellIds + G * 32);           // [G * 32] word index of the cell, -1: not traced
+  float* tThrS = reinterpret_cast<float*>(w0s + G * 32);         // [G * 32] path length at which the intensity threshold ends a ray
+  int* ijk = reinterpret_cast<int*>(tThrS + G * 32);             // [G * 32][3] cell index relative to the level's low corner
+  __shared__ int ctl[4];             // [0] next chunk [1] list length [2] tile group
   __shared__ int warpTot[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int W = 8;
@@ -1092,16 +1100,17 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
     // tiles are handed out dynamically (rays near the centre of the domain are several times longer than those in its corners)
     if (tid == 0) ctl[2] = atomicAdd(tileCounter, 1);
     __syncthreads();
-    const long long tile = ctl[2];
-    if (tile >= a.nTiles) break;
-    // ---- phase 0: the tile's cells (warp 0, lane = cell)
+    const long long tile0 = (long long)ctl[2] * G;
+    if (tile0 >= a.nTiles) break;
+    // ---- phase 0: the cells of the G tiles (warp g < G: tile tile0 + g, lane = cell)
     int i = 0, j = 0, k = 0;
     bool valid = false, flow = false;
     Rec8 r0{0, 0};
     int w0 = -1;
-    if (warp == 0) {
+    if (warp < G) {
+      const long long tile = tile0 + warp;
       const long long t = tile * 32 + lane;
-      valid = t < a.nCells;
+      valid = tile < a.nTiles && t < a.nCells;
       unsigned long long cellId = 0;
       if (valid) {
         patch_cell(a, t, i, j, k);
@@ -1114,30 +1123,29 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
         const int ux = i - bg.lo[0], uy = j - bg.lo[1], uz = k - bg.lo[2];
         if (flow) w0 = 8 * ((ux >> 1) + bg.bx * (uy >> 1) + bg.bxy * (uz >> 1)) + ((ux & 1) | ((uy & 1) << 1) | ((uz & 1) << 2));
       }
-      cellIds[lane] = cellId;
-      w0s[lane] = w0;
-      ijk[lane * 3 + 0] = i - g.lo[0]; ijk[lane * 3 + 1] = j - g.lo[1]; ijk[lane * 3 + 2] = k - g.lo[2];
+      const int gl = warp * 32 + lane;
+      cellIds[gl] = cellId;
+      w0s[gl] = w0;
+      ijk[gl * 3 + 0] = i - g.lo[0]; ijk[gl * 3 + 1] = j - g.lo[1]; ijk[gl * 3 + 2] = k - g.lo[2];
+      // ... or the intensity threshold ends a ray first: optical depth ln(1 / threshold) at the origin cell's abskg (RMCRTCommon.cc:680)
+      tThrS[gl] = w0 >= 0 ? logThr / fmaxf(fabsf(__half2float(__ushort_as_half((unsigned short)(__ldg(blk + w0) >> 16)))), 1e-20f) : 1e30f;
     }
-    double acc = 0;       // warp 0: running sum over the passes
+    double acc = 0;       // warps < G: running sum over the passes
     unsigned steps = 0;
-    for (int ray0 = 0; ray0 < a.nRays; ray0 += RP) {
-      const int nr = min(RP, a.nRays - ray0);
+    const int RPr = RP / G;      // rays of a cell per pass
+    for (int ray0 = 0; ray0 < a.nRays; ray0 += RPr) {
+      const int nr = min(RPr, a.nRays - ray0), V = G * nr;
       for (int q4 = tid; q4 < SORT_BINS; q4 += 256) hist[q4] = 0;
       if (tid == 0) ctl[0] = 0;
       __syncthreads();
-      // ---- phase 1: keys + histogram (thread -> cell = lane, rays warp, warp + W, ...)
-      const int cw0 = w0s[lane];
+      // ---- phase 1: keys + histogram (thread -> cell = lane of every group; (group, ray) pairs warp, warp + W, ...)
       {
-        const unsigned long long cid = cellIds[lane];
-        const float ci = (float)ijk[lane * 3 + 0], cj = (float)ijk[lane * 3 + 1], ck = (float)ijk[lane * 3 + 2];
-        // ... or the intensity threshold ends it first: optical depth ln(1 / threshold) at the origin cell's abskg (RMCRTCommon.cc:680)
-        float tThr = 1e30f;
-        if (cw0 >= 0) {
-          const float k0 = fabsf(__half2float(__ushort_as_half((unsigned short)(__ldg(blk + cw0) >> 16))));
-          tThr = logThr / fmaxf(k0, 1e-20f);
-        }
-        if (cw0 >= 0)
-          for (int r = warp; r < nr; r += W) {
+          for (int v = warp; v < V; v += W) {
+            const int gq = G == 1 ? 0 : v / nr, r = v - gq * nr, gc = gq * 32 + lane;
+            if (w0s[gc] < 0) continue;
+            const unsigned long long cid = cellIds[gc];
+            const float ci = (float)ijk[gc * 3 + 0], cj = (float)ijk[gc * 3 + 1], ck = (float)ijk[gc * 3 + 2];
+            const float tThr = tThrS[gc];
             float dir[3], rayDx[3];
             gen_divq_ray_f32(a.rng, g, ray0 + r, cid, cid, dir, rayDx);
             // cell faces to the outer layer of the level along each axis, from the cell centre
@@ -1178,18 +1186,18 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
             if (twoPart) key = (min(15, (int)(e1 * scale1 + 0.5f)) << 5) | min(31, (int)(e2 * scale2 + 0.5f));
             else key = (min(63, (int)(e1 * scale1 + 0.5f)) << 3) | (px ? 1 : 0) | (py ? 2 : 0) | (pz ? 4 : 0);
             atomicAdd(&hist[key], 1);
-            __stcg(keys + r * 32 + lane, (unsigned short)key);
+            __stcg(keys + v * 32 + lane, (unsigned short)key);
           }
       }
       __syncthreads();
       // ---- phase 2: start of every bin in the sorted list (descending keys), then scatter
       {
         scan_bins();
-        if (cw0 >= 0)
-          for (int r = warp; r < nr; r += W) {
-            const int pos = atomicAdd(&hist[__ldcg(keys + r * 32 + lane)], 1);
-            __stcg(ids + pos, (unsigned short)(r * 32 + lane));
-          }
+        for (int v = warp; v < V; v += W) {
+          if (w0s[(G == 1 ? 0 : v / nr) * 32 + lane] < 0) continue;
+          const int pos = atomicAdd(&hist[__ldcg(keys + v * 32 + lane)], 1);
+          __stcg(ids + pos, (unsigned short)(v * 32 + lane));
+        }
       }
       __syncthreads();
       if constexpr (RESORT) {
@@ -1254,8 +1262,8 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
             const int p = chunk * 32 + lane;
             if (p < nList) {
               const int id = __ldcg(ids + p);
-              const int c = id & 31, r = id >> 5;
-              const unsigned long long cid = cellIds[c];
+              const int gq = G == 1 ? 0 : (id >> 5) / nr, r = (id >> 5) - gq * nr, gc = gq * 32 + (id & 31);
+              const unsigned long long cid = cellIds[gc];
               float dir[3], rayDx[3];
               gen_divq_ray_f32(a.rng, g, ray0 + r, cid, cid, dir, rayDx);
               BlkRay ry;
@@ -1264,7 +1272,7 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
               ry.sum = 0.0f; ry.q.nsteps = 0.0f;
               if (round == 0) {
                 if (1.0f > thr) {
-                  const int rw0 = w0s[c];
+                  const int rw0 = w0s[gc];
                   blk_ray_start(ry, blk, rw0, (unsigned)(rw0 & 7), sy8, sz8, nz<float, float>(dir[0]), nz<float, float>(dir[1]),
                                 nz<float, float>(dir[2]), rayDx[0], rayDx[1], rayDx[2], cx, cy, cz, ddx, ddy, ddz);
                   done = blk_ray_legs(ry, blk, ddx, ddy, ddz, sy8, sz8, thr, a.allowReflect != 0, skipZero, 1);
@@ -1297,14 +1305,14 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
           scan_bins();
           if (tid == 0) ctl[0] = 0;
           if (ctl[1] == 0) break;
-          if (cw0 >= 0)
-            for (int r = warp; r < nr; r += W) {
-              const unsigned short k2 = __ldcg(keys + r * 32 + lane);
-              if (k2 != 0xFFFFu) {
-                const int pos = atomicAdd(&hist[k2], 1);
-                __stcg(ids + pos, (unsigned short)(r * 32 + lane));
-              }
+          for (int v = warp; v < V; v += W) {
+            if (w0s[(G == 1 ? 0 : v / nr) * 32 + lane] < 0) continue;
+            const unsigned short k2 = __ldcg(keys + v * 32 + lane);
+            if (k2 != 0xFFFFu) {
+              const int pos = atomicAdd(&hist[k2], 1);
+              __stcg(ids + pos, (unsigned short)(v * 32 + lane));
             }
+          }
           __syncthreads();
         }
         __syncthreads();
@@ -1323,14 +1331,14 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
           const int p = chunk * 32 + lane;
           if (p < nList) {
             const int id = __ldcg(ids + p);
-            const int c = id & 31, r = id >> 5;
-            const int rw0 = w0s[c];
-            const unsigned long long cid = cellIds[c];
+            const int gq = G == 1 ? 0 : (id >> 5) / nr, r = (id >> 5) - gq * nr, gc = gq * 32 + (id & 31);
+            const int rw0 = w0s[gc];
+            const unsigned long long cid = cellIds[gc];
             float dir[3], rayDx[3];
             gen_divq_ray_f32(a.rng, g, ray0 + r, cid, cid, dir, rayDx);
             float sumI;
             if constexpr (ONION)
-              sumI = march_onion_blk<MAXL>(a.G, ob, ijk[c * 3 + 0] + g.lo[0], ijk[c * 3 + 1] + g.lo[1], ijk[c * 3 + 2] + g.lo[2], rw0,
+              sumI = march_onion_blk<MAXL>(a.G, ob, ijk[gc * 3 + 0] + g.lo[0], ijk[gc * 3 + 1] + g.lo[1], ijk[gc * 3 + 2] + g.lo[2], rw0,
                                             nz<float, float>(dir[0]), nz<float, float>(dir[1]), nz<float, float>(dir[2]), rayDx[0], rayDx[1],
                                             rayDx[2], (float)a.threshold, a.allowReflect != 0, skipZero, steps);
             else
@@ -1347,19 +1355,26 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
       __syncthreads();
       }
       // ---- phase 4: rays of a cell added in ray order (warp w: its contiguous share, then the shares in warp order)
-      {
+      if (G == 1) {
         const int per = (nr + W - 1) / W;
         double s = 0;
-        if (cw0 >= 0)
+        if (w0s[lane] >= 0)
           for (int r = warp * per; r < min(nr, (warp + 1) * per); ++r) s += (double)__ldcg(res + r * 32 + lane);
         part[warp * 32 + lane] = s;
         __syncthreads();
         if (warp == 0)
           for (int w = 0; w < W; ++w) acc += part[w * 32 + lane];
         __syncthreads();       // hist aliases part
+      } else {                 // few rays per cell: warp g adds the rays of its own tile
+        if (warp < G && w0s[warp * 32 + lane] >= 0) {
+          double s = 0;
+          for (int r = 0; r < nr; ++r) s += (double)__ldcg(res + (warp * nr + r) * 32 + lane);
+          acc += s;
+        }
+        __syncthreads();
       }
     }
-    if (warp == 0 && valid) {
+    if (warp < G && valid) {
       const long long q = (long long)(i - a.outLo[0]) +
                           (long long)a.outN[0] * ((long long)(j - a.outLo[1]) + (long long)a.outN[1] * (long long)(k - a.outLo[2]));
       if (flow) {
@@ -2598,7 +2613,7 @@ bool onion_blocked_default(const rmcrt_ctx* ctx, const TraceArgs& a, bool ML) {
   if (!ML || a.G.maxLevels < 2 || a.G.maxLevels > ONION_MAXL || !ctx->p.solveDivQ || ctx->p.marchPrecision != 0 || ctx->p.rayCoherence != 0 ||
       ctx->p.blockedMarch != 3 || ctx->p.genericMarch) return false;
   if (!ctx->p.isSeedRandom || ctx->p.fixedRandom || ctx->p.rayDirSampleAlgo != 0) return false;
-  if (ctx->p.nDivQRays < RMCRT_SORT_MIN_RAYS) return false;      // too few rays per tile to sort: the one-cell kernels
+  if (ctx->p.nDivQRays < 12) return false;      // too few rays per tile to sort one tile at a time (no tile groups here): the one-cell kernels
   for (int d = 0; d < 3; ++d)      // the patch lies inside the ROI (a fixed / dynamic ROI need not contain it)
     if (!(a.G.roiLo[d] <= a.patchLo[d] && a.patchLo[d] + a.patchN[d] <= a.G.roiHi[d])) return false;
   // a ray that leaves the box of level L through an interior cell must land INSIDE the box of level L - 1 (the march tests "marker cell",
@@ -2775,7 +2790,7 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
         unsigned char* base = static_cast<unsigned char*>(ctx->sortScratch.p);
         int* tileCounter = reinterpret_cast<int*>(base);
         CK(cudaMemsetAsync(tileCounter, 0, sizeof(int), st));
-        divq_sorted_kernel<RecT, true, false><<<nb, 256, 0, st>>>(a, bg, ob, RP, base + 256, tileCounter);
+        divq_sorted_kernel<RecT, true, false><<<nb, 256, sorted_cell_smem(1), st>>>(a, bg, ob, RP, 1, base + 256, tileCounter);
       }
     } else if (ML && std::is_same<Real, float>::value && !ctx->p.genericMarch && a.G.maxLevels == 2 && patchInRoi) {
       // 2-level Data Onion fast path: per-patch ROI copy with a marker shell, then the tuned leg loop on both levels
@@ -2848,9 +2863,16 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
         BlkGeom bg;
         int rc = ensure_blocked_level<RecT>(ctx, a.G.maxLevels - 1, bg, st);
         if (rc) return rc;
-        const int RP = std::min(a.nRays, ctx->p.refillLanes > 0 ? ctx->p.refillLanes : 256);      // rays per pass (A/B: refillLanes)
-        // persistent blocks (their scratch is per block), tiles handed out through a counter
-        const int nb = (int)std::min<long long>(a.nTiles, (long long)ctx->smCount * (ctx->p.maxBlocksPerSM > 0 ? ctx->p.maxBlocksPerSM : RMCRT_SORTED_BLOCKS));
+        // few rays per cell: G tiles of 32 cells are sorted and marched together, so that a block still has dozens of 32-ray chunks for
+        // its eight warps.  Measured at 128^3 (profiles/r02v40_few_rays.txt): it pays up to 16 rays per cell (3 / 5 / 10 rays: 4.1 / 4.3 /
+        // 4.5e11 steps/s against 1.3 / 2.1 / 3.6e11 with G = 1 and 3.2 / 3.5 / 3.6e11 unsorted); from 25 rays on one tile sorts better alone
+        int G = 1;
+        if (a.nRays <= 16) while (G < 8 && 2 * G * a.nRays <= 96) G *= 2;
+        // (rays, tile) pairs per lane and pass (A/B: refillLanes = rays of a cell per pass)
+        const int RP = G * std::min(a.nRays, ctx->p.refillLanes > 0 ? ctx->p.refillLanes : 256 / G);
+        // persistent blocks (their scratch is per block), tile groups handed out through a counter
+        const int nb = (int)std::min<long long>((a.nTiles + G - 1) / G,
+                                                (long long)ctx->smCount * (ctx->p.maxBlocksPerSM > 0 ? ctx->p.maxBlocksPerSM : RMCRT_SORTED_BLOCKS));
         const bool mayGoOn = a.allowReflect != 0;      // ... whether rays DO go on after a wall is known on the device only (level status)
         if (ctx->sortScratch.ensure((size_t)nb * sorted_scratch_bytes(RP, mayGoOn) + 256)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc sort scratch");
         unsigned char* base = static_cast<unsigned char*>(ctx->sortScratch.p);
@@ -2860,11 +2882,13 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
         CK(cudaMemsetAsync(tileCounter, 0, sizeof(int), st));
         OnionBlk none;
         memset(&none, 0, sizeof none);
-        divq_sorted_kernel<RecT, false, false><<<nb, 256, 0, st>>>(a2, bg, none, RP, base + 256, tileCounter);
+        if (G > 1) divq_sorted_kernel<RecT, false, false, true><<<nb, 256, sorted_cell_smem(G), st>>>(a2, bg, none, RP, G, base + 256, tileCounter);
+        else       divq_sorted_kernel<RecT, false, false, false><<<nb, 256, sorted_cell_smem(1), st>>>(a2, bg, none, RP, 1, base + 256, tileCounter);
         if (mayGoOn) {
           a2.gate = 2;
           CK(cudaMemsetAsync(tileCounter, 0, sizeof(int), st));
-          divq_sorted_kernel<RecT, false, true><<<nb, 256, 0, st>>>(a2, bg, none, RP, base + 256, tileCounter);
+          if (G > 1) divq_sorted_kernel<RecT, false, true, true><<<nb, 256, sorted_cell_smem(G), st>>>(a2, bg, none, RP, G, base + 256, tileCounter);
+          else       divq_sorted_kernel<RecT, false, true, false><<<nb, 256, sorted_cell_smem(1), st>>>(a2, bg, none, RP, 1, base + 256, tileCounter);
         }
       }
     } else if ((ctx->p.blockedMarch == 2 || ctx->p.blockedMarch == 3) && blocked_default(ctx, a, ML)) {
