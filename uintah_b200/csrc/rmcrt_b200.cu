@@ -39,6 +39,10 @@ using namespace rmcrt;
 namespace {
 
 constexpr int MAXL = 4;   // levels supported by the Data-Onion kernels (reference decks use 2-3)
+// cells of guard in front of a level in its blocked copy (one block: the speculative load past a wall stays inside).  3 cells, which
+// puts the interior of a level with one layer of extra cells -- and with it the origin tiles of divq_sorted_kernel -- on block
+// boundaries, measured 0.6 % SLOWER than 2 (profiles/r02v49)
+constexpr int BLK_PAD = 2;
 #ifndef RMCRT_SORT_MIN_RAYS
 // below this many rays per cell the default runs the unsorted kernel on the same blocked copy (nothing to sort); from here to 16 rays
 // divq_sorted_kernel sorts up to eight tiles together (launch_trace, profiles/r02v40_few_rays.txt)
@@ -94,6 +98,8 @@ struct TraceArgs {
   unsigned long long* counters;   // [0] divQ steps [1] flux steps [2] divQ cells [3] flux cells
   const unsigned* lstat;          // per-level device status words [MAXL][LSTAT_WORDS] (see finalize_kernel)
   int firstLevel;                 // levels [firstLevel, maxLevels) take part in this trace
+  int tcx, tcy, tcz;              // divq_sorted_kernel: compact tiles per patch axis (0: tiles = 32 consecutive cells)
+  int tsx, tsy, tsz;              // ... of tsx x tsy x tsz = 32 origin cells
   int recBytes;                   // sizeof(record)
   RoiBox roi;                     // Data-Onion fast path: shell-wrapped copy of the fine level's ROI (rec == nullptr: generic march)
   double maxRayLength;            // boundedRayLength ROI (RMCRTCommon.cc:680,684); +inf when unbounded
@@ -1111,9 +1117,16 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
       const long long tile = tile0 + warp;
       const long long t = tile * 32 + lane;
       valid = tile < a.nTiles && t < a.nCells;
+      if (a.tcx) {      // compact tiles: 8 x 2 x 2 cells, the rays of a tile share more sectors near their origin
+        const int tz_ = (int)(tile / ((long long)a.tcx * a.tcy)), ty_ = (int)((tile - (long long)tz_ * a.tcx * a.tcy) / a.tcx);
+        const int tx_ = (int)(tile - ((long long)tz_ * a.tcy + ty_) * a.tcx);
+        const int li = a.tsx * tx_ + lane % a.tsx, lj = a.tsy * ty_ + (lane / a.tsx) % a.tsy, lk = a.tsz * tz_ + lane / (a.tsx * a.tsy);
+        valid = tile < a.nTiles && li < a.patchN[0] && lj < a.patchN[1] && lk < a.patchN[2];
+        i = a.patchLo[0] + li; j = a.patchLo[1] + lj; k = a.patchLo[2] + lk;
+      }
       unsigned long long cellId = 0;
       if (valid) {
-        patch_cell(a, t, i, j, k);
+        if (!a.tcx) patch_cell(a, t, i, j, k);
         cellId = (unsigned long long)level_index(g, i, j, k);
         {      // (read once per cell: streaming, so that 8 B per cell of float records do not push the blocked copy out of the L2)
           const float2 v = __ldcs(reinterpret_cast<const float2*>(std::is_same<RecT, Rec4>::value ? g.recFull : g.rec) + cellId);
@@ -1822,8 +1835,8 @@ __global__ void blk_build_kernel(const RecT* __restrict__ recs, Box lb, uint32_t
     uint32_t w[8];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      // block-local coordinate 0 = cell lb.lo - 2
-      const int x = 2 * b0 + (c & 1) - 2, y = 2 * b1 + ((c >> 1) & 1) - 2, z = 2 * b2 + (c >> 2) - 2;
+      // block-local coordinate 0 = cell lb.lo - BLK_PAD
+      const int x = 2 * b0 + (c & 1) - BLK_PAD, y = 2 * b1 + ((c >> 1) & 1) - BLK_PAD, z = 2 * b2 + (c >> 2) - BLK_PAD;
       uint32_t v = 0x80000000u;                     // guard: a wall with abskg 0, sigmaT4 0
       if (x >= 0 && x < lb.n[0] && y >= 0 && y < lb.n[1] && z >= 0 && z < lb.n[2]) {
         const long long f = (long long)x + (long long)lb.n[0] * ((long long)y + (long long)lb.n[1] * (long long)z);
@@ -2592,7 +2605,7 @@ bool blocked_default(const rmcrt_ctx* ctx, const TraceArgs& a, bool ML, bool div
   if (a.maxRayLength < 1e300 || a.sigmaScat > 0) return false;                                        // the generic march
   const rmcrt_level_desc& d = ctx->lv[a.G.maxLevels - 1].d;
   long long nb = 1;
-  for (int k = 0; k < 3; ++k) nb *= (d.hi[k] - d.lo[k] + 4 + 1) / 2;
+  for (int k = 0; k < 3; ++k) nb *= (d.hi[k] - d.lo[k] + BLK_PAD + 2 + 1) / 2;
   return nb < (1LL << 28);      // 32-bit word index
 }
 
@@ -2632,12 +2645,22 @@ bool onion_blocked_default(const rmcrt_ctx* ctx, const TraceArgs& a, bool ML) {
   return true;
 }
 
+// Origin tiles of divq_sorted_kernel: 4 x 4 x 2 cells instead of 32 consecutive cells of a row.  The rays of a tile share sectors while
+// they are near their origin, and a compact tile has half the neighbourhood of a row of 32: 128^3 30.6 -> 27.8 ms, 256^3 536 -> 499 ms
+// (8 x 2 x 2: 28.0, 4 x 2 x 4: 27.8, 2 x 4 x 4: 27.9, 8 x 4 x 1: 28.4, 16 x 2 x 1: 29.1; profiles/r02v48).  Edge tiles of patches whose
+// sizes are not multiples of the shape have idle lanes.
+void compact_tiles(TraceArgs& a) {
+  a.tsx = 4; a.tsy = 4; a.tsz = 2;
+  a.tcx = (a.patchN[0] + a.tsx - 1) / a.tsx; a.tcy = (a.patchN[1] + a.tsy - 1) / a.tsy; a.tcz = (a.patchN[2] + a.tsz - 1) / a.tsz;
+  a.nTiles = (long long)a.tcx * a.tcy * a.tcz;
+}
+
 // blocked half-packed copy of level L (indep.cuh), rebuilt when the level changed since the last build (stream-ordered)
 template <class RecT>
 int ensure_blocked_level(rmcrt_ctx* ctx, int L, BlkGeom& bg, cudaStream_t st, bool persist = true) {
   LevelState& s = ctx->lv[L];
   int nb[3];
-  for (int d = 0; d < 3; ++d) nb[d] = (s.d.hi[d] - s.d.lo[d] + 4 + 1) / 2;        // cells [lo - 2, hi + 2) in 2-cell blocks
+  for (int d = 0; d < 3; ++d) nb[d] = (s.d.hi[d] - s.d.lo[d] + BLK_PAD + 2 + 1) / 2;        // cells [lo - BLK_PAD, hi + 2) in 2-cell blocks
   const size_t bytes = (size_t)nb[0] * nb[1] * nb[2] * 32;
   if ((long long)nb[0] * nb[1] * nb[2] >= (1LL << 28)) return fail(ctx, RMCRT_ERR_INVALID, "level too large for the blocked march");   // 32-bit word index
   if (bytes > s.blkCap) {
@@ -2659,7 +2682,7 @@ int ensure_blocked_level(rmcrt_ctx* ctx, int L, BlkGeom& bg, cudaStream_t st, bo
   if (persist) persist_in_l2(ctx, s.blk, bytes, st);
   bg.blk = static_cast<const uint32_t*>(s.blk);
   bg.bx = nb[0]; bg.bxy = nb[0] * nb[1];
-  for (int d = 0; d < 3; ++d) bg.lo[d] = s.d.lo[d] - 2;
+  for (int d = 0; d < 3; ++d) bg.lo[d] = s.d.lo[d] - BLK_PAD;
   return 0;
 }
 
@@ -2750,6 +2773,7 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
       // visit (ROI / region) wrapped in marker cells
       if constexpr (std::is_same<Real, float>::value && !std::is_same<RecT, Rec16>::value) {
         const int F = a.G.maxLevels - 1;
+        compact_tiles(a);
         OnionBlk ob;
         memset(&ob, 0, sizeof ob);
         size_t fineBytes = 0;
@@ -2863,6 +2887,7 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
         BlkGeom bg;
         int rc = ensure_blocked_level<RecT>(ctx, a.G.maxLevels - 1, bg, st);
         if (rc) return rc;
+        compact_tiles(a);
         // few rays per cell: G tiles of 32 cells are sorted and marched together, so that a block still has dozens of 32-ray chunks for
         // its eight warps.  Measured at 128^3 (profiles/r02v40_few_rays.txt): it pays up to 16 rays per cell (3 / 5 / 10 rays: 4.1 / 4.3 /
         // 4.5e11 steps/s against 1.3 / 2.1 / 3.6e11 with G = 1 and 3.2 / 3.5 / 3.6e11 unsorted); from 25 rays on one tile sorts better alone
