@@ -112,7 +112,7 @@ typedef struct rmcrt_params {
                                   trace the SAME rays (Philox keyed on (cell, ray, timestep)):
                                   3 (DEFAULT): divq_sorted_kernel -- the march runs on a blocked half-packed copy of the level (2 x 2 x 2 cells
                                      per 32-B sector, fp16 abskg / sigmaT4 like recordKind 2, rebuilt when the level changes) and the rays of
-                                     a 32-cell tile are sorted by their expected number of steps, so the 32 lanes of a warp end together
+                                     a 32-cell tile (4 x 4 x 2 cells) are sorted by their expected number of steps, so the 32 lanes of a warp end together
                                      (30.6 instead of 13.4 active lanes) and the second visit to a sector is an L1 hit; per cell the rays are
                                      added in ray order in FP64, so divQ does not depend on the sort, the launch shape or the patch layout.
                                      (With 3 ... 16 rays per cell up to eight tiles are sorted together; below 3 the default runs kernel 2.)

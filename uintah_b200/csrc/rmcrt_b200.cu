@@ -983,7 +983,7 @@ __global__ void __launch_bounds__(256, RMCRT_FAST_MIN_BLOCKS) divq_blk_kernel(co
 // blockedMarch = 3 (the library default): LENGTH-SORTED independent rays on the blocked copy.  Same rays as divq_kernel / divq_blk_kernel
 // (Philox keyed on (cell, ray, timestep)), but the lanes of a warp no longer trace ray r of 32 neighbouring cells -- whose lengths differ
 // by the full range (13.4 of 32 lanes active, ncu) -- they trace 32 rays of the tile that are expected to END TOGETHER:
-//   0. persistent blocks of 8 warps take tiles of 32 x-consecutive origin cells off a counter;
+//   0. persistent blocks of 8 warps take tiles of 4 x 4 x 2 origin cells off a counter (compact_tiles);
 //   1. every (cell, ray) of the tile's 32 cells x RP rays gets a 9-bit key from the number of DDA steps to the far side of the level along
 //      its direction (closed form from the direction and the cell index, ~15 FP instructions; walls inside the domain and the intensity
 //      threshold make it an estimate -- correctness never depends on it);
