@@ -287,7 +287,7 @@ class SingleLevelSolve:
             r = "Rec4" if half else "Rec8"
             self.kernel_name = {1: f"divq_indep_kernel<{r}> (independent rays, blocked half-packed records, per-lane refill)",
                                 2: f"divq_blk_kernel<{r}> (independent rays, blocked half-packed records, one cell per lane)",
-                                3: f"divq_sorted_kernel<{r}> (independent rays sorted by length per 32-cell tile, blocked half-packed records)"}[self.blocked]
+                                3: f"divq_sorted_kernel<{r}> (independent rays sorted by length per 4 x 4 x 2-cell tile, blocked half-packed records)"}[self.blocked]
             self.kernels_per_step += 1          # blk_build_kernel: the blocked copy is rebuilt after every re-pack
             if self.blocked == 3 and int(g.params.allowReflect):
                 self.kernels_per_step += 1      # divq_sorted_kernel<RESORT>: launched behind the plain instantiation, the level's status words pick one

@@ -154,7 +154,7 @@ def test_sorted_kernel_is_independent_of_the_launch_shape(gpu_lib, po):
     for rp in (5, 16, 37):
         d1, v1, n1, c1 = solve(lv, None, refillLanes=rp, **kw)
         assert n0 == n1 and c0 == c1 and np.array_equal(d0, d1) and np.array_equal(v0, v1), rp
-    # two patches (tiles of 32 cells start elsewhere): every cell keeps its rays and their order
+    # two patches (the 4 x 4 x 2-cell tiles start elsewhere): every cell keeps its rays and their order
     g = make(**kw)
     g.upload_level(0, lv)
     a = g.trace_divq(0, patch_lo=(0, 0, 0), patch_hi=(30, 30, 13), timestep=6)["divQ"]
