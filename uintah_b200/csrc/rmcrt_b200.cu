@@ -2808,7 +2808,7 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
         BlkGeom bg;      // the box of the origin cells
         bg.blk = ob.blk[F]; bg.bx = ob.bx[F]; bg.bxy = ob.bxy[F];
         for (int d = 0; d < 3; ++d) bg.lo[d] = ob.lo[F][d];
-        const int RP = std::min(a.nRays, ctx->p.refillLanes > 0 ? ctx->p.refillLanes : 256);
+        const int RP = std::min(a.nRays, ctx->p.refillLanes > 0 ? std::min(ctx->p.refillLanes, 2048) : 256);      // (ray ids are 16 bits: RP * 32 <= 65536)
         const int nb = (int)std::min<long long>(a.nTiles, (long long)ctx->smCount * (ctx->p.maxBlocksPerSM > 0 ? ctx->p.maxBlocksPerSM : RMCRT_SORTED_BLOCKS));
         if (ctx->sortScratch.ensure((size_t)nb * sorted_scratch_bytes(RP, false) + 256)) return fail(ctx, RMCRT_ERR_CUDA, "cudaMalloc sort scratch");
         unsigned char* base = static_cast<unsigned char*>(ctx->sortScratch.p);
@@ -2894,7 +2894,7 @@ int launch_trace(rmcrt_ctx* ctx, TraceArgs& a, bool ML, cudaStream_t st) {
         int G = 1;
         if (a.nRays <= 16) while (G < 8 && 2 * G * a.nRays <= 96) G *= 2;
         // (rays, tile) pairs per lane and pass (A/B: refillLanes = rays of a cell per pass)
-        const int RP = G * std::min(a.nRays, ctx->p.refillLanes > 0 ? ctx->p.refillLanes : 256 / G);
+        const int RP = G * std::min(a.nRays, ctx->p.refillLanes > 0 ? std::min(ctx->p.refillLanes, 2048 / G) : 256 / G);      // (16-bit ray ids)
         // persistent blocks (their scratch is per block), tile groups handed out through a counter
         const int nb = (int)std::min<long long>((a.nTiles + G - 1) / G,
                                                 (long long)ctx->smCount * (ctx->p.maxBlocksPerSM > 0 ? ctx->p.maxBlocksPerSM : RMCRT_SORTED_BLOCKS));
