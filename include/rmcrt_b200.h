@@ -122,7 +122,7 @@ typedef struct rmcrt_params {
                                   Levels too large for a 32-bit blocked index, and every other mode (FP64 march, regression generators,
                                   Latin hyper cube, scattering, bounded rays, Data Onion), march the level's own records. */
   int32_t  refillLanes;        /* implementation knob.  blockedMarch 1: lanes of a warp that must wait for a new ray before ray set-up runs
-                                  (0 = default 8).  blockedMarch 3: rays of a cell sorted per pass (0 = default min(nDivQRays, 256)). */
+                                  (0 = default 8).  blockedMarch 3: rays of a cell sorted per pass (0 = default min(nDivQRays, 256); at most 2048). */
   int32_t  coarsenExtraCells;  /* <coarsenExtraCells> (Ray.cc:256,315; default false): rmcrt_coarsen_level_device also fills the coarse level's
                                   extra cells on the domain faces with the tangential average of the fine level's extra cells (Ray::coarsen_Q,
                                   Ray.cc:2148-2245) instead of leaving them to rmcrt_set_level_extra_cells (setBoundaryConditions) */
