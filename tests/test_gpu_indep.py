@@ -163,6 +163,17 @@ def test_sorted_kernel_is_independent_of_the_launch_shape(gpu_lib, po):
     assert np.array_equal(a + b, d0)
 
 
+def test_sorted_kernel_many_rays_per_pass(gpu_lib, po):
+    """ray ids of a pass are 16 bits (32 cells x at most 2048 rays): a larger refillLanes is clamped, not wrapped -- thousands of rays per
+    cell give bit-identical divQ for any pass length"""
+    lv = po.burns_christon(10, dtype=np.float32)
+    kw = dict(nDivQRays=2500, threshold=0.05, seed=8, blockedMarch=3)
+    d0, v0, n0, c0 = solve(lv, None, **kw)
+    for rp in (2048, 2500, 100000):
+        d1, v1, n1, c1 = solve(lv, None, refillLanes=rp, **kw)
+        assert n0 == n1 and c0 == c1 and np.array_equal(d0, d1) and np.array_equal(v0, v1), rp
+
+
 @pytest.mark.parametrize("case", ["bc", "bc_walls", "plates_mirrors"])
 def test_sorted_data_onion_matches_roi_copy_path(gpu_lib, po, case):
     """2-level Data Onion, library default (divq_sorted_kernel<ONION>: blocked copies of the patch's ROI and of level 0, march_onion2_blk)
