@@ -996,6 +996,9 @@ __global__ void __launch_bounds__(256, RMCRT_FAST_MIN_BLOCKS) divq_blk_kernel(co
 #ifndef RMCRT_SORTED_BLOCKS
 #define RMCRT_SORTED_BLOCKS 4
 #endif
+#ifndef RMCRT_KEY_VARIANT
+#define RMCRT_KEY_VARIANT 2
+#endif
 #ifndef RMCRT_RESORT_ROUNDS
 #define RMCRT_RESORT_ROUNDS 4      // RESORT: rounds of one leg each before whatever is left runs to its end
 #endif
@@ -1057,8 +1060,10 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
   const unsigned mirrors = (a.allowReflect && ls[3] != 0u && ls[6] != 0u) ? (~ls[7] & 63u) : 0u;
   const float logThr = a.threshold > 0 ? (float)log(1.0 / a.threshold) : 1e30f;
   // Sort key.  The lanes of a warp wait for each other at the end of every LEG (a wall, the ROI exit), so rays that are to run together
-  // must agree leg by leg, not just in total.  Single level: the key is that of the FIRST leg, (length: 6 bits | octant of the direction:
-  // 3 bits) -- the 32 rays of a chunk also head the same way (+0.8 % at 128^3 over a 9-bit length, profiles/r02v22) -- and rays that go on
+  // must agree leg by leg, not just in total.  Single level: the key is that of the FIRST leg, (z-hemisphere of the direction: 1 bit |
+  // length: 6 bits | x and y signs: 2 bits) -- the 32 rays of a chunk also head the same way, and so do the chunks the warps of a block
+  // march at one time, so that more of their sectors near the origin are shared (+0.8 % at 128^3 over a 9-bit length with the octant in
+  // the low bits, profiles/r02v22; another +1.1 % with the hemisphere on top, profiles/r02v57_sort_key.txt) -- and rays that go on
   // are sorted again where they stand (RESORT).  Data Onion: (fine steps inside the ROI: 4 bits | coarse steps: 5 bits) -- a chunk of 32
   // out of a tile's ~3200 rays then spans about a sixteenth of the range of the first part and a sixth of the second.
   // goOn: bounces the estimate follows for a ray that goes on after a wall; 0 = rays end at their first wall
@@ -1197,7 +1202,13 @@ __global__ void __launch_bounds__(256, RMCRT_SORTED_BLOCKS) divq_sorted_kernel(c
             }
             int key;
             if (twoPart) key = (min(15, (int)(e1 * scale1 + 0.5f)) << 5) | min(31, (int)(e2 * scale2 + 0.5f));
+#if RMCRT_KEY_VARIANT == 1      // A/B: octant-major (the chunks a block marches at one time head the same way)
+            else key = (((px ? 1 : 0) | (py ? 2 : 0) | (pz ? 4 : 0)) << 6) | min(63, (int)(e1 * scale1 + 0.5f));
+#elif RMCRT_KEY_VARIANT == 2    // shipped: hemisphere-major
+            else key = ((pz ? 1 : 0) << 8) | (min(63, (int)(e1 * scale1 + 0.5f)) << 2) | (px ? 1 : 0) | (py ? 2 : 0);
+#else                           // A/B: (length | octant)
             else key = (min(63, (int)(e1 * scale1 + 0.5f)) << 3) | (px ? 1 : 0) | (py ? 2 : 0) | (pz ? 4 : 0);
+#endif
             atomicAdd(&hist[key], 1);
             __stcg(keys + v * 32 + lane, (unsigned short)key);
           }
